@@ -1,0 +1,327 @@
+// capi.cu -- extern "C" boundary declared in include/athenak_b200.h.
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/athenak_b200.h"
+#include "halo.h"
+#include "mhd_device.cuh"
+#include "mhd_kernels.h"
+
+namespace {
+
+struct Handle {
+  ak_mhd_cfg cfg;
+  akb::Geom g;
+  akb::EosParams eos;
+  int *d_counters = nullptr;                // 3 ints
+  unsigned long long *d_dtmin = nullptr;    // 3 ordered-bit doubles
+  std::string err;
+};
+
+thread_local std::string g_err;  // errors raised before a handle exists
+
+int fail(Handle *h, const std::string &msg) {
+  if (h) h->err = msg; else g_err = msg;
+  return 1;
+}
+int cuda_fail(Handle *h, const char *where, cudaError_t e) {
+  return fail(h, std::string(where) + ": " + cudaGetErrorString(e));
+}
+
+akb::Arrays to_arrays(const ak_mhd_arrays *a) {
+  akb::Arrays r;
+  static_assert(sizeof(akb::Arrays) == sizeof(ak_mhd_arrays), "ak_mhd_arrays / akb::Arrays mismatch");
+  std::memcpy(&r, a, sizeof(r));
+  return r;
+}
+
+int check_cfg(const ak_mhd_cfg *c, std::string &why) {
+  if (!c) { why = "null cfg"; return 1; }
+  if (c->nmb < 1) { why = "nmb < 1"; return 1; }
+  if (c->nx1 < 2 || c->nx2 < 2 || c->nx3 < 2) { why = "only 3-D MeshBlocks (nx1,nx2,nx3 > 1) are supported"; return 1; }
+  if (c->recon < AK_RECON_DC || c->recon > AK_RECON_WENOZ) { why = "unknown reconstruction method"; return 1; }
+  if (c->rsolver < AK_RSOLVER_LLF || c->rsolver > AK_RSOLVER_HLLD) { why = "unknown Riemann solver"; return 1; }
+  // reference src/mhd/mhd.cpp:217-228: 5-point stencils need nghost >= 3, PLM/DC need 2
+  const int need = (c->recon >= AK_RECON_PPM4) ? 3 : 2;
+  if (c->ng < need) { why = "nghost too small for the reconstruction stencil"; return 1; }
+  if (!(c->gamma > 1.0)) { why = "gamma must exceed 1"; return 1; }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *ak_last_error(void *handle) {
+  Handle *h = static_cast<Handle *>(handle);
+  return h ? h->err.c_str() : g_err.c_str();
+}
+
+int ak_mhd_create(const ak_mhd_cfg *cfg, void **handle) {
+  std::string why;
+  if (!handle) return fail(nullptr, "ak_mhd_create: null handle pointer");
+  *handle = nullptr;
+  if (check_cfg(cfg, why)) return fail(nullptr, "ak_mhd_create: " + why);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, std::string("ak_mhd_create: no CUDA device (this engine has no CPU path): ") + cudaGetErrorString(e));
+  Handle *h = new Handle();
+  h->cfg = *cfg;
+  akb::Geom &g = h->g;
+  g.nmb = cfg->nmb; g.ng = cfg->ng; g.nx1 = cfg->nx1; g.nx2 = cfg->nx2; g.nx3 = cfg->nx3;
+  g.n1 = cfg->nx1 + 2 * cfg->ng; g.n2 = cfg->nx2 + 2 * cfg->ng; g.n3 = cfg->nx3 + 2 * cfg->ng;
+  g.is = cfg->ng; g.ie = g.is + cfg->nx1 - 1;   // reference src/mesh/mesh.cpp:285-333
+  g.js = cfg->ng; g.je = g.js + cfg->nx2 - 1;
+  g.ks = cfg->ng; g.ke = g.ks + cfg->nx3 - 1;
+  g.cc = (long)g.n3 * g.n2 * g.n1;
+  g.f1 = (long)g.n3 * g.n2 * (g.n1 + 1); g.f2 = (long)g.n3 * (g.n2 + 1) * g.n1; g.f3 = (long)(g.n3 + 1) * g.n2 * g.n1;
+  g.e1 = (long)(g.n3 + 1) * (g.n2 + 1) * g.n1; g.e2 = (long)(g.n3 + 1) * g.n2 * (g.n1 + 1); g.e3 = (long)g.n3 * (g.n2 + 1) * (g.n1 + 1);
+  h->eos = akb::EosParams{cfg->gamma, cfg->dfloor, cfg->pfloor, cfg->tfloor, cfg->sfloor, cfg->sigma_max};
+  if ((e = cudaMalloc(&h->d_counters, 3 * sizeof(int))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_dtmin, 3 * sizeof(unsigned long long))) != cudaSuccess) {
+    int rc = cuda_fail(nullptr, "ak_mhd_create", e);
+    delete h;
+    return rc;
+  }
+  *handle = h;
+  return 0;
+}
+
+int ak_mhd_destroy(void *handle) {
+  Handle *h = static_cast<Handle *>(handle);
+  if (!h) return 0;
+  cudaFree(h->d_counters);
+  cudaFree(h->d_dtmin);
+  delete h;
+  return 0;
+}
+
+#define AK_PROLOGUE(name)                                          \
+  Handle *h = static_cast<Handle *>(handle);                       \
+  if (!h) return fail(nullptr, name ": null handle");              \
+  if (!a) return fail(h, name ": null arrays");                    \
+  cudaStream_t st = static_cast<cudaStream_t>(s);                  \
+  akb::Arrays A = to_arrays(a);                                    \
+  cudaError_t e = cudaSuccess; (void)e; (void)st; (void)A;
+
+int ak_mhd_copy_cons(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_copy_cons")
+  const akb::Geom &g = h->g;
+  if ((e = akb::launch_copy(A.u0, A.u1, 5L * g.nmb * g.cc, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_copy_cons", e);
+  if ((e = akb::launch_copy(A.b0x1f, A.b1x1f, g.nmb * g.f1, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_copy_cons", e);
+  if ((e = akb::launch_copy(A.b0x2f, A.b1x2f, g.nmb * g.f2, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_copy_cons", e);
+  if ((e = akb::launch_copy(A.b0x3f, A.b1x3f, g.nmb * g.f3, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_copy_cons", e);
+  return 0;
+}
+
+int ak_mhd_fluxes(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_fluxes")
+  if ((e = akb::launch_fluxes(h->cfg.recon, h->cfg.rsolver, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_fluxes", e);
+  return 0;
+}
+
+int ak_mhd_rk_update(void *handle, const ak_mhd_arrays *a, double gam0, double gam1, double beta_dt, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_rk_update")
+  if ((e = akb::launch_update_ct(h->g, A, true, false, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_rk_update", e);
+  return 0;
+}
+
+int ak_mhd_corner_e(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_corner_e")
+  if ((e = akb::launch_corner_e(h->g, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_corner_e", e);
+  return 0;
+}
+
+int ak_mhd_ct(void *handle, const ak_mhd_arrays *a, double gam0, double gam1, double beta_dt, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_ct")
+  if ((e = akb::launch_update_ct(h->g, A, false, true, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_ct", e);
+  return 0;
+}
+
+static int c2p_impl(Handle *h, const akb::Arrays &A, int il, int iu, int jl, int ju, int kl, int ku, int *nfloor,
+                    double *dt3, cudaStream_t st, const char *name) {
+  const akb::Geom &g = h->g;
+  if (il < 0 || jl < 0 || kl < 0 || iu >= g.n1 || ju >= g.n2 || ku >= g.n3 || il > iu || jl > ju || kl > ku)
+    return fail(h, std::string(name) + ": cell box outside the array");
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(h->d_counters, 0, 3 * sizeof(int), st)) != cudaSuccess) return cuda_fail(h, name, e);
+  if (dt3) {
+    const double ident = (double)FLT_MAX;   // reference src/mhd/mhd_newdt.cpp:40-42
+    unsigned long long bits[3];
+    for (int q = 0; q < 3; ++q) std::memcpy(&bits[q], &ident, 8);
+    if ((e = cudaMemcpyAsync(h->d_dtmin, bits, sizeof(bits), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(h, name, e);
+  }
+  if ((e = akb::launch_cons2prim(g, h->eos, A, il, iu, jl, ju, kl, ku, h->d_counters, dt3 != nullptr, h->d_dtmin, st)) != cudaSuccess)
+    return cuda_fail(h, name, e);
+  if (nfloor) {
+    if ((e = cudaMemcpyAsync(nfloor, h->d_counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, name, e);
+  }
+  if (dt3) {
+    if ((e = cudaMemcpyAsync(dt3, h->d_dtmin, 3 * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, name, e);
+  }
+  if (nfloor || dt3) {
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(h, name, e);
+  }
+  return 0;
+}
+
+int ak_mhd_cons2prim(void *handle, const ak_mhd_arrays *a, int il, int iu, int jl, int ju, int kl, int ku,
+                     int *nfloor, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_cons2prim")
+  return c2p_impl(h, A, il, iu, jl, ju, kl, ku, nfloor, nullptr, st, "ak_mhd_cons2prim");
+}
+
+int ak_mhd_cons2prim_newdt(void *handle, const ak_mhd_arrays *a, int *nfloor, double *dt3, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_cons2prim_newdt")
+  if (!dt3) return fail(h, "ak_mhd_cons2prim_newdt: null dt3");
+  return c2p_impl(h, A, 0, h->g.n1 - 1, 0, h->g.n2 - 1, 0, h->g.n3 - 1, nfloor, dt3, st, "ak_mhd_cons2prim_newdt");
+}
+
+int ak_mhd_new_dt(void *handle, const ak_mhd_arrays *a, double *dt3, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_new_dt")
+  if (!dt3) return fail(h, "ak_mhd_new_dt: null dt3");
+  const double ident = (double)FLT_MAX;
+  unsigned long long bits[3];
+  for (int q = 0; q < 3; ++q) std::memcpy(&bits[q], &ident, 8);
+  if ((e = cudaMemcpyAsync(h->d_dtmin, bits, sizeof(bits), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_new_dt", e);
+  if ((e = akb::launch_newdt(h->g, h->eos, A, h->d_dtmin, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_new_dt", e);
+  if ((e = cudaMemcpyAsync(dt3, h->d_dtmin, 3 * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_new_dt", e);
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_new_dt", e);
+  return 0;
+}
+
+int ak_mhd_stage_fused(void *handle, const ak_mhd_arrays *a, int stage, double gam0, double gam1, double beta_dt,
+                       ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_stage_fused")
+  if (stage == 1) {
+    int rc = ak_mhd_copy_cons(handle, a, s);
+    if (rc) return rc;
+  }
+  if ((e = akb::launch_fluxes(h->cfg.recon, h->cfg.rsolver, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_fused", e);
+  if ((e = akb::launch_corner_e(h->g, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_fused", e);
+  if ((e = akb::launch_update_ct(h->g, A, true, true, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_fused", e);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// halo
+
+int ak_halo_create(const ak_mhd_cfg *cfg, const int *nghbr, int my_rank, int gids_start, void **plan) {
+  std::string why;
+  if (!plan) return fail(nullptr, "ak_halo_create: null plan pointer");
+  *plan = nullptr;
+  if (check_cfg(cfg, why)) return fail(nullptr, "ak_halo_create: " + why);
+  if (!nghbr) return fail(nullptr, "ak_halo_create: null neighbour table");
+  akb::HaloPlan *P = akb::halo_build(*cfg, nghbr, my_rank, gids_start, why);
+  if (!P) return fail(nullptr, "ak_halo_create: " + why);
+  *plan = P;
+  return 0;
+}
+
+// Host-side introspection of the resolved copy plan (no device needed): used by the CPU tests
+// of the partition/exchange logic and by hosts that want to drive their own transport.
+// kind: 0 local_cc, 1 local_fc, 2 pack_cc, 3 unpack_cc, 4 pack_fc, 5 unpack_fc (ipeer ignored
+// for 0,1).  out: [max][13] longs = m, src_m, comp, lo[3], hi[3], shift[3], boff.
+int ak_halo_descs(void *plan, int kind, int ipeer, long *out, int max) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P) return -1;
+  const std::vector<akb::HaloDesc> *v = nullptr;
+  if (kind == 0) v = &P->local_cc;
+  else if (kind == 1) v = &P->local_fc;
+  else {
+    if (ipeer < 0 || ipeer >= (int)P->peers.size()) return -1;
+    akb::HaloPeer &p = P->peers[ipeer];
+    v = kind == 2 ? &p.pack_cc : kind == 3 ? &p.unpack_cc : kind == 4 ? &p.pack_fc : kind == 5 ? &p.unpack_fc : nullptr;
+  }
+  if (!v) return -1;
+  const int n = (int)v->size();
+  for (int q = 0; q < n && q < max && out; ++q) {
+    const akb::HaloDesc &d = (*v)[q];
+    long *o = out + (long)q * 13;
+    o[0] = d.m; o[1] = d.src_m; o[2] = d.comp;
+    for (int a = 0; a < 3; ++a) { o[3 + a] = d.lo[a]; o[6 + a] = d.hi[a]; o[9 + a] = d.shift[a]; }
+    o[12] = d.boff;
+  }
+  return n;
+}
+
+int ak_halo_destroy(void *plan) {
+  akb::halo_free(static_cast<akb::HaloPlan *>(plan));
+  return 0;
+}
+
+int ak_halo_npeers(void *plan) { return plan ? (int)static_cast<akb::HaloPlan *>(plan)->peers.size() : 0; }
+
+int ak_halo_peer(void *plan, int ipeer, int *rank, long *cc_count_per_var, long *fc_count) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P || ipeer < 0 || ipeer >= (int)P->peers.size()) return fail(nullptr, "ak_halo_peer: bad peer index");
+  if (rank) *rank = P->peers[ipeer].rank;
+  if (cc_count_per_var) *cc_count_per_var = P->peers[ipeer].cc_count;
+  if (fc_count) *fc_count = P->peers[ipeer].fc_count;
+  return 0;
+}
+
+static int halo_ready(akb::HaloPlan *P, const char *where) {
+  cudaError_t e = akb::halo_ensure_uploaded(P);
+  if (e == cudaSuccess) return 0;
+  P->err = std::string(where) + ": " + cudaGetErrorString(e);
+  g_err = P->err;
+  return 1;
+}
+
+static int halo_rc(akb::HaloPlan *P, const char *where, cudaError_t e) {
+  if (e == cudaSuccess) return 0;
+  P->err = std::string(where) + ": " + cudaGetErrorString(e);
+  g_err = P->err;
+  return 1;
+}
+
+int ak_halo_local_cc(void *plan, double *a, int nvar, ak_stream_t s) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P || !a) return fail(nullptr, "ak_halo_local_cc: null argument");
+  if (halo_ready(P, "ak_halo_local_cc")) return 1;
+  akb::HaloArrays A = akb::halo_arrays_cc(P->cfg, a, nvar);
+  const long cc = A.bstride[0] / nvar;
+  return halo_rc(P, "ak_halo_local_cc", akb::halo_launch(P->local_cc, P->d_local_cc, A, nvar, cc, nullptr, akb::HALO_LOCAL, (cudaStream_t)s));
+}
+
+int ak_halo_local_fc(void *plan, double *x1f, double *x2f, double *x3f, ak_stream_t s) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P || !x1f || !x2f || !x3f) return fail(nullptr, "ak_halo_local_fc: null argument");
+  if (halo_ready(P, "ak_halo_local_fc")) return 1;
+  akb::HaloArrays A = akb::halo_arrays_fc(P->cfg, x1f, x2f, x3f);
+  return halo_rc(P, "ak_halo_local_fc", akb::halo_launch(P->local_fc, P->d_local_fc, A, 1, 0, nullptr, akb::HALO_LOCAL, (cudaStream_t)s));
+}
+
+#define AK_PEER(name)                                                                         \
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);                                      \
+  if (!P || ipeer < 0 || ipeer >= (int)P->peers.size()) return fail(nullptr, name ": bad plan or peer index"); \
+  if (halo_ready(P, name)) return 1;                                                          \
+  akb::HaloPeer &peer = P->peers[ipeer];
+
+int ak_halo_pack_cc(void *plan, const double *a, int nvar, int ipeer, double *sendbuf, ak_stream_t s) {
+  AK_PEER("ak_halo_pack_cc")
+  akb::HaloArrays A = akb::halo_arrays_cc(P->cfg, const_cast<double *>(a), nvar);
+  return halo_rc(P, "ak_halo_pack_cc", akb::halo_launch(peer.pack_cc, peer.d_pack_cc, A, nvar, A.bstride[0] / nvar, sendbuf, akb::HALO_PACK, (cudaStream_t)s));
+}
+int ak_halo_unpack_cc(void *plan, double *a, int nvar, int ipeer, const double *recvbuf, ak_stream_t s) {
+  AK_PEER("ak_halo_unpack_cc")
+  akb::HaloArrays A = akb::halo_arrays_cc(P->cfg, a, nvar);
+  return halo_rc(P, "ak_halo_unpack_cc", akb::halo_launch(peer.unpack_cc, peer.d_unpack_cc, A, nvar, A.bstride[0] / nvar, const_cast<double *>(recvbuf), akb::HALO_UNPACK, (cudaStream_t)s));
+}
+int ak_halo_pack_fc(void *plan, const double *x1f, const double *x2f, const double *x3f, int ipeer, double *sendbuf, ak_stream_t s) {
+  AK_PEER("ak_halo_pack_fc")
+  akb::HaloArrays A = akb::halo_arrays_fc(P->cfg, const_cast<double *>(x1f), const_cast<double *>(x2f), const_cast<double *>(x3f));
+  return halo_rc(P, "ak_halo_pack_fc", akb::halo_launch(peer.pack_fc, peer.d_pack_fc, A, 1, 0, sendbuf, akb::HALO_PACK, (cudaStream_t)s));
+}
+int ak_halo_unpack_fc(void *plan, double *x1f, double *x2f, double *x3f, int ipeer, const double *recvbuf, ak_stream_t s) {
+  AK_PEER("ak_halo_unpack_fc")
+  akb::HaloArrays A = akb::halo_arrays_fc(P->cfg, x1f, x2f, x3f);
+  return halo_rc(P, "ak_halo_unpack_fc", akb::halo_launch(peer.unpack_fc, peer.d_unpack_fc, A, 1, 0, const_cast<double *>(recvbuf), akb::HALO_UNPACK, (cudaStream_t)s));
+}
+
+}  // extern "C"

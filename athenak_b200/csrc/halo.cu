@@ -1,0 +1,250 @@
+// halo.cu -- same-level ghost-zone exchange for cell-centred (CC) and face-centred (FC) data.
+//
+// Reference: src/bvals/bvals_cc.cpp:42-447, bvals_fc.cpp:63-436 and the index tables in
+// buffs_cc.cpp:28-196, buffs_fc.cpp:29-99,388-456.  The reference packs every neighbour slab
+// into a per-slot buffer and unpacks it in a second kernel, even for neighbours on the same
+// rank.  Here the plan is resolved once on the host into flat copy descriptors:
+//   * same-rank neighbours: ONE gather kernel writes ghost zones straight from the
+//     neighbour's active zones (src index = dst index - offset*nx), no buffer round trip;
+//   * off-rank neighbours: pack into / unpack from one contiguous message per peer rank
+//     (entry layout as the reference's rank-packed buffers, bvals_cc.cpp:127,
+//     bvals_fc.cpp:150-156), moved by NCCL send/recv or peer stores.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/athenak_b200.h"
+#include "halo.h"
+
+namespace akb {
+
+// src/mesh/nghbr_index.hpp:28-54
+int neighbor_index(int ix, int iy, int iz, int n1, int n2) {
+  if ((std::abs(ix) + std::abs(iy) + std::abs(iz)) == 0) return -1;
+  if (std::abs(ix * iy * iz) > 1) return -1;
+  if (iz == 0) {
+    if (ix * iy == 0) return std::abs(ix) * 2 * (ix + 1) + std::abs(iy) * 2 * (iy + 5) + (n1 + 2 * n2);
+    return 16 + (ix + 1) + 2 * (iy + 1) + n1;
+  }
+  if (ix * iy == 0) return 24 + std::abs(ix) * (ix + 9) + std::abs(iy) * (iy + 17) + 2 * (iz + 1) + (n1 + 2 * n2);
+  return 48 + (ix + 1) / 2 + (iy + 1) + 2 * (iz + 1);
+}
+
+struct Box { int lo[3], hi[3]; long count() const { return (long)(hi[0]-lo[0]+1)*(hi[1]-lo[1]+1)*(hi[2]-lo[2]+1); } };
+
+// comp = -1: cell-centred; 0,1,2: x1f,x2f,x3f.  d: 0=i,1=j,2=k.  Same-level boxes.
+static Box halo_box(const ak_mhd_cfg &c, int comp, const int o[3], bool send) {
+  const int ng = c.ng, ng1 = ng - 1;
+  const int s[3] = {ng, ng, ng};
+  const int e[3] = {ng + c.nx1 - 1, ng + c.nx2 - 1, ng + c.nx3 - 1};
+  Box b;
+  for (int d = 0; d < 3; ++d) {
+    const int f = (comp == d) ? 1 : 0;  // this component is staggered along d
+    if (send) {                          // buffs_cc.cpp:36-46, buffs_fc.cpp:44-83
+      if (o[d] == 0) { b.lo[d] = s[d]; b.hi[d] = e[d] + f; }
+      else if (o[d] > 0) { b.lo[d] = e[d] - ng1; b.hi[d] = e[d]; }
+      else { b.lo[d] = s[d] + f; b.hi[d] = s[d] + ng1 + f; }
+    } else {                             // buffs_cc.cpp:170-196, buffs_fc.cpp:402-441
+      if (o[d] == 0) { b.lo[d] = s[d]; b.hi[d] = e[d] + f; }
+      else if (o[d] > 0) { b.lo[d] = e[d] + 1 + f; b.hi[d] = e[d] + ng + f; }
+      else { b.lo[d] = s[d] - ng; b.hi[d] = s[d] - 1; }
+    }
+  }
+  return b;
+}
+
+__global__ void __launch_bounds__(256)
+halo_copy_kernel(const HaloDesc *__restrict__ descs, HaloArrays A, int nvar, long varstride,
+                 double *__restrict__ buf, int mode) {
+  const HaloDesc d = descs[blockIdx.y];
+  const int ni = d.hi[0] - d.lo[0] + 1, nj = d.hi[1] - d.lo[1] + 1, nk = d.hi[2] - d.lo[2] + 1;
+  const long per = (long)ni * nj * nk;
+  const long total = per * nvar;
+  const int c = d.comp < 0 ? 0 : d.comp;
+  double *arr = A.p[c];
+  const long e1 = A.ext1[c], e2 = A.ext2[c], bs = A.bstride[c];
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x) {
+    long t = q;
+    const int i = (int)(t % ni); t /= ni;
+    const int j = (int)(t % nj); t /= nj;
+    const int k = (int)(t % nk);
+    const int v = (int)(t / nk);
+    const long a_idx = ((long)(d.lo[2] + k) * e2 + (d.lo[1] + j)) * e1 + (d.lo[0] + i) + v * varstride;
+    const long base = (d.comp < 0) ? d.boff * nvar + v * per : d.boff;
+    if (mode == HALO_LOCAL) {
+      const long s_idx = ((long)(d.lo[2] + k + d.shift[2]) * e2 + (d.lo[1] + j + d.shift[1])) * e1 +
+                         (d.lo[0] + i + d.shift[0]) + v * varstride;
+      arr[(long)d.m * bs + a_idx] = arr[(long)d.src_m * bs + s_idx];
+    } else if (mode == HALO_PACK) {
+      buf[base + i + (long)ni * (j + (long)nj * k)] = arr[(long)d.m * bs + a_idx];
+    } else {
+      arr[(long)d.m * bs + a_idx] = buf[base + i + (long)ni * (j + (long)nj * k)];
+    }
+  }
+}
+
+static const int kOff[26][3] = {
+    {-1,0,0},{1,0,0},{0,-1,0},{0,1,0},{-1,-1,0},{1,-1,0},{-1,1,0},{1,1,0},{0,0,-1},{0,0,1},
+    {-1,0,-1},{1,0,-1},{-1,0,1},{1,0,1},{0,-1,-1},{0,1,-1},{0,-1,1},{0,1,1},
+    {-1,-1,-1},{1,-1,-1},{-1,1,-1},{1,1,-1},{-1,-1,1},{1,-1,1},{-1,1,1},{1,1,1}};
+
+HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int gids_start, std::string &err) {
+  if (cfg.nx2 <= 1 || cfg.nx3 <= 1) { err = "halo: only 3-D meshes are supported"; return nullptr; }
+  if (cfg.nx1 < cfg.ng || cfg.nx2 < cfg.ng || cfg.nx3 < cfg.ng) { err = "halo: block smaller than nghost"; return nullptr; }
+  auto *P = new HaloPlan();
+  P->cfg = cfg;
+  const int nx[3] = {cfg.nx1, cfg.nx2, cfg.nx3};
+  struct Entry { int gid_src, n_src, m, slot; int o[3]; };
+  std::map<int, std::vector<Entry>> send, recv;   // per peer rank
+  for (int m = 0; m < cfg.nmb; ++m) {
+    for (int q = 0; q < 26; ++q) {
+      const int *o = kOff[q];
+      const int slot = neighbor_index(o[0], o[1], o[2], 0, 0);
+      const int *nb = nghbr + ((long)m * 56 + slot) * 4;
+      const int gid = nb[0], rank = nb[2];
+      if (gid < 0) continue;
+      const int no[3] = {-o[0], -o[1], -o[2]};
+      if (rank == my_rank) {
+        // ghost box of m on side o is filled from block gid's active zones
+        const int src_m = gid - gids_start;
+        if (src_m < 0 || src_m >= cfg.nmb) { err = "halo: same-rank neighbour gid outside this pack"; delete P; return nullptr; }
+        for (int comp = -1; comp < 3; ++comp) {
+          Box b = halo_box(cfg, comp, o, false);
+          HaloDesc d{};
+          d.m = m; d.src_m = src_m; d.comp = comp; d.boff = 0;
+          for (int a = 0; a < 3; ++a) { d.lo[a] = b.lo[a]; d.hi[a] = b.hi[a]; d.shift[a] = -o[a] * nx[a]; }
+          (comp < 0 ? P->local_cc : P->local_fc).push_back(d);
+        }
+      } else {
+        // I receive into (m, slot) what the peer sends from (gid, slot(-o)); and I send my
+        // box on side o to the peer's block gid, which receives it in ITS slot(-o).
+        Entry r{gid, neighbor_index(no[0], no[1], no[2], 0, 0), m, slot, {o[0], o[1], o[2]}};
+        recv[rank].push_back(r);
+        Entry s{gids_start + m, slot, m, slot, {o[0], o[1], o[2]}};
+        send[rank].push_back(s);
+      }
+    }
+  }
+  auto key_lt = [](const Entry &a, const Entry &b) { return a.gid_src != b.gid_src ? a.gid_src < b.gid_src : a.n_src < b.n_src; };
+  for (auto &kv : send) {
+    const int rank = kv.first;
+    HaloPeer peer;
+    peer.rank = rank;
+    auto &sv = kv.second;
+    auto &rv = recv[rank];
+    std::sort(sv.begin(), sv.end(), key_lt);
+    std::sort(rv.begin(), rv.end(), key_lt);
+    long cc_off = 0, fc_off = 0;
+    for (const Entry &e : sv) {
+      Box b = halo_box(cfg, -1, e.o, true);
+      HaloDesc d{}; d.m = e.m; d.src_m = e.m; d.comp = -1; d.boff = cc_off;
+      for (int a = 0; a < 3; ++a) { d.lo[a] = b.lo[a]; d.hi[a] = b.hi[a]; }
+      peer.pack_cc.push_back(d);
+      cc_off += b.count();   // per variable; scaled by nvar at launch
+      long ndat = 0;
+      for (int comp = 0; comp < 3; ++comp) ndat = std::max(ndat, halo_box(cfg, comp, e.o, true).count());
+      for (int comp = 0; comp < 3; ++comp) {
+        Box bb = halo_box(cfg, comp, e.o, true);
+        HaloDesc f{}; f.m = e.m; f.src_m = e.m; f.comp = comp; f.boff = fc_off + ndat * comp;
+        for (int a = 0; a < 3; ++a) { f.lo[a] = bb.lo[a]; f.hi[a] = bb.hi[a]; }
+        peer.pack_fc.push_back(f);
+      }
+      fc_off += 3 * ndat;
+    }
+    peer.cc_count = cc_off; peer.fc_count = fc_off;
+    cc_off = 0; fc_off = 0;
+    for (const Entry &e : rv) {
+      // sender's box is its send box on side -o; same extents as my recv box on side o
+      const int so[3] = {-e.o[0], -e.o[1], -e.o[2]};
+      Box b = halo_box(cfg, -1, e.o, false);
+      HaloDesc d{}; d.m = e.m; d.src_m = e.m; d.comp = -1; d.boff = cc_off;
+      for (int a = 0; a < 3; ++a) { d.lo[a] = b.lo[a]; d.hi[a] = b.hi[a]; }
+      peer.unpack_cc.push_back(d);
+      cc_off += b.count();
+      long ndat = 0;
+      for (int comp = 0; comp < 3; ++comp) ndat = std::max(ndat, halo_box(cfg, comp, so, true).count());
+      for (int comp = 0; comp < 3; ++comp) {
+        Box bb = halo_box(cfg, comp, e.o, false);
+        HaloDesc f{}; f.m = e.m; f.src_m = e.m; f.comp = comp; f.boff = fc_off + ndat * comp;
+        for (int a = 0; a < 3; ++a) { f.lo[a] = bb.lo[a]; f.hi[a] = bb.hi[a]; }
+        peer.unpack_fc.push_back(f);
+      }
+      fc_off += 3 * ndat;
+    }
+    if (cc_off != peer.cc_count || fc_off != peer.fc_count) { err = "halo: send/recv message sizes differ"; delete P; return nullptr; }
+    P->peers.push_back(peer);
+  }
+  return P;
+}
+
+cudaError_t halo_ensure_uploaded(HaloPlan *P) {
+  if (P->uploaded) return cudaSuccess;
+  auto up = [&](const std::vector<HaloDesc> &v, HaloDesc **dptr) -> cudaError_t {
+    *dptr = nullptr;
+    if (v.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc(dptr, v.size() * sizeof(HaloDesc));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dptr, v.data(), v.size() * sizeof(HaloDesc), cudaMemcpyHostToDevice);
+  };
+  cudaError_t e;
+  if ((e = up(P->local_cc, &P->d_local_cc)) != cudaSuccess) return e;
+  if ((e = up(P->local_fc, &P->d_local_fc)) != cudaSuccess) return e;
+  for (auto &p : P->peers) {
+    if ((e = up(p.pack_cc, &p.d_pack_cc)) != cudaSuccess) return e;
+    if ((e = up(p.unpack_cc, &p.d_unpack_cc)) != cudaSuccess) return e;
+    if ((e = up(p.pack_fc, &p.d_pack_fc)) != cudaSuccess) return e;
+    if ((e = up(p.unpack_fc, &p.d_unpack_fc)) != cudaSuccess) return e;
+  }
+  P->uploaded = true;
+  return cudaSuccess;
+}
+
+void halo_free(HaloPlan *P) {
+  if (!P) return;
+  cudaFree(P->d_local_cc); cudaFree(P->d_local_fc);
+  for (auto &p : P->peers) { cudaFree(p.d_pack_cc); cudaFree(p.d_unpack_cc); cudaFree(p.d_pack_fc); cudaFree(p.d_unpack_fc); }
+  delete P;
+}
+
+static long max_count(const std::vector<HaloDesc> &v, int nvar) {
+  long mx = 0;
+  for (const auto &d : v) mx = std::max(mx, (long)(d.hi[0]-d.lo[0]+1)*(d.hi[1]-d.lo[1]+1)*(d.hi[2]-d.lo[2]+1) * nvar);
+  return mx;
+}
+
+cudaError_t halo_launch(const std::vector<HaloDesc> &host, const HaloDesc *dev, const HaloArrays &A, int nvar,
+                        long varstride, double *buf, int mode, cudaStream_t st) {
+  if (host.empty()) return cudaSuccess;
+  long mx = max_count(host, nvar);
+  unsigned gx = (unsigned)std::min<long>((mx + 255) / 256, 64);
+  if (gx == 0) gx = 1;
+  dim3 grid(gx, (unsigned)host.size());
+  // gridDim.y is limited to 65535 descriptors per launch
+  for (size_t first = 0; first < host.size(); first += 65535) {
+    unsigned ny = (unsigned)std::min<size_t>(65535, host.size() - first);
+    halo_copy_kernel<<<dim3(gx, ny), 256, 0, st>>>(dev + first, A, nvar, varstride, buf, mode);
+  }
+  return cudaGetLastError();
+}
+
+HaloArrays halo_arrays_cc(const ak_mhd_cfg &c, double *a, int nvar) {
+  const long n1 = c.nx1 + 2 * c.ng, n2 = c.nx2 + 2 * c.ng, n3 = c.nx3 + 2 * c.ng;
+  HaloArrays A{};
+  A.p[0] = a; A.ext1[0] = n1; A.ext2[0] = n2; A.bstride[0] = (long)nvar * n1 * n2 * n3;
+  return A;
+}
+
+HaloArrays halo_arrays_fc(const ak_mhd_cfg &c, double *x1f, double *x2f, double *x3f) {
+  const long n1 = c.nx1 + 2 * c.ng, n2 = c.nx2 + 2 * c.ng, n3 = c.nx3 + 2 * c.ng;
+  HaloArrays A{};
+  A.p[0] = x1f; A.ext1[0] = n1 + 1; A.ext2[0] = n2;     A.bstride[0] = (n1 + 1) * n2 * n3;
+  A.p[1] = x2f; A.ext1[1] = n1;     A.ext2[1] = n2 + 1; A.bstride[1] = n1 * (n2 + 1) * n3;
+  A.p[2] = x3f; A.ext1[2] = n1;     A.ext2[2] = n2;     A.bstride[2] = n1 * n2 * (n3 + 1);
+  return A;
+}
+
+}  // namespace akb

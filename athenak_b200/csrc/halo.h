@@ -1,0 +1,49 @@
+// halo.h -- internal declarations of the ghost-zone exchange plan (see halo.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../../include/athenak_b200.h"
+
+namespace akb {
+
+enum { HALO_LOCAL = 0, HALO_PACK = 1, HALO_UNPACK = 2 };
+
+struct HaloDesc {
+  int m, src_m, comp;      // block written/read; source block (local gather); -1 = CC, 0..2 = x1f..x3f
+  int lo[3], hi[3];        // i,j,k box in the array named by comp
+  int shift[3];            // local gather: src index = dst index + shift
+  long boff;               // message offset (CC: per variable, scaled by nvar in the kernel)
+};
+
+struct HaloArrays {
+  double *p[3];
+  long ext1[3], ext2[3], bstride[3];  // inner, middle extents and per-block stride
+};
+
+struct HaloPeer {
+  int rank;
+  long cc_count, fc_count;  // doubles per message: CC per variable, FC total
+  std::vector<HaloDesc> pack_cc, unpack_cc, pack_fc, unpack_fc;
+  HaloDesc *d_pack_cc = nullptr, *d_unpack_cc = nullptr, *d_pack_fc = nullptr, *d_unpack_fc = nullptr;
+};
+
+struct HaloPlan {
+  ak_mhd_cfg cfg;
+  std::vector<HaloDesc> local_cc, local_fc;
+  HaloDesc *d_local_cc = nullptr, *d_local_fc = nullptr;
+  std::vector<HaloPeer> peers;
+  std::string err;
+  bool uploaded = false;   // descriptor lists are copied to the device on first use
+};
+
+int neighbor_index(int ix, int iy, int iz, int n1, int n2);
+HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int gids_start, std::string &err);
+void halo_free(HaloPlan *P);
+cudaError_t halo_ensure_uploaded(HaloPlan *P);
+cudaError_t halo_launch(const std::vector<HaloDesc> &host, const HaloDesc *dev, const HaloArrays &A, int nvar,
+                        long varstride, double *buf, int mode, cudaStream_t st);
+HaloArrays halo_arrays_cc(const ak_mhd_cfg &c, double *a, int nvar);
+HaloArrays halo_arrays_fc(const ak_mhd_cfg &c, double *x1f, double *x2f, double *x3f);
+
+}  // namespace akb

@@ -1,0 +1,526 @@
+// mhd_kernels.cu -- hand-written sm_100a kernels for the per-MeshBlock ideal-MHD stage update
+// (reference path: src/reconstruct -> src/mhd/rsolvers -> mhd_corner_e -> mhd_update/mhd_ct ->
+// src/eos ConsToPrim).  No tensor cores: the path has no contraction.
+// FP64 SIMT, --fmad=false, bit-faithful to the reference's expression order.
+//
+// Kernel inventory (algorithmic traffic in FP64 words per active cell per stage):
+//   flux_x1        warp = 32 consecutive cells of one i-pencil; 5-point stencils come from L1,
+//                  the left face state from lane-1 by warp shuffle; recon + Riemann in registers.
+//   flux_march<D>  x2/x3: one thread per (transverse, i) column marching along the sweep
+//                  direction, carrying the left face state in registers (coalesced along i).
+//   corner_emf     GS07 upwinded corner EMFs, cell-centred E recomputed on the fly.
+//   update_ct      RK update of u0 and CT update of b0 in one pass (+ CopyCons at stage 1).
+//   cons2prim      c2p over a cell box, floors, floor counters; optional fused new-dt reduce.
+#include "mhd_kernels.h"
+#include "mhd_device.cuh"
+
+namespace akb {
+
+// ---------------------------------------------------------------------------------------
+// x1 sweep.  Flattened cell space (m, k in [ks-1,ke+1], j in [js-1,je+1], c in [0,nx1+2));
+// warp w owns cells 31*w .. 31*w+31 (one-cell overlap), i.e. 31 faces.
+template <int RECON, int RS>
+__global__ void __launch_bounds__(128)
+flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
+               const double *__restrict__ bx1f, double *__restrict__ flx, double *__restrict__ e3x1,
+               double *__restrict__ e2x1) {
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const long cell = (gt >> 5) * 31 + lane;
+  const int nc = g.nx1 + 2, nj = g.nx2 + 2, nk = g.nx3 + 2;
+  const long total = (long)g.nmb * nk * nj * nc;
+  const bool valid = cell < total;
+  int c = 0, j = 0, k = 0, m = 0;
+  if (valid) {
+    long t = cell;
+    c = (int)(t % nc); t /= nc;
+    j = (int)(t % nj) + g.js - 1; t /= nj;
+    k = (int)(t % nk) + g.ks - 1;
+    m = (int)(t / nk);
+  }
+  const int i = g.is - 1 + c;
+  const long cc = g.cc;
+  const long off = ((long)k * g.n2 + j) * g.n1 + i;
+  State7 up, lo;
+  if (valid) {
+    recon_cell<RECON, 0>(w0 + (long)m * 5 * cc + off, bcc + (long)m * 3 * cc + off, cc, 1, eos, up, lo);
+  } else {
+    up.d = up.vx = up.vy = up.vz = up.e = up.by = up.bz = 0.0;
+    lo = up;
+  }
+  State7 L;
+  L.d = __shfl_up_sync(0xffffffffu, up.d, 1);
+  L.vx = __shfl_up_sync(0xffffffffu, up.vx, 1);
+  L.vy = __shfl_up_sync(0xffffffffu, up.vy, 1);
+  L.vz = __shfl_up_sync(0xffffffffu, up.vz, 1);
+  L.e = __shfl_up_sync(0xffffffffu, up.e, 1);
+  L.by = __shfl_up_sync(0xffffffffu, up.by, 1);
+  L.bz = __shfl_up_sync(0xffffffffu, up.bz, 1);
+  if (!valid || lane == 0 || c == 0) return;
+  const double bxi = __ldg(bx1f + (((long)m * g.n3 + k) * g.n2 + j) * (g.n1 + 1) + i);
+  Flux7 f;
+  riemann<RS>(L, lo, bxi, eos, f);
+  const long fs = (long)g.n3 * g.n2 * (g.n1 + 1);
+  double *fp = flx + (long)m * 5 * fs + ((long)k * g.n2 + j) * (g.n1 + 1) + i;
+  fp[IDN * fs] = f.d;
+  fp[IVX * fs] = f.mx;
+  fp[IVY * fs] = f.my;
+  fp[IVZ * fs] = f.mz;
+  fp[IEN * fs] = f.e;
+  e3x1[(long)m * cc + off] = f.ey;  // mhd_fluxes.cpp:146
+  e2x1[(long)m * cc + off] = f.ez;
+}
+
+// x2 / x3 sweeps.  Thread = (m, segment, transverse index, i-cell); marches `len` faces.
+template <int RECON, int RS, int DIR>
+__global__ void __launch_bounds__(128)
+flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
+                  const double *__restrict__ bnf, double *__restrict__ flx, double *__restrict__ eyo,
+                  double *__restrict__ ezo, int seglen, int nseg) {
+  static_assert(DIR == 1 || DIR == 2, "march kernel handles x2 and x3");
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nc = g.nx1 + 2;
+  const int nt = (DIR == 1) ? g.nx3 + 2 : g.nx2 + 2;
+  const long total = (long)g.nmb * nseg * nt * nc;
+  if (gt >= total) return;
+  long t = gt;
+  const int i = g.is - 1 + (int)(t % nc); t /= nc;
+  const int tr = (int)(t % nt); t /= nt;
+  const int seg = (int)(t % nseg);
+  const int m = (int)(t / nseg);
+  const int fs0 = (DIR == 1) ? g.js : g.ks;         // first face along the sweep
+  const int fe0 = (DIR == 1) ? g.je + 1 : g.ke + 1; // last face
+  const int f_lo = fs0 + seg * seglen;
+  int f_hi = f_lo + seglen - 1;
+  if (f_hi > fe0) f_hi = fe0;
+  if (f_lo > f_hi) return;
+  const long cc = g.cc;
+  const long s = (DIR == 1) ? (long)g.n1 : (long)g.n1 * g.n2;
+  // cell (k,j,i) with the sweep index = f_lo-1
+  int k, j;
+  if (DIR == 1) { k = g.ks - 1 + tr; j = f_lo - 1; } else { j = g.js - 1 + tr; k = f_lo - 1; }
+  long off = ((long)k * g.n2 + j) * g.n1 + i;
+  const double *wp = w0 + (long)m * 5 * cc + off;
+  const double *bp = bcc + (long)m * 3 * cc + off;
+  // face-array geometry
+  const long frow = (DIR == 1) ? (long)g.n1 : (long)g.n1 * g.n2;  // stride of the sweep index in the face arrays
+  const long fsz = (DIR == 1) ? (long)g.n3 * (g.n2 + 1) * g.n1 : (long)(g.n3 + 1) * g.n2 * g.n1;
+  long foff = (DIR == 1) ? ((long)k * (g.n2 + 1) + f_lo) * g.n1 + i
+                         : ((long)f_lo * g.n2 + j) * g.n1 + i;
+  const double *bn = bnf + (long)m * fsz + foff;
+  double *fp = flx + (long)m * 5 * fsz + foff;
+  double *eyp = eyo + (long)m * cc + off + s;
+  double *ezp = ezo + (long)m * cc + off + s;
+  constexpr int ivx = IVX + DIR, ivy = IVX + (DIR + 1) % 3, ivz = IVX + (DIR + 2) % 3;
+
+  State7 L, lo_unused;
+  recon_cell<RECON, DIR>(wp, bp, cc, s, eos, L, lo_unused);
+  for (int f = f_lo; f <= f_hi; ++f) {
+    wp += s; bp += s;
+    State7 up, lo;
+    recon_cell<RECON, DIR>(wp, bp, cc, s, eos, up, lo);
+    Flux7 fx;
+    riemann<RS>(L, lo, __ldg(bn), eos, fx);
+    fp[IDN * fsz] = fx.d;
+    fp[ivx * fsz] = fx.mx;
+    fp[ivy * fsz] = fx.my;
+    fp[ivz * fsz] = fx.mz;
+    fp[IEN * fsz] = fx.e;
+    *eyp = fx.ey;  // x2: (e1x2,e3x2)  x3: (e2x3,e1x3)   mhd_fluxes.cpp:196,243
+    *ezp = fx.ez;
+    L = up;
+    bn += frow; fp += frow; eyp += s; ezp += s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// GS07 corner EMFs (mhd_corner_e.cpp:309-318,338-414), one thread per corner
+// k in [ks,ke+1], j in [js,je+1], i in [is,ie+1].
+__global__ void __launch_bounds__(256)
+corner_emf_kernel(Geom g, const double *__restrict__ w0, const double *__restrict__ bcc,
+                  const double *__restrict__ flx1, const double *__restrict__ flx2,
+                  const double *__restrict__ flx3, const double *__restrict__ e3x1,
+                  const double *__restrict__ e2x1, const double *__restrict__ e1x2,
+                  const double *__restrict__ e3x2, const double *__restrict__ e2x3,
+                  const double *__restrict__ e1x3, double *__restrict__ e1, double *__restrict__ e2,
+                  double *__restrict__ e3) {
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ni = g.nx1 + 1, nj = g.nx2 + 1, nk = g.nx3 + 1;
+  const long total = (long)g.nmb * nk * nj * ni;
+  if (gt >= total) return;
+  long t = gt;
+  const int i = g.is + (int)(t % ni); t /= ni;
+  const int j = g.js + (int)(t % nj); t /= nj;
+  const int k = g.ks + (int)(t % nk);
+  const int m = (int)(t / nk);
+  const long cc = g.cc, n1 = g.n1, n12 = (long)g.n1 * g.n2;
+  const double *w = w0 + (long)m * 5 * cc, *b = bcc + (long)m * 3 * cc;
+  auto C = [&](int kk, int jj, int ii) -> long { return ((long)kk * g.n2 + jj) * n1 + ii; };
+  // cell-centred E = -(v x B)  (mhd_corner_e.cpp:310-317)
+  auto e1cc = [&](long o) { return __ldg(w + IVZ * cc + o) * __ldg(b + 1 * cc + o) - __ldg(w + IVY * cc + o) * __ldg(b + 2 * cc + o); };
+  auto e2cc = [&](long o) { return __ldg(w + IVX * cc + o) * __ldg(b + 2 * cc + o) - __ldg(w + IVZ * cc + o) * __ldg(b + 0 * cc + o); };
+  auto e3cc = [&](long o) { return __ldg(w + IVY * cc + o) * __ldg(b + 0 * cc + o) - __ldg(w + IVX * cc + o) * __ldg(b + 1 * cc + o); };
+  // mass fluxes (IDN component) on the three face families
+  const double *f1 = flx1 + (long)m * 5 * g.f1;
+  const double *f2 = flx2 + (long)m * 5 * g.f2;
+  const double *f3 = flx3 + (long)m * 5 * g.f3;
+  auto F1 = [&](int kk, int jj, int ii) { return __ldg(f1 + ((long)kk * g.n2 + jj) * (n1 + 1) + ii); };
+  auto F2 = [&](int kk, int jj, int ii) { return __ldg(f2 + ((long)kk * (g.n2 + 1) + jj) * n1 + ii); };
+  auto F3 = [&](int kk, int jj, int ii) { return __ldg(f3 + ((long)kk * g.n2 + jj) * n1 + ii); };
+  const long mo = (long)m * cc;
+  const long o = C(k, j, i);
+  {
+    const double x3_jm = __ldg(e1x3 + mo + o - n1), x3_j = __ldg(e1x3 + mo + o);
+    const double x2_km = __ldg(e1x2 + mo + o - n12), x2_k = __ldg(e1x2 + mo + o);
+    double l3, r3, l2, r2;
+    if (F2(k - 1, j, i) >= 0.0) l3 = x3_jm - e1cc(o - n12 - n1); else l3 = x3_j - e1cc(o - n12);
+    if (F2(k, j, i) >= 0.0) r3 = x3_jm - e1cc(o - n1); else r3 = x3_j - e1cc(o);
+    if (F3(k, j - 1, i) >= 0.0) l2 = x2_km - e1cc(o - n12 - n1); else l2 = x2_k - e1cc(o - n1);
+    if (F3(k, j, i) >= 0.0) r2 = x2_km - e1cc(o - n12); else r2 = x2_k - e1cc(o);
+    e1[(long)m * g.e1 + ((long)k * (g.n2 + 1) + j) * n1 + i] = 0.25 * (l3 + r3 + l2 + r2 + x2_km + x2_k + x3_jm + x3_j);
+  }
+  {
+    const double x3_im = __ldg(e2x3 + mo + o - 1), x3_i = __ldg(e2x3 + mo + o);
+    const double x1_km = __ldg(e2x1 + mo + o - n12), x1_k = __ldg(e2x1 + mo + o);
+    double l3, r3, l1, r1;
+    if (F1(k - 1, j, i) >= 0.0) l3 = x3_im - e2cc(o - n12 - 1); else l3 = x3_i - e2cc(o - n12);
+    if (F1(k, j, i) >= 0.0) r3 = x3_im - e2cc(o - 1); else r3 = x3_i - e2cc(o);
+    if (F3(k, j, i - 1) >= 0.0) l1 = x1_km - e2cc(o - n12 - 1); else l1 = x1_k - e2cc(o - 1);
+    if (F3(k, j, i) >= 0.0) r1 = x1_km - e2cc(o - n12); else r1 = x1_k - e2cc(o);
+    e2[(long)m * g.e2 + ((long)k * g.n2 + j) * (n1 + 1) + i] = 0.25 * (l3 + r3 + l1 + r1 + x3_im + x3_i + x1_km + x1_k);
+  }
+  {
+    const double x2_im = __ldg(e3x2 + mo + o - 1), x2_i = __ldg(e3x2 + mo + o);
+    const double x1_jm = __ldg(e3x1 + mo + o - n1), x1_j = __ldg(e3x1 + mo + o);
+    double l2, r2, l1, r1;
+    if (F1(k, j - 1, i) >= 0.0) l2 = x2_im - e3cc(o - n1 - 1); else l2 = x2_i - e3cc(o - n1);
+    if (F1(k, j, i) >= 0.0) r2 = x2_im - e3cc(o - 1); else r2 = x2_i - e3cc(o);
+    if (F2(k, j, i - 1) >= 0.0) l1 = x1_jm - e3cc(o - n1 - 1); else l1 = x1_j - e3cc(o - 1);
+    if (F2(k, j, i) >= 0.0) r1 = x1_jm - e3cc(o - n1); else r1 = x1_j - e3cc(o);
+    e3[(long)m * g.e3 + ((long)k * (g.n2 + 1) + j) * (n1 + 1) + i] = 0.25 * (l1 + r1 + l2 + r2 + x2_im + x2_i + x1_jm + x1_j);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// RK update (mhd_update.cpp:51-82) and CT (mhd_ct.cpp:45-77) in one pass.  Thread per
+// (k in [ks,ke+1], j in [js,je+1], i in [is,ie+1]); the cell update runs where all three
+// indices are active, each face update where its own range allows.  SAVE=true also performs
+// CopyCons (u1<-u0, b1<-b0, mhd_tasks.cpp:162-170) for the entries it touches; the caller
+// copies the ghost entries separately when the host contract needs them.
+template <bool DO_U, bool DO_B>
+__global__ void __launch_bounds__(256)
+update_ct_kernel(Geom g, double *__restrict__ u0, const double *__restrict__ u1,
+                 const double *__restrict__ flx1, const double *__restrict__ flx2,
+                 const double *__restrict__ flx3, double *__restrict__ b1f, double *__restrict__ b2f,
+                 double *__restrict__ b3f, const double *__restrict__ o1f, const double *__restrict__ o2f,
+                 const double *__restrict__ o3f, const double *__restrict__ e1, const double *__restrict__ e2,
+                 const double *__restrict__ e3, const double *__restrict__ mb_size, double gam0, double gam1,
+                 double beta_dt) {
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ni = g.nx1 + 1, nj = g.nx2 + 1, nk = g.nx3 + 1;
+  const long total = (long)g.nmb * nk * nj * ni;
+  if (gt >= total) return;
+  long t = gt;
+  const int i = g.is + (int)(t % ni); t /= ni;
+  const int j = g.js + (int)(t % nj); t /= nj;
+  const int k = g.ks + (int)(t % nk);
+  const int m = (int)(t / nk);
+  const double dx1 = __ldg(mb_size + m * 9 + 6), dx2 = __ldg(mb_size + m * 9 + 7), dx3 = __ldg(mb_size + m * 9 + 8);
+  const double rdx1 = 1.0 / dx1, rdx2 = 1.0 / dx2, rdx3 = 1.0 / dx3;
+  const long n1 = g.n1, n2 = g.n2;
+  const bool ia = (i <= g.ie), ja = (j <= g.je), ka = (k <= g.ke);
+  if (DO_U && ia && ja && ka) {
+    const long o = ((long)k * n2 + j) * n1 + i;
+    const long o1 = ((long)k * n2 + j) * (n1 + 1) + i;
+    const long o2 = ((long)k * (n2 + 1) + j) * n1 + i;
+    const long o3 = o;
+#pragma unroll
+    for (int n = 0; n < 5; ++n) {
+      const double *p1 = flx1 + ((long)m * 5 + n) * g.f1 + o1;
+      const double *p2 = flx2 + ((long)m * 5 + n) * g.f2 + o2;
+      const double *p3 = flx3 + ((long)m * 5 + n) * g.f3 + o3;
+      double divf = div_by(__ldg(p1 + 1) - __ldg(p1), dx1, rdx1);
+      divf += div_by(__ldg(p2 + n1) - __ldg(p2), dx2, rdx2);
+      divf += div_by(__ldg(p3 + n1 * n2) - __ldg(p3), dx3, rdx3);
+      const long uo = ((long)m * 5 + n) * g.cc + o;
+      u0[uo] = gam0 * u0[uo] + gam1 * __ldg(u1 + uo) - beta_dt * divf;
+    }
+  }
+  if (DO_B) {
+    const double *E1 = e1 + (long)m * g.e1, *E2 = e2 + (long)m * g.e2, *E3 = e3 + (long)m * g.e3;
+    const long a1 = ((long)k * (n2 + 1) + j) * n1 + i;        // x1e(k,j,i)
+    const long a2 = ((long)k * n2 + j) * (n1 + 1) + i;        // x2e(k,j,i)
+    const long a3 = ((long)k * (n2 + 1) + j) * (n1 + 1) + i;  // x3e(k,j,i)
+    if (ja && ka) {  // x1f(k,j,i), i in [is,ie+1]
+      const long o = (long)m * g.f1 + ((long)k * n2 + j) * (n1 + 1) + i;
+      double b = gam0 * b1f[o] + gam1 * __ldg(o1f + o);
+      b -= div_by(beta_dt * (__ldg(E3 + a3 + (n1 + 1)) - __ldg(E3 + a3)), dx2, rdx2);
+      b += div_by(beta_dt * (__ldg(E2 + a2 + n2 * (n1 + 1)) - __ldg(E2 + a2)), dx3, rdx3);
+      b1f[o] = b;
+    }
+    if (ia && ka) {  // x2f(k,j,i), j in [js,je+1]
+      const long o = (long)m * g.f2 + ((long)k * (n2 + 1) + j) * n1 + i;
+      double b = gam0 * b2f[o] + gam1 * __ldg(o2f + o);
+      b += div_by(beta_dt * (__ldg(E3 + a3 + 1) - __ldg(E3 + a3)), dx1, rdx1);
+      b -= div_by(beta_dt * (__ldg(E1 + a1 + (n2 + 1) * n1) - __ldg(E1 + a1)), dx3, rdx3);
+      b2f[o] = b;
+    }
+    if (ia && ja) {  // x3f(k,j,i), k in [ks,ke+1]
+      const long o = (long)m * g.f3 + ((long)k * n2 + j) * n1 + i;
+      double b = gam0 * b3f[o] + gam1 * __ldg(o3f + o);
+      b -= div_by(beta_dt * (__ldg(E2 + a2 + 1) - __ldg(E2 + a2)), dx1, rdx1);
+      b += div_by(beta_dt * (__ldg(E1 + a1 + n1) - __ldg(E1 + a1)), dx2, rdx2);
+      b3f[o] = b;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// ConsToPrim (ideal_mhd.cpp:47-122 + ideal_c2p_mhd.hpp:20-67) over a cell box, optionally
+// fused with the new-dt reduction over the active cells (mhd_newdt.cpp:76-150).
+// counters: int[3] (dfloor,efloor,tfloor); dtmin: 3 doubles stored as ordered uint64 bits.
+// identity of the min-reduction = (double)FLT_MAX, the reference's initial value (mhd_newdt.cpp:40-42)
+#define DT_IDENT 3.4028234663852886e+38
+__device__ __forceinline__ void atomic_min_pos(unsigned long long *addr, double v) {
+  atomicMin(addr, (unsigned long long)__double_as_longlong(v));  // v > 0: bit order == value order
+}
+
+template <bool NEWDT>
+__global__ void __launch_bounds__(256)
+cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *__restrict__ b1f,
+                 const double *__restrict__ b2f, const double *__restrict__ b3f, double *__restrict__ w0,
+                 double *__restrict__ bcc, int il, int iu, int jl, int ju, int kl, int ku,
+                 int *__restrict__ counters, const double *__restrict__ mb_size,
+                 unsigned long long *__restrict__ dtmin) {
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ni = iu - il + 1, nj = ju - jl + 1, nk = ku - kl + 1;
+  const long total = (long)g.nmb * nk * nj * ni;
+  int nd = 0, ne = 0, nt = 0;
+  double d1 = DT_IDENT, d2 = DT_IDENT, d3 = DT_IDENT;
+  bool act = false;
+  if (gt < total) {
+    long t = gt;
+    const int i = il + (int)(t % ni); t /= ni;
+    const int j = jl + (int)(t % nj); t /= nj;
+    const int k = kl + (int)(t % nk);
+    const int m = (int)(t / nk);
+    const long n1 = g.n1, n2 = g.n2, cc = g.cc;
+    const long o = ((long)k * n2 + j) * n1 + i;
+    double *u = u0 + (long)m * 5 * cc + o;
+    double ud = u[IDN * cc], umx = u[IM1 * cc], umy = u[IM2 * cc], umz = u[IM3 * cc], ue = u[IEN * cc];
+    const double *p1 = b1f + (long)m * g.f1 + ((long)k * n2 + j) * (n1 + 1) + i;
+    const double *p2 = b2f + (long)m * g.f2 + ((long)k * (n2 + 1) + j) * n1 + i;
+    const double *p3 = b3f + (long)m * g.f3 + o;
+    const double ubx = 0.5 * (__ldg(p1) + __ldg(p1 + 1));
+    const double uby = 0.5 * (__ldg(p2) + __ldg(p2 + n1));
+    const double ubz = 0.5 * (__ldg(p3) + __ldg(p3 + n1 * n2));
+    bool dfl = false, efl = false, tfl = false;
+    const double gm1 = eos.gamma - 1.0;
+    const double b2 = sqr(ubx) + sqr(uby) + sqr(ubz);
+    const double dfloor_ = fmax(eos.dfloor, b2 / eos.sigma_max);
+    const double efloor = eos.pfloor / (eos.gamma - 1.0);
+    if (ud < dfloor_) { ud = dfloor_; dfl = true; }
+    const double wd = ud;
+    const double di = 1.0 / ud;
+    const double wvx = di * umx, wvy = di * umy, wvz = di * umz;
+    const double e_k = 0.5 * di * (sqr(umx) + sqr(umy) + sqr(umz));
+    const double e_m = 0.5 * (sqr(ubx) + sqr(uby) + sqr(ubz));
+    double we = (ue - e_k - e_m);
+    if (we < efloor) { we = efloor; ue = efloor + e_k + e_m; efl = true; }
+    if (gm1 * we * di < eos.tfloor) { we = wd * eos.tfloor / gm1; ue = we + e_k + e_m; tfl = true; }
+    // Entropy floor (ideal_c2p_mhd.hpp:59-65).  spe = gm1*we*di / wd^gm1.  pow() is only needed
+    // when spe can be <= sfloor: for 0 < gm1 <= 2, wd^gm1 <= max(1, wd^2), so
+    // gm1*we*di > 4*sfloor*max(1,wd^2) proves spe > sfloor (factor 4 covers rounding) without
+    // evaluating pow; otherwise the reference expression is evaluated as written.
+    const double pow_ub = fmax(1.0, wd * wd);
+    bool need_pow = !(gm1 > 0.0 && gm1 <= 2.0 && (gm1 * we * di) > 4.0 * eos.sfloor * pow_ub);
+    if (need_pow) {
+      const double spe_over_eps = gm1 / pow(wd, gm1);
+      const double spe = spe_over_eps * we * di;
+      if (spe <= eos.sfloor) { we = wd * eos.sfloor / spe_over_eps; efl = true; }
+    }
+    if (dfl) { u[IDN * cc] = ud; nd = 1; }
+    if (efl) { u[IEN * cc] = ue; ne = 1; }
+    if (tfl) { u[IEN * cc] = ue; nt = 1; }
+    double *w = w0 + (long)m * 5 * cc + o;
+    w[IDN * cc] = wd; w[IVX * cc] = wvx; w[IVY * cc] = wvy; w[IVZ * cc] = wvz; w[IEN * cc] = we;
+    double *bc = bcc + (long)m * 3 * cc + o;
+    bc[0] = ubx; bc[cc] = uby; bc[2 * cc] = ubz;
+    if (NEWDT) {
+      act = (i >= g.is && i <= g.ie && j >= g.js && j <= g.je && k >= g.ks && k <= g.ke);
+      if (act) {  // mhd_newdt.cpp:128-138,146-148
+        const double p = gm1 * we;
+        d1 = __ldg(mb_size + m * 9 + 6) / (fabs(wvx) + fast_speed(eos.gamma, wd, p, ubx, uby, ubz));
+        d2 = __ldg(mb_size + m * 9 + 7) / (fabs(wvy) + fast_speed(eos.gamma, wd, p, uby, ubz, ubx));
+        d3 = __ldg(mb_size + m * 9 + 8) / (fabs(wvz) + fast_speed(eos.gamma, wd, p, ubz, ubx, uby));
+      }
+    }
+  }
+  // warp-level reduction, one atomic per warp and only when needed
+  const unsigned any = __ballot_sync(0xffffffffu, nd | ne | nt);
+  if (any) {
+    for (int s = 16; s > 0; s >>= 1) {
+      nd += __shfl_xor_sync(0xffffffffu, nd, s);
+      ne += __shfl_xor_sync(0xffffffffu, ne, s);
+      nt += __shfl_xor_sync(0xffffffffu, nt, s);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (nd) atomicAdd(counters + 0, nd);
+      if (ne) atomicAdd(counters + 1, ne);
+      if (nt) atomicAdd(counters + 2, nt);
+    }
+  }
+  if (NEWDT) {
+    if (__ballot_sync(0xffffffffu, act)) {
+      for (int s = 16; s > 0; s >>= 1) {
+        d1 = fmin(d1, __shfl_xor_sync(0xffffffffu, d1, s));
+        d2 = fmin(d2, __shfl_xor_sync(0xffffffffu, d2, s));
+        d3 = fmin(d3, __shfl_xor_sync(0xffffffffu, d3, s));
+      }
+      if ((threadIdx.x & 31) == 0) {
+        atomic_min_pos(dtmin + 0, d1);
+        atomic_min_pos(dtmin + 1, d2);
+        atomic_min_pos(dtmin + 2, d3);
+      }
+    }
+  }
+}
+
+// MHD::NewTimeStep stand-alone (task 28): reads w0, bcc0 over the active cells.
+__global__ void __launch_bounds__(256)
+newdt_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
+             const double *__restrict__ mb_size, unsigned long long *__restrict__ dtmin) {
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)g.nmb * g.nx3 * g.nx2 * g.nx1;
+  double d1 = DT_IDENT, d2 = DT_IDENT, d3 = DT_IDENT;
+  if (gt < total) {
+    long t = gt;
+    const int i = g.is + (int)(t % g.nx1); t /= g.nx1;
+    const int j = g.js + (int)(t % g.nx2); t /= g.nx2;
+    const int k = g.ks + (int)(t % g.nx3);
+    const int m = (int)(t / g.nx3);
+    const long cc = g.cc, o = ((long)k * g.n2 + j) * g.n1 + i;
+    const double *w = w0 + (long)m * 5 * cc + o, *b = bcc + (long)m * 3 * cc + o;
+    const double wd = __ldg(w), bx = __ldg(b), by = __ldg(b + cc), bz = __ldg(b + 2 * cc);
+    const double p = (eos.gamma - 1.0) * __ldg(w + IEN * cc);
+    d1 = __ldg(mb_size + m * 9 + 6) / (fabs(__ldg(w + IVX * cc)) + fast_speed(eos.gamma, wd, p, bx, by, bz));
+    d2 = __ldg(mb_size + m * 9 + 7) / (fabs(__ldg(w + IVY * cc)) + fast_speed(eos.gamma, wd, p, by, bz, bx));
+    d3 = __ldg(mb_size + m * 9 + 8) / (fabs(__ldg(w + IVZ * cc)) + fast_speed(eos.gamma, wd, p, bz, bx, by));
+  }
+  for (int s = 16; s > 0; s >>= 1) {
+    d1 = fmin(d1, __shfl_xor_sync(0xffffffffu, d1, s));
+    d2 = fmin(d2, __shfl_xor_sync(0xffffffffu, d2, s));
+    d3 = fmin(d3, __shfl_xor_sync(0xffffffffu, d3, s));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomic_min_pos(dtmin + 0, d1);
+    atomic_min_pos(dtmin + 1, d2);
+    atomic_min_pos(dtmin + 2, d3);
+  }
+}
+
+// u1 <- u0 / b1 <- b0 fused into the stage-1 update needs the ghost entries too when the host
+// contract reads them; a plain vectorised copy covers that case (CopyCons, task 1).
+__global__ void __launch_bounds__(256) copy_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, long n2,
+                                                    const double *__restrict__ tail_src, double *__restrict__ tail_dst, int ntail) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n2; q += stride) dst[q] = src[q];
+  if (blockIdx.x == 0 && threadIdx.x < ntail) tail_dst[threadIdx.x] = tail_src[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+
+static inline unsigned nblocks(long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+template <int RECON, int RS>
+static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st) {
+  {  // x1
+    const long cells = (long)g.nmb * (g.nx3 + 2) * (g.nx2 + 2) * (g.nx1 + 2);
+    const long warps = (cells + 30) / 31;
+    flux_x1_kernel<RECON, RS><<<nblocks(warps * 32, 128), 128, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x1f, a.flx1, a.e3x1, a.e2x1);
+  }
+  {  // x2: (ey,ez) = (e1x2,e3x2)
+    const int nf = g.nx2 + 1;
+    const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
+    const long threads = (long)g.nmb * nseg * (g.nx3 + 2) * (g.nx1 + 2);
+    flux_march_kernel<RECON, RS, 1><<<nblocks(threads, 128), 128, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg);
+  }
+  {  // x3: (ey,ez) = (e2x3,e1x3)
+    const int nf = g.nx3 + 1;
+    const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
+    const long threads = (long)g.nmb * nseg * (g.nx2 + 2) * (g.nx1 + 2);
+    flux_march_kernel<RECON, RS, 2><<<nblocks(threads, 128), 128, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
+  }
+  return cudaGetLastError();
+}
+
+template <int RECON>
+static cudaError_t launch_fluxes_r(int rs, const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st) {
+  switch (rs) {
+    case RS_LLF: return launch_fluxes_t<RECON, RS_LLF>(g, eos, a, st);
+    case RS_HLLE: return launch_fluxes_t<RECON, RS_HLLE>(g, eos, a, st);
+    case RS_HLLD: return launch_fluxes_t<RECON, RS_HLLD>(g, eos, a, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_fluxes(int recon, int rs, const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st) {
+  switch (recon) {
+    case RECON_DC: return launch_fluxes_r<RECON_DC>(rs, g, eos, a, st);
+    case RECON_PLM: return launch_fluxes_r<RECON_PLM>(rs, g, eos, a, st);
+    case RECON_PPM4: return launch_fluxes_r<RECON_PPM4>(rs, g, eos, a, st);
+    case RECON_PPMX: return launch_fluxes_r<RECON_PPMX>(rs, g, eos, a, st);
+    case RECON_WENOZ: return launch_fluxes_r<RECON_WENOZ>(rs, g, eos, a, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_corner_e(const Geom &g, const Arrays &a, cudaStream_t st) {
+  const long n = (long)g.nmb * (g.nx3 + 1) * (g.nx2 + 1) * (g.nx1 + 1);
+  corner_emf_kernel<<<nblocks(n, 256), 256, 0, st>>>(g, a.w0, a.bcc0, a.flx1, a.flx2, a.flx3, a.e3x1, a.e2x1, a.e1x2, a.e3x2, a.e2x3, a.e1x3, a.e1, a.e2, a.e3);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_update_ct(const Geom &g, const Arrays &a, bool do_u, bool do_b, double gam0, double gam1,
+                             double beta_dt, cudaStream_t st) {
+  const long n = (long)g.nmb * (g.nx3 + 1) * (g.nx2 + 1) * (g.nx1 + 1);
+#define AKB_UCT_ARGS g, a.u0, a.u1, a.flx1, a.flx2, a.flx3, a.b0x1f, a.b0x2f, a.b0x3f, a.b1x1f, a.b1x2f, a.b1x3f, a.e1, a.e2, a.e3, a.mb_size, gam0, gam1, beta_dt
+  if (do_u && do_b) update_ct_kernel<true, true><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
+  else if (do_u) update_ct_kernel<true, false><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
+  else if (do_b) update_ct_kernel<false, true><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
+#undef AKB_UCT_ARGS
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cons2prim(const Geom &g, const EosParams &eos, const Arrays &a, int il, int iu, int jl, int ju,
+                             int kl, int ku, int *counters, bool newdt, unsigned long long *dtmin, cudaStream_t st) {
+  const long n = (long)g.nmb * (ku - kl + 1) * (ju - jl + 1) * (iu - il + 1);
+  if (n <= 0) return cudaSuccess;
+  if (newdt)
+    cons2prim_kernel<true><<<nblocks(n, 256), 256, 0, st>>>(g, eos, a.u0, a.b0x1f, a.b0x2f, a.b0x3f, a.w0, a.bcc0, il, iu, jl, ju, kl, ku, counters, a.mb_size, dtmin);
+  else
+    cons2prim_kernel<false><<<nblocks(n, 256), 256, 0, st>>>(g, eos, a.u0, a.b0x1f, a.b0x2f, a.b0x3f, a.w0, a.bcc0, il, iu, jl, ju, kl, ku, counters, a.mb_size, dtmin);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_newdt(const Geom &g, const EosParams &eos, const Arrays &a, unsigned long long *dtmin, cudaStream_t st) {
+  const long n = (long)g.nmb * g.nx3 * g.nx2 * g.nx1;
+  newdt_kernel<<<nblocks(n, 256), 256, 0, st>>>(g, eos, a.w0, a.bcc0, a.mb_size, dtmin);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_copy(const double *src, double *dst, long n, cudaStream_t st) {
+  // 16-byte vector copy when both pointers allow it, scalar tail otherwise
+  if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+    const long n2 = n / 2;
+    const int ntail = (int)(n - 2 * n2);
+    long want = (n2 + 255) / 256;
+    unsigned nb = (unsigned)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
+    copy_kernel<<<nb, 256, 0, st>>>((const double2 *)src, (double2 *)dst, n2, src + 2 * n2, dst + 2 * n2, ntail);
+    return cudaGetLastError();
+  }
+  return cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+}
+
+}  // namespace akb

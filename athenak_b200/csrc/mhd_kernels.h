@@ -1,0 +1,37 @@
+// mhd_kernels.h -- host-side declarations of the kernel launchers (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace akb {
+
+struct EosParams;
+
+struct Geom {  // RegionIndcs (src/mesh/mesh.hpp:35-41) + derived array extents
+  int nmb, ng, nx1, nx2, nx3;
+  int n1, n2, n3;
+  int is, ie, js, je, ks, ke;
+  long cc;          // cells per variable per block
+  long f1, f2, f3;  // faces per block
+  long e1, e2, e3;  // edges per block
+};
+
+struct Arrays {  // mirror of ak_mhd_arrays (include/athenak_b200.h)
+  double *u0, *u1, *w0, *bcc0;
+  double *b0x1f, *b0x2f, *b0x3f, *b1x1f, *b1x2f, *b1x3f;
+  double *flx1, *flx2, *flx3;
+  double *e3x1, *e2x1, *e1x2, *e3x2, *e2x3, *e1x3;
+  double *e1, *e2, *e3;
+  const double *mb_size;
+};
+
+cudaError_t launch_fluxes(int recon, int rs, const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st);
+cudaError_t launch_corner_e(const Geom &g, const Arrays &a, cudaStream_t st);
+cudaError_t launch_update_ct(const Geom &g, const Arrays &a, bool do_u, bool do_b, double gam0, double gam1,
+                             double beta_dt, cudaStream_t st);
+cudaError_t launch_cons2prim(const Geom &g, const EosParams &eos, const Arrays &a, int il, int iu, int jl, int ju,
+                             int kl, int ku, int *counters, bool newdt, unsigned long long *dtmin, cudaStream_t st);
+cudaError_t launch_newdt(const Geom &g, const EosParams &eos, const Arrays &a, unsigned long long *dtmin, cudaStream_t st);
+cudaError_t launch_copy(const double *src, double *dst, long n, cudaStream_t st);
+
+}  // namespace akb

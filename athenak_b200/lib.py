@@ -1,0 +1,99 @@
+"""ctypes binding of libathenak_b200.so (the C ABI in include/athenak_b200.h).
+
+The library is the product: there is no Python or CPU implementation behind these calls.
+If the shared object is missing it is built in-tree with nvcc (athenak_b200/build.py); if it
+cannot be loaded, or no CUDA device is present, the calls raise -- nothing falls back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+RECON = {"dc": 0, "plm": 1, "ppm4": 2, "ppmx": 3, "wenoz": 4}
+RSOLVER = {"llf": 0, "hlle": 1, "hlld": 2}
+
+_dp = C.POINTER(C.c_double)
+
+
+class MhdCfg(C.Structure):
+    """ak_mhd_cfg"""
+    _fields_ = [("nmb", C.c_int), ("ng", C.c_int), ("nx1", C.c_int), ("nx2", C.c_int),
+                ("nx3", C.c_int), ("recon", C.c_int), ("rsolver", C.c_int),
+                ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
+                ("tfloor", C.c_double), ("sfloor", C.c_double), ("sigma_max", C.c_double)]
+
+
+ARRAY_FIELDS = ("u0", "u1", "w0", "bcc0", "b0x1f", "b0x2f", "b0x3f", "b1x1f", "b1x2f", "b1x3f",
+                "flx1", "flx2", "flx3", "e3x1", "e2x1", "e1x2", "e3x2", "e2x3", "e1x3",
+                "e1", "e2", "e3", "mb_size")
+
+
+class MhdArrays(C.Structure):
+    """ak_mhd_arrays: borrowed device pointers"""
+    _fields_ = [(n, C.c_void_p) for n in ARRAY_FIELDS]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        path = _build.build()
+    lib = C.CDLL(path)
+    lib.ak_last_error.restype = C.c_char_p
+    lib.ak_last_error.argtypes = [C.c_void_p]
+    vp, ip, d = C.c_void_p, C.c_int, C.c_double
+    ap = C.POINTER(MhdArrays)
+    sig = {
+        "ak_mhd_create": [C.POINTER(MhdCfg), C.POINTER(vp)],
+        "ak_mhd_destroy": [vp],
+        "ak_mhd_copy_cons": [vp, ap, vp],
+        "ak_mhd_fluxes": [vp, ap, vp],
+        "ak_mhd_rk_update": [vp, ap, d, d, d, vp],
+        "ak_mhd_corner_e": [vp, ap, vp],
+        "ak_mhd_ct": [vp, ap, d, d, d, vp],
+        "ak_mhd_cons2prim": [vp, ap, ip, ip, ip, ip, ip, ip, C.POINTER(C.c_int), vp],
+        "ak_mhd_new_dt": [vp, ap, _dp, vp],
+        "ak_mhd_stage_fused": [vp, ap, ip, d, d, d, vp],
+        "ak_mhd_cons2prim_newdt": [vp, ap, C.POINTER(C.c_int), _dp, vp],
+        "ak_halo_create": [C.POINTER(MhdCfg), C.POINTER(C.c_int), ip, ip, C.POINTER(vp)],
+        "ak_halo_destroy": [vp],
+        "ak_halo_npeers": [vp],
+        "ak_halo_peer": [vp, ip, C.POINTER(C.c_int), C.POINTER(C.c_long), C.POINTER(C.c_long)],
+        "ak_halo_descs": [vp, ip, ip, C.POINTER(C.c_long), ip],
+        "ak_halo_local_cc": [vp, vp, ip, vp],
+        "ak_halo_local_fc": [vp, vp, vp, vp, vp],
+        "ak_halo_pack_cc": [vp, vp, ip, ip, vp, vp],
+        "ak_halo_unpack_cc": [vp, vp, ip, ip, vp, vp],
+        "ak_halo_pack_fc": [vp, vp, vp, vp, ip, vp, vp],
+        "ak_halo_unpack_fc": [vp, vp, vp, vp, ip, vp, vp],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, name)      # AttributeError here = header/library mismatch: fail loudly
+        fn.argtypes = args
+        fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_cons", "ak_mhd_fluxes",
+            "ak_mhd_rk_update", "ak_mhd_corner_e", "ak_mhd_ct", "ak_mhd_cons2prim", "ak_mhd_new_dt",
+            "ak_mhd_stage_fused", "ak_mhd_cons2prim_newdt", "ak_halo_create", "ak_halo_destroy",
+            "ak_halo_npeers", "ak_halo_peer", "ak_halo_descs", "ak_halo_local_cc", "ak_halo_local_fc",
+            "ak_halo_pack_cc", "ak_halo_unpack_cc", "ak_halo_pack_fc", "ak_halo_unpack_fc")
+
+
+def check(rc, handle=None):
+    if rc != 0:
+        msg = load().ak_last_error(handle)
+        raise EngineError((msg or b"unknown error").decode())

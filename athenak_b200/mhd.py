@@ -1,0 +1,217 @@
+"""Host-side mirror of the reference's `mhd::MHD` module for the Newtonian ideal-gas path.
+
+Reference: src/mhd/mhd.hpp:87-207 (state owner), src/mhd/mhd_tasks.cpp:38-84 (task list).
+The object owns every array of one MeshBlockPack as FP64 device tensors in the reference
+layout and exposes one method per task with the reference's task signature
+`(driver, stage) -> TaskStatus`; each method body is one call through the C ABI
+(include/athenak_b200.h).  PyTorch is used for device memory, streams and (multi-rank)
+torch.distributed point-to-point only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+
+FLT_MIN = float(np.finfo(np.float32).tiny)
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+class TaskStatus(enum.Enum):  # src/tasklist/task_list.hpp:30
+    fail = 0
+    complete = 1
+    incomplete = 2
+
+
+class MHD:
+    def __init__(self, nmb, ng, nx, mb_size, nghbr, *, recon="ppm4", rsolver="hlld", gamma,
+                 dfloor=FLT_MIN, pfloor=FLT_MIN, tfloor=FLT_MIN, sfloor=FLT_MIN, sigma_max=FLT_MAX,
+                 my_rank=0, gids_start=0, device="cuda", process_group=None, fused=True):
+        if not torch.cuda.is_available():
+            raise _lib.EngineError("athenak_b200: no CUDA device; the engine has no CPU path")
+        self.L = _lib.load()
+        self.device = torch.device(device)
+        self.nmb, self.ng, self.nx = int(nmb), int(ng), tuple(int(v) for v in nx)
+        nx1, nx2, nx3 = self.nx
+        self.n = (nx1 + 2 * ng, nx2 + 2 * ng, nx3 + 2 * ng)
+        self.cfg = _lib.MhdCfg(self.nmb, ng, nx1, nx2, nx3, _lib.RECON[recon], _lib.RSOLVER[rsolver],
+                               gamma, dfloor, pfloor, tfloor, sfloor, sigma_max)
+        self.fused = fused
+        self.my_rank, self.gids_start, self.pg = my_rank, gids_start, process_group
+        n1, n2, n3 = self.n
+        z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=self.device)
+        # src/mhd/mhd.cpp:148-161,329-354
+        self.u0, self.u1, self.w0 = z(nmb, 5, n3, n2, n1), z(nmb, 5, n3, n2, n1), z(nmb, 5, n3, n2, n1)
+        self.bcc0 = z(nmb, 3, n3, n2, n1)
+        self.b0 = [z(nmb, n3, n2, n1 + 1), z(nmb, n3, n2 + 1, n1), z(nmb, n3 + 1, n2, n1)]
+        self.b1 = [torch.zeros_like(a) for a in self.b0]
+        self.uflx = [z(nmb, 5, n3, n2, n1 + 1), z(nmb, 5, n3, n2 + 1, n1), z(nmb, 5, n3 + 1, n2, n1)]
+        self.femf = [z(nmb, n3, n2, n1) for _ in range(6)]   # e3x1,e2x1,e1x2,e3x2,e2x3,e1x3
+        self.efld = [z(nmb, n3 + 1, n2 + 1, n1), z(nmb, n3 + 1, n2, n1 + 1), z(nmb, n3, n2 + 1, n1 + 1)]
+        self.mb_size_h = np.ascontiguousarray(mb_size, dtype=np.float64).reshape(nmb, 9)
+        self.mb_size = torch.from_numpy(self.mb_size_h).to(self.device)
+        self.arrays = _lib.MhdArrays()
+        self._bind()
+        self.h = C.c_void_p()
+        _lib.check(self.L.ak_mhd_create(C.byref(self.cfg), C.byref(self.h)))
+        # neighbour table -> halo plan
+        self.nghbr = np.ascontiguousarray(nghbr, dtype=np.int32).reshape(nmb, 56, 4)
+        self.plan = C.c_void_p()
+        _lib.check(self.L.ak_halo_create(C.byref(self.cfg), self.nghbr.ctypes.data_as(C.POINTER(C.c_int)),
+                                         my_rank, gids_start, C.byref(self.plan)))
+        self.peers = []
+        for ip in range(self.L.ak_halo_npeers(self.plan)):
+            r, ncc, nfc = C.c_int(), C.c_long(), C.c_long()
+            _lib.check(self.L.ak_halo_peer(self.plan, ip, C.byref(r), C.byref(ncc), C.byref(nfc)))
+            self.peers.append(dict(rank=r.value, ncc=ncc.value, nfc=nfc.value,
+                                   scc=z(5 * ncc.value), rcc=z(5 * ncc.value), sfc=z(nfc.value), rfc=z(nfc.value)))
+        self.dtnew = FLT_MAX
+        self.nfloor = [0, 0, 0]       # EventCounters neos_dfloor/efloor/tfloor (src/mesh/mesh.hpp:70-74)
+        self.launches = 0             # kernels this object has launched (bench: gpu_launches)
+
+    def _bind(self):
+        a = self.arrays
+        t = dict(u0=self.u0, u1=self.u1, w0=self.w0, bcc0=self.bcc0,
+                 b0x1f=self.b0[0], b0x2f=self.b0[1], b0x3f=self.b0[2],
+                 b1x1f=self.b1[0], b1x2f=self.b1[1], b1x3f=self.b1[2],
+                 flx1=self.uflx[0], flx2=self.uflx[1], flx3=self.uflx[2],
+                 e3x1=self.femf[0], e2x1=self.femf[1], e1x2=self.femf[2], e3x2=self.femf[3],
+                 e2x3=self.femf[4], e1x3=self.femf[5], e1=self.efld[0], e2=self.efld[1], e3=self.efld[2],
+                 mb_size=self.mb_size)
+        for k, v in t.items():
+            setattr(a, k, v.data_ptr())
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None):
+                self.L.ak_halo_destroy(self.plan)
+            if getattr(self, "h", None):
+                self.L.ak_mhd_destroy(self.h)
+        except Exception:
+            pass
+
+    # -- helpers -------------------------------------------------------------------------
+    def _st(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ck(self, rc):
+        _lib.check(rc, self.h)
+
+    def load_state(self, u0, b1f, b2f, b3f):
+        """Copy host (numpy) conserved state into the device arrays (ICs / restart)."""
+        self.u0.copy_(torch.from_numpy(np.ascontiguousarray(u0)))
+        for dst, src in zip(self.b0, (b1f, b2f, b3f)):
+            dst.copy_(torch.from_numpy(np.ascontiguousarray(src)))
+
+    # -- tasks (src/mhd/mhd_tasks.cpp:48-75), uniform-mesh subset -------------------------
+    def CopyCons(self, driver, stage):
+        if stage == 1:
+            self._ck(self.L.ak_mhd_copy_cons(self.h, C.byref(self.arrays), self._st()))
+            self.launches += 4
+        return TaskStatus.complete
+
+    def Fluxes(self, driver, stage):
+        self._ck(self.L.ak_mhd_fluxes(self.h, C.byref(self.arrays), self._st()))
+        self.launches += 3
+        return TaskStatus.complete
+
+    def RKUpdate(self, driver, stage):
+        g0, g1, bdt = driver.gam0[stage - 1], driver.gam1[stage - 1], driver.beta[stage - 1] * driver.dt
+        self._ck(self.L.ak_mhd_rk_update(self.h, C.byref(self.arrays), g0, g1, bdt, self._st()))
+        self.launches += 1
+        return TaskStatus.complete
+
+    def EField(self, driver, stage):
+        self._ck(self.L.ak_mhd_corner_e(self.h, C.byref(self.arrays), self._st()))
+        self.launches += 1
+        return TaskStatus.complete
+
+    def CT(self, driver, stage):
+        g0, g1, bdt = driver.gam0[stage - 1], driver.gam1[stage - 1], driver.beta[stage - 1] * driver.dt
+        self._ck(self.L.ak_mhd_ct(self.h, C.byref(self.arrays), g0, g1, bdt, self._st()))
+        self.launches += 1
+        return TaskStatus.complete
+
+    def StageFused(self, driver, stage):
+        """Tasks 1,2,5,14,17 in one ABI call (ak_mhd_stage_fused)."""
+        g0, g1, bdt = driver.gam0[stage - 1], driver.gam1[stage - 1], driver.beta[stage - 1] * driver.dt
+        self._ck(self.L.ak_mhd_stage_fused(self.h, C.byref(self.arrays), stage, g0, g1, bdt, self._st()))
+        self.launches += 5 + (4 if stage == 1 else 0)
+        return TaskStatus.complete
+
+    def _exchange(self, which):
+        """SendU/RecvU (which='u') or SendB/RecvB (which='b'): src/bvals/bvals_cc.cpp:42-447,
+        bvals_fc.cpp:63-436.  Off-rank slabs: pack -> one message per peer -> unpack."""
+        st = self._st()
+        L = self.L
+        if self.peers:
+            import torch.distributed as dist
+            ops = []
+            for ip, p in enumerate(self.peers):
+                if which == "u":
+                    _lib.check(L.ak_halo_pack_cc(self.plan, self.u0.data_ptr(), 5, ip, p["scc"].data_ptr(), st))
+                    s, r = p["scc"], p["rcc"]
+                else:
+                    _lib.check(L.ak_halo_pack_fc(self.plan, *[a.data_ptr() for a in self.b0], ip, p["sfc"].data_ptr(), st))
+                    s, r = p["sfc"], p["rfc"]
+                self.launches += 1
+                ops.append(dist.P2POp(dist.isend, s, p["rank"], group=self.pg))
+                ops.append(dist.P2POp(dist.irecv, r, p["rank"], group=self.pg))
+            reqs = dist.batch_isend_irecv(ops)
+        if which == "u":
+            _lib.check(L.ak_halo_local_cc(self.plan, self.u0.data_ptr(), 5, st))
+        else:
+            _lib.check(L.ak_halo_local_fc(self.plan, *[a.data_ptr() for a in self.b0], st))
+        self.launches += 1
+        if self.peers:
+            for rq in reqs:
+                rq.wait()
+            for ip, p in enumerate(self.peers):
+                if which == "u":
+                    _lib.check(L.ak_halo_unpack_cc(self.plan, self.u0.data_ptr(), 5, ip, p["rcc"].data_ptr(), st))
+                else:
+                    _lib.check(L.ak_halo_unpack_fc(self.plan, *[a.data_ptr() for a in self.b0], ip, p["rfc"].data_ptr(), st))
+                self.launches += 1
+
+    def SendRecvU(self, driver, stage):
+        self._exchange("u")
+        return TaskStatus.complete
+
+    def SendRecvB(self, driver, stage):
+        self._exchange("b")
+        return TaskStatus.complete
+
+    def ConToPrim(self, driver, stage, count=True):
+        n1, n2, n3 = self.n
+        nf = (C.c_int * 3)() if count else None
+        self._ck(self.L.ak_mhd_cons2prim(self.h, C.byref(self.arrays), 0, n1 - 1, 0, n2 - 1, 0, n3 - 1, nf, self._st()))
+        self.launches += 1
+        if count:
+            for q in range(3):
+                self.nfloor[q] += nf[q]
+        return TaskStatus.complete
+
+    def NewTimeStep(self, driver, stage):
+        if stage != driver.nexp_stages:      # src/mhd/mhd_newdt.cpp:32-34
+            return TaskStatus.complete
+        dt3 = (C.c_double * 3)()
+        self._ck(self.L.ak_mhd_new_dt(self.h, C.byref(self.arrays), dt3, self._st()))
+        self.launches += 1
+        self.dtnew = min(dt3[0], dt3[1], dt3[2])   # src/mhd/mhd_newdt.cpp:152-155
+        return TaskStatus.complete
+
+    def ConToPrimNewDt(self, driver, stage):
+        """Tasks 27+28 fused on the last stage (ak_mhd_cons2prim_newdt)."""
+        if stage != driver.nexp_stages:
+            return self.ConToPrim(driver, stage)
+        nf, dt3 = (C.c_int * 3)(), (C.c_double * 3)()
+        self._ck(self.L.ak_mhd_cons2prim_newdt(self.h, C.byref(self.arrays), nf, dt3, self._st()))
+        self.launches += 1
+        for q in range(3):
+            self.nfloor[q] += nf[q]
+        self.dtnew = min(dt3[0], dt3[1], dt3[2])
+        return TaskStatus.complete

@@ -1,0 +1,117 @@
+/* athenak_b200.h -- C ABI of the B200-native MHD stage-update engine.
+ *
+ * Drop-in boundary: every entry point replaces the body of one task
+ * that AthenaK's MHD module registers with TaskList::AddTask (reference
+ * src/mhd/mhd_tasks.cpp:38-84; task signature src/tasklist/task_list.hpp:85-110).  The host
+ * keeps owning every array (reference src/mhd/mhd.hpp:99-137); this library only borrows raw
+ * device pointers (Kokkos View::data(), LayoutRight, no padding) for the duration of a call.
+ *
+ * Conventions
+ *  - all functions return 0 on success, non-zero on error; ak_last_error() gives the text.
+ *    A task wrapper turns non-zero into the reference's "### FATAL ERROR" + exit
+ *    (e.g. src/mhd/mhd.cpp:85-87) and otherwise returns TaskStatus::complete.
+ *  - single host thread per handle; all work is enqueued on the given stream, in order;
+ *    only calls that return host scalars (ak_mhd_cons2prim counters, ak_mhd_new_dt)
+ *    synchronise that stream.
+ *  - there is no CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Array layout (reference src/athena.hpp:111-130,178-231), FP64, i fastest:
+ *   cell  (m,n,k,j,i)            n1=nx1+2ng, n2=nx2+2ng, n3=nx3+2ng
+ *   faces x1f (m,[n,]k,j,i)  extents (n3,n2,n1+1); x2f (n3,n2+1,n1); x3f (n3+1,n2,n1)
+ *   edges x1e (m,k,j,i) extents (n3+1,n2+1,n1); x2e (n3+1,n2,n1+1); x3e (n3,n2+1,n1+1)
+ *   face EMFs e3x1,e2x1,e1x2,e3x2,e2x3,e1x3: cell-shaped (m,k,j,i) (src/mhd/mhd.cpp:349-354)
+ */
+#ifndef ATHENAK_B200_H_
+#define ATHENAK_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *ak_stream_t; /* a cudaStream_t (0 = default stream) */
+
+/* reconstruction / Riemann-solver selectors: reference src/athena.hpp:75, src/mhd/mhd.hpp:39 */
+enum { AK_RECON_DC = 0, AK_RECON_PLM = 1, AK_RECON_PPM4 = 2, AK_RECON_PPMX = 3, AK_RECON_WENOZ = 4 };
+enum { AK_RSOLVER_LLF = 0, AK_RSOLVER_HLLE = 1, AK_RSOLVER_HLLD = 2 };
+
+typedef struct {
+  int nmb;           /* MeshBlocks in this pack (reference MeshBlockPack::nmb_thispack) */
+  int ng;            /* ghost cells per side (mesh/nghost)                               */
+  int nx1, nx2, nx3; /* active cells per block (RegionIndcs, src/mesh/mesh.hpp:35-41)    */
+  int recon, rsolver;
+  double gamma, dfloor, pfloor, tfloor, sfloor, sigma_max; /* EOS_Data, src/eos/eos.hpp:27-33 */
+} ak_mhd_cfg;
+
+typedef struct {
+  double *u0, *u1, *w0, *bcc0;                       /* src/mhd/mhd.hpp:99-111 */
+  double *b0x1f, *b0x2f, *b0x3f, *b1x1f, *b1x2f, *b1x3f;
+  double *flx1, *flx2, *flx3;                        /* uflx.x1f/x2f/x3f      */
+  double *e3x1, *e2x1, *e1x2, *e3x2, *e2x3, *e1x3;   /* face-centred EMFs     */
+  double *e1, *e2, *e3;                              /* efld.x1e/x2e/x3e      */
+  const double *mb_size; /* DEVICE [nmb][9]: x1min,x2min,x3min,x1max,x2max,x3max,dx1,dx2,dx3
+                            (RegionSize, src/mesh/mesh.hpp:25-29)                        */
+} ak_mhd_arrays;
+
+int ak_mhd_create(const ak_mhd_cfg *cfg, void **handle);
+int ak_mhd_destroy(void *handle);
+const char *ak_last_error(void *handle);
+
+/* task 1  MHD::CopyCons      src/mhd/mhd_tasks.cpp:162-170  (caller decides stage==1) */
+int ak_mhd_copy_cons(void *h, const ak_mhd_arrays *a, ak_stream_t s);
+/* task 2  MHD::Fluxes -> CalculateFluxes<rsolver>  src/mhd/mhd_fluxes.cpp:85-266 */
+int ak_mhd_fluxes(void *h, const ak_mhd_arrays *a, ak_stream_t s);
+/* task 5  MHD::RKUpdate      src/mhd/mhd_update.cpp:24-84 */
+int ak_mhd_rk_update(void *h, const ak_mhd_arrays *a, double gam0, double gam1, double beta_dt, ak_stream_t s);
+/* task 14 MHD::CornerE       src/mhd/mhd_corner_e.cpp:26-415 (3-D Newtonian branch) */
+int ak_mhd_corner_e(void *h, const ak_mhd_arrays *a, ak_stream_t s);
+/* task 17 MHD::CT            src/mhd/mhd_ct.cpp:23-80 */
+int ak_mhd_ct(void *h, const ak_mhd_arrays *a, double gam0, double gam1, double beta_dt, ak_stream_t s);
+/* task 27 MHD::ConToPrim -> IdealMHD::ConsToPrim  src/eos/ideal_mhd.cpp:30-134.
+ * nfloor (host int[3], may be NULL) receives the dfloor/efloor/tfloor counters; when it is
+ * non-NULL the call synchronises the stream. */
+int ak_mhd_cons2prim(void *h, const ak_mhd_arrays *a, int il, int iu, int jl, int ju, int kl, int ku,
+                     int *nfloor, ak_stream_t s);
+/* task 28 MHD::NewTimeStep   src/mhd/mhd_newdt.cpp:31-174: dt3 (host double[3]) = min over
+ * active cells of dx_d/(|v_d|+c_f,d); synchronises the stream. */
+int ak_mhd_new_dt(void *h, const ak_mhd_arrays *a, double *dt3, ak_stream_t s);
+
+/* Fused stage: tasks 1,2,5,14,17 (CopyCons, Fluxes, RKUpdate, CornerE, CT) with fewer kernels
+ * and no CopyCons pass.  Legal on a same-level mesh with no diffusion/FOFC/source-term
+ * consumers of uflx/efld between the tasks (SendE/RecvE is a bitwise identity there,
+ * SURVEY.md section 0 fact 6).  flx*, e?x?, e1..e3 are still written. */
+int ak_mhd_stage_fused(void *h, const ak_mhd_arrays *a, int stage, double gam0, double gam1,
+                       double beta_dt, ak_stream_t s);
+/* c2p over all cells fused with the task-28 reduction over the active cells (last stage). */
+int ak_mhd_cons2prim_newdt(void *h, const ak_mhd_arrays *a, int *nfloor, double *dt3, ak_stream_t s);
+
+/* ---- ghost-zone exchange (src/bvals): tasks 10/11 SendU/RecvU, 21/22 SendB/RecvB ---------
+ * nghbr: HOST [nmb][56][4] = {gid, lev, rank, dest} per neighbour slot (NeighborBlock,
+ * src/mesh/mesh.hpp:47-52; slot numbering src/mesh/nghbr_index.hpp:28-54).  gids_start is the
+ * first gid owned by my_rank (contiguous ranges, src/mesh/load_balance.cpp:38-88).
+ * Same-rank neighbours are filled by one gather kernel (the reference's direct-write path,
+ * src/bvals/bvals_cc.cpp:122-135, without the intermediate buffer).  Off-rank neighbours go
+ * through per-peer send/recv buffers laid out as the reference's rank-packed messages:
+ * entries ordered by (m, slot), each nvar*ndat values linearised as
+ * (i-il) + ni*((j-jl) + nj*((k-kl) + nk*v))  (src/bvals/bvals_cc.cpp:127). */
+int ak_halo_create(const ak_mhd_cfg *cfg, const int *nghbr, int my_rank, int gids_start, void **plan);
+int ak_halo_destroy(void *plan);
+int ak_halo_npeers(void *plan);
+/* peer rank and message length (doubles) for CC data with nvar variables, and for FC data */
+int ak_halo_peer(void *plan, int ipeer, int *rank, long *cc_count_per_var, long *fc_count);
+/* host-side view of the resolved copy plan (needs no device): kind 0 local_cc, 1 local_fc,
+ * 2 pack_cc, 3 unpack_cc, 4 pack_fc, 5 unpack_fc; out [max][13] longs = m, src_m, comp,
+ * lo[3], hi[3], shift[3], message offset.  Returns the number of descriptors, <0 on error. */
+int ak_halo_descs(void *plan, int kind, int ipeer, long *out, int max);
+int ak_halo_local_cc(void *plan, double *a, int nvar, ak_stream_t s);
+int ak_halo_local_fc(void *plan, double *x1f, double *x2f, double *x3f, ak_stream_t s);
+int ak_halo_pack_cc(void *plan, const double *a, int nvar, int ipeer, double *sendbuf, ak_stream_t s);
+int ak_halo_unpack_cc(void *plan, double *a, int nvar, int ipeer, const double *recvbuf, ak_stream_t s);
+int ak_halo_pack_fc(void *plan, const double *x1f, const double *x2f, const double *x3f, int ipeer,
+                    double *sendbuf, ak_stream_t s);
+int ak_halo_unpack_fc(void *plan, double *x1f, double *x2f, double *x3f, int ipeer,
+                      const double *recvbuf, ak_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATHENAK_B200_H_ */

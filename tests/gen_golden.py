@@ -1,0 +1,55 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref, see oracle/build_ref.sh).
+
+Run in the build container:  python tests/gen_golden.py
+Fixtures hold only the ACTIVE zones (ghosts are a periodic wrap of them and are rebuilt by
+tests/golden_io.py), so each state is a few hundred kB.
+"""
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle_lib as O  # noqa: E402
+from athenak_b200.rst import read_rst  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def active(r):
+    ng = r.mb_indcs["ng"]
+    s = slice(ng, -ng)
+    return dict(u0=r.u0[:, :, s, s, s], b1f=r.b1f[:, s, s, ng:-ng], b2f=r.b2f[:, s, ng:-ng, s],
+                b3f=r.b3f[:, ng:-ng, s, s])
+
+
+def blast(n, cycles, recon="ppm4", rsolver="hlld", integrator="rk3", name=None):
+    tmp = tempfile.mkdtemp(prefix="akgold_")
+    try:
+        ov = [f"mesh/nx1={n}", f"mesh/nx2={n}", f"mesh/nx3={n}", f"meshblock/nx1={n}", f"meshblock/nx2={n}",
+              f"meshblock/nx3={n}", f"time/nlim={max(cycles)}", f"mhd/reconstruct={recon}", f"mhd/rsolver={rsolver}",
+              f"time/integrator={integrator}"]
+        O.run_reference("athena_blast", os.path.join(HERE, "decks", "blast3d.athinput"), tmp, ov)
+        out = {}
+        for c in [0] + list(cycles):
+            r = read_rst(os.path.join(tmp, "rst", "Blast.%05d.rst" % c))
+            assert r.ncycle == c
+            for k, v in active(r).items():
+                out[f"{k}_c{c}"] = v
+            out[f"time_c{c}"] = r.time
+            out[f"dt_c{c}"] = r.dt
+        out["meta"] = np.array([n, 4, max(cycles)])
+        np.savez_compressed(os.path.join(HERE, "golden", name or f"blast{n}_{recon}_{rsolver}_{integrator}.npz"), **out)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    blast(16, (1, 4))
+    blast(16, (2,), recon="plm", rsolver="hlle", integrator="rk2")
+    blast(16, (2,), recon="wenoz", rsolver="llf", integrator="rk3")
+    blast(16, (2,), recon="ppmx", rsolver="hlld", integrator="rk1")
+    print("golden fixtures written")
