@@ -1,0 +1,277 @@
+// host_mesh.cpp -- host-side (CPU, plain C++17) mirror of the reference's uniform-mesh metadata:
+// MeshBlockTree Z-ordering, LoadBalance, MeshBlock sizes/BC flags and the 56-slot neighbour
+// table, plus the blast problem generator that provides the synthetic inputs of the benchmark.
+//
+// Reference: src/mesh/build_tree.cpp:32-307 (BuildTreeFromScratch), meshblock_tree.cpp:60-90
+// (CreateRootGrid), :336-350 (Z-order gids), :355-430 (FindNeighbor), load_balance.cpp:38-88,
+// meshblock.cpp:25-131 (sizes, BC flags), :142-430 (SetNeighbors, same-level branch),
+// nghbr_index.hpp:28-54, coordinates/cell_locations.hpp:24-39, pgen/fluids/blast.cpp:134-402.
+// The integer maps must be bit-exact with the reference (tests/test_host_mesh.py).
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/athenak_b200.h"
+#include "halo.h"
+
+namespace {
+
+struct LLoc { int32_t lx1, lx2, lx3, level; };
+
+struct HostMesh {
+  int nmesh[3], nblock[3], nroot[3];
+  double xmin[3], xmax[3];
+  int bcs[6];          // per mesh face: AK_BC_* (periodic = 0)
+  int nranks;
+  int root_level, nmb_total;
+  std::vector<LLoc> lloc;            // Z-ordered
+  std::vector<int> rank_of, gids_start, nmb_rank;
+  std::vector<double> mb_size;       // [nmb_total][9]
+  std::vector<int> mb_bcs;           // [nmb_total][6]
+  std::vector<int> nghbr;            // [nmb_total][56][4]
+  std::string err;
+};
+
+thread_local std::string g_mesh_err;
+
+// coordinates/cell_locations.hpp:24-39
+inline double LeftEdgeX(int ith, int n, double xmin, double xmax) {
+  double x = (static_cast<double>(ith)) / (static_cast<double>(n));
+  return (x * xmax - x * xmin) - (0.5 * xmax - 0.5 * xmin) + (0.5 * xmin + 0.5 * xmax);
+}
+inline double CellCenterX(int ith, int n, double xmin, double xmax) {
+  double x = (static_cast<double>(ith) + 0.5) / (static_cast<double>(n));
+  return (x * xmax - x * xmin) - (0.5 * xmax - 0.5 * xmin) + (0.5 * xmin + 0.5 * xmax);
+}
+
+// depth-first walk of the (possibly incomplete) root oct-tree: leaf order = gid order
+void walk(const HostMesh &M, int lx, int ly, int lz, int lev, std::vector<LLoc> &out) {
+  if (lev == M.root_level) { out.push_back(LLoc{lx, ly, lz, lev}); return; }
+  const int levfac = 1 << (M.root_level - lev - 1);
+  for (int n = 0; n < 8; ++n) {
+    const int i = n & 1, j = (n >> 1) & 1, k = (n >> 2) & 1;
+    if ((lz * 2 + k) * levfac < M.nroot[2] && (ly * 2 + j) * levfac < M.nroot[1] && (lx * 2 + i) * levfac < M.nroot[0])
+      walk(M, lx * 2 + i, ly * 2 + j, lz * 2 + k, lev + 1, out);
+  }
+}
+
+// load_balance.cpp:38-88 with unit costs
+void load_balance(HostMesh &M) {
+  const int nb = M.nmb_total, nr = M.nranks;
+  std::vector<float> clist(nb, 1.0f);
+  M.rank_of.assign(nb, 0); M.gids_start.assign(nr, 0); M.nmb_rank.assign(nr, 0);
+  float totalcost = 0.0f;
+  for (int i = 0; i < nb; i++) totalcost += clist[i];
+  int j = nr - 1;
+  float targetcost = totalcost / nr;
+  float mycost = 0.0f;
+  for (int i = nb - 1; i >= 0; i--) {
+    mycost += clist[i];
+    M.rank_of[i] = j;
+    if (mycost >= targetcost && j > 0) {
+      j--;
+      totalcost -= mycost;
+      mycost = 0.0f;
+      targetcost = totalcost / (j + 1);
+    }
+  }
+  M.gids_start[0] = 0;
+  j = 0;
+  for (int i = 1; i < nb; i++) {
+    if (M.rank_of[i] != M.rank_of[i - 1]) {
+      M.nmb_rank[j] = i - M.gids_start[j];
+      M.gids_start[++j] = i;
+    }
+  }
+  M.nmb_rank[j] = nb - M.gids_start[j];
+}
+
+}  // namespace
+
+extern "C" {
+
+enum { AK_BC_PERIODIC = 0, AK_BC_OTHER = 1 };
+
+const char *ak_mesh_last_error() { return g_mesh_err.c_str(); }
+
+// nmesh/nblock: cells per direction in the mesh / per MeshBlock; bcs[6]: ix1,ox1,ix2,ox2,ix3,ox3.
+int ak_mesh_create(const int *nmesh, const int *nblock, const double *xmin, const double *xmax, const int *bcs,
+                   int nranks, void **mesh) {
+  if (!mesh) { g_mesh_err = "ak_mesh_create: null output"; return 1; }
+  *mesh = nullptr;
+  auto *M = new HostMesh();
+  for (int d = 0; d < 3; ++d) {
+    M->nmesh[d] = nmesh[d]; M->nblock[d] = nblock[d]; M->xmin[d] = xmin[d]; M->xmax[d] = xmax[d];
+    if (nblock[d] < 1 || nmesh[d] < nblock[d] || nmesh[d] % nblock[d] != 0) {
+      g_mesh_err = "ak_mesh_create: mesh/nx must be a positive multiple of meshblock/nx"; delete M; return 1;
+    }
+    M->nroot[d] = nmesh[d] / nblock[d];                       // build_tree.cpp:34-36
+    if ((bcs[2 * d] == AK_BC_PERIODIC) != (bcs[2 * d + 1] == AK_BC_PERIODIC)) {
+      g_mesh_err = "ak_mesh_create: both inner and outer bcs must be periodic"; delete M; return 1;  // mesh.cpp:86-93
+    }
+  }
+  for (int q = 0; q < 6; ++q) M->bcs[q] = bcs[q];
+  M->nranks = nranks;
+  int nmbmax = std::max(M->nroot[0], std::max(M->nroot[1], M->nroot[2]));
+  for (M->root_level = 0; ((1 << M->root_level) < nmbmax); M->root_level++) {}   // build_tree.cpp:42-45
+  walk(*M, 0, 0, 0, 0, M->lloc);
+  M->nmb_total = (int)M->lloc.size();
+  if (M->nmb_total < nranks) { g_mesh_err = "ak_mesh_create: fewer MeshBlocks than ranks"; delete M; return 1; }
+  load_balance(*M);
+  const int nb = M->nmb_total;
+  // gid lookup by logical location
+  std::vector<int> gid_of((size_t)M->nroot[0] * M->nroot[1] * M->nroot[2], -1);
+  auto at = [&](int x, int y, int z) -> int & { return gid_of[((size_t)z * M->nroot[1] + y) * M->nroot[0] + x]; };
+  for (int g = 0; g < nb; ++g) at(M->lloc[g].lx1, M->lloc[g].lx2, M->lloc[g].lx3) = g;
+  M->mb_size.assign((size_t)nb * 9, 0.0);
+  M->mb_bcs.assign((size_t)nb * 6, 0);
+  M->nghbr.assign((size_t)nb * 56 * 4, -1);
+  const int AK_BC_BLOCK = -1;  // BoundaryFlag::block
+  for (int g = 0; g < nb; ++g) {
+    const int l[3] = {M->lloc[g].lx1, M->lloc[g].lx2, M->lloc[g].lx3};
+    for (int d = 0; d < 3; ++d) {   // meshblock.cpp:44-116
+      const int n = M->nroot[d];
+      double lo, hi;
+      if (l[d] == 0) { lo = M->xmin[d]; M->mb_bcs[g * 6 + 2 * d] = M->bcs[2 * d]; }
+      else { lo = LeftEdgeX(l[d], n, M->xmin[d], M->xmax[d]); M->mb_bcs[g * 6 + 2 * d] = AK_BC_BLOCK; }
+      if (l[d] == n - 1) { hi = M->xmax[d]; M->mb_bcs[g * 6 + 2 * d + 1] = M->bcs[2 * d + 1]; }
+      else { hi = LeftEdgeX(l[d] + 1, n, M->xmin[d], M->xmax[d]); M->mb_bcs[g * 6 + 2 * d + 1] = AK_BC_BLOCK; }
+      M->mb_size[g * 9 + d] = lo;
+      M->mb_size[g * 9 + 3 + d] = hi;
+      M->mb_size[g * 9 + 6 + d] = (hi - lo) / static_cast<double>(M->nblock[d]);
+    }
+    // same-level neighbours: meshblock.cpp:170-425 with FindNeighbor's periodic wrap
+    for (int oz = -1; oz <= 1; ++oz) for (int oy = -1; oy <= 1; ++oy) for (int ox = -1; ox <= 1; ++ox) {
+      if (!ox && !oy && !oz) continue;
+      int q[3] = {l[0] + ox, l[1] + oy, l[2] + oz};
+      bool ok = true;
+      for (int d = 0; d < 3; ++d) {
+        if (q[d] < 0) { if (M->bcs[2 * d] == AK_BC_PERIODIC) q[d] = M->nroot[d] - 1; else ok = false; }
+        else if (q[d] >= M->nroot[d]) { if (M->bcs[2 * d + 1] == AK_BC_PERIODIC) q[d] = 0; else ok = false; }
+      }
+      if (!ok) continue;
+      const int ng = at(q[0], q[1], q[2]);
+      int *e = &M->nghbr[((size_t)g * 56 + akb::neighbor_index(ox, oy, oz, 0, 0)) * 4];
+      e[0] = ng; e[1] = M->root_level; e[2] = M->rank_of[ng]; e[3] = akb::neighbor_index(-ox, -oy, -oz, 0, 0);
+    }
+  }
+  *mesh = M;
+  return 0;
+}
+
+int ak_mesh_destroy(void *mesh) { delete static_cast<HostMesh *>(mesh); return 0; }
+
+int ak_mesh_info(void *mesh, int *nmb_total, int *root_level) {
+  auto *M = static_cast<HostMesh *>(mesh);
+  if (!M) return 1;
+  if (nmb_total) *nmb_total = M->nmb_total;
+  if (root_level) *root_level = M->root_level;
+  return 0;
+}
+
+// lloc [nmb_total][4], rank_of [nmb_total], gids_start/nmb_rank [nranks] (any may be NULL)
+int ak_mesh_tables(void *mesh, int *lloc, int *rank_of, int *gids_start, int *nmb_rank) {
+  auto *M = static_cast<HostMesh *>(mesh);
+  if (!M) return 1;
+  if (lloc) std::memcpy(lloc, M->lloc.data(), sizeof(LLoc) * M->lloc.size());
+  if (rank_of) std::memcpy(rank_of, M->rank_of.data(), sizeof(int) * M->rank_of.size());
+  if (gids_start) std::memcpy(gids_start, M->gids_start.data(), sizeof(int) * M->nranks);
+  if (nmb_rank) std::memcpy(nmb_rank, M->nmb_rank.data(), sizeof(int) * M->nranks);
+  return 0;
+}
+
+// per-rank slices: mb_size [nmb][9], mb_bcs [nmb][6], nghbr [nmb][56][4]
+int ak_mesh_rank_tables(void *mesh, int rank, double *mb_size, int *mb_bcs, int *nghbr) {
+  auto *M = static_cast<HostMesh *>(mesh);
+  if (!M || rank < 0 || rank >= M->nranks) return 1;
+  const size_t g0 = M->gids_start[rank], n = M->nmb_rank[rank];
+  if (mb_size) std::memcpy(mb_size, &M->mb_size[g0 * 9], sizeof(double) * n * 9);
+  if (mb_bcs) std::memcpy(mb_bcs, &M->mb_bcs[g0 * 6], sizeof(int) * n * 6);
+  if (nghbr) std::memcpy(nghbr, &M->nghbr[g0 * 56 * 4], sizeof(int) * n * 56 * 4);
+  return 0;
+}
+
+int ak_neighbor_index(int ix, int iy, int iz, int n1, int n2) { return akb::neighbor_index(ix, iy, iz, n1, n2); }
+
+// Blast problem generator, pgen/fluids/blast.cpp:147-158,236-374 (MHD branch, Cartesian).
+// Fills the ACTIVE zones of the rank's blocks in host arrays laid out like the device arrays
+// (ghosts are left to the halo exchange, as in the reference).  prm = {pi_amb, di_amb, prat,
+// drat, b_amb, inner_radius, outer_radius}.
+int ak_pgen_blast(void *mesh, int rank, int ng, double gamma, const double *prm, double *u0, double *b1f,
+                  double *b2f, double *b3f) {
+  auto *M = static_cast<HostMesh *>(mesh);
+  if (!M || rank < 0 || rank >= M->nranks) return 1;
+  const double pi_amb = prm[0], di_amb = prm[1], prat = prm[2], drat = prm[3], b_amb = prm[4];
+  const double rout = prm[6], rin = rout - prm[5];
+  const int nx1 = M->nblock[0], nx2 = M->nblock[1], nx3 = M->nblock[2];
+  const int n1 = nx1 + 2 * ng, n2 = nx2 + 2 * ng, n3 = nx3 + 2 * ng;
+  const int is = ng, ie = ng + nx1 - 1, js = ng, je = ng + nx2 - 1, ks = ng, ke = ng + nx3 - 1;
+  const size_t cc = (size_t)n3 * n2 * n1, f1 = (size_t)n3 * n2 * (n1 + 1), f2 = (size_t)n3 * (n2 + 1) * n1, f3 = (size_t)(n3 + 1) * n2 * n1;
+  const double gm1 = gamma - 1.0;
+  const int nmb = M->nmb_rank[rank], g0 = M->gids_start[rank];
+  std::vector<double> a3((size_t)n3 * n2 * n1);
+  for (int m = 0; m < nmb; ++m) {
+    const double *sz = &M->mb_size[(size_t)(g0 + m) * 9];
+    const double x1min = sz[0], x2min = sz[1], x3min = sz[2], x1max = sz[3], x2max = sz[4], x3max = sz[5];
+    const double dx1 = sz[6], dx2 = sz[7];
+    double *U = u0 + (size_t)m * 5 * cc;
+    std::vector<double> bcx(cc, 0.0), bcy(cc, 0.0), bcz(cc, 0.0), wd(cc, 0.0), we(cc, 0.0);
+    auto C = [&](int k, int j, int i) { return ((size_t)k * n2 + j) * n1 + i; };
+    for (int k = ks; k <= ke; ++k) for (int j = js; j <= je; ++j) for (int i = is; i <= ie; ++i) {
+      double x1v = CellCenterX(i - is, nx1, x1min, x1max);
+      double x2v = CellCenterX(j - js, nx2, x2min, x2max);
+      double x3v = CellCenterX(k - ks, nx3, x3min, x3max);
+      double rad = std::sqrt(x1v * x1v + x2v * x2v + x3v * x3v);
+      double den = di_amb, pres = pi_amb;
+      if (rad < rout) {
+        if (rad < rin) { den *= drat; pres *= prat; }
+        else {
+          double f = (rad - rin) / (rout - rin);
+          double log_den = (1.0 - f) * std::log(drat * di_amb) + f * std::log(di_amb);
+          den = std::exp(log_den);
+          double log_pres = (1.0 - f) * std::log(prat * pi_amb) + f * std::log(pi_amb);
+          pres = std::exp(log_pres);
+        }
+      }
+      wd[C(k, j, i)] = den;
+      we[C(k, j, i)] = pres / gm1;
+    }
+    // vector potential a3 = b_amb * y on faces (blast.cpp:318-351)
+    for (int k = ks; k <= ke + 1; ++k) for (int j = js; j <= je + 1; ++j) for (int i = is; i <= ie + 1; ++i) {
+      double x2f = LeftEdgeX(j - js, nx2, x2min, x2max);
+      if (k < n3) a3[C(k, j, i)] = b_amb * x2f;
+    }
+    double *B1 = b1f + (size_t)m * f1, *B2 = b2f + (size_t)m * f2, *B3 = b3f + (size_t)m * f3;
+    auto X1 = [&](int k, int j, int i) -> double & { return B1[((size_t)k * n2 + j) * (n1 + 1) + i]; };
+    auto X2 = [&](int k, int j, int i) -> double & { return B2[((size_t)k * (n2 + 1) + j) * n1 + i]; };
+    auto X3 = [&](int k, int j, int i) -> double & { return B3[((size_t)k * n2 + j) * n1 + i]; };
+    for (int k = ks; k <= ke; ++k) for (int j = js; j <= je; ++j) for (int i = is; i <= ie; ++i) {
+      X1(k, j, i) = (a3[C(k, j + 1, i)] - a3[C(k, j, i)]) / dx2;
+      X2(k, j, i) = -(a3[C(k, j, i + 1)] - a3[C(k, j, i)]) / dx1;
+      X3(k, j, i) = 0.0;
+      if (i == ie) X1(k, j, i + 1) = (a3[C(k, j + 1, i + 1)] - a3[C(k, j, i + 1)]) / dx2;
+      if (j == je) X2(k, j + 1, i) = -(a3[C(k, j + 1, i + 1)] - a3[C(k, j + 1, i)]) / dx1;
+      if (k == ke) X3(k + 1, j, i) = 0.0;
+    }
+    for (int k = ks; k <= ke; ++k) for (int j = js; j <= je; ++j) for (int i = is; i <= ie; ++i) {
+      const size_t o = C(k, j, i);
+      double bx = 0.5 * (X1(k, j, i) + X1(k, j, i + 1));
+      double by = 0.5 * (X2(k, j, i) + X2(k, j + 1, i));
+      double bz = 0.5 * (X3(k, j, i) + X3(k + 1, j, i));
+      // SingleP2C_IdealMHD, eos/ideal_c2p_mhd.hpp:75-84, with v = 0
+      const double d = wd[o], vx = 0.0, vy = 0.0, vz = 0.0;
+      U[0 * cc + o] = d;
+      U[1 * cc + o] = d * vx;
+      U[2 * cc + o] = d * vy;
+      U[3 * cc + o] = d * vz;
+      U[4 * cc + o] = we[o] + 0.5 * (d * (vx * vx + vy * vy + vz * vz) + (bx * bx + by * by + bz * bz));
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -78,6 +78,17 @@ def load():
         "ak_halo_pack_fc": [vp, vp, vp, vp, ip, vp, vp],
         "ak_halo_unpack_fc": [vp, vp, vp, vp, ip, vp, vp],
     }
+    ipp, dpp = C.POINTER(C.c_int), _dp
+    sig.update({
+        "ak_mesh_create": [ipp, ipp, dpp, dpp, ipp, ip, C.POINTER(vp)],
+        "ak_mesh_destroy": [vp],
+        "ak_mesh_info": [vp, ipp, ipp],
+        "ak_mesh_tables": [vp, ipp, ipp, ipp, ipp],
+        "ak_mesh_rank_tables": [vp, ip, dpp, ipp, ipp],
+        "ak_neighbor_index": [ip, ip, ip, ip, ip],
+        "ak_pgen_blast": [vp, ip, ip, d, dpp, dpp, dpp, dpp, dpp],
+    })
+    lib.ak_mesh_last_error.restype = C.c_char_p
     for name, args in sig.items():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch: fail loudly
         fn.argtypes = args
@@ -90,7 +101,9 @@ EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_con
             "ak_mhd_rk_update", "ak_mhd_corner_e", "ak_mhd_ct", "ak_mhd_cons2prim", "ak_mhd_new_dt",
             "ak_mhd_stage_fused", "ak_mhd_cons2prim_newdt", "ak_halo_create", "ak_halo_destroy",
             "ak_halo_npeers", "ak_halo_peer", "ak_halo_descs", "ak_halo_local_cc", "ak_halo_local_fc",
-            "ak_halo_pack_cc", "ak_halo_unpack_cc", "ak_halo_pack_fc", "ak_halo_unpack_fc")
+            "ak_halo_pack_cc", "ak_halo_unpack_cc", "ak_halo_pack_fc", "ak_halo_unpack_fc",
+            "ak_mesh_create", "ak_mesh_destroy", "ak_mesh_last_error", "ak_mesh_info", "ak_mesh_tables",
+            "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast")
 
 
 def check(rc, handle=None):

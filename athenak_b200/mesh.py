@@ -1,0 +1,62 @@
+"""Python handle on the C++ host mesh (athenak_b200/csrc/host_mesh.cpp): the uniform-mesh part
+of the reference's Mesh / MeshBlockTree / MeshBlock metadata (src/mesh), kept on the host."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+
+PERIODIC, OTHER = 0, 1
+
+
+class Mesh:
+    def __init__(self, nmesh, nblock, xmin=(-0.5, -0.5, -0.5), xmax=(0.5, 0.5, 0.5), bcs=(0,) * 6, nranks=1):
+        self.L = _lib.load()
+        self.nmesh, self.nblock, self.nranks = tuple(nmesh), tuple(nblock), int(nranks)
+        self.xmin, self.xmax = tuple(xmin), tuple(xmax)
+        i3, d3, i6 = (C.c_int * 3), (C.c_double * 3), (C.c_int * 6)
+        self.h = C.c_void_p()
+        rc = self.L.ak_mesh_create(i3(*nmesh), i3(*nblock), d3(*xmin), d3(*xmax), i6(*bcs), nranks, C.byref(self.h))
+        if rc:
+            raise _lib.EngineError(self.L.ak_mesh_last_error().decode())
+        a, b = C.c_int(), C.c_int()
+        self.L.ak_mesh_info(self.h, C.byref(a), C.byref(b))
+        self.nmb_total, self.root_level = a.value, b.value
+        self.lloc = np.zeros((self.nmb_total, 4), np.int32)
+        self.rank_of = np.zeros(self.nmb_total, np.int32)
+        self.gids_start = np.zeros(nranks, np.int32)
+        self.nmb_rank = np.zeros(nranks, np.int32)
+        ip = lambda x: x.ctypes.data_as(C.POINTER(C.c_int))
+        self.L.ak_mesh_tables(self.h, ip(self.lloc), ip(self.rank_of), ip(self.gids_start), ip(self.nmb_rank))
+
+    def __del__(self):
+        try:
+            self.L.ak_mesh_destroy(self.h)
+        except Exception:
+            pass
+
+    def rank_tables(self, rank):
+        n = int(self.nmb_rank[rank])
+        mb_size = np.zeros((n, 9))
+        mb_bcs = np.zeros((n, 6), np.int32)
+        nghbr = np.zeros((n, 56, 4), np.int32)
+        self.L.ak_mesh_rank_tables(self.h, rank, mb_size.ctypes.data_as(C.POINTER(C.c_double)),
+                                   mb_bcs.ctypes.data_as(C.POINTER(C.c_int)), nghbr.ctypes.data_as(C.POINTER(C.c_int)))
+        return mb_size, mb_bcs, nghbr
+
+    def pgen_blast(self, rank, ng, gamma, pi_amb=0.1, di_amb=1.0, prat=100.0, drat=1.0, b_amb=1.0,
+                   inner_radius=0.1, outer_radius=0.1, pinned=False):
+        """Blast ICs for the rank's blocks as host arrays (u0, b1f, b2f, b3f), active zones filled."""
+        import torch
+        n = int(self.nmb_rank[rank])
+        n1, n2, n3 = (self.nblock[d] + 2 * ng for d in range(3))
+        mk = lambda *s: torch.zeros(*s, dtype=torch.float64, pin_memory=pinned)
+        u0, b1, b2, b3 = mk(n, 5, n3, n2, n1), mk(n, n3, n2, n1 + 1), mk(n, n3, n2 + 1, n1), mk(n, n3 + 1, n2, n1)
+        prm = (C.c_double * 7)(pi_amb, di_amb, prat, drat, b_amb, inner_radius, outer_radius)
+        dp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
+        rc = self.L.ak_pgen_blast(self.h, rank, ng, gamma, prm, dp(u0), dp(b1), dp(b2), dp(b3))
+        if rc:
+            raise _lib.EngineError("ak_pgen_blast failed")
+        return u0, b1, b2, b3

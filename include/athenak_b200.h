@@ -111,6 +111,26 @@ int ak_halo_pack_fc(void *plan, const double *x1f, const double *x2f, const doub
 int ak_halo_unpack_fc(void *plan, double *x1f, double *x2f, double *x3f, int ipeer,
                       const double *recvbuf, ak_stream_t s);
 
+/* ---- host-side mesh metadata (CPU only; reference src/mesh, kept on the host) ---------------
+ * Uniform (single-level) meshes.  Bit-exact mirrors of: Z-ordered gids (meshblock_tree.cpp:
+ * 60-90,336-350), LoadBalance (load_balance.cpp:38-88), MeshBlock sizes and BC flags
+ * (meshblock.cpp:25-131; BoundaryFlag::block = -1), neighbour table {gid,lev,rank,dest}
+ * (meshblock.cpp:142-430).  bcs[6] = ix1,ox1,ix2,ox2,ix3,ox3; 0 = periodic. */
+int ak_mesh_create(const int *nmesh, const int *nblock, const double *xmin, const double *xmax,
+                   const int *bcs, int nranks, void **mesh);
+int ak_mesh_destroy(void *mesh);
+const char *ak_mesh_last_error(void);
+int ak_mesh_info(void *mesh, int *nmb_total, int *root_level);
+int ak_mesh_tables(void *mesh, int *lloc /*[nmb_total][4]*/, int *rank_of, int *gids_start, int *nmb_rank);
+int ak_mesh_rank_tables(void *mesh, int rank, double *mb_size /*[nmb][9]*/, int *mb_bcs /*[nmb][6]*/,
+                        int *nghbr /*[nmb][56][4]*/);
+int ak_neighbor_index(int ix, int iy, int iz, int n1, int n2); /* src/mesh/nghbr_index.hpp:28-54 */
+/* Synthetic input: spherical blast ICs (src/pgen/fluids/blast.cpp:147-158,236-374), active
+ * zones of the rank's blocks, HOST arrays in the device layout.  prm = {pi_amb, di_amb, prat,
+ * drat, b_amb, inner_radius, outer_radius}. */
+int ak_pgen_blast(void *mesh, int rank, int ng, double gamma, const double *prm, double *u0,
+                  double *b1f, double *b2f, double *b3f);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,259 @@
+"""GPU parity tests: every task of the CUDA path, called through the C ABI, against the oracle
+(oracle/mhd_oracle.c, itself pinned bitwise to the reference) on identical inputs.
+
+Tolerance: FP64, bit-faithful build (--fmad=false) => the gate is max|delta| == 0.0
+(north-star tolerance: relative L1 <= 1e-12; exact equality is stricter and is what we assert).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import golden_io as G
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+CASES = [("ppm4", "hlld"), ("plm", "hlle"), ("wenoz", "llf"), ("ppmx", "hlld"), ("plm", "llf"),
+         ("ppm4", "hlle"), ("wenoz", "hlld"), ("dc", "hlld")]
+
+
+def evolved_state(recon, rs, ncyc=3, nb=1, n=16):
+    """Oracle state after `ncyc` blast cycles (non-trivial velocities/fields), 1 or nb^3 blocks."""
+    d = G.load("blast16_ppm4_hlld_rk3")
+    cfg1 = O.make_cfg(1, 4, (n, n, n), "ppm4", "hlld")
+    A1 = O.Arrays(cfg1)
+    G.fill_active(A1, d, 0)
+    _, ngh1, mbs1, _ = O.uniform_mesh((n, n, n), (n, n, n))
+    G.oracle_init(A1, ngh1)
+    st = A1.state()
+    t, dt = C.c_double(0.0), C.c_double(float(d["dt_c0"]))
+    O.lib().oracle_run(C.byref(cfg1), C.byref(st), O.p(mbs1), O.ip(ngh1), 3, C.c_double(0.3), C.c_double(0.3), ncyc,
+                       C.byref(t), C.byref(dt), None)
+    if nb == 1:
+        cfg = O.make_cfg(1, 4, (n, n, n), recon, rs)
+        A = O.Arrays(cfg)
+        A.u0[:] = A1.u0
+        for a, b in zip(A.b0, A1.b0):
+            a[:] = b
+        A.c2p_all()
+        return A, ngh1, mbs1, dt.value
+    # cut the periodic block into nb^3 blocks (Z-order), ghosts via the oracle's exchange
+    m = n // nb
+    lloc, ngh, mbs, _ = O.uniform_mesh((n, n, n), (m, m, m))
+    cfg = O.make_cfg(len(lloc), 4, (m, m, m), recon, rs)
+    A = O.Arrays(cfg)
+    ng = 4
+    for g, (lx, ly, lz) in enumerate(lloc):
+        si, sj, sk = ng + lx * m, ng + ly * m, ng + lz * m
+        A.u0[g, :, ng:-ng, ng:-ng, ng:-ng] = A1.u0[0, :, sk:sk + m, sj:sj + m, si:si + m]
+        A.b0[0][g, ng:-ng, ng:-ng, ng:-ng] = A1.b0[0][0, sk:sk + m, sj:sj + m, si:si + m + 1]
+        A.b0[1][g, ng:-ng, ng:-ng, ng:-ng] = A1.b0[1][0, sk:sk + m, sj:sj + m + 1, si:si + m]
+        A.b0[2][g, ng:-ng, ng:-ng, ng:-ng] = A1.b0[2][0, sk:sk + m + 1, sj:sj + m, si:si + m]
+    G.oracle_init(A, ngh)
+    return A, ngh, mbs, dt.value
+
+
+def nghbr4(ngh_gid, rank=0):
+    """[nmb][56] gids -> [nmb][56][4] {gid, lev, rank, dest} on a single rank."""
+    nmb = ngh_gid.shape[0]
+    out = -np.ones((nmb, 56, 4), np.int32)
+    out[:, :, 0] = ngh_gid
+    out[:, :, 2] = np.where(ngh_gid >= 0, rank, -1)
+    return out
+
+
+def make_engine(A, ngh, mbs, recon, rs, fused=False):
+    from athenak_b200.mhd import MHD
+    cfg = A.cfg
+    e = MHD(cfg.nmb, cfg.ng, (cfg.nx1, cfg.nx2, cfg.nx3), mbs, nghbr4(ngh), recon=recon, rsolver=rs,
+            gamma=cfg.gamma, fused=fused)
+    e.load_state(A.u0, *A.b0)
+    e.u1.copy_(torch.from_numpy(A.u1))
+    e.w0.copy_(torch.from_numpy(A.w0))
+    e.bcc0.copy_(torch.from_numpy(A.bcc0))
+    for d, s in zip(e.b1, A.b1):
+        d.copy_(torch.from_numpy(s))
+    return e
+
+
+class FakeDriver:
+    def __init__(self, g0, g1, beta, dt, nst=3):
+        self.gam0, self.gam1, self.beta, self.dt, self.nexp_stages = [g0] * 3, [g1] * 3, [beta] * 3, dt, nst
+
+
+def maxdiff(t, a):
+    return float(np.abs(t.cpu().numpy() - a).max())
+
+
+@pytest.mark.parametrize("recon,rs", CASES)
+@pytest.mark.parametrize("nb", [1, 2])
+def test_tasks_bitwise(recon, rs, nb):
+    """fluxes -> rk_update -> corner_e -> ct -> cons2prim -> new_dt, each vs the oracle."""
+    A, ngh, mbs, dt = evolved_state(recon, rs, nb=nb)
+    e = make_engine(A, ngh, mbs, recon, rs)
+    cfg = A.cfg
+    L = O.lib()
+    g0, g1, beta = 0.25, 0.75, 0.25
+    A.u1[:] = A.u0 * 1.01
+    for a, b in zip(A.b1, A.b0):
+        a[:] = b * 0.99
+    e.u1.copy_(torch.from_numpy(A.u1))
+    for d, s in zip(e.b1, A.b1):
+        d.copy_(torch.from_numpy(s))
+    drv = FakeDriver(g0, g1, beta, dt)
+    # task 2
+    L.oracle_fluxes(C.byref(cfg), O.p(A.w0), O.p(A.bcc0), *[O.p(a) for a in A.b0], *[O.p(a) for a in A.flx],
+                    *[O.p(a) for a in A.fe])
+    e.Fluxes(drv, 2)
+    ng = cfg.ng
+    # compare only where the reference writes (A.2 ranges); elsewhere both hold zeros
+    for q in range(3):
+        assert maxdiff(e.uflx[q], A.flx[q]) == 0.0, f"flux x{q+1}"
+    for q in range(6):
+        assert maxdiff(e.femf[q], A.fe[q]) == 0.0, f"face emf {q}"
+    # task 5
+    L.oracle_rk_update(C.byref(cfg), O.p(A.u0), O.p(A.u1), *[O.p(a) for a in A.flx], O.p(mbs),
+                       C.c_double(g0), C.c_double(g1), C.c_double(beta * dt))
+    e.RKUpdate(drv, 2)
+    assert maxdiff(e.u0, A.u0) == 0.0
+    # task 14
+    L.oracle_corner_e(C.byref(cfg), O.p(A.w0), O.p(A.bcc0), *[O.p(a) for a in A.flx], *[O.p(a) for a in A.fe],
+                      *[O.p(a) for a in A.e])
+    e.EField(drv, 2)
+    for q in range(3):
+        assert maxdiff(e.efld[q], A.e[q]) == 0.0, f"corner e{q+1}"
+    # task 17
+    L.oracle_ct(C.byref(cfg), *[O.p(a) for a in A.b0], *[O.p(a) for a in A.b1], *[O.p(a) for a in A.e], O.p(mbs),
+                C.c_double(g0), C.c_double(g1), C.c_double(beta * dt))
+    e.CT(drv, 2)
+    for q in range(3):
+        assert maxdiff(e.b0[q], A.b0[q]) == 0.0, f"ct b{q+1}"
+    # tasks 10/11, 21/22
+    L.oracle_halo_cc(C.byref(cfg), O.p(A.u0), 5, O.ip(ngh))
+    L.oracle_halo_fc(C.byref(cfg), *[O.p(a) for a in A.b0], O.ip(ngh))
+    e.SendRecvU(drv, 2)
+    e.SendRecvB(drv, 2)
+    assert maxdiff(e.u0, A.u0) == 0.0
+    for q in range(3):
+        assert maxdiff(e.b0[q], A.b0[q]) == 0.0, f"halo b{q+1}"
+    # task 27
+    nf = A.c2p_all()
+    e.nfloor = [0, 0, 0]
+    e.ConToPrim(drv, 2)
+    assert e.nfloor == nf
+    assert maxdiff(e.w0, A.w0) == 0.0 and maxdiff(e.bcc0, A.bcc0) == 0.0 and maxdiff(e.u0, A.u0) == 0.0
+    # task 28
+    dt3 = np.zeros(3)
+    ref = L.oracle_new_dt(C.byref(cfg), O.p(A.w0), O.p(A.bcc0), O.p(mbs), O.p(dt3))
+    e.NewTimeStep(FakeDriver(g0, g1, beta, dt, nst=2), 2)
+    assert e.dtnew == ref
+
+
+def test_c2p_floors_bitwise():
+    """Density/energy/temperature floors: states that trip each floor, counters included."""
+    A, ngh, mbs, dt = evolved_state("ppm4", "hlld")
+    rng = np.random.default_rng(7)
+    cfg = O.make_cfg(1, 4, (16, 16, 16), "ppm4", "hlld", dfloor=0.9, pfloor=0.05, tfloor=0.04)
+    B = O.Arrays(cfg)
+    B.u0[:] = A.u0
+    B.u0[0, 0] *= rng.uniform(0.5, 1.5, B.u0[0, 0].shape)      # some cells below dfloor
+    B.u0[0, 4] *= rng.uniform(0.2, 1.2, B.u0[0, 4].shape)      # some cells below e/t floors
+    for a, b in zip(B.b0, A.b0):
+        a[:] = b
+    from athenak_b200.mhd import MHD
+    e = MHD(1, 4, (16, 16, 16), mbs, nghbr4(ngh), recon="ppm4", rsolver="hlld", gamma=cfg.gamma,
+            dfloor=0.9, pfloor=0.05, tfloor=0.04)
+    e.load_state(B.u0, *B.b0)
+    nf = B.c2p_all()
+    assert min(nf) > 0
+    e.ConToPrim(None, 1)
+    assert e.nfloor == nf
+    assert maxdiff(e.w0, B.w0) == 0.0 and maxdiff(e.u0, B.u0) == 0.0 and maxdiff(e.bcc0, B.bcc0) == 0.0
+
+
+@pytest.mark.parametrize("name,recon,rs,integ,cycles", [
+    ("blast16_ppm4_hlld_rk3", "ppm4", "hlld", "rk3", (1, 4)),
+    ("blast16_plm_hlle_rk2", "plm", "hlle", "rk2", (2,)),
+    ("blast16_wenoz_llf_rk3", "wenoz", "llf", "rk3", (2,)),
+    ("blast16_ppmx_hlld_rk1", "ppmx", "hlld", "rk1", (2,)),
+])
+@pytest.mark.parametrize("fused", [False, True])
+def test_full_run_matches_golden(name, recon, rs, integ, cycles, fused):
+    """Whole cycles through the TaskList/Driver mirror vs the reference's restart dumps
+    (committed golden fixtures): u0 and b0 bitwise, dt sequence bitwise."""
+    from athenak_b200.driver import Driver, assemble_mhd_tasks
+    from athenak_b200.mhd import MHD
+    d = G.load(name)
+    n = 16
+    cfg = O.make_cfg(1, 4, (n, n, n), recon, rs)
+    A = O.Arrays(cfg)
+    G.fill_active(A, d, 0)
+    _, ngh, mbs, _ = O.uniform_mesh((n, n, n), (n, n, n))
+    e = MHD(1, 4, (n, n, n), mbs, nghbr4(ngh), recon=recon, rsolver=rs, gamma=cfg.gamma)
+    e.load_state(A.u0, *A.b0)
+    drv = Driver(integ, 0.3, tlim=0.3)
+    tl = assemble_mhd_tasks(e, fused=fused)
+    drv.Initialize(e)
+    assert drv.dt == float(d["dt_c0"])
+    done = 0
+    for c in cycles:
+        dt_used = None
+        for _ in range(c - done):
+            dt_used = drv.dt
+            drv.Execute(e, tl, ncycles=1)
+        done = c
+        s = slice(4, -4)
+        assert maxdiff(e.u0[0, :, s, s, s], d[f"u0_c{c}"][0]) == 0.0
+        assert maxdiff(e.b0[0][0, s, s, 4:-4], d[f"b1f_c{c}"][0]) == 0.0
+        assert maxdiff(e.b0[1][0, s, 4:-4, s], d[f"b2f_c{c}"][0]) == 0.0
+        assert maxdiff(e.b0[2][0, 4:-4, s, s], d[f"b3f_c{c}"][0]) == 0.0
+        assert dt_used == float(d[f"dt_c{c}"])
+        assert drv.time == float(d[f"time_c{c}"])
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_multiblock_equals_single_block(fused):
+    """Decomposition independence: 8 blocks of 8^3 evolve to the
+    same bits as one 16^3 block (exercises the gather-halo kernels and the multi-block batching)."""
+    from athenak_b200.driver import Driver, assemble_mhd_tasks
+    d = G.load("blast16_ppm4_hlld_rk3")
+    A, ngh, mbs, dt = evolved_state("ppm4", "hlld", ncyc=0, nb=2)
+    e = make_engine(A, ngh, mbs, "ppm4", "hlld")
+    drv = Driver("rk3", 0.3, tlim=0.3)
+    tl = assemble_mhd_tasks(e, fused=fused)
+    drv.Initialize(e)
+    assert drv.dt == float(d["dt_c0"])
+    drv.Execute(e, tl, ncycles=4)
+    lloc, _, _, _ = O.uniform_mesh((16, 16, 16), (8, 8, 8))
+    u = e.u0.cpu().numpy()
+    b1, b2, b3 = [t.cpu().numpy() for t in e.b0]
+    for g, (lx, ly, lz) in enumerate(lloc):
+        si, sj, sk = lx * 8, ly * 8, lz * 8
+        assert np.abs(u[g, :, 4:-4, 4:-4, 4:-4] - d["u0_c4"][0][:, sk:sk + 8, sj:sj + 8, si:si + 8]).max() == 0.0
+        assert np.abs(b1[g, 4:-4, 4:-4, 4:-4] - d["b1f_c4"][0][sk:sk + 8, sj:sj + 8, si:si + 9]).max() == 0.0
+        assert np.abs(b2[g, 4:-4, 4:-4, 4:-4] - d["b2f_c4"][0][sk:sk + 8, sj:sj + 9, si:si + 8]).max() == 0.0
+        assert np.abs(b3[g, 4:-4, 4:-4, 4:-4] - d["b3f_c4"][0][sk:sk + 9, sj:sj + 8, si:si + 8]).max() == 0.0
+
+
+def test_div_by_is_ieee_division():
+    """The 3-instruction reciprocal+FMA quotient used for /dx and /12 equals '/' bit for bit
+    (checked here through the RK update on random fluxes with awkward dx values)."""
+    rng = np.random.default_rng(3)
+    n = 16
+    _, ngh, mbs, _ = O.uniform_mesh((n, n, n), (n, n, n), xmin=(-0.37, 0.11, -1.3), xmax=(0.93, 0.77, 2.9))
+    cfg = O.make_cfg(1, 4, (n, n, n))
+    A = O.Arrays(cfg)
+    for a in A.flx:
+        a[:] = rng.standard_normal(a.shape) * 10.0 ** rng.integers(-6, 6, a.shape)
+    A.u0[:] = rng.standard_normal(A.u0.shape)
+    A.u1[:] = rng.standard_normal(A.u1.shape)
+    e = make_engine(A, ngh, mbs, "ppm4", "hlld")
+    for d, s in zip(e.uflx, A.flx):
+        d.copy_(torch.from_numpy(s))
+    O.lib().oracle_rk_update(C.byref(cfg), O.p(A.u0), O.p(A.u1), *[O.p(a) for a in A.flx], O.p(mbs),
+                             C.c_double(2.0 / 3.0), C.c_double(1.0 / 3.0), C.c_double(0.0123))
+    e.RKUpdate(FakeDriver(2.0 / 3.0, 1.0 / 3.0, 1.0, 0.0123), 1)
+    assert maxdiff(e.u0, A.u0) == 0.0
