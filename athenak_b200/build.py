@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libathenak_b200.so")
+LIB = os.environ.get("ATHENAK_B200_LIB") or os.path.join(HERE, "libathenak_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false",
               "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math"]
 
@@ -26,29 +26,31 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out/defines: build a tuning variant into another file (used by profiles/ sweeps)."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if out is None else "build_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-x", "cu", "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-x", "cu", "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+            raise RuntimeError(f"nvcc failed on {src}:\n{log}")
         if verbose:
-            print(out)
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-lcudart"])
-    return LIB
+            print(log)
+    target = out or LIB
+    subprocess.check_call([nvcc, "-shared", "-o", target, *objs, "-lcudart"])
+    return target
 
 
 if __name__ == "__main__":

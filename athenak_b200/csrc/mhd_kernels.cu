@@ -14,13 +14,25 @@
 #include "mhd_kernels.h"
 #include "mhd_device.cuh"
 
+#ifndef AKB_MARCH_PREFETCH
+#define AKB_MARCH_PREFETCH 0
+#endif
+#ifndef AKB_X1_MINB
+#define AKB_X1_MINB 4
+#endif
+#ifndef AKB_MARCH_MINB
+#define AKB_MARCH_MINB 4
+#endif
+
 namespace akb {
+
+__device__ __forceinline__ void prefetch_l1(const double *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------------------------------
 // x1 sweep.  Flattened cell space (m, k in [ks-1,ke+1], j in [js-1,je+1], c in [0,nx1+2));
 // warp w owns cells 31*w .. 31*w+31 (one-cell overlap), i.e. 31 faces.
 template <int RECON, int RS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, AKB_X1_MINB)
 flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
                const double *__restrict__ bx1f, double *__restrict__ flx, double *__restrict__ e3x1,
                double *__restrict__ e2x1) {
@@ -73,7 +85,7 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
 
 // x2 / x3 sweeps.  Thread = (m, segment, transverse index, i-cell); marches `len` faces.
 template <int RECON, int RS, int DIR>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, AKB_MARCH_MINB)
 flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
                   const double *__restrict__ bnf, double *__restrict__ flx, double *__restrict__ eyo,
                   double *__restrict__ ezo, int seglen, int nseg) {
@@ -118,6 +130,15 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
   for (int f = f_lo; f <= f_hi; ++f) {
     wp += s; bp += s;
     State7 up, lo;
+#if AKB_MARCH_PREFETCH
+    // the next step's only new stencil row (sweep index +3 from the current cell) -> L1 now
+    if (f < f_hi) {
+      constexpr int pf = (RECON >= RECON_PPM4) ? 3 : 2;
+      prefetch_l1(wp + IDN * cc + pf * s); prefetch_l1(wp + IVX * cc + pf * s); prefetch_l1(wp + IVY * cc + pf * s);
+      prefetch_l1(wp + IVZ * cc + pf * s); prefetch_l1(wp + IEN * cc + pf * s);
+      prefetch_l1(bp + ((DIR + 1) % 3) * cc + pf * s); prefetch_l1(bp + ((DIR + 2) % 3) * cc + pf * s);
+    }
+#endif
     recon_cell<RECON, DIR>(wp, bp, cc, s, eos, up, lo);
     Flux7 fx;
     riemann<RS>(L, lo, __ldg(bn), eos, fx);
@@ -317,7 +338,7 @@ cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *_
     bool dfl = false, efl = false, tfl = false;
     const double gm1 = eos.gamma - 1.0;
     const double b2 = sqr(ubx) + sqr(uby) + sqr(ubz);
-    const double dfloor_ = fmax(eos.dfloor, b2 / eos.sigma_max);
+    const double dfloor_ = dmax(eos.dfloor, b2 / eos.sigma_max);
     const double efloor = eos.pfloor / (eos.gamma - 1.0);
     if (ud < dfloor_) { ud = dfloor_; dfl = true; }
     const double wd = ud;
@@ -332,7 +353,7 @@ cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *_
     // when spe can be <= sfloor: for 0 < gm1 <= 2, wd^gm1 <= max(1, wd^2), so
     // gm1*we*di > 4*sfloor*max(1,wd^2) proves spe > sfloor (factor 4 covers rounding) without
     // evaluating pow; otherwise the reference expression is evaluated as written.
-    const double pow_ub = fmax(1.0, wd * wd);
+    const double pow_ub = dmax(1.0, wd * wd);
     bool need_pow = !(gm1 > 0.0 && gm1 <= 2.0 && (gm1 * we * di) > 4.0 * eos.sfloor * pow_ub);
     if (need_pow) {
       const double spe_over_eps = gm1 / pow(wd, gm1);

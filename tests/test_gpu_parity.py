@@ -257,3 +257,18 @@ def test_div_by_is_ieee_division():
                              C.c_double(2.0 / 3.0), C.c_double(1.0 / 3.0), C.c_double(0.0123))
     e.RKUpdate(FakeDriver(2.0 / 3.0, 1.0 / 3.0, 1.0, 0.0123), 1)
     assert maxdiff(e.u0, A.u0) == 0.0
+
+
+def test_multi_gpu_nccl_matches_reference():
+    """N>1 path on real GPUs (skipped with a single device): tests/multigpu_parity.py."""
+    import os
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "multigpu_parity.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert "MULTIGPU_PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
