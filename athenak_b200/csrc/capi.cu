@@ -31,6 +31,30 @@ int cuda_fail(Handle *h, const char *where, cudaError_t e) {
   return fail(h, std::string(where) + ": " + cudaGetErrorString(e));
 }
 
+// new-dt partial slots: identity = (double)FLT_MAX, the reference's initial value (mhd_newdt.cpp:40-42)
+cudaError_t dt_slots_init(Handle *h, cudaStream_t st) {
+  static unsigned long long init[3 * DT_SLOTS];
+  static bool ready = false;
+  if (!ready) {
+    const double ident = (double)FLT_MAX;
+    for (int q = 0; q < 3 * DT_SLOTS; ++q) std::memcpy(&init[q], &ident, 8);
+    ready = true;
+  }
+  return cudaMemcpyAsync(h->d_dtmin, init, sizeof(init), cudaMemcpyHostToDevice, st);
+}
+cudaError_t dt_slots_fetch(Handle *h, double *dt3, cudaStream_t st) {
+  double part[3 * DT_SLOTS];
+  cudaError_t e = cudaMemcpyAsync(part, h->d_dtmin, sizeof(part), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+  for (int c = 0; c < 3; ++c) {
+    double v = part[c];
+    for (int q = 1; q < DT_SLOTS; ++q) v = (part[3 * q + c] < v) ? part[3 * q + c] : v;
+    dt3[c] = v;
+  }
+  return cudaSuccess;
+}
+
 akb::Arrays to_arrays(const ak_mhd_arrays *a) {
   akb::Arrays r;
   static_assert(sizeof(akb::Arrays) == sizeof(ak_mhd_arrays), "ak_mhd_arrays / akb::Arrays mismatch");
@@ -82,7 +106,12 @@ int ak_mhd_create(const ak_mhd_cfg *cfg, void **handle) {
   g.e1 = (long)(g.n3 + 1) * (g.n2 + 1) * g.n1; g.e2 = (long)(g.n3 + 1) * g.n2 * (g.n1 + 1); g.e3 = (long)g.n3 * (g.n2 + 1) * (g.n1 + 1);
   h->eos = akb::EosParams{cfg->gamma, cfg->dfloor, cfg->pfloor, cfg->tfloor, cfg->sfloor, cfg->sigma_max};
   if ((e = cudaMalloc(&h->d_counters, 3 * sizeof(int))) != cudaSuccess ||
-      (e = cudaMalloc(&h->d_dtmin, 3 * sizeof(unsigned long long))) != cudaSuccess) {
+      (e = cudaMalloc(&h->d_dtmin, 3 * DT_SLOTS * sizeof(unsigned long long))) != cudaSuccess) {
+    int rc = cuda_fail(nullptr, "ak_mhd_create", e);
+    delete h;
+    return rc;
+  }
+  if ((e = cudaMemset(h->d_counters, 0, 3 * sizeof(int))) != cudaSuccess) {
     int rc = cuda_fail(nullptr, "ak_mhd_create", e);
     delete h;
     return rc;
@@ -126,7 +155,7 @@ int ak_mhd_fluxes(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
 
 int ak_mhd_rk_update(void *handle, const ak_mhd_arrays *a, double gam0, double gam1, double beta_dt, ak_stream_t s) {
   AK_PROLOGUE("ak_mhd_rk_update")
-  if ((e = akb::launch_update_ct(h->g, A, true, false, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_rk_update", e);
+  if ((e = akb::launch_update_ct(h->g, A, true, false, false, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_rk_update", e);
   return 0;
 }
 
@@ -138,7 +167,7 @@ int ak_mhd_corner_e(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
 
 int ak_mhd_ct(void *handle, const ak_mhd_arrays *a, double gam0, double gam1, double beta_dt, ak_stream_t s) {
   AK_PROLOGUE("ak_mhd_ct")
-  if ((e = akb::launch_update_ct(h->g, A, false, true, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_ct", e);
+  if ((e = akb::launch_update_ct(h->g, A, false, true, false, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_ct", e);
   return 0;
 }
 
@@ -148,22 +177,19 @@ static int c2p_impl(Handle *h, const akb::Arrays &A, int il, int iu, int jl, int
   if (il < 0 || jl < 0 || kl < 0 || iu >= g.n1 || ju >= g.n2 || ku >= g.n3 || il > iu || jl > ju || kl > ku)
     return fail(h, std::string(name) + ": cell box outside the array");
   cudaError_t e;
-  if ((e = cudaMemsetAsync(h->d_counters, 0, 3 * sizeof(int), st)) != cudaSuccess) return cuda_fail(h, name, e);
+  // floor counters accumulate on the device across calls and are zeroed when they are read
   if (dt3) {
-    const double ident = (double)FLT_MAX;   // reference src/mhd/mhd_newdt.cpp:40-42
-    unsigned long long bits[3];
-    for (int q = 0; q < 3; ++q) std::memcpy(&bits[q], &ident, 8);
-    if ((e = cudaMemcpyAsync(h->d_dtmin, bits, sizeof(bits), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(h, name, e);
+    if ((e = dt_slots_init(h, st)) != cudaSuccess) return cuda_fail(h, name, e);
   }
   if ((e = akb::launch_cons2prim(g, h->eos, A, il, iu, jl, ju, kl, ku, h->d_counters, dt3 != nullptr, h->d_dtmin, st)) != cudaSuccess)
     return cuda_fail(h, name, e);
   if (nfloor) {
     if ((e = cudaMemcpyAsync(nfloor, h->d_counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, name, e);
+    if ((e = cudaMemsetAsync(h->d_counters, 0, 3 * sizeof(int), st)) != cudaSuccess) return cuda_fail(h, name, e);
   }
   if (dt3) {
-    if ((e = cudaMemcpyAsync(dt3, h->d_dtmin, 3 * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, name, e);
-  }
-  if (nfloor || dt3) {
+    if ((e = dt_slots_fetch(h, dt3, st)) != cudaSuccess) return cuda_fail(h, name, e);
+  } else if (nfloor) {
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(h, name, e);
   }
   return 0;
@@ -184,26 +210,20 @@ int ak_mhd_cons2prim_newdt(void *handle, const ak_mhd_arrays *a, int *nfloor, do
 int ak_mhd_new_dt(void *handle, const ak_mhd_arrays *a, double *dt3, ak_stream_t s) {
   AK_PROLOGUE("ak_mhd_new_dt")
   if (!dt3) return fail(h, "ak_mhd_new_dt: null dt3");
-  const double ident = (double)FLT_MAX;
-  unsigned long long bits[3];
-  for (int q = 0; q < 3; ++q) std::memcpy(&bits[q], &ident, 8);
-  if ((e = cudaMemcpyAsync(h->d_dtmin, bits, sizeof(bits), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_new_dt", e);
+  if ((e = dt_slots_init(h, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_new_dt", e);
   if ((e = akb::launch_newdt(h->g, h->eos, A, h->d_dtmin, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_new_dt", e);
-  if ((e = cudaMemcpyAsync(dt3, h->d_dtmin, 3 * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_new_dt", e);
-  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_new_dt", e);
+  if ((e = dt_slots_fetch(h, dt3, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_new_dt", e);
   return 0;
 }
 
 int ak_mhd_stage_fused(void *handle, const ak_mhd_arrays *a, int stage, double gam0, double gam1, double beta_dt,
                        ak_stream_t s) {
   AK_PROLOGUE("ak_mhd_stage_fused")
-  if (stage == 1) {
-    int rc = ak_mhd_copy_cons(handle, a, s);
-    if (rc) return rc;
-  }
+  // stage 1: CopyCons is folded into the update kernel (it saves u1/b1 for the ACTIVE zones it
+  // updates -- the only entries later stages read -- instead of copying whole arrays)
   if ((e = akb::launch_fluxes(h->cfg.recon, h->cfg.rsolver, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_fused", e);
   if ((e = akb::launch_corner_e(h->g, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_fused", e);
-  if ((e = akb::launch_update_ct(h->g, A, true, true, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_fused", e);
+  if ((e = akb::launch_update_ct(h->g, A, true, true, stage == 1, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_fused", e);
   return 0;
 }
 

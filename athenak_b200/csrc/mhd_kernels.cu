@@ -190,34 +190,37 @@ corner_emf_kernel(Geom g, const double *__restrict__ w0, const double *__restric
   auto F3 = [&](int kk, int jj, int ii) { return __ldg(f3 + ((long)kk * g.n2 + jj) * n1 + ii); };
   const long mo = (long)m * cc;
   const long o = C(k, j, i);
+  // Branch-free form of mhd_corner_e.cpp:342-413: all four cell-centred values of a component
+  // are evaluated (loads are independent, shared between components by CSE), both candidate
+  // differences are formed and the mass-flux sign selects one.  Same values, same sum order.
   {
     const double x3_jm = __ldg(e1x3 + mo + o - n1), x3_j = __ldg(e1x3 + mo + o);
     const double x2_km = __ldg(e1x2 + mo + o - n12), x2_k = __ldg(e1x2 + mo + o);
-    double l3, r3, l2, r2;
-    if (F2(k - 1, j, i) >= 0.0) l3 = x3_jm - e1cc(o - n12 - n1); else l3 = x3_j - e1cc(o - n12);
-    if (F2(k, j, i) >= 0.0) r3 = x3_jm - e1cc(o - n1); else r3 = x3_j - e1cc(o);
-    if (F3(k, j - 1, i) >= 0.0) l2 = x2_km - e1cc(o - n12 - n1); else l2 = x2_k - e1cc(o - n1);
-    if (F3(k, j, i) >= 0.0) r2 = x2_km - e1cc(o - n12); else r2 = x2_k - e1cc(o);
+    const double c_mm = e1cc(o - n12 - n1), c_m0 = e1cc(o - n12), c_0m = e1cc(o - n1), c_00 = e1cc(o);
+    const double l3 = (F2(k - 1, j, i) >= 0.0) ? (x3_jm - c_mm) : (x3_j - c_m0);
+    const double r3 = (F2(k, j, i) >= 0.0) ? (x3_jm - c_0m) : (x3_j - c_00);
+    const double l2 = (F3(k, j - 1, i) >= 0.0) ? (x2_km - c_mm) : (x2_k - c_0m);
+    const double r2 = (F3(k, j, i) >= 0.0) ? (x2_km - c_m0) : (x2_k - c_00);
     e1[(long)m * g.e1 + ((long)k * (g.n2 + 1) + j) * n1 + i] = 0.25 * (l3 + r3 + l2 + r2 + x2_km + x2_k + x3_jm + x3_j);
   }
   {
     const double x3_im = __ldg(e2x3 + mo + o - 1), x3_i = __ldg(e2x3 + mo + o);
     const double x1_km = __ldg(e2x1 + mo + o - n12), x1_k = __ldg(e2x1 + mo + o);
-    double l3, r3, l1, r1;
-    if (F1(k - 1, j, i) >= 0.0) l3 = x3_im - e2cc(o - n12 - 1); else l3 = x3_i - e2cc(o - n12);
-    if (F1(k, j, i) >= 0.0) r3 = x3_im - e2cc(o - 1); else r3 = x3_i - e2cc(o);
-    if (F3(k, j, i - 1) >= 0.0) l1 = x1_km - e2cc(o - n12 - 1); else l1 = x1_k - e2cc(o - 1);
-    if (F3(k, j, i) >= 0.0) r1 = x1_km - e2cc(o - n12); else r1 = x1_k - e2cc(o);
+    const double c_mm = e2cc(o - n12 - 1), c_m0 = e2cc(o - n12), c_0m = e2cc(o - 1), c_00 = e2cc(o);
+    const double l3 = (F1(k - 1, j, i) >= 0.0) ? (x3_im - c_mm) : (x3_i - c_m0);
+    const double r3 = (F1(k, j, i) >= 0.0) ? (x3_im - c_0m) : (x3_i - c_00);
+    const double l1 = (F3(k, j, i - 1) >= 0.0) ? (x1_km - c_mm) : (x1_k - c_0m);
+    const double r1 = (F3(k, j, i) >= 0.0) ? (x1_km - c_m0) : (x1_k - c_00);
     e2[(long)m * g.e2 + ((long)k * g.n2 + j) * (n1 + 1) + i] = 0.25 * (l3 + r3 + l1 + r1 + x3_im + x3_i + x1_km + x1_k);
   }
   {
     const double x2_im = __ldg(e3x2 + mo + o - 1), x2_i = __ldg(e3x2 + mo + o);
     const double x1_jm = __ldg(e3x1 + mo + o - n1), x1_j = __ldg(e3x1 + mo + o);
-    double l2, r2, l1, r1;
-    if (F1(k, j - 1, i) >= 0.0) l2 = x2_im - e3cc(o - n1 - 1); else l2 = x2_i - e3cc(o - n1);
-    if (F1(k, j, i) >= 0.0) r2 = x2_im - e3cc(o - 1); else r2 = x2_i - e3cc(o);
-    if (F2(k, j, i - 1) >= 0.0) l1 = x1_jm - e3cc(o - n1 - 1); else l1 = x1_j - e3cc(o - 1);
-    if (F2(k, j, i) >= 0.0) r1 = x1_jm - e3cc(o - n1); else r1 = x1_j - e3cc(o);
+    const double c_mm = e3cc(o - n1 - 1), c_m0 = e3cc(o - n1), c_0m = e3cc(o - 1), c_00 = e3cc(o);
+    const double l2 = (F1(k, j - 1, i) >= 0.0) ? (x2_im - c_mm) : (x2_i - c_m0);
+    const double r2 = (F1(k, j, i) >= 0.0) ? (x2_im - c_0m) : (x2_i - c_00);
+    const double l1 = (F2(k, j, i - 1) >= 0.0) ? (x1_jm - c_mm) : (x1_j - c_0m);
+    const double r1 = (F2(k, j, i) >= 0.0) ? (x1_jm - c_m0) : (x1_j - c_00);
     e3[(long)m * g.e3 + ((long)k * (g.n2 + 1) + j) * (n1 + 1) + i] = 0.25 * (l1 + r1 + l2 + r2 + x2_im + x2_i + x1_jm + x1_j);
   }
 }
@@ -228,13 +231,13 @@ corner_emf_kernel(Geom g, const double *__restrict__ w0, const double *__restric
 // indices are active, each face update where its own range allows.  SAVE=true also performs
 // CopyCons (u1<-u0, b1<-b0, mhd_tasks.cpp:162-170) for the entries it touches; the caller
 // copies the ghost entries separately when the host contract needs them.
-template <bool DO_U, bool DO_B>
+template <bool DO_U, bool DO_B, bool SAVE>
 __global__ void __launch_bounds__(256)
-update_ct_kernel(Geom g, double *__restrict__ u0, const double *__restrict__ u1,
+update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
                  const double *__restrict__ flx1, const double *__restrict__ flx2,
                  const double *__restrict__ flx3, double *__restrict__ b1f, double *__restrict__ b2f,
-                 double *__restrict__ b3f, const double *__restrict__ o1f, const double *__restrict__ o2f,
-                 const double *__restrict__ o3f, const double *__restrict__ e1, const double *__restrict__ e2,
+                 double *__restrict__ b3f, double *__restrict__ o1f, double *__restrict__ o2f,
+                 double *__restrict__ o3f, const double *__restrict__ e1, const double *__restrict__ e2,
                  const double *__restrict__ e3, const double *__restrict__ mb_size, double gam0, double gam1,
                  double beta_dt) {
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -264,7 +267,10 @@ update_ct_kernel(Geom g, double *__restrict__ u0, const double *__restrict__ u1,
       divf += div_by(__ldg(p2 + n1) - __ldg(p2), dx2, rdx2);
       divf += div_by(__ldg(p3 + n1 * n2) - __ldg(p3), dx3, rdx3);
       const long uo = ((long)m * 5 + n) * g.cc + o;
-      u0[uo] = gam0 * u0[uo] + gam1 * __ldg(u1 + uo) - beta_dt * divf;
+      const double uold = u0[uo];
+      double ureg;
+      if (SAVE) { ureg = uold; u1[uo] = uold; } else { ureg = u1[uo]; }   // SAVE: CopyCons fused in
+      u0[uo] = gam0 * uold + gam1 * ureg - beta_dt * divf;
     }
   }
   if (DO_B) {
@@ -274,21 +280,30 @@ update_ct_kernel(Geom g, double *__restrict__ u0, const double *__restrict__ u1,
     const long a3 = ((long)k * (n2 + 1) + j) * (n1 + 1) + i;  // x3e(k,j,i)
     if (ja && ka) {  // x1f(k,j,i), i in [is,ie+1]
       const long o = (long)m * g.f1 + ((long)k * n2 + j) * (n1 + 1) + i;
-      double b = gam0 * b1f[o] + gam1 * __ldg(o1f + o);
+      const double bold = b1f[o];
+      double breg;
+      if (SAVE) { breg = bold; o1f[o] = bold; } else { breg = o1f[o]; }
+      double b = gam0 * bold + gam1 * breg;
       b -= div_by(beta_dt * (__ldg(E3 + a3 + (n1 + 1)) - __ldg(E3 + a3)), dx2, rdx2);
       b += div_by(beta_dt * (__ldg(E2 + a2 + n2 * (n1 + 1)) - __ldg(E2 + a2)), dx3, rdx3);
       b1f[o] = b;
     }
     if (ia && ka) {  // x2f(k,j,i), j in [js,je+1]
       const long o = (long)m * g.f2 + ((long)k * (n2 + 1) + j) * n1 + i;
-      double b = gam0 * b2f[o] + gam1 * __ldg(o2f + o);
+      const double bold = b2f[o];
+      double breg;
+      if (SAVE) { breg = bold; o2f[o] = bold; } else { breg = o2f[o]; }
+      double b = gam0 * bold + gam1 * breg;
       b += div_by(beta_dt * (__ldg(E3 + a3 + 1) - __ldg(E3 + a3)), dx1, rdx1);
       b -= div_by(beta_dt * (__ldg(E1 + a1 + (n2 + 1) * n1) - __ldg(E1 + a1)), dx3, rdx3);
       b2f[o] = b;
     }
     if (ia && ja) {  // x3f(k,j,i), k in [ks,ke+1]
       const long o = (long)m * g.f3 + ((long)k * n2 + j) * n1 + i;
-      double b = gam0 * b3f[o] + gam1 * __ldg(o3f + o);
+      const double bold = b3f[o];
+      double breg;
+      if (SAVE) { breg = bold; o3f[o] = bold; } else { breg = o3f[o]; }
+      double b = gam0 * bold + gam1 * breg;
       b -= div_by(beta_dt * (__ldg(E2 + a2 + 1) - __ldg(E2 + a2)), dx1, rdx1);
       b += div_by(beta_dt * (__ldg(E1 + a1 + n1) - __ldg(E1 + a1)), dx2, rdx2);
       b3f[o] = b;
@@ -304,6 +319,26 @@ update_ct_kernel(Geom g, double *__restrict__ u0, const double *__restrict__ u1,
 #define DT_IDENT 3.4028234663852886e+38
 __device__ __forceinline__ void atomic_min_pos(unsigned long long *addr, double v) {
   atomicMin(addr, (unsigned long long)__double_as_longlong(v));  // v > 0: bit order == value order
+}
+
+// Block-wide min of three positive doubles, then ONE atomic per block and value into one of
+// DT_SLOTS slots (chosen by block index) to keep same-address atomic traffic low; the host
+// takes the min over the slots.  All threads of the block must call it.
+__device__ __forceinline__ void block_min3(double d1, double d2, double d3, unsigned long long *__restrict__ dtmin) {
+  __shared__ double sm[3][8];
+  for (int s = 16; s > 0; s >>= 1) {
+    d1 = dmin(d1, __shfl_xor_sync(0xffffffffu, d1, s));
+    d2 = dmin(d2, __shfl_xor_sync(0xffffffffu, d2, s));
+    d3 = dmin(d3, __shfl_xor_sync(0xffffffffu, d3, s));
+  }
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if ((threadIdx.x & 31) == 0) { sm[0][w] = d1; sm[1][w] = d2; sm[2][w] = d3; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double v = sm[threadIdx.x][0];
+    for (int q = 1; q < nw; ++q) v = dmin(v, sm[threadIdx.x][q]);
+    atomic_min_pos(dtmin + 3 * (blockIdx.x % DT_SLOTS) + threadIdx.x, v);
+  }
 }
 
 template <bool NEWDT>
@@ -391,20 +426,7 @@ cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *_
       if (nt) atomicAdd(counters + 2, nt);
     }
   }
-  if (NEWDT) {
-    if (__ballot_sync(0xffffffffu, act)) {
-      for (int s = 16; s > 0; s >>= 1) {
-        d1 = fmin(d1, __shfl_xor_sync(0xffffffffu, d1, s));
-        d2 = fmin(d2, __shfl_xor_sync(0xffffffffu, d2, s));
-        d3 = fmin(d3, __shfl_xor_sync(0xffffffffu, d3, s));
-      }
-      if ((threadIdx.x & 31) == 0) {
-        atomic_min_pos(dtmin + 0, d1);
-        atomic_min_pos(dtmin + 1, d2);
-        atomic_min_pos(dtmin + 2, d3);
-      }
-    }
-  }
+  if (NEWDT) block_min3(d1, d2, d3, dtmin);
 }
 
 // MHD::NewTimeStep stand-alone (task 28): reads w0, bcc0 over the active cells.
@@ -428,16 +450,7 @@ newdt_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double 
     d2 = __ldg(mb_size + m * 9 + 7) / (fabs(__ldg(w + IVY * cc)) + fast_speed(eos.gamma, wd, p, by, bz, bx));
     d3 = __ldg(mb_size + m * 9 + 8) / (fabs(__ldg(w + IVZ * cc)) + fast_speed(eos.gamma, wd, p, bz, bx, by));
   }
-  for (int s = 16; s > 0; s >>= 1) {
-    d1 = fmin(d1, __shfl_xor_sync(0xffffffffu, d1, s));
-    d2 = fmin(d2, __shfl_xor_sync(0xffffffffu, d2, s));
-    d3 = fmin(d3, __shfl_xor_sync(0xffffffffu, d3, s));
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomic_min_pos(dtmin + 0, d1);
-    atomic_min_pos(dtmin + 1, d2);
-    atomic_min_pos(dtmin + 2, d3);
-  }
+  block_min3(d1, d2, d3, dtmin);
 }
 
 // u1 <- u0 / b1 <- b0 fused into the stage-1 update needs the ghost entries too when the host
@@ -503,13 +516,14 @@ cudaError_t launch_corner_e(const Geom &g, const Arrays &a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_update_ct(const Geom &g, const Arrays &a, bool do_u, bool do_b, double gam0, double gam1,
+cudaError_t launch_update_ct(const Geom &g, const Arrays &a, bool do_u, bool do_b, bool save, double gam0, double gam1,
                              double beta_dt, cudaStream_t st) {
   const long n = (long)g.nmb * (g.nx3 + 1) * (g.nx2 + 1) * (g.nx1 + 1);
 #define AKB_UCT_ARGS g, a.u0, a.u1, a.flx1, a.flx2, a.flx3, a.b0x1f, a.b0x2f, a.b0x3f, a.b1x1f, a.b1x2f, a.b1x3f, a.e1, a.e2, a.e3, a.mb_size, gam0, gam1, beta_dt
-  if (do_u && do_b) update_ct_kernel<true, true><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
-  else if (do_u) update_ct_kernel<true, false><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
-  else if (do_b) update_ct_kernel<false, true><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
+  if (do_u && do_b && save) update_ct_kernel<true, true, true><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
+  else if (do_u && do_b) update_ct_kernel<true, true, false><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
+  else if (do_u) update_ct_kernel<true, false, false><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
+  else if (do_b) update_ct_kernel<false, true, false><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
 #undef AKB_UCT_ARGS
   return cudaGetLastError();
 }

@@ -7,6 +7,9 @@ namespace akb {
 
 struct EosParams;
 
+// number of partial-result slots of the new-dt min-reduction (3 doubles each)
+#define DT_SLOTS 64
+
 struct Geom {  // RegionIndcs (src/mesh/mesh.hpp:35-41) + derived array extents
   int nmb, ng, nx1, nx2, nx3;
   int n1, n2, n3;
@@ -27,7 +30,7 @@ struct Arrays {  // mirror of ak_mhd_arrays (include/athenak_b200.h)
 
 cudaError_t launch_fluxes(int recon, int rs, const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st);
 cudaError_t launch_corner_e(const Geom &g, const Arrays &a, cudaStream_t st);
-cudaError_t launch_update_ct(const Geom &g, const Arrays &a, bool do_u, bool do_b, double gam0, double gam1,
+cudaError_t launch_update_ct(const Geom &g, const Arrays &a, bool do_u, bool do_b, bool save, double gam0, double gam1,
                              double beta_dt, cudaStream_t st);
 cudaError_t launch_cons2prim(const Geom &g, const EosParams &eos, const Arrays &a, int il, int iu, int jl, int ju,
                              int kl, int ku, int *counters, bool newdt, unsigned long long *dtmin, cudaStream_t st);

@@ -140,7 +140,7 @@ class MHD:
         """Tasks 1,2,5,14,17 in one ABI call (ak_mhd_stage_fused)."""
         g0, g1, bdt = driver.gam0[stage - 1], driver.gam1[stage - 1], driver.beta[stage - 1] * driver.dt
         self._ck(self.L.ak_mhd_stage_fused(self.h, C.byref(self.arrays), stage, g0, g1, bdt, self._st()))
-        self.launches += 5 + (4 if stage == 1 else 0)
+        self.launches += 5
         return TaskStatus.complete
 
     def _exchange(self, which):
@@ -207,7 +207,7 @@ class MHD:
     def ConToPrimNewDt(self, driver, stage):
         """Tasks 27+28 fused on the last stage (ak_mhd_cons2prim_newdt)."""
         if stage != driver.nexp_stages:
-            return self.ConToPrim(driver, stage)
+            return self.ConToPrim(driver, stage, count=False)   # counters accumulate on the device
         nf, dt3 = (C.c_int * 3)(), (C.c_double * 3)()
         self._ck(self.L.ak_mhd_cons2prim_newdt(self.h, C.byref(self.arrays), nf, dt3, self._st()))
         self.launches += 1

@@ -67,8 +67,9 @@ int ak_mhd_corner_e(void *h, const ak_mhd_arrays *a, ak_stream_t s);
 /* task 17 MHD::CT            src/mhd/mhd_ct.cpp:23-80 */
 int ak_mhd_ct(void *h, const ak_mhd_arrays *a, double gam0, double gam1, double beta_dt, ak_stream_t s);
 /* task 27 MHD::ConToPrim -> IdealMHD::ConsToPrim  src/eos/ideal_mhd.cpp:30-134.
- * nfloor (host int[3], may be NULL) receives the dfloor/efloor/tfloor counters; when it is
- * non-NULL the call synchronises the stream. */
+ * nfloor (host int[3], may be NULL) receives the dfloor/efloor/tfloor counts accumulated on the
+ * device since they were last read (and zeroes them); when it is non-NULL the call synchronises
+ * the stream, with NULL it is fully asynchronous. */
 int ak_mhd_cons2prim(void *h, const ak_mhd_arrays *a, int il, int iu, int jl, int ju, int kl, int ku,
                      int *nfloor, ak_stream_t s);
 /* task 28 MHD::NewTimeStep   src/mhd/mhd_newdt.cpp:31-174: dt3 (host double[3]) = min over
@@ -78,7 +79,8 @@ int ak_mhd_new_dt(void *h, const ak_mhd_arrays *a, double *dt3, ak_stream_t s);
 /* Fused stage: tasks 1,2,5,14,17 (CopyCons, Fluxes, RKUpdate, CornerE, CT) with fewer kernels
  * and no CopyCons pass.  Legal on a same-level mesh with no diffusion/FOFC/source-term
  * consumers of uflx/efld between the tasks (SendE/RecvE is a bitwise identity there,
- * SURVEY.md section 0 fact 6).  flx*, e?x?, e1..e3 are still written. */
+ * SURVEY.md section 0 fact 6).  flx*, e?x?, e1..e3 are still written; u1/b1 (the RK registers)
+ * are saved for the active zones only (nothing reads their ghost zones). */
 int ak_mhd_stage_fused(void *h, const ak_mhd_arrays *a, int stage, double gam0, double gam1,
                        double beta_dt, ak_stream_t s);
 /* c2p over all cells fused with the task-28 reduction over the active cells (last stage). */
