@@ -84,12 +84,69 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
 }
 
 // x2 / x3 sweeps.  Thread = (m, segment, transverse index, i-cell); marches `len` faces.
+//
+// 5-point reconstructions keep a rolling window of the sweep in SHARED memory: a ring of
+// MARCH_SLOTS rows x 7 variables per thread column (thread-private slots, so no barriers and
+// no bank conflicts: consecutive threads own consecutive doubles).  Each step issues ONE new
+// row per variable with cp.async (global -> shared, no register staging) one step ahead of its
+// use, so the stencil reads are LDS and the HBM/L2 latency of the new row hides behind the
+// Riemann solve of the current face.  3-point methods (PLM/DC) read global memory directly.
+#define TILE_X 32
+#define TILE_Y 4
+#define TILE_Z 2
+#define MARCH_SLOTS 6
+#define MARCH_THREADS 128
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int RECON>
+__device__ __forceinline__ void recon_ring_var(const double *__restrict__ rv, int b0, double &q_up, double &q_lo) {
+  // rv: this thread's ring for one variable (slot stride MARCH_THREADS); b0 = slot of row c-2
+  int b1 = b0 + 1; if (b1 >= MARCH_SLOTS) b1 -= MARCH_SLOTS;
+  int b2 = b1 + 1; if (b2 >= MARCH_SLOTS) b2 -= MARCH_SLOTS;
+  int b3 = b2 + 1; if (b3 >= MARCH_SLOTS) b3 -= MARCH_SLOTS;
+  int b4 = b3 + 1; if (b4 >= MARCH_SLOTS) b4 -= MARCH_SLOTS;
+  const double qm2 = rv[b0 * MARCH_THREADS], qm1 = rv[b1 * MARCH_THREADS], q = rv[b2 * MARCH_THREADS];
+  const double qp1 = rv[b3 * MARCH_THREADS], qp2 = rv[b4 * MARCH_THREADS];
+  if constexpr (RECON == RECON_PPM4) ppm4(qm2, qm1, q, qp1, qp2, q_up, q_lo);
+  else if constexpr (RECON == RECON_PPMX) ppmx(qm2, qm1, q, qp1, qp2, q_up, q_lo);
+  else wenoz(qm2, qm1, q, qp1, qp2, q_up, q_lo);
+}
+
+template <int RECON>
+__device__ __forceinline__ void recon_ring_cell(const double *__restrict__ ring, int b0, const EosParams &eos,
+                                                State7 &up, State7 &lo) {
+  constexpr int VS = MARCH_SLOTS * MARCH_THREADS;   // ring stride between variables
+  recon_ring_var<RECON>(ring + 0 * VS, b0, up.d, lo.d);
+  recon_ring_var<RECON>(ring + 1 * VS, b0, up.vx, lo.vx);
+  recon_ring_var<RECON>(ring + 2 * VS, b0, up.vy, lo.vy);
+  recon_ring_var<RECON>(ring + 3 * VS, b0, up.vz, lo.vz);
+  recon_ring_var<RECON>(ring + 4 * VS, b0, up.e, lo.e);
+  recon_ring_var<RECON>(ring + 5 * VS, b0, up.by, lo.by);
+  recon_ring_var<RECON>(ring + 6 * VS, b0, up.bz, lo.bz);
+  if constexpr (RECON == RECON_PPMX || RECON == RECON_WENOZ) {   // recon.hpp:78-108
+    const double efloor = eos.pfloor / (eos.gamma - 1.0);
+    up.d = dmax(up.d, eos.dfloor);
+    lo.d = dmax(lo.d, eos.dfloor);
+    up.e = dmax(up.e, efloor);
+    lo.e = dmax(lo.e, efloor);
+  }
+}
+
 template <int RECON, int RS, int DIR>
-__global__ void __launch_bounds__(128, AKB_MARCH_MINB)
+__global__ void __launch_bounds__(MARCH_THREADS, AKB_MARCH_MINB)
 flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
                   const double *__restrict__ bnf, double *__restrict__ flx, double *__restrict__ eyo,
                   double *__restrict__ ezo, int seglen, int nseg) {
   static_assert(DIR == 1 || DIR == 2, "march kernel handles x2 and x3");
+  constexpr bool RING = (RECON >= RECON_PPM4);
+  __shared__ double ring_all[RING ? 7 * MARCH_SLOTS * MARCH_THREADS : 1];
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nc = g.nx1 + 2;
   const int nt = (DIR == 1) ? g.nx3 + 2 : g.nx2 + 2;
@@ -124,33 +181,70 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
   double *eyp = eyo + (long)m * cc + off + s;
   double *ezp = ezo + (long)m * cc + off + s;
   constexpr int ivx = IVX + DIR, ivy = IVX + (DIR + 1) % 3, ivz = IVX + (DIR + 2) % 3;
+  constexpr int iby = (DIR + 1) % 3, ibz = (DIR + 2) % 3;
 
   State7 L, lo_unused;
-  recon_cell<RECON, DIR>(wp, bp, cc, s, eos, L, lo_unused);
-  for (int f = f_lo; f <= f_hi; ++f) {
-    wp += s; bp += s;
-    State7 up, lo;
-#if AKB_MARCH_PREFETCH
-    // the next step's only new stencil row (sweep index +3 from the current cell) -> L1 now
-    if (f < f_hi) {
-      constexpr int pf = (RECON >= RECON_PPM4) ? 3 : 2;
-      prefetch_l1(wp + IDN * cc + pf * s); prefetch_l1(wp + IVX * cc + pf * s); prefetch_l1(wp + IVY * cc + pf * s);
-      prefetch_l1(wp + IVZ * cc + pf * s); prefetch_l1(wp + IEN * cc + pf * s);
-      prefetch_l1(bp + ((DIR + 1) % 3) * cc + pf * s); prefetch_l1(bp + ((DIR + 2) % 3) * cc + pf * s);
+  if constexpr (RING) {
+    constexpr int VS = MARCH_SLOTS * MARCH_THREADS;
+    double *ring = ring_all + threadIdx.x;
+    // global columns of the seven variables at the current cell (sweep index c = f_lo-1)
+    const double *gv[7] = {wp + IDN * cc, wp + ivx * cc, wp + ivy * cc, wp + ivz * cc, wp + IEN * cc,
+                           bp + iby * cc, bp + ibz * cc};
+    // prologue: rows c-2 .. c+3 -> slots 0..5 (row c-2 in slot 0)
+#pragma unroll
+    for (int r = 0; r < MARCH_SLOTS; ++r) {
+#pragma unroll
+      for (int v = 0; v < 7; ++v) cp_async8(ring + v * VS + r * MARCH_THREADS, gv[v] + (long)(r - 2) * s);
     }
-#endif
-    recon_cell<RECON, DIR>(wp, bp, cc, s, eos, up, lo);
-    Flux7 fx;
-    riemann<RS>(L, lo, __ldg(bn), eos, fx);
-    fp[IDN * fsz] = fx.d;
-    fp[ivx * fsz] = fx.mx;
-    fp[ivy * fsz] = fx.my;
-    fp[ivz * fsz] = fx.mz;
-    fp[IEN * fsz] = fx.e;
-    *eyp = fx.ey;  // x2: (e1x2,e3x2)  x3: (e2x3,e1x3)   mhd_fluxes.cpp:196,243
-    *ezp = fx.ez;
-    L = up;
-    bn += frow; fp += frow; eyp += s; ezp += s;
+    cp_async_commit();
+    cp_async_wait<0>();
+    recon_ring_cell<RECON>(ring, 0, eos, L, lo_unused);
+    int b0 = 1;                       // slot of row c-2 for the next cell (c = f_lo)
+    for (int f = f_lo; f <= f_hi; ++f) {
+      // cell c = f: rows c-2..c+2 are present (row c+2 arrived with the previous step's group or
+      // the prologue); request row c+3 for the next step into the slot that held row c-3
+      if (f < f_hi) {
+        int bn_slot = b0 + 5; if (bn_slot >= MARCH_SLOTS) bn_slot -= MARCH_SLOTS;
+        const long ro = (long)(f - (f_lo - 1) + 3) * s;
+#pragma unroll
+        for (int v = 0; v < 7; ++v) cp_async8(ring + v * VS + bn_slot * MARCH_THREADS, gv[v] + ro);
+      }
+      cp_async_commit();
+      cp_async_wait<1>();
+      State7 up, lo;
+      recon_ring_cell<RECON>(ring, b0, eos, up, lo);
+      Flux7 fx;
+      riemann<RS>(L, lo, __ldg(bn), eos, fx);
+      fp[IDN * fsz] = fx.d;
+      fp[ivx * fsz] = fx.mx;
+      fp[ivy * fsz] = fx.my;
+      fp[ivz * fsz] = fx.mz;
+      fp[IEN * fsz] = fx.e;
+      *eyp = fx.ey;  // x2: (e1x2,e3x2)  x3: (e2x3,e1x3)   mhd_fluxes.cpp:196,243
+      *ezp = fx.ez;
+      L = up;
+      bn += frow; fp += frow; eyp += s; ezp += s;
+      b0 = (b0 + 1 >= MARCH_SLOTS) ? 0 : b0 + 1;
+    }
+    cp_async_wait<0>();
+  } else {
+    recon_cell<RECON, DIR>(wp, bp, cc, s, eos, L, lo_unused);
+    for (int f = f_lo; f <= f_hi; ++f) {
+      wp += s; bp += s;
+      State7 up, lo;
+      recon_cell<RECON, DIR>(wp, bp, cc, s, eos, up, lo);
+      Flux7 fx;
+      riemann<RS>(L, lo, __ldg(bn), eos, fx);
+      fp[IDN * fsz] = fx.d;
+      fp[ivx * fsz] = fx.mx;
+      fp[ivy * fsz] = fx.my;
+      fp[ivz * fsz] = fx.mz;
+      fp[IEN * fsz] = fx.e;
+      *eyp = fx.ey;
+      *ezp = fx.ez;
+      L = up;
+      bn += frow; fp += frow; eyp += s; ezp += s;
+    }
   }
 }
 
@@ -165,15 +259,15 @@ corner_emf_kernel(Geom g, const double *__restrict__ w0, const double *__restric
                   const double *__restrict__ e3x2, const double *__restrict__ e2x3,
                   const double *__restrict__ e1x3, double *__restrict__ e1, double *__restrict__ e2,
                   double *__restrict__ e3) {
-  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  // 3-D thread tile (32 x 4 x 2): the j-1 / k-1 neighbours of most threads are loaded by the
+  // same block, so they come from L1
   const int ni = g.nx1 + 1, nj = g.nx2 + 1, nk = g.nx3 + 1;
-  const long total = (long)g.nmb * nk * nj * ni;
-  if (gt >= total) return;
-  long t = gt;
-  const int i = g.is + (int)(t % ni); t /= ni;
-  const int j = g.js + (int)(t % nj); t /= nj;
-  const int k = g.ks + (int)(t % nk);
-  const int m = (int)(t / nk);
+  const int nkb = (nk + TILE_Z - 1) / TILE_Z;
+  const int ii = blockIdx.x * TILE_X + threadIdx.x, jj = blockIdx.y * TILE_Y + threadIdx.y;
+  const int kk = (blockIdx.z % nkb) * TILE_Z + threadIdx.z;
+  const int m = blockIdx.z / nkb;
+  if (ii >= ni || jj >= nj || kk >= nk) return;
+  const int i = g.is + ii, j = g.js + jj, k = g.ks + kk;
   const long cc = g.cc, n1 = g.n1, n12 = (long)g.n1 * g.n2;
   const double *w = w0 + (long)m * 5 * cc, *b = bcc + (long)m * 3 * cc;
   auto C = [&](int kk, int jj, int ii) -> long { return ((long)kk * g.n2 + jj) * n1 + ii; };
@@ -240,15 +334,13 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
                  double *__restrict__ o3f, const double *__restrict__ e1, const double *__restrict__ e2,
                  const double *__restrict__ e3, const double *__restrict__ mb_size, double gam0, double gam1,
                  double beta_dt) {
-  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int ni = g.nx1 + 1, nj = g.nx2 + 1, nk = g.nx3 + 1;
-  const long total = (long)g.nmb * nk * nj * ni;
-  if (gt >= total) return;
-  long t = gt;
-  const int i = g.is + (int)(t % ni); t /= ni;
-  const int j = g.js + (int)(t % nj); t /= nj;
-  const int k = g.ks + (int)(t % nk);
-  const int m = (int)(t / nk);
+  const int nkb = (nk + TILE_Z - 1) / TILE_Z;
+  const int ii = blockIdx.x * TILE_X + threadIdx.x, jj = blockIdx.y * TILE_Y + threadIdx.y;
+  const int kk = (blockIdx.z % nkb) * TILE_Z + threadIdx.z;
+  const int m = blockIdx.z / nkb;
+  if (ii >= ni || jj >= nj || kk >= nk) return;
+  const int i = g.is + ii, j = g.js + jj, k = g.ks + kk;
   const double dx1 = __ldg(mb_size + m * 9 + 6), dx2 = __ldg(mb_size + m * 9 + 7), dx3 = __ldg(mb_size + m * 9 + 8);
   const double rdx1 = 1.0 / dx1, rdx2 = 1.0 / dx2, rdx3 = 1.0 / dx3;
   const long n1 = g.n1, n2 = g.n2;
@@ -478,13 +570,13 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
     const int nf = g.nx2 + 1;
     const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
     const long threads = (long)g.nmb * nseg * (g.nx3 + 2) * (g.nx1 + 2);
-    flux_march_kernel<RECON, RS, 1><<<nblocks(threads, 128), 128, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg);
+    flux_march_kernel<RECON, RS, 1><<<nblocks(threads, MARCH_THREADS), MARCH_THREADS, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg);
   }
   {  // x3: (ey,ez) = (e2x3,e1x3)
     const int nf = g.nx3 + 1;
     const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
     const long threads = (long)g.nmb * nseg * (g.nx2 + 2) * (g.nx1 + 2);
-    flux_march_kernel<RECON, RS, 2><<<nblocks(threads, 128), 128, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
+    flux_march_kernel<RECON, RS, 2><<<nblocks(threads, MARCH_THREADS), MARCH_THREADS, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
   }
   return cudaGetLastError();
 }
@@ -511,19 +603,21 @@ cudaError_t launch_fluxes(int recon, int rs, const Geom &g, const EosParams &eos
 }
 
 cudaError_t launch_corner_e(const Geom &g, const Arrays &a, cudaStream_t st) {
-  const long n = (long)g.nmb * (g.nx3 + 1) * (g.nx2 + 1) * (g.nx1 + 1);
-  corner_emf_kernel<<<nblocks(n, 256), 256, 0, st>>>(g, a.w0, a.bcc0, a.flx1, a.flx2, a.flx3, a.e3x1, a.e2x1, a.e1x2, a.e3x2, a.e2x3, a.e1x3, a.e1, a.e2, a.e3);
+  const dim3 tb(TILE_X, TILE_Y, TILE_Z);
+  const dim3 gr((g.nx1 + 1 + TILE_X - 1) / TILE_X, (g.nx2 + 1 + TILE_Y - 1) / TILE_Y, ((g.nx3 + 1 + TILE_Z - 1) / TILE_Z) * g.nmb);
+  corner_emf_kernel<<<gr, tb, 0, st>>>(g, a.w0, a.bcc0, a.flx1, a.flx2, a.flx3, a.e3x1, a.e2x1, a.e1x2, a.e3x2, a.e2x3, a.e1x3, a.e1, a.e2, a.e3);
   return cudaGetLastError();
 }
 
 cudaError_t launch_update_ct(const Geom &g, const Arrays &a, bool do_u, bool do_b, bool save, double gam0, double gam1,
                              double beta_dt, cudaStream_t st) {
-  const long n = (long)g.nmb * (g.nx3 + 1) * (g.nx2 + 1) * (g.nx1 + 1);
+  const dim3 tb(TILE_X, TILE_Y, TILE_Z);
+  const dim3 gr((g.nx1 + 1 + TILE_X - 1) / TILE_X, (g.nx2 + 1 + TILE_Y - 1) / TILE_Y, ((g.nx3 + 1 + TILE_Z - 1) / TILE_Z) * g.nmb);
 #define AKB_UCT_ARGS g, a.u0, a.u1, a.flx1, a.flx2, a.flx3, a.b0x1f, a.b0x2f, a.b0x3f, a.b1x1f, a.b1x2f, a.b1x3f, a.e1, a.e2, a.e3, a.mb_size, gam0, gam1, beta_dt
-  if (do_u && do_b && save) update_ct_kernel<true, true, true><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
-  else if (do_u && do_b) update_ct_kernel<true, true, false><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
-  else if (do_u) update_ct_kernel<true, false, false><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
-  else if (do_b) update_ct_kernel<false, true, false><<<nblocks(n, 256), 256, 0, st>>>(AKB_UCT_ARGS);
+  if (do_u && do_b && save) update_ct_kernel<true, true, true><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
+  else if (do_u && do_b) update_ct_kernel<true, true, false><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
+  else if (do_u) update_ct_kernel<true, false, false><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
+  else if (do_b) update_ct_kernel<false, true, false><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
 #undef AKB_UCT_ARGS
   return cudaGetLastError();
 }
