@@ -104,7 +104,8 @@ int ak_mhd_create(const ak_mhd_cfg *cfg, void **handle) {
   g.cc = (long)g.n3 * g.n2 * g.n1;
   g.f1 = (long)g.n3 * g.n2 * (g.n1 + 1); g.f2 = (long)g.n3 * (g.n2 + 1) * g.n1; g.f3 = (long)(g.n3 + 1) * g.n2 * g.n1;
   g.e1 = (long)(g.n3 + 1) * (g.n2 + 1) * g.n1; g.e2 = (long)(g.n3 + 1) * g.n2 * (g.n1 + 1); g.e3 = (long)g.n3 * (g.n2 + 1) * (g.n1 + 1);
-  h->eos = akb::EosParams{cfg->gamma, cfg->dfloor, cfg->pfloor, cfg->tfloor, cfg->sfloor, cfg->sigma_max};
+  h->eos = akb::EosParams{cfg->gamma, cfg->dfloor, cfg->pfloor, cfg->tfloor, cfg->sfloor, cfg->sigma_max,
+                          1.0 / (cfg->gamma - 1.0)};
   if ((e = cudaMalloc(&h->d_counters, 3 * sizeof(int))) != cudaSuccess ||
       (e = cudaMalloc(&h->d_dtmin, 3 * DT_SLOTS * sizeof(unsigned long long))) != cudaSuccess) {
     int rc = cuda_fail(nullptr, "ak_mhd_create", e);

@@ -342,7 +342,7 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
   if (ii >= ni || jj >= nj || kk >= nk) return;
   const int i = g.is + ii, j = g.js + jj, k = g.ks + kk;
   const double dx1 = __ldg(mb_size + m * 9 + 6), dx2 = __ldg(mb_size + m * 9 + 7), dx3 = __ldg(mb_size + m * 9 + 8);
-  const double rdx1 = 1.0 / dx1, rdx2 = 1.0 / dx2, rdx3 = 1.0 / dx3;
+  const double rdx1 = drcp(dx1), rdx2 = drcp(dx2), rdx3 = drcp(dx3);
   const long n1 = g.n1, n2 = g.n2;
   const bool ia = (i <= g.ie), ja = (j <= g.je), ka = (k <= g.ke);
   if (DO_U && ia && ja && ka) {
@@ -465,11 +465,11 @@ cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *_
     bool dfl = false, efl = false, tfl = false;
     const double gm1 = eos.gamma - 1.0;
     const double b2 = sqr(ubx) + sqr(uby) + sqr(ubz);
-    const double dfloor_ = dmax(eos.dfloor, b2 / eos.sigma_max);
-    const double efloor = eos.pfloor / (eos.gamma - 1.0);
+    const double dfloor_ = dmax(eos.dfloor, ddiv(b2, eos.sigma_max));
+    const double efloor = ddiv(eos.pfloor, eos.gamma - 1.0);
     if (ud < dfloor_) { ud = dfloor_; dfl = true; }
     const double wd = ud;
-    const double di = 1.0 / ud;
+    const double di = drcp(ud);
     const double wvx = di * umx, wvy = di * umy, wvz = di * umz;
     const double e_k = 0.5 * di * (sqr(umx) + sqr(umy) + sqr(umz));
     const double e_m = 0.5 * (sqr(ubx) + sqr(uby) + sqr(ubz));
@@ -498,9 +498,9 @@ cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *_
       act = (i >= g.is && i <= g.ie && j >= g.js && j <= g.je && k >= g.ks && k <= g.ke);
       if (act) {  // mhd_newdt.cpp:128-138,146-148
         const double p = gm1 * we;
-        d1 = __ldg(mb_size + m * 9 + 6) / (fabs(wvx) + fast_speed(eos.gamma, wd, p, ubx, uby, ubz));
-        d2 = __ldg(mb_size + m * 9 + 7) / (fabs(wvy) + fast_speed(eos.gamma, wd, p, uby, ubz, ubx));
-        d3 = __ldg(mb_size + m * 9 + 8) / (fabs(wvz) + fast_speed(eos.gamma, wd, p, ubz, ubx, uby));
+        d1 = ddiv(__ldg(mb_size + m * 9 + 6), fabs(wvx) + fast_speed(eos.gamma, wd, p, ubx, uby, ubz));
+        d2 = ddiv(__ldg(mb_size + m * 9 + 7), fabs(wvy) + fast_speed(eos.gamma, wd, p, uby, ubz, ubx));
+        d3 = ddiv(__ldg(mb_size + m * 9 + 8), fabs(wvz) + fast_speed(eos.gamma, wd, p, ubz, ubx, uby));
       }
     }
   }
@@ -538,9 +538,9 @@ newdt_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double 
     const double *w = w0 + (long)m * 5 * cc + o, *b = bcc + (long)m * 3 * cc + o;
     const double wd = __ldg(w), bx = __ldg(b), by = __ldg(b + cc), bz = __ldg(b + 2 * cc);
     const double p = (eos.gamma - 1.0) * __ldg(w + IEN * cc);
-    d1 = __ldg(mb_size + m * 9 + 6) / (fabs(__ldg(w + IVX * cc)) + fast_speed(eos.gamma, wd, p, bx, by, bz));
-    d2 = __ldg(mb_size + m * 9 + 7) / (fabs(__ldg(w + IVY * cc)) + fast_speed(eos.gamma, wd, p, by, bz, bx));
-    d3 = __ldg(mb_size + m * 9 + 8) / (fabs(__ldg(w + IVZ * cc)) + fast_speed(eos.gamma, wd, p, bz, bx, by));
+    d1 = ddiv(__ldg(mb_size + m * 9 + 6), fabs(__ldg(w + IVX * cc)) + fast_speed(eos.gamma, wd, p, bx, by, bz));
+    d2 = ddiv(__ldg(mb_size + m * 9 + 7), fabs(__ldg(w + IVY * cc)) + fast_speed(eos.gamma, wd, p, by, bz, bx));
+    d3 = ddiv(__ldg(mb_size + m * 9 + 8), fabs(__ldg(w + IVZ * cc)) + fast_speed(eos.gamma, wd, p, bz, bx, by));
   }
   block_min3(d1, d2, d3, dtmin);
 }

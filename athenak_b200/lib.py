@@ -87,6 +87,7 @@ def load():
         "ak_mesh_rank_tables": [vp, ip, dpp, ipp, ipp],
         "ak_neighbor_index": [ip, ip, ip, ip, ip],
         "ak_pgen_blast": [vp, ip, ip, d, dpp, dpp, dpp, dpp, dpp],
+        "ak_selftest_divsqrt": [C.c_long, C.c_ulonglong, ip, C.POINTER(C.c_long)],
     })
     lib.ak_mesh_last_error.restype = C.c_char_p
     for name, args in sig.items():
@@ -103,7 +104,7 @@ EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_con
             "ak_halo_npeers", "ak_halo_peer", "ak_halo_descs", "ak_halo_local_cc", "ak_halo_local_fc",
             "ak_halo_pack_cc", "ak_halo_unpack_cc", "ak_halo_pack_fc", "ak_halo_unpack_fc",
             "ak_mesh_create", "ak_mesh_destroy", "ak_mesh_last_error", "ak_mesh_info", "ak_mesh_tables",
-            "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast")
+            "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast", "ak_selftest_divsqrt")
 
 
 def check(rc, handle=None):

@@ -113,6 +113,11 @@ int ak_halo_pack_fc(void *plan, const double *x1f, const double *x2f, const doub
 int ak_halo_unpack_fc(void *plan, double *x1f, double *x2f, double *x3f, int ipeer,
                       const double *recvbuf, ak_stream_t s);
 
+/* Device self-test: compares the library's slow-path-free FP64 reciprocal / division / sqrt with
+ * the built-in IEEE operators on n random operands (|exponent| <= exponent_span, every 64th
+ * numerator exactly 0); mismatches[3] = differing results for 1/x, a/b, sqrt(x). */
+int ak_selftest_divsqrt(long n, unsigned long long seed, int exponent_span, long *mismatches);
+
 /* ---- host-side mesh metadata (CPU only; reference src/mesh, kept on the host) ---------------
  * Uniform (single-level) meshes.  Bit-exact mirrors of: Z-ordered gids (meshblock_tree.cpp:
  * 60-90,336-350), LoadBalance (load_balance.cpp:38-88), MeshBlock sizes and BC flags

@@ -272,3 +272,14 @@ def test_multi_gpu_nccl_matches_reference():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "multigpu_parity.py")],
                        capture_output=True, text=True, timeout=600)
     assert "MULTIGPU_PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("span", [8, 60, 300])
+def test_fast_div_sqrt(span):
+    """drcp/ddiv/dsqrt (nvcc's fast paths without the range-test branch) == built-in '/', sqrt,
+    bit for bit, on 2^28 random operands per exponent span."""
+    from athenak_b200 import lib as _lib
+    L = _lib.load()
+    bad = (C.c_long * 3)()
+    assert L.ak_selftest_divsqrt(1 << 28, 12345 + span, span, bad) == 0
+    assert list(bad) == [0, 0, 0]
