@@ -1,0 +1,468 @@
+// host_driver.cpp -- C++ host layer above the C ABI: the reference's operator API for this path.
+//
+// Mirrors, with the same names and semantics, the pieces of the reference that stay on the host:
+//   TaskID / Task / TaskList   src/tasklist/task_list.hpp:37-236 (bitmask dependencies, DoAvailable)
+//   Driver                     src/driver/driver.cpp:93-130 (RK tables), :290-307 (ExecuteTaskList),
+//                              :314-371,569-653 (Initialize), :380-459 (Execute)
+//   Mesh::NewTimeStep          src/mesh/mesh.cpp:573-643
+//   MHD (state owner + tasks)  src/mhd/mhd.hpp:87-207, src/mhd/mhd_tasks.cpp:38-84
+// Every MHD task body is one call into the C ABI of this library (include/athenak_b200.h);
+// the task signature is the reference's `TaskStatus(Driver*, int stage)`.  Inter-rank ghost
+// exchange is grouped ncclSend/ncclRecv (one message per peer per exchange) and
+// ncclAllReduce(min) for dt; NCCL is loaded at run time (libnccl.so.2) and only when nranks > 1.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <bitset>
+#include <cfloat>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <list>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/athenak_b200.h"
+
+namespace akh {
+
+enum class TaskStatus { fail, complete, incomplete };
+enum class TaskListStatus { running, stuck, complete, nothing_to_do };
+class Driver;
+
+class TaskID {  // task_list.hpp:37-82
+ public:
+  TaskID() = default;
+  explicit TaskID(unsigned int id) { if (id == 0) bitfld_.reset(); else bitfld_.set(--id); }
+  void Clear() { bitfld_.reset(); }
+  bool CheckDependencies(const TaskID &dep) const { return ((bitfld_ & dep.bitfld_) == dep.bitfld_); }
+  void SetComplete(const TaskID &rhs) { bitfld_ |= rhs.bitfld_; }
+  bool operator==(const TaskID &rhs) const { return bitfld_ == rhs.bitfld_; }
+  TaskID operator|(const TaskID &rhs) const { TaskID r; r.bitfld_ = bitfld_ | rhs.bitfld_; return r; }
+ private:
+  std::bitset<64> bitfld_;
+};
+
+class Task {  // task_list.hpp:85-110
+ public:
+  Task(TaskID id, TaskID dep, std::function<TaskStatus(Driver *, int)> func) : myid_(id), dep_(dep), func_(func) {}
+  TaskStatus operator()(Driver *d, int s) { return func_(d, s); }
+  TaskID GetID() { return myid_; }
+  TaskID GetDependency() { return dep_; }
+  void SetComplete() { complete_ = true; }
+  void SetIncomplete() { complete_ = false; }
+  bool IsComplete() { return complete_; }
+ private:
+  TaskID myid_, dep_;
+  bool complete_ = false;
+  std::function<TaskStatus(Driver *, int)> func_;
+};
+
+class TaskList {  // task_list.hpp:116-236
+ public:
+  bool IsComplete() {
+    for (auto &it : task_list_) if (!(tasks_completed_.CheckDependencies(it.GetID()))) return false;
+    return true;
+  }
+  int Size() { return (int)task_list_.size(); }
+  bool Empty() { return task_list_.empty(); }
+  void Reset() { tasks_completed_.Clear(); for (auto &it : task_list_) it.SetIncomplete(); }
+  TaskListStatus DoAvailable(Driver *d, int s) {
+    for (auto &task : task_list_) {
+      auto dep = task.GetDependency();
+      if (tasks_completed_.CheckDependencies(dep) && !(task.IsComplete())) {
+        TaskStatus status = task(d, s);
+        if (status == TaskStatus::complete) { task.SetComplete(); tasks_completed_.SetComplete(task.GetID()); }
+      }
+    }
+    return IsComplete() ? TaskListStatus::complete : TaskListStatus::running;
+  }
+  template <class F, class T>
+  TaskID AddTask(F func, T *obj, TaskID &dep) {
+    TaskID id((unsigned)task_list_.size() + 1);
+    task_list_.push_back(Task(id, dep, [=](Driver *d, int s) mutable -> TaskStatus { return (obj->*func)(d, s); }));
+    return id;
+  }
+ protected:
+  std::list<Task> task_list_;
+  TaskID tasks_completed_;
+};
+
+// ---- NCCL, loaded lazily -----------------------------------------------------------------
+struct Nccl {
+  typedef struct { char internal[128]; } UniqueId;
+  typedef void *Comm;
+  int (*GetUniqueId)(UniqueId *) = nullptr;
+  int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(Comm) = nullptr;
+  int (*Send)(const void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  static Nccl &get() {
+    static Nccl n;
+    if (!n.ok) {
+      void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+      if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (h) {
+        n.GetUniqueId = (int (*)(UniqueId *))dlsym(h, "ncclGetUniqueId");
+        n.CommInitRank = (int (*)(Comm *, int, UniqueId, int))dlsym(h, "ncclCommInitRank");
+        n.CommDestroy = (int (*)(Comm))dlsym(h, "ncclCommDestroy");
+        n.Send = (int (*)(const void *, size_t, int, int, Comm, cudaStream_t))dlsym(h, "ncclSend");
+        n.Recv = (int (*)(void *, size_t, int, int, Comm, cudaStream_t))dlsym(h, "ncclRecv");
+        n.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+        n.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+        n.AllReduce = (int (*)(const void *, void *, size_t, int, int, Comm, cudaStream_t))dlsym(h, "ncclAllReduce");
+        n.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+        n.ok = n.GetUniqueId && n.CommInitRank && n.Send && n.Recv && n.GroupStart && n.GroupEnd && n.AllReduce;
+      }
+    }
+    return n;
+  }
+};
+enum { kNcclFloat64 = 8, kNcclMin = 3 };  // nccl.h: ncclFloat64 = 8, ncclMin = 3
+
+[[noreturn]] static void Fatal(const char *file, int line, const std::string &msg) {
+  // the reference's fatal-error convention (e.g. src/mhd/mhd.cpp:85-87)
+  std::fprintf(stdout, "### FATAL ERROR in %s at line %d\n%s\n", file, line, msg.c_str());
+  std::fflush(stdout);
+  std::exit(EXIT_FAILURE);
+}
+#define AK_CHECK(h, call) do { if ((call) != 0) Fatal(__FILE__, __LINE__, ak_last_error(h)); } while (0)
+#define CU_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) Fatal(__FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+
+struct MeshState {  // the members of Mesh this path uses (src/mesh/mesh.hpp:120-150)
+  double time = 0.0, dt = (double)FLT_MAX, cfl_no = 0.3;
+  int ncycle = 0, nmb_total = 1;
+};
+
+class MHD;
+
+class Driver {  // driver.hpp / driver.cpp
+ public:
+  Driver(const std::string &integrator, double tlim_, int nlim_) : tlim(tlim_), nlim(nlim_) {
+    if (integrator == "rk1") { nexp_stages = 1; gam0[0] = 0.0; gam1[0] = 1.0; beta[0] = 1.0; }
+    else if (integrator == "rk2") {
+      nexp_stages = 2; gam0[0] = 0.0; gam1[0] = 1.0; beta[0] = 1.0; gam0[1] = 0.5; gam1[1] = 0.5; beta[1] = 0.5;
+    } else if (integrator == "rk3") {
+      nexp_stages = 3; gam0[0] = 0.0; gam1[0] = 1.0; beta[0] = 1.0; gam0[1] = 0.25; gam1[1] = 0.75; beta[1] = 0.25;
+      gam0[2] = 2.0 / 3.0; gam1[2] = 1.0 / 3.0; beta[2] = 2.0 / 3.0;
+    } else {
+      Fatal(__FILE__, __LINE__, "integrator must be rk1, rk2 or rk3 on this path");
+    }
+  }
+  double gam0[4], gam1[4], beta[4];
+  int nexp_stages = 0;
+  double tlim;
+  int nlim;
+  std::uint64_t nmb_updated_ = 0;
+  void ExecuteTaskList(std::map<std::string, std::shared_ptr<TaskList>> &tl_map, const std::string &tl, int stage) {
+    auto &lst = tl_map[tl];                           // driver.cpp:290-307
+    if (lst->Empty()) return;
+    lst->Reset();
+    while (lst->DoAvailable(this, stage) != TaskListStatus::complete) {}
+  }
+  void Initialize(MHD *pmhd);
+  int Execute(MHD *pmhd, int ncycles);
+};
+
+class MHD {  // state owner + tasks
+ public:
+  ak_mhd_cfg cfg;
+  ak_mhd_arrays a;
+  void *h = nullptr, *plan = nullptr;
+  cudaStream_t st = nullptr;
+  MeshState mesh;
+  int my_rank, nranks;
+  bool fused = true;
+  double dtnew = (double)FLT_MAX;
+  long nfloor[3] = {0, 0, 0};
+  long launches = 0;
+  std::map<std::string, std::shared_ptr<TaskList>> tl_map;
+  std::vector<double *> owned;
+  struct Peer { int rank; long ncc, nfc; double *scc, *rcc, *sfc, *rfc; };
+  std::vector<Peer> peers;
+  Nccl::Comm comm = nullptr;
+  double *d_dt = nullptr;
+  size_t n_u, n_f1, n_f2, n_f3;
+
+  MHD(const ak_mhd_cfg &c, const double *mb_size, const int *nghbr, int rank, int nranks_, int gids_start, int nmb_total)
+      : cfg(c), my_rank(rank), nranks(nranks_) {
+    mesh.nmb_total = nmb_total;
+    CU_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const size_t n1 = c.nx1 + 2 * c.ng, n2 = c.nx2 + 2 * c.ng, n3 = c.nx3 + 2 * c.ng, nm = c.nmb;
+    const size_t cc = n1 * n2 * n3;
+    n_u = nm * 5 * cc; n_f1 = nm * n3 * n2 * (n1 + 1); n_f2 = nm * n3 * (n2 + 1) * n1; n_f3 = nm * (n3 + 1) * n2 * n1;
+    auto alloc = [&](size_t n) { double *p; CU_CHECK(cudaMalloc(&p, n * 8)); CU_CHECK(cudaMemsetAsync(p, 0, n * 8, st)); owned.push_back(p); return p; };
+    a.u0 = alloc(n_u); a.u1 = alloc(n_u); a.w0 = alloc(n_u); a.bcc0 = alloc(nm * 3 * cc);   // mhd.cpp:148-161
+    a.b0x1f = alloc(n_f1); a.b0x2f = alloc(n_f2); a.b0x3f = alloc(n_f3);
+    a.b1x1f = alloc(n_f1); a.b1x2f = alloc(n_f2); a.b1x3f = alloc(n_f3);                       // mhd.cpp:329-347
+    a.flx1 = alloc(5 * n_f1); a.flx2 = alloc(5 * n_f2); a.flx3 = alloc(5 * n_f3);
+    a.e3x1 = alloc(nm * cc); a.e2x1 = alloc(nm * cc); a.e1x2 = alloc(nm * cc);
+    a.e3x2 = alloc(nm * cc); a.e2x3 = alloc(nm * cc); a.e1x3 = alloc(nm * cc);
+    a.e1 = alloc(nm * (n3 + 1) * (n2 + 1) * n1); a.e2 = alloc(nm * (n3 + 1) * n2 * (n1 + 1)); a.e3 = alloc(nm * n3 * (n2 + 1) * (n1 + 1));
+    double *ms = alloc(nm * 9);
+    CU_CHECK(cudaMemcpyAsync(ms, mb_size, nm * 9 * 8, cudaMemcpyHostToDevice, st));
+    a.mb_size = ms;
+    d_dt = alloc(1);
+    if (ak_mhd_create(&cfg, &h)) Fatal(__FILE__, __LINE__, ak_last_error(nullptr));
+    if (ak_halo_create(&cfg, nghbr, rank, gids_start, &plan)) Fatal(__FILE__, __LINE__, ak_last_error(nullptr));
+    for (int p = 0; p < ak_halo_npeers(plan); ++p) {
+      Peer pe;
+      ak_halo_peer(plan, p, &pe.rank, &pe.ncc, &pe.nfc);
+      pe.scc = alloc(5 * pe.ncc); pe.rcc = alloc(5 * pe.ncc); pe.sfc = alloc(pe.nfc); pe.rfc = alloc(pe.nfc);
+      peers.push_back(pe);
+    }
+    CU_CHECK(cudaStreamSynchronize(st));
+  }
+  ~MHD() {
+    if (comm && Nccl::get().CommDestroy) Nccl::get().CommDestroy(comm);
+    ak_halo_destroy(plan);
+    ak_mhd_destroy(h);
+    for (double *p : owned) cudaFree(p);
+    if (st) cudaStreamDestroy(st);
+  }
+
+  // MHD::AssembleMHDTasks, mhd_tasks.cpp:38-84 (the tasks that do work on a uniform mesh)
+  void AssembleMHDTasks() {
+    for (const char *n : {"before_timeintegrator", "before_stagen", "stagen", "after_stagen", "after_timeintegrator"})
+      tl_map[n] = std::make_shared<TaskList>();
+    TaskID none(0);
+    auto &tl = tl_map["stagen"];
+    if (fused) {
+      TaskID f = tl->AddTask(&MHD::StageFused, this, none);
+      TaskID su = tl->AddTask(&MHD::SendU, this, f);
+      TaskID ru = tl->AddTask(&MHD::RecvU, this, su);
+      TaskID sb = tl->AddTask(&MHD::SendB, this, ru);
+      TaskID rb = tl->AddTask(&MHD::RecvB, this, sb);
+      tl->AddTask(&MHD::ConToPrimNewDt, this, rb);
+    } else {
+      TaskID copyu = tl->AddTask(&MHD::CopyCons, this, none);
+      TaskID flux = tl->AddTask(&MHD::Fluxes, this, copyu);
+      TaskID rkupdt = tl->AddTask(&MHD::RKUpdate, this, flux);
+      TaskID sendu = tl->AddTask(&MHD::SendU, this, rkupdt);
+      TaskID recvu = tl->AddTask(&MHD::RecvU, this, sendu);
+      TaskID efld = tl->AddTask(&MHD::EField, this, recvu);
+      TaskID ct = tl->AddTask(&MHD::CT, this, efld);
+      TaskID sendb = tl->AddTask(&MHD::SendB, this, ct);
+      TaskID recvb = tl->AddTask(&MHD::RecvB, this, sendb);
+      TaskID c2p = tl->AddTask(&MHD::ConToPrim, this, recvb);
+      tl->AddTask(&MHD::NewTimeStep, this, c2p);
+    }
+  }
+
+  // ---- tasks ------------------------------------------------------------------------------
+  TaskStatus CopyCons(Driver *pd, int stage) {
+    if (stage == 1) { AK_CHECK(h, ak_mhd_copy_cons(h, &a, st)); launches += 4; }
+    return TaskStatus::complete;
+  }
+  TaskStatus Fluxes(Driver *pd, int stage) { AK_CHECK(h, ak_mhd_fluxes(h, &a, st)); launches += 3; return TaskStatus::complete; }
+  TaskStatus RKUpdate(Driver *pd, int stage) {
+    AK_CHECK(h, ak_mhd_rk_update(h, &a, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, st));
+    launches += 1;
+    return TaskStatus::complete;
+  }
+  TaskStatus EField(Driver *pd, int stage) { AK_CHECK(h, ak_mhd_corner_e(h, &a, st)); launches += 1; return TaskStatus::complete; }
+  TaskStatus CT(Driver *pd, int stage) {
+    AK_CHECK(h, ak_mhd_ct(h, &a, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, st));
+    launches += 1;
+    return TaskStatus::complete;
+  }
+  TaskStatus StageFused(Driver *pd, int stage) {
+    AK_CHECK(h, ak_mhd_stage_fused(h, &a, stage, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, st));
+    launches += 5;
+    return TaskStatus::complete;
+  }
+  // SendU/RecvU, SendB/RecvB: bvals_cc.cpp:42-447, bvals_fc.cpp:63-436
+  void Exchange(bool cc_vars) {
+    Nccl &n = Nccl::get();
+    if (!peers.empty()) {
+      if (!comm) Fatal(__FILE__, __LINE__, "MeshBlocks on other ranks but no NCCL communicator (call ak_sim_comm_init)");
+      for (size_t p = 0; p < peers.size(); ++p) {
+        if (cc_vars) AK_CHECK(nullptr, ak_halo_pack_cc(plan, a.u0, 5, (int)p, peers[p].scc, st));
+        else AK_CHECK(nullptr, ak_halo_pack_fc(plan, a.b0x1f, a.b0x2f, a.b0x3f, (int)p, peers[p].sfc, st));
+        launches += 1;
+      }
+      n.GroupStart();
+      for (auto &pe : peers) {
+        const size_t cnt = cc_vars ? (size_t)5 * pe.ncc : (size_t)pe.nfc;
+        n.Send(cc_vars ? pe.scc : pe.sfc, cnt, kNcclFloat64, pe.rank, comm, st);
+        n.Recv(cc_vars ? pe.rcc : pe.rfc, cnt, kNcclFloat64, pe.rank, comm, st);
+      }
+      n.GroupEnd();
+    }
+    if (cc_vars) AK_CHECK(nullptr, ak_halo_local_cc(plan, a.u0, 5, st));
+    else AK_CHECK(nullptr, ak_halo_local_fc(plan, a.b0x1f, a.b0x2f, a.b0x3f, st));
+    launches += 1;
+  }
+  void Unpack(bool cc_vars) {
+    for (size_t p = 0; p < peers.size(); ++p) {
+      if (cc_vars) AK_CHECK(nullptr, ak_halo_unpack_cc(plan, a.u0, 5, (int)p, peers[p].rcc, st));
+      else AK_CHECK(nullptr, ak_halo_unpack_fc(plan, a.b0x1f, a.b0x2f, a.b0x3f, (int)p, peers[p].rfc, st));
+      launches += 1;
+    }
+  }
+  TaskStatus SendU(Driver *pd, int stage) { Exchange(true); return TaskStatus::complete; }
+  TaskStatus RecvU(Driver *pd, int stage) { Unpack(true); return TaskStatus::complete; }   // stream-ordered: never incomplete
+  TaskStatus SendB(Driver *pd, int stage) { Exchange(false); return TaskStatus::complete; }
+  TaskStatus RecvB(Driver *pd, int stage) { Unpack(false); return TaskStatus::complete; }
+  TaskStatus ConToPrim(Driver *pd, int stage) {
+    const int n1 = cfg.nx1 + 2 * cfg.ng, n2 = cfg.nx2 + 2 * cfg.ng, n3 = cfg.nx3 + 2 * cfg.ng;
+    int nf[3];
+    AK_CHECK(h, ak_mhd_cons2prim(h, &a, 0, n1 - 1, 0, n2 - 1, 0, n3 - 1, nf, st));
+    for (int q = 0; q < 3; ++q) nfloor[q] += nf[q];
+    launches += 1;
+    return TaskStatus::complete;
+  }
+  TaskStatus NewTimeStep(Driver *pd, int stage) {
+    if (stage != pd->nexp_stages) return TaskStatus::complete;    // mhd_newdt.cpp:32-34
+    double dt3[3];
+    AK_CHECK(h, ak_mhd_new_dt(h, &a, dt3, st));
+    dtnew = std::min(dt3[0], std::min(dt3[1], dt3[2]));
+    launches += 1;
+    return TaskStatus::complete;
+  }
+  TaskStatus ConToPrimNewDt(Driver *pd, int stage) {              // tasks 27+28 fused on the last stage
+    const int n1 = cfg.nx1 + 2 * cfg.ng, n2 = cfg.nx2 + 2 * cfg.ng, n3 = cfg.nx3 + 2 * cfg.ng;
+    if (stage != pd->nexp_stages) {
+      AK_CHECK(h, ak_mhd_cons2prim(h, &a, 0, n1 - 1, 0, n2 - 1, 0, n3 - 1, nullptr, st));
+    } else {
+      int nf[3];
+      double dt3[3];
+      AK_CHECK(h, ak_mhd_cons2prim_newdt(h, &a, nf, dt3, st));
+      for (int q = 0; q < 3; ++q) nfloor[q] += nf[q];
+      dtnew = std::min(dt3[0], std::min(dt3[1], dt3[2]));
+    }
+    launches += 1;
+    return TaskStatus::complete;
+  }
+
+  // Mesh::NewTimeStep, mesh.cpp:573-643
+  void MeshNewTimeStep(double tlim) {
+    double dt = 2.0 * mesh.dt;
+    dt = std::min(dt, mesh.cfl_no * dtnew);
+    if (nranks > 1) {
+      Nccl &n = Nccl::get();
+      CU_CHECK(cudaMemcpyAsync(d_dt, &dt, 8, cudaMemcpyHostToDevice, st));
+      n.AllReduce(d_dt, d_dt, 1, kNcclFloat64, kNcclMin, comm, st);
+      CU_CHECK(cudaMemcpyAsync(&dt, d_dt, 8, cudaMemcpyDeviceToHost, st));
+      CU_CHECK(cudaStreamSynchronize(st));
+    }
+    if ((mesh.time < tlim) && ((mesh.time + dt) > tlim)) dt = tlim - mesh.time;
+    mesh.dt = dt;
+  }
+};
+
+void Driver::Initialize(MHD *pmhd) {   // driver.cpp:314-371 -> InitBoundaryValuesAndPrimitives :569-653
+  pmhd->SendU(this, 0); pmhd->RecvU(this, 0);
+  pmhd->SendB(this, 0); pmhd->RecvB(this, 0);
+  pmhd->ConToPrim(this, 0);
+  pmhd->NewTimeStep(this, nexp_stages);
+  pmhd->MeshNewTimeStep(tlim);
+}
+
+int Driver::Execute(MHD *pmhd, int ncycles) {   // driver.cpp:380-459
+  int done = 0;
+  auto &m = pmhd->mesh;
+  while ((m.time < tlim) && (m.ncycle < nlim || nlim < 0) && (ncycles < 0 || done < ncycles)) {
+    ExecuteTaskList(pmhd->tl_map, "before_timeintegrator", 0);
+    for (int stage = 1; stage <= nexp_stages; ++stage) {
+      ExecuteTaskList(pmhd->tl_map, "before_stagen", stage);
+      ExecuteTaskList(pmhd->tl_map, "stagen", stage);
+      ExecuteTaskList(pmhd->tl_map, "after_stagen", stage);
+    }
+    ExecuteTaskList(pmhd->tl_map, "after_timeintegrator", 1);
+    m.time = m.time + m.dt;
+    m.ncycle++;
+    nmb_updated_ += m.nmb_total;
+    done++;
+    pmhd->MeshNewTimeStep(tlim);
+  }
+  return done;
+}
+
+struct Sim {
+  std::unique_ptr<MHD> pmhd;
+  std::unique_ptr<Driver> pdriver;
+};
+
+}  // namespace akh
+
+extern "C" {
+
+int ak_sim_create(const ak_sim_cfg *c, const double *mb_size, const int *nghbr, void **sim) {
+  if (!c || !sim || !mb_size || !nghbr) return 1;
+  auto *s = new akh::Sim();
+  s->pmhd.reset(new akh::MHD(c->mhd, mb_size, nghbr, c->my_rank, c->nranks, c->gids_start, c->nmb_total));
+  s->pmhd->fused = c->fused != 0;
+  s->pmhd->mesh.cfl_no = c->cfl_number;
+  s->pmhd->AssembleMHDTasks();
+  s->pdriver.reset(new akh::Driver(c->integrator == 1 ? "rk1" : c->integrator == 2 ? "rk2" : "rk3", c->tlim, c->nlim));
+  *sim = s;
+  return 0;
+}
+int ak_sim_destroy(void *sim) { delete static_cast<akh::Sim *>(sim); return 0; }
+
+int ak_nccl_unique_id(void *out128) {
+  akh::Nccl &n = akh::Nccl::get();
+  if (!n.ok) return 1;
+  return n.GetUniqueId(static_cast<akh::Nccl::UniqueId *>(out128));
+}
+int ak_sim_comm_init(void *sim, const void *unique_id128) {
+  auto *s = static_cast<akh::Sim *>(sim);
+  akh::Nccl &n = akh::Nccl::get();
+  if (!n.ok) return 1;
+  akh::Nccl::UniqueId id;
+  std::memcpy(&id, unique_id128, sizeof(id));
+  return n.CommInitRank(&s->pmhd->comm, s->pmhd->nranks, id, s->pmhd->my_rank);
+}
+int ak_sim_set_state(void *sim, const double *u0, const double *b1f, const double *b2f, const double *b3f) {
+  auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
+  cudaError_t e = cudaMemcpyAsync(m->a.u0, u0, m->n_u * 8, cudaMemcpyHostToDevice, m->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->a.b0x1f, b1f, m->n_f1 * 8, cudaMemcpyHostToDevice, m->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->a.b0x2f, b2f, m->n_f2 * 8, cudaMemcpyHostToDevice, m->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->a.b0x3f, b3f, m->n_f3 * 8, cudaMemcpyHostToDevice, m->st);
+  return e == cudaSuccess ? 0 : 1;
+}
+int ak_sim_get_state(void *sim, double *u0, double *b1f, double *b2f, double *b3f) {
+  auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
+  cudaError_t e = cudaMemcpyAsync(u0, m->a.u0, m->n_u * 8, cudaMemcpyDeviceToHost, m->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b1f, m->a.b0x1f, m->n_f1 * 8, cudaMemcpyDeviceToHost, m->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b2f, m->a.b0x2f, m->n_f2 * 8, cudaMemcpyDeviceToHost, m->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b3f, m->a.b0x3f, m->n_f3 * 8, cudaMemcpyDeviceToHost, m->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(m->st);
+  return e == cudaSuccess ? 0 : 1;
+}
+int ak_sim_initialize(void *sim) {
+  auto *s = static_cast<akh::Sim *>(sim);
+  s->pmhd->mesh.time = 0.0; s->pmhd->mesh.ncycle = 0; s->pmhd->mesh.dt = (double)FLT_MAX; s->pmhd->dtnew = (double)FLT_MAX;
+  s->pdriver->Initialize(s->pmhd.get());
+  return 0;
+}
+int ak_sim_execute(void *sim, int ncycles) {
+  auto *s = static_cast<akh::Sim *>(sim);
+  return s->pdriver->Execute(s->pmhd.get(), ncycles);
+}
+int ak_sim_sync(void *sim) {
+  return cudaStreamSynchronize(static_cast<akh::Sim *>(sim)->pmhd->st) == cudaSuccess ? 0 : 1;
+}
+/* st[0..2] = time, dt, dtnew; cnt[0..5] = ncycle, launches, nfloor d/e/t, stream handle (as integer) */
+int ak_sim_status(void *sim, double *st, long *cnt) {
+  auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
+  st[0] = m->mesh.time; st[1] = m->mesh.dt; st[2] = m->dtnew;
+  cnt[0] = m->mesh.ncycle; cnt[1] = m->launches; cnt[2] = m->nfloor[0]; cnt[3] = m->nfloor[1]; cnt[4] = m->nfloor[2];
+  cnt[5] = (long)(intptr_t)m->st;
+  return 0;
+}
+int ak_sim_arrays(void *sim, ak_mhd_arrays *out) {
+  *out = static_cast<akh::Sim *>(sim)->pmhd->a;
+  return 0;
+}
+
+}  // extern "C"

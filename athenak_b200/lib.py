@@ -35,6 +35,13 @@ class MhdArrays(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ARRAY_FIELDS]
 
 
+class SimCfg(C.Structure):
+    """ak_sim_cfg"""
+    _fields_ = [("mhd", MhdCfg), ("integrator", C.c_int), ("cfl_number", C.c_double), ("tlim", C.c_double),
+                ("nlim", C.c_int), ("my_rank", C.c_int), ("nranks", C.c_int), ("gids_start", C.c_int),
+                ("nmb_total", C.c_int), ("fused", C.c_int)]
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -88,6 +95,17 @@ def load():
         "ak_neighbor_index": [ip, ip, ip, ip, ip],
         "ak_pgen_blast": [vp, ip, ip, d, dpp, dpp, dpp, dpp, dpp],
         "ak_selftest_divsqrt": [C.c_long, C.c_ulonglong, ip, C.POINTER(C.c_long)],
+        "ak_sim_create": [C.POINTER(SimCfg), dpp, ipp, C.POINTER(vp)],
+        "ak_sim_destroy": [vp],
+        "ak_nccl_unique_id": [vp],
+        "ak_sim_comm_init": [vp, vp],
+        "ak_sim_set_state": [vp, vp, vp, vp, vp],
+        "ak_sim_get_state": [vp, vp, vp, vp, vp],
+        "ak_sim_initialize": [vp],
+        "ak_sim_execute": [vp, ip],
+        "ak_sim_sync": [vp],
+        "ak_sim_status": [vp, dpp, C.POINTER(C.c_long)],
+        "ak_sim_arrays": [vp, C.POINTER(MhdArrays)],
     })
     lib.ak_mesh_last_error.restype = C.c_char_p
     for name, args in sig.items():
@@ -104,7 +122,9 @@ EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_con
             "ak_halo_npeers", "ak_halo_peer", "ak_halo_descs", "ak_halo_local_cc", "ak_halo_local_fc",
             "ak_halo_pack_cc", "ak_halo_unpack_cc", "ak_halo_pack_fc", "ak_halo_unpack_fc",
             "ak_mesh_create", "ak_mesh_destroy", "ak_mesh_last_error", "ak_mesh_info", "ak_mesh_tables",
-            "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast", "ak_selftest_divsqrt")
+            "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast", "ak_selftest_divsqrt",
+            "ak_sim_create", "ak_sim_destroy", "ak_nccl_unique_id", "ak_sim_comm_init", "ak_sim_set_state",
+            "ak_sim_get_state", "ak_sim_initialize", "ak_sim_execute", "ak_sim_sync", "ak_sim_status", "ak_sim_arrays")
 
 
 def check(rc, handle=None):

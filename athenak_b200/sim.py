@@ -1,0 +1,80 @@
+"""Python handle on the C++ host driver (athenak_b200/csrc/host_driver.cpp): TaskList + Driver +
+MHD task registration in C++, owning the device arrays; Python only feeds ICs and reads results."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+from .mhd import FLT_MAX, FLT_MIN
+
+INTEGRATOR = {"rk1": 1, "rk2": 2, "rk3": 3}
+
+
+class Simulation:
+    def __init__(self, mesh, rank=0, *, ng=4, recon="ppm4", rsolver="hlld", gamma=1.6666667, integrator="rk3",
+                 cfl_number=0.3, tlim=1.0, nlim=-1, fused=True, dfloor=FLT_MIN, pfloor=FLT_MIN, tfloor=FLT_MIN,
+                 sfloor=FLT_MIN, sigma_max=FLT_MAX):
+        self.L = _lib.load()
+        self.mesh, self.rank, self.ng = mesh, rank, ng
+        nmb = int(mesh.nmb_rank[rank])
+        nx = mesh.nblock
+        mb_size, _, nghbr = mesh.rank_tables(rank)
+        mcfg = _lib.MhdCfg(nmb, ng, nx[0], nx[1], nx[2], _lib.RECON[recon], _lib.RSOLVER[rsolver], gamma,
+                           dfloor, pfloor, tfloor, sfloor, sigma_max)
+        self.cfg = _lib.SimCfg(mcfg, INTEGRATOR[integrator], cfl_number, tlim, nlim, rank, mesh.nranks,
+                               int(mesh.gids_start[rank]), mesh.nmb_total, 1 if fused else 0)
+        self.h = C.c_void_p()
+        rc = self.L.ak_sim_create(C.byref(self.cfg), mb_size.ctypes.data_as(C.POINTER(C.c_double)),
+                                  nghbr.ctypes.data_as(C.POINTER(C.c_int)), C.byref(self.h))
+        if rc:
+            raise _lib.EngineError("ak_sim_create failed: " + (self.L.ak_last_error(None) or b"").decode())
+        n1, n2, n3 = (nx[d] + 2 * ng for d in range(3))
+        self.shapes = [(nmb, 5, n3, n2, n1), (nmb, n3, n2, n1 + 1), (nmb, n3, n2 + 1, n1), (nmb, n3 + 1, n2, n1)]
+
+    def __del__(self):
+        try:
+            self.L.ak_sim_destroy(self.h)
+        except Exception:
+            pass
+
+    def comm_init(self, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        if self.L.ak_sim_comm_init(self.h, buf):
+            raise _lib.EngineError("ak_sim_comm_init failed")
+
+    def unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        if self.L.ak_nccl_unique_id(buf):
+            raise _lib.EngineError("NCCL not available")
+        return buf.raw
+
+    @staticmethod
+    def _ptr(t):
+        return C.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else t.ctypes.data)
+
+    def set_state(self, u0, b1f, b2f, b3f):
+        """Host arrays (numpy or torch CPU tensors, C-contiguous float64, full ghost-inclusive shape)."""
+        if self.L.ak_sim_set_state(self.h, *[self._ptr(t) for t in (u0, b1f, b2f, b3f)]):
+            raise _lib.EngineError("ak_sim_set_state failed")
+
+    def get_state(self, out=None):
+        out = out or [np.empty(s) for s in self.shapes]
+        if self.L.ak_sim_get_state(self.h, *[self._ptr(t) for t in out]):
+            raise _lib.EngineError("ak_sim_get_state failed")
+        return out
+
+    def initialize(self):
+        self.L.ak_sim_initialize(self.h)
+
+    def execute(self, ncycles=-1):
+        return self.L.ak_sim_execute(self.h, ncycles)
+
+    def sync(self):
+        self.L.ak_sim_sync(self.h)
+
+    def status(self):
+        st, cnt = (C.c_double * 3)(), (C.c_long * 6)()
+        self.L.ak_sim_status(self.h, st, cnt)
+        return dict(time=st[0], dt=st[1], dtnew=st[2], ncycle=cnt[0], launches=cnt[1], nfloor=list(cnt[2:5]), stream=cnt[5])

@@ -167,33 +167,41 @@ def bench_native(args):
     assert int(mesh.nmb_rank[rank]) == 1
     mb_size, _, nghbr = mesh.rank_tables(rank)
     hu0, hb1, hb2, hb3 = mesh.pgen_blast(rank, NG, GAMMA, pinned=True)
-    e = MHD(1, NG, (n, n, n), mb_size, nghbr, recon="ppm4", rsolver="hlld", gamma=GAMMA, my_rank=rank,
-            gids_start=int(mesh.gids_start[rank]), device=dev)
-    for dst, src in zip([e.u0] + e.b0, (hu0, hb1, hb2, hb3)):
-        dst.copy_(src, non_blocking=True)
-    drv = Driver("rk3", 0.3, tlim=1.0e9)
-    tl = assemble_mhd_tasks(e, fused=True)
-    drv.Initialize(e)
+    # headline path: the C++ host driver (TaskList/Driver/MHD tasks in csrc/host_driver.cpp) calling
+    # the C ABI; NCCL communicator of its own for N > 1 (id broadcast through torch.distributed)
+    from athenak_b200.sim import Simulation
+    sim = Simulation(mesh, rank, ng=NG, recon="ppm4", rsolver="hlld", gamma=GAMMA, integrator="rk3",
+                     cfl_number=0.3, tlim=1.0e9, fused=True)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(sim.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        sim.comm_init(bytes(idt.cpu().numpy().tobytes()))
+    sim.set_state(hu0, hb1, hb2, hb3)
+    sim.initialize()
+    sstream = torch.cuda.ExternalStream(sim.status()["stream"], device=dev)
 
     def sync_all():
+        sim.sync()
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize(dev)
 
     K, W = args.steps, args.warmup
-    drv.Execute(e, tl, ncycles=W)
+    sim.execute(W)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     sync_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = e.launches
-    ev0.record()
-    drv.Execute(e, tl, ncycles=K)
-    ev1.record()
+    l0 = sim.status()["launches"]
+    ev0.record(sstream)
+    sim.execute(K)
+    ev1.record(sstream)
     sync_all()
-    launches = e.launches - l0
+    launches = sim.status()["launches"] - l0
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -202,30 +210,28 @@ def bench_native(args):
         ms = float(t.item())
     cells = float(n) ** 3 * world
     value = cells * K / (ms * 1e-3) / 1e6
+    dt_now = sim.status()["dt"]
 
     # ---- end to end: host buffers in, host buffers out, every step --------------------------
     # H2D of the conserved state (u0 + 3 face fields, pinned) -> ghost exchange + c2p -> one full
-    # step -> D2H of the updated conserved state.
-    ho = [torch.empty_like(t, device="cpu").pin_memory() for t in [e.u0] + e.b0]
+    # step -> D2H of the updated conserved state, all through the C ABI (ak_sim_*).
+    ho = [torch.empty_like(t).pin_memory() for t in (hu0, hb1, hb2, hb3)]
     ke2e = max(2, min(K, 5))
     h2d = sum(t.numel() * 8 for t in (hu0, hb1, hb2, hb3))
     d2h = sum(t.numel() * 8 for t in ho)
 
     def e2e_step():
-        for dst, src in zip([e.u0] + e.b0, (hu0, hb1, hb2, hb3)):
-            dst.copy_(src, non_blocking=True)
-        d2 = Driver("rk3", 0.3, tlim=1.0e9)
-        d2.Initialize(e)
-        d2.Execute(e, tl, ncycles=1)
-        for dst, src in zip(ho, [e.u0] + e.b0):
-            dst.copy_(src, non_blocking=True)
+        sim.set_state(hu0, hb1, hb2, hb3)
+        sim.initialize()
+        sim.execute(1)
+        sim.get_state(ho)
 
     e2e_step()
     sync_all()
-    ev0.record()
+    ev0.record(sstream)
     for _ in range(ke2e):
         e2e_step()
-    ev1.record()
+    ev1.record(sstream)
     sync_all()
     ms_e2e = ev0.elapsed_time(ev1)
     if world > 1:
@@ -233,6 +239,18 @@ def bench_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     e2e_value = cells * ke2e / (ms_e2e * 1e-3) / 1e6
+    del sim
+    torch.cuda.empty_cache()
+
+    # ---- per-kernel breakdown through the per-task C-ABI entry points -------------------------
+    e = MHD(1, NG, (n, n, n), mb_size, nghbr, recon="ppm4", rsolver="hlld", gamma=GAMMA, my_rank=rank,
+            gids_start=int(mesh.gids_start[rank]), device=dev)
+    for dst, src in zip([e.u0] + e.b0, (hu0, hb1, hb2, hb3)):
+        dst.copy_(src, non_blocking=True)
+    drv = Driver("rk3", 0.3, tlim=1.0e9)
+    tl = assemble_mhd_tasks(e, fused=True)
+    drv.Initialize(e)
+    drv.Execute(e, tl, ncycles=2)
 
     # ---- per-kernel timing (per-task ABI path, CUDA events on the launching stream) ----------
     peaks = {}
@@ -245,7 +263,7 @@ def bench_native(args):
     if True:   # every rank runs the plan (the halo entries are collective); rank 0 reports
         nrep = 3
         class D:  # stage-2 coefficients
-            gam0, gam1, beta, dt, nexp_stages = [0.25] * 3, [0.75] * 3, [0.25] * 3, drv.dt, 3
+            gam0, gam1, beta, dt, nexp_stages = [0.25] * 3, [0.75] * 3, [0.25] * 3, dt_now, 3
         def timeit(fn):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             fn(); torch.cuda.synchronize(dev)

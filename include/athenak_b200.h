@@ -138,6 +138,33 @@ int ak_neighbor_index(int ix, int iy, int iz, int n1, int n2); /* src/mesh/nghbr
 int ak_pgen_blast(void *mesh, int rank, int ng, double gamma, const double *prm, double *u0,
                   double *b1f, double *b2f, double *b3f);
 
+/* ---- C++ host driver (athenak_b200/csrc/host_driver.cpp) -----------------------------------
+ * TaskList / Driver / MHD task registration as in the reference (src/tasklist/task_list.hpp,
+ * src/driver/driver.cpp:93-130,290-307,380-459, src/mhd/mhd_tasks.cpp:38-84, src/mesh/mesh.cpp:
+ * 573-643), owning the device arrays of one MeshBlockPack and sequencing the calls above.
+ * Multi-rank: grouped ncclSend/ncclRecv per exchange + ncclAllReduce(min) for dt. */
+typedef struct {
+  ak_mhd_cfg mhd;
+  int integrator;        /* 1 rk1, 2 rk2, 3 rk3 (src/driver/driver.cpp:93-130) */
+  double cfl_number, tlim;
+  int nlim;              /* <0: no cycle limit */
+  int my_rank, nranks, gids_start, nmb_total;
+  int fused;             /* 1: ak_mhd_stage_fused + ak_mhd_cons2prim_newdt task list */
+} ak_sim_cfg;
+int ak_sim_create(const ak_sim_cfg *cfg, const double *mb_size /*host [nmb][9]*/,
+                  const int *nghbr /*host [nmb][56][4]*/, void **sim);
+int ak_sim_destroy(void *sim);
+int ak_nccl_unique_id(void *out128);                         /* rank 0; broadcast by the launcher */
+int ak_sim_comm_init(void *sim, const void *unique_id128);   /* collective over all ranks */
+int ak_sim_set_state(void *sim, const double *u0, const double *b1f, const double *b2f, const double *b3f);
+int ak_sim_get_state(void *sim, double *u0, double *b1f, double *b2f, double *b3f);
+int ak_sim_initialize(void *sim);            /* Driver::Initialize: ghosts, c2p, first dt */
+int ak_sim_execute(void *sim, int ncycles);  /* Driver::Execute; returns cycles done */
+int ak_sim_sync(void *sim);
+/* st[3] = time, dt, dtnew; cnt[6] = ncycle, kernel launches, nfloor d/e/t, cudaStream_t */
+int ak_sim_status(void *sim, double *st, long *cnt);
+int ak_sim_arrays(void *sim, ak_mhd_arrays *out);            /* the device arrays it owns */
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,28 @@ def main():
             ok &= np.array_equal(bb[1][m, 4:-4, 4:-4, 4:-4], d["b2f_c4"][0][lz:lz + 8, ly:ly + 9, lx:lx + 8])
             ok &= np.array_equal(bb[2][m, 4:-4, 4:-4, 4:-4], d["b3f_c4"][0][lz:lz + 9, ly:ly + 8, lx:lx + 8])
         ok &= drv.time == float(d["time_c4"])
+    # the same run through the C++ host driver with its own NCCL communicator
+    from athenak_b200.sim import Simulation
+    sim = Simulation(mesh, rank, ng=ng, recon="ppm4", rsolver="hlld", gamma=gamma, integrator="rk3",
+                     cfl_number=0.3, tlim=0.3, fused=True)
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(sim.unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    sim.comm_init(bytes(idt.cpu().numpy().tobytes()))
+    sim.set_state(u0, b1, b2, b3)
+    sim.initialize()
+    ok &= sim.status()["dt"] == float(d["dt_c0"])
+    sim.execute(4)
+    u, x1, x2, x3 = sim.get_state()
+    for m in range(n):
+        lx, ly, lz = (int(v) * 8 for v in mesh.lloc[g0 + m, :3])
+        ok &= np.array_equal(u[m, :, 4:-4, 4:-4, 4:-4], d["u0_c4"][0][:, lz:lz + 8, ly:ly + 8, lx:lx + 8])
+        ok &= np.array_equal(x1[m, 4:-4, 4:-4, 4:-4], d["b1f_c4"][0][lz:lz + 8, ly:ly + 8, lx:lx + 9])
+        ok &= np.array_equal(x2[m, 4:-4, 4:-4, 4:-4], d["b2f_c4"][0][lz:lz + 8, ly:ly + 9, lx:lx + 8])
+        ok &= np.array_equal(x3[m, 4:-4, 4:-4, 4:-4], d["b3f_c4"][0][lz:lz + 9, ly:ly + 8, lx:lx + 8])
+    ok &= sim.status()["time"] == float(d["time_c4"])
+    del sim
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

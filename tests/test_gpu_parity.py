@@ -283,3 +283,31 @@ def test_fast_div_sqrt(span):
     bad = (C.c_long * 3)()
     assert L.ak_selftest_divsqrt(1 << 28, 12345 + span, span, bad) == 0
     assert list(bad) == [0, 0, 0]
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("nb", [1, 2])
+def test_cxx_driver_matches_golden(fused, nb):
+    """The C++ host driver (TaskList/Driver/MHD tasks in csrc/host_driver.cpp) + C++ host mesh +
+    C++ blast pgen, end to end: 4 cycles of the 16^3 blast == the reference's restart dump."""
+    from athenak_b200.mesh import Mesh
+    from athenak_b200.sim import Simulation
+    d = G.load("blast16_ppm4_hlld_rk3")
+    m = 16 // nb
+    mesh = Mesh((16, 16, 16), (m, m, m))
+    sim = Simulation(mesh, 0, ng=4, recon="ppm4", rsolver="hlld", gamma=1.6666667, integrator="rk3",
+                     cfl_number=0.3, tlim=0.3, fused=fused)
+    u0, b1, b2, b3 = mesh.pgen_blast(0, 4, 1.6666667)
+    sim.set_state(u0, b1, b2, b3)
+    sim.initialize()
+    assert sim.status()["dt"] == float(d["dt_c0"])
+    assert sim.execute(4) == 4
+    st = sim.status()
+    assert st["time"] == float(d["time_c4"]) and st["ncycle"] == 4 and st["nfloor"] == [0, 0, 0]
+    u, x1, x2, x3 = sim.get_state()
+    for g in range(mesh.nmb_total):
+        lx, ly, lz = (int(v) * m for v in mesh.lloc[g, :3])
+        assert np.array_equal(u[g, :, 4:-4, 4:-4, 4:-4], d["u0_c4"][0][:, lz:lz + m, ly:ly + m, lx:lx + m])
+        assert np.array_equal(x1[g, 4:-4, 4:-4, 4:-4], d["b1f_c4"][0][lz:lz + m, ly:ly + m, lx:lx + m + 1])
+        assert np.array_equal(x2[g, 4:-4, 4:-4, 4:-4], d["b2f_c4"][0][lz:lz + m, ly:ly + m + 1, lx:lx + m])
+        assert np.array_equal(x3[g, 4:-4, 4:-4, 4:-4], d["b3f_c4"][0][lz:lz + m + 1, ly:ly + m, lx:lx + m])
