@@ -1,0 +1,78 @@
+"""BASELINE config 4 on the GPU: 3-D MHD linear-wave convergence (PLM/PPM4/WENOZ x HLLE/HLLD) on a
+multi-block uniform mesh.  Synthetic inputs = the reference's own initial condition (cycle-0
+restart dump of oracle/_ref/athena_builtin, run live); gates:
+  * final u0/b0 after one wave period (36 / 72 cycles) == the reference's final dump, bitwise;
+  * RMS-L1 error (formula of src/pgen/pgen.cpp:680-905) == the value the reference writes to
+    LinWave-errs.dat, and the SURVEY.md section 8c known answers at 32x16x16;
+  * error ratio between 32x16x16 and 64x32x32 below the reference's convergence thresholds.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from athenak_b200.rst import read_rst
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+KNOWN = {("ppm4", "hlld"): (1.059406e-07, 2.296897e-08), ("plm", "hlle"): (2.269293e-07, 7.876275e-08),
+         ("wenoz", "hlld"): (8.389852e-09, 1.638898e-09)}
+
+
+def rms_l1(u, b, u_ic, b_ic, ng):
+    """ProblemGenerator::OutputErrors: volume-weighted L1 per variable (5 cons + 3 cell-centred B),
+    RMS over variables; uniform cells so the volume weights reduce to a mean."""
+    s = slice(ng, -ng)
+    errs = [np.abs(u[:, n, s, s, s] - u_ic[:, n, s, s, s]).mean() for n in range(5)]
+
+    def cc(bf):
+        return (0.5 * (bf[0][:, s, s, ng:-ng - 1] + bf[0][:, s, s, ng + 1:-ng]),
+                0.5 * (bf[1][:, s, ng:-ng - 1, s] + bf[1][:, s, ng + 1:-ng, s]),
+                0.5 * (bf[2][:, ng:-ng - 1, s, s] + bf[2][:, ng + 1:-ng, s, s]))
+    for x, y in zip(cc(b), cc(b_ic)):
+        errs.append(np.abs(x - y).mean())
+    return float(np.sqrt(sum(e * e for e in errs)))
+
+
+def run_case(recon, rs, n):
+    from athenak_b200.mesh import Mesh
+    from athenak_b200.sim import Simulation
+    nmesh, nblock = (n, n // 2, n // 2), (n // 2, n // 8, n // 8)
+    ov = [f"mesh/nx{d+1}={nmesh[d]}" for d in range(3)] + [f"meshblock/nx{d+1}={nblock[d]}" for d in range(3)]
+    ov += [f"mhd/reconstruct={recon}", f"mhd/rsolver={rs}"]
+    with tempfile.TemporaryDirectory() as tmp:
+        O.run_reference("athena_builtin", os.path.join(HERE, "decks", "lwave3d.athinput"), tmp, ov, threads=4)
+        r0 = read_rst(os.path.join(tmp, "rst", "LinWave.00000.rst"))
+        r1 = read_rst(os.path.join(tmp, "rst", "LinWave.00001.rst"))
+        ref_err = float(open(os.path.join(tmp, "LinWave-errs.dat")).read().split("\n")[1].split()[4])
+    mesh = Mesh(nmesh, nblock, xmin=(0.0, 0.0, 0.0), xmax=(3.0, 1.5, 1.5))
+    assert (mesh.lloc == r0.lloc).all()
+    sim = Simulation(mesh, 0, ng=4, recon=recon, rsolver=rs, gamma=1.66666666667, integrator="rk3",
+                     cfl_number=0.3, tlim=r1.time, fused=True)
+    sim.set_state(r0.u0, r0.b1f, r0.b2f, r0.b3f)
+    sim.initialize()
+    assert sim.status()["dt"] == r0.dt
+    sim.execute(-1)
+    st = sim.status()
+    assert st["ncycle"] == r1.ncycle and st["time"] == r1.time
+    u, b1, b2, b3 = sim.get_state()
+    assert np.array_equal(u, r1.u0), f"max|dU| = {np.abs(u - r1.u0).max()}"
+    for x, y in zip((b1, b2, b3), (r1.b1f, r1.b2f, r1.b3f)):
+        assert np.array_equal(x, y)
+    err = rms_l1(u, (b1, b2, b3), r0.u0, (r0.b1f, r0.b2f, r0.b3f), 4)
+    assert abs(err - ref_err) <= 2e-6 * ref_err, (err, ref_err)   # errs.dat prints 7 digits
+    return err
+
+
+@pytest.mark.parametrize("recon,rs", list(KNOWN))
+def test_linear_wave_convergence(recon, rs):
+    if not O.have_reference("athena_builtin"):
+        pytest.skip("oracle/_ref/athena_builtin not built")
+    e32 = run_case(recon, rs, 32)
+    e64 = run_case(recon, rs, 64)
+    k32, k64 = KNOWN[(recon, rs)]
+    assert abs(e32 - k32) <= 2e-6 * k32 and abs(e64 - k64) <= 2e-6 * k64
+    # second-order (PLM) or better: error ratio per doubling (cf. tst/test_suite/nr/test_nr_lwave1d_cpu.py:15-96)
+    assert e64 / e32 < (0.4 if recon == "plm" else 0.25)
