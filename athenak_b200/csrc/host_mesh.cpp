@@ -274,4 +274,59 @@ int ak_pgen_blast(void *mesh, int rank, int ng, double gamma, const double *prm,
   return 0;
 }
 
+// Orszag-Tang vortex, pgen/tests/orszag_tang.cpp:32-123 (x3-invariant; same libm sin/cos as the
+// reference, so the ICs are bit-identical).  Active zones of the rank's blocks.
+int ak_pgen_orszag_tang(void *mesh, int rank, int ng, double gamma, double *u0, double *b1f, double *b2f,
+                        double *b3f) {
+  auto *M = static_cast<HostMesh *>(mesh);
+  if (!M || rank < 0 || rank >= M->nranks) return 1;
+  const double B0 = 1.0 / std::sqrt(4.0 * M_PI);
+  const double d0 = 25.0 / (36.0 * M_PI);
+  const double v0 = 1.0;
+  const double p0 = 5.0 / (12.0 * M_PI);
+  auto A3 = [](double x1, double x2, double B0_) {
+    return (B0_ / (4.0 * M_PI)) * (std::cos(4.0 * M_PI * x1) - 2.0 * std::cos(2.0 * M_PI * x2));
+  };
+  const int nx1 = M->nblock[0], nx2 = M->nblock[1], nx3 = M->nblock[2];
+  const int n1 = nx1 + 2 * ng, n2 = nx2 + 2 * ng, n3 = nx3 + 2 * ng;
+  const int is = ng, ie = ng + nx1 - 1, js = ng, je = ng + nx2 - 1, ks = ng, ke = ng + nx3 - 1;
+  const size_t cc = (size_t)n3 * n2 * n1, f1 = (size_t)n3 * n2 * (n1 + 1), f2 = (size_t)n3 * (n2 + 1) * n1, f3 = (size_t)(n3 + 1) * n2 * n1;
+  const double gm1 = gamma - 1.0;
+  const int nmb = M->nmb_rank[rank], g0 = M->gids_start[rank];
+  for (int m = 0; m < nmb; ++m) {
+    const double *sz = &M->mb_size[(size_t)(g0 + m) * 9];
+    const double x1min = sz[0], x2min = sz[1], x1max = sz[3], x2max = sz[4], dx1 = sz[6], dx2 = sz[7];
+    double *U = u0 + (size_t)m * 5 * cc, *B1 = b1f + (size_t)m * f1, *B2 = b2f + (size_t)m * f2, *B3 = b3f + (size_t)m * f3;
+    auto C = [&](int k, int j, int i) { return ((size_t)k * n2 + j) * n1 + i; };
+    auto X1 = [&](int k, int j, int i) -> double & { return B1[((size_t)k * n2 + j) * (n1 + 1) + i]; };
+    auto X2 = [&](int k, int j, int i) -> double & { return B2[((size_t)k * (n2 + 1) + j) * n1 + i]; };
+    auto X3 = [&](int k, int j, int i) -> double & { return B3[((size_t)k * n2 + j) * n1 + i]; };
+    for (int k = ks; k <= ke; ++k) for (int j = js; j <= je; ++j) for (int i = is; i <= ie; ++i) {
+      double x1v = CellCenterX(i - is, nx1, x1min, x1max);
+      double x2v = CellCenterX(j - js, nx2, x2min, x2max);
+      const size_t o = C(k, j, i);
+      U[0 * cc + o] = d0;
+      U[1 * cc + o] = d0 * v0 * std::sin(2.0 * M_PI * x2v);
+      U[2 * cc + o] = -d0 * v0 * std::sin(2.0 * M_PI * x1v);
+      U[3 * cc + o] = 0.0;
+      double x1f = LeftEdgeX(i - is, nx1, x1min, x1max), x1fp1 = LeftEdgeX(i + 1 - is, nx1, x1min, x1max);
+      double x2f = LeftEdgeX(j - js, nx2, x2min, x2max), x2fp1 = LeftEdgeX(j + 1 - js, nx2, x2min, x2max);
+      X1(k, j, i) = (A3(x1f, x2fp1, B0) - A3(x1f, x2f, B0)) / dx2;
+      X2(k, j, i) = -(A3(x1fp1, x2f, B0) - A3(x1f, x2f, B0)) / dx1;
+      X3(k, j, i) = 0.0;
+      if (i == ie) X1(k, j, i + 1) = (A3(x1fp1, x2fp1, B0) - A3(x1fp1, x2f, B0)) / dx2;
+      if (j == je) X2(k, j + 1, i) = -(A3(x1fp1, x2fp1, B0) - A3(x1f, x2fp1, B0)) / dx1;
+      if (k == ke) X3(k + 1, j, i) = 0.0;
+    }
+    for (int k = ks; k <= ke; ++k) for (int j = js; j <= je; ++j) for (int i = is; i <= ie; ++i) {
+      const size_t o = C(k, j, i);
+      U[4 * cc + o] = p0 / gm1 + (0.5 / U[0 * cc + o]) * (U[1 * cc + o] * U[1 * cc + o] + U[2 * cc + o] * U[2 * cc + o] + U[3 * cc + o] * U[3 * cc + o]) +
+                      0.5 * ((0.5 * (X1(k, j, i) + X1(k, j, i + 1))) * (0.5 * (X1(k, j, i) + X1(k, j, i + 1))) +
+                             (0.5 * (X2(k, j, i) + X2(k, j + 1, i))) * (0.5 * (X2(k, j, i) + X2(k, j + 1, i))) +
+                             (0.5 * (X3(k, j, i) + X3(k + 1, j, i))) * (0.5 * (X3(k, j, i) + X3(k + 1, j, i))));
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -94,6 +94,7 @@ def load():
         "ak_mesh_rank_tables": [vp, ip, dpp, ipp, ipp],
         "ak_neighbor_index": [ip, ip, ip, ip, ip],
         "ak_pgen_blast": [vp, ip, ip, d, dpp, dpp, dpp, dpp, dpp],
+        "ak_pgen_orszag_tang": [vp, ip, ip, d, dpp, dpp, dpp, dpp],
         "ak_selftest_divsqrt": [C.c_long, C.c_ulonglong, ip, C.POINTER(C.c_long)],
         "ak_sim_create": [C.POINTER(SimCfg), dpp, ipp, C.POINTER(vp)],
         "ak_sim_destroy": [vp],
@@ -122,7 +123,7 @@ EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_con
             "ak_halo_npeers", "ak_halo_peer", "ak_halo_descs", "ak_halo_local_cc", "ak_halo_local_fc",
             "ak_halo_pack_cc", "ak_halo_unpack_cc", "ak_halo_pack_fc", "ak_halo_unpack_fc",
             "ak_mesh_create", "ak_mesh_destroy", "ak_mesh_last_error", "ak_mesh_info", "ak_mesh_tables",
-            "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast", "ak_selftest_divsqrt",
+            "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast", "ak_pgen_orszag_tang", "ak_selftest_divsqrt",
             "ak_sim_create", "ak_sim_destroy", "ak_nccl_unique_id", "ak_sim_comm_init", "ak_sim_set_state",
             "ak_sim_get_state", "ak_sim_initialize", "ak_sim_execute", "ak_sim_sync", "ak_sim_status", "ak_sim_arrays")
 

@@ -46,6 +46,18 @@ class Mesh:
                                    mb_bcs.ctypes.data_as(C.POINTER(C.c_int)), nghbr.ctypes.data_as(C.POINTER(C.c_int)))
         return mb_size, mb_bcs, nghbr
 
+    def pgen_orszag_tang(self, rank, ng, gamma, pinned=False):
+        """Orszag-Tang ICs for the rank's blocks as host arrays (u0, b1f, b2f, b3f)."""
+        import torch
+        n = int(self.nmb_rank[rank])
+        n1, n2, n3 = (self.nblock[d] + 2 * ng for d in range(3))
+        mk = lambda *s: torch.zeros(*s, dtype=torch.float64, pin_memory=pinned)
+        u0, b1, b2, b3 = mk(n, 5, n3, n2, n1), mk(n, n3, n2, n1 + 1), mk(n, n3, n2 + 1, n1), mk(n, n3 + 1, n2, n1)
+        dp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
+        if self.L.ak_pgen_orszag_tang(self.h, rank, ng, gamma, dp(u0), dp(b1), dp(b2), dp(b3)):
+            raise _lib.EngineError("ak_pgen_orszag_tang failed")
+        return u0, b1, b2, b3
+
     def pgen_blast(self, rank, ng, gamma, pi_amb=0.1, di_amb=1.0, prat=100.0, drat=1.0, b_amb=1.0,
                    inner_radius=0.1, outer_radius=0.1, pinned=False):
         """Blast ICs for the rank's blocks as host arrays (u0, b1f, b2f, b3f), active zones filled."""

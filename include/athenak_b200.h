@@ -113,6 +113,10 @@ int ak_halo_pack_fc(void *plan, const double *x1f, const double *x2f, const doub
 int ak_halo_unpack_fc(void *plan, double *x1f, double *x2f, double *x3f, int ipeer,
                       const double *recvbuf, ak_stream_t s);
 
+/* Orszag-Tang vortex ICs (src/pgen/tests/orszag_tang.cpp:32-123), BASELINE config 3. */
+int ak_pgen_orszag_tang(void *mesh, int rank, int ng, double gamma, double *u0, double *b1f,
+                        double *b2f, double *b3f);
+
 /* Device self-test: compares the library's slow-path-free FP64 reciprocal / division / sqrt with
  * the built-in IEEE operators on n random operands (|exponent| <= exponent_span, every 64th
  * numerator exactly 0); mismatches[3] = differing results for 1/x, a/b, sqrt(x). */

@@ -76,3 +76,27 @@ def test_linear_wave_convergence(recon, rs):
     assert abs(e32 - k32) <= 2e-6 * k32 and abs(e64 - k64) <= 2e-6 * k64
     # second-order (PLM) or better: error ratio per doubling (cf. tst/test_suite/nr/test_nr_lwave1d_cpu.py:15-96)
     assert e64 / e32 < (0.4 if recon == "plm" else 0.25)
+
+
+def test_orszag_tang_multiblock_matches_reference():
+    """BASELINE config 3 at test size: Orszag-Tang 32^3 in 8 MeshBlocks of 16^3, PPM4+HLLD+RK3,
+    ICs from the C++ host pgen, 6 cycles == the reference's restart dump, bitwise."""
+    from athenak_b200.mesh import Mesh
+    from athenak_b200.sim import Simulation
+    if not O.have_reference("athena_builtin"):
+        pytest.skip("oracle/_ref/athena_builtin not built")
+    with tempfile.TemporaryDirectory() as tmp:
+        O.run_reference("athena_builtin", os.path.join(HERE, "decks", "ot3d.athinput"), tmp, threads=4)
+        r1 = read_rst(os.path.join(tmp, "rst", "OrszagTang.00001.rst"))
+    assert r1.ncycle == 6
+    mesh = Mesh((32, 32, 32), (16, 16, 16))
+    sim = Simulation(mesh, 0, ng=4, recon="ppm4", rsolver="hlld", gamma=1.666666667, integrator="rk3",
+                     cfl_number=0.3, tlim=2.0, fused=True)
+    sim.set_state(*mesh.pgen_orszag_tang(0, 4, 1.666666667))
+    sim.initialize()
+    sim.execute(6)
+    assert sim.status()["time"] == r1.time
+    u, b1, b2, b3 = sim.get_state()
+    assert np.array_equal(u, r1.u0)
+    for x, y in zip((b1, b2, b3), (r1.b1f, r1.b2f, r1.b3f)):
+        assert np.array_equal(x, y)

@@ -179,3 +179,24 @@ def test_halo_plan_equals_reference_exchange(nmesh, nblock, nranks):
     assert np.array_equal(u, ou)
     for x, y in zip(b, ob):
         assert np.array_equal(x, y)
+
+
+def test_pgens_match_live_reference():
+    """ak_pgen_blast / ak_pgen_orszag_tang produce the reference's initial conditions bit for bit
+    (active zones of every block; 8 blocks)."""
+    if not (O.have_reference("athena_blast") and O.have_reference("athena_builtin")):
+        pytest.skip("oracle/_ref not built")
+    for binary, deck, gamma, gen in (("athena_blast", "blast3d.athinput", 1.6666667, "pgen_blast"),
+                                     ("athena_builtin", "ot3d.athinput", 1.666666667, "pgen_orszag_tang")):
+        with tempfile.TemporaryDirectory() as tmp:
+            O.run_reference(binary, os.path.join(HERE, "decks", deck), tmp,
+                            ["time/nlim=0"] + [f"meshblock/nx{d}=16" for d in (1, 2, 3)])
+            base = "Blast" if "blast" in deck else "OrszagTang"
+            r = read_rst(os.path.join(tmp, "rst", base + ".00000.rst"))
+        M = Mesh((32, 32, 32), (16, 16, 16))
+        u0, b1, b2, b3 = getattr(M, gen)(0, 4, gamma)
+        s = slice(4, -4)
+        assert np.array_equal(u0.numpy()[:, :, s, s, s], r.u0[:, :, s, s, s]), gen
+        assert np.array_equal(b1.numpy()[:, s, s, 4:-4], r.b1f[:, s, s, 4:-4])
+        assert np.array_equal(b2.numpy()[:, s, 4:-4, s], r.b2f[:, s, 4:-4, s])
+        assert np.array_equal(b3.numpy()[:, 4:-4, s, s], r.b3f[:, 4:-4, s, s])
