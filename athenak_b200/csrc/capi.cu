@@ -217,15 +217,34 @@ int ak_mhd_new_dt(void *handle, const ak_mhd_arrays *a, double *dt3, ak_stream_t
   return 0;
 }
 
-int ak_mhd_stage_fused(void *handle, const ak_mhd_arrays *a, int stage, double gam0, double gam1, double beta_dt,
-                       ak_stream_t s) {
-  AK_PROLOGUE("ak_mhd_stage_fused")
+int ak_mhd_stage_flux_emf(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_stage_flux_emf")
+  if ((e = akb::launch_fluxes(h->cfg.recon, h->cfg.rsolver, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_flux_emf", e);
+  if ((e = akb::launch_corner_e(h->g, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_flux_emf", e);
+  return 0;
+}
+
+int ak_mhd_stage_update(void *handle, const ak_mhd_arrays *a, int stage, double gam0, double gam1, double beta_dt,
+                        ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_stage_update")
   // stage 1: CopyCons is folded into the update kernel (it saves u1/b1 for the ACTIVE zones it
   // updates -- the only entries later stages read -- instead of copying whole arrays)
-  if ((e = akb::launch_fluxes(h->cfg.recon, h->cfg.rsolver, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_fused", e);
-  if ((e = akb::launch_corner_e(h->g, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_fused", e);
-  if ((e = akb::launch_update_ct(h->g, A, true, true, stage == 1, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_fused", e);
+  if ((e = akb::launch_update_ct(h->g, A, true, true, stage == 1, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_update", e);
   return 0;
+}
+
+int ak_mhd_stage_fused(void *handle, const ak_mhd_arrays *a, int stage, double gam0, double gam1, double beta_dt,
+                       void *halo_plan, ak_stream_t s) {
+  int rc = ak_mhd_stage_flux_emf(handle, a, s);
+  if (rc) return rc;
+  if (halo_plan) {
+    if (ak_halo_npeers(halo_plan) != 0)
+      return fail(static_cast<Handle *>(handle), "ak_mhd_stage_fused: MeshBlocks on other ranks; use ak_mhd_stage_flux_emf + "
+                                                 "ak_halo_emf_* + ak_mhd_stage_update");
+    if ((rc = ak_halo_emf_pack_local(halo_plan, a->e1, a->e2, a->e3, s)) != 0) return rc;
+    if ((rc = ak_halo_emf_sumavg(halo_plan, a->e1, a->e2, a->e3, s)) != 0) return rc;
+  }
+  return ak_mhd_stage_update(handle, a, stage, gam0, gam1, beta_dt, s);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -343,6 +362,33 @@ int ak_halo_unpack_fc(void *plan, double *x1f, double *x2f, double *x3f, int ipe
   AK_PEER("ak_halo_unpack_fc")
   akb::HaloArrays A = akb::halo_arrays_fc(P->cfg, x1f, x2f, x3f);
   return halo_rc(P, "ak_halo_unpack_fc", akb::halo_launch(peer.unpack_fc, peer.d_unpack_fc, A, 1, 0, const_cast<double *>(recvbuf), akb::HALO_UNPACK, (cudaStream_t)s));
+}
+
+// ---- SendE/RecvE: EMF flux correction on a same-level mesh (flux_correct_fc.cpp) ------------
+int ak_halo_emf_peer(void *plan, int ipeer, long *count, double **recv_ptr) {
+  AK_PEER("ak_halo_emf_peer")
+  if (count) *count = peer.emf_count;
+  if (recv_ptr) *recv_ptr = P->d_emf_rbuf + peer.emf_recv_base;
+  return 0;
+}
+int ak_halo_emf_pack_local(void *plan, const double *e1, const double *e2, const double *e3, ak_stream_t s) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P || !e1 || !e2 || !e3) return fail(nullptr, "ak_halo_emf_pack_local: null argument");
+  if (halo_ready(P, "ak_halo_emf_pack_local")) return 1;
+  akb::HaloArrays A = akb::halo_arrays_ec(P->cfg, const_cast<double *>(e1), const_cast<double *>(e2), const_cast<double *>(e3));
+  return halo_rc(P, "ak_halo_emf_pack_local", akb::halo_launch(P->emf_pack_local, P->d_emf_pack_local, A, 1, 0, P->d_emf_rbuf, akb::HALO_PACK, (cudaStream_t)s));
+}
+int ak_halo_emf_pack(void *plan, const double *e1, const double *e2, const double *e3, int ipeer, double *sendbuf, ak_stream_t s) {
+  AK_PEER("ak_halo_emf_pack")
+  akb::HaloArrays A = akb::halo_arrays_ec(P->cfg, const_cast<double *>(e1), const_cast<double *>(e2), const_cast<double *>(e3));
+  return halo_rc(P, "ak_halo_emf_pack", akb::halo_launch(peer.pack_emf, peer.d_pack_emf, A, 1, 0, sendbuf, akb::HALO_PACK, (cudaStream_t)s));
+}
+int ak_halo_emf_sumavg(void *plan, double *e1, double *e2, double *e3, ak_stream_t s) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P || !e1 || !e2 || !e3) return fail(nullptr, "ak_halo_emf_sumavg: null argument");
+  if (halo_ready(P, "ak_halo_emf_sumavg")) return 1;
+  akb::HaloArrays A = akb::halo_arrays_ec(P->cfg, e1, e2, e3);
+  return halo_rc(P, "ak_halo_emf_sumavg", akb::emf_sumavg_launch(P, A, (cudaStream_t)s));
 }
 
 }  // extern "C"

@@ -87,6 +87,48 @@ halo_copy_kernel(const HaloDesc *__restrict__ descs, HaloArrays A, int nvar, lon
   }
 }
 
+// EMF (edge-field) boundary boxes for flux correction, same level: buffs_fc.cpp:327-368 (send)
+// and :892-935 (recv) -- identical formulae.  v: 0 x1e, 1 x2e, 2 x3e.
+static Box emf_box(const ak_mhd_cfg &c, int v, const int o[3]) {
+  const int s[3] = {c.ng, c.ng, c.ng};
+  const int e[3] = {c.ng + c.nx1 - 1, c.ng + c.nx2 - 1, c.ng + c.nx3 - 1};
+  Box b;
+  for (int d = 0; d < 3; ++d) {
+    if (o[d] == 0) { b.lo[d] = s[d]; b.hi[d] = e[d] + (v == d ? 0 : 1); }
+    else if (o[d] > 0) { b.lo[d] = e[d] + 1; b.hi[d] = e[d] + 1; }
+    else { b.lo[d] = s[d]; b.hi[d] = s[d]; }
+  }
+  return b;
+}
+// faces carry the two tangential components, block edges the component along the edge
+// (flux_correct_fc.cpp:517-635); corners carry nothing
+static bool emf_slot_has(const int o[3], int v) {
+  const int nz = (o[0] != 0) + (o[1] != 0) + (o[2] != 0);
+  return (nz == 1 || nz == 2) && o[v] == 0;
+}
+
+__global__ void __launch_bounds__(128)
+emf_sumavg_kernel(const EmfSumDesc *__restrict__ descs, HaloArrays A, const double *__restrict__ rbuf) {
+  const EmfSumDesc d = descs[blockIdx.y];
+  const int ni = d.hi[0] - d.lo[0] + 1, nj = d.hi[1] - d.lo[1] + 1, nk = d.hi[2] - d.lo[2] + 1;
+  const long total = (long)ni * nj * nk;
+  double *arr = A.p[d.v];
+  const long e1 = A.ext1[d.v], e2 = A.ext2[d.v], bs = A.bstride[d.v];
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x) {
+    long t = q;
+    const int i = d.lo[0] + (int)(t % ni); t /= ni;
+    const int j = d.lo[1] + (int)(t % nj);
+    const int k = d.lo[2] + (int)(t / nj);
+    const long idx = (long)d.m * bs + ((long)k * e2 + j) * e1 + i;
+    double val = arr[idx];
+    for (int s = 0; s < d.nsrc; ++s)   // SumBoundaryFluxes: increasing slot order
+      val += rbuf[d.soff[s] + (i - d.slo[s][0]) + (long)d.sni[s] * ((j - d.slo[s][1]) + (long)d.snj[s] * (k - d.slo[s][2]))];
+    if (d.face) val *= 0.5;                       // AverageBoundaryFluxes, face interiors
+    else val /= static_cast<double>(d.count);     // block edges: / nflx
+    arr[idx] = val;
+  }
+}
+
 static const int kOff[26][3] = {
     {-1,0,0},{1,0,0},{0,-1,0},{0,1,0},{-1,-1,0},{1,-1,0},{-1,1,0},{1,1,0},{0,0,-1},{0,0,1},
     {-1,0,-1},{1,0,-1},{-1,0,1},{1,0,1},{0,-1,-1},{0,1,-1},{0,-1,1},{0,1,1},
@@ -178,6 +220,122 @@ HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int g
     if (cc_off != peer.cc_count || fc_off != peer.fc_count) { err = "halo: send/recv message sizes differ"; delete P; return nullptr; }
     P->peers.push_back(peer);
   }
+  // ---- EMF flux correction plan -----------------------------------------------------------
+  {
+    // receive segments: (m, slot, v) -> offset in emf_rbuf.  Same-rank sources first, then one
+    // contiguous range per peer ordered by (source gid, source slot, v) = the sender's order.
+    std::map<long, long> roff;   // key = (m*48 + slot)*3 + v
+    auto key = [](int m, int slot, int v) { return ((long)m * 48 + slot) * 3 + v; };
+    long off = 0;
+    struct RSeg { int gid_src, n_src, v, m, slot; long cnt; };
+    std::map<int, std::vector<RSeg>> rsegs;   // per peer
+    for (int m = 0; m < cfg.nmb; ++m)
+      for (int q = 0; q < 26; ++q) {
+        const int *o = kOff[q];
+        const int nz = (o[0] != 0) + (o[1] != 0) + (o[2] != 0);
+        if (nz == 3) continue;
+        const int slot = neighbor_index(o[0], o[1], o[2], 0, 0);
+        const int *nb = nghbr + ((long)m * 56 + slot) * 4;
+        if (nb[0] < 0) continue;
+        for (int v = 0; v < 3; ++v) {
+          if (!emf_slot_has(o, v)) continue;
+          const long cnt = emf_box(cfg, v, o).count();
+          if (nb[2] == my_rank) { roff[key(m, slot, v)] = off; off += cnt; }
+          else rsegs[nb[2]].push_back(RSeg{nb[0], neighbor_index(-o[0], -o[1], -o[2], 0, 0), v, m, slot, cnt});
+        }
+      }
+    for (auto &peer : P->peers) {
+      auto &v = rsegs[peer.rank];
+      std::sort(v.begin(), v.end(), [](const RSeg &a, const RSeg &b) {
+        if (a.gid_src != b.gid_src) return a.gid_src < b.gid_src;
+        if (a.n_src != b.n_src) return a.n_src < b.n_src;
+        return a.v < b.v; });
+      peer.emf_recv_base = off;
+      for (auto &r : v) { roff[key(r.m, r.slot, r.v)] = off; off += r.cnt; }
+      peer.emf_count = off - peer.emf_recv_base;
+    }
+    P->emf_rbuf_count = off;
+    // pack descriptors: my box on side o goes to the neighbour's segment (its slot(-o))
+    std::map<int, std::vector<std::pair<RSeg, HaloDesc>>> psend;
+    for (int m = 0; m < cfg.nmb; ++m)
+      for (int q = 0; q < 26; ++q) {
+        const int *o = kOff[q];
+        const int nz = (o[0] != 0) + (o[1] != 0) + (o[2] != 0);
+        if (nz == 3) continue;
+        const int slot = neighbor_index(o[0], o[1], o[2], 0, 0);
+        const int *nb = nghbr + ((long)m * 56 + slot) * 4;
+        if (nb[0] < 0) continue;
+        const int dslot = neighbor_index(-o[0], -o[1], -o[2], 0, 0);
+        for (int v = 0; v < 3; ++v) {
+          if (!emf_slot_has(o, v)) continue;
+          Box b = emf_box(cfg, v, o);
+          HaloDesc d{};
+          d.m = m; d.src_m = m; d.comp = v;
+          for (int a = 0; a < 3; ++a) { d.lo[a] = b.lo[a]; d.hi[a] = b.hi[a]; }
+          if (nb[2] == my_rank) {
+            d.boff = roff.at(key(nb[0] - gids_start, dslot, v));
+            P->emf_pack_local.push_back(d);
+          } else {
+            psend[nb[2]].push_back({RSeg{gids_start + m, slot, v, m, slot, b.count()}, d});
+          }
+        }
+      }
+    for (auto &peer : P->peers) {
+      auto &v = psend[peer.rank];
+      std::sort(v.begin(), v.end(), [](const std::pair<RSeg, HaloDesc> &a, const std::pair<RSeg, HaloDesc> &b) {
+        if (a.first.gid_src != b.first.gid_src) return a.first.gid_src < b.first.gid_src;
+        if (a.first.n_src != b.first.n_src) return a.first.n_src < b.first.n_src;
+        return a.first.v < b.first.v; });
+      long so = 0;
+      for (auto &pr : v) { pr.second.boff = so; so += pr.first.cnt; peer.pack_emf.push_back(pr.second); }
+      if (so != peer.emf_count) { err = "halo: EMF send/recv message sizes differ"; delete P; return nullptr; }
+    }
+    // sum/scale regions
+    for (int m = 0; m < cfg.nmb; ++m)
+      for (int q = 0; q < 26; ++q) {
+        const int *o = kOff[q];
+        const int nz = (o[0] != 0) + (o[1] != 0) + (o[2] != 0);
+        if (nz == 3) continue;
+        const int slot = neighbor_index(o[0], o[1], o[2], 0, 0);
+        for (int v = 0; v < 3; ++v) {
+          if (!emf_slot_has(o, v)) continue;
+          EmfSumDesc d{};
+          d.m = m; d.v = v;
+          Box b = emf_box(cfg, v, o);
+          std::vector<std::pair<int, const int *>> src;   // (slot, offsets) of contributing neighbours
+          int fo[2][3];
+          if (nz == 1) {
+            if (nghbr[((long)m * 56 + slot) * 4] < 0) continue;   // physical boundary: nothing to average
+            d.face = 1;
+            for (int a = 0; a < 3; ++a) if (o[a] == 0 && a != v) { b.lo[a] += 1; b.hi[a] -= 1; }   // drop the end lines
+            if (b.count() <= 0) continue;
+            src.push_back({slot, o});
+          } else {
+            d.face = 0;
+            int nf = 0;
+            for (int a = 0; a < 3; ++a) if (o[a] != 0) { fo[nf][0] = fo[nf][1] = fo[nf][2] = 0; fo[nf][a] = o[a]; ++nf; }
+            for (int f = 0; f < 2; ++f) {
+              const int fs = neighbor_index(fo[f][0], fo[f][1], fo[f][2], 0, 0);
+              if (nghbr[((long)m * 56 + fs) * 4] >= 0) src.push_back({fs, fo[f]});
+            }
+            if (nghbr[((long)m * 56 + slot) * 4] >= 0) src.push_back({slot, o});
+            if (src.empty()) continue;
+            std::sort(src.begin(), src.end(), [](const std::pair<int, const int *> &a, const std::pair<int, const int *> &b) { return a.first < b.first; });
+          }
+          for (int a = 0; a < 3; ++a) { d.lo[a] = b.lo[a]; d.hi[a] = b.hi[a]; }
+          d.nsrc = (int)src.size();
+          d.count = 1 + d.nsrc;
+          for (int s = 0; s < d.nsrc; ++s) {
+            Box sb = emf_box(cfg, v, src[s].second);
+            d.soff[s] = roff.at(key(m, src[s].first, v));
+            for (int a = 0; a < 3; ++a) d.slo[s][a] = sb.lo[a];
+            d.sni[s] = sb.hi[0] - sb.lo[0] + 1;
+            d.snj[s] = sb.hi[1] - sb.lo[1] + 1;
+          }
+          P->emf_sum.push_back(d);
+        }
+      }
+  }
   return P;
 }
 
@@ -199,14 +357,35 @@ cudaError_t halo_ensure_uploaded(HaloPlan *P) {
     if ((e = up(p.pack_fc, &p.d_pack_fc)) != cudaSuccess) return e;
     if ((e = up(p.unpack_fc, &p.d_unpack_fc)) != cudaSuccess) return e;
   }
+  if ((e = up(P->emf_pack_local, &P->d_emf_pack_local)) != cudaSuccess) return e;
+  for (auto &p : P->peers)
+    if ((e = up(p.pack_emf, &p.d_pack_emf)) != cudaSuccess) return e;
+  if (!P->emf_sum.empty()) {
+    if ((e = cudaMalloc(&P->d_emf_sum, P->emf_sum.size() * sizeof(EmfSumDesc))) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(P->d_emf_sum, P->emf_sum.data(), P->emf_sum.size() * sizeof(EmfSumDesc), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  }
+  if (P->emf_rbuf_count > 0 && (e = cudaMalloc(&P->d_emf_rbuf, P->emf_rbuf_count * sizeof(double))) != cudaSuccess) return e;
   P->uploaded = true;
   return cudaSuccess;
 }
 
+cudaError_t emf_sumavg_launch(HaloPlan *P, const HaloArrays &A, cudaStream_t st) {
+  if (P->emf_sum.empty()) return cudaSuccess;
+  long mx = 0;
+  for (const auto &d : P->emf_sum) mx = std::max(mx, (long)(d.hi[0]-d.lo[0]+1)*(d.hi[1]-d.lo[1]+1)*(d.hi[2]-d.lo[2]+1));
+  unsigned gx = (unsigned)std::min<long>((mx + 127) / 128, 64);
+  if (gx == 0) gx = 1;
+  for (size_t first = 0; first < P->emf_sum.size(); first += 65535) {
+    unsigned ny = (unsigned)std::min<size_t>(65535, P->emf_sum.size() - first);
+    emf_sumavg_kernel<<<dim3(gx, ny), 128, 0, st>>>(P->d_emf_sum + first, A, P->d_emf_rbuf);
+  }
+  return cudaGetLastError();
+}
+
 void halo_free(HaloPlan *P) {
   if (!P) return;
-  cudaFree(P->d_local_cc); cudaFree(P->d_local_fc);
-  for (auto &p : P->peers) { cudaFree(p.d_pack_cc); cudaFree(p.d_unpack_cc); cudaFree(p.d_pack_fc); cudaFree(p.d_unpack_fc); }
+  cudaFree(P->d_local_cc); cudaFree(P->d_local_fc); cudaFree(P->d_emf_pack_local); cudaFree(P->d_emf_sum); cudaFree(P->d_emf_rbuf);
+  for (auto &p : P->peers) { cudaFree(p.d_pack_cc); cudaFree(p.d_unpack_cc); cudaFree(p.d_pack_fc); cudaFree(p.d_unpack_fc); cudaFree(p.d_pack_emf); }
   delete P;
 }
 
@@ -244,6 +423,15 @@ HaloArrays halo_arrays_fc(const ak_mhd_cfg &c, double *x1f, double *x2f, double 
   A.p[0] = x1f; A.ext1[0] = n1 + 1; A.ext2[0] = n2;     A.bstride[0] = (n1 + 1) * n2 * n3;
   A.p[1] = x2f; A.ext1[1] = n1;     A.ext2[1] = n2 + 1; A.bstride[1] = n1 * (n2 + 1) * n3;
   A.p[2] = x3f; A.ext1[2] = n1;     A.ext2[2] = n2;     A.bstride[2] = n1 * n2 * (n3 + 1);
+  return A;
+}
+
+HaloArrays halo_arrays_ec(const ak_mhd_cfg &c, double *x1e, double *x2e, double *x3e) {
+  const long n1 = c.nx1 + 2 * c.ng, n2 = c.nx2 + 2 * c.ng, n3 = c.nx3 + 2 * c.ng;
+  HaloArrays A{};
+  A.p[0] = x1e; A.ext1[0] = n1;     A.ext2[0] = n2 + 1; A.bstride[0] = n1 * (n2 + 1) * (n3 + 1);
+  A.p[1] = x2e; A.ext1[1] = n1 + 1; A.ext2[1] = n2;     A.bstride[1] = (n1 + 1) * n2 * (n3 + 1);
+  A.p[2] = x3e; A.ext1[2] = n1 + 1; A.ext2[2] = n2 + 1; A.bstride[2] = (n1 + 1) * (n2 + 1) * n3;
   return A;
 }
 

@@ -21,11 +21,26 @@ struct HaloArrays {
   long ext1[3], ext2[3], bstride[3];  // inner, middle extents and per-block stride
 };
 
+// EMF flux correction (SendE/RecvE): one descriptor per region of boundary edges that is
+// summed and scaled together (a face interior, or a block-edge line)
+struct EmfSumDesc {
+  int m, v;                 // block, edge-field component (0 x1e, 1 x2e, 2 x3e)
+  int lo[3], hi[3];         // i,j,k box of the region in the edge array
+  int nsrc;                 // contributing receive segments, in increasing slot order
+  long soff[3];             // their offsets in the receive buffer
+  int slo[3][3], sni[3], snj[3];   // their boxes: low corner and i/j extents (linearisation)
+  int count;                // 1 + nsrc (nflx)
+  int face;                 // 1: face interior (x0.5), 0: block edge (/count)
+};
+
 struct HaloPeer {
   int rank;
   long cc_count, fc_count;  // doubles per message: CC per variable, FC total
   std::vector<HaloDesc> pack_cc, unpack_cc, pack_fc, unpack_fc;
   HaloDesc *d_pack_cc = nullptr, *d_unpack_cc = nullptr, *d_pack_fc = nullptr, *d_unpack_fc = nullptr;
+  std::vector<HaloDesc> pack_emf;      // my boundary EMFs -> message to this peer
+  HaloDesc *d_pack_emf = nullptr;
+  long emf_count = 0, emf_recv_base = 0;   // message length; where the peer's message lands in emf_rbuf
 };
 
 struct HaloPlan {
@@ -33,6 +48,12 @@ struct HaloPlan {
   std::vector<HaloDesc> local_cc, local_fc;
   HaloDesc *d_local_cc = nullptr, *d_local_fc = nullptr;
   std::vector<HaloPeer> peers;
+  std::vector<HaloDesc> emf_pack_local;   // same-rank: straight into the receiver's segment of emf_rbuf
+  std::vector<EmfSumDesc> emf_sum;
+  HaloDesc *d_emf_pack_local = nullptr;
+  EmfSumDesc *d_emf_sum = nullptr;
+  long emf_rbuf_count = 0;
+  double *d_emf_rbuf = nullptr;
   std::string err;
   bool uploaded = false;   // descriptor lists are copied to the device on first use
 };
@@ -45,5 +66,7 @@ cudaError_t halo_launch(const std::vector<HaloDesc> &host, const HaloDesc *dev, 
                         long varstride, double *buf, int mode, cudaStream_t st);
 HaloArrays halo_arrays_cc(const ak_mhd_cfg &c, double *a, int nvar);
 HaloArrays halo_arrays_fc(const ak_mhd_cfg &c, double *x1f, double *x2f, double *x3f);
+HaloArrays halo_arrays_ec(const ak_mhd_cfg &c, double *x1e, double *x2e, double *x3e);
+cudaError_t emf_sumavg_launch(HaloPlan *P, const HaloArrays &A, cudaStream_t st);
 
 }  // namespace akb

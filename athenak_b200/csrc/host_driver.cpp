@@ -186,7 +186,7 @@ class MHD {  // state owner + tasks
   long launches = 0;
   std::map<std::string, std::shared_ptr<TaskList>> tl_map;
   std::vector<double *> owned;
-  struct Peer { int rank; long ncc, nfc; double *scc, *rcc, *sfc, *rfc; };
+  struct Peer { int rank; long ncc, nfc; double *scc, *rcc, *sfc, *rfc; long nemf = 0; double *semf = nullptr, *remf = nullptr; };
   std::vector<Peer> peers;
   Nccl::Comm comm = nullptr;
   double *d_dt = nullptr;
@@ -236,8 +236,11 @@ class MHD {  // state owner + tasks
     TaskID none(0);
     auto &tl = tl_map["stagen"];
     if (fused) {
-      TaskID f = tl->AddTask(&MHD::StageFused, this, none);
-      TaskID su = tl->AddTask(&MHD::SendU, this, f);
+      TaskID f = tl->AddTask(&MHD::StageFluxEmf, this, none);
+      TaskID se = tl->AddTask(&MHD::SendE, this, f);
+      TaskID re = tl->AddTask(&MHD::RecvE, this, se);
+      TaskID up = tl->AddTask(&MHD::StageUpdate, this, re);
+      TaskID su = tl->AddTask(&MHD::SendU, this, up);
       TaskID ru = tl->AddTask(&MHD::RecvU, this, su);
       TaskID sb = tl->AddTask(&MHD::SendB, this, ru);
       TaskID rb = tl->AddTask(&MHD::RecvB, this, sb);
@@ -249,7 +252,9 @@ class MHD {  // state owner + tasks
       TaskID sendu = tl->AddTask(&MHD::SendU, this, rkupdt);
       TaskID recvu = tl->AddTask(&MHD::RecvU, this, sendu);
       TaskID efld = tl->AddTask(&MHD::EField, this, recvu);
-      TaskID ct = tl->AddTask(&MHD::CT, this, efld);
+      TaskID sende = tl->AddTask(&MHD::SendE, this, efld);
+      TaskID recve = tl->AddTask(&MHD::RecvE, this, sende);
+      TaskID ct = tl->AddTask(&MHD::CT, this, recve);
       TaskID sendb = tl->AddTask(&MHD::SendB, this, ct);
       TaskID recvb = tl->AddTask(&MHD::RecvB, this, sendb);
       TaskID c2p = tl->AddTask(&MHD::ConToPrim, this, recvb);
@@ -274,9 +279,44 @@ class MHD {  // state owner + tasks
     launches += 1;
     return TaskStatus::complete;
   }
-  TaskStatus StageFused(Driver *pd, int stage) {
-    AK_CHECK(h, ak_mhd_stage_fused(h, &a, stage, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, st));
-    launches += 5;
+  TaskStatus StageFluxEmf(Driver *pd, int stage) {   // tasks 2 + 14
+    AK_CHECK(h, ak_mhd_stage_flux_emf(h, &a, st));
+    launches += 4;
+    return TaskStatus::complete;
+  }
+  TaskStatus StageUpdate(Driver *pd, int stage) {    // tasks 1 + 5 + 17
+    AK_CHECK(h, ak_mhd_stage_update(h, &a, stage, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, st));
+    launches += 1;
+    return TaskStatus::complete;
+  }
+  // SendE/RecvE: flux_correct_fc.cpp:29-437 (EMF flux correction, always executed as in the reference)
+  TaskStatus SendE(Driver *pd, int stage) {
+    Nccl &n = Nccl::get();
+    if (!peers.empty()) {
+      if (!comm) Fatal(__FILE__, __LINE__, "MeshBlocks on other ranks but no NCCL communicator (call ak_sim_comm_init)");
+      for (size_t p = 0; p < peers.size(); ++p) {
+        if (!peers[p].semf) {
+          AK_CHECK(nullptr, ak_halo_emf_peer(plan, (int)p, &peers[p].nemf, &peers[p].remf));
+          CU_CHECK(cudaMalloc(&peers[p].semf, (size_t)peers[p].nemf * 8));
+          owned.push_back(peers[p].semf);
+        }
+        AK_CHECK(nullptr, ak_halo_emf_pack(plan, a.e1, a.e2, a.e3, (int)p, peers[p].semf, st));
+        launches += 1;
+      }
+      n.GroupStart();
+      for (auto &pe : peers) {
+        n.Send(pe.semf, (size_t)pe.nemf, kNcclFloat64, pe.rank, comm, st);
+        n.Recv(pe.remf, (size_t)pe.nemf, kNcclFloat64, pe.rank, comm, st);   // straight into the plan's segment
+      }
+      n.GroupEnd();
+    }
+    AK_CHECK(nullptr, ak_halo_emf_pack_local(plan, a.e1, a.e2, a.e3, st));
+    launches += 1;
+    return TaskStatus::complete;
+  }
+  TaskStatus RecvE(Driver *pd, int stage) {
+    AK_CHECK(nullptr, ak_halo_emf_sumavg(plan, a.e1, a.e2, a.e3, st));
+    launches += 1;
     return TaskStatus::complete;
   }
   // SendU/RecvU, SendB/RecvB: bvals_cc.cpp:42-447, bvals_fc.cpp:63-436

@@ -48,13 +48,14 @@ class TaskList:
 
 def assemble_mhd_tasks(mhd: MHD, fused=True):
     """MHD::AssembleMHDTasks (mhd_tasks.cpp:38-84) restricted to the tasks that do work on a
-    uniform mesh; `fused` swaps tasks 1,2,5,14,17 for the single fused ABI call (legal
-    because SendE/RecvE is a bitwise identity there)."""
+    uniform mesh; `fused` swaps tasks 1,2,14 / 5,17 / 27,28 for the fused ABI calls."""
     tl = {n: TaskList() for n in ("before_timeintegrator", "before_stagen", "stagen",
                                   "after_stagen", "after_timeintegrator")}
     s = tl["stagen"]
     if fused:
-        t = s.AddTask(mhd.StageFused, 0)
+        t = s.AddTask(mhd.StageFluxEmf, 0)
+        t = s.AddTask(mhd.SendRecvE, t)
+        t = s.AddTask(mhd.StageUpdate, t)
         t = s.AddTask(mhd.SendRecvU, t)
         t = s.AddTask(mhd.SendRecvB, t)
         t = s.AddTask(mhd.ConToPrimNewDt, t)
@@ -64,6 +65,7 @@ def assemble_mhd_tasks(mhd: MHD, fused=True):
         t = s.AddTask(mhd.RKUpdate, t)
         t = s.AddTask(mhd.SendRecvU, t)
         t = s.AddTask(mhd.EField, t)
+        t = s.AddTask(mhd.SendRecvE, t)
         t = s.AddTask(mhd.CT, t)
         t = s.AddTask(mhd.SendRecvB, t)
         t = s.AddTask(mhd.ConToPrim, t)

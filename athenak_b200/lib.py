@@ -71,7 +71,9 @@ def load():
         "ak_mhd_ct": [vp, ap, d, d, d, vp],
         "ak_mhd_cons2prim": [vp, ap, ip, ip, ip, ip, ip, ip, C.POINTER(C.c_int), vp],
         "ak_mhd_new_dt": [vp, ap, _dp, vp],
-        "ak_mhd_stage_fused": [vp, ap, ip, d, d, d, vp],
+        "ak_mhd_stage_fused": [vp, ap, ip, d, d, d, vp, vp],
+        "ak_mhd_stage_flux_emf": [vp, ap, vp],
+        "ak_mhd_stage_update": [vp, ap, ip, d, d, d, vp],
         "ak_mhd_cons2prim_newdt": [vp, ap, C.POINTER(C.c_int), _dp, vp],
         "ak_halo_create": [C.POINTER(MhdCfg), C.POINTER(C.c_int), ip, ip, C.POINTER(vp)],
         "ak_halo_destroy": [vp],
@@ -94,6 +96,10 @@ def load():
         "ak_mesh_rank_tables": [vp, ip, dpp, ipp, ipp],
         "ak_neighbor_index": [ip, ip, ip, ip, ip],
         "ak_pgen_blast": [vp, ip, ip, d, dpp, dpp, dpp, dpp, dpp],
+        "ak_halo_emf_peer": [vp, ip, C.POINTER(C.c_long), C.POINTER(vp)],
+        "ak_halo_emf_pack_local": [vp, vp, vp, vp, vp],
+        "ak_halo_emf_pack": [vp, vp, vp, vp, ip, vp, vp],
+        "ak_halo_emf_sumavg": [vp, vp, vp, vp, vp],
         "ak_pgen_orszag_tang": [vp, ip, ip, d, dpp, dpp, dpp, dpp],
         "ak_selftest_divsqrt": [C.c_long, C.c_ulonglong, ip, C.POINTER(C.c_long)],
         "ak_sim_create": [C.POINTER(SimCfg), dpp, ipp, C.POINTER(vp)],
@@ -119,9 +125,10 @@ def load():
 
 EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_cons", "ak_mhd_fluxes",
             "ak_mhd_rk_update", "ak_mhd_corner_e", "ak_mhd_ct", "ak_mhd_cons2prim", "ak_mhd_new_dt",
-            "ak_mhd_stage_fused", "ak_mhd_cons2prim_newdt", "ak_halo_create", "ak_halo_destroy",
+            "ak_mhd_stage_fused", "ak_mhd_stage_flux_emf", "ak_mhd_stage_update", "ak_mhd_cons2prim_newdt", "ak_halo_create", "ak_halo_destroy",
             "ak_halo_npeers", "ak_halo_peer", "ak_halo_descs", "ak_halo_local_cc", "ak_halo_local_fc",
             "ak_halo_pack_cc", "ak_halo_unpack_cc", "ak_halo_pack_fc", "ak_halo_unpack_fc",
+            "ak_halo_emf_peer", "ak_halo_emf_pack_local", "ak_halo_emf_pack", "ak_halo_emf_sumavg",
             "ak_mesh_create", "ak_mesh_destroy", "ak_mesh_last_error", "ak_mesh_info", "ak_mesh_tables",
             "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast", "ak_pgen_orszag_tang", "ak_selftest_divsqrt",
             "ak_sim_create", "ak_sim_destroy", "ak_nccl_unique_id", "ak_sim_comm_init", "ak_sim_set_state",

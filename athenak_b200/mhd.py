@@ -21,6 +21,13 @@ FLT_MIN = float(np.finfo(np.float32).tiny)
 FLT_MAX = float(np.finfo(np.float32).max)
 
 
+class _DevPtr:
+    """Zero-copy view of library-owned device memory as a torch tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
 class TaskStatus(enum.Enum):  # src/tasklist/task_list.hpp:30
     fail = 0
     complete = 1
@@ -136,11 +143,45 @@ class MHD:
         self.launches += 1
         return TaskStatus.complete
 
-    def StageFused(self, driver, stage):
-        """Tasks 1,2,5,14,17 in one ABI call (ak_mhd_stage_fused)."""
+    def StageFluxEmf(self, driver, stage):
+        """Tasks 2 + 14 in one ABI call (ak_mhd_stage_flux_emf)."""
+        self._ck(self.L.ak_mhd_stage_flux_emf(self.h, C.byref(self.arrays), self._st()))
+        self.launches += 4
+        return TaskStatus.complete
+
+    def StageUpdate(self, driver, stage):
+        """Tasks 1 + 5 + 17 in one ABI call (ak_mhd_stage_update)."""
         g0, g1, bdt = driver.gam0[stage - 1], driver.gam1[stage - 1], driver.beta[stage - 1] * driver.dt
-        self._ck(self.L.ak_mhd_stage_fused(self.h, C.byref(self.arrays), stage, g0, g1, bdt, self._st()))
-        self.launches += 5
+        self._ck(self.L.ak_mhd_stage_update(self.h, C.byref(self.arrays), stage, g0, g1, bdt, self._st()))
+        self.launches += 1
+        return TaskStatus.complete
+
+    def SendRecvE(self, driver, stage):
+        """Tasks 15/16 SendE/RecvE: EMF flux correction (src/bvals/flux_correct_fc.cpp)."""
+        st, L = self._st(), self.L
+        e = [t.data_ptr() for t in self.efld]
+        reqs = []
+        if self.peers:
+            import torch.distributed as dist
+            ops = []
+            for ip, p in enumerate(self.peers):
+                if "semf" not in p:
+                    cnt, ptr = C.c_long(), C.c_void_p()
+                    _lib.check(L.ak_halo_emf_peer(self.plan, ip, C.byref(cnt), C.byref(ptr)))
+                    p["semf"] = torch.zeros(cnt.value, dtype=torch.float64, device=self.device)
+                    # the peer's message is received straight into the plan's receive segment
+                    p["remf"] = torch.as_tensor(_DevPtr(ptr.value, cnt.value), device=self.device)
+                _lib.check(L.ak_halo_emf_pack(self.plan, *e, ip, p["semf"].data_ptr(), st))
+                self.launches += 1
+                ops.append(dist.P2POp(dist.isend, p["semf"], p["rank"], group=self.pg))
+                ops.append(dist.P2POp(dist.irecv, p["remf"], p["rank"], group=self.pg))
+            reqs = dist.batch_isend_irecv(ops)
+        _lib.check(L.ak_halo_emf_pack_local(self.plan, *e, st))
+        self.launches += 1
+        for rq in reqs:
+            rq.wait()
+        _lib.check(L.ak_halo_emf_sumavg(self.plan, *e, st))
+        self.launches += 1
         return TaskStatus.complete
 
     def _exchange(self, which):

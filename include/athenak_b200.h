@@ -76,13 +76,20 @@ int ak_mhd_cons2prim(void *h, const ak_mhd_arrays *a, int il, int iu, int jl, in
  * active cells of dx_d/(|v_d|+c_f,d); synchronises the stream. */
 int ak_mhd_new_dt(void *h, const ak_mhd_arrays *a, double *dt3, ak_stream_t s);
 
-/* Fused stage: tasks 1,2,5,14,17 (CopyCons, Fluxes, RKUpdate, CornerE, CT) with fewer kernels
- * and no CopyCons pass.  Legal on a same-level mesh with no diffusion/FOFC/source-term
- * consumers of uflx/efld between the tasks (SendE/RecvE is a bitwise identity there,
- * SURVEY.md section 0 fact 6).  flx*, e?x?, e1..e3 are still written; u1/b1 (the RK registers)
- * are saved for the active zones only (nothing reads their ghost zones). */
+/* Fused stage pieces (fewer kernels, no CopyCons pass, no e_cc / L-R state arrays):
+ *   ak_mhd_stage_flux_emf : tasks 2 + 14 (Fluxes, CornerE)
+ *   [tasks 15/16 SendE/RecvE: ak_halo_emf_* below]
+ *   ak_mhd_stage_update   : tasks 1 + 5 + 17 (CopyCons folded into the stage-1 update, RKUpdate, CT);
+ *                           u1/b1 (the RK registers) are saved for the active zones only.
+ * Legal whenever nothing else consumes uflx/efld between the tasks (no diffusion/FOFC/source
+ * terms).  ak_mhd_stage_fused = flux_emf + same-rank EMF correction through halo_plan (may be
+ * NULL to skip it; it is a bitwise identity only if neighbouring blocks' shared faces hold
+ * identical bits) + update; it refuses plans that have off-rank neighbours. */
+int ak_mhd_stage_flux_emf(void *h, const ak_mhd_arrays *a, ak_stream_t s);
+int ak_mhd_stage_update(void *h, const ak_mhd_arrays *a, int stage, double gam0, double gam1,
+                        double beta_dt, ak_stream_t s);
 int ak_mhd_stage_fused(void *h, const ak_mhd_arrays *a, int stage, double gam0, double gam1,
-                       double beta_dt, ak_stream_t s);
+                       double beta_dt, void *halo_plan, ak_stream_t s);
 /* c2p over all cells fused with the task-28 reduction over the active cells (last stage). */
 int ak_mhd_cons2prim_newdt(void *h, const ak_mhd_arrays *a, int *nfloor, double *dt3, ak_stream_t s);
 
@@ -116,6 +123,18 @@ int ak_halo_unpack_fc(void *plan, double *x1f, double *x2f, double *x3f, int ipe
 /* Orszag-Tang vortex ICs (src/pgen/tests/orszag_tang.cpp:32-123), BASELINE config 3. */
 int ak_pgen_orszag_tang(void *mesh, int rank, int ng, double gamma, double *u0, double *b1f,
                         double *b2f, double *b3f);
+
+/* tasks 15/16 SendE/RecvE: same-level EMF flux correction (src/bvals/flux_correct_fc.cpp:29-437,
+ * 445-644, 801-1034).  Every block's boundary edge EMFs are copied into the receive segments of
+ * its face/edge neighbours (same rank: ak_halo_emf_pack_local; other ranks: ak_halo_emf_pack into
+ * one message per peer, to be delivered at the address ak_halo_emf_peer returns), then
+ * ak_halo_emf_sumavg adds the segments in increasing slot order and scales (x0.5 in face
+ * interiors, / nflx on block edges) exactly as SumBoundaryFluxes + AverageBoundaryFluxes. */
+int ak_halo_emf_peer(void *plan, int ipeer, long *count, double **recv_ptr);
+int ak_halo_emf_pack_local(void *plan, const double *e1, const double *e2, const double *e3, ak_stream_t s);
+int ak_halo_emf_pack(void *plan, const double *e1, const double *e2, const double *e3, int ipeer,
+                     double *sendbuf, ak_stream_t s);
+int ak_halo_emf_sumavg(void *plan, double *e1, double *e2, double *e3, ak_stream_t s);
 
 /* Device self-test: compares the library's slow-path-free FP64 reciprocal / division / sqrt with
  * the built-in IEEE operators on n random operands (|exponent| <= exponent_span, every 64th

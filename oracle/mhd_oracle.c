@@ -916,9 +916,124 @@ void oracle_halo_fc(const ocfg *c, double *b1f, double *b2f, double *b3f, const 
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* SendE/RecvE: same-level EMF flux correction, flux_correct_fc.cpp:29-366 (pack),
+ * :374-437 (RecvAndUnpackFluxFC), :445-644 (SumBoundaryFluxes), :801-1034
+ * (AverageBoundaryFluxes); index boxes buffs_fc.cpp:327-368,892-935.  Every block sends the
+ * edge EMFs lying on its faces/edges to the face and edge neighbours (slots n<48); the receiver
+ * ADDS the buffers in increasing slot order and then scales: x0.5 in face interiors, / nflx on
+ * block edges (nflx = 1 + number of contributing neighbours). */
+static void emf_box(const odims *Dp, int v, int ox, int oy, int oz, int *b6) {
+  const odims D = *Dp;
+  int s[3] = {D.is, D.js, D.ks}, e[3] = {D.ie, D.je, D.ke}, o[3] = {ox, oy, oz};
+  for (int d = 0; d < 3; ++d) {
+    if (o[d] == 0) { b6[2 * d] = s[d]; b6[2 * d + 1] = e[d] + (v == d ? 0 : 1); }  /* edge field v is cell-like along d==v */
+    else if (o[d] > 0) { b6[2 * d] = e[d] + 1; b6[2 * d + 1] = e[d] + 1; }
+    else { b6[2 * d] = s[d]; b6[2 * d + 1] = s[d]; }
+  }
+}
+
+static double *emf_at(const odims *Dp, double *e1, double *e2, double *e3, int v, int m, int k, int j, int i) {
+  const odims D = *Dp;
+  if (v == 0) return &X1E(e1, m, k, j, i);
+  if (v == 1) return &X2E(e2, m, k, j, i);
+  return &X3E(e3, m, k, j, i);
+}
+
+/* which component(s) a slot carries: faces carry the two tangential ones, edges the one along
+ * the edge (flux_correct_fc.cpp:517-635) */
+static int emf_slot_has(int ox, int oy, int oz, int v) {
+  int nz = (ox != 0) + (oy != 0) + (oz != 0);
+  int o[3] = {ox, oy, oz};
+  if (nz == 1) return o[v] == 0;           /* face: components tangential to the face */
+  if (nz == 2) return o[v] == 0;           /* edge: the component along the edge */
+  return 0;
+}
+
+void oracle_emf_exchange(const ocfg *c, double *e1, double *e2, double *e3, const int *nghbr_gid) {
+  odims D = dims(c);
+  const int nmb = c->nmb;
+  double **rbuf = calloc((size_t)nmb * 48 * 3, sizeof(double *));
+  /* pack + send */
+  for (int m = 0; m < nmb; ++m)
+    for (int oz = -1; oz <= 1; ++oz) for (int oy = -1; oy <= 1; ++oy) for (int ox = -1; ox <= 1; ++ox) {
+      int nz = (ox != 0) + (oy != 0) + (oz != 0);
+      if (nz == 0 || nz == 3) continue;
+      int n = oracle_neighbor_index(ox, oy, oz, 0, 0);
+      int gid = nghbr_gid[m * 56 + n];
+      if (gid < 0) continue;
+      int dn = oracle_neighbor_index(-ox, -oy, -oz, 0, 0);
+      for (int v = 0; v < 3; ++v) {
+        if (!emf_slot_has(ox, oy, oz, v)) continue;
+        int b6[6]; emf_box(&D, v, ox, oy, oz, b6);
+        int ni = b6[1] - b6[0] + 1, nj = b6[3] - b6[2] + 1, nk = b6[5] - b6[4] + 1;
+        double *b = malloc(sizeof(double) * (size_t)ni * nj * nk);
+        for (int k = b6[4]; k <= b6[5]; ++k) for (int j = b6[2]; j <= b6[3]; ++j) for (int i = b6[0]; i <= b6[1]; ++i)
+          b[(i - b6[0]) + ni * ((j - b6[2]) + nj * (k - b6[4]))] = *emf_at(&D, e1, e2, e3, v, m, k, j, i);
+        rbuf[((size_t)gid * 48 + dn) * 3 + v] = b;
+      }
+    }
+  /* sum in increasing slot order (SumBoundaryFluxes), counting contributions per block edge */
+  int *nflx = malloc(sizeof(int) * (size_t)nmb * 48);
+  for (int q = 0; q < nmb * 48; ++q) nflx[q] = 1;
+  for (int m = 0; m < nmb; ++m)
+    for (int n = 0; n < 48; ++n) {
+      int ox = 0, oy = 0, oz = 0, found = 0;
+      for (int z = -1; z <= 1 && !found; ++z) for (int y = -1; y <= 1 && !found; ++y) for (int x = -1; x <= 1 && !found; ++x)
+        if ((x || y || z) && oracle_neighbor_index(x, y, z, 0, 0) == n) { ox = x; oy = y; oz = z; found = 1; }
+      if (!found) continue;
+      if (nghbr_gid[m * 56 + n] < 0) continue;
+      int nz = (ox != 0) + (oy != 0) + (oz != 0);
+      if (nz == 1) {  /* a face neighbour also contributes to the four edges of that face */
+        for (int t = -1; t <= 1; t += 2) {
+          if (ox) { nflx[m * 48 + oracle_neighbor_index(ox, t, 0, 0, 0)]++; nflx[m * 48 + oracle_neighbor_index(ox, 0, t, 0, 0)]++; }
+          if (oy) { nflx[m * 48 + oracle_neighbor_index(t, oy, 0, 0, 0)]++; nflx[m * 48 + oracle_neighbor_index(0, oy, t, 0, 0)]++; }
+          if (oz) { nflx[m * 48 + oracle_neighbor_index(t, 0, oz, 0, 0)]++; nflx[m * 48 + oracle_neighbor_index(0, t, oz, 0, 0)]++; }
+        }
+      } else {
+        nflx[m * 48 + n]++;
+      }
+      for (int v = 0; v < 3; ++v) {
+        double *b = rbuf[((size_t)m * 48 + n) * 3 + v];
+        if (!b) continue;
+        int b6[6]; emf_box(&D, v, ox, oy, oz, b6);
+        int ni = b6[1] - b6[0] + 1, nj = b6[3] - b6[2] + 1;
+        for (int k = b6[4]; k <= b6[5]; ++k) for (int j = b6[2]; j <= b6[3]; ++j) for (int i = b6[0]; i <= b6[1]; ++i)
+          *emf_at(&D, e1, e2, e3, v, m, k, j, i) += b[(i - b6[0]) + ni * ((j - b6[2]) + nj * (k - b6[4]))];
+        free(b);
+      }
+    }
+  /* AverageBoundaryFluxes */
+  for (int m = 0; m < nmb; ++m)
+    for (int oz = -1; oz <= 1; ++oz) for (int oy = -1; oy <= 1; ++oy) for (int ox = -1; ox <= 1; ++ox) {
+      int nz = (ox != 0) + (oy != 0) + (oz != 0);
+      if (nz == 0 || nz == 3) continue;
+      int n = oracle_neighbor_index(ox, oy, oz, 0, 0);
+      for (int v = 0; v < 3; ++v) {
+        if (!emf_slot_has(ox, oy, oz, v)) continue;
+        int b6[6]; emf_box(&D, v, ox, oy, oz, b6);
+        if (nz == 1) {
+          if (nghbr_gid[m * 56 + n] < 0) continue;      /* only where a same-level neighbour exists */
+          /* interior of the face: drop the two end lines in the OTHER tangential direction */
+          int o[3] = {ox, oy, oz};
+          for (int d = 0; d < 3; ++d) if (o[d] == 0 && d != v) { b6[2 * d] += 1; b6[2 * d + 1] -= 1; }
+          for (int k = b6[4]; k <= b6[5]; ++k) for (int j = b6[2]; j <= b6[3]; ++j) for (int i = b6[0]; i <= b6[1]; ++i)
+            *emf_at(&D, e1, e2, e3, v, m, k, j, i) *= 0.5;
+        } else {
+          for (int k = b6[4]; k <= b6[5]; ++k) for (int j = b6[2]; j <= b6[3]; ++j) for (int i = b6[0]; i <= b6[1]; ++i)
+            *emf_at(&D, e1, e2, e3, v, m, k, j, i) /= (double)nflx[m * 48 + n];
+        }
+      }
+    }
+  free(nflx);
+  free(rbuf);
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* One RK stage = the "stagen" task chain of mhd_tasks.cpp:48-75 on a uniform mesh
- * (tasks 1,2,5,10/11,14,17,21/22,27; 15/16 SendE/RecvE are a bitwise identity on uniform
- * meshes -- SURVEY.md section 0 fact 6 -- and are omitted). */
+ * (tasks 1,2,5,10/11,14,15/16,17,21/22,27).  SendE/RecvE is a bitwise identity only when the
+ * faces shared by neighbouring blocks START bit-identical (true for the blast ICs, SURVEY.md
+ * section 0 fact 6; false for vector-potential ICs evaluated on both sides of a periodic
+ * boundary, e.g. linear waves), so it is always executed, as in the reference. */
 typedef struct {
   double *u0, *u1, *w0, *bcc0;
   double *b0x1f, *b0x2f, *b0x3f, *b1x1f, *b1x2f, *b1x3f;
@@ -942,6 +1057,7 @@ void oracle_stage(const ocfg *c, ostate *s, const double *mb_size, const int *ng
   oracle_rk_update(c, s->u0, s->u1, flx1, flx2, flx3, mb_size, gam0, gam1, beta_dt);
   oracle_halo_cc(c, s->u0, 5, nghbr_gid);
   oracle_corner_e(c, s->w0, s->bcc0, flx1, flx2, flx3, fe[0], fe[1], fe[2], fe[3], fe[4], fe[5], e1, e2, e3);
+  oracle_emf_exchange(c, e1, e2, e3, nghbr_gid);
   oracle_ct(c, s->b0x1f, s->b0x2f, s->b0x3f, s->b1x1f, s->b1x2f, s->b1x3f, e1, e2, e3, mb_size, gam0, gam1, beta_dt);
   oracle_halo_fc(c, s->b0x1f, s->b0x2f, s->b0x3f, nghbr_gid);
   int nf[3];

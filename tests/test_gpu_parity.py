@@ -125,6 +125,15 @@ def test_tasks_bitwise(recon, rs, nb):
     e.EField(drv, 2)
     for q in range(3):
         assert maxdiff(e.efld[q], A.e[q]) == 0.0, f"corner e{q+1}"
+    # tasks 15/16: make the copies of shared edges differ first, so the correction is not a no-op
+    rng = np.random.default_rng(5)
+    for a, t in zip(A.e, e.efld):
+        a *= 1.0 + 1e-3 * rng.standard_normal(a.shape)
+        t.copy_(torch.from_numpy(a))
+    L.oracle_emf_exchange(C.byref(cfg), *[O.p(a) for a in A.e], O.ip(ngh))
+    e.SendRecvE(drv, 2)
+    for q in range(3):
+        assert maxdiff(e.efld[q], A.e[q]) == 0.0, f"emf flux correction e{q+1}"
     # task 17
     L.oracle_ct(C.byref(cfg), *[O.p(a) for a in A.b0], *[O.p(a) for a in A.b1], *[O.p(a) for a in A.e], O.p(mbs),
                 C.c_double(g0), C.c_double(g1), C.c_double(beta * dt))
