@@ -21,12 +21,19 @@ NAME     ?= athena_builtin
 OUTDIR   ?= $(abspath ..)
 
 SRCDIR   := $(REF)/src
-CXX      := g++
-CXXFLAGS := -O3 -DNDEBUG -std=c++17 -fopenmp
+# KDEV/KARCH/RCXX select the Kokkos backend: the default is the CPU oracle; the GPU baseline
+# ("the reference's own Kokkos-CUDA kernels on the same B200") uses
+#   KDEV=Cuda,Serial KARCH=Blackwell100 RCXX=$(REF)/kokkos/bin/nvcc_wrapper ROMP=
+KDEV     ?= OpenMP,Serial
+KARCH    ?=
+RCXX     ?= g++
+ROMP     ?= -fopenmp
+CXX      := $(RCXX)
+CXXFLAGS := -O3 -DNDEBUG -std=c++17 $(ROMP)
 
 KOKKOS_PATH    := $(REF)/kokkos
-KOKKOS_DEVICES := OpenMP,Serial
-KOKKOS_ARCH    :=
+KOKKOS_DEVICES := $(KDEV)
+KOKKOS_ARCH    := $(KARCH)
 KOKKOS_OPTIONS := aggressive_vectorization
 KOKKOS_USE_DEPRECATED_MAKEFILES := 1
 KOKKOS_CXX_STANDARD := c++17
@@ -50,7 +57,7 @@ config.hpp: $(REF)/config.hpp.in
 	sed -e 's|@PROBLEM@|$(PROBLEM)|' -e 's|@USER_PROBLEM_ENABLED@|$(USER_PROBLEM_ENABLED)|' \
 	    -e 's|@TWO_PUNCTURES@|0|' -e 's|@athena_VERSION_MAJOR@|1|' -e 's|@athena_VERSION_MINOR@|0|' \
 	    -e 's|@SINGLE_PRECISION_ENABLED@|0|' -e 's|@MPI_PARALLEL_ENABLED@|0|' \
-	    -e 's|@OPENMP_PARALLEL_ENABLED@|1|' -e 's|@COMPILER_CHOICE@|g++|' \
+	    -e 's|@OPENMP_PARALLEL_ENABLED@|$(if $(ROMP),1,0)|' -e 's|@COMPILER_CHOICE@|g++|' \
 	    -e 's|@COMPILER_COMMAND@|g++|' -e 's|@COMPILER_FLAGS@|$(CXXFLAGS)|' \
 	    -e 's|@PAR_LOOP_LAYOUT@|MDRANGE_LOOP|' -e 's|@PAR_LOOP_INNER_LAYOUT@|INNER_TTR_LOOP|' $< > $@
 
