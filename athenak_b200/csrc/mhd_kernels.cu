@@ -17,6 +17,9 @@
 #ifndef AKB_MARCH_PREFETCH
 #define AKB_MARCH_PREFETCH 0
 #endif
+#ifndef AKB_CORNER_MINB
+#define AKB_CORNER_MINB 2   // 128-register budget: measured 0.56 ms vs 0.96 ms unbounded, 0.84-0.88 ms at 3-4
+#endif
 #ifndef AKB_X1_MINB
 #define AKB_X1_MINB 4
 #endif
@@ -94,7 +97,10 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
 #define TILE_X 32
 #define TILE_Y 4
 #define TILE_Z 2
-#define MARCH_SLOTS 6
+#ifndef MARCH_SLOTS
+#define MARCH_SLOTS 6          // 5 stencil rows + prefetch distance (6,7,8 measured: 3.16/3.26/3.27 ms)
+#endif
+#define MARCH_PF (MARCH_SLOTS - 5)
 #define MARCH_THREADS 128
 
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src) {
@@ -146,7 +152,7 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
                   double *__restrict__ ezo, int seglen, int nseg) {
   static_assert(DIR == 1 || DIR == 2, "march kernel handles x2 and x3");
   constexpr bool RING = (RECON >= RECON_PPM4);
-  __shared__ double ring_all[RING ? 7 * MARCH_SLOTS * MARCH_THREADS : 1];
+  extern __shared__ double ring_all[];   // RING: 7 * MARCH_SLOTS * MARCH_THREADS doubles (dynamic)
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nc = g.nx1 + 2;
   const int nt = (DIR == 1) ? g.nx3 + 2 : g.nx2 + 2;
@@ -190,31 +196,36 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
     // global columns of the seven variables at the current cell (sweep index c = f_lo-1)
     const double *gv[7] = {wp + IDN * cc, wp + ivx * cc, wp + ivy * cc, wp + ivz * cc, wp + IEN * cc,
                            bp + iby * cc, bp + ibz * cc};
-    // prologue: rows c-2 .. c+3 -> slots 0..5 (row c-2 in slot 0)
+    // prologue: rows c-2 .. c+2+PF -> slots 0..S-1 (row c-2 in slot 0)
 #pragma unroll
     for (int r = 0; r < MARCH_SLOTS; ++r) {
+      if (r < 5 || (f_lo - 1) + (r - 2) <= f_hi + 2) {   // prefetch rows only if some face of this march needs them
 #pragma unroll
-      for (int v = 0; v < 7; ++v) cp_async8(ring + v * VS + r * MARCH_THREADS, gv[v] + (long)(r - 2) * s);
+        for (int v = 0; v < 7; ++v) cp_async8(ring + v * VS + r * MARCH_THREADS, gv[v] + (long)(r - 2) * s);
+      }
     }
     cp_async_commit();
     cp_async_wait<0>();
     recon_ring_cell<RECON>(ring, 0, eos, L, lo_unused);
     int b0 = 1;                       // slot of row c-2 for the next cell (c = f_lo)
+    double bx_cur = __ldg(bn);        // normal field of the face, fetched one step ahead of its use
     for (int f = f_lo; f <= f_hi; ++f) {
-      // cell c = f: rows c-2..c+2 are present (row c+2 arrived with the previous step's group or
-      // the prologue); request row c+3 for the next step into the slot that held row c-3
-      if (f < f_hi) {
-        int bn_slot = b0 + 5; if (bn_slot >= MARCH_SLOTS) bn_slot -= MARCH_SLOTS;
-        const long ro = (long)(f - (f_lo - 1) + 3) * s;
+      const double bx_next = (f < f_hi) ? __ldg(bn + frow) : 0.0;
+      // cell c = f: rows c-2..c+2 are present; request row c+2+PF (needed PF steps from now)
+      // into the slot that held row c-3
+      if (f + MARCH_PF <= f_hi) {
+        int bn_slot = b0 + MARCH_SLOTS - 1; if (bn_slot >= MARCH_SLOTS) bn_slot -= MARCH_SLOTS;
+        const long ro = (long)(f - (f_lo - 1) + 2 + MARCH_PF) * s;
 #pragma unroll
         for (int v = 0; v < 7; ++v) cp_async8(ring + v * VS + bn_slot * MARCH_THREADS, gv[v] + ro);
       }
       cp_async_commit();
-      cp_async_wait<1>();
+      cp_async_wait<MARCH_PF>();
       State7 up, lo;
       recon_ring_cell<RECON>(ring, b0, eos, up, lo);
       Flux7 fx;
-      riemann<RS>(L, lo, __ldg(bn), eos, fx);
+      riemann<RS>(L, lo, bx_cur, eos, fx);
+      bx_cur = bx_next;
       fp[IDN * fsz] = fx.d;
       fp[ivx * fsz] = fx.mx;
       fp[ivy * fsz] = fx.my;
@@ -251,7 +262,7 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
 // ---------------------------------------------------------------------------------------
 // GS07 corner EMFs (mhd_corner_e.cpp:309-318,338-414), one thread per corner
 // k in [ks,ke+1], j in [js,je+1], i in [is,ie+1].
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, AKB_CORNER_MINB)
 corner_emf_kernel(Geom g, const double *__restrict__ w0, const double *__restrict__ bcc,
                   const double *__restrict__ flx1, const double *__restrict__ flx2,
                   const double *__restrict__ flx3, const double *__restrict__ e3x1,
@@ -570,13 +581,19 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
     const int nf = g.nx2 + 1;
     const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
     const long threads = (long)g.nmb * nseg * (g.nx3 + 2) * (g.nx1 + 2);
-    flux_march_kernel<RECON, RS, 1><<<nblocks(threads, MARCH_THREADS), MARCH_THREADS, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg);
+    const size_t smem = (RECON >= RECON_PPM4) ? sizeof(double) * 7 * MARCH_SLOTS * MARCH_THREADS : 0;
+    static bool attr1 = false;
+    if (!attr1 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr1 = true; }
+    flux_march_kernel<RECON, RS, 1><<<nblocks(threads, MARCH_THREADS), MARCH_THREADS, smem, st>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg);
   }
   {  // x3: (ey,ez) = (e2x3,e1x3)
     const int nf = g.nx3 + 1;
     const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
     const long threads = (long)g.nmb * nseg * (g.nx2 + 2) * (g.nx1 + 2);
-    flux_march_kernel<RECON, RS, 2><<<nblocks(threads, MARCH_THREADS), MARCH_THREADS, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
+    const size_t smem = (RECON >= RECON_PPM4) ? sizeof(double) * 7 * MARCH_SLOTS * MARCH_THREADS : 0;
+    static bool attr2 = false;
+    if (!attr2 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr2 = true; }
+    flux_march_kernel<RECON, RS, 2><<<nblocks(threads, MARCH_THREADS), MARCH_THREADS, smem, st>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
   }
   return cudaGetLastError();
 }
