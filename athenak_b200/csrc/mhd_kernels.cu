@@ -208,9 +208,7 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
     cp_async_wait<0>();
     recon_ring_cell<RECON>(ring, 0, eos, L, lo_unused);
     int b0 = 1;                       // slot of row c-2 for the next cell (c = f_lo)
-    double bx_cur = __ldg(bn);        // normal field of the face, fetched one step ahead of its use
     for (int f = f_lo; f <= f_hi; ++f) {
-      const double bx_next = (f < f_hi) ? __ldg(bn + frow) : 0.0;
       // cell c = f: rows c-2..c+2 are present; request row c+2+PF (needed PF steps from now)
       // into the slot that held row c-3
       if (f + MARCH_PF <= f_hi) {
@@ -224,8 +222,7 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       State7 up, lo;
       recon_ring_cell<RECON>(ring, b0, eos, up, lo);
       Flux7 fx;
-      riemann<RS>(L, lo, bx_cur, eos, fx);
-      bx_cur = bx_next;
+      riemann<RS>(L, lo, __ldg(bn), eos, fx);   // (fetching bn a step ahead costs registers: measured slower)
       fp[IDN * fsz] = fx.d;
       fp[ivx * fsz] = fx.mx;
       fp[ivy * fsz] = fx.my;

@@ -190,10 +190,10 @@ def bench_native(args):
             torch.cuda.synchronize(dev)
 
     K, W = args.steps, args.warmup
-    sim.execute(W)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # sampled from the warm-up on, so short timed regions still get samples under load
+    sim.execute(W)
     sync_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = sim.status()["launches"]
