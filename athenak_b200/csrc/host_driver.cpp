@@ -216,7 +216,9 @@ class MHD {  // state owner + tasks
     for (int p = 0; p < ak_halo_npeers(plan); ++p) {
       Peer pe;
       ak_halo_peer(plan, p, &pe.rank, &pe.ncc, &pe.nfc);
-      pe.scc = alloc(5 * pe.ncc); pe.rcc = alloc(5 * pe.ncc); pe.sfc = alloc(pe.nfc); pe.rfc = alloc(pe.nfc);
+      // one contiguous [U | B] buffer per direction so both exchanges can travel as one message
+      pe.scc = alloc(5 * pe.ncc + pe.nfc); pe.sfc = pe.scc + 5 * pe.ncc;
+      pe.rcc = alloc(5 * pe.ncc + pe.nfc); pe.rfc = pe.rcc + 5 * pe.ncc;
       peers.push_back(pe);
     }
     CU_CHECK(cudaStreamSynchronize(st));
@@ -240,11 +242,9 @@ class MHD {  // state owner + tasks
       TaskID se = tl->AddTask(&MHD::SendE, this, f);
       TaskID re = tl->AddTask(&MHD::RecvE, this, se);
       TaskID up = tl->AddTask(&MHD::StageUpdate, this, re);
-      TaskID su = tl->AddTask(&MHD::SendU, this, up);
-      TaskID ru = tl->AddTask(&MHD::RecvU, this, su);
-      TaskID sb = tl->AddTask(&MHD::SendB, this, ru);
-      TaskID rb = tl->AddTask(&MHD::RecvB, this, sb);
-      tl->AddTask(&MHD::ConToPrimNewDt, this, rb);
+      TaskID su = tl->AddTask(&MHD::SendUB, this, up);     // tasks 10+21 as one message per peer
+      TaskID ru = tl->AddTask(&MHD::RecvUB, this, su);     // tasks 11+22
+      tl->AddTask(&MHD::ConToPrimNewDt, this, ru);
     } else {
       TaskID copyu = tl->AddTask(&MHD::CopyCons, this, none);
       TaskID flux = tl->AddTask(&MHD::Fluxes, this, copyu);
@@ -348,6 +348,31 @@ class MHD {  // state owner + tasks
       launches += 1;
     }
   }
+  // U and B ghost exchange in one round: legal in the fused list because nothing runs between
+  // RecvU and SendB there (CornerE/CT already happened); one ncclSend/ncclRecv pair per peer.
+  TaskStatus SendUB(Driver *pd, int stage) {
+    Nccl &n = Nccl::get();
+    if (!peers.empty()) {
+      if (!comm) Fatal(__FILE__, __LINE__, "MeshBlocks on other ranks but no NCCL communicator (call ak_sim_comm_init)");
+      for (size_t p = 0; p < peers.size(); ++p) {
+        AK_CHECK(nullptr, ak_halo_pack_cc(plan, a.u0, 5, (int)p, peers[p].scc, st));
+        AK_CHECK(nullptr, ak_halo_pack_fc(plan, a.b0x1f, a.b0x2f, a.b0x3f, (int)p, peers[p].sfc, st));
+        launches += 2;
+      }
+      n.GroupStart();
+      for (auto &pe : peers) {
+        const size_t cnt = (size_t)5 * pe.ncc + (size_t)pe.nfc;
+        n.Send(pe.scc, cnt, kNcclFloat64, pe.rank, comm, st);
+        n.Recv(pe.rcc, cnt, kNcclFloat64, pe.rank, comm, st);
+      }
+      n.GroupEnd();
+    }
+    AK_CHECK(nullptr, ak_halo_local_cc(plan, a.u0, 5, st));
+    AK_CHECK(nullptr, ak_halo_local_fc(plan, a.b0x1f, a.b0x2f, a.b0x3f, st));
+    launches += 2;
+    return TaskStatus::complete;
+  }
+  TaskStatus RecvUB(Driver *pd, int stage) { Unpack(true); Unpack(false); return TaskStatus::complete; }
   TaskStatus SendU(Driver *pd, int stage) { Exchange(true); return TaskStatus::complete; }
   TaskStatus RecvU(Driver *pd, int stage) { Unpack(true); return TaskStatus::complete; }   // stream-ordered: never incomplete
   TaskStatus SendB(Driver *pd, int stage) { Exchange(false); return TaskStatus::complete; }
