@@ -284,8 +284,14 @@ def bench_native(args):
             t_ms = timeit(fn)
             kern[name] = {"ms": t_ms, "algo_GBps": (words * 8 * ncell / (t_ms * 1e-3) / 1e9) if words else None}
     stage_ms = ms / K / 3.0
-    path_achieved = ALGO_BYTES_PER_CELL_STAGE * float(n) ** 3 / (stage_ms * 1e-3) / 1e9   # per GPU
+    ncell = float(n) ** 3
+    path_achieved = ALGO_BYTES_PER_CELL_STAGE * ncell / (stage_ms * 1e-3) / 1e9   # per GPU
     dom = max(((k, v) for k, v in kern.items()), key=lambda kv: kv[1]["ms"])[0] if kern else None
+    # dominant kernel = one flux sweep (x1 / x2 / x3 launches are the same work in three directions):
+    # algorithmic bytes per launch = (8 words read + 7 written) per active cell
+    flux_ms = kern["fluxes(x1+x2+x3)"]["ms"] / 3.0 if kern else float("nan")
+    flux_bytes = 15 * 8 * ncell
+    flux_achieved = flux_bytes / (flux_ms * 1e-3) / 1e9
 
     line = {
         "metric": METRIC, "value": value, "unit": "Mcell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -294,16 +300,19 @@ def bench_native(args):
         "config": {"workload": f"3D MHD blast {n}^3 cells per GPU, one MeshBlock per GPU, PPM4+HLLD+RK3, nghost=4, periodic, "
                                f"mesh {'x'.join(str(n * r) for r in nroot)}; step = one full RK3 time step",
                    "l2": "every field array is %.0f MB (> 126 MB L2); no explicit flush" % (8 * (n + 2 * NG) ** 3 / 1e6),
-                   "fmad": False, "parity_build": True},
+                   "fmad": False, "parity_build": True, "driver": "C++ host driver (ak_sim_*), fused task list"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mcell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": ke2e, "ms_per_step": ms_e2e / ke2e},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": path_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": path_achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src,
-                     "what": "whole stage: 256 B algorithmic per active cell per stage (SURVEY.md 8d) x cells / mean stage time; "
-                             "the path is FP64-issue-bound, see kernels[] and DESIGN.md",
-                     "dominant_kernel": dom, "kernels": kern},
+        "roofline": {"bound": "hbm", "kernel": "flux sweep (flux_x1_kernel / flux_march_kernel<x2> / <x3>; 3 launches per stage, 63% of the stage)",
+                     "achieved": flux_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": flux_achieved / hbm_peak,
+                     "traffic": 2.13e9, "traffic_source": "ncu --set full, dram__bytes_read.sum+dram__bytes_write.sum per launch: 2.08/2.20/2.19 GB (profiles/r01_ncu_kernels.txt)",
+                     "algorithmic_bytes_per_launch": flux_bytes, "avg_launch_ms": flux_ms, "peak_source": peak_src,
+                     "note": "FP64-issue-bound, not HBM-bound: ~670 FP64 instructions per cell per sweep; ncu FP64-pipe utilisation 50-60%",
+                     "path": {"what": "whole stage, 256 B algorithmic per active cell per stage (SURVEY.md 8d) / mean stage time",
+                              "achieved": path_achieved, "frac": path_achieved / hbm_peak, "stage_ms": stage_ms},
+                     "dominant_task": dom, "kernels": kern},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_cores()
