@@ -66,7 +66,7 @@ int check_cfg(const ak_mhd_cfg *c, std::string &why) {
   if (!c) { why = "null cfg"; return 1; }
   if (c->nmb < 1) { why = "nmb < 1"; return 1; }
   if (c->nx1 < 2 || c->nx2 < 2 || c->nx3 < 2) { why = "only 3-D MeshBlocks (nx1,nx2,nx3 > 1) are supported"; return 1; }
-  if (c->recon < AK_RECON_DC || c->recon > AK_RECON_WENOZ) { why = "unknown reconstruction method"; return 1; }
+  if (c->recon < AK_RECON_DC || c->recon > AK_RECON_TENO) { why = "unknown reconstruction method"; return 1; }
   if (c->rsolver < AK_RSOLVER_LLF || c->rsolver > AK_RSOLVER_HLLD) { why = "unknown Riemann solver"; return 1; }
   // reference src/mhd/mhd.cpp:217-228: 5-point stencils need nghost >= 3, PLM/DC need 2
   const int need = (c->recon >= AK_RECON_PPM4) ? 3 : 2;

@@ -122,6 +122,7 @@ __device__ __forceinline__ void recon_ring_var(const double *__restrict__ rv, in
   const double qp1 = rv[b3 * MARCH_THREADS], qp2 = rv[b4 * MARCH_THREADS];
   if constexpr (RECON == RECON_PPM4) ppm4(qm2, qm1, q, qp1, qp2, q_up, q_lo);
   else if constexpr (RECON == RECON_PPMX) ppmx(qm2, qm1, q, qp1, qp2, q_up, q_lo);
+  else if constexpr (RECON == RECON_TENO) teno(qm2, qm1, q, qp1, qp2, q_up, q_lo);
   else wenoz(qm2, qm1, q, qp1, qp2, q_up, q_lo);
 }
 
@@ -136,7 +137,7 @@ __device__ __forceinline__ void recon_ring_cell(const double *__restrict__ ring,
   recon_ring_var<RECON>(ring + 4 * VS, b0, up.e, lo.e);
   recon_ring_var<RECON>(ring + 5 * VS, b0, up.by, lo.by);
   recon_ring_var<RECON>(ring + 6 * VS, b0, up.bz, lo.bz);
-  if constexpr (RECON == RECON_PPMX || RECON == RECON_WENOZ) {   // recon.hpp:78-108
+  if constexpr (RECON == RECON_PPMX || RECON == RECON_WENOZ || RECON == RECON_TENO) {   // recon.hpp:78-108
     const double efloor = eos.pfloor / (eos.gamma - 1.0);
     up.d = dmax(up.d, eos.dfloor);
     lo.d = dmax(lo.d, eos.dfloor);
@@ -612,6 +613,7 @@ cudaError_t launch_fluxes(int recon, int rs, const Geom &g, const EosParams &eos
     case RECON_PPM4: return launch_fluxes_r<RECON_PPM4>(rs, g, eos, a, st);
     case RECON_PPMX: return launch_fluxes_r<RECON_PPMX>(rs, g, eos, a, st);
     case RECON_WENOZ: return launch_fluxes_r<RECON_WENOZ>(rs, g, eos, a, st);
+    case RECON_TENO: return launch_fluxes_r<RECON_TENO>(rs, g, eos, a, st);
   }
   return cudaErrorInvalidValue;
 }

@@ -11,7 +11,7 @@ import os
 
 from . import build as _build
 
-RECON = {"dc": 0, "plm": 1, "ppm4": 2, "ppmx": 3, "wenoz": 4}
+RECON = {"dc": 0, "plm": 1, "ppm4": 2, "ppmx": 3, "wenoz": 4, "teno": 5}
 RSOLVER = {"llf": 0, "hlle": 1, "hlld": 2}
 
 _dp = C.POINTER(C.c_double)

@@ -73,3 +73,24 @@ def read_rst(path: str, nmhd: int = 5) -> Restart:
         raise ValueError(f"{path}: {len(raw) - off} trailing bytes")
     return Restart(deck, nmb, root_level, mesh_size, mesh_indcs, mb_indcs, time, dt, ncycle,
                    lloc, cost, u0, b1f, b2f, b3f)
+
+
+def write_rst(path: str, r: Restart) -> None:
+    """Writes a dump the reference can restart from (`athena -r file`): same byte layout as
+    src/outputs/restart.cpp:216-294,312-469 (single file, MHD only)."""
+    nmb = int(r.nmb)
+    with open(path, "wb") as f:
+        f.write(r.deck.encode())
+        f.write(struct.pack("<ii", nmb, int(r.root_level)))
+        f.write(np.ascontiguousarray(r.mesh_size, "<f8").tobytes())
+        f.write(struct.pack("<19i", *[int(r.mesh_indcs[k]) for k in _INDCS]))
+        f.write(struct.pack("<19i", *[int(r.mb_indcs[k]) for k in _INDCS]))
+        f.write(struct.pack("<dd", float(r.time), float(r.dt)))
+        f.write(struct.pack("<i", int(r.ncycle)))
+        f.write(np.ascontiguousarray(r.lloc, "<i4").tobytes())
+        f.write(np.ascontiguousarray(r.cost, "<f4").tobytes())
+        per_block = 8 * (r.u0[0].size + r.b1f[0].size + r.b2f[0].size + r.b3f[0].size)
+        f.write(struct.pack("<Q", per_block))
+        for m in range(nmb):
+            for a in (r.u0, r.b1f, r.b2f, r.b3f):
+                f.write(np.ascontiguousarray(a[m], "<f8").tobytes())

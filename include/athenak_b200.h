@@ -31,7 +31,7 @@ extern "C" {
 typedef void *ak_stream_t; /* a cudaStream_t (0 = default stream) */
 
 /* reconstruction / Riemann-solver selectors: reference src/athena.hpp:75, src/mhd/mhd.hpp:39 */
-enum { AK_RECON_DC = 0, AK_RECON_PLM = 1, AK_RECON_PPM4 = 2, AK_RECON_PPMX = 3, AK_RECON_WENOZ = 4 };
+enum { AK_RECON_DC = 0, AK_RECON_PLM = 1, AK_RECON_PPM4 = 2, AK_RECON_PPMX = 3, AK_RECON_WENOZ = 4, AK_RECON_TENO = 5 };
 enum { AK_RSOLVER_LLF = 0, AK_RSOLVER_HLLE = 1, AK_RSOLVER_HLLD = 2 };
 
 typedef struct {

@@ -21,7 +21,7 @@
 
 typedef struct {
   int nmb, ng, nx1, nx2, nx3;
-  int recon;   /* 0 dc, 1 plm, 2 ppm4, 3 ppmx, 4 wenoz   (athena.hpp:75) */
+  int recon;   /* 0 dc, 1 plm, 2 ppm4, 3 ppmx, 4 wenoz, 5 teno   (athena.hpp:75) */
   int rsolver; /* 0 llf, 1 hlle, 2 hlld                   (mhd.hpp:39)    */
   double gamma, dfloor, pfloor, tfloor, sfloor, sigma_max; /* eos.hpp:27-33 */
 } ocfg;
@@ -179,6 +179,43 @@ static void WENOZ(double qm2, double qm1, double q, double qp1, double qp2, doub
   *qr_i = (f[0] * alpha[0] + f[1] * alpha[1] + f[2] * alpha[2]) / alpha_sum;
 }
 
+/* teno.hpp:29-91 */
+#define CUB(x) ((x) * (x) * (x))
+static void TENO(double qm2, double qm1, double q, double qp1, double qp2, double *ql_ip1,
+                 double *qr_i) {
+  const double bc0 = 13. / 12., bc1 = 0.25;
+  double beta[3];
+  beta[0] = bc0 * SQR(qm2 + q - 2.0 * qm1) + bc1 * SQR(qm2 + 3.0 * q - 4.0 * qm1);
+  beta[1] = bc0 * SQR(qm1 + qp1 - 2.0 * q) + bc1 * SQR(qm1 - qp1);
+  beta[2] = bc0 * SQR(qp2 + q - 2.0 * qp1) + bc1 * SQR(qp2 + 3.0 * q - 4.0 * qp1);
+  const double epsT = 1.0e-40, cT = 1.0e-6;
+  double alpha[3];
+  alpha[0] = 1.0 / SQR(CUB(beta[0] + epsT));
+  alpha[1] = 1.0 / SQR(CUB(beta[1] + epsT));
+  alpha[2] = 1.0 / SQR(CUB(beta[2] + epsT));
+  double alpha_sum = alpha[0] + alpha[1] + alpha[2];
+  double ind[3];
+  ind[0] = (alpha[0] < cT * alpha_sum ? 0.0 : 1.0);
+  ind[1] = (alpha[1] < cT * alpha_sum ? 0.0 : 1.0);
+  ind[2] = (alpha[2] < cT * alpha_sum ? 0.0 : 1.0);
+  double f[3];
+  f[0] = (2.0 * qm2 - 7.0 * qm1 + 11.0 * q);
+  f[1] = (-1.0 * qm1 + 5.0 * q + 2.0 * qp1);
+  f[2] = (2.0 * q + 5.0 * qp1 - qp2);
+  alpha[0] = 0.1 * ind[0];
+  alpha[1] = 0.6 * ind[1];
+  alpha[2] = 0.3 * ind[2];
+  alpha_sum = 6.0 * (alpha[0] + alpha[1] + alpha[2]);
+  *ql_ip1 = (f[0] * alpha[0] + f[1] * alpha[1] + f[2] * alpha[2]) / alpha_sum;
+  f[0] = (2.0 * qp2 - 7.0 * qp1 + 11.0 * q);
+  f[1] = (-1.0 * qp1 + 5.0 * q + 2.0 * qm1);
+  f[2] = (2.0 * q + 5.0 * qm1 - qm2);
+  alpha[0] = 0.1 * ind[2];
+  alpha[2] = 0.3 * ind[0];
+  alpha_sum = 6.0 * (alpha[0] + alpha[1] + alpha[2]);
+  *qr_i = (f[0] * alpha[0] + f[1] * alpha[1] + f[2] * alpha[2]) / alpha_sum;
+}
+
 /* recon.hpp:40-118 (ReconCellT) + :134-185 (ReconDispatch): one variable of q over a cell
  * box; ql -> wl at the upper face index, qr -> wr at the cell's own index. */
 static void recon_pass(const ocfg *c, int dir, int nv, int apply_floors, const double *q,
@@ -206,6 +243,7 @@ static void recon_pass(const ocfg *c, int dir, int nv, int apply_floors, const d
               case 2: PPM4(qm2, qm1, q0, qp1, qp2, &ql, &qr); break;
               case 3: PPMX(qm2, qm1, q0, qp1, qp2, &ql, &qr); break;
               case 4: WENOZ(qm2, qm1, q0, qp1, qp2, &ql, &qr); break;
+              case 5: TENO(qm2, qm1, q0, qp1, qp2, &ql, &qr); break;
               default: ql = q0; qr = q0; break;
             }
             if (apply_floors && c->recon >= 3) { /* recon.hpp:78-108: ppmx/wenoz/teno only */

@@ -52,4 +52,5 @@ if __name__ == "__main__":
     blast(16, (2,), recon="plm", rsolver="hlle", integrator="rk2")
     blast(16, (2,), recon="wenoz", rsolver="llf", integrator="rk3")
     blast(16, (2,), recon="ppmx", rsolver="hlld", integrator="rk1")
+    blast(16, (3,), recon="teno", rsolver="hlle", integrator="rk2")
     print("golden fixtures written")

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_DIR = os.path.join(ORACLE_DIR, "_ref")
 
-RECON = {"dc": 0, "plm": 1, "ppm4": 2, "ppmx": 3, "wenoz": 4}
+RECON = {"dc": 0, "plm": 1, "ppm4": 2, "ppmx": 3, "wenoz": 4, "teno": 5}
 RSOLVER = {"llf": 0, "hlle": 1, "hlld": 2}
 FLT_MIN = float(np.finfo(np.float32).tiny)
 FLT_MAX = float(np.finfo(np.float32).max)

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 CASES = [("ppm4", "hlld"), ("plm", "hlle"), ("wenoz", "llf"), ("ppmx", "hlld"), ("plm", "llf"),
-         ("ppm4", "hlle"), ("wenoz", "hlld"), ("dc", "hlld")]
+         ("ppm4", "hlle"), ("wenoz", "hlld"), ("dc", "hlld"), ("teno", "hlld"), ("teno", "llf")]
 
 
 def evolved_state(recon, rs, ncyc=3, nb=1, n=16):
@@ -188,6 +188,7 @@ def test_c2p_floors_bitwise():
     ("blast16_plm_hlle_rk2", "plm", "hlle", "rk2", (2,)),
     ("blast16_wenoz_llf_rk3", "wenoz", "llf", "rk3", (2,)),
     ("blast16_ppmx_hlld_rk1", "ppmx", "hlld", "rk1", (2,)),
+    ("blast16_teno_hlle_rk2", "teno", "hlle", "rk2", (3,)),
 ])
 @pytest.mark.parametrize("fused", [False, True])
 def test_full_run_matches_golden(name, recon, rs, integ, cycles, fused):

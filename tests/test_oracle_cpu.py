@@ -30,6 +30,7 @@ def run_oracle(A, nghbr, mbs, integ, ncyc, dt0, cfl=0.3, tlim=0.3):
     ("blast16_plm_hlle_rk2", "plm", "hlle", "rk2", (2,)),
     ("blast16_wenoz_llf_rk3", "wenoz", "llf", "rk3", (2,)),
     ("blast16_ppmx_hlld_rk1", "ppmx", "hlld", "rk1", (2,)),
+    ("blast16_teno_hlle_rk2", "teno", "hlle", "rk2", (3,)),
 ])
 def test_oracle_matches_golden(name, recon, rs, integ, cycles):
     """Bitwise (max|delta| = 0) agreement of the C restatement with reference restart dumps."""
