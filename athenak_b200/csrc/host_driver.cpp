@@ -176,7 +176,7 @@ class MHD {  // state owner + tasks
  public:
   ak_mhd_cfg cfg;
   ak_mhd_arrays a;
-  void *h = nullptr, *plan = nullptr;
+  void *h = nullptr, *plan = nullptr, *bcs = nullptr;   // bcs == nullptr: strictly periodic mesh
   cudaStream_t st = nullptr;
   MeshState mesh;
   int my_rank, nranks;
@@ -226,6 +226,7 @@ class MHD {  // state owner + tasks
   ~MHD() {
     if (comm && Nccl::get().CommDestroy) Nccl::get().CommDestroy(comm);
     ak_halo_destroy(plan);
+    ak_bcs_destroy(bcs);
     ak_mhd_destroy(h);
     for (double *p : owned) cudaFree(p);
     if (st) cudaStreamDestroy(st);
@@ -244,7 +245,8 @@ class MHD {  // state owner + tasks
       TaskID up = tl->AddTask(&MHD::StageUpdate, this, re);
       TaskID su = tl->AddTask(&MHD::SendUB, this, up);     // tasks 10+21 as one message per peer
       TaskID ru = tl->AddTask(&MHD::RecvUB, this, su);     // tasks 11+22
-      tl->AddTask(&MHD::ConToPrimNewDt, this, ru);
+      TaskID bc = tl->AddTask(&MHD::ApplyPhysicalBCs, this, ru);
+      tl->AddTask(&MHD::ConToPrimNewDt, this, bc);
     } else {
       TaskID copyu = tl->AddTask(&MHD::CopyCons, this, none);
       TaskID flux = tl->AddTask(&MHD::Fluxes, this, copyu);
@@ -257,7 +259,8 @@ class MHD {  // state owner + tasks
       TaskID ct = tl->AddTask(&MHD::CT, this, recve);
       TaskID sendb = tl->AddTask(&MHD::SendB, this, ct);
       TaskID recvb = tl->AddTask(&MHD::RecvB, this, sendb);
-      TaskID c2p = tl->AddTask(&MHD::ConToPrim, this, recvb);
+      TaskID bc = tl->AddTask(&MHD::ApplyPhysicalBCs, this, recvb);
+      TaskID c2p = tl->AddTask(&MHD::ConToPrim, this, bc);
       tl->AddTask(&MHD::NewTimeStep, this, c2p);
     }
   }
@@ -377,6 +380,14 @@ class MHD {  // state owner + tasks
   TaskStatus RecvU(Driver *pd, int stage) { Unpack(true); return TaskStatus::complete; }   // stream-ordered: never incomplete
   TaskStatus SendB(Driver *pd, int stage) { Exchange(false); return TaskStatus::complete; }
   TaskStatus RecvB(Driver *pd, int stage) { Unpack(false); return TaskStatus::complete; }
+  // task 26, mhd_tasks.cpp:504-520: nothing to do on a strictly periodic mesh
+  TaskStatus ApplyPhysicalBCs(Driver *pd, int stage) {
+    if (!bcs) return TaskStatus::complete;
+    if (ak_bcs_apply(bcs, a.u0, 5, a.b0x1f, a.b0x2f, a.b0x3f, st)) Fatal(__FILE__, __LINE__, ak_bcs_last_error(bcs));
+    launches += nbc_launches;
+    return TaskStatus::complete;
+  }
+  int nbc_launches = 0;
   TaskStatus ConToPrim(Driver *pd, int stage) {
     const int n1 = cfg.nx1 + 2 * cfg.ng, n2 = cfg.nx2 + 2 * cfg.ng, n3 = cfg.nx3 + 2 * cfg.ng;
     int nf[3];
@@ -427,6 +438,7 @@ class MHD {  // state owner + tasks
 void Driver::Initialize(MHD *pmhd) {   // driver.cpp:314-371 -> InitBoundaryValuesAndPrimitives :569-653
   pmhd->SendU(this, 0); pmhd->RecvU(this, 0);
   pmhd->SendB(this, 0); pmhd->RecvB(this, 0);
+  pmhd->ApplyPhysicalBCs(this, 0);                 // driver.cpp:626-627
   pmhd->ConToPrim(this, 0);
   pmhd->NewTimeStep(this, nexp_stages);
   pmhd->MeshNewTimeStep(tlim);
@@ -470,6 +482,18 @@ int ak_sim_create(const ak_sim_cfg *c, const double *mb_size, const int *nghbr, 
   s->pmhd->AssembleMHDTasks();
   s->pdriver.reset(new akh::Driver(c->integrator == 1 ? "rk1" : c->integrator == 2 ? "rk2" : "rk3", c->tlim, c->nlim));
   *sim = s;
+  return 0;
+}
+/* physical boundary flags of the mesh and of this rank's blocks (default: strictly periodic) */
+int ak_sim_set_bcs(void *sim, const int *mesh_bcs, const int *mb_bcs) {
+  auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
+  ak_bcs_destroy(m->bcs);
+  m->bcs = nullptr; m->nbc_launches = 0;
+  void *b = nullptr;
+  if (ak_bcs_create(&m->cfg, mesh_bcs, mb_bcs, &b)) return 1;
+  if (ak_bcs_strictly_periodic(b)) { ak_bcs_destroy(b); return 0; }
+  m->bcs = b;
+  for (int d = 0; d < 3; ++d) m->nbc_launches += (mesh_bcs[2 * d] != AK_BC_PERIODIC);
   return 0;
 }
 int ak_sim_destroy(void *sim) { delete static_cast<akh::Sim *>(sim); return 0; }

@@ -25,7 +25,7 @@ struct LLoc { int32_t lx1, lx2, lx3, level; };
 struct HostMesh {
   int nmesh[3], nblock[3], nroot[3];
   double xmin[3], xmax[3];
-  int bcs[6];          // per mesh face: AK_BC_* (periodic = 0)
+  int bcs[6];          // per mesh face: enum ak_bc_flag
   int nranks;
   int root_level, nmb_total;
   std::vector<LLoc> lloc;            // Z-ordered
@@ -94,7 +94,6 @@ void load_balance(HostMesh &M) {
 
 extern "C" {
 
-enum { AK_BC_PERIODIC = 0, AK_BC_OTHER = 1 };
 
 const char *ak_mesh_last_error() { return g_mesh_err.c_str(); }
 
@@ -130,7 +129,6 @@ int ak_mesh_create(const int *nmesh, const int *nblock, const double *xmin, cons
   M->mb_size.assign((size_t)nb * 9, 0.0);
   M->mb_bcs.assign((size_t)nb * 6, 0);
   M->nghbr.assign((size_t)nb * 56 * 4, -1);
-  const int AK_BC_BLOCK = -1;  // BoundaryFlag::block
   for (int g = 0; g < nb; ++g) {
     const int l[3] = {M->lloc[g].lx1, M->lloc[g].lx2, M->lloc[g].lx3};
     for (int d = 0; d < 3; ++d) {   // meshblock.cpp:44-116

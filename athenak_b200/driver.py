@@ -58,6 +58,7 @@ def assemble_mhd_tasks(mhd: MHD, fused=True):
         t = s.AddTask(mhd.StageUpdate, t)
         t = s.AddTask(mhd.SendRecvU, t)
         t = s.AddTask(mhd.SendRecvB, t)
+        t = s.AddTask(mhd.ApplyPhysicalBCs, t)
         t = s.AddTask(mhd.ConToPrimNewDt, t)
     else:
         t = s.AddTask(mhd.CopyCons, 0)
@@ -68,6 +69,7 @@ def assemble_mhd_tasks(mhd: MHD, fused=True):
         t = s.AddTask(mhd.SendRecvE, t)
         t = s.AddTask(mhd.CT, t)
         t = s.AddTask(mhd.SendRecvB, t)
+        t = s.AddTask(mhd.ApplyPhysicalBCs, t)
         t = s.AddTask(mhd.ConToPrim, t)
         t = s.AddTask(mhd.NewTimeStep, t)
     return tl
@@ -117,6 +119,7 @@ class Driver:
         fill ghost zones of U and B, c2p everywhere, first time step."""
         mhd.SendRecvU(self, 0)
         mhd.SendRecvB(self, 0)
+        mhd.ApplyPhysicalBCs(self, 0)
         mhd.ConToPrim(self, 0)
         save = self.nexp_stages
         mhd.NewTimeStep(self, save)

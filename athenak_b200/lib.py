@@ -113,7 +113,16 @@ def load():
         "ak_sim_sync": [vp],
         "ak_sim_status": [vp, dpp, C.POINTER(C.c_long)],
         "ak_sim_arrays": [vp, C.POINTER(MhdArrays)],
+        "ak_sim_set_bcs": [vp, ipp, ipp],
+        "ak_bcs_create": [C.POINTER(MhdCfg), ipp, ipp, C.POINTER(vp)],
+        "ak_bcs_destroy": [vp],
+        "ak_bcs_strictly_periodic": [vp],
+        "ak_bcs_hydro": [vp, vp, ip, vp],
+        "ak_bcs_bfield": [vp, vp, vp, vp, vp],
+        "ak_bcs_apply": [vp, vp, ip, vp, vp, vp, vp],
     })
+    lib.ak_bcs_last_error.restype = C.c_char_p
+    lib.ak_bcs_last_error.argtypes = [vp]
     lib.ak_mesh_last_error.restype = C.c_char_p
     for name, args in sig.items():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch: fail loudly
@@ -132,7 +141,13 @@ EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_con
             "ak_mesh_create", "ak_mesh_destroy", "ak_mesh_last_error", "ak_mesh_info", "ak_mesh_tables",
             "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast", "ak_pgen_orszag_tang", "ak_selftest_divsqrt",
             "ak_sim_create", "ak_sim_destroy", "ak_nccl_unique_id", "ak_sim_comm_init", "ak_sim_set_state",
-            "ak_sim_get_state", "ak_sim_initialize", "ak_sim_execute", "ak_sim_sync", "ak_sim_status", "ak_sim_arrays")
+            "ak_sim_get_state", "ak_sim_initialize", "ak_sim_execute", "ak_sim_sync", "ak_sim_status", "ak_sim_arrays",
+            "ak_sim_set_bcs", "ak_bcs_create", "ak_bcs_destroy", "ak_bcs_last_error", "ak_bcs_strictly_periodic",
+            "ak_bcs_hydro", "ak_bcs_bfield", "ak_bcs_apply")
+
+# BoundaryFlag (src/bvals/bvals.hpp:19) == enum ak_bc_flag
+BC = {"undef": -1, "block": 0, "reflect": 1, "inflow": 2, "outflow": 3, "diode": 4, "user": 5, "periodic": 6,
+      "shear_periodic": 7, "vacuum": 8}
 
 
 def check(rc, handle=None):

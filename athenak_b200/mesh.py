@@ -8,12 +8,15 @@ import numpy as np
 
 from . import lib as _lib
 
-PERIODIC, OTHER = 0, 1
+BC = _lib.BC          # BoundaryFlag values (src/bvals/bvals.hpp:19)
 
 
 class Mesh:
-    def __init__(self, nmesh, nblock, xmin=(-0.5, -0.5, -0.5), xmax=(0.5, 0.5, 0.5), bcs=(0,) * 6, nranks=1):
+    def __init__(self, nmesh, nblock, xmin=(-0.5, -0.5, -0.5), xmax=(0.5, 0.5, 0.5), bcs=("periodic",) * 6, nranks=1):
+        """bcs: ix1,ox1,ix2,ox2,ix3,ox3 as BoundaryFlag names or values."""
         self.L = _lib.load()
+        bcs = tuple(BC[b] if isinstance(b, str) else int(b) for b in bcs)
+        self.bcs = bcs
         self.nmesh, self.nblock, self.nranks = tuple(nmesh), tuple(nblock), int(nranks)
         self.xmin, self.xmax = tuple(xmin), tuple(xmax)
         i3, d3, i6 = (C.c_int * 3), (C.c_double * 3), (C.c_int * 6)

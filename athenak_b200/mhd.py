@@ -37,7 +37,8 @@ class TaskStatus(enum.Enum):  # src/tasklist/task_list.hpp:30
 class MHD:
     def __init__(self, nmb, ng, nx, mb_size, nghbr, *, recon="ppm4", rsolver="hlld", gamma,
                  dfloor=FLT_MIN, pfloor=FLT_MIN, tfloor=FLT_MIN, sfloor=FLT_MIN, sigma_max=FLT_MAX,
-                 my_rank=0, gids_start=0, device="cuda", process_group=None, fused=True):
+                 my_rank=0, gids_start=0, device="cuda", process_group=None, fused=True,
+                 mesh_bcs=None, mb_bcs=None):
         if not torch.cuda.is_available():
             raise _lib.EngineError("athenak_b200: no CUDA device; the engine has no CPU path")
         self.L = _lib.load()
@@ -76,6 +77,18 @@ class MHD:
             _lib.check(self.L.ak_halo_peer(self.plan, ip, C.byref(r), C.byref(ncc), C.byref(nfc)))
             self.peers.append(dict(rank=r.value, ncc=ncc.value, nfc=nfc.value,
                                    scc=z(5 * ncc.value), rcc=z(5 * ncc.value), sfc=z(nfc.value), rfc=z(nfc.value)))
+        # physical BCs (task 26); None = strictly periodic mesh
+        self.bcs = None
+        if mesh_bcs is not None and any(int(b) != _lib.BC["periodic"] for b in mesh_bcs):
+            mesh_bcs = np.ascontiguousarray(mesh_bcs, dtype=np.int32).reshape(6)
+            mb_bcs = np.ascontiguousarray(mb_bcs, dtype=np.int32).reshape(nmb, 6)
+            ipp = C.POINTER(C.c_int)
+            self.bcs = C.c_void_p()
+            if self.L.ak_bcs_create(C.byref(self.cfg), mesh_bcs.ctypes.data_as(ipp), mb_bcs.ctypes.data_as(ipp),
+                                    C.byref(self.bcs)):
+                self.bcs = None
+                raise _lib.EngineError(self.L.ak_bcs_last_error(None).decode())
+            self.nbc = sum(int(mesh_bcs[2 * d]) != _lib.BC["periodic"] for d in range(3))
         self.dtnew = FLT_MAX
         self.nfloor = [0, 0, 0]       # EventCounters neos_dfloor/efloor/tfloor (src/mesh/mesh.hpp:70-74)
         self.launches = 0             # kernels this object has launched (bench: gpu_launches)
@@ -94,6 +107,8 @@ class MHD:
 
     def __del__(self):
         try:
+            if getattr(self, "bcs", None):
+                self.L.ak_bcs_destroy(self.bcs)
             if getattr(self, "plan", None):
                 self.L.ak_halo_destroy(self.plan)
             if getattr(self, "h", None):
@@ -224,6 +239,15 @@ class MHD:
 
     def SendRecvB(self, driver, stage):
         self._exchange("b")
+        return TaskStatus.complete
+
+    def ApplyPhysicalBCs(self, driver, stage):
+        """Task 26 (src/mhd/mhd_tasks.cpp:504-520): HydroBCs + BFieldBCs; no-op when strictly periodic."""
+        if self.bcs is None:
+            return TaskStatus.complete
+        if self.L.ak_bcs_apply(self.bcs, self.u0.data_ptr(), 5, *[a.data_ptr() for a in self.b0], self._st()):
+            raise _lib.EngineError(self.L.ak_bcs_last_error(self.bcs).decode())
+        self.launches += self.nbc
         return TaskStatus.complete
 
     def ConToPrim(self, driver, stage, count=True):

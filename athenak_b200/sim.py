@@ -20,7 +20,7 @@ class Simulation:
         self.mesh, self.rank, self.ng = mesh, rank, ng
         nmb = int(mesh.nmb_rank[rank])
         nx = mesh.nblock
-        mb_size, _, nghbr = mesh.rank_tables(rank)
+        mb_size, mb_bcs, nghbr = mesh.rank_tables(rank)
         mcfg = _lib.MhdCfg(nmb, ng, nx[0], nx[1], nx[2], _lib.RECON[recon], _lib.RSOLVER[rsolver], gamma,
                            dfloor, pfloor, tfloor, sfloor, sigma_max)
         self.cfg = _lib.SimCfg(mcfg, INTEGRATOR[integrator], cfl_number, tlim, nlim, rank, mesh.nranks,
@@ -30,6 +30,10 @@ class Simulation:
                                   nghbr.ctypes.data_as(C.POINTER(C.c_int)), C.byref(self.h))
         if rc:
             raise _lib.EngineError("ak_sim_create failed: " + (self.L.ak_last_error(None) or b"").decode())
+        ipp = C.POINTER(C.c_int)
+        mesh_bcs = np.asarray(mesh.bcs, np.int32)
+        if self.L.ak_sim_set_bcs(self.h, mesh_bcs.ctypes.data_as(ipp), mb_bcs.ctypes.data_as(ipp)):
+            raise _lib.EngineError(self.L.ak_bcs_last_error(None).decode())
         n1, n2, n3 = (nx[d] + 2 * ng for d in range(3))
         self.shapes = [(nmb, 5, n3, n2, n1), (nmb, n3, n2, n1 + 1), (nmb, n3, n2 + 1, n1), (nmb, n3 + 1, n2, n1)]
 

@@ -136,6 +136,25 @@ int ak_halo_emf_pack(void *plan, const double *e1, const double *e2, const doubl
                      double *sendbuf, ak_stream_t s);
 int ak_halo_emf_sumavg(void *plan, double *e1, double *e2, double *e3, ak_stream_t s);
 
+/* task 26 MHD::ApplyPhysicalBCs (src/mhd/mhd_tasks.cpp:504-520): physical boundary conditions
+ * on the blocks touching the mesh edge, MeshBoundaryValues::HydroBCs (src/bvals/physics/
+ * hydro_bcs.cpp:27-335) and ::BFieldBCs (src/bvals/physics/bfield_bcs.cpp:25-358).  Flags are
+ * the reference's BoundaryFlag values (src/bvals/bvals.hpp:19).  mesh_bcs[6] = ix1,ox1,ix2,ox2,
+ * ix3,ox3 of the mesh; mb_bcs = host [nmb][6] per-block flags (MeshBlock::mb_bcs, block faces =
+ * AK_BC_BLOCK).  The x1, x2, x3 passes run in that order over the full transverse extent.  A
+ * strictly periodic mesh makes every call a no-op.  inflow / user / shear_periodic need
+ * problem-generator data and are rejected by ak_bcs_create. */
+enum ak_bc_flag { AK_BC_UNDEF = -1, AK_BC_BLOCK = 0, AK_BC_REFLECT = 1, AK_BC_INFLOW = 2, AK_BC_OUTFLOW = 3,
+                  AK_BC_DIODE = 4, AK_BC_USER = 5, AK_BC_PERIODIC = 6, AK_BC_SHEAR_PERIODIC = 7, AK_BC_VACUUM = 8 };
+int ak_bcs_create(const ak_mhd_cfg *cfg, const int *mesh_bcs, const int *mb_bcs, void **bcs);
+int ak_bcs_destroy(void *bcs);
+const char *ak_bcs_last_error(void *bcs);
+int ak_bcs_strictly_periodic(void *bcs);
+int ak_bcs_hydro(void *bcs, double *u0, int nvar, ak_stream_t s);
+int ak_bcs_bfield(void *bcs, double *x1f, double *x2f, double *x3f, ak_stream_t s);
+/* both of the above with one launch per direction */
+int ak_bcs_apply(void *bcs, double *u0, int nvar, double *x1f, double *x2f, double *x3f, ak_stream_t s);
+
 /* Device self-test: compares the library's slow-path-free FP64 reciprocal / division / sqrt with
  * the built-in IEEE operators on n random operands (|exponent| <= exponent_span, every 64th
  * numerator exactly 0); mismatches[3] = differing results for 1/x, a/b, sqrt(x). */
@@ -144,8 +163,8 @@ int ak_selftest_divsqrt(long n, unsigned long long seed, int exponent_span, long
 /* ---- host-side mesh metadata (CPU only; reference src/mesh, kept on the host) ---------------
  * Uniform (single-level) meshes.  Bit-exact mirrors of: Z-ordered gids (meshblock_tree.cpp:
  * 60-90,336-350), LoadBalance (load_balance.cpp:38-88), MeshBlock sizes and BC flags
- * (meshblock.cpp:25-131; BoundaryFlag::block = -1), neighbour table {gid,lev,rank,dest}
- * (meshblock.cpp:142-430).  bcs[6] = ix1,ox1,ix2,ox2,ix3,ox3; 0 = periodic. */
+ * (meshblock.cpp:25-131; enum ak_bc_flag), neighbour table {gid,lev,rank,dest}
+ * (meshblock.cpp:142-430).  bcs[6] = ix1,ox1,ix2,ox2,ix3,ox3 as enum ak_bc_flag. */
 int ak_mesh_create(const int *nmesh, const int *nblock, const double *xmin, const double *xmax,
                    const int *bcs, int nranks, void **mesh);
 int ak_mesh_destroy(void *mesh);
@@ -177,6 +196,8 @@ typedef struct {
 int ak_sim_create(const ak_sim_cfg *cfg, const double *mb_size /*host [nmb][9]*/,
                   const int *nghbr /*host [nmb][56][4]*/, void **sim);
 int ak_sim_destroy(void *sim);
+/* physical BCs (default strictly periodic): mesh_bcs[6], mb_bcs host [nmb][6]; errors -> ak_bcs_last_error(NULL) */
+int ak_sim_set_bcs(void *sim, const int *mesh_bcs, const int *mb_bcs);
 int ak_nccl_unique_id(void *out128);                         /* rank 0; broadcast by the launcher */
 int ak_sim_comm_init(void *sim, const void *unique_id128);   /* collective over all ranks */
 int ak_sim_set_state(void *sim, const double *u0, const double *b1f, const double *b2f, const double *b3f);

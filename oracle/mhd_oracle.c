@@ -1067,6 +1067,83 @@ void oracle_emf_exchange(const ocfg *c, double *e1, double *e2, double *e3, cons
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* Task 26 ApplyPhysicalBCs (mhd_tasks.cpp:504-520): HydroBCs (bvals/physics/hydro_bcs.cpp:68-335)
+ * then BFieldBCs (bvals/physics/bfield_bcs.cpp:67-358), skipped on strictly periodic meshes.
+ * Flags follow BoundaryFlag (bvals.hpp:19): block 0, reflect 1, inflow 2, outflow 3, diode 4,
+ * user 5, periodic 6, shear_periodic 7, vacuum 8.  The passes run x1, x2, x3 in that order, each
+ * over the FULL transverse extent (ghosts included), so edge/corner ghosts are filled from the
+ * ghosts the earlier passes wrote.  A pass is gated on the MESH flag of the inner face and then
+ * switches on the per-block flag of each face (block faces: untouched).  inflow/user need
+ * problem-generator data and are not restated (oracle_apply_bcs returns 1 for them). */
+enum { BC_BLOCK = 0, BC_REFLECT = 1, BC_INFLOW = 2, BC_OUTFLOW = 3, BC_DIODE = 4, BC_USER = 5,
+       BC_PERIODIC = 6, BC_SHEAR = 7, BC_VACUUM = 8 };
+
+/* one ghost line: a[base + x*st] for x along the BC direction; cell-like (face_like=0) or the
+ * face component normal to the boundary (face_like=1); s,e = first/last ACTIVE cell index */
+/* clamp: 1 = normal momentum (diode clamps it), 0 = other conserved variable, -1 = magnetic
+ * field (diode and vacuum both act as outflow, bfield_bcs.cpp:90-92) */
+static void bc_line(double *a, size_t st, int ng, int s, int e, int side, int flag, int face_like,
+                    int flip, int clamp) {
+  for (int g = 0; g < ng; ++g) {
+    int dst, mir, edge;
+    if (side == 0) { dst = s - g - 1; mir = s + g + face_like; edge = s; }
+    else { dst = e + g + 1 + face_like; mir = e - g; edge = e + face_like; }
+    switch (flag) {
+      case BC_REFLECT: a[dst * st] = flip ? -a[mir * st] : a[mir * st]; break;
+      case BC_OUTFLOW: a[dst * st] = a[edge * st]; break;
+      case BC_DIODE:
+        if (clamp > 0) a[dst * st] = (side == 0) ? fmin(0.0, a[edge * st]) : fmax(0.0, a[edge * st]);
+        else a[dst * st] = a[edge * st];
+        break;
+      case BC_VACUUM: a[dst * st] = (clamp >= 0) ? 0.0 : a[edge * st]; break;  /* B: vacuum == outflow */
+      default: break;
+    }
+  }
+}
+
+/* all ghost lines of one array [nmb][nvar][x3][x2][x1] for BC direction d.  kind: -1 cell-centred
+ * conserved variables, 0/1/2 face component x1f/x2f/x3f */
+static void bc_array(const ocfg *c, double *a, int nvar, int kind, int d, const int *mb_bcs) {
+  odims D = dims(c);
+  int ext[3] = {D.n1 + (kind == 0), D.n2 + (kind == 1), D.n3 + (kind == 2)};
+  int s3[3] = {D.is, D.js, D.ks}, e3[3] = {D.ie, D.je, D.ke};
+  size_t st[3] = {1, (size_t)ext[0], (size_t)ext[0] * ext[1]};
+  size_t blk = st[2] * ext[2];
+  int ta = (d + 1) % 3, tb = (d + 2) % 3;
+  for (int m = 0; m < c->nmb; ++m)
+    for (int n = 0; n < nvar; ++n)
+      for (int qb = 0; qb < ext[tb]; ++qb) for (int qa = 0; qa < ext[ta]; ++qa) {
+        double *line = a + ((size_t)m * nvar + n) * blk + qa * st[ta] + qb * st[tb];
+        for (int side = 0; side < 2; ++side) {
+          int flag = mb_bcs[m * 6 + 2 * d + side];
+          if (kind < 0) bc_line(line, st[d], c->ng, s3[d], e3[d], side, flag, 0, n == IVX + d, n == IVX + d);
+          else bc_line(line, st[d], c->ng, s3[d], e3[d], side, flag, kind == d, kind == d, -1);
+        }
+      }
+}
+
+int oracle_apply_bcs(const ocfg *c, const int *mesh_bcs, const int *mb_bcs, double *u0, double *b1f,
+                     double *b2f, double *b3f) {
+  for (int q = 0; q < 6 * c->nmb; ++q)
+    if (mb_bcs[q] == BC_INFLOW || mb_bcs[q] == BC_USER || mb_bcs[q] == BC_SHEAR) return 1;
+  for (int d = 0; d < 3; ++d) {        /* hydro_bcs.cpp:80-81,167,252: gate on the mesh flag */
+    if (mesh_bcs[2 * d] == BC_PERIODIC || (d == 0 && mesh_bcs[0] == BC_SHEAR)) continue;
+    bc_array(c, u0, 5, -1, d, mb_bcs);
+  }
+  for (int d = 0; d < 3; ++d) {        /* bfield_bcs.cpp:78,169,262 */
+    if (mesh_bcs[2 * d] == BC_PERIODIC) continue;
+    bc_array(c, b1f, 1, 0, d, mb_bcs);
+    bc_array(c, b2f, 1, 1, d, mb_bcs);
+    bc_array(c, b3f, 1, 2, d, mb_bcs);
+  }
+  return 0;
+}
+
+/* physical BCs used by oracle_stage / oracle_run; NULL = strictly periodic mesh */
+static const int *g_mesh_bcs = NULL, *g_mb_bcs = NULL;
+void oracle_set_bcs(const int *mesh_bcs, const int *mb_bcs) { g_mesh_bcs = mesh_bcs; g_mb_bcs = mb_bcs; }
+
+/* ------------------------------------------------------------------------------------ */
 /* One RK stage = the "stagen" task chain of mhd_tasks.cpp:48-75 on a uniform mesh
  * (tasks 1,2,5,10/11,14,15/16,17,21/22,27).  SendE/RecvE is a bitwise identity only when the
  * faces shared by neighbouring blocks START bit-identical (true for the blast ICs, SURVEY.md
@@ -1098,6 +1175,7 @@ void oracle_stage(const ocfg *c, ostate *s, const double *mb_size, const int *ng
   oracle_emf_exchange(c, e1, e2, e3, nghbr_gid);
   oracle_ct(c, s->b0x1f, s->b0x2f, s->b0x3f, s->b1x1f, s->b1x2f, s->b1x3f, e1, e2, e3, mb_size, gam0, gam1, beta_dt);
   oracle_halo_fc(c, s->b0x1f, s->b0x2f, s->b0x3f, nghbr_gid);
+  if (g_mesh_bcs) oracle_apply_bcs(c, g_mesh_bcs, g_mb_bcs, s->u0, s->b0x1f, s->b0x2f, s->b0x3f);
   int nf[3];
   oracle_cons2prim(c, s->u0, s->b0x1f, s->b0x2f, s->b0x3f, s->w0, s->bcc0, 0, D.n1 - 1, 0, D.n2 - 1, 0, D.n3 - 1, nf);
   free(flx1); free(flx2); free(flx3);

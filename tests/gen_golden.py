@@ -26,12 +26,17 @@ def active(r):
                 b3f=r.b3f[:, ng:-ng, s, s])
 
 
-def blast(n, cycles, recon="ppm4", rsolver="hlld", integrator="rk3", name=None):
+BC_NAMES = ("ix1_bc", "ox1_bc", "ix2_bc", "ox2_bc", "ix3_bc", "ox3_bc")
+
+
+def blast(n, cycles, recon="ppm4", rsolver="hlld", integrator="rk3", name=None, bcs=None, extra=()):
     tmp = tempfile.mkdtemp(prefix="akgold_")
     try:
         ov = [f"mesh/nx1={n}", f"mesh/nx2={n}", f"mesh/nx3={n}", f"meshblock/nx1={n}", f"meshblock/nx2={n}",
               f"meshblock/nx3={n}", f"time/nlim={max(cycles)}", f"mhd/reconstruct={recon}", f"mhd/rsolver={rsolver}",
-              f"time/integrator={integrator}"]
+              f"time/integrator={integrator}", *extra]
+        if bcs:
+            ov += [f"mesh/{k}={v}" for k, v in zip(BC_NAMES, bcs)]
         O.run_reference("athena_blast", os.path.join(HERE, "decks", "blast3d.athinput"), tmp, ov)
         out = {}
         for c in [0] + list(cycles):
@@ -41,6 +46,8 @@ def blast(n, cycles, recon="ppm4", rsolver="hlld", integrator="rk3", name=None):
                 out[f"{k}_c{c}"] = v
             out[f"time_c{c}"] = r.time
             out[f"dt_c{c}"] = r.dt
+            if bcs and c == max(cycles):   # ghost-inclusive final state: the BC fill itself is checked
+                out.update({f"u0g_c{c}": r.u0, f"b1fg_c{c}": r.b1f, f"b2fg_c{c}": r.b2f, f"b3fg_c{c}": r.b3f})
         out["meta"] = np.array([n, 4, max(cycles)])
         np.savez_compressed(os.path.join(HERE, "golden", name or f"blast{n}_{recon}_{rsolver}_{integrator}.npz"), **out)
     finally:
@@ -53,4 +60,7 @@ if __name__ == "__main__":
     blast(16, (2,), recon="wenoz", rsolver="llf", integrator="rk3")
     blast(16, (2,), recon="ppmx", rsolver="hlld", integrator="rk1")
     blast(16, (3,), recon="teno", rsolver="hlle", integrator="rk2")
+    # physical BCs (task 26): a blast wide enough to cross every mesh edge
+    blast(16, (3,), name="blast16_bcs_mixed.npz", bcs=("reflect", "outflow", "diode", "reflect", "outflow", "diode"),
+          extra=("problem/inner_radius=0.42", "problem/outer_radius=0.55"))
     print("golden fixtures written")

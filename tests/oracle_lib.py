@@ -128,7 +128,7 @@ def uniform_mesh(nmesh, nblock, xmin=(-0.5, -0.5, -0.5), xmax=(0.5, 0.5, 0.5), p
                     ok = True
                     for d in range(3):
                         if q[d] < 0 or q[d] >= nmbr[d]:
-                            if periodic:
+                            if (periodic[d] if isinstance(periodic, (tuple, list)) else periodic):
                                 q[d] %= nmbr[d]
                             else:
                                 ok = False
@@ -145,6 +145,22 @@ def uniform_mesh(nmesh, nblock, xmin=(-0.5, -0.5, -0.5), xmax=(0.5, 0.5, 0.5), p
             mb_size[g, d], mb_size[g, 3 + d] = bmin, bmax
             mb_size[g, 6 + d] = (bmax - bmin) / np.float64(nblock[d])
     return np.array(llocs, np.int32), nghbr, mb_size, root_level
+
+
+BC = {"block": 0, "reflect": 1, "inflow": 2, "outflow": 3, "diode": 4, "user": 5, "periodic": 6,
+      "shear_periodic": 7, "vacuum": 8}          # BoundaryFlag, bvals.hpp:19
+
+
+def block_bcs(lloc, nmesh, nblock, mesh_bcs):
+    """mb_bcs[nmb][6] (meshblock.cpp:25-131): the mesh flag on faces lying on the mesh edge,
+    BoundaryFlag::block elsewhere.  mesh_bcs = 6 flags ix1,ox1,ix2,ox2,ix3,ox3."""
+    nmbr = [nmesh[d] // nblock[d] for d in range(3)]
+    out = np.zeros((len(lloc), 6), np.int32)
+    for g, l in enumerate(lloc):
+        for d in range(3):
+            out[g, 2 * d] = mesh_bcs[2 * d] if l[d] == 0 else BC["block"]
+            out[g, 2 * d + 1] = mesh_bcs[2 * d + 1] if l[d] == nmbr[d] - 1 else BC["block"]
+    return out
 
 
 def _left_edge(ith, n, xmin, xmax):

@@ -71,13 +71,14 @@ def test_neighbor_index_table(engine_lib):
 def test_host_mesh_matches_definition(nmesh, nblock, periodic):
     """Z-order gids, block extents and the neighbour table against the independent Python
     restatement in tests/oracle_lib.py (incomplete root octs, non-periodic edges included)."""
-    bcs = (0,) * 6 if periodic else (1,) * 6
+    bcs = ("periodic",) * 6 if periodic else ("outflow",) * 6
     M = Mesh(nmesh, nblock, bcs=bcs, nranks=1)
     lloc, ngh, mbs, rl = O.uniform_mesh(nmesh, nblock, periodic=periodic)
     assert M.root_level == rl and M.nmb_total == len(lloc)
     assert (M.lloc[:, :3] == lloc).all() and (M.lloc[:, 3] == rl).all()
     mb_size, mb_bcs, nghbr = M.rank_tables(0)
     assert np.abs(mb_size - mbs).max() == 0.0
+    assert np.array_equal(mb_bcs, O.block_bcs(lloc, nmesh, nblock, [O.BC[b] for b in bcs]))   # meshblock.cpp:25-131
     assert (nghbr[:, :, 0] == ngh).all()
     has = ngh >= 0
     assert (nghbr[:, :, 1][has] == rl).all() and (nghbr[:, :, 2][has] == 0).all()
