@@ -26,42 +26,70 @@
 #ifndef AKB_MARCH_MINB
 #define AKB_MARCH_MINB 4
 #endif
+#ifndef AKB_MARCH_CARRY
+#define AKB_MARCH_CARRY 0   // PPM4 x2/x3 sweeps: carry the clamped interface value along the march.
+                            // Measured SLOWER (1.12 vs 1.05 ms): -10% FP64 instructions but +14 live registers
+                            // under the 128-register budget turn into local-memory spills inside the loop.
+#endif
 
 namespace akb {
 
 __device__ __forceinline__ void prefetch_l1(const double *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------------------------------
-// x1 sweep.  Flattened cell space (m, k in [ks-1,ke+1], j in [js-1,je+1], c in [0,nx1+2));
-// warp w owns cells 31*w .. 31*w+31 (one-cell overlap), i.e. 31 faces.
+// x1 sweep.  One grid row (blockIdx.y) per (m, k in [ks-1,ke+1]) plane; inside the plane the
+// cells (j in [js-1,je+1], c in [0,nx1+2)) are flattened and warp w owns cells
+// STEP*w .. STEP*w+31.  Index decode is one multiply-high by a host-computed reciprocal of
+// nx1+2 (exact for the extents checked by the launcher) instead of three 64-bit divisions.
+//
+// PPM4: each lane evaluates only the clamped interface value at ITS lower face and takes the
+// one at its upper face from lane+1 (bit-identical, see ppm4_iface), so the interface
+// arithmetic is done once per face instead of twice; lanes 0..30 then hold (up, lo), lane l
+// gets the left state from lane l-1 and solves the face between them: STEP = 30 faces per warp.
+// Each row carries one helper cell (c = nx1+2, i = ie+2) whose only job is the interface at
+// the upper face of the row's last real cell.  Other methods reconstruct per cell from L1:
+// STEP = 31, no helper cell.
+template <int RECON>
+struct X1Step { static constexpr int value = (RECON == RECON_PPM4) ? 30 : 31; };
+
 template <int RECON, int RS>
 __global__ void __launch_bounds__(128, AKB_X1_MINB)
 flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
                const double *__restrict__ bx1f, double *__restrict__ flx, double *__restrict__ e3x1,
-               double *__restrict__ e2x1) {
-  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+               double *__restrict__ e2x1, unsigned rcp_nc) {
+  constexpr int STEP = X1Step<RECON>::value;
   const int lane = threadIdx.x & 31;
-  const long cell = (gt >> 5) * 31 + lane;
-  const int nc = g.nx1 + 2, nj = g.nx2 + 2, nk = g.nx3 + 2;
-  const long total = (long)g.nmb * nk * nj * nc;
-  const bool valid = cell < total;
-  int c = 0, j = 0, k = 0, m = 0;
-  if (valid) {
-    long t = cell;
-    c = (int)(t % nc); t /= nc;
-    j = (int)(t % nj) + g.js - 1; t /= nj;
-    k = (int)(t % nk) + g.ks - 1;
-    m = (int)(t / nk);
-  }
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nc = g.nx1 + 2 + (RECON == RECON_PPM4 ? 1 : 0), nj = g.nx2 + 2, nk = g.nx3 + 2;
+  const unsigned cell = warp * STEP + lane;            // cell index inside the plane
+  const bool valid = cell < (unsigned)(nj * nc);
+  const int m = blockIdx.y / nk;
+  const int k = g.ks - 1 + (blockIdx.y - m * nk);
+  const unsigned jr = valid ? __umulhi(cell, rcp_nc) : 0u;   // cell / nc
+  const int c = valid ? (int)(cell - jr * nc) : 1;
+  const int j = g.js - 1 + (int)jr;
   const int i = g.is - 1 + c;
   const long cc = g.cc;
   const long off = ((long)k * g.n2 + j) * g.n1 + i;
   State7 up, lo;
-  if (valid) {
-    recon_cell<RECON, 0>(w0 + (long)m * 5 * cc + off, bcc + (long)m * 3 * cc + off, cc, 1, eos, up, lo);
+  if constexpr (RECON == RECON_PPM4) {
+    const double *w = w0 + (long)m * 5 * cc + off, *b = bcc + (long)m * 3 * cc + off;
+    const double *vp[7] = {w + IDN * cc, w + IVX * cc, w + IVY * cc, w + IVZ * cc, w + IEN * cc, b + 1 * cc, b + 2 * cc};
+    double q[7], fl[7];
+#pragma unroll
+    for (int v = 0; v < 7; ++v) {
+      q[v] = __ldg(vp[v]);
+      fl[v] = ppm4_iface(__ldg(vp[v] - 2), __ldg(vp[v] - 1), q[v], __ldg(vp[v] + 1));
+    }
+    double *upv[7] = {&up.d, &up.vx, &up.vy, &up.vz, &up.e, &up.by, &up.bz};
+    double *lov[7] = {&lo.d, &lo.vx, &lo.vy, &lo.vz, &lo.e, &lo.by, &lo.bz};
+#pragma unroll
+    for (int v = 0; v < 7; ++v) {
+      const double fh = __shfl_down_sync(0xffffffffu, fl[v], 1);   // interface at this cell's upper face
+      ppm4_mono(q[v], fl[v], fh, *upv[v], *lov[v]);
+    }
   } else {
-    up.d = up.vx = up.vy = up.vz = up.e = up.by = up.bz = 0.0;
-    lo = up;
+    recon_cell<RECON, 0>(w0 + (long)m * 5 * cc + off, bcc + (long)m * 3 * cc + off, cc, 1, eos, up, lo);
   }
   State7 L;
   L.d = __shfl_up_sync(0xffffffffu, up.d, 1);
@@ -71,7 +99,7 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
   L.e = __shfl_up_sync(0xffffffffu, up.e, 1);
   L.by = __shfl_up_sync(0xffffffffu, up.by, 1);
   L.bz = __shfl_up_sync(0xffffffffu, up.bz, 1);
-  if (!valid || lane == 0 || c == 0) return;
+  if (!valid || lane == 0 || lane > STEP || c == 0 || c > g.nx1 + 1) return;
   const double bxi = __ldg(bx1f + (((long)m * g.n3 + k) * g.n2 + j) * (g.n1 + 1) + i);
   Flux7 f;
   riemann<RS>(L, lo, bxi, eos, f);
@@ -146,6 +174,40 @@ __device__ __forceinline__ void recon_ring_cell(const double *__restrict__ ring,
   }
 }
 
+// PPM4 with the interface value carried along the march: the clamped interface at the upper
+// face of cell c (rows c-1..c+2) is computed once and reused as the lower interface of cell
+// c+1 on the next step (bit-identical, see ppm4_iface).  fl[] holds the lower interfaces of
+// the current cell on entry and its upper ones on exit.  b0 = slot of row c-2.
+__device__ __forceinline__ void ppm4_ring_iface(const double *__restrict__ ring, int b0, double fl[7]) {
+  // interface between rows c-1 and c: slots of rows c-2, c-1, c, c+1
+  constexpr int VS = MARCH_SLOTS * MARCH_THREADS;
+  int b1 = b0 + 1; if (b1 >= MARCH_SLOTS) b1 -= MARCH_SLOTS;
+  int b2 = b1 + 1; if (b2 >= MARCH_SLOTS) b2 -= MARCH_SLOTS;
+  int b3 = b2 + 1; if (b3 >= MARCH_SLOTS) b3 -= MARCH_SLOTS;
+#pragma unroll
+  for (int v = 0; v < 7; ++v) {
+    const double *rv = ring + v * VS;
+    fl[v] = ppm4_iface(rv[b0 * MARCH_THREADS], rv[b1 * MARCH_THREADS], rv[b2 * MARCH_THREADS], rv[b3 * MARCH_THREADS]);
+  }
+}
+__device__ __forceinline__ void ppm4_ring_cell(const double *__restrict__ ring, int b0, double fl[7], State7 &up, State7 &lo) {
+  constexpr int VS = MARCH_SLOTS * MARCH_THREADS;
+  int b1 = b0 + 1; if (b1 >= MARCH_SLOTS) b1 -= MARCH_SLOTS;
+  int b2 = b1 + 1; if (b2 >= MARCH_SLOTS) b2 -= MARCH_SLOTS;
+  int b3 = b2 + 1; if (b3 >= MARCH_SLOTS) b3 -= MARCH_SLOTS;
+  int b4 = b3 + 1; if (b4 >= MARCH_SLOTS) b4 -= MARCH_SLOTS;
+  double *upv[7] = {&up.d, &up.vx, &up.vy, &up.vz, &up.e, &up.by, &up.bz};
+  double *lov[7] = {&lo.d, &lo.vx, &lo.vy, &lo.vz, &lo.e, &lo.by, &lo.bz};
+#pragma unroll
+  for (int v = 0; v < 7; ++v) {
+    const double *rv = ring + v * VS;
+    const double q = rv[b2 * MARCH_THREADS];
+    const double fh = ppm4_iface(rv[b1 * MARCH_THREADS], q, rv[b3 * MARCH_THREADS], rv[b4 * MARCH_THREADS]);
+    ppm4_mono(q, fl[v], fh, *upv[v], *lov[v]);
+    fl[v] = fh;
+  }
+}
+
 template <int RECON, int RS, int DIR>
 __global__ void __launch_bounds__(MARCH_THREADS, AKB_MARCH_MINB)
 flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
@@ -207,7 +269,13 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
     }
     cp_async_commit();
     cp_async_wait<0>();
-    recon_ring_cell<RECON>(ring, 0, eos, L, lo_unused);
+    double fl[7];
+    if constexpr (RECON == RECON_PPM4 && AKB_MARCH_CARRY) {
+      ppm4_ring_iface(ring, 0, fl);
+      ppm4_ring_cell(ring, 0, fl, L, lo_unused);
+    } else {
+      recon_ring_cell<RECON>(ring, 0, eos, L, lo_unused);
+    }
     int b0 = 1;                       // slot of row c-2 for the next cell (c = f_lo)
     for (int f = f_lo; f <= f_hi; ++f) {
       // cell c = f: rows c-2..c+2 are present; request row c+2+PF (needed PF steps from now)
@@ -221,7 +289,8 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       cp_async_commit();
       cp_async_wait<MARCH_PF>();
       State7 up, lo;
-      recon_ring_cell<RECON>(ring, b0, eos, up, lo);
+      if constexpr (RECON == RECON_PPM4 && AKB_MARCH_CARRY) ppm4_ring_cell(ring, b0, fl, up, lo);
+      else recon_ring_cell<RECON>(ring, b0, eos, up, lo);
       Flux7 fx;
       riemann<RS>(L, lo, __ldg(bn), eos, fx);   // (fetching bn a step ahead costs registers: measured slower)
       fp[IDN * fsz] = fx.d;
@@ -571,9 +640,14 @@ static inline unsigned nblocks(long n, int bs) { return (unsigned)((n + bs - 1) 
 template <int RECON, int RS>
 static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st) {
   {  // x1
-    const long cells = (long)g.nmb * (g.nx3 + 2) * (g.nx2 + 2) * (g.nx1 + 2);
-    const long warps = (cells + 30) / 31;
-    flux_x1_kernel<RECON, RS><<<nblocks(warps * 32, 128), 128, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x1f, a.flx1, a.e3x1, a.e2x1);
+    constexpr int STEP = X1Step<RECON>::value;
+    const unsigned nc = g.nx1 + 2 + (RECON == RECON_PPM4 ? 1 : 0), plane = (unsigned)(g.nx2 + 2) * nc;
+    // rcp = ceil(2^32 / nc): __umulhi(t, rcp) == t / nc for every t < 2^32 / nc
+    const unsigned rcp = (unsigned)((0x100000000ull + nc - 1) / nc);
+    if ((unsigned long long)plane * nc >= 0x100000000ull || (long)g.nmb * (g.nx3 + 2) > 65535) return cudaErrorInvalidConfiguration;
+    const unsigned warps = (plane + STEP - 1) / STEP;
+    const dim3 gr(nblocks((long)warps * 32, 128), (unsigned)(g.nmb * (g.nx3 + 2)));
+    flux_x1_kernel<RECON, RS><<<gr, 128, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x1f, a.flx1, a.e3x1, a.e2x1, rcp);
   }
   {  // x2: (ey,ez) = (e1x2,e3x2)
     const int nf = g.nx2 + 1;
