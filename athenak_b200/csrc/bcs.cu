@@ -123,8 +123,8 @@ BcArray make_array(const ak_mhd_cfg &c, double *p, int nvar, int kind) {
   BcArray a;
   a.p = p; a.nvar = nvar; a.kind = kind;
   a.ext[0] = c.nx1 + 2 * c.ng + (kind == 0);
-  a.ext[1] = c.nx2 + 2 * c.ng + (kind == 1);
-  a.ext[2] = c.nx3 + 2 * c.ng + (kind == 2);
+  a.ext[1] = (c.nx2 > 1 ? c.nx2 + 2 * c.ng : 1) + (kind == 1);   // inactive dimensions: extent 1, no ghosts
+  a.ext[2] = (c.nx3 > 1 ? c.nx3 + 2 * c.ng : 1) + (kind == 2);
   return a;
 }
 
@@ -132,6 +132,7 @@ BcArray make_array(const ak_mhd_cfg &c, double *p, int nvar, int kind) {
 // bfield_bcs.cpp:78,169,262)
 bool pass_active(const BcPlan *P, int dir, bool hydro) {
   const int f = P->mesh_bcs[2 * dir];
+  if ((dir == 1 && P->cfg.nx2 <= 1) || (dir == 2 && P->cfg.nx3 <= 1)) return false;   // hydro_bcs.cpp:166,251 (multi_d / three_d)
   if (f == AK_BC_PERIODIC) return false;
   if (hydro && dir == 0 && f == AK_BC_SHEAR_PERIODIC) return false;
   return true;

@@ -16,6 +16,7 @@ struct Handle {
   ak_mhd_cfg cfg;
   akb::Geom g;
   akb::EosParams eos;
+  bool hydro = false;                       // hydro twin (ak_hydro_*): no magnetic arrays, 1-D/2-D/3-D
   int *d_counters = nullptr;                // 3 ints
   unsigned long long *d_dtmin = nullptr;    // 3 ordered-bit doubles
   std::string err;
@@ -62,12 +63,19 @@ akb::Arrays to_arrays(const ak_mhd_arrays *a) {
   return r;
 }
 
-int check_cfg(const ak_mhd_cfg *c, std::string &why) {
+int check_cfg(const ak_mhd_cfg *c, bool hydro, std::string &why) {
   if (!c) { why = "null cfg"; return 1; }
   if (c->nmb < 1) { why = "nmb < 1"; return 1; }
-  if (c->nx1 < 2 || c->nx2 < 2 || c->nx3 < 2) { why = "only 3-D MeshBlocks (nx1,nx2,nx3 > 1) are supported"; return 1; }
+  if (hydro) {
+    // mesh.cpp:70-79: 1-D (nx2 = nx3 = 1), 2-D (nx3 = 1) or 3-D
+    if (c->nx1 < 2 || c->nx2 < 1 || c->nx3 < 1 || (c->nx2 == 1 && c->nx3 > 1)) { why = "MeshBlock must be 1-D (nx2=nx3=1), 2-D (nx3=1) or 3-D"; return 1; }
+    if (c->rsolver == AK_RSOLVER_HYD_ADVECT) { why = "rsolver advect needs time/evolution=kinematic (hydro.cpp:255-265), which is not on this path"; return 1; }
+    if (c->rsolver < AK_RSOLVER_HYD_LLF || c->rsolver > AK_RSOLVER_HYD_ROE) { why = "unknown hydro Riemann solver"; return 1; }
+  } else {
+    if (c->nx1 < 2 || c->nx2 < 2 || c->nx3 < 2) { why = "MHD: only 3-D MeshBlocks (nx1,nx2,nx3 > 1) are supported"; return 1; }
+    if (c->rsolver < AK_RSOLVER_LLF || c->rsolver > AK_RSOLVER_HLLD) { why = "unknown Riemann solver"; return 1; }
+  }
   if (c->recon < AK_RECON_DC || c->recon > AK_RECON_TENO) { why = "unknown reconstruction method"; return 1; }
-  if (c->rsolver < AK_RSOLVER_LLF || c->rsolver > AK_RSOLVER_HLLD) { why = "unknown Riemann solver"; return 1; }
   // reference src/mhd/mhd.cpp:217-228: 5-point stencils need nghost >= 3, PLM/DC need 2
   const int need = (c->recon >= AK_RECON_PPM4) ? 3 : 2;
   if (c->ng < need) { why = "nghost too small for the reconstruction stencil"; return 1; }
@@ -84,23 +92,28 @@ const char *ak_last_error(void *handle) {
   return h ? h->err.c_str() : g_err.c_str();
 }
 
-int ak_mhd_create(const ak_mhd_cfg *cfg, void **handle) {
+static int create_impl(const ak_mhd_cfg *cfg, bool hydro, void **handle) {
   std::string why;
   if (!handle) return fail(nullptr, "ak_mhd_create: null handle pointer");
   *handle = nullptr;
-  if (check_cfg(cfg, why)) return fail(nullptr, "ak_mhd_create: " + why);
+  if (check_cfg(cfg, hydro, why)) return fail(nullptr, "ak_mhd_create: " + why);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
     return fail(nullptr, std::string("ak_mhd_create: no CUDA device (this engine has no CPU path): ") + cudaGetErrorString(e));
   Handle *h = new Handle();
   h->cfg = *cfg;
+  h->hydro = hydro;
   akb::Geom &g = h->g;
   g.nmb = cfg->nmb; g.ng = cfg->ng; g.nx1 = cfg->nx1; g.nx2 = cfg->nx2; g.nx3 = cfg->nx3;
-  g.n1 = cfg->nx1 + 2 * cfg->ng; g.n2 = cfg->nx2 + 2 * cfg->ng; g.n3 = cfg->nx3 + 2 * cfg->ng;
+  g.multi_d = cfg->nx2 > 1; g.three_d = cfg->nx3 > 1;          // mesh.cpp:70-79
+  g.n1 = cfg->nx1 + 2 * cfg->ng;
+  g.n2 = g.multi_d ? cfg->nx2 + 2 * cfg->ng : 1;               // mhd.cpp:149-152 / hydro.cpp
+  g.n3 = g.three_d ? cfg->nx3 + 2 * cfg->ng : 1;
   g.is = cfg->ng; g.ie = g.is + cfg->nx1 - 1;   // reference src/mesh/mesh.cpp:285-333
-  g.js = cfg->ng; g.je = g.js + cfg->nx2 - 1;
-  g.ks = cfg->ng; g.ke = g.ks + cfg->nx3 - 1;
+  g.js = g.multi_d ? cfg->ng : 0; g.je = g.js + cfg->nx2 - 1;
+  g.ks = g.three_d ? cfg->ng : 0; g.ke = g.ks + cfg->nx3 - 1;
+  g.ext1 = hydro ? 0 : 1; g.ext2 = (!hydro && g.multi_d) ? 1 : 0; g.ext3 = (!hydro && g.three_d) ? 1 : 0;
   g.cc = (long)g.n3 * g.n2 * g.n1;
   g.f1 = (long)g.n3 * g.n2 * (g.n1 + 1); g.f2 = (long)g.n3 * (g.n2 + 1) * g.n1; g.f3 = (long)(g.n3 + 1) * g.n2 * g.n1;
   g.e1 = (long)(g.n3 + 1) * (g.n2 + 1) * g.n1; g.e2 = (long)(g.n3 + 1) * g.n2 * (g.n1 + 1); g.e3 = (long)g.n3 * (g.n2 + 1) * (g.n1 + 1);
@@ -120,6 +133,10 @@ int ak_mhd_create(const ak_mhd_cfg *cfg, void **handle) {
   *handle = h;
   return 0;
 }
+
+int ak_mhd_create(const ak_mhd_cfg *cfg, void **handle) { return create_impl(cfg, false, handle); }
+int ak_hydro_create(const ak_mhd_cfg *cfg, void **handle) { return create_impl(cfg, true, handle); }
+int ak_hydro_destroy(void *handle) { return ak_mhd_destroy(handle); }
 
 int ak_mhd_destroy(void *handle) {
   Handle *h = static_cast<Handle *>(handle);
@@ -182,8 +199,9 @@ static int c2p_impl(Handle *h, const akb::Arrays &A, int il, int iu, int jl, int
   if (dt3) {
     if ((e = dt_slots_init(h, st)) != cudaSuccess) return cuda_fail(h, name, e);
   }
-  if ((e = akb::launch_cons2prim(g, h->eos, A, il, iu, jl, ju, kl, ku, h->d_counters, dt3 != nullptr, h->d_dtmin, st)) != cudaSuccess)
-    return cuda_fail(h, name, e);
+  e = h->hydro ? akb::launch_hydro_cons2prim(g, h->eos, A, il, iu, jl, ju, kl, ku, h->d_counters, dt3 != nullptr, h->d_dtmin, st)
+               : akb::launch_cons2prim(g, h->eos, A, il, iu, jl, ju, kl, ku, h->d_counters, dt3 != nullptr, h->d_dtmin, st);
+  if (e != cudaSuccess) return cuda_fail(h, name, e);
   if (nfloor) {
     if ((e = cudaMemcpyAsync(nfloor, h->d_counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, name, e);
     if ((e = cudaMemsetAsync(h->d_counters, 0, 3 * sizeof(int), st)) != cudaSuccess) return cuda_fail(h, name, e);
@@ -248,13 +266,59 @@ int ak_mhd_stage_fused(void *handle, const ak_mhd_arrays *a, int stage, double g
 }
 
 // ---------------------------------------------------------------------------------------
+// hydro twin (reference src/hydro/hydro_tasks.cpp:47-79)
+#define AK_HYD_PROLOGUE(name)                                                   \
+  AK_PROLOGUE(name)                                                             \
+  if (!h->hydro) return fail(h, name ": handle was not made by ak_hydro_create");
+
+int ak_hydro_copy_cons(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
+  AK_HYD_PROLOGUE("ak_hydro_copy_cons")
+  if ((e = akb::launch_copy(A.u0, A.u1, 5L * h->g.nmb * h->g.cc, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_copy_cons", e);
+  return 0;
+}
+int ak_hydro_fluxes(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
+  AK_HYD_PROLOGUE("ak_hydro_fluxes")
+  if ((e = akb::launch_hydro_fluxes(h->cfg.recon, h->cfg.rsolver, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_fluxes", e);
+  return 0;
+}
+int ak_hydro_rk_update(void *handle, const ak_mhd_arrays *a, double gam0, double gam1, double beta_dt, ak_stream_t s) {
+  AK_HYD_PROLOGUE("ak_hydro_rk_update")
+  if ((e = akb::launch_update_ct(h->g, A, true, false, false, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_rk_update", e);
+  return 0;
+}
+int ak_hydro_stage_fused(void *handle, const ak_mhd_arrays *a, int stage, double gam0, double gam1, double beta_dt, ak_stream_t s) {
+  AK_HYD_PROLOGUE("ak_hydro_stage_fused")
+  if ((e = akb::launch_hydro_fluxes(h->cfg.recon, h->cfg.rsolver, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_stage_fused", e);
+  if ((e = akb::launch_update_ct(h->g, A, true, false, stage == 1, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_stage_fused", e);
+  return 0;
+}
+int ak_hydro_cons2prim(void *handle, const ak_mhd_arrays *a, int il, int iu, int jl, int ju, int kl, int ku,
+                       int *nfloor, ak_stream_t s) {
+  AK_HYD_PROLOGUE("ak_hydro_cons2prim")
+  return c2p_impl(h, A, il, iu, jl, ju, kl, ku, nfloor, nullptr, st, "ak_hydro_cons2prim");
+}
+int ak_hydro_cons2prim_newdt(void *handle, const ak_mhd_arrays *a, int *nfloor, double *dt3, ak_stream_t s) {
+  AK_HYD_PROLOGUE("ak_hydro_cons2prim_newdt")
+  if (!dt3) return fail(h, "ak_hydro_cons2prim_newdt: null dt3");
+  return c2p_impl(h, A, 0, h->g.n1 - 1, 0, h->g.n2 - 1, 0, h->g.n3 - 1, nfloor, dt3, st, "ak_hydro_cons2prim_newdt");
+}
+int ak_hydro_new_dt(void *handle, const ak_mhd_arrays *a, double *dt3, ak_stream_t s) {
+  AK_HYD_PROLOGUE("ak_hydro_new_dt")
+  if (!dt3) return fail(h, "ak_hydro_new_dt: null dt3");
+  if ((e = dt_slots_init(h, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_new_dt", e);
+  if ((e = akb::launch_hydro_newdt(h->g, h->eos, A, h->d_dtmin, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_new_dt", e);
+  if ((e = dt_slots_fetch(h, dt3, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_new_dt", e);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // halo
 
 int ak_halo_create(const ak_mhd_cfg *cfg, const int *nghbr, int my_rank, int gids_start, void **plan) {
   std::string why;
   if (!plan) return fail(nullptr, "ak_halo_create: null plan pointer");
   *plan = nullptr;
-  if (check_cfg(cfg, why)) return fail(nullptr, "ak_halo_create: " + why);
+  if (check_cfg(cfg, cfg && cfg->rsolver >= AK_RSOLVER_HYD_ADVECT, why)) return fail(nullptr, "ak_halo_create: " + why);
   if (!nghbr) return fail(nullptr, "ak_halo_create: null neighbour table");
   akb::HaloPlan *P = akb::halo_build(*cfg, nghbr, my_rank, gids_start, why);
   if (!P) return fail(nullptr, "ak_halo_create: " + why);

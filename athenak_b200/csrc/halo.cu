@@ -39,8 +39,9 @@ struct Box { int lo[3], hi[3]; long count() const { return (long)(hi[0]-lo[0]+1)
 // comp = -1: cell-centred; 0,1,2: x1f,x2f,x3f.  d: 0=i,1=j,2=k.  Same-level boxes.
 static Box halo_box(const ak_mhd_cfg &c, int comp, const int o[3], bool send) {
   const int ng = c.ng, ng1 = ng - 1;
-  const int s[3] = {ng, ng, ng};
-  const int e[3] = {ng + c.nx1 - 1, ng + c.nx2 - 1, ng + c.nx3 - 1};
+  // inactive dimensions (nx = 1) have no ghost cells: s = e = 0 (mesh.cpp:285-333)
+  const int s[3] = {ng, c.nx2 > 1 ? ng : 0, c.nx3 > 1 ? ng : 0};
+  const int e[3] = {s[0] + c.nx1 - 1, s[1] + c.nx2 - 1, s[2] + c.nx3 - 1};
   Box b;
   for (int d = 0; d < 3; ++d) {
     const int f = (comp == d) ? 1 : 0;  // this component is staggered along d
@@ -135,8 +136,11 @@ static const int kOff[26][3] = {
     {-1,-1,-1},{1,-1,-1},{-1,1,-1},{1,1,-1},{-1,-1,1},{1,-1,1},{-1,1,1},{1,1,1}};
 
 HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int gids_start, std::string &err) {
-  if (cfg.nx2 <= 1 || cfg.nx3 <= 1) { err = "halo: only 3-D meshes are supported"; return nullptr; }
-  if (cfg.nx1 < cfg.ng || cfg.nx2 < cfg.ng || cfg.nx3 < cfg.ng) { err = "halo: block smaller than nghost"; return nullptr; }
+  // hydro twin: cell-centred data only, 1-D/2-D/3-D; MHD (face fields, EMFs): 3-D
+  const bool cc_only = cfg.rsolver >= AK_RSOLVER_HYD_ADVECT;
+  const bool act[3] = {true, cfg.nx2 > 1, cfg.nx3 > 1};
+  if (!cc_only && (!act[1] || !act[2])) { err = "halo: MHD supports only 3-D meshes"; return nullptr; }
+  if (cfg.nx1 < cfg.ng || (act[1] && cfg.nx2 < cfg.ng) || (act[2] && cfg.nx3 < cfg.ng)) { err = "halo: block smaller than nghost"; return nullptr; }
   auto *P = new HaloPlan();
   P->cfg = cfg;
   const int nx[3] = {cfg.nx1, cfg.nx2, cfg.nx3};
@@ -145,6 +149,7 @@ HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int g
   for (int m = 0; m < cfg.nmb; ++m) {
     for (int q = 0; q < 26; ++q) {
       const int *o = kOff[q];
+      if ((o[1] && !act[1]) || (o[2] && !act[2])) continue;   // meshblock.cpp:170-425: neighbours only in active dims
       const int slot = neighbor_index(o[0], o[1], o[2], 0, 0);
       const int *nb = nghbr + ((long)m * 56 + slot) * 4;
       const int gid = nb[0], rank = nb[2];
@@ -154,7 +159,7 @@ HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int g
         // ghost box of m on side o is filled from block gid's active zones
         const int src_m = gid - gids_start;
         if (src_m < 0 || src_m >= cfg.nmb) { err = "halo: same-rank neighbour gid outside this pack"; delete P; return nullptr; }
-        for (int comp = -1; comp < 3; ++comp) {
+        for (int comp = -1; comp < (cc_only ? 0 : 3); ++comp) {
           Box b = halo_box(cfg, comp, o, false);
           HaloDesc d{};
           d.m = m; d.src_m = src_m; d.comp = comp; d.boff = 0;
@@ -187,6 +192,7 @@ HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int g
       for (int a = 0; a < 3; ++a) { d.lo[a] = b.lo[a]; d.hi[a] = b.hi[a]; }
       peer.pack_cc.push_back(d);
       cc_off += b.count();   // per variable; scaled by nvar at launch
+      if (cc_only) continue;
       long ndat = 0;
       for (int comp = 0; comp < 3; ++comp) ndat = std::max(ndat, halo_box(cfg, comp, e.o, true).count());
       for (int comp = 0; comp < 3; ++comp) {
@@ -207,6 +213,7 @@ HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int g
       for (int a = 0; a < 3; ++a) { d.lo[a] = b.lo[a]; d.hi[a] = b.hi[a]; }
       peer.unpack_cc.push_back(d);
       cc_off += b.count();
+      if (cc_only) continue;
       long ndat = 0;
       for (int comp = 0; comp < 3; ++comp) ndat = std::max(ndat, halo_box(cfg, comp, so, true).count());
       for (int comp = 0; comp < 3; ++comp) {
@@ -221,7 +228,7 @@ HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int g
     P->peers.push_back(peer);
   }
   // ---- EMF flux correction plan -----------------------------------------------------------
-  {
+  if (!cc_only) {
     // receive segments: (m, slot, v) -> offset in emf_rbuf.  Same-rank sources first, then one
     // contiguous range per peer ordered by (source gid, source slot, v) = the sender's order.
     std::map<long, long> roff;   // key = (m*48 + slot)*3 + v
@@ -411,7 +418,7 @@ cudaError_t halo_launch(const std::vector<HaloDesc> &host, const HaloDesc *dev, 
 }
 
 HaloArrays halo_arrays_cc(const ak_mhd_cfg &c, double *a, int nvar) {
-  const long n1 = c.nx1 + 2 * c.ng, n2 = c.nx2 + 2 * c.ng, n3 = c.nx3 + 2 * c.ng;
+  const long n1 = c.nx1 + 2 * c.ng, n2 = c.nx2 > 1 ? c.nx2 + 2 * c.ng : 1, n3 = c.nx3 > 1 ? c.nx3 + 2 * c.ng : 1;
   HaloArrays A{};
   A.p[0] = a; A.ext1[0] = n1; A.ext2[0] = n2; A.bstride[0] = (long)nvar * n1 * n2 * n3;
   return A;

@@ -145,6 +145,8 @@ int ak_mesh_create(const int *nmesh, const int *nblock, const double *xmin, cons
     // same-level neighbours: meshblock.cpp:170-425 with FindNeighbor's periodic wrap
     for (int oz = -1; oz <= 1; ++oz) for (int oy = -1; oy <= 1; ++oy) for (int ox = -1; ox <= 1; ++ox) {
       if (!ox && !oy && !oz) continue;
+      // meshblock.cpp:170-425: x2 neighbours only if multi_d, x3 neighbours only if three_d
+      if ((oy && M->nmesh[1] <= 1) || (oz && M->nmesh[2] <= 1)) continue;
       int q[3] = {l[0] + ox, l[1] + oy, l[2] + oz};
       bool ok = true;
       for (int d = 0; d < 3; ++d) {

@@ -12,319 +12,10 @@
 //   update_ct      RK update of u0 and CT update of b0 in one pass (+ CopyCons at stage 1).
 //   cons2prim      c2p over a cell box, floors, floor counters; optional fused new-dt reduce.
 #include "mhd_kernels.h"
-#include "mhd_device.cuh"
-
-#ifndef AKB_MARCH_PREFETCH
-#define AKB_MARCH_PREFETCH 0
-#endif
-#ifndef AKB_CORNER_MINB
-#define AKB_CORNER_MINB 2   // 128-register budget: measured 0.56 ms vs 0.96 ms unbounded, 0.84-0.88 ms at 3-4
-#endif
-#ifndef AKB_X1_MINB
-#define AKB_X1_MINB 4
-#endif
-#ifndef AKB_MARCH_MINB
-#define AKB_MARCH_MINB 4
-#endif
-#ifndef AKB_MARCH_CARRY
-#define AKB_MARCH_CARRY 0   // PPM4 x2/x3 sweeps: carry the clamped interface value along the march.
-                            // Measured SLOWER (1.12 vs 1.05 ms): -10% FP64 instructions but +14 live registers
-                            // under the 128-register budget turn into local-memory spills inside the loop.
-#endif
+#include "flux_kernels.cuh"
+#include "reduce.cuh"
 
 namespace akb {
-
-__device__ __forceinline__ void prefetch_l1(const double *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-// ---------------------------------------------------------------------------------------
-// x1 sweep.  One grid row (blockIdx.y) per (m, k in [ks-1,ke+1]) plane; inside the plane the
-// cells (j in [js-1,je+1], c in [0,nx1+2)) are flattened and warp w owns cells
-// STEP*w .. STEP*w+31.  Index decode is one multiply-high by a host-computed reciprocal of
-// nx1+2 (exact for the extents checked by the launcher) instead of three 64-bit divisions.
-//
-// PPM4: each lane evaluates only the clamped interface value at ITS lower face and takes the
-// one at its upper face from lane+1 (bit-identical, see ppm4_iface), so the interface
-// arithmetic is done once per face instead of twice; lanes 0..30 then hold (up, lo), lane l
-// gets the left state from lane l-1 and solves the face between them: STEP = 30 faces per warp.
-// Each row carries one helper cell (c = nx1+2, i = ie+2) whose only job is the interface at
-// the upper face of the row's last real cell.  Other methods reconstruct per cell from L1:
-// STEP = 31, no helper cell.
-template <int RECON>
-struct X1Step { static constexpr int value = (RECON == RECON_PPM4) ? 30 : 31; };
-
-template <int RECON, int RS>
-__global__ void __launch_bounds__(128, AKB_X1_MINB)
-flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
-               const double *__restrict__ bx1f, double *__restrict__ flx, double *__restrict__ e3x1,
-               double *__restrict__ e2x1, unsigned rcp_nc) {
-  constexpr int STEP = X1Step<RECON>::value;
-  const int lane = threadIdx.x & 31;
-  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nc = g.nx1 + 2 + (RECON == RECON_PPM4 ? 1 : 0), nj = g.nx2 + 2, nk = g.nx3 + 2;
-  const unsigned cell = warp * STEP + lane;            // cell index inside the plane
-  const bool valid = cell < (unsigned)(nj * nc);
-  const int m = blockIdx.y / nk;
-  const int k = g.ks - 1 + (blockIdx.y - m * nk);
-  const unsigned jr = valid ? __umulhi(cell, rcp_nc) : 0u;   // cell / nc
-  const int c = valid ? (int)(cell - jr * nc) : 1;
-  const int j = g.js - 1 + (int)jr;
-  const int i = g.is - 1 + c;
-  const long cc = g.cc;
-  const long off = ((long)k * g.n2 + j) * g.n1 + i;
-  State7 up, lo;
-  if constexpr (RECON == RECON_PPM4) {
-    const double *w = w0 + (long)m * 5 * cc + off, *b = bcc + (long)m * 3 * cc + off;
-    const double *vp[7] = {w + IDN * cc, w + IVX * cc, w + IVY * cc, w + IVZ * cc, w + IEN * cc, b + 1 * cc, b + 2 * cc};
-    double q[7], fl[7];
-#pragma unroll
-    for (int v = 0; v < 7; ++v) {
-      q[v] = __ldg(vp[v]);
-      fl[v] = ppm4_iface(__ldg(vp[v] - 2), __ldg(vp[v] - 1), q[v], __ldg(vp[v] + 1));
-    }
-    double *upv[7] = {&up.d, &up.vx, &up.vy, &up.vz, &up.e, &up.by, &up.bz};
-    double *lov[7] = {&lo.d, &lo.vx, &lo.vy, &lo.vz, &lo.e, &lo.by, &lo.bz};
-#pragma unroll
-    for (int v = 0; v < 7; ++v) {
-      const double fh = __shfl_down_sync(0xffffffffu, fl[v], 1);   // interface at this cell's upper face
-      ppm4_mono(q[v], fl[v], fh, *upv[v], *lov[v]);
-    }
-  } else {
-    recon_cell<RECON, 0>(w0 + (long)m * 5 * cc + off, bcc + (long)m * 3 * cc + off, cc, 1, eos, up, lo);
-  }
-  State7 L;
-  L.d = __shfl_up_sync(0xffffffffu, up.d, 1);
-  L.vx = __shfl_up_sync(0xffffffffu, up.vx, 1);
-  L.vy = __shfl_up_sync(0xffffffffu, up.vy, 1);
-  L.vz = __shfl_up_sync(0xffffffffu, up.vz, 1);
-  L.e = __shfl_up_sync(0xffffffffu, up.e, 1);
-  L.by = __shfl_up_sync(0xffffffffu, up.by, 1);
-  L.bz = __shfl_up_sync(0xffffffffu, up.bz, 1);
-  if (!valid || lane == 0 || lane > STEP || c == 0 || c > g.nx1 + 1) return;
-  const double bxi = __ldg(bx1f + (((long)m * g.n3 + k) * g.n2 + j) * (g.n1 + 1) + i);
-  Flux7 f;
-  riemann<RS>(L, lo, bxi, eos, f);
-  const long fs = (long)g.n3 * g.n2 * (g.n1 + 1);
-  double *fp = flx + (long)m * 5 * fs + ((long)k * g.n2 + j) * (g.n1 + 1) + i;
-  fp[IDN * fs] = f.d;
-  fp[IVX * fs] = f.mx;
-  fp[IVY * fs] = f.my;
-  fp[IVZ * fs] = f.mz;
-  fp[IEN * fs] = f.e;
-  e3x1[(long)m * cc + off] = f.ey;  // mhd_fluxes.cpp:146
-  e2x1[(long)m * cc + off] = f.ez;
-}
-
-// x2 / x3 sweeps.  Thread = (m, segment, transverse index, i-cell); marches `len` faces.
-//
-// 5-point reconstructions keep a rolling window of the sweep in SHARED memory: a ring of
-// MARCH_SLOTS rows x 7 variables per thread column (thread-private slots, so no barriers and
-// no bank conflicts: consecutive threads own consecutive doubles).  Each step issues ONE new
-// row per variable with cp.async (global -> shared, no register staging) one step ahead of its
-// use, so the stencil reads are LDS and the HBM/L2 latency of the new row hides behind the
-// Riemann solve of the current face.  3-point methods (PLM/DC) read global memory directly.
-#define TILE_X 32
-#define TILE_Y 4
-#define TILE_Z 2
-#ifndef MARCH_SLOTS
-#define MARCH_SLOTS 6          // 5 stencil rows + prefetch distance (6,7,8 measured: 3.16/3.26/3.27 ms)
-#endif
-#define MARCH_PF (MARCH_SLOTS - 5)
-#define MARCH_THREADS 128
-
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int RECON>
-__device__ __forceinline__ void recon_ring_var(const double *__restrict__ rv, int b0, double &q_up, double &q_lo) {
-  // rv: this thread's ring for one variable (slot stride MARCH_THREADS); b0 = slot of row c-2
-  int b1 = b0 + 1; if (b1 >= MARCH_SLOTS) b1 -= MARCH_SLOTS;
-  int b2 = b1 + 1; if (b2 >= MARCH_SLOTS) b2 -= MARCH_SLOTS;
-  int b3 = b2 + 1; if (b3 >= MARCH_SLOTS) b3 -= MARCH_SLOTS;
-  int b4 = b3 + 1; if (b4 >= MARCH_SLOTS) b4 -= MARCH_SLOTS;
-  const double qm2 = rv[b0 * MARCH_THREADS], qm1 = rv[b1 * MARCH_THREADS], q = rv[b2 * MARCH_THREADS];
-  const double qp1 = rv[b3 * MARCH_THREADS], qp2 = rv[b4 * MARCH_THREADS];
-  if constexpr (RECON == RECON_PPM4) ppm4(qm2, qm1, q, qp1, qp2, q_up, q_lo);
-  else if constexpr (RECON == RECON_PPMX) ppmx(qm2, qm1, q, qp1, qp2, q_up, q_lo);
-  else if constexpr (RECON == RECON_TENO) teno(qm2, qm1, q, qp1, qp2, q_up, q_lo);
-  else wenoz(qm2, qm1, q, qp1, qp2, q_up, q_lo);
-}
-
-template <int RECON>
-__device__ __forceinline__ void recon_ring_cell(const double *__restrict__ ring, int b0, const EosParams &eos,
-                                                State7 &up, State7 &lo) {
-  constexpr int VS = MARCH_SLOTS * MARCH_THREADS;   // ring stride between variables
-  recon_ring_var<RECON>(ring + 0 * VS, b0, up.d, lo.d);
-  recon_ring_var<RECON>(ring + 1 * VS, b0, up.vx, lo.vx);
-  recon_ring_var<RECON>(ring + 2 * VS, b0, up.vy, lo.vy);
-  recon_ring_var<RECON>(ring + 3 * VS, b0, up.vz, lo.vz);
-  recon_ring_var<RECON>(ring + 4 * VS, b0, up.e, lo.e);
-  recon_ring_var<RECON>(ring + 5 * VS, b0, up.by, lo.by);
-  recon_ring_var<RECON>(ring + 6 * VS, b0, up.bz, lo.bz);
-  if constexpr (RECON == RECON_PPMX || RECON == RECON_WENOZ || RECON == RECON_TENO) {   // recon.hpp:78-108
-    const double efloor = eos.pfloor / (eos.gamma - 1.0);
-    up.d = dmax(up.d, eos.dfloor);
-    lo.d = dmax(lo.d, eos.dfloor);
-    up.e = dmax(up.e, efloor);
-    lo.e = dmax(lo.e, efloor);
-  }
-}
-
-// PPM4 with the interface value carried along the march: the clamped interface at the upper
-// face of cell c (rows c-1..c+2) is computed once and reused as the lower interface of cell
-// c+1 on the next step (bit-identical, see ppm4_iface).  fl[] holds the lower interfaces of
-// the current cell on entry and its upper ones on exit.  b0 = slot of row c-2.
-__device__ __forceinline__ void ppm4_ring_iface(const double *__restrict__ ring, int b0, double fl[7]) {
-  // interface between rows c-1 and c: slots of rows c-2, c-1, c, c+1
-  constexpr int VS = MARCH_SLOTS * MARCH_THREADS;
-  int b1 = b0 + 1; if (b1 >= MARCH_SLOTS) b1 -= MARCH_SLOTS;
-  int b2 = b1 + 1; if (b2 >= MARCH_SLOTS) b2 -= MARCH_SLOTS;
-  int b3 = b2 + 1; if (b3 >= MARCH_SLOTS) b3 -= MARCH_SLOTS;
-#pragma unroll
-  for (int v = 0; v < 7; ++v) {
-    const double *rv = ring + v * VS;
-    fl[v] = ppm4_iface(rv[b0 * MARCH_THREADS], rv[b1 * MARCH_THREADS], rv[b2 * MARCH_THREADS], rv[b3 * MARCH_THREADS]);
-  }
-}
-__device__ __forceinline__ void ppm4_ring_cell(const double *__restrict__ ring, int b0, double fl[7], State7 &up, State7 &lo) {
-  constexpr int VS = MARCH_SLOTS * MARCH_THREADS;
-  int b1 = b0 + 1; if (b1 >= MARCH_SLOTS) b1 -= MARCH_SLOTS;
-  int b2 = b1 + 1; if (b2 >= MARCH_SLOTS) b2 -= MARCH_SLOTS;
-  int b3 = b2 + 1; if (b3 >= MARCH_SLOTS) b3 -= MARCH_SLOTS;
-  int b4 = b3 + 1; if (b4 >= MARCH_SLOTS) b4 -= MARCH_SLOTS;
-  double *upv[7] = {&up.d, &up.vx, &up.vy, &up.vz, &up.e, &up.by, &up.bz};
-  double *lov[7] = {&lo.d, &lo.vx, &lo.vy, &lo.vz, &lo.e, &lo.by, &lo.bz};
-#pragma unroll
-  for (int v = 0; v < 7; ++v) {
-    const double *rv = ring + v * VS;
-    const double q = rv[b2 * MARCH_THREADS];
-    const double fh = ppm4_iface(rv[b1 * MARCH_THREADS], q, rv[b3 * MARCH_THREADS], rv[b4 * MARCH_THREADS]);
-    ppm4_mono(q, fl[v], fh, *upv[v], *lov[v]);
-    fl[v] = fh;
-  }
-}
-
-template <int RECON, int RS, int DIR>
-__global__ void __launch_bounds__(MARCH_THREADS, AKB_MARCH_MINB)
-flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
-                  const double *__restrict__ bnf, double *__restrict__ flx, double *__restrict__ eyo,
-                  double *__restrict__ ezo, int seglen, int nseg) {
-  static_assert(DIR == 1 || DIR == 2, "march kernel handles x2 and x3");
-  constexpr bool RING = (RECON >= RECON_PPM4);
-  extern __shared__ double ring_all[];   // RING: 7 * MARCH_SLOTS * MARCH_THREADS doubles (dynamic)
-  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int nc = g.nx1 + 2;
-  const int nt = (DIR == 1) ? g.nx3 + 2 : g.nx2 + 2;
-  const long total = (long)g.nmb * nseg * nt * nc;
-  if (gt >= total) return;
-  long t = gt;
-  const int i = g.is - 1 + (int)(t % nc); t /= nc;
-  const int tr = (int)(t % nt); t /= nt;
-  const int seg = (int)(t % nseg);
-  const int m = (int)(t / nseg);
-  const int fs0 = (DIR == 1) ? g.js : g.ks;         // first face along the sweep
-  const int fe0 = (DIR == 1) ? g.je + 1 : g.ke + 1; // last face
-  const int f_lo = fs0 + seg * seglen;
-  int f_hi = f_lo + seglen - 1;
-  if (f_hi > fe0) f_hi = fe0;
-  if (f_lo > f_hi) return;
-  const long cc = g.cc;
-  const long s = (DIR == 1) ? (long)g.n1 : (long)g.n1 * g.n2;
-  // cell (k,j,i) with the sweep index = f_lo-1
-  int k, j;
-  if (DIR == 1) { k = g.ks - 1 + tr; j = f_lo - 1; } else { j = g.js - 1 + tr; k = f_lo - 1; }
-  long off = ((long)k * g.n2 + j) * g.n1 + i;
-  const double *wp = w0 + (long)m * 5 * cc + off;
-  const double *bp = bcc + (long)m * 3 * cc + off;
-  // face-array geometry
-  const long frow = (DIR == 1) ? (long)g.n1 : (long)g.n1 * g.n2;  // stride of the sweep index in the face arrays
-  const long fsz = (DIR == 1) ? (long)g.n3 * (g.n2 + 1) * g.n1 : (long)(g.n3 + 1) * g.n2 * g.n1;
-  long foff = (DIR == 1) ? ((long)k * (g.n2 + 1) + f_lo) * g.n1 + i
-                         : ((long)f_lo * g.n2 + j) * g.n1 + i;
-  const double *bn = bnf + (long)m * fsz + foff;
-  double *fp = flx + (long)m * 5 * fsz + foff;
-  double *eyp = eyo + (long)m * cc + off + s;
-  double *ezp = ezo + (long)m * cc + off + s;
-  constexpr int ivx = IVX + DIR, ivy = IVX + (DIR + 1) % 3, ivz = IVX + (DIR + 2) % 3;
-  constexpr int iby = (DIR + 1) % 3, ibz = (DIR + 2) % 3;
-
-  State7 L, lo_unused;
-  if constexpr (RING) {
-    constexpr int VS = MARCH_SLOTS * MARCH_THREADS;
-    double *ring = ring_all + threadIdx.x;
-    // global columns of the seven variables at the current cell (sweep index c = f_lo-1)
-    const double *gv[7] = {wp + IDN * cc, wp + ivx * cc, wp + ivy * cc, wp + ivz * cc, wp + IEN * cc,
-                           bp + iby * cc, bp + ibz * cc};
-    // prologue: rows c-2 .. c+2+PF -> slots 0..S-1 (row c-2 in slot 0)
-#pragma unroll
-    for (int r = 0; r < MARCH_SLOTS; ++r) {
-      if (r < 5 || (f_lo - 1) + (r - 2) <= f_hi + 2) {   // prefetch rows only if some face of this march needs them
-#pragma unroll
-        for (int v = 0; v < 7; ++v) cp_async8(ring + v * VS + r * MARCH_THREADS, gv[v] + (long)(r - 2) * s);
-      }
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    double fl[7];
-    if constexpr (RECON == RECON_PPM4 && AKB_MARCH_CARRY) {
-      ppm4_ring_iface(ring, 0, fl);
-      ppm4_ring_cell(ring, 0, fl, L, lo_unused);
-    } else {
-      recon_ring_cell<RECON>(ring, 0, eos, L, lo_unused);
-    }
-    int b0 = 1;                       // slot of row c-2 for the next cell (c = f_lo)
-    for (int f = f_lo; f <= f_hi; ++f) {
-      // cell c = f: rows c-2..c+2 are present; request row c+2+PF (needed PF steps from now)
-      // into the slot that held row c-3
-      if (f + MARCH_PF <= f_hi) {
-        int bn_slot = b0 + MARCH_SLOTS - 1; if (bn_slot >= MARCH_SLOTS) bn_slot -= MARCH_SLOTS;
-        const long ro = (long)(f - (f_lo - 1) + 2 + MARCH_PF) * s;
-#pragma unroll
-        for (int v = 0; v < 7; ++v) cp_async8(ring + v * VS + bn_slot * MARCH_THREADS, gv[v] + ro);
-      }
-      cp_async_commit();
-      cp_async_wait<MARCH_PF>();
-      State7 up, lo;
-      if constexpr (RECON == RECON_PPM4 && AKB_MARCH_CARRY) ppm4_ring_cell(ring, b0, fl, up, lo);
-      else recon_ring_cell<RECON>(ring, b0, eos, up, lo);
-      Flux7 fx;
-      riemann<RS>(L, lo, __ldg(bn), eos, fx);   // (fetching bn a step ahead costs registers: measured slower)
-      fp[IDN * fsz] = fx.d;
-      fp[ivx * fsz] = fx.mx;
-      fp[ivy * fsz] = fx.my;
-      fp[ivz * fsz] = fx.mz;
-      fp[IEN * fsz] = fx.e;
-      *eyp = fx.ey;  // x2: (e1x2,e3x2)  x3: (e2x3,e1x3)   mhd_fluxes.cpp:196,243
-      *ezp = fx.ez;
-      L = up;
-      bn += frow; fp += frow; eyp += s; ezp += s;
-      b0 = (b0 + 1 >= MARCH_SLOTS) ? 0 : b0 + 1;
-    }
-    cp_async_wait<0>();
-  } else {
-    recon_cell<RECON, DIR>(wp, bp, cc, s, eos, L, lo_unused);
-    for (int f = f_lo; f <= f_hi; ++f) {
-      wp += s; bp += s;
-      State7 up, lo;
-      recon_cell<RECON, DIR>(wp, bp, cc, s, eos, up, lo);
-      Flux7 fx;
-      riemann<RS>(L, lo, __ldg(bn), eos, fx);
-      fp[IDN * fsz] = fx.d;
-      fp[ivx * fsz] = fx.mx;
-      fp[ivy * fsz] = fx.my;
-      fp[ivz * fsz] = fx.mz;
-      fp[IEN * fsz] = fx.e;
-      *eyp = fx.ey;
-      *ezp = fx.ez;
-      L = up;
-      bn += frow; fp += frow; eyp += s; ezp += s;
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------
 // GS07 corner EMFs (mhd_corner_e.cpp:309-318,338-414), one thread per corner
@@ -434,8 +125,8 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
       const double *p2 = flx2 + ((long)m * 5 + n) * g.f2 + o2;
       const double *p3 = flx3 + ((long)m * 5 + n) * g.f3 + o3;
       double divf = div_by(__ldg(p1 + 1) - __ldg(p1), dx1, rdx1);
-      divf += div_by(__ldg(p2 + n1) - __ldg(p2), dx2, rdx2);
-      divf += div_by(__ldg(p3 + n1 * n2) - __ldg(p3), dx3, rdx3);
+      if (g.multi_d) divf += div_by(__ldg(p2 + n1) - __ldg(p2), dx2, rdx2);   // hydro_update.cpp:57-75
+      if (g.three_d) divf += div_by(__ldg(p3 + n1 * n2) - __ldg(p3), dx3, rdx3);
       const long uo = ((long)m * 5 + n) * g.cc + o;
       const double uold = u0[uo];
       double ureg;
@@ -485,32 +176,6 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
 // ConsToPrim (ideal_mhd.cpp:47-122 + ideal_c2p_mhd.hpp:20-67) over a cell box, optionally
 // fused with the new-dt reduction over the active cells (mhd_newdt.cpp:76-150).
 // counters: int[3] (dfloor,efloor,tfloor); dtmin: 3 doubles stored as ordered uint64 bits.
-// identity of the min-reduction = (double)FLT_MAX, the reference's initial value (mhd_newdt.cpp:40-42)
-#define DT_IDENT 3.4028234663852886e+38
-__device__ __forceinline__ void atomic_min_pos(unsigned long long *addr, double v) {
-  atomicMin(addr, (unsigned long long)__double_as_longlong(v));  // v > 0: bit order == value order
-}
-
-// Block-wide min of three positive doubles, then ONE atomic per block and value into one of
-// DT_SLOTS slots (chosen by block index) to keep same-address atomic traffic low; the host
-// takes the min over the slots.  All threads of the block must call it.
-__device__ __forceinline__ void block_min3(double d1, double d2, double d3, unsigned long long *__restrict__ dtmin) {
-  __shared__ double sm[3][8];
-  for (int s = 16; s > 0; s >>= 1) {
-    d1 = dmin(d1, __shfl_xor_sync(0xffffffffu, d1, s));
-    d2 = dmin(d2, __shfl_xor_sync(0xffffffffu, d2, s));
-    d3 = dmin(d3, __shfl_xor_sync(0xffffffffu, d3, s));
-  }
-  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  if ((threadIdx.x & 31) == 0) { sm[0][w] = d1; sm[1][w] = d2; sm[2][w] = d3; }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    double v = sm[threadIdx.x][0];
-    for (int q = 1; q < nw; ++q) v = dmin(v, sm[threadIdx.x][q]);
-    atomic_min_pos(dtmin + 3 * (blockIdx.x % DT_SLOTS) + threadIdx.x, v);
-  }
-}
-
 template <bool NEWDT>
 __global__ void __launch_bounds__(256)
 cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *__restrict__ b1f,
@@ -634,42 +299,6 @@ __global__ void __launch_bounds__(256) copy_kernel(const double2 *__restrict__ s
 
 // ---------------------------------------------------------------------------------------
 // launchers
-
-static inline unsigned nblocks(long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
-
-template <int RECON, int RS>
-static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st) {
-  {  // x1
-    constexpr int STEP = X1Step<RECON>::value;
-    const unsigned nc = g.nx1 + 2 + (RECON == RECON_PPM4 ? 1 : 0), plane = (unsigned)(g.nx2 + 2) * nc;
-    // rcp = ceil(2^32 / nc): __umulhi(t, rcp) == t / nc for every t < 2^32 / nc
-    const unsigned rcp = (unsigned)((0x100000000ull + nc - 1) / nc);
-    if ((unsigned long long)plane * nc >= 0x100000000ull || (long)g.nmb * (g.nx3 + 2) > 65535) return cudaErrorInvalidConfiguration;
-    const unsigned warps = (plane + STEP - 1) / STEP;
-    const dim3 gr(nblocks((long)warps * 32, 128), (unsigned)(g.nmb * (g.nx3 + 2)));
-    flux_x1_kernel<RECON, RS><<<gr, 128, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x1f, a.flx1, a.e3x1, a.e2x1, rcp);
-  }
-  {  // x2: (ey,ez) = (e1x2,e3x2)
-    const int nf = g.nx2 + 1;
-    const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
-    const long threads = (long)g.nmb * nseg * (g.nx3 + 2) * (g.nx1 + 2);
-    const size_t smem = (RECON >= RECON_PPM4) ? sizeof(double) * 7 * MARCH_SLOTS * MARCH_THREADS : 0;
-    static bool attr1 = false;
-    if (!attr1 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr1 = true; }
-    flux_march_kernel<RECON, RS, 1><<<nblocks(threads, MARCH_THREADS), MARCH_THREADS, smem, st>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg);
-  }
-  {  // x3: (ey,ez) = (e2x3,e1x3)
-    const int nf = g.nx3 + 1;
-    const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
-    const long threads = (long)g.nmb * nseg * (g.nx2 + 2) * (g.nx1 + 2);
-    const size_t smem = (RECON >= RECON_PPM4) ? sizeof(double) * 7 * MARCH_SLOTS * MARCH_THREADS : 0;
-    static bool attr2 = false;
-    if (!attr2 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr2 = true; }
-    flux_march_kernel<RECON, RS, 2><<<nblocks(threads, MARCH_THREADS), MARCH_THREADS, smem, st>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
-  }
-  return cudaGetLastError();
-}
-
 template <int RECON>
 static cudaError_t launch_fluxes_r(int rs, const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st) {
   switch (rs) {

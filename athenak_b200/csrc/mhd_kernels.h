@@ -17,6 +17,12 @@ struct Geom {  // RegionIndcs (src/mesh/mesh.hpp:35-41) + derived array extents
   long cc;          // cells per variable per block
   long f1, f2, f3;  // faces per block
   long e1, e2, e3;  // edges per block
+  // dimensionality (mesh.cpp:70-79 multi_d/three_d) and the transverse extension of the flux
+  // sweeps: MHD computes fluxes one cell beyond the active zone in every ACTIVE transverse
+  // direction (the corner EMFs need them, mhd_fluxes.cpp:100-248); hydro does not
+  // (hydro_fluxes.cpp:91-101).  Inactive dimensions have n=1, s=e=0.
+  int multi_d, three_d;
+  int ext1, ext2, ext3;
 };
 
 struct Arrays {  // mirror of ak_mhd_arrays (include/athenak_b200.h)
@@ -29,6 +35,11 @@ struct Arrays {  // mirror of ak_mhd_arrays (include/athenak_b200.h)
 };
 
 cudaError_t launch_fluxes(int recon, int rs, const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st);
+// hydro twin (hydro_kernels.cu): rs = RS_HYD_*; a.bcc0, face fields and EMF arrays are unused
+cudaError_t launch_hydro_fluxes(int recon, int rs, const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st);
+cudaError_t launch_hydro_cons2prim(const Geom &g, const EosParams &eos, const Arrays &a, int il, int iu, int jl, int ju,
+                                   int kl, int ku, int *counters, bool newdt, unsigned long long *dtmin, cudaStream_t st);
+cudaError_t launch_hydro_newdt(const Geom &g, const EosParams &eos, const Arrays &a, unsigned long long *dtmin, cudaStream_t st);
 cudaError_t launch_corner_e(const Geom &g, const Arrays &a, cudaStream_t st);
 cudaError_t launch_update_ct(const Geom &g, const Arrays &a, bool do_u, bool do_b, bool save, double gam0, double gam1,
                              double beta_dt, cudaStream_t st);

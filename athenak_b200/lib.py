@@ -13,6 +13,7 @@ from . import build as _build
 
 RECON = {"dc": 0, "plm": 1, "ppm4": 2, "ppmx": 3, "wenoz": 4, "teno": 5}
 RSOLVER = {"llf": 0, "hlle": 1, "hlld": 2}
+HYD_RSOLVER = {"advect": 10, "llf": 11, "hlle": 12, "hllc": 13, "roe": 14}   # AK_RSOLVER_HYD_*
 
 _dp = C.POINTER(C.c_double)
 
@@ -75,6 +76,15 @@ def load():
         "ak_mhd_stage_flux_emf": [vp, ap, vp],
         "ak_mhd_stage_update": [vp, ap, ip, d, d, d, vp],
         "ak_mhd_cons2prim_newdt": [vp, ap, C.POINTER(C.c_int), _dp, vp],
+        "ak_hydro_create": [C.POINTER(MhdCfg), C.POINTER(vp)],
+        "ak_hydro_destroy": [vp],
+        "ak_hydro_copy_cons": [vp, ap, vp],
+        "ak_hydro_fluxes": [vp, ap, vp],
+        "ak_hydro_rk_update": [vp, ap, d, d, d, vp],
+        "ak_hydro_cons2prim": [vp, ap, ip, ip, ip, ip, ip, ip, C.POINTER(C.c_int), vp],
+        "ak_hydro_new_dt": [vp, ap, _dp, vp],
+        "ak_hydro_stage_fused": [vp, ap, ip, d, d, d, vp],
+        "ak_hydro_cons2prim_newdt": [vp, ap, C.POINTER(C.c_int), _dp, vp],
         "ak_halo_create": [C.POINTER(MhdCfg), C.POINTER(C.c_int), ip, ip, C.POINTER(vp)],
         "ak_halo_destroy": [vp],
         "ak_halo_npeers": [vp],
@@ -143,7 +153,9 @@ EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_con
             "ak_sim_create", "ak_sim_destroy", "ak_nccl_unique_id", "ak_sim_comm_init", "ak_sim_set_state",
             "ak_sim_get_state", "ak_sim_initialize", "ak_sim_execute", "ak_sim_sync", "ak_sim_status", "ak_sim_arrays",
             "ak_sim_set_bcs", "ak_bcs_create", "ak_bcs_destroy", "ak_bcs_last_error", "ak_bcs_strictly_periodic",
-            "ak_bcs_hydro", "ak_bcs_bfield", "ak_bcs_apply")
+            "ak_bcs_hydro", "ak_bcs_bfield", "ak_bcs_apply",
+            "ak_hydro_create", "ak_hydro_destroy", "ak_hydro_copy_cons", "ak_hydro_fluxes", "ak_hydro_rk_update",
+            "ak_hydro_cons2prim", "ak_hydro_new_dt", "ak_hydro_stage_fused", "ak_hydro_cons2prim_newdt")
 
 # BoundaryFlag (src/bvals/bvals.hpp:19) == enum ak_bc_flag
 BC = {"undef": -1, "block": 0, "reflect": 1, "inflow": 2, "outflow": 3, "diode": 4, "user": 5, "periodic": 6,

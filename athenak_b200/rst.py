@@ -39,7 +39,9 @@ class Restart:
     b3f: np.ndarray            # (nmb,n3+1,n2,n1)
 
 
-def read_rst(path: str, nmhd: int = 5) -> Restart:
+def read_rst(path: str, nmhd: int = 5, physics: str = "mhd") -> Restart:
+    """physics="hydro": the dump of a hydro-only run holds just u0 per block (restart.cpp:320-353);
+    b1f/b2f/b3f come back as None."""
     raw = open(path, "rb").read()
     end = raw.index(b"<par_end>\n") + len(b"<par_end>\n")
     deck = raw[:end].decode()
@@ -58,6 +60,16 @@ def read_rst(path: str, nmhd: int = 5) -> Restart:
     n2 = mb_indcs["nx2"] + 2 * ng if mb_indcs["nx2"] > 1 else 1
     n3 = mb_indcs["nx3"] + 2 * ng if mb_indcs["nx3"] > 1 else 1
     ncc, nf1, nf2, nf3 = n3 * n2 * n1, n3 * n2 * (n1 + 1), n3 * (n2 + 1) * n1, (n3 + 1) * n2 * n1
+    if physics == "hydro":
+        if per_block != 8 * nmhd * ncc:
+            raise ValueError(f"{path}: block payload {per_block} B, expected {8 * nmhd * ncc} B (hydro only)")
+        u0 = np.empty((nmb, nmhd, n3, n2, n1))
+        for m in range(nmb):
+            u0[m] = np.frombuffer(raw, "<f8", nmhd * ncc, off).reshape(nmhd, n3, n2, n1); off += 8 * nmhd * ncc
+        if off != len(raw):
+            raise ValueError(f"{path}: {len(raw) - off} trailing bytes")
+        return Restart(deck, nmb, root_level, mesh_size, mesh_indcs, mb_indcs, time, dt, ncycle,
+                       lloc, cost, u0, None, None, None)
     expect = 8 * (nmhd * ncc + nf1 + nf2 + nf3)
     if per_block != expect:
         raise ValueError(f"{path}: block payload {per_block} B, expected {expect} B (MHD only)")

@@ -234,15 +234,18 @@ def bench_native(args):
     sync_all()
     e2e_mode = "serial: H2D -> step -> D2H, one engine instance"
     if world == 1:
-        # Two engine instances (two streams, two host threads, ctypes releases the GIL): while one
-        # instance computes step i, the other uploads step i+1's input and downloads step i-1's result,
+        # Several engine instances (own stream + host thread each, ctypes releases the GIL): while one
+        # instance computes step i, others upload step i+1's input and download step i-1's result,
         # so PCIe (both directions) and the SMs are busy at the same time.  Every step still does its own
         # H2D of the full conserved state from pinned memory, ghost exchange + c2p, one RK3 step, and a
         # D2H of the full result.
-        sim2 = Simulation(mesh, rank, ng=NG, recon="ppm4", rsolver="hlld", gamma=GAMMA, integrator="rk3",
-                          cfl_number=0.3, tlim=1.0e9, fused=True)
-        ho2 = [torch.empty_like(t).pin_memory() for t in ho]
-        ke2e = max(4, min(K, 10)) // 2 * 2
+        NI = 3      # per instance the chain H2D -> step -> D2H is serial (same buffers); three chains in flight keep
+                    # both PCIe directions and the SMs busy
+        sims = [sim] + [Simulation(mesh, rank, ng=NG, recon="ppm4", rsolver="hlld", gamma=GAMMA, integrator="rk3",
+                                   cfl_number=0.3, tlim=1.0e9, fused=True) for _ in range(NI - 1)]
+        outs = [ho] + [[torch.empty_like(t).pin_memory() for t in ho] for _ in range(NI - 1)]
+        per = max(2, min(K, 12) // NI)
+        ke2e = per * NI
 
         def worker(s, out, nsteps):
             for _ in range(nsteps):
@@ -252,21 +255,20 @@ def bench_native(args):
                 s.get_state(out)
             s.sync()
 
-        worker(sim2, ho2, 1)
+        for s_, o_ in zip(sims[1:], outs[1:]):
+            worker(s_, o_, 1)
         sync_all()
-        ths = [threading.Thread(target=worker, args=(sim, ho, ke2e // 2)),
-               threading.Thread(target=worker, args=(sim2, ho2, ke2e // 2))]
-        ev0.record(sstream)           # both streams idle here: the event time-stamps "now" on the device clock
+        ths = [threading.Thread(target=worker, args=(s_, o_, per)) for s_, o_ in zip(sims, outs)]
+        ev0.record(sstream)           # all streams idle here: the event time-stamps "now" on the device clock
         for th in ths:
             th.start()
         for th in ths:
             th.join()
-        sim2.sync()
-        ev1.record(sstream)           # both instances drained: time-stamps the end of the last D2H
+        ev1.record(sstream)           # every instance drained (worker ends with a stream sync): end of the last D2H
         sync_all()
-        e2e_mode = "2 engine instances double-buffered over 2 streams/host threads (H2D, step, D2H of consecutive steps overlap)"
-        assert all(bool(torch.equal(x, y)) for x, y in zip(ho, ho2)), "the two e2e instances disagree"
-        del sim2
+        e2e_mode = f"{NI} engine instances over {NI} streams/host threads (H2D, step, D2H of consecutive steps overlap)"
+        assert all(bool(torch.equal(x, y)) for o_ in outs[1:] for x, y in zip(ho, o_)), "the e2e instances disagree"
+        del sims, outs
     else:
         ev0.record(sstream)
         for _ in range(ke2e):

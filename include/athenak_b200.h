@@ -33,6 +33,9 @@ typedef void *ak_stream_t; /* a cudaStream_t (0 = default stream) */
 /* reconstruction / Riemann-solver selectors: reference src/athena.hpp:75, src/mhd/mhd.hpp:39 */
 enum { AK_RECON_DC = 0, AK_RECON_PLM = 1, AK_RECON_PPM4 = 2, AK_RECON_PPMX = 3, AK_RECON_WENOZ = 4, AK_RECON_TENO = 5 };
 enum { AK_RSOLVER_LLF = 0, AK_RSOLVER_HLLE = 1, AK_RSOLVER_HLLD = 2 };
+/* hydro solvers: reference src/hydro/hydro.hpp:32 (Hydro_RSolver), Newtonian ones only */
+enum { AK_RSOLVER_HYD_ADVECT = 10, AK_RSOLVER_HYD_LLF = 11, AK_RSOLVER_HYD_HLLE = 12, AK_RSOLVER_HYD_HLLC = 13,
+       AK_RSOLVER_HYD_ROE = 14 };
 
 typedef struct {
   int nmb;           /* MeshBlocks in this pack (reference MeshBlockPack::nmb_thispack) */
@@ -92,6 +95,29 @@ int ak_mhd_stage_fused(void *h, const ak_mhd_arrays *a, int stage, double gam0, 
                        double beta_dt, void *halo_plan, ak_stream_t s);
 /* c2p over all cells fused with the task-28 reduction over the active cells (last stage). */
 int ak_mhd_cons2prim_newdt(void *h, const ak_mhd_arrays *a, int *nfloor, double *dt3, ak_stream_t s);
+
+/* ---- hydro twin: the same stage update without magnetic fields --------
+ * Replaces the task bodies Hydro::AssembleHydroTasks registers (reference src/hydro/
+ * hydro_tasks.cpp:47-79): CopyCons :137-160, Fluxes -> CalculateFluxes<rsolver> (src/hydro/
+ * hydro_fluxes.cpp:78-229; solvers src/hydro/rsolvers/{advect,llf,hlle,hllc,roe}_hyd.hpp),
+ * RKUpdate (hydro_update.cpp:23-82), ConToPrim (hydro_tasks.cpp:404-412 -> src/eos/ideal_hyd.cpp:
+ * 28-113), NewTimeStep (hydro_newdt.cpp:31-138).  cfg->rsolver is an AK_RSOLVER_HYD_* value,
+ * sigma_max is ignored; MeshBlocks may be 1-D (nx2 = nx3 = 1), 2-D (nx3 = 1) or 3-D, inactive
+ * dimensions having extent 1 and no ghost cells (reference src/mesh/mesh.cpp:285-333).  Only
+ * u0, u1, w0, flx1..3 and mb_size of ak_mhd_arrays are read.  Ghost exchange: ak_halo_*_cc with
+ * nvar = 5; physical boundaries: ak_bcs_hydro. */
+int ak_hydro_create(const ak_mhd_cfg *cfg, void **handle);
+int ak_hydro_destroy(void *handle);
+int ak_hydro_copy_cons(void *h, const ak_mhd_arrays *a, ak_stream_t s);
+int ak_hydro_fluxes(void *h, const ak_mhd_arrays *a, ak_stream_t s);
+int ak_hydro_rk_update(void *h, const ak_mhd_arrays *a, double gam0, double gam1, double beta_dt, ak_stream_t s);
+int ak_hydro_cons2prim(void *h, const ak_mhd_arrays *a, int il, int iu, int jl, int ju, int kl, int ku,
+                       int *nfloor, ak_stream_t s);
+int ak_hydro_new_dt(void *h, const ak_mhd_arrays *a, double *dt3, ak_stream_t s);
+/* CopyCons (folded into the stage-1 update) + Fluxes + RKUpdate; c2p over all cells + new dt */
+int ak_hydro_stage_fused(void *h, const ak_mhd_arrays *a, int stage, double gam0, double gam1,
+                         double beta_dt, ak_stream_t s);
+int ak_hydro_cons2prim_newdt(void *h, const ak_mhd_arrays *a, int *nfloor, double *dt3, ak_stream_t s);
 
 /* ---- ghost-zone exchange (src/bvals): tasks 10/11 SendU/RecvU, 21/22 SendB/RecvB ---------
  * nghbr: HOST [nmb][56][4] = {gid, lev, rank, dest} per neighbour slot (NeighborBlock,

@@ -38,10 +38,12 @@ typedef struct {
 
 static odims dims(const ocfg *c) {
   odims d;
-  d.n1 = c->nx1 + 2 * c->ng; d.n2 = c->nx2 + 2 * c->ng; d.n3 = c->nx3 + 2 * c->ng;
-  d.is = c->ng; d.ie = d.is + c->nx1 - 1;       /* mesh.cpp:285-333 */
-  d.js = c->ng; d.je = d.js + c->nx2 - 1;
-  d.ks = c->ng; d.ke = d.ks + c->nx3 - 1;
+  /* mesh.cpp:285-333: inactive dimensions (nx = 1) have extent 1 and no ghost cells */
+  const int multi_d = c->nx2 > 1, three_d = c->nx3 > 1;
+  d.n1 = c->nx1 + 2 * c->ng; d.n2 = multi_d ? c->nx2 + 2 * c->ng : 1; d.n3 = three_d ? c->nx3 + 2 * c->ng : 1;
+  d.is = c->ng; d.ie = d.is + c->nx1 - 1;
+  d.js = multi_d ? c->ng : 0; d.je = d.js + c->nx2 - 1;
+  d.ks = three_d ? c->ng : 0; d.ke = d.ks + c->nx3 - 1;
   d.cc = (size_t)d.n3 * d.n2 * d.n1;
   d.f1 = (size_t)d.n3 * d.n2 * (d.n1 + 1);
   d.f2 = (size_t)d.n3 * (d.n2 + 1) * d.n1;
@@ -1127,6 +1129,7 @@ int oracle_apply_bcs(const ocfg *c, const int *mesh_bcs, const int *mb_bcs, doub
   for (int q = 0; q < 6 * c->nmb; ++q)
     if (mb_bcs[q] == BC_INFLOW || mb_bcs[q] == BC_USER || mb_bcs[q] == BC_SHEAR) return 1;
   for (int d = 0; d < 3; ++d) {        /* hydro_bcs.cpp:80-81,167,252: gate on the mesh flag */
+    if ((d == 1 && c->nx2 <= 1) || (d == 2 && c->nx3 <= 1)) continue;   /* :164 one_d, :249 two_d */
     if (mesh_bcs[2 * d] == BC_PERIODIC || (d == 0 && mesh_bcs[0] == BC_SHEAR)) continue;
     bc_array(c, u0, 5, -1, d, mb_bcs);
   }
@@ -1220,3 +1223,5 @@ double oracle_initial_dt(const ocfg *c, const ostate *s, const double *mb_size, 
   if ((time < tlim) && ((time + d) > tlim)) d = tlim - time;
   return d;
 }
+
+#include "hydro_oracle.c"

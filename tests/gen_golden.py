@@ -54,7 +54,29 @@ def blast(n, cycles, recon="ppm4", rsolver="hlld", integrator="rk3", name=None, 
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def hydro(deck, base, name, overrides=()):
+    """Hydro fixtures: ghost-inclusive u0 of the cycle-0 and final restart dumps + the embedded deck."""
+    tmp = tempfile.mkdtemp(prefix="akgold_")
+    try:
+        O.run_reference("athena_builtin", os.path.join(HERE, "decks", deck), tmp, list(overrides))
+        r0 = read_rst(os.path.join(tmp, "rst", base + ".00000.rst"), physics="hydro")
+        r1 = read_rst(os.path.join(tmp, "rst", base + ".00001.rst"), physics="hydro")
+        np.savez_compressed(os.path.join(HERE, "golden", name + ".npz"), deck=np.array(r0.deck), u0_c0=r0.u0, u0_final=r1.u0,
+                            dt_c0=r0.dt, time_final=r1.time, dt_final=r1.dt, ncycle_final=r1.ncycle, lloc=r0.lloc)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 if __name__ == "__main__":
+    hydro("sod1d.athinput", "Sod", "hydro_sod1d_plm_llf_rk2")
+    hydro("sod1d.athinput", "Sod", "hydro_sod1d_wenoz_roe_rk3", ("hydro/rsolver=roe", "hydro/reconstruct=wenoz", "mesh/nghost=3",
+                                                                  "time/integrator=rk3", "time/cfl_number=0.4", "mesh/nx1=128", "meshblock/nx1=32"))
+    hydro("sod2d.athinput", "Sod", "hydro_sod2d_ppm4_hllc_rk3")
+    hydro("lwave3d_hydro.athinput", "LinWave", "hydro_lwave3d_ppmx_hlle_rk2",
+          ("mesh/nx1=16", "mesh/nx2=8", "mesh/nx3=8", "meshblock/nx1=8", "meshblock/nx2=8", "meshblock/nx3=8",
+           "hydro/reconstruct=ppmx", "hydro/rsolver=hlle", "time/integrator=rk2", "time/tlim=0.25"))
+    if "--hydro-only" in sys.argv:
+        sys.exit(0)
     blast(16, (1, 4))
     blast(16, (2,), recon="plm", rsolver="hlle", integrator="rk2")
     blast(16, (2,), recon="wenoz", rsolver="llf", integrator="rk3")

@@ -1,0 +1,87 @@
+"""Helpers of the hydro parity tests.  TEST INFRASTRUCTURE ONLY.
+
+A hydro case is defined by a restart dump of the unmodified reference (oracle/_ref/athena_builtin
+run live, or a committed fixture made from one by tests/gen_golden.py): its embedded input deck
+gives the mesh, boundary flags, reconstruction, Riemann solver, integrator and CFL number; its u0
+is the synthetic input.  `oracle_run` evolves it with oracle/hydro_oracle.c."""
+from __future__ import annotations
+
+import ctypes as C
+import re
+
+import numpy as np
+
+import oracle_lib as O
+
+INTEGRATOR = {"rk1": 1, "rk2": 2, "rk3": 3}
+
+
+def deck_params(deck: str) -> dict:
+    """{'block/key': value} of an athinput text (parameter_input.cpp:120-230: '<block>', 'key = value # comment')."""
+    out, blk = {}, None
+    for ln in deck.splitlines():
+        ln = ln.split("#")[0].strip()
+        m = re.match(r"<(\w+)>", ln)
+        if m:
+            blk = m.group(1)
+        elif "=" in ln and blk:
+            k, v = ln.split("=", 1)
+            out[f"{blk}/{k.strip()}"] = v.strip()
+    return out
+
+
+class Case:
+    def __init__(self, deck: str, overrides=()):
+        p = deck_params(deck)
+        for ov in overrides:
+            k, v = ov.split("=", 1)
+            p[k] = v
+        self.p = p
+        self.nmesh = tuple(int(p[f"mesh/nx{d}"]) for d in (1, 2, 3))
+        self.nblock = tuple(int(p[f"meshblock/nx{d}"]) for d in (1, 2, 3))
+        self.xmin = tuple(float(p[f"mesh/x{d}min"]) for d in (1, 2, 3))
+        self.xmax = tuple(float(p[f"mesh/x{d}max"]) for d in (1, 2, 3))
+        self.bc_names = tuple(p[f"mesh/{s}x{d}_bc"] for d in (1, 2, 3) for s in ("i", "o"))
+        self.mesh_bcs = np.array([O.BC[b] for b in self.bc_names], np.int32)
+        self.ng = int(float(p.get("mesh/nghost", 2)))
+        self.recon, self.rsolver = p["hydro/reconstruct"], p["hydro/rsolver"]
+        self.gamma = float(p["hydro/gamma"])
+        self.integrator = p["time/integrator"]
+        self.cfl, self.tlim = float(p["time/cfl_number"]), float(p["time/tlim"])
+        periodic = [self.mesh_bcs[2 * d] == O.BC["periodic"] for d in range(3)]
+        self.lloc, self.nghbr, self.mb_size, _ = O.uniform_mesh(self.nmesh, self.nblock, self.xmin, self.xmax, periodic)
+        self.mb_bcs = O.block_bcs(self.lloc, self.nmesh, self.nblock, self.mesh_bcs)
+        self.nmb = len(self.lloc)
+        self.strictly_periodic = all(periodic)
+
+    def ocfg(self):
+        return O.OCfg(self.nmb, self.ng, *self.nblock, O.RECON[self.recon], O.HYD_RSOLVER[self.rsolver], self.gamma,
+                      O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX)
+
+
+def oracle_run(case: Case, u_init, ncycles=-1, time0=0.0):
+    """Driver::Initialize + Execute on the oracle.  Returns (u0, w0, time, dt_next, ncycles, dt0)."""
+    L = O.lib()
+    cfg = case.ocfg()
+    u0 = np.ascontiguousarray(u_init, dtype=np.float64).copy()
+    u1, w0 = np.zeros_like(u0), np.zeros_like(u0)
+    if not case.strictly_periodic:
+        L.oracle_set_bcs(O.ip(case.mesh_bcs), O.ip(case.mb_bcs))
+    try:
+        dt0 = L.oracle_hydro_init(C.byref(cfg), O.p(u0), O.p(w0), O.p(case.mb_size), O.ip(case.nghbr),
+                                  C.c_double(case.cfl), C.c_double(case.tlim), C.c_double(time0))
+        t, dt = C.c_double(time0), C.c_double(dt0)
+        n = L.oracle_hydro_run(C.byref(cfg), O.p(u0), O.p(u1), O.p(w0), O.p(case.mb_size), O.ip(case.nghbr),
+                               INTEGRATOR[case.integrator], C.c_double(case.cfl), C.c_double(case.tlim), ncycles,
+                               C.byref(t), C.byref(dt), None)
+    finally:
+        L.oracle_set_bcs(None, None)
+    return u0, w0, t.value, dt.value, n, dt0
+
+
+def sod_density(x, tlim=0.25):
+    """Analytic Sod density as tabulated by the reference's own test
+    (tst/test_suite/nr/test_nr_sod_cpu.py:20-46): shock, contact, foot and head of the rarefaction."""
+    xs, xc, xf, xh = 1.7522 * tlim, 0.92745 * tlim, -0.07027 * tlim, -1.1832 * tlim
+    fan = 0.42632 * (1.0 + 0.20046 * (0.92745 - (0.92745 * (x - xh) / (xf - xh)))) ** 5
+    return np.where(x > xs, 0.125, np.where(x > xc, 0.26557, np.where(x > xf, 0.42632, np.where(x > xh, fan, 1.0))))

@@ -13,6 +13,7 @@ REF_DIR = os.path.join(ORACLE_DIR, "_ref")
 
 RECON = {"dc": 0, "plm": 1, "ppm4": 2, "ppmx": 3, "wenoz": 4, "teno": 5}
 RSOLVER = {"llf": 0, "hlle": 1, "hlld": 2}
+HYD_RSOLVER = {"advect": 10, "llf": 11, "hlle": 12, "hllc": 13, "roe": 14}
 FLT_MIN = float(np.finfo(np.float32).tiny)
 FLT_MAX = float(np.finfo(np.float32).max)
 
@@ -43,13 +44,16 @@ def lib():
     global _lib
     if _lib is None:
         so = os.path.join(ORACLE_DIR, "liboracle.so")
-        src = os.path.join(ORACLE_DIR, "mhd_oracle.c")
-        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        srcs = [os.path.join(ORACLE_DIR, f) for f in ("mhd_oracle.c", "hydro_oracle.c")]
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
             subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "liboracle.so"])
         _lib = C.CDLL(so)
         _lib.oracle_new_dt.restype = C.c_double
         _lib.oracle_initial_dt.restype = C.c_double
         _lib.oracle_run.restype = C.c_int
+        _lib.oracle_hydro_new_dt.restype = C.c_double
+        _lib.oracle_hydro_init.restype = C.c_double
+        _lib.oracle_hydro_run.restype = C.c_int
     return _lib
 
 
@@ -124,6 +128,8 @@ def uniform_mesh(nmesh, nblock, xmin=(-0.5, -0.5, -0.5), xmax=(0.5, 0.5, 0.5), p
                 for ox in (-1, 0, 1):
                     if ox == oy == oz == 0:
                         continue
+                    if (oy and nmesh[1] == 1) or (oz and nmesh[2] == 1):
+                        continue      # meshblock.cpp:170-425: neighbours only in active dimensions
                     q = [lx + ox, ly + oy, lz + oz]
                     ok = True
                     for d in range(3):
