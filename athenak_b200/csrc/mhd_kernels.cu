@@ -335,6 +335,7 @@ cudaError_t launch_update_ct(const Geom &g, const Arrays &a, bool do_u, bool do_
 #define AKB_UCT_ARGS g, a.u0, a.u1, a.flx1, a.flx2, a.flx3, a.b0x1f, a.b0x2f, a.b0x3f, a.b1x1f, a.b1x2f, a.b1x3f, a.e1, a.e2, a.e3, a.mb_size, gam0, gam1, beta_dt
   if (do_u && do_b && save) update_ct_kernel<true, true, true><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
   else if (do_u && do_b) update_ct_kernel<true, true, false><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
+  else if (do_u && save) update_ct_kernel<true, false, true><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);   // hydro twin, stage 1
   else if (do_u) update_ct_kernel<true, false, false><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
   else if (do_b) update_ct_kernel<false, true, false><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
 #undef AKB_UCT_ARGS
