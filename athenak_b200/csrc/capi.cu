@@ -19,6 +19,7 @@ struct Handle {
   bool hydro = false;                       // hydro twin (ak_hydro_*): no magnetic arrays, 1-D/2-D/3-D
   int *d_counters = nullptr;                // 3 ints
   unsigned long long *d_dtmin = nullptr;    // 3 ordered-bit doubles
+  double *d_hst = nullptr;                  // history-sum scratch, allocated on first use
   std::string err;
 };
 
@@ -143,6 +144,7 @@ int ak_mhd_destroy(void *handle) {
   if (!h) return 0;
   cudaFree(h->d_counters);
   cudaFree(h->d_dtmin);
+  cudaFree(h->d_hst);
   delete h;
   return 0;
 }
@@ -263,6 +265,20 @@ int ak_mhd_stage_fused(void *handle, const ak_mhd_arrays *a, int stage, double g
     if ((rc = ak_halo_emf_sumavg(halo_plan, a->e1, a->e2, a->e3, s)) != 0) return rc;
   }
   return ak_mhd_stage_update(handle, a, stage, gam0, gam1, beta_dt, s);
+}
+
+// history sums (src/outputs/history.cpp:78-160,272-372); synchronises the stream
+int ak_hst_sums(void *handle, const ak_mhd_arrays *a, double *sums, int *nhist, ak_stream_t s) {
+  AK_PROLOGUE("ak_hst_sums")
+  if (!sums) return fail(h, "ak_hst_sums: null output");
+  const int nb = 148 * 4;
+  if (!h->d_hst && (e = cudaMalloc(&h->d_hst, sizeof(double) * 11 * (nb + 1))) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
+  if ((e = akb::launch_hst_sums(h->g, A, !h->hydro, h->d_hst, nb, st)) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
+  const int n = h->hydro ? 8 : 11;
+  if ((e = cudaMemcpyAsync(sums, h->d_hst + 11L * nb, sizeof(double) * n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
+  if (nhist) *nhist = n;
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -191,27 +191,34 @@ class MHD {  // state owner + tasks
   Nccl::Comm comm = nullptr;
   double *d_dt = nullptr;
   size_t n_u, n_f1, n_f2, n_f3;
+  bool hydro = false, multi_d = true, three_d = true;
 
   MHD(const ak_mhd_cfg &c, const double *mb_size, const int *nghbr, int rank, int nranks_, int gids_start, int nmb_total)
       : cfg(c), my_rank(rank), nranks(nranks_) {
     mesh.nmb_total = nmb_total;
     CU_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    const size_t n1 = c.nx1 + 2 * c.ng, n2 = c.nx2 + 2 * c.ng, n3 = c.nx3 + 2 * c.ng, nm = c.nmb;
+    hydro = c.rsolver >= AK_RSOLVER_HYD_ADVECT;     // hydro twin: Hydro::Hydro, hydro.cpp:100-120,268-290
+    multi_d = c.nx2 > 1; three_d = c.nx3 > 1;       // mesh.cpp:70-79
+    const size_t n1 = c.nx1 + 2 * c.ng, n2 = multi_d ? c.nx2 + 2 * c.ng : 1, n3 = three_d ? c.nx3 + 2 * c.ng : 1, nm = c.nmb;
     const size_t cc = n1 * n2 * n3;
     n_u = nm * 5 * cc; n_f1 = nm * n3 * n2 * (n1 + 1); n_f2 = nm * n3 * (n2 + 1) * n1; n_f3 = nm * (n3 + 1) * n2 * n1;
     auto alloc = [&](size_t n) { double *p; CU_CHECK(cudaMalloc(&p, n * 8)); CU_CHECK(cudaMemsetAsync(p, 0, n * 8, st)); owned.push_back(p); return p; };
-    a.u0 = alloc(n_u); a.u1 = alloc(n_u); a.w0 = alloc(n_u); a.bcc0 = alloc(nm * 3 * cc);   // mhd.cpp:148-161
-    a.b0x1f = alloc(n_f1); a.b0x2f = alloc(n_f2); a.b0x3f = alloc(n_f3);
-    a.b1x1f = alloc(n_f1); a.b1x2f = alloc(n_f2); a.b1x3f = alloc(n_f3);                       // mhd.cpp:329-347
+    std::memset(&a, 0, sizeof(a));
+    a.u0 = alloc(n_u); a.u1 = alloc(n_u); a.w0 = alloc(n_u);
     a.flx1 = alloc(5 * n_f1); a.flx2 = alloc(5 * n_f2); a.flx3 = alloc(5 * n_f3);
-    a.e3x1 = alloc(nm * cc); a.e2x1 = alloc(nm * cc); a.e1x2 = alloc(nm * cc);
-    a.e3x2 = alloc(nm * cc); a.e2x3 = alloc(nm * cc); a.e1x3 = alloc(nm * cc);
-    a.e1 = alloc(nm * (n3 + 1) * (n2 + 1) * n1); a.e2 = alloc(nm * (n3 + 1) * n2 * (n1 + 1)); a.e3 = alloc(nm * n3 * (n2 + 1) * (n1 + 1));
+    if (!hydro) {
+      a.bcc0 = alloc(nm * 3 * cc);   // mhd.cpp:148-161
+      a.b0x1f = alloc(n_f1); a.b0x2f = alloc(n_f2); a.b0x3f = alloc(n_f3);
+      a.b1x1f = alloc(n_f1); a.b1x2f = alloc(n_f2); a.b1x3f = alloc(n_f3);                       // mhd.cpp:329-347
+      a.e3x1 = alloc(nm * cc); a.e2x1 = alloc(nm * cc); a.e1x2 = alloc(nm * cc);
+      a.e3x2 = alloc(nm * cc); a.e2x3 = alloc(nm * cc); a.e1x3 = alloc(nm * cc);
+      a.e1 = alloc(nm * (n3 + 1) * (n2 + 1) * n1); a.e2 = alloc(nm * (n3 + 1) * n2 * (n1 + 1)); a.e3 = alloc(nm * n3 * (n2 + 1) * (n1 + 1));
+    }
     double *ms = alloc(nm * 9);
     CU_CHECK(cudaMemcpyAsync(ms, mb_size, nm * 9 * 8, cudaMemcpyHostToDevice, st));
     a.mb_size = ms;
     d_dt = alloc(1);
-    if (ak_mhd_create(&cfg, &h)) Fatal(__FILE__, __LINE__, ak_last_error(nullptr));
+    if (hydro ? ak_hydro_create(&cfg, &h) : ak_mhd_create(&cfg, &h)) Fatal(__FILE__, __LINE__, ak_last_error(nullptr));
     if (ak_halo_create(&cfg, nghbr, rank, gids_start, &plan)) Fatal(__FILE__, __LINE__, ak_last_error(nullptr));
     for (int p = 0; p < ak_halo_npeers(plan); ++p) {
       Peer pe;
@@ -238,6 +245,25 @@ class MHD {  // state owner + tasks
       tl_map[n] = std::make_shared<TaskList>();
     TaskID none(0);
     auto &tl = tl_map["stagen"];
+    if (hydro) {   // Hydro::AssembleHydroTasks, hydro_tasks.cpp:47-79 (uniform mesh, no source terms)
+      if (fused) {
+        TaskID f = tl->AddTask(&MHD::HydroStageFused, this, none);
+        TaskID su = tl->AddTask(&MHD::SendU, this, f);
+        TaskID ru = tl->AddTask(&MHD::RecvU, this, su);
+        TaskID bc = tl->AddTask(&MHD::ApplyPhysicalBCs, this, ru);
+        tl->AddTask(&MHD::ConToPrimNewDt, this, bc);
+      } else {
+        TaskID copyu = tl->AddTask(&MHD::CopyCons, this, none);
+        TaskID flux = tl->AddTask(&MHD::Fluxes, this, copyu);
+        TaskID rkupdt = tl->AddTask(&MHD::RKUpdate, this, flux);
+        TaskID sendu = tl->AddTask(&MHD::SendU, this, rkupdt);
+        TaskID recvu = tl->AddTask(&MHD::RecvU, this, sendu);
+        TaskID bc = tl->AddTask(&MHD::ApplyPhysicalBCs, this, recvu);
+        TaskID c2p = tl->AddTask(&MHD::ConToPrim, this, bc);
+        tl->AddTask(&MHD::NewTimeStep, this, c2p);
+      }
+      return;
+    }
     if (fused) {
       TaskID f = tl->AddTask(&MHD::StageFluxEmf, this, none);
       TaskID se = tl->AddTask(&MHD::SendE, this, f);
@@ -266,14 +292,28 @@ class MHD {  // state owner + tasks
   }
 
   // ---- tasks ------------------------------------------------------------------------------
+  int nsweeps() const { return 1 + (multi_d ? 1 : 0) + (three_d ? 1 : 0); }
   TaskStatus CopyCons(Driver *pd, int stage) {
-    if (stage == 1) { AK_CHECK(h, ak_mhd_copy_cons(h, &a, st)); launches += 4; }
+    if (stage == 1) {
+      if (hydro) { AK_CHECK(h, ak_hydro_copy_cons(h, &a, st)); launches += 1; }
+      else { AK_CHECK(h, ak_mhd_copy_cons(h, &a, st)); launches += 4; }
+    }
     return TaskStatus::complete;
   }
-  TaskStatus Fluxes(Driver *pd, int stage) { AK_CHECK(h, ak_mhd_fluxes(h, &a, st)); launches += 3; return TaskStatus::complete; }
+  TaskStatus Fluxes(Driver *pd, int stage) {
+    if (hydro) AK_CHECK(h, ak_hydro_fluxes(h, &a, st)); else AK_CHECK(h, ak_mhd_fluxes(h, &a, st));
+    launches += nsweeps();
+    return TaskStatus::complete;
+  }
   TaskStatus RKUpdate(Driver *pd, int stage) {
-    AK_CHECK(h, ak_mhd_rk_update(h, &a, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, st));
+    const double g0 = pd->gam0[stage - 1], g1 = pd->gam1[stage - 1], bdt = pd->beta[stage - 1] * mesh.dt;
+    if (hydro) AK_CHECK(h, ak_hydro_rk_update(h, &a, g0, g1, bdt, st)); else AK_CHECK(h, ak_mhd_rk_update(h, &a, g0, g1, bdt, st));
     launches += 1;
+    return TaskStatus::complete;
+  }
+  TaskStatus HydroStageFused(Driver *pd, int stage) {   // CopyCons + Fluxes + RKUpdate
+    AK_CHECK(h, ak_hydro_stage_fused(h, &a, stage, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, st));
+    launches += nsweeps() + 1;
     return TaskStatus::complete;
   }
   TaskStatus EField(Driver *pd, int stage) { AK_CHECK(h, ak_mhd_corner_e(h, &a, st)); launches += 1; return TaskStatus::complete; }
@@ -383,15 +423,24 @@ class MHD {  // state owner + tasks
   // task 26, mhd_tasks.cpp:504-520: nothing to do on a strictly periodic mesh
   TaskStatus ApplyPhysicalBCs(Driver *pd, int stage) {
     if (!bcs) return TaskStatus::complete;
-    if (ak_bcs_apply(bcs, a.u0, 5, a.b0x1f, a.b0x2f, a.b0x3f, st)) Fatal(__FILE__, __LINE__, ak_bcs_last_error(bcs));
+    if (hydro ? ak_bcs_hydro(bcs, a.u0, 5, st) : ak_bcs_apply(bcs, a.u0, 5, a.b0x1f, a.b0x2f, a.b0x3f, st))
+      Fatal(__FILE__, __LINE__, ak_bcs_last_error(bcs));
     launches += nbc_launches;
     return TaskStatus::complete;
   }
   int nbc_launches = 0;
+  // new dt over the active dimensions only (mhd_newdt.cpp:152-155, hydro_newdt.cpp:122-125)
+  double MinDt(const double *dt3) const {
+    double d = dt3[0];
+    if (multi_d) d = std::min(d, dt3[1]);
+    if (three_d) d = std::min(d, dt3[2]);
+    return d;
+  }
   TaskStatus ConToPrim(Driver *pd, int stage) {
-    const int n1 = cfg.nx1 + 2 * cfg.ng, n2 = cfg.nx2 + 2 * cfg.ng, n3 = cfg.nx3 + 2 * cfg.ng;
+    const int n1 = cfg.nx1 + 2 * cfg.ng, n2 = multi_d ? cfg.nx2 + 2 * cfg.ng : 1, n3 = three_d ? cfg.nx3 + 2 * cfg.ng : 1;
     int nf[3];
-    AK_CHECK(h, ak_mhd_cons2prim(h, &a, 0, n1 - 1, 0, n2 - 1, 0, n3 - 1, nf, st));
+    if (hydro) AK_CHECK(h, ak_hydro_cons2prim(h, &a, 0, n1 - 1, 0, n2 - 1, 0, n3 - 1, nf, st));
+    else AK_CHECK(h, ak_mhd_cons2prim(h, &a, 0, n1 - 1, 0, n2 - 1, 0, n3 - 1, nf, st));
     for (int q = 0; q < 3; ++q) nfloor[q] += nf[q];
     launches += 1;
     return TaskStatus::complete;
@@ -399,21 +448,22 @@ class MHD {  // state owner + tasks
   TaskStatus NewTimeStep(Driver *pd, int stage) {
     if (stage != pd->nexp_stages) return TaskStatus::complete;    // mhd_newdt.cpp:32-34
     double dt3[3];
-    AK_CHECK(h, ak_mhd_new_dt(h, &a, dt3, st));
-    dtnew = std::min(dt3[0], std::min(dt3[1], dt3[2]));
+    if (hydro) AK_CHECK(h, ak_hydro_new_dt(h, &a, dt3, st)); else AK_CHECK(h, ak_mhd_new_dt(h, &a, dt3, st));
+    dtnew = MinDt(dt3);
     launches += 1;
     return TaskStatus::complete;
   }
   TaskStatus ConToPrimNewDt(Driver *pd, int stage) {              // tasks 27+28 fused on the last stage
-    const int n1 = cfg.nx1 + 2 * cfg.ng, n2 = cfg.nx2 + 2 * cfg.ng, n3 = cfg.nx3 + 2 * cfg.ng;
+    const int n1 = cfg.nx1 + 2 * cfg.ng, n2 = multi_d ? cfg.nx2 + 2 * cfg.ng : 1, n3 = three_d ? cfg.nx3 + 2 * cfg.ng : 1;
     if (stage != pd->nexp_stages) {
-      AK_CHECK(h, ak_mhd_cons2prim(h, &a, 0, n1 - 1, 0, n2 - 1, 0, n3 - 1, nullptr, st));
+      if (hydro) AK_CHECK(h, ak_hydro_cons2prim(h, &a, 0, n1 - 1, 0, n2 - 1, 0, n3 - 1, nullptr, st));
+      else AK_CHECK(h, ak_mhd_cons2prim(h, &a, 0, n1 - 1, 0, n2 - 1, 0, n3 - 1, nullptr, st));
     } else {
       int nf[3];
       double dt3[3];
-      AK_CHECK(h, ak_mhd_cons2prim_newdt(h, &a, nf, dt3, st));
+      if (hydro) AK_CHECK(h, ak_hydro_cons2prim_newdt(h, &a, nf, dt3, st)); else AK_CHECK(h, ak_mhd_cons2prim_newdt(h, &a, nf, dt3, st));
       for (int q = 0; q < 3; ++q) nfloor[q] += nf[q];
-      dtnew = std::min(dt3[0], std::min(dt3[1], dt3[2]));
+      dtnew = MinDt(dt3);
     }
     launches += 1;
     return TaskStatus::complete;
@@ -437,7 +487,7 @@ class MHD {  // state owner + tasks
 
 void Driver::Initialize(MHD *pmhd) {   // driver.cpp:314-371 -> InitBoundaryValuesAndPrimitives :569-653
   pmhd->SendU(this, 0); pmhd->RecvU(this, 0);
-  pmhd->SendB(this, 0); pmhd->RecvB(this, 0);
+  if (!pmhd->hydro) { pmhd->SendB(this, 0); pmhd->RecvB(this, 0); }
   pmhd->ApplyPhysicalBCs(this, 0);                 // driver.cpp:626-627
   pmhd->ConToPrim(this, 0);
   pmhd->NewTimeStep(this, nexp_stages);
@@ -493,7 +543,8 @@ int ak_sim_set_bcs(void *sim, const int *mesh_bcs, const int *mb_bcs) {
   if (ak_bcs_create(&m->cfg, mesh_bcs, mb_bcs, &b)) return 1;
   if (ak_bcs_strictly_periodic(b)) { ak_bcs_destroy(b); return 0; }
   m->bcs = b;
-  for (int d = 0; d < 3; ++d) m->nbc_launches += (mesh_bcs[2 * d] != AK_BC_PERIODIC);
+  const bool act[3] = {true, m->multi_d, m->three_d};
+  for (int d = 0; d < 3; ++d) m->nbc_launches += (act[d] && mesh_bcs[2 * d] != AK_BC_PERIODIC);
   return 0;
 }
 int ak_sim_destroy(void *sim) { delete static_cast<akh::Sim *>(sim); return 0; }
@@ -514,6 +565,7 @@ int ak_sim_comm_init(void *sim, const void *unique_id128) {
 int ak_sim_set_state(void *sim, const double *u0, const double *b1f, const double *b2f, const double *b3f) {
   auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
   cudaError_t e = cudaMemcpyAsync(m->a.u0, u0, m->n_u * 8, cudaMemcpyHostToDevice, m->st);
+  if (m->hydro) return e == cudaSuccess ? 0 : 1;     // hydro twin: u0 only, the face-field pointers are ignored
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->a.b0x1f, b1f, m->n_f1 * 8, cudaMemcpyHostToDevice, m->st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->a.b0x2f, b2f, m->n_f2 * 8, cudaMemcpyHostToDevice, m->st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->a.b0x3f, b3f, m->n_f3 * 8, cudaMemcpyHostToDevice, m->st);
@@ -522,6 +574,7 @@ int ak_sim_set_state(void *sim, const double *u0, const double *b1f, const doubl
 int ak_sim_get_state(void *sim, double *u0, double *b1f, double *b2f, double *b3f) {
   auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
   cudaError_t e = cudaMemcpyAsync(u0, m->a.u0, m->n_u * 8, cudaMemcpyDeviceToHost, m->st);
+  if (m->hydro) { if (e == cudaSuccess) e = cudaStreamSynchronize(m->st); return e == cudaSuccess ? 0 : 1; }
   if (e == cudaSuccess) e = cudaMemcpyAsync(b1f, m->a.b0x1f, m->n_f1 * 8, cudaMemcpyDeviceToHost, m->st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(b2f, m->a.b0x2f, m->n_f2 * 8, cudaMemcpyDeviceToHost, m->st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(b3f, m->a.b0x3f, m->n_f3 * 8, cudaMemcpyDeviceToHost, m->st);

@@ -46,6 +46,8 @@ cudaError_t launch_update_ct(const Geom &g, const Arrays &a, bool do_u, bool do_
 cudaError_t launch_cons2prim(const Geom &g, const EosParams &eos, const Arrays &a, int il, int iu, int jl, int ju,
                              int kl, int ku, int *counters, bool newdt, unsigned long long *dtmin, cudaStream_t st);
 cudaError_t launch_newdt(const Geom &g, const EosParams &eos, const Arrays &a, unsigned long long *dtmin, cudaStream_t st);
+// history sums (hst.cu): scratch holds (nblocks+1)*11 doubles, the 11 results are its last row
+cudaError_t launch_hst_sums(const Geom &g, const Arrays &a, bool mhd, double *scratch, int nblocks, cudaStream_t st);
 cudaError_t launch_copy(const double *src, double *dst, long n, cudaStream_t st);
 
 }  // namespace akb

@@ -138,6 +138,14 @@ class Hydro:
             self.launches += 1
         return TaskStatus.complete
 
+    def HistorySums(self):
+        """History-output sums over this pack's active cells (src/outputs/history.cpp:78-160,272-372):
+        mass, 1/2/3-mom, tot-E, 1/2/3-KE (+ 1/2/3-ME for MHD)."""
+        out, n = (C.c_double * 11)(), C.c_int()
+        self._ck(self.L.ak_hst_sums(self.h, C.byref(self.arrays), out, C.byref(n), self._st()))
+        self.launches += 2
+        return np.array(out[:n.value])
+
     def SendRecvB(self, driver, stage):     # no magnetic field: lets Driver.Initialize treat both modules alike
         return TaskStatus.complete
 

@@ -233,6 +233,14 @@ class MHD:
                     _lib.check(L.ak_halo_unpack_fc(self.plan, *[a.data_ptr() for a in self.b0], ip, p["rfc"].data_ptr(), st))
                 self.launches += 1
 
+    def HistorySums(self):
+        """History-output sums over this pack's active cells (src/outputs/history.cpp:78-160,272-372):
+        mass, 1/2/3-mom, tot-E, 1/2/3-KE (+ 1/2/3-ME for MHD)."""
+        out, n = (C.c_double * 11)(), C.c_int()
+        self._ck(self.L.ak_hst_sums(self.h, C.byref(self.arrays), out, C.byref(n), self._st()))
+        self.launches += 2
+        return np.array(out[:n.value])
+
     def SendRecvU(self, driver, stage):
         self._exchange("u")
         return TaskStatus.complete

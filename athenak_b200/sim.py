@@ -15,13 +15,16 @@ INTEGRATOR = {"rk1": 1, "rk2": 2, "rk3": 3}
 class Simulation:
     def __init__(self, mesh, rank=0, *, ng=4, recon="ppm4", rsolver="hlld", gamma=1.6666667, integrator="rk3",
                  cfl_number=0.3, tlim=1.0, nlim=-1, fused=True, dfloor=FLT_MIN, pfloor=FLT_MIN, tfloor=FLT_MIN,
-                 sfloor=FLT_MIN, sigma_max=FLT_MAX):
+                 sfloor=FLT_MIN, sigma_max=FLT_MAX, physics="mhd"):
+        """physics="hydro": the hydro twin (rsolver in llf/hlle/hllc/roe; 1-D/2-D/3-D blocks); the state is u0 only."""
         self.L = _lib.load()
         self.mesh, self.rank, self.ng = mesh, rank, ng
         nmb = int(mesh.nmb_rank[rank])
         nx = mesh.nblock
         mb_size, mb_bcs, nghbr = mesh.rank_tables(rank)
-        mcfg = _lib.MhdCfg(nmb, ng, nx[0], nx[1], nx[2], _lib.RECON[recon], _lib.RSOLVER[rsolver], gamma,
+        self.hydro = physics == "hydro"
+        rs = _lib.HYD_RSOLVER[rsolver] if self.hydro else _lib.RSOLVER[rsolver]
+        mcfg = _lib.MhdCfg(nmb, ng, nx[0], nx[1], nx[2], _lib.RECON[recon], rs, gamma,
                            dfloor, pfloor, tfloor, sfloor, sigma_max)
         self.cfg = _lib.SimCfg(mcfg, INTEGRATOR[integrator], cfl_number, tlim, nlim, rank, mesh.nranks,
                                int(mesh.gids_start[rank]), mesh.nmb_total, 1 if fused else 0)
@@ -34,8 +37,10 @@ class Simulation:
         mesh_bcs = np.asarray(mesh.bcs, np.int32)
         if self.L.ak_sim_set_bcs(self.h, mesh_bcs.ctypes.data_as(ipp), mb_bcs.ctypes.data_as(ipp)):
             raise _lib.EngineError(self.L.ak_bcs_last_error(None).decode())
-        n1, n2, n3 = (nx[d] + 2 * ng for d in range(3))
+        n1, n2, n3 = (nx[d] + 2 * ng if (d == 0 or nx[d] > 1) else 1 for d in range(3))
         self.shapes = [(nmb, 5, n3, n2, n1), (nmb, n3, n2, n1 + 1), (nmb, n3, n2 + 1, n1), (nmb, n3 + 1, n2, n1)]
+        if self.hydro:
+            self.shapes = self.shapes[:1]
 
     def __del__(self):
         try:
@@ -56,16 +61,21 @@ class Simulation:
 
     @staticmethod
     def _ptr(t):
+        if t is None:
+            return C.c_void_p(None)
         return C.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else t.ctypes.data)
 
-    def set_state(self, u0, b1f, b2f, b3f):
+    def set_state(self, u0, b1f=None, b2f=None, b3f=None):
         """Host arrays (numpy or torch CPU tensors, C-contiguous float64, full ghost-inclusive shape)."""
+        if not self.hydro and (b1f is None or b2f is None or b3f is None):
+            raise _lib.EngineError("set_state: MHD needs the three face fields")
         if self.L.ak_sim_set_state(self.h, *[self._ptr(t) for t in (u0, b1f, b2f, b3f)]):
             raise _lib.EngineError("ak_sim_set_state failed")
 
     def get_state(self, out=None):
         out = out or [np.empty(s) for s in self.shapes]
-        if self.L.ak_sim_get_state(self.h, *[self._ptr(t) for t in out]):
+        ptrs = [self._ptr(t) for t in out] + [self._ptr(None)] * (4 - len(out))
+        if self.L.ak_sim_get_state(self.h, *ptrs):
             raise _lib.EngineError("ak_sim_get_state failed")
         return out
 

@@ -119,6 +119,13 @@ int ak_hydro_stage_fused(void *h, const ak_mhd_arrays *a, int stage, double gam0
                          double beta_dt, ak_stream_t s);
 int ak_hydro_cons2prim_newdt(void *h, const ak_mhd_arrays *a, int *nfloor, double *dt3, ak_stream_t s);
 
+/* History-output sums over the active cells of the pack (reference src/outputs/history.cpp:78-160
+ * LoadHydroHistoryData, :272-372 LoadMHDHistoryData): sums[0..4] = volume-weighted mass, 1/2/3-mom,
+ * tot-E; [5..7] = 1/2/3-KE; MHD handles add [8..10] = 1/2/3-ME.  *nhist = 8 (hydro) or 11 (MHD).
+ * h from ak_mhd_create or ak_hydro_create.  Deterministic two-pass device reduction; the caller
+ * adds the per-rank results (the reference's MPI_Reduce, history.cpp:385-392).  Synchronises. */
+int ak_hst_sums(void *h, const ak_mhd_arrays *a, double *sums, int *nhist, ak_stream_t s);
+
 /* ---- ghost-zone exchange (src/bvals): tasks 10/11 SendU/RecvU, 21/22 SendB/RecvB ---------
  * nghbr: HOST [nmb][56][4] = {gid, lev, rank, dest} per neighbour slot (NeighborBlock,
  * src/mesh/mesh.hpp:47-52; slot numbering src/mesh/nghbr_index.hpp:28-54).  gids_start is the

@@ -137,3 +137,66 @@ def test_hydro_linear_wave_convergence(recon, rs):
         assert abs(e - ref_err) <= 2e-6 * ref_err, (e, ref_err)
         errs.append(e)
     assert errs[1] / errs[0] < (0.4 if recon == "plm" else 0.25)
+
+
+@pytest.mark.parametrize("deck,base,ov", [CASES[0], CASES[5], CASES[8]], ids=["sod1d", "sod2d", "lwave3d"])
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "pertask"])
+def test_hydro_cxx_host_driver(deck, base, ov, fused):
+    """The same cases through the C++ host driver (TaskList/Driver/Hydro tasks in csrc/host_driver.cpp, ak_sim_*)."""
+    from athenak_b200.mesh import Mesh
+    from athenak_b200.sim import Simulation
+    r0, r1, _ = reference(deck, base, ov)
+    case = H.Case(r0.deck)
+    mesh = Mesh(case.nmesh, case.nblock, xmin=case.xmin, xmax=case.xmax, bcs=case.bc_names)
+    sim = Simulation(mesh, 0, ng=case.ng, recon=case.recon, rsolver=case.rsolver, gamma=case.gamma,
+                     integrator=case.integrator, cfl_number=case.cfl, tlim=case.tlim, fused=fused, physics="hydro")
+    sim.set_state(np.ascontiguousarray(r0.u0))
+    sim.initialize()
+    assert sim.status()["dt"] == r0.dt
+    sim.execute(-1)
+    st = sim.status()
+    assert st["ncycle"] == r1.ncycle and st["time"] == r1.time
+    (u,) = sim.get_state()
+    assert np.array_equal(u, r1.u0), f"max|dU| = {np.abs(u - r1.u0).max()}"
+
+
+def _read_hst(path):
+    rows = [ln.split() for ln in open(path) if not ln.startswith("#")]
+    return np.array(rows, dtype=np.float64)
+
+
+def test_history_sums_hydro_and_mhd():
+    """the hst sums as a device reduction == the reference's .hst rows (written
+    with %24.16e) to reassociation accuracy, for the hydro twin (2-D Sod, 8 blocks) and for MHD
+    (3-D linear wave, 32 blocks)."""
+    if not O.have_reference("athena_builtin"):
+        pytest.skip("oracle/_ref/athena_builtin not built")
+    # hydro
+    with tempfile.TemporaryDirectory() as tmp:
+        O.run_reference("athena_builtin", os.path.join(DECKS, "sod2d.athinput"), tmp, threads=4)
+        r0 = read_rst(os.path.join(tmp, "rst", "Sod.00000.rst"), physics="hydro")
+        hst = _read_hst(os.path.join(tmp, "Sod.hydro.hst"))
+    case = H.Case(r0.deck)
+    u, w, drv, dt0, hyd = run_engine(case, r0.u0, True, ncycles=0)
+    s0 = hyd.HistorySums()
+    assert s0.shape == (8,)
+    assert np.allclose(s0, hst[0, 2:10], rtol=1e-13, atol=1e-15), (s0, hst[0, 2:10])
+    u, w, drv, dt0, hyd = run_engine(case, r0.u0, True)
+    s1 = hyd.HistorySums()
+    assert drv.time == hst[-1, 0]
+    assert np.allclose(s1, hst[-1, 2:10], rtol=1e-12, atol=1e-14), (s1, hst[-1, 2:10])
+    # MHD
+    from athenak_b200.driver import Driver
+    from athenak_b200.mesh import Mesh
+    from athenak_b200.mhd import MHD
+    with tempfile.TemporaryDirectory() as tmp:
+        O.run_reference("athena_builtin", os.path.join(DECKS, "lwave3d.athinput"), tmp, ["time/tlim=0.0"], threads=4)
+        r0 = read_rst(os.path.join(tmp, "rst", "LinWave.00000.rst"))
+        hst = _read_hst(os.path.join(tmp, "LinWave.mhd.hst"))
+    mesh = Mesh((32, 16, 16), (16, 4, 4), xmin=(0.0, 0.0, 0.0), xmax=(3.0, 1.5, 1.5))
+    mb_size, _, nghbr = mesh.rank_tables(0)
+    e = MHD(mesh.nmb_total, 4, (16, 4, 4), mb_size, nghbr, recon="ppm4", rsolver="hlld", gamma=1.66666666667)
+    e.load_state(r0.u0, r0.b1f, r0.b2f, r0.b3f)
+    sm = e.HistorySums()
+    assert sm.shape == (11,)
+    assert np.allclose(sm, hst[0, 2:13], rtol=1e-13, atol=1e-15), (sm, hst[0, 2:13])
