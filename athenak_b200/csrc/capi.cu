@@ -67,13 +67,12 @@ akb::Arrays to_arrays(const ak_mhd_arrays *a) {
 int check_cfg(const ak_mhd_cfg *c, bool hydro, std::string &why) {
   if (!c) { why = "null cfg"; return 1; }
   if (c->nmb < 1) { why = "nmb < 1"; return 1; }
+  // mesh.cpp:70-79: 1-D (nx2 = nx3 = 1), 2-D (nx3 = 1) or 3-D
+  if (c->nx1 < 2 || c->nx2 < 1 || c->nx3 < 1 || (c->nx2 == 1 && c->nx3 > 1)) { why = "MeshBlock must be 1-D (nx2=nx3=1), 2-D (nx3=1) or 3-D"; return 1; }
   if (hydro) {
-    // mesh.cpp:70-79: 1-D (nx2 = nx3 = 1), 2-D (nx3 = 1) or 3-D
-    if (c->nx1 < 2 || c->nx2 < 1 || c->nx3 < 1 || (c->nx2 == 1 && c->nx3 > 1)) { why = "MeshBlock must be 1-D (nx2=nx3=1), 2-D (nx3=1) or 3-D"; return 1; }
     if (c->rsolver == AK_RSOLVER_HYD_ADVECT) { why = "rsolver advect needs time/evolution=kinematic (hydro.cpp:255-265), which is not on this path"; return 1; }
     if (c->rsolver < AK_RSOLVER_HYD_LLF || c->rsolver > AK_RSOLVER_HYD_ROE) { why = "unknown hydro Riemann solver"; return 1; }
   } else {
-    if (c->nx1 < 2 || c->nx2 < 2 || c->nx3 < 2) { why = "MHD: only 3-D MeshBlocks (nx1,nx2,nx3 > 1) are supported"; return 1; }
     if (c->rsolver < AK_RSOLVER_LLF || c->rsolver > AK_RSOLVER_HLLD) { why = "unknown Riemann solver"; return 1; }
   }
   if (c->recon < AK_RECON_DC || c->recon > AK_RECON_TENO) { why = "unknown reconstruction method"; return 1; }

@@ -91,8 +91,8 @@ halo_copy_kernel(const HaloDesc *__restrict__ descs, HaloArrays A, int nvar, lon
 // EMF (edge-field) boundary boxes for flux correction, same level: buffs_fc.cpp:327-368 (send)
 // and :892-935 (recv) -- identical formulae.  v: 0 x1e, 1 x2e, 2 x3e.
 static Box emf_box(const ak_mhd_cfg &c, int v, const int o[3]) {
-  const int s[3] = {c.ng, c.ng, c.ng};
-  const int e[3] = {c.ng + c.nx1 - 1, c.ng + c.nx2 - 1, c.ng + c.nx3 - 1};
+  const int s[3] = {c.ng, c.nx2 > 1 ? c.ng : 0, c.nx3 > 1 ? c.ng : 0};
+  const int e[3] = {s[0] + c.nx1 - 1, s[1] + c.nx2 - 1, s[2] + c.nx3 - 1};
   Box b;
   for (int d = 0; d < 3; ++d) {
     if (o[d] == 0) { b.lo[d] = s[d]; b.hi[d] = e[d] + (v == d ? 0 : 1); }
@@ -136,10 +136,10 @@ static const int kOff[26][3] = {
     {-1,-1,-1},{1,-1,-1},{-1,1,-1},{1,1,-1},{-1,-1,1},{1,-1,1},{-1,1,1},{1,1,1}};
 
 HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int gids_start, std::string &err) {
-  // hydro twin: cell-centred data only, 1-D/2-D/3-D; MHD (face fields, EMFs): 3-D
+  // hydro twin: cell-centred data only; MHD adds the face fields and the EMF correction.
+  // 1-D/2-D/3-D: only the active dimensions have neighbours, ghost cells and end lines.
   const bool cc_only = cfg.rsolver >= AK_RSOLVER_HYD_ADVECT;
   const bool act[3] = {true, cfg.nx2 > 1, cfg.nx3 > 1};
-  if (!cc_only && (!act[1] || !act[2])) { err = "halo: MHD supports only 3-D meshes"; return nullptr; }
   if (cfg.nx1 < cfg.ng || (act[1] && cfg.nx2 < cfg.ng) || (act[2] && cfg.nx3 < cfg.ng)) { err = "halo: block smaller than nghost"; return nullptr; }
   auto *P = new HaloPlan();
   P->cfg = cfg;
@@ -241,6 +241,7 @@ HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int g
         const int *o = kOff[q];
         const int nz = (o[0] != 0) + (o[1] != 0) + (o[2] != 0);
         if (nz == 3) continue;
+        if ((o[1] && !act[1]) || (o[2] && !act[2])) continue;   // flux_correct_fc.cpp:898,953,963,1013,1023
         const int slot = neighbor_index(o[0], o[1], o[2], 0, 0);
         const int *nb = nghbr + ((long)m * 56 + slot) * 4;
         if (nb[0] < 0) continue;
@@ -269,6 +270,7 @@ HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int g
         const int *o = kOff[q];
         const int nz = (o[0] != 0) + (o[1] != 0) + (o[2] != 0);
         if (nz == 3) continue;
+        if ((o[1] && !act[1]) || (o[2] && !act[2])) continue;   // flux_correct_fc.cpp:898,953,963,1013,1023
         const int slot = neighbor_index(o[0], o[1], o[2], 0, 0);
         const int *nb = nghbr + ((long)m * 56 + slot) * 4;
         if (nb[0] < 0) continue;
@@ -303,6 +305,7 @@ HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int g
         const int *o = kOff[q];
         const int nz = (o[0] != 0) + (o[1] != 0) + (o[2] != 0);
         if (nz == 3) continue;
+        if ((o[1] && !act[1]) || (o[2] && !act[2])) continue;   // flux_correct_fc.cpp:898,953,963,1013,1023
         const int slot = neighbor_index(o[0], o[1], o[2], 0, 0);
         for (int v = 0; v < 3; ++v) {
           if (!emf_slot_has(o, v)) continue;
@@ -314,7 +317,7 @@ HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int g
           if (nz == 1) {
             if (nghbr[((long)m * 56 + slot) * 4] < 0) continue;   // physical boundary: nothing to average
             d.face = 1;
-            for (int a = 0; a < 3; ++a) if (o[a] == 0 && a != v) { b.lo[a] += 1; b.hi[a] -= 1; }   // drop the end lines
+            for (int a = 0; a < 3; ++a) if (o[a] == 0 && a != v && act[a]) { b.lo[a] += 1; b.hi[a] -= 1; }   // drop the end lines (active dims only, :846,873)
             if (b.count() <= 0) continue;
             src.push_back({slot, o});
           } else {
@@ -425,7 +428,7 @@ HaloArrays halo_arrays_cc(const ak_mhd_cfg &c, double *a, int nvar) {
 }
 
 HaloArrays halo_arrays_fc(const ak_mhd_cfg &c, double *x1f, double *x2f, double *x3f) {
-  const long n1 = c.nx1 + 2 * c.ng, n2 = c.nx2 + 2 * c.ng, n3 = c.nx3 + 2 * c.ng;
+  const long n1 = c.nx1 + 2 * c.ng, n2 = c.nx2 > 1 ? c.nx2 + 2 * c.ng : 1, n3 = c.nx3 > 1 ? c.nx3 + 2 * c.ng : 1;
   HaloArrays A{};
   A.p[0] = x1f; A.ext1[0] = n1 + 1; A.ext2[0] = n2;     A.bstride[0] = (n1 + 1) * n2 * n3;
   A.p[1] = x2f; A.ext1[1] = n1;     A.ext2[1] = n2 + 1; A.bstride[1] = n1 * (n2 + 1) * n3;
@@ -434,7 +437,7 @@ HaloArrays halo_arrays_fc(const ak_mhd_cfg &c, double *x1f, double *x2f, double 
 }
 
 HaloArrays halo_arrays_ec(const ak_mhd_cfg &c, double *x1e, double *x2e, double *x3e) {
-  const long n1 = c.nx1 + 2 * c.ng, n2 = c.nx2 + 2 * c.ng, n3 = c.nx3 + 2 * c.ng;
+  const long n1 = c.nx1 + 2 * c.ng, n2 = c.nx2 > 1 ? c.nx2 + 2 * c.ng : 1, n3 = c.nx3 > 1 ? c.nx3 + 2 * c.ng : 1;
   HaloArrays A{};
   A.p[0] = x1e; A.ext1[0] = n1;     A.ext2[0] = n2 + 1; A.bstride[0] = n1 * (n2 + 1) * (n3 + 1);
   A.p[1] = x2e; A.ext1[1] = n1 + 1; A.ext2[1] = n2;     A.bstride[1] = (n1 + 1) * n2 * (n3 + 1);

@@ -324,7 +324,7 @@ class MHD {  // state owner + tasks
   }
   TaskStatus StageFluxEmf(Driver *pd, int stage) {   // tasks 2 + 14
     AK_CHECK(h, ak_mhd_stage_flux_emf(h, &a, st));
-    launches += 4;
+    launches += nsweeps() + 1;
     return TaskStatus::complete;
   }
   TaskStatus StageUpdate(Driver *pd, int stage) {    // tasks 1 + 5 + 17

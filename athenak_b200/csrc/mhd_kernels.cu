@@ -88,6 +88,59 @@ corner_emf_kernel(Geom g, const double *__restrict__ w0, const double *__restric
   }
 }
 
+// 1-D: the face-centred EMFs are the edge EMFs (mhd_corner_e.cpp:41-54).  One thread per x1-face.
+__global__ void __launch_bounds__(128)
+corner_emf_1d_kernel(Geom g, const double *__restrict__ e3x1, const double *__restrict__ e2x1,
+                     double *__restrict__ e2, double *__restrict__ e3) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ni = g.nx1 + 1;
+  if (t >= (long)g.nmb * ni) return;
+  const int m = (int)(t / ni), i = g.is + (int)(t % ni);
+  const double v2 = __ldg(e2x1 + (long)m * g.cc + i), v3 = __ldg(e3x1 + (long)m * g.cc + i);
+  double *E2 = e2 + (long)m * g.e2, *E3 = e3 + (long)m * g.e3;   // x2e (2,1,n1+1), x3e (1,2,n1+1)
+  E2[i] = v2;
+  E2[(long)(g.n1 + 1) + i] = v2;          // k = ke+1
+  E3[i] = v3;
+  E3[(long)(g.n1 + 1) + i] = v3;          // j = je+1
+}
+
+// 2-D: E1, E2 copied from the face EMFs, E3 by the GS07 upwinding (mhd_corner_e.cpp:59-201,
+// Newtonian branch).  One thread per corner j in [js,je+1], i in [is,ie+1]; branch-free form of
+// the selection as in corner_emf_kernel.
+__global__ void __launch_bounds__(128)
+corner_emf_2d_kernel(Geom g, const double *__restrict__ w0, const double *__restrict__ bcc,
+                     const double *__restrict__ flx1, const double *__restrict__ flx2,
+                     const double *__restrict__ e3x1, const double *__restrict__ e2x1,
+                     const double *__restrict__ e1x2, const double *__restrict__ e3x2,
+                     double *__restrict__ e1, double *__restrict__ e2, double *__restrict__ e3) {
+  const int ii = blockIdx.x * 32 + threadIdx.x, jj = blockIdx.y * 4 + threadIdx.y;
+  const int m = blockIdx.z;
+  if (ii > g.nx1 || jj > g.nx2) return;
+  const int i = g.is + ii, j = g.js + jj;
+  const long cc = g.cc, n1 = g.n1;
+  const long o = (long)j * n1 + i, mo = (long)m * cc;
+  const double *w = w0 + (long)m * 5 * cc, *b = bcc + (long)m * 3 * cc;
+  auto e3cc = [&](long q) { return __ldg(w + IVY * cc + q) * __ldg(b + 0 * cc + q) - __ldg(w + IVX * cc + q) * __ldg(b + 1 * cc + q); };
+  const double *f1 = flx1 + (long)m * 5 * g.f1, *f2 = flx2 + (long)m * 5 * g.f2;
+  auto F1 = [&](int jq, int iq) { return __ldg(f1 + (long)jq * (n1 + 1) + iq); };
+  auto F2 = [&](int jq, int iq) { return __ldg(f2 + (long)jq * n1 + iq); };
+  const double v2 = __ldg(e2x1 + mo + o), v1 = __ldg(e1x2 + mo + o);
+  double *E1 = e1 + (long)m * g.e1, *E2 = e2 + (long)m * g.e2, *E3 = e3 + (long)m * g.e3;
+  // x1e (2, n2+1, n1); x2e (2, n2, n1+1); x3e (1, n2+1, n1+1)
+  E2[(long)j * (n1 + 1) + i] = v2;
+  E2[(long)g.n2 * (n1 + 1) + (long)j * (n1 + 1) + i] = v2;
+  E1[(long)j * n1 + i] = v1;
+  E1[(long)(g.n2 + 1) * n1 + (long)j * n1 + i] = v1;
+  const double x2_im = __ldg(e3x2 + mo + o - 1), x2_i = __ldg(e3x2 + mo + o);
+  const double x1_jm = __ldg(e3x1 + mo + o - n1), x1_j = __ldg(e3x1 + mo + o);
+  const double c_mm = e3cc(o - n1 - 1), c_m0 = e3cc(o - n1), c_0m = e3cc(o - 1), c_00 = e3cc(o);
+  const double l2 = (F1(j - 1, i) >= 0.0) ? (x2_im - c_mm) : (x2_i - c_m0);
+  const double r2 = (F1(j, i) >= 0.0) ? (x2_im - c_0m) : (x2_i - c_00);
+  const double l1 = (F2(j, i - 1) >= 0.0) ? (x1_jm - c_mm) : (x1_j - c_0m);
+  const double r1 = (F2(j, i) >= 0.0) ? (x1_jm - c_m0) : (x1_j - c_00);
+  E3[(long)j * (n1 + 1) + i] = 0.25 * (l1 + r1 + l2 + r2 + x2_im + x2_i + x1_jm + x1_j);
+}
+
 // ---------------------------------------------------------------------------------------
 // RK update (mhd_update.cpp:51-82) and CT (mhd_ct.cpp:45-77) in one pass.  Thread per
 // (k in [ks,ke+1], j in [js,je+1], i in [is,ie+1]); the cell update runs where all three
@@ -139,14 +192,14 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
     const long a1 = ((long)k * (n2 + 1) + j) * n1 + i;        // x1e(k,j,i)
     const long a2 = ((long)k * n2 + j) * (n1 + 1) + i;        // x2e(k,j,i)
     const long a3 = ((long)k * (n2 + 1) + j) * (n1 + 1) + i;  // x3e(k,j,i)
-    if (ja && ka) {  // x1f(k,j,i), i in [is,ie+1]
+    if (ja && ka && g.multi_d) {  // x1f(k,j,i), i in [is,ie+1]; B1 is not touched in 1-D (mhd_ct.cpp:41-53)
       const long o = (long)m * g.f1 + ((long)k * n2 + j) * (n1 + 1) + i;
       const double bold = b1f[o];
       double breg;
       if (SAVE) { breg = bold; o1f[o] = bold; } else { breg = o1f[o]; }
       double b = gam0 * bold + gam1 * breg;
       b -= div_by(beta_dt * (__ldg(E3 + a3 + (n1 + 1)) - __ldg(E3 + a3)), dx2, rdx2);
-      b += div_by(beta_dt * (__ldg(E2 + a2 + n2 * (n1 + 1)) - __ldg(E2 + a2)), dx3, rdx3);
+      if (g.three_d) b += div_by(beta_dt * (__ldg(E2 + a2 + n2 * (n1 + 1)) - __ldg(E2 + a2)), dx3, rdx3);
       b1f[o] = b;
     }
     if (ia && ka) {  // x2f(k,j,i), j in [js,je+1]
@@ -156,7 +209,7 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
       if (SAVE) { breg = bold; o2f[o] = bold; } else { breg = o2f[o]; }
       double b = gam0 * bold + gam1 * breg;
       b += div_by(beta_dt * (__ldg(E3 + a3 + 1) - __ldg(E3 + a3)), dx1, rdx1);
-      b -= div_by(beta_dt * (__ldg(E1 + a1 + (n2 + 1) * n1) - __ldg(E1 + a1)), dx3, rdx3);
+      if (g.three_d) b -= div_by(beta_dt * (__ldg(E1 + a1 + (n2 + 1) * n1) - __ldg(E1 + a1)), dx3, rdx3);
       b2f[o] = b;
     }
     if (ia && ja) {  // x3f(k,j,i), k in [ks,ke+1]
@@ -166,7 +219,7 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
       if (SAVE) { breg = bold; o3f[o] = bold; } else { breg = o3f[o]; }
       double b = gam0 * bold + gam1 * breg;
       b -= div_by(beta_dt * (__ldg(E2 + a2 + 1) - __ldg(E2 + a2)), dx1, rdx1);
-      b += div_by(beta_dt * (__ldg(E1 + a1 + n1) - __ldg(E1 + a1)), dx2, rdx2);
+      if (g.multi_d) b += div_by(beta_dt * (__ldg(E1 + a1 + n1) - __ldg(E1 + a1)), dx2, rdx2);
       b3f[o] = b;
     }
   }
@@ -322,6 +375,15 @@ cudaError_t launch_fluxes(int recon, int rs, const Geom &g, const EosParams &eos
 }
 
 cudaError_t launch_corner_e(const Geom &g, const Arrays &a, cudaStream_t st) {
+  if (!g.multi_d) {
+    corner_emf_1d_kernel<<<nblocks((long)g.nmb * (g.nx1 + 1), 128), 128, 0, st>>>(g, a.e3x1, a.e2x1, a.e2, a.e3);
+    return cudaGetLastError();
+  }
+  if (!g.three_d) {
+    const dim3 gr2((g.nx1 + 1 + 31) / 32, (g.nx2 + 1 + 3) / 4, g.nmb);
+    corner_emf_2d_kernel<<<gr2, dim3(32, 4, 1), 0, st>>>(g, a.w0, a.bcc0, a.flx1, a.flx2, a.e3x1, a.e2x1, a.e1x2, a.e3x2, a.e1, a.e2, a.e3);
+    return cudaGetLastError();
+  }
   const dim3 tb(TILE_X, TILE_Y, TILE_Z);
   const dim3 gr((g.nx1 + 1 + TILE_X - 1) / TILE_X, (g.nx2 + 1 + TILE_Y - 1) / TILE_Y, ((g.nx3 + 1 + TILE_Z - 1) / TILE_Z) * g.nmb);
   corner_emf_kernel<<<gr, tb, 0, st>>>(g, a.w0, a.bcc0, a.flx1, a.flx2, a.flx3, a.e3x1, a.e2x1, a.e1x2, a.e3x2, a.e2x3, a.e1x3, a.e1, a.e2, a.e3);

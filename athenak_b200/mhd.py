@@ -45,7 +45,9 @@ class MHD:
         self.device = torch.device(device)
         self.nmb, self.ng, self.nx = int(nmb), int(ng), tuple(int(v) for v in nx)
         nx1, nx2, nx3 = self.nx
-        self.n = (nx1 + 2 * ng, nx2 + 2 * ng, nx3 + 2 * ng)
+        self.multi_d, self.three_d = nx2 > 1, nx3 > 1      # src/mesh/mesh.cpp:70-79
+        self.n = (nx1 + 2 * ng, nx2 + 2 * ng if self.multi_d else 1, nx3 + 2 * ng if self.three_d else 1)
+        self.nsweeps = 1 + int(self.multi_d) + int(self.three_d)
         self.cfg = _lib.MhdCfg(self.nmb, ng, nx1, nx2, nx3, _lib.RECON[recon], _lib.RSOLVER[rsolver],
                                gamma, dfloor, pfloor, tfloor, sfloor, sigma_max)
         self.fused = fused
@@ -88,7 +90,8 @@ class MHD:
                                     C.byref(self.bcs)):
                 self.bcs = None
                 raise _lib.EngineError(self.L.ak_bcs_last_error(None).decode())
-            self.nbc = sum(int(mesh_bcs[2 * d]) != _lib.BC["periodic"] for d in range(3))
+            act = (True, self.multi_d, self.three_d)
+            self.nbc = sum(act[d] and int(mesh_bcs[2 * d]) != _lib.BC["periodic"] for d in range(3))
         self.dtnew = FLT_MAX
         self.nfloor = [0, 0, 0]       # EventCounters neos_dfloor/efloor/tfloor (src/mesh/mesh.hpp:70-74)
         self.launches = 0             # kernels this object has launched (bench: gpu_launches)
@@ -138,7 +141,7 @@ class MHD:
 
     def Fluxes(self, driver, stage):
         self._ck(self.L.ak_mhd_fluxes(self.h, C.byref(self.arrays), self._st()))
-        self.launches += 3
+        self.launches += self.nsweeps
         return TaskStatus.complete
 
     def RKUpdate(self, driver, stage):
@@ -161,7 +164,7 @@ class MHD:
     def StageFluxEmf(self, driver, stage):
         """Tasks 2 + 14 in one ABI call (ak_mhd_stage_flux_emf)."""
         self._ck(self.L.ak_mhd_stage_flux_emf(self.h, C.byref(self.arrays), self._st()))
-        self.launches += 4
+        self.launches += self.nsweeps + 1
         return TaskStatus.complete
 
     def StageUpdate(self, driver, stage):
@@ -274,8 +277,15 @@ class MHD:
         dt3 = (C.c_double * 3)()
         self._ck(self.L.ak_mhd_new_dt(self.h, C.byref(self.arrays), dt3, self._st()))
         self.launches += 1
-        self.dtnew = min(dt3[0], dt3[1], dt3[2])   # src/mhd/mhd_newdt.cpp:152-155
+        self._set_dtnew(dt3)
         return TaskStatus.complete
+
+    def _set_dtnew(self, dt3):
+        self.dtnew = dt3[0]                        # src/mhd/mhd_newdt.cpp:152-155
+        if self.multi_d:
+            self.dtnew = min(self.dtnew, dt3[1])
+        if self.three_d:
+            self.dtnew = min(self.dtnew, dt3[2])
 
     def ConToPrimNewDt(self, driver, stage):
         """Tasks 27+28 fused on the last stage (ak_mhd_cons2prim_newdt)."""
@@ -286,5 +296,5 @@ class MHD:
         self.launches += 1
         for q in range(3):
             self.nfloor[q] += nf[q]
-        self.dtnew = min(dt3[0], dt3[1], dt3[2])
+        self._set_dtnew(dt3)
         return TaskStatus.complete

@@ -596,19 +596,15 @@ void oracle_fluxes(const ocfg *c, const double *w0, const double *bcc0, const do
   double *wl = calloc(5 * ncc, 8), *wr = calloc(5 * ncc, 8);
   double *bl = calloc(3 * ncc, 8), *br = calloc(3 * ncc, 8);
   const int is = D.is, ie = D.ie, js = D.js, je = D.je, ks = D.ks, ke = D.ke;
-  for (int dir = 0; dir < 3; ++dir) {
-    int kl, ku, jl, ju, il, iu;       /* recon cell box   (mhd_fluxes.cpp:131,181,228) */
-    int fkl, fku, fjl, fju, fil, fiu; /* face box         (mhd_fluxes.cpp:138,188,235) */
-    if (dir == 0) {
-      kl = ks - 1; ku = ke + 1; jl = js - 1; ju = je + 1; il = is - 1; iu = ie + 1;
-      fkl = kl; fku = ku; fjl = jl; fju = ju; fil = is; fiu = ie + 1;
-    } else if (dir == 1) {
-      kl = ks - 1; ku = ke + 1; jl = js - 1; ju = je + 1; il = is - 1; iu = ie + 1;
-      fkl = kl; fku = ku; fjl = js; fju = je + 1; fil = il; fiu = iu;
-    } else {
-      kl = ks - 1; ku = ke + 1; jl = js - 1; ju = je + 1; il = is - 1; iu = ie + 1;
-      fkl = ks; fku = ke + 1; fjl = jl; fju = ju; fil = il; fiu = iu;
-    }
+  const int multi_d = c->nx2 > 1, three_d = c->nx3 > 1;
+  const int ndir = 1 + multi_d + three_d;
+  for (int dir = 0; dir < ndir; ++dir) {
+    /* CT-extended transverse ranges only in ACTIVE dimensions (mhd_fluxes.cpp:126-128,176-178,225-226) */
+    int kl = ks - three_d, ku = ke + three_d, jl = js - multi_d, ju = je + multi_d, il = is - 1, iu = ie + 1;   /* recon cell box */
+    int fkl = kl, fku = ku, fjl = jl, fju = ju, fil = il, fiu = iu;                                               /* face box */
+    if (dir == 0) { fil = is; fiu = ie + 1; }
+    else if (dir == 1) { fjl = js; fju = je + 1; }
+    else { fkl = ks; fku = ke + 1; }
     recon_pass(c, dir, 5, 1, w0, wl, wr, kl, ku, jl, ju, il, iu);
     recon_pass(c, dir, 3, 0, bcc0, bl, br, kl, ku, jl, ju, il, iu);
     for (int m = 0; m < c->nmb; ++m)
@@ -649,8 +645,8 @@ void oracle_rk_update(const ocfg *c, double *u0, const double *u1, const double 
         for (int j = D.js; j <= D.je; ++j)
           for (int i = D.is; i <= D.ie; ++i) {
             double divf = (F1(flx1, m, n, k, j, i + 1) - F1(flx1, m, n, k, j, i)) / dx1;
-            divf += (F2(flx2, m, n, k, j + 1, i) - F2(flx2, m, n, k, j, i)) / dx2;
-            divf += (F3(flx3, m, n, k + 1, j, i) - F3(flx3, m, n, k, j, i)) / dx3;
+            if (c->nx2 > 1) divf += (F2(flx2, m, n, k, j + 1, i) - F2(flx2, m, n, k, j, i)) / dx2;   /* mhd_update.cpp:63-69 multi_d */
+            if (c->nx3 > 1) divf += (F3(flx3, m, n, k + 1, j, i) - F3(flx3, m, n, k, j, i)) / dx3;   /* :72-78 three_d */
             CC(u0, 5, m, n, k, j, i) = gam0 * CC(u0, 5, m, n, k, j, i) + gam1 * CC(u1, 5, m, n, k, j, i) - beta_dt * divf;
           }
   }
@@ -663,8 +659,45 @@ void oracle_corner_e(const ocfg *c, const double *w0, const double *bcc, const d
                      double *e1, double *e2, double *e3) {
   odims D = dims(c);
   size_t ncc = (size_t)c->nmb * D.cc;
-  double *e1cc = calloc(ncc, 8), *e2cc = calloc(ncc, 8), *e3cc = calloc(ncc, 8);
   const int is = D.is, ie = D.ie, js = D.js, je = D.je, ks = D.ks, ke = D.ke;
+  if (c->nx2 == 1) {   /* 1-D: copy face-centred E to the edges, mhd_corner_e.cpp:41-54 */
+    for (int m = 0; m < c->nmb; ++m)
+      for (int i = is; i <= ie + 1; ++i) {
+        X2E(e2, m, ks, js, i) = S4(e2x1, m, ks, js, i);
+        X2E(e2, m, ke + 1, js, i) = S4(e2x1, m, ks, js, i);
+        X3E(e3, m, ks, js, i) = S4(e3x1, m, ks, js, i);
+        X3E(e3, m, ks, je + 1, i) = S4(e3x1, m, ks, js, i);
+      }
+    return;
+  }
+  if (c->nx3 == 1) {   /* 2-D: E1, E2 copied, E3 by GS07, mhd_corner_e.cpp:59-201 */
+    double *e3c = calloc(ncc, 8);
+    for (int m = 0; m < c->nmb; ++m)
+      for (int j = js - 1; j <= je + 1; ++j)
+        for (int i = is - 1; i <= ie + 1; ++i)
+          S4(e3c, m, ks, j, i) = CC(w0, 5, m, IVY, ks, j, i) * CC(bcc, 3, m, 0, ks, j, i) - CC(w0, 5, m, IVX, ks, j, i) * CC(bcc, 3, m, 1, ks, j, i);
+    for (int m = 0; m < c->nmb; ++m)
+      for (int j = js; j <= je + 1; ++j)
+        for (int i = is; i <= ie + 1; ++i) {
+          X2E(e2, m, ks, j, i) = S4(e2x1, m, ks, j, i);
+          X2E(e2, m, ke + 1, j, i) = S4(e2x1, m, ks, j, i);
+          X1E(e1, m, ks, j, i) = S4(e1x2, m, ks, j, i);
+          X1E(e1, m, ke + 1, j, i) = S4(e1x2, m, ks, j, i);
+          double e3_l2, e3_r2, e3_l1, e3_r1;
+          if (F1(flx1, m, IDN, ks, j - 1, i) >= 0.0) e3_l2 = S4(e3x2, m, ks, j, i - 1) - S4(e3c, m, ks, j - 1, i - 1);
+          else e3_l2 = S4(e3x2, m, ks, j, i) - S4(e3c, m, ks, j - 1, i);
+          if (F1(flx1, m, IDN, ks, j, i) >= 0.0) e3_r2 = S4(e3x2, m, ks, j, i - 1) - S4(e3c, m, ks, j, i - 1);
+          else e3_r2 = S4(e3x2, m, ks, j, i) - S4(e3c, m, ks, j, i);
+          if (F2(flx2, m, IDN, ks, j, i - 1) >= 0.0) e3_l1 = S4(e3x1, m, ks, j - 1, i) - S4(e3c, m, ks, j - 1, i - 1);
+          else e3_l1 = S4(e3x1, m, ks, j, i) - S4(e3c, m, ks, j, i - 1);
+          if (F2(flx2, m, IDN, ks, j, i) >= 0.0) e3_r1 = S4(e3x1, m, ks, j - 1, i) - S4(e3c, m, ks, j - 1, i);
+          else e3_r1 = S4(e3x1, m, ks, j, i) - S4(e3c, m, ks, j, i);
+          X3E(e3, m, ks, j, i) = 0.25 * (e3_l1 + e3_r1 + e3_l2 + e3_r2 + S4(e3x2, m, ks, j, i - 1) + S4(e3x2, m, ks, j, i) + S4(e3x1, m, ks, j - 1, i) + S4(e3x1, m, ks, j, i));
+        }
+    free(e3c);
+    return;
+  }
+  double *e1cc = calloc(ncc, 8), *e2cc = calloc(ncc, 8), *e3cc = calloc(ncc, 8);
   for (int m = 0; m < c->nmb; ++m)
     for (int k = ks - 1; k <= ke + 1; ++k)
       for (int j = js - 1; j <= je + 1; ++j)
@@ -720,12 +753,14 @@ void oracle_ct(const ocfg *c, double *b1f, double *b2f, double *b3f, const doubl
   odims D = dims(c);
   for (int m = 0; m < c->nmb; ++m) {
     const double dx1 = mb_size[m * 9 + 6], dx2 = mb_size[m * 9 + 7], dx3 = mb_size[m * 9 + 8];
+    const int multi_d = c->nx2 > 1, three_d = c->nx3 > 1;
+    if (multi_d)   /* B1 is not touched at all in 1-D (mhd_ct.cpp:41-53) */
     for (int k = D.ks; k <= D.ke; ++k)
       for (int j = D.js; j <= D.je; ++j)
         for (int i = D.is; i <= D.ie + 1; ++i) {
           double b = gam0 * X1F(b1f, m, k, j, i) + gam1 * X1F(o1f, m, k, j, i);
           b -= beta_dt * (X3E(e3, m, k, j + 1, i) - X3E(e3, m, k, j, i)) / dx2;
-          b += beta_dt * (X2E(e2, m, k + 1, j, i) - X2E(e2, m, k, j, i)) / dx3;
+          if (three_d) b += beta_dt * (X2E(e2, m, k + 1, j, i) - X2E(e2, m, k, j, i)) / dx3;
           X1F(b1f, m, k, j, i) = b;
         }
     for (int k = D.ks; k <= D.ke; ++k)
@@ -733,7 +768,7 @@ void oracle_ct(const ocfg *c, double *b1f, double *b2f, double *b3f, const doubl
         for (int i = D.is; i <= D.ie; ++i) {
           double b = gam0 * X2F(b2f, m, k, j, i) + gam1 * X2F(o2f, m, k, j, i);
           b += beta_dt * (X3E(e3, m, k, j, i + 1) - X3E(e3, m, k, j, i)) / dx1;
-          b -= beta_dt * (X1E(e1, m, k + 1, j, i) - X1E(e1, m, k, j, i)) / dx3;
+          if (three_d) b -= beta_dt * (X1E(e1, m, k + 1, j, i) - X1E(e1, m, k, j, i)) / dx3;
           X2F(b2f, m, k, j, i) = b;
         }
     for (int k = D.ks; k <= D.ke + 1; ++k)
@@ -741,7 +776,7 @@ void oracle_ct(const ocfg *c, double *b1f, double *b2f, double *b3f, const doubl
         for (int i = D.is; i <= D.ie; ++i) {
           double b = gam0 * X3F(b3f, m, k, j, i) + gam1 * X3F(o3f, m, k, j, i);
           b -= beta_dt * (X2E(e2, m, k, j, i + 1) - X2E(e2, m, k, j, i)) / dx1;
-          b += beta_dt * (X1E(e1, m, k, j + 1, i) - X1E(e1, m, k, j, i)) / dx2;
+          if (multi_d) b += beta_dt * (X1E(e1, m, k, j + 1, i) - X1E(e1, m, k, j, i)) / dx2;
           X3F(b3f, m, k, j, i) = b;
         }
   }
@@ -819,9 +854,9 @@ double oracle_new_dt(const ocfg *c, const double *w0, const double *bcc, const d
         }
   }
   if (dt3) { dt3[0] = dt1; dt3[1] = dt2; dt3[2] = dtz; }
-  double dtnew = dt1;
-  if (dt2 < dtnew) dtnew = dt2;
-  if (dtz < dtnew) dtnew = dtz;
+  double dtnew = dt1;                                  /* mhd_newdt.cpp:152-155 */
+  if (c->nx2 > 1 && dt2 < dtnew) dtnew = dt2;
+  if (c->nx3 > 1 && dtz < dtnew) dtnew = dtz;
   return dtnew;
 }
 
@@ -992,12 +1027,16 @@ static int emf_slot_has(int ox, int oy, int oz, int v) {
 void oracle_emf_exchange(const ocfg *c, double *e1, double *e2, double *e3, const int *nghbr_gid) {
   odims D = dims(c);
   const int nmb = c->nmb;
+  /* 1-D / 2-D: only slots in the active dimensions exist (flux_correct_fc.cpp:898,953,963,1013,1023:
+   * multi_d / three_d gates), and a face interior keeps its full extent along an inactive one (:846,873) */
+  const int act[3] = {1, c->nx2 > 1, c->nx3 > 1};
   double **rbuf = calloc((size_t)nmb * 48 * 3, sizeof(double *));
   /* pack + send */
   for (int m = 0; m < nmb; ++m)
     for (int oz = -1; oz <= 1; ++oz) for (int oy = -1; oy <= 1; ++oy) for (int ox = -1; ox <= 1; ++ox) {
       int nz = (ox != 0) + (oy != 0) + (oz != 0);
       if (nz == 0 || nz == 3) continue;
+      if ((oy && !act[1]) || (oz && !act[2])) continue;
       int n = oracle_neighbor_index(ox, oy, oz, 0, 0);
       int gid = nghbr_gid[m * 56 + n];
       if (gid < 0) continue;
@@ -1021,12 +1060,13 @@ void oracle_emf_exchange(const ocfg *c, double *e1, double *e2, double *e3, cons
       for (int z = -1; z <= 1 && !found; ++z) for (int y = -1; y <= 1 && !found; ++y) for (int x = -1; x <= 1 && !found; ++x)
         if ((x || y || z) && oracle_neighbor_index(x, y, z, 0, 0) == n) { ox = x; oy = y; oz = z; found = 1; }
       if (!found) continue;
+      if ((oy && !act[1]) || (oz && !act[2])) continue;
       if (nghbr_gid[m * 56 + n] < 0) continue;
       int nz = (ox != 0) + (oy != 0) + (oz != 0);
       if (nz == 1) {  /* a face neighbour also contributes to the four edges of that face */
         for (int t = -1; t <= 1; t += 2) {
-          if (ox) { nflx[m * 48 + oracle_neighbor_index(ox, t, 0, 0, 0)]++; nflx[m * 48 + oracle_neighbor_index(ox, 0, t, 0, 0)]++; }
-          if (oy) { nflx[m * 48 + oracle_neighbor_index(t, oy, 0, 0, 0)]++; nflx[m * 48 + oracle_neighbor_index(0, oy, t, 0, 0)]++; }
+          if (ox) { if (act[1]) nflx[m * 48 + oracle_neighbor_index(ox, t, 0, 0, 0)]++; if (act[2]) nflx[m * 48 + oracle_neighbor_index(ox, 0, t, 0, 0)]++; }
+          if (oy) { nflx[m * 48 + oracle_neighbor_index(t, oy, 0, 0, 0)]++; if (act[2]) nflx[m * 48 + oracle_neighbor_index(0, oy, t, 0, 0)]++; }
           if (oz) { nflx[m * 48 + oracle_neighbor_index(t, 0, oz, 0, 0)]++; nflx[m * 48 + oracle_neighbor_index(0, t, oz, 0, 0)]++; }
         }
       } else {
@@ -1047,6 +1087,7 @@ void oracle_emf_exchange(const ocfg *c, double *e1, double *e2, double *e3, cons
     for (int oz = -1; oz <= 1; ++oz) for (int oy = -1; oy <= 1; ++oy) for (int ox = -1; ox <= 1; ++ox) {
       int nz = (ox != 0) + (oy != 0) + (oz != 0);
       if (nz == 0 || nz == 3) continue;
+      if ((oy && !act[1]) || (oz && !act[2])) continue;
       int n = oracle_neighbor_index(ox, oy, oz, 0, 0);
       for (int v = 0; v < 3; ++v) {
         if (!emf_slot_has(ox, oy, oz, v)) continue;
@@ -1055,7 +1096,7 @@ void oracle_emf_exchange(const ocfg *c, double *e1, double *e2, double *e3, cons
           if (nghbr_gid[m * 56 + n] < 0) continue;      /* only where a same-level neighbour exists */
           /* interior of the face: drop the two end lines in the OTHER tangential direction */
           int o[3] = {ox, oy, oz};
-          for (int d = 0; d < 3; ++d) if (o[d] == 0 && d != v) { b6[2 * d] += 1; b6[2 * d + 1] -= 1; }
+          for (int d = 0; d < 3; ++d) if (o[d] == 0 && d != v && act[d]) { b6[2 * d] += 1; b6[2 * d + 1] -= 1; }
           for (int k = b6[4]; k <= b6[5]; ++k) for (int j = b6[2]; j <= b6[3]; ++j) for (int i = b6[0]; i <= b6[1]; ++i)
             *emf_at(&D, e1, e2, e3, v, m, k, j, i) *= 0.5;
         } else {
@@ -1134,6 +1175,7 @@ int oracle_apply_bcs(const ocfg *c, const int *mesh_bcs, const int *mb_bcs, doub
     bc_array(c, u0, 5, -1, d, mb_bcs);
   }
   for (int d = 0; d < 3; ++d) {        /* bfield_bcs.cpp:78,169,262 */
+    if ((d == 1 && c->nx2 <= 1) || (d == 2 && c->nx3 <= 1)) continue;   /* :165 one_d, :258 two_d */
     if (mesh_bcs[2 * d] == BC_PERIODIC) continue;
     bc_array(c, b1f, 1, 0, d, mb_bcs);
     bc_array(c, b2f, 1, 1, d, mb_bcs);

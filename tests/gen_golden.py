@@ -67,7 +67,28 @@ def hydro(deck, base, name, overrides=()):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def mhd_lowd(deck, base, name, overrides=()):
+    """1-D / 2-D MHD fixtures: ghost-inclusive u0 and face fields of the cycle-0 and final dumps."""
+    tmp = tempfile.mkdtemp(prefix="akgold_")
+    try:
+        O.run_reference("athena_builtin", os.path.join(HERE, "decks", deck), tmp, list(overrides))
+        r0 = read_rst(os.path.join(tmp, "rst", base + ".00000.rst"))
+        r1 = read_rst(os.path.join(tmp, "rst", base + ".00001.rst"))
+        np.savez_compressed(os.path.join(HERE, "golden", name + ".npz"), deck=np.array(r0.deck), lloc=r0.lloc,
+                            u0_c0=r0.u0, b1f_c0=r0.b1f, b2f_c0=r0.b2f, b3f_c0=r0.b3f,
+                            u0_final=r1.u0, b1f_final=r1.b1f, b2f_final=r1.b2f, b3f_final=r1.b3f,
+                            dt_c0=r0.dt, time_final=r1.time, dt_final=r1.dt, ncycle_final=r1.ncycle)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 if __name__ == "__main__":
+    mhd_lowd("bw1d.athinput", "BrioWu", "mhd_bw1d_ppm4_hlld_rk3",
+             ("mhd/rsolver=hlld", "mhd/reconstruct=ppm4", "mesh/nghost=3", "time/integrator=rk3", "mesh/nx1=128", "meshblock/nx1=32"))
+    mhd_lowd("bw2d.athinput", "BrioWu", "mhd_bw2d_ppm4_hlld_rk3", ("time/tlim=0.03",))
+    mhd_lowd("ot2d.athinput", "OrszagTang", "mhd_ot2d_plm_hlle_rk2",
+             ("mesh/nx1=32", "mesh/nx2=32", "meshblock/nx1=16", "meshblock/nx2=16", "mhd/reconstruct=plm", "mhd/rsolver=hlle",
+              "time/integrator=rk2", "mesh/nghost=2", "time/tlim=0.1"))
     hydro("sod1d.athinput", "Sod", "hydro_sod1d_plm_llf_rk2")
     hydro("sod1d.athinput", "Sod", "hydro_sod1d_wenoz_roe_rk3", ("hydro/rsolver=roe", "hydro/reconstruct=wenoz", "mesh/nghost=3",
                                                                   "time/integrator=rk3", "time/cfl_number=0.4", "mesh/nx1=128", "meshblock/nx1=32"))
@@ -75,7 +96,7 @@ if __name__ == "__main__":
     hydro("lwave3d_hydro.athinput", "LinWave", "hydro_lwave3d_ppmx_hlle_rk2",
           ("mesh/nx1=16", "mesh/nx2=8", "mesh/nx3=8", "meshblock/nx1=8", "meshblock/nx2=8", "meshblock/nx3=8",
            "hydro/reconstruct=ppmx", "hydro/rsolver=hlle", "time/integrator=rk2", "time/tlim=0.25"))
-    if "--hydro-only" in sys.argv:
+    if "--hydro-only" in sys.argv or "--new-only" in sys.argv:
         sys.exit(0)
     blast(16, (1, 4))
     blast(16, (2,), recon="plm", rsolver="hlle", integrator="rk2")

@@ -44,8 +44,10 @@ class Case:
         self.bc_names = tuple(p[f"mesh/{s}x{d}_bc"] for d in (1, 2, 3) for s in ("i", "o"))
         self.mesh_bcs = np.array([O.BC[b] for b in self.bc_names], np.int32)
         self.ng = int(float(p.get("mesh/nghost", 2)))
-        self.recon, self.rsolver = p["hydro/reconstruct"], p["hydro/rsolver"]
-        self.gamma = float(p["hydro/gamma"])
+        self.physics = "mhd" if "mhd/rsolver" in p else "hydro"
+        ph = self.physics
+        self.recon, self.rsolver = p[ph + "/reconstruct"], p[ph + "/rsolver"]
+        self.gamma = float(p[ph + "/gamma"])
         self.integrator = p["time/integrator"]
         self.cfl, self.tlim = float(p["time/cfl_number"]), float(p["time/tlim"])
         periodic = [self.mesh_bcs[2 * d] == O.BC["periodic"] for d in range(3)]
@@ -55,7 +57,8 @@ class Case:
         self.strictly_periodic = all(periodic)
 
     def ocfg(self):
-        return O.OCfg(self.nmb, self.ng, *self.nblock, O.RECON[self.recon], O.HYD_RSOLVER[self.rsolver], self.gamma,
+        rs = O.RSOLVER[self.rsolver] if self.physics == "mhd" else O.HYD_RSOLVER[self.rsolver]
+        return O.OCfg(self.nmb, self.ng, *self.nblock, O.RECON[self.recon], rs, self.gamma,
                       O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX)
 
 
@@ -77,6 +80,34 @@ def oracle_run(case: Case, u_init, ncycles=-1, time0=0.0):
     finally:
         L.oracle_set_bcs(None, None)
     return u0, w0, t.value, dt.value, n, dt0
+
+
+def oracle_run_mhd(case: Case, u_init, b_init, ncycles=-1, time0=0.0):
+    """Driver::Initialize + Execute on the MHD oracle (oracle/mhd_oracle.c), 1-D / 2-D / 3-D.
+    Returns (Arrays, time, dt_next, ncycles, dt0)."""
+    L = O.lib()
+    cfg = case.ocfg()
+    A = O.Arrays(cfg)
+    A.u0[:] = u_init
+    for dst, src in zip(A.b0, b_init):
+        dst[:] = src
+    if not case.strictly_periodic:
+        L.oracle_set_bcs(O.ip(case.mesh_bcs), O.ip(case.mb_bcs))
+    try:
+        L.oracle_halo_cc(C.byref(cfg), O.p(A.u0), 5, O.ip(case.nghbr))
+        L.oracle_halo_fc(C.byref(cfg), *[O.p(a) for a in A.b0], O.ip(case.nghbr))
+        if not case.strictly_periodic:
+            assert L.oracle_apply_bcs(C.byref(cfg), O.ip(case.mesh_bcs), O.ip(case.mb_bcs), O.p(A.u0), *[O.p(a) for a in A.b0]) == 0
+        A.c2p_all()
+        st = A.state()
+        dt0 = L.oracle_initial_dt(C.byref(cfg), C.byref(st), O.p(case.mb_size), C.c_double(case.cfl), C.c_double(case.tlim), C.c_double(time0))
+        t, dt = C.c_double(time0), C.c_double(dt0)
+        n = L.oracle_run(C.byref(cfg), C.byref(st), O.p(case.mb_size), O.ip(case.nghbr), INTEGRATOR[case.integrator],
+                         C.c_double(case.cfl), C.c_double(case.tlim), ncycles if ncycles >= 0 else 1 << 30,
+                         C.byref(t), C.byref(dt), None)
+    finally:
+        L.oracle_set_bcs(None, None)
+    return A, t.value, dt.value, n, dt0
 
 
 def sod_density(x, tlim=0.25):

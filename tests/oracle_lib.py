@@ -72,7 +72,8 @@ class Arrays:
 
     def __init__(self, cfg: OCfg):
         nmb, ng = cfg.nmb, cfg.ng
-        n1, n2, n3 = cfg.nx1 + 2 * ng, cfg.nx2 + 2 * ng, cfg.nx3 + 2 * ng
+        # inactive dimensions (nx = 1): extent 1, no ghost cells (mesh.cpp:285-333)
+        n1, n2, n3 = cfg.nx1 + 2 * ng, (cfg.nx2 + 2 * ng if cfg.nx2 > 1 else 1), (cfg.nx3 + 2 * ng if cfg.nx3 > 1 else 1)
         self.cfg, self.n = cfg, (n1, n2, n3)
         z = np.zeros
         self.u0, self.u1, self.w0 = (z((nmb, 5, n3, n2, n1)) for _ in range(3))

@@ -42,7 +42,7 @@ def test_create_fails_loudly_without_gpu(engine_lib):
 def test_cfg_validation(engine_lib):
     h = C.c_void_p()
     bad = [_lib.MhdCfg(1, 2, 16, 16, 16, 2, 2, 1.6666667, 0, 0, 0, 0, 1e38),    # ppm4 needs ng>=3
-           _lib.MhdCfg(1, 4, 16, 16, 1, 2, 2, 1.6666667, 0, 0, 0, 0, 1e38),     # not 3-D
+           _lib.MhdCfg(1, 4, 16, 1, 16, 2, 2, 1.6666667, 0, 0, 0, 0, 1e38),     # nx2 = 1 with nx3 > 1
            _lib.MhdCfg(1, 4, 16, 16, 16, 9, 2, 1.6666667, 0, 0, 0, 0, 1e38),    # unknown recon
            _lib.MhdCfg(0, 4, 16, 16, 16, 2, 2, 1.6666667, 0, 0, 0, 0, 1e38)]    # no blocks
     for cfg in bad:
@@ -171,7 +171,9 @@ def _exchange_multi_rank(nmesh, nblock, nranks, rng):
 
 @pytest.mark.parametrize("nmesh,nblock,nranks", [((16, 16, 16), (16, 16, 16), 1), ((16, 16, 16), (8, 8, 8), 1),
                                                  ((16, 16, 16), (8, 8, 8), 2), ((32, 16, 16), (8, 8, 8), 3),
-                                                 ((16, 16, 16), (8, 8, 8), 8), ((32, 16, 16), (16, 16, 16), 2)])
+                                                 ((16, 16, 16), (8, 8, 8), 8), ((32, 16, 16), (16, 16, 16), 2),
+                                                 ((32, 32, 1), (16, 16, 1), 1), ((32, 32, 1), (8, 8, 1), 3),      # 2-D
+                                                 ((64, 1, 1), (64, 1, 1), 1), ((64, 1, 1), (16, 1, 1), 2)])       # 1-D
 def test_halo_plan_equals_reference_exchange(nmesh, nblock, nranks):
     """The resolved copy plan (same-rank gather + per-peer messages) reproduces the reference's
     pack/unpack exchange bit for bit for every rank count, incl. a block that is its own

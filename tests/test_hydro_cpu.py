@@ -100,3 +100,16 @@ def test_hydro_halo_plan_1d_2d():
         assert (d[:, 5] == 0).all() and (d[:, 8] == 0).all()               # k box is [0,0]
         assert lib.ak_halo_descs(plan, 1, 0, out.ctypes.data_as(C.POINTER(C.c_long)), 4096) == 0   # no face-field descriptors
         lib.ak_halo_destroy(plan)
+
+
+@pytest.mark.parametrize("name", ["mhd_bw1d_ppm4_hlld_rk3", "mhd_bw2d_ppm4_hlld_rk3", "mhd_ot2d_plm_hlle_rk2"])
+def test_mhd_oracle_1d_2d_matches_golden(name):
+    """oracle/mhd_oracle.c on 1-D / 2-D meshes (CornerE 1-D/2-D branches, CT, EMF correction, BCs)
+    against fixtures made from the unmodified reference."""
+    d = G.load(name)
+    case = H.Case(str(d["deck"]))
+    A, t, dt, n, dt0 = H.oracle_run_mhd(case, d["u0_c0"], (d["b1f_c0"], d["b2f_c0"], d["b3f_c0"]))
+    assert dt0 == float(d["dt_c0"]) and n == int(d["ncycle_final"]) and t == float(d["time_final"])
+    assert np.array_equal(A.u0, d["u0_final"])
+    for x, k in zip(A.b0, ("b1f_final", "b2f_final", "b3f_final")):
+        assert np.array_equal(x, d[k])
