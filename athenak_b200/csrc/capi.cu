@@ -470,4 +470,85 @@ int ak_halo_emf_sumavg(void *plan, double *e1, double *e2, double *e3, ak_stream
   return halo_rc(P, "ak_halo_emf_sumavg", akb::emf_sumavg_launch(P, A, (cudaStream_t)s));
 }
 
+// ---- peer-memory ghost exchange ---------------------------------------------------------------
+int ak_halo_push_setup(void *plan, int ipeer, int peer_gids_start, double *pu0, double *px1f, double *px2f, double *px3f) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P || ipeer < 0 || ipeer >= (int)P->peers.size() || ipeer >= AKB_MAX_PUSH_PEERS) return fail(nullptr, "ak_halo_push_setup: bad peer");
+  if (!pu0) return fail(nullptr, "ak_halo_push_setup: null peer array");
+  P->push_ptrs.p[ipeer][0] = pu0; P->push_ptrs.p[ipeer][1] = px1f; P->push_ptrs.p[ipeer][2] = px2f; P->push_ptrs.p[ipeer][3] = px3f;
+  for (auto &d : P->push)
+    if (d.peer == ipeer) {
+      d.dst_m = d.dst_gid - peer_gids_start;
+      if (d.dst_m < 0) return fail(nullptr, "ak_halo_push_setup: neighbour gid below the peer's first gid");
+      if (d.comp >= 0 && !P->push_ptrs.p[ipeer][1 + d.comp]) return fail(nullptr, "ak_halo_push_setup: null peer face array");
+    }
+  return 0;
+}
+
+int ak_halo_push_flags(void *plan, int my_rank, int nranks, unsigned long long *local_flags,
+                       unsigned long long *const *peer_flags) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P || !local_flags || !peer_flags) return fail(nullptr, "ak_halo_push_flags: null argument");
+  const int np = (int)P->peers.size();
+  std::vector<unsigned long long *> sf(np), sr(np);
+  std::vector<int> ws(2 * np);
+  for (int p = 0; p < np; ++p) {
+    sf[p] = peer_flags[p] + 0 * nranks + my_rank;        // my "free" slot in peer p's memory
+    sr[p] = peer_flags[p] + 1 * nranks + my_rank;        // my "ready" slot
+    ws[p] = 0 * nranks + P->peers[p].rank;               // where peer p writes its "free" counter in MY memory
+    ws[np + p] = 1 * nranks + P->peers[p].rank;
+  }
+  cudaError_t e;
+  if ((e = cudaMalloc(&P->d_sig_free, sizeof(void *) * std::max(np, 1))) != cudaSuccess ||
+      (e = cudaMalloc(&P->d_sig_ready, sizeof(void *) * std::max(np, 1))) != cudaSuccess ||
+      (e = cudaMalloc(&P->d_wait_slots, sizeof(int) * std::max(2 * np, 1))) != cudaSuccess)
+    return cuda_fail(nullptr, "ak_halo_push_flags", e);
+  if (np) {
+    cudaMemcpy(P->d_sig_free, sf.data(), sizeof(void *) * np, cudaMemcpyHostToDevice);
+    cudaMemcpy(P->d_sig_ready, sr.data(), sizeof(void *) * np, cudaMemcpyHostToDevice);
+    cudaMemcpy(P->d_wait_slots, ws.data(), sizeof(int) * 2 * np, cudaMemcpyHostToDevice);
+  }
+  P->flags_local = local_flags; P->my_rank = my_rank; P->nranks = nranks;
+  return 0;
+}
+
+int ak_halo_push_commit(void *plan) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P) return fail(nullptr, "ak_halo_push_commit: null plan");
+  for (const auto &d : P->push) if (d.dst_m < 0) return fail(nullptr, "ak_halo_push_commit: a peer was not set up");
+  if (!P->flags_local) return fail(nullptr, "ak_halo_push_commit: flags were not set up");
+  cudaFree(P->d_push); P->d_push = nullptr;
+  if (!P->push.empty()) {
+    cudaError_t e = cudaMalloc(&P->d_push, sizeof(akb::PushDesc) * P->push.size());
+    if (e == cudaSuccess) e = cudaMemcpy(P->d_push, P->push.data(), sizeof(akb::PushDesc) * P->push.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(nullptr, "ak_halo_push_commit", e);
+  }
+  P->push_ready = true;
+  return 0;
+}
+
+int ak_halo_push(void *plan, double *u0, int nvar, double *x1f, double *x2f, double *x3f, ak_stream_t s) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P || !P->push_ready) return fail(nullptr, "ak_halo_push: plan has no committed peer-memory set-up");
+  const bool do_cc = u0 != nullptr, do_fc = x1f != nullptr;
+  if (do_fc && (!x2f || !x3f)) return fail(nullptr, "ak_halo_push: null face array");
+  akb::HaloArrays CCa = akb::halo_arrays_cc(P->cfg, u0, nvar > 0 ? nvar : 1);
+  akb::HaloArrays FCa = akb::halo_arrays_fc(P->cfg, x1f, x2f, x3f);
+  const long cc = CCa.bstride[0] / (nvar > 0 ? nvar : 1);
+  return halo_rc(P, "ak_halo_push", akb::halo_push_launch(P, CCa, nvar, cc, FCa, do_cc, do_fc, (cudaStream_t)s));
+}
+
+int ak_halo_signal(void *plan, int kind, unsigned long long value, ak_stream_t s) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P || !P->push_ready || kind < 0 || kind > 1) return fail(nullptr, "ak_halo_signal: bad argument");
+  return halo_rc(P, "ak_halo_signal", akb::peer_signal_launch(kind == 0 ? P->d_sig_free : P->d_sig_ready, (int)P->peers.size(), value, (cudaStream_t)s));
+}
+
+int ak_halo_wait(void *plan, int kind, unsigned long long value, ak_stream_t s) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P || !P->push_ready || kind < 0 || kind > 1) return fail(nullptr, "ak_halo_wait: bad argument");
+  const int np = (int)P->peers.size();
+  return halo_rc(P, "ak_halo_wait", akb::peer_wait_launch(P->flags_local, P->d_wait_slots + kind * np, np, value, (cudaStream_t)s));
+}
+
 }  // extern "C"

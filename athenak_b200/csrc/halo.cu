@@ -191,6 +191,18 @@ HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int g
       HaloDesc d{}; d.m = e.m; d.src_m = e.m; d.comp = -1; d.boff = cc_off;
       for (int a = 0; a < 3; ++a) { d.lo[a] = b.lo[a]; d.hi[a] = b.hi[a]; }
       peer.pack_cc.push_back(d);
+      {  // peer-memory path: my send box on side o lands in the neighbour's ghost box on ITS side -o
+        const int no[3] = {-e.o[0], -e.o[1], -e.o[2]};
+        const int ngid = nghbr[((long)e.m * 56 + e.slot) * 4];
+        for (int comp = -1; comp < (cc_only ? 0 : 3); ++comp) {
+          Box sb = halo_box(cfg, comp, e.o, true), rb = halo_box(cfg, comp, no, false);
+          PushDesc pd{};
+          pd.m = e.m; pd.comp = comp; pd.peer = (int)P->peers.size(); pd.dst_gid = ngid; pd.dst_m = -1;
+          for (int a = 0; a < 3; ++a) { pd.lo[a] = sb.lo[a]; pd.hi[a] = sb.hi[a]; pd.dlo[a] = rb.lo[a]; }
+          if (sb.count() != rb.count()) { err = "halo: push source/destination boxes differ"; delete P; return nullptr; }
+          P->push.push_back(pd);
+        }
+      }
       cc_off += b.count();   // per variable; scaled by nvar at launch
       if (cc_only) continue;
       long ndat = 0;
@@ -226,6 +238,10 @@ HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int g
     }
     if (cc_off != peer.cc_count || fc_off != peer.fc_count) { err = "halo: send/recv message sizes differ"; delete P; return nullptr; }
     P->peers.push_back(peer);
+  }
+  {  // push descriptors: CC entries first, then FC (one launch can take either range)
+    auto mid = std::stable_partition(P->push.begin(), P->push.end(), [](const PushDesc &d) { return d.comp < 0; });
+    P->n_push_cc = (long)(mid - P->push.begin());
   }
   // ---- EMF flux correction plan -----------------------------------------------------------
   if (!cc_only) {
@@ -396,6 +412,7 @@ void halo_free(HaloPlan *P) {
   if (!P) return;
   cudaFree(P->d_local_cc); cudaFree(P->d_local_fc); cudaFree(P->d_emf_pack_local); cudaFree(P->d_emf_sum); cudaFree(P->d_emf_rbuf);
   for (auto &p : P->peers) { cudaFree(p.d_pack_cc); cudaFree(p.d_unpack_cc); cudaFree(p.d_pack_fc); cudaFree(p.d_unpack_fc); cudaFree(p.d_pack_emf); }
+  cudaFree(P->d_push); cudaFree(P->d_sig_free); cudaFree(P->d_sig_ready); cudaFree(P->d_wait_slots);
   delete P;
 }
 
@@ -417,6 +434,85 @@ cudaError_t halo_launch(const std::vector<HaloDesc> &host, const HaloDesc *dev, 
     unsigned ny = (unsigned)std::min<size_t>(65535, host.size() - first);
     halo_copy_kernel<<<dim3(gx, ny), 256, 0, st>>>(dev + first, A, nvar, varstride, buf, mode);
   }
+  return cudaGetLastError();
+}
+
+// ---- peer-memory exchange ------------------------------------------------------------------
+// One launch moves every off-rank slab of this rank (all peers, CC and/or FC): coalesced reads of
+// my arrays, stores straight into the peer GPUs' arrays over NVLink (mapped with cudaIpc by the
+// host layer).  grid.y = descriptor.
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const PushDesc *__restrict__ descs, HaloArrays CCa, int nvar, long varstride, HaloArrays FCa,
+                 PushPeerPtrs ptrs) {
+  const PushDesc d = descs[blockIdx.y];
+  const int ni = d.hi[0] - d.lo[0] + 1, nj = d.hi[1] - d.lo[1] + 1, nk = d.hi[2] - d.lo[2] + 1;
+  const long per = (long)ni * nj * nk;
+  const bool cc = d.comp < 0;
+  const int c = cc ? 0 : d.comp;
+  const HaloArrays &A = cc ? CCa : FCa;
+  const double *src = A.p[c] + (long)d.m * A.bstride[c];
+  double *dst = ptrs.p[d.peer][cc ? 0 : 1 + d.comp] + (long)d.dst_m * A.bstride[c];
+  const long e1 = A.ext1[c], e2 = A.ext2[c];
+  const long total = per * (cc ? nvar : 1);
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x) {
+    long t = q;
+    const int i = (int)(t % ni); t /= ni;
+    const int j = (int)(t % nj); t /= nj;
+    const int k = (int)(t % nk);
+    const long v = (t / nk) * (cc ? varstride : 0);
+    dst[((long)(d.dlo[2] + k) * e2 + (d.dlo[1] + j)) * e1 + (d.dlo[0] + i) + v] =
+        src[((long)(d.lo[2] + k) * e2 + (d.lo[1] + j)) * e1 + (d.lo[0] + i) + v];
+  }
+}
+
+cudaError_t halo_push_launch(HaloPlan *P, const HaloArrays &cc, int nvar, long varstride, const HaloArrays &fc, bool do_cc,
+                             bool do_fc, cudaStream_t st) {
+  if (P->push.empty()) return cudaSuccess;
+  const long first = do_cc ? 0 : P->n_push_cc;
+  const long last = do_fc ? (long)P->push.size() : P->n_push_cc;
+  if (last <= first) return cudaSuccess;
+  long mx = 1;
+  for (long q = first; q < last; ++q) {
+    const PushDesc &d = P->push[q];
+    long n = (long)(d.hi[0] - d.lo[0] + 1) * (d.hi[1] - d.lo[1] + 1) * (d.hi[2] - d.lo[2] + 1) * (d.comp < 0 ? nvar : 1);
+    mx = std::max(mx, n);
+  }
+  const unsigned gx = (unsigned)std::min<long>((mx + 255) / 256, 64);
+  for (long f = first; f < last; f += 65535) {
+    const unsigned ny = (unsigned)std::min<long>(65535, last - f);
+    halo_push_kernel<<<dim3(gx, ny), 256, 0, st>>>(P->d_push + f, cc, nvar, varstride, fc, P->push_ptrs);
+  }
+  return cudaGetLastError();
+}
+
+// Cross-GPU flags: monotone counters in each rank's memory, one slot per (kind, writer rank).
+// signal: runs after the producing kernel in stream order (its stores are complete and visible
+// system-wide at the kernel boundary), then publishes the counter in every peer's memory.
+__global__ void peer_signal_kernel(unsigned long long **slots, int n, unsigned long long value) {
+  const int p = threadIdx.x;
+  if (p < n) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(slots[p]) = value;
+    __threadfence_system();
+  }
+}
+// wait: spins (one thread per awaited peer) until every peer's counter has reached `value`
+__global__ void peer_wait_kernel(const unsigned long long *flags, const int *slots, int n, unsigned long long value) {
+  const int p = threadIdx.x;
+  if (p < n) {
+    const volatile unsigned long long *f = flags + slots[p];
+    while (*f < value) __nanosleep(200);
+    __threadfence_system();
+  }
+}
+cudaError_t peer_signal_launch(unsigned long long **slots, int n, unsigned long long value, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  peer_signal_kernel<<<1, 32 * ((n + 31) / 32), 0, st>>>(slots, n, value);
+  return cudaGetLastError();
+}
+cudaError_t peer_wait_launch(const unsigned long long *flags, const int *slots, int n, unsigned long long value, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  peer_wait_kernel<<<1, 32 * ((n + 31) / 32), 0, st>>>(flags, slots, n, value);
   return cudaGetLastError();
 }
 

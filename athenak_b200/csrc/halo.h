@@ -33,6 +33,18 @@ struct EmfSumDesc {
   int face;                 // 1: face interior (x0.5), 0: block edge (/count)
 };
 
+// Peer-memory exchange ("push"): one boundary slab of one of MY blocks written straight into the
+// ghost zones of the neighbouring block in the PEER GPU's array (no pack buffer, no message, no
+// unpack pass).  Source box = the pack box, destination box = the peer's unpack box.
+struct PushDesc {
+  int m, comp, peer;       // my block; -1 = CC, 0..2 = x1f..x3f; index into the peer pointer table
+  int dst_gid, dst_m;      // neighbour's gid; its index in the peer's pack (set by push setup)
+  int lo[3], hi[3];        // i,j,k source box
+  int dlo[3];              // low corner of the destination box (same extents)
+};
+#define AKB_MAX_PUSH_PEERS 32
+struct PushPeerPtrs { double *p[AKB_MAX_PUSH_PEERS][4]; };   // [peer][u0, x1f, x2f, x3f] mapped peer arrays
+
 struct HaloPeer {
   int rank;
   long cc_count, fc_count;  // doubles per message: CC per variable, FC total
@@ -54,6 +66,16 @@ struct HaloPlan {
   EmfSumDesc *d_emf_sum = nullptr;
   long emf_rbuf_count = 0;
   double *d_emf_rbuf = nullptr;
+  // peer-memory exchange state
+  std::vector<PushDesc> push;             // all peers, CC entries first then FC
+  PushDesc *d_push = nullptr;
+  long n_push_cc = 0;
+  PushPeerPtrs push_ptrs{};
+  bool push_ready = false;
+  unsigned long long *flags_local = nullptr;                 // [2][nranks]: free / ready counters written by peers
+  unsigned long long **d_sig_free = nullptr, **d_sig_ready = nullptr;   // device arrays of remote slot addresses
+  int *d_wait_slots = nullptr;            // peer ranks to wait for
+  int my_rank = 0, nranks = 1;
   std::string err;
   bool uploaded = false;   // descriptor lists are copied to the device on first use
 };
@@ -68,5 +90,9 @@ HaloArrays halo_arrays_cc(const ak_mhd_cfg &c, double *a, int nvar);
 HaloArrays halo_arrays_fc(const ak_mhd_cfg &c, double *x1f, double *x2f, double *x3f);
 HaloArrays halo_arrays_ec(const ak_mhd_cfg &c, double *x1e, double *x2e, double *x3e);
 cudaError_t emf_sumavg_launch(HaloPlan *P, const HaloArrays &A, cudaStream_t st);
+cudaError_t halo_push_launch(HaloPlan *P, const HaloArrays &cc, int nvar, long varstride, const HaloArrays &fc, bool do_cc,
+                             bool do_fc, cudaStream_t st);
+cudaError_t peer_signal_launch(unsigned long long **slots, int n, unsigned long long value, cudaStream_t st);
+cudaError_t peer_wait_launch(const unsigned long long *flags, const int *slots, int n, unsigned long long value, cudaStream_t st);
 
 }  // namespace akb

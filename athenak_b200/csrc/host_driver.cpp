@@ -27,6 +27,8 @@
 
 #include "../../include/athenak_b200.h"
 
+#define AKB_MAX_PUSH_PEERS_HOST 32   // == AKB_MAX_PUSH_PEERS (csrc/halo.h)
+
 namespace akh {
 
 enum class TaskStatus { fail, complete, incomplete };
@@ -103,6 +105,7 @@ struct Nccl {
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, Comm, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
   bool ok = false;
   static Nccl &get() {
@@ -119,6 +122,7 @@ struct Nccl {
         n.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
         n.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
         n.AllReduce = (int (*)(const void *, void *, size_t, int, int, Comm, cudaStream_t))dlsym(h, "ncclAllReduce");
+        n.AllGather = (int (*)(const void *, void *, size_t, int, Comm, cudaStream_t))dlsym(h, "ncclAllGather");
         n.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
         n.ok = n.GetUniqueId && n.CommInitRank && n.Send && n.Recv && n.GroupStart && n.GroupEnd && n.AllReduce;
       }
@@ -126,7 +130,7 @@ struct Nccl {
     return n;
   }
 };
-enum { kNcclFloat64 = 8, kNcclMin = 3 };  // nccl.h: ncclFloat64 = 8, ncclMin = 3
+enum { kNcclFloat64 = 8, kNcclMin = 3, kNcclInt8 = 0 };  // nccl.h: ncclFloat64 = 8, ncclMin = 3, ncclInt8 = 0
 
 [[noreturn]] static void Fatal(const char *file, int line, const std::string &msg) {
   // the reference's fatal-error convention (e.g. src/mhd/mhd.cpp:85-87)
@@ -192,9 +196,15 @@ class MHD {  // state owner + tasks
   double *d_dt = nullptr;
   size_t n_u, n_f1, n_f2, n_f3;
   bool hydro = false, multi_d = true, three_d = true;
+  // peer-memory ghost exchange (ak_halo_push_*): set up by SetupPeerPush() after the communicator exists
+  int gids_start_ = 0;
+  bool push = false;
+  unsigned long long nexch = 0;               // exchanges completed (sequence number of the flags)
+  unsigned long long *d_flags = nullptr;      // [2][nranks] counters written by the peers
+  std::vector<void *> ipc_opened;
 
   MHD(const ak_mhd_cfg &c, const double *mb_size, const int *nghbr, int rank, int nranks_, int gids_start, int nmb_total)
-      : cfg(c), my_rank(rank), nranks(nranks_) {
+      : cfg(c), my_rank(rank), nranks(nranks_), gids_start_(gids_start) {
     mesh.nmb_total = nmb_total;
     CU_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     hydro = c.rsolver >= AK_RSOLVER_HYD_ADVECT;     // hydro twin: Hydro::Hydro, hydro.cpp:100-120,268-290
@@ -231,12 +241,79 @@ class MHD {  // state owner + tasks
     CU_CHECK(cudaStreamSynchronize(st));
   }
   ~MHD() {
+    if (st) cudaStreamSynchronize(st);
+    for (void *p : ipc_opened) cudaIpcCloseMemHandle(p);
+    if (d_flags) cudaFree(d_flags);
     if (comm && Nccl::get().CommDestroy) Nccl::get().CommDestroy(comm);
     ak_halo_destroy(plan);
     ak_bcs_destroy(bcs);
     ak_mhd_destroy(h);
     for (double *p : owned) cudaFree(p);
     if (st) cudaStreamDestroy(st);
+  }
+
+  // Peer-memory ghost exchange: every rank publishes cudaIpc handles of its u0 / face fields / flag
+  // array (ncclAllGather), maps its neighbours' arrays and registers them with the halo plan.  All
+  // ranks must agree: the outcome is min-reduced, and anything short of unanimous success leaves the
+  // grouped ncclSend/ncclRecv path in place.  AKB_PEER_PUSH=0 disables it.
+  struct PeerInfo { cudaIpcMemHandle_t h[5]; int gids_start; int ok; int pad[2]; };
+  void SetupPeerPush(int gids_start) {
+    Nccl &n = Nccl::get();
+    const char *env = std::getenv("AKB_PEER_PUSH");
+    if (nranks < 2 || !comm || !n.AllGather || (env && env[0] == '0')) return;
+    int ok = 1;
+    if (cudaMalloc(&d_flags, sizeof(unsigned long long) * 2 * nranks) != cudaSuccess) { ok = 0; d_flags = nullptr; }
+    if (d_flags) CU_CHECK(cudaMemset(d_flags, 0, sizeof(unsigned long long) * 2 * nranks));
+    PeerInfo mine;
+    std::memset(&mine, 0, sizeof(mine));
+    mine.gids_start = gids_start;
+    double *arr[4] = {a.u0, a.b0x1f, a.b0x2f, a.b0x3f};
+    for (int q = 0; q < 4 && ok; ++q)
+      if (arr[q] && cudaIpcGetMemHandle(&mine.h[q], arr[q]) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine.h[4], d_flags) != cudaSuccess) ok = 0;
+    if ((int)peers.size() > AKB_MAX_PUSH_PEERS_HOST) ok = 0;
+    mine.ok = ok;
+    cudaGetLastError();
+    char *d_send = nullptr, *d_recv = nullptr;
+    CU_CHECK(cudaMalloc(&d_send, sizeof(PeerInfo)));
+    CU_CHECK(cudaMalloc(&d_recv, sizeof(PeerInfo) * nranks));
+    CU_CHECK(cudaMemcpyAsync(d_send, &mine, sizeof(PeerInfo), cudaMemcpyHostToDevice, st));
+    n.AllGather(d_send, d_recv, sizeof(PeerInfo), kNcclInt8, comm, st);
+    std::vector<PeerInfo> all(nranks);
+    CU_CHECK(cudaMemcpyAsync(all.data(), d_recv, sizeof(PeerInfo) * nranks, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    for (int r = 0; r < nranks; ++r) ok = ok && all[r].ok;
+    std::vector<unsigned long long *> pflags(peers.size(), nullptr);
+    for (size_t p = 0; p < peers.size() && ok; ++p) {
+      const PeerInfo &pi = all[peers[p].rank];
+      void *ptr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+      for (int q = 0; q < 5 && ok; ++q) {
+        if (q >= 1 && q <= 3 && hydro) continue;
+        if (cudaIpcOpenMemHandle(&ptr[q], pi.h[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+        ipc_opened.push_back(ptr[q]);
+      }
+      if (!ok) break;
+      if (ak_halo_push_setup(plan, (int)p, pi.gids_start, (double *)ptr[0], (double *)ptr[1], (double *)ptr[2], (double *)ptr[3])) ok = 0;
+      pflags[p] = (unsigned long long *)ptr[4];
+    }
+    if (ok && ak_halo_push_flags(plan, my_rank, nranks, d_flags, pflags.data())) ok = 0;
+    if (ok && ak_halo_push_commit(plan)) ok = 0;
+    cudaGetLastError();
+    // unanimous?
+    double flag = ok ? 1.0 : 0.0;
+    CU_CHECK(cudaMemcpyAsync(d_dt, &flag, 8, cudaMemcpyHostToDevice, st));
+    n.AllReduce(d_dt, d_dt, 1, kNcclFloat64, kNcclMin, comm, st);
+    CU_CHECK(cudaMemcpyAsync(&flag, d_dt, 8, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    cudaFree(d_send); cudaFree(d_recv);
+    push = flag > 0.5;
+    if (!push && my_rank == 0) std::fprintf(stderr, "athenak_b200: peer-memory ghost exchange unavailable, using ncclSend/ncclRecv\n");
+  }
+  // receiver side: nothing of this rank reads its ghost zones any more -> peers may overwrite them
+  void SignalFree() {
+    if (!push) return;
+    AK_CHECK(nullptr, ak_halo_signal(plan, 0, nexch + 1, st));
+    launches += 1;
   }
 
   // MHD::AssembleMHDTasks, mhd_tasks.cpp:38-84 (the tasks that do work on a uniform mesh)
@@ -312,6 +389,7 @@ class MHD {  // state owner + tasks
     return TaskStatus::complete;
   }
   TaskStatus HydroStageFused(Driver *pd, int stage) {   // CopyCons + Fluxes + RKUpdate
+    SignalFree();    // u0 ghost zones were last read by the previous c2p
     AK_CHECK(h, ak_hydro_stage_fused(h, &a, stage, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, st));
     launches += nsweeps() + 1;
     return TaskStatus::complete;
@@ -325,6 +403,7 @@ class MHD {  // state owner + tasks
   TaskStatus StageFluxEmf(Driver *pd, int stage) {   // tasks 2 + 14
     AK_CHECK(h, ak_mhd_stage_flux_emf(h, &a, st));
     launches += nsweeps() + 1;
+    SignalFree();    // the flux sweeps were the last readers of the b0 ghost faces (u0 ghosts: c2p of the previous stage)
     return TaskStatus::complete;
   }
   TaskStatus StageUpdate(Driver *pd, int stage) {    // tasks 1 + 5 + 17
@@ -393,8 +472,30 @@ class MHD {  // state owner + tasks
   }
   // U and B ghost exchange in one round: legal in the fused list because nothing runs between
   // RecvU and SendB there (CornerE/CT already happened); one ncclSend/ncclRecv pair per peer.
+  // Peer-memory variant of one exchange (sequence number nexch+1): wait until every neighbour has
+  // released its ghost zones, write my boundary slabs into them, publish "filled".
+  void PushExchange(bool with_b) {
+    const unsigned long long seq = nexch + 1;
+    AK_CHECK(nullptr, ak_halo_wait(plan, 0, seq, st));
+    AK_CHECK(nullptr, ak_halo_push(plan, a.u0, 5, with_b ? a.b0x1f : nullptr, a.b0x2f, a.b0x3f, st));
+    AK_CHECK(nullptr, ak_halo_signal(plan, 1, seq, st));
+    launches += 3;
+  }
+  void PushComplete() {   // receiver side: my ghost zones have been filled by every neighbour
+    AK_CHECK(nullptr, ak_halo_wait(plan, 1, nexch + 1, st));
+    launches += 1;
+    nexch += 1;
+  }
+  bool UsePush() const { return push && fused && !peers.empty(); }
   TaskStatus SendUB(Driver *pd, int stage) {
     Nccl &n = Nccl::get();
+    if (UsePush()) {
+      PushExchange(true);
+      AK_CHECK(nullptr, ak_halo_local_cc(plan, a.u0, 5, st));
+      AK_CHECK(nullptr, ak_halo_local_fc(plan, a.b0x1f, a.b0x2f, a.b0x3f, st));
+      launches += 2;
+      return TaskStatus::complete;
+    }
     if (!peers.empty()) {
       if (!comm) Fatal(__FILE__, __LINE__, "MeshBlocks on other ranks but no NCCL communicator (call ak_sim_comm_init)");
       for (size_t p = 0; p < peers.size(); ++p) {
@@ -415,9 +516,26 @@ class MHD {  // state owner + tasks
     launches += 2;
     return TaskStatus::complete;
   }
-  TaskStatus RecvUB(Driver *pd, int stage) { Unpack(true); Unpack(false); return TaskStatus::complete; }
-  TaskStatus SendU(Driver *pd, int stage) { Exchange(true); return TaskStatus::complete; }
-  TaskStatus RecvU(Driver *pd, int stage) { Unpack(true); return TaskStatus::complete; }   // stream-ordered: never incomplete
+  TaskStatus RecvUB(Driver *pd, int stage) {
+    if (UsePush()) { PushComplete(); return TaskStatus::complete; }
+    Unpack(true); Unpack(false);
+    return TaskStatus::complete;
+  }
+  TaskStatus SendU(Driver *pd, int stage) {
+    if (hydro && UsePush()) {     // hydro twin, fused list: u0 is the only exchanged array
+      PushExchange(false);
+      AK_CHECK(nullptr, ak_halo_local_cc(plan, a.u0, 5, st));
+      launches += 1;
+      return TaskStatus::complete;
+    }
+    Exchange(true);
+    return TaskStatus::complete;
+  }
+  TaskStatus RecvU(Driver *pd, int stage) {   // stream-ordered: never incomplete
+    if (hydro && UsePush()) { PushComplete(); return TaskStatus::complete; }
+    Unpack(true);
+    return TaskStatus::complete;
+  }
   TaskStatus SendB(Driver *pd, int stage) { Exchange(false); return TaskStatus::complete; }
   TaskStatus RecvB(Driver *pd, int stage) { Unpack(false); return TaskStatus::complete; }
   // task 26, mhd_tasks.cpp:504-520: nothing to do on a strictly periodic mesh
@@ -486,8 +604,14 @@ class MHD {  // state owner + tasks
 };
 
 void Driver::Initialize(MHD *pmhd) {   // driver.cpp:314-371 -> InitBoundaryValuesAndPrimitives :569-653
-  pmhd->SendU(this, 0); pmhd->RecvU(this, 0);
-  if (!pmhd->hydro) { pmhd->SendB(this, 0); pmhd->RecvB(this, 0); }
+  if (pmhd->UsePush()) {          // peer-memory exchange: same protocol as inside a stage
+    pmhd->SignalFree();
+    if (pmhd->hydro) { pmhd->SendU(this, 0); pmhd->RecvU(this, 0); }
+    else { pmhd->SendUB(this, 0); pmhd->RecvUB(this, 0); }
+  } else {
+    pmhd->SendU(this, 0); pmhd->RecvU(this, 0);
+    if (!pmhd->hydro) { pmhd->SendB(this, 0); pmhd->RecvB(this, 0); }
+  }
   pmhd->ApplyPhysicalBCs(this, 0);                 // driver.cpp:626-627
   pmhd->ConToPrim(this, 0);
   pmhd->NewTimeStep(this, nexp_stages);
@@ -560,7 +684,9 @@ int ak_sim_comm_init(void *sim, const void *unique_id128) {
   if (!n.ok) return 1;
   akh::Nccl::UniqueId id;
   std::memcpy(&id, unique_id128, sizeof(id));
-  return n.CommInitRank(&s->pmhd->comm, s->pmhd->nranks, id, s->pmhd->my_rank);
+  if (n.CommInitRank(&s->pmhd->comm, s->pmhd->nranks, id, s->pmhd->my_rank)) return 1;
+  s->pmhd->SetupPeerPush(s->pmhd->gids_start_);
+  return 0;
 }
 int ak_sim_set_state(void *sim, const double *u0, const double *b1f, const double *b2f, const double *b3f) {
   auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
@@ -594,12 +720,15 @@ int ak_sim_execute(void *sim, int ncycles) {
 int ak_sim_sync(void *sim) {
   return cudaStreamSynchronize(static_cast<akh::Sim *>(sim)->pmhd->st) == cudaSuccess ? 0 : 1;
 }
-/* st[0..2] = time, dt, dtnew; cnt[0..5] = ncycle, launches, nfloor d/e/t, stream handle (as integer) */
+/* st[0..2] = time, dt, dtnew; cnt[0..7] = ncycle, launches, nfloor d/e/t, stream handle (as integer),
+ * peer-memory ghost exchange active (0/1), exchanges done through it */
 int ak_sim_status(void *sim, double *st, long *cnt) {
   auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
   st[0] = m->mesh.time; st[1] = m->mesh.dt; st[2] = m->dtnew;
   cnt[0] = m->mesh.ncycle; cnt[1] = m->launches; cnt[2] = m->nfloor[0]; cnt[3] = m->nfloor[1]; cnt[4] = m->nfloor[2];
   cnt[5] = (long)(intptr_t)m->st;
+  cnt[6] = m->push ? 1 : 0;
+  cnt[7] = (long)m->nexch;
   return 0;
 }
 int ak_sim_arrays(void *sim, ak_mhd_arrays *out) {

@@ -77,6 +77,12 @@ def load():
         "ak_mhd_stage_update": [vp, ap, ip, d, d, d, vp],
         "ak_mhd_cons2prim_newdt": [vp, ap, C.POINTER(C.c_int), _dp, vp],
         "ak_hst_sums": [vp, ap, _dp, C.POINTER(C.c_int), vp],
+        "ak_halo_push_setup": [vp, ip, ip, vp, vp, vp, vp],
+        "ak_halo_push_flags": [vp, ip, ip, vp, vp],
+        "ak_halo_push_commit": [vp],
+        "ak_halo_push": [vp, vp, ip, vp, vp, vp, vp],
+        "ak_halo_signal": [vp, ip, C.c_ulonglong, vp],
+        "ak_halo_wait": [vp, ip, C.c_ulonglong, vp],
         "ak_hydro_create": [C.POINTER(MhdCfg), C.POINTER(vp)],
         "ak_hydro_destroy": [vp],
         "ak_hydro_copy_cons": [vp, ap, vp],
@@ -155,7 +161,8 @@ EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_con
             "ak_sim_get_state", "ak_sim_initialize", "ak_sim_execute", "ak_sim_sync", "ak_sim_status", "ak_sim_arrays",
             "ak_sim_set_bcs", "ak_bcs_create", "ak_bcs_destroy", "ak_bcs_last_error", "ak_bcs_strictly_periodic",
             "ak_bcs_hydro", "ak_bcs_bfield", "ak_bcs_apply",
-            "ak_hst_sums", "ak_hydro_create", "ak_hydro_destroy", "ak_hydro_copy_cons", "ak_hydro_fluxes", "ak_hydro_rk_update",
+            "ak_hst_sums", "ak_halo_push_setup", "ak_halo_push_flags", "ak_halo_push_commit", "ak_halo_push",
+            "ak_halo_signal", "ak_halo_wait", "ak_hydro_create", "ak_hydro_destroy", "ak_hydro_copy_cons", "ak_hydro_fluxes", "ak_hydro_rk_update",
             "ak_hydro_cons2prim", "ak_hydro_new_dt", "ak_hydro_stage_fused", "ak_hydro_cons2prim_newdt")
 
 # BoundaryFlag (src/bvals/bvals.hpp:19) == enum ak_bc_flag

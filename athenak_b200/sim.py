@@ -89,6 +89,7 @@ class Simulation:
         self.L.ak_sim_sync(self.h)
 
     def status(self):
-        st, cnt = (C.c_double * 3)(), (C.c_long * 6)()
+        st, cnt = (C.c_double * 3)(), (C.c_long * 8)()
         self.L.ak_sim_status(self.h, st, cnt)
-        return dict(time=st[0], dt=st[1], dtnew=st[2], ncycle=cnt[0], launches=cnt[1], nfloor=list(cnt[2:5]), stream=cnt[5])
+        return dict(time=st[0], dt=st[1], dtnew=st[2], ncycle=cnt[0], launches=cnt[1], nfloor=list(cnt[2:5]), stream=cnt[5],
+                    peer_push=bool(cnt[6]), peer_exchanges=cnt[7])

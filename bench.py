@@ -207,6 +207,9 @@ def bench_native(args):
     sync_all()
     launches = sim.status()["launches"] - l0
     ms = ev0.elapsed_time(ev1)
+    halo_mode = ("same-rank gather kernel only" if world == 1 else
+                 "peer-memory push kernel over NVLink (cudaIpc-mapped neighbour arrays, flag handshake); EMF correction + dt via NCCL"
+                 if sim.status()["peer_push"] else "grouped ncclSend/ncclRecv, one message per peer")
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -342,7 +345,8 @@ def bench_native(args):
         "config": {"workload": f"3D MHD blast {n}^3 cells per GPU, one MeshBlock per GPU, PPM4+HLLD+RK3, nghost=4, periodic, "
                                f"mesh {'x'.join(str(n * r) for r in nroot)}; step = one full RK3 time step",
                    "l2": "every field array is %.0f MB (> 126 MB L2); no explicit flush" % (8 * (n + 2 * NG) ** 3 / 1e6),
-                   "fmad": False, "parity_build": True, "driver": "C++ host driver (ak_sim_*), fused task list"},
+                   "fmad": False, "parity_build": True, "driver": "C++ host driver (ak_sim_*), fused task list",
+                   "ghost_exchange": halo_mode},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mcell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": ke2e, "ms_per_step": ms_e2e / ke2e, "mode": e2e_mode},

@@ -153,6 +153,28 @@ int ak_halo_pack_fc(void *plan, const double *x1f, const double *x2f, const doub
 int ak_halo_unpack_fc(void *plan, double *x1f, double *x2f, double *x3f, int ipeer,
                       const double *recvbuf, ak_stream_t s);
 
+/* Peer-memory ghost exchange (one process per GPU on one NVLink/NVSwitch node).  Instead of
+ * pack -> message -> unpack, ONE kernel writes every off-rank boundary slab of this rank straight
+ * into the ghost zones of the neighbouring blocks inside the peer GPUs' arrays.  The host layer maps
+ * each peer's u0 / x1f / x2f / x3f and flag array into this process (cudaIpcOpenMemHandle) and
+ * registers them per peer (ipeer as in ak_halo_peer) together with the peer's first gid; flags are
+ * 2*nranks monotone counters per rank ([kind][writer rank], kind 0 = "my ghost zones may be
+ * overwritten", 1 = "your ghost zones are filled").  Protocol per exchange with sequence number n:
+ *   receiver: ak_halo_signal(plan, 0, n) once nothing reads its ghost zones any more
+ *   sender:   ak_halo_wait(plan, 0, n); ak_halo_push(...); ak_halo_signal(plan, 1, n)
+ *   receiver: ak_halo_wait(plan, 1, n) before the ghost zones are read
+ * all stream-ordered (the waits are spinning single-block kernels).  Same bytes land in the same
+ * places as with ak_halo_pack_* + message + ak_halo_unpack_*. */
+int ak_halo_push_setup(void *plan, int ipeer, int peer_gids_start, double *peer_u0, double *peer_x1f,
+                       double *peer_x2f, double *peer_x3f);
+int ak_halo_push_flags(void *plan, int my_rank, int nranks, unsigned long long *local_flags,
+                       unsigned long long *const *peer_flags /* host [npeers] */);
+int ak_halo_push_commit(void *plan);
+/* u0 == NULL skips the cell-centred data, x1f == NULL the face fields */
+int ak_halo_push(void *plan, double *u0, int nvar, double *x1f, double *x2f, double *x3f, ak_stream_t s);
+int ak_halo_signal(void *plan, int kind, unsigned long long value, ak_stream_t s);
+int ak_halo_wait(void *plan, int kind, unsigned long long value, ak_stream_t s);
+
 /* Orszag-Tang vortex ICs (src/pgen/tests/orszag_tang.cpp:32-123), BASELINE config 3. */
 int ak_pgen_orszag_tang(void *mesh, int rank, int ng, double gamma, double *u0, double *b1f,
                         double *b2f, double *b3f);
@@ -232,13 +254,17 @@ int ak_sim_destroy(void *sim);
 /* physical BCs (default strictly periodic): mesh_bcs[6], mb_bcs host [nmb][6]; errors -> ak_bcs_last_error(NULL) */
 int ak_sim_set_bcs(void *sim, const int *mesh_bcs, const int *mb_bcs);
 int ak_nccl_unique_id(void *out128);                         /* rank 0; broadcast by the launcher */
-int ak_sim_comm_init(void *sim, const void *unique_id128);   /* collective over all ranks */
+/* collective over all ranks: creates the NCCL communicator, then tries to set up the peer-memory
+ * ghost exchange (cudaIpc handles of u0 / face fields / flags all-gathered and mapped; used by the
+ * fused task list when EVERY rank succeeded, AKB_PEER_PUSH=0 disables it) */
+int ak_sim_comm_init(void *sim, const void *unique_id128);
 int ak_sim_set_state(void *sim, const double *u0, const double *b1f, const double *b2f, const double *b3f);
 int ak_sim_get_state(void *sim, double *u0, double *b1f, double *b2f, double *b3f);
 int ak_sim_initialize(void *sim);            /* Driver::Initialize: ghosts, c2p, first dt */
 int ak_sim_execute(void *sim, int ncycles);  /* Driver::Execute; returns cycles done */
 int ak_sim_sync(void *sim);
-/* st[3] = time, dt, dtnew; cnt[6] = ncycle, kernel launches, nfloor d/e/t, cudaStream_t */
+/* st[3] = time, dt, dtnew; cnt[8] = ncycle, kernel launches, nfloor d/e/t, cudaStream_t,
+ * peer-memory ghost exchange active (0/1), exchanges done through it */
 int ak_sim_status(void *sim, double *st, long *cnt);
 int ak_sim_arrays(void *sim, ak_mhd_arrays *out);            /* the device arrays it owns */
 

@@ -70,11 +70,13 @@ def main():
         ok &= np.array_equal(x2[m, 4:-4, 4:-4, 4:-4], d["b2f_c4"][0][lz:lz + 8, ly:ly + 9, lx:lx + 8])
         ok &= np.array_equal(x3[m, 4:-4, 4:-4, 4:-4], d["b3f_c4"][0][lz:lz + 9, ly:ly + 8, lx:lx + 8])
     ok &= sim.status()["time"] == float(d["time_c4"])
+    push_used = sim.status()["peer_push"]
+    ok &= (sim.status()["peer_exchanges"] > 0) == push_used
     del sim
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("MULTIGPU_PARITY", "OK" if int(t.item()) == 1 else "FAIL", "world", world)
+        print("MULTIGPU_PARITY", "OK" if int(t.item()) == 1 else "FAIL", "world", world, "peer_push", push_used)
     dist.destroy_process_group()
     sys.exit(0 if int(t.item()) == 1 else 1)
 
