@@ -80,6 +80,7 @@ int check_cfg(const ak_mhd_cfg *c, bool hydro, std::string &why) {
   const int need = (c->recon >= AK_RECON_PPM4) ? 3 : 2;
   if (c->ng < need) { why = "nghost too small for the reconstruction stencil"; return 1; }
   if (!(c->gamma > 1.0)) { why = "gamma must exceed 1"; return 1; }
+  if (c->nscalars < 0 || c->nscalars > 64) { why = "nscalars must be in [0, 64]"; return 1; }
   return 0;
 }
 
@@ -106,6 +107,7 @@ static int create_impl(const ak_mhd_cfg *cfg, bool hydro, void **handle) {
   h->hydro = hydro;
   akb::Geom &g = h->g;
   g.nmb = cfg->nmb; g.ng = cfg->ng; g.nx1 = cfg->nx1; g.nx2 = cfg->nx2; g.nx3 = cfg->nx3;
+  g.nvar = 5 + cfg->nscalars;
   g.multi_d = cfg->nx2 > 1; g.three_d = cfg->nx3 > 1;          // mesh.cpp:70-79
   g.n1 = cfg->nx1 + 2 * cfg->ng;
   g.n2 = g.multi_d ? cfg->nx2 + 2 * cfg->ng : 1;               // mhd.cpp:149-152 / hydro.cpp
@@ -159,7 +161,7 @@ int ak_mhd_destroy(void *handle) {
 int ak_mhd_copy_cons(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
   AK_PROLOGUE("ak_mhd_copy_cons")
   const akb::Geom &g = h->g;
-  if ((e = akb::launch_copy(A.u0, A.u1, 5L * g.nmb * g.cc, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_copy_cons", e);
+  if ((e = akb::launch_copy(A.u0, A.u1, (long)g.nvar * g.nmb * g.cc, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_copy_cons", e);
   if ((e = akb::launch_copy(A.b0x1f, A.b1x1f, g.nmb * g.f1, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_copy_cons", e);
   if ((e = akb::launch_copy(A.b0x2f, A.b1x2f, g.nmb * g.f2, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_copy_cons", e);
   if ((e = akb::launch_copy(A.b0x3f, A.b1x3f, g.nmb * g.f3, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_copy_cons", e);
@@ -288,7 +290,7 @@ int ak_hst_sums(void *handle, const ak_mhd_arrays *a, double *sums, int *nhist, 
 
 int ak_hydro_copy_cons(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
   AK_HYD_PROLOGUE("ak_hydro_copy_cons")
-  if ((e = akb::launch_copy(A.u0, A.u1, 5L * h->g.nmb * h->g.cc, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_copy_cons", e);
+  if ((e = akb::launch_copy(A.u0, A.u1, (long)h->g.nvar * h->g.nmb * h->g.cc, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_copy_cons", e);
   return 0;
 }
 int ak_hydro_fluxes(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {

@@ -67,7 +67,7 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
   const long off = ((long)k * g.n2 + j) * g.n1 + i;
   State7 up, lo;
   if constexpr (RECON == RECON_PPM4) {
-    const double *w = w0 + (long)m * 5 * cc + off, *b = MHD ? bcc + (long)m * 3 * cc + off : w;
+    const double *w = w0 + (long)m * g.nvar * cc + off, *b = MHD ? bcc + (long)m * 3 * cc + off : w;
     const double *vp[7] = {w + IDN * cc, w + IVX * cc, w + IVY * cc, w + IVZ * cc, w + IEN * cc, b + 1 * cc, b + 2 * cc};
     double q[NV], fl[NV];
 #pragma unroll
@@ -83,7 +83,7 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
       ppm4_mono(q[v], fl[v], fh, *upv[v], *lov[v]);
     }
   } else {
-    recon_cell<RECON, 0, MHD>(w0 + (long)m * 5 * cc + off, bcc + (long)m * 3 * cc + off, cc, 1, eos, up, lo);
+    recon_cell<RECON, 0, MHD>(w0 + (long)m * g.nvar * cc + off, bcc + (long)m * 3 * cc + off, cc, 1, eos, up, lo);
   }
   State7 L;
   L.d = __shfl_up_sync(0xffffffffu, up.d, 1);
@@ -104,7 +104,7 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
     riemann_hyd<RS>(L, lo, eos, f);
   }
   const long fs = (long)g.n3 * g.n2 * (g.n1 + 1);
-  double *fp = flx + (long)m * 5 * fs + ((long)k * g.n2 + j) * (g.n1 + 1) + i;
+  double *fp = flx + (long)m * g.nvar * fs + ((long)k * g.n2 + j) * (g.n1 + 1) + i;
   fp[IDN * fs] = f.d;
   fp[IVX * fs] = f.mx;
   fp[IVY * fs] = f.my;
@@ -244,7 +244,7 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
   int k, j;
   if (DIR == 1) { k = g.ks - g.ext3 + tr; j = f_lo - 1; } else { j = g.js - g.ext2 + tr; k = f_lo - 1; }
   long off = ((long)k * g.n2 + j) * g.n1 + i;
-  const double *wp = w0 + (long)m * 5 * cc + off;
+  const double *wp = w0 + (long)m * g.nvar * cc + off;
   const double *bp = MHD ? bcc + (long)m * 3 * cc + off : wp;
   // face-array geometry
   const long frow = (DIR == 1) ? (long)g.n1 : (long)g.n1 * g.n2;  // stride of the sweep index in the face arrays
@@ -252,7 +252,7 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
   long foff = (DIR == 1) ? ((long)k * (g.n2 + 1) + f_lo) * g.n1 + i
                          : ((long)f_lo * g.n2 + j) * g.n1 + i;
   const double *bn = MHD ? bnf + (long)m * fsz + foff : wp;
-  double *fp = flx + (long)m * 5 * fsz + foff;
+  double *fp = flx + (long)m * g.nvar * fsz + foff;
   double *eyp = MHD ? eyo + (long)m * cc + off + s : nullptr;
   double *ezp = MHD ? ezo + (long)m * cc + off + s : nullptr;
   constexpr int ivx = IVX + DIR, ivy = IVX + (DIR + 1) % 3, ivz = IVX + (DIR + 2) % 3;
@@ -341,6 +341,56 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
 }
 
 // ---------------------------------------------------------------------------------------
+// Passive-scalar fluxes (mhd_fluxes.cpp:153-166,203-216,250-263; hydro_fluxes.cpp:126-138,...):
+// flx(n) = flx(IDN) * (flx(IDN) >= 0 ? wl(n) : wr(n)) over the faces of the ACTIVE transverse
+// range.  One thread per (face, scalar); only the upwind side is reconstructed (the value is the
+// reference's wl or wr entry bit for bit).  Runs after the sweep that wrote the mass flux.
+template <int RECON, int DIR>
+__global__ void __launch_bounds__(256)
+scalar_flux_kernel(Geom g, const double *__restrict__ w0, double *__restrict__ flx) {
+  const int nfi = g.nx1 + (DIR == 0), nfj = g.nx2 + (DIR == 1), nfk = g.nx3 + (DIR == 2);
+  const int ns = g.nvar - 5;
+  const long total = (long)g.nmb * ns * nfk * nfj * nfi;
+  const long t0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t0 >= total) return;
+  long t = t0;
+  const int i = g.is + (int)(t % nfi); t /= nfi;
+  const int j = g.js + (int)(t % nfj); t /= nfj;
+  const int k = g.ks + (int)(t % nfk); t /= nfk;
+  const int n = 5 + (int)(t % ns);
+  const int m = (int)(t / ns);
+  const long s = (DIR == 0) ? 1 : (DIR == 1) ? (long)g.n1 : (long)g.n1 * g.n2;
+  const long fsz = (DIR == 0) ? g.f1 : (DIR == 1) ? g.f2 : g.f3;
+  const long foff = (DIR == 0) ? ((long)k * g.n2 + j) * (g.n1 + 1) + i
+                  : (DIR == 1) ? ((long)k * (g.n2 + 1) + j) * g.n1 + i : ((long)k * g.n2 + j) * g.n1 + i;
+  double *fb = flx + (long)m * g.nvar * fsz + foff;
+  const double fd = fb[IDN * fsz];
+  const double *q = w0 + ((long)m * g.nvar + n) * g.cc + ((long)k * g.n2 + j) * g.n1 + i;   // cell on the upper side of the face
+  double up, lo;
+  if (fd >= 0.0) { recon_var<RECON>(q - s, s, up, lo); fb[n * fsz] = fd * up; }   // wl = upper-face value of the cell below
+  else { recon_var<RECON>(q, s, up, lo); fb[n * fsz] = fd * lo; }                 // wr = lower-face value of this cell
+}
+
+template <int RECON>
+static cudaError_t launch_scalar_fluxes(const Geom &g, const Arrays &a, cudaStream_t st) {
+  const int ns = g.nvar - 5;
+  if (ns <= 0) return cudaSuccess;
+  {
+    const long n = (long)g.nmb * ns * g.nx3 * g.nx2 * (g.nx1 + 1);
+    scalar_flux_kernel<RECON, 0><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, a.w0, a.flx1);
+  }
+  if (g.multi_d) {
+    const long n = (long)g.nmb * ns * g.nx3 * (g.nx2 + 1) * g.nx1;
+    scalar_flux_kernel<RECON, 1><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, a.w0, a.flx2);
+  }
+  if (g.three_d) {
+    const long n = (long)g.nmb * ns * (g.nx3 + 1) * g.nx2 * g.nx1;
+    scalar_flux_kernel<RECON, 2><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, a.w0, a.flx3);
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
 // launchers
 
 static inline unsigned nblocks(long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
@@ -376,6 +426,7 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
     if (!attr2 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr2 = true; }
     flux_march_kernel<RECON, RS, 2><<<nblocks(threads, MARCH_THREADS), MARCH_THREADS, smem, st>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
   }
+  if (g.nvar > 5) return launch_scalar_fluxes<RECON>(g, a, st);
   return cudaGetLastError();
 }
 

@@ -195,6 +195,7 @@ class MHD {  // state owner + tasks
   Nccl::Comm comm = nullptr;
   double *d_dt = nullptr;
   size_t n_u, n_f1, n_f2, n_f3;
+  int nvar = 5;
   bool hydro = false, multi_d = true, three_d = true;
   // peer-memory ghost exchange (ak_halo_push_*): set up by SetupPeerPush() after the communicator exists
   int gids_start_ = 0;
@@ -211,11 +212,12 @@ class MHD {  // state owner + tasks
     multi_d = c.nx2 > 1; three_d = c.nx3 > 1;       // mesh.cpp:70-79
     const size_t n1 = c.nx1 + 2 * c.ng, n2 = multi_d ? c.nx2 + 2 * c.ng : 1, n3 = three_d ? c.nx3 + 2 * c.ng : 1, nm = c.nmb;
     const size_t cc = n1 * n2 * n3;
-    n_u = nm * 5 * cc; n_f1 = nm * n3 * n2 * (n1 + 1); n_f2 = nm * n3 * (n2 + 1) * n1; n_f3 = nm * (n3 + 1) * n2 * n1;
+    nvar = 5 + c.nscalars;
+    n_u = nm * nvar * cc; n_f1 = nm * n3 * n2 * (n1 + 1); n_f2 = nm * n3 * (n2 + 1) * n1; n_f3 = nm * (n3 + 1) * n2 * n1;
     auto alloc = [&](size_t n) { double *p; CU_CHECK(cudaMalloc(&p, n * 8)); CU_CHECK(cudaMemsetAsync(p, 0, n * 8, st)); owned.push_back(p); return p; };
     std::memset(&a, 0, sizeof(a));
     a.u0 = alloc(n_u); a.u1 = alloc(n_u); a.w0 = alloc(n_u);
-    a.flx1 = alloc(5 * n_f1); a.flx2 = alloc(5 * n_f2); a.flx3 = alloc(5 * n_f3);
+    a.flx1 = alloc(nvar * n_f1); a.flx2 = alloc(nvar * n_f2); a.flx3 = alloc(nvar * n_f3);
     if (!hydro) {
       a.bcc0 = alloc(nm * 3 * cc);   // mhd.cpp:148-161
       a.b0x1f = alloc(n_f1); a.b0x2f = alloc(n_f2); a.b0x3f = alloc(n_f3);
@@ -234,8 +236,8 @@ class MHD {  // state owner + tasks
       Peer pe;
       ak_halo_peer(plan, p, &pe.rank, &pe.ncc, &pe.nfc);
       // one contiguous [U | B] buffer per direction so both exchanges can travel as one message
-      pe.scc = alloc(5 * pe.ncc + pe.nfc); pe.sfc = pe.scc + 5 * pe.ncc;
-      pe.rcc = alloc(5 * pe.ncc + pe.nfc); pe.rfc = pe.rcc + 5 * pe.ncc;
+      pe.scc = alloc(nvar * pe.ncc + pe.nfc); pe.sfc = pe.scc + nvar * pe.ncc;
+      pe.rcc = alloc(nvar * pe.ncc + pe.nfc); pe.rfc = pe.rcc + nvar * pe.ncc;
       peers.push_back(pe);
     }
     CU_CHECK(cudaStreamSynchronize(st));
@@ -447,25 +449,25 @@ class MHD {  // state owner + tasks
     if (!peers.empty()) {
       if (!comm) Fatal(__FILE__, __LINE__, "MeshBlocks on other ranks but no NCCL communicator (call ak_sim_comm_init)");
       for (size_t p = 0; p < peers.size(); ++p) {
-        if (cc_vars) AK_CHECK(nullptr, ak_halo_pack_cc(plan, a.u0, 5, (int)p, peers[p].scc, st));
+        if (cc_vars) AK_CHECK(nullptr, ak_halo_pack_cc(plan, a.u0, nvar, (int)p, peers[p].scc, st));
         else AK_CHECK(nullptr, ak_halo_pack_fc(plan, a.b0x1f, a.b0x2f, a.b0x3f, (int)p, peers[p].sfc, st));
         launches += 1;
       }
       n.GroupStart();
       for (auto &pe : peers) {
-        const size_t cnt = cc_vars ? (size_t)5 * pe.ncc : (size_t)pe.nfc;
+        const size_t cnt = cc_vars ? (size_t)nvar * pe.ncc : (size_t)pe.nfc;
         n.Send(cc_vars ? pe.scc : pe.sfc, cnt, kNcclFloat64, pe.rank, comm, st);
         n.Recv(cc_vars ? pe.rcc : pe.rfc, cnt, kNcclFloat64, pe.rank, comm, st);
       }
       n.GroupEnd();
     }
-    if (cc_vars) AK_CHECK(nullptr, ak_halo_local_cc(plan, a.u0, 5, st));
+    if (cc_vars) AK_CHECK(nullptr, ak_halo_local_cc(plan, a.u0, nvar, st));
     else AK_CHECK(nullptr, ak_halo_local_fc(plan, a.b0x1f, a.b0x2f, a.b0x3f, st));
     launches += 1;
   }
   void Unpack(bool cc_vars) {
     for (size_t p = 0; p < peers.size(); ++p) {
-      if (cc_vars) AK_CHECK(nullptr, ak_halo_unpack_cc(plan, a.u0, 5, (int)p, peers[p].rcc, st));
+      if (cc_vars) AK_CHECK(nullptr, ak_halo_unpack_cc(plan, a.u0, nvar, (int)p, peers[p].rcc, st));
       else AK_CHECK(nullptr, ak_halo_unpack_fc(plan, a.b0x1f, a.b0x2f, a.b0x3f, (int)p, peers[p].rfc, st));
       launches += 1;
     }
@@ -477,7 +479,7 @@ class MHD {  // state owner + tasks
   void PushExchange(bool with_b) {
     const unsigned long long seq = nexch + 1;
     AK_CHECK(nullptr, ak_halo_wait(plan, 0, seq, st));
-    AK_CHECK(nullptr, ak_halo_push(plan, a.u0, 5, with_b ? a.b0x1f : nullptr, a.b0x2f, a.b0x3f, st));
+    AK_CHECK(nullptr, ak_halo_push(plan, a.u0, nvar, with_b ? a.b0x1f : nullptr, a.b0x2f, a.b0x3f, st));
     AK_CHECK(nullptr, ak_halo_signal(plan, 1, seq, st));
     launches += 3;
   }
@@ -491,7 +493,7 @@ class MHD {  // state owner + tasks
     Nccl &n = Nccl::get();
     if (UsePush()) {
       PushExchange(true);
-      AK_CHECK(nullptr, ak_halo_local_cc(plan, a.u0, 5, st));
+      AK_CHECK(nullptr, ak_halo_local_cc(plan, a.u0, nvar, st));
       AK_CHECK(nullptr, ak_halo_local_fc(plan, a.b0x1f, a.b0x2f, a.b0x3f, st));
       launches += 2;
       return TaskStatus::complete;
@@ -499,19 +501,19 @@ class MHD {  // state owner + tasks
     if (!peers.empty()) {
       if (!comm) Fatal(__FILE__, __LINE__, "MeshBlocks on other ranks but no NCCL communicator (call ak_sim_comm_init)");
       for (size_t p = 0; p < peers.size(); ++p) {
-        AK_CHECK(nullptr, ak_halo_pack_cc(plan, a.u0, 5, (int)p, peers[p].scc, st));
+        AK_CHECK(nullptr, ak_halo_pack_cc(plan, a.u0, nvar, (int)p, peers[p].scc, st));
         AK_CHECK(nullptr, ak_halo_pack_fc(plan, a.b0x1f, a.b0x2f, a.b0x3f, (int)p, peers[p].sfc, st));
         launches += 2;
       }
       n.GroupStart();
       for (auto &pe : peers) {
-        const size_t cnt = (size_t)5 * pe.ncc + (size_t)pe.nfc;
+        const size_t cnt = (size_t)nvar * pe.ncc + (size_t)pe.nfc;
         n.Send(pe.scc, cnt, kNcclFloat64, pe.rank, comm, st);
         n.Recv(pe.rcc, cnt, kNcclFloat64, pe.rank, comm, st);
       }
       n.GroupEnd();
     }
-    AK_CHECK(nullptr, ak_halo_local_cc(plan, a.u0, 5, st));
+    AK_CHECK(nullptr, ak_halo_local_cc(plan, a.u0, nvar, st));
     AK_CHECK(nullptr, ak_halo_local_fc(plan, a.b0x1f, a.b0x2f, a.b0x3f, st));
     launches += 2;
     return TaskStatus::complete;
@@ -524,7 +526,7 @@ class MHD {  // state owner + tasks
   TaskStatus SendU(Driver *pd, int stage) {
     if (hydro && UsePush()) {     // hydro twin, fused list: u0 is the only exchanged array
       PushExchange(false);
-      AK_CHECK(nullptr, ak_halo_local_cc(plan, a.u0, 5, st));
+      AK_CHECK(nullptr, ak_halo_local_cc(plan, a.u0, nvar, st));
       launches += 1;
       return TaskStatus::complete;
     }
@@ -541,7 +543,7 @@ class MHD {  // state owner + tasks
   // task 26, mhd_tasks.cpp:504-520: nothing to do on a strictly periodic mesh
   TaskStatus ApplyPhysicalBCs(Driver *pd, int stage) {
     if (!bcs) return TaskStatus::complete;
-    if (hydro ? ak_bcs_hydro(bcs, a.u0, 5, st) : ak_bcs_apply(bcs, a.u0, 5, a.b0x1f, a.b0x2f, a.b0x3f, st))
+    if (hydro ? ak_bcs_hydro(bcs, a.u0, nvar, st) : ak_bcs_apply(bcs, a.u0, nvar, a.b0x1f, a.b0x2f, a.b0x3f, st))
       Fatal(__FILE__, __LINE__, ak_bcs_last_error(bcs));
     launches += nbc_launches;
     return TaskStatus::complete;

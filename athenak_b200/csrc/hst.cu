@@ -30,7 +30,7 @@ hst_partial_kernel(Geom g, bool mhd, const double *__restrict__ u0, const double
     const int m = (int)(r / g.nx3);
     const double vol = mb_size[m * 9 + 6] * mb_size[m * 9 + 7] * mb_size[m * 9 + 8];
     const long o = ((long)k * g.n2 + j) * g.n1 + i;
-    const double *u = u0 + (long)m * 5 * g.cc + o;
+    const double *u = u0 + (long)m * g.nvar * g.cc + o;
     const double d = u[0], m1 = u[g.cc], m2 = u[2 * g.cc], m3 = u[3 * g.cc], e = u[4 * g.cc];
     acc[0] += vol * d; acc[1] += vol * m1; acc[2] += vol * m2; acc[3] += vol * m3; acc[4] += vol * e;
     acc[5] += vol * 0.5 * sqr(m1) / d;

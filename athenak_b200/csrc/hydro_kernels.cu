@@ -28,7 +28,7 @@ hydro_cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, double *_
     const int m = (int)(t / nk);
     const long cc = g.cc;
     const long o = ((long)k * g.n2 + j) * g.n1 + i;
-    double *u = u0 + (long)m * 5 * cc + o;
+    double *u = u0 + (long)m * g.nvar * cc + o;
     double ud = u[IDN * cc], ue = u[IEN * cc];
     const double umx = u[IM1 * cc], umy = u[IM2 * cc], umz = u[IM3 * cc];
     bool dfl = false, efl = false, tfl = false;
@@ -53,8 +53,13 @@ hydro_cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, double *_
     if (dfl) { u[IDN * cc] = ud; nd = 1; }
     if (efl) { u[IEN * cc] = ue; ne = 1; }
     if (tfl) { u[IEN * cc] = ue; nt = 1; }
-    double *w = w0 + (long)m * 5 * cc + o;
+    double *w = w0 + (long)m * g.nvar * cc + o;
     w[IDN * cc] = wd; w[IVX * cc] = wvx; w[IVY * cc] = wvy; w[IVZ * cc] = wvz; w[IEN * cc] = we;
+    for (int n = 5; n < g.nvar; ++n) {   // ideal_hyd.cpp:95-101: scalar floor, then s / d (floored density)
+      double sc = u[n * cc];
+      if (sc < 0.0) { sc = 0.0; u[n * cc] = 0.0; }
+      w[n * cc] = sc / ud;
+    }
     if (NEWDT) {
       if (i >= g.is && i <= g.ie && j >= g.js && j <= g.je && k >= g.ks && k <= g.ke) {
         const double cs = sound_speed(eos.gamma, wd, gm1 * we);
@@ -82,7 +87,7 @@ hydro_newdt_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const d
     const int k = g.ks + (int)(t % g.nx3);
     const int m = (int)(t / g.nx3);
     const long cc = g.cc, o = ((long)k * g.n2 + j) * g.n1 + i;
-    const double *w = w0 + (long)m * 5 * cc + o;
+    const double *w = w0 + (long)m * g.nvar * cc + o;
     const double p = (eos.gamma - 1.0) * __ldg(w + IEN * cc);
     const double cs = sound_speed(eos.gamma, __ldg(w), p);
     d1 = ddiv(__ldg(mb_size + m * 9 + 6), fabs(__ldg(w + IVX * cc)) + cs);

@@ -38,16 +38,16 @@ corner_emf_kernel(Geom g, const double *__restrict__ w0, const double *__restric
   if (ii >= ni || jj >= nj || kk >= nk) return;
   const int i = g.is + ii, j = g.js + jj, k = g.ks + kk;
   const long cc = g.cc, n1 = g.n1, n12 = (long)g.n1 * g.n2;
-  const double *w = w0 + (long)m * 5 * cc, *b = bcc + (long)m * 3 * cc;
+  const double *w = w0 + (long)m * g.nvar * cc, *b = bcc + (long)m * 3 * cc;
   auto C = [&](int kk, int jj, int ii) -> long { return ((long)kk * g.n2 + jj) * n1 + ii; };
   // cell-centred E = -(v x B)  (mhd_corner_e.cpp:310-317)
   auto e1cc = [&](long o) { return __ldg(w + IVZ * cc + o) * __ldg(b + 1 * cc + o) - __ldg(w + IVY * cc + o) * __ldg(b + 2 * cc + o); };
   auto e2cc = [&](long o) { return __ldg(w + IVX * cc + o) * __ldg(b + 2 * cc + o) - __ldg(w + IVZ * cc + o) * __ldg(b + 0 * cc + o); };
   auto e3cc = [&](long o) { return __ldg(w + IVY * cc + o) * __ldg(b + 0 * cc + o) - __ldg(w + IVX * cc + o) * __ldg(b + 1 * cc + o); };
   // mass fluxes (IDN component) on the three face families
-  const double *f1 = flx1 + (long)m * 5 * g.f1;
-  const double *f2 = flx2 + (long)m * 5 * g.f2;
-  const double *f3 = flx3 + (long)m * 5 * g.f3;
+  const double *f1 = flx1 + (long)m * g.nvar * g.f1;
+  const double *f2 = flx2 + (long)m * g.nvar * g.f2;
+  const double *f3 = flx3 + (long)m * g.nvar * g.f3;
   auto F1 = [&](int kk, int jj, int ii) { return __ldg(f1 + ((long)kk * g.n2 + jj) * (n1 + 1) + ii); };
   auto F2 = [&](int kk, int jj, int ii) { return __ldg(f2 + ((long)kk * (g.n2 + 1) + jj) * n1 + ii); };
   auto F3 = [&](int kk, int jj, int ii) { return __ldg(f3 + ((long)kk * g.n2 + jj) * n1 + ii); };
@@ -119,9 +119,9 @@ corner_emf_2d_kernel(Geom g, const double *__restrict__ w0, const double *__rest
   const int i = g.is + ii, j = g.js + jj;
   const long cc = g.cc, n1 = g.n1;
   const long o = (long)j * n1 + i, mo = (long)m * cc;
-  const double *w = w0 + (long)m * 5 * cc, *b = bcc + (long)m * 3 * cc;
+  const double *w = w0 + (long)m * g.nvar * cc, *b = bcc + (long)m * 3 * cc;
   auto e3cc = [&](long q) { return __ldg(w + IVY * cc + q) * __ldg(b + 0 * cc + q) - __ldg(w + IVX * cc + q) * __ldg(b + 1 * cc + q); };
-  const double *f1 = flx1 + (long)m * 5 * g.f1, *f2 = flx2 + (long)m * 5 * g.f2;
+  const double *f1 = flx1 + (long)m * g.nvar * g.f1, *f2 = flx2 + (long)m * g.nvar * g.f2;
   auto F1 = [&](int jq, int iq) { return __ldg(f1 + (long)jq * (n1 + 1) + iq); };
   auto F2 = [&](int jq, int iq) { return __ldg(f2 + (long)jq * n1 + iq); };
   const double v2 = __ldg(e2x1 + mo + o), v1 = __ldg(e1x2 + mo + o);
@@ -172,20 +172,22 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
     const long o1 = ((long)k * n2 + j) * (n1 + 1) + i;
     const long o2 = ((long)k * (n2 + 1) + j) * n1 + i;
     const long o3 = o;
-#pragma unroll
-    for (int n = 0; n < 5; ++n) {
-      const double *p1 = flx1 + ((long)m * 5 + n) * g.f1 + o1;
-      const double *p2 = flx2 + ((long)m * 5 + n) * g.f2 + o2;
-      const double *p3 = flx3 + ((long)m * 5 + n) * g.f3 + o3;
+    auto update_var = [&](int n) {
+      const double *p1 = flx1 + ((long)m * g.nvar + n) * g.f1 + o1;
+      const double *p2 = flx2 + ((long)m * g.nvar + n) * g.f2 + o2;
+      const double *p3 = flx3 + ((long)m * g.nvar + n) * g.f3 + o3;
       double divf = div_by(__ldg(p1 + 1) - __ldg(p1), dx1, rdx1);
       if (g.multi_d) divf += div_by(__ldg(p2 + n1) - __ldg(p2), dx2, rdx2);   // hydro_update.cpp:57-75
       if (g.three_d) divf += div_by(__ldg(p3 + n1 * n2) - __ldg(p3), dx3, rdx3);
-      const long uo = ((long)m * 5 + n) * g.cc + o;
+      const long uo = ((long)m * g.nvar + n) * g.cc + o;
       const double uold = u0[uo];
       double ureg;
       if (SAVE) { ureg = uold; u1[uo] = uold; } else { ureg = u1[uo]; }   // SAVE: CopyCons fused in
       u0[uo] = gam0 * uold + gam1 * ureg - beta_dt * divf;
-    }
+    };
+#pragma unroll
+    for (int n = 0; n < 5; ++n) update_var(n);
+    for (int n = 5; n < g.nvar; ++n) update_var(n);   // passive scalars (mhd_update.cpp:51: n over nmhd+nscalars)
   }
   if (DO_B) {
     const double *E1 = e1 + (long)m * g.e1, *E2 = e2 + (long)m * g.e2, *E3 = e3 + (long)m * g.e3;
@@ -250,7 +252,7 @@ cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *_
     const int m = (int)(t / nk);
     const long n1 = g.n1, n2 = g.n2, cc = g.cc;
     const long o = ((long)k * n2 + j) * n1 + i;
-    double *u = u0 + (long)m * 5 * cc + o;
+    double *u = u0 + (long)m * g.nvar * cc + o;
     double ud = u[IDN * cc], umx = u[IM1 * cc], umy = u[IM2 * cc], umz = u[IM3 * cc], ue = u[IEN * cc];
     const double *p1 = b1f + (long)m * g.f1 + ((long)k * n2 + j) * (n1 + 1) + i;
     const double *p2 = b2f + (long)m * g.f2 + ((long)k * (n2 + 1) + j) * n1 + i;
@@ -286,10 +288,15 @@ cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *_
     if (dfl) { u[IDN * cc] = ud; nd = 1; }
     if (efl) { u[IEN * cc] = ue; ne = 1; }
     if (tfl) { u[IEN * cc] = ue; nt = 1; }
-    double *w = w0 + (long)m * 5 * cc + o;
+    double *w = w0 + (long)m * g.nvar * cc + o;
     w[IDN * cc] = wd; w[IVX * cc] = wvx; w[IVY * cc] = wvy; w[IVZ * cc] = wvz; w[IEN * cc] = we;
     double *bc = bcc + (long)m * 3 * cc + o;
     bc[0] = ubx; bc[cc] = uby; bc[2 * cc] = ubz;
+    for (int n = 5; n < g.nvar; ++n) {   // ideal_mhd.cpp:113-120: scalar floor, then s / d (floored density)
+      double sc = u[n * cc];
+      if (sc < 0.0) { sc = 0.0; u[n * cc] = 0.0; }
+      w[n * cc] = sc / ud;
+    }
     if (NEWDT) {
       act = (i >= g.is && i <= g.ie && j >= g.js && j <= g.je && k >= g.ks && k <= g.ke);
       if (act) {  // mhd_newdt.cpp:128-138,146-148
@@ -331,7 +338,7 @@ newdt_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double 
     const int k = g.ks + (int)(t % g.nx3);
     const int m = (int)(t / g.nx3);
     const long cc = g.cc, o = ((long)k * g.n2 + j) * g.n1 + i;
-    const double *w = w0 + (long)m * 5 * cc + o, *b = bcc + (long)m * 3 * cc + o;
+    const double *w = w0 + (long)m * g.nvar * cc + o, *b = bcc + (long)m * 3 * cc + o;
     const double wd = __ldg(w), bx = __ldg(b), by = __ldg(b + cc), bz = __ldg(b + 2 * cc);
     const double p = (eos.gamma - 1.0) * __ldg(w + IEN * cc);
     d1 = ddiv(__ldg(mb_size + m * 9 + 6), fabs(__ldg(w + IVX * cc)) + fast_speed(eos.gamma, wd, p, bx, by, bz));

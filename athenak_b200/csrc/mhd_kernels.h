@@ -12,6 +12,7 @@ struct EosParams;
 
 struct Geom {  // RegionIndcs (src/mesh/mesh.hpp:35-41) + derived array extents
   int nmb, ng, nx1, nx2, nx3;
+  int nvar;         // 5 fluid variables + passive scalars per cell-centred / flux array
   int n1, n2, n3;
   int is, ie, js, je, ks, ke;
   long cc;          // cells per variable per block

@@ -20,7 +20,7 @@ from .mhd import FLT_MAX, FLT_MIN, TaskStatus
 class Hydro:
     def __init__(self, nmb, ng, nx, mb_size, nghbr, *, recon="plm", rsolver="hllc", gamma,
                  dfloor=FLT_MIN, pfloor=FLT_MIN, tfloor=FLT_MIN, sfloor=FLT_MIN,
-                 my_rank=0, gids_start=0, device="cuda", process_group=None, mesh_bcs=None, mb_bcs=None):
+                 my_rank=0, gids_start=0, device="cuda", process_group=None, mesh_bcs=None, mb_bcs=None, nscalars=0):
         if not torch.cuda.is_available():
             raise _lib.EngineError("athenak_b200: no CUDA device; the engine has no CPU path")
         self.L = _lib.load()
@@ -29,14 +29,15 @@ class Hydro:
         nx1, nx2, nx3 = self.nx
         self.multi_d, self.three_d = nx2 > 1, nx3 > 1
         self.n = (nx1 + 2 * ng, nx2 + 2 * ng if self.multi_d else 1, nx3 + 2 * ng if self.three_d else 1)
+        self.nvar = nv = 5 + int(nscalars)      # src/hydro/hydro.cpp:75,117: nhydro + nscalars
         self.cfg = _lib.MhdCfg(self.nmb, ng, nx1, nx2, nx3, _lib.RECON[recon], _lib.HYD_RSOLVER[rsolver],
-                               gamma, dfloor, pfloor, tfloor, sfloor, FLT_MAX)
+                               gamma, dfloor, pfloor, tfloor, sfloor, FLT_MAX, int(nscalars))
         self.my_rank, self.gids_start, self.pg = my_rank, gids_start, process_group
         n1, n2, n3 = self.n
         z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=self.device)
         # src/hydro/hydro.cpp:100-120,268-290
-        self.u0, self.u1, self.w0 = z(nmb, 5, n3, n2, n1), z(nmb, 5, n3, n2, n1), z(nmb, 5, n3, n2, n1)
-        self.uflx = [z(nmb, 5, n3, n2, n1 + 1), z(nmb, 5, n3, n2 + 1, n1), z(nmb, 5, n3 + 1, n2, n1)]
+        self.u0, self.u1, self.w0 = z(nmb, nv, n3, n2, n1), z(nmb, nv, n3, n2, n1), z(nmb, nv, n3, n2, n1)
+        self.uflx = [z(nmb, nv, n3, n2, n1 + 1), z(nmb, nv, n3, n2 + 1, n1), z(nmb, nv, n3 + 1, n2, n1)]
         self.mb_size_h = np.ascontiguousarray(mb_size, dtype=np.float64).reshape(nmb, 9)
         self.mb_size = torch.from_numpy(self.mb_size_h).to(self.device)
         self.arrays = _lib.MhdArrays()
@@ -53,7 +54,7 @@ class Hydro:
         for ip in range(self.L.ak_halo_npeers(self.plan)):
             r, ncc, nfc = C.c_int(), C.c_long(), C.c_long()
             _lib.check(self.L.ak_halo_peer(self.plan, ip, C.byref(r), C.byref(ncc), C.byref(nfc)))
-            self.peers.append(dict(rank=r.value, ncc=ncc.value, scc=z(5 * ncc.value), rcc=z(5 * ncc.value)))
+            self.peers.append(dict(rank=r.value, ncc=ncc.value, scc=z(nv * ncc.value), rcc=z(nv * ncc.value)))
         self.bcs = None
         if mesh_bcs is not None and any(int(b) != _lib.BC["periodic"] for b in mesh_bcs):
             mesh_bcs = np.ascontiguousarray(mesh_bcs, dtype=np.int32).reshape(6)
@@ -124,17 +125,17 @@ class Hydro:
             import torch.distributed as dist
             ops = []
             for ip, p in enumerate(self.peers):
-                _lib.check(L.ak_halo_pack_cc(self.plan, self.u0.data_ptr(), 5, ip, p["scc"].data_ptr(), st))
+                _lib.check(L.ak_halo_pack_cc(self.plan, self.u0.data_ptr(), self.nvar, ip, p["scc"].data_ptr(), st))
                 self.launches += 1
                 ops.append(dist.P2POp(dist.isend, p["scc"], p["rank"], group=self.pg))
                 ops.append(dist.P2POp(dist.irecv, p["rcc"], p["rank"], group=self.pg))
             reqs = dist.batch_isend_irecv(ops)
-        _lib.check(L.ak_halo_local_cc(self.plan, self.u0.data_ptr(), 5, st))
+        _lib.check(L.ak_halo_local_cc(self.plan, self.u0.data_ptr(), self.nvar, st))
         self.launches += 1
         for rq in reqs:
             rq.wait()
         for ip, p in enumerate(self.peers):
-            _lib.check(L.ak_halo_unpack_cc(self.plan, self.u0.data_ptr(), 5, ip, p["rcc"].data_ptr(), st))
+            _lib.check(L.ak_halo_unpack_cc(self.plan, self.u0.data_ptr(), self.nvar, ip, p["rcc"].data_ptr(), st))
             self.launches += 1
         return TaskStatus.complete
 
@@ -153,7 +154,7 @@ class Hydro:
         """hydro_tasks.cpp:357-371: HydroBCs on u0; no-op when strictly periodic."""
         if self.bcs is None:
             return TaskStatus.complete
-        if self.L.ak_bcs_hydro(self.bcs, self.u0.data_ptr(), 5, self._st()):
+        if self.L.ak_bcs_hydro(self.bcs, self.u0.data_ptr(), self.nvar, self._st()):
             raise _lib.EngineError(self.L.ak_bcs_last_error(self.bcs).decode())
         self.launches += self.nbc
         return TaskStatus.complete

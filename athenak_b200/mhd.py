@@ -38,7 +38,7 @@ class MHD:
     def __init__(self, nmb, ng, nx, mb_size, nghbr, *, recon="ppm4", rsolver="hlld", gamma,
                  dfloor=FLT_MIN, pfloor=FLT_MIN, tfloor=FLT_MIN, sfloor=FLT_MIN, sigma_max=FLT_MAX,
                  my_rank=0, gids_start=0, device="cuda", process_group=None, fused=True,
-                 mesh_bcs=None, mb_bcs=None):
+                 mesh_bcs=None, mb_bcs=None, nscalars=0):
         if not torch.cuda.is_available():
             raise _lib.EngineError("athenak_b200: no CUDA device; the engine has no CPU path")
         self.L = _lib.load()
@@ -48,18 +48,20 @@ class MHD:
         self.multi_d, self.three_d = nx2 > 1, nx3 > 1      # src/mesh/mesh.cpp:70-79
         self.n = (nx1 + 2 * ng, nx2 + 2 * ng if self.multi_d else 1, nx3 + 2 * ng if self.three_d else 1)
         self.nsweeps = 1 + int(self.multi_d) + int(self.three_d)
+        self.nvar = 5 + int(nscalars)      # src/mhd/mhd.cpp: nmhd + nscalars
         self.cfg = _lib.MhdCfg(self.nmb, ng, nx1, nx2, nx3, _lib.RECON[recon], _lib.RSOLVER[rsolver],
-                               gamma, dfloor, pfloor, tfloor, sfloor, sigma_max)
+                               gamma, dfloor, pfloor, tfloor, sfloor, sigma_max, int(nscalars))
         self.fused = fused
         self.my_rank, self.gids_start, self.pg = my_rank, gids_start, process_group
         n1, n2, n3 = self.n
         z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=self.device)
         # src/mhd/mhd.cpp:148-161,329-354
-        self.u0, self.u1, self.w0 = z(nmb, 5, n3, n2, n1), z(nmb, 5, n3, n2, n1), z(nmb, 5, n3, n2, n1)
+        nv = self.nvar
+        self.u0, self.u1, self.w0 = z(nmb, nv, n3, n2, n1), z(nmb, nv, n3, n2, n1), z(nmb, nv, n3, n2, n1)
         self.bcc0 = z(nmb, 3, n3, n2, n1)
         self.b0 = [z(nmb, n3, n2, n1 + 1), z(nmb, n3, n2 + 1, n1), z(nmb, n3 + 1, n2, n1)]
         self.b1 = [torch.zeros_like(a) for a in self.b0]
-        self.uflx = [z(nmb, 5, n3, n2, n1 + 1), z(nmb, 5, n3, n2 + 1, n1), z(nmb, 5, n3 + 1, n2, n1)]
+        self.uflx = [z(nmb, nv, n3, n2, n1 + 1), z(nmb, nv, n3, n2 + 1, n1), z(nmb, nv, n3 + 1, n2, n1)]
         self.femf = [z(nmb, n3, n2, n1) for _ in range(6)]   # e3x1,e2x1,e1x2,e3x2,e2x3,e1x3
         self.efld = [z(nmb, n3 + 1, n2 + 1, n1), z(nmb, n3 + 1, n2, n1 + 1), z(nmb, n3, n2 + 1, n1 + 1)]
         self.mb_size_h = np.ascontiguousarray(mb_size, dtype=np.float64).reshape(nmb, 9)
@@ -78,7 +80,7 @@ class MHD:
             r, ncc, nfc = C.c_int(), C.c_long(), C.c_long()
             _lib.check(self.L.ak_halo_peer(self.plan, ip, C.byref(r), C.byref(ncc), C.byref(nfc)))
             self.peers.append(dict(rank=r.value, ncc=ncc.value, nfc=nfc.value,
-                                   scc=z(5 * ncc.value), rcc=z(5 * ncc.value), sfc=z(nfc.value), rfc=z(nfc.value)))
+                                   scc=z(nv * ncc.value), rcc=z(nv * ncc.value), sfc=z(nfc.value), rfc=z(nfc.value)))
         # physical BCs (task 26); None = strictly periodic mesh
         self.bcs = None
         if mesh_bcs is not None and any(int(b) != _lib.BC["periodic"] for b in mesh_bcs):
@@ -212,7 +214,7 @@ class MHD:
             ops = []
             for ip, p in enumerate(self.peers):
                 if which == "u":
-                    _lib.check(L.ak_halo_pack_cc(self.plan, self.u0.data_ptr(), 5, ip, p["scc"].data_ptr(), st))
+                    _lib.check(L.ak_halo_pack_cc(self.plan, self.u0.data_ptr(), self.nvar, ip, p["scc"].data_ptr(), st))
                     s, r = p["scc"], p["rcc"]
                 else:
                     _lib.check(L.ak_halo_pack_fc(self.plan, *[a.data_ptr() for a in self.b0], ip, p["sfc"].data_ptr(), st))
@@ -222,7 +224,7 @@ class MHD:
                 ops.append(dist.P2POp(dist.irecv, r, p["rank"], group=self.pg))
             reqs = dist.batch_isend_irecv(ops)
         if which == "u":
-            _lib.check(L.ak_halo_local_cc(self.plan, self.u0.data_ptr(), 5, st))
+            _lib.check(L.ak_halo_local_cc(self.plan, self.u0.data_ptr(), self.nvar, st))
         else:
             _lib.check(L.ak_halo_local_fc(self.plan, *[a.data_ptr() for a in self.b0], st))
         self.launches += 1
@@ -231,7 +233,7 @@ class MHD:
                 rq.wait()
             for ip, p in enumerate(self.peers):
                 if which == "u":
-                    _lib.check(L.ak_halo_unpack_cc(self.plan, self.u0.data_ptr(), 5, ip, p["rcc"].data_ptr(), st))
+                    _lib.check(L.ak_halo_unpack_cc(self.plan, self.u0.data_ptr(), self.nvar, ip, p["rcc"].data_ptr(), st))
                 else:
                     _lib.check(L.ak_halo_unpack_fc(self.plan, *[a.data_ptr() for a in self.b0], ip, p["rfc"].data_ptr(), st))
                 self.launches += 1
@@ -256,7 +258,7 @@ class MHD:
         """Task 26 (src/mhd/mhd_tasks.cpp:504-520): HydroBCs + BFieldBCs; no-op when strictly periodic."""
         if self.bcs is None:
             return TaskStatus.complete
-        if self.L.ak_bcs_apply(self.bcs, self.u0.data_ptr(), 5, *[a.data_ptr() for a in self.b0], self._st()):
+        if self.L.ak_bcs_apply(self.bcs, self.u0.data_ptr(), self.nvar, *[a.data_ptr() for a in self.b0], self._st()):
             raise _lib.EngineError(self.L.ak_bcs_last_error(self.bcs).decode())
         self.launches += self.nbc
         return TaskStatus.complete

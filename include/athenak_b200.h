@@ -43,6 +43,8 @@ typedef struct {
   int nx1, nx2, nx3; /* active cells per block (RegionIndcs, src/mesh/mesh.hpp:35-41)    */
   int recon, rsolver;
   double gamma, dfloor, pfloor, tfloor, sfloor, sigma_max; /* EOS_Data, src/eos/eos.hpp:27-33 */
+  int nscalars;      /* passive scalars (<mhd>/<hydro> nscalars, src/mhd/mhd.cpp, src/hydro/hydro.cpp:75):
+                        stored after the 5 fluid variables in u0, u1, w0 and the flux arrays */
 } ak_mhd_cfg;
 
 typedef struct {

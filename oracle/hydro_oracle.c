@@ -268,7 +268,7 @@ static void hyd_roe(const ocfg *c, const hprim1d *l, const hprim1d *r, hcons1d *
 void oracle_hydro_fluxes(const ocfg *c, const double *w0, double *flx1, double *flx2, double *flx3) {
   odims D = dims(c);
   size_t ncc = (size_t)c->nmb * D.cc;
-  double *wl = calloc(5 * ncc, 8), *wr = calloc(5 * ncc, 8);
+  double *wl = calloc(D.nv * ncc, 8), *wr = calloc(D.nv * ncc, 8);
   const int is = D.is, ie = D.ie, js = D.js, je = D.je, ks = D.ks, ke = D.ke;
   const int ndir = 1 + (c->nx2 > 1) + (c->nx3 > 1);
   for (int dir = 0; dir < ndir; ++dir) {
@@ -277,7 +277,7 @@ void oracle_hydro_fluxes(const ocfg *c, const double *w0, double *flx1, double *
     if (dir == 0) { il = is - 1; iu = ie + 1; fiu = ie + 1; }
     else if (dir == 1) { jl = js - 1; ju = je + 1; fju = je + 1; }
     else { kl = ks - 1; ku = ke + 1; fku = ke + 1; }
-    recon_pass(c, dir, 5, 1, w0, wl, wr, kl, ku, jl, ju, il, iu);
+    recon_pass(c, dir, D.nv, 1, w0, wl, wr, kl, ku, jl, ju, il, iu);
     const int ivx = IVX + dir, ivy = IVX + (dir + 1) % 3, ivz = IVX + (dir + 2) % 3;
     for (int m = 0; m < c->nmb; ++m)
       for (int k = fkl; k <= fku; ++k)
@@ -285,10 +285,10 @@ void oracle_hydro_fluxes(const ocfg *c, const double *w0, double *flx1, double *
           for (int i = fil; i <= fiu; ++i) {
             hprim1d l, r;
             hcons1d f;
-            l.d = CC(wl, 5, m, IDN, k, j, i); l.vx = CC(wl, 5, m, ivx, k, j, i); l.vy = CC(wl, 5, m, ivy, k, j, i);
-            l.vz = CC(wl, 5, m, ivz, k, j, i); l.e = CC(wl, 5, m, IEN, k, j, i);
-            r.d = CC(wr, 5, m, IDN, k, j, i); r.vx = CC(wr, 5, m, ivx, k, j, i); r.vy = CC(wr, 5, m, ivy, k, j, i);
-            r.vz = CC(wr, 5, m, ivz, k, j, i); r.e = CC(wr, 5, m, IEN, k, j, i);
+            l.d = CC(wl, D.nv, m, IDN, k, j, i); l.vx = CC(wl, D.nv, m, ivx, k, j, i); l.vy = CC(wl, D.nv, m, ivy, k, j, i);
+            l.vz = CC(wl, D.nv, m, ivz, k, j, i); l.e = CC(wl, D.nv, m, IEN, k, j, i);
+            r.d = CC(wr, D.nv, m, IDN, k, j, i); r.vx = CC(wr, D.nv, m, ivx, k, j, i); r.vy = CC(wr, D.nv, m, ivy, k, j, i);
+            r.vz = CC(wr, D.nv, m, ivz, k, j, i); r.e = CC(wr, D.nv, m, IEN, k, j, i);
             switch (c->rsolver) {
               case 10: hyd_advect(&l, &r, &f); break;
               case 11: hyd_llf(c, &l, &r, &f); break;
@@ -303,6 +303,13 @@ void oracle_hydro_fluxes(const ocfg *c, const double *w0, double *flx1, double *
               else if (dir == 1) F2(flx2, m, n, k, j, i) = f5[n];
               else F3(flx3, m, n, k, j, i) = f5[n];
             }
+            for (int n = 5; n < D.nv; ++n) {   /* scalar fluxes, hydro_fluxes.cpp:126-138,165-177,204-216 */
+              double fd = f5[IDN];
+              double v = fd * ((fd >= 0.0) ? CC(wl, D.nv, m, n, k, j, i) : CC(wr, D.nv, m, n, k, j, i));
+              if (dir == 0) F1(flx1, m, n, k, j, i) = v;
+              else if (dir == 1) F2(flx2, m, n, k, j, i) = v;
+              else F3(flx3, m, n, k, j, i) = v;
+            }
           }
   }
   free(wl); free(wr);
@@ -316,14 +323,14 @@ void oracle_hydro_rk_update(const ocfg *c, double *u0, const double *u1, const d
   const int multi_d = c->nx2 > 1, three_d = c->nx3 > 1;
   for (int m = 0; m < c->nmb; ++m) {
     const double dx1 = mb_size[m * 9 + 6], dx2 = mb_size[m * 9 + 7], dx3 = mb_size[m * 9 + 8];
-    for (int n = 0; n < 5; ++n)
+    for (int n = 0; n < D.nv; ++n)
       for (int k = D.ks; k <= D.ke; ++k)
         for (int j = D.js; j <= D.je; ++j)
           for (int i = D.is; i <= D.ie; ++i) {
             double divf = (F1(flx1, m, n, k, j, i + 1) - F1(flx1, m, n, k, j, i)) / dx1;
             if (multi_d) divf += (F2(flx2, m, n, k, j + 1, i) - F2(flx2, m, n, k, j, i)) / dx2;
             if (three_d) divf += (F3(flx3, m, n, k + 1, j, i) - F3(flx3, m, n, k, j, i)) / dx3;
-            CC(u0, 5, m, n, k, j, i) = gam0 * CC(u0, 5, m, n, k, j, i) + gam1 * CC(u1, 5, m, n, k, j, i) - beta_dt * divf;
+            CC(u0, D.nv, m, n, k, j, i) = gam0 * CC(u0, D.nv, m, n, k, j, i) + gam1 * CC(u1, D.nv, m, n, k, j, i) - beta_dt * divf;
           }
   }
 }
@@ -338,8 +345,8 @@ void oracle_hydro_cons2prim(const ocfg *c, double *u0, double *w0, int il, int i
     for (int k = kl; k <= ku; ++k)
       for (int j = jl; j <= ju; ++j)
         for (int i = il; i <= iu; ++i) {
-          double ud = CC(u0, 5, m, IDN, k, j, i), ue = CC(u0, 5, m, IEN, k, j, i);
-          double umx = CC(u0, 5, m, IM1, k, j, i), umy = CC(u0, 5, m, IM2, k, j, i), umz = CC(u0, 5, m, IM3, k, j, i);
+          double ud = CC(u0, D.nv, m, IDN, k, j, i), ue = CC(u0, D.nv, m, IEN, k, j, i);
+          double umx = CC(u0, D.nv, m, IM1, k, j, i), umy = CC(u0, D.nv, m, IM2, k, j, i), umz = CC(u0, D.nv, m, IM3, k, j, i);
           int dfl = 0, efl = 0, tfl = 0;
           double efloor = c->pfloor / (c->gamma - 1.0);
           if (ud < c->dfloor) { ud = c->dfloor; dfl = 1; }
@@ -353,11 +360,15 @@ void oracle_hydro_cons2prim(const ocfg *c, double *u0, double *w0, int il, int i
           double spe_over_eps = gm1 / pow(wd, gm1);
           double spe = spe_over_eps * we * di;
           if (spe <= c->sfloor) { we = wd * c->sfloor / spe_over_eps; efl = 1; }
-          if (dfl) { CC(u0, 5, m, IDN, k, j, i) = ud; nd++; }
-          if (efl) { CC(u0, 5, m, IEN, k, j, i) = ue; ne++; }
-          if (tfl) { CC(u0, 5, m, IEN, k, j, i) = ue; nt++; }
-          CC(w0, 5, m, IDN, k, j, i) = wd; CC(w0, 5, m, IVX, k, j, i) = wvx; CC(w0, 5, m, IVY, k, j, i) = wvy;
-          CC(w0, 5, m, IVZ, k, j, i) = wvz; CC(w0, 5, m, IEN, k, j, i) = we;
+          if (dfl) { CC(u0, D.nv, m, IDN, k, j, i) = ud; nd++; }
+          if (efl) { CC(u0, D.nv, m, IEN, k, j, i) = ue; ne++; }
+          if (tfl) { CC(u0, D.nv, m, IEN, k, j, i) = ue; nt++; }
+          CC(w0, D.nv, m, IDN, k, j, i) = wd; CC(w0, D.nv, m, IVX, k, j, i) = wvx; CC(w0, D.nv, m, IVY, k, j, i) = wvy;
+          CC(w0, D.nv, m, IVZ, k, j, i) = wvz; CC(w0, D.nv, m, IEN, k, j, i) = we;
+          for (int n = 5; n < D.nv; ++n) {   /* ideal_hyd.cpp:95-101 */
+            if (CC(u0, D.nv, m, n, k, j, i) < 0.0) CC(u0, D.nv, m, n, k, j, i) = 0.0;
+            CC(w0, D.nv, m, n, k, j, i) = CC(u0, D.nv, m, n, k, j, i) / ud;
+          }
         }
   if (nfloor) { nfloor[0] = nd; nfloor[1] = ne; nfloor[2] = nt; }
 }
@@ -371,11 +382,11 @@ double oracle_hydro_new_dt(const ocfg *c, const double *w0, const double *mb_siz
     for (int k = D.ks; k <= D.ke; ++k)
       for (int j = D.js; j <= D.je; ++j)
         for (int i = D.is; i <= D.ie; ++i) {
-          double p = (c->gamma - 1.0) * CC(w0, 5, m, IEN, k, j, i);
-          double cs = sound_speed(c->gamma, CC(w0, 5, m, IDN, k, j, i), p);
-          double max_dv1 = fabs(CC(w0, 5, m, IVX, k, j, i)) + cs;
-          double max_dv2 = fabs(CC(w0, 5, m, IVY, k, j, i)) + cs;
-          double max_dv3 = fabs(CC(w0, 5, m, IVZ, k, j, i)) + cs;
+          double p = (c->gamma - 1.0) * CC(w0, D.nv, m, IEN, k, j, i);
+          double cs = sound_speed(c->gamma, CC(w0, D.nv, m, IDN, k, j, i), p);
+          double max_dv1 = fabs(CC(w0, D.nv, m, IVX, k, j, i)) + cs;
+          double max_dv2 = fabs(CC(w0, D.nv, m, IVY, k, j, i)) + cs;
+          double max_dv3 = fabs(CC(w0, D.nv, m, IVZ, k, j, i)) + cs;
           dt1 = fmin((mb_size[m * 9 + 6] / max_dv1), dt1);
           dt2 = fmin((mb_size[m * 9 + 7] / max_dv2), dt2);
           dt3_ = fmin((mb_size[m * 9 + 8] / max_dv3), dt3_);
@@ -394,7 +405,7 @@ int oracle_hydro_apply_bcs(const ocfg *c, const int *mesh_bcs, const int *mb_bcs
   for (int d = 0; d < 3; ++d) {
     if ((d == 1 && c->nx2 <= 1) || (d == 2 && c->nx3 <= 1)) continue;
     if (mesh_bcs[2 * d] == BC_PERIODIC || (d == 0 && mesh_bcs[0] == BC_SHEAR)) continue;
-    bc_array(c, u0, 5, -1, d, mb_bcs);
+    bc_array(c, u0, 5 + c->nscalars, -1, d, mb_bcs);
   }
   return 0;
 }
@@ -404,11 +415,11 @@ void oracle_hydro_stage(const ocfg *c, double *u0, double *u1, double *w0, const
                         const int *nghbr_gid, int stage, double gam0, double gam1, double beta_dt) {
   odims D = dims(c);
   size_t nm = (size_t)c->nmb;
-  if (stage == 1) memcpy(u1, u0, 8 * 5 * nm * D.cc);   /* CopyCons hydro_tasks.cpp:137-141 */
-  double *flx1 = calloc(5 * nm * D.f1, 8), *flx2 = calloc(5 * nm * D.f2, 8), *flx3 = calloc(5 * nm * D.f3, 8);
+  if (stage == 1) memcpy(u1, u0, 8 * D.nv * nm * D.cc);   /* CopyCons hydro_tasks.cpp:137-141 */
+  double *flx1 = calloc(D.nv * nm * D.f1, 8), *flx2 = calloc(D.nv * nm * D.f2, 8), *flx3 = calloc(D.nv * nm * D.f3, 8);
   oracle_hydro_fluxes(c, w0, flx1, flx2, flx3);
   oracle_hydro_rk_update(c, u0, u1, flx1, flx2, flx3, mb_size, gam0, gam1, beta_dt);
-  oracle_halo_cc(c, u0, 5, nghbr_gid);
+  oracle_halo_cc(c, u0, D.nv, nghbr_gid);
   if (g_mesh_bcs) oracle_hydro_apply_bcs(c, g_mesh_bcs, g_mb_bcs, u0);
   oracle_hydro_cons2prim(c, u0, w0, 0, D.n1 - 1, 0, D.n2 - 1, 0, D.n3 - 1, NULL);
   free(flx1); free(flx2); free(flx3);
@@ -418,7 +429,7 @@ void oracle_hydro_stage(const ocfg *c, double *u0, double *u1, double *w0, const
 double oracle_hydro_init(const ocfg *c, double *u0, double *w0, const double *mb_size, const int *nghbr_gid,
                          double cfl, double tlim, double time) {
   odims D = dims(c);
-  oracle_halo_cc(c, u0, 5, nghbr_gid);
+  oracle_halo_cc(c, u0, D.nv, nghbr_gid);
   if (g_mesh_bcs) oracle_hydro_apply_bcs(c, g_mesh_bcs, g_mb_bcs, u0);
   oracle_hydro_cons2prim(c, u0, w0, 0, D.n1 - 1, 0, D.n2 - 1, 0, D.n3 - 1, NULL);
   double dtnew = oracle_hydro_new_dt(c, w0, mb_size, NULL);

@@ -24,6 +24,7 @@ typedef struct {
   int recon;   /* 0 dc, 1 plm, 2 ppm4, 3 ppmx, 4 wenoz, 5 teno   (athena.hpp:75) */
   int rsolver; /* 0 llf, 1 hlle, 2 hlld                   (mhd.hpp:39)    */
   double gamma, dfloor, pfloor, tfloor, sfloor, sigma_max; /* eos.hpp:27-33 */
+  int nscalars; /* passive scalars stored after the 5 fluid variables (mhd.cpp / hydro.cpp:75) */
 } ocfg;
 
 enum { IDN = 0, IM1 = 1, IM2 = 2, IM3 = 3, IEN = 4, IVX = 1, IVY = 2, IVZ = 3 };
@@ -31,6 +32,7 @@ enum { IDN = 0, IM1 = 1, IM2 = 2, IM3 = 3, IEN = 4, IVX = 1, IVY = 2, IVZ = 3 };
 
 typedef struct {
   int n1, n2, n3, is, ie, js, je, ks, ke;
+  int nv;                    /* 5 + nscalars: variables per cell-centred / flux array */
   size_t cc;                 /* cells per variable per block  */
   size_t f1, f2, f3;         /* faces per block               */
   size_t e1, e2, e3;         /* edges per block               */
@@ -44,6 +46,7 @@ static odims dims(const ocfg *c) {
   d.is = c->ng; d.ie = d.is + c->nx1 - 1;
   d.js = multi_d ? c->ng : 0; d.je = d.js + c->nx2 - 1;
   d.ks = three_d ? c->ng : 0; d.ke = d.ks + c->nx3 - 1;
+  d.nv = 5 + c->nscalars;
   d.cc = (size_t)d.n3 * d.n2 * d.n1;
   d.f1 = (size_t)d.n3 * d.n2 * (d.n1 + 1);
   d.f2 = (size_t)d.n3 * (d.n2 + 1) * d.n1;
@@ -60,9 +63,9 @@ static odims dims(const ocfg *c) {
 #define X1F(a, m, k, j, i) (a)[(((size_t)(m) * D.n3 + (k)) * D.n2 + (j)) * (D.n1 + 1) + (i)]
 #define X2F(a, m, k, j, i) (a)[(((size_t)(m) * D.n3 + (k)) * (D.n2 + 1) + (j)) * D.n1 + (i)]
 #define X3F(a, m, k, j, i) (a)[(((size_t)(m) * (D.n3 + 1) + (k)) * D.n2 + (j)) * D.n1 + (i)]
-#define F1(a, m, n, k, j, i) (a)[((((size_t)(m) * 5 + (n)) * D.n3 + (k)) * D.n2 + (j)) * (D.n1 + 1) + (i)]
-#define F2(a, m, n, k, j, i) (a)[((((size_t)(m) * 5 + (n)) * D.n3 + (k)) * (D.n2 + 1) + (j)) * D.n1 + (i)]
-#define F3(a, m, n, k, j, i) (a)[((((size_t)(m) * 5 + (n)) * (D.n3 + 1) + (k)) * D.n2 + (j)) * D.n1 + (i)]
+#define F1(a, m, n, k, j, i) (a)[((((size_t)(m) * D.nv + (n)) * D.n3 + (k)) * D.n2 + (j)) * (D.n1 + 1) + (i)]
+#define F2(a, m, n, k, j, i) (a)[((((size_t)(m) * D.nv + (n)) * D.n3 + (k)) * (D.n2 + 1) + (j)) * D.n1 + (i)]
+#define F3(a, m, n, k, j, i) (a)[((((size_t)(m) * D.nv + (n)) * (D.n3 + 1) + (k)) * D.n2 + (j)) * D.n1 + (i)]
 #define X1E(a, m, k, j, i) (a)[(((size_t)(m) * (D.n3 + 1) + (k)) * (D.n2 + 1) + (j)) * D.n1 + (i)]
 #define X2E(a, m, k, j, i) (a)[(((size_t)(m) * (D.n3 + 1) + (k)) * D.n2 + (j)) * (D.n1 + 1) + (i)]
 #define X3E(a, m, k, j, i) (a)[(((size_t)(m) * D.n3 + (k)) * (D.n2 + 1) + (j)) * (D.n1 + 1) + (i)]
@@ -593,7 +596,7 @@ void oracle_fluxes(const ocfg *c, const double *w0, const double *bcc0, const do
                    double *e1x3) {
   odims D = dims(c);
   size_t ncc = (size_t)c->nmb * D.cc;
-  double *wl = calloc(5 * ncc, 8), *wr = calloc(5 * ncc, 8);
+  double *wl = calloc(D.nv * ncc, 8), *wr = calloc(D.nv * ncc, 8);
   double *bl = calloc(3 * ncc, 8), *br = calloc(3 * ncc, 8);
   const int is = D.is, ie = D.ie, js = D.js, je = D.je, ks = D.ks, ke = D.ke;
   const int multi_d = c->nx2 > 1, three_d = c->nx3 > 1;
@@ -605,14 +608,14 @@ void oracle_fluxes(const ocfg *c, const double *w0, const double *bcc0, const do
     if (dir == 0) { fil = is; fiu = ie + 1; }
     else if (dir == 1) { fjl = js; fju = je + 1; }
     else { fkl = ks; fku = ke + 1; }
-    recon_pass(c, dir, 5, 1, w0, wl, wr, kl, ku, jl, ju, il, iu);
+    recon_pass(c, dir, D.nv, 1, w0, wl, wr, kl, ku, jl, ju, il, iu);
     recon_pass(c, dir, 3, 0, bcc0, bl, br, kl, ku, jl, ju, il, iu);
     for (int m = 0; m < c->nmb; ++m)
       for (int k = fkl; k <= fku; ++k)
         for (int j = fjl; j <= fju; ++j)
           for (int i = fil; i <= fiu; ++i) {
             double wl5[5], wr5[5], bl3[3], br3[3], f5[5], ey, ez, bxi;
-            for (int n = 0; n < 5; ++n) { wl5[n] = CC(wl, 5, m, n, k, j, i); wr5[n] = CC(wr, 5, m, n, k, j, i); }
+            for (int n = 0; n < 5; ++n) { wl5[n] = CC(wl, D.nv, m, n, k, j, i); wr5[n] = CC(wr, D.nv, m, n, k, j, i); }
             for (int n = 0; n < 3; ++n) { bl3[n] = CC(bl, 3, m, n, k, j, i); br3[n] = CC(br, 3, m, n, k, j, i); }
             if (dir == 0) bxi = X1F(b1f, m, k, j, i);
             else if (dir == 1) bxi = X2F(b2f, m, k, j, i);
@@ -629,6 +632,18 @@ void oracle_fluxes(const ocfg *c, const double *w0, const double *bcc0, const do
               S4(e2x3, m, k, j, i) = ey; S4(e1x3, m, k, j, i) = ez;   /* :243 */
             }
           }
+    /* scalar fluxes, upwinded by the sign of the mass flux, ACTIVE transverse range only
+     * (mhd_fluxes.cpp:153-166,203-216,250-263) */
+    if (D.nv > 5)
+      for (int m = 0; m < c->nmb; ++m)
+        for (int k = ks; k <= ke + (dir == 2); ++k)
+          for (int j = js; j <= je + (dir == 1); ++j)
+            for (int i = is; i <= ie + (dir == 0); ++i)
+              for (int n = 5; n < D.nv; ++n) {
+                if (dir == 0) F1(flx1, m, n, k, j, i) = F1(flx1, m, IDN, k, j, i) * ((F1(flx1, m, IDN, k, j, i) >= 0.0) ? CC(wl, D.nv, m, n, k, j, i) : CC(wr, D.nv, m, n, k, j, i));
+                else if (dir == 1) F2(flx2, m, n, k, j, i) = F2(flx2, m, IDN, k, j, i) * ((F2(flx2, m, IDN, k, j, i) >= 0.0) ? CC(wl, D.nv, m, n, k, j, i) : CC(wr, D.nv, m, n, k, j, i));
+                else F3(flx3, m, n, k, j, i) = F3(flx3, m, IDN, k, j, i) * ((F3(flx3, m, IDN, k, j, i) >= 0.0) ? CC(wl, D.nv, m, n, k, j, i) : CC(wr, D.nv, m, n, k, j, i));
+              }
   }
   free(wl); free(wr); free(bl); free(br);
 }
@@ -640,14 +655,14 @@ void oracle_rk_update(const ocfg *c, double *u0, const double *u1, const double 
   odims D = dims(c);
   for (int m = 0; m < c->nmb; ++m) {
     const double dx1 = mb_size[m * 9 + 6], dx2 = mb_size[m * 9 + 7], dx3 = mb_size[m * 9 + 8];
-    for (int n = 0; n < 5; ++n)
+    for (int n = 0; n < D.nv; ++n)
       for (int k = D.ks; k <= D.ke; ++k)
         for (int j = D.js; j <= D.je; ++j)
           for (int i = D.is; i <= D.ie; ++i) {
             double divf = (F1(flx1, m, n, k, j, i + 1) - F1(flx1, m, n, k, j, i)) / dx1;
             if (c->nx2 > 1) divf += (F2(flx2, m, n, k, j + 1, i) - F2(flx2, m, n, k, j, i)) / dx2;   /* mhd_update.cpp:63-69 multi_d */
             if (c->nx3 > 1) divf += (F3(flx3, m, n, k + 1, j, i) - F3(flx3, m, n, k, j, i)) / dx3;   /* :72-78 three_d */
-            CC(u0, 5, m, n, k, j, i) = gam0 * CC(u0, 5, m, n, k, j, i) + gam1 * CC(u1, 5, m, n, k, j, i) - beta_dt * divf;
+            CC(u0, D.nv, m, n, k, j, i) = gam0 * CC(u0, D.nv, m, n, k, j, i) + gam1 * CC(u1, D.nv, m, n, k, j, i) - beta_dt * divf;
           }
   }
 }
@@ -675,7 +690,7 @@ void oracle_corner_e(const ocfg *c, const double *w0, const double *bcc, const d
     for (int m = 0; m < c->nmb; ++m)
       for (int j = js - 1; j <= je + 1; ++j)
         for (int i = is - 1; i <= ie + 1; ++i)
-          S4(e3c, m, ks, j, i) = CC(w0, 5, m, IVY, ks, j, i) * CC(bcc, 3, m, 0, ks, j, i) - CC(w0, 5, m, IVX, ks, j, i) * CC(bcc, 3, m, 1, ks, j, i);
+          S4(e3c, m, ks, j, i) = CC(w0, D.nv, m, IVY, ks, j, i) * CC(bcc, 3, m, 0, ks, j, i) - CC(w0, D.nv, m, IVX, ks, j, i) * CC(bcc, 3, m, 1, ks, j, i);
     for (int m = 0; m < c->nmb; ++m)
       for (int j = js; j <= je + 1; ++j)
         for (int i = is; i <= ie + 1; ++i) {
@@ -702,9 +717,9 @@ void oracle_corner_e(const ocfg *c, const double *w0, const double *bcc, const d
     for (int k = ks - 1; k <= ke + 1; ++k)
       for (int j = js - 1; j <= je + 1; ++j)
         for (int i = is - 1; i <= ie + 1; ++i) {
-          S4(e1cc, m, k, j, i) = CC(w0, 5, m, IVZ, k, j, i) * CC(bcc, 3, m, 1, k, j, i) - CC(w0, 5, m, IVY, k, j, i) * CC(bcc, 3, m, 2, k, j, i);
-          S4(e2cc, m, k, j, i) = CC(w0, 5, m, IVX, k, j, i) * CC(bcc, 3, m, 2, k, j, i) - CC(w0, 5, m, IVZ, k, j, i) * CC(bcc, 3, m, 0, k, j, i);
-          S4(e3cc, m, k, j, i) = CC(w0, 5, m, IVY, k, j, i) * CC(bcc, 3, m, 0, k, j, i) - CC(w0, 5, m, IVX, k, j, i) * CC(bcc, 3, m, 1, k, j, i);
+          S4(e1cc, m, k, j, i) = CC(w0, D.nv, m, IVZ, k, j, i) * CC(bcc, 3, m, 1, k, j, i) - CC(w0, D.nv, m, IVY, k, j, i) * CC(bcc, 3, m, 2, k, j, i);
+          S4(e2cc, m, k, j, i) = CC(w0, D.nv, m, IVX, k, j, i) * CC(bcc, 3, m, 2, k, j, i) - CC(w0, D.nv, m, IVZ, k, j, i) * CC(bcc, 3, m, 0, k, j, i);
+          S4(e3cc, m, k, j, i) = CC(w0, D.nv, m, IVY, k, j, i) * CC(bcc, 3, m, 0, k, j, i) - CC(w0, D.nv, m, IVX, k, j, i) * CC(bcc, 3, m, 1, k, j, i);
         }
   for (int m = 0; m < c->nmb; ++m)
     for (int k = ks; k <= ke + 1; ++k)
@@ -793,9 +808,9 @@ void oracle_cons2prim(const ocfg *c, double *u0, const double *b1f, const double
     for (int k = kl; k <= ku; ++k)
       for (int j = jl; j <= ju; ++j)
         for (int i = il; i <= iu; ++i) {
-          double ud = CC(u0, 5, m, IDN, k, j, i), umx = CC(u0, 5, m, IM1, k, j, i);
-          double umy = CC(u0, 5, m, IM2, k, j, i), umz = CC(u0, 5, m, IM3, k, j, i);
-          double ue = CC(u0, 5, m, IEN, k, j, i);
+          double ud = CC(u0, D.nv, m, IDN, k, j, i), umx = CC(u0, D.nv, m, IM1, k, j, i);
+          double umy = CC(u0, D.nv, m, IM2, k, j, i), umz = CC(u0, D.nv, m, IM3, k, j, i);
+          double ue = CC(u0, D.nv, m, IEN, k, j, i);
           double ubx = 0.5 * (X1F(b1f, m, k, j, i) + X1F(b1f, m, k, j, i + 1));
           double uby = 0.5 * (X2F(b2f, m, k, j, i) + X2F(b2f, m, k, j + 1, i));
           double ubz = 0.5 * (X3F(b3f, m, k, j, i) + X3F(b3f, m, k + 1, j, i));
@@ -816,13 +831,17 @@ void oracle_cons2prim(const ocfg *c, double *u0, const double *b1f, const double
           double spe_over_eps = gm1 / pow(wd, gm1);
           double spe = spe_over_eps * we * di;
           if (spe <= sfloor) { we = wd * sfloor / spe_over_eps; efl = 1; }
-          if (dfl) { CC(u0, 5, m, IDN, k, j, i) = ud; nd++; }
-          if (efl) { CC(u0, 5, m, IEN, k, j, i) = ue; ne++; }
-          if (tfl) { CC(u0, 5, m, IEN, k, j, i) = ue; nt++; }
-          CC(w0, 5, m, IDN, k, j, i) = wd; CC(w0, 5, m, IVX, k, j, i) = wvx;
-          CC(w0, 5, m, IVY, k, j, i) = wvy; CC(w0, 5, m, IVZ, k, j, i) = wvz;
-          CC(w0, 5, m, IEN, k, j, i) = we;
+          if (dfl) { CC(u0, D.nv, m, IDN, k, j, i) = ud; nd++; }
+          if (efl) { CC(u0, D.nv, m, IEN, k, j, i) = ue; ne++; }
+          if (tfl) { CC(u0, D.nv, m, IEN, k, j, i) = ue; nt++; }
+          CC(w0, D.nv, m, IDN, k, j, i) = wd; CC(w0, D.nv, m, IVX, k, j, i) = wvx;
+          CC(w0, D.nv, m, IVY, k, j, i) = wvy; CC(w0, D.nv, m, IVZ, k, j, i) = wvz;
+          CC(w0, D.nv, m, IEN, k, j, i) = we;
           CC(bcc, 3, m, 0, k, j, i) = ubx; CC(bcc, 3, m, 1, k, j, i) = uby; CC(bcc, 3, m, 2, k, j, i) = ubz;
+          for (int n = 5; n < D.nv; ++n) {   /* ideal_mhd.cpp:113-120: scalar floor, then s/d */
+            if (CC(u0, D.nv, m, n, k, j, i) < 0.0) CC(u0, D.nv, m, n, k, j, i) = 0.0;
+            CC(w0, D.nv, m, n, k, j, i) = CC(u0, D.nv, m, n, k, j, i) / ud;
+          }
         }
   if (nfloor) { nfloor[0] = nd; nfloor[1] = ne; nfloor[2] = nt; }
 }
@@ -839,15 +858,15 @@ double oracle_new_dt(const ocfg *c, const double *w0, const double *bcc, const d
     for (int k = D.ks; k <= D.ke; ++k)
       for (int j = D.js; j <= D.je; ++j)
         for (int i = D.is; i <= D.ie; ++i) {
-          double w_d = CC(w0, 5, m, IDN, k, j, i);
+          double w_d = CC(w0, D.nv, m, IDN, k, j, i);
           double w_bx = CC(bcc, 3, m, 0, k, j, i), w_by = CC(bcc, 3, m, 1, k, j, i), w_bz = CC(bcc, 3, m, 2, k, j, i);
-          double p = gm1 * CC(w0, 5, m, IEN, k, j, i);
+          double p = gm1 * CC(w0, D.nv, m, IEN, k, j, i);
           double cf = fast_speed(c->gamma, w_d, p, w_bx, w_by, w_bz);
-          double max_dv1 = fabs(CC(w0, 5, m, IVX, k, j, i)) + cf;
+          double max_dv1 = fabs(CC(w0, D.nv, m, IVX, k, j, i)) + cf;
           cf = fast_speed(c->gamma, w_d, p, w_by, w_bz, w_bx);
-          double max_dv2 = fabs(CC(w0, 5, m, IVY, k, j, i)) + cf;
+          double max_dv2 = fabs(CC(w0, D.nv, m, IVY, k, j, i)) + cf;
           cf = fast_speed(c->gamma, w_d, p, w_bz, w_bx, w_by);
-          double max_dv3 = fabs(CC(w0, 5, m, IVZ, k, j, i)) + cf;
+          double max_dv3 = fabs(CC(w0, D.nv, m, IVZ, k, j, i)) + cf;
           dt1 = fmin((dx1 / max_dv1), dt1);
           dt2 = fmin((dx2 / max_dv2), dt2);
           dtz = fmin((dx3 / max_dv3), dtz);
@@ -1172,7 +1191,7 @@ int oracle_apply_bcs(const ocfg *c, const int *mesh_bcs, const int *mb_bcs, doub
   for (int d = 0; d < 3; ++d) {        /* hydro_bcs.cpp:80-81,167,252: gate on the mesh flag */
     if ((d == 1 && c->nx2 <= 1) || (d == 2 && c->nx3 <= 1)) continue;   /* :164 one_d, :249 two_d */
     if (mesh_bcs[2 * d] == BC_PERIODIC || (d == 0 && mesh_bcs[0] == BC_SHEAR)) continue;
-    bc_array(c, u0, 5, -1, d, mb_bcs);
+    bc_array(c, u0, 5 + c->nscalars, -1, d, mb_bcs);
   }
   for (int d = 0; d < 3; ++d) {        /* bfield_bcs.cpp:78,169,262 */
     if ((d == 1 && c->nx2 <= 1) || (d == 2 && c->nx3 <= 1)) continue;   /* :165 one_d, :258 two_d */
@@ -1204,18 +1223,18 @@ void oracle_stage(const ocfg *c, ostate *s, const double *mb_size, const int *ng
   odims D = dims(c);
   size_t nm = (size_t)c->nmb;
   if (stage == 1) { /* CopyCons mhd_tasks.cpp:162-170 */
-    memcpy(s->u1, s->u0, 8 * 5 * nm * D.cc);
+    memcpy(s->u1, s->u0, 8 * D.nv * nm * D.cc);
     memcpy(s->b1x1f, s->b0x1f, 8 * nm * D.f1);
     memcpy(s->b1x2f, s->b0x2f, 8 * nm * D.f2);
     memcpy(s->b1x3f, s->b0x3f, 8 * nm * D.f3);
   }
-  double *flx1 = calloc(5 * nm * D.f1, 8), *flx2 = calloc(5 * nm * D.f2, 8), *flx3 = calloc(5 * nm * D.f3, 8);
+  double *flx1 = calloc(D.nv * nm * D.f1, 8), *flx2 = calloc(D.nv * nm * D.f2, 8), *flx3 = calloc(D.nv * nm * D.f3, 8);
   double *fe[6];
   for (int q = 0; q < 6; ++q) fe[q] = calloc(nm * D.cc, 8);
   double *e1 = calloc(nm * D.e1, 8), *e2 = calloc(nm * D.e2, 8), *e3 = calloc(nm * D.e3, 8);
   oracle_fluxes(c, s->w0, s->bcc0, s->b0x1f, s->b0x2f, s->b0x3f, flx1, flx2, flx3, fe[0], fe[1], fe[2], fe[3], fe[4], fe[5]);
   oracle_rk_update(c, s->u0, s->u1, flx1, flx2, flx3, mb_size, gam0, gam1, beta_dt);
-  oracle_halo_cc(c, s->u0, 5, nghbr_gid);
+  oracle_halo_cc(c, s->u0, D.nv, nghbr_gid);
   oracle_corner_e(c, s->w0, s->bcc0, flx1, flx2, flx3, fe[0], fe[1], fe[2], fe[3], fe[4], fe[5], e1, e2, e3);
   oracle_emf_exchange(c, e1, e2, e3, nghbr_gid);
   oracle_ct(c, s->b0x1f, s->b0x2f, s->b0x3f, s->b1x1f, s->b1x2f, s->b1x3f, e1, e2, e3, mb_size, gam0, gam1, beta_dt);

@@ -48,6 +48,7 @@ class Case:
         ph = self.physics
         self.recon, self.rsolver = p[ph + "/reconstruct"], p[ph + "/rsolver"]
         self.gamma = float(p[ph + "/gamma"])
+        self.nscalars = int(p.get(ph + "/nscalars", 0))
         self.integrator = p["time/integrator"]
         self.cfl, self.tlim = float(p["time/cfl_number"]), float(p["time/tlim"])
         periodic = [self.mesh_bcs[2 * d] == O.BC["periodic"] for d in range(3)]
@@ -59,7 +60,7 @@ class Case:
     def ocfg(self):
         rs = O.RSOLVER[self.rsolver] if self.physics == "mhd" else O.HYD_RSOLVER[self.rsolver]
         return O.OCfg(self.nmb, self.ng, *self.nblock, O.RECON[self.recon], rs, self.gamma,
-                      O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX)
+                      O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, self.nscalars)
 
 
 def oracle_run(case: Case, u_init, ncycles=-1, time0=0.0):
@@ -94,7 +95,7 @@ def oracle_run_mhd(case: Case, u_init, b_init, ncycles=-1, time0=0.0):
     if not case.strictly_periodic:
         L.oracle_set_bcs(O.ip(case.mesh_bcs), O.ip(case.mb_bcs))
     try:
-        L.oracle_halo_cc(C.byref(cfg), O.p(A.u0), 5, O.ip(case.nghbr))
+        L.oracle_halo_cc(C.byref(cfg), O.p(A.u0), 5 + case.nscalars, O.ip(case.nghbr))
         L.oracle_halo_fc(C.byref(cfg), *[O.p(a) for a in A.b0], O.ip(case.nghbr))
         if not case.strictly_periodic:
             assert L.oracle_apply_bcs(C.byref(cfg), O.ip(case.mesh_bcs), O.ip(case.mb_bcs), O.p(A.u0), *[O.p(a) for a in A.b0]) == 0

@@ -22,7 +22,7 @@ class OCfg(C.Structure):
     _fields_ = [("nmb", C.c_int), ("ng", C.c_int), ("nx1", C.c_int), ("nx2", C.c_int),
                 ("nx3", C.c_int), ("recon", C.c_int), ("rsolver", C.c_int),
                 ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
-                ("tfloor", C.c_double), ("sfloor", C.c_double), ("sigma_max", C.c_double)]
+                ("tfloor", C.c_double), ("sfloor", C.c_double), ("sigma_max", C.c_double), ("nscalars", C.c_int)]
 
 
 class OState(C.Structure):
@@ -31,10 +31,10 @@ class OState(C.Structure):
 
 
 def make_cfg(nmb, ng, nx, recon="ppm4", rsolver="hlld", gamma=1.6666667, dfloor=FLT_MIN,
-             pfloor=FLT_MIN, tfloor=FLT_MIN, sfloor=FLT_MIN, sigma_max=FLT_MAX):
+             pfloor=FLT_MIN, tfloor=FLT_MIN, sfloor=FLT_MIN, sigma_max=FLT_MAX, nscalars=0):
     nx1, nx2, nx3 = nx
     return OCfg(nmb, ng, nx1, nx2, nx3, RECON[recon], RSOLVER[rsolver], gamma, dfloor, pfloor,
-                tfloor, sfloor, sigma_max)
+                tfloor, sfloor, sigma_max, nscalars)
 
 
 _lib = None
@@ -76,11 +76,12 @@ class Arrays:
         n1, n2, n3 = cfg.nx1 + 2 * ng, (cfg.nx2 + 2 * ng if cfg.nx2 > 1 else 1), (cfg.nx3 + 2 * ng if cfg.nx3 > 1 else 1)
         self.cfg, self.n = cfg, (n1, n2, n3)
         z = np.zeros
-        self.u0, self.u1, self.w0 = (z((nmb, 5, n3, n2, n1)) for _ in range(3))
+        nv = 5 + cfg.nscalars
+        self.u0, self.u1, self.w0 = (z((nmb, nv, n3, n2, n1)) for _ in range(3))
         self.bcc0 = z((nmb, 3, n3, n2, n1))
         self.b0 = [z((nmb, n3, n2, n1 + 1)), z((nmb, n3, n2 + 1, n1)), z((nmb, n3 + 1, n2, n1))]
         self.b1 = [np.zeros_like(a) for a in self.b0]
-        self.flx = [z((nmb, 5, n3, n2, n1 + 1)), z((nmb, 5, n3, n2 + 1, n1)), z((nmb, 5, n3 + 1, n2, n1))]
+        self.flx = [z((nmb, nv, n3, n2, n1 + 1)), z((nmb, nv, n3, n2 + 1, n1)), z((nmb, nv, n3 + 1, n2, n1))]
         # face EMFs in the order e3x1,e2x1,e1x2,e3x2,e2x3,e1x3 (mhd.cpp:349-354)
         self.fe = [z((nmb, n3, n2, n1)) for _ in range(6)]
         self.e = [z((nmb, n3 + 1, n2 + 1, n1)), z((nmb, n3 + 1, n2, n1 + 1)), z((nmb, n3, n2 + 1, n1 + 1))]

@@ -39,8 +39,9 @@ def reference(deck, base, overrides=(), want_errs=False):
 def _reference(deck, base, overrides, want_errs):
     with tempfile.TemporaryDirectory() as tmp:
         O.run_reference("athena_builtin", os.path.join(DECKS, deck), tmp, list(overrides), threads=4)
-        r0 = read_rst(os.path.join(tmp, "rst", base + ".00000.rst"), physics="hydro")
-        r1 = read_rst(os.path.join(tmp, "rst", base + ".00001.rst"), physics="hydro")
+        ns = max([int(o.split("=")[1]) for o in overrides if o.startswith("hydro/nscalars=")] + [0])
+        r0 = read_rst(os.path.join(tmp, "rst", base + ".00000.rst"), physics="hydro", nmhd=5 + ns)
+        r1 = read_rst(os.path.join(tmp, "rst", base + ".00001.rst"), physics="hydro", nmhd=5 + ns)
         err = None
         if want_errs:
             err = float(open(os.path.join(tmp, base + "-errs.dat")).read().split("\n")[1].split()[4])
@@ -57,7 +58,7 @@ def run_engine(case: H.Case, u_init, fused, tlim=None, ncycles=None):
     assert np.array_equal(mb_size, case.mb_size) and np.array_equal(mb_bcs, case.mb_bcs)
     assert np.array_equal(nghbr[:, :, 0], case.nghbr)
     hyd = Hydro(case.nmb, case.ng, case.nblock, mb_size, nghbr, recon=case.recon, rsolver=case.rsolver,
-                gamma=case.gamma, mesh_bcs=mesh.bcs, mb_bcs=mb_bcs)
+                gamma=case.gamma, mesh_bcs=mesh.bcs, mb_bcs=mb_bcs, nscalars=case.nscalars)
     hyd.load_state(u_init)
     drv = Driver(case.integrator, case.cfl, tlim=case.tlim if tlim is None else tlim)
     tl = assemble_hydro_tasks(hyd, fused=fused)
@@ -77,6 +78,9 @@ CASES = [
     ("sod2d.athinput", "Sod", ("hydro/rsolver=roe", "hydro/reconstruct=teno")),
     ("sod2d.athinput", "Sod", ("hydro/rsolver=llf", "hydro/reconstruct=plm", "mesh/nghost=2", "time/integrator=rk2")),
     ("lwave3d_hydro.athinput", "LinWave", ("hydro/rsolver=hlle", "hydro/reconstruct=wenoz")),
+    ("sod1d.athinput", "Sod", ("hydro/nscalars=2",)),                                # passive scalars
+    ("sod2d.athinput", "Sod", ("hydro/nscalars=1",)),
+    ("sod2d.athinput", "Sod", ("hydro/nscalars=3", "hydro/rsolver=llf", "hydro/reconstruct=wenoz")),
 ]
 
 
@@ -139,7 +143,7 @@ def test_hydro_linear_wave_convergence(recon, rs):
     assert errs[1] / errs[0] < (0.4 if recon == "plm" else 0.25)
 
 
-@pytest.mark.parametrize("deck,base,ov", [CASES[0], CASES[5], CASES[8]], ids=["sod1d", "sod2d", "lwave3d"])
+@pytest.mark.parametrize("deck,base,ov", [CASES[0], CASES[5], CASES[8], CASES[11]], ids=["sod1d", "sod2d", "lwave3d", "sod2d-3scalars"])
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "pertask"])
 def test_hydro_cxx_host_driver(deck, base, ov, fused):
     """The same cases through the C++ host driver (TaskList/Driver/Hydro tasks in csrc/host_driver.cpp, ak_sim_*)."""
@@ -149,7 +153,8 @@ def test_hydro_cxx_host_driver(deck, base, ov, fused):
     case = H.Case(r0.deck)
     mesh = Mesh(case.nmesh, case.nblock, xmin=case.xmin, xmax=case.xmax, bcs=case.bc_names)
     sim = Simulation(mesh, 0, ng=case.ng, recon=case.recon, rsolver=case.rsolver, gamma=case.gamma,
-                     integrator=case.integrator, cfl_number=case.cfl, tlim=case.tlim, fused=fused, physics="hydro")
+                     integrator=case.integrator, cfl_number=case.cfl, tlim=case.tlim, fused=fused, physics="hydro",
+                     nscalars=case.nscalars)
     sim.set_state(np.ascontiguousarray(r0.u0))
     sim.initialize()
     assert sim.status()["dt"] == r0.dt

@@ -26,6 +26,8 @@ CASES = [
     ("bw2d.athinput", "BrioWu", ()),
     ("bw2d.athinput", "BrioWu", ("mhd/rsolver=llf", "mhd/reconstruct=plm", "mesh/nghost=2", "time/integrator=rk2")),
     ("ot2d.athinput", "OrszagTang", ()),
+    ("bw1d.athinput", "BrioWu", ("mhd/nscalars=1",)),                                 # passive scalars
+    ("bw2d.athinput", "BrioWu", ("mhd/nscalars=2",)),
 ]
 IDS = [f"{c[0].split('.')[0]}-{'-'.join(o.split('=')[1] for o in c[2]) or 'deck'}" for c in CASES]
 
@@ -37,8 +39,9 @@ def reference(deck, base, overrides=()):
     if key not in _CACHE:
         with tempfile.TemporaryDirectory() as tmp:
             O.run_reference("athena_builtin", os.path.join(DECKS, deck), tmp, list(overrides), threads=4)
-            _CACHE[key] = (read_rst(os.path.join(tmp, "rst", base + ".00000.rst")),
-                           read_rst(os.path.join(tmp, "rst", base + ".00001.rst")))
+            ns = max([int(o.split("=")[1]) for o in overrides if o.startswith("mhd/nscalars=")] + [0])
+            _CACHE[key] = (read_rst(os.path.join(tmp, "rst", base + ".00000.rst"), nmhd=5 + ns),
+                           read_rst(os.path.join(tmp, "rst", base + ".00001.rst"), nmhd=5 + ns))
     return _CACHE[key]
 
 
@@ -60,7 +63,7 @@ def test_mhd_1d_2d_matches_reference_bitwise(deck, base, ov, fused):
     mb_size, mb_bcs, nghbr = mesh.rank_tables(0)
     assert np.array_equal(nghbr[:, :, 0], case.nghbr)
     e = MHD(case.nmb, case.ng, case.nblock, mb_size, nghbr, recon=case.recon, rsolver=case.rsolver, gamma=case.gamma,
-            mesh_bcs=mesh.bcs, mb_bcs=mb_bcs)
+            mesh_bcs=mesh.bcs, mb_bcs=mb_bcs, nscalars=case.nscalars)
     e.load_state(r0.u0, r0.b1f, r0.b2f, r0.b3f)
     drv = Driver(case.integrator, case.cfl, tlim=case.tlim)
     tl = assemble_mhd_tasks(e, fused=fused)
@@ -71,7 +74,7 @@ def test_mhd_1d_2d_matches_reference_bitwise(deck, base, ov, fused):
     check(e.u0.cpu().numpy(), [x.cpu().numpy() for x in e.b0], r1)
 
 
-@pytest.mark.parametrize("deck,base,ov", [CASES[1], CASES[3], CASES[5]], ids=[IDS[1], IDS[3], IDS[5]])
+@pytest.mark.parametrize("deck,base,ov", [CASES[1], CASES[3], CASES[5], CASES[7]], ids=[IDS[1], IDS[3], IDS[5], IDS[7]])
 def test_mhd_1d_2d_cxx_host_driver(deck, base, ov):
     from athenak_b200.mesh import Mesh
     from athenak_b200.sim import Simulation
@@ -79,7 +82,7 @@ def test_mhd_1d_2d_cxx_host_driver(deck, base, ov):
     case = H.Case(r0.deck)
     mesh = Mesh(case.nmesh, case.nblock, xmin=case.xmin, xmax=case.xmax, bcs=case.bc_names)
     sim = Simulation(mesh, 0, ng=case.ng, recon=case.recon, rsolver=case.rsolver, gamma=case.gamma,
-                     integrator=case.integrator, cfl_number=case.cfl, tlim=case.tlim, fused=True)
+                     integrator=case.integrator, cfl_number=case.cfl, tlim=case.tlim, fused=True, nscalars=case.nscalars)
     sim.set_state(*[np.ascontiguousarray(a) for a in (r0.u0, r0.b1f, r0.b2f, r0.b3f)])
     sim.initialize()
     assert sim.status()["dt"] == r0.dt
