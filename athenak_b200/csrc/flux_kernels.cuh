@@ -65,6 +65,10 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
   const int i = g.is - 1 + c;
   const long cc = g.cc;
   const long off = ((long)k * g.n2 + j) * g.n1 + i;
+  // The face field is fetched FIRST, with the stencil loads: issued next to its use (after the
+  // early exit) it was the single largest stall site of the kernel (14% of the samples).
+  double bxi = 0.0;
+  if constexpr (MHD) bxi = __ldg(bx1f + (((long)m * g.n3 + k) * g.n2 + j) * (g.n1 + 1) + i);
   State7 up, lo;
   if constexpr (RECON == RECON_PPM4) {
     const double *w = w0 + (long)m * g.nvar * cc + off, *b = MHD ? bcc + (long)m * 3 * cc + off : w;
@@ -98,7 +102,6 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
   if (!valid || lane == 0 || lane > STEP || c == 0 || c > g.nx1 + 1) return;
   Flux7 f;
   if constexpr (MHD) {
-    const double bxi = __ldg(bx1f + (((long)m * g.n3 + k) * g.n2 + j) * (g.n1 + 1) + i);
     riemann<RS>(L, lo, bxi, eos, f);
   } else {
     riemann_hyd<RS>(L, lo, eos, f);
@@ -212,6 +215,12 @@ __device__ __forceinline__ void ppm4_ring_cell(const double *__restrict__ ring, 
   }
 }
 
+// Addressing is kept out of the register file on purpose: the block's (MeshBlock, segment) come
+// from blockIdx.y, so every array base is block-uniform, and a thread carries only two 32-bit
+// running offsets (cell, face) that advance by the sweep stride.  The earlier version carried a
+// dozen 64-bit pointers through the loop; under the 128-register budget ptxas spilled loop
+// invariants to local memory and their reloads (L1-thrashed, long scoreboard) were the top stall
+// site of the kernel (profiles/r01_ncu_kernels_session2.txt).
 template <int RECON, int RS, int DIR>
 __global__ void __launch_bounds__(MARCH_THREADS, AKB_MARCH_MINB)
 flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
@@ -222,16 +231,13 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
   constexpr bool MHD = (RS < RS_HYD_ADVECT);
   constexpr int NV = MHD ? 7 : 5;
   extern __shared__ double ring_all[];   // RING: NV * MARCH_SLOTS * MARCH_THREADS doubles (dynamic)
-  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nc = g.nx1 + 2 * g.ext1;
   const int nt = (DIR == 1) ? g.nx3 + 2 * g.ext3 : g.nx2 + 2 * g.ext2;
-  const long total = (long)g.nmb * nseg * nt * nc;
-  if (gt >= total) return;
-  long t = gt;
-  const int i = g.is - g.ext1 + (int)(t % nc); t /= nc;
-  const int tr = (int)(t % nt); t /= nt;
-  const int seg = (int)(t % nseg);
-  const int m = (int)(t / nseg);
+  const int m = blockIdx.y / nseg, seg = blockIdx.y - m * nseg;       // block-uniform
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= nt * nc) return;
+  const int tr = col / nc;
+  const int i = g.is - g.ext1 + (col - tr * nc);
   const int fs0 = (DIR == 1) ? g.js : g.ks;         // first face along the sweep
   const int fe0 = (DIR == 1) ? g.je + 1 : g.ke + 1; // last face
   const int f_lo = fs0 + seg * seglen;
@@ -239,38 +245,38 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
   if (f_hi > fe0) f_hi = fe0;
   if (f_lo > f_hi) return;
   const long cc = g.cc;
-  const long s = (DIR == 1) ? (long)g.n1 : (long)g.n1 * g.n2;
-  // cell (k,j,i) with the sweep index = f_lo-1
+  const int s = (DIR == 1) ? g.n1 : g.n1 * g.n2;    // sweep stride (cells and faces alike)
+  // cell (k,j,i) with the sweep index = f_lo-1, and the face f_lo above it
   int k, j;
   if (DIR == 1) { k = g.ks - g.ext3 + tr; j = f_lo - 1; } else { j = g.js - g.ext2 + tr; k = f_lo - 1; }
-  long off = ((long)k * g.n2 + j) * g.n1 + i;
-  const double *wp = w0 + (long)m * g.nvar * cc + off;
-  const double *bp = MHD ? bcc + (long)m * 3 * cc + off : wp;
-  // face-array geometry
-  const long frow = (DIR == 1) ? (long)g.n1 : (long)g.n1 * g.n2;  // stride of the sweep index in the face arrays
-  const long fsz = (DIR == 1) ? (long)g.n3 * (g.n2 + 1) * g.n1 : (long)(g.n3 + 1) * g.n2 * g.n1;
-  long foff = (DIR == 1) ? ((long)k * (g.n2 + 1) + f_lo) * g.n1 + i
-                         : ((long)f_lo * g.n2 + j) * g.n1 + i;
-  const double *bn = MHD ? bnf + (long)m * fsz + foff : wp;
-  double *fp = flx + (long)m * g.nvar * fsz + foff;
-  double *eyp = MHD ? eyo + (long)m * cc + off + s : nullptr;
-  double *ezp = MHD ? ezo + (long)m * cc + off + s : nullptr;
+  int co = (k * g.n2 + j) * g.n1 + i;               // running cell offset inside one variable of the block
+  int fo = (DIR == 1) ? (k * (g.n2 + 1) + f_lo) * g.n1 + i : (f_lo * g.n2 + j) * g.n1 + i;   // running face offset
+  const long fsz = (DIR == 1) ? g.f2 : g.f3;
+  // block-uniform bases
+  const double *wb = w0 + (long)m * g.nvar * cc;
+  const double *bb = MHD ? bcc + (long)m * 3 * cc : wb;
+  const double *bnb = MHD ? bnf + (long)m * fsz : wb;
+  double *fb = flx + (long)m * g.nvar * fsz;
+  double *eyb = MHD ? eyo + (long)m * cc : nullptr;
+  double *ezb = MHD ? ezo + (long)m * cc : nullptr;
   constexpr int ivx = IVX + DIR, ivy = IVX + (DIR + 1) % 3, ivz = IVX + (DIR + 2) % 3;
   constexpr int iby = (DIR + 1) % 3, ibz = (DIR + 2) % 3;
+  // the NV reconstructed variables: source array and variable index (block-uniform)
+  auto vsrc = [&](int v) -> const double * {
+    return v == 0 ? wb + IDN * cc : v == 1 ? wb + ivx * cc : v == 2 ? wb + ivy * cc : v == 3 ? wb + ivz * cc
+         : v == 4 ? wb + IEN * cc : v == 5 ? bb + iby * cc : bb + ibz * cc;
+  };
 
   State7 L, lo_unused;
   if constexpr (RING) {
     constexpr int VS = MARCH_SLOTS * MARCH_THREADS;
     double *ring = ring_all + threadIdx.x;
-    // global columns of the seven variables at the current cell (sweep index c = f_lo-1)
-    const double *gv[7] = {wp + IDN * cc, wp + ivx * cc, wp + ivy * cc, wp + ivz * cc, wp + IEN * cc,
-                           bp + iby * cc, bp + ibz * cc};
-    // prologue: rows c-2 .. c+2+PF -> slots 0..S-1 (row c-2 in slot 0)
+    // prologue: rows c-2 .. c+2+PF -> slots 0..S-1 (row c-2 in slot 0), c = f_lo-1
 #pragma unroll
     for (int r = 0; r < MARCH_SLOTS; ++r) {
       if (r < 5 || (f_lo - 1) + (r - 2) <= f_hi + 2) {   // prefetch rows only if some face of this march needs them
 #pragma unroll
-        for (int v = 0; v < NV; ++v) cp_async8(ring + v * VS + r * MARCH_THREADS, gv[v] + (long)(r - 2) * s);
+        for (int v = 0; v < NV; ++v) cp_async8(ring + v * VS + r * MARCH_THREADS, vsrc(v) + (co + (r - 2) * s));
       }
     }
     cp_async_commit();
@@ -284,13 +290,13 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
     }
     int b0 = 1;                       // slot of row c-2 for the next cell (c = f_lo)
     for (int f = f_lo; f <= f_hi; ++f) {
-      // cell c = f: rows c-2..c+2 are present; request row c+2+PF (needed PF steps from now)
-      // into the slot that held row c-3
+      co += s;                        // cell c = f
+      // rows c-2..c+2 are present; request row c+2+PF (needed PF steps from now) into the slot that held row c-3
       if (f + MARCH_PF <= f_hi) {
         int bn_slot = b0 + MARCH_SLOTS - 1; if (bn_slot >= MARCH_SLOTS) bn_slot -= MARCH_SLOTS;
-        const long ro = (long)(f - (f_lo - 1) + 2 + MARCH_PF) * s;
+        const int ro = co + (2 + MARCH_PF) * s;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) cp_async8(ring + v * VS + bn_slot * MARCH_THREADS, gv[v] + ro);
+        for (int v = 0; v < NV; ++v) cp_async8(ring + v * VS + bn_slot * MARCH_THREADS, vsrc(v) + ro);
       }
       cp_async_commit();
       cp_async_wait<MARCH_PF>();
@@ -298,44 +304,44 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       if constexpr (RECON == RECON_PPM4 && AKB_MARCH_CARRY && MHD) ppm4_ring_cell(ring, b0, fl, up, lo);
       else recon_ring_cell<RECON, MHD>(ring, b0, eos, up, lo);
       Flux7 fx;
-      if constexpr (MHD) riemann<RS>(L, lo, __ldg(bn), eos, fx);   // (fetching bn a step ahead costs registers: measured slower)
+      if constexpr (MHD) riemann<RS>(L, lo, __ldg(bnb + fo), eos, fx);
       else riemann_hyd<RS>(L, lo, eos, fx);
+      double *fp = fb + fo;
       fp[IDN * fsz] = fx.d;
       fp[ivx * fsz] = fx.mx;
       fp[ivy * fsz] = fx.my;
       fp[ivz * fsz] = fx.mz;
       fp[IEN * fsz] = fx.e;
       if constexpr (MHD) {
-        *eyp = fx.ey;  // x2: (e1x2,e3x2)  x3: (e2x3,e1x3)   mhd_fluxes.cpp:196,243
-        *ezp = fx.ez;
-        bn += frow; eyp += s; ezp += s;
+        eyb[co] = fx.ey;  // x2: (e1x2,e3x2)  x3: (e2x3,e1x3)   mhd_fluxes.cpp:196,243
+        ezb[co] = fx.ez;
       }
       L = up;
-      fp += frow;
+      fo += s;
       b0 = (b0 + 1 >= MARCH_SLOTS) ? 0 : b0 + 1;
     }
     cp_async_wait<0>();
   } else {
-    recon_cell<RECON, DIR, MHD>(wp, bp, cc, s, eos, L, lo_unused);
+    recon_cell<RECON, DIR, MHD>(wb + co, bb + co, cc, s, eos, L, lo_unused);
     for (int f = f_lo; f <= f_hi; ++f) {
-      wp += s; bp += s;
+      co += s;
       State7 up, lo;
-      recon_cell<RECON, DIR, MHD>(wp, bp, cc, s, eos, up, lo);
+      recon_cell<RECON, DIR, MHD>(wb + co, bb + co, cc, s, eos, up, lo);
       Flux7 fx;
-      if constexpr (MHD) riemann<RS>(L, lo, __ldg(bn), eos, fx);
+      if constexpr (MHD) riemann<RS>(L, lo, __ldg(bnb + fo), eos, fx);
       else riemann_hyd<RS>(L, lo, eos, fx);
+      double *fp = fb + fo;
       fp[IDN * fsz] = fx.d;
       fp[ivx * fsz] = fx.mx;
       fp[ivy * fsz] = fx.my;
       fp[ivz * fsz] = fx.mz;
       fp[IEN * fsz] = fx.e;
       if constexpr (MHD) {
-        *eyp = fx.ey;
-        *ezp = fx.ez;
-        bn += frow; eyp += s; ezp += s;
+        eyb[co] = fx.ey;
+        ezb[co] = fx.ez;
       }
       L = up;
-      fp += frow;
+      fo += s;
     }
   }
 }
@@ -413,18 +419,20 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
   if (g.multi_d) {  // x2: (ey,ez) = (e1x2,e3x2)
     const int nf = g.nx2 + 1;
     const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
-    const long threads = (long)g.nmb * nseg * (g.nx3 + 2 * g.ext3) * (g.nx1 + 2 * g.ext1);
+    const long cols = (long)(g.nx3 + 2 * g.ext3) * (g.nx1 + 2 * g.ext1);
+    if ((long)g.nmb * nseg > 65535 || (long)g.nvar * g.cc >= 0x7fffffffL) return cudaErrorInvalidConfiguration;
     static bool attr1 = false;
     if (!attr1 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr1 = true; }
-    flux_march_kernel<RECON, RS, 1><<<nblocks(threads, MARCH_THREADS), MARCH_THREADS, smem, st>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg);
+    flux_march_kernel<RECON, RS, 1><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg);
   }
   if (g.three_d) {  // x3: (ey,ez) = (e2x3,e1x3)
     const int nf = g.nx3 + 1;
     const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
-    const long threads = (long)g.nmb * nseg * (g.nx2 + 2 * g.ext2) * (g.nx1 + 2 * g.ext1);
+    const long cols = (long)(g.nx2 + 2 * g.ext2) * (g.nx1 + 2 * g.ext1);
+    if ((long)g.nmb * nseg > 65535 || (long)g.nvar * g.cc >= 0x7fffffffL) return cudaErrorInvalidConfiguration;
     static bool attr2 = false;
     if (!attr2 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr2 = true; }
-    flux_march_kernel<RECON, RS, 2><<<nblocks(threads, MARCH_THREADS), MARCH_THREADS, smem, st>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
+    flux_march_kernel<RECON, RS, 2><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
   }
   if (g.nvar > 5) return launch_scalar_fluxes<RECON>(g, a, st);
   return cudaGetLastError();
