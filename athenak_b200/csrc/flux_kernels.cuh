@@ -18,6 +18,9 @@
 #ifndef AKB_MARCH_MINB
 #define AKB_MARCH_MINB 4
 #endif
+#ifndef AKB_X1_L2PF
+#define AKB_X1_L2PF 0       // x1 sweep: planes ahead whose stencil lines each warp prefetches into L2 (0 = off)
+#endif
 #ifndef AKB_MARCH_CARRY
 #define AKB_MARCH_CARRY 0   // PPM4 x2/x3 sweeps: carry the clamped interface value along the march.
                             // Measured SLOWER (1.12 vs 1.05 ms): -10% FP64 instructions but +14 live registers
@@ -69,6 +72,16 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
   // early exit) it was the single largest stall site of the kernel (14% of the samples).
   double bxi = 0.0;
   if constexpr (MHD) bxi = __ldg(bx1f + (((long)m * g.n3 + k) * g.n2 + j) * (g.n1 + 1) + i);
+  if constexpr (AKB_X1_L2PF > 0) {
+    // One instruction per warp: lane l touches variable (l mod NV) at its own cell, AKB_X1_L2PF planes
+    // ahead, so every 128-byte line the counterpart warp of that plane will read is requested once.
+    if (k + AKB_X1_L2PF <= g.ke + g.ext3) {
+      const int v = lane % NV;
+      constexpr int vidx[7] = {IDN, IVX, IVY, IVZ, IEN, 1, 2};
+      const double *src = (v < 5) ? w0 + ((long)m * g.nvar + vidx[v]) * cc : bcc + ((long)m * 3 + vidx[v]) * cc;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off + (long)AKB_X1_L2PF * g.n1 * g.n2));
+    }
+  }
   State7 up, lo;
   if constexpr (RECON == RECON_PPM4) {
     const double *w = w0 + (long)m * g.nvar * cc + off, *b = MHD ? bcc + (long)m * 3 * cc + off : w;
