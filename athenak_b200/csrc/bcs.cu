@@ -194,7 +194,7 @@ int ak_bcs_hydro(void *bcs, double *u0, int nvar, ak_stream_t s) {
   BcPlan *P = static_cast<BcPlan *>(bcs);
   if (!P) { g_bc_err = "ak_bcs_hydro: null plan"; return 1; }
   if (!P->any) return 0;
-  if (!u0 || nvar < 5) { P->err = "ak_bcs_hydro: null array or nvar < 5"; return 1; }
+  if (!u0 || nvar < 4) { P->err = "ak_bcs_hydro: null array or nvar < 4"; return 1; }
   BcArray a = make_array(P->cfg, u0, nvar, -1);
   for (int d = 0; d < 3; ++d)
     if (pass_active(P, d, true) && launch_dir(P, d, &a, 1, static_cast<cudaStream_t>(s))) return 1;
@@ -217,7 +217,7 @@ int ak_bcs_apply(void *bcs, double *u0, int nvar, double *x1f, double *x2f, doub
   BcPlan *P = static_cast<BcPlan *>(bcs);
   if (!P) { g_bc_err = "ak_bcs_apply: null plan"; return 1; }
   if (!P->any) return 0;
-  if (!u0 || !x1f || !x2f || !x3f || nvar < 5) { P->err = "ak_bcs_apply: null array or nvar < 5"; return 1; }
+  if (!u0 || !x1f || !x2f || !x3f || nvar < 4) { P->err = "ak_bcs_apply: null array or nvar < 4"; return 1; }
   BcArray a[4] = {make_array(P->cfg, u0, nvar, -1), make_array(P->cfg, x1f, 1, 0), make_array(P->cfg, x2f, 1, 1),
                   make_array(P->cfg, x3f, 1, 2)};
   for (int d = 0; d < 3; ++d) {

@@ -17,6 +17,7 @@ struct Handle {
   akb::Geom g;
   akb::EosParams eos;
   bool hydro = false;                       // hydro twin (ak_hydro_*): no magnetic arrays, 1-D/2-D/3-D
+  int rs = 0;                               // internal solver code (cfg.rsolver, + 20 when isothermal)
   int *d_counters = nullptr;                // 3 ints
   unsigned long long *d_dtmin = nullptr;    // 3 ordered-bit doubles
   double *d_hst = nullptr;                  // history-sum scratch, allocated on first use
@@ -79,7 +80,12 @@ int check_cfg(const ak_mhd_cfg *c, bool hydro, std::string &why) {
   // reference src/mhd/mhd.cpp:217-228: 5-point stencils need nghost >= 3, PLM/DC need 2
   const int need = (c->recon >= AK_RECON_PPM4) ? 3 : 2;
   if (c->ng < need) { why = "nghost too small for the reconstruction stencil"; return 1; }
-  if (!(c->gamma > 1.0)) { why = "gamma must exceed 1"; return 1; }
+  if (c->eos != AK_EOS_IDEAL && c->eos != AK_EOS_ISOTHERMAL) { why = "unknown eos"; return 1; }
+  if (c->eos == AK_EOS_ISOTHERMAL) {
+    // hydro.cpp:252-262: hllc cannot be used with the isothermal EOS
+    if (hydro && c->rsolver == AK_RSOLVER_HYD_HLLC) { why = "rsolver hllc cannot be used with isothermal EOS"; return 1; }
+    if (!(c->iso_sound_speed > 0.0)) { why = "iso_sound_speed must be positive"; return 1; }
+  } else if (!(c->gamma > 1.0)) { why = "gamma must exceed 1"; return 1; }
   if (c->nscalars < 0 || c->nscalars > 64) { why = "nscalars must be in [0, 64]"; return 1; }
   return 0;
 }
@@ -107,7 +113,9 @@ static int create_impl(const ak_mhd_cfg *cfg, bool hydro, void **handle) {
   h->hydro = hydro;
   akb::Geom &g = h->g;
   g.nmb = cfg->nmb; g.ng = cfg->ng; g.nx1 = cfg->nx1; g.nx2 = cfg->nx2; g.nx3 = cfg->nx3;
-  g.nvar = 5 + cfg->nscalars;
+  g.nfl = (cfg->eos == AK_EOS_ISOTHERMAL) ? 4 : 5;
+  g.nvar = g.nfl + cfg->nscalars;
+  h->rs = akb::internal_rsolver(cfg->rsolver, cfg->eos);
   g.multi_d = cfg->nx2 > 1; g.three_d = cfg->nx3 > 1;          // mesh.cpp:70-79
   g.n1 = cfg->nx1 + 2 * cfg->ng;
   g.n2 = g.multi_d ? cfg->nx2 + 2 * cfg->ng : 1;               // mhd.cpp:149-152 / hydro.cpp
@@ -120,7 +128,7 @@ static int create_impl(const ak_mhd_cfg *cfg, bool hydro, void **handle) {
   g.f1 = (long)g.n3 * g.n2 * (g.n1 + 1); g.f2 = (long)g.n3 * (g.n2 + 1) * g.n1; g.f3 = (long)(g.n3 + 1) * g.n2 * g.n1;
   g.e1 = (long)(g.n3 + 1) * (g.n2 + 1) * g.n1; g.e2 = (long)(g.n3 + 1) * g.n2 * (g.n1 + 1); g.e3 = (long)g.n3 * (g.n2 + 1) * (g.n1 + 1);
   h->eos = akb::EosParams{cfg->gamma, cfg->dfloor, cfg->pfloor, cfg->tfloor, cfg->sfloor, cfg->sigma_max,
-                          1.0 / (cfg->gamma - 1.0)};
+                          1.0 / (cfg->gamma - 1.0), cfg->iso_sound_speed};
   if ((e = cudaMalloc(&h->d_counters, 3 * sizeof(int))) != cudaSuccess ||
       (e = cudaMalloc(&h->d_dtmin, 3 * DT_SLOTS * sizeof(unsigned long long))) != cudaSuccess) {
     int rc = cuda_fail(nullptr, "ak_mhd_create", e);
@@ -170,7 +178,7 @@ int ak_mhd_copy_cons(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
 
 int ak_mhd_fluxes(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
   AK_PROLOGUE("ak_mhd_fluxes")
-  if ((e = akb::launch_fluxes(h->cfg.recon, h->cfg.rsolver, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_fluxes", e);
+  if ((e = akb::launch_fluxes(h->cfg.recon, h->rs, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_fluxes", e);
   return 0;
 }
 
@@ -240,7 +248,7 @@ int ak_mhd_new_dt(void *handle, const ak_mhd_arrays *a, double *dt3, ak_stream_t
 
 int ak_mhd_stage_flux_emf(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
   AK_PROLOGUE("ak_mhd_stage_flux_emf")
-  if ((e = akb::launch_fluxes(h->cfg.recon, h->cfg.rsolver, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_flux_emf", e);
+  if ((e = akb::launch_fluxes(h->cfg.recon, h->rs, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_flux_emf", e);
   if ((e = akb::launch_corner_e(h->g, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_flux_emf", e);
   return 0;
 }
@@ -275,7 +283,7 @@ int ak_hst_sums(void *handle, const ak_mhd_arrays *a, double *sums, int *nhist, 
   const int nb = 148 * 4;
   if (!h->d_hst && (e = cudaMalloc(&h->d_hst, sizeof(double) * 11 * (nb + 1))) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
   if ((e = akb::launch_hst_sums(h->g, A, !h->hydro, h->d_hst, nb, st)) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
-  const int n = h->hydro ? 8 : 11;
+  const int n = (h->hydro ? 8 : 11) - (5 - h->g.nfl);   // isothermal: no tot-E column (history.cpp:84-88,278-282)
   if ((e = cudaMemcpyAsync(sums, h->d_hst + 11L * nb, sizeof(double) * n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
   if (nhist) *nhist = n;
@@ -295,7 +303,7 @@ int ak_hydro_copy_cons(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
 }
 int ak_hydro_fluxes(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
   AK_HYD_PROLOGUE("ak_hydro_fluxes")
-  if ((e = akb::launch_hydro_fluxes(h->cfg.recon, h->cfg.rsolver, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_fluxes", e);
+  if ((e = akb::launch_hydro_fluxes(h->cfg.recon, h->rs, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_fluxes", e);
   return 0;
 }
 int ak_hydro_rk_update(void *handle, const ak_mhd_arrays *a, double gam0, double gam1, double beta_dt, ak_stream_t s) {
@@ -305,7 +313,7 @@ int ak_hydro_rk_update(void *handle, const ak_mhd_arrays *a, double gam0, double
 }
 int ak_hydro_stage_fused(void *handle, const ak_mhd_arrays *a, int stage, double gam0, double gam1, double beta_dt, ak_stream_t s) {
   AK_HYD_PROLOGUE("ak_hydro_stage_fused")
-  if ((e = akb::launch_hydro_fluxes(h->cfg.recon, h->cfg.rsolver, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_stage_fused", e);
+  if ((e = akb::launch_hydro_fluxes(h->cfg.recon, h->rs, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_stage_fused", e);
   if ((e = akb::launch_update_ct(h->g, A, true, false, stage == 1, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_hydro_stage_fused", e);
   return 0;
 }

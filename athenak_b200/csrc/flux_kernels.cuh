@@ -5,6 +5,7 @@
 #include "mhd_kernels.h"
 #include "mhd_device.cuh"
 #include "hydro_device.cuh"
+#include "iso_device.cuh"
 
 #ifndef AKB_MARCH_PREFETCH
 #define AKB_MARCH_PREFETCH 0
@@ -28,6 +29,29 @@
 #endif
 
 namespace akb {
+
+// Which of the seven State7 members (d, vx, vy, vz, e, by, bz) a solver family reconstructs:
+// ideal MHD all seven, isothermal MHD six (no e), ideal hydro five, isothermal hydro four.
+template <int RS>
+struct SolverTraits {
+  static constexpr bool MHD = !rs_is_hydro(RS);
+  static constexpr bool IDEAL = !rs_is_iso(RS);
+  static constexpr int NV = (MHD ? 6 : 4) + (IDEAL ? 1 : 0);
+  // member index of reconstructed variable v
+  __host__ __device__ static constexpr int member(int v) { return (IDEAL || v < 4) ? v : v + 1; }
+};
+
+template <int RS>
+__device__ __forceinline__ void riemann_any(const State7 &l, const State7 &r, double bxi, const EosParams &eos, Flux7 &f) {
+  if constexpr (RS == RS_LLF_ISO) llf_iso(l, r, bxi, eos, f);
+  else if constexpr (RS == RS_HLLE_ISO) hlle_iso(l, r, bxi, eos, f);
+  else if constexpr (RS == RS_HLLD_ISO) hlld_iso(l, r, bxi, eos, f);
+  else if constexpr (RS == RS_HYD_LLF_ISO) hyd_llf_iso(l, r, eos, f);
+  else if constexpr (RS == RS_HYD_HLLE_ISO) hyd_hlle_iso(l, r, eos, f);
+  else if constexpr (RS == RS_HYD_ROE_ISO) hyd_roe_iso(l, r, eos, f);
+  else if constexpr (rs_is_hydro(RS)) riemann_hyd<RS>(l, r, eos, f);
+  else riemann<RS>(l, r, bxi, eos, f);
+}
 
 __device__ __forceinline__ void prefetch_l1(const double *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -53,8 +77,10 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
                const double *__restrict__ bx1f, double *__restrict__ flx, double *__restrict__ e3x1,
                double *__restrict__ e2x1, unsigned rcp_nc) {
   constexpr int STEP = X1Step<RECON>::value;
-  constexpr bool MHD = (RS < RS_HYD_ADVECT);     // hydro twin: 5 variables, no face field, no EMFs
-  constexpr int NV = MHD ? 7 : 5;
+  using T = SolverTraits<RS>;
+  constexpr bool MHD = T::MHD;       // hydro twin: no face field, no EMFs
+  constexpr bool IDEAL = T::IDEAL;   // isothermal EOS: no energy variable
+  constexpr int NV = T::NV;
   const int lane = threadIdx.x & 31;
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nc = g.nx1 + 2 + (RECON == RECON_PPM4 ? 1 : 0), nj = g.nx2 + 2 * g.ext2, nk = g.nx3 + 2 * g.ext3;
@@ -76,7 +102,7 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
     // One instruction per warp: lane l touches variable (l mod NV) at its own cell, AKB_X1_L2PF planes
     // ahead, so every 128-byte line the counterpart warp of that plane will read is requested once.
     if (k + AKB_X1_L2PF <= g.ke + g.ext3) {
-      const int v = lane % NV;
+      const int v = T::member(lane % NV);
       constexpr int vidx[7] = {IDN, IVX, IVY, IVZ, IEN, 1, 2};
       const double *src = (v < 5) ? w0 + ((long)m * g.nvar + vidx[v]) * cc : bcc + ((long)m * 3 + vidx[v]) * cc;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off + (long)AKB_X1_L2PF * g.n1 * g.n2));
@@ -89,43 +115,40 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
     double q[NV], fl[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      q[v] = __ldg(vp[v]);
-      fl[v] = ppm4_iface(__ldg(vp[v] - 2), __ldg(vp[v] - 1), q[v], __ldg(vp[v] + 1));
+      const double *pv = vp[T::member(v)];
+      q[v] = __ldg(pv);
+      fl[v] = ppm4_iface(__ldg(pv - 2), __ldg(pv - 1), q[v], __ldg(pv + 1));
     }
     double *upv[7] = {&up.d, &up.vx, &up.vy, &up.vz, &up.e, &up.by, &up.bz};
     double *lov[7] = {&lo.d, &lo.vx, &lo.vy, &lo.vz, &lo.e, &lo.by, &lo.bz};
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const double fh = __shfl_down_sync(0xffffffffu, fl[v], 1);   // interface at this cell's upper face
-      ppm4_mono(q[v], fl[v], fh, *upv[v], *lov[v]);
+      ppm4_mono(q[v], fl[v], fh, *upv[T::member(v)], *lov[T::member(v)]);
     }
   } else {
-    recon_cell<RECON, 0, MHD>(w0 + (long)m * g.nvar * cc + off, bcc + (long)m * 3 * cc + off, cc, 1, eos, up, lo);
+    recon_cell<RECON, 0, MHD, IDEAL>(w0 + (long)m * g.nvar * cc + off, bcc + (long)m * 3 * cc + off, cc, 1, eos, up, lo);
   }
   State7 L;
   L.d = __shfl_up_sync(0xffffffffu, up.d, 1);
   L.vx = __shfl_up_sync(0xffffffffu, up.vx, 1);
   L.vy = __shfl_up_sync(0xffffffffu, up.vy, 1);
   L.vz = __shfl_up_sync(0xffffffffu, up.vz, 1);
-  L.e = __shfl_up_sync(0xffffffffu, up.e, 1);
+  if constexpr (IDEAL) L.e = __shfl_up_sync(0xffffffffu, up.e, 1);
   if constexpr (MHD) {
     L.by = __shfl_up_sync(0xffffffffu, up.by, 1);
     L.bz = __shfl_up_sync(0xffffffffu, up.bz, 1);
   }
   if (!valid || lane == 0 || lane > STEP || c == 0 || c > g.nx1 + 1) return;
   Flux7 f;
-  if constexpr (MHD) {
-    riemann<RS>(L, lo, bxi, eos, f);
-  } else {
-    riemann_hyd<RS>(L, lo, eos, f);
-  }
+  riemann_any<RS>(L, lo, bxi, eos, f);
   const long fs = (long)g.n3 * g.n2 * (g.n1 + 1);
   double *fp = flx + (long)m * g.nvar * fs + ((long)k * g.n2 + j) * (g.n1 + 1) + i;
   fp[IDN * fs] = f.d;
   fp[IVX * fs] = f.mx;
   fp[IVY * fs] = f.my;
   fp[IVZ * fs] = f.mz;
-  fp[IEN * fs] = f.e;
+  if constexpr (IDEAL) fp[IEN * fs] = f.e;
   if constexpr (MHD) {
     e3x1[(long)m * cc + off] = f.ey;  // mhd_fluxes.cpp:146
     e2x1[(long)m * cc + off] = f.ez;
@@ -172,25 +195,23 @@ __device__ __forceinline__ void recon_ring_var(const double *__restrict__ rv, in
   else wenoz(qm2, qm1, q, qp1, qp2, q_up, q_lo);
 }
 
-template <int RECON, bool MHD>
+template <int RECON, int RS>
 __device__ __forceinline__ void recon_ring_cell(const double *__restrict__ ring, int b0, const EosParams &eos,
                                                 State7 &up, State7 &lo) {
+  using T = SolverTraits<RS>;
   constexpr int VS = MARCH_SLOTS * MARCH_THREADS;   // ring stride between variables
-  recon_ring_var<RECON>(ring + 0 * VS, b0, up.d, lo.d);
-  recon_ring_var<RECON>(ring + 1 * VS, b0, up.vx, lo.vx);
-  recon_ring_var<RECON>(ring + 2 * VS, b0, up.vy, lo.vy);
-  recon_ring_var<RECON>(ring + 3 * VS, b0, up.vz, lo.vz);
-  recon_ring_var<RECON>(ring + 4 * VS, b0, up.e, lo.e);
-  if constexpr (MHD) {
-    recon_ring_var<RECON>(ring + 5 * VS, b0, up.by, lo.by);
-    recon_ring_var<RECON>(ring + 6 * VS, b0, up.bz, lo.bz);
-  }
+  double *upv[7] = {&up.d, &up.vx, &up.vy, &up.vz, &up.e, &up.by, &up.bz};
+  double *lov[7] = {&lo.d, &lo.vx, &lo.vy, &lo.vz, &lo.e, &lo.by, &lo.bz};
+#pragma unroll
+  for (int v = 0; v < T::NV; ++v) recon_ring_var<RECON>(ring + v * VS, b0, *upv[T::member(v)], *lov[T::member(v)]);
   if constexpr (RECON == RECON_PPMX || RECON == RECON_WENOZ || RECON == RECON_TENO) {   // recon.hpp:78-108
-    const double efloor = eos.pfloor / (eos.gamma - 1.0);
     up.d = dmax(up.d, eos.dfloor);
     lo.d = dmax(lo.d, eos.dfloor);
-    up.e = dmax(up.e, efloor);
-    lo.e = dmax(lo.e, efloor);
+    if constexpr (T::IDEAL) {
+      const double efloor = eos.pfloor / (eos.gamma - 1.0);
+      up.e = dmax(up.e, efloor);
+      lo.e = dmax(lo.e, efloor);
+    }
   }
 }
 
@@ -241,8 +262,10 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
                   double *__restrict__ ezo, int seglen, int nseg) {
   static_assert(DIR == 1 || DIR == 2, "march kernel handles x2 and x3");
   constexpr bool RING = (RECON >= RECON_PPM4);
-  constexpr bool MHD = (RS < RS_HYD_ADVECT);
-  constexpr int NV = MHD ? 7 : 5;
+  using T = SolverTraits<RS>;
+  constexpr bool MHD = T::MHD;
+  constexpr bool IDEAL = T::IDEAL;
+  constexpr int NV = T::NV;
   extern __shared__ double ring_all[];   // RING: NV * MARCH_SLOTS * MARCH_THREADS doubles (dynamic)
   const int nc = g.nx1 + 2 * g.ext1;
   const int nt = (DIR == 1) ? g.nx3 + 2 * g.ext3 : g.nx2 + 2 * g.ext2;
@@ -275,7 +298,8 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
   constexpr int ivx = IVX + DIR, ivy = IVX + (DIR + 1) % 3, ivz = IVX + (DIR + 2) % 3;
   constexpr int iby = (DIR + 1) % 3, ibz = (DIR + 2) % 3;
   // the NV reconstructed variables: source array and variable index (block-uniform)
-  auto vsrc = [&](int v) -> const double * {
+  auto vsrc = [&](int vv) -> const double * {
+    const int v = T::member(vv);
     return v == 0 ? wb + IDN * cc : v == 1 ? wb + ivx * cc : v == 2 ? wb + ivy * cc : v == 3 ? wb + ivz * cc
          : v == 4 ? wb + IEN * cc : v == 5 ? bb + iby * cc : bb + ibz * cc;
   };
@@ -295,11 +319,11 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
     cp_async_commit();
     cp_async_wait<0>();
     double fl[7];
-    if constexpr (RECON == RECON_PPM4 && AKB_MARCH_CARRY && MHD) {
+    if constexpr (RECON == RECON_PPM4 && AKB_MARCH_CARRY && MHD && IDEAL) {
       ppm4_ring_iface(ring, 0, fl);
       ppm4_ring_cell(ring, 0, fl, L, lo_unused);
     } else {
-      recon_ring_cell<RECON, MHD>(ring, 0, eos, L, lo_unused);
+      recon_ring_cell<RECON, RS>(ring, 0, eos, L, lo_unused);
     }
     int b0 = 1;                       // slot of row c-2 for the next cell (c = f_lo)
     for (int f = f_lo; f <= f_hi; ++f) {
@@ -314,17 +338,18 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       cp_async_commit();
       cp_async_wait<MARCH_PF>();
       State7 up, lo;
-      if constexpr (RECON == RECON_PPM4 && AKB_MARCH_CARRY && MHD) ppm4_ring_cell(ring, b0, fl, up, lo);
-      else recon_ring_cell<RECON, MHD>(ring, b0, eos, up, lo);
+      if constexpr (RECON == RECON_PPM4 && AKB_MARCH_CARRY && MHD && IDEAL) ppm4_ring_cell(ring, b0, fl, up, lo);
+      else recon_ring_cell<RECON, RS>(ring, b0, eos, up, lo);
       Flux7 fx;
-      if constexpr (MHD) riemann<RS>(L, lo, __ldg(bnb + fo), eos, fx);
-      else riemann_hyd<RS>(L, lo, eos, fx);
+      double bni = 0.0;
+      if constexpr (MHD) bni = __ldg(bnb + fo);
+      riemann_any<RS>(L, lo, bni, eos, fx);
       double *fp = fb + fo;
       fp[IDN * fsz] = fx.d;
       fp[ivx * fsz] = fx.mx;
       fp[ivy * fsz] = fx.my;
       fp[ivz * fsz] = fx.mz;
-      fp[IEN * fsz] = fx.e;
+      if constexpr (IDEAL) fp[IEN * fsz] = fx.e;
       if constexpr (MHD) {
         eyb[co] = fx.ey;  // x2: (e1x2,e3x2)  x3: (e2x3,e1x3)   mhd_fluxes.cpp:196,243
         ezb[co] = fx.ez;
@@ -335,20 +360,21 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
     }
     cp_async_wait<0>();
   } else {
-    recon_cell<RECON, DIR, MHD>(wb + co, bb + co, cc, s, eos, L, lo_unused);
+    recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, L, lo_unused);
     for (int f = f_lo; f <= f_hi; ++f) {
       co += s;
       State7 up, lo;
-      recon_cell<RECON, DIR, MHD>(wb + co, bb + co, cc, s, eos, up, lo);
+      recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, up, lo);
       Flux7 fx;
-      if constexpr (MHD) riemann<RS>(L, lo, __ldg(bnb + fo), eos, fx);
-      else riemann_hyd<RS>(L, lo, eos, fx);
+      double bni = 0.0;
+      if constexpr (MHD) bni = __ldg(bnb + fo);
+      riemann_any<RS>(L, lo, bni, eos, fx);
       double *fp = fb + fo;
       fp[IDN * fsz] = fx.d;
       fp[ivx * fsz] = fx.mx;
       fp[ivy * fsz] = fx.my;
       fp[ivz * fsz] = fx.mz;
-      fp[IEN * fsz] = fx.e;
+      if constexpr (IDEAL) fp[IEN * fsz] = fx.e;
       if constexpr (MHD) {
         eyb[co] = fx.ey;
         ezb[co] = fx.ez;
@@ -368,7 +394,7 @@ template <int RECON, int DIR>
 __global__ void __launch_bounds__(256)
 scalar_flux_kernel(Geom g, const double *__restrict__ w0, double *__restrict__ flx) {
   const int nfi = g.nx1 + (DIR == 0), nfj = g.nx2 + (DIR == 1), nfk = g.nx3 + (DIR == 2);
-  const int ns = g.nvar - 5;
+  const int ns = g.nvar - g.nfl;
   const long total = (long)g.nmb * ns * nfk * nfj * nfi;
   const long t0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t0 >= total) return;
@@ -376,7 +402,7 @@ scalar_flux_kernel(Geom g, const double *__restrict__ w0, double *__restrict__ f
   const int i = g.is + (int)(t % nfi); t /= nfi;
   const int j = g.js + (int)(t % nfj); t /= nfj;
   const int k = g.ks + (int)(t % nfk); t /= nfk;
-  const int n = 5 + (int)(t % ns);
+  const int n = g.nfl + (int)(t % ns);
   const int m = (int)(t / ns);
   const long s = (DIR == 0) ? 1 : (DIR == 1) ? (long)g.n1 : (long)g.n1 * g.n2;
   const long fsz = (DIR == 0) ? g.f1 : (DIR == 1) ? g.f2 : g.f3;
@@ -392,7 +418,7 @@ scalar_flux_kernel(Geom g, const double *__restrict__ w0, double *__restrict__ f
 
 template <int RECON>
 static cudaError_t launch_scalar_fluxes(const Geom &g, const Arrays &a, cudaStream_t st) {
-  const int ns = g.nvar - 5;
+  const int ns = g.nvar - g.nfl;
   if (ns <= 0) return cudaSuccess;
   {
     const long n = (long)g.nmb * ns * g.nx3 * g.nx2 * (g.nx1 + 1);
@@ -416,7 +442,7 @@ static inline unsigned nblocks(long n, int bs) { return (unsigned)((n + bs - 1) 
 
 template <int RECON, int RS>
 static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st) {
-  constexpr int NV = (RS < RS_HYD_ADVECT) ? 7 : 5;
+  constexpr int NV = SolverTraits<RS>::NV;
   const size_t smem = (RECON >= RECON_PPM4) ? sizeof(double) * NV * MARCH_SLOTS * MARCH_THREADS : 0;
   {  // x1
     constexpr int STEP = X1Step<RECON>::value;
@@ -447,7 +473,7 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
     if (!attr2 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr2 = true; }
     flux_march_kernel<RECON, RS, 2><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
   }
-  if (g.nvar > 5) return launch_scalar_fluxes<RECON>(g, a, st);
+  if (g.nvar > g.nfl) return launch_scalar_fluxes<RECON>(g, a, st);
   return cudaGetLastError();
 }
 

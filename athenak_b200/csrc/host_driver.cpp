@@ -212,7 +212,7 @@ class MHD {  // state owner + tasks
     multi_d = c.nx2 > 1; three_d = c.nx3 > 1;       // mesh.cpp:70-79
     const size_t n1 = c.nx1 + 2 * c.ng, n2 = multi_d ? c.nx2 + 2 * c.ng : 1, n3 = three_d ? c.nx3 + 2 * c.ng : 1, nm = c.nmb;
     const size_t cc = n1 * n2 * n3;
-    nvar = 5 + c.nscalars;
+    nvar = (c.eos == AK_EOS_ISOTHERMAL ? 4 : 5) + c.nscalars;   // mhd.cpp:148 nmhd, hydro.cpp:75 nhydro
     n_u = nm * nvar * cc; n_f1 = nm * n3 * n2 * (n1 + 1); n_f2 = nm * n3 * (n2 + 1) * n1; n_f3 = nm * (n3 + 1) * n2 * n1;
     auto alloc = [&](size_t n) { double *p; CU_CHECK(cudaMalloc(&p, n * 8)); CU_CHECK(cudaMemsetAsync(p, 0, n * 8, st)); owned.push_back(p); return p; };
     std::memset(&a, 0, sizeof(a));

@@ -31,7 +31,8 @@ hst_partial_kernel(Geom g, bool mhd, const double *__restrict__ u0, const double
     const double vol = mb_size[m * 9 + 6] * mb_size[m * 9 + 7] * mb_size[m * 9 + 8];
     const long o = ((long)k * g.n2 + j) * g.n1 + i;
     const double *u = u0 + (long)m * g.nvar * g.cc + o;
-    const double d = u[0], m1 = u[g.cc], m2 = u[2 * g.cc], m3 = u[3 * g.cc], e = u[4 * g.cc];
+    const double d = u[0], m1 = u[g.cc], m2 = u[2 * g.cc], m3 = u[3 * g.cc];
+    const double e = (g.nfl == 5) ? u[4 * g.cc] : 0.0;   // isothermal: no energy variable (history.cpp:140-142)
     acc[0] += vol * d; acc[1] += vol * m1; acc[2] += vol * m2; acc[3] += vol * m3; acc[4] += vol * e;
     acc[5] += vol * 0.5 * sqr(m1) / d;
     acc[6] += vol * 0.5 * sqr(m2) / d;
@@ -60,18 +61,20 @@ hst_partial_kernel(Geom g, bool mhd, const double *__restrict__ u0, const double
   }
 }
 
-__global__ void hst_final_kernel(const double *__restrict__ partial, int nblocks, double *__restrict__ out) {
+// skip_e: isothermal runs have no tot-E column, the later columns move up by one (history.cpp:84-88)
+__global__ void hst_final_kernel(const double *__restrict__ partial, int nblocks, double *__restrict__ out, int skip_e) {
   if (threadIdx.x < HST_NV) {
     double v = 0.0;
     for (int b = 0; b < nblocks; ++b) v += partial[(long)b * HST_NV + threadIdx.x];
-    out[threadIdx.x] = v;
+    if (!skip_e) out[threadIdx.x] = v;
+    else if (threadIdx.x != 4) out[threadIdx.x < 4 ? threadIdx.x : threadIdx.x - 1] = v;
   }
 }
 
 // scratch: at least (nblocks+1)*HST_NV doubles; result in scratch[nblocks*HST_NV ..]
 cudaError_t launch_hst_sums(const Geom &g, const Arrays &a, bool mhd, double *scratch, int nblocks, cudaStream_t st) {
   hst_partial_kernel<<<nblocks, HST_THREADS, 0, st>>>(g, mhd, a.u0, a.b0x1f, a.b0x2f, a.b0x3f, a.mb_size, scratch);
-  hst_final_kernel<<<1, 32, 0, st>>>(scratch, nblocks, scratch + (long)nblocks * HST_NV);
+  hst_final_kernel<<<1, 32, 0, st>>>(scratch, nblocks, scratch + (long)nblocks * HST_NV, g.nfl == 4 ? 1 : 0);
   return cudaGetLastError();
 }
 

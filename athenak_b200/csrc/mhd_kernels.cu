@@ -186,8 +186,9 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
       u0[uo] = gam0 * uold + gam1 * ureg - beta_dt * divf;
     };
 #pragma unroll
-    for (int n = 0; n < 5; ++n) update_var(n);
-    for (int n = 5; n < g.nvar; ++n) update_var(n);   // passive scalars (mhd_update.cpp:51: n over nmhd+nscalars)
+    for (int n = 0; n < 4; ++n) update_var(n);
+    if (g.nfl == 5) update_var(IEN);                        // no energy equation with the isothermal EOS
+    for (int n = g.nfl; n < g.nvar; ++n) update_var(n);   // passive scalars (mhd_update.cpp:51: n over nmhd+nscalars)
   }
   if (DO_B) {
     const double *E1 = e1 + (long)m * g.e1, *E2 = e2 + (long)m * g.e2, *E3 = e3 + (long)m * g.e3;
@@ -231,7 +232,7 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
 // ConsToPrim (ideal_mhd.cpp:47-122 + ideal_c2p_mhd.hpp:20-67) over a cell box, optionally
 // fused with the new-dt reduction over the active cells (mhd_newdt.cpp:76-150).
 // counters: int[3] (dfloor,efloor,tfloor); dtmin: 3 doubles stored as ordered uint64 bits.
-template <bool NEWDT>
+template <bool NEWDT, bool IDEAL>
 __global__ void __launch_bounds__(256)
 cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *__restrict__ b1f,
                  const double *__restrict__ b2f, const double *__restrict__ b3f, double *__restrict__ w0,
@@ -253,7 +254,8 @@ cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *_
     const long n1 = g.n1, n2 = g.n2, cc = g.cc;
     const long o = ((long)k * n2 + j) * n1 + i;
     double *u = u0 + (long)m * g.nvar * cc + o;
-    double ud = u[IDN * cc], umx = u[IM1 * cc], umy = u[IM2 * cc], umz = u[IM3 * cc], ue = u[IEN * cc];
+    double ud = u[IDN * cc], umx = u[IM1 * cc], umy = u[IM2 * cc], umz = u[IM3 * cc], ue = 0.0;
+    if constexpr (IDEAL) ue = u[IEN * cc];
     const double *p1 = b1f + (long)m * g.f1 + ((long)k * n2 + j) * (n1 + 1) + i;
     const double *p2 = b2f + (long)m * g.f2 + ((long)k * (n2 + 1) + j) * n1 + i;
     const double *p3 = b3f + (long)m * g.f3 + o;
@@ -264,14 +266,17 @@ cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *_
     const double gm1 = eos.gamma - 1.0;
     const double b2 = sqr(ubx) + sqr(uby) + sqr(ubz);
     const double dfloor_ = dmax(eos.dfloor, ddiv(b2, eos.sigma_max));
-    const double efloor = ddiv(eos.pfloor, eos.gamma - 1.0);
     if (ud < dfloor_) { ud = dfloor_; dfl = true; }
     const double wd = ud;
     const double di = drcp(ud);
     const double wvx = di * umx, wvy = di * umy, wvz = di * umz;
+    double we = 0.0;
+    double *w = w0 + (long)m * g.nvar * cc + o;
+    if constexpr (IDEAL) {
+    const double efloor = ddiv(eos.pfloor, eos.gamma - 1.0);
     const double e_k = 0.5 * di * (sqr(umx) + sqr(umy) + sqr(umz));
     const double e_m = 0.5 * (sqr(ubx) + sqr(uby) + sqr(ubz));
-    double we = (ue - e_k - e_m);
+    we = (ue - e_k - e_m);
     if (we < efloor) { we = efloor; ue = efloor + e_k + e_m; efl = true; }
     if (gm1 * we * di < eos.tfloor) { we = wd * eos.tfloor / gm1; ue = we + e_k + e_m; tfl = true; }
     // Entropy floor (ideal_c2p_mhd.hpp:59-65).  spe = gm1*we*di / wd^gm1.  pow() is only needed
@@ -285,25 +290,30 @@ cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *_
       const double spe = spe_over_eps * we * di;
       if (spe <= eos.sfloor) { we = wd * eos.sfloor / spe_over_eps; efl = true; }
     }
-    if (dfl) { u[IDN * cc] = ud; nd = 1; }
     if (efl) { u[IEN * cc] = ue; ne = 1; }
     if (tfl) { u[IEN * cc] = ue; nt = 1; }
-    double *w = w0 + (long)m * g.nvar * cc + o;
-    w[IDN * cc] = wd; w[IVX * cc] = wvx; w[IVY * cc] = wvy; w[IVZ * cc] = wvz; w[IEN * cc] = we;
+    w[IEN * cc] = we;
+    }  // IDEAL; isothermal_mhd.cpp:28-46,95-135 has the density floor only
+    if (dfl) { u[IDN * cc] = ud; nd = 1; }
+    w[IDN * cc] = wd; w[IVX * cc] = wvx; w[IVY * cc] = wvy; w[IVZ * cc] = wvz;
     double *bc = bcc + (long)m * 3 * cc + o;
     bc[0] = ubx; bc[cc] = uby; bc[2 * cc] = ubz;
-    for (int n = 5; n < g.nvar; ++n) {   // ideal_mhd.cpp:113-120: scalar floor, then s / d (floored density)
+    for (int n = g.nfl; n < g.nvar; ++n) {   // ideal_mhd.cpp:113-120: scalar floor, then s / d (floored density)
       double sc = u[n * cc];
-      if (sc < 0.0) { sc = 0.0; u[n * cc] = 0.0; }
+      if (IDEAL && sc < 0.0) { sc = 0.0; u[n * cc] = 0.0; }   // isothermal_mhd.cpp:130-132: no scalar floor
       w[n * cc] = sc / ud;
     }
     if (NEWDT) {
       act = (i >= g.is && i <= g.ie && j >= g.js && j <= g.je && k >= g.ks && k <= g.ke);
       if (act) {  // mhd_newdt.cpp:128-138,146-148
         const double p = gm1 * we;
-        d1 = ddiv(__ldg(mb_size + m * 9 + 6), fabs(wvx) + fast_speed(eos.gamma, wd, p, ubx, uby, ubz));
-        d2 = ddiv(__ldg(mb_size + m * 9 + 7), fabs(wvy) + fast_speed(eos.gamma, wd, p, uby, ubz, ubx));
-        d3 = ddiv(__ldg(mb_size + m * 9 + 8), fabs(wvz) + fast_speed(eos.gamma, wd, p, ubz, ubx, uby));
+        auto cf = [&](double bx, double by, double bz) {   // mhd_newdt.cpp:128-138
+          if constexpr (IDEAL) return fast_speed(eos.gamma, wd, p, bx, by, bz);
+          else return fast_speed_iso(eos.iso_cs, wd, bx, by, bz);
+        };
+        d1 = ddiv(__ldg(mb_size + m * 9 + 6), fabs(wvx) + cf(ubx, uby, ubz));
+        d2 = ddiv(__ldg(mb_size + m * 9 + 7), fabs(wvy) + cf(uby, ubz, ubx));
+        d3 = ddiv(__ldg(mb_size + m * 9 + 8), fabs(wvz) + cf(ubz, ubx, uby));
       }
     }
   }
@@ -325,6 +335,7 @@ cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *_
 }
 
 // MHD::NewTimeStep stand-alone (task 28): reads w0, bcc0 over the active cells.
+template <bool IDEAL>
 __global__ void __launch_bounds__(256)
 newdt_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
              const double *__restrict__ mb_size, unsigned long long *__restrict__ dtmin) {
@@ -340,10 +351,15 @@ newdt_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double 
     const long cc = g.cc, o = ((long)k * g.n2 + j) * g.n1 + i;
     const double *w = w0 + (long)m * g.nvar * cc + o, *b = bcc + (long)m * 3 * cc + o;
     const double wd = __ldg(w), bx = __ldg(b), by = __ldg(b + cc), bz = __ldg(b + 2 * cc);
-    const double p = (eos.gamma - 1.0) * __ldg(w + IEN * cc);
-    d1 = ddiv(__ldg(mb_size + m * 9 + 6), fabs(__ldg(w + IVX * cc)) + fast_speed(eos.gamma, wd, p, bx, by, bz));
-    d2 = ddiv(__ldg(mb_size + m * 9 + 7), fabs(__ldg(w + IVY * cc)) + fast_speed(eos.gamma, wd, p, by, bz, bx));
-    d3 = ddiv(__ldg(mb_size + m * 9 + 8), fabs(__ldg(w + IVZ * cc)) + fast_speed(eos.gamma, wd, p, bz, bx, by));
+    double p = 0.0;
+    if constexpr (IDEAL) p = (eos.gamma - 1.0) * __ldg(w + IEN * cc);
+    auto cf = [&](double b1, double b2, double b3) {
+      if constexpr (IDEAL) return fast_speed(eos.gamma, wd, p, b1, b2, b3);
+      else return fast_speed_iso(eos.iso_cs, wd, b1, b2, b3);
+    };
+    d1 = ddiv(__ldg(mb_size + m * 9 + 6), fabs(__ldg(w + IVX * cc)) + cf(bx, by, bz));
+    d2 = ddiv(__ldg(mb_size + m * 9 + 7), fabs(__ldg(w + IVY * cc)) + cf(by, bz, bx));
+    d3 = ddiv(__ldg(mb_size + m * 9 + 8), fabs(__ldg(w + IVZ * cc)) + cf(bz, bx, by));
   }
   block_min3(d1, d2, d3, dtmin);
 }
@@ -365,6 +381,9 @@ static cudaError_t launch_fluxes_r(int rs, const Geom &g, const EosParams &eos, 
     case RS_LLF: return launch_fluxes_t<RECON, RS_LLF>(g, eos, a, st);
     case RS_HLLE: return launch_fluxes_t<RECON, RS_HLLE>(g, eos, a, st);
     case RS_HLLD: return launch_fluxes_t<RECON, RS_HLLD>(g, eos, a, st);
+    case RS_LLF_ISO: return launch_fluxes_t<RECON, RS_LLF_ISO>(g, eos, a, st);
+    case RS_HLLE_ISO: return launch_fluxes_t<RECON, RS_HLLE_ISO>(g, eos, a, st);
+    case RS_HLLD_ISO: return launch_fluxes_t<RECON, RS_HLLD_ISO>(g, eos, a, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -415,16 +434,20 @@ cudaError_t launch_cons2prim(const Geom &g, const EosParams &eos, const Arrays &
                              int kl, int ku, int *counters, bool newdt, unsigned long long *dtmin, cudaStream_t st) {
   const long n = (long)g.nmb * (ku - kl + 1) * (ju - jl + 1) * (iu - il + 1);
   if (n <= 0) return cudaSuccess;
-  if (newdt)
-    cons2prim_kernel<true><<<nblocks(n, 256), 256, 0, st>>>(g, eos, a.u0, a.b0x1f, a.b0x2f, a.b0x3f, a.w0, a.bcc0, il, iu, jl, ju, kl, ku, counters, a.mb_size, dtmin);
-  else
-    cons2prim_kernel<false><<<nblocks(n, 256), 256, 0, st>>>(g, eos, a.u0, a.b0x1f, a.b0x2f, a.b0x3f, a.w0, a.bcc0, il, iu, jl, ju, kl, ku, counters, a.mb_size, dtmin);
+#define AKB_C2P_ARGS g, eos, a.u0, a.b0x1f, a.b0x2f, a.b0x3f, a.w0, a.bcc0, il, iu, jl, ju, kl, ku, counters, a.mb_size, dtmin
+  const bool ideal = (g.nfl == 5);
+  if (newdt && ideal) cons2prim_kernel<true, true><<<nblocks(n, 256), 256, 0, st>>>(AKB_C2P_ARGS);
+  else if (ideal) cons2prim_kernel<false, true><<<nblocks(n, 256), 256, 0, st>>>(AKB_C2P_ARGS);
+  else if (newdt) cons2prim_kernel<true, false><<<nblocks(n, 256), 256, 0, st>>>(AKB_C2P_ARGS);
+  else cons2prim_kernel<false, false><<<nblocks(n, 256), 256, 0, st>>>(AKB_C2P_ARGS);
+#undef AKB_C2P_ARGS
   return cudaGetLastError();
 }
 
 cudaError_t launch_newdt(const Geom &g, const EosParams &eos, const Arrays &a, unsigned long long *dtmin, cudaStream_t st) {
   const long n = (long)g.nmb * g.nx3 * g.nx2 * g.nx1;
-  newdt_kernel<<<nblocks(n, 256), 256, 0, st>>>(g, eos, a.w0, a.bcc0, a.mb_size, dtmin);
+  if (g.nfl == 5) newdt_kernel<true><<<nblocks(n, 256), 256, 0, st>>>(g, eos, a.w0, a.bcc0, a.mb_size, dtmin);
+  else newdt_kernel<false><<<nblocks(n, 256), 256, 0, st>>>(g, eos, a.w0, a.bcc0, a.mb_size, dtmin);
   return cudaGetLastError();
 }
 

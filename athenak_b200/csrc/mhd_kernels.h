@@ -12,7 +12,8 @@ struct EosParams;
 
 struct Geom {  // RegionIndcs (src/mesh/mesh.hpp:35-41) + derived array extents
   int nmb, ng, nx1, nx2, nx3;
-  int nvar;         // 5 fluid variables + passive scalars per cell-centred / flux array
+  int nvar;         // fluid variables + passive scalars per cell-centred / flux array
+  int nfl;          // fluid variables: 5 (ideal gas) or 4 (isothermal EOS: no IEN)
   int n1, n2, n3;
   int is, ie, js, je, ks, ke;
   long cc;          // cells per variable per block
@@ -49,6 +50,8 @@ cudaError_t launch_cons2prim(const Geom &g, const EosParams &eos, const Arrays &
 cudaError_t launch_newdt(const Geom &g, const EosParams &eos, const Arrays &a, unsigned long long *dtmin, cudaStream_t st);
 // history sums (hst.cu): scratch holds (nblocks+1)*11 doubles, the 11 results are its last row
 cudaError_t launch_hst_sums(const Geom &g, const Arrays &a, bool mhd, double *scratch, int nblocks, cudaStream_t st);
+// internal solver code: public AK_RSOLVER_* value, + 20 for the isothermal variant (iso_device.cuh)
+inline int internal_rsolver(int rsolver, int eos) { return rsolver + (eos == 1 ? 20 : 0); }
 cudaError_t launch_copy(const double *src, double *dst, long n, cudaStream_t st);
 
 }  // namespace akb

@@ -20,7 +20,8 @@ from .mhd import FLT_MAX, FLT_MIN, TaskStatus
 class Hydro:
     def __init__(self, nmb, ng, nx, mb_size, nghbr, *, recon="plm", rsolver="hllc", gamma,
                  dfloor=FLT_MIN, pfloor=FLT_MIN, tfloor=FLT_MIN, sfloor=FLT_MIN,
-                 my_rank=0, gids_start=0, device="cuda", process_group=None, mesh_bcs=None, mb_bcs=None, nscalars=0):
+                 my_rank=0, gids_start=0, device="cuda", process_group=None, mesh_bcs=None, mb_bcs=None, nscalars=0,
+                 eos="ideal", iso_sound_speed=1.0):
         if not torch.cuda.is_available():
             raise _lib.EngineError("athenak_b200: no CUDA device; the engine has no CPU path")
         self.L = _lib.load()
@@ -29,9 +30,10 @@ class Hydro:
         nx1, nx2, nx3 = self.nx
         self.multi_d, self.three_d = nx2 > 1, nx3 > 1
         self.n = (nx1 + 2 * ng, nx2 + 2 * ng if self.multi_d else 1, nx3 + 2 * ng if self.three_d else 1)
-        self.nvar = nv = 5 + int(nscalars)      # src/hydro/hydro.cpp:75,117: nhydro + nscalars
+        self.nfl = 4 if eos == "isothermal" else 5
+        self.nvar = nv = self.nfl + int(nscalars)      # src/hydro/hydro.cpp:75,117: nhydro + nscalars
         self.cfg = _lib.MhdCfg(self.nmb, ng, nx1, nx2, nx3, _lib.RECON[recon], _lib.HYD_RSOLVER[rsolver],
-                               gamma, dfloor, pfloor, tfloor, sfloor, FLT_MAX, int(nscalars))
+                               gamma, dfloor, pfloor, tfloor, sfloor, FLT_MAX, int(nscalars), _lib.EOS[eos], iso_sound_speed)
         self.my_rank, self.gids_start, self.pg = my_rank, gids_start, process_group
         n1, n2, n3 = self.n
         z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=self.device)

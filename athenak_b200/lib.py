@@ -23,7 +23,11 @@ class MhdCfg(C.Structure):
     _fields_ = [("nmb", C.c_int), ("ng", C.c_int), ("nx1", C.c_int), ("nx2", C.c_int),
                 ("nx3", C.c_int), ("recon", C.c_int), ("rsolver", C.c_int),
                 ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
-                ("tfloor", C.c_double), ("sfloor", C.c_double), ("sigma_max", C.c_double), ("nscalars", C.c_int)]
+                ("tfloor", C.c_double), ("sfloor", C.c_double), ("sigma_max", C.c_double), ("nscalars", C.c_int),
+                ("eos", C.c_int), ("iso_sound_speed", C.c_double)]
+
+
+EOS = {"ideal": 0, "isothermal": 1}      # AK_EOS_*
 
 
 ARRAY_FIELDS = ("u0", "u1", "w0", "bcc0", "b0x1f", "b0x2f", "b0x3f", "b1x1f", "b1x2f", "b1x3f",

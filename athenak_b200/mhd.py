@@ -38,7 +38,7 @@ class MHD:
     def __init__(self, nmb, ng, nx, mb_size, nghbr, *, recon="ppm4", rsolver="hlld", gamma,
                  dfloor=FLT_MIN, pfloor=FLT_MIN, tfloor=FLT_MIN, sfloor=FLT_MIN, sigma_max=FLT_MAX,
                  my_rank=0, gids_start=0, device="cuda", process_group=None, fused=True,
-                 mesh_bcs=None, mb_bcs=None, nscalars=0):
+                 mesh_bcs=None, mb_bcs=None, nscalars=0, eos="ideal", iso_sound_speed=1.0):
         if not torch.cuda.is_available():
             raise _lib.EngineError("athenak_b200: no CUDA device; the engine has no CPU path")
         self.L = _lib.load()
@@ -48,9 +48,10 @@ class MHD:
         self.multi_d, self.three_d = nx2 > 1, nx3 > 1      # src/mesh/mesh.cpp:70-79
         self.n = (nx1 + 2 * ng, nx2 + 2 * ng if self.multi_d else 1, nx3 + 2 * ng if self.three_d else 1)
         self.nsweeps = 1 + int(self.multi_d) + int(self.three_d)
-        self.nvar = 5 + int(nscalars)      # src/mhd/mhd.cpp: nmhd + nscalars
+        self.nfl = 4 if eos == "isothermal" else 5       # src/mhd/mhd.cpp:100-108: nmhd
+        self.nvar = self.nfl + int(nscalars)      # src/mhd/mhd.cpp: nmhd + nscalars
         self.cfg = _lib.MhdCfg(self.nmb, ng, nx1, nx2, nx3, _lib.RECON[recon], _lib.RSOLVER[rsolver],
-                               gamma, dfloor, pfloor, tfloor, sfloor, sigma_max, int(nscalars))
+                               gamma, dfloor, pfloor, tfloor, sfloor, sigma_max, int(nscalars), _lib.EOS[eos], iso_sound_speed)
         self.fused = fused
         self.my_rank, self.gids_start, self.pg = my_rank, gids_start, process_group
         n1, n2, n3 = self.n

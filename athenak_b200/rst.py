@@ -89,7 +89,7 @@ def read_rst(path: str, nmhd: int = 5, physics: str = "mhd") -> Restart:
 
 def write_rst(path: str, r: Restart) -> None:
     """Writes a dump the reference can restart from (`athena -r file`): same byte layout as
-    src/outputs/restart.cpp:216-294,312-469 (single file, MHD only)."""
+    src/outputs/restart.cpp:216-294,312-469 (single file; MHD, or hydro when r.b1f is None)."""
     nmb = int(r.nmb)
     with open(path, "wb") as f:
         f.write(r.deck.encode())
@@ -101,8 +101,9 @@ def write_rst(path: str, r: Restart) -> None:
         f.write(struct.pack("<i", int(r.ncycle)))
         f.write(np.ascontiguousarray(r.lloc, "<i4").tobytes())
         f.write(np.ascontiguousarray(r.cost, "<f4").tobytes())
-        per_block = 8 * (r.u0[0].size + r.b1f[0].size + r.b2f[0].size + r.b3f[0].size)
+        arrays = [a for a in (r.u0, r.b1f, r.b2f, r.b3f) if a is not None]
+        per_block = 8 * sum(a[0].size for a in arrays)
         f.write(struct.pack("<Q", per_block))
         for m in range(nmb):
-            for a in (r.u0, r.b1f, r.b2f, r.b3f):
+            for a in arrays:
                 f.write(np.ascontiguousarray(a[m], "<f8").tobytes())

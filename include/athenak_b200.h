@@ -33,6 +33,10 @@ typedef void *ak_stream_t; /* a cudaStream_t (0 = default stream) */
 /* reconstruction / Riemann-solver selectors: reference src/athena.hpp:75, src/mhd/mhd.hpp:39 */
 enum { AK_RECON_DC = 0, AK_RECON_PLM = 1, AK_RECON_PPM4 = 2, AK_RECON_PPMX = 3, AK_RECON_WENOZ = 4, AK_RECON_TENO = 5 };
 enum { AK_RSOLVER_LLF = 0, AK_RSOLVER_HLLE = 1, AK_RSOLVER_HLLD = 2 };
+/* equation of state: reference src/eos/eos.hpp:27-33 (EOS_Data::is_ideal).  The isothermal MHD solvers are the
+ * `else` branches of llf/hlle (src/mhd/rsolvers) and HLLD of hlld_mhd.hpp:350-546; isothermal hydro has
+ * llf, hlle and roe only (hydro.cpp:252-262 rejects hllc). */
+enum { AK_EOS_IDEAL = 0, AK_EOS_ISOTHERMAL = 1 };
 /* hydro solvers: reference src/hydro/hydro.hpp:32 (Hydro_RSolver), Newtonian ones only */
 enum { AK_RSOLVER_HYD_ADVECT = 10, AK_RSOLVER_HYD_LLF = 11, AK_RSOLVER_HYD_HLLE = 12, AK_RSOLVER_HYD_HLLC = 13,
        AK_RSOLVER_HYD_ROE = 14 };
@@ -44,7 +48,10 @@ typedef struct {
   int recon, rsolver;
   double gamma, dfloor, pfloor, tfloor, sfloor, sigma_max; /* EOS_Data, src/eos/eos.hpp:27-33 */
   int nscalars;      /* passive scalars (<mhd>/<hydro> nscalars, src/mhd/mhd.cpp, src/hydro/hydro.cpp:75):
-                        stored after the 5 fluid variables in u0, u1, w0 and the flux arrays */
+                        stored after the fluid variables in u0, u1, w0 and the flux arrays */
+  int eos;           /* AK_EOS_IDEAL (5 fluid variables) or AK_EOS_ISOTHERMAL (4: no IEN; <mhd>/<hydro> eos,
+                        src/eos/isothermal_mhd.cpp, isothermal_hyd.cpp; gamma and the p/T/s floors are ignored) */
+  double iso_sound_speed; /* EOS_Data::iso_cs (src/eos/eos.hpp:28), isothermal only */
 } ak_mhd_cfg;
 
 typedef struct {

@@ -262,6 +262,123 @@ static void hyd_roe(const ocfg *c, const hprim1d *l, const hprim1d *r, hcons1d *
   flux->d = flxi[IDN]; flux->mx = flxi[IVX]; flux->my = flxi[IVY]; flux->mz = flxi[IVZ]; flux->e = flxi[IEN];
 }
 
+/* isothermal branches of llf_hyd_singlestate.hpp:27-82 */
+static void hyd_llf_iso(const ocfg *c, const hprim1d *wl, const hprim1d *wr, hcons1d *flux) {
+  double qa = wl->d * wl->vx;
+  double qb = wr->d * wr->vx;
+  hcons1d fsum, du;
+  fsum.d = qa + qb;
+  fsum.mx = qa * wl->vx + qb * wr->vx;
+  fsum.my = qa * wl->vy + qb * wr->vy;
+  fsum.mz = qa * wl->vz + qb * wr->vz;
+  fsum.mx += SQR(c->iso_cs) * (wl->d + wr->d);
+  qa = c->iso_cs;
+  qb = c->iso_cs;
+  double a = fmax((fabs(wl->vx) + qa), (fabs(wr->vx) + qb));
+  du.d = a * (wr->d - wl->d);
+  du.mx = a * (wr->d * wr->vx - wl->d * wl->vx);
+  du.my = a * (wr->d * wr->vy - wl->d * wl->vy);
+  du.mz = a * (wr->d * wr->vz - wl->d * wl->vz);
+  flux->d = 0.5 * (fsum.d - du.d);
+  flux->mx = 0.5 * (fsum.mx - du.mx);
+  flux->my = 0.5 * (fsum.my - du.my);
+  flux->mz = 0.5 * (fsum.mz - du.mz);
+  flux->e = 0.0;
+}
+
+/* isothermal branches of hlle_hyd.hpp:26-129 */
+static void hyd_hlle_iso(const ocfg *c, const hprim1d *wl, const hprim1d *wr, hcons1d *flux) {
+  const double iso_cs = c->iso_cs;
+  double sqrtdl = sqrt(wl->d);
+  double sqrtdr = sqrt(wr->d);
+  double isdlpdr = 1.0 / (sqrtdl + sqrtdr);
+  double wroe_ivx = (sqrtdl * wl->vx + sqrtdr * wr->vx) * isdlpdr;
+  double qa = iso_cs, qb = iso_cs, a = iso_cs;
+  double al = fmin((wroe_ivx - a), (wl->vx - qa));
+  double ar = fmax((wroe_ivx + a), (wr->vx + qb));
+  double bp = (ar > 0.0) ? ar : 1.0e-20;
+  double bm = (al < 0.0) ? al : -1.0e-20;
+  qa = wl->vx - bm;
+  qb = wr->vx - bp;
+  hcons1d fl, fr;
+  fl.d = wl->d * qa;              fr.d = wr->d * qb;
+  fl.mx = wl->d * wl->vx * qa;    fr.mx = wr->d * wr->vx * qb;
+  fl.my = wl->d * wl->vy * qa;    fr.my = wr->d * wr->vy * qb;
+  fl.mz = wl->d * wl->vz * qa;    fr.mz = wr->d * wr->vz * qb;
+  fl.mx += (iso_cs * iso_cs) * wl->d;
+  fr.mx += (iso_cs * iso_cs) * wr->d;
+  qa = 0.0;
+  if (bp != bm) { qa = 0.5 * (bp + bm) / (bp - bm); }
+  flux->d = 0.5 * (fl.d + fr.d) + qa * (fl.d - fr.d);
+  flux->mx = 0.5 * (fl.mx + fr.mx) + qa * (fl.mx - fr.mx);
+  flux->my = 0.5 * (fl.my + fr.my) + qa * (fl.my - fr.my);
+  flux->mz = 0.5 * (fl.mz + fr.mz) + qa * (fl.mz - fr.mz);
+  flux->e = 0.0;
+}
+
+/* roe_hyd.hpp:38-176 isothermal branches + RoeFluxIso :290-345 */
+static void hyd_roe_iso(const ocfg *c, const hprim1d *l, const hprim1d *r, hcons1d *flux) {
+  const double iso_cs = c->iso_cs;
+  double wli[4], wri[4], fl[4], fr[4], flxi[4], ev[4], du[4];
+  wli[IDN] = l->d; wli[IVX] = l->vx; wli[IVY] = l->vy; wli[IVZ] = l->vz;
+  wri[IDN] = r->d; wri[IVX] = r->vx; wri[IVY] = r->vy; wri[IVZ] = r->vz;
+  double sqrtdl = sqrt(wli[IDN]);
+  double sqrtdr = sqrt(wri[IDN]);
+  double isdlpdr = 1.0 / (sqrtdl + sqrtdr);
+  double v1 = (sqrtdl * wli[IVX] + sqrtdr * wri[IVX]) * isdlpdr;
+  double v2 = (sqrtdl * wli[IVY] + sqrtdr * wri[IVY]) * isdlpdr;
+  double v3 = (sqrtdl * wli[IVZ] + sqrtdr * wri[IVZ]) * isdlpdr;
+  double mxl = wli[IDN] * wli[IVX];
+  double mxr = wri[IDN] * wri[IVX];
+  fl[IDN] = mxl;             fr[IDN] = mxr;
+  fl[IVX] = mxl * wli[IVX];  fr[IVX] = mxr * wri[IVX];
+  fl[IVY] = mxl * wli[IVY];  fr[IVY] = mxr * wri[IVY];
+  fl[IVZ] = mxl * wli[IVZ];  fr[IVZ] = mxr * wri[IVZ];
+  fl[IVX] += (iso_cs * iso_cs) * wli[IDN];
+  fr[IVX] += (iso_cs * iso_cs) * wri[IDN];
+  du[IDN] = wri[IDN] - wli[IDN];
+  du[IVX] = wri[IDN] * wri[IVX] - wli[IDN] * wli[IVX];
+  du[IVY] = wri[IDN] * wri[IVY] - wli[IDN] * wli[IVY];
+  du[IVZ] = wri[IDN] * wri[IVZ] - wli[IDN] * wli[IVZ];
+  for (int n = 0; n < 4; ++n) flxi[n] = 0.5 * (fl[n] + fr[n]);
+  int llf_flag = 0;
+  {
+    ev[0] = v1 - iso_cs; ev[1] = v1; ev[2] = v1; ev[3] = v1 + iso_cs;
+    double a[4];
+    a[0] = du[0] * (0.5 + 0.5 * v1 / iso_cs);
+    a[0] -= du[1] * 0.5 / iso_cs;
+    a[1] = du[0] * (-v2);
+    a[1] += du[2];
+    a[2] = du[0] * (-v3);
+    a[2] += du[3];
+    a[3] = du[0] * (0.5 - 0.5 * v1 / iso_cs);
+    a[3] += du[1] * 0.5 / iso_cs;
+    double coeff[4];
+    for (int n = 0; n < 4; ++n) coeff[n] = -0.5 * fabs(ev[n]) * a[n];
+    double dens = wli[IDN] + a[0];
+    if (dens < 0.0) llf_flag = 1;
+    dens += a[3];
+    if (dens < 0.0) llf_flag = 1;
+    flxi[0] += coeff[0];
+    flxi[0] += coeff[3];
+    flxi[1] += coeff[0] * (v1 - iso_cs);
+    flxi[1] += coeff[3] * (v1 + iso_cs);
+    flxi[2] += coeff[0] * v2;
+    flxi[2] += coeff[1];
+    flxi[2] += coeff[3] * v2;
+    flxi[3] += coeff[0] * v3;
+    flxi[3] += coeff[2];
+    flxi[3] += coeff[3] * v3;
+  }
+  if (ev[0] >= 0.0) for (int n = 0; n < 4; ++n) flxi[n] = fl[n];
+  if (ev[3] <= 0.0) for (int n = 0; n < 4; ++n) flxi[n] = fr[n];
+  if (llf_flag != 0) {
+    double a = 0.5 * fmax((fabs(wli[IVX]) + iso_cs), (fabs(wri[IVX]) + iso_cs));
+    for (int n = 0; n < 4; ++n) flxi[n] = 0.5 * (fl[n] + fr[n]) - a * du[n];
+  }
+  flux->d = flxi[IDN]; flux->mx = flxi[IVX]; flux->my = flxi[IVY]; flux->mz = flxi[IVZ]; flux->e = 0.0;
+}
+
 /* Hydro::CalculateFluxes, hydro_fluxes.cpp:78-229 (no FOFC, no scalars): reconstruction over
  * [il1-1,iu1] then a Riemann solve on faces [il1,iu1]; no transverse extension; x2 only if
  * multi_d, x3 only if three_d. */
@@ -286,9 +403,14 @@ void oracle_hydro_fluxes(const ocfg *c, const double *w0, double *flx1, double *
             hprim1d l, r;
             hcons1d f;
             l.d = CC(wl, D.nv, m, IDN, k, j, i); l.vx = CC(wl, D.nv, m, ivx, k, j, i); l.vy = CC(wl, D.nv, m, ivy, k, j, i);
-            l.vz = CC(wl, D.nv, m, ivz, k, j, i); l.e = CC(wl, D.nv, m, IEN, k, j, i);
+            l.vz = CC(wl, D.nv, m, ivz, k, j, i); l.e = c->is_iso ? 0.0 : CC(wl, D.nv, m, IEN, k, j, i);
             r.d = CC(wr, D.nv, m, IDN, k, j, i); r.vx = CC(wr, D.nv, m, ivx, k, j, i); r.vy = CC(wr, D.nv, m, ivy, k, j, i);
-            r.vz = CC(wr, D.nv, m, ivz, k, j, i); r.e = CC(wr, D.nv, m, IEN, k, j, i);
+            r.vz = CC(wr, D.nv, m, ivz, k, j, i); r.e = c->is_iso ? 0.0 : CC(wr, D.nv, m, IEN, k, j, i);
+            if (c->is_iso) {
+              if (c->rsolver == 11) hyd_llf_iso(c, &l, &r, &f);
+              else if (c->rsolver == 12) hyd_hlle_iso(c, &l, &r, &f);
+              else hyd_roe_iso(c, &l, &r, &f);
+            } else
             switch (c->rsolver) {
               case 10: hyd_advect(&l, &r, &f); break;
               case 11: hyd_llf(c, &l, &r, &f); break;
@@ -298,12 +420,12 @@ void oracle_hydro_fluxes(const ocfg *c, const double *w0, double *flx1, double *
             }
             double f5[5];
             f5[IDN] = f.d; f5[ivx] = f.mx; f5[ivy] = f.my; f5[ivz] = f.mz; f5[IEN] = f.e;
-            for (int n = 0; n < 5; ++n) {
+            for (int n = 0; n < D.nfl; ++n) {
               if (dir == 0) F1(flx1, m, n, k, j, i) = f5[n];
               else if (dir == 1) F2(flx2, m, n, k, j, i) = f5[n];
               else F3(flx3, m, n, k, j, i) = f5[n];
             }
-            for (int n = 5; n < D.nv; ++n) {   /* scalar fluxes, hydro_fluxes.cpp:126-138,165-177,204-216 */
+            for (int n = D.nfl; n < D.nv; ++n) {   /* scalar fluxes, hydro_fluxes.cpp:126-138,165-177,204-216 */
               double fd = f5[IDN];
               double v = fd * ((fd >= 0.0) ? CC(wl, D.nv, m, n, k, j, i) : CC(wr, D.nv, m, n, k, j, i));
               if (dir == 0) F1(flx1, m, n, k, j, i) = v;
@@ -345,8 +467,18 @@ void oracle_hydro_cons2prim(const ocfg *c, double *u0, double *w0, int il, int i
     for (int k = kl; k <= ku; ++k)
       for (int j = jl; j <= ju; ++j)
         for (int i = il; i <= iu; ++i) {
-          double ud = CC(u0, D.nv, m, IDN, k, j, i), ue = CC(u0, D.nv, m, IEN, k, j, i);
+          double ud = CC(u0, D.nv, m, IDN, k, j, i);
           double umx = CC(u0, D.nv, m, IM1, k, j, i), umy = CC(u0, D.nv, m, IM2, k, j, i), umz = CC(u0, D.nv, m, IM3, k, j, i);
+          if (c->is_iso) {   /* isothermal_hyd.cpp:25-45,60-130 */
+            if (ud < c->dfloor) { ud = c->dfloor; CC(u0, D.nv, m, IDN, k, j, i) = ud; nd++; }
+            double dii = 1.0 / ud;
+            CC(w0, D.nv, m, IDN, k, j, i) = ud; CC(w0, D.nv, m, IVX, k, j, i) = dii * umx;
+            CC(w0, D.nv, m, IVY, k, j, i) = dii * umy; CC(w0, D.nv, m, IVZ, k, j, i) = dii * umz;
+            for (int n = D.nfl; n < D.nv; ++n)   /* no scalar floor in the isothermal c2p */
+              CC(w0, D.nv, m, n, k, j, i) = CC(u0, D.nv, m, n, k, j, i) / ud;
+            continue;
+          }
+          double ue = CC(u0, D.nv, m, IEN, k, j, i);
           int dfl = 0, efl = 0, tfl = 0;
           double efloor = c->pfloor / (c->gamma - 1.0);
           if (ud < c->dfloor) { ud = c->dfloor; dfl = 1; }
@@ -365,7 +497,7 @@ void oracle_hydro_cons2prim(const ocfg *c, double *u0, double *w0, int il, int i
           if (tfl) { CC(u0, D.nv, m, IEN, k, j, i) = ue; nt++; }
           CC(w0, D.nv, m, IDN, k, j, i) = wd; CC(w0, D.nv, m, IVX, k, j, i) = wvx; CC(w0, D.nv, m, IVY, k, j, i) = wvy;
           CC(w0, D.nv, m, IVZ, k, j, i) = wvz; CC(w0, D.nv, m, IEN, k, j, i) = we;
-          for (int n = 5; n < D.nv; ++n) {   /* ideal_hyd.cpp:95-101 */
+          for (int n = D.nfl; n < D.nv; ++n) {   /* ideal_hyd.cpp:95-101 */
             if (CC(u0, D.nv, m, n, k, j, i) < 0.0) CC(u0, D.nv, m, n, k, j, i) = 0.0;
             CC(w0, D.nv, m, n, k, j, i) = CC(u0, D.nv, m, n, k, j, i) / ud;
           }
@@ -382,8 +514,11 @@ double oracle_hydro_new_dt(const ocfg *c, const double *w0, const double *mb_siz
     for (int k = D.ks; k <= D.ke; ++k)
       for (int j = D.js; j <= D.je; ++j)
         for (int i = D.is; i <= D.ie; ++i) {
-          double p = (c->gamma - 1.0) * CC(w0, D.nv, m, IEN, k, j, i);
-          double cs = sound_speed(c->gamma, CC(w0, D.nv, m, IDN, k, j, i), p);
+          double cs = c->iso_cs;                                    /* hydro_newdt.cpp:107-112 */
+          if (!c->is_iso) {
+            double p = (c->gamma - 1.0) * CC(w0, D.nv, m, IEN, k, j, i);
+            cs = sound_speed(c->gamma, CC(w0, D.nv, m, IDN, k, j, i), p);
+          }
           double max_dv1 = fabs(CC(w0, D.nv, m, IVX, k, j, i)) + cs;
           double max_dv2 = fabs(CC(w0, D.nv, m, IVY, k, j, i)) + cs;
           double max_dv3 = fabs(CC(w0, D.nv, m, IVZ, k, j, i)) + cs;
@@ -405,7 +540,7 @@ int oracle_hydro_apply_bcs(const ocfg *c, const int *mesh_bcs, const int *mb_bcs
   for (int d = 0; d < 3; ++d) {
     if ((d == 1 && c->nx2 <= 1) || (d == 2 && c->nx3 <= 1)) continue;
     if (mesh_bcs[2 * d] == BC_PERIODIC || (d == 0 && mesh_bcs[0] == BC_SHEAR)) continue;
-    bc_array(c, u0, 5 + c->nscalars, -1, d, mb_bcs);
+    bc_array(c, u0, (c->is_iso ? 4 : 5) + c->nscalars, -1, d, mb_bcs);
   }
   return 0;
 }

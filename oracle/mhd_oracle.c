@@ -24,7 +24,9 @@ typedef struct {
   int recon;   /* 0 dc, 1 plm, 2 ppm4, 3 ppmx, 4 wenoz, 5 teno   (athena.hpp:75) */
   int rsolver; /* 0 llf, 1 hlle, 2 hlld                   (mhd.hpp:39)    */
   double gamma, dfloor, pfloor, tfloor, sfloor, sigma_max; /* eos.hpp:27-33 */
-  int nscalars; /* passive scalars stored after the 5 fluid variables (mhd.cpp / hydro.cpp:75) */
+  int nscalars; /* passive scalars stored after the fluid variables (mhd.cpp / hydro.cpp:75) */
+  int is_iso;   /* 1: isothermal EOS (eos/isothermal_mhd.cpp, isothermal_hyd.cpp): 4 fluid variables, no IEN */
+  double iso_cs;
 } ocfg;
 
 enum { IDN = 0, IM1 = 1, IM2 = 2, IM3 = 3, IEN = 4, IVX = 1, IVY = 2, IVZ = 3 };
@@ -32,7 +34,8 @@ enum { IDN = 0, IM1 = 1, IM2 = 2, IM3 = 3, IEN = 4, IVX = 1, IVY = 2, IVZ = 3 };
 
 typedef struct {
   int n1, n2, n3, is, ie, js, je, ks, ke;
-  int nv;                    /* 5 + nscalars: variables per cell-centred / flux array */
+  int nfl;                   /* fluid variables: 5 (ideal gas) or 4 (isothermal) */
+  int nv;                    /* nfl + nscalars: variables per cell-centred / flux array */
   size_t cc;                 /* cells per variable per block  */
   size_t f1, f2, f3;         /* faces per block               */
   size_t e1, e2, e3;         /* edges per block               */
@@ -46,7 +49,8 @@ static odims dims(const ocfg *c) {
   d.is = c->ng; d.ie = d.is + c->nx1 - 1;
   d.js = multi_d ? c->ng : 0; d.je = d.js + c->nx2 - 1;
   d.ks = three_d ? c->ng : 0; d.ke = d.ks + c->nx3 - 1;
-  d.nv = 5 + c->nscalars;
+  d.nfl = c->is_iso ? 4 : 5;
+  d.nv = d.nfl + c->nscalars;
   d.cc = (size_t)d.n3 * d.n2 * d.n1;
   d.f1 = (size_t)d.n3 * d.n2 * (d.n1 + 1);
   d.f2 = (size_t)d.n3 * (d.n2 + 1) * d.n1;
@@ -253,7 +257,7 @@ static void recon_pass(const ocfg *c, int dir, int nv, int apply_floors, const d
             }
             if (apply_floors && c->recon >= 3) { /* recon.hpp:78-108: ppmx/wenoz/teno only */
               if (n == IDN) { ql = fmax(ql, dfloor); qr = fmax(qr, dfloor); }
-              if (n == IEN) { ql = fmax(ql, efloor); qr = fmax(qr, efloor); }
+              if (n == IEN && !c->is_iso) { ql = fmax(ql, efloor); qr = fmax(qr, efloor); }   /* recon.hpp:80: is_ideal */
             }
             CC(wl, nv, m, n, k + dk, j + dj, i + di) = ql;
             CC(wr, nv, m, n, k, j, i) = qr;
@@ -563,6 +567,194 @@ static void hlld_face(const ocfg *c, const prim1d *wl, const prim1d *wr, double 
   }
 }
 
+/* eos.hpp:60-68: isothermal fast speed */
+static double fast_speed_iso(double iso_cs, double d, double bx, double by, double bz) {
+  double asq = (iso_cs * iso_cs) * d;
+  double ct2 = by * by + bz * bz;
+  double qsq = bx * bx + ct2 + asq;
+  double tmp = bx * bx + ct2 - asq;
+  return sqrt(0.5 * (qsq + sqrt(tmp * tmp + 4.0 * asq * ct2)) / d);
+}
+
+/* llf_mhd_singlestate.hpp:27-89, isothermal branches */
+static void llf_face_iso(const ocfg *c, const prim1d *wl, const prim1d *wr, double bxi, cons1d *flux) {
+  double qa = wl->d * wl->vx;
+  double qb = wr->d * wr->vx;
+  double qc = 0.5 * (SQR(wl->by) + SQR(wl->bz) - SQR(bxi));
+  double qd = 0.5 * (SQR(wr->by) + SQR(wr->bz) - SQR(bxi));
+  cons1d fsum, du;
+  fsum.d = qa + qb;
+  fsum.mx = qa * wl->vx + qb * wr->vx + qc + qd;
+  fsum.my = qa * wl->vy + qb * wr->vy - bxi * (wl->by + wr->by);
+  fsum.mz = qa * wl->vz + qb * wr->vz - bxi * (wl->bz + wr->bz);
+  fsum.by = wl->by * wl->vx + wr->by * wr->vx - bxi * (wl->vy + wr->vy);
+  fsum.bz = wl->bz * wl->vx + wr->bz * wr->vx - bxi * (wl->vz + wr->vz);
+  fsum.mx += SQR(c->iso_cs) * (wl->d + wr->d);
+  qa = fast_speed_iso(c->iso_cs, wl->d, bxi, wl->by, wl->bz);
+  qb = fast_speed_iso(c->iso_cs, wr->d, bxi, wr->by, wr->bz);
+  double a = fmax((fabs(wl->vx) + qa), (fabs(wr->vx) + qb));
+  du.d = a * (wr->d - wl->d);
+  du.mx = a * (wr->d * wr->vx - wl->d * wl->vx);
+  du.my = a * (wr->d * wr->vy - wl->d * wl->vy);
+  du.mz = a * (wr->d * wr->vz - wl->d * wl->vz);
+  du.by = a * (wr->by - wl->by);
+  du.bz = a * (wr->bz - wl->bz);
+  flux->d = 0.5 * (fsum.d - du.d);
+  flux->mx = 0.5 * (fsum.mx - du.mx);
+  flux->my = 0.5 * (fsum.my - du.my);
+  flux->mz = 0.5 * (fsum.mz - du.mz);
+  flux->e = 0.0;
+  flux->by = -0.5 * (fsum.by - du.by);
+  flux->bz = 0.5 * (fsum.bz - du.bz);
+}
+
+/* hlle_mhd.hpp:24-179, isothermal branches; ey/ez as stored by the reference */
+static void hlle_face_iso(const ocfg *c, const prim1d *wl, const prim1d *wr, double bxi, cons1d *flux, double *ey, double *ez) {
+  const double iso_cs = c->iso_cs;
+  double sqrtdl = sqrt(wl->d), sqrtdr = sqrt(wr->d);
+  double isdlpdr = 1.0 / (sqrtdl + sqrtdr);
+  double wroe_idn = sqrtdl * sqrtdr;
+  double wroe_ivx = (sqrtdl * wl->vx + sqrtdr * wr->vx) * isdlpdr;
+  double wroe_iby = (sqrtdr * wl->by + sqrtdl * wr->by) * isdlpdr;
+  double wroe_ibz = (sqrtdr * wl->bz + sqrtdl * wr->bz) * isdlpdr;
+  double x = 0.5 * (SQR(wl->by - wr->by) + SQR(wl->bz - wr->bz)) / (SQR(sqrtdl + sqrtdr));
+  double y = 0.5 * (wl->d + wr->d) / wroe_idn;
+  double pbl = 0.5 * (bxi * bxi + SQR(wl->by) + SQR(wl->bz));
+  double pbr = 0.5 * (bxi * bxi + SQR(wr->by) + SQR(wr->bz));
+  double cl = fast_speed_iso(iso_cs, wl->d, bxi, wl->by, wl->bz);
+  double cr = fast_speed_iso(iso_cs, wr->d, bxi, wr->by, wr->bz);
+  double btsq = SQR(wroe_iby) + SQR(wroe_ibz);
+  double vaxsq = bxi * bxi / wroe_idn;
+  double bt_starsq = btsq * y;
+  double twid_asq = iso_cs * iso_cs + x;
+  double ct2 = bt_starsq / wroe_idn;
+  double tsum = vaxsq + ct2 + twid_asq;
+  double tdif = vaxsq + ct2 - twid_asq;
+  double cf2_cs2 = sqrt(tdif * tdif + 4.0 * twid_asq * ct2);
+  double cfsq = 0.5 * (tsum + cf2_cs2);
+  double a = sqrt(cfsq);
+  double al = fmin((wroe_ivx - a), (wl->vx - cl));
+  double ar = fmax((wroe_ivx + a), (wr->vx + cr));
+  double bp = ar > 0.0 ? ar : 1.0e-20;
+  double bm = al < 0.0 ? al : -1.0e-20;
+  double vxl = wl->vx - bm, vxr = wr->vx - bp;
+  cons1d fl, fr;
+  fl.d = wl->d * vxl;                                  fr.d = wr->d * vxr;
+  fl.mx = wl->d * wl->vx * vxl + pbl - SQR(bxi);       fr.mx = wr->d * wr->vx * vxr + pbr - SQR(bxi);
+  fl.my = wl->d * wl->vy * vxl - bxi * wl->by;         fr.my = wr->d * wr->vy * vxr - bxi * wr->by;
+  fl.mz = wl->d * wl->vz * vxl - bxi * wl->bz;         fr.mz = wr->d * wr->vz * vxr - bxi * wr->bz;
+  fl.mx += (iso_cs * iso_cs) * wl->d;                  fr.mx += (iso_cs * iso_cs) * wr->d;
+  fl.by = wl->by * vxl - bxi * wl->vy;                 fr.by = wr->by * vxr - bxi * wr->vy;
+  fl.bz = wl->bz * vxl - bxi * wl->vz;                 fr.bz = wr->bz * vxr - bxi * wr->vz;
+  double tmp = 0.0;
+  if (bp != bm) tmp = 0.5 * (bp + bm) / (bp - bm);
+  flux->d = 0.5 * (fl.d + fr.d) + (fl.d - fr.d) * tmp;
+  flux->mx = 0.5 * (fl.mx + fr.mx) + (fl.mx - fr.mx) * tmp;
+  flux->my = 0.5 * (fl.my + fr.my) + (fl.my - fr.my) * tmp;
+  flux->mz = 0.5 * (fl.mz + fr.mz) + (fl.mz - fr.mz) * tmp;
+  flux->e = 0.0;
+  *ey = -0.5 * (fl.by + fr.by) - (fl.by - fr.by) * tmp;
+  *ez = 0.5 * (fl.bz + fr.bz) + (fl.bz - fr.bz) * tmp;
+}
+
+/* hlld_mhd.hpp:350-546: isothermal HLLD (Mignone 2007) */
+static void hlld_face_iso(const ocfg *c, const prim1d *wl, const prim1d *wr, double bxi, cons1d *flxi) {
+  const double dfloor_ = c->dfloor, iso_cs = c->iso_cs;
+  double spd[5];
+  cons1d ul, ur;
+  ul.d = wl->d; ul.mx = wl->vx * ul.d; ul.my = wl->vy * ul.d; ul.mz = wl->vz * ul.d; ul.by = wl->by; ul.bz = wl->bz;
+  ur.d = wr->d; ur.mx = wr->vx * ur.d; ur.my = wr->vy * ur.d; ur.mz = wr->vz * ur.d; ur.by = wr->by; ur.bz = wr->bz;
+  double cfl = fast_speed_iso(iso_cs, wl->d, bxi, wl->by, wl->bz);
+  double cfr = fast_speed_iso(iso_cs, wr->d, bxi, wr->by, wr->bz);
+  spd[0] = fmin(wl->vx - cfl, wr->vx - cfr);
+  spd[4] = fmax(wl->vx + cfl, wr->vx + cfr);
+  double bxsq = bxi * bxi;
+  double ptl = SQR(iso_cs) * wl->d + 0.5 * (bxsq + SQR(wl->by) + SQR(wl->bz));
+  double ptr = SQR(iso_cs) * wr->d + 0.5 * (bxsq + SQR(wr->by) + SQR(wr->bz));
+  cons1d fl, fr;
+  fl.d = ul.mx;
+  fl.mx = ul.mx * wl->vx + ptl - bxsq;
+  fl.my = ul.my * wl->vx - bxi * ul.by;
+  fl.mz = ul.mz * wl->vx - bxi * ul.bz;
+  fl.by = ul.by * wl->vx - bxi * wl->vy;
+  fl.bz = ul.bz * wl->vx - bxi * wl->vz;
+  fr.d = ur.mx;
+  fr.mx = ur.mx * wr->vx + ptr - bxsq;
+  fr.my = ur.my * wr->vx - bxi * ur.by;
+  fr.mz = ur.mz * wr->vx - bxi * ur.bz;
+  fr.by = ur.by * wr->vx - bxi * wr->vy;
+  fr.bz = ur.bz * wr->vx - bxi * wr->vz;
+  double idspd = 1.0 / (spd[4] - spd[0]);
+  double dhll = (spd[4] * ur.d - spd[0] * ul.d - fr.d + fl.d) * idspd;
+  dhll = fmax(dhll, dfloor_);
+  double sqrtdhll = sqrt(dhll);
+  double fdhll = (spd[4] * fl.d - spd[0] * fr.d + spd[4] * spd[0] * (ur.d - ul.d)) * idspd;
+  double fmxhll = (spd[4] * fl.mx - spd[0] * fr.mx + spd[4] * spd[0] * (ur.mx - ul.mx)) * idspd;
+  double ustar = fdhll / dhll;
+  double mxhll = (spd[4] * ur.mx - spd[0] * ul.mx - fr.mx + fl.mx) * idspd;
+  spd[1] = ustar - fabs(bxi) / sqrtdhll;
+  spd[3] = ustar + fabs(bxi) / sqrtdhll;
+  cons1d ulst, urst, ucst;
+  ulst.d = dhll; ulst.mx = mxhll;
+  double tmp = (spd[0] - spd[1]) * (spd[0] - spd[3]);
+  if (fabs(spd[0] - spd[1]) < (HLLD_SMALL_NUMBER)*iso_cs) {
+    ulst.my = ul.my; ulst.mz = ul.mz; ulst.by = ul.by; ulst.bz = ul.bz;
+  } else {
+    double mfact = bxi * (ustar - wl->vx) / tmp;
+    double bfact = (ul.d * SQR(spd[0] - wl->vx) - bxsq) / (dhll * tmp);
+    ulst.my = dhll * wl->vy - ul.by * mfact;
+    ulst.mz = dhll * wl->vz - ul.bz * mfact;
+    ulst.by = ul.by * bfact;
+    ulst.bz = ul.bz * bfact;
+  }
+  urst.d = dhll; urst.mx = mxhll;
+  tmp = (spd[4] - spd[1]) * (spd[4] - spd[3]);
+  if (fabs(spd[4] - spd[3]) < (HLLD_SMALL_NUMBER)*iso_cs) {
+    urst.my = ur.my; urst.mz = ur.mz; urst.by = ur.by; urst.bz = ur.bz;
+  } else {
+    double mfact = bxi * (ustar - wr->vx) / tmp;
+    double bfact = (ur.d * SQR(spd[4] - wr->vx) - bxsq) / (dhll * tmp);
+    urst.my = dhll * wr->vy - ur.by * mfact;
+    urst.mz = dhll * wr->vz - ur.bz * mfact;
+    urst.by = ur.by * bfact;
+    urst.bz = ur.bz * bfact;
+  }
+  double x = sqrtdhll * (bxi > 0.0 ? 1.0 : -1.0);
+  ucst.d = dhll; ucst.mx = mxhll;
+  ucst.my = 0.5 * (ulst.my + urst.my + (urst.by - ulst.by) * x);
+  ucst.mz = 0.5 * (ulst.mz + urst.mz + (urst.bz - ulst.bz) * x);
+  ucst.by = 0.5 * (ulst.by + urst.by + (urst.my - ulst.my) / x);
+  ucst.bz = 0.5 * (ulst.bz + urst.bz + (urst.mz - ulst.mz) / x);
+  if (spd[0] >= 0.0) {
+    *flxi = fl;
+  } else if (spd[4] <= 0.0) {
+    *flxi = fr;
+  } else if (spd[1] >= 0.0) {
+    flxi->d = fl.d + spd[0] * (ulst.d - ul.d);
+    flxi->mx = fl.mx + spd[0] * (ulst.mx - ul.mx);
+    flxi->my = fl.my + spd[0] * (ulst.my - ul.my);
+    flxi->mz = fl.mz + spd[0] * (ulst.mz - ul.mz);
+    flxi->by = fl.by + spd[0] * (ulst.by - ul.by);
+    flxi->bz = fl.bz + spd[0] * (ulst.bz - ul.bz);
+  } else if (spd[3] <= 0.0) {
+    flxi->d = fr.d + spd[4] * (urst.d - ur.d);
+    flxi->mx = fr.mx + spd[4] * (urst.mx - ur.mx);
+    flxi->my = fr.my + spd[4] * (urst.my - ur.my);
+    flxi->mz = fr.mz + spd[4] * (urst.mz - ur.mz);
+    flxi->by = fr.by + spd[4] * (urst.by - ur.by);
+    flxi->bz = fr.bz + spd[4] * (urst.bz - ur.bz);
+  } else {
+    flxi->d = dhll * ustar;
+    flxi->mx = fmxhll;
+    flxi->my = ucst.my * ustar - bxi * ucst.by;
+    flxi->mz = ucst.mz * ustar - bxi * ucst.bz;
+    flxi->by = ucst.by * ustar - bxi * ucst.my / ucst.d;
+    flxi->bz = ucst.bz * ustar - bxi * ucst.mz / ucst.d;
+  }
+  flxi->e = 0.0;
+}
+
+
 /* mhd_fluxes.cpp:47-77 (SolveFaceMHD) for one face; writes 5 fluxes into f[0..4] in the
  * UNROTATED variable order and the two EMFs (ey,ez). */
 static void solve_face(const ocfg *c, int dir, const double *wl5, const double *wr5,
@@ -571,11 +763,18 @@ static void solve_face(const ocfg *c, int dir, const double *wl5, const double *
   const int ivx = IVX + dir, ivy = IVX + (dir + 1) % 3, ivz = IVX + (dir + 2) % 3;
   const int iby = (dir + 1) % 3, ibz = (dir + 2) % 3;
   prim1d l, r;
-  l.d = wl5[IDN]; l.vx = wl5[ivx]; l.vy = wl5[ivy]; l.vz = wl5[ivz]; l.e = wl5[IEN];
+  l.d = wl5[IDN]; l.vx = wl5[ivx]; l.vy = wl5[ivy]; l.vz = wl5[ivz]; l.e = c->is_iso ? 0.0 : wl5[IEN];
   l.by = bl3[iby]; l.bz = bl3[ibz];
-  r.d = wr5[IDN]; r.vx = wr5[ivx]; r.vy = wr5[ivy]; r.vz = wr5[ivz]; r.e = wr5[IEN];
+  r.d = wr5[IDN]; r.vx = wr5[ivx]; r.vy = wr5[ivy]; r.vz = wr5[ivz]; r.e = c->is_iso ? 0.0 : wr5[IEN];
   r.by = br3[iby]; r.bz = br3[ibz];
   cons1d fx;
+  if (c->is_iso) {
+    if (c->rsolver == 2) { hlld_face_iso(c, &l, &r, bxi, &fx); *ey = -fx.by; *ez = fx.bz; }
+    else if (c->rsolver == 1) { hlle_face_iso(c, &l, &r, bxi, &fx, ey, ez); }
+    else { llf_face_iso(c, &l, &r, bxi, &fx); *ey = fx.by; *ez = fx.bz; }
+    f5[IDN] = fx.d; f5[ivx] = fx.mx; f5[ivy] = fx.my; f5[ivz] = fx.mz;
+    return;
+  }
   if (c->rsolver == 2) {
     hlld_face(c, &l, &r, bxi, &fx);
     *ey = -fx.by; *ez = fx.bz;                     /* hlld_mhd.hpp:346-347 */
@@ -615,31 +814,31 @@ void oracle_fluxes(const ocfg *c, const double *w0, const double *bcc0, const do
         for (int j = fjl; j <= fju; ++j)
           for (int i = fil; i <= fiu; ++i) {
             double wl5[5], wr5[5], bl3[3], br3[3], f5[5], ey, ez, bxi;
-            for (int n = 0; n < 5; ++n) { wl5[n] = CC(wl, D.nv, m, n, k, j, i); wr5[n] = CC(wr, D.nv, m, n, k, j, i); }
+            for (int n = 0; n < D.nfl; ++n) { wl5[n] = CC(wl, D.nv, m, n, k, j, i); wr5[n] = CC(wr, D.nv, m, n, k, j, i); }
             for (int n = 0; n < 3; ++n) { bl3[n] = CC(bl, 3, m, n, k, j, i); br3[n] = CC(br, 3, m, n, k, j, i); }
             if (dir == 0) bxi = X1F(b1f, m, k, j, i);
             else if (dir == 1) bxi = X2F(b2f, m, k, j, i);
             else bxi = X3F(b3f, m, k, j, i);
             solve_face(c, dir, wl5, wr5, bl3, br3, bxi, f5, &ey, &ez);
             if (dir == 0) {
-              for (int n = 0; n < 5; ++n) F1(flx1, m, n, k, j, i) = f5[n];
+              for (int n = 0; n < D.nfl; ++n) F1(flx1, m, n, k, j, i) = f5[n];
               S4(e3x1, m, k, j, i) = ey; S4(e2x1, m, k, j, i) = ez;   /* mhd_fluxes.cpp:146 */
             } else if (dir == 1) {
-              for (int n = 0; n < 5; ++n) F2(flx2, m, n, k, j, i) = f5[n];
+              for (int n = 0; n < D.nfl; ++n) F2(flx2, m, n, k, j, i) = f5[n];
               S4(e1x2, m, k, j, i) = ey; S4(e3x2, m, k, j, i) = ez;   /* :196 */
             } else {
-              for (int n = 0; n < 5; ++n) F3(flx3, m, n, k, j, i) = f5[n];
+              for (int n = 0; n < D.nfl; ++n) F3(flx3, m, n, k, j, i) = f5[n];
               S4(e2x3, m, k, j, i) = ey; S4(e1x3, m, k, j, i) = ez;   /* :243 */
             }
           }
     /* scalar fluxes, upwinded by the sign of the mass flux, ACTIVE transverse range only
      * (mhd_fluxes.cpp:153-166,203-216,250-263) */
-    if (D.nv > 5)
+    if (D.nv > D.nfl)
       for (int m = 0; m < c->nmb; ++m)
         for (int k = ks; k <= ke + (dir == 2); ++k)
           for (int j = js; j <= je + (dir == 1); ++j)
             for (int i = is; i <= ie + (dir == 0); ++i)
-              for (int n = 5; n < D.nv; ++n) {
+              for (int n = D.nfl; n < D.nv; ++n) {
                 if (dir == 0) F1(flx1, m, n, k, j, i) = F1(flx1, m, IDN, k, j, i) * ((F1(flx1, m, IDN, k, j, i) >= 0.0) ? CC(wl, D.nv, m, n, k, j, i) : CC(wr, D.nv, m, n, k, j, i));
                 else if (dir == 1) F2(flx2, m, n, k, j, i) = F2(flx2, m, IDN, k, j, i) * ((F2(flx2, m, IDN, k, j, i) >= 0.0) ? CC(wl, D.nv, m, n, k, j, i) : CC(wr, D.nv, m, n, k, j, i));
                 else F3(flx3, m, n, k, j, i) = F3(flx3, m, IDN, k, j, i) * ((F3(flx3, m, IDN, k, j, i) >= 0.0) ? CC(wl, D.nv, m, n, k, j, i) : CC(wr, D.nv, m, n, k, j, i));
@@ -810,10 +1009,22 @@ void oracle_cons2prim(const ocfg *c, double *u0, const double *b1f, const double
         for (int i = il; i <= iu; ++i) {
           double ud = CC(u0, D.nv, m, IDN, k, j, i), umx = CC(u0, D.nv, m, IM1, k, j, i);
           double umy = CC(u0, D.nv, m, IM2, k, j, i), umz = CC(u0, D.nv, m, IM3, k, j, i);
-          double ue = CC(u0, D.nv, m, IEN, k, j, i);
           double ubx = 0.5 * (X1F(b1f, m, k, j, i) + X1F(b1f, m, k, j, i + 1));
           double uby = 0.5 * (X2F(b2f, m, k, j, i) + X2F(b2f, m, k, j + 1, i));
           double ubz = 0.5 * (X3F(b3f, m, k, j, i) + X3F(b3f, m, k + 1, j, i));
+          if (c->is_iso) {   /* isothermal_mhd.cpp:28-46,95-135 */
+            const double b2i = SQR(ubx) + SQR(uby) + SQR(ubz);
+            const double dfl_ = fmax(c->dfloor, b2i / c->sigma_max);
+            if (ud < dfl_) { ud = dfl_; CC(u0, D.nv, m, IDN, k, j, i) = ud; nd++; }
+            double dii = 1.0 / ud;
+            CC(w0, D.nv, m, IDN, k, j, i) = ud; CC(w0, D.nv, m, IVX, k, j, i) = dii * umx;
+            CC(w0, D.nv, m, IVY, k, j, i) = dii * umy; CC(w0, D.nv, m, IVZ, k, j, i) = dii * umz;
+            CC(bcc, 3, m, 0, k, j, i) = ubx; CC(bcc, 3, m, 1, k, j, i) = uby; CC(bcc, 3, m, 2, k, j, i) = ubz;
+            for (int n = D.nfl; n < D.nv; ++n)   /* no scalar floor in the isothermal c2p */
+              CC(w0, D.nv, m, n, k, j, i) = CC(u0, D.nv, m, n, k, j, i) / ud;
+            continue;
+          }
+          double ue = CC(u0, D.nv, m, IEN, k, j, i);
           int dfl = 0, efl = 0, tfl = 0;
           const double b2 = SQR(ubx) + SQR(uby) + SQR(ubz);
           const double dfloor_ = fmax(c->dfloor, b2 / c->sigma_max);
@@ -838,7 +1049,7 @@ void oracle_cons2prim(const ocfg *c, double *u0, const double *b1f, const double
           CC(w0, D.nv, m, IVY, k, j, i) = wvy; CC(w0, D.nv, m, IVZ, k, j, i) = wvz;
           CC(w0, D.nv, m, IEN, k, j, i) = we;
           CC(bcc, 3, m, 0, k, j, i) = ubx; CC(bcc, 3, m, 1, k, j, i) = uby; CC(bcc, 3, m, 2, k, j, i) = ubz;
-          for (int n = 5; n < D.nv; ++n) {   /* ideal_mhd.cpp:113-120: scalar floor, then s/d */
+          for (int n = D.nfl; n < D.nv; ++n) {   /* ideal_mhd.cpp:113-120: scalar floor, then s/d */
             if (CC(u0, D.nv, m, n, k, j, i) < 0.0) CC(u0, D.nv, m, n, k, j, i) = 0.0;
             CC(w0, D.nv, m, n, k, j, i) = CC(u0, D.nv, m, n, k, j, i) / ud;
           }
@@ -860,12 +1071,12 @@ double oracle_new_dt(const ocfg *c, const double *w0, const double *bcc, const d
         for (int i = D.is; i <= D.ie; ++i) {
           double w_d = CC(w0, D.nv, m, IDN, k, j, i);
           double w_bx = CC(bcc, 3, m, 0, k, j, i), w_by = CC(bcc, 3, m, 1, k, j, i), w_bz = CC(bcc, 3, m, 2, k, j, i);
-          double p = gm1 * CC(w0, D.nv, m, IEN, k, j, i);
-          double cf = fast_speed(c->gamma, w_d, p, w_bx, w_by, w_bz);
+          double p = c->is_iso ? 0.0 : gm1 * CC(w0, D.nv, m, IEN, k, j, i);
+          double cf = c->is_iso ? fast_speed_iso(c->iso_cs, w_d, w_bx, w_by, w_bz) : fast_speed(c->gamma, w_d, p, w_bx, w_by, w_bz);
           double max_dv1 = fabs(CC(w0, D.nv, m, IVX, k, j, i)) + cf;
-          cf = fast_speed(c->gamma, w_d, p, w_by, w_bz, w_bx);
+          cf = c->is_iso ? fast_speed_iso(c->iso_cs, w_d, w_by, w_bz, w_bx) : fast_speed(c->gamma, w_d, p, w_by, w_bz, w_bx);
           double max_dv2 = fabs(CC(w0, D.nv, m, IVY, k, j, i)) + cf;
-          cf = fast_speed(c->gamma, w_d, p, w_bz, w_bx, w_by);
+          cf = c->is_iso ? fast_speed_iso(c->iso_cs, w_d, w_bz, w_bx, w_by) : fast_speed(c->gamma, w_d, p, w_bz, w_bx, w_by);
           double max_dv3 = fabs(CC(w0, D.nv, m, IVZ, k, j, i)) + cf;
           dt1 = fmin((dx1 / max_dv1), dt1);
           dt2 = fmin((dx2 / max_dv2), dt2);
@@ -1191,7 +1402,7 @@ int oracle_apply_bcs(const ocfg *c, const int *mesh_bcs, const int *mb_bcs, doub
   for (int d = 0; d < 3; ++d) {        /* hydro_bcs.cpp:80-81,167,252: gate on the mesh flag */
     if ((d == 1 && c->nx2 <= 1) || (d == 2 && c->nx3 <= 1)) continue;   /* :164 one_d, :249 two_d */
     if (mesh_bcs[2 * d] == BC_PERIODIC || (d == 0 && mesh_bcs[0] == BC_SHEAR)) continue;
-    bc_array(c, u0, 5 + c->nscalars, -1, d, mb_bcs);
+    bc_array(c, u0, (c->is_iso ? 4 : 5) + c->nscalars, -1, d, mb_bcs);
   }
   for (int d = 0; d < 3; ++d) {        /* bfield_bcs.cpp:78,169,262 */
     if ((d == 1 && c->nx2 <= 1) || (d == 2 && c->nx3 <= 1)) continue;   /* :165 one_d, :258 two_d */

@@ -82,7 +82,22 @@ def mhd_lowd(deck, base, name, overrides=()):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def iso():
+    """Isothermal-EOS fixtures (tests/iso_util.py CASES): ghost-inclusive initial and final dumps."""
+    import iso_util as I
+    for name, c in I.CASES.items():
+        r0, r1 = I.reference(name)
+        out = dict(deck=np.array(r0.deck), lloc=r0.lloc, u0_c0=r0.u0, u0_final=r1.u0, time_final=r1.time,
+                   dt_final=r1.dt, ncycle_final=r1.ncycle)
+        if c[3] == "mhd":
+            out.update(b1f_c0=r0.b1f, b2f_c0=r0.b2f, b3f_c0=r0.b3f, b1f_final=r1.b1f, b2f_final=r1.b2f, b3f_final=r1.b3f)
+        np.savez_compressed(os.path.join(HERE, "golden", name + ".npz"), **out)
+
+
 if __name__ == "__main__":
+    iso()
+    if "--iso-only" in sys.argv:
+        sys.exit(0)
     mhd_lowd("bw1d.athinput", "BrioWu", "mhd_bw1d_ppm4_hlld_rk3",
              ("mhd/rsolver=hlld", "mhd/reconstruct=ppm4", "mesh/nghost=3", "time/integrator=rk3", "mesh/nx1=128", "meshblock/nx1=32"))
     mhd_lowd("bw2d.athinput", "BrioWu", "mhd_bw2d_ppm4_hlld_rk3", ("time/tlim=0.03",))

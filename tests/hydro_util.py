@@ -49,6 +49,10 @@ class Case:
         self.recon, self.rsolver = p[ph + "/reconstruct"], p[ph + "/rsolver"]
         self.gamma = float(p[ph + "/gamma"])
         self.nscalars = int(p.get(ph + "/nscalars", 0))
+        self.iso = p.get(ph + "/eos", "ideal") == "isothermal"
+        self.iso_cs = float(p.get(ph + "/iso_sound_speed", 1.0))
+        self.nfl = 4 if self.iso else 5
+        self.nvar = self.nfl + self.nscalars
         self.integrator = p["time/integrator"]
         self.cfl, self.tlim = float(p["time/cfl_number"]), float(p["time/tlim"])
         periodic = [self.mesh_bcs[2 * d] == O.BC["periodic"] for d in range(3)]
@@ -60,7 +64,7 @@ class Case:
     def ocfg(self):
         rs = O.RSOLVER[self.rsolver] if self.physics == "mhd" else O.HYD_RSOLVER[self.rsolver]
         return O.OCfg(self.nmb, self.ng, *self.nblock, O.RECON[self.recon], rs, self.gamma,
-                      O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, self.nscalars)
+                      O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, self.nscalars, 1 if self.iso else 0, self.iso_cs)
 
 
 def oracle_run(case: Case, u_init, ncycles=-1, time0=0.0):
@@ -95,7 +99,7 @@ def oracle_run_mhd(case: Case, u_init, b_init, ncycles=-1, time0=0.0):
     if not case.strictly_periodic:
         L.oracle_set_bcs(O.ip(case.mesh_bcs), O.ip(case.mb_bcs))
     try:
-        L.oracle_halo_cc(C.byref(cfg), O.p(A.u0), 5 + case.nscalars, O.ip(case.nghbr))
+        L.oracle_halo_cc(C.byref(cfg), O.p(A.u0), case.nvar, O.ip(case.nghbr))
         L.oracle_halo_fc(C.byref(cfg), *[O.p(a) for a in A.b0], O.ip(case.nghbr))
         if not case.strictly_periodic:
             assert L.oracle_apply_bcs(C.byref(cfg), O.ip(case.mesh_bcs), O.ip(case.mb_bcs), O.p(A.u0), *[O.p(a) for a in A.b0]) == 0

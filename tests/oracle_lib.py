@@ -22,7 +22,8 @@ class OCfg(C.Structure):
     _fields_ = [("nmb", C.c_int), ("ng", C.c_int), ("nx1", C.c_int), ("nx2", C.c_int),
                 ("nx3", C.c_int), ("recon", C.c_int), ("rsolver", C.c_int),
                 ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
-                ("tfloor", C.c_double), ("sfloor", C.c_double), ("sigma_max", C.c_double), ("nscalars", C.c_int)]
+                ("tfloor", C.c_double), ("sfloor", C.c_double), ("sigma_max", C.c_double), ("nscalars", C.c_int),
+                ("is_iso", C.c_int), ("iso_cs", C.c_double)]
 
 
 class OState(C.Structure):
@@ -76,7 +77,7 @@ class Arrays:
         n1, n2, n3 = cfg.nx1 + 2 * ng, (cfg.nx2 + 2 * ng if cfg.nx2 > 1 else 1), (cfg.nx3 + 2 * ng if cfg.nx3 > 1 else 1)
         self.cfg, self.n = cfg, (n1, n2, n3)
         z = np.zeros
-        nv = 5 + cfg.nscalars
+        nv = (4 if cfg.is_iso else 5) + cfg.nscalars
         self.u0, self.u1, self.w0 = (z((nmb, nv, n3, n2, n1)) for _ in range(3))
         self.bcc0 = z((nmb, 3, n3, n2, n1))
         self.b0 = [z((nmb, n3, n2, n1 + 1)), z((nmb, n3, n2 + 1, n1)), z((nmb, n3 + 1, n2, n1))]
