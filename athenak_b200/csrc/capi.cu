@@ -18,7 +18,9 @@ struct Handle {
   akb::EosParams eos;
   bool hydro = false;                       // hydro twin (ak_hydro_*): no magnetic arrays, 1-D/2-D/3-D
   int rs = 0;                               // internal solver code (cfg.rsolver, + 20 when isothermal)
-  int *d_counters = nullptr;                // 3 ints
+  int *d_counters = nullptr;                // 4 ints: dfloor, efloor, tfloor, fofc
+  unsigned char *d_fofc = nullptr;          // FOFC cell flags, nmb*cc bytes (cfg.fofc)
+  double stage_rk[3] = {0.0, 1.0, 0.0};     // gam0, gam1, beta*dt for the fused FOFC call (ak_mhd_set_stage)
   unsigned long long *d_dtmin = nullptr;    // 3 ordered-bit doubles
   double *d_hst = nullptr;                  // history-sum scratch, allocated on first use
   std::string err;
@@ -86,6 +88,12 @@ int check_cfg(const ak_mhd_cfg *c, bool hydro, std::string &why) {
     if (hydro && c->rsolver == AK_RSOLVER_HYD_HLLC) { why = "rsolver hllc cannot be used with isothermal EOS"; return 1; }
     if (!(c->iso_sound_speed > 0.0)) { why = "iso_sound_speed must be positive"; return 1; }
   } else if (!(c->gamma > 1.0)) { why = "gamma must exceed 1"; return 1; }
+  if (c->fofc != 0 && c->fofc != 1) { why = "fofc must be 0 or 1"; return 1; }
+  if (c->fofc) {
+    if (hydro) { why = "hydro FOFC is not built: the reference's Hydro never allocates utest/fofc (hydro.cpp:38-39) and crashes"; return 1; }
+    // mhd.cpp:209-235: FOFC needs one more ghost cell than the stencil
+    if (c->ng < need + 1 && c->recon != AK_RECON_DC) { why = "FOFC requires one more ghost zone than the reconstruction stencil"; return 1; }
+  }
   if (c->nscalars < 0 || c->nscalars > 64) { why = "nscalars must be in [0, 64]"; return 1; }
   return 0;
 }
@@ -123,19 +131,21 @@ static int create_impl(const ak_mhd_cfg *cfg, bool hydro, void **handle) {
   g.is = cfg->ng; g.ie = g.is + cfg->nx1 - 1;   // reference src/mesh/mesh.cpp:285-333
   g.js = g.multi_d ? cfg->ng : 0; g.je = g.js + cfg->nx2 - 1;
   g.ks = g.three_d ? cfg->ng : 0; g.ke = g.ks + cfg->nx3 - 1;
+  g.next = cfg->fofc ? 1 : 0;
   g.ext1 = hydro ? 0 : 1; g.ext2 = (!hydro && g.multi_d) ? 1 : 0; g.ext3 = (!hydro && g.three_d) ? 1 : 0;
   g.cc = (long)g.n3 * g.n2 * g.n1;
   g.f1 = (long)g.n3 * g.n2 * (g.n1 + 1); g.f2 = (long)g.n3 * (g.n2 + 1) * g.n1; g.f3 = (long)(g.n3 + 1) * g.n2 * g.n1;
   g.e1 = (long)(g.n3 + 1) * (g.n2 + 1) * g.n1; g.e2 = (long)(g.n3 + 1) * g.n2 * (g.n1 + 1); g.e3 = (long)g.n3 * (g.n2 + 1) * (g.n1 + 1);
   h->eos = akb::EosParams{cfg->gamma, cfg->dfloor, cfg->pfloor, cfg->tfloor, cfg->sfloor, cfg->sigma_max,
                           1.0 / (cfg->gamma - 1.0), cfg->iso_sound_speed};
-  if ((e = cudaMalloc(&h->d_counters, 3 * sizeof(int))) != cudaSuccess ||
+  if ((e = cudaMalloc(&h->d_counters, 4 * sizeof(int))) != cudaSuccess ||
+      (cfg->fofc && (e = cudaMalloc(&h->d_fofc, (size_t)g.nmb * g.cc)) != cudaSuccess) ||
       (e = cudaMalloc(&h->d_dtmin, 3 * DT_SLOTS * sizeof(unsigned long long))) != cudaSuccess) {
     int rc = cuda_fail(nullptr, "ak_mhd_create", e);
     delete h;
     return rc;
   }
-  if ((e = cudaMemset(h->d_counters, 0, 3 * sizeof(int))) != cudaSuccess) {
+  if ((e = cudaMemset(h->d_counters, 0, 4 * sizeof(int))) != cudaSuccess) {
     int rc = cuda_fail(nullptr, "ak_mhd_create", e);
     delete h;
     return rc;
@@ -152,6 +162,7 @@ int ak_mhd_destroy(void *handle) {
   Handle *h = static_cast<Handle *>(handle);
   if (!h) return 0;
   cudaFree(h->d_counters);
+  cudaFree(h->d_fofc);
   cudaFree(h->d_dtmin);
   cudaFree(h->d_hst);
   delete h;
@@ -246,9 +257,30 @@ int ak_mhd_new_dt(void *handle, const ak_mhd_arrays *a, double *dt3, ak_stream_t
   return 0;
 }
 
+int ak_mhd_fofc(void *handle, const ak_mhd_arrays *a, double gam0, double gam1, double beta_dt, int *nfofc, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_fofc")
+  if (!h->cfg.fofc || h->hydro) return fail(h, "ak_mhd_fofc: handle was not created with cfg.fofc = 1");
+  if ((e = akb::launch_fofc(h->g, h->eos, A, gam0, gam1, beta_dt, h->d_fofc, h->d_counters + 3, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_fofc", e);
+  if (nfofc) {
+    if ((e = cudaMemcpyAsync(nfofc, h->d_counters + 3, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_fofc", e);
+    if ((e = cudaMemsetAsync(h->d_counters + 3, 0, sizeof(int), st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_fofc", e);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_fofc", e);
+  }
+  return 0;
+}
+
+int ak_mhd_set_stage(void *handle, double gam0, double gam1, double beta_dt) {
+  Handle *h = static_cast<Handle *>(handle);
+  if (!h) return fail(nullptr, "ak_mhd_set_stage: null handle");
+  h->stage_rk[0] = gam0; h->stage_rk[1] = gam1; h->stage_rk[2] = beta_dt;
+  return 0;
+}
+
 int ak_mhd_stage_flux_emf(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
   AK_PROLOGUE("ak_mhd_stage_flux_emf")
   if ((e = akb::launch_fluxes(h->cfg.recon, h->rs, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_flux_emf", e);
+  if (h->cfg.fofc && (e = akb::launch_fofc(h->g, h->eos, A, h->stage_rk[0], h->stage_rk[1], h->stage_rk[2], h->d_fofc, h->d_counters + 3, st)) != cudaSuccess)
+    return cuda_fail(h, "ak_mhd_stage_flux_emf", e);
   if ((e = akb::launch_corner_e(h->g, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_flux_emf", e);
   return 0;
 }
@@ -258,14 +290,20 @@ int ak_mhd_stage_update(void *handle, const ak_mhd_arrays *a, int stage, double 
   AK_PROLOGUE("ak_mhd_stage_update")
   // stage 1: CopyCons is folded into the update kernel (it saves u1/b1 for the ACTIVE zones it
   // updates -- the only entries later stages read -- instead of copying whole arrays)
-  if ((e = akb::launch_update_ct(h->g, A, true, true, stage == 1, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_update", e);
+  // With FOFC the estimate reads u1/b1 in the ghost zones too, so the caller ran the full CopyCons.
+  if ((e = akb::launch_update_ct(h->g, A, true, true, stage == 1 && !h->cfg.fofc, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_update", e);
   return 0;
 }
 
 int ak_mhd_stage_fused(void *handle, const ak_mhd_arrays *a, int stage, double gam0, double gam1, double beta_dt,
                        void *halo_plan, ak_stream_t s) {
-  int rc = ak_mhd_stage_flux_emf(handle, a, s);
-  if (rc) return rc;
+  int rc = 0;
+  Handle *hh = static_cast<Handle *>(handle);
+  if (hh && hh->cfg.fofc) {       // CopyCons over the whole arrays at stage 1, RK coefficients for the FOFC estimate
+    if (stage == 1 && (rc = ak_mhd_copy_cons(handle, a, s)) != 0) return rc;
+    ak_mhd_set_stage(handle, gam0, gam1, beta_dt);
+  }
+  if ((rc = ak_mhd_stage_flux_emf(handle, a, s)) != 0) return rc;
   if (halo_plan) {
     if (ak_halo_npeers(halo_plan) != 0)
       return fail(static_cast<Handle *>(handle), "ak_mhd_stage_fused: MeshBlocks on other ranks; use ak_mhd_stage_flux_emf + "

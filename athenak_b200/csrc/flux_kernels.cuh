@@ -83,7 +83,8 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
   constexpr int NV = T::NV;
   const int lane = threadIdx.x & 31;
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nc = g.nx1 + 2 + (RECON == RECON_PPM4 ? 1 : 0), nj = g.nx2 + 2 * g.ext2, nk = g.nx3 + 2 * g.ext3;
+  // g.next = 1 (FOFC): faces [is-1,ie+2] instead of [is,ie+1] (mhd_fluxes.cpp:96-106)
+  const int nc = g.nx1 + 2 + 2 * g.next + (RECON == RECON_PPM4 ? 1 : 0), nj = g.nx2 + 2 * g.ext2, nk = g.nx3 + 2 * g.ext3;
   const unsigned cell = warp * STEP + lane;            // cell index inside the plane
   const bool valid = cell < (unsigned)(nj * nc);
   const int m = blockIdx.y / nk;
@@ -91,7 +92,7 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
   const unsigned jr = valid ? __umulhi(cell, rcp_nc) : 0u;   // cell / nc
   const int c = valid ? (int)(cell - jr * nc) : 1;
   const int j = g.js - g.ext2 + (int)jr;
-  const int i = g.is - 1 + c;
+  const int i = g.is - 1 - g.next + c;
   const long cc = g.cc;
   const long off = ((long)k * g.n2 + j) * g.n1 + i;
   // The face field is fetched FIRST, with the stencil loads: issued next to its use (after the
@@ -139,7 +140,7 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
     L.by = __shfl_up_sync(0xffffffffu, up.by, 1);
     L.bz = __shfl_up_sync(0xffffffffu, up.bz, 1);
   }
-  if (!valid || lane == 0 || lane > STEP || c == 0 || c > g.nx1 + 1) return;
+  if (!valid || lane == 0 || lane > STEP || c == 0 || c > g.nx1 + 1 + 2 * g.next) return;
   Flux7 f;
   riemann_any<RS>(L, lo, bxi, eos, f);
   const long fs = (long)g.n3 * g.n2 * (g.n1 + 1);
@@ -274,8 +275,8 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
   if (col >= nt * nc) return;
   const int tr = col / nc;
   const int i = g.is - g.ext1 + (col - tr * nc);
-  const int fs0 = (DIR == 1) ? g.js : g.ks;         // first face along the sweep
-  const int fe0 = (DIR == 1) ? g.je + 1 : g.ke + 1; // last face
+  const int fs0 = ((DIR == 1) ? g.js : g.ks) - g.next;         // first face along the sweep (one more with FOFC)
+  const int fe0 = ((DIR == 1) ? g.je + 1 : g.ke + 1) + g.next; // last face
   const int f_lo = fs0 + seg * seglen;
   int f_hi = f_lo + seglen - 1;
   if (f_hi > fe0) f_hi = fe0;
@@ -446,7 +447,7 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
   const size_t smem = (RECON >= RECON_PPM4) ? sizeof(double) * NV * MARCH_SLOTS * MARCH_THREADS : 0;
   {  // x1
     constexpr int STEP = X1Step<RECON>::value;
-    const unsigned nc = g.nx1 + 2 + (RECON == RECON_PPM4 ? 1 : 0), plane = (unsigned)(g.nx2 + 2 * g.ext2) * nc;
+    const unsigned nc = g.nx1 + 2 + 2 * g.next + (RECON == RECON_PPM4 ? 1 : 0), plane = (unsigned)(g.nx2 + 2 * g.ext2) * nc;
     // rcp = ceil(2^32 / nc): __umulhi(t, rcp) == t / nc for every t < 2^32 / nc
     const unsigned rcp = (unsigned)((0x100000000ull + nc - 1) / nc);
     const long planes = (long)g.nmb * (g.nx3 + 2 * g.ext3);
@@ -456,7 +457,7 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
     flux_x1_kernel<RECON, RS><<<gr, 128, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x1f, a.flx1, a.e3x1, a.e2x1, rcp);
   }
   if (g.multi_d) {  // x2: (ey,ez) = (e1x2,e3x2)
-    const int nf = g.nx2 + 1;
+    const int nf = g.nx2 + 1 + 2 * g.next;
     const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
     const long cols = (long)(g.nx3 + 2 * g.ext3) * (g.nx1 + 2 * g.ext1);
     if ((long)g.nmb * nseg > 65535 || (long)g.nvar * g.cc >= 0x7fffffffL) return cudaErrorInvalidConfiguration;
@@ -465,7 +466,7 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
     flux_march_kernel<RECON, RS, 1><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg);
   }
   if (g.three_d) {  // x3: (ey,ez) = (e2x3,e1x3)
-    const int nf = g.nx3 + 1;
+    const int nf = g.nx3 + 1 + 2 * g.next;
     const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
     const long cols = (long)(g.nx2 + 2 * g.ext2) * (g.nx1 + 2 * g.ext1);
     if ((long)g.nmb * nseg > 65535 || (long)g.nvar * g.cc >= 0x7fffffffL) return cudaErrorInvalidConfiguration;

@@ -187,6 +187,7 @@ class MHD {  // state owner + tasks
   bool fused = true;
   double dtnew = (double)FLT_MAX;
   long nfloor[3] = {0, 0, 0};
+  long nfofc = 0;          // EventCounters::nfofc (per-task list only; the fused list leaves the count on the device)
   long launches = 0;
   std::map<std::string, std::shared_ptr<TaskList>> tl_map;
   std::vector<double *> owned;
@@ -382,6 +383,12 @@ class MHD {  // state owner + tasks
   TaskStatus Fluxes(Driver *pd, int stage) {
     if (hydro) AK_CHECK(h, ak_hydro_fluxes(h, &a, st)); else AK_CHECK(h, ak_mhd_fluxes(h, &a, st));
     launches += nsweeps();
+    if (cfg.fofc) {     // mhd_tasks.cpp:208-211
+      int n = 0;
+      AK_CHECK(h, ak_mhd_fofc(h, &a, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, &n, st));
+      nfofc += n;
+      launches += 1 + nsweeps();
+    }
     return TaskStatus::complete;
   }
   TaskStatus RKUpdate(Driver *pd, int stage) {
@@ -403,6 +410,11 @@ class MHD {  // state owner + tasks
     return TaskStatus::complete;
   }
   TaskStatus StageFluxEmf(Driver *pd, int stage) {   // tasks 2 + 14
+    if (cfg.fofc) {     // the FOFC estimate reads u1/b1 in the ghost zones: whole-array CopyCons, RK coefficients
+      CopyCons(pd, stage);
+      AK_CHECK(h, ak_mhd_set_stage(h, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt));
+      launches += 1 + nsweeps();
+    }
     AK_CHECK(h, ak_mhd_stage_flux_emf(h, &a, st));
     launches += nsweeps() + 1;
     SignalFree();    // the flux sweeps were the last readers of the b0 ghost faces (u0 ghosts: c2p of the previous stage)

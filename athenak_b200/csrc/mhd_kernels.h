@@ -25,6 +25,7 @@ struct Geom {  // RegionIndcs (src/mesh/mesh.hpp:35-41) + derived array extents
   // (hydro_fluxes.cpp:91-101).  Inactive dimensions have n=1, s=e=0.
   int multi_d, three_d;
   int ext1, ext2, ext3;
+  int next;         // 1 with FOFC: the sweeps cover one more face on each side along the face normal
 };
 
 struct Arrays {  // mirror of ak_mhd_arrays (include/athenak_b200.h)
@@ -51,6 +52,9 @@ cudaError_t launch_newdt(const Geom &g, const EosParams &eos, const Arrays &a, u
 // history sums (hst.cu): scratch holds (nblocks+1)*11 doubles, the 11 results are its last row
 cudaError_t launch_hst_sums(const Geom &g, const Arrays &a, bool mhd, double *scratch, int nblocks, cudaStream_t st);
 // internal solver code: public AK_RSOLVER_* value, + 20 for the isothermal variant (iso_device.cuh)
+// FOFC (fofc.cu): flag = nmb*cc bytes, counter = device int accumulating ecounter.nfofc
+cudaError_t launch_fofc(const Geom &g, const EosParams &eos, const Arrays &a, double gam0, double gam1, double beta_dt,
+                        unsigned char *flag, int *counter, cudaStream_t st);
 inline int internal_rsolver(int rsolver, int eos) { return rsolver + (eos == 1 ? 20 : 0); }
 cudaError_t launch_copy(const double *src, double *dst, long n, cudaStream_t st);
 

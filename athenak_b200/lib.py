@@ -24,7 +24,7 @@ class MhdCfg(C.Structure):
                 ("nx3", C.c_int), ("recon", C.c_int), ("rsolver", C.c_int),
                 ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
                 ("tfloor", C.c_double), ("sfloor", C.c_double), ("sigma_max", C.c_double), ("nscalars", C.c_int),
-                ("eos", C.c_int), ("iso_sound_speed", C.c_double)]
+                ("eos", C.c_int), ("iso_sound_speed", C.c_double), ("fofc", C.c_int)]
 
 
 EOS = {"ideal": 0, "isothermal": 1}      # AK_EOS_*
@@ -78,6 +78,8 @@ def load():
         "ak_mhd_new_dt": [vp, ap, _dp, vp],
         "ak_mhd_stage_fused": [vp, ap, ip, d, d, d, vp, vp],
         "ak_mhd_stage_flux_emf": [vp, ap, vp],
+        "ak_mhd_fofc": [vp, ap, d, d, d, C.POINTER(C.c_int), vp],
+        "ak_mhd_set_stage": [vp, d, d, d],
         "ak_mhd_stage_update": [vp, ap, ip, d, d, d, vp],
         "ak_mhd_cons2prim_newdt": [vp, ap, C.POINTER(C.c_int), _dp, vp],
         "ak_hst_sums": [vp, ap, _dp, C.POINTER(C.c_int), vp],
@@ -155,7 +157,7 @@ def load():
 
 EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_cons", "ak_mhd_fluxes",
             "ak_mhd_rk_update", "ak_mhd_corner_e", "ak_mhd_ct", "ak_mhd_cons2prim", "ak_mhd_new_dt",
-            "ak_mhd_stage_fused", "ak_mhd_stage_flux_emf", "ak_mhd_stage_update", "ak_mhd_cons2prim_newdt", "ak_halo_create", "ak_halo_destroy",
+            "ak_mhd_stage_fused", "ak_mhd_stage_flux_emf", "ak_mhd_fofc", "ak_mhd_set_stage", "ak_mhd_stage_update", "ak_mhd_cons2prim_newdt", "ak_halo_create", "ak_halo_destroy",
             "ak_halo_npeers", "ak_halo_peer", "ak_halo_descs", "ak_halo_local_cc", "ak_halo_local_fc",
             "ak_halo_pack_cc", "ak_halo_unpack_cc", "ak_halo_pack_fc", "ak_halo_unpack_fc",
             "ak_halo_emf_peer", "ak_halo_emf_pack_local", "ak_halo_emf_pack", "ak_halo_emf_sumavg",

@@ -38,7 +38,8 @@ class MHD:
     def __init__(self, nmb, ng, nx, mb_size, nghbr, *, recon="ppm4", rsolver="hlld", gamma,
                  dfloor=FLT_MIN, pfloor=FLT_MIN, tfloor=FLT_MIN, sfloor=FLT_MIN, sigma_max=FLT_MAX,
                  my_rank=0, gids_start=0, device="cuda", process_group=None, fused=True,
-                 mesh_bcs=None, mb_bcs=None, nscalars=0, eos="ideal", iso_sound_speed=1.0):
+                 mesh_bcs=None, mb_bcs=None, nscalars=0, eos="ideal", iso_sound_speed=1.0,
+                 fofc=False):
         if not torch.cuda.is_available():
             raise _lib.EngineError("athenak_b200: no CUDA device; the engine has no CPU path")
         self.L = _lib.load()
@@ -51,7 +52,8 @@ class MHD:
         self.nfl = 4 if eos == "isothermal" else 5       # src/mhd/mhd.cpp:100-108: nmhd
         self.nvar = self.nfl + int(nscalars)      # src/mhd/mhd.cpp: nmhd + nscalars
         self.cfg = _lib.MhdCfg(self.nmb, ng, nx1, nx2, nx3, _lib.RECON[recon], _lib.RSOLVER[rsolver],
-                               gamma, dfloor, pfloor, tfloor, sfloor, sigma_max, int(nscalars), _lib.EOS[eos], iso_sound_speed)
+                               gamma, dfloor, pfloor, tfloor, sfloor, sigma_max, int(nscalars), _lib.EOS[eos], iso_sound_speed, 1 if fofc else 0)
+        self.fofc, self.nfofc = bool(fofc), 0     # <mhd>/fofc, EventCounters::nfofc (src/mesh/mesh.hpp:70-74)
         self.fused = fused
         self.my_rank, self.gids_start, self.pg = my_rank, gids_start, process_group
         n1, n2, n3 = self.n
@@ -143,8 +145,15 @@ class MHD:
         return TaskStatus.complete
 
     def Fluxes(self, driver, stage):
+        """mhd_tasks.cpp:177-218: CalculateFluxes, then FOFC when enabled."""
         self._ck(self.L.ak_mhd_fluxes(self.h, C.byref(self.arrays), self._st()))
         self.launches += self.nsweeps
+        if self.fofc:
+            g0, g1, bdt = driver.gam0[stage - 1], driver.gam1[stage - 1], driver.beta[stage - 1] * driver.dt
+            n = C.c_int()
+            self._ck(self.L.ak_mhd_fofc(self.h, C.byref(self.arrays), g0, g1, bdt, C.byref(n), self._st()))
+            self.nfofc += n.value
+            self.launches += 1 + self.nsweeps
         return TaskStatus.complete
 
     def RKUpdate(self, driver, stage):
@@ -166,6 +175,11 @@ class MHD:
 
     def StageFluxEmf(self, driver, stage):
         """Tasks 2 + 14 in one ABI call (ak_mhd_stage_flux_emf)."""
+        if self.fofc:       # the FOFC estimate needs CopyCons over the whole arrays and the RK coefficients
+            self.CopyCons(driver, stage)
+            g0, g1, bdt = driver.gam0[stage - 1], driver.gam1[stage - 1], driver.beta[stage - 1] * driver.dt
+            self._ck(self.L.ak_mhd_set_stage(self.h, g0, g1, bdt))
+            self.launches += 1 + self.nsweeps
         self._ck(self.L.ak_mhd_stage_flux_emf(self.h, C.byref(self.arrays), self._st()))
         self.launches += self.nsweeps + 1
         return TaskStatus.complete

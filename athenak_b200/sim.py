@@ -15,7 +15,7 @@ INTEGRATOR = {"rk1": 1, "rk2": 2, "rk3": 3}
 class Simulation:
     def __init__(self, mesh, rank=0, *, ng=4, recon="ppm4", rsolver="hlld", gamma=1.6666667, integrator="rk3",
                  cfl_number=0.3, tlim=1.0, nlim=-1, fused=True, dfloor=FLT_MIN, pfloor=FLT_MIN, tfloor=FLT_MIN,
-                 sfloor=FLT_MIN, sigma_max=FLT_MAX, physics="mhd", nscalars=0, eos="ideal", iso_sound_speed=1.0):
+                 sfloor=FLT_MIN, sigma_max=FLT_MAX, physics="mhd", nscalars=0, eos="ideal", iso_sound_speed=1.0, fofc=False):
         """physics="hydro": the hydro twin (rsolver in llf/hlle/hllc/roe; 1-D/2-D/3-D blocks); the state is u0 only."""
         self.L = _lib.load()
         self.mesh, self.rank, self.ng = mesh, rank, ng
@@ -25,7 +25,7 @@ class Simulation:
         self.hydro = physics == "hydro"
         rs = _lib.HYD_RSOLVER[rsolver] if self.hydro else _lib.RSOLVER[rsolver]
         mcfg = _lib.MhdCfg(nmb, ng, nx[0], nx[1], nx[2], _lib.RECON[recon], rs, gamma,
-                           dfloor, pfloor, tfloor, sfloor, sigma_max, int(nscalars), _lib.EOS[eos], iso_sound_speed)
+                           dfloor, pfloor, tfloor, sfloor, sigma_max, int(nscalars), _lib.EOS[eos], iso_sound_speed, 1 if fofc else 0)
         self.cfg = _lib.SimCfg(mcfg, INTEGRATOR[integrator], cfl_number, tlim, nlim, rank, mesh.nranks,
                                int(mesh.gids_start[rank]), mesh.nmb_total, 1 if fused else 0)
         self.h = C.c_void_p()

@@ -52,6 +52,11 @@ typedef struct {
   int eos;           /* AK_EOS_IDEAL (5 fluid variables) or AK_EOS_ISOTHERMAL (4: no IEN; <mhd>/<hydro> eos,
                         src/eos/isothermal_mhd.cpp, isothermal_hyd.cpp; gamma and the p/T/s floors are ignored) */
   double iso_sound_speed; /* EOS_Data::iso_cs (src/eos/eos.hpp:28), isothermal only */
+  int fofc;          /* 1: first-order flux correction (<mhd>/fofc, src/mhd/mhd.cpp:197-201): ak_mhd_fluxes covers one
+                        more face on each side along the face normal (src/mhd/mhd_fluxes.cpp:96-106) and the Fluxes task
+                        must call ak_mhd_fofc after it.  Needs nghost >= 3 (dc/plm) or 4 (5-point stencils),
+                        src/mhd/mhd.cpp:209-235.  MHD only: the reference's hydro FOFC never allocates its
+                        utest / fofc arrays (src/hydro/hydro.cpp:38-39 vs src/mhd/mhd.cpp:369-374) and crashes. */
 } ak_mhd_cfg;
 
 typedef struct {
@@ -98,6 +103,16 @@ int ak_mhd_new_dt(void *h, const ak_mhd_arrays *a, double *dt3, ak_stream_t s);
  * NULL to skip it; it is a bitwise identity only if neighbouring blocks' shared faces hold
  * identical bits) + update; it refuses plans that have off-rank neighbours. */
 int ak_mhd_stage_flux_emf(void *h, const ak_mhd_arrays *a, ak_stream_t s);
+/* second half of task 2 when cfg.fofc = 1: MHD::FOFC, src/mhd/mhd_fofc.cpp:31-489 (Newtonian, no excision).
+ * Estimates the updated state over [is-1,ie+1]^d from uflx / the face EMFs, u0, u1, bcc0 and b1 (so CopyCons must have
+ * filled u1/b1 INCLUDING ghost zones: call ak_mhd_copy_cons at stage 1; ak_mhd_stage_update then skips its folded
+ * copy), flags the cells whose ConsToPrim would need a floor and replaces the fluxes and face EMFs on every face of
+ * a flagged cell with single-state LLF values.  nfofc (host int, may be NULL) receives the cells flagged since the
+ * count was last read (EventCounters::nfofc, src/mesh/mesh.hpp:70-74) and makes the call synchronise.
+ * With cfg.fofc = 1 ak_mhd_stage_flux_emf / ak_mhd_stage_fused take gam0 = gam1 = beta_dt from
+ * ak_mhd_set_stage, which must precede them. */
+int ak_mhd_fofc(void *h, const ak_mhd_arrays *a, double gam0, double gam1, double beta_dt, int *nfofc, ak_stream_t s);
+int ak_mhd_set_stage(void *h, double gam0, double gam1, double beta_dt);
 int ak_mhd_stage_update(void *h, const ak_mhd_arrays *a, int stage, double gam0, double gam1,
                         double beta_dt, ak_stream_t s);
 int ak_mhd_stage_fused(void *h, const ak_mhd_arrays *a, int stage, double gam0, double gam1,

@@ -27,6 +27,7 @@ typedef struct {
   int nscalars; /* passive scalars stored after the fluid variables (mhd.cpp / hydro.cpp:75) */
   int is_iso;   /* 1: isothermal EOS (eos/isothermal_mhd.cpp, isothermal_hyd.cpp): 4 fluid variables, no IEN */
   double iso_cs;
+  int fofc;     /* 1: first-order flux correction (<mhd>/<hydro> fofc, mhd_fofc.cpp, hydro_fofc.cpp) */
 } ocfg;
 
 enum { IDN = 0, IM1 = 1, IM2 = 2, IM3 = 3, IEN = 4, IVX = 1, IVY = 2, IVZ = 3 };
@@ -804,9 +805,10 @@ void oracle_fluxes(const ocfg *c, const double *w0, const double *bcc0, const do
     /* CT-extended transverse ranges only in ACTIVE dimensions (mhd_fluxes.cpp:126-128,176-178,225-226) */
     int kl = ks - three_d, ku = ke + three_d, jl = js - multi_d, ju = je + multi_d, il = is - 1, iu = ie + 1;   /* recon cell box */
     int fkl = kl, fku = ku, fjl = jl, fju = ju, fil = il, fiu = iu;                                               /* face box */
-    if (dir == 0) { fil = is; fiu = ie + 1; }
-    else if (dir == 1) { fjl = js; fju = je + 1; }
-    else { fkl = ks; fku = ke + 1; }
+    const int nx = c->fofc ? 1 : 0;   /* mhd_fluxes.cpp:100-106: face-normal range one cell wider with FOFC */
+    if (dir == 0) { fil = is - nx; fiu = ie + 1 + nx; il = fil - 1; iu = fiu; }
+    else if (dir == 1) { fjl = js - nx; fju = je + 1 + nx; jl = fjl - 1; ju = fju; }
+    else { fkl = ks - nx; fku = ke + 1 + nx; kl = fkl - 1; ku = fku; }
     recon_pass(c, dir, D.nv, 1, w0, wl, wr, kl, ku, jl, ju, il, iu);
     recon_pass(c, dir, 3, 0, bcc0, bl, br, kl, ku, jl, ju, il, iu);
     for (int m = 0; m < c->nmb; ++m)
@@ -1418,6 +1420,127 @@ int oracle_apply_bcs(const ocfg *c, const int *mesh_bcs, const int *mb_bcs, doub
 static const int *g_mesh_bcs = NULL, *g_mb_bcs = NULL;
 void oracle_set_bcs(const int *mesh_bcs, const int *mb_bcs) { g_mesh_bcs = mesh_bcs; g_mb_bcs = mb_bcs; }
 
+/* MHD::FOFC, mhd_fofc.cpp:31-489 (Newtonian, no excision).  Estimates the updated state over
+ * [is-1,ie+1] (x [js-1,je+1] x [ks-1,ke+1] in active dimensions), flags the cells whose c2p would
+ * need a floor (ideal_mhd.cpp:57-88 / isothermal_mhd.cpp:105-118 with only_testfloors), then replaces
+ * the fluxes and face EMFs on all faces of flagged cells with first-order LLF values.  Returns
+ * the number of flagged cells (ecounter.nfofc). */
+static int g_nfofc = 0;
+int oracle_get_nfofc(int reset) { int n = g_nfofc; if (reset) g_nfofc = 0; return n; }
+
+static void fofc_llf(const ocfg *c, int dir, const double *w0, const double *bcc0, int nv, int m, int kl_, int jl_, int il_,
+                     int kr_, int jr_, int ir_, double bxi, double *f5, double *ey, double *ez) {
+  odims D = dims(c);
+  const int ivx = IVX + dir, ivy = IVX + (dir + 1) % 3, ivz = IVX + (dir + 2) % 3;
+  const int iby = (dir + 1) % 3, ibz = (dir + 2) % 3;
+  prim1d l, r;
+  l.d = CC(w0, nv, m, IDN, kl_, jl_, il_); l.vx = CC(w0, nv, m, ivx, kl_, jl_, il_); l.vy = CC(w0, nv, m, ivy, kl_, jl_, il_);
+  l.vz = CC(w0, nv, m, ivz, kl_, jl_, il_); l.e = c->is_iso ? 0.0 : CC(w0, nv, m, IEN, kl_, jl_, il_);
+  l.by = CC(bcc0, 3, m, iby, kl_, jl_, il_); l.bz = CC(bcc0, 3, m, ibz, kl_, jl_, il_);
+  r.d = CC(w0, nv, m, IDN, kr_, jr_, ir_); r.vx = CC(w0, nv, m, ivx, kr_, jr_, ir_); r.vy = CC(w0, nv, m, ivy, kr_, jr_, ir_);
+  r.vz = CC(w0, nv, m, ivz, kr_, jr_, ir_); r.e = c->is_iso ? 0.0 : CC(w0, nv, m, IEN, kr_, jr_, ir_);
+  r.by = CC(bcc0, 3, m, iby, kr_, jr_, ir_); r.bz = CC(bcc0, 3, m, ibz, kr_, jr_, ir_);
+  cons1d fx;
+  if (c->is_iso) llf_face_iso(c, &l, &r, bxi, &fx); else llf_face(c, &l, &r, bxi, &fx);
+  f5[IDN] = fx.d; f5[ivx] = fx.mx; f5[ivy] = fx.my; f5[ivz] = fx.mz; f5[IEN] = fx.e;
+  *ey = fx.by; *ez = fx.bz;     /* mhd_fofc.cpp:196-197: the single-state LLF already carries the EMF signs */
+}
+
+int oracle_fofc(const ocfg *c, const double *u0, const double *u1, const double *w0, const double *bcc0,
+                const double *b0x1f, const double *b0x2f, const double *b0x3f,
+                const double *b1x1f, const double *b1x2f, const double *b1x3f,
+                double *flx1, double *flx2, double *flx3, double *e3x1, double *e2x1, double *e1x2,
+                double *e3x2, double *e2x3, double *e1x3, const double *mb_size, double gam0, double gam1,
+                double beta_dt) {
+  odims D = dims(c);
+  const int multi_d = c->nx2 > 1, three_d = c->nx3 > 1;
+  const int il = D.is - 1, iu = D.ie + 1, jl = D.js - multi_d, ju = D.je + multi_d, kl = D.ks - three_d, ku = D.ke + three_d;
+  unsigned char *flag = calloc((size_t)c->nmb * D.cc, 1);
+  int count = 0;
+  const double gm1 = c->gamma - 1.0;
+  for (int m = 0; m < c->nmb; ++m) {
+    const double dtodx1 = beta_dt / mb_size[m * 9 + 6], dtodx2 = beta_dt / mb_size[m * 9 + 7], dtodx3 = beta_dt / mb_size[m * 9 + 8];
+    for (int k = kl; k <= ku; ++k)
+      for (int j = jl; j <= ju; ++j)
+        for (int i = il; i <= iu; ++i) {
+          double ut[5] = {0, 0, 0, 0, 0};
+          for (int n = 0; n < D.nfl; ++n) {   /* mhd_fofc.cpp:78-88 */
+            double divf = dtodx1 * (F1(flx1, m, n, k, j, i + 1) - F1(flx1, m, n, k, j, i));
+            if (multi_d) divf += dtodx2 * (F2(flx2, m, n, k, j + 1, i) - F2(flx2, m, n, k, j, i));
+            if (three_d) divf += dtodx3 * (F3(flx3, m, n, k + 1, j, i) - F3(flx3, m, n, k, j, i));
+            ut[n] = gam0 * CC(u0, D.nv, m, n, k, j, i) + gam1 * CC(u1, D.nv, m, n, k, j, i) - divf;
+          }
+          double b1old = 0.5 * (X1F(b1x1f, m, k, j, i) + X1F(b1x1f, m, k, j, i + 1));   /* :91-107 */
+          double b2old = 0.5 * (X2F(b1x2f, m, k, j, i) + X2F(b1x2f, m, k, j + 1, i));
+          double b3old = 0.5 * (X3F(b1x3f, m, k, j, i) + X3F(b1x3f, m, k + 1, j, i));
+          double bx = gam0 * CC(bcc0, 3, m, 0, k, j, i) + gam1 * b1old;
+          double by = gam0 * CC(bcc0, 3, m, 1, k, j, i) + gam1 * b2old;
+          double bz = gam0 * CC(bcc0, 3, m, 2, k, j, i) + gam1 * b3old;
+          by += dtodx1 * (S4(e3x1, m, k, j, i + 1) - S4(e3x1, m, k, j, i));
+          bz -= dtodx1 * (S4(e2x1, m, k, j, i + 1) - S4(e2x1, m, k, j, i));
+          if (multi_d) {
+            bx -= dtodx2 * (S4(e3x2, m, k, j + 1, i) - S4(e3x2, m, k, j, i));
+            bz += dtodx2 * (S4(e1x2, m, k, j + 1, i) - S4(e1x2, m, k, j, i));
+          }
+          if (three_d) {
+            bx += dtodx3 * (S4(e2x3, m, k + 1, j, i) - S4(e2x3, m, k, j, i));
+            by -= dtodx3 * (S4(e1x3, m, k + 1, j, i) - S4(e1x3, m, k, j, i));
+          }
+          int used = 0;
+          if (c->is_iso) {   /* isothermal_mhd.cpp:95-118: the floor test averages the b0 FACES it is handed */
+            double fbx = 0.5 * (X1F(b0x1f, m, k, j, i) + X1F(b0x1f, m, k, j, i + 1));
+            double fby = 0.5 * (X2F(b0x2f, m, k, j, i) + X2F(b0x2f, m, k, j + 1, i));
+            double fbz = 0.5 * (X3F(b0x3f, m, k, j, i) + X3F(b0x3f, m, k + 1, j, i));
+            const double b2 = SQR(fbx) + SQR(fby) + SQR(fbz);
+            if (ut[IDN] < fmax(c->dfloor, b2 / c->sigma_max)) used = 1;
+          } else {           /* ideal_c2p_mhd.hpp:20-67 on (utest, bcctest) */
+            const double b2 = SQR(bx) + SQR(by) + SQR(bz);
+            const double dfloor_ = fmax(c->dfloor, b2 / c->sigma_max);
+            double efloor = c->pfloor / (c->gamma - 1.0);
+            double ud = ut[IDN];
+            if (ud < dfloor_) { ud = dfloor_; used = 1; }
+            double wd = ud, di = 1.0 / ud;
+            double e_k = 0.5 * di * (SQR(ut[IM1]) + SQR(ut[IM2]) + SQR(ut[IM3]));
+            double e_m = 0.5 * (SQR(bx) + SQR(by) + SQR(bz));
+            double we = (ut[IEN] - e_k - e_m);
+            if (we < efloor) { we = efloor; used = 1; }
+            if (gm1 * we * di < c->tfloor) { we = wd * c->tfloor / gm1; used = 1; }
+            double spe_over_eps = gm1 / pow(wd, gm1);
+            double spe = spe_over_eps * we * di;
+            if (spe <= c->sfloor) used = 1;
+          }
+          if (used) { flag[(size_t)m * D.cc + ((size_t)k * D.n2 + j) * D.n1 + i] = 1; count++; }
+        }
+  }
+  /* mhd_fofc.cpp:131-474: lower faces of flagged cells, then upper faces (a face shared by two flagged
+   * cells gets the same value twice) */
+  for (int pass = 0; pass < 2; ++pass)
+    for (int m = 0; m < c->nmb; ++m)
+      for (int k = kl; k <= ku; ++k)
+        for (int j = jl; j <= ju; ++j)
+          for (int i = il; i <= iu; ++i) {
+            if (!flag[(size_t)m * D.cc + ((size_t)k * D.n2 + j) * D.n1 + i]) continue;
+            double f5[5], ey, ez;
+            const int s = pass;   /* 0: faces (i,j,k); 1: faces (i+1), (j+1), (k+1) */
+            fofc_llf(c, 0, w0, bcc0, D.nv, m, k, j, i - 1 + s, k, j, i + s, X1F(b0x1f, m, k, j, i + s), f5, &ey, &ez);
+            for (int n = 0; n < D.nfl; ++n) F1(flx1, m, n, k, j, i + s) = f5[n];
+            S4(e3x1, m, k, j, i + s) = ey; S4(e2x1, m, k, j, i + s) = ez;
+            if (multi_d) {
+              fofc_llf(c, 1, w0, bcc0, D.nv, m, k, j - 1 + s, i, k, j + s, i, X2F(b0x2f, m, k, j + s, i), f5, &ey, &ez);
+              for (int n = 0; n < D.nfl; ++n) F2(flx2, m, n, k, j + s, i) = f5[n];
+              S4(e1x2, m, k, j + s, i) = ey; S4(e3x2, m, k, j + s, i) = ez;
+            }
+            if (three_d) {
+              fofc_llf(c, 2, w0, bcc0, D.nv, m, k - 1 + s, j, i, k + s, j, i, X3F(b0x3f, m, k + s, j, i), f5, &ey, &ez);
+              for (int n = 0; n < D.nfl; ++n) F3(flx3, m, n, k + s, j, i) = f5[n];
+              S4(e2x3, m, k + s, j, i) = ey; S4(e1x3, m, k + s, j, i) = ez;
+            }
+          }
+  free(flag);
+  g_nfofc += count;
+  return count;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* One RK stage = the "stagen" task chain of mhd_tasks.cpp:48-75 on a uniform mesh
  * (tasks 1,2,5,10/11,14,15/16,17,21/22,27).  SendE/RecvE is a bitwise identity only when the
@@ -1444,6 +1567,9 @@ void oracle_stage(const ocfg *c, ostate *s, const double *mb_size, const int *ng
   for (int q = 0; q < 6; ++q) fe[q] = calloc(nm * D.cc, 8);
   double *e1 = calloc(nm * D.e1, 8), *e2 = calloc(nm * D.e2, 8), *e3 = calloc(nm * D.e3, 8);
   oracle_fluxes(c, s->w0, s->bcc0, s->b0x1f, s->b0x2f, s->b0x3f, flx1, flx2, flx3, fe[0], fe[1], fe[2], fe[3], fe[4], fe[5]);
+  if (c->fofc)   /* mhd_tasks.cpp:208-211 */
+    oracle_fofc(c, s->u0, s->u1, s->w0, s->bcc0, s->b0x1f, s->b0x2f, s->b0x3f, s->b1x1f, s->b1x2f, s->b1x3f, flx1, flx2, flx3,
+                fe[0], fe[1], fe[2], fe[3], fe[4], fe[5], mb_size, gam0, gam1, beta_dt);
   oracle_rk_update(c, s->u0, s->u1, flx1, flx2, flx3, mb_size, gam0, gam1, beta_dt);
   oracle_halo_cc(c, s->u0, D.nv, nghbr_gid);
   oracle_corner_e(c, s->w0, s->bcc0, flx1, flx2, flx3, fe[0], fe[1], fe[2], fe[3], fe[4], fe[5], e1, e2, e3);

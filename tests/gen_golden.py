@@ -88,7 +88,7 @@ def iso():
     for name, c in I.CASES.items():
         r0, r1 = I.reference(name)
         out = dict(deck=np.array(r0.deck), lloc=r0.lloc, u0_c0=r0.u0, u0_final=r1.u0, time_final=r1.time,
-                   dt_final=r1.dt, ncycle_final=r1.ncycle)
+                   dt_final=r1.dt, ncycle_final=r1.ncycle, nfofc=r1.nfofc)
         if c[3] == "mhd":
             out.update(b1f_c0=r0.b1f, b2f_c0=r0.b2f, b3f_c0=r0.b3f, b1f_final=r1.b1f, b2f_final=r1.b2f, b3f_final=r1.b3f)
         np.savez_compressed(os.path.join(HERE, "golden", name + ".npz"), **out)

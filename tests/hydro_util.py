@@ -48,10 +48,12 @@ class Case:
         ph = self.physics
         self.recon, self.rsolver = p[ph + "/reconstruct"], p[ph + "/rsolver"]
         self.gamma = float(p[ph + "/gamma"])
+        self.dfloor = float(p.get(ph + "/dfloor", O.FLT_MIN))      # eos.cpp:22-25 defaults
         self.nscalars = int(p.get(ph + "/nscalars", 0))
         self.iso = p.get(ph + "/eos", "ideal") == "isothermal"
         self.iso_cs = float(p.get(ph + "/iso_sound_speed", 1.0))
         self.nfl = 4 if self.iso else 5
+        self.fofc = p.get(ph + "/fofc", "false").strip().lower() in ("true", "1")
         self.nvar = self.nfl + self.nscalars
         self.integrator = p["time/integrator"]
         self.cfl, self.tlim = float(p["time/cfl_number"]), float(p["time/tlim"])
@@ -64,7 +66,8 @@ class Case:
     def ocfg(self):
         rs = O.RSOLVER[self.rsolver] if self.physics == "mhd" else O.HYD_RSOLVER[self.rsolver]
         return O.OCfg(self.nmb, self.ng, *self.nblock, O.RECON[self.recon], rs, self.gamma,
-                      O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, self.nscalars, 1 if self.iso else 0, self.iso_cs)
+                      self.dfloor, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, self.nscalars, 1 if self.iso else 0, self.iso_cs,
+                      1 if self.fofc else 0)
 
 
 def oracle_run(case: Case, u_init, ncycles=-1, time0=0.0):

@@ -23,7 +23,7 @@ class OCfg(C.Structure):
                 ("nx3", C.c_int), ("recon", C.c_int), ("rsolver", C.c_int),
                 ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
                 ("tfloor", C.c_double), ("sfloor", C.c_double), ("sigma_max", C.c_double), ("nscalars", C.c_int),
-                ("is_iso", C.c_int), ("iso_cs", C.c_double)]
+                ("is_iso", C.c_int), ("iso_cs", C.c_double), ("fofc", C.c_int)]
 
 
 class OState(C.Structure):

@@ -1,10 +1,11 @@
-"""Isothermal EOS on the GPU: isothermal LLF / HLLE / HLLD (MHD) and LLF / HLLE / Roe
+"""Isothermal EOS and first-order flux correction (FOFC) on the GPU: isothermal LLF / HLLE / HLLD (MHD) and LLF / HLLE / Roe
 (hydro) through the same sweep kernels with four fluid variables, density-floor-only ConsToPrim and the
 isothermal fast / sound speed in NewTimeStep; 1-D / 2-D / 3-D, multi-block, physical boundaries, passive
 scalars.  Gate: final u0 and face fields (ghost zones included) == the unmodified reference's final
 dump, bitwise -- against the committed fixtures always, and against live reference runs of more
 combinations when oracle/_ref is present -- through the per-task ABI, the fused ABI and the C++ host
-driver; history sums have no tot-E column."""
+driver; history sums have no tot-E column.  FOFC cases (mhd_fofc.cpp) are ones in which the correction fires:
+the number of flagged cells must equal the count in the reference's event log."""
 import numpy as np
 import pytest
 
@@ -34,7 +35,7 @@ def initial_and_final(name, live):
     d = G.load(name)
     case = H.Case(str(d["deck"]))
     r1 = _Dump()
-    r1.u0, r1.ncycle, r1.time = d["u0_final"], int(d["ncycle_final"]), float(d["time_final"])
+    r1.u0, r1.ncycle, r1.time, r1.nfofc = d["u0_final"], int(d["ncycle_final"]), float(d["time_final"]), int(d["nfofc"])
     b = None
     if case.physics == "mhd":
         b = (d["b1f_c0"], d["b2f_c0"], d["b3f_c0"])
@@ -42,7 +43,7 @@ def initial_and_final(name, live):
     return case, d["u0_c0"], b, r1
 
 
-def run_python_driver(case, u_init, b_init, fused):
+def run_python_driver(case, u_init, b_init, fused, ncycles=None):
     from athenak_b200.driver import Driver, assemble_mhd_tasks
     from athenak_b200.hydro import Hydro, assemble_hydro_tasks
     from athenak_b200.mesh import Mesh
@@ -50,18 +51,18 @@ def run_python_driver(case, u_init, b_init, fused):
     mesh = Mesh(case.nmesh, case.nblock, xmin=case.xmin, xmax=case.xmax, bcs=case.bc_names)
     mb_size, mb_bcs, nghbr = mesh.rank_tables(0)
     kw = dict(recon=case.recon, rsolver=case.rsolver, gamma=case.gamma, mesh_bcs=mesh.bcs, mb_bcs=mb_bcs,
-              nscalars=case.nscalars, eos="isothermal", iso_sound_speed=case.iso_cs)
+              nscalars=case.nscalars, eos="isothermal" if case.iso else "ideal", iso_sound_speed=case.iso_cs, dfloor=case.dfloor)
     if case.physics == "hydro":
         e = Hydro(case.nmb, case.ng, case.nblock, mb_size, nghbr, **kw)
         e.load_state(u_init)
         tl = assemble_hydro_tasks(e, fused=fused)
     else:
-        e = MHD(case.nmb, case.ng, case.nblock, mb_size, nghbr, **kw)
+        e = MHD(case.nmb, case.ng, case.nblock, mb_size, nghbr, fofc=case.fofc, **kw)
         e.load_state(u_init, *b_init)
         tl = assemble_mhd_tasks(e, fused=fused)
     drv = Driver(case.integrator, case.cfl, tlim=case.tlim)
     drv.Initialize(e)
-    drv.Execute(e, tl)
+    drv.Execute(e, tl, ncycles=ncycles)
     return e, drv
 
 
@@ -76,18 +77,23 @@ def check(u, b, r1):
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "pertask"])
 def test_iso_matches_golden_bitwise(name, fused):
     case, u0, b0, r1 = initial_and_final(name, live=False)
-    e, drv = run_python_driver(case, u0, b0, fused)
+    e, drv = run_python_driver(case, u0, b0, fused, ncycles=r1.ncycle)
     assert drv.ncycle == r1.ncycle and drv.time == r1.time
     check(e.u0.cpu().numpy(), None if b0 is None else [x.cpu().numpy() for x in e.b0], r1)
-    assert e.launches > 0 and e.u0.shape[1] == 4 + case.nscalars
+    assert e.launches > 0 and e.u0.shape[1] == case.nfl + case.nscalars
+    if case.fofc and not fused:       # the per-task list reads the device counter back every stage
+        assert e.nfofc == r1.nfofc > 0
 
 
 @pytest.mark.parametrize("name", sorted(set(I.LIVE_CASES) - set(I.CASES)))
 def test_iso_matches_live_reference_bitwise(name):
     case, u0, b0, r1 = initial_and_final(name, live=True)
-    e, drv = run_python_driver(case, u0, b0, True)
+    fused = not case.fofc
+    e, drv = run_python_driver(case, u0, b0, fused, ncycles=r1.ncycle)
     assert drv.ncycle == r1.ncycle and drv.time == r1.time
     check(e.u0.cpu().numpy(), None if b0 is None else [x.cpu().numpy() for x in e.b0], r1)
+    if case.fofc:
+        assert e.nfofc == r1.nfofc
 
 
 @pytest.mark.parametrize("name", sorted(I.CASES))
@@ -99,10 +105,11 @@ def test_iso_cxx_host_driver(name):
     mesh = Mesh(case.nmesh, case.nblock, xmin=case.xmin, xmax=case.xmax, bcs=case.bc_names)
     sim = Simulation(mesh, 0, ng=case.ng, recon=case.recon, rsolver=case.rsolver, gamma=case.gamma,
                      integrator=case.integrator, cfl_number=case.cfl, tlim=case.tlim, fused=True, physics=case.physics,
-                     nscalars=case.nscalars, eos="isothermal", iso_sound_speed=case.iso_cs)
+                     nscalars=case.nscalars, eos="isothermal" if case.iso else "ideal", iso_sound_speed=case.iso_cs,
+                     dfloor=case.dfloor, fofc=case.fofc)
     sim.set_state(*[np.ascontiguousarray(a) for a in ((u0,) if b0 is None else (u0, *b0))])
     sim.initialize()
-    sim.execute(-1)
+    sim.execute(r1.ncycle)
     st = sim.status()
     assert st["ncycle"] == r1.ncycle and st["time"] == r1.time
     out = sim.get_state()
