@@ -498,6 +498,14 @@ int ak_halo_emf_peer(void *plan, int ipeer, long *count, double **recv_ptr) {
   if (recv_ptr) *recv_ptr = P->d_emf_rbuf + peer.emf_recv_base;
   return 0;
 }
+int ak_halo_emf_rbuf(void *plan, double **base, long *count) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P) return fail(nullptr, "ak_halo_emf_rbuf: null plan");
+  if (halo_ready(P, "ak_halo_emf_rbuf")) return 1;
+  if (base) *base = P->d_emf_rbuf;
+  if (count) *count = P->emf_rbuf_count;
+  return 0;
+}
 int ak_halo_emf_pack_local(void *plan, const double *e1, const double *e2, const double *e3, ak_stream_t s) {
   akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
   if (!P || !e1 || !e2 || !e3) return fail(nullptr, "ak_halo_emf_pack_local: null argument");
@@ -538,24 +546,20 @@ int ak_halo_push_flags(void *plan, int my_rank, int nranks, unsigned long long *
   akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
   if (!P || !local_flags || !peer_flags) return fail(nullptr, "ak_halo_push_flags: null argument");
   const int np = (int)P->peers.size();
-  std::vector<unsigned long long *> sf(np), sr(np);
-  std::vector<int> ws(2 * np);
-  for (int p = 0; p < np; ++p) {
-    sf[p] = peer_flags[p] + 0 * nranks + my_rank;        // my "free" slot in peer p's memory
-    sr[p] = peer_flags[p] + 1 * nranks + my_rank;        // my "ready" slot
-    ws[p] = 0 * nranks + P->peers[p].rank;               // where peer p writes its "free" counter in MY memory
-    ws[np + p] = 1 * nranks + P->peers[p].rank;
-  }
+  // kinds: 0/1 = ghost zones free / filled, 2/3 = EMF receive segment free / filled
+  std::vector<unsigned long long *> sg(np);
+  std::vector<int> ws(4 * np);
   cudaError_t e;
-  if ((e = cudaMalloc(&P->d_sig_free, sizeof(void *) * std::max(np, 1))) != cudaSuccess ||
-      (e = cudaMalloc(&P->d_sig_ready, sizeof(void *) * std::max(np, 1))) != cudaSuccess ||
-      (e = cudaMalloc(&P->d_wait_slots, sizeof(int) * std::max(2 * np, 1))) != cudaSuccess)
-    return cuda_fail(nullptr, "ak_halo_push_flags", e);
-  if (np) {
-    cudaMemcpy(P->d_sig_free, sf.data(), sizeof(void *) * np, cudaMemcpyHostToDevice);
-    cudaMemcpy(P->d_sig_ready, sr.data(), sizeof(void *) * np, cudaMemcpyHostToDevice);
-    cudaMemcpy(P->d_wait_slots, ws.data(), sizeof(int) * 2 * np, cudaMemcpyHostToDevice);
+  if ((e = cudaMalloc(&P->d_wait_slots, sizeof(int) * std::max(4 * np, 1))) != cudaSuccess) return cuda_fail(nullptr, "ak_halo_push_flags", e);
+  for (int kind = 0; kind < 4; ++kind) {
+    for (int p = 0; p < np; ++p) {
+      sg[p] = peer_flags[p] + kind * nranks + my_rank;       // my slot of this kind in peer p's memory
+      ws[kind * np + p] = kind * nranks + P->peers[p].rank;  // where peer p writes its counter in MY memory
+    }
+    if ((e = cudaMalloc(&P->d_sig[kind], sizeof(void *) * std::max(np, 1))) != cudaSuccess) return cuda_fail(nullptr, "ak_halo_push_flags", e);
+    if (np) cudaMemcpy(P->d_sig[kind], sg.data(), sizeof(void *) * np, cudaMemcpyHostToDevice);
   }
+  if (np) cudaMemcpy(P->d_wait_slots, ws.data(), sizeof(int) * 4 * np, cudaMemcpyHostToDevice);
   P->flags_local = local_flags; P->my_rank = my_rank; P->nranks = nranks;
   return 0;
 }
@@ -588,13 +592,13 @@ int ak_halo_push(void *plan, double *u0, int nvar, double *x1f, double *x2f, dou
 
 int ak_halo_signal(void *plan, int kind, unsigned long long value, ak_stream_t s) {
   akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
-  if (!P || !P->push_ready || kind < 0 || kind > 1) return fail(nullptr, "ak_halo_signal: bad argument");
-  return halo_rc(P, "ak_halo_signal", akb::peer_signal_launch(kind == 0 ? P->d_sig_free : P->d_sig_ready, (int)P->peers.size(), value, (cudaStream_t)s));
+  if (!P || !P->push_ready || kind < 0 || kind > 3) return fail(nullptr, "ak_halo_signal: bad argument");
+  return halo_rc(P, "ak_halo_signal", akb::peer_signal_launch(P->d_sig[kind], (int)P->peers.size(), value, (cudaStream_t)s));
 }
 
 int ak_halo_wait(void *plan, int kind, unsigned long long value, ak_stream_t s) {
   akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
-  if (!P || !P->push_ready || kind < 0 || kind > 1) return fail(nullptr, "ak_halo_wait: bad argument");
+  if (!P || !P->push_ready || kind < 0 || kind > 3) return fail(nullptr, "ak_halo_wait: bad argument");
   const int np = (int)P->peers.size();
   return halo_rc(P, "ak_halo_wait", akb::peer_wait_launch(P->flags_local, P->d_wait_slots + kind * np, np, value, (cudaStream_t)s));
 }

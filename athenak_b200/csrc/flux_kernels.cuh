@@ -2,6 +2,7 @@
 // (mhd_kernels.cu instantiates them for LLF/HLLE/HLLD) and its hydro twin (hydro_kernels.cu:
 // advect/LLF/HLLE/HLLC/Roe).  See mhd_kernels.cu for the kernel inventory.
 #pragma once
+#include <cstdlib>
 #include "mhd_kernels.h"
 #include "mhd_device.cuh"
 #include "hydro_device.cuh"
@@ -441,9 +442,40 @@ static cudaError_t launch_scalar_fluxes(const Geom &g, const Arrays &a, cudaStre
 
 static inline unsigned nblocks(long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+// The three sweeps are independent (they read w0/bcc0/b0 and write disjoint arrays), so x2 and x3 go to
+// two auxiliary streams forked from and joined back into the caller's stream: the block scheduler
+// fills the partial last wave of one sweep with blocks of the next instead of idling those SMs.
+// One pool per host thread (a handle is driven by one thread).  AKB_SWEEP_STREAMS=0 disables it.
+struct SweepFork {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  bool ok = false;
+  SweepFork() {
+    const char *env = getenv("AKB_SWEEP_STREAMS");
+    if (env && env[0] == '0') return;
+    ok = cudaStreamCreateWithFlags(&s[0], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&s[1], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&join[0], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&join[1], cudaEventDisableTiming) == cudaSuccess;
+  }
+};
+inline SweepFork *sweep_fork() {
+  thread_local SweepFork f;
+  return f.ok ? &f : nullptr;
+}
+
 template <int RECON, int RS>
 static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st) {
   constexpr int NV = SolverTraits<RS>::NV;
+  SweepFork *sf = g.multi_d ? sweep_fork() : nullptr;
+  cudaStream_t st2 = st, st3 = st;
+  if (sf) {
+    cudaEventRecord(sf->fork, st);
+    cudaStreamWaitEvent(sf->s[0], sf->fork, 0);
+    st2 = sf->s[0];
+    if (g.three_d) { cudaStreamWaitEvent(sf->s[1], sf->fork, 0); st3 = sf->s[1]; }
+  }
   const size_t smem = (RECON >= RECON_PPM4) ? sizeof(double) * NV * MARCH_SLOTS * MARCH_THREADS : 0;
   {  // x1
     constexpr int STEP = X1Step<RECON>::value;
@@ -463,7 +495,7 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
     if ((long)g.nmb * nseg > 65535 || (long)g.nvar * g.cc >= 0x7fffffffL) return cudaErrorInvalidConfiguration;
     static bool attr1 = false;
     if (!attr1 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr1 = true; }
-    flux_march_kernel<RECON, RS, 1><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg);
+    flux_march_kernel<RECON, RS, 1><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st2>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg);
   }
   if (g.three_d) {  // x3: (ey,ez) = (e2x3,e1x3)
     const int nf = g.nx3 + 1 + 2 * g.next;
@@ -472,7 +504,12 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
     if ((long)g.nmb * nseg > 65535 || (long)g.nvar * g.cc >= 0x7fffffffL) return cudaErrorInvalidConfiguration;
     static bool attr2 = false;
     if (!attr2 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr2 = true; }
-    flux_march_kernel<RECON, RS, 2><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
+    flux_march_kernel<RECON, RS, 2><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st3>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
+  }
+  if (sf) {   // join
+    cudaEventRecord(sf->join[0], st2);
+    cudaStreamWaitEvent(st, sf->join[0], 0);
+    if (g.three_d) { cudaEventRecord(sf->join[1], st3); cudaStreamWaitEvent(st, sf->join[1], 0); }
   }
   if (g.nvar > g.nfl) return launch_scalar_fluxes<RECON>(g, a, st);
   return cudaGetLastError();

@@ -412,7 +412,7 @@ void halo_free(HaloPlan *P) {
   if (!P) return;
   cudaFree(P->d_local_cc); cudaFree(P->d_local_fc); cudaFree(P->d_emf_pack_local); cudaFree(P->d_emf_sum); cudaFree(P->d_emf_rbuf);
   for (auto &p : P->peers) { cudaFree(p.d_pack_cc); cudaFree(p.d_unpack_cc); cudaFree(p.d_pack_fc); cudaFree(p.d_unpack_fc); cudaFree(p.d_pack_emf); }
-  cudaFree(P->d_push); cudaFree(P->d_sig_free); cudaFree(P->d_sig_ready); cudaFree(P->d_wait_slots);
+  cudaFree(P->d_push); for (auto *q : P->d_sig) cudaFree(q); cudaFree(P->d_wait_slots);
   delete P;
 }
 

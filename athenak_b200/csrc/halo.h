@@ -73,7 +73,7 @@ struct HaloPlan {
   PushPeerPtrs push_ptrs{};
   bool push_ready = false;
   unsigned long long *flags_local = nullptr;                 // [2][nranks]: free / ready counters written by peers
-  unsigned long long **d_sig_free = nullptr, **d_sig_ready = nullptr;   // device arrays of remote slot addresses
+  unsigned long long **d_sig[4] = {nullptr, nullptr, nullptr, nullptr};   // per flag kind: device array of remote slot addresses
   int *d_wait_slots = nullptr;            // peer ranks to wait for
   int my_rank = 0, nranks = 1;
   std::string err;

@@ -191,7 +191,8 @@ class MHD {  // state owner + tasks
   long launches = 0;
   std::map<std::string, std::shared_ptr<TaskList>> tl_map;
   std::vector<double *> owned;
-  struct Peer { int rank; long ncc, nfc; double *scc, *rcc, *sfc, *rfc; long nemf = 0; double *semf = nullptr, *remf = nullptr; };
+  struct Peer { int rank; long ncc, nfc; double *scc, *rcc, *sfc, *rfc; long nemf = 0; double *semf = nullptr, *remf = nullptr;
+                double *pemf = nullptr; /* my segment inside the peer's EMF receive buffer, mapped over NVLink */ };
   std::vector<Peer> peers;
   Nccl::Comm comm = nullptr;
   double *d_dt = nullptr;
@@ -200,6 +201,7 @@ class MHD {  // state owner + tasks
   bool hydro = false, multi_d = true, three_d = true;
   // peer-memory ghost exchange (ak_halo_push_*): set up by SetupPeerPush() after the communicator exists
   int gids_start_ = 0;
+  unsigned long long nemfx = 0;      // EMF exchanges completed through peer memory
   bool push = false;
   unsigned long long nexch = 0;               // exchanges completed (sequence number of the flags)
   unsigned long long *d_flags = nullptr;      // [2][nranks] counters written by the peers
@@ -259,14 +261,17 @@ class MHD {  // state owner + tasks
   // array (ncclAllGather), maps its neighbours' arrays and registers them with the halo plan.  All
   // ranks must agree: the outcome is min-reduced, and anything short of unanimous success leaves the
   // grouped ncclSend/ncclRecv path in place.  AKB_PEER_PUSH=0 disables it.
-  struct PeerInfo { cudaIpcMemHandle_t h[5]; int gids_start; int ok; int pad[2]; };
+  // h[0..3] u0 / face fields, h[4] flags, h[5] EMF receive buffer; emf_rank/emf_off: where each of MY peers'
+  // EMF messages lands inside that buffer (doubles from its base)
+  struct PeerInfo { cudaIpcMemHandle_t h[6]; int gids_start; int ok; int npeers; int pad;
+                    int emf_rank[AKB_MAX_PUSH_PEERS_HOST]; long emf_off[AKB_MAX_PUSH_PEERS_HOST]; };
   void SetupPeerPush(int gids_start) {
     Nccl &n = Nccl::get();
     const char *env = std::getenv("AKB_PEER_PUSH");
     if (nranks < 2 || !comm || !n.AllGather || (env && env[0] == '0')) return;
     int ok = 1;
-    if (cudaMalloc(&d_flags, sizeof(unsigned long long) * 2 * nranks) != cudaSuccess) { ok = 0; d_flags = nullptr; }
-    if (d_flags) CU_CHECK(cudaMemset(d_flags, 0, sizeof(unsigned long long) * 2 * nranks));
+    if (cudaMalloc(&d_flags, sizeof(unsigned long long) * 4 * nranks) != cudaSuccess) { ok = 0; d_flags = nullptr; }
+    if (d_flags) CU_CHECK(cudaMemset(d_flags, 0, sizeof(unsigned long long) * 4 * nranks));
     PeerInfo mine;
     std::memset(&mine, 0, sizeof(mine));
     mine.gids_start = gids_start;
@@ -275,6 +280,17 @@ class MHD {  // state owner + tasks
       if (arr[q] && cudaIpcGetMemHandle(&mine.h[q], arr[q]) != cudaSuccess) ok = 0;
     if (ok && cudaIpcGetMemHandle(&mine.h[4], d_flags) != cudaSuccess) ok = 0;
     if ((int)peers.size() > AKB_MAX_PUSH_PEERS_HOST) ok = 0;
+    double *emf_base = nullptr;
+    if (ok && !hydro) {    // EMF correction (SendE/RecvE) through peer memory as well
+      long cnt = 0;
+      if (ak_halo_emf_rbuf(plan, &emf_base, &cnt) || !emf_base || cudaIpcGetMemHandle(&mine.h[5], emf_base) != cudaSuccess) ok = 0;
+      mine.npeers = (int)peers.size();
+      for (size_t p = 0; p < peers.size() && ok; ++p) {
+        if (ak_halo_emf_peer(plan, (int)p, &peers[p].nemf, &peers[p].remf)) { ok = 0; break; }
+        mine.emf_rank[p] = peers[p].rank;
+        mine.emf_off[p] = (long)(peers[p].remf - emf_base);
+      }
+    }
     mine.ok = ok;
     cudaGetLastError();
     char *d_send = nullptr, *d_recv = nullptr;
@@ -289,15 +305,21 @@ class MHD {  // state owner + tasks
     std::vector<unsigned long long *> pflags(peers.size(), nullptr);
     for (size_t p = 0; p < peers.size() && ok; ++p) {
       const PeerInfo &pi = all[peers[p].rank];
-      void *ptr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-      for (int q = 0; q < 5 && ok; ++q) {
-        if (q >= 1 && q <= 3 && hydro) continue;
+      void *ptr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+      for (int q = 0; q < 6 && ok; ++q) {
+        if ((q >= 1 && q <= 3 || q == 5) && hydro) continue;
         if (cudaIpcOpenMemHandle(&ptr[q], pi.h[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
         ipc_opened.push_back(ptr[q]);
       }
       if (!ok) break;
       if (ak_halo_push_setup(plan, (int)p, pi.gids_start, (double *)ptr[0], (double *)ptr[1], (double *)ptr[2], (double *)ptr[3])) ok = 0;
       pflags[p] = (unsigned long long *)ptr[4];
+      if (!hydro) {      // my segment in the peer's EMF receive buffer
+        peers[p].pemf = nullptr;
+        for (int q = 0; q < pi.npeers; ++q)
+          if (pi.emf_rank[q] == my_rank) peers[p].pemf = (double *)ptr[5] + pi.emf_off[q];
+        if (!peers[p].pemf) ok = 0;
+      }
     }
     if (ok && ak_halo_push_flags(plan, my_rank, nranks, d_flags, pflags.data())) ok = 0;
     if (ok && ak_halo_push_commit(plan)) ok = 0;
@@ -310,6 +332,8 @@ class MHD {  // state owner + tasks
     CU_CHECK(cudaStreamSynchronize(st));
     cudaFree(d_send); cudaFree(d_recv);
     push = flag > 0.5;
+    // the EMF receive segments start out free: first exchange has sequence number 1
+    if (push && !hydro) AK_CHECK(nullptr, ak_halo_signal(plan, 2, 1, st));
     if (!push && my_rank == 0) std::fprintf(stderr, "athenak_b200: peer-memory ghost exchange unavailable, using ncclSend/ncclRecv\n");
   }
   // receiver side: nothing of this rank reads its ghost zones any more -> peers may overwrite them
@@ -428,6 +452,17 @@ class MHD {  // state owner + tasks
   // SendE/RecvE: flux_correct_fc.cpp:29-437 (EMF flux correction, always executed as in the reference)
   TaskStatus SendE(Driver *pd, int stage) {
     Nccl &n = Nccl::get();
+    if (UsePush()) {
+      // peer-memory variant: the pack kernel of each peer stores straight into my segment of that peer's
+      // receive buffer over NVLink (no send buffer, no message); handshake kinds 2 ("segment free") / 3 ("filled")
+      const unsigned long long seq = nemfx + 1;
+      AK_CHECK(nullptr, ak_halo_wait(plan, 2, seq, st));
+      for (size_t p = 0; p < peers.size(); ++p) AK_CHECK(nullptr, ak_halo_emf_pack(plan, a.e1, a.e2, a.e3, (int)p, peers[p].pemf, st));
+      AK_CHECK(nullptr, ak_halo_signal(plan, 3, seq, st));
+      AK_CHECK(nullptr, ak_halo_emf_pack_local(plan, a.e1, a.e2, a.e3, st));
+      launches += 3 + (long)peers.size();
+      return TaskStatus::complete;
+    }
     if (!peers.empty()) {
       if (!comm) Fatal(__FILE__, __LINE__, "MeshBlocks on other ranks but no NCCL communicator (call ak_sim_comm_init)");
       for (size_t p = 0; p < peers.size(); ++p) {
@@ -451,8 +486,14 @@ class MHD {  // state owner + tasks
     return TaskStatus::complete;
   }
   TaskStatus RecvE(Driver *pd, int stage) {
+    if (UsePush()) { AK_CHECK(nullptr, ak_halo_wait(plan, 3, nemfx + 1, st)); launches += 1; }
     AK_CHECK(nullptr, ak_halo_emf_sumavg(plan, a.e1, a.e2, a.e3, st));
     launches += 1;
+    if (UsePush()) {      // segments consumed: peers may fill them for the next exchange
+      nemfx += 1;
+      AK_CHECK(nullptr, ak_halo_signal(plan, 2, nemfx + 1, st));
+      launches += 1;
+    }
     return TaskStatus::complete;
   }
   // SendU/RecvU, SendB/RecvB: bvals_cc.cpp:42-447, bvals_fc.cpp:63-436

@@ -167,7 +167,7 @@ EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_con
             "ak_sim_get_state", "ak_sim_initialize", "ak_sim_execute", "ak_sim_sync", "ak_sim_status", "ak_sim_arrays",
             "ak_sim_set_bcs", "ak_bcs_create", "ak_bcs_destroy", "ak_bcs_last_error", "ak_bcs_strictly_periodic",
             "ak_bcs_hydro", "ak_bcs_bfield", "ak_bcs_apply",
-            "ak_hst_sums", "ak_halo_push_setup", "ak_halo_push_flags", "ak_halo_push_commit", "ak_halo_push",
+            "ak_hst_sums", "ak_halo_emf_rbuf", "ak_halo_push_setup", "ak_halo_push_flags", "ak_halo_push_commit", "ak_halo_push",
             "ak_halo_signal", "ak_halo_wait", "ak_hydro_create", "ak_hydro_destroy", "ak_hydro_copy_cons", "ak_hydro_fluxes", "ak_hydro_rk_update",
             "ak_hydro_cons2prim", "ak_hydro_new_dt", "ak_hydro_stage_fused", "ak_hydro_cons2prim_newdt")
 

@@ -182,8 +182,10 @@ int ak_halo_unpack_fc(void *plan, double *x1f, double *x2f, double *x3f, int ipe
  * into the ghost zones of the neighbouring blocks inside the peer GPUs' arrays.  The host layer maps
  * each peer's u0 / x1f / x2f / x3f and flag array into this process (cudaIpcOpenMemHandle) and
  * registers them per peer (ipeer as in ak_halo_peer) together with the peer's first gid; flags are
- * 2*nranks monotone counters per rank ([kind][writer rank], kind 0 = "my ghost zones may be
- * overwritten", 1 = "your ghost zones are filled").  Protocol per exchange with sequence number n:
+ * 4*nranks monotone counters per rank ([kind][writer rank], kind 0 = "my ghost zones may be
+ * overwritten", 1 = "your ghost zones are filled"; kinds 2 / 3 are the same pair for the EMF
+ * receive segments: ak_halo_emf_pack may be handed a peer-mapped pointer into the neighbour's
+ * segment (ak_halo_emf_rbuf base + that rank's ak_halo_emf_peer offset) instead of a send buffer).  Protocol per exchange with sequence number n:
  *   receiver: ak_halo_signal(plan, 0, n) once nothing reads its ghost zones any more
  *   sender:   ak_halo_wait(plan, 0, n); ak_halo_push(...); ak_halo_signal(plan, 1, n)
  *   receiver: ak_halo_wait(plan, 1, n) before the ghost zones are read
@@ -197,6 +199,8 @@ int ak_halo_push_commit(void *plan);
 /* u0 == NULL skips the cell-centred data, x1f == NULL the face fields */
 int ak_halo_push(void *plan, double *u0, int nvar, double *x1f, double *x2f, double *x3f, ak_stream_t s);
 int ak_halo_signal(void *plan, int kind, unsigned long long value, ak_stream_t s);
+/* base and length (doubles) of this rank's EMF receive buffer (all local + per-peer segments) */
+int ak_halo_emf_rbuf(void *plan, double **base, long *count);
 int ak_halo_wait(void *plan, int kind, unsigned long long value, ak_stream_t s);
 
 /* Orszag-Tang vortex ICs (src/pgen/tests/orszag_tang.cpp:32-123), BASELINE config 3. */

@@ -19,6 +19,45 @@ from athenak_b200.mesh import Mesh  # noqa: E402
 from athenak_b200.mhd import MHD  # noqa: E402
 
 
+def orszag_tang_leg(rank, world, dev):
+    """Orszag-Tang 16^3 on 8 blocks over the ranks, 3 cycles, C++ host driver (peer-memory U/B and EMF exchange
+    when available) against oracle/mhd_oracle.c run on all 8 blocks by every rank.  Unlike the blast, these ICs
+    come from a vector potential evaluated on both sides of the periodic boundary, so the two copies of a shared
+    face differ by an ulp and the SendE/RecvE correction changes bits: a lost or misplaced EMF
+    message fails this leg."""
+    import hydro_util as H
+    from athenak_b200.sim import Simulation
+    deck = open(os.path.join(HERE, "decks", "ot3d.athinput")).read()
+    case = H.Case(deck, overrides=[f"mesh/nx{d}=16" for d in (1, 2, 3)] + [f"meshblock/nx{d}=8" for d in (1, 2, 3)])
+    ncyc = 3
+    full = Mesh(case.nmesh, case.nblock, nranks=1)
+    fu, f1, f2, f3 = (t.numpy() for t in full.pgen_orszag_tang(0, case.ng, case.gamma))
+    A, t_or, dt_or, n_or, dt0 = H.oracle_run_mhd(case, fu, (f1, f2, f3), ncycles=ncyc)
+    mesh = Mesh(case.nmesh, case.nblock, nranks=world)
+    g0, n = int(mesh.gids_start[rank]), int(mesh.nmb_rank[rank])
+    ok = True
+    for fused in (True, False):
+        sim = Simulation(mesh, rank, ng=case.ng, recon=case.recon, rsolver=case.rsolver, gamma=case.gamma,
+                         integrator=case.integrator, cfl_number=case.cfl, tlim=case.tlim, fused=fused)
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(sim.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        sim.comm_init(bytes(idt.cpu().numpy().tobytes()))
+        sim.set_state(*mesh.pgen_orszag_tang(rank, case.ng, case.gamma))
+        sim.initialize()
+        ok &= sim.status()["dt"] == dt0
+        sim.execute(ncyc)
+        u, x1, x2, x3 = sim.get_state()
+        s = slice(case.ng, -case.ng)
+        ok &= np.array_equal(u[:, :, s, s, s], A.u0[g0:g0 + n, :, s, s, s])
+        for x, y in zip((x1, x2, x3), A.b0):
+            ok &= np.array_equal(x, y[g0:g0 + n])       # face fields: ghost zones included
+        ok &= sim.status()["time"] == t_or and sim.status()["dt"] == dt_or
+        del sim
+    return bool(ok)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -73,6 +112,7 @@ def main():
     push_used = sim.status()["peer_push"]
     ok &= (sim.status()["peer_exchanges"] > 0) == push_used
     del sim
+    ok &= orszag_tang_leg(rank, world, dev)
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
