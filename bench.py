@@ -208,7 +208,7 @@ def bench_native(args):
     launches = sim.status()["launches"] - l0
     ms = ev0.elapsed_time(ev1)
     halo_mode = ("same-rank gather kernel only" if world == 1 else
-                 "peer-memory push kernel over NVLink (cudaIpc-mapped neighbour arrays, flag handshake); EMF correction + dt via NCCL"
+                 "peer-memory push kernel over NVLink (cudaIpc-mapped neighbour arrays, flag handshake); EMF correction packed straight into the neighbours' receive segments the same way; dt via ncclAllReduce(min)"
                  if sim.status()["peer_push"] else "grouped ncclSend/ncclRecv, one message per peer")
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
