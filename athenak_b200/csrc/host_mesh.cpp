@@ -28,6 +28,8 @@ struct HostMesh {
   int bcs[6];          // per mesh face: enum ak_bc_flag
   int nranks;
   int root_level, nmb_total;
+  int max_level = 0;
+  bool multilevel = false;     // <mesh_refinement>/refinement != none: neighbour sub-block slots are in use
   std::vector<LLoc> lloc;            // Z-ordered
   std::vector<int> rank_of, gids_start, nmb_rank;
   std::vector<double> mb_size;       // [nmb_total][9]
@@ -48,16 +50,107 @@ inline double CellCenterX(int ith, int n, double xmin, double xmax) {
   return (x * xmax - x * xmin) - (0.5 * xmax - 0.5 * xmin) + (0.5 * xmin + 0.5 * xmax);
 }
 
-// depth-first walk of the (possibly incomplete) root oct-tree: leaf order = gid order
-void walk(const HostMesh &M, int lx, int ly, int lz, int lev, std::vector<LLoc> &out) {
-  if (lev == M.root_level) { out.push_back(LLoc{lx, ly, lz, lev}); return; }
-  const int levfac = 1 << (M.root_level - lev - 1);
-  for (int n = 0; n < 8; ++n) {
-    const int i = n & 1, j = (n >> 1) & 1, k = (n >> 2) & 1;
-    if ((lz * 2 + k) * levfac < M.nroot[2] && (ly * 2 + j) * levfac < M.nroot[1] && (lx * 2 + i) * levfac < M.nroot[0])
-      walk(M, lx * 2 + i, ly * 2 + j, lz * 2 + k, lev + 1, out);
+// MeshBlockTree (meshblock_tree.cpp:28-479): oct-/quad-/binary tree over logical locations.  The root
+// grid can be incomplete; refining a node also refines its neighbours as needed so that adjacent
+// leaves differ by at most one level (Refine -> AddNode on the 26 neighbours of the refined node).
+struct HostMesh;
+struct Tree {
+  struct Node {
+    LLoc l{0, 0, 0, 0};
+    int gid = -1;
+    Node *leaf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool split = false;          // pleaf_ != nullptr
+    ~Node() { for (Node *c : leaf) delete c; }
+  };
+  const int *nroot; const int *bcs; int root_level; bool multi_d, three_d; int nleaf;
+  Node *root = nullptr;
+  Tree(const int *nroot_, const int *bcs_, int root_level_, bool multi_d_, bool three_d_)
+      : nroot(nroot_), bcs(bcs_), root_level(root_level_), multi_d(multi_d_), three_d(three_d_) {
+    nleaf = three_d ? 8 : (multi_d ? 4 : 2);          // meshblock_tree.cpp:64-69
+    root = new Node();
+    CreateRootGrid(root);
   }
-}
+  ~Tree() { delete root; }
+  static Node *child(Node *p, int i, int j, int k) {
+    Node *c = new Node();
+    c->l = LLoc{(p->l.lx1 << 1) + i, (p->l.lx2 << 1) + j, (p->l.lx3 << 1) + k, p->l.level + 1};   // meshblock_tree.cpp:38-47
+    return c;
+  }
+  void CreateRootGrid(Node *t) {                       // meshblock_tree.cpp:64-91
+    if (t->l.level == root_level) return;
+    t->split = true;
+    const int levfac = 1 << (root_level - t->l.level - 1);
+    for (int n = 0; n < nleaf; ++n) {
+      const int i = n & 1, j = (n >> 1) & 1, k = (n >> 2) & 1;
+      if ((t->l.lx3 * 2 + k) * levfac < nroot[2] && (t->l.lx2 * 2 + j) * levfac < nroot[1] && (t->l.lx1 * 2 + i) * levfac < nroot[0]) {
+        t->leaf[n] = child(t, i, j, k);
+        CreateRootGrid(t->leaf[n]);
+      }
+    }
+  }
+  static int leaf_index(const LLoc &r, int level) {    // leaf of a node at `level` on the way to r
+    const int sh = r.level - level - 1;
+    return ((r.lx1 >> sh) & 1) + (((r.lx2 >> sh) & 1) << 1) + (((r.lx3 >> sh) & 1) << 2);
+  }
+  void AddNode(Node *t, const LLoc &r, int &nnew) {    // meshblock_tree.cpp:97-114
+    if (t->l.level == r.level) return;
+    if (!t->split) Refine(t, nnew);
+    AddNode(t->leaf[leaf_index(r, t->l.level)], r, nnew);
+  }
+  bool periodic(int face) const { return bcs[face] == AK_BC_PERIODIC || (face < 2 && bcs[face] == AK_BC_SHEAR_PERIODIC); }
+  void Refine(Node *t, int &nnew) {                    // meshblock_tree.cpp:151-249
+    if (t->split) return;
+    t->split = true;
+    for (int n = 0; n < nleaf; ++n) t->leaf[n] = child(t, n & 1, (n >> 1) & 1, (n >> 2) & 1);
+    const int sh = t->l.level - root_level;
+    const int nmax[3] = {nroot[0] << sh, multi_d ? nroot[1] << sh : 1, three_d ? nroot[2] << sh : 1};
+    const int oy0 = multi_d ? -1 : 0, oz0 = three_d ? -1 : 0;
+    for (int oz = oz0; oz <= -oz0; ++oz) {
+      int lz = t->l.lx3 + oz;
+      if (lz < 0) { if (!periodic(4)) continue; lz = nmax[2] - 1; }
+      if (lz >= nmax[2]) { if (!periodic(5)) continue; lz = 0; }
+      for (int oy = oy0; oy <= -oy0; ++oy) {
+        int ly = t->l.lx2 + oy;
+        if (ly < 0) { if (!periodic(2)) continue; ly = nmax[1] - 1; }
+        if (ly >= nmax[1]) { if (!periodic(3)) continue; ly = 0; }
+        for (int ox = -1; ox <= 1; ++ox) {
+          if (ox == 0 && oy == 0 && oz == 0) continue;
+          int lx = t->l.lx1 + ox;
+          if (lx < 0) { if (!periodic(0)) continue; lx = nmax[0] - 1; }
+          if (lx >= nmax[0]) { if (!periodic(1)) continue; lx = 0; }
+          AddNode(root, LLoc{lx, ly, lz, t->l.level}, nnew);
+        }
+      }
+    }
+    t->gid = -1;
+    nnew += nleaf - 1;
+  }
+  // meshblock_tree.cpp:361-448: the block at (myloc + offset) if it is a leaf at the same level, the
+  // coarser leaf that contains it, or -- when that position is refined -- the node whose leaves are finer
+  Node *FindNeighbor(const LLoc &my, int ox1, int ox2, int ox3) const {
+    int lx = my.lx1 + ox1, ly = my.lx2 + ox2, lz = my.lx3 + ox3;
+    const int ll = my.level, sh = ll - root_level;
+    if (lx < 0) { if (!periodic(0)) return nullptr; lx = (nroot[0] << sh) - 1; }
+    if (lx >= (nroot[0] << sh)) { if (!periodic(1)) return nullptr; lx = 0; }
+    if (ly < 0) { if (!periodic(2)) return nullptr; ly = (nroot[1] << sh) - 1; }
+    if (ly >= (nroot[1] << sh)) { if (!periodic(3)) return nullptr; ly = 0; }
+    if (lz < 0) { if (!periodic(4)) return nullptr; lz = (nroot[2] << sh) - 1; }
+    if (lz >= (nroot[2] << sh)) { if (!periodic(5)) return nullptr; lz = 0; }
+    if (ll < 1) return root;
+    Node *bt = root;
+    for (int level = 0; level < ll; ++level) {
+      if (!bt->split) return bt;                       // coarser leaf (the reference insists level == ll-1)
+      const int s = ll - level - 1;
+      bt = bt->leaf[((lx >> s) & 1) + (((ly >> s) & 1) << 1) + (((lz >> s) & 1) << 2)];
+      if (!bt) return nullptr;
+    }
+    return bt;     // leaf at the same level, or a split node: its leaves are one level finer
+  }
+  void ZOrder(Node *t, std::vector<LLoc> &out) {       // meshblock_tree.cpp:336-350
+    if (!t->split) { t->gid = (int)out.size(); out.push_back(t->l); return; }
+    for (int n = 0; n < nleaf; ++n) if (t->leaf[n]) ZOrder(t->leaf[n], out);
+  }
+};
 
 // load_balance.cpp:38-88 with unit costs
 void load_balance(HostMesh &M) {
@@ -97,9 +190,91 @@ extern "C" {
 
 const char *ak_mesh_last_error() { return g_mesh_err.c_str(); }
 
-// nmesh/nblock: cells per direction in the mesh / per MeshBlock; bcs[6]: ix1,ox1,ix2,ox2,ix3,ox3.
-int ak_mesh_create(const int *nmesh, const int *nblock, const double *xmin, const double *xmax, const int *bcs,
-                   int nranks, void **mesh) {
+// Fills the per-block tables from the Z-ordered leaf list: sizes / BC flags (meshblock.cpp:25-131) and the
+// 56-slot neighbour table with levels and sub-block indices (meshblock.cpp:142-430).
+static void fill_tables(HostMesh *M, Tree &T) {
+  const int nb = M->nmb_total;
+  const bool multi_d = M->nmesh[1] > 1, three_d = M->nmesh[2] > 1;
+  M->mb_size.assign((size_t)nb * 9, 0.0);
+  M->mb_bcs.assign((size_t)nb * 6, 0);
+  M->nghbr.assign((size_t)nb * 56 * 4, -1);
+  const int nfx = M->multilevel ? 2 : 1, nfy = (M->multilevel && multi_d) ? 2 : 1, nfz = (M->multilevel && three_d) ? 2 : 1;
+  (void)nfx;
+  for (int g = 0; g < nb; ++g) {
+    const LLoc &ll = M->lloc[g];
+    const int l[3] = {ll.lx1, ll.lx2, ll.lx3};
+    const bool act[3] = {true, multi_d, three_d};
+    for (int d = 0; d < 3; ++d) {
+      if (!act[d]) {      // meshblock.cpp:63-67,90-94: the whole mesh extent, mesh flags
+        M->mb_size[g * 9 + d] = M->xmin[d]; M->mb_size[g * 9 + 3 + d] = M->xmax[d];
+        M->mb_bcs[g * 6 + 2 * d] = M->bcs[2 * d]; M->mb_bcs[g * 6 + 2 * d + 1] = M->bcs[2 * d + 1];
+      } else {
+        const int n = M->nroot[d] << (ll.level - M->root_level);
+        double lo, hi;
+        if (l[d] == 0) { lo = M->xmin[d]; M->mb_bcs[g * 6 + 2 * d] = M->bcs[2 * d]; }
+        else { lo = LeftEdgeX(l[d], n, M->xmin[d], M->xmax[d]); M->mb_bcs[g * 6 + 2 * d] = AK_BC_BLOCK; }
+        if (l[d] == n - 1) { hi = M->xmax[d]; M->mb_bcs[g * 6 + 2 * d + 1] = M->bcs[2 * d + 1]; }
+        else { hi = LeftEdgeX(l[d] + 1, n, M->xmin[d], M->xmax[d]); M->mb_bcs[g * 6 + 2 * d + 1] = AK_BC_BLOCK; }
+        M->mb_size[g * 9 + d] = lo;
+        M->mb_size[g * 9 + 3 + d] = hi;
+      }
+      M->mb_size[g * 9 + 6 + d] = (M->mb_size[g * 9 + 3 + d] - M->mb_size[g * 9 + d]) / static_cast<double>(M->nblock[d]);
+    }
+    // position of this block inside its parent
+    const int myfx1 = ll.lx1 & 1, myfx2 = ll.lx2 & 1, myfx3 = ll.lx3 & 1;
+    const int myox1 = myfx1 * 2 - 1, myox2 = multi_d ? myfx2 * 2 - 1 : 0, myox3 = three_d ? myfx3 * 2 - 1 : 0;
+    auto set = [&](int slot, const Tree::Node *nt, int dest) {
+      int *e = &M->nghbr[((size_t)g * 56 + slot) * 4];
+      e[0] = nt->gid; e[1] = nt->l.level; e[2] = M->rank_of[nt->gid]; e[3] = dest;
+    };
+    using akb::neighbor_index;
+    for (int oz = -1; oz <= 1; ++oz) for (int oy = -1; oy <= 1; ++oy) for (int ox = -1; ox <= 1; ++ox) {
+      if (!ox && !oy && !oz) continue;
+      if ((oy && !multi_d) || (oz && !three_d)) continue;
+      Tree::Node *nt = T.FindNeighbor(ll, ox, oy, oz);
+      if (!nt) continue;
+      const int nzero = (ox == 0) + (oy == 0) + (oz == 0);      // 2: face, 1: edge, 0: corner
+      if (nt->split) {   // finer neighbour(s): the leaves of nt that touch this block
+        const int ffx = 1 - (ox + 1) / 2, ffy = 1 - (oy + 1) / 2, ffz = 1 - (oz + 1) / 2;   // 0 toward +, 1 toward -
+        if (nzero == 2) {
+          // sub-block indices (f1,f2) run over the two transverse directions in the order (x1|x2, x2|x3)
+          for (int f2 = 0; f2 < ((ox || oy) ? nfz : nfy); ++f2)
+            for (int f1 = 0; f1 < (ox ? nfy : nfx); ++f1) {
+              const Tree::Node *nf = ox ? nt->leaf[ffx + 2 * f1 + 4 * f2] : oy ? nt->leaf[f1 + 2 * ffy + 4 * f2] : nt->leaf[f1 + 2 * f2 + 4 * ffz];
+              set(neighbor_index(ox, oy, oz, f1, f2), nf, neighbor_index(-ox, -oy, -oz, f1, f2));
+            }
+        } else if (nzero == 1) {
+          const int nf1 = (oz == 0) ? nfz : (oy == 0) ? nfy : nfy;   // meshblock.cpp:373 loops fx over nfy
+          for (int f1 = 0; f1 < nf1; ++f1) {
+            const Tree::Node *nf = (oz == 0) ? nt->leaf[ffx + 2 * ffy + 4 * f1] : (oy == 0) ? nt->leaf[ffx + 2 * f1 + 4 * ffz] : nt->leaf[f1 + 2 * ffy + 4 * ffz];
+            set(neighbor_index(ox, oy, oz, f1, 0), nf, neighbor_index(-ox, -oy, -oz, f1, 0));
+          }
+        } else {
+          set(neighbor_index(ox, oy, oz, 0, 0), nt->leaf[ffx + 2 * ffy + 4 * ffz], neighbor_index(-ox, -oy, -oz, 0, 0));
+        }
+      } else if (nt->l.level == ll.level) {   // same level
+        set(neighbor_index(ox, oy, oz, 0, 0), nt, neighbor_index(-ox, -oy, -oz, 0, 0));
+      } else {                                // coarser: slot and destination carry MY sub-block position
+        if (nzero == 2) {
+          const int f1 = ox ? myfx2 : myfx1, f2 = (ox || oy) ? myfx3 : myfx2;
+          set(neighbor_index(ox, oy, oz, f1, f2), nt, neighbor_index(-ox, -oy, -oz, f1, f2));
+        } else if (nzero == 1) {
+          // only the exterior edges of the coarser block's face (meshblock.cpp:263,333,383)
+          const int f1 = (oz == 0) ? myfx3 : (oy == 0) ? myfx2 : myfx1;
+          const bool exterior = (oz == 0) ? (myox1 == ox && myox2 == oy) : (oy == 0) ? (myox1 == ox && myox3 == oz) : (myox2 == oy && myox3 == oz);
+          if (exterior) set(neighbor_index(ox, oy, oz, f1, 0), nt, neighbor_index(-ox, -oy, -oz, f1, 0));
+        } else if (myox1 == ox && myox2 == oy && myox3 == oz) {   // :410
+          set(neighbor_index(ox, oy, oz, 0, 0), nt, neighbor_index(-ox, -oy, -oz, 0, 0));
+        }
+      }
+    }
+  }
+}
+
+// regions: [nregions][7] = physical level (>= 1), x1min, x1max, x2min, x2max, x3min, x3max of each
+// <refined_region> block (build_tree.cpp:79-230); multilevel = <mesh_refinement>/refinement != none.
+static int mesh_build(const int *nmesh, const int *nblock, const double *xmin, const double *xmax, const int *bcs,
+                      int nranks, int multilevel, int nregions, const double *regions, void **mesh) {
   if (!mesh) { g_mesh_err = "ak_mesh_create: null output"; return 1; }
   *mesh = nullptr;
   auto *M = new HostMesh();
@@ -115,52 +290,62 @@ int ak_mesh_create(const int *nmesh, const int *nblock, const double *xmin, cons
   }
   for (int q = 0; q < 6; ++q) M->bcs[q] = bcs[q];
   M->nranks = nranks;
+  M->multilevel = multilevel != 0 || nregions > 0;
+  const bool multi_d = nmesh[1] > 1, three_d = nmesh[2] > 1;
+  if (M->multilevel && (nblock[0] % 2 || (multi_d && nblock[1] % 2) || (three_d && nblock[2] % 2))) {
+    g_mesh_err = "ak_mesh_create: number of cells in MeshBlock must be divisible by 2 with SMR or AMR"; delete M; return 1;   // build_tree.cpp:68-76
+  }
   int nmbmax = std::max(M->nroot[0], std::max(M->nroot[1], M->nroot[2]));
   for (M->root_level = 0; ((1 << M->root_level) < nmbmax); M->root_level++) {}   // build_tree.cpp:42-45
-  walk(*M, 0, 0, 0, 0, M->lloc);
+  Tree T(M->nroot, M->bcs, M->root_level, multi_d, three_d);
+  M->max_level = M->root_level;
+  for (int r = 0; r < nregions; ++r) {        // build_tree.cpp:79-230
+    const double *R = regions + 7 * r;
+    const int phy = (int)R[0], logl = phy + M->root_level;
+    double rmin[3] = {R[1], multi_d ? R[3] : xmin[1], three_d ? R[5] : xmin[2]};
+    double rmax[3] = {R[2], multi_d ? R[4] : xmax[1], three_d ? R[6] : xmax[2]};
+    if (phy < 1) { g_mesh_err = "ak_mesh_create: <refined_region> level must be larger than 0"; delete M; return 1; }
+    for (int d = 0; d < 3; ++d)
+      if (rmin[d] > rmax[d] || rmin[d] < xmin[d] || rmax[d] > xmax[d]) {
+        g_mesh_err = "ak_mesh_create: <refined_region> must be valid and fully contained within the root mesh"; delete M; return 1;
+      }
+    if (logl > M->max_level) M->max_level = logl;
+    int lmin[3] = {0, 0, 0}, lmax[3] = {0, 0, 0};
+    const bool act[3] = {true, multi_d, three_d};
+    for (int d = 0; d < 3; ++d) {
+      if (!act[d]) continue;
+      const int lxmax = M->nroot[d] * (1 << phy);
+      for (lmin[d] = 0; lmin[d] < lxmax; lmin[d]++) if (LeftEdgeX(lmin[d] + 1, lxmax, xmin[d], xmax[d]) > rmin[d]) break;
+      for (lmax[d] = lmin[d]; lmax[d] < lxmax; lmax[d]++) if (LeftEdgeX(lmax[d] + 1, lxmax, xmin[d], xmax[d]) >= rmax[d]) break;
+      if (lmin[d] % 2 == 1) lmin[d]--;
+      if (lmax[d] % 2 == 0) lmax[d]++;
+    }
+    int nnew = 0;
+    for (int k = lmin[2]; k < (three_d ? lmax[2] : lmin[2] + 1); k += 2)
+      for (int j = lmin[1]; j < (multi_d ? lmax[1] : lmin[1] + 1); j += 2)
+        for (int i = lmin[0]; i < lmax[0]; i += 2) T.AddNode(T.root, LLoc{i, multi_d ? j : 0, three_d ? k : 0, logl}, nnew);
+  }
+  T.ZOrder(T.root, M->lloc);
   M->nmb_total = (int)M->lloc.size();
   if (M->nmb_total < nranks) { g_mesh_err = "ak_mesh_create: fewer MeshBlocks than ranks"; delete M; return 1; }
   load_balance(*M);
-  const int nb = M->nmb_total;
-  // gid lookup by logical location
-  std::vector<int> gid_of((size_t)M->nroot[0] * M->nroot[1] * M->nroot[2], -1);
-  auto at = [&](int x, int y, int z) -> int & { return gid_of[((size_t)z * M->nroot[1] + y) * M->nroot[0] + x]; };
-  for (int g = 0; g < nb; ++g) at(M->lloc[g].lx1, M->lloc[g].lx2, M->lloc[g].lx3) = g;
-  M->mb_size.assign((size_t)nb * 9, 0.0);
-  M->mb_bcs.assign((size_t)nb * 6, 0);
-  M->nghbr.assign((size_t)nb * 56 * 4, -1);
-  for (int g = 0; g < nb; ++g) {
-    const int l[3] = {M->lloc[g].lx1, M->lloc[g].lx2, M->lloc[g].lx3};
-    for (int d = 0; d < 3; ++d) {   // meshblock.cpp:44-116
-      const int n = M->nroot[d];
-      double lo, hi;
-      if (l[d] == 0) { lo = M->xmin[d]; M->mb_bcs[g * 6 + 2 * d] = M->bcs[2 * d]; }
-      else { lo = LeftEdgeX(l[d], n, M->xmin[d], M->xmax[d]); M->mb_bcs[g * 6 + 2 * d] = AK_BC_BLOCK; }
-      if (l[d] == n - 1) { hi = M->xmax[d]; M->mb_bcs[g * 6 + 2 * d + 1] = M->bcs[2 * d + 1]; }
-      else { hi = LeftEdgeX(l[d] + 1, n, M->xmin[d], M->xmax[d]); M->mb_bcs[g * 6 + 2 * d + 1] = AK_BC_BLOCK; }
-      M->mb_size[g * 9 + d] = lo;
-      M->mb_size[g * 9 + 3 + d] = hi;
-      M->mb_size[g * 9 + 6 + d] = (hi - lo) / static_cast<double>(M->nblock[d]);
-    }
-    // same-level neighbours: meshblock.cpp:170-425 with FindNeighbor's periodic wrap
-    for (int oz = -1; oz <= 1; ++oz) for (int oy = -1; oy <= 1; ++oy) for (int ox = -1; ox <= 1; ++ox) {
-      if (!ox && !oy && !oz) continue;
-      // meshblock.cpp:170-425: x2 neighbours only if multi_d, x3 neighbours only if three_d
-      if ((oy && M->nmesh[1] <= 1) || (oz && M->nmesh[2] <= 1)) continue;
-      int q[3] = {l[0] + ox, l[1] + oy, l[2] + oz};
-      bool ok = true;
-      for (int d = 0; d < 3; ++d) {
-        if (q[d] < 0) { if (M->bcs[2 * d] == AK_BC_PERIODIC) q[d] = M->nroot[d] - 1; else ok = false; }
-        else if (q[d] >= M->nroot[d]) { if (M->bcs[2 * d + 1] == AK_BC_PERIODIC) q[d] = 0; else ok = false; }
-      }
-      if (!ok) continue;
-      const int ng = at(q[0], q[1], q[2]);
-      int *e = &M->nghbr[((size_t)g * 56 + akb::neighbor_index(ox, oy, oz, 0, 0)) * 4];
-      e[0] = ng; e[1] = M->root_level; e[2] = M->rank_of[ng]; e[3] = akb::neighbor_index(-ox, -oy, -oz, 0, 0);
-    }
-  }
+  fill_tables(M, T);
   *mesh = M;
   return 0;
+}
+
+// nmesh/nblock: cells per direction in the mesh / per MeshBlock; bcs[6]: ix1,ox1,ix2,ox2,ix3,ox3.
+int ak_mesh_create(const int *nmesh, const int *nblock, const double *xmin, const double *xmax, const int *bcs,
+                   int nranks, void **mesh) {
+  return mesh_build(nmesh, nblock, xmin, xmax, bcs, nranks, 0, 0, nullptr, mesh);
+}
+
+// Static mesh refinement (host maps only): the same tables for a mesh with
+// <refined_region> blocks; NeighborBlock.lev and the sub-block slots / destinations are filled as in
+// meshblock.cpp:142-430.  lloc[.][3] (ak_mesh_tables) is the logical level of each block.
+int ak_mesh_create_smr(const int *nmesh, const int *nblock, const double *xmin, const double *xmax, const int *bcs,
+                       int nranks, int nregions, const double *regions, void **mesh) {
+  return mesh_build(nmesh, nblock, xmin, xmax, bcs, nranks, 1, nregions, regions, mesh);
 }
 
 int ak_mesh_destroy(void *mesh) { delete static_cast<HostMesh *>(mesh); return 0; }

@@ -12,8 +12,10 @@ BC = _lib.BC          # BoundaryFlag values (src/bvals/bvals.hpp:19)
 
 
 class Mesh:
-    def __init__(self, nmesh, nblock, xmin=(-0.5, -0.5, -0.5), xmax=(0.5, 0.5, 0.5), bcs=("periodic",) * 6, nranks=1):
-        """bcs: ix1,ox1,ix2,ox2,ix3,ox3 as BoundaryFlag names or values."""
+    def __init__(self, nmesh, nblock, xmin=(-0.5, -0.5, -0.5), xmax=(0.5, 0.5, 0.5), bcs=("periodic",) * 6, nranks=1, refined_regions=None):
+        """bcs: ix1,ox1,ix2,ox2,ix3,ox3 as BoundaryFlag names or values.
+        refined_regions: None (uniform mesh) or a list of (level, x1min, x1max, x2min, x2max, x3min, x3max), the
+        <refined_region> blocks of a static-mesh-refinement deck (host maps only, see ak_mesh_create_smr)."""
         self.L = _lib.load()
         bcs = tuple(BC[b] if isinstance(b, str) else int(b) for b in bcs)
         self.bcs = bcs
@@ -21,7 +23,12 @@ class Mesh:
         self.xmin, self.xmax = tuple(xmin), tuple(xmax)
         i3, d3, i6 = (C.c_int * 3), (C.c_double * 3), (C.c_int * 6)
         self.h = C.c_void_p()
-        rc = self.L.ak_mesh_create(i3(*nmesh), i3(*nblock), d3(*xmin), d3(*xmax), i6(*bcs), nranks, C.byref(self.h))
+        if refined_regions is None:
+            rc = self.L.ak_mesh_create(i3(*nmesh), i3(*nblock), d3(*xmin), d3(*xmax), i6(*bcs), nranks, C.byref(self.h))
+        else:
+            reg = np.ascontiguousarray(np.array(refined_regions, np.float64).reshape(-1, 7))
+            rc = self.L.ak_mesh_create_smr(i3(*nmesh), i3(*nblock), d3(*xmin), d3(*xmax), i6(*bcs), nranks, len(reg),
+                                           reg.ctypes.data_as(C.POINTER(C.c_double)), C.byref(self.h))
         if rc:
             raise _lib.EngineError(self.L.ak_mesh_last_error().decode())
         a, b = C.c_int(), C.c_int()

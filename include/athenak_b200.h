@@ -250,6 +250,14 @@ int ak_selftest_divsqrt(long n, unsigned long long seed, int exponent_span, long
  * (meshblock.cpp:142-430).  bcs[6] = ix1,ox1,ix2,ox2,ix3,ox3 as enum ak_bc_flag. */
 int ak_mesh_create(const int *nmesh, const int *nblock, const double *xmin, const double *xmax,
                    const int *bcs, int nranks, void **mesh);
+/* Static mesh refinement, host maps: the same tables for a mesh with <refined_region>
+ * blocks (src/mesh/build_tree.cpp:79-230 -> MeshBlockTree::AddNode/Refine, src/mesh/meshblock_tree.cpp:97-249, which
+ * keeps adjacent leaves within one level of each other).  regions = [nregions][7] doubles: physical level
+ * (>= 1), x1min, x1max, x2min, x2max, x3min, x3max.  Z-ordered gids across levels, lloc[.][3] = logical level,
+ * NeighborBlock.lev and the sub-block slots / destinations of coarser and finer neighbours as in
+ * src/mesh/meshblock.cpp:142-430.  The device path for fine/coarse boundaries is not built yet. */
+int ak_mesh_create_smr(const int *nmesh, const int *nblock, const double *xmin, const double *xmax, const int *bcs,
+                       int nranks, int nregions, const double *regions, void **mesh);
 int ak_mesh_destroy(void *mesh);
 const char *ak_mesh_last_error(void);
 int ak_mesh_info(void *mesh, int *nmb_total, int *root_level);

@@ -94,8 +94,46 @@ def iso():
         np.savez_compressed(os.path.join(HERE, "golden", name + ".npz"), **out)
 
 
+SMR_TREES = {   # name -> overrides on tests/decks/lwave3d_hydro_smr.athinput (time/nlim=0: only the mesh is built)
+    "smr3d_periodic": (),
+    "smr3d_outflow_l3": ("mesh/ix1_bc=outflow", "mesh/ox1_bc=outflow", "mesh/ix3_bc=reflect", "mesh/ox3_bc=reflect",
+                         "refined_region1/level=3", "refined_region1/x1min=2.9", "refined_region1/x1max=3.0",
+                         "refined_region1/x3min=0.0", "refined_region1/x3max=0.05"),
+    "smr2d_mixed": ("mesh/nx3=1", "meshblock/nx3=1", "mesh/nx2=32", "meshblock/nx2=8", "mesh/ix2_bc=outflow", "mesh/ox2_bc=reflect",
+                    "refined_region2/level=3", "refined_region2/x1min=2.6", "refined_region2/x1max=3.0", "refined_region2/x2min=1.3",
+                    "refined_region2/x2max=1.5"),
+    "smr1d": ("mesh/nx2=1", "meshblock/nx2=1", "mesh/nx3=1", "meshblock/nx3=1", "mesh/nx1=128", "meshblock/nx1=8",
+              "refined_region2/level=3"),
+}
+
+
+def smr_trees():
+    """Z-ordered LogicalLocation lists (lx1, lx2, lx3, level per gid) of the unmodified reference for static-mesh-
+    refinement decks -> tests/golden/smr_trees.npz (a few kB).  Read from the header of its cycle-0 restart dump."""
+    import struct
+    out = {}
+    for name, ov in SMR_TREES.items():
+        tmp = tempfile.mkdtemp(prefix="akgold_")
+        try:
+            O.run_reference("athena_builtin", os.path.join(HERE, "decks", "lwave3d_hydro_smr.athinput"), tmp, list(ov) + ["time/nlim=0"])
+            raw = open(os.path.join(tmp, "rst", "LinWave.00000.rst"), "rb").read()
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        end = raw.index(b"<par_end>\n") + 10
+        nmb, root = struct.unpack_from("<ii", raw, end)
+        off = end + 8 + 72 + 76 + 76 + 16 + 4          # restart.cpp:216-294 header
+        out[name + "_lloc"] = np.frombuffer(raw, "<i4", 4 * nmb, off).reshape(nmb, 4).copy()
+        out[name + "_root"] = root
+        out[name + "_deck"] = np.array(raw[:end].decode())
+    np.savez_compressed(os.path.join(HERE, "golden", "smr_trees.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--smr-only" in sys.argv:
+        smr_trees()
+        sys.exit(0)
     iso()
+    smr_trees()
     if "--iso-only" in sys.argv:
         sys.exit(0)
     mhd_lowd("bw1d.athinput", "BrioWu", "mhd_bw1d_ppm4_hlld_rk3",
