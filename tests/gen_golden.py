@@ -128,12 +128,27 @@ def smr_trees():
     np.savez_compressed(os.path.join(HERE, "golden", "smr_trees.npz"), **out)
 
 
+def smr():
+    """Hydro SMR fixtures (tests/smr_util.py CASES): ghost-inclusive initial and final dumps on refined meshes."""
+    import smr_util as S
+    for name in S.CASES:
+        r0, r1 = S.reference(name)
+        ng = r0.mb_indcs["ng"]
+        if r0.u0.shape[2] > 1:      # 3-D: active zones only (ghost zones are rebuilt by Driver::Initialize)
+            s = slice(ng, -ng)
+            r0.u0, r1.u0 = r0.u0[:, :, s, s, s], r1.u0[:, :, s, s, s]
+        np.savez_compressed(os.path.join(HERE, "golden", name + ".npz"), deck=np.array(r0.deck), lloc=r0.lloc, u0_c0=r0.u0,
+                            u0_final=r1.u0, dt_c0=r0.dt, ng=ng, time_final=r1.time, dt_final=r1.dt, ncycle_final=r1.ncycle)
+
+
 if __name__ == "__main__":
     if "--smr-only" in sys.argv:
         smr_trees()
+        smr()
         sys.exit(0)
     iso()
     smr_trees()
+    smr()
     if "--iso-only" in sys.argv:
         sys.exit(0)
     mhd_lowd("bw1d.athinput", "BrioWu", "mhd_bw1d_ppm4_hlld_rk3",
