@@ -21,7 +21,9 @@ class Hydro:
     def __init__(self, nmb, ng, nx, mb_size, nghbr, *, recon="plm", rsolver="hllc", gamma,
                  dfloor=FLT_MIN, pfloor=FLT_MIN, tfloor=FLT_MIN, sfloor=FLT_MIN,
                  my_rank=0, gids_start=0, device="cuda", process_group=None, mesh_bcs=None, mb_bcs=None, nscalars=0,
-                 eos="ideal", iso_sound_speed=1.0):
+                 eos="ideal", iso_sound_speed=1.0, mb_lev=None):
+        """mb_lev: logical level of every block (Mesh.lloc[:, 3]) on a statically refined mesh; enables the
+        fine/coarse boundary path (ak_smr_*: restriction, multi-level exchange, prolongation, flux correction)."""
         if not torch.cuda.is_available():
             raise _lib.EngineError("athenak_b200: no CUDA device; the engine has no CPU path")
         self.L = _lib.load()
@@ -50,10 +52,23 @@ class Hydro:
         _lib.check(self.L.ak_hydro_create(C.byref(self.cfg), C.byref(self.h)))
         self.nghbr = np.ascontiguousarray(nghbr, dtype=np.int32).reshape(nmb, 56, 4)
         self.plan = C.c_void_p()
-        _lib.check(self.L.ak_halo_create(C.byref(self.cfg), self.nghbr.ctypes.data_as(C.POINTER(C.c_int)),
-                                         my_rank, gids_start, C.byref(self.plan)))
+        self.smr = None
+        if mb_lev is not None:       # multilevel mesh (src/mesh/mesh.hpp multilevel): coarse array + SMR plan
+            self.mb_lev = np.ascontiguousarray(mb_lev, dtype=np.int32).reshape(nmb)
+            self.smr = C.c_void_p()
+            ipp = C.POINTER(C.c_int)
+            if self.L.ak_smr_create(C.byref(self.cfg), self.nghbr.ctypes.data_as(ipp), self.mb_lev.ctypes.data_as(ipp),
+                                    my_rank, gids_start, C.byref(self.smr)):
+                self.smr = None
+                raise _lib.EngineError(self.L.ak_smr_last_error(None).decode())
+            if mesh_bcs is not None and any(int(b) != _lib.BC["periodic"] for b in mesh_bcs):
+                raise _lib.EngineError("SMR with physical boundaries needs HydroBCsCoarse (hydro_tasks.cpp:382-386): not built yet")
+            self.coarse_u0 = z(nmb, nv, self.L.ak_smr_coarse_cells(self.smr))      # hydro.cpp:121-128
+        else:
+            _lib.check(self.L.ak_halo_create(C.byref(self.cfg), self.nghbr.ctypes.data_as(C.POINTER(C.c_int)),
+                                             my_rank, gids_start, C.byref(self.plan)))
         self.peers = []
-        for ip in range(self.L.ak_halo_npeers(self.plan)):
+        for ip in range(self.L.ak_halo_npeers(self.plan) if self.smr is None else 0):
             r, ncc, nfc = C.c_int(), C.c_long(), C.c_long()
             _lib.check(self.L.ak_halo_peer(self.plan, ip, C.byref(r), C.byref(ncc), C.byref(nfc)))
             self.peers.append(dict(rank=r.value, ncc=ncc.value, scc=z(nv * ncc.value), rcc=z(nv * ncc.value)))
@@ -80,6 +95,8 @@ class Hydro:
                 self.L.ak_bcs_destroy(self.bcs)
             if getattr(self, "plan", None):
                 self.L.ak_halo_destroy(self.plan)
+            if getattr(self, "smr", None):
+                self.L.ak_smr_destroy(self.smr)
             if getattr(self, "h", None):
                 self.L.ak_hydro_destroy(self.h)
         except Exception:
@@ -119,9 +136,28 @@ class Hydro:
         self.launches += self.nsweeps + 1
         return TaskStatus.complete
 
+    def _smr_ck(self, rc):
+        if rc:
+            raise _lib.EngineError(self.L.ak_smr_last_error(self.smr).decode())
+
+    def FluxCorrect(self, driver, stage):
+        """SendFlux/RecvFlux (hydro_tasks.cpp:58-59 -> flux_correct_cc.cpp): multilevel meshes only."""
+        if self.smr is not None:
+            self._smr_ck(self.L.ak_smr_flux_correct_cc(self.smr, *[f.data_ptr() for f in self.uflx], self.nvar, self._st()))
+            self.launches += 1
+        return TaskStatus.complete
+
     def SendRecvU(self, driver, stage):
-        """SendU/RecvU (src/bvals/bvals_cc.cpp:42-447): same-rank gather + one message per peer."""
+        """SendU/RecvU (src/bvals/bvals_cc.cpp:42-447): same-rank gather + one message per peer.  On a multilevel
+        mesh: RestrictU, SendU/RecvU across levels and Prolongate (hydro_tasks.cpp:63-68)."""
         st, L = self._st(), self.L
+        if self.smr is not None:
+            u, cu = self.u0.data_ptr(), self.coarse_u0.data_ptr()
+            self._smr_ck(L.ak_smr_restrict_cc(self.smr, u, cu, self.nvar, st))
+            self._smr_ck(L.ak_smr_exchange_cc(self.smr, u, cu, self.nvar, st))
+            self._smr_ck(L.ak_smr_prolongate_cc(self.smr, u, cu, self.nvar, st))
+            self.launches += 4
+            return TaskStatus.complete
         reqs = []
         if self.peers:
             import torch.distributed as dist
@@ -207,7 +243,19 @@ def assemble_hydro_tasks(hyd: Hydro, fused=True):
     tl = {n: TaskList() for n in ("before_timeintegrator", "before_stagen", "stagen",
                                   "after_stagen", "after_timeintegrator")}
     s = tl["stagen"]
-    if fused:
+    if hyd.smr is not None:     # flux correction sits between Fluxes and RKUpdate: no fused flux+update call
+        t = s.AddTask(hyd.CopyCons, 0)
+        t = s.AddTask(hyd.Fluxes, t)
+        t = s.AddTask(hyd.FluxCorrect, t)
+        t = s.AddTask(hyd.RKUpdate, t)
+        t = s.AddTask(hyd.SendRecvU, t)
+        t = s.AddTask(hyd.ApplyPhysicalBCs, t)
+        if fused:
+            t = s.AddTask(hyd.ConToPrimNewDt, t)
+        else:
+            t = s.AddTask(hyd.ConToPrim, t)
+            t = s.AddTask(hyd.NewTimeStep, t)
+    elif fused:
         t = s.AddTask(hyd.StageFused, 0)
         t = s.AddTask(hyd.SendRecvU, t)
         t = s.AddTask(hyd.ApplyPhysicalBCs, t)

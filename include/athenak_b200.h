@@ -259,6 +259,27 @@ int ak_mesh_create(const int *nmesh, const int *nblock, const double *xmin, cons
 int ak_mesh_create_smr(const int *nmesh, const int *nblock, const double *xmin, const double *xmax, const int *bcs,
                        int nranks, int nregions, const double *regions, void **mesh);
 int ak_mesh_destroy(void *mesh);
+
+/* ---- fine/coarse boundaries of cell-centred data on a statically refined mesh, hydro ----
+ * Replaces, for a pack whose neighbours are all on this rank, the multilevel parts of the tasks RestrictU
+ * (src/mesh/mesh_refinement.cpp:1226-1284), SendU/RecvU (src/bvals/bvals_cc.cpp:42-167,273-402 with the
+ * same/coarser/finer index tables of src/bvals/buffs_cc.cpp:28-484), Prolongate (src/bvals/prolongation.cpp:
+ * 366-547: FillCoarseInBndryCC + ProlongateCC, operator src/mesh/prolongation.hpp:21-60) and SendFlux/RecvFlux
+ * (src/bvals/flux_correct_cc.cpp:28-290), in the order of src/hydro/hydro_tasks.cpp:55-71:
+ *   Fluxes -> ak_smr_flux_correct_cc -> RKUpdate -> ak_smr_restrict_cc -> ak_smr_exchange_cc ->
+ *   ak_smr_prolongate_cc -> [physical BCs] -> ConToPrim.
+ * nghbr = [nmb][56][4] NeighborBlock entries (gid, lev, rank, dest), mb_lev = [nmb] logical levels
+ * (ak_mesh_create_smr); u / cu are the fine array and the host's coarse array coarse_u0
+ * (nmb, nvar, cnx3+2ng, cnx2+2ng, cnx1+2ng in active dimensions; ak_smr_coarse_cells per variable and block). */
+int ak_smr_create(const ak_mhd_cfg *cfg, const int *nghbr, const int *mb_lev, int my_rank, int gids_start, void **plan);
+int ak_smr_destroy(void *plan);
+const char *ak_smr_last_error(void *plan);
+long ak_smr_coarse_cells(void *plan);
+int ak_smr_counts(void *plan, long *counts /* [4]: exchange, fill, prolongation, flux descriptors */);
+int ak_smr_restrict_cc(void *plan, const double *u, double *cu, int nvar, ak_stream_t s);
+int ak_smr_exchange_cc(void *plan, double *u, double *cu, int nvar, ak_stream_t s);
+int ak_smr_prolongate_cc(void *plan, double *u, double *cu, int nvar, ak_stream_t s);
+int ak_smr_flux_correct_cc(void *plan, double *flx1, double *flx2, double *flx3, int nvar, ak_stream_t s);
 const char *ak_mesh_last_error(void);
 int ak_mesh_info(void *mesh, int *nmb_total, int *root_level);
 int ak_mesh_tables(void *mesh, int *lloc /*[nmb_total][4]*/, int *rank_of, int *gids_start, int *nmb_rank);

@@ -163,3 +163,38 @@ def test_smr_block_sizes(name):
 def test_smr_rejects_odd_blocks():
     with pytest.raises(Exception):
         Mesh((30, 30, 30), (15, 15, 15), refined_regions=[(1, -0.1, 0.1, -0.1, 0.1, -0.1, 0.1)])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_smr_plan_descriptor_counts(name):
+    """ak_smr_create (host-side plan, no device needed): one exchange descriptor per neighbour entry, one fill
+    descriptor per same-level entry (multi-D), one prolongation descriptor per coarser entry, one flux descriptor per
+    coarser FACE entry -- and the totals are symmetric: every fine->coarse flux box has a finer entry on the other side."""
+    import ctypes as C
+    from athenak_b200 import lib as L
+    lib = L.load()
+    mesh, bcs = mesh_of(str(GOLD[name + "_deck"]))
+    p = H.deck_params(str(GOLD[name + "_deck"]))
+    _, _, ngh = mesh.rank_tables(0)
+    lev = np.ascontiguousarray(mesh.lloc[:, 3], np.int32)
+    ng = 4
+    nb = mesh.nblock
+    if any(n > 1 and n < 2 * ng for n in nb):
+        ng = 2
+    cfg = L.MhdCfg(mesh.nmb_total, ng, *nb, L.RECON["plm"], L.HYD_RSOLVER["hllc"], 1.4, 0, 0, 0, 0, 0)
+    plan = C.c_void_p()
+    ipp = C.POINTER(C.c_int)
+    rc = lib.ak_smr_create(C.byref(cfg), ngh.ctypes.data_as(ipp), lev.ctypes.data_as(ipp), 0, 0, C.byref(plan))
+    assert rc == 0, lib.ak_smr_last_error(None)
+    cnt = (C.c_long * 4)()
+    assert lib.ak_smr_counts(plan, cnt) == 0
+    have = ngh[:, :, 0] >= 0
+    same = have & (ngh[:, :, 1] == lev[:, None])
+    coarser = have & (ngh[:, :, 1] < lev[:, None])
+    finer = have & (ngh[:, :, 1] > lev[:, None])
+    face = np.zeros(56, bool); face[:16] = True; face[24:32] = True
+    assert cnt[0] == have.sum()
+    assert cnt[1] == (same.sum() if mesh.nmesh[1] > 1 else 0)
+    assert cnt[2] == coarser.sum()
+    assert cnt[3] == (coarser & face[None, :]).sum() == (finer & face[None, :]).sum()
+    lib.ak_smr_destroy(plan)
