@@ -439,10 +439,14 @@ int ak_smr_exchange_cc(void *plan, double *u, double *cu, int nvar, ak_stream_t 
 }
 
 int ak_smr_prolongate_cc(void *plan, double *u, double *cu, int nvar, ak_stream_t s) {
+  return ak_smr_prolongate_cc_steps(plan, u, cu, nvar, 3, s);
+}
+
+int ak_smr_prolongate_cc_steps(void *plan, double *u, double *cu, int nvar, int steps, ak_stream_t s) {
   SMR_PROLOGUE("ak_smr_prolongate_cc")
-  if (!P->fill.empty())
+  if ((steps & 1) && !P->fill.empty())
     smr_fill_kernel<<<dim3((unsigned)P->fill.size(), gx(P->max_fill * nvar, 256)), 256, 0, st>>>(D, nvar, P->d_fill, u, cu);
-  if (!P->prol.empty())
+  if ((steps & 2) && !P->prol.empty())
     smr_prolong_kernel<<<dim3((unsigned)P->prol.size(), gx(P->max_prol * nvar, 256)), 256, 0, st>>>(D, nvar, P->d_prol, u, cu);
   SMR_EPILOGUE("ak_smr_prolongate_cc")
 }

@@ -61,8 +61,6 @@ class Hydro:
                                     my_rank, gids_start, C.byref(self.smr)):
                 self.smr = None
                 raise _lib.EngineError(self.L.ak_smr_last_error(None).decode())
-            if mesh_bcs is not None and any(int(b) != _lib.BC["periodic"] for b in mesh_bcs):
-                raise _lib.EngineError("SMR with physical boundaries needs HydroBCsCoarse (hydro_tasks.cpp:382-386): not built yet")
             self.coarse_u0 = z(nmb, nv, self.L.ak_smr_coarse_cells(self.smr))      # hydro.cpp:121-128
         else:
             _lib.check(self.L.ak_halo_create(C.byref(self.cfg), self.nghbr.ctypes.data_as(C.POINTER(C.c_int)),
@@ -84,6 +82,14 @@ class Hydro:
                 raise _lib.EngineError(self.L.ak_bcs_last_error(None).decode())
             act = (True, self.multi_d, self.three_d)
             self.nbc = sum(act[d] and int(mesh_bcs[2 * d]) != _lib.BC["periodic"] for d in range(3))
+            self.bcs_coarse = None
+            if self.smr is not None:     # HydroBCsCoarse (hydro_bcs.cpp:51-67): the same fill on the coarse index space
+                ccfg = _lib.MhdCfg.from_buffer_copy(self.cfg)
+                ccfg.nx1, ccfg.nx2, ccfg.nx3 = nx1 // 2, max(1, nx2 // 2), max(1, nx3 // 2)
+                self.bcs_coarse = C.c_void_p()
+                if self.L.ak_bcs_create(C.byref(ccfg), mesh_bcs.ctypes.data_as(ipp), mb_bcs.ctypes.data_as(ipp),
+                                        C.byref(self.bcs_coarse)):
+                    raise _lib.EngineError(self.L.ak_bcs_last_error(None).decode())
         self.dtnew = FLT_MAX
         self.nfloor = [0, 0, 0]
         self.launches = 0
@@ -93,6 +99,8 @@ class Hydro:
         try:
             if getattr(self, "bcs", None):
                 self.L.ak_bcs_destroy(self.bcs)
+            if getattr(self, "bcs_coarse", None):
+                self.L.ak_bcs_destroy(self.bcs_coarse)
             if getattr(self, "plan", None):
                 self.L.ak_halo_destroy(self.plan)
             if getattr(self, "smr", None):
@@ -155,7 +163,14 @@ class Hydro:
             u, cu = self.u0.data_ptr(), self.coarse_u0.data_ptr()
             self._smr_ck(L.ak_smr_restrict_cc(self.smr, u, cu, self.nvar, st))
             self._smr_ck(L.ak_smr_exchange_cc(self.smr, u, cu, self.nvar, st))
-            self._smr_ck(L.ak_smr_prolongate_cc(self.smr, u, cu, self.nvar, st))
+            if self.bcs is None:
+                self._smr_ck(L.ak_smr_prolongate_cc(self.smr, u, cu, self.nvar, st))
+            else:       # Prolongate (hydro_tasks.cpp:378-398): coarse-array BCs between the coarse fill and the prolongation
+                self._smr_ck(L.ak_smr_prolongate_cc_steps(self.smr, u, cu, self.nvar, 1, st))
+                if L.ak_bcs_hydro(self.bcs_coarse, cu, self.nvar, st):
+                    raise _lib.EngineError(L.ak_bcs_last_error(self.bcs_coarse).decode())
+                self._smr_ck(L.ak_smr_prolongate_cc_steps(self.smr, u, cu, self.nvar, 2, st))
+                self.launches += self.nbc
             self.launches += 4
             return TaskStatus.complete
         reqs = []

@@ -279,6 +279,10 @@ int ak_smr_counts(void *plan, long *counts /* [4]: exchange, fill, prolongation,
 int ak_smr_restrict_cc(void *plan, const double *u, double *cu, int nvar, ak_stream_t s);
 int ak_smr_exchange_cc(void *plan, double *u, double *cu, int nvar, ak_stream_t s);
 int ak_smr_prolongate_cc(void *plan, double *u, double *cu, int nvar, ak_stream_t s);
+/* steps: 1 = FillCoarseInBndryCC only, 2 = ProlongateCC only, 3 = both.  With physical boundaries the host applies
+ * them to the COARSE array between the two steps (HydroBCsCoarse, src/bvals/physics/hydro_bcs.cpp:51-67: ak_bcs_hydro
+ * on a plan created with nx -> nx/2) and to the fine array after prolongation (src/hydro/hydro_tasks.cpp:357-398). */
+int ak_smr_prolongate_cc_steps(void *plan, double *u, double *cu, int nvar, int steps, ak_stream_t s);
 int ak_smr_flux_correct_cc(void *plan, double *flx1, double *flx2, double *flx3, int nvar, ak_stream_t s);
 const char *ak_mesh_last_error(void);
 int ak_mesh_info(void *mesh, int *nmb_total, int *root_level);

@@ -232,12 +232,13 @@ void oracle_smr_halo_cc(const ocfg *c, double *u, double *cu, int nv, const int 
 
 static double smr_sign(double x) { return (x < 0.0) ? -1.0 : 1.0; }   /* athena.hpp SIGN(): ((x) < 0.0 ? -1.0 : 1.0) */
 
-/* prolongation.cpp:366-547 */
-void oracle_smr_prolongate_cc(const ocfg *c, double *u, double *cu, int nv, const int *nghbr, const int *mblev) {
+/* prolongation.cpp:366-547.  steps: 1 = FillCoarseInBndryCC, 2 = ProlongateCC, 3 = both (physical BCs on the
+ * coarse array go between the two, hydro_tasks.cpp:380-394) */
+void oracle_smr_prolongate_cc_steps(const ocfg *c, double *u, double *cu, int nv, const int *nghbr, const int *mblev, int steps) {
   odims D = dims(c);
   sidx I = smr_indcs(c);
   cdims CD = smr_cdims(&I);
-  if (I.multi_d)    /* FillCoarseInBndryCC: restrict the same-level ghost data into the coarse array */
+  if (I.multi_d && (steps & 1))    /* FillCoarseInBndryCC: restrict the same-level ghost data into the coarse array */
     for (int m = 0; m < c->nmb; ++m)
       for (int n = 0; n < 56; ++n) {
         const int *e = nghbr + ((size_t)m * 56 + n) * 4;
@@ -263,6 +264,7 @@ void oracle_smr_prolongate_cc(const ocfg *c, double *u, double *cu, int nv, cons
                              + CC(u, nv, m, v, fk + 1, fj + 1, fi) + CC(u, nv, m, v, fk + 1, fj + 1, fi + 1));
               }
       }
+  if (steps & 2)
   for (int m = 0; m < c->nmb; ++m)   /* ProlongateCC: slots whose neighbour is coarser */
     for (int n = 0; n < 56; ++n) {
       const int *e = nghbr + ((size_t)m * 56 + n) * 4;
@@ -301,6 +303,10 @@ void oracle_smr_prolongate_cc(const ocfg *c, double *u, double *cu, int nv, cons
               }
             }
     }
+}
+
+void oracle_smr_prolongate_cc(const ocfg *c, double *u, double *cu, int nv, const int *nghbr, const int *mblev) {
+  oracle_smr_prolongate_cc_steps(c, u, cu, nv, nghbr, mblev, 3);
 }
 
 /* flux_correct_cc.cpp:28-167 + :173-290: fine blocks restrict their boundary-face fluxes onto the coarse
@@ -383,12 +389,21 @@ void oracle_smr_flux_correct_cc(const ocfg *c, double *flx1, double *flx2, doubl
   free(rbuf);
 }
 
-/* Driver::InitBoundaryValuesAndPrimitives for hydro on a multilevel mesh (driver.cpp:587-604), strictly periodic */
+/* Driver::InitBoundaryValuesAndPrimitives for hydro on a multilevel mesh (driver.cpp:587-604); coarse-array BCs:
+ * src/bvals/physics/hydro_bcs.cpp:51-67 (HydroBCsCoarse), between FillCoarseInBndryCC and ProlongateCC */
 static void smr_hydro_ghosts_and_prims(const ocfg *c, double *u0, double *cu0, double *w0, const int *nghbr, const int *mblev) {
   odims D = dims(c);
   oracle_smr_restrict_cc(c, u0, cu0, D.nv);
   oracle_smr_halo_cc(c, u0, cu0, D.nv, nghbr, mblev);
-  oracle_smr_prolongate_cc(c, u0, cu0, D.nv, nghbr, mblev);
+  oracle_smr_prolongate_cc_steps(c, u0, cu0, D.nv, nghbr, mblev, 1);
+  if (g_mesh_bcs) {   /* HydroBCsCoarse (hydro_bcs.cpp:51-67): the same fill on the coarse array's index space */
+    ocfg cc = *c;
+    sidx I = smr_indcs(c);
+    cc.nx1 = I.cnx1; cc.nx2 = I.multi_d ? I.cnx2 : 1; cc.nx3 = I.three_d ? I.cnx3 : 1;
+    oracle_hydro_apply_bcs(&cc, g_mesh_bcs, g_mb_bcs, cu0);
+  }
+  oracle_smr_prolongate_cc_steps(c, u0, cu0, D.nv, nghbr, mblev, 2);
+  if (g_mesh_bcs) oracle_hydro_apply_bcs(c, g_mesh_bcs, g_mb_bcs, u0);     /* hydro_tasks.cpp:357-371, after prolongation */
   oracle_hydro_cons2prim(c, u0, w0, 0, D.n1 - 1, 0, D.n2 - 1, 0, D.n3 - 1, NULL);
 }
 

@@ -31,8 +31,17 @@ CASES = {
                                   "refined_region2/level=1", "refined_region2/x1min=0.1", "refined_region2/x1max=0.2",
                                   "refined_region2/x2min=0.1", "refined_region2/x2max=0.2", "refined_region2/x3min=0.1", "refined_region2/x3max=0.2"),
 }
+# physical boundaries on a refined mesh: HydroBCsCoarse before the prolongation, HydroBCs after it
+CASES["hydro_smr2d_bcs_ppm4_hllc_rk3"] = (
+    "problem/amp=0.1", "time/tlim=0.05", "mesh/nx3=1", "meshblock/nx3=1", "mesh/nx2=32", "meshblock/nx2=8",
+    "mesh/ix1_bc=outflow", "mesh/ox1_bc=reflect", "mesh/ix2_bc=reflect", "mesh/ox2_bc=diode",
+    "refined_region1/x1min=0.0", "refined_region1/x1max=0.3", "refined_region1/x2min=0.0", "refined_region1/x2max=0.2",
+    "refined_region2/level=2", "refined_region2/x1min=2.8", "refined_region2/x1max=3.0", "refined_region2/x2min=1.4", "refined_region2/x2max=1.5")
 LIVE_CASES = dict(CASES)
 LIVE_CASES.update({
+    "hydro_smr3d_bcs": ("problem/amp=0.1", "time/tlim=0.03", *_B8, "mesh/ix1_bc=reflect", "mesh/ox1_bc=outflow", "mesh/ix3_bc=outflow",
+                        "mesh/ox3_bc=reflect", "refined_region1/x1min=0.0", "refined_region1/x1max=0.2", "refined_region1/x3min=1.3",
+                        "refined_region1/x3max=1.5", "refined_region2/level=1"),
     "hydro_smr3d_3levels": ("problem/amp=0.1", "time/tlim=0.05", *_B8),                        # 135 blocks, levels 2-4
     "hydro_smr3d_wenoz_roe": ("problem/amp=0.1", "time/tlim=0.03", *_B8, "hydro/reconstruct=wenoz", "hydro/rsolver=roe", "refined_region2/level=1"),
     "hydro_smr2d_ppm4_hlle_l3": ("problem/amp=0.1", "time/tlim=0.05", "mesh/nx3=1", "meshblock/nx3=1", "mesh/nx2=32", "meshblock/nx2=8",
@@ -80,10 +89,29 @@ def mesh_of(deck_text, nranks=1):
     return Mesh(nmesh, nblock, xmin=xmin, xmax=xmax, bcs=bcs, nranks=nranks, refined_regions=regs), p
 
 
+def block_bcs(mesh, p):
+    """mb_bcs from the definition (meshblock.cpp:25-131) at each block's own level; (mesh_bcs, mb_bcs, strictly periodic)."""
+    names = tuple(p[f"mesh/{s}x{d}_bc"] for d in (1, 2, 3) for s in ("i", "o"))
+    flags = np.array([O.BC[b] for b in names], np.int32)
+    out = np.zeros((mesh.nmb_total, 6), np.int32)
+    for g, l in enumerate(mesh.lloc):
+        for d in range(3):
+            if mesh.nmesh[d] == 1:
+                out[g, 2 * d], out[g, 2 * d + 1] = flags[2 * d], flags[2 * d + 1]
+                continue
+            n = (mesh.nmesh[d] // mesh.nblock[d]) << (int(l[3]) - mesh.root_level)
+            out[g, 2 * d] = flags[2 * d] if l[d] == 0 else O.BC["block"]
+            out[g, 2 * d + 1] = flags[2 * d + 1] if l[d] == n - 1 else O.BC["block"]
+    active = [d for d in range(3) if mesh.nmesh[d] > 1]
+    return flags, out, all(flags[2 * d] == O.BC["periodic"] for d in active)
+
+
 def oracle_run(deck_text, u_init, ncycles=-1):
     """Driver::Initialize + Execute on the SMR oracle; returns (u0, w0, time, dt_next, ncycles, dt0)."""
     mesh, p = mesh_of(deck_text)
-    mbs, _, ngh = mesh.rank_tables(0)
+    mbs, mbb, ngh = mesh.rank_tables(0)
+    flags, mb_bcs, periodic = block_bcs(mesh, p)
+    assert np.array_equal(mbb, mb_bcs)
     cfg = O.OCfg(mesh.nmb_total, int(p["mesh/nghost"]), *mesh.nblock, O.RECON[p["hydro/reconstruct"]], O.HYD_RSOLVER[p["hydro/rsolver"]],
                  float(p["hydro/gamma"]), O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, 0, 0, 1.0, 0)
     L = O.lib()
@@ -97,6 +125,15 @@ def oracle_run(deck_text, u_init, ncycles=-1):
     ngh = np.ascontiguousarray(ngh, np.int32)
     lev = np.ascontiguousarray(mesh.lloc[:, 3], np.int32)
     cfl, tlim = float(p["time/cfl_number"]), float(p["time/tlim"])
+    if not periodic:
+        L.oracle_set_bcs(O.ip(flags), O.ip(mb_bcs))
+    try:
+        return _oracle_run(L, cfg, u0, u1, cu0, w0, mbs, ngh, lev, p, cfl, tlim, ncycles)
+    finally:
+        L.oracle_set_bcs(None, None)
+
+
+def _oracle_run(L, cfg, u0, u1, cu0, w0, mbs, ngh, lev, p, cfl, tlim, ncycles):
     dt0 = L.oracle_hydro_smr_init(C.byref(cfg), O.p(u0), O.p(cu0), O.p(w0), O.p(mbs), O.ip(ngh), O.ip(lev), C.c_double(cfl),
                                   C.c_double(tlim), C.c_double(0.0))
     t, dt = C.c_double(0.0), C.c_double(dt0)

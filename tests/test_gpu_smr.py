@@ -22,7 +22,7 @@ def run_engine(deck_text, u_init, fused, ncycles=None):
     mesh, p = S.mesh_of(deck_text)
     mb_size, mb_bcs, nghbr = mesh.rank_tables(0)
     hyd = Hydro(mesh.nmb_total, int(p["mesh/nghost"]), mesh.nblock, mb_size, nghbr, recon=p["hydro/reconstruct"],
-                rsolver=p["hydro/rsolver"], gamma=float(p["hydro/gamma"]), mb_lev=mesh.lloc[:, 3])
+                rsolver=p["hydro/rsolver"], gamma=float(p["hydro/gamma"]), mb_lev=mesh.lloc[:, 3], mesh_bcs=mesh.bcs, mb_bcs=mb_bcs)
     hyd.load_state(u_init)
     drv = Driver(p["time/integrator"], float(p["time/cfl_number"]), tlim=float(p["time/tlim"]))
     tl = assemble_hydro_tasks(hyd, fused=fused)
