@@ -206,6 +206,12 @@ class MHD {  // state owner + tasks
   unsigned long long nexch = 0;               // exchanges completed (sequence number of the flags)
   unsigned long long *d_flags = nullptr;      // [2][nranks] counters written by the peers
   std::vector<void *> ipc_opened;
+  // static mesh refinement (hydro): multi-level plan, coarse array, coarse-array BC plan (ak_sim_set_levels)
+  std::vector<int> nghbr_h;
+  void *smr = nullptr, *bcs_coarse = nullptr;
+  int mesh_bcs_h[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<int> mb_bcs_h;
+  double *coarse_u0 = nullptr;
 
   MHD(const ak_mhd_cfg &c, const double *mb_size, const int *nghbr, int rank, int nranks_, int gids_start, int nmb_total)
       : cfg(c), my_rank(rank), nranks(nranks_), gids_start_(gids_start) {
@@ -234,6 +240,7 @@ class MHD {  // state owner + tasks
     a.mb_size = ms;
     d_dt = alloc(1);
     if (hydro ? ak_hydro_create(&cfg, &h) : ak_mhd_create(&cfg, &h)) Fatal(__FILE__, __LINE__, ak_last_error(nullptr));
+    nghbr_h.assign(nghbr, nghbr + nm * 56 * 4);
     if (ak_halo_create(&cfg, nghbr, rank, gids_start, &plan)) Fatal(__FILE__, __LINE__, ak_last_error(nullptr));
     for (int p = 0; p < ak_halo_npeers(plan); ++p) {
       Peer pe;
@@ -252,6 +259,8 @@ class MHD {  // state owner + tasks
     if (comm && Nccl::get().CommDestroy) Nccl::get().CommDestroy(comm);
     ak_halo_destroy(plan);
     ak_bcs_destroy(bcs);
+    ak_bcs_destroy(bcs_coarse);
+    ak_smr_destroy(smr);
     ak_mhd_destroy(h);
     for (double *p : owned) cudaFree(p);
     if (st) cudaStreamDestroy(st);
@@ -349,6 +358,22 @@ class MHD {  // state owner + tasks
       tl_map[n] = std::make_shared<TaskList>();
     TaskID none(0);
     auto &tl = tl_map["stagen"];
+    if (hydro && smr) {   // multilevel mesh: SendFlux/RecvFlux between Fluxes and RKUpdate, RestrictU + Prolongate around SendU/RecvU
+      TaskID copyu = tl->AddTask(&MHD::CopyCons, this, none);
+      TaskID flux = tl->AddTask(&MHD::Fluxes, this, copyu);
+      TaskID fc = tl->AddTask(&MHD::FluxCorrect, this, flux);
+      TaskID rkupdt = tl->AddTask(&MHD::RKUpdate, this, fc);
+      TaskID sendu = tl->AddTask(&MHD::SendU, this, rkupdt);
+      TaskID recvu = tl->AddTask(&MHD::RecvU, this, sendu);
+      TaskID bc = tl->AddTask(&MHD::ApplyPhysicalBCs, this, recvu);
+      if (fused) {
+        tl->AddTask(&MHD::ConToPrimNewDt, this, bc);
+      } else {
+        TaskID c2p = tl->AddTask(&MHD::ConToPrim, this, bc);
+        tl->AddTask(&MHD::NewTimeStep, this, c2p);
+      }
+      return;
+    }
     if (hydro) {   // Hydro::AssembleHydroTasks, hydro_tasks.cpp:47-79 (uniform mesh, no source terms)
       if (fused) {
         TaskID f = tl->AddTask(&MHD::HydroStageFused, this, none);
@@ -576,7 +601,29 @@ class MHD {  // state owner + tasks
     Unpack(true); Unpack(false);
     return TaskStatus::complete;
   }
+  // SendFlux/RecvFlux (hydro_tasks.cpp:58-59 -> flux_correct_cc.cpp)
+  TaskStatus FluxCorrect(Driver *pd, int stage) {
+    if (ak_smr_flux_correct_cc(smr, a.flx1, a.flx2, a.flx3, nvar, st)) Fatal(__FILE__, __LINE__, ak_smr_last_error(smr));
+    launches += 1;
+    return TaskStatus::complete;
+  }
+  // RestrictU + SendU/RecvU across levels + Prolongate (hydro_tasks.cpp:63-68,296-398)
+  void SmrGhosts() {
+    auto ck = [&](int rc) { if (rc) Fatal(__FILE__, __LINE__, ak_smr_last_error(smr)); };
+    ck(ak_smr_restrict_cc(smr, a.u0, coarse_u0, nvar, st));
+    ck(ak_smr_exchange_cc(smr, a.u0, coarse_u0, nvar, st));
+    if (!bcs) {
+      ck(ak_smr_prolongate_cc(smr, a.u0, coarse_u0, nvar, st));
+    } else {   // coarse-array BCs between the coarse fill and the prolongation (HydroBCsCoarse)
+      ck(ak_smr_prolongate_cc_steps(smr, a.u0, coarse_u0, nvar, 1, st));
+      if (ak_bcs_hydro(bcs_coarse, coarse_u0, nvar, st)) Fatal(__FILE__, __LINE__, ak_bcs_last_error(bcs_coarse));
+      ck(ak_smr_prolongate_cc_steps(smr, a.u0, coarse_u0, nvar, 2, st));
+      launches += nbc_launches;
+    }
+    launches += 4;
+  }
   TaskStatus SendU(Driver *pd, int stage) {
+    if (smr) { SmrGhosts(); return TaskStatus::complete; }
     if (hydro && UsePush()) {     // hydro twin, fused list: u0 is the only exchanged array
       PushExchange(false);
       AK_CHECK(nullptr, ak_halo_local_cc(plan, a.u0, nvar, st));
@@ -587,6 +634,7 @@ class MHD {  // state owner + tasks
     return TaskStatus::complete;
   }
   TaskStatus RecvU(Driver *pd, int stage) {   // stream-ordered: never incomplete
+    if (smr) return TaskStatus::complete;
     if (hydro && UsePush()) { PushComplete(); return TaskStatus::complete; }
     Unpack(true);
     return TaskStatus::complete;
@@ -722,8 +770,29 @@ int ak_sim_set_bcs(void *sim, const int *mesh_bcs, const int *mb_bcs) {
   if (ak_bcs_create(&m->cfg, mesh_bcs, mb_bcs, &b)) return 1;
   if (ak_bcs_strictly_periodic(b)) { ak_bcs_destroy(b); return 0; }
   m->bcs = b;
+  std::memcpy(m->mesh_bcs_h, mesh_bcs, sizeof(m->mesh_bcs_h));
+  m->mb_bcs_h.assign(mb_bcs, mb_bcs + (size_t)m->cfg.nmb * 6);
   const bool act[3] = {true, m->multi_d, m->three_d};
   for (int d = 0; d < 3; ++d) m->nbc_launches += (act[d] && mesh_bcs[2 * d] != AK_BC_PERIODIC);
+  return 0;
+}
+/* static mesh refinement (hydro, one rank): logical level of every block of the pack (ak_mesh_create_smr).  Builds the
+ * multi-level plan from the neighbour table given to ak_sim_create, allocates coarse_u0 and switches to the multilevel
+ * task list.  Call before ak_sim_initialize; with physical boundaries call ak_sim_set_bcs first. */
+int ak_sim_set_levels(void *sim, const int *mb_lev) {
+  auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
+  if (!m->hydro || m->nranks != 1 || !mb_lev) return 1;
+  if (ak_smr_create(&m->cfg, m->nghbr_h.data(), mb_lev, m->my_rank, m->gids_start_, &m->smr)) return 1;
+  const size_t n = (size_t)m->cfg.nmb * m->nvar * ak_smr_coarse_cells(m->smr);
+  if (cudaMalloc(&m->coarse_u0, n * 8) != cudaSuccess || cudaMemsetAsync(m->coarse_u0, 0, n * 8, m->st) != cudaSuccess) return 1;
+  m->owned.push_back(m->coarse_u0);
+  if (m->bcs) {      // HydroBCsCoarse: the same flags on the coarse index space
+    ak_mhd_cfg cc = m->cfg;
+    cc.nx1 = m->cfg.nx1 / 2; cc.nx2 = std::max(1, m->cfg.nx2 / 2); cc.nx3 = std::max(1, m->cfg.nx3 / 2);
+    if (ak_bcs_create(&cc, m->mesh_bcs_h, m->mb_bcs_h.data(), &m->bcs_coarse)) return 1;
+  }
+  m->tl_map.clear();
+  m->AssembleMHDTasks();
   return 0;
 }
 int ak_sim_destroy(void *sim) { delete static_cast<akh::Sim *>(sim); return 0; }

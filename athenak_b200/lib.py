@@ -136,6 +136,7 @@ def load():
         "ak_selftest_divsqrt": [C.c_long, C.c_ulonglong, ip, C.POINTER(C.c_long)],
         "ak_sim_create": [C.POINTER(SimCfg), dpp, ipp, C.POINTER(vp)],
         "ak_sim_destroy": [vp],
+        "ak_sim_set_levels": [vp, ipp],
         "ak_nccl_unique_id": [vp],
         "ak_sim_comm_init": [vp, vp],
         "ak_sim_set_state": [vp, vp, vp, vp, vp],
@@ -177,7 +178,7 @@ EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_con
             "ak_mesh_create", "ak_mesh_create_smr", "ak_mesh_destroy", "ak_smr_create", "ak_smr_destroy", "ak_smr_last_error",
             "ak_smr_coarse_cells", "ak_smr_counts", "ak_smr_restrict_cc", "ak_smr_exchange_cc", "ak_smr_prolongate_cc", "ak_smr_prolongate_cc_steps", "ak_smr_flux_correct_cc", "ak_mesh_last_error", "ak_mesh_info", "ak_mesh_tables",
             "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast", "ak_pgen_orszag_tang", "ak_selftest_divsqrt",
-            "ak_sim_create", "ak_sim_destroy", "ak_nccl_unique_id", "ak_sim_comm_init", "ak_sim_set_state",
+            "ak_sim_create", "ak_sim_destroy", "ak_sim_set_levels", "ak_nccl_unique_id", "ak_sim_comm_init", "ak_sim_set_state",
             "ak_sim_get_state", "ak_sim_initialize", "ak_sim_execute", "ak_sim_sync", "ak_sim_status", "ak_sim_arrays",
             "ak_sim_set_bcs", "ak_bcs_create", "ak_bcs_destroy", "ak_bcs_last_error", "ak_bcs_strictly_periodic",
             "ak_bcs_hydro", "ak_bcs_bfield", "ak_bcs_apply",

@@ -15,7 +15,7 @@ INTEGRATOR = {"rk1": 1, "rk2": 2, "rk3": 3}
 class Simulation:
     def __init__(self, mesh, rank=0, *, ng=4, recon="ppm4", rsolver="hlld", gamma=1.6666667, integrator="rk3",
                  cfl_number=0.3, tlim=1.0, nlim=-1, fused=True, dfloor=FLT_MIN, pfloor=FLT_MIN, tfloor=FLT_MIN,
-                 sfloor=FLT_MIN, sigma_max=FLT_MAX, physics="mhd", nscalars=0, eos="ideal", iso_sound_speed=1.0, fofc=False):
+                 sfloor=FLT_MIN, sigma_max=FLT_MAX, physics="mhd", nscalars=0, eos="ideal", iso_sound_speed=1.0, fofc=False, multilevel=False):
         """physics="hydro": the hydro twin (rsolver in llf/hlle/hllc/roe; 1-D/2-D/3-D blocks); the state is u0 only."""
         self.L = _lib.load()
         self.mesh, self.rank, self.ng = mesh, rank, ng
@@ -37,6 +37,10 @@ class Simulation:
         mesh_bcs = np.asarray(mesh.bcs, np.int32)
         if self.L.ak_sim_set_bcs(self.h, mesh_bcs.ctypes.data_as(ipp), mb_bcs.ctypes.data_as(ipp)):
             raise _lib.EngineError(self.L.ak_bcs_last_error(None).decode())
+        if multilevel:       # statically refined mesh: levels from the mesh (hydro, one rank)
+            lev = np.ascontiguousarray(mesh.lloc[int(mesh.gids_start[rank]):int(mesh.gids_start[rank]) + nmb, 3], np.int32)
+            if self.L.ak_sim_set_levels(self.h, lev.ctypes.data_as(ipp)):
+                raise _lib.EngineError("ak_sim_set_levels failed: " + (self.L.ak_smr_last_error(None) or b"").decode())
         n1, n2, n3 = (nx[d] + 2 * ng if (d == 0 or nx[d] > 1) else 1 for d in range(3))
         self.shapes = [(nmb, (4 if eos == "isothermal" else 5) + int(nscalars), n3, n2, n1), (nmb, n3, n2, n1 + 1), (nmb, n3, n2 + 1, n1), (nmb, n3 + 1, n2, n1)]
         if self.hydro:

@@ -312,6 +312,9 @@ typedef struct {
 int ak_sim_create(const ak_sim_cfg *cfg, const double *mb_size /*host [nmb][9]*/,
                   const int *nghbr /*host [nmb][56][4]*/, void **sim);
 int ak_sim_destroy(void *sim);
+/* statically refined mesh (hydro, one rank): logical level per block; switches to the multilevel task list
+ * (RestrictU, SendU/RecvU across levels, Prolongate, SendFlux/RecvFlux).  After ak_sim_set_bcs, before ak_sim_initialize. */
+int ak_sim_set_levels(void *sim, const int *mb_lev);
 /* physical BCs (default strictly periodic): mesh_bcs[6], mb_bcs host [nmb][6]; errors -> ak_bcs_last_error(NULL) */
 int ak_sim_set_bcs(void *sim, const int *mesh_bcs, const int *mb_bcs);
 int ak_nccl_unique_id(void *out128);                         /* rank 0; broadcast by the launcher */

@@ -67,3 +67,25 @@ def test_smr_matches_oracle_every_cycle():
         uo, wo, t, dtn, n, dt0o = S.oracle_run(str(d["deck"]), d["u0_c0"], ncycles=nc)
         assert n == nc and dt0 == dt0o and drv.time == t and drv.dt == dtn
         assert np.array_equal(hyd.u0.cpu().numpy(), uo) and np.array_equal(hyd.w0.cpu().numpy(), wo)
+
+
+@pytest.mark.parametrize("name", sorted(S.CASES))
+@pytest.mark.parametrize("fused", [True, False], ids=["fused_c2p", "pertask"])
+def test_smr_cxx_host_driver(name, fused):
+    """The same fixtures through the C++ host driver (csrc/host_driver.cpp: ak_sim_set_levels, multilevel task list)."""
+    from athenak_b200.sim import Simulation
+    d = G.load(name)
+    u_init, u_final, act = S.with_ghosts(d)
+    mesh, p = S.mesh_of(str(d["deck"]))
+    sim = Simulation(mesh, 0, ng=int(p["mesh/nghost"]), recon=p["hydro/reconstruct"], rsolver=p["hydro/rsolver"],
+                     gamma=float(p["hydro/gamma"]), integrator=p["time/integrator"], cfl_number=float(p["time/cfl_number"]),
+                     tlim=float(p["time/tlim"]), fused=fused, physics="hydro", multilevel=True)
+    sim.set_state(np.ascontiguousarray(u_init))
+    sim.initialize()
+    assert sim.status()["dt"] == float(d["dt_c0"])
+    sim.execute(-1)
+    st = sim.status()
+    assert st["ncycle"] == int(d["ncycle_final"]) and st["time"] == float(d["time_final"]) and st["dt"] == float(d["dt_final"])
+    (u,) = sim.get_state()
+    u = u[:, :, act[0], act[1], act[2]]
+    assert np.array_equal(u, u_final), f"max|dU| = {np.abs(u - u_final).max()}"
