@@ -461,11 +461,13 @@ class MHD {  // state owner + tasks
   TaskStatus StageFluxEmf(Driver *pd, int stage) {   // tasks 2 + 14
     if (cfg.fofc) {     // the FOFC estimate reads u1/b1 in the ghost zones: whole-array CopyCons, RK coefficients
       CopyCons(pd, stage);
-      AK_CHECK(h, ak_mhd_set_stage(h, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt));
       launches += 1 + nsweeps();
     }
+    // RK coefficients for FOFC + the U half of the update overlapped with the corner-EMF kernel
+    AK_CHECK(h, ak_mhd_stage_begin(h, stage, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt));
     AK_CHECK(h, ak_mhd_stage_flux_emf(h, &a, st));
-    launches += nsweeps() + 1;
+    static const bool overlap_u = !(std::getenv("AKB_OVERLAP_U") && std::getenv("AKB_OVERLAP_U")[0] == '0');
+    launches += nsweeps() + 1 + (overlap_u ? 1 : 0);    // sweeps, corner EMFs, (early U update)
     SignalFree();    // the flux sweeps were the last readers of the b0 ghost faces (u0 ghosts: c2p of the previous stage)
     return TaskStatus::complete;
   }

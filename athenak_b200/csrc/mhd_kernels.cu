@@ -425,6 +425,7 @@ cudaError_t launch_update_ct(const Geom &g, const Arrays &a, bool do_u, bool do_
   else if (do_u && do_b) update_ct_kernel<true, true, false><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
   else if (do_u && save) update_ct_kernel<true, false, true><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);   // hydro twin, stage 1
   else if (do_u) update_ct_kernel<true, false, false><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
+  else if (do_b && save) update_ct_kernel<false, true, true><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);   // CT after an overlapped U update, stage 1
   else if (do_b) update_ct_kernel<false, true, false><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
 #undef AKB_UCT_ARGS
   return cudaGetLastError();

@@ -80,6 +80,7 @@ def load():
         "ak_mhd_stage_flux_emf": [vp, ap, vp],
         "ak_mhd_fofc": [vp, ap, d, d, d, C.POINTER(C.c_int), vp],
         "ak_mhd_set_stage": [vp, d, d, d],
+        "ak_mhd_stage_begin": [vp, ip, d, d, d],
         "ak_mhd_stage_update": [vp, ap, ip, d, d, d, vp],
         "ak_mhd_cons2prim_newdt": [vp, ap, C.POINTER(C.c_int), _dp, vp],
         "ak_hst_sums": [vp, ap, _dp, C.POINTER(C.c_int), vp],
@@ -171,7 +172,7 @@ def load():
 
 EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_cons", "ak_mhd_fluxes",
             "ak_mhd_rk_update", "ak_mhd_corner_e", "ak_mhd_ct", "ak_mhd_cons2prim", "ak_mhd_new_dt",
-            "ak_mhd_stage_fused", "ak_mhd_stage_flux_emf", "ak_mhd_fofc", "ak_mhd_set_stage", "ak_mhd_stage_update", "ak_mhd_cons2prim_newdt", "ak_halo_create", "ak_halo_destroy",
+            "ak_mhd_stage_fused", "ak_mhd_stage_flux_emf", "ak_mhd_fofc", "ak_mhd_set_stage", "ak_mhd_stage_begin", "ak_mhd_stage_update", "ak_mhd_cons2prim_newdt", "ak_halo_create", "ak_halo_destroy",
             "ak_halo_npeers", "ak_halo_peer", "ak_halo_descs", "ak_halo_local_cc", "ak_halo_local_fc",
             "ak_halo_pack_cc", "ak_halo_unpack_cc", "ak_halo_pack_fc", "ak_halo_unpack_fc",
             "ak_halo_emf_peer", "ak_halo_emf_pack_local", "ak_halo_emf_pack", "ak_halo_emf_sumavg",

@@ -113,6 +113,11 @@ int ak_mhd_stage_flux_emf(void *h, const ak_mhd_arrays *a, ak_stream_t s);
  * ak_mhd_set_stage, which must precede them. */
 int ak_mhd_fofc(void *h, const ak_mhd_arrays *a, double gam0, double gam1, double beta_dt, int *nfofc, ak_stream_t s);
 int ak_mhd_set_stage(void *h, double gam0, double gam1, double beta_dt);
+/* Optional, before ak_mhd_stage_flux_emf: announces the stage and its RK coefficients (as ak_mhd_set_stage) and lets the
+ * library start the conserved-variable half of the stage update on an auxiliary stream as soon as the fluxes (and FOFC)
+ * are done, concurrently with the corner-EMF kernel; the following ak_mhd_stage_update(h, a, stage, same coefficients)
+ * joins it and performs the CT half only.  Same kernels, same results; AKB_OVERLAP_U=0 disables the overlap. */
+int ak_mhd_stage_begin(void *h, int stage, double gam0, double gam1, double beta_dt);
 int ak_mhd_stage_update(void *h, const ak_mhd_arrays *a, int stage, double gam0, double gam1,
                         double beta_dt, ak_stream_t s);
 int ak_mhd_stage_fused(void *h, const ak_mhd_arrays *a, int stage, double gam0, double gam1,
