@@ -400,3 +400,216 @@ void oracle_mhd_smr_ghosts_and_prims(const ocfg *c, ostate *s, double *cu0, doub
   int nf[3];
   oracle_cons2prim(c, s->u0, s->b0x1f, s->b0x2f, s->b0x3f, s->w0, s->bcc0, 0, D.n1 - 1, 0, D.n2 - 1, 0, D.n3 - 1, nf);
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * SendE / RecvE on a multilevel mesh: flux_correct_fc.cpp:29-366 (pack: same level, or restricted onto the
+ * coarser neighbour), :374-437 (RecvAndUnpackFluxFC), :445-644 (SumBoundaryFluxes), :655-796
+ * (ZeroFluxesAtBoundaryWithFiner), :801-1034 (AverageBoundaryFluxes); index tables buffs_fc.cpp:282-385 (send)
+ * and :785-935 (recv).  No shear-periodic boundaries. */
+enum { EMF_SAME = 0, EMF_COAR_SEND = 1, EMF_COAR_RECV = 2 };
+static sbox emf_flux_box(const sidx *I, const int o[3], int f1, int f2, int kind, int v) {
+  const int s_[3] = {I->is, I->js, I->ks}, e_[3] = {I->ie, I->je, I->ke};
+  const int cs_[3] = {I->cis, I->cjs, I->cks}, ce_[3] = {I->cie, I->cje, I->cke};
+  const int cnx[3] = {I->cnx1, I->cnx2, I->cnx3};
+  const int act[3] = {1, I->nx2 > 1, I->nx3 > 1};
+  int lo[3], hi[3];
+  for (int d = 0; d < 3; ++d) {
+    const int node = (v != d);      /* an edge field is cell-like along its own direction, node-like across */
+    const int s = (kind == EMF_COAR_SEND) ? cs_[d] : s_[d], e = (kind == EMF_COAR_SEND) ? ce_[d] : e_[d];
+    if (o[d] == 0) {
+      lo[d] = s; hi[d] = e + node;
+      if (kind == EMF_COAR_RECV && (d == 0 || act[d])) {
+        const int sub = (d == 0) ? f1 : (d == 1) ? ((o[0] != 0) ? f1 : f2) : ((o[0] != 0 && o[1] != 0) ? f1 : f2);
+        if (sub == 1) lo[d] += cnx[d]; else hi[d] -= cnx[d];
+      }
+    } else if (o[d] > 0) { lo[d] = hi[d] = e + 1; }
+    else { lo[d] = hi[d] = s; }
+  }
+  sbox b = {lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]};
+  return b;
+}
+/* which edge-field component(s) a slot carries: faces the two tangential ones, edges the one along the edge */
+static int emf_carries(int n, int v) {
+  if (n < 8) return v != 0;
+  if (n < 16) return v != 1;
+  if (n < 24) return v == 2;
+  if (n < 32) return v != 2;
+  if (n < 40) return v == 1;
+  if (n < 48) return v == 0;
+  return 0;
+}
+static void emf_nflx_faces(int *nf, int n, int add) {   /* the four edge counters of a face slot with sub-block (0,0) */
+  static const int tab[6][5] = {{0, 16, 20, 32, 36}, {4, 18, 22, 34, 38}, {8, 16, 18, 40, 44}, {12, 20, 22, 42, 46}, {24, 32, 34, 40, 42}, {28, 36, 38, 44, 46}};
+  for (int q = 0; q < 6; ++q)
+    if (tab[q][0] == n) for (int r = 1; r <= 4; ++r) { if (add) nf[tab[q][r]] += 1; else nf[tab[q][r]] = 0; }
+}
+
+void oracle_smr_emf_correct(const ocfg *c, double *e1, double *e2, double *e3, const int *nghbr, const int *mblev) {
+  odims D = dims(c);
+  sidx I = smr_indcs(c);
+  const int nmb = c->nmb, multi_d = I.multi_d, three_d = I.three_d;
+  const int actv[3] = {1, multi_d, three_d};
+  double **rbuf = calloc((size_t)nmb * 48 * 3, sizeof(double *));
+  /* ---- pack */
+  for (int m = 0; m < nmb; ++m)
+    for (int n = 0; n < 48; ++n) {
+      const int *e = nghbr + ((size_t)m * 56 + n) * 4;
+      if (e[0] < 0 || e[1] > mblev[m]) continue;
+      int o[3], f1, f2;
+      smr_slot_decode(n, &o[0], &o[1], &o[2], &f1, &f2);
+      const int coarser = e[1] < mblev[m];
+      for (int v = 0; v < 3; ++v) {
+        if (!emf_carries(n, v)) continue;
+        sbox x = emf_flux_box(&I, o, f1, f2, coarser ? EMF_COAR_SEND : EMF_SAME, v);
+        const int ni = x.ie - x.is + 1, nj = x.je - x.js + 1, nk = x.ke - x.ks + 1;
+        double *buf = malloc(sizeof(double) * (size_t)ni * nj * nk);
+        for (int k = x.ks; k <= x.ke; ++k)
+          for (int j = x.js; j <= x.je; ++j)
+            for (int i = x.is; i <= x.ie; ++i) {
+              double r;
+              if (!coarser) r = *emf_at(&D, e1, e2, e3, v, m, k, j, i);
+              else {
+                /* flux_correct_fc.cpp:108-113,131-136: inactive directions always read index 0 of the fine array */
+                const int fi = 2 * i - I.cis, fj = multi_d ? 2 * j - I.cjs : 0, fk = three_d ? 2 * k - I.cks : 0;
+                const int d1 = (v == 0), d2 = (v == 1), d3 = (v == 2);
+                if (actv[v]) r = 0.5 * (*emf_at(&D, e1, e2, e3, v, m, fk, fj, fi) + *emf_at(&D, e1, e2, e3, v, m, fk + d3, fj + d2, fi + d1));
+                else r = *emf_at(&D, e1, e2, e3, v, m, fk, fj, fi);
+              }
+              buf[(i - x.is) + ni * ((j - x.js) + nj * (k - x.ks))] = r;
+            }
+        rbuf[((size_t)e[0] * 48 + e[3]) * 3 + v] = buf;
+      }
+    }
+  int *nflx = malloc(sizeof(int) * (size_t)nmb * 48);
+  for (int q = 0; q < nmb * 48; ++q) nflx[q] = 1;
+  const int multilevel = 1;
+  for (int pass = 0; pass < (multilevel ? 2 : 1); ++pass) {
+    const int same_level = (pass == 0);
+    if (!same_level) {   /* ZeroFluxesAtBoundaryWithFiner */
+      for (int m = 0; m < nmb; ++m)
+        for (int n = 0; n < 48; ++n) {
+          const int *e = nghbr + ((size_t)m * 56 + n) * 4;
+          if (e[0] < 0 || e[1] <= mblev[m]) continue;
+          int o[3], f1, f2;
+          smr_slot_decode(n, &o[0], &o[1], &o[2], &f1, &f2);
+          if (n < 16 || (n >= 24 && n < 32)) emf_nflx_faces(nflx + (size_t)m * 48, n, 0);
+          else nflx[(size_t)m * 48 + n] = 0;
+          for (int v = 0; v < 3; ++v) {
+            if (!emf_carries(n, v)) continue;
+            sbox x = emf_flux_box(&I, o, f1, f2, EMF_COAR_RECV, v);
+            for (int k = x.ks; k <= x.ke; ++k) for (int j = x.js; j <= x.je; ++j) for (int i = x.is; i <= x.ie; ++i)
+              *emf_at(&D, e1, e2, e3, v, m, k, j, i) = 0.0;
+          }
+        }
+    }
+    /* SumBoundaryFluxes: per (block, component) in increasing slot order */
+    for (int m = 0; m < nmb; ++m)
+      for (int n = 0; n < 48; ++n) {
+        const int *e = nghbr + ((size_t)m * 56 + n) * 4;
+        if (e[0] < 0) continue;
+        if (same_level ? (e[1] != mblev[m]) : (e[1] <= mblev[m])) continue;
+        int o[3], f1, f2;
+        smr_slot_decode(n, &o[0], &o[1], &o[2], &f1, &f2);
+        if (n < 16 || (n >= 24 && n < 32)) emf_nflx_faces(nflx + (size_t)m * 48, n, 1);     /* only n == 0,4,8,12,24,28 are in the table */
+        else nflx[(size_t)m * 48 + n] += 1;
+        for (int v = 0; v < 3; ++v) {
+          if (!emf_carries(n, v)) continue;
+          sbox x = emf_flux_box(&I, o, f1, f2, same_level ? EMF_SAME : EMF_COAR_RECV, v);
+          const int ni = x.ie - x.is + 1, nj = x.je - x.js + 1;
+          const double *buf = rbuf[((size_t)m * 48 + n) * 3 + v];
+          for (int k = x.ks; k <= x.ke; ++k) for (int j = x.js; j <= x.je; ++j) for (int i = x.is; i <= x.ie; ++i)
+            *emf_at(&D, e1, e2, e3, v, m, k, j, i) += buf[(i - x.is) + ni * ((j - x.js) + nj * (k - x.ks))];
+        }
+      }
+  }
+  /* AverageBoundaryFluxes: slots with sub-block (0,0) only; boxes = the same-level receive boxes */
+  for (int m = 0; m < nmb; ++m)
+    for (int n = 0; n < 48; ++n) {
+      int o[3], f1, f2;
+      smr_slot_decode(n, &o[0], &o[1], &o[2], &f1, &f2);
+      if (f1 || f2) continue;
+      if ((o[1] && !multi_d) || (o[2] && !three_d)) continue;
+      const int *e = nghbr + ((size_t)m * 56 + n) * 4;
+      const int nz = (o[0] != 0) + (o[1] != 0) + (o[2] != 0);
+      for (int v = 0; v < 3; ++v) {
+        if (!emf_carries(n, v)) continue;
+        sbox x = emf_flux_box(&I, o, 0, 0, EMF_SAME, v);
+        int lo[3] = {x.is, x.js, x.ks}, hi[3] = {x.ie, x.je, x.ke};
+        if (nz == 2) {     /* block edge: divide by the number of contributions */
+          for (int k = lo[2]; k <= hi[2]; ++k) for (int j = lo[1]; j <= hi[1]; ++j) for (int i = lo[0]; i <= hi[0]; ++i)
+            *emf_at(&D, e1, e2, e3, v, m, k, j, i) /= (double)nflx[(size_t)m * 48 + n];
+          continue;
+        }
+        /* face: t = the tangential direction ACROSS the edge field (the node-like one) */
+        int t = -1;
+        for (int d = 0; d < 3; ++d) if (o[d] == 0 && d != v) t = d;
+        if (e[1] == mblev[m]) {              /* same level: halve the face interior, excluding the edge lines */
+          if (actv[t] || t == 0) { if (t == 0 || (t == 1 ? multi_d : three_d)) { lo[t] += 1; hi[t] -= 1; } }
+          for (int k = lo[2]; k <= hi[2]; ++k) for (int j = lo[1]; j <= hi[1]; ++j) for (int i = lo[0]; i <= hi[0]; ++i)
+            *emf_at(&D, e1, e2, e3, v, m, k, j, i) *= 0.5;
+        } else if (e[1] >= mblev[m]) {       /* finer: halve the line where two fine faces meet */
+          if (!(t == 0 || (t == 1 ? multi_d : three_d))) continue;
+          const int mid = lo[t] + (hi[t] - lo[t] + 1) / 2;
+          lo[t] = hi[t] = mid;
+          for (int k = lo[2]; k <= hi[2]; ++k) for (int j = lo[1]; j <= hi[1]; ++j) for (int i = lo[0]; i <= hi[0]; ++i)
+            *emf_at(&D, e1, e2, e3, v, m, k, j, i) *= 0.5;
+        }
+      }
+    }
+  for (size_t q = 0; q < (size_t)nmb * 48 * 3; ++q) free(rbuf[q]);
+  free(rbuf);
+  free(nflx);
+}
+
+/* MHD stage on a multilevel, strictly periodic mesh: mhd_tasks.cpp:48-75 */
+int oracle_mhd_smr_run(const ocfg *c, ostate *s, double *cu0, double *cb1, double *cb2, double *cb3, const double *mb_size,
+                       const int *nghbr, const int *mblev, int integrator, double cfl, double tlim, int ncycles,
+                       double *time, double *dt) {
+  odims D = dims(c);
+  size_t nm = (size_t)c->nmb;
+  double g0[3] = {0.0, 0.0, 0.0}, g1[3] = {1.0, 0.0, 0.0}, be[3] = {1.0, 0.0, 0.0};
+  if (integrator == 2) { g0[1] = 0.5; g1[1] = 0.5; be[1] = 0.5; }
+  if (integrator == 3) { g0[1] = 0.25; g1[1] = 0.75; be[1] = 0.25; g0[2] = 2.0 / 3.0; g1[2] = 1.0 / 3.0; be[2] = 2.0 / 3.0; }
+  double *flx1 = calloc(D.nv * nm * D.f1, 8), *flx2 = calloc(D.nv * nm * D.f2, 8), *flx3 = calloc(D.nv * nm * D.f3, 8);
+  double *fe[6];
+  for (int q = 0; q < 6; ++q) fe[q] = calloc(nm * D.cc, 8);
+  double *e1 = calloc(nm * D.e1, 8), *e2 = calloc(nm * D.e2, 8), *e3 = calloc(nm * D.e3, 8);
+  int n = 0;
+  while (*time < tlim && (ncycles < 0 || n < ncycles)) {
+    for (int st = 1; st <= integrator; ++st) {
+      const double bdt = be[st - 1] * (*dt);
+      if (st == 1) {
+        memcpy(s->u1, s->u0, 8 * D.nv * nm * D.cc);
+        memcpy(s->b1x1f, s->b0x1f, 8 * nm * D.f1); memcpy(s->b1x2f, s->b0x2f, 8 * nm * D.f2); memcpy(s->b1x3f, s->b0x3f, 8 * nm * D.f3);
+      }
+      oracle_fluxes(c, s->w0, s->bcc0, s->b0x1f, s->b0x2f, s->b0x3f, flx1, flx2, flx3, fe[0], fe[1], fe[2], fe[3], fe[4], fe[5]);
+      oracle_smr_flux_correct_cc(c, flx1, flx2, flx3, D.nv, nghbr, mblev);                      /* SendFlux / RecvFlux */
+      oracle_rk_update(c, s->u0, s->u1, flx1, flx2, flx3, mb_size, g0[st - 1], g1[st - 1], bdt);
+      oracle_smr_restrict_cc(c, s->u0, cu0, D.nv);                                                /* RestrictU, SendU, RecvU */
+      oracle_smr_halo_cc(c, s->u0, cu0, D.nv, nghbr, mblev);
+      oracle_corner_e(c, s->w0, s->bcc0, flx1, flx2, flx3, fe[0], fe[1], fe[2], fe[3], fe[4], fe[5], e1, e2, e3);
+      oracle_smr_emf_correct(c, e1, e2, e3, nghbr, mblev);                                        /* SendE / RecvE */
+      oracle_ct(c, s->b0x1f, s->b0x2f, s->b0x3f, s->b1x1f, s->b1x2f, s->b1x3f, e1, e2, e3, mb_size, g0[st - 1], g1[st - 1], bdt);
+      oracle_smr_restrict_fc(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3);                     /* RestrictB, SendB, RecvB */
+      oracle_smr_halo_fc(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3, nghbr, mblev);
+      oracle_smr_prolongate_cc_steps(c, s->u0, cu0, D.nv, nghbr, mblev, 1);                       /* Prolongate */
+      oracle_smr_prolongate_fc_steps(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3, nghbr, mblev, 1);
+      oracle_smr_prolongate_cc_steps(c, s->u0, cu0, D.nv, nghbr, mblev, 2);
+      oracle_smr_prolongate_fc_steps(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3, nghbr, mblev, 2);
+      int nf[3];
+      oracle_cons2prim(c, s->u0, s->b0x1f, s->b0x2f, s->b0x3f, s->w0, s->bcc0, 0, D.n1 - 1, 0, D.n2 - 1, 0, D.n3 - 1, nf);
+    }
+    double dtnew = oracle_new_dt(c, s->w0, s->bcc0, mb_size, NULL);
+    *time = *time + *dt;
+    n++;
+    double d = 2.0 * (*dt);
+    double lim = cfl * dtnew;
+    if (lim < d) d = lim;
+    if ((*time < tlim) && ((*time + d) > tlim)) d = tlim - *time;
+    *dt = d;
+  }
+  free(flx1); free(flx2); free(flx3);
+  for (int q = 0; q < 6; ++q) free(fe[q]);
+  free(e1); free(e2); free(e3);
+  return n;
+}

@@ -141,14 +141,40 @@ def smr():
                             u0_final=r1.u0, dt_c0=r0.dt, ng=ng, time_final=r1.time, dt_final=r1.dt, ncycle_final=r1.ncycle)
 
 
+def smr_mhd():
+    """MHD SMR fixtures (tests/smr_util.py MHD_CASES); 3-D ones keep the active zones / faces only."""
+    import smr_util as S
+    for name in S.MHD_CASES:
+        r0, r1 = S.reference_mhd(name)
+        ng = r0.mb_indcs["ng"]
+        nb = (r0.mb_indcs["nx1"], r0.mb_indcs["nx2"], r0.mb_indcs["nx3"])
+        out = dict(deck=np.array(r0.deck), lloc=r0.lloc, dt_c0=r0.dt, time_final=r1.time, dt_final=r1.dt, ncycle_final=r1.ncycle)
+        active_only = nb[2] > 1
+        for tag, r in (("c0", r0), ("final", r1)):
+            u, b = r.u0, (r.b1f, r.b2f, r.b3f)
+            if active_only:
+                s = slice(ng, -ng)
+                u, b = u[:, :, s, s, s], S.active_faces(b, ng, nb)
+            out["u0_" + tag] = u
+            for k, x in zip(("b1f_", "b2f_", "b3f_"), b):
+                out[k + tag] = x
+        out["active_only"] = active_only
+        np.savez_compressed(os.path.join(HERE, "golden", name + ".npz"), **out)
+
+
 if __name__ == "__main__":
     if "--smr-only" in sys.argv:
         smr_trees()
         smr()
+        smr_mhd()
+        sys.exit(0)
+    if "--smr-mhd-only" in sys.argv:
+        smr_mhd()
         sys.exit(0)
     iso()
     smr_trees()
     smr()
+    smr_mhd()
     if "--iso-only" in sys.argv:
         sys.exit(0)
     mhd_lowd("bw1d.athinput", "BrioWu", "mhd_bw1d_ppm4_hlld_rk3",

@@ -140,3 +140,87 @@ def _oracle_run(L, cfg, u0, u1, cu0, w0, mbs, ngh, lev, p, cfl, tlim, ncycles):
     n = L.oracle_hydro_smr_run(C.byref(cfg), O.p(u0), O.p(u1), O.p(cu0), O.p(w0), O.p(mbs), O.ip(ngh), O.ip(lev),
                                H.INTEGRATOR[p["time/integrator"]], C.c_double(cfl), C.c_double(tlim), ncycles, C.byref(t), C.byref(dt))
     return u0, w0, t.value, dt.value, n, dt0
+
+
+# ---- MHD on refined meshes (tests/decks/lwave3d_smr.athinput: nonlinear fast wave, nested regions, periodic) -------
+MHD_DECK = os.path.join(HERE, "decks", "lwave3d_smr.athinput")
+MHD_CASES = {
+    "mhd_smr2d_ppm4_hlld_rk3": ("problem/amp=0.1", "time/tlim=0.05", "mesh/nx3=1", "meshblock/nx3=1", "mesh/nx2=32", "meshblock/nx2=8"),
+    # 3-D: 16 root blocks, one refined (23 blocks); fixture keeps the ACTIVE zones / faces only
+    "mhd_smr3d_ppm4_hlld_rk3": ("problem/amp=0.1", "time/tlim=0.02", *_B8,
+                                "refined_region1/x1min=0.1", "refined_region1/x1max=0.2", "refined_region1/x2min=0.1", "refined_region1/x2max=0.2",
+                                "refined_region1/x3min=0.1", "refined_region1/x3max=0.2",
+                                "refined_region2/level=1", "refined_region2/x1min=0.1", "refined_region2/x1max=0.2",
+                                "refined_region2/x2min=0.1", "refined_region2/x2max=0.2", "refined_region2/x3min=0.1", "refined_region2/x3max=0.2"),
+}
+MHD_LIVE_CASES = dict(MHD_CASES)
+MHD_LIVE_CASES.update({
+    "mhd_smr3d_3levels": ("problem/amp=0.1", "time/tlim=0.02", *_B8),                       # 135 blocks, levels 2-4
+    "mhd_smr3d_plm_hlle_rk2": ("problem/amp=0.1", "time/tlim=0.03", *_B8, "mhd/reconstruct=plm", "mhd/rsolver=hlle", "time/integrator=rk2",
+                               "refined_region2/level=1"),
+    "mhd_smr2d_wenoz_llf_l3": ("problem/amp=0.1", "time/tlim=0.04", "mesh/nx3=1", "meshblock/nx3=1", "mesh/nx2=32", "meshblock/nx2=8",
+                               "mhd/reconstruct=wenoz", "mhd/rsolver=llf", "refined_region2/level=3", "refined_region2/x1min=2.6",
+                               "refined_region2/x1max=3.0", "refined_region2/x2min=1.3", "refined_region2/x2max=1.5"),
+    "mhd_smr1d_plm_hlld": ("problem/amp=0.1", "time/tlim=0.2", "mesh/nx2=1", "meshblock/nx2=1", "mesh/nx3=1", "meshblock/nx3=1",
+                           "mesh/nx1=128", "meshblock/nx1=8", "problem/along_x1=true", "mhd/reconstruct=plm", "mesh/nghost=2",
+                           "refined_region2/level=3"),
+})
+
+
+def reference_mhd(name, threads=4):
+    with tempfile.TemporaryDirectory() as tmp:
+        O.run_reference("athena_builtin", MHD_DECK, tmp, list(MHD_LIVE_CASES[name]), threads=threads)
+        r0 = read_rst(os.path.join(tmp, "rst", "LinWave.00000.rst"))
+        r1 = read_rst(os.path.join(tmp, "rst", "LinWave.00001.rst"))
+    return r0, r1
+
+
+def active_faces(b, ng, nblock):
+    """Active faces (block-boundary faces included) of ghost-inclusive face arrays (b1f, b2f, b3f)."""
+    out = []
+    for v, a in enumerate(b):
+        sl = [slice(None)]
+        for d in (2, 1, 0):           # array axes k, j, i
+            if nblock[d] > 1 or d == 0:
+                sl.append(slice(ng, -ng))       # n (+1 along the staggered axis) entries: s .. e (+1)
+            else:
+                sl.append(slice(None))
+        out.append(a[tuple(sl)])
+    return out
+
+
+def oracle_run_mhd(deck_text, u_init, b_init, ncycles=-1, active_only=False):
+    """Driver::Initialize + Execute of the MHD SMR oracle.  active_only: u_init / b_init hold active zones / faces
+    only (ghost zones start at zero; Initialize rebuilds them).  Returns (Arrays, time, dt_next, ncycles, dt0)."""
+    mesh, p = mesh_of(deck_text)
+    mbs, _, ngh = mesh.rank_tables(0)
+    cfg = O.OCfg(mesh.nmb_total, int(p["mesh/nghost"]), *mesh.nblock, O.RECON[p["mhd/reconstruct"]], O.RSOLVER[p["mhd/rsolver"]],
+                 float(p["mhd/gamma"]), O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, 0, 0, 1.0, 0)
+    L = O.lib()
+    L.oracle_smr_coarse_cells.restype = C.c_size_t
+    L.oracle_smr_coarse_faces.restype = C.c_size_t
+    L.oracle_mhd_smr_run.restype = C.c_int
+    L.oracle_initial_dt.restype = C.c_double
+    A = O.Arrays(cfg)
+    ng = cfg.ng
+    if active_only:
+        act = tuple(slice(ng, -ng) if n > 1 else slice(None) for n in mesh.nblock[::-1])
+        A.u0[(slice(None), slice(None)) + act] = u_init
+        for dst, src in zip(active_faces(A.b0, ng, mesh.nblock), b_init):
+            dst[:] = src
+    else:
+        A.u0[:] = u_init
+        for dst, src in zip(A.b0, b_init):
+            dst[:] = src
+    cu0 = np.zeros((mesh.nmb_total, A.u0.shape[1], L.oracle_smr_coarse_cells(C.byref(cfg))))
+    cb = [np.zeros((mesh.nmb_total, L.oracle_smr_coarse_faces(C.byref(cfg), v))) for v in range(3)]
+    ngh = np.ascontiguousarray(ngh, np.int32)
+    lev = np.ascontiguousarray(mesh.lloc[:, 3], np.int32)
+    st = A.state()
+    L.oracle_mhd_smr_ghosts_and_prims(C.byref(cfg), C.byref(st), O.p(cu0), *[O.p(x) for x in cb], O.ip(ngh), O.ip(lev))
+    cfl, tlim = float(p["time/cfl_number"]), float(p["time/tlim"])
+    dt0 = L.oracle_initial_dt(C.byref(cfg), C.byref(st), O.p(mbs), C.c_double(cfl), C.c_double(tlim), C.c_double(0.0))
+    t, dt = C.c_double(0.0), C.c_double(dt0)
+    n = L.oracle_mhd_smr_run(C.byref(cfg), C.byref(st), O.p(cu0), *[O.p(x) for x in cb], O.p(mbs), O.ip(ngh), O.ip(lev),
+                             H.INTEGRATOR[p["time/integrator"]], C.c_double(cfl), C.c_double(tlim), ncycles, C.byref(t), C.byref(dt))
+    return A, t.value, dt.value, n, dt0

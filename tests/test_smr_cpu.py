@@ -33,3 +33,37 @@ def test_smr_oracle_matches_live_reference(name):
     u, w, t, dt, n, dt0 = S.oracle_run(r0.deck, r0.u0)
     assert dt0 == r0.dt and n == r1.ncycle and t == r1.time and dt == r1.dt
     assert np.array_equal(u, r1.u0), f"max|dU| = {np.abs(u - r1.u0).max()}"
+
+
+@pytest.mark.parametrize("name", sorted(S.MHD_CASES))
+def test_mhd_smr_oracle_matches_golden(name):
+    """MHD on refined meshes (oracle/smr_fc_oracle.c: RestrictFC, face-field exchange across levels, divergence-
+    preserving ProlongateFC, fine/coarse EMF correction) against fixtures made from the unmodified reference."""
+    d = G.load(name)
+    mesh, p = S.mesh_of(str(d["deck"]))
+    assert np.array_equal(mesh.lloc, d["lloc"]) and len(np.unique(mesh.lloc[:, 3])) >= 2
+    active_only = bool(d["active_only"])
+    b0 = (d["b1f_c0"], d["b2f_c0"], d["b3f_c0"])
+    A, t, dt, n, dt0 = S.oracle_run_mhd(str(d["deck"]), d["u0_c0"], b0, active_only=active_only)
+    assert dt0 == float(d["dt_c0"]) and n == int(d["ncycle_final"]) and t == float(d["time_final"]) and dt == float(d["dt_final"])
+    ng = int(p["mesh/nghost"])
+    if active_only:
+        act = tuple(slice(ng, -ng) if k > 1 else slice(None) for k in mesh.nblock[::-1])
+        u, b = A.u0[(slice(None), slice(None)) + act], S.active_faces(A.b0, ng, mesh.nblock)
+    else:
+        u, b = A.u0, A.b0
+    assert np.array_equal(u, d["u0_final"]), f"max|dU| = {np.abs(u - d['u0_final']).max()}"
+    for x, k in zip(b, ("b1f_final", "b2f_final", "b3f_final")):
+        assert np.array_equal(x, d[k]), k
+
+
+@pytest.mark.parametrize("name", sorted(set(S.MHD_LIVE_CASES) - set(S.MHD_CASES)))
+def test_mhd_smr_oracle_matches_live_reference(name):
+    if not O.have_reference("athena_builtin"):
+        pytest.skip("oracle/_ref/athena_builtin not built")
+    r0, r1 = S.reference_mhd(name)
+    A, t, dt, n, dt0 = S.oracle_run_mhd(r0.deck, r0.u0, (r0.b1f, r0.b2f, r0.b3f))
+    assert dt0 == r0.dt and n == r1.ncycle and t == r1.time and dt == r1.dt
+    assert np.array_equal(A.u0, r1.u0), f"max|dU| = {np.abs(A.u0 - r1.u0).max()}"        # ghost zones included
+    for x, y in zip(A.b0, (r1.b1f, r1.b2f, r1.b3f)):
+        assert np.array_equal(x, y)
