@@ -21,6 +21,7 @@
 
 #include "../../include/athenak_b200.h"
 #include "halo.h"
+#include "smr_fc_body.h"
 
 namespace {
 
@@ -126,6 +127,22 @@ struct Plan {
   long max_copy = 0, max_fill = 0, max_prol = 0, max_flux = 0;
   bool uploaded = false;
   std::string err;
+  // ---- face-centred fields and edge EMFs across levels (MHD); bodies in smr_fc_body.h
+  akb_smr::FcDims FD;
+  std::vector<unsigned char> fmap[3], cmap[3];      // winning neighbour slot per fine / coarse face, 255 = not received
+  std::vector<akb_smr::FcSrc> fsrc;                 // [nmb][56][3]
+  std::vector<akb_smr::FcBox> ffill, fshared;
+  std::vector<akb_smr::FcCell> fint;
+  std::vector<akb_smr::EmfPack> epack;
+  std::vector<akb_smr::EmfOp> eops;
+  std::vector<akb_smr::EmfRange> erange;            // [nmb][3]
+  long emf_buf = 0;
+  long max_ffill = 0, max_fshared = 0, max_fint = 0, max_epack = 0;
+  unsigned char *d_fmap[3] = {nullptr, nullptr, nullptr}, *d_cmap[3] = {nullptr, nullptr, nullptr};
+  akb_smr::FcSrc *d_fsrc = nullptr; akb_smr::FcBox *d_ffill = nullptr, *d_fshared = nullptr; akb_smr::FcCell *d_fint = nullptr;
+  akb_smr::EmfPack *d_epack = nullptr; akb_smr::EmfOp *d_eops = nullptr; akb_smr::EmfRange *d_erange = nullptr;
+  double *d_emfbuf = nullptr;
+  bool fc_uploaded = false;
 };
 
 thread_local std::string g_smr_err;
@@ -304,6 +321,370 @@ int ensure_uploaded(Plan *P) {
 
 inline unsigned gx(long maxcount, int bs) { return (unsigned)std::max(1L, std::min((maxcount + bs - 1) / bs, 64L)); }
 
+
+// ---------------------------------------------------------------------------------------------------
+// face-centred fields and edge EMFs across levels: host tables
+
+using namespace akb_smr;
+
+FcDims fcdims_of(const Idx &I, int nmb) {
+  FcDims D;
+  for (int d = 0; d < 3; ++d) { D.n[d] = I.n[d]; D.cn[d] = I.cn[d]; D.s[d] = I.s[d]; D.e[d] = I.e[d]; D.cs[d] = I.cs[d]; D.ce[d] = I.ce[d]; }
+  D.multi_d = I.act[1]; D.three_d = I.act[2]; D.ng = I.ng; D.nmb = nmb;
+  for (int v = 0; v < 3; ++v) {
+    D.f[v] = (long)(I.n[0] + (v == 0)) * (I.n[1] + (v == 1)) * (I.n[2] + (v == 2));
+    D.cf[v] = (long)(I.cn[0] + (v == 0)) * (I.cn[1] + (v == 1)) * (I.cn[2] + (v == 2));
+    D.ef[v] = (long)(I.n[0] + (v != 0)) * (I.n[1] + (v != 1)) * (I.n[2] + (v != 2));
+  }
+  return D;
+}
+
+// buffs_fc.cpp:29-326 (send) and :388-790 (receive, prolongation): box of component v, staggered along d == v
+Box fc_box(const Idx &I, const int o[3], int f1, int f2, Kind kind, int v, bool send) {
+  Box b;
+  const int ng = I.ng, ng1 = ng - 1;
+  for (int d = 0; d < 3; ++d) {
+    const int st = (v == d);
+    const int sub = sub_of(d, o, f1, f2);
+    const bool others = (o[(d + 1) % 3] != 0) || (o[(d + 2) % 3] != 0);
+    const bool splits = (d == 0) || I.act[d];
+    int lo, hi;
+    if (send) {
+      if (kind == SAME || kind == COAR) {
+        const int s = (kind == COAR) ? I.cs[d] : I.s[d], e = (kind == COAR) ? I.ce[d] : I.e[d];
+        if (o[d] == 0) { lo = s; hi = e + st; }
+        else if (o[d] > 0) { lo = e - ng1; hi = e; }
+        else { lo = s + st; hi = s + ng1 + st; }
+        if (st && others) { if (o[d] > 0) hi++; if (o[d] < 0) lo--; }      // overlapping faces on edges / corners
+      } else {   // FINE
+        if (o[d] == 0) {
+          lo = I.s[d]; hi = I.e[d] + st;
+          if (splits) { if (sub == 1) lo += I.cnx[d] - ng; else hi -= I.cnx[d] - ng; }
+        } else if (o[d] > 0) { lo = I.e[d] - ng1; hi = I.e[d] + st; }
+        else { lo = I.s[d]; hi = I.s[d] + ng1 + st; }
+      }
+    } else {
+      if (kind == SAME || kind == FINE) {
+        if (o[d] == 0) {
+          lo = I.s[d]; hi = I.e[d] + st;
+          if (kind == FINE && splits) { if (sub == 1) lo += I.cnx[d]; else hi -= I.cnx[d]; }
+        } else if (o[d] > 0) { lo = I.e[d] + 1 + st; hi = I.e[d] + ng + st; }
+        else { lo = I.s[d] - ng; hi = I.s[d] - 1; }
+        if (st && others) { if (o[d] > 0) lo--; if (o[d] < 0) hi++; }
+      } else if (kind == COAR) {
+        if (o[d] == 0) {
+          lo = I.cs[d]; hi = I.ce[d] + st;
+          if (splits) { if (sub == 0) hi += ng; else lo -= ng; }
+        } else if (o[d] > 0) { lo = I.ce[d] + 1; hi = I.ce[d] + ng + st; }
+        else { lo = I.cs[d] - ng; hi = I.cs[d] - 1 + st; }
+      } else {   // PROL
+        const int cn = ng / 2;
+        if (o[d] == 0) {
+          lo = I.cs[d]; hi = I.ce[d] + st;
+          if (splits) { if (sub == 0) hi += cn; else lo -= cn; }
+        } else if (o[d] > 0) { lo = I.ce[d] + 1 + st; hi = I.ce[d] + cn + st; }
+        else { lo = I.cs[d] - cn; hi = I.cs[d] - 1; }
+      }
+    }
+    b.lo[d] = lo; b.hi[d] = hi;
+  }
+  return b;
+}
+
+// buffs_fc.cpp:282-385 (send) and :785-935 (receive): boundary edges of component v.  kind: SAME, COAR = packed
+// on the coarse index space for a coarser neighbour, FINE = received from a finer neighbour (half a face / edge)
+Box emf_box(const Idx &I, const int o[3], int f1, int f2, Kind kind, int v) {
+  Box b;
+  for (int d = 0; d < 3; ++d) {
+    const int node = (v != d);
+    const int s = (kind == COAR) ? I.cs[d] : I.s[d], e = (kind == COAR) ? I.ce[d] : I.e[d];
+    if (o[d] == 0) {
+      b.lo[d] = s; b.hi[d] = e + node;
+      if (kind == FINE && ((d == 0) || I.act[d])) { if (sub_of(d, o, f1, f2) == 1) b.lo[d] += I.cnx[d]; else b.hi[d] -= I.cnx[d]; }
+    } else if (o[d] > 0) { b.lo[d] = b.hi[d] = e + 1; }
+    else { b.lo[d] = b.hi[d] = s; }
+  }
+  return b;
+}
+// faces carry the two tangential EMF components, edges the one along the edge (flux_correct_fc.cpp:64-100)
+inline bool emf_carries(int n, int v) {
+  if (n < 8) return v != 0;
+  if (n < 16) return v != 1;
+  if (n < 24) return v == 2;
+  if (n < 32) return v != 2;
+  if (n < 40) return v == 1;
+  if (n < 48) return v == 0;
+  return false;
+}
+// the four edge counters a face slot with sub-block (0,0) adds to (flux_correct_fc.cpp:489-520)
+void nflx_faces(int *nf, int n, bool add) {
+  static const int tab[6][5] = {{0, 16, 20, 32, 36}, {4, 18, 22, 34, 38}, {8, 16, 18, 40, 44}, {12, 20, 22, 42, 46}, {24, 32, 34, 40, 42}, {28, 36, 38, 44, 46}};
+  for (int q = 0; q < 6; ++q)
+    if (tab[q][0] == n) for (int r = 1; r <= 4; ++r) { if (add) nf[tab[q][r]] += 1; else nf[tab[q][r]] = 0; }
+}
+// prolongation.cpp:28-50: the reference's own slot -> offset search (tries every (n1,n2) for every offset)
+void ref_offset(int n, int o[3]) {
+  o[0] = o[1] = o[2] = 0;
+  for (int iz = -1; iz <= 1; ++iz) for (int iy = -1; iy <= 1; ++iy) for (int ix = -1; ix <= 1; ++ix) {
+    if (!ix && !iy && !iz) continue;
+    for (int n1 = 0; n1 <= 1; ++n1) for (int n2 = 0; n2 <= 1; ++n2)
+      if (akb::neighbor_index(ix, iy, iz, n1, n2) == n) { o[0] = ix; o[1] = iy; o[2] = iz; return; }
+  }
+}
+int max_lev_at(const int *nghbr, int m, const int o[3]) {      // prolongation.cpp:53-68
+  int mx = -1;
+  for (int n1 = 0; n1 <= 1; ++n1) for (int n2 = 0; n2 <= 1; ++n2) {
+    const int idx = akb::neighbor_index(o[0], o[1], o[2], n1, n2);
+    if (idx >= 0 && idx < 56 && nghbr[((size_t)m * 56 + idx) * 4] >= 0) mx = std::max(mx, nghbr[((size_t)m * 56 + idx) * 4 + 1]);
+  }
+  return mx;
+}
+inline long box_count(const Box &b) { return (long)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1); }
+inline bool same_shape(const Box &a, const Box &b) {
+  for (int d = 0; d < 3; ++d) if (a.hi[d] - a.lo[d] != b.hi[d] - b.lo[d]) return false;
+  return true;
+}
+
+// all tables of the face-centred path; returns an error text or ""
+std::string build_fc(Plan *P, const int *nghbr, const int *mb_lev, int gids_start) {
+  const Idx &I = P->I;
+  auto cnt = [](const int n[3]) { return (long)n[0] * n[1] * n[2]; };
+  const int nmb = P->cfg.nmb;
+  P->FD = fcdims_of(I, nmb);
+  const FcDims &D = P->FD;
+  for (int v = 0; v < 3; ++v) { P->fmap[v].assign((size_t)nmb * D.f[v], 255); P->cmap[v].assign((size_t)nmb * D.cf[v], 255); }
+  P->fsrc.assign((size_t)nmb * 56 * 3, FcSrc{-1, 0, {0, 0, 0}});
+  std::vector<long> bufoff((size_t)nmb * 48 * 3, -1), bufcnt((size_t)nmb * 48 * 3, 0);
+  auto E = [&](int m, int n) { return nghbr + ((size_t)m * 56 + n) * 4; };
+  for (int m = 0; m < nmb; ++m)
+    for (int n = 0; n < 56; ++n) {
+      const int *e = E(m, n);
+      if (e[0] < 0) continue;
+      int o[3], f1, f2, ro[3], rf1, rf2;
+      slot_decode(n, o, f1, f2);
+      const int dm = e[0] - gids_start, dn = e[3];
+      const int mylev = mb_lev[m], nlev = e[1];
+      slot_decode(dn, ro, rf1, rf2);
+      const Kind sk = (nlev < mylev) ? COAR : (nlev == mylev) ? SAME : FINE;
+      const Kind rk = (mylev < nlev) ? COAR : (mylev == nlev) ? SAME : FINE;      // how the receiver sees me
+      for (int v = 0; v < 3; ++v) {
+        // ---- SendB / RecvB (bvals_fc.cpp:63-436)
+        const Box sb = fc_box(I, o, f1, f2, sk, v, true), rb = fc_box(I, ro, rf1, rf2, rk, v, false);
+        if (!same_shape(sb, rb)) return "face-field send/receive boxes differ in size";
+        FcSrc &S = P->fsrc[((size_t)dm * 56 + dn) * 3 + v];
+        if (S.src_m >= 0) return "two senders for one receive slot";
+        S.src_m = m; S.src_coarse = (sk == COAR);
+        for (int d = 0; d < 3; ++d) S.off[d] = sb.lo[d] - rb.lo[d];
+        std::vector<unsigned char> &map = (rk == COAR) ? P->cmap[v] : P->fmap[v];
+        const long per = (rk == COAR) ? D.cf[v] : D.f[v];
+        for (int k = rb.lo[2]; k <= rb.hi[2]; ++k) for (int j = rb.lo[1]; j <= rb.hi[1]; ++j) for (int i = rb.lo[0]; i <= rb.hi[0]; ++i) {
+          if (rk != COAR && fc_is_active(D, v, k, j, i)) continue;                 // bvals_fc.cpp:372-374
+          unsigned char &c = map[(size_t)dm * per + ((rk == COAR) ? cidx(D, v, k, j, i) : fidx(D, v, k, j, i))];
+          if (c == 255 || dn >= c) c = (unsigned char)dn;                          // serial unpack order: the highest slot wins
+        }
+        // ---- FillCoarseInBndryFC (prolongation.cpp:556-650): same-level neighbours, multi-D
+        if (nlev == mylev && I.act[1]) {
+          const Box r = fc_box(I, o, 0, 0, SAME, v, false);
+          FcBox d; d.m = m; d.v = v; d.own_axis = -1; d.own_sign = 0;
+          for (int q = 0; q < 3; ++q) {
+            if (I.act[q]) { d.lo[q] = (r.lo[q] + I.cs[q]) / 2; d.n[q] = (r.hi[q] + I.cs[q]) / 2 - d.lo[q] + 1; }
+            else { d.lo[q] = 0; d.n[q] = 1 + (v == q); }
+          }
+          P->ffill.push_back(d);
+          P->max_ffill = std::max(P->max_ffill, cnt(d.n));
+        }
+        // ---- ProlongateFC, shared faces (prolongation.cpp:651-760): coarser neighbours
+        if (nlev < mylev) {
+          const Box x = fc_box(I, o, f1, f2, PROL, v, false);
+          int rx[3];
+          ref_offset(n, rx);
+          FcBox d; d.m = m; d.v = v; d.own_axis = -1; d.own_sign = 0;
+          if ((rx[0] != 0) + (rx[1] != 0) + (rx[2] != 0) == 1 && max_lev_at(nghbr, m, rx) < mylev) {
+            d.own_axis = rx[0] ? 0 : rx[1] ? 1 : 2;
+            d.own_sign = rx[d.own_axis];
+          }
+          for (int q = 0; q < 3; ++q) { d.lo[q] = x.lo[q]; d.n[q] = x.hi[q] - x.lo[q] + 1; }
+          P->fshared.push_back(d);
+          P->max_fshared = std::max(P->max_fshared, cnt(d.n));
+        }
+      }
+      // ---- ProlongateFC, interior faces (prolongation.cpp:761-785): coarse cells of the prolongation region
+      if (nlev < mylev) {
+        const Box p0 = fc_box(I, o, f1, f2, PROL, 0, false), p1 = fc_box(I, o, f1, f2, PROL, 1, false), p2 = fc_box(I, o, f1, f2, PROL, 2, false);
+        FcCell d; d.m = m;
+        d.lo[0] = p2.lo[0]; d.n[0] = p2.hi[0] - p2.lo[0] + 1;
+        d.lo[1] = p0.lo[1]; d.n[1] = p0.hi[1] - p0.lo[1] + 1;
+        d.lo[2] = p1.lo[2]; d.n[2] = p1.hi[2] - p1.lo[2] + 1;
+        P->fint.push_back(d);
+        P->max_fint = std::max(P->max_fint, cnt(d.n));
+      }
+      // ---- SendE, pack (flux_correct_fc.cpp:29-366): to same-level and coarser neighbours
+      if (n < 48 && nlev <= mylev)
+        for (int v = 0; v < 3; ++v) {
+          if (!emf_carries(n, v)) continue;
+          const Box x = emf_box(I, o, f1, f2, (nlev < mylev) ? COAR : SAME, v);
+          EmfPack d; d.src_m = m; d.v = v; d.coarser = (nlev < mylev); d.off = P->emf_buf;
+          for (int q = 0; q < 3; ++q) { d.lo[q] = x.lo[q]; d.n[q] = x.hi[q] - x.lo[q] + 1; }
+          if (dn >= 48) return "EMF destination slot is a corner";
+          bufoff[((size_t)dm * 48 + dn) * 3 + v] = d.off;
+          bufcnt[((size_t)dm * 48 + dn) * 3 + v] = cnt(d.n);
+          P->emf_buf += cnt(d.n);
+          P->epack.push_back(d);
+          P->max_epack = std::max(P->max_epack, cnt(d.n));
+        }
+    }
+  // ---- RecvE: per (block, component) the sums in slot order, then the average
+  P->erange.assign((size_t)nmb * 3, EmfRange{0, 0, 0, 0});
+  std::vector<int> nflx(48);
+  for (int m = 0; m < nmb; ++m) {
+    const int mylev = mb_lev[m];
+    // contribution counters (flux_correct_fc.cpp:445-644, 655-796), pass by pass as the reference runs them
+    std::fill(nflx.begin(), nflx.end(), 1);
+    auto is_face = [](int n) { return n < 16 || (n >= 24 && n < 32); };
+    for (int n = 0; n < 48; ++n) { const int *e = E(m, n); if (e[0] >= 0 && e[1] == mylev) { if (is_face(n)) nflx_faces(nflx.data(), n, true); else nflx[n] += 1; } }
+    for (int n = 0; n < 48; ++n) { const int *e = E(m, n); if (e[0] >= 0 && e[1] > mylev) { if (is_face(n)) nflx_faces(nflx.data(), n, false); else nflx[n] = 0; } }
+    for (int n = 0; n < 48; ++n) { const int *e = E(m, n); if (e[0] >= 0 && e[1] > mylev) { if (is_face(n)) nflx_faces(nflx.data(), n, true); else nflx[n] += 1; } }
+    for (int v = 0; v < 3; ++v) {
+      EmfRange &R = P->erange[(size_t)m * 3 + v];
+      R.sum0 = (int)P->eops.size();
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) R.sum1 = (int)P->eops.size();
+        for (int n = 0; n < 48; ++n) {
+          const int *e = E(m, n);
+          if (e[0] < 0 || !emf_carries(n, v)) continue;
+          if (pass == 0 ? (e[1] != mylev) : (e[1] <= mylev)) continue;
+          int o[3], f1, f2;
+          slot_decode(n, o, f1, f2);
+          const Box x = emf_box(I, o, f1, f2, pass == 0 ? SAME : FINE, v);
+          EmfOp op; op.type = pass == 0 ? EMF_SUM0 : EMF_SUM1; op.div = 1.0;
+          op.off = bufoff[((size_t)m * 48 + n) * 3 + v];
+          if (op.off < 0 || bufcnt[((size_t)m * 48 + n) * 3 + v] != box_count(x)) return "EMF send/receive boxes differ in size";
+          for (int q = 0; q < 3; ++q) { op.lo[q] = x.lo[q]; op.hi[q] = x.hi[q]; }
+          P->eops.push_back(op);
+        }
+      }
+      R.avg = (int)P->eops.size();
+      // AverageBoundaryFluxes (flux_correct_fc.cpp:801-1034): slots with sub-block (0,0), same-level boxes
+      for (int n = 0; n < 48; ++n) {
+        int o[3], f1, f2;
+        slot_decode(n, o, f1, f2);
+        if (f1 || f2 || !emf_carries(n, v)) continue;
+        if ((o[1] && !I.act[1]) || (o[2] && !I.act[2])) continue;
+        const int *e = E(m, n);
+        const Box x = emf_box(I, o, 0, 0, SAME, v);
+        EmfOp op; op.off = -1; op.div = 1.0;
+        for (int q = 0; q < 3; ++q) { op.lo[q] = x.lo[q]; op.hi[q] = x.hi[q]; }
+        const int nz = (o[0] != 0) + (o[1] != 0) + (o[2] != 0);
+        if (nz == 2) {                               // block edge: divide by the number of contributions
+          op.type = EMF_DIV; op.div = (double)nflx[n];
+          P->eops.push_back(op);
+          continue;
+        }
+        if (e[0] < 0) continue;
+        int t = -1;                                  // the tangential direction across the edge field
+        for (int d = 0; d < 3; ++d) if (o[d] == 0 && d != v) t = d;
+        const bool tact = (t == 0) || I.act[t];
+        op.type = EMF_MUL;
+        if (e[1] == mylev) {                         // same level: halve the face interior, not its edge lines
+          if (tact) { op.lo[t] += 1; op.hi[t] -= 1; }
+          P->eops.push_back(op);
+        } else if (e[1] > mylev) {                   // finer: halve the line where two fine faces meet
+          if (!tact) continue;
+          const int mid = op.lo[t] + (op.hi[t] - op.lo[t] + 1) / 2;
+          op.lo[t] = op.hi[t] = mid;
+          P->eops.push_back(op);
+        }
+      }
+      R.end = (int)P->eops.size();
+    }
+  }
+  return "";
+}
+
+int ensure_fc_uploaded(Plan *P) {
+  if (P->fc_uploaded) return 0;
+  cudaError_t e = cudaSuccess;
+  for (int v = 0; v < 3 && e == cudaSuccess; ++v) { e = upload(P->fmap[v], &P->d_fmap[v]); if (e == cudaSuccess) e = upload(P->cmap[v], &P->d_cmap[v]); }
+  if (e == cudaSuccess) e = upload(P->fsrc, &P->d_fsrc);
+  if (e == cudaSuccess) e = upload(P->ffill, &P->d_ffill);
+  if (e == cudaSuccess) e = upload(P->fshared, &P->d_fshared);
+  if (e == cudaSuccess) e = upload(P->fint, &P->d_fint);
+  if (e == cudaSuccess) e = upload(P->epack, &P->d_epack);
+  if (e == cudaSuccess) e = upload(P->eops, &P->d_eops);
+  if (e == cudaSuccess) e = upload(P->erange, &P->d_erange);
+  if (e == cudaSuccess && P->emf_buf > 0) e = cudaMalloc(&P->d_emfbuf, sizeof(double) * P->emf_buf);
+  if (e != cudaSuccess) return smr_fail(P, std::string("ak_smr (face-centred tables): ") + cudaGetErrorString(e));
+  P->fc_uploaded = true;
+  return 0;
+}
+
+// ---- kernels: one launch per step over all blocks / descriptors; bodies in smr_fc_body.h
+
+__global__ void __launch_bounds__(256)
+fc_restrict_kernel(FcDims D, const double *__restrict__ b1, const double *__restrict__ b2, const double *__restrict__ b3,
+                   double *__restrict__ cb1, double *__restrict__ cb2, double *__restrict__ cb3) {
+  const int v = blockIdx.y;
+  const long cnt = fc_restrict_count(D, v);
+  const double *b = v == 0 ? b1 : v == 1 ? b2 : b3;
+  double *cb = v == 0 ? cb1 : v == 1 ? cb2 : cb3;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.x * blockDim.x) fc_restrict_elem(D, v, t, b, cb);
+}
+
+struct FcMaps { const unsigned char *f[3], *c[3]; };
+
+// blockIdx.y = component x {fine, coarse} destination
+__global__ void __launch_bounds__(256)
+fc_exchange_kernel(FcDims D, FcMaps M, const FcSrc *__restrict__ src, double *b1, double *b2, double *b3, double *cb1, double *cb2, double *cb3) {
+  const int v = blockIdx.y % 3, coarse = blockIdx.y / 3;
+  const long cnt = (long)D.nmb * (coarse ? D.cf[v] : D.f[v]);
+  double *b = v == 0 ? b1 : v == 1 ? b2 : b3;
+  double *cb = v == 0 ? cb1 : v == 1 ? cb2 : cb3;
+  const unsigned char *map = coarse ? M.c[v] : M.f[v];
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.x * blockDim.x) fc_exchange_elem(D, v, coarse, t, map, src, b, cb);
+}
+
+__global__ void __launch_bounds__(128)
+fc_fill_kernel(FcDims D, const FcBox *__restrict__ descs, const double *__restrict__ b1, const double *__restrict__ b2,
+               const double *__restrict__ b3, double *cb1, double *cb2, double *cb3) {
+  const FcBox d = descs[blockIdx.x];
+  const long cnt = (long)d.n[0] * d.n[1] * d.n[2];
+  for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) fc_fill_elem(D, d, t, b1, b2, b3, cb1, cb2, cb3);
+}
+
+__global__ void __launch_bounds__(128)
+fc_prolong_shared_kernel(FcDims D, const FcBox *__restrict__ descs, double *b1, double *b2, double *b3, const double *__restrict__ cb1,
+                         const double *__restrict__ cb2, const double *__restrict__ cb3) {
+  const FcBox d = descs[blockIdx.x];
+  const long cnt = (long)d.n[0] * d.n[1] * d.n[2];
+  for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) fc_prolong_shared_elem(D, d, t, b1, b2, b3, cb1, cb2, cb3);
+}
+
+__global__ void __launch_bounds__(128)
+fc_prolong_interior_kernel(FcDims D, const FcCell *__restrict__ descs, double *b1, double *b2, double *b3) {
+  const FcCell d = descs[blockIdx.x];
+  const long cnt = (long)d.n[0] * d.n[1] * d.n[2];
+  for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) fc_prolong_interior_elem(D, d, t, b1, b2, b3);
+}
+
+__global__ void __launch_bounds__(128)
+emf_pack_kernel(FcDims D, const EmfPack *__restrict__ descs, const double *__restrict__ e1, const double *__restrict__ e2,
+                const double *__restrict__ e3, double *__restrict__ buf) {
+  const EmfPack d = descs[blockIdx.x];
+  const long cnt = (long)d.n[0] * d.n[1] * d.n[2];
+  for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) emf_pack_elem(D, d, t, e1, e2, e3, buf);
+}
+
+__global__ void __launch_bounds__(256)
+emf_apply_kernel(FcDims D, const EmfRange *__restrict__ ranges, const EmfOp *__restrict__ ops, const double *__restrict__ buf,
+                 double *e1, double *e2, double *e3) {
+  const int v = blockIdx.y;
+  const long cnt = (long)D.nmb * D.ef[v];
+  double *e = v == 0 ? e1 : v == 1 ? e2 : e3;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.x * blockDim.x) emf_apply_elem(D, v, t, ranges, ops, buf, e);
+}
+
+inline unsigned gflat(long count, int bs) { return (unsigned)std::max(1L, std::min((count + bs - 1) / bs, 148L * 16)); }
+
 }  // namespace
 
 extern "C" {
@@ -386,6 +767,10 @@ int ak_smr_create(const ak_mhd_cfg *cfg, const int *nghbr, const int *mb_lev, in
         P->max_flux = std::max(P->max_flux, cnt(d.n));
       }
     }
+  {
+    const std::string msg = build_fc(P, nghbr, mb_lev, gids_start);
+    if (!msg.empty()) { delete P; return smr_fail(nullptr, "ak_smr_create: " + msg); }
+  }
   *plan = P;
   return 0;
 }
@@ -394,6 +779,9 @@ int ak_smr_destroy(void *plan) {
   Plan *P = static_cast<Plan *>(plan);
   if (!P) return 0;
   cudaFree(P->d_copy); cudaFree(P->d_fill); cudaFree(P->d_prol); cudaFree(P->d_flux);
+  for (int v = 0; v < 3; ++v) { cudaFree(P->d_fmap[v]); cudaFree(P->d_cmap[v]); }
+  cudaFree(P->d_fsrc); cudaFree(P->d_ffill); cudaFree(P->d_fshared); cudaFree(P->d_fint);
+  cudaFree(P->d_epack); cudaFree(P->d_eops); cudaFree(P->d_erange); cudaFree(P->d_emfbuf);
   delete P;
   return 0;
 }
@@ -456,6 +844,78 @@ int ak_smr_flux_correct_cc(void *plan, double *flx1, double *flx2, double *flx3,
   if (!P->flux.empty())
     smr_flux_kernel<<<dim3((unsigned)P->flux.size(), gx(P->max_flux * nvar, 128)), 128, 0, st>>>(D, nvar, P->d_flux, flx1, flx2, flx3);
   SMR_EPILOGUE("ak_smr_flux_correct_cc")
+}
+
+/* ---- face-centred fields and edge EMFs across levels (MHD) ---- */
+long ak_smr_coarse_faces(void *plan, int v) {
+  Plan *P = static_cast<Plan *>(plan);
+  return (P && v >= 0 && v < 3) ? P->FD.cf[v] : 0;
+}
+
+#define SMR_FC_PROLOGUE(name)                                            \
+  Plan *P = static_cast<Plan *>(plan);                                   \
+  if (!P) return smr_fail(nullptr, name ": null plan");                  \
+  if (ensure_fc_uploaded(P)) return 1;                                   \
+  cudaStream_t st = static_cast<cudaStream_t>(s);                        \
+  const FcDims &D = P->FD;
+
+int ak_smr_restrict_fc(void *plan, const double *b1, const double *b2, const double *b3, double *cb1, double *cb2, double *cb3, ak_stream_t s) {
+  SMR_FC_PROLOGUE("ak_smr_restrict_fc")
+  long mx = 0;
+  for (int v = 0; v < 3; ++v) mx = std::max(mx, fc_restrict_count(D, v));
+  fc_restrict_kernel<<<dim3(gflat(mx, 256), 3), 256, 0, st>>>(D, b1, b2, b3, cb1, cb2, cb3);
+  SMR_EPILOGUE("ak_smr_restrict_fc")
+}
+
+int ak_smr_exchange_fc(void *plan, double *b1, double *b2, double *b3, double *cb1, double *cb2, double *cb3, ak_stream_t s) {
+  SMR_FC_PROLOGUE("ak_smr_exchange_fc")
+  FcMaps M;
+  for (int v = 0; v < 3; ++v) { M.f[v] = P->d_fmap[v]; M.c[v] = P->d_cmap[v]; }
+  const long mx = (long)D.nmb * std::max(D.f[0], std::max(D.f[1], D.f[2]));
+  fc_exchange_kernel<<<dim3(gflat(mx, 256), 6), 256, 0, st>>>(D, M, P->d_fsrc, b1, b2, b3, cb1, cb2, cb3);
+  SMR_EPILOGUE("ak_smr_exchange_fc")
+}
+
+int ak_smr_prolongate_fc_steps(void *plan, double *b1, double *b2, double *b3, double *cb1, double *cb2, double *cb3, int steps, ak_stream_t s) {
+  SMR_FC_PROLOGUE("ak_smr_prolongate_fc")
+  if ((steps & 1) && !P->ffill.empty())
+    fc_fill_kernel<<<dim3((unsigned)P->ffill.size(), gx(P->max_ffill, 128)), 128, 0, st>>>(D, P->d_ffill, b1, b2, b3, cb1, cb2, cb3);
+  if ((steps & 2) && !P->fshared.empty()) {
+    fc_prolong_shared_kernel<<<dim3((unsigned)P->fshared.size(), gx(P->max_fshared, 128)), 128, 0, st>>>(D, P->d_fshared, b1, b2, b3, cb1, cb2, cb3);
+    fc_prolong_interior_kernel<<<dim3((unsigned)P->fint.size(), gx(P->max_fint, 128)), 128, 0, st>>>(D, P->d_fint, b1, b2, b3);
+  }
+  SMR_EPILOGUE("ak_smr_prolongate_fc")
+}
+
+int ak_smr_emf_correct(void *plan, double *e1, double *e2, double *e3, ak_stream_t s) {
+  SMR_FC_PROLOGUE("ak_smr_emf_correct")
+  if (!P->epack.empty())
+    emf_pack_kernel<<<dim3((unsigned)P->epack.size(), gx(P->max_epack, 128)), 128, 0, st>>>(D, P->d_epack, e1, e2, e3, P->d_emfbuf);
+  const long mx = (long)D.nmb * std::max(D.ef[0], std::max(D.ef[1], D.ef[2]));
+  emf_apply_kernel<<<dim3(gflat(mx, 256), 3), 256, 0, st>>>(D, P->d_erange, P->d_eops, P->d_emfbuf, e1, e2, e3);
+  SMR_EPILOGUE("ak_smr_emf_correct")
+}
+
+/* host tables of the face-centred path (no device needed): 0 FcDims, 1-3 fine maps, 4-6 coarse maps, 7 sources,
+ * 8 fill boxes, 9 shared-face boxes, 10 interior boxes, 11 EMF pack, 12 EMF ops, 13 EMF ranges, 14 EMF buffer size */
+int ak_smr_fc_tables(void *plan, int which, const void **ptr, long *count) {
+  Plan *P = static_cast<Plan *>(plan);
+  if (!P || !ptr || !count) return 1;
+  switch (which) {
+    case 0: *ptr = &P->FD; *count = 1; break;
+    case 1: case 2: case 3: *ptr = P->fmap[which - 1].data(); *count = (long)P->fmap[which - 1].size(); break;
+    case 4: case 5: case 6: *ptr = P->cmap[which - 4].data(); *count = (long)P->cmap[which - 4].size(); break;
+    case 7: *ptr = P->fsrc.data(); *count = (long)P->fsrc.size(); break;
+    case 8: *ptr = P->ffill.data(); *count = (long)P->ffill.size(); break;
+    case 9: *ptr = P->fshared.data(); *count = (long)P->fshared.size(); break;
+    case 10: *ptr = P->fint.data(); *count = (long)P->fint.size(); break;
+    case 11: *ptr = P->epack.data(); *count = (long)P->epack.size(); break;
+    case 12: *ptr = P->eops.data(); *count = (long)P->eops.size(); break;
+    case 13: *ptr = P->erange.data(); *count = (long)P->erange.size(); break;
+    case 14: *ptr = nullptr; *count = P->emf_buf; break;
+    default: return 1;
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -124,6 +124,11 @@ def load():
         "ak_smr_prolongate_cc": [vp, vp, vp, ip, vp],
         "ak_smr_prolongate_cc_steps": [vp, vp, vp, ip, ip, vp],
         "ak_smr_flux_correct_cc": [vp, vp, vp, vp, ip, vp],
+        "ak_smr_restrict_fc": [vp, vp, vp, vp, vp, vp, vp, vp],
+        "ak_smr_exchange_fc": [vp, vp, vp, vp, vp, vp, vp, vp],
+        "ak_smr_prolongate_fc_steps": [vp, vp, vp, vp, vp, vp, vp, ip, vp],
+        "ak_smr_emf_correct": [vp, vp, vp, vp, vp],
+        "ak_smr_fc_tables": [vp, ip, C.POINTER(vp), C.POINTER(C.c_long)],
         "ak_mesh_info": [vp, ipp, ipp],
         "ak_mesh_tables": [vp, ipp, ipp, ipp, ipp],
         "ak_mesh_rank_tables": [vp, ip, dpp, ipp, ipp],
@@ -162,6 +167,8 @@ def load():
     lib.ak_smr_last_error.argtypes = [vp]
     lib.ak_smr_coarse_cells.restype = C.c_long
     lib.ak_smr_coarse_cells.argtypes = [vp]
+    lib.ak_smr_coarse_faces.restype = C.c_long
+    lib.ak_smr_coarse_faces.argtypes = [vp, ip]
     for name, args in sig.items():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch: fail loudly
         fn.argtypes = args
@@ -177,7 +184,7 @@ EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_con
             "ak_halo_pack_cc", "ak_halo_unpack_cc", "ak_halo_pack_fc", "ak_halo_unpack_fc",
             "ak_halo_emf_peer", "ak_halo_emf_pack_local", "ak_halo_emf_pack", "ak_halo_emf_sumavg",
             "ak_mesh_create", "ak_mesh_create_smr", "ak_mesh_destroy", "ak_smr_create", "ak_smr_destroy", "ak_smr_last_error",
-            "ak_smr_coarse_cells", "ak_smr_counts", "ak_smr_restrict_cc", "ak_smr_exchange_cc", "ak_smr_prolongate_cc", "ak_smr_prolongate_cc_steps", "ak_smr_flux_correct_cc", "ak_mesh_last_error", "ak_mesh_info", "ak_mesh_tables",
+            "ak_smr_coarse_cells", "ak_smr_counts", "ak_smr_restrict_cc", "ak_smr_exchange_cc", "ak_smr_prolongate_cc", "ak_smr_prolongate_cc_steps", "ak_smr_flux_correct_cc", "ak_smr_coarse_faces", "ak_smr_restrict_fc", "ak_smr_exchange_fc", "ak_smr_prolongate_fc_steps", "ak_smr_emf_correct", "ak_smr_fc_tables", "ak_mesh_last_error", "ak_mesh_info", "ak_mesh_tables",
             "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast", "ak_pgen_orszag_tang", "ak_selftest_divsqrt",
             "ak_sim_create", "ak_sim_destroy", "ak_sim_set_levels", "ak_nccl_unique_id", "ak_sim_comm_init", "ak_sim_set_state",
             "ak_sim_get_state", "ak_sim_initialize", "ak_sim_execute", "ak_sim_sync", "ak_sim_status", "ak_sim_arrays",

@@ -260,7 +260,7 @@ int ak_mesh_create(const int *nmesh, const int *nblock, const double *xmin, cons
  * keeps adjacent leaves within one level of each other).  regions = [nregions][7] doubles: physical level
  * (>= 1), x1min, x1max, x2min, x2max, x3min, x3max.  Z-ordered gids across levels, lloc[.][3] = logical level,
  * NeighborBlock.lev and the sub-block slots / destinations of coarser and finer neighbours as in
- * src/mesh/meshblock.cpp:142-430.  The device path for fine/coarse boundaries is not built yet. */
+ * src/mesh/meshblock.cpp:142-430.  The device path for fine/coarse boundaries is ak_smr_* below. */
 int ak_mesh_create_smr(const int *nmesh, const int *nblock, const double *xmin, const double *xmax, const int *bcs,
                        int nranks, int nregions, const double *regions, void **mesh);
 int ak_mesh_destroy(void *mesh);
@@ -289,6 +289,27 @@ int ak_smr_prolongate_cc(void *plan, double *u, double *cu, int nvar, ak_stream_
  * on a plan created with nx -> nx/2) and to the fine array after prolongation (src/hydro/hydro_tasks.cpp:357-398). */
 int ak_smr_prolongate_cc_steps(void *plan, double *u, double *cu, int nvar, int steps, ak_stream_t s);
 int ak_smr_flux_correct_cc(void *plan, double *flx1, double *flx2, double *flx3, int nvar, ak_stream_t s);
+/* ---- the same boundaries for FACE-CENTRED fields and edge EMFs: MHD on a statically refined mesh ----
+ * Replaces the multilevel parts of RestrictB (src/mesh/mesh_refinement.cpp:1290-1383), SendB/RecvB
+ * (src/bvals/bvals_fc.cpp:63-436 with the tables of src/bvals/buffs_fc.cpp:29-790), Prolongate for B
+ * (src/bvals/prolongation.cpp:556-785: FillCoarseInBndryFC, shared faces with the ownership rule of :92-133, then the
+ * divergence-preserving interior faces of :253-357) and SendE/RecvE with coarser and finer neighbours
+ * (src/bvals/flux_correct_fc.cpp:29-1034), in the order of src/mhd/mhd_tasks.cpp:48-75:
+ *   Fluxes -> ak_smr_flux_correct_cc -> RKUpdate -> ak_smr_restrict_cc -> ak_smr_exchange_cc -> CornerE ->
+ *   ak_smr_emf_correct -> CT -> ak_smr_restrict_fc -> ak_smr_exchange_fc -> prolongate_cc(1) -> prolongate_fc(1)
+ *   -> prolongate_cc(2) -> prolongate_fc(2) -> ConToPrim.
+ * b1..b3 = b0.x1f/x2f/x3f, cb1..cb3 = the host's coarse_b0 (ak_smr_coarse_faces(plan, v) doubles per block),
+ * e1..e3 = efld.x1e/x2e/x3e.  Where several neighbours deliver the same ghost face the reference's serial unpack
+ * order decides (the highest slot wins); the plan resolves that once on the host.  Strictly periodic meshes. */
+long ak_smr_coarse_faces(void *plan, int v);
+int ak_smr_restrict_fc(void *plan, const double *b1, const double *b2, const double *b3, double *cb1, double *cb2, double *cb3, ak_stream_t s);
+int ak_smr_exchange_fc(void *plan, double *b1, double *b2, double *b3, double *cb1, double *cb2, double *cb3, ak_stream_t s);
+/* steps: 1 = FillCoarseInBndryFC, 2 = ProlongateFC, 3 = both */
+int ak_smr_prolongate_fc_steps(void *plan, double *b1, double *b2, double *b3, double *cb1, double *cb2, double *cb3, int steps, ak_stream_t s);
+int ak_smr_emf_correct(void *plan, double *e1, double *e2, double *e3, ak_stream_t s);
+/* host-side tables of the plan (no device needed; consumed by tests/emul): which = 0 dims, 1-3 fine maps, 4-6 coarse
+ * maps, 7 sources, 8 fill, 9 shared-face, 10 interior boxes, 11 EMF pack, 12 EMF ops, 13 EMF ranges, 14 EMF buffer size */
+int ak_smr_fc_tables(void *plan, int which, const void **ptr, long *count);
 const char *ak_mesh_last_error(void);
 int ak_mesh_info(void *mesh, int *nmb_total, int *root_level);
 int ak_mesh_tables(void *mesh, int *lloc /*[nmb_total][4]*/, int *rank_of, int *gids_start, int *nmb_rank);

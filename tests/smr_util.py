@@ -73,8 +73,12 @@ def with_ghosts(d):
     return u0, uf, (slice(None),) * 3
 
 
-def mesh_of(deck_text, nranks=1):
+def mesh_of(deck_text, nranks=1, overrides=()):
+    """Mesh of a deck; overrides = command-line style "block/key=value" strings applied on top (as the reference does)."""
     p = H.deck_params(deck_text)
+    for o in overrides:
+        k, v = o.split("=", 1)
+        p[k] = v
     nmesh = tuple(int(p[f"mesh/nx{d}"]) for d in (1, 2, 3))
     nblock = tuple(int(p[f"meshblock/nx{d}"]) for d in (1, 2, 3))
     xmin = tuple(float(p[f"mesh/x{d}min"]) for d in (1, 2, 3))
