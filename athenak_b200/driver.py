@@ -52,7 +52,25 @@ def assemble_mhd_tasks(mhd: MHD, fused=True):
     tl = {n: TaskList() for n in ("before_timeintegrator", "before_stagen", "stagen",
                                   "after_stagen", "after_timeintegrator")}
     s = tl["stagen"]
-    if fused:
+    if getattr(mhd, "smr", None) is not None:
+        # multilevel mesh (mhd_tasks.cpp:48-75): flux correction sits between Fluxes and RKUpdate, so the fused
+        # flux+EMF / update+CT calls do not apply; `fused` only folds the new time step into the last c2p
+        t = s.AddTask(mhd.CopyCons, 0)
+        t = s.AddTask(mhd.Fluxes, t)
+        t = s.AddTask(mhd.FluxCorrect, t)
+        t = s.AddTask(mhd.RKUpdate, t)
+        t = s.AddTask(mhd.SendRecvU, t)
+        t = s.AddTask(mhd.EField, t)
+        t = s.AddTask(mhd.SendRecvE, t)
+        t = s.AddTask(mhd.CT, t)
+        t = s.AddTask(mhd.SendRecvB, t)
+        t = s.AddTask(mhd.Prolongate, t)
+        if fused:
+            t = s.AddTask(mhd.ConToPrimNewDt, t)
+        else:
+            t = s.AddTask(mhd.ConToPrim, t)
+            t = s.AddTask(mhd.NewTimeStep, t)
+    elif fused:
         t = s.AddTask(mhd.StageFluxEmf, 0)
         t = s.AddTask(mhd.SendRecvE, t)
         t = s.AddTask(mhd.StageUpdate, t)
@@ -119,6 +137,8 @@ class Driver:
         fill ghost zones of U and B, c2p everywhere, first time step."""
         mhd.SendRecvU(self, 0)
         mhd.SendRecvB(self, 0)
+        if getattr(mhd, "smr", None) is not None and hasattr(mhd, "Prolongate"):     # driver.cpp:607-653 on a multilevel mesh
+            mhd.Prolongate(self, 0)
         mhd.ApplyPhysicalBCs(self, 0)
         mhd.ConToPrim(self, 0)
         save = self.nexp_stages

@@ -39,7 +39,9 @@ class MHD:
                  dfloor=FLT_MIN, pfloor=FLT_MIN, tfloor=FLT_MIN, sfloor=FLT_MIN, sigma_max=FLT_MAX,
                  my_rank=0, gids_start=0, device="cuda", process_group=None, fused=True,
                  mesh_bcs=None, mb_bcs=None, nscalars=0, eos="ideal", iso_sound_speed=1.0,
-                 fofc=False):
+                 fofc=False, mb_lev=None):
+        """mb_lev: logical level of every block (Mesh.lloc[:, 3]) on a statically refined mesh; enables the fine/coarse
+        boundary path for U, B and the edge EMFs (ak_smr_*; strictly periodic meshes, one rank)."""
         if not torch.cuda.is_available():
             raise _lib.EngineError("athenak_b200: no CUDA device; the engine has no CPU path")
         self.L = _lib.load()
@@ -78,8 +80,23 @@ class MHD:
         self.plan = C.c_void_p()
         _lib.check(self.L.ak_halo_create(C.byref(self.cfg), self.nghbr.ctypes.data_as(C.POINTER(C.c_int)),
                                          my_rank, gids_start, C.byref(self.plan)))
+        self.smr = None
+        if mb_lev is not None:       # multilevel mesh: coarse arrays (mhd.cpp:163-176) + SMR plan
+            if mesh_bcs is not None and any(int(b) != _lib.BC["periodic"] for b in mesh_bcs):
+                raise _lib.EngineError("athenak_b200: MHD on a refined mesh needs strictly periodic boundaries")
+            if fofc or nscalars:
+                raise _lib.EngineError("athenak_b200: MHD on a refined mesh: fofc / passive scalars are not wired in")
+            self.mb_lev = np.ascontiguousarray(mb_lev, dtype=np.int32).reshape(nmb)
+            self.smr = C.c_void_p()
+            ipp = C.POINTER(C.c_int)
+            if self.L.ak_smr_create(C.byref(self.cfg), self.nghbr.ctypes.data_as(ipp), self.mb_lev.ctypes.data_as(ipp),
+                                    my_rank, gids_start, C.byref(self.smr)):
+                self.smr = None
+                raise _lib.EngineError(self.L.ak_smr_last_error(None).decode())
+            self.coarse_u0 = z(nmb, nv, self.L.ak_smr_coarse_cells(self.smr))
+            self.coarse_b0 = [z(nmb, self.L.ak_smr_coarse_faces(self.smr, v)) for v in range(3)]
         self.peers = []
-        for ip in range(self.L.ak_halo_npeers(self.plan)):
+        for ip in range(self.L.ak_halo_npeers(self.plan) if self.smr is None else 0):
             r, ncc, nfc = C.c_int(), C.c_long(), C.c_long()
             _lib.check(self.L.ak_halo_peer(self.plan, ip, C.byref(r), C.byref(ncc), C.byref(nfc)))
             self.peers.append(dict(rank=r.value, ncc=ncc.value, nfc=nfc.value,
@@ -117,6 +134,8 @@ class MHD:
         try:
             if getattr(self, "bcs", None):
                 self.L.ak_bcs_destroy(self.bcs)
+            if getattr(self, "smr", None):
+                self.L.ak_smr_destroy(self.smr)
             if getattr(self, "plan", None):
                 self.L.ak_halo_destroy(self.plan)
             if getattr(self, "h", None):
@@ -191,10 +210,39 @@ class MHD:
         self.launches += 1
         return TaskStatus.complete
 
+    def _smr_ck(self, rc):
+        if rc:
+            raise _lib.EngineError(self.L.ak_smr_last_error(self.smr).decode())
+
+    def FluxCorrect(self, driver, stage):
+        """SendFlux/RecvFlux (mhd_tasks.cpp:52-53 -> flux_correct_cc.cpp): multilevel meshes only."""
+        if self.smr is not None:
+            self._smr_ck(self.L.ak_smr_flux_correct_cc(self.smr, *[f.data_ptr() for f in self.uflx], self.nvar, self._st()))
+            self.launches += 1
+        return TaskStatus.complete
+
+    def Prolongate(self, driver, stage):
+        """mhd_tasks.cpp:527-551: FillCoarseInBndryCC/FC, then ProlongateCC/FC (multilevel meshes only)."""
+        if self.smr is None:
+            return TaskStatus.complete
+        st, L = self._st(), self.L
+        u, cu = self.u0.data_ptr(), self.coarse_u0.data_ptr()
+        b, cb = [a.data_ptr() for a in self.b0], [a.data_ptr() for a in self.coarse_b0]
+        self._smr_ck(L.ak_smr_prolongate_cc_steps(self.smr, u, cu, self.nvar, 1, st))
+        self._smr_ck(L.ak_smr_prolongate_fc_steps(self.smr, *b, *cb, 1, st))
+        self._smr_ck(L.ak_smr_prolongate_cc_steps(self.smr, u, cu, self.nvar, 2, st))
+        self._smr_ck(L.ak_smr_prolongate_fc_steps(self.smr, *b, *cb, 2, st))
+        self.launches += 5
+        return TaskStatus.complete
+
     def SendRecvE(self, driver, stage):
         """Tasks 15/16 SendE/RecvE: EMF flux correction (src/bvals/flux_correct_fc.cpp)."""
         st, L = self._st(), self.L
         e = [t.data_ptr() for t in self.efld]
+        if self.smr is not None:     # with coarser / finer neighbours: pack (restricted) + gather-form sum / zero / average
+            self._smr_ck(L.ak_smr_emf_correct(self.smr, *e, st))
+            self.launches += 2
+            return TaskStatus.complete
         reqs = []
         if self.peers:
             import torch.distributed as dist
@@ -224,6 +272,17 @@ class MHD:
         bvals_fc.cpp:63-436.  Off-rank slabs: pack -> one message per peer -> unpack."""
         st = self._st()
         L = self.L
+        if self.smr is not None:     # RestrictU/B + SendU/B + RecvU/B across levels (mhd_tasks.cpp:55-57, 63-65)
+            if which == "u":
+                u, cu = self.u0.data_ptr(), self.coarse_u0.data_ptr()
+                self._smr_ck(L.ak_smr_restrict_cc(self.smr, u, cu, self.nvar, st))
+                self._smr_ck(L.ak_smr_exchange_cc(self.smr, u, cu, self.nvar, st))
+            else:
+                b, cb = [a.data_ptr() for a in self.b0], [a.data_ptr() for a in self.coarse_b0]
+                self._smr_ck(L.ak_smr_restrict_fc(self.smr, *b, *cb, st))
+                self._smr_ck(L.ak_smr_exchange_fc(self.smr, *b, *cb, st))
+            self.launches += 2
+            return
         if self.peers:
             import torch.distributed as dist
             ops = []
