@@ -212,6 +212,7 @@ class MHD {  // state owner + tasks
   int mesh_bcs_h[6] = {0, 0, 0, 0, 0, 0};
   std::vector<int> mb_bcs_h;
   double *coarse_u0 = nullptr;
+  double *coarse_b0[3] = {nullptr, nullptr, nullptr};     // MHD: coarse face fields (mhd.cpp:163-176)
 
   MHD(const ak_mhd_cfg &c, const double *mb_size, const int *nghbr, int rank, int nranks_, int gids_start, int nmb_total)
       : cfg(c), my_rank(rank), nranks(nranks_), gids_start_(gids_start) {
@@ -374,6 +375,29 @@ class MHD {  // state owner + tasks
       }
       return;
     }
+    if (smr) {     // MHD on a multilevel mesh, mhd_tasks.cpp:48-75: no fused flux+EMF / update+CT calls (flux correction
+                   // sits between Fluxes and RKUpdate); Restrict* ride with the sends, Prolongate after RecvB
+      TaskID copyu = tl->AddTask(&MHD::CopyCons, this, none);
+      TaskID flux = tl->AddTask(&MHD::Fluxes, this, copyu);
+      TaskID fc = tl->AddTask(&MHD::FluxCorrect, this, flux);
+      TaskID rkupdt = tl->AddTask(&MHD::RKUpdate, this, fc);
+      TaskID sendu = tl->AddTask(&MHD::SendU, this, rkupdt);
+      TaskID recvu = tl->AddTask(&MHD::RecvU, this, sendu);
+      TaskID efld = tl->AddTask(&MHD::EField, this, recvu);
+      TaskID sende = tl->AddTask(&MHD::SendE, this, efld);
+      TaskID recve = tl->AddTask(&MHD::RecvE, this, sende);
+      TaskID ct = tl->AddTask(&MHD::CT, this, recve);
+      TaskID sendb = tl->AddTask(&MHD::SendB, this, ct);
+      TaskID recvb = tl->AddTask(&MHD::RecvB, this, sendb);
+      TaskID prol = tl->AddTask(&MHD::Prolongate, this, recvb);
+      if (fused) {
+        tl->AddTask(&MHD::ConToPrimNewDt, this, prol);
+      } else {
+        TaskID c2p = tl->AddTask(&MHD::ConToPrim, this, prol);
+        tl->AddTask(&MHD::NewTimeStep, this, c2p);
+      }
+      return;
+    }
     if (hydro) {   // Hydro::AssembleHydroTasks, hydro_tasks.cpp:47-79 (uniform mesh, no source terms)
       if (fused) {
         TaskID f = tl->AddTask(&MHD::HydroStageFused, this, none);
@@ -478,6 +502,11 @@ class MHD {  // state owner + tasks
   }
   // SendE/RecvE: flux_correct_fc.cpp:29-437 (EMF flux correction, always executed as in the reference)
   TaskStatus SendE(Driver *pd, int stage) {
+    if (smr) {       // coarser / finer neighbours: restricted pack + gather-form sum / zero / average (flux_correct_fc.cpp)
+      if (ak_smr_emf_correct(smr, a.e1, a.e2, a.e3, st)) Fatal(__FILE__, __LINE__, ak_smr_last_error(smr));
+      launches += 2;
+      return TaskStatus::complete;
+    }
     Nccl &n = Nccl::get();
     if (UsePush()) {
       // peer-memory variant: the pack kernel of each peer stores straight into my segment of that peer's
@@ -513,6 +542,7 @@ class MHD {  // state owner + tasks
     return TaskStatus::complete;
   }
   TaskStatus RecvE(Driver *pd, int stage) {
+    if (smr) return TaskStatus::complete;
     if (UsePush()) { AK_CHECK(nullptr, ak_halo_wait(plan, 3, nemfx + 1, st)); launches += 1; }
     AK_CHECK(nullptr, ak_halo_emf_sumavg(plan, a.e1, a.e2, a.e3, st));
     launches += 1;
@@ -624,7 +654,31 @@ class MHD {  // state owner + tasks
     }
     launches += 4;
   }
+  // MHD on a multilevel mesh: RestrictU + SendU/RecvU and RestrictB + SendB/RecvB across levels (mhd_tasks.cpp:55-57,
+  // 63-65), then Prolongate (:527-551): coarse fills of U and B first, then both prolongations
+  void SmrExchangeU() {
+    auto ck = [&](int rc) { if (rc) Fatal(__FILE__, __LINE__, ak_smr_last_error(smr)); };
+    ck(ak_smr_restrict_cc(smr, a.u0, coarse_u0, nvar, st));
+    ck(ak_smr_exchange_cc(smr, a.u0, coarse_u0, nvar, st));
+    launches += 2;
+  }
+  void SmrExchangeB() {
+    auto ck = [&](int rc) { if (rc) Fatal(__FILE__, __LINE__, ak_smr_last_error(smr)); };
+    ck(ak_smr_restrict_fc(smr, a.b0x1f, a.b0x2f, a.b0x3f, coarse_b0[0], coarse_b0[1], coarse_b0[2], st));
+    ck(ak_smr_exchange_fc(smr, a.b0x1f, a.b0x2f, a.b0x3f, coarse_b0[0], coarse_b0[1], coarse_b0[2], st));
+    launches += 2;
+  }
+  TaskStatus Prolongate(Driver *pd, int stage) {
+    auto ck = [&](int rc) { if (rc) Fatal(__FILE__, __LINE__, ak_smr_last_error(smr)); };
+    ck(ak_smr_prolongate_cc_steps(smr, a.u0, coarse_u0, nvar, 1, st));
+    ck(ak_smr_prolongate_fc_steps(smr, a.b0x1f, a.b0x2f, a.b0x3f, coarse_b0[0], coarse_b0[1], coarse_b0[2], 1, st));
+    ck(ak_smr_prolongate_cc_steps(smr, a.u0, coarse_u0, nvar, 2, st));
+    ck(ak_smr_prolongate_fc_steps(smr, a.b0x1f, a.b0x2f, a.b0x3f, coarse_b0[0], coarse_b0[1], coarse_b0[2], 2, st));
+    launches += 5;
+    return TaskStatus::complete;
+  }
   TaskStatus SendU(Driver *pd, int stage) {
+    if (smr && !hydro) { SmrExchangeU(); return TaskStatus::complete; }
     if (smr) { SmrGhosts(); return TaskStatus::complete; }
     if (hydro && UsePush()) {     // hydro twin, fused list: u0 is the only exchanged array
       PushExchange(false);
@@ -641,8 +695,16 @@ class MHD {  // state owner + tasks
     Unpack(true);
     return TaskStatus::complete;
   }
-  TaskStatus SendB(Driver *pd, int stage) { Exchange(false); return TaskStatus::complete; }
-  TaskStatus RecvB(Driver *pd, int stage) { Unpack(false); return TaskStatus::complete; }
+  TaskStatus SendB(Driver *pd, int stage) {
+    if (smr) { SmrExchangeB(); return TaskStatus::complete; }
+    Exchange(false);
+    return TaskStatus::complete;
+  }
+  TaskStatus RecvB(Driver *pd, int stage) {
+    if (smr) return TaskStatus::complete;
+    Unpack(false);
+    return TaskStatus::complete;
+  }
   // task 26, mhd_tasks.cpp:504-520: nothing to do on a strictly periodic mesh
   TaskStatus ApplyPhysicalBCs(Driver *pd, int stage) {
     if (!bcs) return TaskStatus::complete;
@@ -716,6 +778,7 @@ void Driver::Initialize(MHD *pmhd) {   // driver.cpp:314-371 -> InitBoundaryValu
   } else {
     pmhd->SendU(this, 0); pmhd->RecvU(this, 0);
     if (!pmhd->hydro) { pmhd->SendB(this, 0); pmhd->RecvB(this, 0); }
+    if (!pmhd->hydro && pmhd->smr) pmhd->Prolongate(this, 0);     // driver.cpp:607-653 on a multilevel mesh
   }
   pmhd->ApplyPhysicalBCs(this, 0);                 // driver.cpp:626-627
   pmhd->ConToPrim(this, 0);
@@ -778,16 +841,23 @@ int ak_sim_set_bcs(void *sim, const int *mesh_bcs, const int *mb_bcs) {
   for (int d = 0; d < 3; ++d) m->nbc_launches += (act[d] && mesh_bcs[2 * d] != AK_BC_PERIODIC);
   return 0;
 }
-/* static mesh refinement (hydro, one rank): logical level of every block of the pack (ak_mesh_create_smr).  Builds the
+/* static mesh refinement (hydro and MHD, one rank; MHD: strictly periodic meshes): logical level of every block of the pack (ak_mesh_create_smr).  Builds the
  * multi-level plan from the neighbour table given to ak_sim_create, allocates coarse_u0 and switches to the multilevel
  * task list.  Call before ak_sim_initialize; with physical boundaries call ak_sim_set_bcs first. */
 int ak_sim_set_levels(void *sim, const int *mb_lev) {
   auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
-  if (!m->hydro || m->nranks != 1 || !mb_lev) return 1;
+  if (m->nranks != 1 || !mb_lev || m->smr) return 1;
+  if (!m->hydro && (m->bcs || m->cfg.fofc || m->cfg.nscalars)) return 1;
   if (ak_smr_create(&m->cfg, m->nghbr_h.data(), mb_lev, m->my_rank, m->gids_start_, &m->smr)) return 1;
   const size_t n = (size_t)m->cfg.nmb * m->nvar * ak_smr_coarse_cells(m->smr);
   if (cudaMalloc(&m->coarse_u0, n * 8) != cudaSuccess || cudaMemsetAsync(m->coarse_u0, 0, n * 8, m->st) != cudaSuccess) return 1;
   m->owned.push_back(m->coarse_u0);
+  if (!m->hydro)
+    for (int v = 0; v < 3; ++v) {
+      const size_t nf = (size_t)m->cfg.nmb * ak_smr_coarse_faces(m->smr, v);
+      if (cudaMalloc(&m->coarse_b0[v], nf * 8) != cudaSuccess || cudaMemsetAsync(m->coarse_b0[v], 0, nf * 8, m->st) != cudaSuccess) return 1;
+      m->owned.push_back(m->coarse_b0[v]);
+    }
   if (m->bcs) {      // HydroBCsCoarse: the same flags on the coarse index space
     ak_mhd_cfg cc = m->cfg;
     cc.nx1 = m->cfg.nx1 / 2; cc.nx2 = std::max(1, m->cfg.nx2 / 2); cc.nx3 = std::max(1, m->cfg.nx3 / 2);

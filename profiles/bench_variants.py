@@ -19,7 +19,12 @@ from athenak_b200.sim import Simulation  # noqa: E402
 GAMMA, NG = 1.6666667, 4
 
 
+ONLY = None
+
+
 def run(tag, mesh, state, steps, **kw):
+    if ONLY and ONLY not in tag:
+        return
     sim = Simulation(mesh, 0, ng=NG, gamma=GAMMA, cfl_number=0.3, tlim=1.0e9, fused=True, **kw)
     sim.set_state(*state)
     sim.initialize()
@@ -42,7 +47,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nx", type=int, default=256)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--only", default=None, help="run only the variants whose tag contains this text")
     a = ap.parse_args()
+    global ONLY
+    ONLY = a.only
     n = a.nx
     mesh = Mesh((n, n, n), (n, n, n))
     u0, b1, b2, b3 = mesh.pgen_blast(0, NG, GAMMA)
@@ -73,6 +81,12 @@ def main():
     us[:, 4, NG + q // 4: NG + q // 2, NG + q // 4: NG + q // 2, NG + q // 4: NG + q // 2] = 15.0       # a hot spot in every block
     run("hydro SMR ppm4+hllc rk3, 2 levels", ms, (us,), a.steps, recon="ppm4", rsolver="hllc", integrator="rk3", physics="hydro",
         multilevel=True)
+    # the same refined mesh for MHD: face fields, EMF correction and divergence-preserving prolongation across levels
+    ub = us.clone()
+    ub[:, 4] += 0.5                      # + B^2/2 of the uniform field B = (1, 0, 0)
+    fb = [torch.zeros(ms.nmb_total, q + 2 * NG + (d == 2), q + 2 * NG + (d == 1), q + 2 * NG + (d == 0), dtype=torch.float64) for d in range(3)]
+    fb[0][:] = 1.0
+    run("mhd SMR ppm4+hlld rk3, 2 levels", ms, (ub, *fb), a.steps, recon="ppm4", rsolver="hlld", integrator="rk3", multilevel=True)
 
 
 if __name__ == "__main__":

@@ -169,6 +169,36 @@ def test_mhd_smr_matches_live_reference_bitwise(name):
         assert np.array_equal(x.cpu().numpy(), y)
 
 
+def _sim_of(mesh, p, fused):
+    from athenak_b200.sim import Simulation
+    return Simulation(mesh, 0, ng=int(p["mesh/nghost"]), recon=p["mhd/reconstruct"], rsolver=p["mhd/rsolver"], gamma=float(p["mhd/gamma"]),
+                      integrator=p["time/integrator"], cfl_number=float(p["time/cfl_number"]), tlim=float(p["time/tlim"]), fused=fused,
+                      physics="mhd", multilevel=True)
+
+
+@pytest.mark.parametrize("name", sorted(S.MHD_LIVE_CASES))
+@pytest.mark.parametrize("fused", [True, False], ids=["fused_c2p", "pertask"])
+def test_mhd_smr_cxx_host_driver(name, fused):
+    """The C++ host driver (csrc/host_driver.cpp: ak_sim_set_levels for MHD, multilevel MHD task list) against the
+    oracle from the same synthetic start: ghost zones, dt sequence and cycle count included."""
+    deck = open(S.MHD_DECK).read()
+    txt = deck_with(deck, S.MHD_LIVE_CASES[name])
+    mesh, p = S.mesh_of(txt)
+    u, b = synthetic_state(mesh, p)
+    A, t, dt, n, dt0 = S.oracle_run_mhd(txt, u, b, ncycles=2)
+    sim = _sim_of(mesh, p, fused)
+    sim.set_state(np.ascontiguousarray(u), *[np.ascontiguousarray(x) for x in b])
+    sim.initialize()
+    assert sim.status()["dt"] == dt0
+    sim.execute(2)
+    st = sim.status()
+    assert st["ncycle"] == n and st["time"] == t and st["dt"] == dt and st["launches"] > 0
+    out = sim.get_state()
+    assert np.array_equal(out[0], A.u0), f"max|dU| = {np.abs(out[0] - A.u0).max()}"
+    for x, y in zip(out[1:], A.b0):
+        assert np.array_equal(x, y)
+
+
 def deck_with(deck_text, overrides):
     """Deck text with command-line style overrides folded in (the engine and the oracle both parse text)."""
     import hydro_util as H
