@@ -377,6 +377,23 @@ class MHD {  // state owner + tasks
     }
     if (smr) {     // MHD on a multilevel mesh, mhd_tasks.cpp:48-75: no fused flux+EMF / update+CT calls (flux correction
                    // sits between Fluxes and RKUpdate); Restrict* ride with the sends, Prolongate after RecvB
+      if (fused) {   // corner EMFs + their correction ahead of the update (they read w0 / bcc0 / the corrected fluxes
+                     // only), then CopyCons + RKUpdate + CT as one kernel; new dt on the last c2p
+        TaskID flux = tl->AddTask(&MHD::Fluxes, this, none);
+        TaskID fc = tl->AddTask(&MHD::FluxCorrect, this, flux);
+        TaskID efld = tl->AddTask(&MHD::EField, this, fc);
+        TaskID sende = tl->AddTask(&MHD::SendE, this, efld);
+        TaskID recve = tl->AddTask(&MHD::RecvE, this, sende);
+        TaskID up = tl->AddTask(&MHD::StageUpdate, this, recve);
+        TaskID sendu = tl->AddTask(&MHD::SendU, this, up);
+        TaskID recvu = tl->AddTask(&MHD::RecvU, this, sendu);
+        TaskID sendb = tl->AddTask(&MHD::SendB, this, recvu);
+        TaskID recvb = tl->AddTask(&MHD::RecvB, this, sendb);
+        TaskID prol = tl->AddTask(&MHD::Prolongate, this, recvb);
+        TaskID bc = tl->AddTask(&MHD::ApplyPhysicalBCs, this, prol);
+        tl->AddTask(&MHD::ConToPrimNewDt, this, bc);
+        return;
+      }
       TaskID copyu = tl->AddTask(&MHD::CopyCons, this, none);
       TaskID flux = tl->AddTask(&MHD::Fluxes, this, copyu);
       TaskID fc = tl->AddTask(&MHD::FluxCorrect, this, flux);
@@ -390,12 +407,9 @@ class MHD {  // state owner + tasks
       TaskID sendb = tl->AddTask(&MHD::SendB, this, ct);
       TaskID recvb = tl->AddTask(&MHD::RecvB, this, sendb);
       TaskID prol = tl->AddTask(&MHD::Prolongate, this, recvb);
-      if (fused) {
-        tl->AddTask(&MHD::ConToPrimNewDt, this, prol);
-      } else {
-        TaskID c2p = tl->AddTask(&MHD::ConToPrim, this, prol);
-        tl->AddTask(&MHD::NewTimeStep, this, c2p);
-      }
+      TaskID bc = tl->AddTask(&MHD::ApplyPhysicalBCs, this, prol);
+      TaskID c2p = tl->AddTask(&MHD::ConToPrim, this, bc);
+      tl->AddTask(&MHD::NewTimeStep, this, c2p);
       return;
     }
     if (hydro) {   // Hydro::AssembleHydroTasks, hydro_tasks.cpp:47-79 (uniform mesh, no source terms)
@@ -672,6 +686,10 @@ class MHD {  // state owner + tasks
     auto ck = [&](int rc) { if (rc) Fatal(__FILE__, __LINE__, ak_smr_last_error(smr)); };
     ck(ak_smr_prolongate_cc_steps(smr, a.u0, coarse_u0, nvar, 1, st));
     ck(ak_smr_prolongate_fc_steps(smr, a.b0x1f, a.b0x2f, a.b0x3f, coarse_b0[0], coarse_b0[1], coarse_b0[2], 1, st));
+    if (bcs) {     // HydroBCsCoarse + BFieldBCsCoarse before the prolongation reads the coarse arrays (mhd_tasks.cpp:532-537)
+      if (ak_bcs_apply(bcs_coarse, coarse_u0, nvar, coarse_b0[0], coarse_b0[1], coarse_b0[2], st)) Fatal(__FILE__, __LINE__, ak_bcs_last_error(bcs_coarse));
+      launches += nbc_launches;
+    }
     ck(ak_smr_prolongate_cc_steps(smr, a.u0, coarse_u0, nvar, 2, st));
     ck(ak_smr_prolongate_fc_steps(smr, a.b0x1f, a.b0x2f, a.b0x3f, coarse_b0[0], coarse_b0[1], coarse_b0[2], 2, st));
     launches += 5;
@@ -841,13 +859,13 @@ int ak_sim_set_bcs(void *sim, const int *mesh_bcs, const int *mb_bcs) {
   for (int d = 0; d < 3; ++d) m->nbc_launches += (act[d] && mesh_bcs[2 * d] != AK_BC_PERIODIC);
   return 0;
 }
-/* static mesh refinement (hydro and MHD, one rank; MHD: strictly periodic meshes): logical level of every block of the pack (ak_mesh_create_smr).  Builds the
+/* static mesh refinement (hydro and MHD, one rank): logical level of every block of the pack (ak_mesh_create_smr).  Builds the
  * multi-level plan from the neighbour table given to ak_sim_create, allocates coarse_u0 and switches to the multilevel
  * task list.  Call before ak_sim_initialize; with physical boundaries call ak_sim_set_bcs first. */
 int ak_sim_set_levels(void *sim, const int *mb_lev) {
   auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
   if (m->nranks != 1 || !mb_lev || m->smr) return 1;
-  if (!m->hydro && (m->bcs || m->cfg.fofc || m->cfg.nscalars)) return 1;
+  if (!m->hydro && (m->cfg.fofc || m->cfg.nscalars)) return 1;
   if (ak_smr_create(&m->cfg, m->nghbr_h.data(), mb_lev, m->my_rank, m->gids_start_, &m->smr)) return 1;
   const size_t n = (size_t)m->cfg.nmb * m->nvar * ak_smr_coarse_cells(m->smr);
   if (cudaMalloc(&m->coarse_u0, n * 8) != cudaSuccess || cudaMemsetAsync(m->coarse_u0, 0, n * 8, m->st) != cudaSuccess) return 1;

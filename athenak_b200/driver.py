@@ -53,21 +53,33 @@ def assemble_mhd_tasks(mhd: MHD, fused=True):
                                   "after_stagen", "after_timeintegrator")}
     s = tl["stagen"]
     if getattr(mhd, "smr", None) is not None:
-        # multilevel mesh (mhd_tasks.cpp:48-75): flux correction sits between Fluxes and RKUpdate, so the fused
-        # flux+EMF / update+CT calls do not apply; `fused` only folds the new time step into the last c2p
-        t = s.AddTask(mhd.CopyCons, 0)
-        t = s.AddTask(mhd.Fluxes, t)
-        t = s.AddTask(mhd.FluxCorrect, t)
-        t = s.AddTask(mhd.RKUpdate, t)
-        t = s.AddTask(mhd.SendRecvU, t)
-        t = s.AddTask(mhd.EField, t)
-        t = s.AddTask(mhd.SendRecvE, t)
-        t = s.AddTask(mhd.CT, t)
-        t = s.AddTask(mhd.SendRecvB, t)
-        t = s.AddTask(mhd.Prolongate, t)
+        # multilevel mesh (mhd_tasks.cpp:48-75): flux correction sits between Fluxes and the corner EMFs (CornerE
+        # upwinds with the CORRECTED mass fluxes), so the fused flux+EMF call does not apply.  `fused`: the corner
+        # EMFs and their correction move ahead of the update (they read w0 / bcc0 / fluxes only), then one
+        # kernel does CopyCons + RKUpdate + CT (ak_mhd_stage_update); the new time step rides on the last c2p.
         if fused:
+            t = s.AddTask(mhd.Fluxes, 0)
+            t = s.AddTask(mhd.FluxCorrect, t)
+            t = s.AddTask(mhd.EField, t)
+            t = s.AddTask(mhd.SendRecvE, t)
+            t = s.AddTask(mhd.StageUpdate, t)
+            t = s.AddTask(mhd.SendRecvU, t)
+            t = s.AddTask(mhd.SendRecvB, t)
+            t = s.AddTask(mhd.Prolongate, t)
+            t = s.AddTask(mhd.ApplyPhysicalBCs, t)
             t = s.AddTask(mhd.ConToPrimNewDt, t)
         else:
+            t = s.AddTask(mhd.CopyCons, 0)
+            t = s.AddTask(mhd.Fluxes, t)
+            t = s.AddTask(mhd.FluxCorrect, t)
+            t = s.AddTask(mhd.RKUpdate, t)
+            t = s.AddTask(mhd.SendRecvU, t)
+            t = s.AddTask(mhd.EField, t)
+            t = s.AddTask(mhd.SendRecvE, t)
+            t = s.AddTask(mhd.CT, t)
+            t = s.AddTask(mhd.SendRecvB, t)
+            t = s.AddTask(mhd.Prolongate, t)
+            t = s.AddTask(mhd.ApplyPhysicalBCs, t)
             t = s.AddTask(mhd.ConToPrim, t)
             t = s.AddTask(mhd.NewTimeStep, t)
     elif fused:

@@ -41,7 +41,7 @@ class MHD:
                  mesh_bcs=None, mb_bcs=None, nscalars=0, eos="ideal", iso_sound_speed=1.0,
                  fofc=False, mb_lev=None):
         """mb_lev: logical level of every block (Mesh.lloc[:, 3]) on a statically refined mesh; enables the fine/coarse
-        boundary path for U, B and the edge EMFs (ak_smr_*; strictly periodic meshes, one rank)."""
+        boundary path for U, B and the edge EMFs (ak_smr_*; one rank)."""
         if not torch.cuda.is_available():
             raise _lib.EngineError("athenak_b200: no CUDA device; the engine has no CPU path")
         self.L = _lib.load()
@@ -82,8 +82,6 @@ class MHD:
                                          my_rank, gids_start, C.byref(self.plan)))
         self.smr = None
         if mb_lev is not None:       # multilevel mesh: coarse arrays (mhd.cpp:163-176) + SMR plan
-            if mesh_bcs is not None and any(int(b) != _lib.BC["periodic"] for b in mesh_bcs):
-                raise _lib.EngineError("athenak_b200: MHD on a refined mesh needs strictly periodic boundaries")
             if fofc or nscalars:
                 raise _lib.EngineError("athenak_b200: MHD on a refined mesh: fofc / passive scalars are not wired in")
             self.mb_lev = np.ascontiguousarray(mb_lev, dtype=np.int32).reshape(nmb)
@@ -114,6 +112,15 @@ class MHD:
                 raise _lib.EngineError(self.L.ak_bcs_last_error(None).decode())
             act = (True, self.multi_d, self.three_d)
             self.nbc = sum(act[d] and int(mesh_bcs[2 * d]) != _lib.BC["periodic"] for d in range(3))
+            self.bcs_coarse = None
+            if self.smr is not None:     # HydroBCsCoarse / BFieldBCsCoarse (bfield_bcs.cpp:44-63): the same fill on the coarse index space
+                ccfg = _lib.MhdCfg.from_buffer_copy(self.cfg)
+                ccfg.nx1, ccfg.nx2, ccfg.nx3 = nx1 // 2, max(1, nx2 // 2), max(1, nx3 // 2)
+                self.bcs_coarse = C.c_void_p()
+                if self.L.ak_bcs_create(C.byref(ccfg), mesh_bcs.ctypes.data_as(ipp), mb_bcs.ctypes.data_as(ipp),
+                                        C.byref(self.bcs_coarse)):
+                    self.bcs_coarse = None
+                    raise _lib.EngineError(self.L.ak_bcs_last_error(None).decode())
         self.dtnew = FLT_MAX
         self.nfloor = [0, 0, 0]       # EventCounters neos_dfloor/efloor/tfloor (src/mesh/mesh.hpp:70-74)
         self.launches = 0             # kernels this object has launched (bench: gpu_launches)
@@ -132,6 +139,8 @@ class MHD:
 
     def __del__(self):
         try:
+            if getattr(self, "bcs_coarse", None):
+                self.L.ak_bcs_destroy(self.bcs_coarse)
             if getattr(self, "bcs", None):
                 self.L.ak_bcs_destroy(self.bcs)
             if getattr(self, "smr", None):
@@ -230,6 +239,10 @@ class MHD:
         b, cb = [a.data_ptr() for a in self.b0], [a.data_ptr() for a in self.coarse_b0]
         self._smr_ck(L.ak_smr_prolongate_cc_steps(self.smr, u, cu, self.nvar, 1, st))
         self._smr_ck(L.ak_smr_prolongate_fc_steps(self.smr, *b, *cb, 1, st))
+        if self.bcs is not None:     # physical BCs on the coarse arrays before the prolongation reads them
+            if L.ak_bcs_apply(self.bcs_coarse, cu, self.nvar, *cb, st):
+                raise _lib.EngineError(L.ak_bcs_last_error(self.bcs_coarse).decode())
+            self.launches += self.nbc
         self._smr_ck(L.ak_smr_prolongate_cc_steps(self.smr, u, cu, self.nvar, 2, st))
         self._smr_ck(L.ak_smr_prolongate_fc_steps(self.smr, *b, *cb, 2, st))
         self.launches += 5

@@ -300,7 +300,9 @@ int ak_smr_flux_correct_cc(void *plan, double *flx1, double *flx2, double *flx3,
  *   -> prolongate_cc(2) -> prolongate_fc(2) -> ConToPrim.
  * b1..b3 = b0.x1f/x2f/x3f, cb1..cb3 = the host's coarse_b0 (ak_smr_coarse_faces(plan, v) doubles per block),
  * e1..e3 = efld.x1e/x2e/x3e.  Where several neighbours deliver the same ghost face the reference's serial unpack
- * order decides (the highest slot wins); the plan resolves that once on the host.  Strictly periodic meshes. */
+ * order decides (the highest slot wins); the plan resolves that once on the host.  With physical boundaries the host
+ * applies them to the coarse arrays between steps 1 and 2 (BFieldBCsCoarse, src/bvals/physics/bfield_bcs.cpp:44-63:
+ * ak_bcs_apply on a plan created with nx -> nx/2) and to the fine arrays after the prolongation. */
 long ak_smr_coarse_faces(void *plan, int v);
 int ak_smr_restrict_fc(void *plan, const double *b1, const double *b2, const double *b3, double *cb1, double *cb2, double *cb3, ak_stream_t s);
 int ak_smr_exchange_fc(void *plan, double *b1, double *b2, double *b3, double *cb1, double *cb2, double *cb3, ak_stream_t s);

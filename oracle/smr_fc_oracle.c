@@ -384,7 +384,26 @@ void oracle_smr_prolongate_fc_steps(const ocfg *c, double *b1, double *b2, doubl
 #undef FC_STORE
 }
 
-/* Driver::InitBoundaryValuesAndPrimitives for MHD on a multilevel, strictly periodic mesh (driver.cpp:607-653):
+/* MHD::Prolongate (mhd_tasks.cpp:527-551) + MHD::ApplyPhysicalBCs (:504-520): coarse fills of U and B, physical BCs on
+ * the COARSE arrays (HydroBCsCoarse / BFieldBCsCoarse, bvals/physics/bfield_bcs.cpp:44-63: the same fill on the coarse
+ * index space), prolongation of U and B, then physical BCs on the fine arrays */
+static void mhd_smr_prolongate_and_bcs(const ocfg *c, ostate *s, double *cu0, double *cb1, double *cb2, double *cb3,
+                                       const int *nghbr, const int *mblev) {
+  odims D = dims(c);
+  oracle_smr_prolongate_cc_steps(c, s->u0, cu0, D.nv, nghbr, mblev, 1);
+  oracle_smr_prolongate_fc_steps(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3, nghbr, mblev, 1);
+  if (g_mesh_bcs) {
+    ocfg cc = *c;
+    sidx I = smr_indcs(c);
+    cc.nx1 = I.cnx1; cc.nx2 = I.multi_d ? I.cnx2 : 1; cc.nx3 = I.three_d ? I.cnx3 : 1;
+    oracle_apply_bcs(&cc, g_mesh_bcs, g_mb_bcs, cu0, cb1, cb2, cb3);
+  }
+  oracle_smr_prolongate_cc_steps(c, s->u0, cu0, D.nv, nghbr, mblev, 2);
+  oracle_smr_prolongate_fc_steps(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3, nghbr, mblev, 2);
+  if (g_mesh_bcs) oracle_apply_bcs(c, g_mesh_bcs, g_mb_bcs, s->u0, s->b0x1f, s->b0x2f, s->b0x3f);
+}
+
+/* Driver::InitBoundaryValuesAndPrimitives for MHD on a multilevel mesh (driver.cpp:607-653):
  * RestrictU/B, SendU/B, RecvU/B, Prolongate (mhd_tasks.cpp:527-551), ConToPrim */
 void oracle_mhd_smr_ghosts_and_prims(const ocfg *c, ostate *s, double *cu0, double *cb1, double *cb2, double *cb3,
                                      const int *nghbr, const int *mblev) {
@@ -393,10 +412,7 @@ void oracle_mhd_smr_ghosts_and_prims(const ocfg *c, ostate *s, double *cu0, doub
   oracle_smr_restrict_fc(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3);
   oracle_smr_halo_cc(c, s->u0, cu0, D.nv, nghbr, mblev);
   oracle_smr_halo_fc(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3, nghbr, mblev);
-  oracle_smr_prolongate_cc_steps(c, s->u0, cu0, D.nv, nghbr, mblev, 1);
-  oracle_smr_prolongate_fc_steps(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3, nghbr, mblev, 1);
-  oracle_smr_prolongate_cc_steps(c, s->u0, cu0, D.nv, nghbr, mblev, 2);
-  oracle_smr_prolongate_fc_steps(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3, nghbr, mblev, 2);
+  mhd_smr_prolongate_and_bcs(c, s, cu0, cb1, cb2, cb3, nghbr, mblev);
   int nf[3];
   oracle_cons2prim(c, s->u0, s->b0x1f, s->b0x2f, s->b0x3f, s->w0, s->bcc0, 0, D.n1 - 1, 0, D.n2 - 1, 0, D.n3 - 1, nf);
 }
@@ -561,7 +577,7 @@ void oracle_smr_emf_correct(const ocfg *c, double *e1, double *e2, double *e3, c
   free(nflx);
 }
 
-/* MHD stage on a multilevel, strictly periodic mesh: mhd_tasks.cpp:48-75 */
+/* MHD stage on a multilevel mesh: mhd_tasks.cpp:48-75 (physical BCs: oracle_set_bcs) */
 int oracle_mhd_smr_run(const ocfg *c, ostate *s, double *cu0, double *cb1, double *cb2, double *cb3, const double *mb_size,
                        const int *nghbr, const int *mblev, int integrator, double cfl, double tlim, int ncycles,
                        double *time, double *dt) {
@@ -592,10 +608,7 @@ int oracle_mhd_smr_run(const ocfg *c, ostate *s, double *cu0, double *cb1, doubl
       oracle_ct(c, s->b0x1f, s->b0x2f, s->b0x3f, s->b1x1f, s->b1x2f, s->b1x3f, e1, e2, e3, mb_size, g0[st - 1], g1[st - 1], bdt);
       oracle_smr_restrict_fc(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3);                     /* RestrictB, SendB, RecvB */
       oracle_smr_halo_fc(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3, nghbr, mblev);
-      oracle_smr_prolongate_cc_steps(c, s->u0, cu0, D.nv, nghbr, mblev, 1);                       /* Prolongate */
-      oracle_smr_prolongate_fc_steps(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3, nghbr, mblev, 1);
-      oracle_smr_prolongate_cc_steps(c, s->u0, cu0, D.nv, nghbr, mblev, 2);
-      oracle_smr_prolongate_fc_steps(c, s->b0x1f, s->b0x2f, s->b0x3f, cb1, cb2, cb3, nghbr, mblev, 2);
+      mhd_smr_prolongate_and_bcs(c, s, cu0, cb1, cb2, cb3, nghbr, mblev);                         /* Prolongate, ApplyPhysicalBCs */
       int nf[3];
       oracle_cons2prim(c, s->u0, s->b0x1f, s->b0x2f, s->b0x3f, s->w0, s->bcc0, 0, D.n1 - 1, 0, D.n2 - 1, 0, D.n3 - 1, nf);
     }

@@ -156,6 +156,12 @@ MHD_CASES = {
                                 "refined_region1/x3min=0.1", "refined_region1/x3max=0.2",
                                 "refined_region2/level=1", "refined_region2/x1min=0.1", "refined_region2/x1max=0.2",
                                 "refined_region2/x2min=0.1", "refined_region2/x2max=0.2", "refined_region2/x3min=0.1", "refined_region2/x3max=0.2"),
+    # physical boundaries: coarse-array BCs (HydroBCsCoarse / BFieldBCsCoarse) before the prolongation, fine BCs after
+    "mhd_smr2d_bcs": ("problem/amp=0.1", "time/tlim=0.05", "mesh/nx3=1", "meshblock/nx3=1", "mesh/nx2=32", "meshblock/nx2=8",
+                      "mesh/ix1_bc=outflow", "mesh/ox1_bc=reflect", "mesh/ix2_bc=reflect", "mesh/ox2_bc=diode",
+                      "refined_region1/x1min=0.0", "refined_region1/x1max=0.3", "refined_region1/x2min=0.0", "refined_region1/x2max=0.2",
+                      "refined_region2/level=2", "refined_region2/x1min=2.8", "refined_region2/x1max=3.0", "refined_region2/x2min=1.4",
+                      "refined_region2/x2max=1.5"),
 }
 MHD_LIVE_CASES = dict(MHD_CASES)
 MHD_LIVE_CASES.update({
@@ -165,6 +171,9 @@ MHD_LIVE_CASES.update({
     "mhd_smr2d_wenoz_llf_l3": ("problem/amp=0.1", "time/tlim=0.04", "mesh/nx3=1", "meshblock/nx3=1", "mesh/nx2=32", "meshblock/nx2=8",
                                "mhd/reconstruct=wenoz", "mhd/rsolver=llf", "refined_region2/level=3", "refined_region2/x1min=2.6",
                                "refined_region2/x1max=3.0", "refined_region2/x2min=1.3", "refined_region2/x2max=1.5"),
+    "mhd_smr3d_bcs": ("problem/amp=0.1", "time/tlim=0.02", *_B8, "mesh/ix1_bc=reflect", "mesh/ox1_bc=outflow", "mesh/ix3_bc=outflow",
+                      "mesh/ox3_bc=reflect", "refined_region1/x1min=0.0", "refined_region1/x1max=0.2", "refined_region1/x3min=1.3",
+                      "refined_region1/x3max=1.5", "refined_region2/level=1"),
     "mhd_smr1d_plm_hlld": ("problem/amp=0.1", "time/tlim=0.2", "mesh/nx2=1", "meshblock/nx2=1", "mesh/nx3=1", "meshblock/nx3=1",
                            "mesh/nx1=128", "meshblock/nx1=8", "problem/along_x1=true", "mhd/reconstruct=plm", "mesh/nghost=2",
                            "refined_region2/level=3"),
@@ -221,6 +230,16 @@ def oracle_run_mhd(deck_text, u_init, b_init, ncycles=-1, active_only=False):
     ngh = np.ascontiguousarray(ngh, np.int32)
     lev = np.ascontiguousarray(mesh.lloc[:, 3], np.int32)
     st = A.state()
+    flags, mb_bcs, periodic = block_bcs(mesh, p)
+    if not periodic:
+        L.oracle_set_bcs(O.ip(flags), O.ip(mb_bcs))
+    try:
+        return _oracle_run_mhd(L, cfg, st, A, cu0, cb, mbs, ngh, lev, p, ncycles)
+    finally:
+        L.oracle_set_bcs(None, None)
+
+
+def _oracle_run_mhd(L, cfg, st, A, cu0, cb, mbs, ngh, lev, p, ncycles):
     L.oracle_mhd_smr_ghosts_and_prims(C.byref(cfg), C.byref(st), O.p(cu0), *[O.p(x) for x in cb], O.ip(ngh), O.ip(lev))
     cfl, tlim = float(p["time/cfl_number"]), float(p["time/tlim"])
     dt0 = L.oracle_initial_dt(C.byref(cfg), C.byref(st), O.p(mbs), C.c_double(cfl), C.c_double(tlim), C.c_double(0.0))

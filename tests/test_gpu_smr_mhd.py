@@ -24,7 +24,7 @@ def make_engine(deck_text, overrides=()):
     mesh, p = S.mesh_of(deck_text, overrides=overrides)
     mb_size, mb_bcs, nghbr = mesh.rank_tables(0)
     mhd = MHD(mesh.nmb_total, int(p["mesh/nghost"]), mesh.nblock, mb_size, nghbr, recon=p["mhd/reconstruct"], rsolver=p["mhd/rsolver"],
-              gamma=float(p["mhd/gamma"]), mb_lev=mesh.lloc[:, 3])
+              gamma=float(p["mhd/gamma"]), mb_lev=mesh.lloc[:, 3], mesh_bcs=mesh.bcs, mb_bcs=mb_bcs)
     return mhd, mesh, p
 
 
