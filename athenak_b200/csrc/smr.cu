@@ -640,7 +640,17 @@ fc_exchange_kernel(FcDims D, FcMaps M, const FcSrc *__restrict__ src, double *b1
   double *b = v == 0 ? b1 : v == 1 ? b2 : b3;
   double *cb = v == 0 ? cb1 : v == 1 ? cb2 : cb3;
   const unsigned char *map = coarse ? M.c[v] : M.f[v];
-  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.x * blockDim.x) fc_exchange_elem(D, v, coarse, t, map, src, b, cb);
+  // eight map bytes per step: the interior of a block (nothing received) is skipped with one 64-bit load
+  const long nchunk = (cnt + 7) / 8;
+  for (long c = (long)blockIdx.x * blockDim.x + threadIdx.x; c < nchunk; c += (long)gridDim.x * blockDim.x) {
+    const long t0 = c * 8;
+    unsigned long long w;
+    if (t0 + 8 <= cnt) w = *reinterpret_cast<const unsigned long long *>(map + t0);
+    else { w = ~0ull; for (int q = 0; t0 + q < cnt; ++q) w = (w & ~(0xFFull << (8 * q))) | ((unsigned long long)map[t0 + q] << (8 * q)); }
+    if (w == ~0ull) continue;
+    for (int q = 0; q < 8; ++q)
+      if (((w >> (8 * q)) & 0xFF) != 255) fc_exchange_elem(D, v, coarse, t0 + q, map, src, b, cb);
+  }
 }
 
 __global__ void __launch_bounds__(128)
@@ -674,13 +684,14 @@ emf_pack_kernel(FcDims D, const EmfPack *__restrict__ descs, const double *__res
   for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) emf_pack_elem(D, d, t, e1, e2, e3, buf);
 }
 
-__global__ void __launch_bounds__(256)
+// blockIdx.y = block, blockIdx.z = component; threads over the surface elements only
+__global__ void __launch_bounds__(128)
 emf_apply_kernel(FcDims D, const EmfRange *__restrict__ ranges, const EmfOp *__restrict__ ops, const double *__restrict__ buf,
                  double *e1, double *e2, double *e3) {
-  const int v = blockIdx.y;
-  const long cnt = (long)D.nmb * D.ef[v];
+  const int v = blockIdx.z, m = blockIdx.y;
+  const int ns = emf_surface_count(D, v);
   double *e = v == 0 ? e1 : v == 1 ? e2 : e3;
-  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.x * blockDim.x) emf_apply_elem(D, v, t, ranges, ops, buf, e);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ns; q += gridDim.x * blockDim.x) emf_apply_elem(D, v, m, q, ranges, ops, buf, e);
 }
 
 inline unsigned gflat(long count, int bs) { return (unsigned)std::max(1L, std::min((count + bs - 1) / bs, 148L * 16)); }
@@ -871,7 +882,7 @@ int ak_smr_exchange_fc(void *plan, double *b1, double *b2, double *b3, double *c
   SMR_FC_PROLOGUE("ak_smr_exchange_fc")
   FcMaps M;
   for (int v = 0; v < 3; ++v) { M.f[v] = P->d_fmap[v]; M.c[v] = P->d_cmap[v]; }
-  const long mx = (long)D.nmb * std::max(D.f[0], std::max(D.f[1], D.f[2]));
+  const long mx = ((long)D.nmb * std::max(D.f[0], std::max(D.f[1], D.f[2])) + 7) / 8;
   fc_exchange_kernel<<<dim3(gflat(mx, 256), 6), 256, 0, st>>>(D, M, P->d_fsrc, b1, b2, b3, cb1, cb2, cb3);
   SMR_EPILOGUE("ak_smr_exchange_fc")
 }
@@ -891,8 +902,8 @@ int ak_smr_emf_correct(void *plan, double *e1, double *e2, double *e3, ak_stream
   SMR_FC_PROLOGUE("ak_smr_emf_correct")
   if (!P->epack.empty())
     emf_pack_kernel<<<dim3((unsigned)P->epack.size(), gx(P->max_epack, 128)), 128, 0, st>>>(D, P->d_epack, e1, e2, e3, P->d_emfbuf);
-  const long mx = (long)D.nmb * std::max(D.ef[0], std::max(D.ef[1], D.ef[2]));
-  emf_apply_kernel<<<dim3(gflat(mx, 256), 3), 256, 0, st>>>(D, P->d_erange, P->d_eops, P->d_emfbuf, e1, e2, e3);
+  const int ns = std::max(emf_surface_count(D, 0), std::max(emf_surface_count(D, 1), emf_surface_count(D, 2)));
+  emf_apply_kernel<<<dim3((unsigned)((ns + 127) / 128), (unsigned)D.nmb, 3), 128, 0, st>>>(D, P->d_erange, P->d_eops, P->d_emfbuf, e1, e2, e3);
   SMR_EPILOGUE("ak_smr_emf_correct")
 }
 

@@ -254,23 +254,40 @@ AK_HD void emf_pack_elem(const FcDims &D, const EmfPack &d, long t, const double
   buf[slot] = r;
 }
 
-// RecvE (flux_correct_fc.cpp:374-1034) as a gather over the elements of one block's edge field: same-level sums in
-// slot order, zero where a finer neighbour covers the element, sums from finer neighbours in slot order, then
-// the average (x0.5 on faces, / number of contributions on block edges).  t over (block, element of component v).
-AK_HD void emf_apply_elem(const FcDims &D, int v, long t, const EmfRange *ranges, const EmfOp *ops, const double *buf, double *e) {
-  const long per = D.ef[v];
-  const long m = t / per;
-  long r = t - m * per;
-  const int x0 = D.n[0] + (v != 0), x1 = D.n[1] + (v != 1);
-  const int i = (int)(r % x0); r /= x0;
-  const int j = (int)(r % x1);
-  const int k = (int)(r / x1);
-  // quick reject: only elements on the block surface are touched
-  bool surf = false;
-  if (v != 0) surf |= (i == D.s[0] || i == D.e[0] + 1);
-  if (v != 1) surf |= (j == D.s[1] || j == D.e[1] + 1);
-  if (v != 2) surf |= (k == D.s[2] || k == D.e[2] + 1);
-  if (!surf) return;
+// The elements of one block's edge field that lie on the block surface (node-like coordinate at either end in at
+// least one of the two directions across the field), enumerated without duplicates: first the two planes at the ends
+// of direction a = (v+1)%3, then the two planes at the ends of b = (v+2)%3 minus the lines already counted.
+AK_HD int emf_surface_count(const FcDims &D, int v) {
+  const int a = (v + 1) % 3, b = (v + 2) % 3;
+  const int na1 = D.e[a] - D.s[a] + 2, nb1 = D.e[b] - D.s[b] + 2, nc = D.e[v] - D.s[v] + 1;
+  return 2 * nb1 * nc + 2 * (na1 - 2) * nc;
+}
+AK_HD void emf_surface_decode(const FcDims &D, int v, int q, int x[3]) {
+  const int a = (v + 1) % 3, b = (v + 2) % 3;
+  const int na1 = D.e[a] - D.s[a] + 2, nb1 = D.e[b] - D.s[b] + 2, nc = D.e[v] - D.s[v] + 1;
+  const int s1 = 2 * nb1 * nc;
+  if (q < s1) {
+    const int side = q / (nb1 * nc), r = q - side * (nb1 * nc);
+    x[a] = side ? D.e[a] + 1 : D.s[a];
+    x[b] = D.s[b] + r / nc;
+    x[v] = D.s[v] + r % nc;
+  } else {
+    q -= s1;
+    const int per = (na1 - 2) * nc, side = q / per, r = q - side * per;
+    x[a] = D.s[a] + 1 + r / nc;
+    x[b] = side ? D.e[b] + 1 : D.s[b];
+    x[v] = D.s[v] + r % nc;
+  }
+}
+
+// RecvE (flux_correct_fc.cpp:374-1034) as a gather over the SURFACE elements of one block's edge field: same-level
+// sums in slot order, zero where a finer neighbour covers the element, sums from finer neighbours in slot order,
+// then the average (x0.5 on faces, / number of contributions on block edges).  q = surface element of (m, v).
+AK_HD void emf_apply_elem(const FcDims &D, int v, int m, int q, const EmfRange *ranges, const EmfOp *ops, const double *buf, double *e) {
+  int x[3];
+  emf_surface_decode(D, v, q, x);
+  const int i = x[0], j = x[1], k = x[2];
+  const long t = (long)m * D.ef[v] + eidx(D, v, k, j, i);
   const EmfRange R = ranges[m * 3 + v];
   double val = e[t];
   bool touched = false;
@@ -279,15 +296,15 @@ AK_HD void emf_apply_elem(const FcDims &D, int v, long t, const EmfRange *ranges
     const int ni = o.hi[0] - o.lo[0] + 1, nj = o.hi[1] - o.lo[1] + 1;
     return buf[o.off + (i - o.lo[0]) + (long)ni * ((j - o.lo[1]) + (long)nj * (k - o.lo[2]))];
   };
-  for (int q = R.sum0; q < R.sum1; ++q) if (inside(ops[q])) { val += bufat(ops[q]); touched = true; }
+  for (int p = R.sum0; p < R.sum1; ++p) if (inside(ops[p])) { val += bufat(ops[p]); touched = true; }
   bool zero = false;
-  for (int q = R.sum1; q < R.avg; ++q) zero |= inside(ops[q]);
+  for (int p = R.sum1; p < R.avg; ++p) zero |= inside(ops[p]);
   if (zero) {
     val = 0.0; touched = true;
-    for (int q = R.sum1; q < R.avg; ++q) if (inside(ops[q])) val += bufat(ops[q]);
+    for (int p = R.sum1; p < R.avg; ++p) if (inside(ops[p])) val += bufat(ops[p]);
   }
-  for (int q = R.avg; q < R.end; ++q) if (inside(ops[q])) {
-    if (ops[q].type == EMF_MUL) val *= 0.5; else val /= ops[q].div;
+  for (int p = R.avg; p < R.end; ++p) if (inside(ops[p])) {
+    if (ops[p].type == EMF_MUL) val *= 0.5; else val /= ops[p].div;
     touched = true;
   }
   if (touched) e[t] = val;

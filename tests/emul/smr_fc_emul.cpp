@@ -53,8 +53,9 @@ void emul_emf_correct(const FcDims *D, const EmfPack *pack, long npack, const Em
   }
   double *e[3] = {e1, e2, e3};
   for (int v = 0; v < 3; ++v) {
-    const long cnt = (long)D->nmb * D->ef[v];
-    for (long q = 0; q < cnt; ++q) emf_apply_elem(*D, v, reverse ? cnt - 1 - q : q, ranges, ops, buf, e[v]);
+    const int ns = emf_surface_count(*D, v);
+    for (int m = 0; m < D->nmb; ++m)
+      for (int q = 0; q < ns; ++q) emf_apply_elem(*D, v, reverse ? D->nmb - 1 - m : m, reverse ? ns - 1 - q : q, ranges, ops, buf, e[v]);
   }
 }
 
