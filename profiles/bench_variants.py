@@ -53,7 +53,8 @@ def main():
     ONLY = a.only
     n = a.nx
     mesh = Mesh((n, n, n), (n, n, n))
-    u0, b1, b2, b3 = mesh.pgen_blast(0, NG, GAMMA)
+    small = bool(ONLY) and ("SMR" in ONLY or "config 5" in ONLY)      # the refined-mesh lines build their own states
+    u0, b1, b2, b3 = mesh.pgen_blast(0, NG, GAMMA) if not small else (torch.zeros(1, 5, 1, 1, 1, dtype=torch.float64),) * 4
     mhd = (u0, b1, b2, b3)
     run("mhd ideal ppm4+hlld rk3 (headline)", mesh, mhd, a.steps, recon="ppm4", rsolver="hlld", integrator="rk3")
     run("mhd ideal plm+hlle rk2", mesh, mhd, a.steps, recon="plm", rsolver="hlle", integrator="rk2")
@@ -70,7 +71,7 @@ def main():
         physics="hydro", eos="isothermal", iso_sound_speed=1.0)
     # many small blocks: 64 blocks of 64^3 (BASELINE config 3's per-GPU layout)
     m64 = Mesh((n, n, n), (n // 4, n // 4, n // 4))
-    run("mhd ideal ppm4+hlld rk3, 64 blocks of (nx/4)^3", m64, m64.pgen_blast(0, NG, GAMMA), a.steps, recon="ppm4", rsolver="hlld",
+    run("mhd ideal ppm4+hlld rk3, 64 blocks of (nx/4)^3", m64, m64.pgen_blast(0, NG, GAMMA) if not small else None, a.steps, recon="ppm4", rsolver="hlld",
         integrator="rk3")
     # statically refined hydro mesh: 8 root blocks of (nx/4)^3 ... one octant refined
     q = n // 4
@@ -87,6 +88,13 @@ def main():
     fb = [torch.zeros(ms.nmb_total, q + 2 * NG + (d == 2), q + 2 * NG + (d == 1), q + 2 * NG + (d == 0), dtype=torch.float64) for d in range(3)]
     fb[0][:] = 1.0
     run("mhd SMR ppm4+hlld rk3, 2 levels", ms, (ub, *fb), a.steps, recon="ppm4", rsolver="hlld", integrator="rk3", multilevel=True)
+
+    # BASELINE config 5, static variant on ONE GPU: 3-D MHD blast, three levels, 32^3 blocks (nx root cells per dimension:
+    # 1408 blocks = 46 M cells at nx = 256)
+    if ONLY and "config 5" in ONLY:
+        m5 = Mesh((n, n, n), (32, 32, 32), refined_regions=[(1, -0.25, 0.25, -0.25, 0.25, -0.25, 0.25), (2, -0.125, 0.125, -0.125, 0.125, -0.125, 0.125)])
+        run("mhd SMR blast, config 5 static: 3 levels, 32^3 blocks", m5, m5.pgen_blast(0, NG, GAMMA), a.steps, recon="ppm4", rsolver="hlld",
+            integrator="rk3", multilevel=True)
 
 
 if __name__ == "__main__":

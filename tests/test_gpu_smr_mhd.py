@@ -199,6 +199,74 @@ def test_mhd_smr_cxx_host_driver(name, fused):
         assert np.array_equal(x, y)
 
 
+def _blast_smr_mesh(nroot=128, nb=32):
+    from athenak_b200.mesh import Mesh
+    return Mesh((nroot,) * 3, (nb,) * 3, refined_regions=[(1, -0.25, 0.25, -0.25, 0.25, -0.25, 0.25), (2, -0.125, 0.125, -0.125, 0.125, -0.125, 0.125)])
+
+
+def test_mhd_smr_blast_three_levels_divb_conservation_and_oracle():
+    """BASELINE config 5's static variant at working size: 3-D MHD blast, three levels, 176 blocks of 32^3 (5.8 M cells),
+    PPM4+HLLD+RK3.  Size-independent properties: div B = 0 to round-off in every active cell of every level after
+    several cycles (divergence-preserving prolongation + EMF correction), mass / momentum / energy conserved to
+    round-off on the refined mesh (flux correction); and the first cycles equal the oracle bitwise, ghost zones included."""
+    from athenak_b200.sim import Simulation
+    ng, gamma = 4, 1.6666667
+    mesh = _blast_smr_mesh()
+    assert mesh.nmb_total == 176 and len(np.unique(mesh.lloc[:, 3])) == 3
+    u0, b1, b2, b3 = [t.numpy() for t in mesh.pgen_blast(0, ng, gamma)]
+    mbs = np.asarray(mesh.rank_tables(0)[0]).reshape(-1, 9)
+    vol = (mbs[:, 6] * mbs[:, 7] * mbs[:, 8])[:, None]
+    a = slice(ng, -ng)
+
+    def totals(u):
+        return (u[:, :, a, a, a].sum(axis=(2, 3, 4)) * vol).sum(axis=0)
+
+    def max_divb(b):
+        d = ((b[0][:, a, a, ng + 1:-ng] - b[0][:, a, a, ng:-ng - 1]) / mbs[:, 6, None, None, None]
+             + (b[1][:, a, ng + 1:-ng, a] - b[1][:, a, ng:-ng - 1, a]) / mbs[:, 7, None, None, None]
+             + (b[2][:, ng + 1:-ng, a, a] - b[2][:, ng:-ng - 1, a, a]) / mbs[:, 8, None, None, None])
+        return np.abs(d * mbs[:, 6, None, None, None]).max()
+
+    def sim_of():
+        sim = Simulation(mesh, 0, ng=ng, recon="ppm4", rsolver="hlld", gamma=gamma, integrator="rk3", cfl_number=0.3, tlim=1.0,
+                         fused=True, physics="mhd", multilevel=True)
+        sim.set_state(u0, b1, b2, b3)
+        sim.initialize()
+        return sim
+
+    sim = sim_of()
+    t0 = totals(u0)
+    sim.execute(6)
+    out = sim.get_state()
+    assert sim.status()["ncycle"] == 6 and np.isfinite(out[0]).all()
+    t1 = totals(out[0])
+    assert abs(t1[0] - t0[0]) <= 1e-12 * abs(t0[0]), (t0[0], t1[0])             # mass
+    assert abs(t1[4] - t0[4]) <= 1e-12 * abs(t0[4]), (t0[4], t1[4])             # total energy
+    assert np.abs(t1[1:4] - t0[1:4]).max() <= 1e-12 * abs(t0[4])                 # momentum (zero initially)
+    assert max_divb(out[1:]) <= 1e-12, max_divb(out[1:])                         # |div B| dx / B0, B0 = 1
+    assert np.abs(out[0][:, 1:4]).max() > 1e-3                                   # the blast is moving
+    # first cycles against the oracle (same ICs), bitwise with ghost zones
+    deck = ("<mesh>\nnghost = 4\nnx1 = 128\nx1min = -0.5\nx1max = 0.5\nix1_bc = periodic\nox1_bc = periodic\n"
+            "nx2 = 128\nx2min = -0.5\nx2max = 0.5\nix2_bc = periodic\nox2_bc = periodic\n"
+            "nx3 = 128\nx3min = -0.5\nx3max = 0.5\nix3_bc = periodic\nox3_bc = periodic\n\n"
+            "<meshblock>\nnx1 = 32\nnx2 = 32\nnx3 = 32\n\n<mesh_refinement>\nrefinement = static\n\n"
+            "<refined_region1>\nlevel = 1\nx1min = -0.25\nx1max = 0.25\nx2min = -0.25\nx2max = 0.25\nx3min = -0.25\nx3max = 0.25\n\n"
+            "<refined_region2>\nlevel = 2\nx1min = -0.125\nx1max = 0.125\nx2min = -0.125\nx2max = 0.125\nx3min = -0.125\nx3max = 0.125\n\n"
+            "<time>\nintegrator = rk3\ncfl_number = 0.3\ntlim = 1.0\n\n<mhd>\nreconstruct = ppm4\nrsolver = hlld\ngamma = 1.6666667\n")
+    m2, _ = S.mesh_of(deck)
+    assert np.array_equal(m2.lloc, mesh.lloc)
+    A, t, dt, n, dt0 = S.oracle_run_mhd(deck, u0, (b1, b2, b3), ncycles=1)
+    sim = sim_of()
+    assert sim.status()["dt"] == dt0
+    sim.execute(1)
+    st = sim.status()
+    assert st["time"] == t and st["dt"] == dt
+    out = sim.get_state()
+    assert np.array_equal(out[0], A.u0)
+    for x, y in zip(out[1:], A.b0):
+        assert np.array_equal(x, y)
+
+
 def deck_with(deck_text, overrides):
     """Deck text with command-line style overrides folded in (the engine and the oracle both parse text)."""
     import hydro_util as H
@@ -231,7 +299,7 @@ def synthetic_state(mesh, p):
     s = [ng if act3[d] else 0 for d in range(3)]
     two_pi = 2.0 * np.pi
     for m in range(nmb):
-        x1min, x1max, x2min, x2max, x3min, x3max, dx1, dx2, dx3 = mbs[m]
+        x1min, x2min, x3min, x1max, x2max, x3max, dx1, dx2, dx3 = mbs[m]       # RegionSize (mesh.hpp:25-29)
         lo, dx = [x1min, x2min, x3min], [dx1, dx2, dx3]
         # node and centre coordinates of the active region
         nd = [lo[d] + dx[d] * np.arange(nb[d] + 1) for d in range(3)]
