@@ -186,13 +186,13 @@ smr_restrict_kernel(Dims D, int nmb, int nvar, int cnx1, int cnx2, int cnx3, con
 __global__ void __launch_bounds__(256)
 smr_copy_kernel(Dims D, int nvar, const CopyDesc *__restrict__ descs, double *__restrict__ u, double *__restrict__ cu) {
   const CopyDesc d = descs[blockIdx.x];
-  const long cnt = (long)d.n[0] * d.n[1] * d.n[2] * nvar;
-  for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) {
-    long r = t;
-    const int i = (int)(r % d.n[0]); r /= d.n[0];
-    const int j = (int)(r % d.n[1]); r /= d.n[1];
-    const int k = (int)(r % d.n[2]);
-    const int v = (int)(r / d.n[2]);
+  const int cnt = d.n[0] * d.n[1] * d.n[2] * nvar;      // 32-bit index math: a box holds far fewer than 2^31 elements
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) {
+    int r = t;
+    const int i = r % d.n[0]; r /= d.n[0];
+    const int j = r % d.n[1]; r /= d.n[1];
+    const int k = r % d.n[2];
+    const int v = r / d.n[2];
     const double *src = d.src_coarse ? cu + ((long)d.src_m * nvar + v) * D.ccc + ((long)(d.slo[2] + k) * D.c2 + d.slo[1] + j) * D.c1 + d.slo[0] + i
                                      : u + ((long)d.src_m * nvar + v) * D.cc + ((long)(d.slo[2] + k) * D.n2 + d.slo[1] + j) * D.n1 + d.slo[0] + i;
     double *dst = d.dst_coarse ? cu + ((long)d.dst_m * nvar + v) * D.ccc + ((long)(d.dlo[2] + k) * D.c2 + d.dlo[1] + j) * D.c1 + d.dlo[0] + i
@@ -205,13 +205,13 @@ smr_copy_kernel(Dims D, int nvar, const CopyDesc *__restrict__ descs, double *__
 __global__ void __launch_bounds__(256)
 smr_fill_kernel(Dims D, int nvar, const BoxDesc *__restrict__ descs, const double *__restrict__ u, double *__restrict__ cu) {
   const BoxDesc d = descs[blockIdx.x];
-  const long cnt = (long)d.n[0] * d.n[1] * d.n[2] * nvar;
-  for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) {
-    long r = t;
-    const int i = d.lo[0] + (int)(r % d.n[0]); r /= d.n[0];
-    const int j = d.lo[1] + (int)(r % d.n[1]); r /= d.n[1];
-    const int k = d.lo[2] + (int)(r % d.n[2]);
-    const int v = (int)(r / d.n[2]);
+  const int cnt = d.n[0] * d.n[1] * d.n[2] * nvar;      // 32-bit index math: a box holds far fewer than 2^31 elements
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) {
+    int r = t;
+    const int i = d.lo[0] + r % d.n[0]; r /= d.n[0];
+    const int j = d.lo[1] + r % d.n[1]; r /= d.n[1];
+    const int k = d.lo[2] + r % d.n[2];
+    const int v = r / d.n[2];
     const int fi = (i - D.cs[0]) * 2 + D.s[0], fj = (j - D.cs[1]) * 2 + D.s[1], fk = (k - D.cs[2]) * 2 + D.s[2];
     const double *a = u + ((long)d.m * nvar + v) * D.cc;
     auto A = [&](int kk, int jj, int ii) { return a[((long)kk * D.n2 + jj) * D.n1 + ii]; };
@@ -233,13 +233,13 @@ __device__ __forceinline__ double minmod_slope(double dl, double dr) {          
 __global__ void __launch_bounds__(256)
 smr_prolong_kernel(Dims D, int nvar, const BoxDesc *__restrict__ descs, double *__restrict__ u, const double *__restrict__ cu) {
   const BoxDesc d = descs[blockIdx.x];
-  const long cnt = (long)d.n[0] * d.n[1] * d.n[2] * nvar;
-  for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) {
-    long r = t;
-    const int i = d.lo[0] + (int)(r % d.n[0]); r /= d.n[0];
-    const int j = d.lo[1] + (int)(r % d.n[1]); r /= d.n[1];
-    const int k = d.lo[2] + (int)(r % d.n[2]);
-    const int v = (int)(r / d.n[2]);
+  const int cnt = d.n[0] * d.n[1] * d.n[2] * nvar;      // 32-bit index math: a box holds far fewer than 2^31 elements
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) {
+    int r = t;
+    const int i = d.lo[0] + r % d.n[0]; r /= d.n[0];
+    const int j = d.lo[1] + r % d.n[1]; r /= d.n[1];
+    const int k = d.lo[2] + r % d.n[2];
+    const int v = r / d.n[2];
     const int fi = (i - D.cs[0]) * 2 + D.s[0], fj = (j - D.cs[1]) * 2 + D.s[1], fk = (k - D.cs[2]) * 2 + D.s[2];
     const double *c = cu + ((long)d.m * nvar + v) * D.ccc + ((long)k * D.c2 + j) * D.c1 + i;
     const long sj = D.c1, sk = (long)D.c1 * D.c2;
@@ -276,10 +276,10 @@ smr_flux_kernel(Dims D, int nvar, const FluxDesc *__restrict__ descs, double *__
   const long fsz = D.f[d.dir];
   for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) {
     long r = t;
-    const int a = (int)(r % d.n[0]); r /= d.n[0];
-    const int b = (int)(r % d.n[1]); r /= d.n[1];
-    const int c = (int)(r % d.n[2]);
-    const int v = (int)(r / d.n[2]);
+    const int a = r % d.n[0]; r /= d.n[0];
+    const int b = r % d.n[1]; r /= d.n[1];
+    const int c = r % d.n[2];
+    const int v = r / d.n[2];
     const int i = d.slo[0] + a, j = d.slo[1] + b, k = d.slo[2] + c;          // coarse indices on the sender
     const int fi = 2 * i - D.cs[0], fj = 2 * j - D.cs[1], fk = 2 * k - D.cs[2];
     const double *s = flx + ((long)d.src_m * nvar + v) * fsz;
@@ -657,31 +657,31 @@ __global__ void __launch_bounds__(128)
 fc_fill_kernel(FcDims D, const FcBox *__restrict__ descs, const double *__restrict__ b1, const double *__restrict__ b2,
                const double *__restrict__ b3, double *cb1, double *cb2, double *cb3) {
   const FcBox d = descs[blockIdx.x];
-  const long cnt = (long)d.n[0] * d.n[1] * d.n[2];
-  for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) fc_fill_elem(D, d, t, b1, b2, b3, cb1, cb2, cb3);
+  const int cnt = d.n[0] * d.n[1] * d.n[2];
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) fc_fill_elem(D, d, t, b1, b2, b3, cb1, cb2, cb3);
 }
 
 __global__ void __launch_bounds__(128)
 fc_prolong_shared_kernel(FcDims D, const FcBox *__restrict__ descs, double *b1, double *b2, double *b3, const double *__restrict__ cb1,
                          const double *__restrict__ cb2, const double *__restrict__ cb3) {
   const FcBox d = descs[blockIdx.x];
-  const long cnt = (long)d.n[0] * d.n[1] * d.n[2];
-  for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) fc_prolong_shared_elem(D, d, t, b1, b2, b3, cb1, cb2, cb3);
+  const int cnt = d.n[0] * d.n[1] * d.n[2];
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) fc_prolong_shared_elem(D, d, t, b1, b2, b3, cb1, cb2, cb3);
 }
 
 __global__ void __launch_bounds__(128)
 fc_prolong_interior_kernel(FcDims D, const FcCell *__restrict__ descs, double *b1, double *b2, double *b3) {
   const FcCell d = descs[blockIdx.x];
-  const long cnt = (long)d.n[0] * d.n[1] * d.n[2];
-  for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) fc_prolong_interior_elem(D, d, t, b1, b2, b3);
+  const int cnt = d.n[0] * d.n[1] * d.n[2];
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) fc_prolong_interior_elem(D, d, t, b1, b2, b3);
 }
 
 __global__ void __launch_bounds__(128)
 emf_pack_kernel(FcDims D, const EmfPack *__restrict__ descs, const double *__restrict__ e1, const double *__restrict__ e2,
                 const double *__restrict__ e3, double *__restrict__ buf) {
   const EmfPack d = descs[blockIdx.x];
-  const long cnt = (long)d.n[0] * d.n[1] * d.n[2];
-  for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) emf_pack_elem(D, d, t, e1, e2, e3, buf);
+  const int cnt = d.n[0] * d.n[1] * d.n[2];
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) emf_pack_elem(D, d, t, e1, e2, e3, buf);
 }
 
 // blockIdx.y = block, blockIdx.z = component; threads over the surface elements only

@@ -106,11 +106,11 @@ AK_HD void fc_exchange_elem(const FcDims &D, int v, int dst_coarse, long t, cons
 }
 
 // FillCoarseInBndryFC (prolongation.cpp:556-650): t over (descriptor box)
-AK_HD void fc_fill_elem(const FcDims &D, const FcBox &d, long t, const double *b1, const double *b2, const double *b3,
+AK_HD void fc_fill_elem(const FcDims &D, const FcBox &d, int t, const double *b1, const double *b2, const double *b3,
                         double *cb1, double *cb2, double *cb3) {
-  const int i = d.lo[0] + (int)(t % d.n[0]); t /= d.n[0];
-  const int j = d.lo[1] + (int)(t % d.n[1]);
-  const int k = d.lo[2] + (int)(t / d.n[1]);
+  const int i = d.lo[0] + t % d.n[0]; t /= d.n[0];      // 32-bit index math: a box holds far fewer than 2^31 elements
+  const int j = d.lo[1] + t % d.n[1];
+  const int k = d.lo[2] + t / d.n[1];
   const double *a = (d.v == 0 ? b1 : d.v == 1 ? b2 : b3) + (long)d.m * D.f[d.v];
   double *c = (d.v == 0 ? cb1 : d.v == 1 ? cb2 : cb3) + (long)d.m * D.cf[d.v];
   c[cidx(D, d.v, k, j, i)] = restrict_face(D, d.v, a, k, j, i);
@@ -133,11 +133,11 @@ AK_HD bool fc_can_store(const FcDims &D, int v, int k, int j, int i, int own_axi
 }
 
 // ProlongateFC, shared faces (prolongation.cpp:651-760): t over (descriptor box of coarse faces)
-AK_HD void fc_prolong_shared_elem(const FcDims &D, const FcBox &d, long t, double *b1, double *b2, double *b3,
+AK_HD void fc_prolong_shared_elem(const FcDims &D, const FcBox &d, int t, double *b1, double *b2, double *b3,
                                   const double *cb1, const double *cb2, const double *cb3) {
-  const int i = d.lo[0] + (int)(t % d.n[0]); t /= d.n[0];
-  const int j = d.lo[1] + (int)(t % d.n[1]);
-  const int k = d.lo[2] + (int)(t / d.n[1]);
+  const int i = d.lo[0] + t % d.n[0]; t /= d.n[0];      // 32-bit index math: a box holds far fewer than 2^31 elements
+  const int j = d.lo[1] + t % d.n[1];
+  const int k = d.lo[2] + t / d.n[1];
   const int v = d.v;
   const int fi = (i - D.cs[0]) * 2 + D.s[0], fj = D.multi_d ? ((j - D.cs[1]) * 2 + D.s[1]) : j, fk = D.three_d ? ((k - D.cs[2]) * 2 + D.s[2]) : k;
   const double *c = (v == 0 ? cb1 : v == 1 ? cb2 : cb3) + (long)d.m * D.cf[v];
@@ -180,10 +180,10 @@ AK_HD void fc_prolong_shared_elem(const FcDims &D, const FcBox &d, long t, doubl
 
 // ProlongateFC, interior faces of the refined ghost cells (prolongation.cpp:253-357, Toth & Roe 2002): reads only
 // faces shared with the coarse cell (even offsets), writes only the faces between them (odd offsets).
-AK_HD void fc_prolong_interior_elem(const FcDims &D, const FcCell &d, long t, double *b1, double *b2, double *b3) {
-  const int i = d.lo[0] + (int)(t % d.n[0]); t /= d.n[0];
-  const int j = d.lo[1] + (int)(t % d.n[1]);
-  const int k = d.lo[2] + (int)(t / d.n[1]);
+AK_HD void fc_prolong_interior_elem(const FcDims &D, const FcCell &d, int t, double *b1, double *b2, double *b3) {
+  const int i = d.lo[0] + t % d.n[0]; t /= d.n[0];      // 32-bit index math: a box holds far fewer than 2^31 elements
+  const int j = d.lo[1] + t % d.n[1];
+  const int k = d.lo[2] + t / d.n[1];
   const int fi = (i - D.cs[0]) * 2 + D.s[0], fj = (j - D.cs[1]) * 2 + D.s[1], fk = (k - D.cs[2]) * 2 + D.s[2];
   double *x1 = b1 + (long)d.m * D.f[0], *x2 = b2 + (long)d.m * D.f[1], *x3 = b3 + (long)d.m * D.f[2];
 #define B1(K_, J_, I_) x1[fidx(D, 0, K_, J_, I_)]
@@ -236,11 +236,11 @@ AK_HD void fc_prolong_interior_elem(const FcDims &D, const FcCell &d, long t, do
 
 // SendE, pack (flux_correct_fc.cpp:29-366): the boundary EMFs toward a same-level neighbour as they are, toward a
 // coarser neighbour averaged over the two fine edges of a coarse edge (inactive directions read index 0).
-AK_HD void emf_pack_elem(const FcDims &D, const EmfPack &d, long t, const double *e1, const double *e2, const double *e3, double *buf) {
+AK_HD void emf_pack_elem(const FcDims &D, const EmfPack &d, int t, const double *e1, const double *e2, const double *e3, double *buf) {
   const long slot = d.off + t;
-  const int i = d.lo[0] + (int)(t % d.n[0]); t /= d.n[0];
-  const int j = d.lo[1] + (int)(t % d.n[1]);
-  const int k = d.lo[2] + (int)(t / d.n[1]);
+  const int i = d.lo[0] + t % d.n[0]; t /= d.n[0];      // 32-bit index math: a box holds far fewer than 2^31 elements
+  const int j = d.lo[1] + t % d.n[1];
+  const int k = d.lo[2] + t / d.n[1];
   const int v = d.v;
   const double *a = (v == 0 ? e1 : v == 1 ? e2 : e3) + (long)d.src_m * D.ef[v];
   double r;
