@@ -1,19 +1,22 @@
-// smr.cu -- fine/coarse boundaries of CELL-CENTRED data on a statically refined mesh (SURVEY.md 8f item 2,
-// hydro path): restriction into the coarse arrays, ghost exchange across refinement levels, coarse-buffer
-// fill + slope-limited prolongation of the fine ghost zones, and flux correction at fine/coarse faces.
+// smr.cu -- fine/coarse boundaries on a statically refined mesh: restriction into the coarse
+// arrays, ghost exchange across refinement levels, coarse-buffer fill + prolongation of the fine ghost zones, and
+// flux / EMF correction at fine/coarse faces -- for CELL-CENTRED data (hydro and MHD) and for FACE-CENTRED fields
+// and EDGE EMFs (MHD; per-element bodies in smr_fc_body.h).
 //
-// Reference: src/mesh/mesh_refinement.cpp:1226-1284 (RestrictCC), src/bvals/buffs_cc.cpp:28-484 (index
-// tables), bvals_cc.cpp:42-167,273-402 (PackAndSendCC / RecvAndUnpackCC with coarser and finer neighbours),
-// prolongation.cpp:366-547 (FillCoarseInBndryCC, ProlongateCC), mesh/prolongation.hpp:21-60 (ProlongCC),
-// flux_correct_cc.cpp:28-290; task order src/hydro/hydro_tasks.cpp:55-71.
+// Reference: src/mesh/mesh_refinement.cpp:1226-1383 (RestrictCC / RestrictFC), src/bvals/buffs_cc.cpp:28-484 and
+// buffs_fc.cpp:29-935 (index tables), bvals_cc.cpp:42-167,273-402 and bvals_fc.cpp:63-436 (exchange with coarser and
+// finer neighbours), prolongation.cpp:28-785 (FillCoarseInBndry*, Prolongate*), mesh/prolongation.hpp:21-60 (ProlongCC),
+// flux_correct_cc.cpp:28-290, flux_correct_fc.cpp:29-1034; task order src/hydro/hydro_tasks.cpp:55-71,
+// src/mhd/mhd_tasks.cpp:48-75.
 //
-// Design: the host resolves the neighbour table once into flat descriptor lists (box copies between the
-// fine and coarse arrays of two blocks, coarse boxes to fill / prolongate, flux boxes); each step is ONE
-// launch over all descriptors of all blocks -- no pack buffers, no per-neighbour kernels.  Where two
-// descriptors write the same cell they carry the same bits (a physical cell has one owner; both
-// prolongations read the same coarse data), so launch-internal order does not matter; the order BETWEEN the
-// steps (exchange, fill, prolongate) is the reference's and is kept by the stream.  Single rank: every
-// neighbour must live in this pack (the multi-rank plan is the next step).
+// Design: the host resolves the neighbour table once into flat tables (box copies between the fine and coarse
+// arrays of two blocks, coarse boxes to fill / prolongate, flux boxes; for face fields a per-face "winning slot"
+// map and per-slot source records; for EMFs pack boxes and per-block op lists); each step is ONE launch over all
+// blocks -- no per-neighbour kernels, no host loop.  Cell data: where two descriptors write the same cell they carry
+// the same bits (a physical cell has one owner), so launch-internal order does not matter.  Face data: several
+// neighbours deliver the same ghost face with different last bits, so the exchange is a gather whose winner (the
+// reference's serial unpack order) is fixed on the host.  The order BETWEEN the steps is the reference's and is kept
+// by the stream.  Single rank: every neighbour must live in this pack (the multi-rank plan is the next step).
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <string>
@@ -632,15 +635,21 @@ fc_restrict_kernel(FcDims D, const double *__restrict__ b1, const double *__rest
 
 struct FcMaps { const unsigned char *f[3], *c[3]; };
 
-// blockIdx.y = component x {fine, coarse} destination
+// blockIdx.y = component x {fine, coarse} destination.  A resident-size grid strides over 8-byte chunks of the winner
+// map: one 64-bit load skips eight faces of a block's interior; a chunk with received faces pays ONE 64-bit division
+// (its block index), everything per face is 32-bit, and the eight source loads are issued before the stores.
+// Measured on 15 blocks of 64^3 (5 M ghost faces), ncu per launch: one thread per face with 64-bit index math 89 us;
+// one tiny block per 256 faces 221 us (block scheduling dominates); 8 faces per thread, 64-bit math per face 114 us;
+// this form 97-100 us.  Index math is NOT the limiter: the time follows the scattered 8-32 B ghost-face sectors
+// (the uniform-mesh halo_copy_kernel moves the same number of faces in 50 us), so the simpler variants are equivalent.
 __global__ void __launch_bounds__(256)
 fc_exchange_kernel(FcDims D, FcMaps M, const FcSrc *__restrict__ src, double *b1, double *b2, double *b3, double *cb1, double *cb2, double *cb3) {
   const int v = blockIdx.y % 3, coarse = blockIdx.y / 3;
-  const long cnt = (long)D.nmb * (coarse ? D.cf[v] : D.f[v]);
+  const long per = coarse ? D.cf[v] : D.f[v];
+  const long cnt = (long)D.nmb * per;
   double *b = v == 0 ? b1 : v == 1 ? b2 : b3;
   double *cb = v == 0 ? cb1 : v == 1 ? cb2 : cb3;
   const unsigned char *map = coarse ? M.c[v] : M.f[v];
-  // eight map bytes per step: the interior of a block (nothing received) is skipped with one 64-bit load
   const long nchunk = (cnt + 7) / 8;
   for (long c = (long)blockIdx.x * blockDim.x + threadIdx.x; c < nchunk; c += (long)gridDim.x * blockDim.x) {
     const long t0 = c * 8;
@@ -648,8 +657,21 @@ fc_exchange_kernel(FcDims D, FcMaps M, const FcSrc *__restrict__ src, double *b1
     if (t0 + 8 <= cnt) w = *reinterpret_cast<const unsigned long long *>(map + t0);
     else { w = ~0ull; for (int q = 0; t0 + q < cnt; ++q) w = (w & ~(0xFFull << (8 * q))) | ((unsigned long long)map[t0 + q] << (8 * q)); }
     if (w == ~0ull) continue;
+    const int m = (int)(t0 / per), r = (int)(t0 - (long)m * per);
+    // all source values first (eight independent load chains in flight), then the stores: sources are active faces,
+    // destinations ghost / coarse faces, so reading everything before writing anything changes no value
+    double val[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int n = (int)((w >> (8 * q)) & 0xFF);
+      int mm = m, rr = r + q;
+      if (rr >= per) { rr -= (int)per; mm += 1; }          // a chunk may straddle two blocks (per >= 8)
+      val[q] = (n != 255) ? fc_exchange_value(D, v, coarse, mm, rr, n, src, b) : 0.0;
+    }
+    double *dst = (coarse ? cb : b) + t0;
+#pragma unroll
     for (int q = 0; q < 8; ++q)
-      if (((w >> (8 * q)) & 0xFF) != 255) fc_exchange_elem(D, v, coarse, t0 + q, map, src, b, cb);
+      if (((w >> (8 * q)) & 0xFF) != 255) dst[q] = val[q];
   }
 }
 

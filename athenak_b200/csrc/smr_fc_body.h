@@ -87,21 +87,22 @@ AK_HD long fc_restrict_count(const FcDims &D, int v) {
 // it LAST in the reference's serial unpack order; that slot's source element is read directly.  A coarse source
 // (data sent to a coarser neighbour) is restricted on the fly from the sender's ACTIVE fine faces, which this
 // step never writes, so the launch has no read-after-write hazard.
-AK_HD void fc_exchange_elem(const FcDims &D, int v, int dst_coarse, long t, const unsigned char *map, const FcSrc *src,
-                            double *b, double *cb) {
-  const unsigned char n = map[t];
-  if (n == 255) return;
-  const long per = dst_coarse ? D.cf[v] : D.f[v];
-  const long m = t / per;
-  long r = t - m * per;
+AK_HD double fc_exchange_value(const FcDims &D, int v, int dst_coarse, int m, int r, int n, const FcSrc *src, const double *b) {
   const int x0 = (dst_coarse ? D.cn[0] : D.n[0]) + (v == 0), x1 = (dst_coarse ? D.cn[1] : D.n[1]) + (v == 1);
-  const int i = (int)(r % x0); r /= x0;
-  const int j = (int)(r % x1);
-  const int k = (int)(r / x1);
-  const FcSrc S = src[(m * 56 + n) * 3 + v];
+  const int i = r % x0; r /= x0;              // r = element of block m's array, n = the winning slot (32-bit index math)
+  const int j = r % x1;
+  const int k = r / x1;
+  const FcSrc S = src[((long)m * 56 + n) * 3 + v];
   const int si = i + S.off[0], sj = j + S.off[1], sk = k + S.off[2];
   const double *a = b + (long)S.src_m * D.f[v];
-  const double val = S.src_coarse ? restrict_face(D, v, a, sk, sj, si) : a[fidx(D, v, sk, sj, si)];
+  return S.src_coarse ? restrict_face(D, v, a, sk, sj, si) : a[fidx(D, v, sk, sj, si)];
+}
+AK_HD void fc_exchange_elem(const FcDims &D, int v, int dst_coarse, int m, int r, const unsigned char *map, const FcSrc *src,
+                            double *b, double *cb) {
+  const long t = (long)m * (dst_coarse ? D.cf[v] : D.f[v]) + r;
+  const unsigned char n = map[t];
+  if (n == 255) return;
+  const double val = fc_exchange_value(D, v, dst_coarse, m, r, n, src, b);
   if (dst_coarse) cb[t] = val; else b[t] = val;
 }
 

@@ -21,8 +21,10 @@ void emul_exchange_fc(const FcDims *D, const unsigned char *const *maps /* f0,f1
   double *b[3] = {b1, b2, b3}, *cb[3] = {cb1, cb2, cb3};
   for (int seg = 0; seg < 6; ++seg) {
     const int s = reverse ? 5 - seg : seg, v = s % 3, coarse = s / 3;
-    const long cnt = (long)D->nmb * (coarse ? D->cf[v] : D->f[v]);
-    for (long q = 0; q < cnt; ++q) fc_exchange_elem(*D, v, coarse, reverse ? cnt - 1 - q : q, maps[s], src, b[v], cb[v]);
+    const int per = (int)(coarse ? D->cf[v] : D->f[v]);
+    for (int mm = 0; mm < D->nmb; ++mm)
+      for (int q = 0; q < per; ++q)
+        fc_exchange_elem(*D, v, coarse, reverse ? D->nmb - 1 - mm : mm, reverse ? per - 1 - q : q, maps[s], src, b[v], cb[v]);
   }
 }
 
