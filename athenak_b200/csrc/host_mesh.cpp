@@ -7,6 +7,7 @@
 // meshblock.cpp:25-131 (sizes, BC flags), :142-430 (SetNeighbors, same-level branch),
 // nghbr_index.hpp:28-54, coordinates/cell_locations.hpp:24-39, pgen/fluids/blast.cpp:134-402.
 // The integer maps must be bit-exact with the reference (tests/test_host_mesh.py).
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -36,6 +37,12 @@ struct HostMesh {
   std::vector<int> mb_bcs;           // [nmb_total][6]
   std::vector<int> nghbr;            // [nmb_total][56][4]
   std::string err;
+  struct Tree *tree = nullptr;       // kept for adaptive refinement (ak_mesh_adapt)
+  // MeshRefinement state (mesh_refinement.cpp:46-131)
+  int ncyc_check_amr = 1, refinement_interval = 5;
+  bool adaptive = false;
+  std::vector<int> ncyc_since_ref;   // [nmb_total]
+  std::vector<int> newtoold, oldtonew, old_flag;      // maps of the last ak_mesh_adapt that changed the mesh
 };
 
 thread_local std::string g_mesh_err;
@@ -53,7 +60,6 @@ inline double CellCenterX(int ith, int n, double xmin, double xmax) {
 // MeshBlockTree (meshblock_tree.cpp:28-479): oct-/quad-/binary tree over logical locations.  The root
 // grid can be incomplete; refining a node also refines its neighbours as needed so that adjacent
 // leaves differ by at most one level (Refine -> AddNode on the 26 neighbours of the refined node).
-struct HostMesh;
 struct Tree {
   struct Node {
     LLoc l{0, 0, 0, 0};
@@ -74,6 +80,7 @@ struct Tree {
   static Node *child(Node *p, int i, int j, int k) {
     Node *c = new Node();
     c->l = LLoc{(p->l.lx1 << 1) + i, (p->l.lx2 << 1) + j, (p->l.lx3 << 1) + k, p->l.level + 1};   // meshblock_tree.cpp:38-47
+    c->gid = p->gid;            // a new leaf carries its parent's gid until the next Z-ordering (AMR: new -> old map)
     return c;
   }
   void CreateRootGrid(Node *t) {                       // meshblock_tree.cpp:64-91
@@ -146,9 +153,36 @@ struct Tree {
     }
     return bt;     // leaf at the same level, or a split node: its leaves are one level finer
   }
-  void ZOrder(Node *t, std::vector<LLoc> &out) {       // meshblock_tree.cpp:336-350
-    if (!t->split) { t->gid = (int)out.size(); out.push_back(t->l); return; }
-    for (int n = 0; n < nleaf; ++n) if (t->leaf[n]) ZOrder(t->leaf[n], out);
+  void ZOrder(Node *t, std::vector<LLoc> &out, std::vector<int> *oldgid = nullptr) {       // meshblock_tree.cpp:336-350
+    if (!t->split) { if (oldgid) oldgid->push_back(t->gid); t->gid = (int)out.size(); out.push_back(t->l); return; }
+    for (int n = 0; n < nleaf; ++n) if (t->leaf[n]) ZOrder(t->leaf[n], out, oldgid);
+  }
+  Node *FindMeshBlock(const LLoc &r) const {          // meshblock_tree.cpp:453-479
+    Node *bt = root;
+    for (int level = 0; level < r.level; ++level) {
+      if (!bt || !bt->split) return nullptr;
+      bt = bt->leaf[leaf_index(r, level)];
+    }
+    return bt;
+  }
+  // meshblock_tree.cpp:256-304: make this node a leaf again unless a neighbouring leaf that touches it is itself
+  // refined (adjacent leaves may differ by one level only)
+  void Derefine(Node *t, int &ndel) {
+    const int s2 = multi_d ? -1 : 0, s3 = three_d ? -1 : 0;
+    for (int ox3 = s3; ox3 <= -s3; ++ox3) for (int ox2 = s2; ox2 <= -s2; ++ox2) for (int ox1 = -1; ox1 <= 1; ++ox1) {
+      Node *bt = FindNeighbor(t->l, ox1, ox2, ox3);
+      if (!bt || !bt->split) continue;
+      int lis, lie, ljs, lje, lks, lke;
+      if (ox1 == -1) lis = lie = 1; else if (ox1 == 1) lis = lie = 0; else { lis = 0; lie = 1; }
+      if (multi_d) { if (ox2 == -1) ljs = lje = 1; else if (ox2 == 1) ljs = lje = 0; else { ljs = 0; lje = 1; } } else ljs = lje = 0;
+      if (three_d) { if (ox3 == -1) lks = lke = 1; else if (ox3 == 1) lks = lke = 0; else { lks = 0; lke = 1; } } else lks = lke = 0;
+      for (int lk = lks; lk <= lke; ++lk) for (int lj = ljs; lj <= lje; ++lj) for (int li = lis; li <= lie; ++li)
+        if (bt->leaf[li + (lj << 1) + (lk << 2)]->split) return;
+    }
+    t->gid = t->leaf[0]->gid;      // inherits the first leaf's gid
+    for (Node *&c : t->leaf) { delete c; c = nullptr; }
+    t->split = false;
+    ndel += nleaf - 1;
   }
 };
 
@@ -271,6 +305,8 @@ static void fill_tables(HostMesh *M, Tree &T) {
   }
 }
 
+static void free_mesh(HostMesh *M) { if (M) { delete M->tree; delete M; } }
+
 // regions: [nregions][7] = physical level (>= 1), x1min, x1max, x2min, x2max, x3min, x3max of each
 // <refined_region> block (build_tree.cpp:79-230); multilevel = <mesh_refinement>/refinement != none.
 static int mesh_build(const int *nmesh, const int *nblock, const double *xmin, const double *xmax, const int *bcs,
@@ -281,11 +317,11 @@ static int mesh_build(const int *nmesh, const int *nblock, const double *xmin, c
   for (int d = 0; d < 3; ++d) {
     M->nmesh[d] = nmesh[d]; M->nblock[d] = nblock[d]; M->xmin[d] = xmin[d]; M->xmax[d] = xmax[d];
     if (nblock[d] < 1 || nmesh[d] < nblock[d] || nmesh[d] % nblock[d] != 0) {
-      g_mesh_err = "ak_mesh_create: mesh/nx must be a positive multiple of meshblock/nx"; delete M; return 1;
+      g_mesh_err = "ak_mesh_create: mesh/nx must be a positive multiple of meshblock/nx"; free_mesh(M); return 1;
     }
     M->nroot[d] = nmesh[d] / nblock[d];                       // build_tree.cpp:34-36
     if ((bcs[2 * d] == AK_BC_PERIODIC) != (bcs[2 * d + 1] == AK_BC_PERIODIC)) {
-      g_mesh_err = "ak_mesh_create: both inner and outer bcs must be periodic"; delete M; return 1;  // mesh.cpp:86-93
+      g_mesh_err = "ak_mesh_create: both inner and outer bcs must be periodic"; free_mesh(M); return 1;  // mesh.cpp:86-93
     }
   }
   for (int q = 0; q < 6; ++q) M->bcs[q] = bcs[q];
@@ -293,21 +329,22 @@ static int mesh_build(const int *nmesh, const int *nblock, const double *xmin, c
   M->multilevel = multilevel != 0 || nregions > 0;
   const bool multi_d = nmesh[1] > 1, three_d = nmesh[2] > 1;
   if (M->multilevel && (nblock[0] % 2 || (multi_d && nblock[1] % 2) || (three_d && nblock[2] % 2))) {
-    g_mesh_err = "ak_mesh_create: number of cells in MeshBlock must be divisible by 2 with SMR or AMR"; delete M; return 1;   // build_tree.cpp:68-76
+    g_mesh_err = "ak_mesh_create: number of cells in MeshBlock must be divisible by 2 with SMR or AMR"; free_mesh(M); return 1;   // build_tree.cpp:68-76
   }
   int nmbmax = std::max(M->nroot[0], std::max(M->nroot[1], M->nroot[2]));
   for (M->root_level = 0; ((1 << M->root_level) < nmbmax); M->root_level++) {}   // build_tree.cpp:42-45
-  Tree T(M->nroot, M->bcs, M->root_level, multi_d, three_d);
+  M->tree = new Tree(M->nroot, M->bcs, M->root_level, multi_d, three_d);
+  Tree &T = *M->tree;
   M->max_level = M->root_level;
   for (int r = 0; r < nregions; ++r) {        // build_tree.cpp:79-230
     const double *R = regions + 7 * r;
     const int phy = (int)R[0], logl = phy + M->root_level;
     double rmin[3] = {R[1], multi_d ? R[3] : xmin[1], three_d ? R[5] : xmin[2]};
     double rmax[3] = {R[2], multi_d ? R[4] : xmax[1], three_d ? R[6] : xmax[2]};
-    if (phy < 1) { g_mesh_err = "ak_mesh_create: <refined_region> level must be larger than 0"; delete M; return 1; }
+    if (phy < 1) { g_mesh_err = "ak_mesh_create: <refined_region> level must be larger than 0"; free_mesh(M); return 1; }
     for (int d = 0; d < 3; ++d)
       if (rmin[d] > rmax[d] || rmin[d] < xmin[d] || rmax[d] > xmax[d]) {
-        g_mesh_err = "ak_mesh_create: <refined_region> must be valid and fully contained within the root mesh"; delete M; return 1;
+        g_mesh_err = "ak_mesh_create: <refined_region> must be valid and fully contained within the root mesh"; free_mesh(M); return 1;
       }
     if (logl > M->max_level) M->max_level = logl;
     int lmin[3] = {0, 0, 0}, lmax[3] = {0, 0, 0};
@@ -327,7 +364,7 @@ static int mesh_build(const int *nmesh, const int *nblock, const double *xmin, c
   }
   T.ZOrder(T.root, M->lloc);
   M->nmb_total = (int)M->lloc.size();
-  if (M->nmb_total < nranks) { g_mesh_err = "ak_mesh_create: fewer MeshBlocks than ranks"; delete M; return 1; }
+  if (M->nmb_total < nranks) { g_mesh_err = "ak_mesh_create: fewer MeshBlocks than ranks"; free_mesh(M); return 1; }
   load_balance(*M);
   fill_tables(M, T);
   *mesh = M;
@@ -348,7 +385,7 @@ int ak_mesh_create_smr(const int *nmesh, const int *nblock, const double *xmin, 
   return mesh_build(nmesh, nblock, xmin, xmax, bcs, nranks, 1, nregions, regions, mesh);
 }
 
-int ak_mesh_destroy(void *mesh) { delete static_cast<HostMesh *>(mesh); return 0; }
+int ak_mesh_destroy(void *mesh) { free_mesh(static_cast<HostMesh *>(mesh)); return 0; }
 
 int ak_mesh_info(void *mesh, int *nmb_total, int *root_level) {
   auto *M = static_cast<HostMesh *>(mesh);
@@ -377,6 +414,113 @@ int ak_mesh_rank_tables(void *mesh, int rank, double *mb_size, int *mb_bcs, int 
   if (mb_size) std::memcpy(mb_size, &M->mb_size[g0 * 9], sizeof(double) * n * 9);
   if (mb_bcs) std::memcpy(mb_bcs, &M->mb_bcs[g0 * 6], sizeof(int) * n * 6);
   if (nghbr) std::memcpy(nghbr, &M->nghbr[g0 * 56 * 4], sizeof(int) * n * 56 * 4);
+  return 0;
+}
+
+// ---- adaptive mesh refinement, host maps: mesh_refinement.cpp:46-131 (parameters),
+// :196-266 (CheckForRefinement: cycle counters, level limits, refinement interval), :274-419 (UpdateMeshBlockTree:
+// refine flagged leaves with the 2:1 rule, derefine complete sibling sets that the tree allows), :427-510
+// (new Z-ordered list, new -> old and old -> new gid maps, per-old-block flags) and :611-656 (housekeeping).
+// One rank's view of the whole mesh, as every rank of the reference holds it.
+int ak_mesh_set_amr(void *mesh, int num_levels, int refinement_interval, int ncycle_check) {
+  auto *M = static_cast<HostMesh *>(mesh);
+  if (!M || !M->tree || num_levels < 1 || refinement_interval < 0 || ncycle_check < 1) return 1;
+  M->adaptive = true;
+  M->multilevel = true;
+  M->max_level = std::max(M->max_level, M->root_level + num_levels - 1);      // build_tree.cpp:232-246
+  M->refinement_interval = refinement_interval;
+  M->ncyc_check_amr = ncycle_check;
+  M->ncyc_since_ref.assign(M->nmb_total, 0);
+  fill_tables(M, *M->tree);       // neighbour sub-block slots are in use on a multilevel mesh
+  return 0;
+}
+
+// refine_flag [nmb_total]: in = the criteria's verdict per block (+1 refine, -1 derefine, 0), ignored on cycles that
+// are not check cycles; out = what happened to each OLD block (+1 refined, -nleaf derefined, 0).  ncycle = the mesh's
+// cycle counter when the reference calls AdaptiveMeshRefinement (after it was incremented).  Returns the number of
+// blocks created / deleted; when either is non-zero the mesh tables are those of the NEW mesh afterwards.
+int ak_mesh_adapt(void *mesh, int ncycle, int *refine_flag, int *nnew_out, int *ndel_out) {
+  auto *M = static_cast<HostMesh *>(mesh);
+  if (!M || !M->tree || !M->adaptive || !refine_flag) { g_mesh_err = "ak_mesh_adapt: mesh is not adaptive (ak_mesh_set_amr)"; return 1; }
+  Tree &T = *M->tree;
+  const int nb = M->nmb_total;
+  const bool multi_d = M->nmesh[1] > 1, three_d = M->nmesh[2] > 1;
+  const int nleaf = T.nleaf;
+  if (nnew_out) *nnew_out = 0;
+  if (ndel_out) *ndel_out = 0;
+  for (int m = 0; m < nb; ++m) M->ncyc_since_ref[m] += 1;
+  if (ncycle % M->ncyc_check_amr != 0) { std::fill(refine_flag, refine_flag + nb, 0); return 0; }
+  for (int m = 0; m < nb; ++m) {
+    if (M->lloc[m].level == M->max_level && refine_flag[m] > 0) refine_flag[m] = 0;
+    if (M->lloc[m].level == M->root_level && refine_flag[m] < 0) refine_flag[m] = 0;
+    if (M->ncyc_since_ref[m] < M->refinement_interval) refine_flag[m] = 0;
+  }
+  // UpdateMeshBlockTree
+  std::vector<LLoc> llref, llderef, cllderef;
+  for (int m = 0; m < nb; ++m) if (refine_flag[m] == 1) llref.push_back(M->lloc[m]);
+  int tnderef = 0;
+  for (int m = 0; m < nb; ++m) if (refine_flag[m] == -1) tnderef++;
+  int nnew = 0, ndel = 0;
+  if (!(llref.empty() && tnderef < nleaf)) {
+    if (tnderef >= nleaf) for (int m = 0; m < nb; ++m) if (refine_flag[m] == -1) llderef.push_back(M->lloc[m]);
+    const int lj = multi_d ? 1 : 0, lk = three_d ? 1 : 0;
+    for (int n = 0; n < (int)llderef.size(); ++n) {
+      if ((llderef[n].lx1 & 1) || (llderef[n].lx2 & 1) || (llderef[n].lx3 & 1)) continue;
+      int r = n, rr = 0;
+      for (int k = 0; k <= lk; ++k) for (int j = 0; j <= lj; ++j) for (int i = 0; i <= 1; ++i) {
+        if (r < (int)llderef.size()) {
+          if (llderef[n].lx1 + i == llderef[r].lx1 && llderef[n].lx2 + j == llderef[r].lx2 && llderef[n].lx3 + k == llderef[r].lx3 &&
+              llderef[n].level == llderef[r].level) rr++;
+          r++;
+        }
+      }
+      if (rr == nleaf) cllderef.push_back(LLoc{llderef[n].lx1 >> 1, llderef[n].lx2 >> 1, llderef[n].lx3 >> 1, llderef[n].level - 1});
+    }
+    // mesh_refinement.cpp:393-395 sorts [first, last-1) by decreasing level: the last entry stays where it is
+    if (cllderef.size() > 1) std::sort(cllderef.begin(), cllderef.end() - 1, [](const LLoc &a, const LLoc &b) { return a.level > b.level; });
+    for (const LLoc &l : llref) { Tree::Node *bt = T.FindMeshBlock(l); if (bt) T.Refine(bt, nnew); }
+    for (const LLoc &l : cllderef) { Tree::Node *bt = T.FindMeshBlock(l); if (bt && bt->split) T.Derefine(bt, ndel); }
+  }
+  if (nnew == 0 && ndel == 0) { std::fill(refine_flag, refine_flag + nb, 0); return 0; }
+  // RedistAndRefineMeshBlocks, steps 1-3 and 10
+  std::vector<LLoc> new_lloc;
+  std::vector<int> newtoold;
+  T.ZOrder(T.root, new_lloc, &newtoold);
+  const int new_nmb = (int)new_lloc.size();
+  if (new_nmb != nb + nnew - ndel) { g_mesh_err = "ak_mesh_adapt: number of MeshBlocks in the new tree differs from the expected value"; return 1; }
+  std::vector<int> oldtonew(nb, 0);
+  int mb_idx = 1;
+  for (int n = 1; n < new_nmb; ++n) {
+    if (newtoold[n] == newtoold[n - 1] + 1) oldtonew[mb_idx++] = n;
+    else if (newtoold[n] == newtoold[n - 1] + nleaf) { for (int j = 0; j < nleaf - 1; ++j) oldtonew[mb_idx++] = n - 1; oldtonew[mb_idx++] = n; }
+  }
+  while (mb_idx < nb) oldtonew[mb_idx++] = new_nmb - 1;
+  for (int oldm = 0; oldm < nb; ++oldm) {
+    const int ol = M->lloc[oldm].level, nl = new_lloc[oldtonew[oldm]].level;
+    refine_flag[oldm] = (ol > nl) ? -nleaf : (ol < nl) ? 1 : 0;
+  }
+  std::vector<int> ncyc(new_nmb);
+  for (int m = 0; m < new_nmb; ++m) ncyc[m] = refine_flag[newtoold[m]] != 0 ? 0 : M->ncyc_since_ref[newtoold[m]];
+  M->old_flag.assign(refine_flag, refine_flag + nb);
+  M->newtoold = newtoold; M->oldtonew = oldtonew;
+  M->ncyc_since_ref = ncyc;
+  M->lloc = new_lloc;
+  M->nmb_total = new_nmb;
+  load_balance(*M);
+  fill_tables(M, T);
+  if (nnew_out) *nnew_out = nnew;
+  if (ndel_out) *ndel_out = ndel;
+  return 0;
+}
+
+// maps of the last ak_mesh_adapt that changed the mesh: newtoold [new nmb_total], oldtonew / old_flag [old nmb_total]
+int ak_mesh_amr_maps(void *mesh, int *newtoold, int *oldtonew, int *old_flag, int *old_nmb) {
+  auto *M = static_cast<HostMesh *>(mesh);
+  if (!M) return 1;
+  if (newtoold) std::memcpy(newtoold, M->newtoold.data(), sizeof(int) * M->newtoold.size());
+  if (oldtonew) std::memcpy(oldtonew, M->oldtonew.data(), sizeof(int) * M->oldtonew.size());
+  if (old_flag) std::memcpy(old_flag, M->old_flag.data(), sizeof(int) * M->old_flag.size());
+  if (old_nmb) *old_nmb = (int)M->oldtonew.size();
   return 0;
 }
 

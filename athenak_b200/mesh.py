@@ -31,15 +31,42 @@ class Mesh:
                                            reg.ctypes.data_as(C.POINTER(C.c_double)), C.byref(self.h))
         if rc:
             raise _lib.EngineError(self.L.ak_mesh_last_error().decode())
+        self._refresh()
+
+    def _refresh(self):
         a, b = C.c_int(), C.c_int()
         self.L.ak_mesh_info(self.h, C.byref(a), C.byref(b))
         self.nmb_total, self.root_level = a.value, b.value
         self.lloc = np.zeros((self.nmb_total, 4), np.int32)
         self.rank_of = np.zeros(self.nmb_total, np.int32)
-        self.gids_start = np.zeros(nranks, np.int32)
-        self.nmb_rank = np.zeros(nranks, np.int32)
+        self.gids_start = np.zeros(self.nranks, np.int32)
+        self.nmb_rank = np.zeros(self.nranks, np.int32)
         ip = lambda x: x.ctypes.data_as(C.POINTER(C.c_int))
         self.L.ak_mesh_tables(self.h, ip(self.lloc), ip(self.rank_of), ip(self.gids_start), ip(self.nmb_rank))
+
+    # -- adaptive mesh refinement, host maps (src/mesh/mesh_refinement.cpp:196-510) ---------------------------
+    def set_amr(self, num_levels, refinement_interval=5, ncycle_check=1):
+        """<mesh_refinement> refinement=adaptive: num_levels, refinement_interval, ncycle_check."""
+        if self.L.ak_mesh_set_amr(self.h, int(num_levels), int(refinement_interval), int(ncycle_check)):
+            raise _lib.EngineError("ak_mesh_set_amr failed")
+
+    def adapt(self, ncycle, refine_flag):
+        """One AdaptiveMeshRefinement bookkeeping step.  refine_flag: the criteria's verdict per block (+1 / -1 / 0).
+        Returns (nnew, ndel, what happened to each OLD block); when the mesh changed, self.lloc etc. describe the
+        new mesh and self.newtoold / self.oldtonew map the block indices."""
+        flag = np.ascontiguousarray(refine_flag, np.int32).copy()
+        assert flag.shape == (self.nmb_total,)
+        ip = lambda x: x.ctypes.data_as(C.POINTER(C.c_int))
+        nnew, ndel = C.c_int(), C.c_int()
+        if self.L.ak_mesh_adapt(self.h, int(ncycle), ip(flag), C.byref(nnew), C.byref(ndel)):
+            raise _lib.EngineError(self.L.ak_mesh_last_error().decode())
+        if nnew.value or ndel.value:
+            old_nmb = self.nmb_total
+            self._refresh()
+            self.newtoold = np.zeros(self.nmb_total, np.int32)
+            self.oldtonew = np.zeros(old_nmb, np.int32)
+            self.L.ak_mesh_amr_maps(self.h, ip(self.newtoold), ip(self.oldtonew), None, None)
+        return nnew.value, ndel.value, flag
 
     def __del__(self):
         try:

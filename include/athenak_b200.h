@@ -264,6 +264,18 @@ int ak_mesh_create(const int *nmesh, const int *nblock, const double *xmin, cons
 int ak_mesh_create_smr(const int *nmesh, const int *nblock, const double *xmin, const double *xmax, const int *bcs,
                        int nranks, int nregions, const double *regions, void **mesh);
 int ak_mesh_destroy(void *mesh);
+/* Adaptive mesh refinement, host maps: the reference's MeshRefinement bookkeeping for one cycle --
+ * src/mesh/mesh_refinement.cpp:196-266 (cycle counters, level limits, <mesh_refinement>/refinement_interval and
+ * ncycle_check), :274-419 (UpdateMeshBlockTree: refine flagged leaves keeping adjacent leaves within one level,
+ * derefine complete sibling sets the tree allows), :427-510 (new Z-ordered block list and the new->old / old->new gid
+ * maps) and :611-656.  ak_mesh_set_amr switches a mesh created by ak_mesh_create[_smr] to adaptive; ak_mesh_adapt takes
+ * the refinement criteria's verdict per block (+1 / -1 / 0; ignored on cycles that are not check cycles), returns in the
+ * same array what happened to each OLD block (+1 refined, -nleaf derefined, 0) and the number of blocks created /
+ * deleted; when either is non-zero every ak_mesh_* table describes the NEW mesh afterwards.  The data movement that goes
+ * with it (refine / derefine copies, RepairAMRFC) is not built yet. */
+int ak_mesh_set_amr(void *mesh, int num_levels, int refinement_interval, int ncycle_check);
+int ak_mesh_adapt(void *mesh, int ncycle, int *refine_flag /*[nmb_total] in/out*/, int *nnew, int *ndel);
+int ak_mesh_amr_maps(void *mesh, int *newtoold, int *oldtonew, int *old_flag, int *old_nmb);
 
 /* ---- fine/coarse boundaries of cell-centred data on a statically refined mesh, hydro ----
  * Replaces, for a pack whose neighbours are all on this rank, the multilevel parts of the tasks RestrictU

@@ -1625,3 +1625,4 @@ double oracle_initial_dt(const ocfg *c, const ostate *s, const double *mb_size, 
 #include "hydro_oracle.c"
 #include "smr_oracle.c"
 #include "smr_fc_oracle.c"
+#include "amr_oracle.c"

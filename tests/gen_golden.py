@@ -162,7 +162,22 @@ def smr_mhd():
         np.savez_compressed(os.path.join(HERE, "golden", name + ".npz"), **out)
 
 
+def amr():
+    """AMR host-map fixture (tests/test_amr_cpu.py): block list + ghost-inclusive density of every cycle of the
+    unmodified reference on tests/decks/blast2d_amr.athinput -> tests/golden/amr_blast2d_llocs.npz."""
+    import test_amr_cpu as T
+    seq = T.reference_sequence()
+    out = dict(deck=np.array(open(T.DECK).read()), ncycles=len(seq))
+    for k, (l, d) in enumerate(seq):
+        out[f"lloc_{k}"] = l
+        out[f"dens_{k}"] = d
+    np.savez_compressed(os.path.join(HERE, "golden", "amr_blast2d_llocs.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--amr-only" in sys.argv:
+        amr()
+        sys.exit(0)
     if "--smr-only" in sys.argv:
         smr_trees()
         smr()
