@@ -174,9 +174,40 @@ def amr():
     np.savez_compressed(os.path.join(HERE, "golden", "amr_blast2d_llocs.npz"), **out)
 
 
+AMR_EVENTS_OVERRIDES = ("mesh/nx1=64", "mesh/nx2=64", "time/nlim=16", "mesh_refinement/refinement_interval=2",
+                        "problem/inner_radius=0.2", "problem/outer_radius=0.2")
+
+
+def amr_events():
+    """AMR data-path fixture (tests/test_amr_data_cpu.py): 64^2 blast, 8^2 blocks; block list + density of every cycle,
+    full ghost-inclusive states of the cycles around the first refinement and the first derefinement
+    -> tests/golden/amr_blast2d_events.npz."""
+    import amr_util as AU
+    dumps = AU.reference_dumps(AMR_EVENTS_OVERRIDES)
+    p = AU.params(AMR_EVENTS_OVERRIDES)
+    deck = "".join(f"<{b}>\n" + "".join(f"{k.split('/', 1)[1]} = {v}\n" for k, v in p.items() if k.split("/")[0] == b) + "\n"
+                   for b in dict.fromkeys(k.split("/")[0] for k in p))
+    out = dict(deck=np.array(deck), ncycles=len(dumps))
+    events, seen = [], set()
+    for k in range(1, len(dumps) - 1):
+        kind = np.sign(dumps[k + 1].nmb - dumps[k].nmb)
+        if kind != 0 and kind not in seen:
+            seen.add(kind)
+            events.append(k)
+    for k, r in enumerate(dumps):
+        out[f"lloc_{k}"] = r.lloc
+        out[f"dens_{k}"] = r.u0[:, 0]
+        if k in events or (k - 1) in events:
+            out[f"u0_{k}"], out[f"b1f_{k}"], out[f"b2f_{k}"], out[f"b3f_{k}"] = r.u0, r.b1f, r.b2f, r.b3f
+            out[f"time_{k}"], out[f"dt_{k}"] = r.time, r.dt
+    out["events"] = np.array(events)
+    np.savez_compressed(os.path.join(HERE, "golden", "amr_blast2d_events.npz"), **out)
+
+
 if __name__ == "__main__":
     if "--amr-only" in sys.argv:
         amr()
+        amr_events()
         sys.exit(0)
     if "--smr-only" in sys.argv:
         smr_trees()
