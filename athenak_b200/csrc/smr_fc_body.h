@@ -181,7 +181,7 @@ AK_HD void fc_prolong_shared_elem(const FcDims &D, const FcBox &d, int t, double
 
 // ProlongateFC, interior faces of the refined ghost cells (prolongation.cpp:253-357, Toth & Roe 2002): reads only
 // faces shared with the coarse cell (even offsets), writes only the faces between them (odd offsets).
-AK_HD void fc_prolong_interior_elem(const FcDims &D, const FcCell &d, int t, double *b1, double *b2, double *b3) {
+AK_HD void fc_prolong_interior_elem(const FcDims &D, const FcCell &d, int t, double *b1, double *b2, double *b3, bool force = false) {
   const int i = d.lo[0] + t % d.n[0]; t /= d.n[0];      // 32-bit index math: a box holds far fewer than 2^31 elements
   const int j = d.lo[1] + t % d.n[1];
   const int k = d.lo[2] + t / d.n[1];
@@ -190,7 +190,8 @@ AK_HD void fc_prolong_interior_elem(const FcDims &D, const FcCell &d, int t, dou
 #define B1(K_, J_, I_) x1[fidx(D, 0, K_, J_, I_)]
 #define B2(K_, J_, I_) x2[fidx(D, 1, K_, J_, I_)]
 #define B3(K_, J_, I_) x3[fidx(D, 2, K_, J_, I_)]
-#define ST(v_, X_, K_, J_, I_, val_) do { if (!fc_is_active(D, v_, K_, J_, I_)) X_(K_, J_, I_) = (val_); } while (0)
+// force: write active faces too (blocks created by refinement, RepairAMRFC); ghost-zone prolongation never does
+#define ST(v_, X_, K_, J_, I_, val_) do { if (force || !fc_is_active(D, v_, K_, J_, I_)) X_(K_, J_, I_) = (val_); } while (0)
   if (!D.multi_d) {
     ST(0, B1, fk, fj, fi + 1, 0.5 * (B1(fk, fj, fi) + B1(fk, fj, fi + 2)));
   } else if (D.three_d) {

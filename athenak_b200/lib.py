@@ -119,6 +119,10 @@ def load():
         "ak_mesh_set_amr": [vp, ip, ip, ip],
         "ak_mesh_adapt": [vp, ip, ipp, ipp, ipp],
         "ak_mesh_amr_maps": [vp, ipp, ipp, ipp, ipp],
+        "ak_amr_criterion": [C.POINTER(MhdCfg), ip, vp, ip, ip, d, d, dpp, dpp, ipp, vp],
+        "ak_amr_plan": [C.POINTER(MhdCfg), ip, ipp, ipp, ipp, ipp],
+        "ak_amr_move": [C.POINTER(MhdCfg), ipp, vp, vp, ip, vp, vp, vp, vp, vp, vp, vp],
+        "ak_amr_repair_fc": [C.POINTER(MhdCfg), ipp, vp, vp, vp, vp],
         "ak_smr_create": [C.POINTER(MhdCfg), ipp, ipp, ip, ip, C.POINTER(vp)],
         "ak_smr_destroy": [vp],
         "ak_smr_counts": [vp, C.POINTER(C.c_long)],
@@ -170,6 +174,8 @@ def load():
     lib.ak_smr_last_error.argtypes = [vp]
     lib.ak_smr_coarse_cells.restype = C.c_long
     lib.ak_smr_coarse_cells.argtypes = [vp]
+    lib.ak_amr_last_error.restype = C.c_char_p
+    lib.ak_amr_last_error.argtypes = []
     lib.ak_smr_coarse_faces.restype = C.c_long
     lib.ak_smr_coarse_faces.argtypes = [vp, ip]
     for name, args in sig.items():
@@ -186,7 +192,7 @@ EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_con
             "ak_halo_npeers", "ak_halo_peer", "ak_halo_descs", "ak_halo_local_cc", "ak_halo_local_fc",
             "ak_halo_pack_cc", "ak_halo_unpack_cc", "ak_halo_pack_fc", "ak_halo_unpack_fc",
             "ak_halo_emf_peer", "ak_halo_emf_pack_local", "ak_halo_emf_pack", "ak_halo_emf_sumavg",
-            "ak_mesh_create", "ak_mesh_create_smr", "ak_mesh_destroy", "ak_mesh_set_amr", "ak_mesh_adapt", "ak_mesh_amr_maps", "ak_smr_create", "ak_smr_destroy", "ak_smr_last_error",
+            "ak_mesh_create", "ak_mesh_create_smr", "ak_mesh_destroy", "ak_mesh_set_amr", "ak_mesh_adapt", "ak_mesh_amr_maps", "ak_amr_last_error", "ak_amr_criterion", "ak_amr_plan", "ak_amr_move", "ak_amr_repair_fc", "ak_smr_create", "ak_smr_destroy", "ak_smr_last_error",
             "ak_smr_coarse_cells", "ak_smr_counts", "ak_smr_restrict_cc", "ak_smr_exchange_cc", "ak_smr_prolongate_cc", "ak_smr_prolongate_cc_steps", "ak_smr_flux_correct_cc", "ak_smr_coarse_faces", "ak_smr_restrict_fc", "ak_smr_exchange_fc", "ak_smr_prolongate_fc_steps", "ak_smr_emf_correct", "ak_smr_fc_tables", "ak_mesh_last_error", "ak_mesh_info", "ak_mesh_tables",
             "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast", "ak_pgen_orszag_tang", "ak_selftest_divsqrt",
             "ak_sim_create", "ak_sim_destroy", "ak_sim_set_levels", "ak_nccl_unique_id", "ak_sim_comm_init", "ak_sim_set_state",

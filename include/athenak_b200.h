@@ -271,11 +271,28 @@ int ak_mesh_destroy(void *mesh);
  * maps) and :611-656.  ak_mesh_set_amr switches a mesh created by ak_mesh_create[_smr] to adaptive; ak_mesh_adapt takes
  * the refinement criteria's verdict per block (+1 / -1 / 0; ignored on cycles that are not check cycles), returns in the
  * same array what happened to each OLD block (+1 refined, -nleaf derefined, 0) and the number of blocks created /
- * deleted; when either is non-zero every ak_mesh_* table describes the NEW mesh afterwards.  The data movement that goes
- * with it (refine / derefine copies, RepairAMRFC) is not built yet. */
+ * deleted; when either is non-zero every ak_mesh_* table describes the NEW mesh afterwards.  Data movement: ak_amr_* below. */
 int ak_mesh_set_amr(void *mesh, int num_levels, int refinement_interval, int ncycle_check);
 int ak_mesh_adapt(void *mesh, int ncycle, int *refine_flag /*[nmb_total] in/out*/, int *nnew, int *ndel);
 int ak_mesh_amr_maps(void *mesh, int *newtoold, int *oldtonew, int *old_flag, int *old_nmb);
+/* ---- adaptive mesh refinement on the device (dynamic refinement) ----
+ * ak_amr_criterion: one <amr_criterion> block (src/mesh/refinement_criteria.cpp:177-386; method 0 min_max, 1 slope,
+ * 2 second_deriv, 3 location) as per-block extrema on the device + the reference's flag rules on the host.
+ * ak_amr_plan / ak_amr_move: the data movement of MeshRefinement::RedistAndRefineMeshBlocks (src/mesh/mesh_refinement.cpp:
+ * 523-603: DerefineCC/FC, CopyCC/FC, CopyForRefinementCC/FC, RefineCC/FC) as gathers from the OLD arrays into the NEW
+ * arrays: the reference moves blocks in place inside over-allocated Views and stages through the coarse arrays; here
+ * the host hands over both sets of arrays and every element of the new ones is computed in one launch per field with
+ * the reference's expressions (RestrictCC/FC for derefined blocks, ProlongCC and the divergence-preserving face
+ * operators for blocks created by refinement).  ak_amr_repair_fc: RepairAMRFC (:1189-1221).  Host sequence
+ * (AdaptiveMeshRefinement, :145-190): criteria -> ak_mesh_adapt -> ak_amr_plan + ak_amr_move -> ghost exchange +
+ * ConToPrim -> ak_amr_repair_fc -> ghost exchange + ConToPrim -> NewTimeStep.  plan rows = {kind, old block, offset[3]}. */
+const char *ak_amr_last_error(void);
+int ak_amr_criterion(const ak_mhd_cfg *cfg, int method, const double *q, int nvar, int var, double value_min, double value_max,
+                     const double *loc4, const double *mb_size, int *flag /* host [nmb], in/out */, ak_stream_t s);
+int ak_amr_plan(const ak_mhd_cfg *cfg_new, int old_nmb, const int *newtoold, const int *old_flag, const int *lloc_new, int *plan /*[new_nmb][5]*/);
+int ak_amr_move(const ak_mhd_cfg *cfg_new, const int *plan, const double *u_old, double *u_new, int nvar,
+                const double *b1_old, const double *b2_old, const double *b3_old, double *b1_new, double *b2_new, double *b3_new, ak_stream_t s);
+int ak_amr_repair_fc(const ak_mhd_cfg *cfg, const int *blockflag /* host [nmb] */, double *b1, double *b2, double *b3, ak_stream_t s);
 
 /* ---- fine/coarse boundaries of cell-centred data on a statically refined mesh, hydro ----
  * Replaces, for a pack whose neighbours are all on this rank, the multilevel parts of the tasks RestrictU

@@ -93,6 +93,28 @@ class Stepper:
         return (np.zeros((nmb, 5, L.oracle_smr_coarse_cells(C.byref(cfg)))),
                 [np.zeros((nmb, L.oracle_smr_coarse_faces(C.byref(cfg), v))) for v in range(3)])
 
+    def move(self, cfg, A, what, n2o, o2n, lloc_old, lloc_new, refined):
+        """RedistAndRefineMeshBlocks steps 5-9 with the oracle (in place, the reference's copy order)."""
+        L, mesh = self.L, self.mesh
+        old_nmb, new_nmb = cfg.nmb, mesh.nmb_total
+        cap = max(old_nmb, new_nmb)
+        pad = lambda a: np.concatenate([a, np.zeros((cap - old_nmb,) + a.shape[1:])]) if cap > old_nmb else a.copy()
+        u = pad(A.u0)
+        b = [pad(x) for x in A.b0]
+        cu, cb = self.coarse(cfg, cap)
+        L.oracle_smr_restrict_cc(C.byref(cfg), O.p(u), O.p(cu), 5)       # coarse_u0 as the last stage's RestrictU left it
+        L.oracle_amr_redistribute(C.byref(cfg), new_nmb, O.p(u), O.p(cu), 5, *[O.p(x) for x in b], *[O.p(x) for x in cb],
+                                  O.ip(what), O.ip(n2o), O.ip(o2n), O.ip(lloc_old), O.ip(lloc_new))
+        cfgn = ocfg(mesh, self.p)
+        L.oracle_amr_refine_fc(C.byref(cfgn), *[O.p(x) for x in b], *[O.p(x) for x in cb], O.ip(refined), 1)
+        return u, b
+
+    def repair(self, cfg, A, cbn, repair):
+        self.L.oracle_amr_refine_fc(C.byref(cfg), *[O.p(x) for x in A.b0], *[O.p(x) for x in cbn], O.ip(repair), 2)
+
+    def flags(self, cfg, A, mbs):
+        return criteria_flags(self.L, cfg, self.p, A.w0, mbs)
+
     def advance(self, r, ncycle):
         """r = the reference's state of cycle `ncycle` (before its AMR step).  Returns (Arrays, time, dt_used) after the
         AMR step and one more cycle."""
@@ -105,7 +127,7 @@ class Stepper:
             dst[:] = src
         A.c2p_all()
         mbs, ngh, lev = self.tables()
-        flag = criteria_flags(L, cfg, p, A.w0, mbs)
+        flag = self.flags(cfg, A, mbs)
         lloc_old = np.ascontiguousarray(mesh.lloc, np.int32).copy()
         nnew, ndel, what = mesh.adapt(ncycle, flag)
         if nnew or ndel:
@@ -113,20 +135,12 @@ class Stepper:
             self.ncreated += nnew
             self.ndeleted += ndel
             old_nmb, new_nmb = cfg.nmb, mesh.nmb_total
-            cap = max(old_nmb, new_nmb)
-            pad = lambda a: np.concatenate([a, np.zeros((cap - old_nmb,) + a.shape[1:])]) if cap > old_nmb else a.copy()
-            u = pad(A.u0)
-            b = [pad(x) for x in A.b0]
-            cu, cb = self.coarse(cfg, cap)
-            L.oracle_smr_restrict_cc(C.byref(cfg), O.p(u), O.p(cu), 5)       # coarse_u0 as the last stage's RestrictU left it
             lloc_new = np.ascontiguousarray(mesh.lloc, np.int32)
             n2o, o2n = np.ascontiguousarray(mesh.newtoold, np.int32), np.ascontiguousarray(mesh.oldtonew, np.int32)
-            L.oracle_amr_redistribute(C.byref(cfg), new_nmb, O.p(u), O.p(cu), 5, *[O.p(x) for x in b], *[O.p(x) for x in cb],
-                                      O.ip(what), O.ip(n2o), O.ip(o2n), O.ip(lloc_old), O.ip(lloc_new))
-            cfg = ocfg(mesh, p)
             refined = np.ascontiguousarray(what[n2o] > 0, np.int32)
             repair = np.ascontiguousarray(what[n2o] != 0, np.int32)
-            L.oracle_amr_refine_fc(C.byref(cfg), *[O.p(x) for x in b], *[O.p(x) for x in cb], O.ip(refined), 1)
+            u, b = self.move(cfg, A, what, n2o, o2n, lloc_old, lloc_new, refined)
+            cfg = ocfg(mesh, p)
             A = O.Arrays(cfg)
             A.u0[:] = u[:new_nmb]
             for dst, src in zip(A.b0, b):
@@ -135,7 +149,7 @@ class Stepper:
             cu0, cbn = self.coarse(cfg, new_nmb)
             st = A.state()
             L.oracle_mhd_smr_ghosts_and_prims(C.byref(cfg), C.byref(st), O.p(cu0), *[O.p(x) for x in cbn], O.ip(ngh), O.ip(lev))
-            L.oracle_amr_refine_fc(C.byref(cfg), *[O.p(x) for x in A.b0], *[O.p(x) for x in cbn], O.ip(repair), 2)      # RepairAMRFC
+            self.repair(cfg, A, cbn, repair)                                                                             # RepairAMRFC
             L.oracle_mhd_smr_ghosts_and_prims(C.byref(cfg), C.byref(st), O.p(cu0), *[O.p(x) for x in cbn], O.ip(ngh), O.ip(lev))
         else:
             cu0, cbn = self.coarse(cfg, cfg.nmb)

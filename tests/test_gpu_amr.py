@@ -1,0 +1,104 @@
+"""Adaptive mesh refinement on the GPU (dynamic refinement): refinement criteria (ak_amr_criterion),
+mesh bookkeeping (ak_mesh_adapt), data movement as gathers from the old arrays into the new ones (ak_amr_plan / ak_amr_move),
+RepairAMRFC (ak_amr_repair_fc) and the AdaptiveMeshRefinement sequence (athenak_b200/amr.py) around the multilevel MHD task
+list.  Gate: from the unmodified reference's state of cycle k the engine reproduces the reference's state of cycle k+1
+BITWISE -- U and B with ghost zones, block list, time, dt -- across one refinement and one derefinement event (committed
+fixture), and across whole live runs when oracle/_ref/athena_blast is present."""
+import numpy as np
+import pytest
+
+import amr_util as AU
+import golden_io as G
+import hydro_util as H
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+class EngineStepper:
+    def __init__(self, p):
+        self.p, self.mesh = p, AU.make_mesh(p)
+        self.nadapt = self.ncreated = self.ndeleted = 0
+
+    def make_mhd(self, mesh):
+        from athenak_b200.mhd import MHD
+        p = self.p
+        mb_size, mb_bcs, nghbr = mesh.rank_tables(0)
+        return MHD(mesh.nmb_total, int(p["mesh/nghost"]), mesh.nblock, mb_size, nghbr, recon=p["mhd/reconstruct"], rsolver=p["mhd/rsolver"],
+                   gamma=float(p["mhd/gamma"]), mb_lev=mesh.lloc[:, 3], mesh_bcs=mesh.bcs, mb_bcs=mb_bcs)
+
+    def advance(self, r, ncycle, fused=True):
+        import torch
+        from athenak_b200 import amr
+        from athenak_b200.driver import Driver, assemble_mhd_tasks
+        p, mesh = self.p, self.mesh
+        assert np.array_equal(mesh.lloc, r.lloc)
+        mhd = self.make_mhd(mesh)
+        mhd.load_state(r.u0, r.b1f, r.b2f, r.b3f)
+        drv = Driver(p["time/integrator"], float(p["time/cfl_number"]), tlim=float(p["time/tlim"]))
+        drv.time, drv.dt, drv.ncycle = r.time, r.dt, ncycle
+        mhd.ConToPrim(drv, 0)
+        mhd.NewTimeStep(drv, drv.nexp_stages)        # dtnew as the last stage of the cycle left it
+        nmb0 = mhd.nmb
+        mhd, changed = amr.adaptive_mesh_refinement(mhd, mesh, drv, amr.criteria_from_params(p), self.make_mhd)
+        if changed:
+            self.nadapt += 1
+            self.ncreated += max(0, mhd.nmb - nmb0)
+            self.ndeleted += max(0, nmb0 - mhd.nmb)
+        drv.NewTimeStep(mhd)                          # Mesh::NewTimeStep after AMR (driver.cpp:449-450)
+        dt = drv.dt
+        drv.Execute(mhd, assemble_mhd_tasks(mhd, fused=fused), ncycles=1)
+        torch.cuda.synchronize()
+        return mhd, drv.time, dt
+
+
+def check_step(S, r, rn, k, fused=True):
+    mhd, t, dt = S.advance(r, k, fused)
+    assert np.array_equal(S.mesh.lloc, rn.lloc), f"block list after cycle {k}"
+    assert t == rn.time and dt == rn.dt, f"time / dt after cycle {k}: {t} {rn.time} {dt} {rn.dt}"
+    u = mhd.u0.cpu().numpy()
+    assert np.array_equal(u, rn.u0), f"cycle {k}: max|dU| = {np.abs(u - rn.u0).max()}"
+    for x, y in zip(mhd.b0, (rn.b1f, rn.b2f, rn.b3f)):
+        assert np.array_equal(x.cpu().numpy(), y), f"cycle {k}: face field differs"
+    assert mhd.launches > 0
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "pertask"])
+def test_amr_events_match_fixture_bitwise(fused):
+    d = G.load("amr_blast2d_events")
+    p = H.deck_params(str(d["deck"]))
+    S = EngineStepper(p)
+
+    class R:
+        pass
+
+    def state(k):
+        r = R()
+        r.lloc, r.u0, r.b1f, r.b2f, r.b3f = d[f"lloc_{k}"], d[f"u0_{k}"], d[f"b1f_{k}"], d[f"b2f_{k}"], d[f"b3f_{k}"]
+        r.time, r.dt = float(d[f"time_{k}"]), float(d[f"dt_{k}"])
+        return r
+
+    events = [int(k) for k in d["events"]]
+    L = O.lib()
+    for k in range(1, int(d["ncycles"]) - 1):
+        if k in events:
+            check_step(S, state(k), state(k + 1), k, fused)
+        else:       # replay the mesh bookkeeping only (criteria verdict from the oracle on the stored density)
+            cfg = AU.ocfg(S.mesh, p)
+            mbs = np.ascontiguousarray(S.mesh.rank_tables(0)[0])
+            S.mesh.adapt(k, AU.criteria_flags(L, cfg, p, np.ascontiguousarray(d[f"dens_{k}"][:, None]), mbs))
+        assert np.array_equal(S.mesh.lloc, d[f"lloc_{k + 1}"])
+    assert S.ncreated > 0 and S.ndeleted > 0
+
+
+@pytest.mark.parametrize("name", ["2d_3levels", "3d"])
+def test_amr_cycle_by_cycle_matches_live_reference_bitwise(name):
+    if not O.have_reference("athena_blast"):
+        pytest.skip("oracle/_ref/athena_blast not built")
+    from test_amr_data_cpu import CASES
+    ov = CASES[name]
+    dumps = AU.reference_dumps(ov)
+    S = EngineStepper(AU.params(ov))
+    for k in range(1, len(dumps) - 1):
+        check_step(S, dumps[k], dumps[k + 1], k)
+    assert S.nadapt >= 1 and S.ncreated > 0
