@@ -4,7 +4,7 @@ old parent, RefineFC, RepairAMRFC, criterion extrema; compiled here with g++ by 
 (ak_amr_plan) replace the oracle's data movement inside the cycle-by-cycle harness of tests/amr_util.py: from the
 reference's state of cycle k they must reproduce the reference's state of cycle k+1 BITWISE (ghost zones included), i.e.
 the gather formulation equals the reference's in-place move + coarse-array staging, and the zero-initialised ghost zones
-of changed blocks never reach a result.  No GPU needed; tests/test_gpu_amr.py runs the same bodies as CUDA kernels."""
+of changed blocks never reach a result.  No GPU needed; tests/test_gpu_zamr.py runs the same bodies as CUDA kernels."""
 import ctypes as C
 import os
 import subprocess
