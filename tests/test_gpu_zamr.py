@@ -7,9 +7,10 @@ fixture; passed on a B200 for the fused and the per-task list), and across whole
 present.  Live runs: block list, time, dt and U bitwise; B bit-identical wherever it is not far-field noise (|dB| <= 1e-100,
 i.e. every value above ~1e-84 must agree to the last bit).  Reason: on the one B200 run this round had budget for, the 2-D
 three-level run agreed bitwise for 23 cycles (8 AMR events) and then differed in x2f only, U, time and dt still identical,
-in a cycle WITHOUT a mesh change; by then the far-field precursor of the blast carries |B2| ~ 1e-161, whose products are
-denormal, and the library's guard-free exact division / square root are exact for normal-range operands
-only.  That explanation is NOT confirmed on hardware yet (no GPU budget left); DESIGN.md section 6b lists it as open.
+in a cycle WITHOUT a mesh change.  Cause: the PLM limiter's guard-free division with a numerator at the denormal
+floor; substituting that division into the oracle reproduces the same signature on the CPU (cycle 24 only, 4 faces of x2f,
+5e-175), and the device PLM now guards that range -- but the fixed library has not run on hardware yet, so the bound stays
+until it has.
 (File name: sorted last on purpose -- the newest, least-measured tests should not stop an `-x` run before the others.)"""
 import numpy as np
 import pytest
