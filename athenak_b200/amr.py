@@ -97,3 +97,27 @@ def adaptive_mesh_refinement(mhd, mesh, driver, criteria, make_mhd):
     init_boundary_values_and_primitives(new, driver)
     new.NewTimeStep(driver, driver.nexp_stages)
     return new, True
+
+
+def execute(mhd, mesh, driver, criteria, make_mhd, ncycles=None, fused=True):
+    """Driver::Execute with AMR (driver.cpp:380-459): cycle, then AdaptiveMeshRefinement, then Mesh::NewTimeStep.  Returns the
+    MHD object of the final mesh and the number of mesh changes."""
+    from .driver import assemble_mhd_tasks
+    tl = assemble_mhd_tasks(mhd, fused=fused)
+    done = nchanged = 0
+    while driver.time < driver.tlim and (driver.nlim < 0 or driver.ncycle < driver.nlim):
+        if ncycles is not None and done >= ncycles:
+            break
+        for stage in range(1, driver.nexp_stages + 1):
+            driver.ExecuteTaskList(tl, "stagen", stage)
+        driver.time += driver.dt
+        driver.ncycle += 1
+        driver.nmb_updated += mhd.nmb
+        done += 1
+        mhd, changed = adaptive_mesh_refinement(mhd, mesh, driver, criteria, make_mhd)
+        if changed:
+            nchanged += 1
+            tl = assemble_mhd_tasks(mhd, fused=fused)      # the task bodies are bound to the MHD object
+        driver.NewTimeStep(mhd)
+    return mhd, nchanged
+

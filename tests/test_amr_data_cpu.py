@@ -18,6 +18,9 @@ CASES = {
     "2d_3levels": ("mesh_refinement/num_levels=3", "time/nlim=36"),
     "3d": ("mesh/nx1=32", "mesh/nx2=32", "mesh/nx3=32", "meshblock/nx3=8", "time/nlim=14", "mesh_refinement/refinement_interval=2",
            "problem/inner_radius=0.2", "problem/outer_radius=0.2"),
+    # refinement and derefinement alternate (interval 1): the 8-sibling restriction in 3-D
+    "3d_deref": ("mesh/nx1=32", "mesh/nx2=32", "mesh/nx3=32", "meshblock/nx3=8", "time/nlim=12", "mesh_refinement/refinement_interval=1",
+                 "problem/inner_radius=0.2", "problem/outer_radius=0.2", "amr_criterion0/value_max=0.3"),
     "2d_ppm4_rk3_ng4": ("mesh/nghost=4", "mhd/reconstruct=ppm4", "time/integrator=rk3", "time/nlim=24", "mesh/nx1=64", "mesh/nx2=64"),
 }
 
@@ -41,7 +44,7 @@ def test_amr_cycle_by_cycle_matches_live_reference(name):
     for k in range(1, len(dumps) - 1):
         check_step(S, dumps[k], dumps[k + 1], k)
     assert S.nadapt >= 1 and S.ncreated > 0
-    if name.startswith("2d_3levels") or name == "2d_2levels":
+    if name in ("2d_3levels", "2d_2levels", "3d_deref"):
         assert S.ndeleted > 0
 
 

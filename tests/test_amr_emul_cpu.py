@@ -126,7 +126,7 @@ def test_amr_emulated_device_path_matches_fixture(emul):
     assert S.ncreated > 0 and S.ndeleted > 0
 
 
-@pytest.mark.parametrize("name", ["2d_3levels", "3d"])
+@pytest.mark.parametrize("name", ["2d_3levels", "3d", "3d_deref"])
 def test_amr_emulated_device_path_matches_live_reference(name, emul):
     if not O.have_reference("athena_blast"):
         pytest.skip("oracle/_ref/athena_blast not built")

@@ -104,7 +104,7 @@ def test_amr_events_match_fixture_bitwise(fused):
     assert S.ncreated > 0 and S.ndeleted > 0
 
 
-@pytest.mark.parametrize("name", ["2d_3levels", "3d"])
+@pytest.mark.parametrize("name", ["2d_3levels", "3d", "3d_deref"])
 def test_amr_cycle_by_cycle_matches_live_reference_bitwise(name):
     if not O.have_reference("athena_blast"):
         pytest.skip("oracle/_ref/athena_blast not built")
