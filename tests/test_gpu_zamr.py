@@ -104,6 +104,44 @@ def test_amr_events_match_fixture_bitwise(fused):
     assert S.ncreated > 0 and S.ndeleted > 0
 
 
+def test_amr_execute_loop_across_both_events():
+    """athenak_b200.amr.execute (cycle -> AdaptiveMeshRefinement -> new dt, task lists rebuilt on a mesh change) from the
+    fixture's state of the refinement cycle to the state after the derefinement cycle, without reloading in between."""
+    import torch
+    from athenak_b200 import amr
+    from athenak_b200.driver import Driver, assemble_mhd_tasks
+    d = G.load("amr_blast2d_events")
+    p = H.deck_params(str(d["deck"]))
+    events = [int(k) for k in d["events"]]
+    k0, k1 = events[0], events[-1] + 1
+    assert all(f"u0_{k}" in d for k in (k0, k1))
+    S = EngineStepper(p)
+    L = O.lib()
+    for k in range(1, k0):          # mesh bookkeeping up to the first event
+        cfg = AU.ocfg(S.mesh, p)
+        mbs = np.ascontiguousarray(S.mesh.rank_tables(0)[0])
+        S.mesh.adapt(k, AU.criteria_flags(L, cfg, p, np.ascontiguousarray(d[f"dens_{k}"][:, None]), mbs))
+    mhd = S.make_mhd(S.mesh)
+    mhd.load_state(d[f"u0_{k0}"], d[f"b1f_{k0}"], d[f"b2f_{k0}"], d[f"b3f_{k0}"])
+    drv = Driver(p["time/integrator"], float(p["time/cfl_number"]), tlim=float(p["time/tlim"]))
+    drv.time, drv.dt, drv.ncycle = float(d[f"time_{k0}"]), float(d[f"dt_{k0}"]), k0
+    mhd.ConToPrim(drv, 0)
+    mhd.NewTimeStep(drv, drv.nexp_stages)
+    crit = amr.criteria_from_params(p)
+    mhd, changed = amr.adaptive_mesh_refinement(mhd, S.mesh, drv, crit, S.make_mhd)     # the AMR step of cycle k0
+    assert changed
+    drv.NewTimeStep(mhd)
+    mhd, nchanged = amr.execute(mhd, S.mesh, drv, crit, S.make_mhd, ncycles=k1 - 1 - k0)    # cycles k0+1 .. k1-1, each followed by AMR
+    assert nchanged >= 1 and drv.ncycle == k1 - 1
+    drv.Execute(mhd, assemble_mhd_tasks(mhd), ncycles=1)                                  # cycle k1 (its AMR step comes after the dump)
+    torch.cuda.synchronize()
+    assert drv.ncycle == k1 and drv.time == float(d[f"time_{k1}"])
+    assert np.array_equal(S.mesh.lloc, d[f"lloc_{k1}"])
+    assert np.array_equal(mhd.u0.cpu().numpy(), d[f"u0_{k1}"])
+    for x, key in zip(mhd.b0, ("b1f", "b2f", "b3f")):
+        assert np.array_equal(x.cpu().numpy(), d[f"{key}_{k1}"])
+
+
 @pytest.mark.parametrize("name", ["2d_3levels", "3d", "3d_deref"])
 def test_amr_cycle_by_cycle_matches_live_reference_bitwise(name):
     if not O.have_reference("athena_blast"):
