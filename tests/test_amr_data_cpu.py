@@ -76,3 +76,20 @@ def test_amr_events_match_fixture():
             S.mesh.adapt(k, flag)
         assert np.array_equal(S.mesh.lloc, d[f"lloc_{k + 1}"])
     assert S.ncreated > 0 and S.ndeleted > 0
+
+
+@pytest.mark.parametrize("name,overrides", [("2d_plm_hllc_rk2", ()), ("2d_ppm4_hlle_rk3_3levels", ("hydro/reconstruct=ppm4", "hydro/rsolver=hlle",
+                                            "time/integrator=rk3", "mesh/nghost=4", "mesh_refinement/num_levels=3", "mesh/nx1=64", "mesh/nx2=64"))])
+def test_hydro_amr_cycle_by_cycle_matches_live_reference(name, overrides):
+    """The hydro twin (tests/decks/blast2d_hydro_amr.athinput; one ghost-zone rebuild after the data movement, no RepairAMRFC)."""
+    if not O.have_reference("athena_blast"):
+        pytest.skip("oracle/_ref/athena_blast not built")
+    dumps = AU.reference_dumps(overrides, deck=AU.HYDRO_DECK, physics="hydro")
+    S = AU.HydroStepper(AU.params(overrides, deck=AU.HYDRO_DECK))
+    for k in range(1, len(dumps) - 1):
+        r, rn = dumps[k], dumps[k + 1]
+        u, t, dt = S.advance(r, k)
+        assert np.array_equal(S.mesh.lloc, rn.lloc) and t == rn.time and dt == rn.dt, f"cycle {k}"
+        assert np.array_equal(u, rn.u0), f"cycle {k}: max|dU| = {np.abs(u - rn.u0).max()}"
+    assert S.nadapt >= 2 and S.ncreated > 0 and (S.ndeleted > 0 or name != "2d_plm_hllc_rk2")
+
