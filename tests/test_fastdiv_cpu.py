@@ -1,0 +1,39 @@
+"""The one bitwise difference the GPU showed in a long AMR run, pinned on the CPU: the oracle with the DEVICE's
+guard-free division formula in the PLM limiter (oracle/tools/fastdiv_experiment.py) differs from the unmodified reference in
+exactly one cycle of the 2-D three-level AMR blast, in a handful of x2f faces at the 1e-175 level, U / time / dt equal; with the
+guard that athenak_b200/csrc/mhd_device.cuh::plm now has (numerator below 2^-900 and non-zero -> IEEE division) every cycle is
+bitwise.  Needs oracle/_ref/athena_blast (live reference run)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+import oracle_lib as O
+
+TOOL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "tools", "fastdiv_experiment.py")
+
+
+def run(*args):
+    return subprocess.run([sys.executable, TOOL, *args], capture_output=True, text=True, timeout=600, check=True).stdout
+
+
+def test_guard_free_division_reproduces_the_gpu_difference_and_the_guard_removes_it():
+    if not O.have_reference("athena_blast"):
+        pytest.skip("oracle/_ref/athena_blast not built")
+    out = run()
+    m = re.search(r"guard=False: (\d+) of (\d+) cycles differ", out)
+    assert m and int(m.group(1)) == 1, out
+    line = [l for l in out.splitlines() if l.startswith("cycle ")]
+    assert len(line) == 1 and "U faces differing 0" in line[0] and "time equal True, dt equal True" in line[0], out
+    mx = [float(x) for x in re.search(r"max\|dB\| \[(.*?)\]", line[0]).group(1).split(",")]
+    assert mx[0] == 0.0 and 0.0 < mx[1] < 1e-150 and mx[2] == 0.0, out
+    out = run("--guard")
+    assert re.search(r"guard=True: 0 of \d+ cycles differ", out), out
+
+
+def test_device_plm_has_the_guard():
+    src = open(os.path.join(os.path.dirname(TOOL), "..", "..", "athenak_b200", "csrc", "mhd_device.cuh")).read()
+    body = src[src.index("void plm("):src.index("void plm(") + 1600]
+    assert "0x1p-900" in body and "dq2 != 0.0" in body and "dq2 / (dql + dqr)" in body
