@@ -110,3 +110,37 @@ def test_amr_block_lists_match_live_reference(name, overrides):
     seq = reference_sequence(overrides)
     nchanged, ncreated, ndeleted = follow(p, seq)
     assert nchanged >= 1 and ncreated > 0
+
+
+def test_amr_adapt_with_two_ranks_keeps_the_partition_consistent():
+    """ak_mesh_adapt on a mesh distributed over two ranks (every rank holds the whole tree, as in the reference): after each
+    change the Z-ordered list is re-partitioned by LoadBalance (load_balance.cpp:38-88, unit costs) -- contiguous gid ranges,
+    sizes within one block of each other -- and every neighbour entry carries the rank that owns that gid."""
+    d = G.load("amr_blast2d_llocs")
+    p = H.deck_params(str(d["deck"]))
+    nmesh = tuple(int(p[f"mesh/nx{q}"]) for q in (1, 2, 3))
+    nblock = tuple(int(p[f"meshblock/nx{q}"]) for q in (1, 2, 3))
+    mesh = Mesh(nmesh, nblock, nranks=2)
+    mesh.set_amr(int(p["mesh_refinement/num_levels"]), int(p["mesh_refinement/refinement_interval"]), 1)
+    L = O.lib()
+    nchanged = 0
+    for k in range(1, int(d["ncycles"]) - 1):
+        cfg = O.OCfg(mesh.nmb_total, int(p["mesh/nghost"]), *nblock, 1, 2, 5.0 / 3.0, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, 0, 0, 1.0, 0)
+        flag = np.zeros(mesh.nmb_total, np.int32)
+        mbs = np.concatenate([mesh.rank_tables(r)[0] for r in range(2)])
+        q = np.ascontiguousarray(d[f"dens_{k}"][:, None])
+        L.oracle_amr_criterion(C.byref(cfg), 1, O.p(q), 1, 0, C.c_double(-O.FLT_MAX), C.c_double(float(p["amr_criterion0/value_max"])),
+                               O.p(np.zeros(4)), O.p(np.ascontiguousarray(mbs)), O.ip(flag))
+        nnew, ndel, _ = mesh.adapt(k, flag)
+        assert np.array_equal(mesh.lloc, d[f"lloc_{k + 1}"])            # the same block lists as with one rank
+        if nnew or ndel:
+            nchanged += 1
+        assert int(mesh.nmb_rank.sum()) == mesh.nmb_total and abs(int(mesh.nmb_rank[0]) - int(mesh.nmb_rank[1])) <= 1
+        assert mesh.gids_start[0] == 0 and mesh.gids_start[1] == mesh.nmb_rank[0]
+        assert np.array_equal(mesh.rank_of, np.repeat([0, 1], mesh.nmb_rank))
+        for r in range(2):
+            ngh = mesh.rank_tables(r)[2]
+            valid = ngh[:, :, 0] >= 0
+            assert np.array_equal(ngh[:, :, 2][valid], mesh.rank_of[ngh[:, :, 0][valid]])
+    assert nchanged >= 3
+
