@@ -99,6 +99,9 @@ def test_amr_block_lists_match_fixture():
 @pytest.mark.parametrize("name,overrides", [
     ("levels3", ("mesh_refinement/num_levels=3", "time/nlim=40")),
     ("second_deriv", ("amr_criterion0/method=second_deriv", "amr_criterion0/value_max=0.05", "time/nlim=25", "mesh_refinement/refinement_interval=2")),
+    ("min_max", ("amr_criterion0/method=min_max", "amr_criterion0/value_max=1.02", "time/nlim=40")),
+    ("location", ("amr_criterion0/method=location", "amr_criterion0/location_x1=0.21", "amr_criterion0/location_x2=-0.13",
+                  "amr_criterion0/location_rad=0.06", "time/nlim=8", "mesh_refinement/num_levels=3", "mesh_refinement/refinement_interval=1")),
 ])
 def test_amr_block_lists_match_live_reference(name, overrides):
     if not O.have_reference("athena_blast"):
@@ -143,4 +146,35 @@ def test_amr_adapt_with_two_ranks_keeps_the_partition_consistent():
             valid = ngh[:, :, 0] >= 0
             assert np.array_equal(ngh[:, :, 2][valid], mesh.rank_of[ngh[:, :, 0][valid]])
     assert nchanged >= 3
+
+
+def test_location_criterion_through_the_abi_matches_the_oracle():
+    """ak_amr_criterion's location branch is host-only (refinement_criteria.cpp:341-386 never touches the device): the C ABI
+    itself can be compared with the oracle here, on a three-level refined mesh, for points inside blocks, on block edges and
+    outside the domain, in 2-D and 3-D."""
+    from athenak_b200 import lib as _lib
+    K = _lib.load()
+    L = O.lib()
+    rng = np.random.default_rng(5)
+    for nmesh, nblock in (((64, 64, 1), (8, 8, 1)), ((32, 32, 32), (8, 8, 8))):
+        mesh = Mesh(nmesh, nblock, refined_regions=[(1, -0.3, 0.1, -0.2, 0.2, -0.1, 0.3), (2, -0.1, 0.0, -0.1, 0.05, 0.0, 0.1)])
+        mbs = np.ascontiguousarray(mesh.rank_tables(0)[0])
+        ocfg = O.OCfg(mesh.nmb_total, 2, *nblock, 1, 2, 5.0 / 3.0, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, 0, 0, 1.0, 0)
+        ecfg = _lib.MhdCfg(mesh.nmb_total, 2, *nblock, 1, 2, 5.0 / 3.0, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, 0, 0, 1.0, 0)
+        pts = [rng.uniform(-0.6, 0.6, 3).tolist() + [float(rng.uniform(0.0, 0.3))] for _ in range(40)]
+        pts += [[0.0, 0.0, 0.0, 0.125], [-0.25, 0.125, 0.0, 0.0], [0.5, 0.5, 0.5, 0.01]]
+        nset = 0
+        for pt in pts:
+            loc = np.array(pt)
+            fo = np.zeros(mesh.nmb_total, np.int32)
+            fe = np.zeros(mesh.nmb_total, np.int32)
+            fe[::3] = -1                                   # a location criterion overrides an earlier derefinement verdict
+            fo[::3] = -1
+            L.oracle_amr_criterion(C.byref(ocfg), 3, None, 1, 0, C.c_double(-O.FLT_MAX), C.c_double(O.FLT_MAX), O.p(loc), O.p(mbs), O.ip(fo))
+            dp, ipp = C.POINTER(C.c_double), C.POINTER(C.c_int)
+            assert K.ak_amr_criterion(C.byref(ecfg), 3, None, 1, 0, -O.FLT_MAX, O.FLT_MAX, loc.ctypes.data_as(dp), mbs.ctypes.data_as(dp),
+                                      fe.ctypes.data_as(ipp), None) == 0
+            assert np.array_equal(fe, fo)
+            nset += int((fo == 1).sum())
+        assert nset > 0
 
