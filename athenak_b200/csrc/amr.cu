@@ -39,16 +39,12 @@ FcDims dims_from_cfg(const ak_mhd_cfg &c) {
   return D;
 }
 
-// blockIdx.y = new block, blockIdx.z = variable; threads over the cells of the block
+// blockIdx.y = new block, blockIdx.z = variable; threads over the cells of the block (decode + body: amr_body.h)
 __global__ void __launch_bounds__(256)
 amr_move_cc_kernel(FcDims D, const AmrBlock *__restrict__ blocks, int nvar, const double *__restrict__ uo, double *__restrict__ un) {
   const int m = blockIdx.y, v = blockIdx.z;
   const AmrBlock B = blocks[m];
-  const int ncell = D.n[0] * D.n[1] * D.n[2];
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ncell; t += gridDim.x * blockDim.x) {
-    const int i = t % D.n[0], r = t / D.n[0];
-    amr_move_cc_elem(D, B, m, nvar, v, r / D.n[1], r % D.n[1], i, uo, un);
-  }
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < amr_move_cc_count(D); t += gridDim.x * blockDim.x) amr_move_cc_flat(D, B, m, nvar, v, t, uo, un);
 }
 
 struct Fc3 { const double *o[3]; double *n[3]; };
@@ -58,12 +54,7 @@ __global__ void __launch_bounds__(256)
 amr_move_fc_kernel(FcDims D, const AmrBlock *__restrict__ blocks, Fc3 F) {
   const int m = blockIdx.y, v = blockIdx.z;
   const AmrBlock B = blocks[m];
-  const int x0 = D.n[0] + (v == 0), x1 = D.n[1] + (v == 1);
-  const int nface = (int)D.f[v];
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nface; t += gridDim.x * blockDim.x) {
-    const int i = t % x0, r = t / x0;
-    amr_move_fc_elem(D, B, m, v, r / x1, r % x1, i, F.o[v], F.n[v]);
-  }
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < (int)D.f[v]; t += gridDim.x * blockDim.x) amr_move_fc_flat(D, B, m, v, t, F.o[v], F.n[v]);
 }
 
 // blockIdx.y = new block (only blocks created by refinement do work), blockIdx.z = component; threads over the coarse faces
@@ -72,11 +63,8 @@ amr_refine_fc_shared_kernel(FcDims D, const AmrBlock *__restrict__ blocks, Fc3 F
   const int m = blockIdx.y, v = blockIdx.z;
   const AmrBlock B = blocks[m];
   if (B.kind != AMR_REFINE) return;
-  const int e0 = (D.ce[0] - D.cs[0] + 1) + (v == 0), e1 = (D.ce[1] - D.cs[1] + 1) + (v == 1), e2 = (D.ce[2] - D.cs[2] + 1) + (v == 2);
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < e0 * e1 * e2; t += gridDim.x * blockDim.x) {
-    const int i = D.cs[0] + t % e0, r = t / e0;
-    amr_refine_fc_shared_elem(D, B, m, v, D.cs[2] + r / e1, D.cs[1] + r % e1, i, F.o[v], F.n[v]);
-  }
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < amr_refine_fc_shared_count(D, v); t += gridDim.x * blockDim.x)
+    amr_refine_fc_shared_flat(D, B, m, v, t, F.o[v], F.n[v]);
 }
 
 // interior faces of every refined coarse cell of the flagged blocks (RefineFC second half, and RepairAMRFC)
@@ -84,11 +72,8 @@ __global__ void __launch_bounds__(128)
 amr_fc_interior_kernel(FcDims D, const int *__restrict__ blockflag, double *b1, double *b2, double *b3) {
   const int m = blockIdx.y;
   if (!blockflag[m]) return;
-  FcCell d;
-  d.m = m;
-  for (int q = 0; q < 3; ++q) { d.lo[q] = D.cs[q]; d.n[q] = D.ce[q] - D.cs[q] + 1; }
-  const int cnt = d.n[0] * d.n[1] * d.n[2];
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += gridDim.x * blockDim.x) fc_prolong_interior_elem(D, d, t, b1, b2, b3, true);
+  const FcCell d = amr_whole_block(D, m);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < d.n[0] * d.n[1] * d.n[2]; t += gridDim.x * blockDim.x) fc_prolong_interior_elem(D, d, t, b1, b2, b3, true);
 }
 
 // per-block max and min of the criterion value over the active cells: out[m][0] = max, out[m][1] = min.  One CTA per block;
@@ -97,11 +82,9 @@ __global__ void __launch_bounds__(256)
 amr_extrema_kernel(FcDims D, int method, int nvar, int var, const double *__restrict__ q, double *__restrict__ out) {
   const int m = blockIdx.x;
   const double *a = q + ((long)m * nvar + var) * ((long)D.n[0] * D.n[1] * D.n[2]);
-  const int nx1 = D.e[0] - D.s[0] + 1, nx2 = D.e[1] - D.s[1] + 1, nx3 = D.e[2] - D.s[2] + 1;
   double vmax = -DBL_MAX, vmin = DBL_MAX;
-  for (int t = threadIdx.x; t < nx1 * nx2 * nx3; t += blockDim.x) {
-    const int i = D.s[0] + t % nx1, r = t / nx1;
-    const double x = amr_criterion_value(D, method, a, D.s[2] + r / nx2, D.s[1] + r % nx2, i);
+  for (int t = threadIdx.x; t < amr_active_count(D); t += blockDim.x) {
+    const double x = amr_criterion_flat(D, method, a, t);
     vmax = fmax(x, vmax); vmin = fmin(x, vmin);
   }
   __shared__ double smax[256], smin[256];

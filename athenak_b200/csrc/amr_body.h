@@ -126,4 +126,37 @@ AK_HD double amr_criterion_value(const FcDims &D, int method, const double *a, i
   return fabs(d2q) / q;
 }
 
+// ---- flat-index entry points: the index decode lives here too, so that the g++ emulation harness of the tests exercises it and
+// the CUDA wrappers in amr.cu contain nothing but their grid-stride loops
+AK_HD void amr_move_cc_flat(const FcDims &D, const AmrBlock &B, int m, int nvar, int v, int t, const double *uo, double *un) {
+  const int i = t % D.n[0], r = t / D.n[0];
+  amr_move_cc_elem(D, B, m, nvar, v, r / D.n[1], r % D.n[1], i, uo, un);
+}
+AK_HD int amr_move_cc_count(const FcDims &D) { return D.n[0] * D.n[1] * D.n[2]; }
+AK_HD void amr_move_fc_flat(const FcDims &D, const AmrBlock &B, int m, int v, int t, const double *bo, double *bn) {
+  const int x0 = D.n[0] + (v == 0), x1 = D.n[1] + (v == 1);
+  const int i = t % x0, r = t / x0;
+  amr_move_fc_elem(D, B, m, v, r / x1, r % x1, i, bo, bn);
+}
+AK_HD int amr_refine_fc_shared_count(const FcDims &D, int v) {
+  return ((D.ce[0] - D.cs[0] + 1) + (v == 0)) * ((D.ce[1] - D.cs[1] + 1) + (v == 1)) * ((D.ce[2] - D.cs[2] + 1) + (v == 2));
+}
+AK_HD void amr_refine_fc_shared_flat(const FcDims &D, const AmrBlock &B, int m, int v, int t, const double *bo, double *bn) {
+  const int e0 = (D.ce[0] - D.cs[0] + 1) + (v == 0), e1 = (D.ce[1] - D.cs[1] + 1) + (v == 1);
+  const int i = D.cs[0] + t % e0, r = t / e0;
+  amr_refine_fc_shared_elem(D, B, m, v, D.cs[2] + r / e1, D.cs[1] + r % e1, i, bo, bn);
+}
+AK_HD int amr_active_count(const FcDims &D) { return (D.e[0] - D.s[0] + 1) * (D.e[1] - D.s[1] + 1) * (D.e[2] - D.s[2] + 1); }
+AK_HD double amr_criterion_flat(const FcDims &D, int method, const double *a, int t) {
+  const int nx1 = D.e[0] - D.s[0] + 1, nx2 = D.e[1] - D.s[1] + 1;
+  const int i = D.s[0] + t % nx1, r = t / nx1;
+  return amr_criterion_value(D, method, a, D.s[2] + r / nx2, D.s[1] + r % nx2, i);
+}
+AK_HD FcCell amr_whole_block(const FcDims &D, int m) {      // all coarse cells of block m (RefineFC / RepairAMRFC interior faces)
+  FcCell d;
+  d.m = m;
+  for (int q = 0; q < 3; ++q) { d.lo[q] = D.cs[q]; d.n[q] = D.ce[q] - D.cs[q] + 1; }
+  return d;
+}
+
 }  // namespace akb_smr

@@ -17,17 +17,15 @@ void emul_amr_move(const FcDims *Dp, int new_nmb, const int *plan, const double 
   for (int m = new_nmb - 1; m >= 0; --m) {          // any order: a gather
     const AmrBlock B = blocks[m];
     for (int v = 0; v < nvar; ++v)
-      for (int k = 0; k < D.n[2]; ++k) for (int j = 0; j < D.n[1]; ++j) for (int i = 0; i < D.n[0]; ++i) amr_move_cc_elem(D, B, m, nvar, v, k, j, i, uo, un);
+      for (int t = amr_move_cc_count(D) - 1; t >= 0; --t) amr_move_cc_flat(D, B, m, nvar, v, t, uo, un);
     for (int v = 0; v < 3; ++v)
-      for (int k = 0; k < D.n[2] + (v == 2); ++k) for (int j = 0; j < D.n[1] + (v == 1); ++j) for (int i = 0; i < D.n[0] + (v == 0); ++i)
-        amr_move_fc_elem(D, B, m, v, k, j, i, bo[v], bn[v]);
+      for (int t = (int)D.f[v] - 1; t >= 0; --t) amr_move_fc_flat(D, B, m, v, t, bo[v], bn[v]);
   }
   for (int m = 0; m < new_nmb; ++m) {
     const AmrBlock B = blocks[m];
     if (B.kind != AMR_REFINE) continue;
     for (int v = 0; v < 3; ++v)
-      for (int k = D.cs[2]; k <= D.ce[2] + (v == 2); ++k) for (int j = D.cs[1]; j <= D.ce[1] + (v == 1); ++j) for (int i = D.cs[0]; i <= D.ce[0] + (v == 0); ++i)
-        amr_refine_fc_shared_elem(D, B, m, v, k, j, i, bo[v], bn[v]);
+      for (int t = 0; t < amr_refine_fc_shared_count(D, v); ++t) amr_refine_fc_shared_flat(D, B, m, v, t, bo[v], bn[v]);
   }
 }
 
@@ -35,9 +33,7 @@ void emul_amr_interior(const FcDims *Dp, int nmb, const int *blockflag, double *
   const FcDims &D = *Dp;
   for (int m = 0; m < nmb; ++m) {
     if (!blockflag[m]) continue;
-    FcCell d;
-    d.m = m;
-    for (int q = 0; q < 3; ++q) { d.lo[q] = D.cs[q]; d.n[q] = D.ce[q] - D.cs[q] + 1; }
+    const FcCell d = amr_whole_block(D, m);
     for (int t = d.n[0] * d.n[1] * d.n[2] - 1; t >= 0; --t) fc_prolong_interior_elem(D, d, t, b1, b2, b3, true);
   }
 }
@@ -47,8 +43,8 @@ void emul_amr_extrema(const FcDims *Dp, int nmb, int method, int nvar, int var, 
   for (int m = 0; m < nmb; ++m) {
     const double *a = q + ((long)m * nvar + var) * ((long)D.n[0] * D.n[1] * D.n[2]);
     double vmax = -DBL_MAX, vmin = DBL_MAX;
-    for (int k = D.e[2]; k >= D.s[2]; --k) for (int j = D.e[1]; j >= D.s[1]; --j) for (int i = D.e[0]; i >= D.s[0]; --i) {
-      const double x = amr_criterion_value(D, method, a, k, j, i);
+    for (int t = amr_active_count(D) - 1; t >= 0; --t) {
+      const double x = amr_criterion_flat(D, method, a, t);
       vmax = fmax(x, vmax); vmin = fmin(x, vmin);
     }
     out[2 * m] = vmax; out[2 * m + 1] = vmin;
