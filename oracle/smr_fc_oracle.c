@@ -599,6 +599,9 @@ int oracle_mhd_smr_run(const ocfg *c, ostate *s, double *cu0, double *cb1, doubl
         memcpy(s->b1x1f, s->b0x1f, 8 * nm * D.f1); memcpy(s->b1x2f, s->b0x2f, 8 * nm * D.f2); memcpy(s->b1x3f, s->b0x3f, 8 * nm * D.f3);
       }
       oracle_fluxes(c, s->w0, s->bcc0, s->b0x1f, s->b0x2f, s->b0x3f, flx1, flx2, flx3, fe[0], fe[1], fe[2], fe[3], fe[4], fe[5]);
+      if (c->fofc)   /* mhd_tasks.cpp:208-211: first-order flux correction inside the Fluxes task, before SendFlux */
+        oracle_fofc(c, s->u0, s->u1, s->w0, s->bcc0, s->b0x1f, s->b0x2f, s->b0x3f, s->b1x1f, s->b1x2f, s->b1x3f, flx1, flx2, flx3,
+                    fe[0], fe[1], fe[2], fe[3], fe[4], fe[5], mb_size, g0[st - 1], g1[st - 1], bdt);
       oracle_smr_flux_correct_cc(c, flx1, flx2, flx3, D.nv, nghbr, mblev);                      /* SendFlux / RecvFlux */
       oracle_rk_update(c, s->u0, s->u1, flx1, flx2, flx3, mb_size, g0[st - 1], g1[st - 1], bdt);
       oracle_smr_restrict_cc(c, s->u0, cu0, D.nv);                                                /* RestrictU, SendU, RecvU */

@@ -59,7 +59,8 @@ def make_mesh(p):
 
 def ocfg(mesh, p, nmb=None):
     return O.OCfg(mesh.nmb_total if nmb is None else nmb, int(p["mesh/nghost"]), *mesh.nblock, O.RECON[p["mhd/reconstruct"]],
-                  O.RSOLVER[p["mhd/rsolver"]], float(p["mhd/gamma"]), O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, 0, 0, 1.0, 0)
+                  O.RSOLVER[p["mhd/rsolver"]], float(p["mhd/gamma"]), O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, 0, 0, 1.0,
+                  1 if p.get("mhd/fofc", "false") == "true" else 0)
 
 
 def criteria_flags(L, cfg, p, w0, mbs):
