@@ -57,7 +57,7 @@ def assemble_mhd_tasks(mhd: MHD, fused=True):
         # upwinds with the CORRECTED mass fluxes), so the fused flux+EMF call does not apply.  `fused`: the corner
         # EMFs and their correction move ahead of the update (they read w0 / bcc0 / fluxes only), then one
         # kernel does CopyCons + RKUpdate + CT (ak_mhd_stage_update); the new time step rides on the last c2p.
-        if fused:
+        if fused and not mhd.fofc:      # FOFC estimates the update from u1 / b1 over the whole arrays: it needs CopyCons first
             t = s.AddTask(mhd.Fluxes, 0)
             t = s.AddTask(mhd.FluxCorrect, t)
             t = s.AddTask(mhd.EField, t)
@@ -80,8 +80,11 @@ def assemble_mhd_tasks(mhd: MHD, fused=True):
             t = s.AddTask(mhd.SendRecvB, t)
             t = s.AddTask(mhd.Prolongate, t)
             t = s.AddTask(mhd.ApplyPhysicalBCs, t)
-            t = s.AddTask(mhd.ConToPrim, t)
-            t = s.AddTask(mhd.NewTimeStep, t)
+            if fused:
+                t = s.AddTask(mhd.ConToPrimNewDt, t)
+            else:
+                t = s.AddTask(mhd.ConToPrim, t)
+                t = s.AddTask(mhd.NewTimeStep, t)
     elif fused:
         t = s.AddTask(mhd.StageFluxEmf, 0)
         t = s.AddTask(mhd.SendRecvE, t)

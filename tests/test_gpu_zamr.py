@@ -26,14 +26,15 @@ pytestmark = pytest.mark.gpu
 class EngineStepper:
     def __init__(self, p):
         self.p, self.mesh = p, AU.make_mesh(p)
-        self.nadapt = self.ncreated = self.ndeleted = 0
+        self.nadapt = self.ncreated = self.ndeleted = self.nfofc = 0
 
     def make_mhd(self, mesh):
         from athenak_b200.mhd import MHD
         p = self.p
         mb_size, mb_bcs, nghbr = mesh.rank_tables(0)
         return MHD(mesh.nmb_total, int(p["mesh/nghost"]), mesh.nblock, mb_size, nghbr, recon=p["mhd/reconstruct"], rsolver=p["mhd/rsolver"],
-                   gamma=float(p["mhd/gamma"]), mb_lev=mesh.lloc[:, 3], mesh_bcs=mesh.bcs, mb_bcs=mb_bcs)
+                   gamma=float(p["mhd/gamma"]), mb_lev=mesh.lloc[:, 3], mesh_bcs=mesh.bcs, mb_bcs=mb_bcs,
+                   fofc=p.get("mhd/fofc", "false") == "true")
 
     def advance(self, r, ncycle, fused=True):
         import torch
@@ -57,6 +58,7 @@ class EngineStepper:
         dt = drv.dt
         drv.Execute(mhd, assemble_mhd_tasks(mhd, fused=fused), ncycles=1)
         torch.cuda.synchronize()
+        self.nfofc += mhd.nfofc
         return mhd, drv.time, dt
 
 
@@ -153,3 +155,18 @@ def test_amr_cycle_by_cycle_matches_live_reference_bitwise(name):
     for k in range(1, len(dumps) - 1):
         check_step(S, dumps[k], dumps[k + 1], k, b_atol=1e-100)
     assert S.nadapt >= 1 and S.ncreated > 0
+
+
+def test_fofc_on_a_refined_mesh_matches_live_reference():
+    """FOFC inside the multilevel stage (per-task order: CopyCons, Fluxes + FOFC, flux correction, ...) on a strong magnetised
+    blast where the correction fires, with an AMR event on the way; same tolerance rule as the other live runs."""
+    if not O.have_reference("athena_blast"):
+        pytest.skip("oracle/_ref/athena_blast not built")
+    from test_amr_data_cpu import _FOFC
+    ov = _FOFC + ("mhd/reconstruct=ppm4", "time/integrator=rk3")
+    dumps = AU.reference_dumps(ov)
+    S = EngineStepper(AU.params(ov))
+    for k in range(1, len(dumps) - 1):
+        check_step(S, dumps[k], dumps[k + 1], k, b_atol=1e-100)
+    assert S.nfofc > 100 and S.nadapt >= 1
+
