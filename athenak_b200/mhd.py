@@ -82,8 +82,6 @@ class MHD:
                                          my_rank, gids_start, C.byref(self.plan)))
         self.smr = None
         if mb_lev is not None:       # multilevel mesh: coarse arrays (mhd.cpp:163-176) + SMR plan
-            if nscalars:
-                raise _lib.EngineError("athenak_b200: MHD on a refined mesh: passive scalars are not wired in")
             self.mb_lev = np.ascontiguousarray(mb_lev, dtype=np.int32).reshape(nmb)
             self.smr = C.c_void_p()
             ipp = C.POINTER(C.c_int)

@@ -208,7 +208,8 @@ def oracle_run_mhd(deck_text, u_init, b_init, ncycles=-1, active_only=False):
     mesh, p = mesh_of(deck_text)
     mbs, _, ngh = mesh.rank_tables(0)
     cfg = O.OCfg(mesh.nmb_total, int(p["mesh/nghost"]), *mesh.nblock, O.RECON[p["mhd/reconstruct"]], O.RSOLVER[p["mhd/rsolver"]],
-                 float(p["mhd/gamma"]), O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, 0, 0, 1.0, 0)
+                 float(p["mhd/gamma"]), O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MIN, O.FLT_MAX, int(p.get("mhd/nscalars", 0)), 0, 1.0,
+                 1 if p.get("mhd/fofc", "false") == "true" else 0)
     L = O.lib()
     L.oracle_smr_coarse_cells.restype = C.c_size_t
     L.oracle_smr_coarse_faces.restype = C.c_size_t
@@ -247,3 +248,15 @@ def _oracle_run_mhd(L, cfg, st, A, cu0, cb, mbs, ngh, lev, p, ncycles):
     n = L.oracle_mhd_smr_run(C.byref(cfg), C.byref(st), O.p(cu0), *[O.p(x) for x in cb], O.p(mbs), O.ip(ngh), O.ip(lev),
                              H.INTEGRATOR[p["time/integrator"]], C.c_double(cfl), C.c_double(tlim), ncycles, C.byref(t), C.byref(dt))
     return A, t.value, dt.value, n, dt0
+
+
+SCALAR_DECK = os.path.join(HERE, "decks", "bw2d_smr_scalars.athinput")
+
+
+def reference_mhd_deck(deck, nmhd, threads=4):
+    """First and last restart dump of athena_builtin on a deck (nmhd = number of cell-centred variables incl. scalars)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        O.run_reference("athena_builtin", deck, tmp, [], threads=threads)
+        files = sorted(f for f in os.listdir(os.path.join(tmp, "rst")) if f.endswith(".rst"))
+        return read_rst(os.path.join(tmp, "rst", files[0]), nmhd=nmhd), read_rst(os.path.join(tmp, "rst", files[-1]), nmhd=nmhd)
+

@@ -170,3 +170,31 @@ def test_fofc_on_a_refined_mesh_matches_live_reference():
         check_step(S, dumps[k], dumps[k + 1], k, b_atol=1e-100)
     assert S.nfofc > 100 and S.nadapt >= 1
 
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "pertask"])
+def test_mhd_smr_with_passive_scalar_and_bcs_matches_live_reference(fused):
+    """Static refinement + physical boundaries + one passive scalar (nvar = 6) through the engine's multilevel MHD list:
+    Brio-Wu along x2, 49 cycles, bitwise with ghost zones."""
+    import smr_util as SU
+    import torch
+    from athenak_b200.driver import Driver, assemble_mhd_tasks
+    from athenak_b200.mhd import MHD
+    if not O.have_reference("athena_builtin"):
+        pytest.skip("oracle/_ref/athena_builtin not built")
+    r0, r1 = SU.reference_mhd_deck(SU.SCALAR_DECK, 6)
+    mesh, p = SU.mesh_of(r0.deck)
+    mb_size, mb_bcs, nghbr = mesh.rank_tables(0)
+    mhd = MHD(mesh.nmb_total, int(p["mesh/nghost"]), mesh.nblock, mb_size, nghbr, recon=p["mhd/reconstruct"], rsolver=p["mhd/rsolver"],
+              gamma=float(p["mhd/gamma"]), mb_lev=mesh.lloc[:, 3], mesh_bcs=mesh.bcs, mb_bcs=mb_bcs, nscalars=1)
+    mhd.load_state(r0.u0, r0.b1f, r0.b2f, r0.b3f)
+    drv = Driver(p["time/integrator"], float(p["time/cfl_number"]), tlim=float(p["time/tlim"]))
+    drv.Initialize(mhd)
+    assert drv.dt == r0.dt
+    drv.Execute(mhd, assemble_mhd_tasks(mhd, fused=fused))
+    torch.cuda.synchronize()
+    assert drv.ncycle == r1.ncycle and drv.time == r1.time and drv.dt == r1.dt
+    u = mhd.u0.cpu().numpy()
+    assert np.array_equal(u, r1.u0), f"max|dU| = {np.abs(u - r1.u0).max()}"
+    for x, y in zip(mhd.b0, (r1.b1f, r1.b2f, r1.b3f)):
+        assert np.array_equal(x.cpu().numpy(), y)
+

@@ -67,3 +67,20 @@ def test_mhd_smr_oracle_matches_live_reference(name):
     assert np.array_equal(A.u0, r1.u0), f"max|dU| = {np.abs(A.u0 - r1.u0).max()}"        # ghost zones included
     for x, y in zip(A.b0, (r1.b1f, r1.b2f, r1.b3f)):
         assert np.array_equal(x, y)
+
+
+def test_mhd_smr_with_passive_scalar_and_bcs_matches_live_reference():
+    """Brio-Wu along x2 on a statically refined 2-D mesh with reflect / outflow / diode boundaries and one passive scalar
+    (tests/decks/bw2d_smr_scalars.athinput): the multilevel stage with nvar = 6 -- scalar fluxes, flux correction, restriction
+    and prolongation of the scalar -- 49 cycles, ghost zones included."""
+    if not O.have_reference("athena_builtin"):
+        pytest.skip("oracle/_ref/athena_builtin not built")
+    r0, r1 = S.reference_mhd_deck(S.SCALAR_DECK, 6)
+    assert len(np.unique(r0.lloc[:, 3])) == 2 and r0.u0.shape[1] == 6
+    A, t, dt, n, dt0 = S.oracle_run_mhd(r0.deck, r0.u0, (r0.b1f, r0.b2f, r0.b3f))
+    assert dt0 == r0.dt and n == r1.ncycle and t == r1.time and dt == r1.dt
+    assert np.array_equal(A.u0, r1.u0), f"max|dU| = {np.abs(A.u0 - r1.u0).max()}"
+    for x, y in zip(A.b0, (r1.b1f, r1.b2f, r1.b3f)):
+        assert np.array_equal(x, y)
+    assert r1.u0[:, 5].max() - r1.u0[:, 5].min() > 0.5          # the scalar is not trivial
+
