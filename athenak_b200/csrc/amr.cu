@@ -135,6 +135,7 @@ int ak_amr_move(const ak_mhd_cfg *cfg_new, const int *plan, const double *u_old,
   cudaStream_t st = static_cast<cudaStream_t>(s);
   const FcDims D = dims_from_cfg(*cfg_new);
   const int nmb = cfg_new->nmb;
+  if (nmb < 1 || nmb > 65535 || nvar < 1 || nvar > 65535) return amr_fail("ak_amr_move: nmb and nvar must be in 1..65535 (grid dimensions y, z)");
   static_assert(sizeof(AmrBlock) == 5 * sizeof(int), "plan layout");
   AmrBlock *d_plan = static_cast<AmrBlock *>(scratch(sizeof(AmrBlock) * nmb + sizeof(int) * nmb));
   if (!d_plan) return amr_fail("ak_amr_move: out of device memory");
@@ -166,6 +167,7 @@ int ak_amr_repair_fc(const ak_mhd_cfg *cfg, const int *blockflag, double *b1, do
   if (!cfg || !blockflag || !b1 || !b2 || !b3) return amr_fail("ak_amr_repair_fc: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(s);
   const FcDims D = dims_from_cfg(*cfg);
+  if (cfg->nmb < 1 || cfg->nmb > 65535) return amr_fail("ak_amr_repair_fc: nmb must be in 1..65535 (grid dimension y)");
   int *d_flag = static_cast<int *>(scratch(sizeof(int) * cfg->nmb));
   if (!d_flag) return amr_fail("ak_amr_repair_fc: out of device memory");
   cudaMemcpyAsync(d_flag, blockflag, sizeof(int) * cfg->nmb, cudaMemcpyHostToDevice, st);

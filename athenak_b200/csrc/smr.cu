@@ -922,6 +922,7 @@ int ak_smr_prolongate_fc_steps(void *plan, double *b1, double *b2, double *b3, d
 
 int ak_smr_emf_correct(void *plan, double *e1, double *e2, double *e3, ak_stream_t s) {
   SMR_FC_PROLOGUE("ak_smr_emf_correct")
+  if (D.nmb > 65535) return smr_fail(P, "ak_smr_emf_correct: more than 65535 MeshBlocks per pack (grid dimension y)");
   if (!P->epack.empty())
     emf_pack_kernel<<<dim3((unsigned)P->epack.size(), gx(P->max_epack, 128)), 128, 0, st>>>(D, P->d_epack, e1, e2, e3, P->d_emfbuf);
   const int ns = std::max(emf_surface_count(D, 0), std::max(emf_surface_count(D, 1), emf_surface_count(D, 2)));
