@@ -46,9 +46,9 @@ def refinement_flags(mhd, mesh, criteria):
     for c in criteria:
         if c.method not in METHOD:
             raise _lib.EngineError(f"athenak_b200: refinement method {c.method!r} not supported")
-        if c.method != "location" and c.variable not in ("mhd_w_d", "mhd_u_d"):
+        if c.method != "location" and c.variable not in ("mhd_w_d", "mhd_u_d", "hydro_w_d", "hydro_u_d"):
             raise _lib.EngineError(f"athenak_b200: refinement variable {c.variable!r} not supported")
-        q = mhd.w0 if c.variable == "mhd_w_d" else mhd.u0
+        q = mhd.w0 if c.variable.endswith("_w_d") else mhd.u0
         loc = (C.c_double * 4)(*c.location)
         if L.ak_amr_criterion(C.byref(mhd.cfg), METHOD[c.method], q.data_ptr(), mhd.nvar, 0, c.value_min, c.value_max, loc,
                               mbs.ctypes.data_as(dp), flag.ctypes.data_as(ipp), mhd._st()):
@@ -58,10 +58,12 @@ def refinement_flags(mhd, mesh, criteria):
 
 
 def init_boundary_values_and_primitives(mhd, driver):
-    """Driver::InitBoundaryValuesAndPrimitives (driver.cpp:569-653) for the MHD mirror."""
+    """Driver::InitBoundaryValuesAndPrimitives (driver.cpp:569-653) for the MHD mirror, or for the hydro twin (whose SendRecvU
+    already restricts, exchanges and prolongates)."""
     mhd.SendRecvU(driver, 0)
-    mhd.SendRecvB(driver, 0)
-    mhd.Prolongate(driver, 0)
+    if hasattr(mhd, "Prolongate"):
+        mhd.SendRecvB(driver, 0)
+        mhd.Prolongate(driver, 0)
     mhd.ApplyPhysicalBCs(driver, 0)
     mhd.ConToPrim(driver, 0)
 
@@ -84,26 +86,36 @@ def adaptive_mesh_refinement(mhd, mesh, driver, criteria, make_mhd):
                      plan.ctypes.data_as(ipp)):
         raise _lib.EngineError(L.ak_amr_last_error().decode())
     st = new._st()
-    if L.ak_amr_move(C.byref(new.cfg), plan.ctypes.data_as(ipp), mhd.u0.data_ptr(), new.u0.data_ptr(), new.nvar,
-                     *[a.data_ptr() for a in mhd.b0], *[a.data_ptr() for a in new.b0], st):
+    is_mhd = hasattr(mhd, "b0")
+    bo = [a.data_ptr() for a in mhd.b0] if is_mhd else [None] * 3
+    bn = [a.data_ptr() for a in new.b0] if is_mhd else [None] * 3
+    if L.ak_amr_move(C.byref(new.cfg), plan.ctypes.data_as(ipp), mhd.u0.data_ptr(), new.u0.data_ptr(), new.nvar, *bo, *bn, st):
         raise _lib.EngineError(L.ak_amr_last_error().decode())
-    new.launches = mhd.launches + 4
+    new.launches = mhd.launches + (4 if is_mhd else 1)
     new.nfloor = list(mhd.nfloor)
     init_boundary_values_and_primitives(new, driver)
-    repair = np.ascontiguousarray(what[n2o] != 0, np.int32)
-    if L.ak_amr_repair_fc(C.byref(new.cfg), repair.ctypes.data_as(ipp), *[a.data_ptr() for a in new.b0], st):
-        raise _lib.EngineError(L.ak_amr_last_error().decode())
-    new.launches += 1
-    init_boundary_values_and_primitives(new, driver)
+    if is_mhd:       # mesh_refinement.cpp:164-171: only MHD repairs the interior faces and rebuilds the ghost zones a second time
+        repair = np.ascontiguousarray(what[n2o] != 0, np.int32)
+        if L.ak_amr_repair_fc(C.byref(new.cfg), repair.ctypes.data_as(ipp), *bn, st):
+            raise _lib.EngineError(L.ak_amr_last_error().decode())
+        new.launches += 1
+        init_boundary_values_and_primitives(new, driver)
     new.NewTimeStep(driver, driver.nexp_stages)
     return new, True
+
+
+def _assemble(obj, fused):
+    if hasattr(obj, "b0"):
+        from .driver import assemble_mhd_tasks
+        return assemble_mhd_tasks(obj, fused=fused)
+    from .hydro import assemble_hydro_tasks
+    return assemble_hydro_tasks(obj, fused=fused)
 
 
 def execute(mhd, mesh, driver, criteria, make_mhd, ncycles=None, fused=True):
     """Driver::Execute with AMR (driver.cpp:380-459): cycle, then AdaptiveMeshRefinement, then Mesh::NewTimeStep.  Returns the
     MHD object of the final mesh and the number of mesh changes."""
-    from .driver import assemble_mhd_tasks
-    tl = assemble_mhd_tasks(mhd, fused=fused)
+    tl = _assemble(mhd, fused)
     done = nchanged = 0
     while driver.time < driver.tlim and (driver.nlim < 0 or driver.ncycle < driver.nlim):
         if ncycles is not None and done >= ncycles:
@@ -117,7 +129,7 @@ def execute(mhd, mesh, driver, criteria, make_mhd, ncycles=None, fused=True):
         mhd, changed = adaptive_mesh_refinement(mhd, mesh, driver, criteria, make_mhd)
         if changed:
             nchanged += 1
-            tl = assemble_mhd_tasks(mhd, fused=fused)      # the task bodies are bound to the MHD object
+            tl = _assemble(mhd, fused)      # the task bodies are bound to the MHD / Hydro object
         driver.NewTimeStep(mhd)
     return mhd, nchanged
 

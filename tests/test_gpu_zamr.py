@@ -198,3 +198,44 @@ def test_mhd_smr_with_passive_scalar_and_bcs_matches_live_reference(fused):
     for x, y in zip(mhd.b0, (r1.b1f, r1.b2f, r1.b3f)):
         assert np.array_equal(x.cpu().numpy(), y)
 
+
+def test_hydro_amr_cycle_by_cycle_matches_live_reference_bitwise():
+    """The hydro twin through the same AMR sequence (cell-centred gather only, one ghost-zone rebuild, no RepairAMRFC):
+    PLM+HLLC+RK2 blast, 39 cycles with refinement and derefinement events."""
+    import torch
+    from athenak_b200 import amr
+    from athenak_b200.driver import Driver
+    from athenak_b200.hydro import Hydro, assemble_hydro_tasks
+    if not O.have_reference("athena_blast"):
+        pytest.skip("oracle/_ref/athena_blast not built")
+    p = AU.params(deck=AU.HYDRO_DECK)
+    dumps = AU.reference_dumps(deck=AU.HYDRO_DECK, physics="hydro")
+    mesh = AU.make_mesh(p)
+
+    def make(mesh):
+        mb_size, mb_bcs, nghbr = mesh.rank_tables(0)
+        return Hydro(mesh.nmb_total, int(p["mesh/nghost"]), mesh.nblock, mb_size, nghbr, recon=p["hydro/reconstruct"], rsolver=p["hydro/rsolver"],
+                     gamma=float(p["hydro/gamma"]), mb_lev=mesh.lloc[:, 3], mesh_bcs=mesh.bcs, mb_bcs=mb_bcs)
+
+    crit = amr.criteria_from_params(p)
+    nchanged = 0
+    for k in range(1, len(dumps) - 1):
+        r, rn = dumps[k], dumps[k + 1]
+        assert np.array_equal(mesh.lloc, r.lloc)
+        hyd = make(mesh)
+        hyd.load_state(r.u0)
+        drv = Driver(p["time/integrator"], float(p["time/cfl_number"]), tlim=float(p["time/tlim"]))
+        drv.time, drv.dt, drv.ncycle = r.time, r.dt, k
+        hyd.ConToPrim(drv, 0)
+        hyd.NewTimeStep(drv, drv.nexp_stages)
+        hyd, changed = amr.adaptive_mesh_refinement(hyd, mesh, drv, crit, make)
+        nchanged += int(changed)
+        drv.NewTimeStep(hyd)
+        dt = drv.dt
+        drv.Execute(hyd, assemble_hydro_tasks(hyd), ncycles=1)
+        torch.cuda.synchronize()
+        assert np.array_equal(mesh.lloc, rn.lloc) and drv.time == rn.time and dt == rn.dt, f"cycle {k}"
+        u = hyd.u0.cpu().numpy()
+        assert np.array_equal(u, rn.u0), f"cycle {k}: max|dU| = {np.abs(u - rn.u0).max()}"
+    assert nchanged >= 2
+
