@@ -243,10 +243,20 @@ int ak_bcs_bfield(void *bcs, double *x1f, double *x2f, double *x3f, ak_stream_t 
 /* both of the above with one launch per direction */
 int ak_bcs_apply(void *bcs, double *u0, int nvar, double *x1f, double *x2f, double *x3f, ak_stream_t s);
 
-/* Device self-test: compares the library's slow-path-free FP64 reciprocal / division / sqrt with
- * the built-in IEEE operators on n random operands (|exponent| <= exponent_span, every 64th
- * numerator exactly 0); mismatches[3] = differing results for 1/x, a/b, sqrt(x). */
+/* Device self-test: compares the library's FP64 reciprocal / division / sqrt (nvcc's fast paths + a zero-aware
+ * range guard, csrc/mhd_device.cuh) with the built-in IEEE operators on n random operands.  exponent_span <= 1022:
+ * |exponent| <= exponent_span, every 64th numerator exactly 0.  exponent_span > 1022: the whole double range --
+ * subnormals, the denormal floor, +-0, infinities, NaNs, negative sqrt arguments -- in every operand position.
+ * mismatches[4] = differing results for 1/x, a/b, sqrt(x), and a/y by the reciprocal+FMA quotient used for the
+ * launch-uniform divisors (dx, 12, 6). */
 int ak_selftest_divsqrt(long n, unsigned long long seed, int exponent_span, long *mismatches);
+
+/* Measured FP64 issue peak of the current device (csrc/peaks.cu): a register-only kernel of dependent chains of
+ * one FP64 instruction.  op: 0 DFMA, 1 DADD, 2 DMUL, 3 alternating DADD/DMUL (what an --fmad=false build issues);
+ * ilp = independent chains per thread (1, 2, 4, 8); warps_per_smsp = resident warps per SM sub-partition (1..16);
+ * iters x 16 instructions per chain.  Returns thread-level FP64 instructions per second (the denominator of
+ * bench.py's roofline.fp64) and the best-of-3 kernel time. */
+int ak_peak_fp64(int op, int ilp, int warps_per_smsp, int iters, double *lane_instr_per_s, double *ms);
 
 /* ---- host-side mesh metadata (CPU only; reference src/mesh, kept on the host) ---------------
  * Uniform (single-level) meshes.  Bit-exact mirrors of: Z-ordered gids (meshblock_tree.cpp:

@@ -1,8 +1,9 @@
 """The one bitwise difference the GPU showed in a long AMR run, pinned on the CPU: the oracle with the DEVICE's
 guard-free division formula in the PLM limiter (oracle/tools/fastdiv_experiment.py) differs from the unmodified reference in
 exactly one cycle of the 2-D three-level AMR blast, in a handful of x2f faces at the 1e-175 level, U / time / dt equal; with the
-guard that athenak_b200/csrc/mhd_device.cuh::plm now has (numerator below 2^-900 and non-zero -> IEEE division) every cycle is
-bitwise.  Needs oracle/_ref/athena_blast (live reference run)."""
+guard (numerator below the fast path's range and non-zero -> IEEE division) every cycle is bitwise.  Round 2 moved that guard
+from plm() into ddiv / drcp / dsqrt themselves (athenak_b200/csrc/mhd_device.cuh), so EVERY division site has it.
+Needs oracle/_ref/athena_blast (live reference run)."""
 import os
 import re
 import subprocess
@@ -33,7 +34,12 @@ def test_guard_free_division_reproduces_the_gpu_difference_and_the_guard_removes
     assert re.search(r"guard=True: 0 of \d+ cycles differ", out), out
 
 
-def test_device_plm_has_the_guard():
+def test_device_division_has_the_guard_at_every_site():
+    """The range guard lives inside ddiv / drcp / dsqrt (one policy for every call site) and is on by default."""
     src = open(os.path.join(os.path.dirname(TOOL), "..", "..", "athenak_b200", "csrc", "mhd_device.cuh")).read()
-    body = src[src.index("void plm("):src.index("void plm(") + 1600]
-    assert "0x1p-900" in body and "dq2 != 0.0" in body and "dq2 / (dql + dqr)" in body
+    assert re.search(r"#ifndef AKB_DIV_GUARD\s*\n#define AKB_DIV_GUARD 1", src)
+    for fn, cold in (("double drcp(", "drcp_cold(x)"), ("double ddiv(", "ddiv_cold(a, b)"), ("double dsqrt(", "dsqrt_cold(x)")):
+        body = src[src.index(fn):src.index(fn) + 1800]
+        assert "#if AKB_DIV_GUARD" in body and cold in body, fn
+    plm = src[src.index("void plm("):src.index("void plm(") + 600]
+    assert "ddiv(dq2, dql + dqr)" in plm and " / " not in plm.replace("// ", "")

@@ -284,15 +284,16 @@ def test_multi_gpu_nccl_matches_reference():
     assert "MULTIGPU_PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("span", [8, 60, 300])
+@pytest.mark.parametrize("span", [8, 60, 300, 1022, 2000])
 def test_fast_div_sqrt(span):
-    """drcp/ddiv/dsqrt (nvcc's fast paths without the range-test branch) == built-in '/', sqrt,
-    bit for bit, on 2^28 random operands per exponent span."""
+    """drcp/ddiv/dsqrt (nvcc's fast paths + the zero-aware range guard) == built-in '/', sqrt, bit for
+    bit, on 2^28 random operands per exponent span; span 2000 draws the WHOLE double range (subnormals,
+    the denormal floor below 2^-969, +-0, infinities, NaNs, negative sqrt arguments) in every position."""
     from athenak_b200 import lib as _lib
     L = _lib.load()
-    bad = (C.c_long * 3)()
+    bad = (C.c_long * 4)()
     assert L.ak_selftest_divsqrt(1 << 28, 12345 + span, span, bad) == 0
-    assert list(bad) == [0, 0, 0]
+    assert list(bad) == [0, 0, 0, 0]
 
 
 @pytest.mark.parametrize("fused", [True, False])
