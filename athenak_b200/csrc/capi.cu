@@ -362,6 +362,75 @@ int ak_mhd_stage_fused(void *handle, const ak_mhd_arrays *a, int stage, double g
   return ak_mhd_stage_update(handle, a, stage, gam0, gam1, beta_dt, s);
 }
 
+// ---------------------------------------------------------------------------------------
+// Two-kernel stage: flux sweeps (ak_mhd_fluxes) + ONE tail kernel for tasks 14, 1, 5, 17, 27 (and 28 on
+// the last stage), plus the two shell kernels for the outermost layer around SendE/RecvE and the ghost exchange.
+static akb::TailArrays tail_arrays(const akb::Arrays &in, const akb::Arrays &out, bool stage1) {
+  akb::TailArrays T;
+  T.u_in = in.u0; T.u1r = stage1 ? nullptr : in.u1; T.u_out = out.u0; T.u1w = stage1 ? in.u1 : nullptr;
+  T.b_in[0] = in.b0x1f; T.b_in[1] = in.b0x2f; T.b_in[2] = in.b0x3f;
+  T.b1[0] = stage1 ? nullptr : in.b1x1f; T.b1[1] = stage1 ? nullptr : in.b1x2f; T.b1[2] = stage1 ? nullptr : in.b1x3f;
+  T.b_out[0] = out.b0x1f; T.b_out[1] = out.b0x2f; T.b_out[2] = out.b0x3f;
+  T.w_in = in.w0; T.bcc_in = in.bcc0; T.w_out = out.w0; T.bcc_out = out.bcc0;
+  T.flx[0] = in.flx1; T.flx[1] = in.flx2; T.flx[2] = in.flx3;
+  T.e3x1 = in.e3x1; T.e2x1 = in.e2x1; T.e1x2 = in.e1x2; T.e3x2 = in.e3x2; T.e2x3 = in.e2x3; T.e1x3 = in.e1x3;
+  T.e1 = in.e1; T.e2 = in.e2; T.e3 = in.e3;
+  T.mb_size = in.mb_size;
+  return T;
+}
+static int tail_check(Handle *h, const ak_mhd_arrays *a, const ak_mhd_arrays *out, const char *name) {
+  if (h->hydro) return fail(h, std::string(name) + ": MHD handles only");
+  if (!akb::stage_tail_supported(h->g)) return fail(h, std::string(name) + ": needs 3-D blocks of at least 3 cells per direction, nghost >= 2, no FOFC");
+  if (!out) return fail(h, std::string(name) + ": null output arrays");
+  if (out->b0x1f == a->b0x1f || out->b0x2f == a->b0x2f || out->b0x3f == a->b0x3f || out->w0 == a->w0 || out->bcc0 == a->bcc0)
+    return fail(h, std::string(name) + ": the face field and the primitives are written out of place (out->b0x?f, out->w0, out->bcc0 must be other buffers)");
+  return 0;
+}
+
+int ak_mhd_tail_supported(void *handle) {
+  Handle *h = static_cast<Handle *>(handle);
+  return (h && !h->hydro && akb::stage_tail_supported(h->g)) ? 1 : 0;
+}
+
+int ak_mhd_stage_tail(void *handle, const ak_mhd_arrays *a, const ak_mhd_arrays *out, int stage, double gam0, double gam1,
+                      double beta_dt, int want_dt, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_stage_tail")
+  if (tail_check(h, a, out, "ak_mhd_stage_tail")) return 1;
+  if (stage < 1) return fail(h, "ak_mhd_stage_tail: stage is 1-based");
+  if (want_dt && (e = dt_slots_init(h, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_tail", e);
+  const akb::TailArrays T = tail_arrays(A, to_arrays(out), stage == 1);
+  // AKB_TAIL_SPLIT=1: field kernel (corner EMFs + CT) + cell kernel (update + c2p) instead of the single tail kernel
+  static const bool split = [] { const char *v = getenv("AKB_TAIL_SPLIT"); return v && v[0] == '1'; }();
+  if ((e = akb::launch_stage_tail(h->g, h->eos, T, stage == 1, gam0, gam1, beta_dt, h->d_counters, want_dt != 0, h->d_dtmin, split, st)) != cudaSuccess)
+    return cuda_fail(h, "ak_mhd_stage_tail", e);
+  return 0;
+}
+
+int ak_mhd_stage_shell_ct(void *handle, const ak_mhd_arrays *a, const ak_mhd_arrays *out, int stage, double gam0, double gam1,
+                          double beta_dt, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_stage_shell_ct")
+  if (tail_check(h, a, out, "ak_mhd_stage_shell_ct")) return 1;
+  const akb::TailArrays T = tail_arrays(A, to_arrays(out), stage == 1);
+  if ((e = akb::launch_shell_ct(h->g, T, stage == 1, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_shell_ct", e);
+  return 0;
+}
+
+int ak_mhd_stage_shell_c2p(void *handle, const ak_mhd_arrays *a, int *nfloor, double *dt3, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_stage_shell_c2p")
+  if (h->hydro || !akb::stage_tail_supported(h->g)) return fail(h, "ak_mhd_stage_shell_c2p: not available for this handle (see ak_mhd_tail_supported)");
+  if ((e = akb::launch_shell_c2p(h->g, h->eos, A, h->d_counters, dt3 != nullptr, h->d_dtmin, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_shell_c2p", e);
+  if (nfloor) {
+    if ((e = cudaMemcpyAsync(nfloor, h->d_counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_shell_c2p", e);
+    if ((e = cudaMemsetAsync(h->d_counters, 0, 3 * sizeof(int), st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_shell_c2p", e);
+  }
+  if (dt3) {
+    if ((e = dt_slots_fetch(h, dt3, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_shell_c2p", e);
+  } else if (nfloor) {
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_shell_c2p", e);
+  }
+  return 0;
+}
+
 // history sums (src/outputs/history.cpp:78-160,272-372); synchronises the stream
 int ak_hst_sums(void *handle, const ak_mhd_arrays *a, double *sums, int *nhist, ak_stream_t s) {
   AK_PROLOGUE("ak_hst_sums")
@@ -586,6 +655,16 @@ int ak_halo_push_setup(void *plan, int ipeer, int peer_gids_start, double *pu0, 
       if (d.dst_m < 0) return fail(nullptr, "ak_halo_push_setup: neighbour gid below the peer's first gid");
       if (d.comp >= 0 && !P->push_ptrs.p[ipeer][1 + d.comp]) return fail(nullptr, "ak_halo_push_setup: null peer face array");
     }
+  return 0;
+}
+
+// the peer's face-field arrays of the next push (the two-kernel stage rotates its face-field buffers; every rank does so at
+// the same point of the task list, so the sender follows the receiver's rotation with its own copy of the mapped pointers)
+int ak_halo_push_set_faces(void *plan, int ipeer, double *px1f, double *px2f, double *px3f) {
+  akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
+  if (!P || ipeer < 0 || ipeer >= (int)P->peers.size() || ipeer >= AKB_MAX_PUSH_PEERS) return fail(nullptr, "ak_halo_push_set_faces: bad peer");
+  if (!px1f || !px2f || !px3f) return fail(nullptr, "ak_halo_push_set_faces: null peer face array");
+  P->push_ptrs.p[ipeer][1] = px1f; P->push_ptrs.p[ipeer][2] = px2f; P->push_ptrs.p[ipeer][3] = px3f;
   return 0;
 }
 

@@ -43,7 +43,8 @@ struct SolverTraits {
 };
 
 template <int RS>
-__device__ __forceinline__ void riemann_any(const State7 &l, const State7 &r, double bxi, const EosParams &eos, Flux7 &f) {
+__device__ __forceinline__ void riemann_any(const State7 &l, const State7 &r, double bxi, const EosParams &eos, Flux7 &f,
+                                            bool *oor = nullptr) {   // oor: deferred range guard (mhd_device.cuh), threaded through the headline solver
   if constexpr (RS == RS_LLF_ISO) llf_iso(l, r, bxi, eos, f);
   else if constexpr (RS == RS_HLLE_ISO) hlle_iso(l, r, bxi, eos, f);
   else if constexpr (RS == RS_HLLD_ISO) hlld_iso(l, r, bxi, eos, f);
@@ -51,7 +52,7 @@ __device__ __forceinline__ void riemann_any(const State7 &l, const State7 &r, do
   else if constexpr (RS == RS_HYD_HLLE_ISO) hyd_hlle_iso(l, r, eos, f);
   else if constexpr (RS == RS_HYD_ROE_ISO) hyd_roe_iso(l, r, eos, f);
   else if constexpr (rs_is_hydro(RS)) riemann_hyd<RS>(l, r, eos, f);
-  else riemann<RS>(l, r, bxi, eos, f);
+  else riemann<RS>(l, r, bxi, eos, f, oor);
 }
 
 __device__ __forceinline__ void prefetch_l1(const double *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -71,6 +72,47 @@ __device__ __forceinline__ void prefetch_l1(const double *p) { asm volatile("pre
 // STEP = 31, no helper cell.
 template <int RECON>
 struct X1Step { static constexpr int value = (RECON == RECON_PPM4) ? 30 : 31; };
+
+// left state of a face = upper-face state of the cell in lane-1
+template <int RS>
+__device__ __forceinline__ void shift_up_state(const State7 &up, State7 &L) {
+  using T = SolverTraits<RS>;
+  L.d = __shfl_up_sync(0xffffffffu, up.d, 1);
+  L.vx = __shfl_up_sync(0xffffffffu, up.vx, 1);
+  L.vy = __shfl_up_sync(0xffffffffu, up.vy, 1);
+  L.vz = __shfl_up_sync(0xffffffffu, up.vz, 1);
+  if constexpr (T::IDEAL) L.e = __shfl_up_sync(0xffffffffu, up.e, 1);
+  if constexpr (T::MHD) {
+    L.by = __shfl_up_sync(0xffffffffu, up.by, 1);
+    L.bz = __shfl_up_sync(0xffffffffu, up.bz, 1);
+  }
+}
+
+// Cold side of the x1 sweep's deferred range guard: the whole warp repeats reconstruction and Riemann solve with the
+// guarded (IEEE-exact for every operand) operators, re-reading the stencil.  Called warp-uniformly.
+template <int RECON, int RS>
+__device__ __noinline__ void x1_face_guarded(const double *__restrict__ wc, const double *__restrict__ bc, long cc, double bxi,
+                                             bool act, EosParams eos, Flux7 &f) {
+  using T = SolverTraits<RS>;
+  State7 up, lo, L;
+  if constexpr (RECON == RECON_PPM4) {
+    const double *vp[7] = {wc + IDN * cc, wc + IVX * cc, wc + IVY * cc, wc + IVZ * cc, wc + IEN * cc, bc + 1 * cc, bc + 2 * cc};
+    double *upv[7] = {&up.d, &up.vx, &up.vy, &up.vz, &up.e, &up.by, &up.bz};
+    double *lov[7] = {&lo.d, &lo.vx, &lo.vy, &lo.vz, &lo.e, &lo.by, &lo.bz};
+#pragma unroll
+    for (int v = 0; v < T::NV; ++v) {
+      const double *pv = vp[T::member(v)];
+      const double q = __ldg(pv);
+      const double fl = ppm4_iface(__ldg(pv - 2), __ldg(pv - 1), q, __ldg(pv + 1));
+      const double fh = __shfl_down_sync(0xffffffffu, fl, 1);
+      ppm4_mono(q, fl, fh, *upv[T::member(v)], *lov[T::member(v)]);
+    }
+  } else {
+    recon_cell<RECON, 0, T::MHD, T::IDEAL>(wc, bc, cc, 1, eos, up, lo);
+  }
+  shift_up_state<RS>(up, L);
+  if (act) riemann_any<RS>(L, lo, bxi, eos, f);
+}
 
 template <int RECON, int RS>
 __global__ void __launch_bounds__(128, AKB_X1_MINB)
@@ -110,16 +152,24 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
       asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off + (long)AKB_X1_L2PF * g.n1 * g.n2));
     }
   }
+  // Range guard of the guard-free division / square root (mhd_device.cuh), deferred form: the arithmetic below only
+  // accumulates "an operand left the fast path's exact range" into oor; a warp that sees the flag anywhere (a lane's
+  // interface value feeds lane-1, its upper state lane+1) repeats recon + Riemann with the guarded operators in a
+  // separate function that re-reads its inputs, so nothing stays live across the hot path for its sake.
+  bool oor = false;
   State7 up, lo;
+  const bool act = valid && lane != 0 && lane <= STEP && c != 0 && c <= g.nx1 + 1 + 2 * g.next;
+  State7 L;
+  Flux7 f;
+  const double *wc = w0 + (long)m * g.nvar * cc + off, *bc = MHD ? bcc + (long)m * 3 * cc + off : wc;
   if constexpr (RECON == RECON_PPM4) {
-    const double *w = w0 + (long)m * g.nvar * cc + off, *b = MHD ? bcc + (long)m * 3 * cc + off : w;
-    const double *vp[7] = {w + IDN * cc, w + IVX * cc, w + IVY * cc, w + IVZ * cc, w + IEN * cc, b + 1 * cc, b + 2 * cc};
+    const double *vp[7] = {wc + IDN * cc, wc + IVX * cc, wc + IVY * cc, wc + IVZ * cc, wc + IEN * cc, bc + 1 * cc, bc + 2 * cc};
     double q[NV], fl[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const double *pv = vp[T::member(v)];
       q[v] = __ldg(pv);
-      fl[v] = ppm4_iface(__ldg(pv - 2), __ldg(pv - 1), q[v], __ldg(pv + 1));
+      fl[v] = ppm4_iface(__ldg(pv - 2), __ldg(pv - 1), q[v], __ldg(pv + 1), &oor);
     }
     double *upv[7] = {&up.d, &up.vx, &up.vy, &up.vz, &up.e, &up.by, &up.bz};
     double *lov[7] = {&lo.d, &lo.vx, &lo.vy, &lo.vz, &lo.e, &lo.by, &lo.bz};
@@ -129,21 +179,16 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
       ppm4_mono(q[v], fl[v], fh, *upv[T::member(v)], *lov[T::member(v)]);
     }
   } else {
-    recon_cell<RECON, 0, MHD, IDEAL>(w0 + (long)m * g.nvar * cc + off, bcc + (long)m * 3 * cc + off, cc, 1, eos, up, lo);
+    recon_cell<RECON, 0, MHD, IDEAL>(wc, bc, cc, 1, eos, up, lo);
   }
-  State7 L;
-  L.d = __shfl_up_sync(0xffffffffu, up.d, 1);
-  L.vx = __shfl_up_sync(0xffffffffu, up.vx, 1);
-  L.vy = __shfl_up_sync(0xffffffffu, up.vy, 1);
-  L.vz = __shfl_up_sync(0xffffffffu, up.vz, 1);
-  if constexpr (IDEAL) L.e = __shfl_up_sync(0xffffffffu, up.e, 1);
-  if constexpr (MHD) {
-    L.by = __shfl_up_sync(0xffffffffu, up.by, 1);
-    L.bz = __shfl_up_sync(0xffffffffu, up.bz, 1);
+  shift_up_state<RS>(up, L);
+  if (act) riemann_any<RS>(L, lo, bxi, eos, f, &oor);
+  if (__any_sync(0xffffffffu, oor)) {     // results come back through a separate object so that f itself stays in registers
+    Flux7 fg;
+    x1_face_guarded<RECON, RS>(wc, bc, cc, bxi, act, eos, fg);
+    f = fg;
   }
-  if (!valid || lane == 0 || lane > STEP || c == 0 || c > g.nx1 + 1 + 2 * g.next) return;
-  Flux7 f;
-  riemann_any<RS>(L, lo, bxi, eos, f);
+  if (!act) return;
   const long fs = (long)g.n3 * g.n2 * (g.n1 + 1);
   double *fp = flx + (long)m * g.nvar * fs + ((long)k * g.n2 + j) * (g.n1 + 1) + i;
   fp[IDN * fs] = f.d;
@@ -183,7 +228,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int RECON>
-__device__ __forceinline__ void recon_ring_var(const double *__restrict__ rv, int b0, double &q_up, double &q_lo) {
+__device__ __forceinline__ void recon_ring_var(const double *__restrict__ rv, int b0, double &q_up, double &q_lo, bool *oor = nullptr) {
   // rv: this thread's ring for one variable (slot stride MARCH_THREADS); b0 = slot of row c-2
   int b1 = b0 + 1; if (b1 >= MARCH_SLOTS) b1 -= MARCH_SLOTS;
   int b2 = b1 + 1; if (b2 >= MARCH_SLOTS) b2 -= MARCH_SLOTS;
@@ -191,7 +236,7 @@ __device__ __forceinline__ void recon_ring_var(const double *__restrict__ rv, in
   int b4 = b3 + 1; if (b4 >= MARCH_SLOTS) b4 -= MARCH_SLOTS;
   const double qm2 = rv[b0 * MARCH_THREADS], qm1 = rv[b1 * MARCH_THREADS], q = rv[b2 * MARCH_THREADS];
   const double qp1 = rv[b3 * MARCH_THREADS], qp2 = rv[b4 * MARCH_THREADS];
-  if constexpr (RECON == RECON_PPM4) ppm4(qm2, qm1, q, qp1, qp2, q_up, q_lo);
+  if constexpr (RECON == RECON_PPM4) ppm4(qm2, qm1, q, qp1, qp2, q_up, q_lo, oor);
   else if constexpr (RECON == RECON_PPMX) ppmx(qm2, qm1, q, qp1, qp2, q_up, q_lo);
   else if constexpr (RECON == RECON_TENO) teno(qm2, qm1, q, qp1, qp2, q_up, q_lo);
   else wenoz(qm2, qm1, q, qp1, qp2, q_up, q_lo);
@@ -199,13 +244,13 @@ __device__ __forceinline__ void recon_ring_var(const double *__restrict__ rv, in
 
 template <int RECON, int RS>
 __device__ __forceinline__ void recon_ring_cell(const double *__restrict__ ring, int b0, const EosParams &eos,
-                                                State7 &up, State7 &lo) {
+                                                State7 &up, State7 &lo, bool *oor = nullptr) {
   using T = SolverTraits<RS>;
   constexpr int VS = MARCH_SLOTS * MARCH_THREADS;   // ring stride between variables
   double *upv[7] = {&up.d, &up.vx, &up.vy, &up.vz, &up.e, &up.by, &up.bz};
   double *lov[7] = {&lo.d, &lo.vx, &lo.vy, &lo.vz, &lo.e, &lo.by, &lo.bz};
 #pragma unroll
-  for (int v = 0; v < T::NV; ++v) recon_ring_var<RECON>(ring + v * VS, b0, *upv[T::member(v)], *lov[T::member(v)]);
+  for (int v = 0; v < T::NV; ++v) recon_ring_var<RECON>(ring + v * VS, b0, *upv[T::member(v)], *lov[T::member(v)], oor);
   if constexpr (RECON == RECON_PPMX || RECON == RECON_WENOZ || RECON == RECON_TENO) {   // recon.hpp:78-108
     up.d = dmax(up.d, eos.dfloor);
     lo.d = dmax(lo.d, eos.dfloor);
@@ -251,6 +296,28 @@ __device__ __forceinline__ void ppm4_ring_cell(const double *__restrict__ ring, 
   }
 }
 
+// Cold side of the march kernels' deferred range guard (see flux_x1_kernel): one face repeated with the guarded operators.
+// The left state comes back from the thread's shared-memory copy (the hot path does not keep it live for this), the cell's
+// own states are re-reconstructed from the ring.
+template <int RECON, int RS>
+__device__ __noinline__ void march_face_guarded(const double *__restrict__ ring, int b0, const double *__restrict__ lsm, double bni,
+                                                EosParams eos, State7 &up, Flux7 &fx) {
+  State7 L, lo;
+  L.d = lsm[0 * MARCH_THREADS]; L.vx = lsm[1 * MARCH_THREADS]; L.vy = lsm[2 * MARCH_THREADS]; L.vz = lsm[3 * MARCH_THREADS];
+  L.e = lsm[4 * MARCH_THREADS]; L.by = lsm[5 * MARCH_THREADS]; L.bz = lsm[6 * MARCH_THREADS];
+  recon_ring_cell<RECON, RS>(ring, b0, eos, up, lo);
+  riemann_any<RS>(L, lo, bni, eos, fx);
+}
+template <int RECON, int RS>
+__device__ __noinline__ void march_recon_guarded(const double *__restrict__ ring, int b0, EosParams eos, State7 &up) {
+  State7 lo;
+  recon_ring_cell<RECON, RS>(ring, b0, eos, up, lo);
+}
+__device__ __forceinline__ void store_left_state(double *lsm, const State7 &s) {
+  lsm[0 * MARCH_THREADS] = s.d; lsm[1 * MARCH_THREADS] = s.vx; lsm[2 * MARCH_THREADS] = s.vy; lsm[3 * MARCH_THREADS] = s.vz;
+  lsm[4 * MARCH_THREADS] = s.e; lsm[5 * MARCH_THREADS] = s.by; lsm[6 * MARCH_THREADS] = s.bz;
+}
+
 // Addressing is kept out of the register file on purpose: the block's (MeshBlock, segment) come
 // from blockIdx.y, so every array base is block-uniform, and a thread carries only two 32-bit
 // running offsets (cell, face) that advance by the sweep stride.  The earlier version carried a
@@ -268,7 +335,7 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
   constexpr bool MHD = T::MHD;
   constexpr bool IDEAL = T::IDEAL;
   constexpr int NV = T::NV;
-  extern __shared__ double ring_all[];   // RING: NV * MARCH_SLOTS * MARCH_THREADS doubles (dynamic)
+  extern __shared__ double ring_all[];   // RING: (NV * MARCH_SLOTS + 7) * MARCH_THREADS doubles (dynamic): ring + left-state copy
   const int nc = g.nx1 + 2 * g.ext1;
   const int nt = (DIR == 1) ? g.nx3 + 2 * g.ext3 : g.nx2 + 2 * g.ext2;
   const int m = blockIdx.y / nseg, seg = blockIdx.y - m * nseg;       // block-uniform
@@ -325,8 +392,12 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       ppm4_ring_iface(ring, 0, fl);
       ppm4_ring_cell(ring, 0, fl, L, lo_unused);
     } else {
-      recon_ring_cell<RECON, RS>(ring, 0, eos, L, lo_unused);
+      bool oor0 = false;      // deferred range guard (mhd_device.cuh): repeat with the guarded operators when flagged
+      recon_ring_cell<RECON, RS>(ring, 0, eos, L, lo_unused, &oor0);
+      if (oor0) { State7 lg; march_recon_guarded<RECON, RS>(ring, 0, eos, lg); L = lg; }
     }
+    double *lsm = ring_all + NV * VS + threadIdx.x;     // this thread's copy of the left state, for the cold path only
+    store_left_state(lsm, L);
     int b0 = 1;                       // slot of row c-2 for the next cell (c = f_lo)
     for (int f = f_lo; f <= f_hi; ++f) {
       co += s;                        // cell c = f
@@ -340,12 +411,19 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       cp_async_commit();
       cp_async_wait<MARCH_PF>();
       State7 up, lo;
+      bool oor = false;
       if constexpr (RECON == RECON_PPM4 && AKB_MARCH_CARRY && MHD && IDEAL) ppm4_ring_cell(ring, b0, fl, up, lo);
-      else recon_ring_cell<RECON, RS>(ring, b0, eos, up, lo);
+      else recon_ring_cell<RECON, RS>(ring, b0, eos, up, lo, &oor);
       Flux7 fx;
       double bni = 0.0;
       if constexpr (MHD) bni = __ldg(bnb + fo);
-      riemann_any<RS>(L, lo, bni, eos, fx);
+      riemann_any<RS>(L, lo, bni, eos, fx, &oor);
+      if (oor) {       // cold: an operand left the fast path's exact range (separate result objects keep up / fx in registers)
+        State7 ug; Flux7 fg;
+        march_face_guarded<RECON, RS>(ring, b0, lsm, bni, eos, ug, fg);
+        up = ug; fx = fg;
+      }
+      store_left_state(lsm, up);
       double *fp = fb + fo;
       fp[IDN * fsz] = fx.d;
       fp[ivx * fsz] = fx.mx;
@@ -370,7 +448,9 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       Flux7 fx;
       double bni = 0.0;
       if constexpr (MHD) bni = __ldg(bnb + fo);
-      riemann_any<RS>(L, lo, bni, eos, fx);
+      bool oor = false;
+      riemann_any<RS>(L, lo, bni, eos, fx, &oor);
+      if (oor) riemann_any<RS>(L, lo, bni, eos, fx);
       double *fp = fb + fo;
       fp[IDN * fsz] = fx.d;
       fp[ivx * fsz] = fx.mx;
@@ -476,7 +556,7 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
     st2 = sf->s[0];
     if (g.three_d) { cudaStreamWaitEvent(sf->s[1], sf->fork, 0); st3 = sf->s[1]; }
   }
-  const size_t smem = (RECON >= RECON_PPM4) ? sizeof(double) * NV * MARCH_SLOTS * MARCH_THREADS : 0;
+  const size_t smem = (RECON >= RECON_PPM4) ? sizeof(double) * (NV * MARCH_SLOTS + 7) * MARCH_THREADS : 0;   // ring + left-state copy
   {  // x1
     constexpr int STEP = X1Step<RECON>::value;
     const unsigned nc = g.nx1 + 2 + 2 * g.next + (RECON == RECON_PPM4 ? 1 : 0), plane = (unsigned)(g.nx2 + 2 * g.ext2) * nc;

@@ -213,6 +213,15 @@ class MHD {  // state owner + tasks
   std::vector<int> mb_bcs_h;
   double *coarse_u0 = nullptr;
   double *coarse_b0[3] = {nullptr, nullptr, nullptr};     // MHD: coarse face fields (mhd.cpp:163-176)
+  // Two-kernel stage (ak_mhd_stage_tail): the face field and the primitives are written out of place, so the state owner
+  // keeps one spare buffer of each and rotates the pointers in `a` after every stage; at stage 1 the old b0 buffers BECOME b1
+  // (no CopyCons pass over the face field).  Peer-memory pushes follow the rotation through per-peer copies of the same
+  // three buffer sets (every rank rotates at the same point of the task list).
+  bool tail = false;
+  double *spare_b[3] = {nullptr, nullptr, nullptr}, *spare_w = nullptr, *spare_bcc = nullptr;
+  ak_mhd_arrays tail_out;                 // outputs of the stage in flight (u0 in place, b0x?f / w0 / bcc0 = the spares)
+  struct PeerFaces { double *b[3][3]; };  // [set][component]: a peer's three face-field buffer sets, in MY rotation order
+  std::vector<PeerFaces> peer_faces;      // set 0 = its current b0, 1 = its b1, 2 = its spare
 
   MHD(const ak_mhd_cfg &c, const double *mb_size, const int *nghbr, int rank, int nranks_, int gids_start, int nmb_total)
       : cfg(c), my_rank(rank), nranks(nranks_), gids_start_(gids_start) {
@@ -241,6 +250,14 @@ class MHD {  // state owner + tasks
     a.mb_size = ms;
     d_dt = alloc(1);
     if (hydro ? ak_hydro_create(&cfg, &h) : ak_mhd_create(&cfg, &h)) Fatal(__FILE__, __LINE__, ak_last_error(nullptr));
+    {
+      const char *env = std::getenv("AKB_TAIL");
+      tail = !hydro && !cfg.fofc && ak_mhd_tail_supported(h) && !(env && env[0] == '0');
+      if (tail) {
+        spare_b[0] = alloc(n_f1); spare_b[1] = alloc(n_f2); spare_b[2] = alloc(n_f3);
+        spare_w = alloc(n_u); spare_bcc = alloc(nm * 3 * cc);
+      }
+    }
     nghbr_h.assign(nghbr, nghbr + nm * 56 * 4);
     if (ak_halo_create(&cfg, nghbr, rank, gids_start, &plan)) Fatal(__FILE__, __LINE__, ak_last_error(nullptr));
     for (int p = 0; p < ak_halo_npeers(plan); ++p) {
@@ -273,7 +290,7 @@ class MHD {  // state owner + tasks
   // grouped ncclSend/ncclRecv path in place.  AKB_PEER_PUSH=0 disables it.
   // h[0..3] u0 / face fields, h[4] flags, h[5] EMF receive buffer; emf_rank/emf_off: where each of MY peers'
   // EMF messages lands inside that buffer (doubles from its base)
-  struct PeerInfo { cudaIpcMemHandle_t h[6]; int gids_start; int ok; int npeers; int pad;
+  struct PeerInfo { cudaIpcMemHandle_t h[12]; int gids_start; int ok; int npeers; int pad;
                     int emf_rank[AKB_MAX_PUSH_PEERS_HOST]; long emf_off[AKB_MAX_PUSH_PEERS_HOST]; };
   void SetupPeerPush(int gids_start) {
     Nccl &n = Nccl::get();
@@ -288,6 +305,11 @@ class MHD {  // state owner + tasks
     double *arr[4] = {a.u0, a.b0x1f, a.b0x2f, a.b0x3f};
     for (int q = 0; q < 4 && ok; ++q)
       if (arr[q] && cudaIpcGetMemHandle(&mine.h[q], arr[q]) != cudaSuccess) ok = 0;
+    if (tail) {      // the two other face-field buffer sets of the rotation: h[6..8] = b1, h[9..11] = spare
+      double *more[6] = {a.b1x1f, a.b1x2f, a.b1x3f, spare_b[0], spare_b[1], spare_b[2]};
+      for (int q = 0; q < 6 && ok; ++q)
+        if (cudaIpcGetMemHandle(&mine.h[6 + q], more[q]) != cudaSuccess) ok = 0;
+    }
     if (ok && cudaIpcGetMemHandle(&mine.h[4], d_flags) != cudaSuccess) ok = 0;
     if ((int)peers.size() > AKB_MAX_PUSH_PEERS_HOST) ok = 0;
     double *emf_base = nullptr;
@@ -315,15 +337,21 @@ class MHD {  // state owner + tasks
     std::vector<unsigned long long *> pflags(peers.size(), nullptr);
     for (size_t p = 0; p < peers.size() && ok; ++p) {
       const PeerInfo &pi = all[peers[p].rank];
-      void *ptr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-      for (int q = 0; q < 6 && ok; ++q) {
+      void *ptr[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+      for (int q = 0; q < 12 && ok; ++q) {
         if ((q >= 1 && q <= 3 || q == 5) && hydro) continue;
+        if (q >= 6 && !tail) continue;
         if (cudaIpcOpenMemHandle(&ptr[q], pi.h[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
         ipc_opened.push_back(ptr[q]);
       }
       if (!ok) break;
       if (ak_halo_push_setup(plan, (int)p, pi.gids_start, (double *)ptr[0], (double *)ptr[1], (double *)ptr[2], (double *)ptr[3])) ok = 0;
       pflags[p] = (unsigned long long *)ptr[4];
+      if (tail) {
+        PeerFaces pf;
+        for (int c = 0; c < 3; ++c) { pf.b[0][c] = (double *)ptr[1 + c]; pf.b[1][c] = (double *)ptr[6 + c]; pf.b[2][c] = (double *)ptr[9 + c]; }
+        peer_faces.push_back(pf);
+      }
       if (!hydro) {      // my segment in the peer's EMF receive buffer
         peers[p].pemf = nullptr;
         for (int q = 0; q < pi.npeers; ++q)
@@ -431,7 +459,17 @@ class MHD {  // state owner + tasks
       }
       return;
     }
-    if (fused) {
+    if (fused && tail) {     // two-kernel stage: flux sweeps + ONE tail kernel; the outermost layer waits for the EMF correction
+      TaskID f = tl->AddTask(&MHD::StageFluxes, this, none);                // task 2
+      TaskID t = tl->AddTask(&MHD::StageTail, this, f);                     // tasks 14, 1, 5, 17, 27 (28) for everything but the outermost layer
+      TaskID se = tl->AddTask(&MHD::SendE, this, t);                        // tasks 15/16 on the surface EMFs the tail kernel left in HBM
+      TaskID re = tl->AddTask(&MHD::RecvE, this, se);
+      TaskID sc = tl->AddTask(&MHD::ShellCT, this, re);                     // task 17 for the faces that touch the block surface
+      TaskID su = tl->AddTask(&MHD::SendUB, this, sc);
+      TaskID ru = tl->AddTask(&MHD::RecvUB, this, su);
+      TaskID bc = tl->AddTask(&MHD::ApplyPhysicalBCs, this, ru);
+      tl->AddTask(&MHD::ShellC2PNewDt, this, bc);                           // tasks 27 (28) for the ghost zones + the outermost layer
+    } else if (fused) {
       TaskID f = tl->AddTask(&MHD::StageFluxEmf, this, none);
       TaskID se = tl->AddTask(&MHD::SendE, this, f);
       TaskID re = tl->AddTask(&MHD::RecvE, this, se);
@@ -511,6 +549,56 @@ class MHD {  // state owner + tasks
   }
   TaskStatus StageUpdate(Driver *pd, int stage) {    // tasks 1 + 5 + 17
     AK_CHECK(h, ak_mhd_stage_update(h, &a, stage, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, st));
+    launches += 1;
+    return TaskStatus::complete;
+  }
+  // ---- two-kernel stage -------------------------------------------------------------------
+  TaskStatus StageFluxes(Driver *pd, int stage) {
+    AK_CHECK(h, ak_mhd_fluxes(h, &a, st));
+    launches += nsweeps();
+    SignalFree();    // the sweeps were the last readers of the b0 ghost faces (u0 ghosts: the shell c2p of the previous stage)
+    return TaskStatus::complete;
+  }
+  TaskStatus StageTail(Driver *pd, int stage) {
+    tail_out = a;
+    tail_out.b0x1f = spare_b[0]; tail_out.b0x2f = spare_b[1]; tail_out.b0x3f = spare_b[2];
+    tail_out.w0 = spare_w; tail_out.bcc0 = spare_bcc;
+    AK_CHECK(h, ak_mhd_stage_tail(h, &a, &tail_out, stage, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt,
+                                  stage == pd->nexp_stages ? 1 : 0, st));
+    launches += 1;
+    return TaskStatus::complete;
+  }
+  TaskStatus ShellCT(Driver *pd, int stage) {
+    AK_CHECK(h, ak_mhd_stage_shell_ct(h, &a, &tail_out, stage, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, st));
+    launches += 1;
+    // rotate: the outputs become the state; at stage 1 the old b0 buffers become the register b1 (CopyCons without a copy)
+    double **cur[3] = {&a.b0x1f, &a.b0x2f, &a.b0x3f}, **reg[3] = {&a.b1x1f, &a.b1x2f, &a.b1x3f};
+    for (int c = 0; c < 3; ++c) {
+      double *oc = *cur[c], *orr = *reg[c], *osp = spare_b[c];
+      *cur[c] = osp;
+      if (stage == 1) { *reg[c] = oc; spare_b[c] = orr; } else { spare_b[c] = oc; }
+      for (auto &pf : peer_faces) {       // the same permutation on every neighbour's buffer sets
+        double *pc = pf.b[0][c], *pr = pf.b[1][c], *ps = pf.b[2][c];
+        pf.b[0][c] = ps;
+        if (stage == 1) { pf.b[1][c] = pc; pf.b[2][c] = pr; } else { pf.b[2][c] = pc; }
+      }
+    }
+    std::swap(a.w0, spare_w);
+    std::swap(a.bcc0, spare_bcc);
+    for (size_t p = 0; p < peer_faces.size(); ++p)
+      AK_CHECK(nullptr, ak_halo_push_set_faces(plan, (int)p, peer_faces[p].b[0][0], peer_faces[p].b[0][1], peer_faces[p].b[0][2]));
+    return TaskStatus::complete;
+  }
+  TaskStatus ShellC2PNewDt(Driver *pd, int stage) {
+    if (stage != pd->nexp_stages) {
+      AK_CHECK(h, ak_mhd_stage_shell_c2p(h, &a, nullptr, nullptr, st));
+    } else {
+      int nf[3];
+      double dt3[3];
+      AK_CHECK(h, ak_mhd_stage_shell_c2p(h, &a, nf, dt3, st));
+      for (int q = 0; q < 3; ++q) nfloor[q] += nf[q];
+      dtnew = MinDt(dt3);
+    }
     launches += 1;
     return TaskStatus::complete;
   }
@@ -918,6 +1006,15 @@ int ak_sim_get_state(void *sim, double *u0, double *b1f, double *b2f, double *b3
   if (e == cudaSuccess) e = cudaMemcpyAsync(b1f, m->a.b0x1f, m->n_f1 * 8, cudaMemcpyDeviceToHost, m->st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(b2f, m->a.b0x2f, m->n_f2 * 8, cudaMemcpyDeviceToHost, m->st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(b3f, m->a.b0x3f, m->n_f3 * 8, cudaMemcpyDeviceToHost, m->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(m->st);
+  return e == cudaSuccess ? 0 : 1;
+}
+/* primitives and cell-centred field of the current state, ghost zones included (test / diagnostic read-back) */
+int ak_sim_get_prim(void *sim, double *w0, double *bcc0) {
+  auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
+  cudaError_t e = cudaMemcpyAsync(w0, m->a.w0, m->n_u * 8, cudaMemcpyDeviceToHost, m->st);
+  if (e == cudaSuccess && !m->hydro && bcc0)
+    e = cudaMemcpyAsync(bcc0, m->a.bcc0, (m->n_u / m->nvar) * 3 * 8, cudaMemcpyDeviceToHost, m->st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(m->st);
   return e == cudaSuccess ? 0 : 1;
 }

@@ -58,4 +58,25 @@ cudaError_t launch_fofc(const Geom &g, const EosParams &eos, const Arrays &a, do
 inline int internal_rsolver(int rsolver, int eos) { return rsolver + (eos == 1 ? 20 : 0); }
 cudaError_t launch_copy(const double *src, double *dst, long n, cudaStream_t st);
 
+// fused stage tail (stage_tail.cu): corner EMFs + conserved update + CT + ConsToPrim (+ new dt) in one kernel, out of place
+// for the face field and the primitives; shell kernels for the outermost layer
+struct TailArrays {
+  const double *u_in, *u1r;          // u1r: register copy read at stages > 1 (nullptr at stage 1)
+  double *u_out, *u1w;               // u1w: stage-1 save of the old state (nullptr otherwise, or when the host rotates u too)
+  const double *b_in[3], *b1[3];     // b1 == nullptr at stage 1 (the register IS the old field)
+  double *b_out[3];
+  const double *w_in, *bcc_in;
+  double *w_out, *bcc_out;
+  const double *flx[3];
+  const double *e3x1, *e2x1, *e1x2, *e3x2, *e2x3, *e1x3;
+  double *e1, *e2, *e3;
+  const double *mb_size;
+};
+bool stage_tail_supported(const Geom &g);
+cudaError_t launch_stage_tail(const Geom &g, const EosParams &eos, const TailArrays &A, bool stage1, double gam0, double gam1,
+                              double beta_dt, int *counters, bool newdt, unsigned long long *dtmin, bool split, cudaStream_t st);
+cudaError_t launch_shell_ct(const Geom &g, const TailArrays &A, bool stage1, double gam0, double gam1, double beta_dt, cudaStream_t st);
+cudaError_t launch_shell_c2p(const Geom &g, const EosParams &eos, const Arrays &a, int *counters, bool newdt, unsigned long long *dtmin,
+                             cudaStream_t st);
+
 }  // namespace akb

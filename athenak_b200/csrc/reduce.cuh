@@ -15,7 +15,7 @@ __device__ __forceinline__ void atomic_min_pos(unsigned long long *addr, double 
 // DT_SLOTS slots (chosen by block index) to keep same-address atomic traffic low; the host
 // takes the min over the slots.  All threads of the block must call it.
 __device__ __forceinline__ void block_min3(double d1, double d2, double d3, unsigned long long *__restrict__ dtmin) {
-  __shared__ double sm[3][8];
+  __shared__ double sm[3][32];    // up to 1024 threads per block
   for (int s = 16; s > 0; s >>= 1) {
     d1 = dmin(d1, __shfl_xor_sync(0xffffffffu, d1, s));
     d2 = dmin(d2, __shfl_xor_sync(0xffffffffu, d2, s));

@@ -34,7 +34,7 @@ __device__ __forceinline__ double rnd(unsigned long long &st, int span) {
 
 __global__ void selftest_kernel(long n, unsigned long long seed, int span, unsigned long long *bad) {
   unsigned long long st = seed ^ (0x632be59bd9b4e019ULL * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1));
-  unsigned long long b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  unsigned long long b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0;
   for (long q = blockIdx.x * (long)blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
     double a = rnd(st, span), b = rnd(st, span);
     if ((q & 63) == 0) a = 0.0;                       // exact-zero numerators are common on this path
@@ -43,6 +43,7 @@ __global__ void selftest_kernel(long n, unsigned long long seed, int span, unsig
     volatile double vsb = sb;
     const double r_ref = 1.0 / vb, q_ref = va / vb, s_ref = sqrt(vsb);
     auto differ = [](double x, double y) { return (x != x || y != y) ? ((x != x) != (y != y)) : (__double_as_longlong(x) != __double_as_longlong(y)); };
+    auto differ_v = [&](double x, double y) { return (x == 0.0 && y == 0.0) ? false : differ(x, y); };   // deferred form: the sign of a zero quotient is not kept
     b0 += differ(akb::drcp(b), r_ref);
     b1 += differ(akb::ddiv(a, b), q_ref);
     b2 += differ(akb::dsqrt(sb), s_ref);
@@ -51,25 +52,31 @@ __global__ void selftest_kernel(long n, unsigned long long seed, int span, unsig
       volatile double vy = ys[q % 6];
       const double y = vy, ry = 1.0 / vy, d_ref = va / vy;
       b3 += differ(akb::div_by(a, y, ry), d_ref);
+      // deferred form of the guard (flux sweeps, fused stage tail): whenever the flag stays clear the fast result must be the
+      // IEEE one (up to the sign of a zero); a set flag sends the caller to the guarded operators checked above
+      bool o1 = false, o2 = false, o3 = false, o4 = false;
+      const double r1 = akb::drcp(b, &o1), r2 = akb::ddiv(a, b, &o2), r3 = akb::dsqrt(sb, &o3), r4 = akb::div_by(a, y, ry, &o4);
+      b4 += (!o1 && differ_v(r1, r_ref)) + (!o2 && differ_v(r2, q_ref)) + (!o3 && differ_v(r3, s_ref)) + (!o4 && differ_v(r4, d_ref));
     }
   }
   if (b0) atomicAdd(bad + 0, b0);
   if (b1) atomicAdd(bad + 1, b1);
   if (b2) atomicAdd(bad + 2, b2);
   if (b3) atomicAdd(bad + 3, b3);
+  if (b4) atomicAdd(bad + 4, b4);
 }
 
 }  // namespace
 
 extern "C" int ak_selftest_divsqrt(long n, unsigned long long seed, int exponent_span, long *mismatches) {
   unsigned long long *d = nullptr;
-  if (cudaMalloc(&d, 4 * sizeof(unsigned long long)) != cudaSuccess) return 1;
-  cudaMemset(d, 0, 4 * sizeof(unsigned long long));
+  if (cudaMalloc(&d, 5 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+  cudaMemset(d, 0, 5 * sizeof(unsigned long long));
   selftest_kernel<<<148 * 8, 256>>>(n, seed, exponent_span, d);
-  unsigned long long h[4];
+  unsigned long long h[5];
   cudaError_t e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
   cudaFree(d);
   if (e != cudaSuccess) return 1;
-  for (int q = 0; q < 4; ++q) mismatches[q] = (long)h[q];
+  for (int q = 0; q < 5; ++q) mismatches[q] = (long)h[q];
   return 0;
 }

@@ -99,6 +99,11 @@ def load():
         "ak_hydro_new_dt": [vp, ap, _dp, vp],
         "ak_hydro_stage_fused": [vp, ap, ip, d, d, d, vp],
         "ak_hydro_cons2prim_newdt": [vp, ap, C.POINTER(C.c_int), _dp, vp],
+        "ak_mhd_tail_supported": [vp],
+        "ak_mhd_stage_tail": [vp, ap, ap, ip, d, d, d, ip, vp],
+        "ak_mhd_stage_shell_ct": [vp, ap, ap, ip, d, d, d, vp],
+        "ak_mhd_stage_shell_c2p": [vp, ap, C.POINTER(C.c_int), _dp, vp],
+        "ak_halo_push_set_faces": [vp, ip, vp, vp, vp],
         "ak_halo_create": [C.POINTER(MhdCfg), C.POINTER(C.c_int), ip, ip, C.POINTER(vp)],
         "ak_halo_destroy": [vp],
         "ak_halo_npeers": [vp],
@@ -155,6 +160,7 @@ def load():
         "ak_sim_comm_init": [vp, vp],
         "ak_sim_set_state": [vp, vp, vp, vp, vp],
         "ak_sim_get_state": [vp, vp, vp, vp, vp],
+        "ak_sim_get_prim": [vp, vp, vp],
         "ak_sim_initialize": [vp],
         "ak_sim_execute": [vp, ip],
         "ak_sim_sync": [vp],
@@ -189,7 +195,7 @@ def load():
 
 EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_cons", "ak_mhd_fluxes",
             "ak_mhd_rk_update", "ak_mhd_corner_e", "ak_mhd_ct", "ak_mhd_cons2prim", "ak_mhd_new_dt",
-            "ak_mhd_stage_fused", "ak_mhd_stage_flux_emf", "ak_mhd_fofc", "ak_mhd_set_stage", "ak_mhd_stage_begin", "ak_mhd_stage_update", "ak_mhd_cons2prim_newdt", "ak_halo_create", "ak_halo_destroy",
+            "ak_mhd_stage_fused", "ak_mhd_tail_supported", "ak_mhd_stage_tail", "ak_mhd_stage_shell_ct", "ak_mhd_stage_shell_c2p", "ak_halo_push_set_faces", "ak_mhd_stage_flux_emf", "ak_mhd_fofc", "ak_mhd_set_stage", "ak_mhd_stage_begin", "ak_mhd_stage_update", "ak_mhd_cons2prim_newdt", "ak_halo_create", "ak_halo_destroy",
             "ak_halo_npeers", "ak_halo_peer", "ak_halo_descs", "ak_halo_local_cc", "ak_halo_local_fc",
             "ak_halo_pack_cc", "ak_halo_unpack_cc", "ak_halo_pack_fc", "ak_halo_unpack_fc",
             "ak_halo_emf_peer", "ak_halo_emf_pack_local", "ak_halo_emf_pack", "ak_halo_emf_sumavg",
@@ -197,7 +203,7 @@ EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_con
             "ak_smr_coarse_cells", "ak_smr_counts", "ak_smr_restrict_cc", "ak_smr_exchange_cc", "ak_smr_prolongate_cc", "ak_smr_prolongate_cc_steps", "ak_smr_flux_correct_cc", "ak_smr_coarse_faces", "ak_smr_restrict_fc", "ak_smr_exchange_fc", "ak_smr_prolongate_fc_steps", "ak_smr_emf_correct", "ak_smr_fc_tables", "ak_mesh_last_error", "ak_mesh_info", "ak_mesh_tables",
             "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast", "ak_pgen_orszag_tang", "ak_selftest_divsqrt", "ak_peak_fp64",
             "ak_sim_create", "ak_sim_destroy", "ak_sim_set_levels", "ak_nccl_unique_id", "ak_sim_comm_init", "ak_sim_set_state",
-            "ak_sim_get_state", "ak_sim_initialize", "ak_sim_execute", "ak_sim_sync", "ak_sim_status", "ak_sim_arrays",
+            "ak_sim_get_state", "ak_sim_get_prim", "ak_sim_initialize", "ak_sim_execute", "ak_sim_sync", "ak_sim_status", "ak_sim_arrays",
             "ak_sim_set_bcs", "ak_bcs_create", "ak_bcs_destroy", "ak_bcs_last_error", "ak_bcs_strictly_periodic",
             "ak_bcs_hydro", "ak_bcs_bfield", "ak_bcs_apply",
             "ak_hst_sums", "ak_halo_emf_rbuf", "ak_halo_push_setup", "ak_halo_push_flags", "ak_halo_push_commit", "ak_halo_push",

@@ -83,6 +83,14 @@ class Simulation:
             raise _lib.EngineError("ak_sim_get_state failed")
         return out
 
+    def get_prim(self):
+        """(w0, bcc0) of the current state as numpy arrays, ghost zones included (bcc0 is None for the hydro twin)."""
+        w0 = np.empty(self.shapes[0])
+        bcc = None if self.hydro else np.empty((self.shapes[0][0], 3) + tuple(self.shapes[0][2:]))
+        if self.L.ak_sim_get_prim(self.h, self._ptr(w0), self._ptr(bcc)):
+            raise _lib.EngineError("ak_sim_get_prim failed")
+        return w0, bcc
+
     def initialize(self):
         self.L.ak_sim_initialize(self.h)
 

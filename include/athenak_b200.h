@@ -122,6 +122,33 @@ int ak_mhd_stage_update(void *h, const ak_mhd_arrays *a, int stage, double gam0,
                         double beta_dt, ak_stream_t s);
 int ak_mhd_stage_fused(void *h, const ak_mhd_arrays *a, int stage, double gam0, double gam1,
                        double beta_dt, void *halo_plan, ak_stream_t s);
+
+/* ---- the two-kernel stage (north star: "one or two hand-written kernels" per MeshBlock update) --------------------------
+ * Kernel 1 = ak_mhd_fluxes (task 2: reconstruction + Riemann solve, three sweeps in one forked launch group).
+ * Kernel 2 = ak_mhd_stage_tail: tasks 14 (MHD::CornerE, mhd_corner_e.cpp:206-414), 1 (CopyCons, mhd_tasks.cpp:162-170),
+ * 5 (RKUpdate, mhd_update.cpp:24-84), 17 (CT, mhd_ct.cpp:23-80), 27 (ConToPrim, eos/ideal_mhd.cpp:30-134,
+ * isothermal_mhd.cpp:20-135) and, with want_dt = 1, the reduction of 28 (NewTimeStep, mhd_newdt.cpp:31-174) in ONE launch:
+ * corner EMFs never leave the chip except within two edges of the block surface.  3-D blocks, same-level mesh, no FOFC
+ * (ak_mhd_tail_supported says whether the handle qualifies; otherwise use the per-task or ak_mhd_stage_* calls above).
+ *
+ * in  a:   u0, u1 (read at stage > 1; at stage 1 its active cells receive the old u0, as CopyCons does), b0x?f, b1x?f
+ *          (stage > 1), w0, bcc0, flx?, the six face EMFs; e1,e2,e3 are WRITTEN within two edges of the block surface.
+ * out out: u0 (may be a->u0: updated in place), b0x?f, w0, bcc0 -- these three MUST be other buffers than a's: neighbouring
+ *          tiles still read the old values.  The caller rotates its pointers afterwards (std::swap on the Views); at
+ *          stage 1 the old b0 buffers ARE b1 from then on, so no face-field copy is made.
+ * The tail kernel finishes every cell and face that does not touch the block surface.  The rest needs other blocks:
+ *   SendE/RecvE on a->e1,e2,e3 (ak_halo_emf_*), then
+ *   ak_mhd_stage_shell_ct  : task 17 for the faces with an edge on the block surface (same in / out convention), then
+ *   the ghost exchange of out->u0, out->b0x?f and the physical boundaries, then
+ *   ak_mhd_stage_shell_c2p : task 27 for the ghost zones and the outermost active layer of the NEW state a (= the rotated
+ *          pointers); nfloor (3 ints) and dt3 (3 doubles), when not NULL, return the floor counters and the new-dt minima
+ *          accumulated by both kernels (dt3 requires want_dt = 1 in the tail call) and synchronise the stream. */
+int ak_mhd_tail_supported(void *h);
+int ak_mhd_stage_tail(void *h, const ak_mhd_arrays *a, const ak_mhd_arrays *out, int stage, double gam0, double gam1,
+                      double beta_dt, int want_dt, ak_stream_t s);
+int ak_mhd_stage_shell_ct(void *h, const ak_mhd_arrays *a, const ak_mhd_arrays *out, int stage, double gam0, double gam1,
+                          double beta_dt, ak_stream_t s);
+int ak_mhd_stage_shell_c2p(void *h, const ak_mhd_arrays *a, int *nfloor, double *dt3, ak_stream_t s);
 /* c2p over all cells fused with the task-28 reduction over the active cells (last stage). */
 int ak_mhd_cons2prim_newdt(void *h, const ak_mhd_arrays *a, int *nfloor, double *dt3, ak_stream_t s);
 
@@ -198,6 +225,8 @@ int ak_halo_unpack_fc(void *plan, double *x1f, double *x2f, double *x3f, int ipe
  * places as with ak_halo_pack_* + message + ak_halo_unpack_*. */
 int ak_halo_push_setup(void *plan, int ipeer, int peer_gids_start, double *peer_u0, double *peer_x1f,
                        double *peer_x2f, double *peer_x3f);
+/* the peer's face-field arrays for the pushes that follow (the two-kernel stage below rotates its face-field buffers) */
+int ak_halo_push_set_faces(void *plan, int ipeer, double *peer_x1f, double *peer_x2f, double *peer_x3f);
 int ak_halo_push_flags(void *plan, int my_rank, int nranks, unsigned long long *local_flags,
                        unsigned long long *const *peer_flags /* host [npeers] */);
 int ak_halo_push_commit(void *plan);
@@ -247,8 +276,9 @@ int ak_bcs_apply(void *bcs, double *u0, int nvar, double *x1f, double *x2f, doub
  * range guard, csrc/mhd_device.cuh) with the built-in IEEE operators on n random operands.  exponent_span <= 1022:
  * |exponent| <= exponent_span, every 64th numerator exactly 0.  exponent_span > 1022: the whole double range --
  * subnormals, the denormal floor, +-0, infinities, NaNs, negative sqrt arguments -- in every operand position.
- * mismatches[4] = differing results for 1/x, a/b, sqrt(x), and a/y by the reciprocal+FMA quotient used for the
- * launch-uniform divisors (dx, 12, 6). */
+ * mismatches[5] = differing results for 1/x, a/b, sqrt(x), a/y by the reciprocal+FMA quotient used for the
+ * launch-uniform divisors (dx, 12, 6), and -- [4] -- results of the DEFERRED form of the guard (flag accumulated, caller
+ * re-evaluates) that differ from IEEE although the flag stayed clear. */
 int ak_selftest_divsqrt(long n, unsigned long long seed, int exponent_span, long *mismatches);
 
 /* Measured FP64 issue peak of the current device (csrc/peaks.cu): a register-only kernel of dependent chains of
@@ -391,6 +421,8 @@ int ak_nccl_unique_id(void *out128);                         /* rank 0; broadcas
 int ak_sim_comm_init(void *sim, const void *unique_id128);
 int ak_sim_set_state(void *sim, const double *u0, const double *b1f, const double *b2f, const double *b3f);
 int ak_sim_get_state(void *sim, double *u0, double *b1f, double *b2f, double *b3f);
+/* primitives w0 and cell-centred field bcc0 of the current state, ghost zones included, to host buffers (diagnostics) */
+int ak_sim_get_prim(void *sim, double *w0, double *bcc0);
 int ak_sim_initialize(void *sim);            /* Driver::Initialize: ghosts, c2p, first dt */
 int ak_sim_execute(void *sim, int ncycles);  /* Driver::Execute; returns cycles done */
 int ak_sim_sync(void *sim);
