@@ -305,6 +305,15 @@ int ak_mhd_stage_begin(void *handle, int stage, double gam0, double gam1, double
   return 0;
 }
 
+/* the auxiliary stream ak_mhd_stage_begin / ak_mhd_stage_flux_emf run the early U update on (NULL when that overlap is off):
+ * the host layer queues the ghost-zone push of u0 behind it, so the push overlaps the corner EMFs, SendE/RecvE and CT */
+int ak_mhd_aux_stream(void *handle, ak_stream_t *aux) {
+  Handle *h = static_cast<Handle *>(handle);
+  if (!h || !aux) return fail(h, "ak_mhd_aux_stream: null argument");
+  *aux = h->u_pending ? static_cast<ak_stream_t>(h->aux) : nullptr;
+  return 0;
+}
+
 int ak_mhd_stage_flux_emf(void *handle, const ak_mhd_arrays *a, ak_stream_t s) {
   AK_PROLOGUE("ak_mhd_stage_flux_emf")
   if ((e = akb::launch_fluxes(h->cfg.recon, h->rs, h->g, h->eos, A, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_flux_emf", e);
@@ -365,6 +374,32 @@ int ak_mhd_stage_fused(void *handle, const ak_mhd_arrays *a, int stage, double g
 // ---------------------------------------------------------------------------------------
 // Two-kernel stage: flux sweeps (ak_mhd_fluxes) + ONE tail kernel for tasks 14, 1, 5, 17, 27 (and 28 on
 // the last stage), plus the two shell kernels for the outermost layer around SendE/RecvE and the ghost exchange.
+// Flux + update fusion: tasks 2 + 1 + 5 (Fluxes, CopyCons of u, RKUpdate) as the three sweeps alone -- the flux arrays are never
+// written (only their IDN component, for the corner EMFs) and no update kernel runs; du = scratch, 2 * nmb * nfl * cells doubles.
+int ak_mhd_fluxes_update_supported(void *handle) {
+  Handle *h = static_cast<Handle *>(handle);
+  return (h && !h->hydro && !h->cfg.fofc && akb::fluxes_update_supported(h->g)) ? 1 : 0;
+}
+int ak_mhd_fluxes_update(void *handle, const ak_mhd_arrays *a, double *du, int stage, double gam0, double gam1, double beta_dt,
+                         ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_fluxes_update")
+  if (!ak_mhd_fluxes_update_supported(handle)) return fail(h, "ak_mhd_fluxes_update: needs 3-D MHD without passive scalars or FOFC");
+  if (!du) return fail(h, "ak_mhd_fluxes_update: null scratch array");
+  if (stage < 1) return fail(h, "ak_mhd_fluxes_update: stage is 1-based");
+  if ((e = akb::launch_fluxes_update(h->cfg.recon, h->rs, h->g, h->eos, A, du, stage == 1, gam0, gam1, beta_dt, st)) != cudaSuccess)
+    return cuda_fail(h, "ak_mhd_fluxes_update", e);
+  return 0;
+}
+
+// task 17 with the stage-1 CopyCons of the face field folded in (b1 <- old b0 on the faces it updates): the CT half of
+// ak_mhd_stage_update for callers whose conserved update already happened (ak_mhd_fluxes_update)
+int ak_mhd_ct_save(void *handle, const ak_mhd_arrays *a, int stage, double gam0, double gam1, double beta_dt, ak_stream_t s) {
+  AK_PROLOGUE("ak_mhd_ct_save")
+  if (h->hydro) return fail(h, "ak_mhd_ct_save: MHD handles only");
+  if ((e = akb::launch_update_ct(h->g, A, false, true, stage == 1 && !h->cfg.fofc, gam0, gam1, beta_dt, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_ct_save", e);
+  return 0;
+}
+
 static akb::TailArrays tail_arrays(const akb::Arrays &in, const akb::Arrays &out, bool stage1) {
   akb::TailArrays T;
   T.u_in = in.u0; T.u1r = stage1 ? nullptr : in.u1; T.u_out = out.u0; T.u1w = stage1 ? in.u1 : nullptr;

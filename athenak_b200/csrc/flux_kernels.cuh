@@ -73,6 +73,22 @@ __device__ __forceinline__ void prefetch_l1(const double *p) { asm volatile("pre
 template <int RECON>
 struct X1Step { static constexpr int value = (RECON == RECON_PPM4) ? 30 : 31; };
 
+// Flux + update fusion (ak_mhd_fluxes_update): the sweeps never write the flux arrays.  Each sweep turns the fluxes at the
+// two faces of a cell into that direction's term of the flux divergence while they are in registers -- x1 by a shuffle from
+// lane+1, x2 / x3 from the previous step of the march -- and stores 5 words per cell instead of 5 per face:
+//   x1: d1 = (F1(i+1) - F1(i)) / dx1 -> du1;   x2: d2 -> du2;   x3: divf = du1; divf += du2; divf += d3;
+//       u0 = gam0*u0 + gam1*u1 - beta_dt*divf (+ the stage-1 CopyCons of u)       [mhd_update.cpp:51-82, same operation order]
+// Only the mass flux (corner-EMF upwinding) and the face EMFs still go to HBM.  Against flux arrays + update kernel this
+// removes 15 words written + 15 read per cell per stage and one kernel; the divisions ride in kernels that are bound by FP64
+// issue, not by HBM.  ACC: 0 = plain sweep, 1 = store this direction's term, 2 = x3: finish the update.
+struct AccArgs {
+  double *du1, *du2;             // nmb x nfl x cc each
+  const double *mb_size;
+  double *u0, *u1;
+  double gam0, gam1, beta_dt;
+  int save;                      // stage 1: u1 <- old u0 on the updated cells
+};
+
 // left state of a face = upper-face state of the cell in lane-1
 template <int RS>
 __device__ __forceinline__ void shift_up_state(const State7 &up, State7 &L) {
@@ -114,12 +130,13 @@ __device__ __noinline__ void x1_face_guarded(const double *__restrict__ wc, cons
   if (act) riemann_any<RS>(L, lo, bxi, eos, f);
 }
 
-template <int RECON, int RS>
+template <int RECON, int RS, bool ACC = false>
 __global__ void __launch_bounds__(128, AKB_X1_MINB)
 flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
                const double *__restrict__ bx1f, double *__restrict__ flx, double *__restrict__ e3x1,
-               double *__restrict__ e2x1, unsigned rcp_nc) {
-  constexpr int STEP = X1Step<RECON>::value;
+               double *__restrict__ e2x1, unsigned rcp_nc, AccArgs acc) {
+  constexpr int NFL = X1Step<RECON>::value;     // lanes 1..NFL solve a face
+  constexpr int STEP = NFL - (ACC ? 1 : 0);     // warp stride; ACC: lane NFL's face only closes lane NFL-1's cell
   using T = SolverTraits<RS>;
   constexpr bool MHD = T::MHD;       // hydro twin: no face field, no EMFs
   constexpr bool IDEAL = T::IDEAL;   // isothermal EOS: no energy variable
@@ -158,7 +175,7 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
   // separate function that re-reads its inputs, so nothing stays live across the hot path for its sake.
   bool oor = false;
   State7 up, lo;
-  const bool act = valid && lane != 0 && lane <= STEP && c != 0 && c <= g.nx1 + 1 + 2 * g.next;
+  const bool act = valid && lane != 0 && lane <= NFL && c != 0 && c <= g.nx1 + 1 + 2 * g.next;
   State7 L;
   Flux7 f;
   const double *wc = w0 + (long)m * g.nvar * cc + off, *bc = MHD ? bcc + (long)m * 3 * cc + off : wc;
@@ -188,14 +205,38 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
     x1_face_guarded<RECON, RS>(wc, bc, cc, bxi, act, eos, fg);
     f = fg;
   }
-  if (!act) return;
   const long fs = (long)g.n3 * g.n2 * (g.n1 + 1);
   double *fp = flx + (long)m * g.nvar * fs + ((long)k * g.n2 + j) * (g.n1 + 1) + i;
-  fp[IDN * fs] = f.d;
-  fp[IVX * fs] = f.mx;
-  fp[IVY * fs] = f.my;
-  fp[IVZ * fs] = f.mz;
-  if constexpr (IDEAL) fp[IEN * fs] = f.e;
+  if constexpr (ACC) {
+    // x1 term of the flux divergence of this lane's cell: its upper face is lane+1's (every lane takes part in the shuffles)
+    const double nd = __shfl_down_sync(0xffffffffu, f.d, 1), nmx = __shfl_down_sync(0xffffffffu, f.mx, 1);
+    const double nmy = __shfl_down_sync(0xffffffffu, f.my, 1), nmz = __shfl_down_sync(0xffffffffu, f.mz, 1);
+    double ne = 0.0;
+    if constexpr (IDEAL) ne = __shfl_down_sync(0xffffffffu, f.e, 1);
+    const bool cell = act && lane < NFL && i >= g.is && i <= g.ie && j >= g.js && j <= g.je && k >= g.ks && k <= g.ke;
+    if (cell) {
+      const double dx1 = __ldg(acc.mb_size + m * 9 + 6), rdx1 = drcp(dx1);
+      bool o2 = false;
+      double d0 = div_by(nd - f.d, dx1, rdx1, &o2), d1 = div_by(nmx - f.mx, dx1, rdx1, &o2), d2 = div_by(nmy - f.my, dx1, rdx1, &o2);
+      double d3 = div_by(nmz - f.mz, dx1, rdx1, &o2), d4 = IDEAL ? div_by(ne - f.e, dx1, rdx1, &o2) : 0.0;
+      if (o2) {
+        d0 = div_by(nd - f.d, dx1, rdx1); d1 = div_by(nmx - f.mx, dx1, rdx1); d2 = div_by(nmy - f.my, dx1, rdx1);
+        d3 = div_by(nmz - f.mz, dx1, rdx1); if (IDEAL) d4 = div_by(ne - f.e, dx1, rdx1);
+      }
+      double *dp = acc.du1 + (long)m * g.nfl * cc + off;
+      dp[IDN * cc] = d0; dp[IM1 * cc] = d1; dp[IM2 * cc] = d2; dp[IM3 * cc] = d3;
+      if constexpr (IDEAL) dp[IEN * cc] = d4;
+    }
+    if (!act) return;
+    fp[IDN * fs] = f.d;               // mass flux: upwinding of the corner EMFs (mhd_corner_e.cpp:342-413)
+  } else {
+    if (!act) return;
+    fp[IDN * fs] = f.d;
+    fp[IVX * fs] = f.mx;
+    fp[IVY * fs] = f.my;
+    fp[IVZ * fs] = f.mz;
+    if constexpr (IDEAL) fp[IEN * fs] = f.e;
+  }
   if constexpr (MHD) {
     e3x1[(long)m * cc + off] = f.ey;  // mhd_fluxes.cpp:146
     e2x1[(long)m * cc + off] = f.ez;
@@ -324,18 +365,18 @@ __device__ __forceinline__ void store_left_state(double *lsm, const State7 &s) {
 // dozen 64-bit pointers through the loop; under the 128-register budget ptxas spilled loop
 // invariants to local memory and their reloads (L1-thrashed, long scoreboard) were the top stall
 // site of the kernel (profiles/r01_ncu_kernels_session2.txt).
-template <int RECON, int RS, int DIR>
+template <int RECON, int RS, int DIR, int ACC = 0>
 __global__ void __launch_bounds__(MARCH_THREADS, AKB_MARCH_MINB)
 flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
                   const double *__restrict__ bnf, double *__restrict__ flx, double *__restrict__ eyo,
-                  double *__restrict__ ezo, int seglen, int nseg) {
+                  double *__restrict__ ezo, int seglen, int nseg, AccArgs acc) {
   static_assert(DIR == 1 || DIR == 2, "march kernel handles x2 and x3");
   constexpr bool RING = (RECON >= RECON_PPM4);
   using T = SolverTraits<RS>;
   constexpr bool MHD = T::MHD;
   constexpr bool IDEAL = T::IDEAL;
   constexpr int NV = T::NV;
-  extern __shared__ double ring_all[];   // RING: (NV * MARCH_SLOTS + 7) * MARCH_THREADS doubles (dynamic): ring + left-state copy
+  extern __shared__ double ring_all[];   // dynamic: RING: (NV * MARCH_SLOTS + 7) * MARCH_THREADS doubles (ring + left-state copy); ACC: + 5 * MARCH_THREADS
   const int nc = g.nx1 + 2 * g.ext1;
   const int nt = (DIR == 1) ? g.nx3 + 2 * g.ext3 : g.nx2 + 2 * g.ext2;
   const int m = blockIdx.y / nseg, seg = blockIdx.y - m * nseg;       // block-uniform
@@ -346,9 +387,9 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
   const int fs0 = ((DIR == 1) ? g.js : g.ks) - g.next;         // first face along the sweep (one more with FOFC)
   const int fe0 = ((DIR == 1) ? g.je + 1 : g.ke + 1) + g.next; // last face
   const int f_lo = fs0 + seg * seglen;
-  int f_hi = f_lo + seglen - 1;
+  int f_hi = f_lo + seglen - 1 + (ACC ? 1 : 0);     // ACC: a segment is seglen CELLS, closed by one more face (solved twice)
   if (f_hi > fe0) f_hi = fe0;
-  if (f_lo > f_hi) return;
+  if (f_lo > f_hi - (ACC ? 1 : 0)) return;
   const long cc = g.cc;
   const int s = (DIR == 1) ? g.n1 : g.n1 * g.n2;    // sweep stride (cells and faces alike)
   // cell (k,j,i) with the sweep index = f_lo-1, and the face f_lo above it
@@ -371,6 +412,65 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
     const int v = T::member(vv);
     return v == 0 ? wb + IDN * cc : v == 1 ? wb + ivx * cc : v == 2 ? wb + ivy * cc : v == 3 ? wb + ivz * cc
          : v == 4 ? wb + IEN * cc : v == 5 ? bb + iby * cc : bb + ibz * cc;
+  };
+
+  // ACC (flux + update fusion, see AccArgs): this direction's term of the flux divergence of the cell BELOW face f, from the
+  // flux just solved and the previous step's (kept in thread-private shared memory, not in registers)
+  double *pfs = ring_all + (RING ? (NV * MARCH_SLOTS + 7) * MARCH_THREADS : 0) + threadIdx.x;
+  const bool tact = (DIR == 1) ? (k >= g.ks && k <= g.ke && i >= g.is && i <= g.ie) : (j >= g.js && j <= g.je && i >= g.is && i <= g.ie);
+  double dxn = 1.0, rdxn = 1.0;
+  if constexpr (ACC != 0) { dxn = __ldg(acc.mb_size + m * 9 + 6 + DIR); rdxn = drcp(dxn); }
+  auto emit = [&](int f, const Flux7 &fx, int cof, int fof) {      // cof: cell above face f, fof: face f
+    double *fp = fb + fof;
+    fp[IDN * fsz] = fx.d;
+    if constexpr (ACC == 0) {
+      fp[ivx * fsz] = fx.mx;
+      fp[ivy * fsz] = fx.my;
+      fp[ivz * fsz] = fx.mz;
+      if constexpr (IDEAL) fp[IEN * fsz] = fx.e;
+    }
+    if constexpr (MHD) {
+      eyb[cof] = fx.ey;  // x2: (e1x2,e3x2)  x3: (e2x3,e1x3)   mhd_fluxes.cpp:196,243
+      ezb[cof] = fx.ez;
+    }
+    if constexpr (ACC != 0) {
+      const int cs = (DIR == 1) ? g.js : g.ks, ce = (DIR == 1) ? g.je : g.ke;
+      if (f > f_lo && tact && f - 1 >= cs && f - 1 <= ce) {
+        const int cb = cof - s;                                    // the cell below face f
+        const double p0 = pfs[0 * MARCH_THREADS], p1 = pfs[1 * MARCH_THREADS], p2 = pfs[2 * MARCH_THREADS], p3 = pfs[3 * MARCH_THREADS];
+        const double p4 = IDEAL ? pfs[4 * MARCH_THREADS] : 0.0;
+        bool o2 = false;
+        double d0 = div_by(fx.d - p0, dxn, rdxn, &o2), d1 = div_by(fx.mx - p1, dxn, rdxn, &o2), d2 = div_by(fx.my - p2, dxn, rdxn, &o2);
+        double d3 = div_by(fx.mz - p3, dxn, rdxn, &o2), d4 = IDEAL ? div_by(fx.e - p4, dxn, rdxn, &o2) : 0.0;
+        if (o2) {
+          d0 = div_by(fx.d - p0, dxn, rdxn); d1 = div_by(fx.mx - p1, dxn, rdxn); d2 = div_by(fx.my - p2, dxn, rdxn);
+          d3 = div_by(fx.mz - p3, dxn, rdxn); if (IDEAL) d4 = div_by(fx.e - p4, dxn, rdxn);
+        }
+        const long mb = (long)m * g.nfl * cc;
+        if constexpr (ACC == 1) {
+          double *dp = acc.du2 + mb + cb;
+          dp[IDN * cc] = d0; dp[ivx * cc] = d1; dp[ivy * cc] = d2; dp[ivz * cc] = d3;
+          if constexpr (IDEAL) dp[IEN * cc] = d4;
+        } else {
+          // x3: mhd_update.cpp:51-82 -- divf = x1 term; += x2 term; += x3 term; u0 = gam0*u0 + gam1*u1 - beta_dt*divf
+          const double *q1 = acc.du1 + mb + cb, *q2 = acc.du2 + mb + cb;
+          double *u0p = acc.u0 + mb + cb, *u1p = acc.u1 + mb + cb;
+          auto upd = [&](int n, double d3rd) {
+            double divf = q1[n * cc];
+            divf += q2[n * cc];
+            divf += d3rd;
+            const double uold = u0p[n * cc];
+            double ureg;
+            if (acc.save) { ureg = uold; u1p[n * cc] = uold; } else { ureg = u1p[n * cc]; }
+            u0p[n * cc] = acc.gam0 * uold + acc.gam1 * ureg - acc.beta_dt * divf;
+          };
+          upd(IDN, d0); upd(ivx, d1); upd(ivy, d2); upd(ivz, d3);
+          if constexpr (IDEAL) upd(IEN, d4);
+        }
+      }
+      pfs[0 * MARCH_THREADS] = fx.d; pfs[1 * MARCH_THREADS] = fx.mx; pfs[2 * MARCH_THREADS] = fx.my; pfs[3 * MARCH_THREADS] = fx.mz;
+      if constexpr (IDEAL) pfs[4 * MARCH_THREADS] = fx.e;
+    }
   };
 
   State7 L, lo_unused;
@@ -399,8 +499,13 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
     double *lsm = ring_all + NV * VS + threadIdx.x;     // this thread's copy of the left state, for the cold path only
     store_left_state(lsm, L);
     int b0 = 1;                       // slot of row c-2 for the next cell (c = f_lo)
+    // the normal field of a face is fetched one step ahead: issued next to its use it was the top stall site of the kernel
+    double bn_next = 0.0;
+    if constexpr (MHD) bn_next = __ldg(bnb + fo);
     for (int f = f_lo; f <= f_hi; ++f) {
       co += s;                        // cell c = f
+      const double bni = bn_next;
+      if constexpr (MHD) { if (f < f_hi) bn_next = __ldg(bnb + fo + s); }
       // rows c-2..c+2 are present; request row c+2+PF (needed PF steps from now) into the slot that held row c-3
       if (f + MARCH_PF <= f_hi) {
         int bn_slot = b0 + MARCH_SLOTS - 1; if (bn_slot >= MARCH_SLOTS) bn_slot -= MARCH_SLOTS;
@@ -415,8 +520,6 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       if constexpr (RECON == RECON_PPM4 && AKB_MARCH_CARRY && MHD && IDEAL) ppm4_ring_cell(ring, b0, fl, up, lo);
       else recon_ring_cell<RECON, RS>(ring, b0, eos, up, lo, &oor);
       Flux7 fx;
-      double bni = 0.0;
-      if constexpr (MHD) bni = __ldg(bnb + fo);
       riemann_any<RS>(L, lo, bni, eos, fx, &oor);
       if (oor) {       // cold: an operand left the fast path's exact range (separate result objects keep up / fx in registers)
         State7 ug; Flux7 fg;
@@ -424,16 +527,7 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
         up = ug; fx = fg;
       }
       store_left_state(lsm, up);
-      double *fp = fb + fo;
-      fp[IDN * fsz] = fx.d;
-      fp[ivx * fsz] = fx.mx;
-      fp[ivy * fsz] = fx.my;
-      fp[ivz * fsz] = fx.mz;
-      if constexpr (IDEAL) fp[IEN * fsz] = fx.e;
-      if constexpr (MHD) {
-        eyb[co] = fx.ey;  // x2: (e1x2,e3x2)  x3: (e2x3,e1x3)   mhd_fluxes.cpp:196,243
-        ezb[co] = fx.ez;
-      }
+      emit(f, fx, co, fo);
       L = up;
       fo += s;
       b0 = (b0 + 1 >= MARCH_SLOTS) ? 0 : b0 + 1;
@@ -451,16 +545,7 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       bool oor = false;
       riemann_any<RS>(L, lo, bni, eos, fx, &oor);
       if (oor) riemann_any<RS>(L, lo, bni, eos, fx);
-      double *fp = fb + fo;
-      fp[IDN * fsz] = fx.d;
-      fp[ivx * fsz] = fx.mx;
-      fp[ivy * fsz] = fx.my;
-      fp[ivz * fsz] = fx.mz;
-      if constexpr (IDEAL) fp[IEN * fsz] = fx.e;
-      if constexpr (MHD) {
-        eyb[co] = fx.ey;
-        ezb[co] = fx.ez;
-      }
+      emit(f, fx, co, fo);
       L = up;
       fo += s;
     }
@@ -545,10 +630,11 @@ inline SweepFork *sweep_fork() {
   return f.ok ? &f : nullptr;
 }
 
-template <int RECON, int RS>
-static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st) {
+template <int RECON, int RS, bool ACC = false>
+static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st, const AccArgs *accp = nullptr) {
   constexpr int NV = SolverTraits<RS>::NV;
-  SweepFork *sf = g.multi_d ? sweep_fork() : nullptr;
+  // ACC (flux + update fusion): x3 consumes what x1 and x2 stored, so the sweeps run in order on the caller's stream
+  SweepFork *sf = (g.multi_d && !ACC) ? sweep_fork() : nullptr;
   cudaStream_t st2 = st, st3 = st;
   if (sf) {
     cudaEventRecord(sf->fork, st);
@@ -556,9 +642,12 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
     st2 = sf->s[0];
     if (g.three_d) { cudaStreamWaitEvent(sf->s[1], sf->fork, 0); st3 = sf->s[1]; }
   }
-  const size_t smem = (RECON >= RECON_PPM4) ? sizeof(double) * (NV * MARCH_SLOTS + 7) * MARCH_THREADS : 0;   // ring + left-state copy
+  AccArgs acc{};
+  if (ACC) acc = *accp;
+  // ring + left-state copy (5-point reconstructions), + the previous face's fluxes (ACC)
+  const size_t smem = sizeof(double) * (((RECON >= RECON_PPM4) ? (NV * MARCH_SLOTS + 7) : 0) + (ACC ? 5 : 0)) * MARCH_THREADS;
   {  // x1
-    constexpr int STEP = X1Step<RECON>::value;
+    constexpr int STEP = X1Step<RECON>::value - (ACC ? 1 : 0);
     const unsigned nc = g.nx1 + 2 + 2 * g.next + (RECON == RECON_PPM4 ? 1 : 0), plane = (unsigned)(g.nx2 + 2 * g.ext2) * nc;
     // rcp = ceil(2^32 / nc): __umulhi(t, rcp) == t / nc for every t < 2^32 / nc
     const unsigned rcp = (unsigned)((0x100000000ull + nc - 1) / nc);
@@ -566,32 +655,32 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
     if ((unsigned long long)plane * nc >= 0x100000000ull || planes > 65535) return cudaErrorInvalidConfiguration;
     const unsigned warps = (plane + STEP - 1) / STEP;
     const dim3 gr(nblocks((long)warps * 32, 128), (unsigned)planes);
-    flux_x1_kernel<RECON, RS><<<gr, 128, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x1f, a.flx1, a.e3x1, a.e2x1, rcp);
+    flux_x1_kernel<RECON, RS, ACC><<<gr, 128, 0, st>>>(g, eos, a.w0, a.bcc0, a.b0x1f, a.flx1, a.e3x1, a.e2x1, rcp, acc);
   }
   if (g.multi_d) {  // x2: (ey,ez) = (e1x2,e3x2)
-    const int nf = g.nx2 + 1 + 2 * g.next;
-    const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
+    const int nf = g.nx2 + (ACC ? 0 : 1) + 2 * g.next;      // ACC: segments count cells, each closed by one more face
+    const int nseg = (nf + 31 - (ACC ? 1 : 0)) / (32 - (ACC ? 1 : 0)), seglen = (nf + nseg - 1) / nseg;
     const long cols = (long)(g.nx3 + 2 * g.ext3) * (g.nx1 + 2 * g.ext1);
     if ((long)g.nmb * nseg > 65535 || (long)g.nvar * g.cc >= 0x7fffffffL) return cudaErrorInvalidConfiguration;
     static bool attr1 = false;
-    if (!attr1 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr1 = true; }
-    flux_march_kernel<RECON, RS, 1><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st2>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg);
+    if (!attr1 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 1, ACC ? 1 : 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr1 = true; }
+    flux_march_kernel<RECON, RS, 1, ACC ? 1 : 0><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st2>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg, acc);
   }
   if (g.three_d) {  // x3: (ey,ez) = (e2x3,e1x3)
-    const int nf = g.nx3 + 1 + 2 * g.next;
-    const int nseg = (nf + 31) / 32, seglen = (nf + nseg - 1) / nseg;
+    const int nf = g.nx3 + (ACC ? 0 : 1) + 2 * g.next;
+    const int nseg = (nf + 31 - (ACC ? 1 : 0)) / (32 - (ACC ? 1 : 0)), seglen = (nf + nseg - 1) / nseg;
     const long cols = (long)(g.nx2 + 2 * g.ext2) * (g.nx1 + 2 * g.ext1);
     if ((long)g.nmb * nseg > 65535 || (long)g.nvar * g.cc >= 0x7fffffffL) return cudaErrorInvalidConfiguration;
     static bool attr2 = false;
-    if (!attr2 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr2 = true; }
-    flux_march_kernel<RECON, RS, 2><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st3>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
+    if (!attr2 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 2, ACC ? 2 : 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr2 = true; }
+    flux_march_kernel<RECON, RS, 2, ACC ? 2 : 0><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st3>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg, acc);
   }
   if (sf) {   // join
     cudaEventRecord(sf->join[0], st2);
     cudaStreamWaitEvent(st, sf->join[0], 0);
     if (g.three_d) { cudaEventRecord(sf->join[1], st3); cudaStreamWaitEvent(st, sf->join[1], 0); }
   }
-  if (g.nvar > g.nfl) return launch_scalar_fluxes<RECON>(g, a, st);
+  if (!ACC && g.nvar > g.nfl) return launch_scalar_fluxes<RECON>(g, a, st);
   return cudaGetLastError();
 }
 

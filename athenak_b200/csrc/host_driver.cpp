@@ -184,6 +184,7 @@ class MHD {  // state owner + tasks
   cudaStream_t st = nullptr;
   MeshState mesh;
   int my_rank, nranks;
+  int device = 0;          // CUDA device this state lives on (the current device at construction); ak_sim_* calls select it
   bool fused = true;
   double dtnew = (double)FLT_MAX;
   long nfloor[3] = {0, 0, 0};
@@ -203,6 +204,8 @@ class MHD {  // state owner + tasks
   int gids_start_ = 0;
   unsigned long long nemfx = 0;      // EMF exchanges completed through peer memory
   bool push = false;
+  bool u_pushed = false;                      // this stage's u0 push is already in flight on the auxiliary stream
+  cudaEvent_t ev_upush = nullptr;
   unsigned long long nexch = 0;               // exchanges completed (sequence number of the flags)
   unsigned long long *d_flags = nullptr;      // [2][nranks] counters written by the peers
   std::vector<void *> ipc_opened;
@@ -217,6 +220,9 @@ class MHD {  // state owner + tasks
   // keeps one spare buffer of each and rotates the pointers in `a` after every stage; at stage 1 the old b0 buffers BECOME b1
   // (no CopyCons pass over the face field).  Peer-memory pushes follow the rotation through per-peer copies of the same
   // three buffer sets (every rank rotates at the same point of the task list).
+  // Flux + update fusion (ak_mhd_fluxes_update): the sweeps finish the conserved update themselves; du = their scratch
+  bool fluxupd = false;
+  double *du = nullptr;
   bool tail = false;
   double *spare_b[3] = {nullptr, nullptr, nullptr}, *spare_w = nullptr, *spare_bcc = nullptr;
   ak_mhd_arrays tail_out;                 // outputs of the stage in flight (u0 in place, b0x?f / w0 / bcc0 = the spares)
@@ -226,6 +232,7 @@ class MHD {  // state owner + tasks
   MHD(const ak_mhd_cfg &c, const double *mb_size, const int *nghbr, int rank, int nranks_, int gids_start, int nmb_total)
       : cfg(c), my_rank(rank), nranks(nranks_), gids_start_(gids_start) {
     mesh.nmb_total = nmb_total;
+    CU_CHECK(cudaGetDevice(&device));
     CU_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     hydro = c.rsolver >= AK_RSOLVER_HYD_ADVECT;     // hydro twin: Hydro::Hydro, hydro.cpp:100-120,268-290
     multi_d = c.nx2 > 1; three_d = c.nx3 > 1;       // mesh.cpp:70-79
@@ -252,7 +259,10 @@ class MHD {  // state owner + tasks
     if (hydro ? ak_hydro_create(&cfg, &h) : ak_mhd_create(&cfg, &h)) Fatal(__FILE__, __LINE__, ak_last_error(nullptr));
     {
       const char *env = std::getenv("AKB_TAIL");
-      tail = !hydro && !cfg.fofc && ak_mhd_tail_supported(h) && !(env && env[0] == '0');
+      tail = !hydro && !cfg.fofc && ak_mhd_tail_supported(h) && (env && env[0] == '1');      // measured slower than the task kernels so far: opt-in
+      const char *envf = std::getenv("AKB_FLUXUPD");
+      fluxupd = !tail && !hydro && ak_mhd_fluxes_update_supported(h) && (envf && envf[0] == '1');     // measured slower than the task kernels so far: opt-in
+      if (fluxupd) du = alloc(2 * nm * (size_t)(c.eos == AK_EOS_ISOTHERMAL ? 4 : 5) * cc);
       if (tail) {
         spare_b[0] = alloc(n_f1); spare_b[1] = alloc(n_f2); spare_b[2] = alloc(n_f3);
         spare_w = alloc(n_u); spare_bcc = alloc(nm * 3 * cc);
@@ -273,6 +283,7 @@ class MHD {  // state owner + tasks
   ~MHD() {
     if (st) cudaStreamSynchronize(st);
     for (void *p : ipc_opened) cudaIpcCloseMemHandle(p);
+    if (ev_upush) cudaEventDestroy(ev_upush);
     if (d_flags) cudaFree(d_flags);
     if (comm && Nccl::get().CommDestroy) Nccl::get().CommDestroy(comm);
     ak_halo_destroy(plan);
@@ -469,6 +480,16 @@ class MHD {  // state owner + tasks
       TaskID ru = tl->AddTask(&MHD::RecvUB, this, su);
       TaskID bc = tl->AddTask(&MHD::ApplyPhysicalBCs, this, ru);
       tl->AddTask(&MHD::ShellC2PNewDt, this, bc);                           // tasks 27 (28) for the ghost zones + the outermost layer
+    } else if (fused && fluxupd) {     // flux + update fusion: no flux arrays, no update kernel
+      TaskID f = tl->AddTask(&MHD::StageFluxUpdate, this, none);           // tasks 2 + 1 + 5
+      TaskID ef = tl->AddTask(&MHD::EField, this, f);                       // task 14
+      TaskID se = tl->AddTask(&MHD::SendE, this, ef);
+      TaskID re = tl->AddTask(&MHD::RecvE, this, se);
+      TaskID ct = tl->AddTask(&MHD::CTSave, this, re);                      // task 17 (+ CopyCons of b at stage 1)
+      TaskID su = tl->AddTask(&MHD::SendUB, this, ct);
+      TaskID ru = tl->AddTask(&MHD::RecvUB, this, su);
+      TaskID bc = tl->AddTask(&MHD::ApplyPhysicalBCs, this, ru);
+      tl->AddTask(&MHD::ConToPrimNewDt, this, bc);
     } else if (fused) {
       TaskID f = tl->AddTask(&MHD::StageFluxEmf, this, none);
       TaskID se = tl->AddTask(&MHD::SendE, this, f);
@@ -544,11 +565,41 @@ class MHD {  // state owner + tasks
     AK_CHECK(h, ak_mhd_stage_flux_emf(h, &a, st));
     static const bool overlap_u = !(std::getenv("AKB_OVERLAP_U") && std::getenv("AKB_OVERLAP_U")[0] == '0');
     launches += nsweeps() + 1 + (overlap_u ? 1 : 0);    // sweeps, corner EMFs, (early U update)
-    SignalFree();    // the flux sweeps were the last readers of the b0 ghost faces (u0 ghosts: c2p of the previous stage)
+    // Overlapped ghost exchange: the U update already ran on the library's auxiliary stream beside the corner-EMF kernel, so the
+    // push of u0 (5 of the 8 exchanged fields) is queued right behind it there -- "my ghost zones are free", wait for the
+    // neighbours' same signal, push -- and overlaps corner EMFs, SendE/RecvE and CT; SendUB then pushes the face field only and
+    // publishes "filled" once both pushes are done.  AKB_OVERLAP_PUSH=0 keeps the single push after CT.
+    static const bool overlap_push = !(std::getenv("AKB_OVERLAP_PUSH") && std::getenv("AKB_OVERLAP_PUSH")[0] == '0');
+    cudaStream_t aux = nullptr;
+    if (UsePush() && overlap_push) AK_CHECK(h, ak_mhd_aux_stream(h, reinterpret_cast<ak_stream_t *>(&aux)));
+    if (aux) {
+      if (!ev_upush) CU_CHECK(cudaEventCreateWithFlags(&ev_upush, cudaEventDisableTiming));
+      const unsigned long long seq = nexch + 1;
+      AK_CHECK(nullptr, ak_halo_signal(plan, 0, seq, aux));      // the sweeps (joined before the fork) were the last readers of my ghost zones
+      AK_CHECK(nullptr, ak_halo_wait(plan, 0, seq, aux));
+      AK_CHECK(nullptr, ak_halo_push(plan, a.u0, nvar, nullptr, nullptr, nullptr, aux));
+      CU_CHECK(cudaEventRecord(ev_upush, aux));
+      u_pushed = true;
+      launches += 3;
+    } else {
+      SignalFree();    // the flux sweeps were the last readers of the b0 ghost faces (u0 ghosts: c2p of the previous stage)
+    }
     return TaskStatus::complete;
   }
   TaskStatus StageUpdate(Driver *pd, int stage) {    // tasks 1 + 5 + 17
     AK_CHECK(h, ak_mhd_stage_update(h, &a, stage, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, st));
+    launches += 1;
+    return TaskStatus::complete;
+  }
+  // ---- flux + update fusion ---------------------------------------------------------------
+  TaskStatus StageFluxUpdate(Driver *pd, int stage) {
+    AK_CHECK(h, ak_mhd_fluxes_update(h, &a, du, stage, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, st));
+    launches += nsweeps();
+    SignalFree();    // the sweeps were the last readers of the b0 ghost faces (u0 ghosts: the c2p of the previous stage)
+    return TaskStatus::complete;
+  }
+  TaskStatus CTSave(Driver *pd, int stage) {
+    AK_CHECK(h, ak_mhd_ct_save(h, &a, stage, pd->gam0[stage - 1], pd->gam1[stage - 1], pd->beta[stage - 1] * mesh.dt, st));
     launches += 1;
     return TaskStatus::complete;
   }
@@ -691,7 +742,13 @@ class MHD {  // state owner + tasks
   void PushExchange(bool with_b) {
     const unsigned long long seq = nexch + 1;
     AK_CHECK(nullptr, ak_halo_wait(plan, 0, seq, st));
-    AK_CHECK(nullptr, ak_halo_push(plan, a.u0, nvar, with_b ? a.b0x1f : nullptr, a.b0x2f, a.b0x3f, st));
+    if (u_pushed) {        // u0 went out early on the auxiliary stream (StageFluxEmf): face field only, then join
+      AK_CHECK(nullptr, ak_halo_push(plan, nullptr, nvar, a.b0x1f, a.b0x2f, a.b0x3f, st));
+      CU_CHECK(cudaStreamWaitEvent(st, ev_upush, 0));
+      u_pushed = false;
+    } else {
+      AK_CHECK(nullptr, ak_halo_push(plan, a.u0, nvar, with_b ? a.b0x1f : nullptr, a.b0x2f, a.b0x3f, st));
+    }
     AK_CHECK(nullptr, ak_halo_signal(plan, 1, seq, st));
     launches += 3;
   }
@@ -992,6 +1049,7 @@ int ak_sim_comm_init(void *sim, const void *unique_id128) {
 }
 int ak_sim_set_state(void *sim, const double *u0, const double *b1f, const double *b2f, const double *b3f) {
   auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
+  cudaSetDevice(m->device);      // a host thread other than the creating one may drive this handle
   cudaError_t e = cudaMemcpyAsync(m->a.u0, u0, m->n_u * 8, cudaMemcpyHostToDevice, m->st);
   if (m->hydro) return e == cudaSuccess ? 0 : 1;     // hydro twin: u0 only, the face-field pointers are ignored
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->a.b0x1f, b1f, m->n_f1 * 8, cudaMemcpyHostToDevice, m->st);
@@ -1001,6 +1059,7 @@ int ak_sim_set_state(void *sim, const double *u0, const double *b1f, const doubl
 }
 int ak_sim_get_state(void *sim, double *u0, double *b1f, double *b2f, double *b3f) {
   auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
+  cudaSetDevice(m->device);
   cudaError_t e = cudaMemcpyAsync(u0, m->a.u0, m->n_u * 8, cudaMemcpyDeviceToHost, m->st);
   if (m->hydro) { if (e == cudaSuccess) e = cudaStreamSynchronize(m->st); return e == cudaSuccess ? 0 : 1; }
   if (e == cudaSuccess) e = cudaMemcpyAsync(b1f, m->a.b0x1f, m->n_f1 * 8, cudaMemcpyDeviceToHost, m->st);
@@ -1012,6 +1071,7 @@ int ak_sim_get_state(void *sim, double *u0, double *b1f, double *b2f, double *b3
 /* primitives and cell-centred field of the current state, ghost zones included (test / diagnostic read-back) */
 int ak_sim_get_prim(void *sim, double *w0, double *bcc0) {
   auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
+  cudaSetDevice(m->device);
   cudaError_t e = cudaMemcpyAsync(w0, m->a.w0, m->n_u * 8, cudaMemcpyDeviceToHost, m->st);
   if (e == cudaSuccess && !m->hydro && bcc0)
     e = cudaMemcpyAsync(bcc0, m->a.bcc0, (m->n_u / m->nvar) * 3 * 8, cudaMemcpyDeviceToHost, m->st);
@@ -1020,15 +1080,18 @@ int ak_sim_get_prim(void *sim, double *w0, double *bcc0) {
 }
 int ak_sim_initialize(void *sim) {
   auto *s = static_cast<akh::Sim *>(sim);
+  cudaSetDevice(s->pmhd->device);
   s->pmhd->mesh.time = 0.0; s->pmhd->mesh.ncycle = 0; s->pmhd->mesh.dt = (double)FLT_MAX; s->pmhd->dtnew = (double)FLT_MAX;
   s->pdriver->Initialize(s->pmhd.get());
   return 0;
 }
 int ak_sim_execute(void *sim, int ncycles) {
   auto *s = static_cast<akh::Sim *>(sim);
+  cudaSetDevice(s->pmhd->device);
   return s->pdriver->Execute(s->pmhd.get(), ncycles);
 }
 int ak_sim_sync(void *sim) {
+  cudaSetDevice(static_cast<akh::Sim *>(sim)->pmhd->device);
   return cudaStreamSynchronize(static_cast<akh::Sim *>(sim)->pmhd->st) == cudaSuccess ? 0 : 1;
 }
 /* st[0..2] = time, dt, dtnew; cnt[0..7] = ncycle, launches, nfloor d/e/t, stream handle (as integer),

@@ -176,9 +176,19 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
       const double *p1 = flx1 + ((long)m * g.nvar + n) * g.f1 + o1;
       const double *p2 = flx2 + ((long)m * g.nvar + n) * g.f2 + o2;
       const double *p3 = flx3 + ((long)m * g.nvar + n) * g.f3 + o3;
-      double divf = div_by(__ldg(p1 + 1) - __ldg(p1), dx1, rdx1);
-      if (g.multi_d) divf += div_by(__ldg(p2 + n1) - __ldg(p2), dx2, rdx2);   // hydro_update.cpp:57-75
-      if (g.three_d) divf += div_by(__ldg(p3 + n1 * n2) - __ldg(p3), dx3, rdx3);
+      // deferred range guard (mhd_device.cuh): flux differences are exact zeros wherever the flow is uniform, so the guard must
+      // not branch on them; the rare out-of-range operand repeats the three quotients with the guarded operator
+      const double df1 = __ldg(p1 + 1) - __ldg(p1), df2 = g.multi_d ? __ldg(p2 + n1) - __ldg(p2) : 0.0;
+      const double df3 = g.three_d ? __ldg(p3 + n1 * n2) - __ldg(p3) : 0.0;
+      bool oor = false;
+      double divf = div_by(df1, dx1, rdx1, &oor);
+      if (g.multi_d) divf += div_by(df2, dx2, rdx2, &oor);   // hydro_update.cpp:57-75
+      if (g.three_d) divf += div_by(df3, dx3, rdx3, &oor);
+      if (oor) {
+        divf = div_by(df1, dx1, rdx1);
+        if (g.multi_d) divf += div_by(df2, dx2, rdx2);
+        if (g.three_d) divf += div_by(df3, dx3, rdx3);
+      }
       const long uo = ((long)m * g.nvar + n) * g.cc + o;
       const double uold = u0[uo];
       double ureg;
@@ -201,8 +211,13 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
       double breg;
       if (SAVE) { breg = bold; o1f[o] = bold; } else { breg = o1f[o]; }
       double b = gam0 * bold + gam1 * breg;
-      b -= div_by(beta_dt * (__ldg(E3 + a3 + (n1 + 1)) - __ldg(E3 + a3)), dx2, rdx2);
-      if (g.three_d) b += div_by(beta_dt * (__ldg(E2 + a2 + n2 * (n1 + 1)) - __ldg(E2 + a2)), dx3, rdx3);
+      const double de3 = beta_dt * (__ldg(E3 + a3 + (n1 + 1)) - __ldg(E3 + a3));
+      const double de2 = g.three_d ? beta_dt * (__ldg(E2 + a2 + n2 * (n1 + 1)) - __ldg(E2 + a2)) : 0.0;
+      bool oor = false;
+      double q3 = div_by(de3, dx2, rdx2, &oor), q2 = g.three_d ? div_by(de2, dx3, rdx3, &oor) : 0.0;
+      if (oor) { q3 = div_by(de3, dx2, rdx2); if (g.three_d) q2 = div_by(de2, dx3, rdx3); }
+      b -= q3;
+      if (g.three_d) b += q2;
       b1f[o] = b;
     }
     if (ia && ka) {  // x2f(k,j,i), j in [js,je+1]
@@ -211,8 +226,13 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
       double breg;
       if (SAVE) { breg = bold; o2f[o] = bold; } else { breg = o2f[o]; }
       double b = gam0 * bold + gam1 * breg;
-      b += div_by(beta_dt * (__ldg(E3 + a3 + 1) - __ldg(E3 + a3)), dx1, rdx1);
-      if (g.three_d) b -= div_by(beta_dt * (__ldg(E1 + a1 + (n2 + 1) * n1) - __ldg(E1 + a1)), dx3, rdx3);
+      const double de3 = beta_dt * (__ldg(E3 + a3 + 1) - __ldg(E3 + a3));
+      const double de1 = g.three_d ? beta_dt * (__ldg(E1 + a1 + (n2 + 1) * n1) - __ldg(E1 + a1)) : 0.0;
+      bool oor = false;
+      double q3 = div_by(de3, dx1, rdx1, &oor), q1 = g.three_d ? div_by(de1, dx3, rdx3, &oor) : 0.0;
+      if (oor) { q3 = div_by(de3, dx1, rdx1); if (g.three_d) q1 = div_by(de1, dx3, rdx3); }
+      b += q3;
+      if (g.three_d) b -= q1;
       b2f[o] = b;
     }
     if (ia && ja) {  // x3f(k,j,i), k in [ks,ke+1]
@@ -221,8 +241,13 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
       double breg;
       if (SAVE) { breg = bold; o3f[o] = bold; } else { breg = o3f[o]; }
       double b = gam0 * bold + gam1 * breg;
-      b -= div_by(beta_dt * (__ldg(E2 + a2 + 1) - __ldg(E2 + a2)), dx1, rdx1);
-      if (g.multi_d) b += div_by(beta_dt * (__ldg(E1 + a1 + n1) - __ldg(E1 + a1)), dx2, rdx2);
+      const double de2 = beta_dt * (__ldg(E2 + a2 + 1) - __ldg(E2 + a2));
+      const double de1 = g.multi_d ? beta_dt * (__ldg(E1 + a1 + n1) - __ldg(E1 + a1)) : 0.0;
+      bool oor = false;
+      double q2 = div_by(de2, dx1, rdx1, &oor), q1 = g.multi_d ? div_by(de1, dx2, rdx2, &oor) : 0.0;
+      if (oor) { q2 = div_by(de2, dx1, rdx1); if (g.multi_d) q1 = div_by(de1, dx2, rdx2); }
+      b -= q2;
+      if (g.multi_d) b += q1;
       b3f[o] = b;
     }
   }

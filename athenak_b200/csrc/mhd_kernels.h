@@ -38,6 +38,11 @@ struct Arrays {  // mirror of ak_mhd_arrays (include/athenak_b200.h)
 };
 
 cudaError_t launch_fluxes(int recon, int rs, const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st);
+// flux + update fusion: sweeps that turn the fluxes into the divergence terms on chip and finish the conserved update in the
+// x3 sweep; du = scratch of 2 * nmb * nfl * cc doubles.  3-D MHD without passive scalars / FOFC (fluxes_update_supported).
+bool fluxes_update_supported(const Geom &g);
+cudaError_t launch_fluxes_update(int recon, int rs, const Geom &g, const EosParams &eos, const Arrays &a, double *du, bool save,
+                                 double gam0, double gam1, double beta_dt, cudaStream_t st);
 // hydro twin (hydro_kernels.cu): rs = RS_HYD_*; a.bcc0, face fields and EMF arrays are unused
 cudaError_t launch_hydro_fluxes(int recon, int rs, const Geom &g, const EosParams &eos, const Arrays &a, cudaStream_t st);
 cudaError_t launch_hydro_cons2prim(const Geom &g, const EosParams &eos, const Arrays &a, int il, int iu, int jl, int ju,

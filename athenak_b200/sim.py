@@ -69,15 +69,27 @@ class Simulation:
             return C.c_void_p(None)
         return C.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else t.ctypes.data)
 
+    def _check_buffers(self, arrays, what):
+        """The C side copies exactly prod(shape) doubles per array: anything else is an out-of-bounds host access."""
+        for t, shape in zip(arrays, self.shapes):
+            tshape = tuple(t.shape)
+            dt = str(t.dtype)
+            contig = t.is_contiguous() if hasattr(t, "is_contiguous") else t.flags["C_CONTIGUOUS"]
+            on_host = (not hasattr(t, "is_cuda")) or (not t.is_cuda)
+            if tshape != tuple(shape) or "float64" not in dt or not contig or not on_host:
+                raise _lib.EngineError(f"{what}: expected a C-contiguous float64 host array of shape {tuple(shape)}, got {tshape} {dt}")
+
     def set_state(self, u0, b1f=None, b2f=None, b3f=None):
         """Host arrays (numpy or torch CPU tensors, C-contiguous float64, full ghost-inclusive shape)."""
         if not self.hydro and (b1f is None or b2f is None or b3f is None):
             raise _lib.EngineError("set_state: MHD needs the three face fields")
+        self._check_buffers([u0] if self.hydro else [u0, b1f, b2f, b3f], "set_state")
         if self.L.ak_sim_set_state(self.h, *[self._ptr(t) for t in (u0, b1f, b2f, b3f)]):
             raise _lib.EngineError("ak_sim_set_state failed")
 
     def get_state(self, out=None):
         out = out or [np.empty(s) for s in self.shapes]
+        self._check_buffers(out, "get_state")
         ptrs = [self._ptr(t) for t in out] + [self._ptr(None)] * (4 - len(out))
         if self.L.ak_sim_get_state(self.h, *ptrs):
             raise _lib.EngineError("ak_sim_get_state failed")
@@ -92,7 +104,8 @@ class Simulation:
         return w0, bcc
 
     def initialize(self):
-        self.L.ak_sim_initialize(self.h)
+        if self.L.ak_sim_initialize(self.h):
+            raise _lib.EngineError("ak_sim_initialize failed")
 
     def execute(self, ncycles=-1):
         return self.L.ak_sim_execute(self.h, ncycles)

@@ -23,6 +23,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# The pipelined end-to-end leg drives several engine instances per GPU, each with its own compute, auxiliary and sweep streams
+# and with spinning flag-wait kernels on some of them: with the default 8 hardware work queues two unrelated streams can share a
+# queue and a spinning kernel then blocks the very signal it waits for.  One queue per stream (set before CUDA initialises).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 GAMMA = 1.6666667
 NG = 4
@@ -30,6 +34,13 @@ DECK = os.path.join(ROOT, "tests", "decks", "blast3d.athinput")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "athena_blast")
 ALGO_BYTES_PER_CELL_STAGE = 256.0      # 32 FP64 words per active cell per stage
 METRIC = "Mcell-updates/s on 3D MHD blast 256^3/GPU"
+NCU_FLUX = os.path.join(ROOT, "profiles", "r02_flux_fp64.json")     # committed ncu summary the roofline's traffic / FP64 counts come from
+
+
+def workload(n):
+    """One string for both arms (the driver compares the two config.workload values)."""
+    return (f"3D MHD blast {n}^3 cells per GPU, one MeshBlock per GPU, PPM4+HLLD+RK3, nghost=4, periodic; "
+            "step = one full RK3 time step")
 
 
 def host_cores():
@@ -90,7 +101,8 @@ def bench_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mcell-updates/s", "n_gpus": args.gpus,
         "steps": len(timed), "warmup": W, "ms_per_step": 1e3 * tsum / len(timed), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D MHD blast, PPM4+HLLD+RK3, nghost=4, reference Kokkos::OpenMP CPU build", "sample": sample},
+        "config": {"workload": workload(args.nx), "implementation": "reference Kokkos::OpenMP CPU build (oracle/_ref/athena_blast), unmodified",
+                   "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Mcell-updates/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -144,10 +156,98 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
+def measure_fp64_peak(L):
+    """FP64 issue peak of this device (csrc/peaks.cu): best lane-instruction rate over the DADD/DMUL mix an --fmad=false
+    build issues, ILP 4 and 8, 8 to 16 resident warps per SM sub-partition."""
+    import ctypes as C
+    best, how = 0.0, None
+    for op, name in ((3, "DADD/DMUL"), (0, "DFMA")):
+        for ilp in (4, 8):
+            for w in (8, 12, 16):
+                r, ms = C.c_double(), C.c_double()
+                if L.ak_peak_fp64(op, ilp, w, 2048 // ilp, C.byref(r), C.byref(ms)) == 0 and r.value > best:
+                    best, how = r.value, f"{name} chains, ilp {ilp}, {w} warps/SMSP"
+    return best, how
+
+
+def make_sim(mesh, rank, world, dev, dist, **kw):
+    """Simulation on the C++ host driver with its own NCCL communicator for N > 1 (id broadcast through torch.distributed)."""
+    import torch
+    from athenak_b200.sim import Simulation
+    sim = Simulation(mesh, rank, ng=NG, gamma=GAMMA, cfl_number=0.3, tlim=1.0e9, fused=True, **kw)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(sim.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        sim.comm_init(bytes(idt.cpu().numpy().tobytes()))
+    return sim
+
+
+def parity_leg(rank, world, dev, dist):
+    """N > 1 only, before the timed region: two small runs through the SAME driver / exchange path the bench times.
+    (1) 16^3 blast, 8 MeshBlocks of 8^3 over the ranks, 4 cycles, against the reference's own restart dump
+        (tests/golden/blast16_ppm4_hlld_rk3.npz, made by tests/gen_golden.py from oracle/_ref).
+    (2) Orszag-Tang 16^3 on the same 8 blocks, 3 cycles -- there the SendE/RecvE correction changes bits, so a lost or
+        misplaced EMF message shows -- against the same run on ONE rank (every rank repeats it locally), ghost faces included.
+    Returns the max |difference| over all ranks (must be exactly 0) and whether the peer-memory push carried the exchange."""
+    import numpy as np
+    import torch
+    from athenak_b200.mesh import Mesh
+    d = np.load(os.path.join(ROOT, "tests", "golden", "blast16_ppm4_hlld_rk3.npz"))
+    worst, push = 0.0, False
+    mesh = Mesh((16, 16, 16), (8, 8, 8), nranks=world)
+    g0, n = int(mesh.gids_start[rank]), int(mesh.nmb_rank[rank])
+    sim = make_sim(mesh, rank, world, dev, dist, recon="ppm4", rsolver="hlld", integrator="rk3")
+    sim.set_state(*mesh.pgen_blast(rank, NG, GAMMA))
+    sim.initialize()
+    worst = max(worst, abs(sim.status()["dt"] - float(d["dt_c0"])))
+    sim.execute(4)
+    u, x1, x2, x3 = sim.get_state()
+    for m in range(n):
+        lx, ly, lz = (int(v) * 8 for v in mesh.lloc[g0 + m, :3])
+        for got, ref in ((u[m, :, 4:-4, 4:-4, 4:-4], d["u0_c4"][0][:, lz:lz + 8, ly:ly + 8, lx:lx + 8]),
+                         (x1[m, 4:-4, 4:-4, 4:-4], d["b1f_c4"][0][lz:lz + 8, ly:ly + 8, lx:lx + 9]),
+                         (x2[m, 4:-4, 4:-4, 4:-4], d["b2f_c4"][0][lz:lz + 8, ly:ly + 9, lx:lx + 8]),
+                         (x3[m, 4:-4, 4:-4, 4:-4], d["b3f_c4"][0][lz:lz + 9, ly:ly + 8, lx:lx + 8])):
+            worst = max(worst, float(np.abs(got - ref).max()))
+    worst = max(worst, abs(sim.status()["time"] - float(d["time_c4"])))
+    push = sim.status()["peer_push"]
+    del sim
+    # Orszag-Tang: N ranks against one rank
+    from athenak_b200.sim import Simulation
+    one = Mesh((16, 16, 16), (8, 8, 8), nranks=1)
+    ref = Simulation(one, 0, ng=NG, gamma=GAMMA, cfl_number=0.3, tlim=1.0e9, fused=True, recon="ppm4", rsolver="hlld", integrator="rk3")
+    ref.set_state(*one.pgen_orszag_tang(0, NG, GAMMA))
+    ref.initialize()
+    ref.execute(3)
+    r = ref.get_state()
+    rt = ref.status()
+    del ref
+    sim = make_sim(mesh, rank, world, dev, dist, recon="ppm4", rsolver="hlld", integrator="rk3")
+    sim.set_state(*mesh.pgen_orszag_tang(rank, NG, GAMMA))
+    sim.initialize()
+    sim.execute(3)
+    got = sim.get_state()
+    s = slice(NG, -NG)
+    worst = max(worst, float(np.abs(got[0][:, :, s, s, s] - r[0][g0:g0 + n, :, s, s, s]).max()))
+    for x, y in zip(got[1:], r[1:]):
+        worst = max(worst, float(np.abs(x - y[g0:g0 + n]).max()))       # face fields: ghost zones included
+    worst = max(worst, abs(sim.status()["time"] - rt["time"]), abs(sim.status()["dt"] - rt["dt"]))
+    del sim
+    t = torch.tensor([worst], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), bool(push)
+
+
 def bench_native(args):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
+    from athenak_b200 import lib as _lib
     from athenak_b200.driver import Driver, assemble_mhd_tasks
     from athenak_b200.mesh import Mesh
     from athenak_b200.mhd import MHD
@@ -166,55 +266,66 @@ def bench_native(args):
     nroot = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world)
     if nroot is None:
         raise SystemExit("bench.py: --gpus must be 1, 2, 4 or 8")
+
+    def sync_all(sim=None):
+        if sim is not None:
+            sim.sync()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def maxrank(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- N > 1: bitwise parity of the multi-rank path, before anything is timed -----------------
+    parity = None
+    if world > 1:
+        diff, push = parity_leg(rank, world, dev, dist)
+        parity = {"checked": True, "max_abs_diff": diff, "peer_push": push,
+                  "what": "16^3 blast on 8 MeshBlocks over the ranks vs the reference's restart dump (tests/golden), "
+                          "Orszag-Tang 16^3 (EMF correction changes bits) vs the same run on one rank; C++ driver, same exchange path as the timed run"}
+        if diff != 0.0 or os.environ.get("AKB_BENCH_PARITY_ONLY") == "1":
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "multi-rank parity failed" if diff != 0.0 else None, "parity": parity}))
+            dist.destroy_process_group()
+            raise SystemExit(2 if diff != 0.0 else 0)
+
     mesh = Mesh(tuple(n * r for r in nroot), (n, n, n), xmin=tuple(-0.5 * r for r in nroot),
                 xmax=tuple(0.5 * r for r in nroot), nranks=world)
     assert int(mesh.nmb_rank[rank]) == 1
     mb_size, _, nghbr = mesh.rank_tables(rank)
     hu0, hb1, hb2, hb3 = mesh.pgen_blast(rank, NG, GAMMA, pinned=True)
-    # headline path: the C++ host driver (TaskList/Driver/MHD tasks in csrc/host_driver.cpp) calling
-    # the C ABI; NCCL communicator of its own for N > 1 (id broadcast through torch.distributed)
-    from athenak_b200.sim import Simulation
-    sim = Simulation(mesh, rank, ng=NG, recon="ppm4", rsolver="hlld", gamma=GAMMA, integrator="rk3",
-                     cfl_number=0.3, tlim=1.0e9, fused=True)
-    if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(sim.unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        sim.comm_init(bytes(idt.cpu().numpy().tobytes()))
+    # headline path: the C++ host driver (TaskList/Driver/MHD tasks in csrc/host_driver.cpp) calling the C ABI
+    HEAD = dict(recon="ppm4", rsolver="hlld", integrator="rk3")
+    sim = make_sim(mesh, rank, world, dev, dist, **HEAD)
     sim.set_state(hu0, hb1, hb2, hb3)
     sim.initialize()
     sstream = torch.cuda.ExternalStream(sim.status()["stream"], device=dev)
-
-    def sync_all():
-        sim.sync()
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
 
     K, W = args.steps, args.warmup
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # sampled from the warm-up on, so short timed regions still get samples under load
     sim.execute(W)
-    sync_all()
+    sync_all(sim)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = sim.status()["launches"]
     ev0.record(sstream)
     sim.execute(K)
     ev1.record(sstream)
-    sync_all()
+    sync_all(sim)
     launches = sim.status()["launches"] - l0
     ms = ev0.elapsed_time(ev1)
     halo_mode = ("same-rank gather kernel only" if world == 1 else
                  "peer-memory push kernel over NVLink (cudaIpc-mapped neighbour arrays, flag handshake); EMF correction packed straight into the neighbours' receive segments the same way; dt via ncclAllReduce(min)"
                  if sim.status()["peer_push"] else "grouped ncclSend/ncclRecv, one message per peer")
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = maxrank(ms)
     cells = float(n) ** 3 * world
     value = cells * K / (ms * 1e-3) / 1e6
     dt_now = sim.status()["dt"]
@@ -223,69 +334,119 @@ def bench_native(args):
     # H2D of the conserved state (u0 + 3 face fields, pinned) -> ghost exchange + c2p -> one full
     # step -> D2H of the updated conserved state, all through the C ABI (ak_sim_*).
     ho = [torch.empty_like(t).pin_memory() for t in (hu0, hb1, hb2, hb3)]
-    ke2e = max(2, min(K, 5))
     h2d = sum(t.numel() * 8 for t in (hu0, hb1, hb2, hb3))
     d2h = sum(t.numel() * 8 for t in ho)
 
-    def e2e_step():
-        sim.set_state(hu0, hb1, hb2, hb3)
-        sim.initialize()
-        sim.execute(1)
-        sim.get_state(ho)
+    def e2e_step(s_, out):
+        s_.set_state(hu0, hb1, hb2, hb3)
+        s_.initialize()
+        s_.execute(1)
+        s_.get_state(out)
 
-    e2e_step()
-    sync_all()
+    e2e_step(sim, ho)
+    sync_all(sim)
+    # (a) serial reference point: one engine instance, H2D -> step -> D2H
+    ks = 2
+    ev0.record(sstream)
+    for _ in range(ks):
+        e2e_step(sim, ho)
+    ev1.record(sstream)
+    sync_all(sim)
+    ms_serial = maxrank(ev0.elapsed_time(ev1)) / ks
+    # (b) pipelined: several engine instances (own stream + host thread each, ctypes releases the GIL; at N > 1 each has
+    # its own NCCL communicator and peer-memory mapping): while one instance computes step i, others upload step i+1's
+    # input and download step i-1's result, so both PCIe directions and the SMs are busy at the same time.  Every step
+    # still does its own H2D of the full conserved state from pinned memory, ghost exchange + c2p, one RK3 step, and a
+    # D2H of the full result.  Guarded by a watchdog: if the instances do not finish, the serial figure is reported.
+    NI = 3
     e2e_mode = "serial: H2D -> step -> D2H, one engine instance"
-    if world == 1:
-        # Several engine instances (own stream + host thread each, ctypes releases the GIL): while one
-        # instance computes step i, others upload step i+1's input and download step i-1's result,
-        # so PCIe (both directions) and the SMs are busy at the same time.  Every step still does its own
-        # H2D of the full conserved state from pinned memory, ghost exchange + c2p, one RK3 step, and a
-        # D2H of the full result.
-        NI = 3      # per instance the chain H2D -> step -> D2H is serial (same buffers); three chains in flight keep
-                    # both PCIe directions and the SMs busy
-        sims = [sim] + [Simulation(mesh, rank, ng=NG, recon="ppm4", rsolver="hlld", gamma=GAMMA, integrator="rk3",
-                                   cfl_number=0.3, tlim=1.0e9, fused=True) for _ in range(NI - 1)]
+    ms_e2e, ke2e = ms_serial * ks, ks
+    try:
+        sims = [sim] + [make_sim(mesh, rank, world, dev, dist, **HEAD) for _ in range(NI - 1)]
         outs = [ho] + [[torch.empty_like(t).pin_memory() for t in ho] for _ in range(NI - 1)]
         per = max(2, min(K, 12) // NI)
-        ke2e = per * NI
 
-        def worker(s, out, nsteps):
+        def worker(s_, out, nsteps):
+            torch.cuda.set_device(local)       # a new host thread starts on device 0
             for _ in range(nsteps):
-                s.set_state(hu0, hb1, hb2, hb3)
-                s.initialize()
-                s.execute(1)
-                s.get_state(out)
-            s.sync()
+                e2e_step(s_, out)
+            s_.sync()
 
         for s_, o_ in zip(sims[1:], outs[1:]):
             worker(s_, o_, 1)
-        sync_all()
-        ths = [threading.Thread(target=worker, args=(s_, o_, per)) for s_, o_ in zip(sims, outs)]
+        sync_all(sim)
+        ths = [threading.Thread(target=worker, args=(s_, o_, per), daemon=True) for s_, o_ in zip(sims, outs)]
         ev0.record(sstream)           # all streams idle here: the event time-stamps "now" on the device clock
         for th in ths:
             th.start()
+        deadline = time.time() + 180.0
         for th in ths:
-            th.join()
+            th.join(max(0.0, deadline - time.time()))
+        if any(th.is_alive() for th in ths):
+            raise TimeoutError("pipelined e2e instances did not finish in 180 s")
         ev1.record(sstream)           # every instance drained (worker ends with a stream sync): end of the last D2H
-        sync_all()
-        e2e_mode = f"{NI} engine instances over {NI} streams/host threads (H2D, step, D2H of consecutive steps overlap)"
+        sync_all(sim)
         assert all(bool(torch.equal(x, y)) for o_ in outs[1:] for x, y in zip(ho, o_)), "the e2e instances disagree"
+        ms_e2e, ke2e = maxrank(ev0.elapsed_time(ev1)), per * NI
+        e2e_mode = f"{NI} engine instances over {NI} streams/host threads per rank (H2D, step, D2H of consecutive steps overlap)"
         del sims, outs
+    except TimeoutError as ex:
+        e2e_mode += f" (pipelined mode abandoned: {ex})"
+        hung = True
     else:
-        ev0.record(sstream)
-        for _ in range(ke2e):
-            e2e_step()
-        ev1.record(sstream)
-        sync_all()
-    ms_e2e = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+        hung = False
     e2e_value = cells * ke2e / (ms_e2e * 1e-3) / 1e6
-    del sim
-    torch.cuda.empty_cache()
+    if not hung:
+        del sim
+        torch.cuda.empty_cache()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mcell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload(n), "mesh": "x".join(str(n * r) for r in nroot),
+                   "l2": "every field array is %.0f MB (> 126 MB L2); no explicit flush" % (8 * (n + 2 * NG) ** 3 / 1e6),
+                   "fmad": False, "parity_build": True, "division_guard": "deferred range guard on (IEEE result for every operand)",
+                   "driver": "C++ host driver (ak_sim_*), fused task list", "ghost_exchange": halo_mode},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mcell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": ke2e, "ms_per_step": ms_e2e / ke2e, "mode": e2e_mode,
+                "serial_ms_per_step": ms_serial, "serial_value": cells / (ms_serial * 1e-3) / 1e6},
+        "gpu_launches": launches,
+    }
+    if parity is not None:
+        line["parity"] = parity
+    if hung:      # threads stuck inside the library cannot be joined: report what was measured and leave
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+
+    # ---- BASELINE config 3's per-GPU layout as a secondary block: Orszag-Tang, 64 MeshBlocks of (n/4)^3 per GPU ---------
+    try:
+        q = n // 4
+        m3 = Mesh(tuple(n * r for r in nroot), (q, q, q), xmin=tuple(-0.5 * r for r in nroot), xmax=tuple(0.5 * r for r in nroot),
+                  nranks=world)
+        s3 = make_sim(m3, rank, world, dev, dist, **HEAD)
+        s3.set_state(*m3.pgen_orszag_tang(rank, NG, GAMMA))
+        s3.initialize()
+        st3 = torch.cuda.ExternalStream(s3.status()["stream"], device=dev)
+        k3 = max(3, min(K, 10))
+        s3.execute(3)
+        sync_all(s3)
+        l3 = s3.status()["launches"]
+        ev0.record(st3)
+        s3.execute(k3)
+        ev1.record(st3)
+        sync_all(s3)
+        ms3 = maxrank(ev0.elapsed_time(ev1))
+        line["config3_ot"] = {"workload": f"Orszag-Tang 3D MHD, {'x'.join(str(n * r) for r in nroot)} cells, {int(m3.nmb_rank[rank])} MeshBlocks of {q}^3 per GPU, "
+                                          "PPM4+HLLD+RK3, nghost=4, uniform mesh (BASELINE config 3 layout)",
+                              "value": cells * k3 / (ms3 * 1e-3) / 1e6, "unit": "Mcell-updates/s", "steps": k3, "ms_per_step": ms3 / k3,
+                              "gpu_launches": s3.status()["launches"] - l3, "peer_push": s3.status()["peer_push"]}
+        del s3
+        torch.cuda.empty_cache()
+    except Exception as ex:      # secondary block: never takes the headline down
+        line["config3_ot"] = {"error": str(ex)[:200]}
 
     # ---- per-kernel breakdown through the per-task C-ABI entry points -------------------------
     e = MHD(1, NG, (n, n, n), mb_size, nghbr, recon="ppm4", rsolver="hlld", gamma=GAMMA, my_rank=rank,
@@ -337,37 +498,43 @@ def bench_native(args):
     flux_ms = kern["fluxes(x1+x2+x3)"]["ms"] / 3.0 if kern else float("nan")
     flux_bytes = 15 * 8 * ncell
     flux_achieved = flux_bytes / (flux_ms * 1e-3) / 1e9
-
-    line = {
-        "metric": METRIC, "value": value, "unit": "Mcell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": f"3D MHD blast {n}^3 cells per GPU, one MeshBlock per GPU, PPM4+HLLD+RK3, nghost=4, periodic, "
-                               f"mesh {'x'.join(str(n * r) for r in nroot)}; step = one full RK3 time step",
-                   "l2": "every field array is %.0f MB (> 126 MB L2); no explicit flush" % (8 * (n + 2 * NG) ** 3 / 1e6),
-                   "fmad": False, "parity_build": True, "driver": "C++ host driver (ak_sim_*), fused task list",
-                   "ghost_exchange": halo_mode},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "Mcell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": ke2e, "ms_per_step": ms_e2e / ke2e, "mode": e2e_mode},
-        "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "flux sweep (flux_x1_kernel / flux_march_kernel<x2> / <x3>; 3 launches per stage, 63% of the stage)",
-                     "achieved": flux_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": flux_achieved / hbm_peak,
-                     "traffic": 2.13e9, "traffic_source": "ncu --set full, dram__bytes_read.sum+dram__bytes_write.sum per launch: 2.08/2.20/2.19 GB (profiles/r01_ncu_kernels.txt)",
-                     "algorithmic_bytes_per_launch": flux_bytes, "avg_launch_ms": flux_ms, "peak_source": peak_src,
-                     "note": "FP64-issue-bound, not HBM-bound: ~670 FP64 instructions per cell per sweep; ncu FP64-pipe utilisation 50-60%",
-                     "path": {"what": "whole stage, 256 B algorithmic per active cell per stage (SURVEY.md 8d) / mean stage time",
-                              "achieved": path_achieved, "frac": path_achieved / hbm_peak, "stage_ms": stage_ms},
-                     "dominant_task": dom, "kernels": kern},
-    }
+    flux_share = 3.0 * flux_ms / sum(v["ms"] for v in kern.values()) if kern else float("nan")
+    # measured DRAM traffic and FP64 instruction counts of the sweeps: committed ncu summary (256^3 launches only)
+    ncu = {}
+    try:
+        ncu = json.load(open(NCU_FLUX))
+    except Exception:
+        pass
+    traffic = ncu.get("per_launch_mean", {}).get("dram_bytes") if n == 256 else None
+    fp64_inst = ncu.get("per_launch_mean", {}).get("fp64_warp_inst") if n == 256 else None
+    fp64_peak, fp64_how = measure_fp64_peak(_lib.load())
+    fp64 = None
+    if fp64_inst and fp64_peak:
+        ach = 32.0 * fp64_inst / (flux_ms * 1e-3)
+        fp64 = {"what": "FP64 issue roofline of the same kernel: warp-level FP64 instructions (DADD/DMUL/DFMA/DSETP) per launch x 32 lanes / launch time, "
+                        "against the lane-instruction rate of a register-only FP64 chain kernel measured in this run (ak_peak_fp64)",
+                "achieved": ach, "peak": fp64_peak, "unit": "FP64 lane-instructions/s", "frac": ach / fp64_peak,
+                "peak_how": fp64_how, "fp64_warp_inst_per_launch": fp64_inst, "counts_source": os.path.relpath(NCU_FLUX, ROOT)}
+    line["roofline"] = {
+        "bound": "hbm", "kernel": "flux sweep (flux_x1_kernel / flux_march_kernel<x2> / <x3>; 3 launches per stage, "
+                                  f"{100.0 * flux_share:.0f}% of the per-task stage time measured below)",
+        "achieved": flux_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": flux_achieved / hbm_peak,
+        "traffic": traffic, "traffic_source": f"{os.path.relpath(NCU_FLUX, ROOT)}: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean of the "
+                                              f"three sweep launches, kernel regex '{ncu.get('kernel_regex')}'" if traffic else None,
+        "algorithmic_bytes_per_launch": flux_bytes, "avg_launch_ms": flux_ms, "peak_source": peak_src,
+        "note": "the sweeps are bound by FP64 issue, not by HBM: see fp64 (measured issue peak) next to the HBM figure",
+        "fp64": fp64,
+        "path": {"what": "whole stage, 256 B algorithmic per active cell per stage (SURVEY.md 8d) / mean stage time",
+                 "achieved": path_achieved, "frac": path_achieved / hbm_peak, "stage_ms": stage_ms},
+        "dominant_task": dom, "kernels": kern}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_cores()
         try:
-            ncpu, rate = pick_reference_size(threads, budget_s=25.0, ncycles=3)
-            r = run_reference_cpu(ncpu, 3, threads)
+            ncpu, rate = pick_reference_size(threads, budget_s=25.0, ncycles=4)
+            r = run_reference_cpu(ncpu, 4, threads)
             v = ncpu ** 3 * len(r["per_cycle"][1:]) / sum(r["per_cycle"][1:]) / 1e6
             line["cpu_baseline"] = {"value": v, "unit": "Mcell-updates/s", "cores": threads, "kind": "reference",
-                                    "sample": f"{ncpu}^3 single MeshBlock, 2 timed cycles after 1 warm-up, reference Kokkos::OpenMP build (oracle/_ref/athena_blast), all host threads"}
+                                    "sample": f"{ncpu}^3 single MeshBlock, {len(r['per_cycle'][1:])} timed cycles after 1 warm-up, reference Kokkos::OpenMP build (oracle/_ref/athena_blast), all host threads"}
         except Exception as ex:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "Mcell-updates/s", "cores": threads, "kind": "reference",
                                     "sample": f"failed: {ex}"[:200]}

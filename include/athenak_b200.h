@@ -118,6 +118,9 @@ int ak_mhd_set_stage(void *h, double gam0, double gam1, double beta_dt);
  * are done, concurrently with the corner-EMF kernel; the following ak_mhd_stage_update(h, a, stage, same coefficients)
  * joins it and performs the CT half only.  Same kernels, same results; AKB_OVERLAP_U=0 disables the overlap. */
 int ak_mhd_stage_begin(void *h, int stage, double gam0, double gam1, double beta_dt);
+/* after ak_mhd_stage_flux_emf: the auxiliary stream its early U update was queued on (NULL when that overlap is off); work queued
+ * there runs after the U update and beside the corner-EMF kernel -- the host driver uses it for the ghost-zone push of u0 */
+int ak_mhd_aux_stream(void *h, ak_stream_t *aux);
 int ak_mhd_stage_update(void *h, const ak_mhd_arrays *a, int stage, double gam0, double gam1,
                         double beta_dt, ak_stream_t s);
 int ak_mhd_stage_fused(void *h, const ak_mhd_arrays *a, int stage, double gam0, double gam1,
@@ -144,6 +147,20 @@ int ak_mhd_stage_fused(void *h, const ak_mhd_arrays *a, int stage, double gam0, 
  *          pointers); nfloor (3 ints) and dt3 (3 doubles), when not NULL, return the floor counters and the new-dt minima
  *          accumulated by both kernels (dt3 requires want_dt = 1 in the tail call) and synchronise the stream. */
 int ak_mhd_tail_supported(void *h);
+
+/* Flux + update fusion: tasks 2 (Fluxes, mhd_fluxes.cpp:85-266), 1 (CopyCons of u) and 5 (RKUpdate, mhd_update.cpp:24-84) as the
+ * three sweep kernels alone.  Each sweep turns the fluxes at the two faces of a cell into its term of the flux divergence while
+ * they are in registers; x1 and x2 store theirs in du, x3 adds its own in the reference's order and writes
+ * u0 = gam0*u0 + gam1*u1 - beta_dt*divf (stage 1: u1's active cells receive the old u0).  a->flx1/2/3 receive ONLY their IDN
+ * component (the corner EMFs upwind with it), the face EMFs are written as by ak_mhd_fluxes.  du = scratch of
+ * 2 * nmb * nfl * n3*n2*n1 doubles.  3-D MHD without passive scalars / FOFC (ak_mhd_fluxes_update_supported).
+ * Follow with ak_mhd_corner_e, SendE/RecvE, ak_mhd_ct (ak_mhd_stage_update with the U half already done), the ghost exchange
+ * and ak_mhd_cons2prim. */
+int ak_mhd_fluxes_update_supported(void *h);
+/* task 17 (CT) with the stage-1 CopyCons of the face field folded in, for callers of ak_mhd_fluxes_update */
+int ak_mhd_ct_save(void *h, const ak_mhd_arrays *a, int stage, double gam0, double gam1, double beta_dt, ak_stream_t s);
+int ak_mhd_fluxes_update(void *h, const ak_mhd_arrays *a, double *du, int stage, double gam0, double gam1, double beta_dt,
+                         ak_stream_t s);
 int ak_mhd_stage_tail(void *h, const ak_mhd_arrays *a, const ak_mhd_arrays *out, int stage, double gam0, double gam1,
                       double beta_dt, int want_dt, ak_stream_t s);
 int ak_mhd_stage_shell_ct(void *h, const ak_mhd_arrays *a, const ak_mhd_arrays *out, int stage, double gam0, double gam1,

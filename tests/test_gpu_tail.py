@@ -1,4 +1,5 @@
-"""The two-kernel stage (ak_mhd_stage_tail + shell kernels, csrc/stage_tail.cu) against (i) the task-by-task kernels of the same
+"""The fused forms of the stage -- the flux + update fusion (ak_mhd_fluxes_update: sweeps that finish the conserved update, no flux
+arrays) and the two-kernel stage (ak_mhd_stage_tail + shell kernels, csrc/stage_tail.cu) -- against (i) the task-by-task kernels of the same
 library (AKB_TAIL=0: flux sweeps, corner_emf, update_ct, cons2prim as separate launches -- themselves bitwise against the oracle
 and the reference in test_gpu_parity.py) and (ii) the reference's golden dumps.  Everything is compared bit for bit, ghost zones
 and primitives included, after several cycles, so a wrong frame cell, a missed shell face, a wrong buffer rotation or a lost
@@ -14,17 +15,25 @@ import golden_io as G
 pytestmark = pytest.mark.gpu
 
 
-def _run(mesh, state, ncycles, tail, **kw):
+MODES = {"tail": {"AKB_TAIL": "1", "AKB_FLUXUPD": "0"},        # two-kernel stage (stage_tail.cu)
+         "fluxupd": {"AKB_TAIL": "0", "AKB_FLUXUPD": "1"},     # flux + update fusion (AccArgs, flux_kernels.cuh)
+         "tasks": {"AKB_TAIL": "0", "AKB_FLUXUPD": "0"}}       # one kernel per task group (round-1 fused list)
+
+
+def _run(mesh, state, ncycles, mode, **kw):
     from athenak_b200.sim import Simulation
-    old = os.environ.get("AKB_TAIL")
-    os.environ["AKB_TAIL"] = "1" if tail else "0"
+    if mode is True:
+        mode = "tail"
+    old = {k: os.environ.get(k) for k in MODES[mode]}
+    os.environ.update(MODES[mode])
     try:
         sim = Simulation(mesh, 0, ng=kw.pop("ng", 4), cfl_number=0.3, tlim=1.0e9, fused=True, **kw)
     finally:
-        if old is None:
-            os.environ.pop("AKB_TAIL", None)
-        else:
-            os.environ["AKB_TAIL"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     sim.set_state(*state)
     sim.initialize()
     dts = [sim.status()["dt"]]
@@ -37,14 +46,17 @@ def _run(mesh, state, ncycles, tail, **kw):
 
 
 def _compare(mesh, state, ncycles, **kw):
-    a, dta, sta = _run(mesh, state, ncycles, True, **kw)
-    b, dtb, stb = _run(mesh, state, ncycles, False, **kw)
-    assert dta == dtb, (dta, dtb)
-    assert sta["time"] == stb["time"] and sta["nfloor"] == stb["nfloor"]
-    assert sta["launches"] < stb["launches"]          # the tail path really ran (fewer launches per stage)
-    for name, x, y in zip(("u0", "b1f", "b2f", "b3f", "w0", "bcc0"), a, b):
-        bad = np.argwhere(x != y)
-        assert len(bad) == 0, f"{name}: {len(bad)} entries differ, first {bad[0]}, {x[tuple(bad[0])]!r} vs {y[tuple(bad[0])]!r}"
+    b, dtb, stb = _run(mesh, state, ncycles, "tasks", **dict(kw))
+    scal = kw.get("nscalars", 0) > 0
+    for mode in ("tail", "fluxupd"):
+        a, dta, sta = _run(mesh, state, ncycles, mode, **dict(kw))
+        assert dta == dtb, (mode, dta, dtb)
+        assert sta["time"] == stb["time"] and sta["nfloor"] == stb["nfloor"], mode
+        if not (mode == "fluxupd" and scal):        # passive scalars: the flux + update fusion falls back to the task kernels
+            assert sta["launches"] < stb["launches"], mode          # the fused path really ran (fewer launches per stage)
+        for name, x, y in zip(("u0", "b1f", "b2f", "b3f", "w0", "bcc0"), a, b):
+            bad = np.argwhere(x != y)
+            assert len(bad) == 0, f"{mode} {name}: {len(bad)} entries differ, first {bad[0]}, {x[tuple(bad[0])]!r} vs {y[tuple(bad[0])]!r}"
     return a
 
 
@@ -99,14 +111,15 @@ def test_tail_floors_fire():
     assert np.isfinite(a[0]).all()
 
 
+@pytest.mark.parametrize("mode", ["tail", "fluxupd"])
 @pytest.mark.parametrize("nb", [1, 2])
-def test_tail_matches_reference_golden(nb):
+def test_tail_matches_reference_golden(nb, mode):
     """End to end against the reference's restart dump (16^3 blast, 4 cycles), through the two-kernel stage."""
     from athenak_b200.mesh import Mesh
     d = G.load("blast16_ppm4_hlld_rk3")
     m = 16 // nb
     mesh = Mesh((16, 16, 16), (m, m, m))
-    (u, x1, x2, x3, _, _), dts, st = _run(mesh, mesh.pgen_blast(0, 4, 1.6666667), 4, True, recon="ppm4", rsolver="hlld",
+    (u, x1, x2, x3, _, _), dts, st = _run(mesh, mesh.pgen_blast(0, 4, 1.6666667), 4, mode, recon="ppm4", rsolver="hlld",
                                            gamma=1.6666667, integrator="rk3")
     assert dts[0] == float(d["dt_c0"]) and st["time"] == float(d["time_c4"])
     for g in range(mesh.nmb_total):
