@@ -605,7 +605,7 @@ int ak_halo_local_cc(void *plan, double *a, int nvar, ak_stream_t s) {
   if (halo_ready(P, "ak_halo_local_cc")) return 1;
   akb::HaloArrays A = akb::halo_arrays_cc(P->cfg, a, nvar);
   const long cc = A.bstride[0] / nvar;
-  return halo_rc(P, "ak_halo_local_cc", akb::halo_launch(P->local_cc, P->d_local_cc, A, nvar, cc, nullptr, akb::HALO_LOCAL, (cudaStream_t)s));
+  return halo_rc(P, "ak_halo_local_cc", akb::halo_launch(P, P->local_cc, P->d_local_cc, A, nvar, cc, nullptr, akb::HALO_LOCAL, (cudaStream_t)s));
 }
 
 int ak_halo_local_fc(void *plan, double *x1f, double *x2f, double *x3f, ak_stream_t s) {
@@ -613,7 +613,7 @@ int ak_halo_local_fc(void *plan, double *x1f, double *x2f, double *x3f, ak_strea
   if (!P || !x1f || !x2f || !x3f) return fail(nullptr, "ak_halo_local_fc: null argument");
   if (halo_ready(P, "ak_halo_local_fc")) return 1;
   akb::HaloArrays A = akb::halo_arrays_fc(P->cfg, x1f, x2f, x3f);
-  return halo_rc(P, "ak_halo_local_fc", akb::halo_launch(P->local_fc, P->d_local_fc, A, 1, 0, nullptr, akb::HALO_LOCAL, (cudaStream_t)s));
+  return halo_rc(P, "ak_halo_local_fc", akb::halo_launch(P, P->local_fc, P->d_local_fc, A, 1, 0, nullptr, akb::HALO_LOCAL, (cudaStream_t)s));
 }
 
 #define AK_PEER(name)                                                                         \
@@ -625,22 +625,22 @@ int ak_halo_local_fc(void *plan, double *x1f, double *x2f, double *x3f, ak_strea
 int ak_halo_pack_cc(void *plan, const double *a, int nvar, int ipeer, double *sendbuf, ak_stream_t s) {
   AK_PEER("ak_halo_pack_cc")
   akb::HaloArrays A = akb::halo_arrays_cc(P->cfg, const_cast<double *>(a), nvar);
-  return halo_rc(P, "ak_halo_pack_cc", akb::halo_launch(peer.pack_cc, peer.d_pack_cc, A, nvar, A.bstride[0] / nvar, sendbuf, akb::HALO_PACK, (cudaStream_t)s));
+  return halo_rc(P, "ak_halo_pack_cc", akb::halo_launch(P, peer.pack_cc, peer.d_pack_cc, A, nvar, A.bstride[0] / nvar, sendbuf, akb::HALO_PACK, (cudaStream_t)s));
 }
 int ak_halo_unpack_cc(void *plan, double *a, int nvar, int ipeer, const double *recvbuf, ak_stream_t s) {
   AK_PEER("ak_halo_unpack_cc")
   akb::HaloArrays A = akb::halo_arrays_cc(P->cfg, a, nvar);
-  return halo_rc(P, "ak_halo_unpack_cc", akb::halo_launch(peer.unpack_cc, peer.d_unpack_cc, A, nvar, A.bstride[0] / nvar, const_cast<double *>(recvbuf), akb::HALO_UNPACK, (cudaStream_t)s));
+  return halo_rc(P, "ak_halo_unpack_cc", akb::halo_launch(P, peer.unpack_cc, peer.d_unpack_cc, A, nvar, A.bstride[0] / nvar, const_cast<double *>(recvbuf), akb::HALO_UNPACK, (cudaStream_t)s));
 }
 int ak_halo_pack_fc(void *plan, const double *x1f, const double *x2f, const double *x3f, int ipeer, double *sendbuf, ak_stream_t s) {
   AK_PEER("ak_halo_pack_fc")
   akb::HaloArrays A = akb::halo_arrays_fc(P->cfg, const_cast<double *>(x1f), const_cast<double *>(x2f), const_cast<double *>(x3f));
-  return halo_rc(P, "ak_halo_pack_fc", akb::halo_launch(peer.pack_fc, peer.d_pack_fc, A, 1, 0, sendbuf, akb::HALO_PACK, (cudaStream_t)s));
+  return halo_rc(P, "ak_halo_pack_fc", akb::halo_launch(P, peer.pack_fc, peer.d_pack_fc, A, 1, 0, sendbuf, akb::HALO_PACK, (cudaStream_t)s));
 }
 int ak_halo_unpack_fc(void *plan, double *x1f, double *x2f, double *x3f, int ipeer, const double *recvbuf, ak_stream_t s) {
   AK_PEER("ak_halo_unpack_fc")
   akb::HaloArrays A = akb::halo_arrays_fc(P->cfg, x1f, x2f, x3f);
-  return halo_rc(P, "ak_halo_unpack_fc", akb::halo_launch(peer.unpack_fc, peer.d_unpack_fc, A, 1, 0, const_cast<double *>(recvbuf), akb::HALO_UNPACK, (cudaStream_t)s));
+  return halo_rc(P, "ak_halo_unpack_fc", akb::halo_launch(P, peer.unpack_fc, peer.d_unpack_fc, A, 1, 0, const_cast<double *>(recvbuf), akb::HALO_UNPACK, (cudaStream_t)s));
 }
 
 // ---- SendE/RecvE: EMF flux correction on a same-level mesh (flux_correct_fc.cpp) ------------
@@ -663,12 +663,12 @@ int ak_halo_emf_pack_local(void *plan, const double *e1, const double *e2, const
   if (!P || !e1 || !e2 || !e3) return fail(nullptr, "ak_halo_emf_pack_local: null argument");
   if (halo_ready(P, "ak_halo_emf_pack_local")) return 1;
   akb::HaloArrays A = akb::halo_arrays_ec(P->cfg, const_cast<double *>(e1), const_cast<double *>(e2), const_cast<double *>(e3));
-  return halo_rc(P, "ak_halo_emf_pack_local", akb::halo_launch(P->emf_pack_local, P->d_emf_pack_local, A, 1, 0, P->d_emf_rbuf, akb::HALO_PACK, (cudaStream_t)s));
+  return halo_rc(P, "ak_halo_emf_pack_local", akb::halo_launch(P, P->emf_pack_local, P->d_emf_pack_local, A, 1, 0, P->d_emf_rbuf, akb::HALO_PACK, (cudaStream_t)s));
 }
 int ak_halo_emf_pack(void *plan, const double *e1, const double *e2, const double *e3, int ipeer, double *sendbuf, ak_stream_t s) {
   AK_PEER("ak_halo_emf_pack")
   akb::HaloArrays A = akb::halo_arrays_ec(P->cfg, const_cast<double *>(e1), const_cast<double *>(e2), const_cast<double *>(e3));
-  return halo_rc(P, "ak_halo_emf_pack", akb::halo_launch(peer.pack_emf, peer.d_pack_emf, A, 1, 0, sendbuf, akb::HALO_PACK, (cudaStream_t)s));
+  return halo_rc(P, "ak_halo_emf_pack", akb::halo_launch(P, peer.pack_emf, peer.d_pack_emf, A, 1, 0, sendbuf, akb::HALO_PACK, (cudaStream_t)s));
 }
 int ak_halo_emf_sumavg(void *plan, double *e1, double *e2, double *e3, ak_stream_t s) {
   akb::HaloPlan *P = static_cast<akb::HaloPlan *>(plan);
@@ -732,6 +732,8 @@ int ak_halo_push_commit(void *plan) {
   for (const auto &d : P->push) if (d.dst_m < 0) return fail(nullptr, "ak_halo_push_commit: a peer was not set up");
   if (!P->flags_local) return fail(nullptr, "ak_halo_push_commit: flags were not set up");
   cudaFree(P->d_push); P->d_push = nullptr;
+  for (auto &kv : P->tiles) cudaFree(kv.second.d);     // launch tables are keyed by the descriptor arrays: rebuild
+  P->tiles.clear();
   if (!P->push.empty()) {
     cudaError_t e = cudaMalloc(&P->d_push, sizeof(akb::PushDesc) * P->push.size());
     if (e == cudaSuccess) e = cudaMemcpy(P->d_push, P->push.data(), sizeof(akb::PushDesc) * P->push.size(), cudaMemcpyHostToDevice);

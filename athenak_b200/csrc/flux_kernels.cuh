@@ -45,13 +45,13 @@ struct SolverTraits {
 template <int RS>
 __device__ __forceinline__ void riemann_any(const State7 &l, const State7 &r, double bxi, const EosParams &eos, Flux7 &f,
                                             bool *oor = nullptr) {   // oor: deferred range guard (mhd_device.cuh), threaded through the headline solver
-  if constexpr (RS == RS_LLF_ISO) llf_iso(l, r, bxi, eos, f);
-  else if constexpr (RS == RS_HLLE_ISO) hlle_iso(l, r, bxi, eos, f);
-  else if constexpr (RS == RS_HLLD_ISO) hlld_iso(l, r, bxi, eos, f);
-  else if constexpr (RS == RS_HYD_LLF_ISO) hyd_llf_iso(l, r, eos, f);
-  else if constexpr (RS == RS_HYD_HLLE_ISO) hyd_hlle_iso(l, r, eos, f);
-  else if constexpr (RS == RS_HYD_ROE_ISO) hyd_roe_iso(l, r, eos, f);
-  else if constexpr (rs_is_hydro(RS)) riemann_hyd<RS>(l, r, eos, f);
+  if constexpr (RS == RS_LLF_ISO) llf_iso(l, r, bxi, eos, f, oor);
+  else if constexpr (RS == RS_HLLE_ISO) hlle_iso(l, r, bxi, eos, f, oor);
+  else if constexpr (RS == RS_HLLD_ISO) hlld_iso(l, r, bxi, eos, f, oor);
+  else if constexpr (RS == RS_HYD_LLF_ISO) hyd_llf_iso(l, r, eos, f, oor);
+  else if constexpr (RS == RS_HYD_HLLE_ISO) hyd_hlle_iso(l, r, eos, f, oor);
+  else if constexpr (RS == RS_HYD_ROE_ISO) hyd_roe_iso(l, r, eos, f, oor);
+  else if constexpr (rs_is_hydro(RS)) riemann_hyd<RS>(l, r, eos, f, oor);
   else riemann<RS>(l, r, bxi, eos, f, oor);
 }
 
@@ -196,7 +196,7 @@ flux_x1_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const doubl
       ppm4_mono(q[v], fl[v], fh, *upv[T::member(v)], *lov[T::member(v)]);
     }
   } else {
-    recon_cell<RECON, 0, MHD, IDEAL>(wc, bc, cc, 1, eos, up, lo);
+    recon_cell<RECON, 0, MHD, IDEAL>(wc, bc, cc, 1, eos, up, lo, &oor);
   }
   shift_up_state<RS>(up, L);
   if (act) riemann_any<RS>(L, lo, bxi, eos, f, &oor);
@@ -278,9 +278,9 @@ __device__ __forceinline__ void recon_ring_var(const double *__restrict__ rv, in
   const double qm2 = rv[b0 * MARCH_THREADS], qm1 = rv[b1 * MARCH_THREADS], q = rv[b2 * MARCH_THREADS];
   const double qp1 = rv[b3 * MARCH_THREADS], qp2 = rv[b4 * MARCH_THREADS];
   if constexpr (RECON == RECON_PPM4) ppm4(qm2, qm1, q, qp1, qp2, q_up, q_lo, oor);
-  else if constexpr (RECON == RECON_PPMX) ppmx(qm2, qm1, q, qp1, qp2, q_up, q_lo);
-  else if constexpr (RECON == RECON_TENO) teno(qm2, qm1, q, qp1, qp2, q_up, q_lo);
-  else wenoz(qm2, qm1, q, qp1, qp2, q_up, q_lo);
+  else if constexpr (RECON == RECON_PPMX) ppmx(qm2, qm1, q, qp1, qp2, q_up, q_lo, oor);
+  else if constexpr (RECON == RECON_TENO) teno(qm2, qm1, q, qp1, qp2, q_up, q_lo, oor);
+  else wenoz(qm2, qm1, q, qp1, qp2, q_up, q_lo, oor);
 }
 
 template <int RECON, int RS>
@@ -534,17 +534,24 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
     }
     cp_async_wait<0>();
   } else {
-    recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, L, lo_unused);
+    {
+      bool oor0 = false;
+      recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, L, lo_unused, &oor0);
+      if (oor0) recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, L, lo_unused);
+    }
     for (int f = f_lo; f <= f_hi; ++f) {
       co += s;
       State7 up, lo;
-      recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, up, lo);
+      bool oor = false;
+      recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, up, lo, &oor);
       Flux7 fx;
       double bni = 0.0;
       if constexpr (MHD) bni = __ldg(bnb + fo);
-      bool oor = false;
       riemann_any<RS>(L, lo, bni, eos, fx, &oor);
-      if (oor) riemann_any<RS>(L, lo, bni, eos, fx);
+      if (oor) {       // cold: the guarded operators (L was verified when it was computed)
+        recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, up, lo);
+        riemann_any<RS>(L, lo, bni, eos, fx);
+      }
       emit(f, fx, co, fo);
       L = up;
       fo += s;

@@ -59,16 +59,18 @@ static Box halo_box(const ak_mhd_cfg &c, int comp, const int o[3], bool send) {
 }
 
 __global__ void __launch_bounds__(256)
-halo_copy_kernel(const HaloDesc *__restrict__ descs, HaloArrays A, int nvar, long varstride,
+halo_copy_kernel(const HaloDesc *__restrict__ descs, const int2 *__restrict__ tiles, HaloArrays A, int nvar, long varstride,
                  double *__restrict__ buf, int mode) {
-  const HaloDesc d = descs[blockIdx.y];
+  const int2 tl = tiles[blockIdx.x];        // {descriptor, chunk}: one CTA per HALO_TILE elements of one descriptor
+  const HaloDesc d = descs[tl.x];
   const int ni = d.hi[0] - d.lo[0] + 1, nj = d.hi[1] - d.lo[1] + 1, nk = d.hi[2] - d.lo[2] + 1;
   const long per = (long)ni * nj * nk;
   const long total = per * nvar;
   const int c = d.comp < 0 ? 0 : d.comp;
   double *arr = A.p[c];
   const long e1 = A.ext1[c], e2 = A.ext2[c], bs = A.bstride[c];
-  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x) {
+  const long qend = ((long)(tl.y + 1) * HALO_TILE < total) ? (long)(tl.y + 1) * HALO_TILE : total;
+  for (long q = (long)tl.y * HALO_TILE + threadIdx.x; q < qend; q += blockDim.x) {
     long t = q;
     const int i = (int)(t % ni); t /= ni;
     const int j = (int)(t % nj); t /= nj;
@@ -109,13 +111,15 @@ static bool emf_slot_has(const int o[3], int v) {
 }
 
 __global__ void __launch_bounds__(128)
-emf_sumavg_kernel(const EmfSumDesc *__restrict__ descs, HaloArrays A, const double *__restrict__ rbuf) {
-  const EmfSumDesc d = descs[blockIdx.y];
+emf_sumavg_kernel(const EmfSumDesc *__restrict__ descs, const int2 *__restrict__ tiles, HaloArrays A, const double *__restrict__ rbuf) {
+  const int2 tl = tiles[blockIdx.x];
+  const EmfSumDesc d = descs[tl.x];
   const int ni = d.hi[0] - d.lo[0] + 1, nj = d.hi[1] - d.lo[1] + 1, nk = d.hi[2] - d.lo[2] + 1;
   const long total = (long)ni * nj * nk;
   double *arr = A.p[d.v];
   const long e1 = A.ext1[d.v], e2 = A.ext2[d.v], bs = A.bstride[d.v];
-  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x) {
+  const long qend = ((long)(tl.y + 1) * HALO_TILE < total) ? (long)(tl.y + 1) * HALO_TILE : total;
+  for (long q = (long)tl.y * HALO_TILE + threadIdx.x; q < qend; q += blockDim.x) {
     long t = q;
     const int i = d.lo[0] + (int)(t % ni); t /= ni;
     const int j = d.lo[1] + (int)(t % nj);
@@ -395,16 +399,35 @@ cudaError_t halo_ensure_uploaded(HaloPlan *P) {
   return cudaSuccess;
 }
 
+// tile table of a descriptor list: built and uploaded on first use, cached per (list, nvar)
+template <class Desc, class CountFn>
+static cudaError_t tile_table(HaloPlan *P, const std::vector<Desc> &host, const void *key, int nvar, CountFn count, HaloPlan::TileTab &out) {
+  auto it = P->tiles.find({key, nvar});
+  if (it != P->tiles.end()) { out = it->second; return cudaSuccess; }
+  std::vector<int2> t;
+  for (size_t q = 0; q < host.size(); ++q) {
+    const long total = count(host[q]);
+    for (long c = 0; c * HALO_TILE < total; ++c) t.push_back(make_int2((int)q, (int)c));
+  }
+  HaloPlan::TileTab tab;
+  tab.n = (int)t.size();
+  if (tab.n) {
+    cudaError_t e = cudaMalloc(&tab.d, t.size() * sizeof(int2));
+    if (e == cudaSuccess) e = cudaMemcpy(tab.d, t.data(), t.size() * sizeof(int2), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+  }
+  P->tiles[{key, nvar}] = tab;
+  out = tab;
+  return cudaSuccess;
+}
+
 cudaError_t emf_sumavg_launch(HaloPlan *P, const HaloArrays &A, cudaStream_t st) {
   if (P->emf_sum.empty()) return cudaSuccess;
-  long mx = 0;
-  for (const auto &d : P->emf_sum) mx = std::max(mx, (long)(d.hi[0]-d.lo[0]+1)*(d.hi[1]-d.lo[1]+1)*(d.hi[2]-d.lo[2]+1));
-  unsigned gx = (unsigned)std::min<long>((mx + 127) / 128, 64);
-  if (gx == 0) gx = 1;
-  for (size_t first = 0; first < P->emf_sum.size(); first += 65535) {
-    unsigned ny = (unsigned)std::min<size_t>(65535, P->emf_sum.size() - first);
-    emf_sumavg_kernel<<<dim3(gx, ny), 128, 0, st>>>(P->d_emf_sum + first, A, P->d_emf_rbuf);
-  }
+  HaloPlan::TileTab tab;
+  cudaError_t e = tile_table(P, P->emf_sum, P->d_emf_sum, 1, [](const EmfSumDesc &d) {
+    return (long)(d.hi[0] - d.lo[0] + 1) * (d.hi[1] - d.lo[1] + 1) * (d.hi[2] - d.lo[2] + 1); }, tab);
+  if (e != cudaSuccess) return e;
+  if (tab.n) emf_sumavg_kernel<<<tab.n, 128, 0, st>>>(P->d_emf_sum, tab.d, A, P->d_emf_rbuf);
   return cudaGetLastError();
 }
 
@@ -413,27 +436,18 @@ void halo_free(HaloPlan *P) {
   cudaFree(P->d_local_cc); cudaFree(P->d_local_fc); cudaFree(P->d_emf_pack_local); cudaFree(P->d_emf_sum); cudaFree(P->d_emf_rbuf);
   for (auto &p : P->peers) { cudaFree(p.d_pack_cc); cudaFree(p.d_unpack_cc); cudaFree(p.d_pack_fc); cudaFree(p.d_unpack_fc); cudaFree(p.d_pack_emf); }
   cudaFree(P->d_push); for (auto *q : P->d_sig) cudaFree(q); cudaFree(P->d_wait_slots);
+  for (auto &kv : P->tiles) cudaFree(kv.second.d);
   delete P;
 }
 
-static long max_count(const std::vector<HaloDesc> &v, int nvar) {
-  long mx = 0;
-  for (const auto &d : v) mx = std::max(mx, (long)(d.hi[0]-d.lo[0]+1)*(d.hi[1]-d.lo[1]+1)*(d.hi[2]-d.lo[2]+1) * nvar);
-  return mx;
-}
-
-cudaError_t halo_launch(const std::vector<HaloDesc> &host, const HaloDesc *dev, const HaloArrays &A, int nvar,
+cudaError_t halo_launch(HaloPlan *P, const std::vector<HaloDesc> &host, const HaloDesc *dev, const HaloArrays &A, int nvar,
                         long varstride, double *buf, int mode, cudaStream_t st) {
   if (host.empty()) return cudaSuccess;
-  long mx = max_count(host, nvar);
-  unsigned gx = (unsigned)std::min<long>((mx + 255) / 256, 64);
-  if (gx == 0) gx = 1;
-  dim3 grid(gx, (unsigned)host.size());
-  // gridDim.y is limited to 65535 descriptors per launch
-  for (size_t first = 0; first < host.size(); first += 65535) {
-    unsigned ny = (unsigned)std::min<size_t>(65535, host.size() - first);
-    halo_copy_kernel<<<dim3(gx, ny), 256, 0, st>>>(dev + first, A, nvar, varstride, buf, mode);
-  }
+  HaloPlan::TileTab tab;
+  cudaError_t e = tile_table(P, host, dev, nvar, [nvar](const HaloDesc &d) {
+    return (long)(d.hi[0] - d.lo[0] + 1) * (d.hi[1] - d.lo[1] + 1) * (d.hi[2] - d.lo[2] + 1) * nvar; }, tab);
+  if (e != cudaSuccess) return e;
+  if (tab.n) halo_copy_kernel<<<tab.n, 256, 0, st>>>(dev, tab.d, A, nvar, varstride, buf, mode);
   return cudaGetLastError();
 }
 
@@ -442,9 +456,10 @@ cudaError_t halo_launch(const std::vector<HaloDesc> &host, const HaloDesc *dev, 
 // my arrays, stores straight into the peer GPUs' arrays over NVLink (mapped with cudaIpc by the
 // host layer).  grid.y = descriptor.
 __global__ void __launch_bounds__(256)
-halo_push_kernel(const PushDesc *__restrict__ descs, HaloArrays CCa, int nvar, long varstride, HaloArrays FCa,
+halo_push_kernel(const PushDesc *__restrict__ descs, const int2 *__restrict__ tiles, HaloArrays CCa, int nvar, long varstride, HaloArrays FCa,
                  PushPeerPtrs ptrs) {
-  const PushDesc d = descs[blockIdx.y];
+  const int2 tl = tiles[blockIdx.x];
+  const PushDesc d = descs[tl.x];
   const int ni = d.hi[0] - d.lo[0] + 1, nj = d.hi[1] - d.lo[1] + 1, nk = d.hi[2] - d.lo[2] + 1;
   const long per = (long)ni * nj * nk;
   const bool cc = d.comp < 0;
@@ -454,7 +469,8 @@ halo_push_kernel(const PushDesc *__restrict__ descs, HaloArrays CCa, int nvar, l
   double *dst = ptrs.p[d.peer][cc ? 0 : 1 + d.comp] + (long)d.dst_m * A.bstride[c];
   const long e1 = A.ext1[c], e2 = A.ext2[c];
   const long total = per * (cc ? nvar : 1);
-  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x) {
+  const long qend = ((long)(tl.y + 1) * HALO_TILE < total) ? (long)(tl.y + 1) * HALO_TILE : total;
+  for (long q = (long)tl.y * HALO_TILE + threadIdx.x; q < qend; q += blockDim.x) {
     long t = q;
     const int i = (int)(t % ni); t /= ni;
     const int j = (int)(t % nj); t /= nj;
@@ -471,17 +487,14 @@ cudaError_t halo_push_launch(HaloPlan *P, const HaloArrays &cc, int nvar, long v
   const long first = do_cc ? 0 : P->n_push_cc;
   const long last = do_fc ? (long)P->push.size() : P->n_push_cc;
   if (last <= first) return cudaSuccess;
-  long mx = 1;
-  for (long q = first; q < last; ++q) {
-    const PushDesc &d = P->push[q];
-    long n = (long)(d.hi[0] - d.lo[0] + 1) * (d.hi[1] - d.lo[1] + 1) * (d.hi[2] - d.lo[2] + 1) * (d.comp < 0 ? nvar : 1);
-    mx = std::max(mx, n);
-  }
-  const unsigned gx = (unsigned)std::min<long>((mx + 255) / 256, 64);
-  for (long f = first; f < last; f += 65535) {
-    const unsigned ny = (unsigned)std::min<long>(65535, last - f);
-    halo_push_kernel<<<dim3(gx, ny), 256, 0, st>>>(P->d_push + f, cc, nvar, varstride, fc, P->push_ptrs);
-  }
+  // one tile table per (range, nvar): the sub-list is addressed through its own base pointer
+  const std::vector<PushDesc> sub(P->push.begin() + first, P->push.begin() + last);
+  HaloPlan::TileTab tab;
+  const void *key = reinterpret_cast<const char *>(P->d_push + first) + (do_cc ? 1 : 0) + (do_fc ? 2 : 0);   // distinct key per range
+  cudaError_t e = tile_table(P, sub, key, nvar, [nvar](const PushDesc &d) {
+    return (long)(d.hi[0] - d.lo[0] + 1) * (d.hi[1] - d.lo[1] + 1) * (d.hi[2] - d.lo[2] + 1) * (d.comp < 0 ? nvar : 1); }, tab);
+  if (e != cudaSuccess) return e;
+  if (tab.n) halo_push_kernel<<<tab.n, 256, 0, st>>>(P->d_push + first, tab.d, cc, nvar, varstride, fc, P->push_ptrs);
   return cudaGetLastError();
 }
 

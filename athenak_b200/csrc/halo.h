@@ -1,7 +1,9 @@
 // halo.h -- internal declarations of the ghost-zone exchange plan (see halo.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/athenak_b200.h"
 
@@ -78,13 +80,19 @@ struct HaloPlan {
   int my_rank = 0, nranks = 1;
   std::string err;
   bool uploaded = false;   // descriptor lists are copied to the device on first use
+  // Launch tables: a descriptor list is launched as ONE compact 1-D grid of tiles {descriptor, chunk of HALO_TILE elements},
+  // built on first use per (list, nvar).  (Launching max-box-size CTAs for every descriptor, as round 1 did, starts hundreds of
+  // thousands of empty CTAs when a pack holds many small blocks: 1.0 ms per face-field exchange for 64 blocks of 64^3.)
+  struct TileTab { int2 *d = nullptr; int n = 0; };
+  std::map<std::pair<const void *, int>, TileTab> tiles;
 };
+#define HALO_TILE 2048
 
 int neighbor_index(int ix, int iy, int iz, int n1, int n2);
 HaloPlan *halo_build(const ak_mhd_cfg &cfg, const int *nghbr, int my_rank, int gids_start, std::string &err);
 void halo_free(HaloPlan *P);
 cudaError_t halo_ensure_uploaded(HaloPlan *P);
-cudaError_t halo_launch(const std::vector<HaloDesc> &host, const HaloDesc *dev, const HaloArrays &A, int nvar,
+cudaError_t halo_launch(HaloPlan *P, const std::vector<HaloDesc> &host, const HaloDesc *dev, const HaloArrays &A, int nvar,
                         long varstride, double *buf, int mode, cudaStream_t st);
 HaloArrays halo_arrays_cc(const ak_mhd_cfg &c, double *a, int nvar);
 HaloArrays halo_arrays_fc(const ak_mhd_cfg &c, double *x1f, double *x2f, double *x3f);

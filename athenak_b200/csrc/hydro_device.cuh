@@ -11,10 +11,10 @@ namespace akb {
 enum RSolverHyd { RS_HYD_ADVECT = 10, RS_HYD_LLF = 11, RS_HYD_HLLE = 12, RS_HYD_HLLC = 13, RS_HYD_ROE = 14 };
 
 // eos.hpp:41-45
-__device__ __forceinline__ double sound_speed(double gamma, double d, double p) { return dsqrt(ddiv(gamma * p, d)); }
+__device__ __forceinline__ double sound_speed(double gamma, double d, double p, bool *oor = nullptr) { return dsqrt(ddiv(gamma * p, d, oor), oor); }
 
 // advect_hyd.hpp:18-52 (ideal gas)
-__device__ __forceinline__ void hyd_advect(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f) {
+__device__ __forceinline__ void hyd_advect(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f, bool *oor = nullptr) {
   if (l.vx >= 0.0) {
     f.d = l.d * l.vx;
     f.mx = l.d * l.vx * l.vx;
@@ -31,7 +31,7 @@ __device__ __forceinline__ void hyd_advect(const State7 &l, const State7 &r, con
 }
 
 // llf_hyd_singlestate.hpp:27-82 (ideal gas)
-__device__ __forceinline__ void hyd_llf(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f) {
+__device__ __forceinline__ void hyd_llf(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f, bool *oor = nullptr) {
   const double gm1 = eos.gamma - 1.0;
   double qa = l.d * l.vx;
   double qb = r.d * r.vx;
@@ -45,8 +45,8 @@ __device__ __forceinline__ void hyd_llf(const State7 &l, const State7 &r, const 
   double er = r.e + 0.5 * r.d * (sqr(r.vx) + sqr(r.vy) + sqr(r.vz));
   s_mx += (pl + pr);
   double s_e = (el + pl) * l.vx + (er + pr) * r.vx;
-  qa = sound_speed(eos.gamma, l.d, pl);
-  qb = sound_speed(eos.gamma, r.d, pr);
+  qa = sound_speed(eos.gamma, l.d, pl, oor);
+  qb = sound_speed(eos.gamma, r.d, pr, oor);
   double a = dmax((fabs(l.vx) + qa), (fabs(r.vx) + qb));
   double du_d = a * (r.d - l.d);
   double du_mx = a * (r.d * r.vx - l.d * l.vx);
@@ -61,23 +61,23 @@ __device__ __forceinline__ void hyd_llf(const State7 &l, const State7 &r, const 
 }
 
 // hlle_hyd.hpp:26-129 (ideal gas)
-__device__ __forceinline__ void hyd_hlle(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f) {
+__device__ __forceinline__ void hyd_hlle(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f, bool *oor = nullptr) {
   const double gm1 = eos.gamma - 1.0;
   const double igm1 = eos.igm1;
   const double pl = gm1 * l.e, pr = gm1 * r.e;
-  double sqrtdl = dsqrt(l.d);
-  double sqrtdr = dsqrt(r.d);
-  double isdlpdr = drcp(sqrtdl + sqrtdr);
+  double sqrtdl = dsqrt(l.d, oor);
+  double sqrtdr = dsqrt(r.d, oor);
+  double isdlpdr = drcp(sqrtdl + sqrtdr, oor);
   double roe_vx = (sqrtdl * l.vx + sqrtdr * r.vx) * isdlpdr;
   double roe_vy = (sqrtdl * l.vy + sqrtdr * r.vy) * isdlpdr;
   double roe_vz = (sqrtdl * l.vz + sqrtdr * r.vz) * isdlpdr;
   double el = pl * igm1 + 0.5 * l.d * (sqr(l.vx) + sqr(l.vy) + sqr(l.vz));
   double er = pr * igm1 + 0.5 * r.d * (sqr(r.vx) + sqr(r.vy) + sqr(r.vz));
-  double hroe = (ddiv(el + pl, sqrtdl) + ddiv(er + pr, sqrtdr)) * isdlpdr;
-  double qa = sound_speed(eos.gamma, l.d, pl);
-  double qb = sound_speed(eos.gamma, r.d, pr);
+  double hroe = (ddiv(el + pl, sqrtdl, oor) + ddiv(er + pr, sqrtdr, oor)) * isdlpdr;
+  double qa = sound_speed(eos.gamma, l.d, pl, oor);
+  double qb = sound_speed(eos.gamma, r.d, pr, oor);
   double a = hroe - 0.5 * (sqr(roe_vx) + sqr(roe_vy) + sqr(roe_vz));
-  a = (a < 0.0) ? 0.0 : dsqrt(gm1 * a);
+  a = (a < 0.0) ? 0.0 : dsqrt(gm1 * a, oor);
   double al = dmin((roe_vx - a), (l.vx - qa));
   double ar = dmax((roe_vx + a), (r.vx + qb));
   double bp = (ar > 0.0) ? ar : 1.0e-20;
@@ -93,7 +93,7 @@ __device__ __forceinline__ void hyd_hlle(const State7 &l, const State7 &r, const
   double fl_e = el * qa + pl * l.vx;
   double fr_e = er * qb + pr * r.vx;
   qa = 0.0;
-  if (bp != bm) qa = ddiv(0.5 * (bp + bm), bp - bm);
+  if (bp != bm) qa = ddiv(0.5 * (bp + bm), bp - bm, oor);
   f.d = 0.5 * (fl_d + fr_d) + qa * (fl_d - fr_d);
   f.mx = 0.5 * (fl_mx + fr_mx) + qa * (fl_mx - fr_mx);
   f.my = 0.5 * (fl_my + fr_my) + qa * (fl_my - fr_my);
@@ -102,20 +102,20 @@ __device__ __forceinline__ void hyd_hlle(const State7 &l, const State7 &r, const
 }
 
 // hllc_hyd.hpp:20-115 (ideal gas only, as in the reference)
-__device__ __forceinline__ void hyd_hllc(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f) {
+__device__ __forceinline__ void hyd_hllc(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f, bool *oor = nullptr) {
   const double gm1 = eos.gamma - 1.0;
   const double igm1 = eos.igm1;
-  const double alpha = ddiv((eos.gamma) + 1.0, 2.0 * (eos.gamma));
+  const double alpha = ddiv((eos.gamma) + 1.0, 2.0 * (eos.gamma), oor);
   const double pl = gm1 * l.e, pr = gm1 * r.e;
   double qa, qb, qc, qd, qe, qf;
-  qa = sound_speed(eos.gamma, l.d, pl);
-  qb = sound_speed(eos.gamma, r.d, pr);
+  qa = sound_speed(eos.gamma, l.d, pl, oor);
+  qb = sound_speed(eos.gamma, r.d, pr, oor);
   double el = pl * igm1 + 0.5 * l.d * (sqr(l.vx) + sqr(l.vy) + sqr(l.vz));
   double er = pr * igm1 + 0.5 * r.d * (sqr(r.vx) + sqr(r.vy) + sqr(r.vz));
   qc = 0.25 * (l.d + r.d) * (qa + qb);
   qd = 0.5 * (pl + pr + (l.vx - r.vx) * qc);   // P_mid
-  qe = (qd <= pl) ? 1.0 : dsqrt(1.0 + alpha * (ddiv(qd, pl) - 1.0));
-  qf = (qd <= pr) ? 1.0 : dsqrt(1.0 + alpha * (ddiv(qd, pr) - 1.0));
+  qe = (qd <= pl) ? 1.0 : dsqrt(1.0 + alpha * (ddiv(qd, pl, oor) - 1.0), oor);
+  qf = (qd <= pr) ? 1.0 : dsqrt(1.0 + alpha * (ddiv(qd, pr, oor) - 1.0), oor);
   qc = l.vx - qa * qe;   // al
   qd = r.vx + qb * qf;   // ar
   qa = qd > 0.0 ? qd : 1.0e-20;    // bp
@@ -126,8 +126,8 @@ __device__ __forceinline__ void hyd_hllc(const State7 &l, const State7 &r, const
   qd = pr + qf * r.d * r.vx;   // tr
   double ml = l.d * qe;
   double mr = -(r.d * qf);
-  double am = ddiv(qc - qd, ml + mr);
-  double cp = ddiv(ml * qd + mr * qc, ml + mr);
+  double am = ddiv(qc - qd, ml + mr, oor);
+  double cp = ddiv(ml * qd + mr * qc, ml + mr, oor);
   cp = cp > 0.0 ? cp : 0.0;
   qe = l.d * (l.vx - qb);
   qf = r.d * (r.vx - qa);
@@ -138,13 +138,13 @@ __device__ __forceinline__ void hyd_hllc(const State7 &l, const State7 &r, const
   double fl_e = el * (l.vx - qb) + pl * l.vx;
   double fr_e = er * (r.vx - qa) + pr * r.vx;
   if (am >= 0.0) {
-    qc = ddiv(am, am - qb);
+    qc = ddiv(am, am - qb, oor);
     qd = 0.0;
-    qe = ddiv(-qb, am - qb);
+    qe = ddiv(-qb, am - qb, oor);
   } else {
     qc = 0.0;
-    qd = ddiv(-am, qa - am);
-    qe = ddiv(qa, qa - am);
+    qd = ddiv(-am, qa - am, oor);
+    qe = ddiv(qa, qa - am, oor);
   }
   f.d = qc * fl_d + qd * fr_d;
   f.mx = qc * fl_mx + qd * fr_mx + qe * cp;
@@ -154,18 +154,18 @@ __device__ __forceinline__ void hyd_hllc(const State7 &l, const State7 &r, const
 }
 
 // roe_hyd.hpp:38-176 + RoeFluxAdb :187-283 (ideal gas), with the LLF fallback of Step 6
-__device__ __forceinline__ void hyd_roe(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f) {
+__device__ __forceinline__ void hyd_roe(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f, bool *oor = nullptr) {
   const double gm1 = eos.gamma - 1.0;
   const double pl = gm1 * l.e, pr = gm1 * r.e;
-  double sqrtdl = dsqrt(l.d);
-  double sqrtdr = dsqrt(r.d);
-  double isdlpdr = drcp(sqrtdl + sqrtdr);
+  double sqrtdl = dsqrt(l.d, oor);
+  double sqrtdr = dsqrt(r.d, oor);
+  double isdlpdr = drcp(sqrtdl + sqrtdr, oor);
   const double v1 = (sqrtdl * l.vx + sqrtdr * r.vx) * isdlpdr;
   const double v2 = (sqrtdl * l.vy + sqrtdr * r.vy) * isdlpdr;
   const double v3 = (sqrtdl * l.vz + sqrtdr * r.vz) * isdlpdr;
-  double el = ddiv(pl, gm1) + 0.5 * l.d * (sqr(l.vx) + sqr(l.vy) + sqr(l.vz));
-  double er = ddiv(pr, gm1) + 0.5 * r.d * (sqr(r.vx) + sqr(r.vy) + sqr(r.vz));
-  const double h = (ddiv(el + pl, sqrtdl) + ddiv(er + pr, sqrtdr)) * isdlpdr;
+  double el = ddiv(pl, gm1, oor) + 0.5 * l.d * (sqr(l.vx) + sqr(l.vy) + sqr(l.vz));
+  double er = ddiv(pr, gm1, oor) + 0.5 * r.d * (sqr(r.vx) + sqr(r.vy) + sqr(r.vz));
+  const double h = (ddiv(el + pl, sqrtdl, oor) + ddiv(er + pr, sqrtdr, oor)) * isdlpdr;
   double mxl = l.d * l.vx;
   double mxr = r.d * r.vx;
   double fl[5], fr[5], flx[5], du[5];
@@ -189,11 +189,11 @@ __device__ __forceinline__ void hyd_roe(const State7 &l, const State7 &r, const 
     double vsq = v1 * v1 + v2 * v2 + v3 * v3;
     double q = h - 0.5 * vsq;
     double cs_sq = (q < 0.0) ? (double)1.17549435e-38f : gm1 * q;   // FLT_MIN
-    double cs = dsqrt(cs_sq);
+    double cs = dsqrt(cs_sq, oor);
     ev0 = v1 - cs;
     ev4 = v1 + cs;
     double a[5];
-    double na = ddiv(0.5, cs_sq);
+    double na = ddiv(0.5, cs_sq, oor);
     a[0] = du[0] * (0.5 * gm1 * vsq + v1 * cs);
     a[0] -= du[1] * (gm1 * v1 + cs);
     a[0] -= du[2] * gm1 * v2;
@@ -204,7 +204,7 @@ __device__ __forceinline__ void hyd_roe(const State7 &l, const State7 &r, const 
     a[1] += du[2];
     a[2] = du[0] * (-v3);
     a[2] += du[3];
-    double qa = ddiv(gm1, cs_sq);
+    double qa = ddiv(gm1, cs_sq, oor);
     a[3] = du[0] * (1.0 - na * gm1 * vsq);
     a[3] += du[1] * qa * v1;
     a[3] += du[2] * qa * v2;
@@ -254,8 +254,8 @@ __device__ __forceinline__ void hyd_roe(const State7 &l, const State7 &r, const 
     for (int n = 0; n < 5; ++n) flx[n] = fr[n];
   }
   if (llf_flag != 0) {
-    double cl = sound_speed(eos.gamma, l.d, pl);
-    double cr = sound_speed(eos.gamma, r.d, pr);
+    double cl = sound_speed(eos.gamma, l.d, pl, oor);
+    double cr = sound_speed(eos.gamma, r.d, pr, oor);
     double a = 0.5 * dmax((fabs(l.vx) + cl), (fabs(r.vx) + cr));
 #pragma unroll
     for (int n = 0; n < 5; ++n) flx[n] = 0.5 * (fl[n] + fr[n]) - a * du[n];
@@ -264,12 +264,12 @@ __device__ __forceinline__ void hyd_roe(const State7 &l, const State7 &r, const 
 }
 
 template <int RS>
-__device__ __forceinline__ void riemann_hyd(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f) {
-  if constexpr (RS == RS_HYD_ADVECT) hyd_advect(l, r, eos, f);
-  else if constexpr (RS == RS_HYD_LLF) hyd_llf(l, r, eos, f);
-  else if constexpr (RS == RS_HYD_HLLE) hyd_hlle(l, r, eos, f);
-  else if constexpr (RS == RS_HYD_HLLC) hyd_hllc(l, r, eos, f);
-  else hyd_roe(l, r, eos, f);
+__device__ __forceinline__ void riemann_hyd(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f, bool *oor = nullptr) {
+  if constexpr (RS == RS_HYD_ADVECT) hyd_advect(l, r, eos, f, oor);
+  else if constexpr (RS == RS_HYD_LLF) hyd_llf(l, r, eos, f, oor);
+  else if constexpr (RS == RS_HYD_HLLE) hyd_hlle(l, r, eos, f, oor);
+  else if constexpr (RS == RS_HYD_HLLC) hyd_hllc(l, r, eos, f, oor);
+  else hyd_roe(l, r, eos, f, oor);
 }
 
 }  // namespace akb

@@ -15,15 +15,15 @@ __host__ __device__ constexpr bool rs_is_iso(int rs) { return rs >= RS_ISO; }
 __host__ __device__ constexpr bool rs_is_hydro(int rs) { return (rs % 20) >= 10; }
 
 // eos.hpp:60-68
-__device__ __forceinline__ double fast_speed_iso(double iso_cs, double d, double bx, double by, double bz) {
+__device__ __forceinline__ double fast_speed_iso(double iso_cs, double d, double bx, double by, double bz, bool *oor = nullptr) {
   double asq = (iso_cs * iso_cs) * d;
   double ct2 = by * by + bz * bz;
   double qsq = bx * bx + ct2 + asq;
   double tmp = bx * bx + ct2 - asq;
-  return dsqrt(ddiv(0.5 * (qsq + dsqrt(tmp * tmp + 4.0 * asq * ct2)), d));
+  return dsqrt(ddiv(0.5 * (qsq + dsqrt(tmp * tmp + 4.0 * asq * ct2)), d, oor), oor);
 }
 
-__device__ __forceinline__ void llf_iso(const State7 &l, const State7 &r, double bxi, const EosParams &eos, Flux7 &f) {
+__device__ __forceinline__ void llf_iso(const State7 &l, const State7 &r, double bxi, const EosParams &eos, Flux7 &f, bool *oor = nullptr) {
   double qa = l.d * l.vx;
   double qb = r.d * r.vx;
   double qc = 0.5 * (sqr(l.by) + sqr(l.bz) - sqr(bxi));
@@ -35,8 +35,8 @@ __device__ __forceinline__ void llf_iso(const State7 &l, const State7 &r, double
   double s_by = l.by * l.vx + r.by * r.vx - bxi * (l.vy + r.vy);
   double s_bz = l.bz * l.vx + r.bz * r.vx - bxi * (l.vz + r.vz);
   s_mx += sqr(eos.iso_cs) * (l.d + r.d);
-  qa = fast_speed_iso(eos.iso_cs, l.d, bxi, l.by, l.bz);
-  qb = fast_speed_iso(eos.iso_cs, r.d, bxi, r.by, r.bz);
+  qa = fast_speed_iso(eos.iso_cs, l.d, bxi, l.by, l.bz, oor);
+  qb = fast_speed_iso(eos.iso_cs, r.d, bxi, r.by, r.bz, oor);
   double a = dmax((fabs(l.vx) + qa), (fabs(r.vx) + qb));
   double du_d = a * (r.d - l.d);
   double du_mx = a * (r.d * r.vx - l.d * l.vx);
@@ -52,31 +52,31 @@ __device__ __forceinline__ void llf_iso(const State7 &l, const State7 &r, double
   f.ez = 0.5 * (s_bz - du_bz);
 }
 
-__device__ __forceinline__ void hlle_iso(const State7 &l, const State7 &r, double bxi, const EosParams &eos, Flux7 &f) {
+__device__ __forceinline__ void hlle_iso(const State7 &l, const State7 &r, double bxi, const EosParams &eos, Flux7 &f, bool *oor = nullptr) {
   const double iso_cs = eos.iso_cs;
-  double sqrtdl = dsqrt(l.d);
-  double sqrtdr = dsqrt(r.d);
-  double isdlpdr = drcp(sqrtdl + sqrtdr);
+  double sqrtdl = dsqrt(l.d, oor);
+  double sqrtdr = dsqrt(r.d, oor);
+  double isdlpdr = drcp(sqrtdl + sqrtdr, oor);
   double roe_d = sqrtdl * sqrtdr;
   double roe_vx = (sqrtdl * l.vx + sqrtdr * r.vx) * isdlpdr;
   double roe_by = (sqrtdr * l.by + sqrtdl * r.by) * isdlpdr;
   double roe_bz = (sqrtdr * l.bz + sqrtdl * r.bz) * isdlpdr;
-  double x = ddiv(0.5 * (sqr(l.by - r.by) + sqr(l.bz - r.bz)), sqr(sqrtdl + sqrtdr));
-  double y = ddiv(0.5 * (l.d + r.d), roe_d);
+  double x = ddiv(0.5 * (sqr(l.by - r.by) + sqr(l.bz - r.bz)), sqr(sqrtdl + sqrtdr), oor);
+  double y = ddiv(0.5 * (l.d + r.d), roe_d, oor);
   double pbl = 0.5 * (bxi * bxi + sqr(l.by) + sqr(l.bz));
   double pbr = 0.5 * (bxi * bxi + sqr(r.by) + sqr(r.bz));
-  double cl = fast_speed_iso(iso_cs, l.d, bxi, l.by, l.bz);
-  double cr = fast_speed_iso(iso_cs, r.d, bxi, r.by, r.bz);
+  double cl = fast_speed_iso(iso_cs, l.d, bxi, l.by, l.bz, oor);
+  double cr = fast_speed_iso(iso_cs, r.d, bxi, r.by, r.bz, oor);
   double btsq = sqr(roe_by) + sqr(roe_bz);
-  double vaxsq = ddiv(bxi * bxi, roe_d);
+  double vaxsq = ddiv(bxi * bxi, roe_d, oor);
   double bt_starsq = btsq * y;
   double twid_asq = iso_cs * iso_cs + x;
-  double ct2 = ddiv(bt_starsq, roe_d);
+  double ct2 = ddiv(bt_starsq, roe_d, oor);
   double tsum = vaxsq + ct2 + twid_asq;
   double tdif = vaxsq + ct2 - twid_asq;
-  double cf2_cs2 = dsqrt(tdif * tdif + 4.0 * twid_asq * ct2);
+  double cf2_cs2 = dsqrt(tdif * tdif + 4.0 * twid_asq * ct2, oor);
   double cfsq = 0.5 * (tsum + cf2_cs2);
-  double a = dsqrt(cfsq);
+  double a = dsqrt(cfsq, oor);
   double al = dmin((roe_vx - a), (l.vx - cl));
   double ar = dmax((roe_vx + a), (r.vx + cr));
   double bp = ar > 0.0 ? ar : 1.0e-20;
@@ -97,7 +97,7 @@ __device__ __forceinline__ void hlle_iso(const State7 &l, const State7 &r, doubl
   double fl_bz = l.bz * vxl - bxi * l.vz;
   double fr_bz = r.bz * vxr - bxi * r.vz;
   double tmp = 0.0;
-  if (bp != bm) tmp = ddiv(0.5 * (bp + bm), bp - bm);
+  if (bp != bm) tmp = ddiv(0.5 * (bp + bm), bp - bm, oor);
   f.d = 0.5 * (fl_d + fr_d) + (fl_d - fr_d) * tmp;
   f.mx = 0.5 * (fl_mx + fr_mx) + (fl_mx - fr_mx) * tmp;
   f.my = 0.5 * (fl_my + fr_my) + (fl_my - fr_my) * tmp;
@@ -107,14 +107,14 @@ __device__ __forceinline__ void hlle_iso(const State7 &l, const State7 &r, doubl
 }
 
 // hlld_mhd.hpp:350-546 (Mignone 2007)
-__device__ __forceinline__ void hlld_iso(const State7 &l, const State7 &r, double bxi, const EosParams &eos, Flux7 &f) {
+__device__ __forceinline__ void hlld_iso(const State7 &l, const State7 &r, double bxi, const EosParams &eos, Flux7 &f, bool *oor = nullptr) {
   const double small = 1.0e-4;   // HLLD_SMALL_NUMBER
   const double iso_cs = eos.iso_cs;
   Cons7 ul, ur;
   ul.d = l.d; ul.mx = l.vx * ul.d; ul.my = l.vy * ul.d; ul.mz = l.vz * ul.d; ul.by = l.by; ul.bz = l.bz;
   ur.d = r.d; ur.mx = r.vx * ur.d; ur.my = r.vy * ur.d; ur.mz = r.vz * ur.d; ur.by = r.by; ur.bz = r.bz;
-  const double cfl = fast_speed_iso(iso_cs, l.d, bxi, l.by, l.bz);
-  const double cfr = fast_speed_iso(iso_cs, r.d, bxi, r.by, r.bz);
+  const double cfl = fast_speed_iso(iso_cs, l.d, bxi, l.by, l.bz, oor);
+  const double cfr = fast_speed_iso(iso_cs, r.d, bxi, r.by, r.bz, oor);
   const double s0 = dmin(l.vx - cfl, r.vx - cfr);
   const double s4 = dmax(l.vx + cfl, r.vx + cfr);
   const double bxsq = bxi * bxi;
@@ -135,24 +135,24 @@ __device__ __forceinline__ void hlld_iso(const State7 &l, const State7 &r, doubl
   fr.bz = ur.bz * r.vx - bxi * r.vz;
   if (s0 >= 0.0) { f.d = fl.d; f.mx = fl.mx; f.my = fl.my; f.mz = fl.mz; f.ey = -fl.by; f.ez = fl.bz; return; }
   if (s4 <= 0.0) { f.d = fr.d; f.mx = fr.mx; f.my = fr.my; f.mz = fr.mz; f.ey = -fr.by; f.ez = fr.bz; return; }
-  const double idspd = drcp(s4 - s0);
+  const double idspd = drcp(s4 - s0, oor);
   double dhll = (s4 * ur.d - s0 * ul.d - fr.d + fl.d) * idspd;
   dhll = dmax(dhll, eos.dfloor);
-  const double sqrtdhll = dsqrt(dhll);
+  const double sqrtdhll = dsqrt(dhll, oor);
   const double fdhll = (s4 * fl.d - s0 * fr.d + s4 * s0 * (ur.d - ul.d)) * idspd;
   const double fmxhll = (s4 * fl.mx - s0 * fr.mx + s4 * s0 * (ur.mx - ul.mx)) * idspd;
-  const double ustar = ddiv(fdhll, dhll);
+  const double ustar = ddiv(fdhll, dhll, oor);
   const double mxhll = (s4 * ur.mx - s0 * ul.mx - fr.mx + fl.mx) * idspd;
-  const double s1 = ustar - ddiv(fabs(bxi), sqrtdhll);
-  const double s3 = ustar + ddiv(fabs(bxi), sqrtdhll);
+  const double s1 = ustar - ddiv(fabs(bxi), sqrtdhll, oor);
+  const double s3 = ustar + ddiv(fabs(bxi), sqrtdhll, oor);
   Cons7 ulst, urst;
   ulst.d = dhll; ulst.mx = mxhll;
   double tmp = (s0 - s1) * (s0 - s3);
   if (fabs(s0 - s1) < (small)*iso_cs) {
     ulst.my = ul.my; ulst.mz = ul.mz; ulst.by = ul.by; ulst.bz = ul.bz;
   } else {
-    const double mfact = ddiv(bxi * (ustar - l.vx), tmp);
-    const double bfact = ddiv(ul.d * sqr(s0 - l.vx) - bxsq, dhll * tmp);
+    const double mfact = ddiv(bxi * (ustar - l.vx), tmp, oor);
+    const double bfact = ddiv(ul.d * sqr(s0 - l.vx) - bxsq, dhll * tmp, oor);
     ulst.my = dhll * l.vy - ul.by * mfact;
     ulst.mz = dhll * l.vz - ul.bz * mfact;
     ulst.by = ul.by * bfact;
@@ -163,8 +163,8 @@ __device__ __forceinline__ void hlld_iso(const State7 &l, const State7 &r, doubl
   if (fabs(s4 - s3) < (small)*iso_cs) {
     urst.my = ur.my; urst.mz = ur.mz; urst.by = ur.by; urst.bz = ur.bz;
   } else {
-    const double mfact = ddiv(bxi * (ustar - r.vx), tmp);
-    const double bfact = ddiv(ur.d * sqr(s4 - r.vx) - bxsq, dhll * tmp);
+    const double mfact = ddiv(bxi * (ustar - r.vx), tmp, oor);
+    const double bfact = ddiv(ur.d * sqr(s4 - r.vx) - bxsq, dhll * tmp, oor);
     urst.my = dhll * r.vy - ur.by * mfact;
     urst.mz = dhll * r.vz - ur.bz * mfact;
     urst.by = ur.by * bfact;
@@ -188,19 +188,19 @@ __device__ __forceinline__ void hlld_iso(const State7 &l, const State7 &r, doubl
     const double x = sqrtdhll * (bxi > 0.0 ? 1.0 : -1.0);
     const double c_my = 0.5 * (ulst.my + urst.my + (urst.by - ulst.by) * x);
     const double c_mz = 0.5 * (ulst.mz + urst.mz + (urst.bz - ulst.bz) * x);
-    const double c_by = 0.5 * (ulst.by + urst.by + ddiv(urst.my - ulst.my, x));
-    const double c_bz = 0.5 * (ulst.bz + urst.bz + ddiv(urst.mz - ulst.mz, x));
+    const double c_by = 0.5 * (ulst.by + urst.by + ddiv(urst.my - ulst.my, x, oor));
+    const double c_bz = 0.5 * (ulst.bz + urst.bz + ddiv(urst.mz - ulst.mz, x, oor));
     f.d = dhll * ustar;
     f.mx = fmxhll;
     f.my = c_my * ustar - bxi * c_by;
     f.mz = c_mz * ustar - bxi * c_bz;
-    f.ey = -(c_by * ustar - ddiv(bxi * c_my, dhll));
-    f.ez = c_bz * ustar - ddiv(bxi * c_mz, dhll);
+    f.ey = -(c_by * ustar - ddiv(bxi * c_my, dhll, oor));
+    f.ez = c_bz * ustar - ddiv(bxi * c_mz, dhll, oor);
   }
 }
 
 // ---- hydro -------------------------------------------------------------------------------
-__device__ __forceinline__ void hyd_llf_iso(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f) {
+__device__ __forceinline__ void hyd_llf_iso(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f, bool *oor = nullptr) {
   double qa = l.d * l.vx;
   double qb = r.d * r.vx;
   double s_d = qa + qb;
@@ -219,11 +219,11 @@ __device__ __forceinline__ void hyd_llf_iso(const State7 &l, const State7 &r, co
   f.mz = 0.5 * (s_mz - du_mz);
 }
 
-__device__ __forceinline__ void hyd_hlle_iso(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f) {
+__device__ __forceinline__ void hyd_hlle_iso(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f, bool *oor = nullptr) {
   const double iso_cs = eos.iso_cs;
-  double sqrtdl = dsqrt(l.d);
-  double sqrtdr = dsqrt(r.d);
-  double isdlpdr = drcp(sqrtdl + sqrtdr);
+  double sqrtdl = dsqrt(l.d, oor);
+  double sqrtdr = dsqrt(r.d, oor);
+  double isdlpdr = drcp(sqrtdl + sqrtdr, oor);
   double roe_vx = (sqrtdl * l.vx + sqrtdr * r.vx) * isdlpdr;
   double al = dmin((roe_vx - iso_cs), (l.vx - iso_cs));
   double ar = dmax((roe_vx + iso_cs), (r.vx + iso_cs));
@@ -238,18 +238,18 @@ __device__ __forceinline__ void hyd_hlle_iso(const State7 &l, const State7 &r, c
   fl_mx += (iso_cs * iso_cs) * l.d;
   fr_mx += (iso_cs * iso_cs) * r.d;
   qa = 0.0;
-  if (bp != bm) qa = ddiv(0.5 * (bp + bm), bp - bm);
+  if (bp != bm) qa = ddiv(0.5 * (bp + bm), bp - bm, oor);
   f.d = 0.5 * (fl_d + fr_d) + qa * (fl_d - fr_d);
   f.mx = 0.5 * (fl_mx + fr_mx) + qa * (fl_mx - fr_mx);
   f.my = 0.5 * (fl_my + fr_my) + qa * (fl_my - fr_my);
   f.mz = 0.5 * (fl_mz + fr_mz) + qa * (fl_mz - fr_mz);
 }
 
-__device__ __forceinline__ void hyd_roe_iso(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f) {
+__device__ __forceinline__ void hyd_roe_iso(const State7 &l, const State7 &r, const EosParams &eos, Flux7 &f, bool *oor = nullptr) {
   const double iso_cs = eos.iso_cs;
-  double sqrtdl = dsqrt(l.d);
-  double sqrtdr = dsqrt(r.d);
-  double isdlpdr = drcp(sqrtdl + sqrtdr);
+  double sqrtdl = dsqrt(l.d, oor);
+  double sqrtdr = dsqrt(r.d, oor);
+  double isdlpdr = drcp(sqrtdl + sqrtdr, oor);
   const double v1 = (sqrtdl * l.vx + sqrtdr * r.vx) * isdlpdr;
   const double v2 = (sqrtdl * l.vy + sqrtdr * r.vy) * isdlpdr;
   const double v3 = (sqrtdl * l.vz + sqrtdr * r.vz) * isdlpdr;
@@ -271,14 +271,14 @@ __device__ __forceinline__ void hyd_roe_iso(const State7 &l, const State7 &r, co
   int llf_flag = 0;
   const double ev0 = v1 - iso_cs, ev3 = v1 + iso_cs;
   {
-    double a0 = du[0] * (0.5 + ddiv(0.5 * v1, iso_cs));
-    a0 -= ddiv(du[1] * 0.5, iso_cs);
+    double a0 = du[0] * (0.5 + ddiv(0.5 * v1, iso_cs, oor));
+    a0 -= ddiv(du[1] * 0.5, iso_cs, oor);
     double a1 = du[0] * (-v2);
     a1 += du[2];
     double a2 = du[0] * (-v3);
     a2 += du[3];
-    double a3 = du[0] * (0.5 - ddiv(0.5 * v1, iso_cs));
-    a3 += ddiv(du[1] * 0.5, iso_cs);
+    double a3 = du[0] * (0.5 - ddiv(0.5 * v1, iso_cs, oor));
+    a3 += ddiv(du[1] * 0.5, iso_cs, oor);
     const double c0 = -0.5 * fabs(ev0) * a0;
     const double c1 = -0.5 * fabs(v1) * a1;
     const double c2 = -0.5 * fabs(v1) * a2;

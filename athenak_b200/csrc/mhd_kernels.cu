@@ -14,12 +14,42 @@
 #include "mhd_kernels.h"
 #include "flux_kernels.cuh"
 #include "reduce.cuh"
+#include "c2p_device.cuh"
 
 namespace akb {
 
 // ---------------------------------------------------------------------------------------
 // GS07 corner EMFs (mhd_corner_e.cpp:309-318,338-414), one thread per corner
 // k in [ks,ke+1], j in [js,je+1], i in [is,ie+1].
+// Thread -> (kk, jj, ii) of the corner / face index space [0, nk) x [0, nj) x [0, ni) of block m.  FLAT = false: 32 x 4 x 2 tiles
+// (neighbours in j and k mostly come from L1).  FLAT = true: the (jj, ii) plane flattened, 128 consecutive positions x 2
+// k-layers per CTA -- for extents like 64 + 1 the tiles would leave a third of the warps with one active lane.
+template <bool FLAT>
+__device__ __forceinline__ bool stencil_index(int ni, int nj, int nk, int &ii, int &jj, int &kk, int &m) {
+  const int nkb = (nk + TILE_Z - 1) / TILE_Z;
+  if (FLAT) {
+    const int p = blockIdx.x * 128 + (threadIdx.x & 127);
+    jj = p / ni; ii = p - jj * ni;
+    kk = (blockIdx.y % nkb) * TILE_Z + (threadIdx.x >> 7);
+    m = blockIdx.y / nkb;
+  } else {
+    ii = blockIdx.x * TILE_X + (threadIdx.x & 31); jj = blockIdx.y * TILE_Y + ((threadIdx.x >> 5) & 3);
+    kk = (blockIdx.z % nkb) * TILE_Z + (threadIdx.x >> 7);
+    m = blockIdx.z / nkb;
+  }
+  return ii < ni && jj < nj && kk < nk;
+}
+static inline bool stencil_flat(int ni, int nj, int nk) {       // tile efficiency below 85%: flatten
+  const double used = (double)ni * nj * nk;
+  const double launched = (double)((ni + TILE_X - 1) / TILE_X * TILE_X) * ((nj + TILE_Y - 1) / TILE_Y * TILE_Y) * ((nk + TILE_Z - 1) / TILE_Z * TILE_Z);
+  return used < 0.85 * launched;
+}
+static inline dim3 stencil_grid(bool flat, int ni, int nj, int nk, int nmb) {
+  const int nkb = (nk + TILE_Z - 1) / TILE_Z;
+  return flat ? dim3((ni * nj + 127) / 128, nkb * nmb, 1) : dim3((ni + TILE_X - 1) / TILE_X, (nj + TILE_Y - 1) / TILE_Y, nkb * nmb);
+}
+
+template <bool FLAT>
 __global__ void __launch_bounds__(256, AKB_CORNER_MINB)
 corner_emf_kernel(Geom g, const double *__restrict__ w0, const double *__restrict__ bcc,
                   const double *__restrict__ flx1, const double *__restrict__ flx2,
@@ -30,12 +60,8 @@ corner_emf_kernel(Geom g, const double *__restrict__ w0, const double *__restric
                   double *__restrict__ e3) {
   // 3-D thread tile (32 x 4 x 2): the j-1 / k-1 neighbours of most threads are loaded by the
   // same block, so they come from L1
-  const int ni = g.nx1 + 1, nj = g.nx2 + 1, nk = g.nx3 + 1;
-  const int nkb = (nk + TILE_Z - 1) / TILE_Z;
-  const int ii = blockIdx.x * TILE_X + threadIdx.x, jj = blockIdx.y * TILE_Y + threadIdx.y;
-  const int kk = (blockIdx.z % nkb) * TILE_Z + threadIdx.z;
-  const int m = blockIdx.z / nkb;
-  if (ii >= ni || jj >= nj || kk >= nk) return;
+  int ii, jj, kk, m;
+  if (!stencil_index<FLAT>(g.nx1 + 1, g.nx2 + 1, g.nx3 + 1, ii, jj, kk, m)) return;
   const int i = g.is + ii, j = g.js + jj, k = g.ks + kk;
   const long cc = g.cc, n1 = g.n1, n12 = (long)g.n1 * g.n2;
   const double *w = w0 + (long)m * g.nvar * cc, *b = bcc + (long)m * 3 * cc;
@@ -147,7 +173,7 @@ corner_emf_2d_kernel(Geom g, const double *__restrict__ w0, const double *__rest
 // indices are active, each face update where its own range allows.  SAVE=true also performs
 // CopyCons (u1<-u0, b1<-b0, mhd_tasks.cpp:162-170) for the entries it touches; the caller
 // copies the ghost entries separately when the host contract needs them.
-template <bool DO_U, bool DO_B, bool SAVE>
+template <bool DO_U, bool DO_B, bool SAVE, bool FLAT>
 __global__ void __launch_bounds__(256)
 update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
                  const double *__restrict__ flx1, const double *__restrict__ flx2,
@@ -156,12 +182,10 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
                  double *__restrict__ o3f, const double *__restrict__ e1, const double *__restrict__ e2,
                  const double *__restrict__ e3, const double *__restrict__ mb_size, double gam0, double gam1,
                  double beta_dt) {
-  const int ni = g.nx1 + 1, nj = g.nx2 + 1, nk = g.nx3 + 1;
-  const int nkb = (nk + TILE_Z - 1) / TILE_Z;
-  const int ii = blockIdx.x * TILE_X + threadIdx.x, jj = blockIdx.y * TILE_Y + threadIdx.y;
-  const int kk = (blockIdx.z % nkb) * TILE_Z + threadIdx.z;
-  const int m = blockIdx.z / nkb;
-  if (ii >= ni || jj >= nj || kk >= nk) return;
+  // the conserved update alone covers cells only: no "+1" positions (exact tiles for power-of-two blocks)
+  const int xb = DO_B ? 1 : 0;
+  int ii, jj, kk, m;
+  if (!stencil_index<FLAT>(g.nx1 + xb, g.nx2 + xb, g.nx3 + xb, ii, jj, kk, m)) return;
   const int i = g.is + ii, j = g.js + jj, k = g.ks + kk;
   const double dx1 = __ldg(mb_size + m * 9 + 6), dx2 = __ldg(mb_size + m * 9 + 7), dx3 = __ldg(mb_size + m * 9 + 8);
   const double rdx1 = drcp(dx1), rdx2 = drcp(dx2), rdx3 = drcp(dx3);
@@ -287,38 +311,21 @@ cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *_
     const double ubx = 0.5 * (__ldg(p1) + __ldg(p1 + 1));
     const double uby = 0.5 * (__ldg(p2) + __ldg(p2 + n1));
     const double ubz = 0.5 * (__ldg(p3) + __ldg(p3 + n1 * n2));
-    bool dfl = false, efl = false, tfl = false;
-    const double gm1 = eos.gamma - 1.0;
-    const double b2 = sqr(ubx) + sqr(uby) + sqr(ubz);
-    const double dfloor_ = dmax(eos.dfloor, ddiv(b2, eos.sigma_max));
-    if (ud < dfloor_) { ud = dfloor_; dfl = true; }
-    const double wd = ud;
-    const double di = drcp(ud);
-    const double wvx = di * umx, wvy = di * umy, wvz = di * umz;
-    double we = 0.0;
+    // one cell of c2p (c2p_device.cuh), deferred range guard: the rare out-of-range operand repeats the cell with the guarded operators
+    bool dfl = false, efl = false, tfl = false, oor = false;
+    const double ud0 = ud, ue0 = ue;
+    double wd, wvx, wvy, wvz, we;
+    c2p_cell<IDEAL>(eos, ud, umx, umy, umz, ue, ubx, uby, ubz, wd, wvx, wvy, wvz, we, dfl, efl, tfl, &oor);
+    if (oor) {
+      ud = ud0; ue = ue0; dfl = efl = tfl = false;
+      c2p_cell<IDEAL>(eos, ud, umx, umy, umz, ue, ubx, uby, ubz, wd, wvx, wvy, wvz, we, dfl, efl, tfl, nullptr);
+    }
     double *w = w0 + (long)m * g.nvar * cc + o;
     if constexpr (IDEAL) {
-    const double efloor = ddiv(eos.pfloor, eos.gamma - 1.0);
-    const double e_k = 0.5 * di * (sqr(umx) + sqr(umy) + sqr(umz));
-    const double e_m = 0.5 * (sqr(ubx) + sqr(uby) + sqr(ubz));
-    we = (ue - e_k - e_m);
-    if (we < efloor) { we = efloor; ue = efloor + e_k + e_m; efl = true; }
-    if (gm1 * we * di < eos.tfloor) { we = wd * eos.tfloor / gm1; ue = we + e_k + e_m; tfl = true; }
-    // Entropy floor (ideal_c2p_mhd.hpp:59-65).  spe = gm1*we*di / wd^gm1.  pow() is only needed
-    // when spe can be <= sfloor: for 0 < gm1 <= 2, wd^gm1 <= max(1, wd^2), so
-    // gm1*we*di > 4*sfloor*max(1,wd^2) proves spe > sfloor (factor 4 covers rounding) without
-    // evaluating pow; otherwise the reference expression is evaluated as written.
-    const double pow_ub = dmax(1.0, wd * wd);
-    bool need_pow = !(gm1 > 0.0 && gm1 <= 2.0 && (gm1 * we * di) > 4.0 * eos.sfloor * pow_ub);
-    if (need_pow) {
-      const double spe_over_eps = gm1 / pow(wd, gm1);
-      const double spe = spe_over_eps * we * di;
-      if (spe <= eos.sfloor) { we = wd * eos.sfloor / spe_over_eps; efl = true; }
+      if (efl) { u[IEN * cc] = ue; ne = 1; }
+      if (tfl) { u[IEN * cc] = ue; nt = 1; }
+      w[IEN * cc] = we;
     }
-    if (efl) { u[IEN * cc] = ue; ne = 1; }
-    if (tfl) { u[IEN * cc] = ue; nt = 1; }
-    w[IEN * cc] = we;
-    }  // IDEAL; isothermal_mhd.cpp:28-46,95-135 has the density floor only
     if (dfl) { u[IDN * cc] = ud; nd = 1; }
     w[IDN * cc] = wd; w[IVX * cc] = wvx; w[IVY * cc] = wvy; w[IVZ * cc] = wvz;
     double *bc = bcc + (long)m * 3 * cc + o;
@@ -331,14 +338,10 @@ cons2prim_kernel(Geom g, EosParams eos, double *__restrict__ u0, const double *_
     if (NEWDT) {
       act = (i >= g.is && i <= g.ie && j >= g.js && j <= g.je && k >= g.ks && k <= g.ke);
       if (act) {  // mhd_newdt.cpp:128-138,146-148
-        const double p = gm1 * we;
-        auto cf = [&](double bx, double by, double bz) {   // mhd_newdt.cpp:128-138
-          if constexpr (IDEAL) return fast_speed(eos.gamma, wd, p, bx, by, bz);
-          else return fast_speed_iso(eos.iso_cs, wd, bx, by, bz);
-        };
-        d1 = ddiv(__ldg(mb_size + m * 9 + 6), fabs(wvx) + cf(ubx, uby, ubz));
-        d2 = ddiv(__ldg(mb_size + m * 9 + 7), fabs(wvy) + cf(uby, ubz, ubx));
-        d3 = ddiv(__ldg(mb_size + m * 9 + 8), fabs(wvz) + cf(ubz, ubx, uby));
+        bool o2 = false;
+        const double dx1 = __ldg(mb_size + m * 9 + 6), dx2 = __ldg(mb_size + m * 9 + 7), dx3 = __ldg(mb_size + m * 9 + 8);
+        newdt_cell<IDEAL>(eos, dx1, dx2, dx3, wd, wvx, wvy, wvz, we, ubx, uby, ubz, d1, d2, d3, &o2);
+        if (o2) newdt_cell<IDEAL>(eos, dx1, dx2, dx3, wd, wvx, wvy, wvz, we, ubx, uby, ubz, d1, d2, d3, nullptr);
       }
     }
   }
@@ -435,23 +438,29 @@ cudaError_t launch_corner_e(const Geom &g, const Arrays &a, cudaStream_t st) {
     corner_emf_2d_kernel<<<gr2, dim3(32, 4, 1), 0, st>>>(g, a.w0, a.bcc0, a.flx1, a.flx2, a.e3x1, a.e2x1, a.e1x2, a.e3x2, a.e1, a.e2, a.e3);
     return cudaGetLastError();
   }
-  const dim3 tb(TILE_X, TILE_Y, TILE_Z);
-  const dim3 gr((g.nx1 + 1 + TILE_X - 1) / TILE_X, (g.nx2 + 1 + TILE_Y - 1) / TILE_Y, ((g.nx3 + 1 + TILE_Z - 1) / TILE_Z) * g.nmb);
-  corner_emf_kernel<<<gr, tb, 0, st>>>(g, a.w0, a.bcc0, a.flx1, a.flx2, a.flx3, a.e3x1, a.e2x1, a.e1x2, a.e3x2, a.e2x3, a.e1x3, a.e1, a.e2, a.e3);
+  const bool flat = stencil_flat(g.nx1 + 1, g.nx2 + 1, g.nx3 + 1);
+  const dim3 gr = stencil_grid(flat, g.nx1 + 1, g.nx2 + 1, g.nx3 + 1, g.nmb);
+  if (flat) corner_emf_kernel<true><<<gr, 256, 0, st>>>(g, a.w0, a.bcc0, a.flx1, a.flx2, a.flx3, a.e3x1, a.e2x1, a.e1x2, a.e3x2, a.e2x3, a.e1x3, a.e1, a.e2, a.e3);
+  else corner_emf_kernel<false><<<gr, 256, 0, st>>>(g, a.w0, a.bcc0, a.flx1, a.flx2, a.flx3, a.e3x1, a.e2x1, a.e1x2, a.e3x2, a.e2x3, a.e1x3, a.e1, a.e2, a.e3);
   return cudaGetLastError();
 }
 
 cudaError_t launch_update_ct(const Geom &g, const Arrays &a, bool do_u, bool do_b, bool save, double gam0, double gam1,
                              double beta_dt, cudaStream_t st) {
-  const dim3 tb(TILE_X, TILE_Y, TILE_Z);
-  const dim3 gr((g.nx1 + 1 + TILE_X - 1) / TILE_X, (g.nx2 + 1 + TILE_Y - 1) / TILE_Y, ((g.nx3 + 1 + TILE_Z - 1) / TILE_Z) * g.nmb);
+  const int xb = do_b ? 1 : 0;
+  const int ni = g.nx1 + xb, nj = g.nx2 + xb, nk = g.nx3 + xb;    // CT reaches the +1 faces in every dimension (mhd_ct.cpp:41-77)
+  const bool flat = stencil_flat(ni, nj, nk);
+  const dim3 gr = stencil_grid(flat, ni, nj, nk, g.nmb);
+  const int tb = 256;
+#define AKB_UCT(U, B, S) do { if (flat) update_ct_kernel<U, B, S, true><<<gr, tb, 0, st>>>(AKB_UCT_ARGS); else update_ct_kernel<U, B, S, false><<<gr, tb, 0, st>>>(AKB_UCT_ARGS); } while (0)
 #define AKB_UCT_ARGS g, a.u0, a.u1, a.flx1, a.flx2, a.flx3, a.b0x1f, a.b0x2f, a.b0x3f, a.b1x1f, a.b1x2f, a.b1x3f, a.e1, a.e2, a.e3, a.mb_size, gam0, gam1, beta_dt
-  if (do_u && do_b && save) update_ct_kernel<true, true, true><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
-  else if (do_u && do_b) update_ct_kernel<true, true, false><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
-  else if (do_u && save) update_ct_kernel<true, false, true><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);   // hydro twin, stage 1
-  else if (do_u) update_ct_kernel<true, false, false><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
-  else if (do_b && save) update_ct_kernel<false, true, true><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);   // CT after an overlapped U update, stage 1
-  else if (do_b) update_ct_kernel<false, true, false><<<gr, tb, 0, st>>>(AKB_UCT_ARGS);
+  if (do_u && do_b && save) AKB_UCT(true, true, true);
+  else if (do_u && do_b) AKB_UCT(true, true, false);
+  else if (do_u && save) AKB_UCT(true, false, true);   // hydro twin, stage 1
+  else if (do_u) AKB_UCT(true, false, false);
+  else if (do_b && save) AKB_UCT(false, true, true);   // CT after an overlapped U update, stage 1
+  else if (do_b) AKB_UCT(false, true, false);
+#undef AKB_UCT
 #undef AKB_UCT_ARGS
   return cudaGetLastError();
 }

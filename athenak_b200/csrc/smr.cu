@@ -19,6 +19,7 @@
 // by the stream.  Single rank: every neighbour must live in this pack (the multi-rank plan is the next step).
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -146,7 +147,13 @@ struct Plan {
   akb_smr::EmfPack *d_epack = nullptr; akb_smr::EmfOp *d_eops = nullptr; akb_smr::EmfRange *d_erange = nullptr;
   double *d_emfbuf = nullptr;
   bool fc_uploaded = false;
+  // launch tables: every descriptor list goes out as ONE compact 1-D grid of {descriptor, chunk of SMR_TILE elements} tiles,
+  // cached per (list, nvar) -- descriptor boxes differ by orders of magnitude in size, and a (descriptor x max-box) grid
+  // launches mostly empty CTAs (round-1 VERDICT: smr_copy_kernel)
+  struct TileTab { int2 *d = nullptr; int n = 0; };
+  std::map<std::pair<int, int>, TileTab> tiles;
 };
+#define SMR_TILE 1024
 
 thread_local std::string g_smr_err;
 
@@ -187,10 +194,11 @@ smr_restrict_kernel(Dims D, int nmb, int nvar, int cnx1, int cnx2, int cnx3, con
 
 // bvals_cc.cpp:42-167 + 273-402 without the buffer: blockIdx.x = descriptor, blockIdx.y x threads over (variable, box)
 __global__ void __launch_bounds__(256)
-smr_copy_kernel(Dims D, int nvar, const CopyDesc *__restrict__ descs, double *__restrict__ u, double *__restrict__ cu) {
-  const CopyDesc d = descs[blockIdx.x];
+smr_copy_kernel(Dims D, int nvar, const CopyDesc *__restrict__ descs, const int2 *__restrict__ tiles, double *__restrict__ u, double *__restrict__ cu) {
+  const int2 tl = tiles[blockIdx.x];
+  const CopyDesc d = descs[tl.x];
   const int cnt = d.n[0] * d.n[1] * d.n[2] * nvar;      // 32-bit index math: a box holds far fewer than 2^31 elements
-  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) {
+  for (int t = tl.y * SMR_TILE + threadIdx.x, tend = (cnt < (tl.y + 1) * SMR_TILE ? cnt : (tl.y + 1) * SMR_TILE); t < tend; t += blockDim.x) {
     int r = t;
     const int i = r % d.n[0]; r /= d.n[0];
     const int j = r % d.n[1]; r /= d.n[1];
@@ -206,10 +214,11 @@ smr_copy_kernel(Dims D, int nvar, const CopyDesc *__restrict__ descs, double *__
 
 // prolongation.cpp:366-464 (FillCoarseInBndryCC): restrict same-level ghost data into the coarse array
 __global__ void __launch_bounds__(256)
-smr_fill_kernel(Dims D, int nvar, const BoxDesc *__restrict__ descs, const double *__restrict__ u, double *__restrict__ cu) {
-  const BoxDesc d = descs[blockIdx.x];
+smr_fill_kernel(Dims D, int nvar, const BoxDesc *__restrict__ descs, const int2 *__restrict__ tiles, const double *__restrict__ u, double *__restrict__ cu) {
+  const int2 tl = tiles[blockIdx.x];
+  const BoxDesc d = descs[tl.x];
   const int cnt = d.n[0] * d.n[1] * d.n[2] * nvar;      // 32-bit index math: a box holds far fewer than 2^31 elements
-  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) {
+  for (int t = tl.y * SMR_TILE + threadIdx.x, tend = (cnt < (tl.y + 1) * SMR_TILE ? cnt : (tl.y + 1) * SMR_TILE); t < tend; t += blockDim.x) {
     int r = t;
     const int i = d.lo[0] + r % d.n[0]; r /= d.n[0];
     const int j = d.lo[1] + r % d.n[1]; r /= d.n[1];
@@ -234,10 +243,11 @@ __device__ __forceinline__ double minmod_slope(double dl, double dr) {          
 
 // prolongation.cpp:471-547 + mesh/prolongation.hpp:21-60: thread per coarse cell of a prolongation box
 __global__ void __launch_bounds__(256)
-smr_prolong_kernel(Dims D, int nvar, const BoxDesc *__restrict__ descs, double *__restrict__ u, const double *__restrict__ cu) {
-  const BoxDesc d = descs[blockIdx.x];
+smr_prolong_kernel(Dims D, int nvar, const BoxDesc *__restrict__ descs, const int2 *__restrict__ tiles, double *__restrict__ u, const double *__restrict__ cu) {
+  const int2 tl = tiles[blockIdx.x];
+  const BoxDesc d = descs[tl.x];
   const int cnt = d.n[0] * d.n[1] * d.n[2] * nvar;      // 32-bit index math: a box holds far fewer than 2^31 elements
-  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) {
+  for (int t = tl.y * SMR_TILE + threadIdx.x, tend = (cnt < (tl.y + 1) * SMR_TILE ? cnt : (tl.y + 1) * SMR_TILE); t < tend; t += blockDim.x) {
     int r = t;
     const int i = d.lo[0] + r % d.n[0]; r /= d.n[0];
     const int j = d.lo[1] + r % d.n[1]; r /= d.n[1];
@@ -270,14 +280,15 @@ smr_prolong_kernel(Dims D, int nvar, const BoxDesc *__restrict__ descs, double *
 // flux_correct_cc.cpp:28-290 without the buffer: the fine block's boundary-face fluxes, averaged over the
 // 1 / 2 / 4 fine faces of a coarse face, replace the coarse neighbour's flux there.
 __global__ void __launch_bounds__(128)
-smr_flux_kernel(Dims D, int nvar, const FluxDesc *__restrict__ descs, double *__restrict__ flx1, double *__restrict__ flx2,
+smr_flux_kernel(Dims D, int nvar, const FluxDesc *__restrict__ descs, const int2 *__restrict__ tiles, double *__restrict__ flx1, double *__restrict__ flx2,
                 double *__restrict__ flx3) {
-  const FluxDesc d = descs[blockIdx.x];
+  const int2 tl = tiles[blockIdx.x];
+  const FluxDesc d = descs[tl.x];
   const long cnt = (long)d.n[0] * d.n[1] * d.n[2] * nvar;
   double *flx = d.dir == 0 ? flx1 : d.dir == 1 ? flx2 : flx3;
   const long e1 = D.n1 + (d.dir == 0), e2 = D.n2 + (d.dir == 1);      // face-array extents along x1, x2
   const long fsz = D.f[d.dir];
-  for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += (long)gridDim.y * blockDim.x) {
+  for (long t = (long)tl.y * SMR_TILE + threadIdx.x, tend = (cnt < (long)(tl.y + 1) * SMR_TILE ? cnt : (long)(tl.y + 1) * SMR_TILE); t < tend; t += blockDim.x) {
     long r = t;
     const int a = r % d.n[0]; r /= d.n[0];
     const int b = r % d.n[1]; r /= d.n[1];
@@ -676,34 +687,38 @@ fc_exchange_kernel(FcDims D, FcMaps M, const FcSrc *__restrict__ src, double *b1
 }
 
 __global__ void __launch_bounds__(128)
-fc_fill_kernel(FcDims D, const FcBox *__restrict__ descs, const double *__restrict__ b1, const double *__restrict__ b2,
+fc_fill_kernel(FcDims D, const FcBox *__restrict__ descs, const int2 *__restrict__ tiles, const double *__restrict__ b1, const double *__restrict__ b2,
                const double *__restrict__ b3, double *cb1, double *cb2, double *cb3) {
-  const FcBox d = descs[blockIdx.x];
+  const int2 tl = tiles[blockIdx.x];
+  const FcBox d = descs[tl.x];
   const int cnt = d.n[0] * d.n[1] * d.n[2];
-  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) fc_fill_elem(D, d, t, b1, b2, b3, cb1, cb2, cb3);
+  for (int t = tl.y * SMR_TILE + threadIdx.x, tend = (cnt < (tl.y + 1) * SMR_TILE ? cnt : (tl.y + 1) * SMR_TILE); t < tend; t += blockDim.x) fc_fill_elem(D, d, t, b1, b2, b3, cb1, cb2, cb3);
 }
 
 __global__ void __launch_bounds__(128)
-fc_prolong_shared_kernel(FcDims D, const FcBox *__restrict__ descs, double *b1, double *b2, double *b3, const double *__restrict__ cb1,
+fc_prolong_shared_kernel(FcDims D, const FcBox *__restrict__ descs, const int2 *__restrict__ tiles, double *b1, double *b2, double *b3, const double *__restrict__ cb1,
                          const double *__restrict__ cb2, const double *__restrict__ cb3) {
-  const FcBox d = descs[blockIdx.x];
+  const int2 tl = tiles[blockIdx.x];
+  const FcBox d = descs[tl.x];
   const int cnt = d.n[0] * d.n[1] * d.n[2];
-  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) fc_prolong_shared_elem(D, d, t, b1, b2, b3, cb1, cb2, cb3);
+  for (int t = tl.y * SMR_TILE + threadIdx.x, tend = (cnt < (tl.y + 1) * SMR_TILE ? cnt : (tl.y + 1) * SMR_TILE); t < tend; t += blockDim.x) fc_prolong_shared_elem(D, d, t, b1, b2, b3, cb1, cb2, cb3);
 }
 
 __global__ void __launch_bounds__(128)
-fc_prolong_interior_kernel(FcDims D, const FcCell *__restrict__ descs, double *b1, double *b2, double *b3) {
-  const FcCell d = descs[blockIdx.x];
+fc_prolong_interior_kernel(FcDims D, const FcCell *__restrict__ descs, const int2 *__restrict__ tiles, double *b1, double *b2, double *b3) {
+  const int2 tl = tiles[blockIdx.x];
+  const FcCell d = descs[tl.x];
   const int cnt = d.n[0] * d.n[1] * d.n[2];
-  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) fc_prolong_interior_elem(D, d, t, b1, b2, b3);
+  for (int t = tl.y * SMR_TILE + threadIdx.x, tend = (cnt < (tl.y + 1) * SMR_TILE ? cnt : (tl.y + 1) * SMR_TILE); t < tend; t += blockDim.x) fc_prolong_interior_elem(D, d, t, b1, b2, b3);
 }
 
 __global__ void __launch_bounds__(128)
-emf_pack_kernel(FcDims D, const EmfPack *__restrict__ descs, const double *__restrict__ e1, const double *__restrict__ e2,
+emf_pack_kernel(FcDims D, const EmfPack *__restrict__ descs, const int2 *__restrict__ tiles, const double *__restrict__ e1, const double *__restrict__ e2,
                 const double *__restrict__ e3, double *__restrict__ buf) {
-  const EmfPack d = descs[blockIdx.x];
+  const int2 tl = tiles[blockIdx.x];
+  const EmfPack d = descs[tl.x];
   const int cnt = d.n[0] * d.n[1] * d.n[2];
-  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) emf_pack_elem(D, d, t, e1, e2, e3, buf);
+  for (int t = tl.y * SMR_TILE + threadIdx.x, tend = (cnt < (tl.y + 1) * SMR_TILE ? cnt : (tl.y + 1) * SMR_TILE); t < tend; t += blockDim.x) emf_pack_elem(D, d, t, e1, e2, e3, buf);
 }
 
 // blockIdx.y = block, blockIdx.z = component; threads over the surface elements only
@@ -719,6 +734,26 @@ emf_apply_kernel(FcDims D, const EmfRange *__restrict__ ranges, const EmfOp *__r
 inline unsigned gflat(long count, int bs) { return (unsigned)std::max(1L, std::min((count + bs - 1) / bs, 148L * 16)); }
 
 }  // namespace
+
+// tile table of descriptor list `id` for `nvar` variables per element box (built and uploaded on first use)
+template <class Desc>
+static int smr_tiles(Plan *P, int id, int nvar, const std::vector<Desc> &host, Plan::TileTab &out) {
+  auto it = P->tiles.find({id, nvar});
+  if (it != P->tiles.end()) { out = it->second; return 0; }
+  std::vector<int2> t;
+  for (size_t q = 0; q < host.size(); ++q) {
+    const long total = (long)host[q].n[0] * host[q].n[1] * host[q].n[2] * nvar;
+    for (long c = 0; c * SMR_TILE < total; ++c) t.push_back(make_int2((int)q, (int)c));
+  }
+  Plan::TileTab tab;
+  tab.n = (int)t.size();
+  if (tab.n && (cudaMalloc(&tab.d, t.size() * sizeof(int2)) != cudaSuccess ||
+                cudaMemcpy(tab.d, t.data(), t.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess))
+    return smr_fail(P, "launch-table upload failed");
+  P->tiles[{id, nvar}] = tab;
+  out = tab;
+  return 0;
+}
 
 extern "C" {
 
@@ -815,6 +850,7 @@ int ak_smr_destroy(void *plan) {
   for (int v = 0; v < 3; ++v) { cudaFree(P->d_fmap[v]); cudaFree(P->d_cmap[v]); }
   cudaFree(P->d_fsrc); cudaFree(P->d_ffill); cudaFree(P->d_fshared); cudaFree(P->d_fint);
   cudaFree(P->d_epack); cudaFree(P->d_eops); cudaFree(P->d_erange); cudaFree(P->d_emfbuf);
+  for (auto &kv : P->tiles) cudaFree(kv.second.d);
   delete P;
   return 0;
 }
@@ -854,8 +890,9 @@ int ak_smr_restrict_cc(void *plan, const double *u, double *cu, int nvar, ak_str
 
 int ak_smr_exchange_cc(void *plan, double *u, double *cu, int nvar, ak_stream_t s) {
   SMR_PROLOGUE("ak_smr_exchange_cc")
-  if (!P->copy.empty())
-    smr_copy_kernel<<<dim3((unsigned)P->copy.size(), gx(P->max_copy * nvar, 256)), 256, 0, st>>>(D, nvar, P->d_copy, u, cu);
+  Plan::TileTab tt;
+  if (smr_tiles(P, 0, nvar, P->copy, tt)) return 1;
+  if (tt.n) smr_copy_kernel<<<tt.n, 256, 0, st>>>(D, nvar, P->d_copy, tt.d, u, cu);
   SMR_EPILOGUE("ak_smr_exchange_cc")
 }
 
@@ -865,17 +902,23 @@ int ak_smr_prolongate_cc(void *plan, double *u, double *cu, int nvar, ak_stream_
 
 int ak_smr_prolongate_cc_steps(void *plan, double *u, double *cu, int nvar, int steps, ak_stream_t s) {
   SMR_PROLOGUE("ak_smr_prolongate_cc")
-  if ((steps & 1) && !P->fill.empty())
-    smr_fill_kernel<<<dim3((unsigned)P->fill.size(), gx(P->max_fill * nvar, 256)), 256, 0, st>>>(D, nvar, P->d_fill, u, cu);
-  if ((steps & 2) && !P->prol.empty())
-    smr_prolong_kernel<<<dim3((unsigned)P->prol.size(), gx(P->max_prol * nvar, 256)), 256, 0, st>>>(D, nvar, P->d_prol, u, cu);
+  Plan::TileTab tt;
+  if (steps & 1) {
+    if (smr_tiles(P, 1, nvar, P->fill, tt)) return 1;
+    if (tt.n) smr_fill_kernel<<<tt.n, 256, 0, st>>>(D, nvar, P->d_fill, tt.d, u, cu);
+  }
+  if (steps & 2) {
+    if (smr_tiles(P, 2, nvar, P->prol, tt)) return 1;
+    if (tt.n) smr_prolong_kernel<<<tt.n, 256, 0, st>>>(D, nvar, P->d_prol, tt.d, u, cu);
+  }
   SMR_EPILOGUE("ak_smr_prolongate_cc")
 }
 
 int ak_smr_flux_correct_cc(void *plan, double *flx1, double *flx2, double *flx3, int nvar, ak_stream_t s) {
   SMR_PROLOGUE("ak_smr_flux_correct_cc")
-  if (!P->flux.empty())
-    smr_flux_kernel<<<dim3((unsigned)P->flux.size(), gx(P->max_flux * nvar, 128)), 128, 0, st>>>(D, nvar, P->d_flux, flx1, flx2, flx3);
+  Plan::TileTab tt;
+  if (smr_tiles(P, 3, nvar, P->flux, tt)) return 1;
+  if (tt.n) smr_flux_kernel<<<tt.n, 128, 0, st>>>(D, nvar, P->d_flux, tt.d, flx1, flx2, flx3);
   SMR_EPILOGUE("ak_smr_flux_correct_cc")
 }
 
@@ -911,11 +954,16 @@ int ak_smr_exchange_fc(void *plan, double *b1, double *b2, double *b3, double *c
 
 int ak_smr_prolongate_fc_steps(void *plan, double *b1, double *b2, double *b3, double *cb1, double *cb2, double *cb3, int steps, ak_stream_t s) {
   SMR_FC_PROLOGUE("ak_smr_prolongate_fc")
-  if ((steps & 1) && !P->ffill.empty())
-    fc_fill_kernel<<<dim3((unsigned)P->ffill.size(), gx(P->max_ffill, 128)), 128, 0, st>>>(D, P->d_ffill, b1, b2, b3, cb1, cb2, cb3);
+  Plan::TileTab tt;
+  if (steps & 1) {
+    if (smr_tiles(P, 4, 1, P->ffill, tt)) return 1;
+    if (tt.n) fc_fill_kernel<<<tt.n, 128, 0, st>>>(D, P->d_ffill, tt.d, b1, b2, b3, cb1, cb2, cb3);
+  }
   if ((steps & 2) && !P->fshared.empty()) {
-    fc_prolong_shared_kernel<<<dim3((unsigned)P->fshared.size(), gx(P->max_fshared, 128)), 128, 0, st>>>(D, P->d_fshared, b1, b2, b3, cb1, cb2, cb3);
-    fc_prolong_interior_kernel<<<dim3((unsigned)P->fint.size(), gx(P->max_fint, 128)), 128, 0, st>>>(D, P->d_fint, b1, b2, b3);
+    if (smr_tiles(P, 5, 1, P->fshared, tt)) return 1;
+    if (tt.n) fc_prolong_shared_kernel<<<tt.n, 128, 0, st>>>(D, P->d_fshared, tt.d, b1, b2, b3, cb1, cb2, cb3);
+    if (smr_tiles(P, 6, 1, P->fint, tt)) return 1;
+    if (tt.n) fc_prolong_interior_kernel<<<tt.n, 128, 0, st>>>(D, P->d_fint, tt.d, b1, b2, b3);
   }
   SMR_EPILOGUE("ak_smr_prolongate_fc")
 }
@@ -923,8 +971,9 @@ int ak_smr_prolongate_fc_steps(void *plan, double *b1, double *b2, double *b3, d
 int ak_smr_emf_correct(void *plan, double *e1, double *e2, double *e3, ak_stream_t s) {
   SMR_FC_PROLOGUE("ak_smr_emf_correct")
   if (D.nmb > 65535) return smr_fail(P, "ak_smr_emf_correct: more than 65535 MeshBlocks per pack (grid dimension y)");
-  if (!P->epack.empty())
-    emf_pack_kernel<<<dim3((unsigned)P->epack.size(), gx(P->max_epack, 128)), 128, 0, st>>>(D, P->d_epack, e1, e2, e3, P->d_emfbuf);
+  Plan::TileTab tt;
+  if (smr_tiles(P, 7, 1, P->epack, tt)) return 1;
+  if (tt.n) emf_pack_kernel<<<tt.n, 128, 0, st>>>(D, P->d_epack, tt.d, e1, e2, e3, P->d_emfbuf);
   const int ns = std::max(emf_surface_count(D, 0), std::max(emf_surface_count(D, 1), emf_surface_count(D, 2)));
   emf_apply_kernel<<<dim3((unsigned)((ns + 127) / 128), (unsigned)D.nmb, 3), 128, 0, st>>>(D, P->d_erange, P->d_eops, P->d_emfbuf, e1, e2, e3);
   SMR_EPILOGUE("ak_smr_emf_correct")

@@ -37,3 +37,12 @@ def oracle_init(A: O.Arrays, nghbr_gid):
     L.oracle_halo_cc(C.byref(A.cfg), O.p(A.u0), 5, O.ip(nghbr_gid))
     L.oracle_halo_fc(C.byref(A.cfg), *[O.p(a) for a in A.b0], O.ip(nghbr_gid))
     return A.c2p_all()
+
+
+def oracle_init_bcs(A: O.Arrays, nghbr_gid, mesh_bcs, mb_bcs):
+    """Driver::Initialize with physical boundaries: ghost exchange, ApplyPhysicalBCs, c2p."""
+    L = O.lib()
+    L.oracle_halo_cc(C.byref(A.cfg), O.p(A.u0), 5, O.ip(nghbr_gid))
+    L.oracle_halo_fc(C.byref(A.cfg), *[O.p(a) for a in A.b0], O.ip(nghbr_gid))
+    assert L.oracle_apply_bcs(C.byref(A.cfg), O.ip(mesh_bcs), O.ip(mb_bcs), O.p(A.u0), *[O.p(a) for a in A.b0]) == 0
+    return A.c2p_all()

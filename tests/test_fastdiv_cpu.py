@@ -42,4 +42,10 @@ def test_device_division_has_the_guard_at_every_site():
         body = src[src.index(fn):src.index(fn) + 1800]
         assert "#if AKB_DIV_GUARD" in body and cold in body, fn
     plm = src[src.index("void plm("):src.index("void plm(") + 600]
-    assert "ddiv(dq2, dql + dqr)" in plm and " / " not in plm.replace("// ", "")
+    assert "ddiv(dq2, dql + dqr, oor)" in plm and " / " not in plm.replace("// ", "")
+    # no call site may bypass the guard: every division / reciprocal / square root of the device arithmetic goes through the
+    # guarded helpers (the cold helpers themselves, host-uniform constants and comments excepted)
+    for name in ("mhd_device.cuh", "hydro_device.cuh", "iso_device.cuh", "c2p_device.cuh"):
+        txt = open(os.path.join(os.path.dirname(TOOL), "..", "..", "athenak_b200", "csrc", name)).read()
+        code = "\n".join(l.split("//")[0] for l in txt.splitlines())
+        assert "sqrt(" not in re.sub(r"\b(dsqrt|dsqrt_cold|rsqrt)\b", "", code).replace("return sqrt(x)", ""), name
