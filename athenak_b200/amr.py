@@ -5,7 +5,11 @@ The host (athenak_b200.mesh.Mesh = the C++ host mesh) owns the tree and the bloc
 refinement criteria (ak_amr_criterion) and moves the data (ak_amr_plan + ak_amr_move: every element of the NEW arrays is
 gathered from the OLD ones -- copy / on-the-fly restriction / direct prolongation -- and ak_amr_repair_fc).  Because the
 arrays of the mirror are sized by the number of MeshBlocks, a mesh change builds a new MHD object for the new mesh
-(`make_mhd(mesh)`), which is also what re-creates the ghost-exchange and refinement plans for the new neighbour table."""
+(`make_mhd(mesh)`), which is also what re-creates the ghost-exchange and refinement plans for the new neighbour table.
+
+ONE RANK ONLY: the flag array, ak_mesh_adapt, ak_amr_plan and the new-to-old maps all index the GLOBAL block list, and no block
+migrates between ranks after the load balance (reference: src/mesh/load_balance.cpp:97-1024, not built); adaptive_mesh_refinement
+raises EngineError for a mesh sharded over several ranks."""
 from __future__ import annotations
 
 import ctypes as C
@@ -72,7 +76,16 @@ def adaptive_mesh_refinement(mhd, mesh, driver, criteria, make_mhd):
     """One AdaptiveMeshRefinement call.  Returns (mhd, changed): the same object when the mesh did not change, otherwise
     a new MHD object (from make_mhd(mesh)) holding the moved data, rebuilt ghost zones / primitives and its new dtnew."""
     L = mhd.L
-    flag = refinement_flags(mhd, mesh, criteria)
+    if getattr(mesh, "nranks", 1) != 1 or mhd.nmb != mesh.nmb_total:
+        raise _lib.EngineError("athenak_b200: adaptive mesh refinement is built for one rank holding every MeshBlock "
+                               f"(mesh.nranks = {getattr(mesh, 'nranks', 1)}, blocks here {mhd.nmb} of {mesh.nmb_total})")
+    # CheckForRefinement returns before evaluating any criterion on a non-check cycle (mesh_refinement.cpp:196-215): zero flags
+    # still go through ak_mesh_adapt so that its cycle counters advance
+    ncheck = getattr(mesh, "ncycle_check", 1)
+    if ncheck > 1 and driver.ncycle % ncheck != 0:
+        flag = np.zeros(mhd.nmb, np.int32)
+    else:
+        flag = refinement_flags(mhd, mesh, criteria)
     old_nmb = mhd.nmb
     nnew, ndel, what = mesh.adapt(driver.ncycle, flag)
     if not (nnew or ndel):
@@ -93,6 +106,8 @@ def adaptive_mesh_refinement(mhd, mesh, driver, criteria, make_mhd):
         raise _lib.EngineError(L.ak_amr_last_error().decode())
     new.launches = mhd.launches + (4 if is_mhd else 1)
     new.nfloor = list(mhd.nfloor)
+    if hasattr(mhd, "nfofc"):
+        new.nfofc = mhd.nfofc              # EventCounters accumulate over the whole run (src/mesh/mesh.hpp:70-74)
     init_boundary_values_and_primitives(new, driver)
     if is_mhd:       # mesh_refinement.cpp:164-171: only MHD repairs the interior faces and rebuilds the ghost zones a second time
         repair = np.ascontiguousarray(what[n2o] != 0, np.int32)

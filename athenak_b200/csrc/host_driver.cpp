@@ -70,6 +70,7 @@ class TaskList {  // task_list.hpp:116-236
     return true;
   }
   int Size() { return (int)task_list_.size(); }
+  static void TraceTask(Driver *d);     // AKB_TRACE=1: an event on the state owner's stream after every task body
   bool Empty() { return task_list_.empty(); }
   void Reset() { tasks_completed_.Clear(); for (auto &it : task_list_) it.SetIncomplete(); }
   TaskListStatus DoAvailable(Driver *d, int s) {
@@ -77,6 +78,7 @@ class TaskList {  // task_list.hpp:116-236
       auto dep = task.GetDependency();
       if (tasks_completed_.CheckDependencies(dep) && !(task.IsComplete())) {
         TaskStatus status = task(d, s);
+        TraceTask(d);
         if (status == TaskStatus::complete) { task.SetComplete(); tasks_completed_.SetComplete(task.GetID()); }
       }
     }
@@ -166,6 +168,9 @@ class Driver {  // driver.hpp / driver.cpp
   double tlim;
   int nlim;
   std::uint64_t nmb_updated_ = 0;
+  // AKB_TRACE=1: device time between consecutive task bodies of one cycle (diagnostic; printed to stderr by Execute)
+  cudaStream_t trace_stream = nullptr;
+  std::vector<cudaEvent_t> trace_events;
   void ExecuteTaskList(std::map<std::string, std::shared_ptr<TaskList>> &tl_map, const std::string &tl, int stage) {
     auto &lst = tl_map[tl];                           // driver.cpp:290-307
     if (lst->Empty()) return;
@@ -175,6 +180,14 @@ class Driver {  // driver.hpp / driver.cpp
   void Initialize(MHD *pmhd);
   int Execute(MHD *pmhd, int ncycles);
 };
+
+void TaskList::TraceTask(Driver *d) {
+  if (!d->trace_stream) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, d->trace_stream);
+  d->trace_events.push_back(e);
+}
 
 class MHD {  // state owner + tasks
  public:
@@ -211,6 +224,7 @@ class MHD {  // state owner + tasks
   std::vector<void *> ipc_opened;
   // static mesh refinement (hydro): multi-level plan, coarse array, coarse-array BC plan (ak_sim_set_levels)
   std::vector<int> nghbr_h;
+  std::vector<double> mb_size_h;     // host copy of the block extents (refinement criteria, AMR)
   void *smr = nullptr, *bcs_coarse = nullptr;
   int mesh_bcs_h[6] = {0, 0, 0, 0, 0, 0};
   std::vector<int> mb_bcs_h;
@@ -269,6 +283,7 @@ class MHD {  // state owner + tasks
       }
     }
     nghbr_h.assign(nghbr, nghbr + nm * 56 * 4);
+    mb_size_h.assign(mb_size, mb_size + nm * 9);
     if (ak_halo_create(&cfg, nghbr, rank, gids_start, &plan)) Fatal(__FILE__, __LINE__, ak_last_error(nullptr));
     for (int p = 0; p < ak_halo_npeers(plan); ++p) {
       Peer pe;
@@ -952,7 +967,13 @@ void Driver::Initialize(MHD *pmhd) {   // driver.cpp:314-371 -> InitBoundaryValu
 int Driver::Execute(MHD *pmhd, int ncycles) {   // driver.cpp:380-459
   int done = 0;
   auto &m = pmhd->mesh;
+  static const bool trace = std::getenv("AKB_TRACE") && std::getenv("AKB_TRACE")[0] == '1';
   while ((m.time < tlim) && (m.ncycle < nlim || nlim < 0) && (ncycles < 0 || done < ncycles)) {
+    if (trace && done == ncycles - 1) {       // last cycle of this call: event after every task body
+      cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, pmhd->st);
+      trace_events.assign(1, e);
+      trace_stream = pmhd->st;
+    }
     ExecuteTaskList(pmhd->tl_map, "before_timeintegrator", 0);
     for (int stage = 1; stage <= nexp_stages; ++stage) {
       ExecuteTaskList(pmhd->tl_map, "before_stagen", stage);
@@ -960,6 +981,21 @@ int Driver::Execute(MHD *pmhd, int ncycles) {   // driver.cpp:380-459
       ExecuteTaskList(pmhd->tl_map, "after_stagen", stage);
     }
     ExecuteTaskList(pmhd->tl_map, "after_timeintegrator", 1);
+    if (trace_stream) {
+      cudaStreamSynchronize(trace_stream);
+      std::fprintf(stderr, "AKB_TRACE cycle %d: ms after each task body (stage-major):", m.ncycle);
+      float tot = 0.f;
+      for (size_t q = 1; q < trace_events.size(); ++q) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, trace_events[q - 1], trace_events[q]);
+        tot += ms;
+        std::fprintf(stderr, " %.3f", ms);
+      }
+      std::fprintf(stderr, "  total %.3f\n", tot);
+      for (auto e : trace_events) cudaEventDestroy(e);
+      trace_events.clear();
+      trace_stream = nullptr;
+    }
     m.time = m.time + m.dt;
     m.ncycle++;
     nmb_updated_ += m.nmb_total;
@@ -972,6 +1008,8 @@ int Driver::Execute(MHD *pmhd, int ncycles) {   // driver.cpp:380-459
 struct Sim {
   std::unique_ptr<MHD> pmhd;
   std::unique_ptr<Driver> pdriver;
+  ak_sim_cfg cfg;                  // as given to ak_sim_create: an AMR mesh change re-creates the state owner from it
+  long nadapt = 0, ncreated = 0, ndeleted = 0;
 };
 
 }  // namespace akh
@@ -981,6 +1019,7 @@ extern "C" {
 int ak_sim_create(const ak_sim_cfg *c, const double *mb_size, const int *nghbr, void **sim) {
   if (!c || !sim || !mb_size || !nghbr) return 1;
   auto *s = new akh::Sim();
+  s->cfg = *c;
   s->pmhd.reset(new akh::MHD(c->mhd, mb_size, nghbr, c->my_rank, c->nranks, c->gids_start, c->nmb_total));
   s->pmhd->fused = c->fused != 0;
   s->pmhd->mesh.cfl_no = c->cfl_number;
@@ -1028,6 +1067,141 @@ int ak_sim_set_levels(void *sim, const int *mb_lev) {
   }
   m->tl_map.clear();
   m->AssembleMHDTasks();
+  return 0;
+}
+
+/* ---- adaptive mesh refinement inside the C++ host driver (one rank) ----------------------------------------------------
+ * MeshRefinement::AdaptiveMeshRefinement (src/mesh/mesh_refinement.cpp:145-190) as Driver::Execute calls it after every
+ * cycle (src/driver/driver.cpp:447-450): criteria on the device (ak_amr_criterion) -> ak_mesh_adapt on the host mesh ->
+ * a new state owner for the new block list (arrays, ghost-exchange and multilevel plans) -> ak_amr_plan + ak_amr_move
+ * (every element of the new arrays gathered from the old ones) -> ghost zones + primitives -> ak_amr_repair_fc -> ghost
+ * zones + primitives again -> new dt.  mesh = the adaptive host mesh (ak_mesh_create[_smr] + ak_mesh_set_amr) whose tables
+ * the simulation was created from; crit = ncrit rows {method, use_primitive, value_min, value_max, loc x1, x2, x3, rad}. */
+static int sim_init_bvp(akh::Sim *s) {       // Driver::InitBoundaryValuesAndPrimitives, driver.cpp:569-653
+  akh::MHD *m = s->pmhd.get();
+  akh::Driver *d = s->pdriver.get();
+  m->SendU(d, 0); m->RecvU(d, 0);
+  if (!m->hydro) { m->SendB(d, 0); m->RecvB(d, 0); if (m->smr) m->Prolongate(d, 0); }
+  m->ApplyPhysicalBCs(d, 0);
+  m->ConToPrim(d, 0);
+  return 0;
+}
+
+int ak_sim_adapt(void *sim, void *mesh, const double *crit, int ncrit, int *changed) {
+  auto *s = static_cast<akh::Sim *>(sim);
+  akh::MHD *old = s->pmhd.get();
+  if (changed) *changed = 0;
+  if (!mesh || (ncrit > 0 && !crit)) return 1;
+  if (old->nranks != 1) return 1;                       // block migration across ranks is not built
+  cudaSetDevice(old->device);
+  const int onmb = old->cfg.nmb;
+  std::vector<int> flag(onmb, 0);
+  for (int q = 0; q < ncrit; ++q) {
+    const double *c = crit + 8 * q;
+    const double *field = (c[1] != 0.0) ? old->a.w0 : old->a.u0;
+    if (ak_amr_criterion(&old->cfg, (int)c[0], field, old->nvar, 0, c[2], c[3], c + 4, old->mb_size_h.data(), flag.data(), old->st)) return 1;
+    old->launches += 1;
+  }
+  int nnew = 0, ndel = 0;
+  if (ak_mesh_adapt(mesh, old->mesh.ncycle, flag.data(), &nnew, &ndel)) return 1;
+  if (!nnew && !ndel) return 0;
+  // tables of the NEW mesh
+  int nmb = 0, root = 0;
+  if (ak_mesh_info(mesh, &nmb, &root)) return 1;
+  std::vector<int> lloc(4 * (size_t)nmb), rank_of(nmb), gs(1), nr(1);
+  if (ak_mesh_tables(mesh, lloc.data(), rank_of.data(), gs.data(), nr.data())) return 1;
+  std::vector<double> mbs(9 * (size_t)nmb);
+  std::vector<int> bcs(6 * (size_t)nmb), ngh(56 * 4 * (size_t)nmb);
+  if (ak_mesh_rank_tables(mesh, 0, mbs.data(), bcs.data(), ngh.data())) return 1;
+  std::vector<int> n2o(nmb), o2n(onmb), oflag(onmb);
+  int old_nmb = 0;
+  if (ak_mesh_amr_maps(mesh, n2o.data(), o2n.data(), oflag.data(), &old_nmb) || old_nmb != onmb) return 1;
+  // new state owner
+  ak_sim_cfg nc = s->cfg;
+  nc.mhd.nmb = nmb; nc.nmb_total = nmb;
+  std::unique_ptr<akh::MHD> nw(new akh::MHD(nc.mhd, mbs.data(), ngh.data(), nc.my_rank, nc.nranks, nc.gids_start, nmb));
+  nw->fused = old->fused;
+  nw->mesh = old->mesh;
+  nw->mesh.nmb_total = nmb;
+  nw->launches = old->launches;
+  for (int q = 0; q < 3; ++q) nw->nfloor[q] = old->nfloor[q];
+  nw->nfofc = old->nfofc;
+  nw->dtnew = old->dtnew;
+  std::unique_ptr<akh::MHD> keep = std::move(s->pmhd);
+  s->pmhd = std::move(nw);
+  akh::MHD *m = s->pmhd.get();
+  if (keep->bcs && ak_sim_set_bcs(sim, keep->mesh_bcs_h, bcs.data())) return 1;
+  std::vector<int> lev(nmb);
+  for (int q = 0; q < nmb; ++q) lev[q] = lloc[4 * q + 3];
+  if (ak_sim_set_levels(sim, lev.data())) return 1;
+  // data movement
+  std::vector<int> plan(5 * (size_t)nmb);
+  if (ak_amr_plan(&m->cfg, onmb, n2o.data(), oflag.data(), lloc.data(), plan.data())) return 1;
+  if (ak_amr_move(&m->cfg, plan.data(), keep->a.u0, m->a.u0, m->nvar, keep->a.b0x1f, keep->a.b0x2f, keep->a.b0x3f,
+                  m->a.b0x1f, m->a.b0x2f, m->a.b0x3f, m->st)) return 1;
+  m->launches += m->hydro ? 1 : 4;
+  if (cudaStreamSynchronize(m->st) != cudaSuccess) return 1;       // the old arrays go away with `keep`
+  keep.reset();
+  sim_init_bvp(s);
+  if (!m->hydro) {      // mesh_refinement.cpp:164-171: MHD repairs the interior faces of new fine blocks, then rebuilds the ghost zones
+    std::vector<int> rep(nmb);
+    for (int q = 0; q < nmb; ++q) rep[q] = oflag[n2o[q]] != 0;
+    if (ak_amr_repair_fc(&m->cfg, rep.data(), m->a.b0x1f, m->a.b0x2f, m->a.b0x3f, m->st)) return 1;
+    m->launches += 1;
+    sim_init_bvp(s);
+  }
+  m->NewTimeStep(s->pdriver.get(), s->pdriver->nexp_stages);
+  s->nadapt += 1; s->ncreated += nnew; s->ndeleted += ndel;
+  if (changed) *changed = 1;
+  return 0;
+}
+
+/* Driver::Execute with AMR (driver.cpp:380-459): cycle -> AdaptiveMeshRefinement -> Mesh::NewTimeStep.  Returns the cycles done. */
+int ak_sim_execute_amr(void *sim, void *mesh, const double *crit, int ncrit, int ncycles) {
+  auto *s = static_cast<akh::Sim *>(sim);
+  akh::Driver *d = s->pdriver.get();
+  cudaSetDevice(s->pmhd->device);
+  int done = 0;
+  while ((s->pmhd->mesh.time < d->tlim) && (s->pmhd->mesh.ncycle < d->nlim || d->nlim < 0) && (ncycles < 0 || done < ncycles)) {
+    akh::MHD *m = s->pmhd.get();
+    for (int stage = 1; stage <= d->nexp_stages; ++stage) {
+      d->ExecuteTaskList(m->tl_map, "before_stagen", stage);
+      d->ExecuteTaskList(m->tl_map, "stagen", stage);
+      d->ExecuteTaskList(m->tl_map, "after_stagen", stage);
+    }
+    m->mesh.time = m->mesh.time + m->mesh.dt;
+    m->mesh.ncycle++;
+    done++;
+    int changed = 0;
+    if (ak_sim_adapt(sim, mesh, crit, ncrit, &changed)) return -1;
+    s->pmhd->MeshNewTimeStep(d->tlim);
+  }
+  return done;
+}
+/* restart-style entry: the state just loaded with ak_sim_set_state belongs to (time, dt, ncycle) */
+int ak_sim_set_time(void *sim, double time, double dt, int ncycle) {
+  auto *m = static_cast<akh::Sim *>(sim)->pmhd.get();
+  m->mesh.time = time; m->mesh.dt = dt; m->mesh.ncycle = ncycle;
+  return 0;
+}
+/* ConToPrim over every cell of the loaded state (ghost zones as loaded) + MHD::NewTimeStep: what the last stage of a cycle leaves */
+int ak_sim_prims_newdt(void *sim) {
+  auto *s = static_cast<akh::Sim *>(sim);
+  cudaSetDevice(s->pmhd->device);
+  s->pmhd->ConToPrim(s->pdriver.get(), 0);
+  s->pmhd->NewTimeStep(s->pdriver.get(), s->pdriver->nexp_stages);
+  return 0;
+}
+/* Mesh::NewTimeStep (mesh.cpp:573-643): dt = min(2 dt, cfl * dtnew), clipped at tlim */
+int ak_sim_mesh_new_dt(void *sim) {
+  auto *s = static_cast<akh::Sim *>(sim);
+  s->pmhd->MeshNewTimeStep(s->pdriver->tlim);
+  return 0;
+}
+/* cnt[0..3] = MeshBlocks now, mesh changes so far, blocks created, blocks deleted by refinement */
+int ak_sim_amr_status(void *sim, long *cnt) {
+  auto *s = static_cast<akh::Sim *>(sim);
+  cnt[0] = s->pmhd->cfg.nmb; cnt[1] = s->nadapt; cnt[2] = s->ncreated; cnt[3] = s->ndeleted;
   return 0;
 }
 int ak_sim_destroy(void *sim) { delete static_cast<akh::Sim *>(sim); return 0; }

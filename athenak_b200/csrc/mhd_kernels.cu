@@ -196,33 +196,46 @@ update_ct_kernel(Geom g, double *__restrict__ u0, double *__restrict__ u1,
     const long o1 = ((long)k * n2 + j) * (n1 + 1) + i;
     const long o2 = ((long)k * (n2 + 1) + j) * n1 + i;
     const long o3 = o;
-    auto update_var = [&](int n) {
+    // Deferred range guard (mhd_device.cuh): flux differences are exact zeros wherever the flow is uniform, so the guard must not
+    // branch on them.  All variables first (no branch between their loads, so every load of the cell is in flight together),
+    // ONE check for the cell, and the rare out-of-range operand repeats the quotients with the guarded operator.
+    auto divergence = [&](int n, bool *oor) -> double {
       const double *p1 = flx1 + ((long)m * g.nvar + n) * g.f1 + o1;
       const double *p2 = flx2 + ((long)m * g.nvar + n) * g.f2 + o2;
       const double *p3 = flx3 + ((long)m * g.nvar + n) * g.f3 + o3;
-      // deferred range guard (mhd_device.cuh): flux differences are exact zeros wherever the flow is uniform, so the guard must
-      // not branch on them; the rare out-of-range operand repeats the three quotients with the guarded operator
-      const double df1 = __ldg(p1 + 1) - __ldg(p1), df2 = g.multi_d ? __ldg(p2 + n1) - __ldg(p2) : 0.0;
-      const double df3 = g.three_d ? __ldg(p3 + n1 * n2) - __ldg(p3) : 0.0;
-      bool oor = false;
-      double divf = div_by(df1, dx1, rdx1, &oor);
-      if (g.multi_d) divf += div_by(df2, dx2, rdx2, &oor);   // hydro_update.cpp:57-75
-      if (g.three_d) divf += div_by(df3, dx3, rdx3, &oor);
-      if (oor) {
-        divf = div_by(df1, dx1, rdx1);
-        if (g.multi_d) divf += div_by(df2, dx2, rdx2);
-        if (g.three_d) divf += div_by(df3, dx3, rdx3);
-      }
+      double divf = div_by(__ldg(p1 + 1) - __ldg(p1), dx1, rdx1, oor);
+      if (g.multi_d) divf += div_by(__ldg(p2 + n1) - __ldg(p2), dx2, rdx2, oor);   // hydro_update.cpp:57-75
+      if (g.three_d) divf += div_by(__ldg(p3 + n1 * n2) - __ldg(p3), dx3, rdx3, oor);
+      return divf;
+    };
+    // the state loads do not wait for the guard's branch either: gam0*u0 + gam1*u1 is formed with the divergences
+    auto combine_var = [&](int n) -> double {
       const long uo = ((long)m * g.nvar + n) * g.cc + o;
       const double uold = u0[uo];
       double ureg;
       if (SAVE) { ureg = uold; u1[uo] = uold; } else { ureg = u1[uo]; }   // SAVE: CopyCons fused in
-      u0[uo] = gam0 * uold + gam1 * ureg - beta_dt * divf;
+      return gam0 * uold + gam1 * ureg;
     };
+    const bool energy = (g.nfl == 5);                       // no energy equation with the isothermal EOS
+    bool oor = false;
+    double dv[5], uc[5];
 #pragma unroll
-    for (int n = 0; n < 4; ++n) update_var(n);
-    if (g.nfl == 5) update_var(IEN);                        // no energy equation with the isothermal EOS
-    for (int n = g.nfl; n < g.nvar; ++n) update_var(n);   // passive scalars (mhd_update.cpp:51: n over nmhd+nscalars)
+    for (int n = 0; n < 4; ++n) { dv[n] = divergence(n, &oor); uc[n] = combine_var(n); }
+    dv[4] = 0.0; uc[4] = 0.0;
+    if (energy) { dv[4] = divergence(IEN, &oor); uc[4] = combine_var(IEN); }
+    if (oor) {
+#pragma unroll
+      for (int n = 0; n < 4; ++n) dv[n] = divergence(n, nullptr);
+      if (energy) dv[4] = divergence(IEN, nullptr);
+    }
+    double *ub = u0 + (long)m * g.nvar * g.cc + o;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) ub[n * g.cc] = uc[n] - beta_dt * dv[n];
+    if (energy) ub[IEN * g.cc] = uc[4] - beta_dt * dv[4];
+    for (int n = g.nfl; n < g.nvar; ++n) {                  // passive scalars (mhd_update.cpp:51: n over nmhd+nscalars)
+      const double c = combine_var(n);
+      ub[n * g.cc] = c - beta_dt * divergence(n, nullptr);
+    }
   }
   if (DO_B) {
     const double *E1 = e1 + (long)m * g.e1, *E2 = e2 + (long)m * g.e2, *E3 = e3 + (long)m * g.e3;

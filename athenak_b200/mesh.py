@@ -49,6 +49,7 @@ class Mesh:
         """<mesh_refinement> refinement=adaptive: num_levels, refinement_interval, ncycle_check."""
         if self.L.ak_mesh_set_amr(self.h, int(num_levels), int(refinement_interval), int(ncycle_check)):
             raise _lib.EngineError("ak_mesh_set_amr failed")
+        self.ncycle_check = int(ncycle_check)
 
     def adapt(self, ncycle, refine_flag):
         """One AdaptiveMeshRefinement bookkeeping step.  refine_flag: the criteria's verdict per block (+1 / -1 / 0).

@@ -110,6 +110,48 @@ class Simulation:
     def execute(self, ncycles=-1):
         return self.L.ak_sim_execute(self.h, ncycles)
 
+    # ---- adaptive mesh refinement inside the C++ driver (one rank) ----
+    @staticmethod
+    def _crit_rows(criteria):
+        from .amr import METHOD
+        rows = []
+        for c in criteria:
+            if c.method != "location" and c.variable not in ("mhd_w_d", "mhd_u_d", "hydro_w_d", "hydro_u_d"):
+                raise _lib.EngineError(f"athenak_b200: refinement variable {c.variable!r} not supported")
+            rows.append([float(METHOD[c.method]), 1.0 if c.variable.endswith("_w_d") else 0.0, c.value_min, c.value_max, *c.location])
+        return np.ascontiguousarray(rows, np.float64).reshape(-1, 8)
+
+    def _after_mesh_change(self):
+        cnt = (C.c_long * 4)()
+        self.L.ak_sim_amr_status(self.h, cnt)
+        self.shapes = [(int(cnt[0]),) + tuple(s[1:]) for s in self.shapes]
+        return dict(nmb=int(cnt[0]), nadapt=int(cnt[1]), ncreated=int(cnt[2]), ndeleted=int(cnt[3]))
+
+    def restart_from(self, time, dt, ncycle):
+        """After set_state: the loaded arrays (ghost zones included) are the state of (time, dt, ncycle); primitives and dtnew follow."""
+        self.L.ak_sim_set_time(self.h, float(time), float(dt), int(ncycle))
+        self.L.ak_sim_prims_newdt(self.h)
+
+    def adapt(self, criteria):
+        """One AdaptiveMeshRefinement call followed by Mesh::NewTimeStep; returns (changed, status dict)."""
+        rows = self._crit_rows(criteria)
+        ch = C.c_int()
+        if self.L.ak_sim_adapt(self.h, self.mesh.h, rows.ctypes.data_as(C.POINTER(C.c_double)), len(rows), C.byref(ch)):
+            raise _lib.EngineError("ak_sim_adapt failed: " + (self.L.ak_amr_last_error() or b"").decode())
+        self.L.ak_sim_mesh_new_dt(self.h)
+        self.mesh._refresh()
+        return bool(ch.value), self._after_mesh_change()
+
+    def execute_amr(self, criteria, ncycles=-1):
+        """Driver::Execute with AdaptiveMeshRefinement after every cycle; self.mesh must be adaptive (Mesh.set_amr) and the
+        simulation multilevel.  Returns (cycles done, status dict)."""
+        rows = self._crit_rows(criteria)
+        n = self.L.ak_sim_execute_amr(self.h, self.mesh.h, rows.ctypes.data_as(C.POINTER(C.c_double)), len(rows), int(ncycles))
+        if n < 0:
+            raise _lib.EngineError("ak_sim_execute_amr failed: " + (self.L.ak_amr_last_error() or b"").decode())
+        self.mesh._refresh()
+        return n, self._after_mesh_change()
+
     def sync(self):
         self.L.ak_sim_sync(self.h)
 

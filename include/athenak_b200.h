@@ -429,6 +429,22 @@ int ak_sim_destroy(void *sim);
 /* statically refined mesh (hydro, one rank): logical level per block; switches to the multilevel task list
  * (RestrictU, SendU/RecvU across levels, Prolongate, SendFlux/RecvFlux).  After ak_sim_set_bcs, before ak_sim_initialize. */
 int ak_sim_set_levels(void *sim, const int *mb_lev);
+/* Adaptive mesh refinement inside the C++ host driver, one rank (MeshRefinement::AdaptiveMeshRefinement, src/mesh/
+ * mesh_refinement.cpp:145-190, called by Driver::Execute after every cycle, src/driver/driver.cpp:447-450).  mesh = the adaptive host
+ * mesh (ak_mesh_create[_smr] + ak_mesh_set_amr) the simulation was created from (with ak_sim_set_levels); crit = ncrit rows of 8
+ * doubles {method (0 min_max, 1 slope, 2 second_deriv, 3 location), 1 = primitive density / 0 = conserved, value_min, value_max,
+ * location x1, x2, x3, radius}.  ak_sim_adapt = one AdaptiveMeshRefinement call (criteria -> ak_mesh_adapt -> new state owner ->
+ * ak_amr_plan / ak_amr_move -> ghost zones + primitives -> ak_amr_repair_fc -> ghost zones + primitives -> new dt);
+ * ak_sim_execute_amr = Driver::Execute with it (returns cycles done, -1 on error); ak_sim_amr_status: cnt[4] = MeshBlocks now,
+ * mesh changes, blocks created, blocks deleted.  No FOFC / passive scalars on this path. */
+int ak_sim_adapt(void *sim, void *mesh, const double *crit, int ncrit, int *changed);
+int ak_sim_execute_amr(void *sim, void *mesh, const double *crit, int ncrit, int ncycles);
+int ak_sim_amr_status(void *sim, long *cnt);
+/* restart-style entries: (time, dt, ncycle) of a state loaded with ak_sim_set_state; ConToPrim over every cell + MHD::NewTimeStep of
+ * that state (ghost zones as loaded); Mesh::NewTimeStep */
+int ak_sim_set_time(void *sim, double time, double dt, int ncycle);
+int ak_sim_prims_newdt(void *sim);
+int ak_sim_mesh_new_dt(void *sim);
 /* physical BCs (default strictly periodic): mesh_bcs[6], mb_bcs host [nmb][6]; errors -> ak_bcs_last_error(NULL) */
 int ak_sim_set_bcs(void *sim, const int *mesh_bcs, const int *mb_bcs);
 int ak_nccl_unique_id(void *out128);                         /* rank 0; broadcast by the launcher */

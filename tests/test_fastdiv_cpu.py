@@ -41,8 +41,8 @@ def test_device_division_has_the_guard_at_every_site():
     for fn, cold in (("double drcp(", "drcp_cold(x)"), ("double ddiv(", "ddiv_cold(a, b)"), ("double dsqrt(", "dsqrt_cold(x)")):
         body = src[src.index(fn):src.index(fn) + 1800]
         assert "#if AKB_DIV_GUARD" in body and cold in body, fn
-    plm = src[src.index("void plm("):src.index("void plm(") + 600]
-    assert "ddiv(dq2, dql + dqr, oor)" in plm and " / " not in plm.replace("// ", "")
+    plm = src[src.index("void plm("):src.index("// ppm.hpp:44-77")]
+    assert "ddiv(dq2, dql + dqr, &o)" in plm and "ddiv(dq2, dql + dqr)" in plm and " / " not in "\n".join(l.split("//")[0] for l in plm.splitlines())
     # no call site may bypass the guard: every division / reciprocal / square root of the device arithmetic goes through the
     # guarded helpers (the cold helpers themselves, host-uniform constants and comments excepted)
     for name in ("mhd_device.cuh", "hydro_device.cuh", "iso_device.cuh", "c2p_device.cuh"):

@@ -4,13 +4,11 @@ RepairAMRFC (ak_amr_repair_fc) and the AdaptiveMeshRefinement sequence (athenak_
 list.  Gate: from the unmodified reference's state of cycle k the engine reproduces the reference's state of cycle k+1
 BITWISE -- U and B with ghost zones, block list, time, dt -- across one refinement and one derefinement event (committed
 fixture; passed on a B200 for the fused and the per-task list), and across whole live runs when oracle/_ref/athena_blast is
-present.  Live runs: block list, time, dt and U bitwise; B bit-identical wherever it is not far-field noise (|dB| <= 1e-100,
-i.e. every value above ~1e-84 must agree to the last bit).  Reason: on the one B200 run this round had budget for, the 2-D
-three-level run agreed bitwise for 23 cycles (8 AMR events) and then differed in x2f only, U, time and dt still identical,
-in a cycle WITHOUT a mesh change.  Cause: the PLM limiter's guard-free division with a numerator at the denormal
-floor; substituting that division into the oracle reproduces the same signature on the CPU (cycle 24 only, 4 faces of x2f,
-5e-175), and the device PLM now guards that range -- but the fixed library has not run on hardware yet, so the bound stays
-until it has.
+present -- U, B (every face, far-field values at the denormal floor included), block list, time and dt, all bit for bit.
+History: in round 1 the 2-D three-level live run differed after 23 cycles in four faces of x2f at the 5e-175 level (the PLM
+limiter's guard-free division with a numerator at the denormal floor) and B was compared with |dB| <= 1e-100; the
+range guard now lives inside every division / reciprocal / square root (csrc/mhd_device.cuh) and the tolerance is 0.
+The AMR loop exists twice: athenak_b200/amr.py around the per-task ABI, and inside the C++ host driver (ak_sim_execute_amr).
 (File name: sorted last on purpose -- the newest, least-measured tests should not stop an `-x` run before the others.)"""
 import numpy as np
 import pytest
@@ -142,6 +140,43 @@ def test_amr_execute_loop_across_both_events():
     assert np.array_equal(mhd.u0.cpu().numpy(), d[f"u0_{k1}"])
     for x, key in zip(mhd.b0, ("b1f", "b2f", "b3f")):
         assert np.array_equal(x.cpu().numpy(), d[f"{key}_{k1}"])
+
+
+def test_amr_loop_of_the_cxx_driver_across_both_events():
+    """The same stretch through the C++ host driver's own AMR loop (ak_sim_adapt / ak_sim_execute_amr, csrc/host_driver.cpp):
+    state of the refinement cycle loaded restart-style, AMR step, then cycle -> AdaptiveMeshRefinement -> new dt up to the
+    cycle after the derefinement; block list, time, U and B must equal the reference's dump bit for bit."""
+    from athenak_b200 import amr
+    from athenak_b200.sim import Simulation
+    d = G.load("amr_blast2d_events")
+    p = H.deck_params(str(d["deck"]))
+    events = [int(k) for k in d["events"]]
+    k0, k1 = events[0], events[-1] + 1
+    S = EngineStepper(p)
+    L = O.lib()
+    for k in range(1, k0):          # mesh bookkeeping up to the first event
+        cfg = AU.ocfg(S.mesh, p)
+        mbs = np.ascontiguousarray(S.mesh.rank_tables(0)[0])
+        S.mesh.adapt(k, AU.criteria_flags(L, cfg, p, np.ascontiguousarray(d[f"dens_{k}"][:, None]), mbs))
+    mesh = S.mesh
+    sim = Simulation(mesh, 0, ng=int(p["mesh/nghost"]), recon=p["mhd/reconstruct"], rsolver=p["mhd/rsolver"], gamma=float(p["mhd/gamma"]),
+                     integrator=p["time/integrator"], cfl_number=float(p["time/cfl_number"]), tlim=float(p["time/tlim"]), fused=True,
+                     multilevel=True)
+    sim.set_state(*[np.ascontiguousarray(d[f"{q}_{k0}"]) for q in ("u0", "b1f", "b2f", "b3f")])
+    sim.restart_from(float(d[f"time_{k0}"]), float(d[f"dt_{k0}"]), k0)
+    crit = amr.criteria_from_params(p)
+    changed, st = sim.adapt(crit)                       # the AMR step of cycle k0 (+ Mesh::NewTimeStep)
+    assert changed and st["nadapt"] == 1
+    n, st = sim.execute_amr(crit, ncycles=k1 - 1 - k0)  # cycles k0+1 .. k1-1, each followed by AMR
+    assert n == k1 - 1 - k0 and st["nadapt"] >= 2 and st["ndeleted"] > 0
+    assert sim.execute(1) == 1                          # cycle k1 (its AMR step comes after the dump)
+    stt = sim.status()
+    assert stt["ncycle"] == k1 and stt["time"] == float(d[f"time_{k1}"])
+    assert np.array_equal(mesh.lloc, d[f"lloc_{k1}"])
+    u, x1, x2, x3 = sim.get_state()
+    assert np.array_equal(u, d[f"u0_{k1}"])
+    for x, key in zip((x1, x2, x3), ("b1f", "b2f", "b3f")):
+        assert np.array_equal(x, d[f"{key}_{k1}"])
 
 
 @pytest.mark.parametrize("name", ["2d_3levels", "3d", "3d_deref"])
