@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/athenak_b200.h"
 #include "halo.h"
@@ -42,6 +43,47 @@ int cuda_fail(Handle *h, const char *where, cudaError_t e) {
   return fail(h, std::string(where) + ": " + cudaGetErrorString(e));
 }
 
+// Small device -> host reads (new-dt slots, floor / FOFC counters, history sums, the all-reduced dt) do NOT use cudaMemcpyAsync:
+// a D2H copy of any size queues on the device's download copy engine behind whatever bulk download another stream has in
+// flight.  Under ak_pipe_* (host_driver.cpp) that is the previous job's 1.2 GB state, 21 ms: every step's first dt read waited
+// for it and steps and downloads ran strictly one after the other.  Instead a one-block kernel stores the words into mapped
+// pinned host memory (posted PCIe writes from the SM, no copy engine); the values are handed over after the stream sync that
+// every such read is followed by anyway.  One mirror per host thread (a handle is driven by one thread at a time).
+__global__ void mirror_words_kernel(const unsigned *__restrict__ src, unsigned *__restrict__ dst, int n) {
+  for (int q = threadIdx.x; q < n; q += blockDim.x) dst[q] = src[q];
+  __threadfence_system();
+}
+struct Mirror {
+  static constexpr size_t CAP = 8192;
+  unsigned char *host = nullptr;
+  size_t used = 0;
+  struct Pend { void *dst; size_t off, bytes; };
+  std::vector<Pend> pend;
+  bool failed = false;
+  ~Mirror() { if (host) cudaFreeHost(host); }
+};
+thread_local Mirror t_mirror;
+cudaError_t small_d2h(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+  Mirror &m = t_mirror;
+  if (!m.host && !m.failed) {
+    if (cudaHostAlloc((void **)&m.host, Mirror::CAP, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { m.host = nullptr; m.failed = true; cudaGetLastError(); }
+  }
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (!m.host || (bytes & 3) || m.used + need > Mirror::CAP) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+  mirror_words_kernel<<<1, 128, 0, st>>>((const unsigned *)src, (unsigned *)(m.host + m.used), (int)(bytes / 4));
+  m.pend.push_back({dst, m.used, bytes});
+  m.used += need;
+  return cudaGetLastError();
+}
+cudaError_t small_sync(cudaStream_t st) {
+  const cudaError_t e = cudaStreamSynchronize(st);
+  Mirror &m = t_mirror;
+  for (const auto &p : m.pend) std::memcpy(p.dst, m.host + p.off, p.bytes);
+  m.pend.clear();
+  m.used = 0;
+  return e;
+}
+
 // new-dt partial slots: identity = (double)FLT_MAX, the reference's initial value (mhd_newdt.cpp:40-42)
 cudaError_t dt_slots_init(Handle *h, cudaStream_t st) {
   static unsigned long long init[3 * DT_SLOTS];
@@ -55,9 +97,9 @@ cudaError_t dt_slots_init(Handle *h, cudaStream_t st) {
 }
 cudaError_t dt_slots_fetch(Handle *h, double *dt3, cudaStream_t st) {
   double part[3 * DT_SLOTS];
-  cudaError_t e = cudaMemcpyAsync(part, h->d_dtmin, sizeof(part), cudaMemcpyDeviceToHost, st);
+  cudaError_t e = small_d2h(part, h->d_dtmin, sizeof(part), st);
   if (e != cudaSuccess) return e;
-  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+  if ((e = small_sync(st)) != cudaSuccess) return e;
   for (int c = 0; c < 3; ++c) {
     double v = part[c];
     for (int q = 1; q < DT_SLOTS; ++q) v = (part[3 * q + c] < v) ? part[3 * q + c] : v;
@@ -234,13 +276,13 @@ static int c2p_impl(Handle *h, const akb::Arrays &A, int il, int iu, int jl, int
                : akb::launch_cons2prim(g, h->eos, A, il, iu, jl, ju, kl, ku, h->d_counters, dt3 != nullptr, h->d_dtmin, st);
   if (e != cudaSuccess) return cuda_fail(h, name, e);
   if (nfloor) {
-    if ((e = cudaMemcpyAsync(nfloor, h->d_counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, name, e);
+    if ((e = small_d2h(nfloor, h->d_counters, 3 * sizeof(int), st)) != cudaSuccess) return cuda_fail(h, name, e);
     if ((e = cudaMemsetAsync(h->d_counters, 0, 3 * sizeof(int), st)) != cudaSuccess) return cuda_fail(h, name, e);
   }
   if (dt3) {
     if ((e = dt_slots_fetch(h, dt3, st)) != cudaSuccess) return cuda_fail(h, name, e);
   } else if (nfloor) {
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(h, name, e);
+    if ((e = small_sync(st)) != cudaSuccess) return cuda_fail(h, name, e);
   }
   return 0;
 }
@@ -271,9 +313,9 @@ int ak_mhd_fofc(void *handle, const ak_mhd_arrays *a, double gam0, double gam1, 
   if (!h->cfg.fofc || h->hydro) return fail(h, "ak_mhd_fofc: handle was not created with cfg.fofc = 1");
   if ((e = akb::launch_fofc(h->g, h->eos, A, gam0, gam1, beta_dt, h->d_fofc, h->d_counters + 3, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_fofc", e);
   if (nfofc) {
-    if ((e = cudaMemcpyAsync(nfofc, h->d_counters + 3, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_fofc", e);
+    if ((e = small_d2h(nfofc, h->d_counters + 3, sizeof(int), st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_fofc", e);
     if ((e = cudaMemsetAsync(h->d_counters + 3, 0, sizeof(int), st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_fofc", e);
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_fofc", e);
+    if ((e = small_sync(st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_fofc", e);
   }
   return 0;
 }
@@ -455,13 +497,13 @@ int ak_mhd_stage_shell_c2p(void *handle, const ak_mhd_arrays *a, int *nfloor, do
   if (h->hydro || !akb::stage_tail_supported(h->g)) return fail(h, "ak_mhd_stage_shell_c2p: not available for this handle (see ak_mhd_tail_supported)");
   if ((e = akb::launch_shell_c2p(h->g, h->eos, A, h->d_counters, dt3 != nullptr, h->d_dtmin, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_shell_c2p", e);
   if (nfloor) {
-    if ((e = cudaMemcpyAsync(nfloor, h->d_counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_shell_c2p", e);
+    if ((e = small_d2h(nfloor, h->d_counters, 3 * sizeof(int), st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_shell_c2p", e);
     if ((e = cudaMemsetAsync(h->d_counters, 0, 3 * sizeof(int), st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_shell_c2p", e);
   }
   if (dt3) {
     if ((e = dt_slots_fetch(h, dt3, st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_shell_c2p", e);
   } else if (nfloor) {
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_shell_c2p", e);
+    if ((e = small_sync(st)) != cudaSuccess) return cuda_fail(h, "ak_mhd_stage_shell_c2p", e);
   }
   return 0;
 }
@@ -474,8 +516,8 @@ int ak_hst_sums(void *handle, const ak_mhd_arrays *a, double *sums, int *nhist, 
   if (!h->d_hst && (e = cudaMalloc(&h->d_hst, sizeof(double) * 11 * (nb + 1))) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
   if ((e = akb::launch_hst_sums(h->g, A, !h->hydro, h->d_hst, nb, st)) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
   const int n = (h->hydro ? 8 : 11) - (5 - h->g.nfl);   // isothermal: no tot-E column (history.cpp:84-88,278-282)
-  if ((e = cudaMemcpyAsync(sums, h->d_hst + 11L * nb, sizeof(double) * n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
-  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
+  if ((e = small_d2h(sums, h->d_hst + 11L * nb, sizeof(double) * n, st)) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
+  if ((e = small_sync(st)) != cudaSuccess) return cuda_fail(h, "ak_hst_sums", e);
   if (nhist) *nhist = n;
   return 0;
 }
@@ -765,6 +807,14 @@ int ak_halo_wait(void *plan, int kind, unsigned long long value, ak_stream_t s) 
   if (!P || !P->push_ready || kind < 0 || kind > 3) return fail(nullptr, "ak_halo_wait: bad argument");
   const int np = (int)P->peers.size();
   return halo_rc(P, "ak_halo_wait", akb::peer_wait_launch(P->flags_local, P->d_wait_slots + kind * np, np, value, (cudaStream_t)s));
+}
+
+/* Synchronous read of a few words of device memory into host memory WITHOUT the download copy engine (see small_d2h above):
+ * the host driver's all-reduced dt.  bytes must be a multiple of 4. */
+int ak_small_d2h_sync(void *dst_host, const void *src_dev, long bytes, ak_stream_t s) {
+  cudaError_t e = small_d2h(dst_host, src_dev, (size_t)bytes, (cudaStream_t)s);
+  if (e == cudaSuccess) e = small_sync((cudaStream_t)s);
+  return e == cudaSuccess ? 0 : cuda_fail(nullptr, "ak_small_d2h_sync", e);
 }
 
 }  // extern "C"

@@ -12,6 +12,10 @@
 // ncclAllReduce(min) for dt; NCCL is loaded at run time (libnccl.so.2) and only when nranks > 1.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 
 #include <bitset>
 #include <cfloat>
@@ -940,8 +944,7 @@ class MHD {  // state owner + tasks
       Nccl &n = Nccl::get();
       CU_CHECK(cudaMemcpyAsync(d_dt, &dt, 8, cudaMemcpyHostToDevice, st));
       n.AllReduce(d_dt, d_dt, 1, kNcclFloat64, kNcclMin, comm, st);
-      CU_CHECK(cudaMemcpyAsync(&dt, d_dt, 8, cudaMemcpyDeviceToHost, st));
-      CU_CHECK(cudaStreamSynchronize(st));
+      AK_CHECK(nullptr, ak_small_d2h_sync(&dt, d_dt, 8, st));     // not cudaMemcpyAsync: see small_d2h in capi.cu
     }
     if ((mesh.time < tlim) && ((mesh.time + dt) > tlim)) dt = tlim - mesh.time;
     mesh.dt = dt;
@@ -1283,5 +1286,180 @@ int ak_sim_arrays(void *sim, ak_mhd_arrays *out) {
   *out = static_cast<akh::Sim *>(sim)->pmhd->a;
   return 0;
 }
+
+}  // extern "C"
+
+/* ---- pipelined host-buffer stepping -----------------------------------------------------------------------------------------
+ * The reference-facing call with HOST buffers is  set_state (H2D) -> initialize -> execute(n) -> get_state (D2H).  Issued back to
+ * back on one engine instance the three phases serialise (PCIe idle while the SMs work and the other way round); several
+ * instances driven by independent threads drift into lockstep (all uploading, then all computing, then all downloading) and share
+ * the link instead of overlapping.  The pipe owns ONE upload stream and ONE download stream for all its engine instances (slots):
+ * copies of one direction queue behind each other at full link speed, uploads, steps and downloads of consecutive jobs overlap,
+ * and both PCIe directions stay busy.  A job is exactly the serial sequence above on its slot; jobs are independent of each other
+ * (job k runs on slot k mod nslots, each slot has a worker thread because Driver::Execute reads dt back every cycle). */
+namespace akh {
+struct Pipe {
+  struct Job { const double *in[4]; double *out[4]; int ncycles; long ticket; };
+  struct Slot {
+    Sim *sim = nullptr;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Job> q;
+    bool stop = false;
+    long completed = -1;        // last ticket of this slot whose result is in its host buffers
+    int rc = 0;                 // sticky error
+    cudaEvent_t up = nullptr, comp = nullptr, down = nullptr;
+    cudaEvent_t t_up0 = nullptr, t_down0 = nullptr;      // AKB_PIPE_TRACE=1: when each copy phase actually started
+  };
+  std::vector<std::unique_ptr<Slot>> slots;
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  int device = 0;
+  long next_ticket = 0;
+  bool trace = false;
+  cudaEvent_t epoch = nullptr;
+  std::mutex tmu;
+  // Turnstiles: uploads are queued and steps are run strictly in job order.  Steps of different slots left to run side by
+  // side only time-slice the SMs (every job finishes late, every slot stays occupied longer); and on several ranks the same
+  // job must be stepping everywhere at the same time, because its ghost exchange pairs the slots of equal index.
+  struct Turn {
+    std::mutex mu;
+    std::condition_variable cv;
+    long serving = 0;
+    void enter(long t) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return serving == t; }); }
+    void leave() { { std::lock_guard<std::mutex> lk(mu); ++serving; } cv.notify_all(); }
+  } up_turn, step_turn;
+
+  static bool ok(cudaError_t e) { return e == cudaSuccess; }
+  int RunJob(Slot &sl, const Job &j) {
+    MHD *m = sl.sim->pmhd.get();
+    const size_t nb[4] = {(size_t)m->n_u * 8, (size_t)m->n_f1 * 8, (size_t)m->n_f2 * 8, (size_t)m->n_f3 * 8};
+    double *dev[4] = {m->a.u0, m->a.b0x1f, m->a.b0x2f, m->a.b0x3f};
+    const int nf = m->hydro ? 1 : 4;
+    // upload: the slot's previous download has completed (the worker waited for it), so the state arrays are free
+    int rc = 0;
+    up_turn.enter(j.ticket);
+    if (trace) cudaEventRecord(sl.t_up0, h2d);
+    for (int q = 0; q < nf && !rc; ++q)
+      if (!ok(cudaMemcpyAsync(dev[q], j.in[q], nb[q], cudaMemcpyHostToDevice, h2d))) rc = 1;
+    if (!rc && (!ok(cudaEventRecord(sl.up, h2d)) || !ok(cudaStreamWaitEvent(m->st, sl.up, 0)))) rc = 1;
+    up_turn.leave();
+    step_turn.enter(j.ticket);          // a failed job still takes and passes its turns, or every later job would wait for ever
+    if (!rc && ak_sim_initialize(sl.sim)) rc = 1;
+    if (!rc && ak_sim_execute(sl.sim, j.ncycles) != j.ncycles) rc = 1;
+    step_turn.leave();
+    if (rc) return rc;
+    if (!ok(cudaEventRecord(sl.comp, m->st)) || !ok(cudaStreamWaitEvent(d2h, sl.comp, 0))) return 1;
+    if (trace) cudaEventRecord(sl.t_down0, d2h);
+    for (int q = 0; q < nf; ++q)
+      if (!ok(cudaMemcpyAsync(j.out[q], dev[q], nb[q], cudaMemcpyDeviceToHost, d2h))) return 1;
+    if (!ok(cudaEventRecord(sl.down, d2h)) || !ok(cudaEventSynchronize(sl.down))) return 1;
+    if (trace) {
+      float t[5] = {0, 0, 0, 0, 0};
+      cudaEvent_t ev[5] = {sl.t_up0, sl.up, sl.comp, sl.t_down0, sl.down};
+      for (int q = 0; q < 5; ++q) cudaEventElapsedTime(&t[q], epoch, ev[q]);
+      std::lock_guard<std::mutex> lk(tmu);
+      std::fprintf(stderr, "AKB_PIPE_TRACE job %ld slot %ld: h2d %.2f-%.2f  step done %.2f  d2h %.2f-%.2f ms\n", j.ticket,
+                   j.ticket % (long)slots.size(), t[0], t[1], t[2], t[3], t[4]);
+    }
+    return 0;
+  }
+  void Work(Slot *sl) {
+    cudaSetDevice(device);
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(sl->mu);
+        sl->cv.wait(lk, [&] { return sl->stop || !sl->q.empty(); });
+        if (sl->q.empty()) return;
+        j = sl->q.front();
+      }
+      const int rc = RunJob(*sl, j);
+      {
+        std::lock_guard<std::mutex> lk(sl->mu);
+        sl->q.pop_front();
+        sl->completed = j.ticket;
+        if (rc) sl->rc = rc;
+      }
+      sl->cv.notify_all();
+    }
+  }
+  ~Pipe() {
+    for (auto &sl : slots) {
+      { std::lock_guard<std::mutex> lk(sl->mu); sl->stop = true; }
+      sl->cv.notify_all();
+      if (sl->th.joinable()) sl->th.join();       // drains the slot's queue first
+      cudaSetDevice(device);
+      for (cudaEvent_t e : {sl->up, sl->comp, sl->down, sl->t_up0, sl->t_down0}) if (e) cudaEventDestroy(e);
+    }
+    if (h2d) cudaStreamDestroy(h2d);
+    if (d2h) cudaStreamDestroy(d2h);
+  }
+};
+}  // namespace akh
+
+extern "C" {
+
+int ak_pipe_create(void *const *sims, int nsims, void **pipe) {
+  if (!sims || nsims < 1 || !pipe) return 1;
+  std::unique_ptr<akh::Pipe> p(new akh::Pipe());
+  p->device = static_cast<akh::Sim *>(sims[0])->pmhd->device;
+  for (int q = 0; q < nsims; ++q)
+    if (!sims[q] || static_cast<akh::Sim *>(sims[q])->pmhd->device != p->device) return 1;
+  cudaSetDevice(p->device);
+  if (cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking) != cudaSuccess) return 1;
+  p->trace = std::getenv("AKB_PIPE_TRACE") && std::getenv("AKB_PIPE_TRACE")[0] == '1';
+  if (p->trace) { cudaEventCreate(&p->epoch); cudaEventRecord(p->epoch, p->h2d); }
+  for (int q = 0; q < nsims; ++q) {
+    std::unique_ptr<akh::Pipe::Slot> sl(new akh::Pipe::Slot());
+    sl->sim = static_cast<akh::Sim *>(sims[q]);
+    for (cudaEvent_t *e : {&sl->up, &sl->comp, &sl->down, &sl->t_up0, &sl->t_down0})
+      if (cudaEventCreateWithFlags(e, p->trace ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) return 1;
+    p->slots.push_back(std::move(sl));
+  }
+  for (auto &sl : p->slots) sl->th = std::thread(&akh::Pipe::Work, p.get(), sl.get());
+  *pipe = p.release();
+  return 0;
+}
+/* One job: the HOST arrays of (u0, b1f, b2f, b3f) in, n cycles from time 0 (ak_sim_initialize + ak_sim_execute), the HOST arrays
+ * of the result out.  Buffers must stay valid (and should be pinned) until ak_pipe_wait(ticket) returns.  Returns the ticket. */
+long ak_pipe_submit(void *pipe, const double *u0, const double *b1f, const double *b2f, const double *b3f,
+                    double *ou0, double *ob1f, double *ob2f, double *ob3f, int ncycles) {
+  auto *p = static_cast<akh::Pipe *>(pipe);
+  if (!p || !u0 || !ou0 || ncycles < 0) return -1;
+  const long t = p->next_ticket++;
+  auto &sl = *p->slots[(size_t)(t % (long)p->slots.size())];
+  {
+    std::lock_guard<std::mutex> lk(sl.mu);
+    sl.q.push_back(akh::Pipe::Job{{u0, b1f, b2f, b3f}, {ou0, ob1f, ob2f, ob3f}, ncycles, t});
+  }
+  sl.cv.notify_all();
+  return t;
+}
+/* blocks until the job's result is in its host buffers; ticket < 0: every job submitted so far */
+int ak_pipe_wait(void *pipe, long ticket) {
+  auto *p = static_cast<akh::Pipe *>(pipe);
+  if (!p) return 1;
+  int rc = 0;
+  const long ns = (long)p->slots.size();
+  for (long s = 0; s < ns; ++s) {
+    long want;
+    if (ticket >= 0) { if (ticket % ns != s) continue; want = ticket; }
+    else { want = p->next_ticket - 1; while (want >= 0 && want % ns != s) --want; }
+    auto &sl = *p->slots[(size_t)s];
+    std::unique_lock<std::mutex> lk(sl.mu);
+    sl.cv.wait(lk, [&] { return sl.completed >= want; });
+    rc |= sl.rc;
+  }
+  return rc;
+}
+int ak_pipe_streams(void *pipe, ak_stream_t *h2d, ak_stream_t *d2h) {
+  auto *p = static_cast<akh::Pipe *>(pipe);
+  if (h2d) *h2d = p->h2d;
+  if (d2h) *d2h = p->d2h;
+  return 0;
+}
+int ak_pipe_destroy(void *pipe) { delete static_cast<akh::Pipe *>(pipe); return 0; }
 
 }  // extern "C"

@@ -160,3 +160,55 @@ class Simulation:
         self.L.ak_sim_status(self.h, st, cnt)
         return dict(time=st[0], dt=st[1], dtnew=st[2], ncycle=cnt[0], launches=cnt[1], nfloor=list(cnt[2:5]), stream=cnt[5],
                     peer_push=bool(cnt[6]), peer_exchanges=cnt[7])
+
+
+class HostPipeline:
+    """Pipelined host-buffer stepping (ak_pipe_*, include/athenak_b200.h): a stream of independent jobs, each
+    `set_state(host in) -> initialize -> execute(ncycles) -> get_state(host out)`, over several Simulation instances on one
+    device.  One upload and one download stream are shared by all instances, so consecutive jobs' H2D, step and D2H overlap and
+    both PCIe directions stay busy; every job's result equals the serial sequence on one instance bit for bit."""
+
+    def __init__(self, sims):
+        self.sims = list(sims)          # keeps the engine instances alive
+        self.L = self.sims[0].L
+        arr = (C.c_void_p * len(self.sims))(*[s.h for s in self.sims])
+        self.h = C.c_void_p()
+        if self.L.ak_pipe_create(arr, len(self.sims), C.byref(self.h)):
+            raise _lib.EngineError("ak_pipe_create failed (instances must live on one device)")
+        self._keep = {}
+
+    def streams(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self.L.ak_pipe_streams(self.h, C.byref(a), C.byref(b))
+        return int(a.value or 0), int(b.value or 0)
+
+    def submit(self, state_in, state_out, ncycles=1):
+        s0 = self.sims[0]
+        s0._check_buffers(list(state_in), "HostPipeline.submit (in)")
+        s0._check_buffers(list(state_out), "HostPipeline.submit (out)")
+        pin = [s0._ptr(t) for t in state_in] + [s0._ptr(None)] * (4 - len(state_in))
+        pout = [s0._ptr(t) for t in state_out] + [s0._ptr(None)] * (4 - len(state_out))
+        t = self.L.ak_pipe_submit(self.h, *pin, *pout, int(ncycles))
+        if t < 0:
+            raise _lib.EngineError("ak_pipe_submit failed")
+        self._keep[t] = (state_in, state_out)       # the buffers must outlive the job
+        return t
+
+    def wait(self, ticket=-1):
+        if self.L.ak_pipe_wait(self.h, int(ticket)):
+            raise _lib.EngineError("a pipelined job failed: " + (self.L.ak_last_error(None) or b"").decode())
+        if ticket < 0:
+            self._keep.clear()
+        else:
+            self._keep.pop(ticket, None)
+
+    def close(self):
+        if self.h:
+            self.L.ak_pipe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -121,6 +121,37 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        # NVML in-process (what nvidia-smi itself reads), one light query per 50 ms: a looping nvidia-smi process re-queries the
+        # whole device record every period and measurably slows kernel launches of a launch-heavy step (seen: -10% on `value`).
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.stop_flag, self.idle = pynvml, False, 0
+
+            def poll():
+                bits = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+                while not self.stop_flag:
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        try:
+                            r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            r = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        f = ["", str(sm), str(mx), "", ""] + ["Active" if r & b else "Not Active" for b, _ in bits]
+                        self.lines.append(",".join(f))
+                    except Exception:
+                        pass
+                    time.sleep(0.05)
+
+            threading.Thread(target=poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
                                           "--format=csv,noheader,nounits", "-lms", "50"],
@@ -138,6 +169,8 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if getattr(self, "nvml", None):
+            self.stop_flag = True
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
@@ -153,7 +186,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if getattr(self, "nvml", None) else "nvidia-smi"}
 
 
 
@@ -353,48 +386,61 @@ def bench_native(args):
     ev1.record(sstream)
     sync_all(sim)
     ms_serial = maxrank(ev0.elapsed_time(ev1)) / ks
-    # (b) pipelined: several engine instances (own stream + host thread each, ctypes releases the GIL; at N > 1 each has
-    # its own NCCL communicator and peer-memory mapping): while one instance computes step i, others upload step i+1's
-    # input and download step i-1's result, so both PCIe directions and the SMs are busy at the same time.  Every step
-    # still does its own H2D of the full conserved state from pinned memory, ghost exchange + c2p, one RK3 step, and a
-    # D2H of the full result.  Guarded by a watchdog: if the instances do not finish, the serial figure is reported.
-    NI = 3
+    # (b) pipelined: ak_pipe_* (csrc/host_driver.cpp) over several engine instances -- one upload and one download stream
+    # shared by all of them, one worker thread per instance (at N > 1 each instance has its own NCCL communicator and
+    # peer-memory mapping): while one instance computes step i, the upload of step i+1 and the download of step i-1 run, so
+    # both PCIe directions and the SMs are busy at the same time.  Every step still does its own H2D of the full conserved
+    # state from pinned memory, ghost exchange + c2p, one RK3 step, and a D2H of the full result, and the outputs are checked
+    # against the serial leg's bit for bit.  Guarded by a watchdog: if the jobs do not finish, the serial figure is reported.
+    NI = int(os.environ.get("AKB_E2E_SLOTS", "5"))
     e2e_mode = "serial: H2D -> step -> D2H, one engine instance"
     ms_e2e, ke2e = ms_serial * ks, ks
+    hung = False
     try:
+        from athenak_b200.sim import HostPipeline
         sims = [sim] + [make_sim(mesh, rank, world, dev, dist, **HEAD) for _ in range(NI - 1)]
         outs = [ho] + [[torch.empty_like(t).pin_memory() for t in ho] for _ in range(NI - 1)]
-        per = max(2, min(K, 12) // NI)
+        pipe = HostPipeline(sims)
+        up_s, down_s = (torch.cuda.ExternalStream(h, device=dev) for h in pipe.streams())
+        hin = (hu0, hb1, hb2, hb3)
+        njobs = max(2 * NI, min(K, 30))
 
-        def worker(s_, out, nsteps):
-            torch.cuda.set_device(local)       # a new host thread starts on device 0
-            for _ in range(nsteps):
-                e2e_step(s_, out)
-            s_.sync()
+        def run_jobs(nj, result):
+            try:
+                for j in range(nj):
+                    pipe.submit(hin, outs[j % NI], 1)
+                    if j >= NI - 1:              # a slot's output buffer is reused only after its previous job is done
+                        pipe.wait(j - (NI - 1))
+                pipe.wait(-1)
+                result.append(True)
+            except Exception as ex:      # noqa: BLE001
+                result.append(ex)
 
-        for s_, o_ in zip(sims[1:], outs[1:]):
-            worker(s_, o_, 1)
-        sync_all(sim)
-        ths = [threading.Thread(target=worker, args=(s_, o_, per), daemon=True) for s_, o_ in zip(sims, outs)]
-        ev0.record(sstream)           # all streams idle here: the event time-stamps "now" on the device clock
-        for th in ths:
+        def guarded(nj):
+            res = []
+            th = threading.Thread(target=run_jobs, args=(nj, res), daemon=True)
             th.start()
-        deadline = time.time() + 180.0
-        for th in ths:
-            th.join(max(0.0, deadline - time.time()))
-        if any(th.is_alive() for th in ths):
-            raise TimeoutError("pipelined e2e instances did not finish in 180 s")
-        ev1.record(sstream)           # every instance drained (worker ends with a stream sync): end of the last D2H
+            th.join(240.0)
+            if th.is_alive():
+                raise TimeoutError("pipelined e2e jobs did not finish in 240 s")
+            if res[0] is not True:
+                raise res[0]
+
+        guarded(NI)                   # warm-up: every slot once
+        sync_all(sim)
+        ev0.record(up_s)              # all streams idle here: the event time-stamps "now" on the device clock
+        guarded(njobs)
+        ev1.record(down_s)            # behind the last download
         sync_all(sim)
         assert all(bool(torch.equal(x, y)) for o_ in outs[1:] for x, y in zip(ho, o_)), "the e2e instances disagree"
-        ms_e2e, ke2e = maxrank(ev0.elapsed_time(ev1)), per * NI
-        e2e_mode = f"{NI} engine instances over {NI} streams/host threads per rank (H2D, step, D2H of consecutive steps overlap)"
-        del sims, outs
+        ms_e2e, ke2e = maxrank(ev0.elapsed_time(ev1)), njobs
+        e2e_mode = (f"ak_pipe_*: {NI} engine instances per rank, one shared upload stream + one shared download stream "
+                    "(H2D of step i+1, RK3 step i, D2H of step i-1 overlap; each step = full H2D -> ghost exchange + c2p -> step -> full D2H)")
+        pipe.close()
+        del pipe, sims, outs
     except TimeoutError as ex:
         e2e_mode += f" (pipelined mode abandoned: {ex})"
         hung = True
-    else:
-        hung = False
     e2e_value = cells * ke2e / (ms_e2e * 1e-3) / 1e6
     if not hung:
         del sim

@@ -463,6 +463,24 @@ int ak_sim_sync(void *sim);
  * peer-memory ghost exchange active (0/1), exchanges done through it */
 int ak_sim_status(void *sim, double *st, long *cnt);
 int ak_sim_arrays(void *sim, ak_mhd_arrays *out);            /* the device arrays it owns */
+/* a few words device -> host, synchronously, by a kernel storing into mapped pinned memory instead of a D2H copy (which would
+ * queue behind any bulk download in flight on the copy engine); bytes % 4 == 0 */
+int ak_small_d2h_sync(void *dst_host, const void *src_dev, long bytes, ak_stream_t s);
+
+/* ---- pipelined host-buffer stepping (csrc/host_driver.cpp) -----------------------------------
+ * What a caller that keeps its state in HOST memory does per step is ak_sim_set_state (H2D) -> ak_sim_initialize ->
+ * ak_sim_execute(n) -> ak_sim_get_state (D2H); in the reference that is the restart-file round trip around Driver::Execute
+ * (src/outputs/restart.cpp, src/pgen/pgen.cpp:140-330, src/driver/driver.cpp:380-459).  A pipe runs that sequence for a stream of
+ * independent jobs over several engine instances ("slots", created by ak_sim_create on the same device, owned by the caller): one
+ * upload stream and one download stream shared by all slots, one worker thread per slot, so the upload of job k+1, the step of
+ * job k and the download of job k-1 overlap and both PCIe directions stay busy.  Job k runs on slot k mod nsims and gives bit for
+ * bit what the serial sequence gives.  Host buffers must stay valid until ak_pipe_wait returns (pinned memory for full speed). */
+int ak_pipe_create(void *const *sims, int nsims, void **pipe);
+long ak_pipe_submit(void *pipe, const double *u0, const double *b1f, const double *b2f, const double *b3f,
+                    double *out_u0, double *out_b1f, double *out_b2f, double *out_b3f, int ncycles);   /* ticket >= 0, -1 on error */
+int ak_pipe_wait(void *pipe, long ticket);                   /* ticket < 0: all jobs submitted so far; non-zero: a job failed */
+int ak_pipe_streams(void *pipe, ak_stream_t *h2d, ak_stream_t *d2h);   /* for device-side timing of the pipe */
+int ak_pipe_destroy(void *pipe);                             /* drains, joins the workers; the sims stay alive */
 
 #ifdef __cplusplus
 }

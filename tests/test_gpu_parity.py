@@ -322,3 +322,44 @@ def test_cxx_driver_matches_golden(fused, nb):
         assert np.array_equal(x1[g, 4:-4, 4:-4, 4:-4], d["b1f_c4"][0][lz:lz + m, ly:ly + m, lx:lx + m + 1])
         assert np.array_equal(x2[g, 4:-4, 4:-4, 4:-4], d["b2f_c4"][0][lz:lz + m, ly:ly + m + 1, lx:lx + m])
         assert np.array_equal(x3[g, 4:-4, 4:-4, 4:-4], d["b3f_c4"][0][lz:lz + m + 1, ly:ly + m, lx:lx + m])
+
+
+def test_host_pipeline_equals_serial_sequence_and_golden():
+    """ak_pipe_* (pipelined host-buffer stepping, csrc/host_driver.cpp): a stream of jobs over three engine instances, each job
+    = H2D -> initialize -> execute(n) -> D2H on shared upload / download streams.  Jobs with the blast state give the reference's
+    restart dump bit for bit; jobs with the Orszag-Tang state interleaved between them equal the serial sequence on one
+    instance -- so neither slot reuse nor copy/step overlap mixes jobs up."""
+    from athenak_b200.mesh import Mesh
+    from athenak_b200.sim import HostPipeline, Simulation
+    d = G.load("blast16_ppm4_hlld_rk3")
+    mesh = Mesh((16, 16, 16), (8, 8, 8))
+    kw = dict(ng=4, recon="ppm4", rsolver="hlld", gamma=1.6666667, integrator="rk3", cfl_number=0.3, tlim=0.3, fused=True)
+    blast = [t.numpy() for t in mesh.pgen_blast(0, 4, 1.6666667)]
+    ot = [t.numpy() for t in mesh.pgen_orszag_tang(0, 4, 1.6666667)]
+    ref = Simulation(mesh, 0, **kw)
+    ref.set_state(*ot)
+    ref.initialize()
+    assert ref.execute(3) == 3
+    ot_ref = ref.get_state()
+    del ref
+    pipe = HostPipeline([Simulation(mesh, 0, **kw) for _ in range(3)])
+    jobs = []
+    for j in range(8):
+        src, n = (blast, 4) if j % 2 == 0 else (ot, 3)
+        out = [np.full_like(a, np.nan) for a in src]
+        jobs.append((pipe.submit(src, out, n), j % 2 == 0, out))
+    pipe.wait(jobs[2][0])
+    pipe.wait(-1)
+    m = 8
+    for _, is_blast, (u, x1, x2, x3) in jobs:
+        if is_blast:
+            for g in range(mesh.nmb_total):
+                lx, ly, lz = (int(v) * m for v in mesh.lloc[g, :3])
+                assert np.array_equal(u[g, :, 4:-4, 4:-4, 4:-4], d["u0_c4"][0][:, lz:lz + m, ly:ly + m, lx:lx + m])
+                assert np.array_equal(x1[g, 4:-4, 4:-4, 4:-4], d["b1f_c4"][0][lz:lz + m, ly:ly + m, lx:lx + m + 1])
+                assert np.array_equal(x2[g, 4:-4, 4:-4, 4:-4], d["b2f_c4"][0][lz:lz + m, ly:ly + m + 1, lx:lx + m])
+                assert np.array_equal(x3[g, 4:-4, 4:-4, 4:-4], d["b3f_c4"][0][lz:lz + m + 1, ly:ly + m, lx:lx + m])
+        else:
+            for a, b in zip((u, x1, x2, x3), ot_ref):
+                assert np.array_equal(a, b)
+    pipe.close()
