@@ -35,9 +35,19 @@ def build(force=False, verbose=False, out=None, defines=()):
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []
+    # an object is reused when it is newer than its source, every header of csrc/ and include/, this file and the flag set
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [
+        os.path.join(HERE, "..", "include", "athenak_b200.h"), os.path.abspath(__file__)]
+    stamp = os.path.join(objdir, "flags.txt")
+    flagtext = " ".join(NVCC_FLAGS + [f"-D{d}" for d in defines])
+    same_flags = os.path.exists(stamp) and open(stamp).read() == flagtext
+    newest_hdr = max(os.path.getmtime(h) for h in hdrs)
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
         objs.append(obj)
+        if (not force and same_flags and os.path.exists(obj)
+                and os.path.getmtime(obj) > max(os.path.getmtime(src), newest_hdr)):
+            continue
         cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-x", "cu", "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -48,6 +58,8 @@ def build(force=False, verbose=False, out=None, defines=()):
             raise RuntimeError(f"nvcc failed on {src}:\n{log}")
         if verbose:
             print(log)
+    with open(stamp, "w") as f:
+        f.write(flagtext)
     target = out or LIB
     subprocess.check_call([nvcc, "-shared", "-o", target, *objs, "-lcudart"])
     return target

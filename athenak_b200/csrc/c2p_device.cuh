@@ -4,7 +4,19 @@
 #include "mhd_device.cuh"
 #include "iso_device.cuh"
 
+#ifndef AKB_C2P_SCALED
+#define AKB_C2P_SCALED 1      // ConsToPrim divisions through ddiv_x (exact for every numerator, no repeat): 0.52 -> 0.42 ms at 256^3
+#endif
+
 namespace akb {
+
+__device__ __forceinline__ double c2p_div(double a, double b, bool *oor) {
+#if AKB_C2P_SCALED
+  return oor ? ddiv_x(a, b, oor) : ddiv(a, b);
+#else
+  return ddiv(a, b, oor);
+#endif
+}
 
 // One cell of ConsToPrim (ideal_mhd.cpp:47-122 + ideal_c2p_mhd.hpp:20-67; isothermal_mhd.cpp:28-46,95-135), shared by the
 // fused tail and the shell kernel.  u[]: conserved (floors applied in place, flags say which), b: cell-centred field,
@@ -15,14 +27,14 @@ __device__ __forceinline__ void c2p_cell(const EosParams &eos, double &ud, doubl
                                          double &we, bool &dfl, bool &efl, bool &tfl, bool *oor) {
   const double gm1 = eos.gamma - 1.0;
   const double b2 = sqr(ubx) + sqr(uby) + sqr(ubz);
-  const double dfloor_ = dmax(eos.dfloor, ddiv(b2, eos.sigma_max, oor));
+  const double dfloor_ = dmax(eos.dfloor, c2p_div(b2, eos.sigma_max, oor));
   if (ud < dfloor_) { ud = dfloor_; dfl = true; }
   wd = ud;
   const double di = drcp(ud, oor);
   wvx = di * umx; wvy = di * umy; wvz = di * umz;
   we = 0.0;
   if constexpr (IDEAL) {
-    const double efloor = ddiv(eos.pfloor, eos.gamma - 1.0, oor);
+    const double efloor = c2p_div(eos.pfloor, eos.gamma - 1.0, oor);
     const double e_k = 0.5 * di * (sqr(umx) + sqr(umy) + sqr(umz));
     const double e_m = 0.5 * (sqr(ubx) + sqr(uby) + sqr(ubz));
     we = (ue - e_k - e_m);
@@ -49,9 +61,9 @@ __device__ __forceinline__ void newdt_cell(const EosParams &eos, double dx1, dou
     if constexpr (IDEAL) return fast_speed(eos.gamma, wd, p, b1, b2, b3, oor);
     else return fast_speed_iso(eos.iso_cs, wd, b1, b2, b3, oor);
   };
-  d1 = ddiv(dx1, fabs(wvx) + cf(bx, by, bz), oor);
-  d2 = ddiv(dx2, fabs(wvy) + cf(by, bz, bx), oor);
-  d3 = ddiv(dx3, fabs(wvz) + cf(bz, bx, by), oor);
+  d1 = c2p_div(dx1, fabs(wvx) + cf(bx, by, bz), oor);
+  d2 = c2p_div(dx2, fabs(wvy) + cf(by, bz, bx), oor);
+  d3 = c2p_div(dx3, fabs(wvz) + cf(bz, bx, by), oor);
 }
 
 }  // namespace akb

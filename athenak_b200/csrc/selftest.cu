@@ -57,6 +57,14 @@ __global__ void selftest_kernel(long n, unsigned long long seed, int span, unsig
       bool o1 = false, o2 = false, o3 = false, o4 = false;
       const double r1 = akb::drcp(b, &o1), r2 = akb::ddiv(a, b, &o2), r3 = akb::dsqrt(sb, &o3), r4 = akb::div_by(a, y, ry, &o4);
       b4 += (!o1 && differ_v(r1, r_ref)) + (!o2 && differ_v(r2, q_ref)) + (!o3 && differ_v(r3, s_ref)) + (!o4 && differ_v(r4, d_ref));
+      // ddiv_x / div_by_x: exact for EVERY numerator (scaled fast path + subnormal tie repair); the flag may only be raised by an
+      // odd divisor, an overflow or a NaN -- never by a zero, subnormal or tiny numerator over a normal divisor of moderate size
+      bool o5 = false, o6 = false;
+      const double r5 = akb::ddiv_x(a, b, &o5), r6 = akb::div_by_x(a, y, ry, &o6);
+      b4 += (!o5 && differ_v(r5, q_ref)) + (!o6 && differ_v(r6, d_ref));
+      const double ab = fabs(b);
+      const bool tame = (a == a) && fabs(a) < 1.0e-200 && ab > 1.0e-60 && ab < 1.0e60;
+      b4 += (tame && o5) + (tame && o6);
     }
   }
   if (b0) atomicAdd(bad + 0, b0);

@@ -363,3 +363,40 @@ def test_host_pipeline_equals_serial_sequence_and_golden():
             for a, b in zip((u, x1, x2, x3), ot_ref):
                 assert np.array_equal(a, b)
     pipe.close()
+
+
+@pytest.mark.parametrize("recon,rs", [("ppm4", "hlld"), ("plm", "hlle"), ("wenoz", "hlld"), ("ppmx", "llf")])
+@pytest.mark.parametrize("nb", [1, 2])
+def test_fluxes_bitwise_with_values_at_the_denormal_floor(recon, rs, nb):
+    """Range guard of the sweeps (flag_face / flux_fixup_kernel): velocities and transverse fields scaled into the range where
+    the guard-free division and square root are not exact (products near 1e-324, subnormals, exact zeros in between) over a
+    part of the domain.  Fluxes and face EMFs must still equal the oracle's IEEE arithmetic bit for bit, the marked-face map
+    must come back clean (a second launch on the unscaled state is exact too), and the fix-up must not touch anything else."""
+    A, ngh, mbs, dt = evolved_state(recon, rs, nb=nb)
+    cfg = A.cfg
+    L = O.lib()
+    w_keep, b_keep = A.w0.copy(), A.bcc0.copy()
+    rng = np.random.default_rng(11)
+    n3, n2, n1 = A.w0.shape[2:]
+    scale = np.ones((n3, n2, n1))
+    scale[:, :, : n1 // 2] = 10.0 ** rng.choice([-162.0, -170.0, -155.0, -300.0, -320.0], size=(n3, n2, n1 // 2))
+    scale[:, : n2 // 3, : n1 // 2] = 0.0                  # exact zeros next to the tiny values
+    A.w0[:, 1:4] *= scale
+    A.bcc0[:, 1:3] *= scale
+    e = make_engine(A, ngh, mbs, recon, rs)
+    drv = FakeDriver(0.25, 0.75, 0.25, dt)
+
+    def compare(tag):
+        L.oracle_fluxes(C.byref(cfg), O.p(A.w0), O.p(A.bcc0), *[O.p(a) for a in A.b0], *[O.p(a) for a in A.flx],
+                        *[O.p(a) for a in A.fe])
+        e.Fluxes(drv, 2)
+        for q in range(3):
+            assert np.array_equal(e.uflx[q].cpu().numpy(), A.flx[q]), f"{tag}: flux x{q + 1}"
+        for q in range(6):
+            assert np.array_equal(e.femf[q].cpu().numpy(), A.fe[q]), f"{tag}: face emf {q}"
+
+    compare("denormal floor")
+    A.w0[:], A.bcc0[:] = w_keep, b_keep
+    e.w0.copy_(torch.from_numpy(A.w0))
+    e.bcc0.copy_(torch.from_numpy(A.bcc0))
+    compare("unscaled state afterwards")
