@@ -817,4 +817,8 @@ int ak_small_d2h_sync(void *dst_host, const void *src_dev, long bytes, ak_stream
   return e == cudaSuccess ? 0 : cuda_fail(nullptr, "ak_small_d2h_sync", e);
 }
 
+/* x2 / x3 flux sweeps of the PPM4 path through the TMA form (flux_march_tma_kernel: ring rows fetched by cp.async.bulk, one issuing
+ * thread per CTA) instead of per-thread cp.async; process-wide, returns the previous setting.  Same bits either way. */
+int ak_mhd_set_march_tma(int on) { return akb::set_march_tma(on); }
+
 }  // extern "C"

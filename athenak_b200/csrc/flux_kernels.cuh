@@ -23,6 +23,9 @@
 #ifndef AKB_X1_L2PF
 #define AKB_X1_L2PF 0       // x1 sweep: planes ahead whose stencil lines each warp prefetches into L2 (0 = off)
 #endif
+#ifndef AKB_MARCH_TMA_DEFAULT
+#define AKB_MARCH_TMA_DEFAULT 0   // x2/x3 sweeps of the 5-point reconstructions through flux_march_tma_kernel (AKB_MARCH_TMA=0/1 overrides)
+#endif
 #ifndef AKB_MARCH_CARRY
 #define AKB_MARCH_CARRY 0   // PPM4 x2/x3 sweeps: carry the clamped interface value along the march.
                             // Measured SLOWER (1.12 vs 1.05 ms): -10% FP64 instructions but +14 live registers
@@ -268,30 +271,30 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int RECON>
+template <int RECON, int SS = MARCH_THREADS>
 __device__ __forceinline__ void recon_ring_var(const double *__restrict__ rv, int b0, double &q_up, double &q_lo, bool *oor = nullptr) {
-  // rv: this thread's ring for one variable (slot stride MARCH_THREADS); b0 = slot of row c-2
+  // rv: this thread's ring for one variable (slot stride SS doubles); b0 = slot of row c-2
   int b1 = b0 + 1; if (b1 >= MARCH_SLOTS) b1 -= MARCH_SLOTS;
   int b2 = b1 + 1; if (b2 >= MARCH_SLOTS) b2 -= MARCH_SLOTS;
   int b3 = b2 + 1; if (b3 >= MARCH_SLOTS) b3 -= MARCH_SLOTS;
   int b4 = b3 + 1; if (b4 >= MARCH_SLOTS) b4 -= MARCH_SLOTS;
-  const double qm2 = rv[b0 * MARCH_THREADS], qm1 = rv[b1 * MARCH_THREADS], q = rv[b2 * MARCH_THREADS];
-  const double qp1 = rv[b3 * MARCH_THREADS], qp2 = rv[b4 * MARCH_THREADS];
+  const double qm2 = rv[b0 * SS], qm1 = rv[b1 * SS], q = rv[b2 * SS];
+  const double qp1 = rv[b3 * SS], qp2 = rv[b4 * SS];
   if constexpr (RECON == RECON_PPM4) ppm4(qm2, qm1, q, qp1, qp2, q_up, q_lo, oor);
   else if constexpr (RECON == RECON_PPMX) ppmx(qm2, qm1, q, qp1, qp2, q_up, q_lo, oor);
   else if constexpr (RECON == RECON_TENO) teno(qm2, qm1, q, qp1, qp2, q_up, q_lo, oor);
   else wenoz(qm2, qm1, q, qp1, qp2, q_up, q_lo, oor);
 }
 
-template <int RECON, int RS>
+template <int RECON, int RS, int SS = MARCH_THREADS>
 __device__ __forceinline__ void recon_ring_cell(const double *__restrict__ ring, int b0, const EosParams &eos,
                                                 State7 &up, State7 &lo, bool *oor = nullptr) {
   using T = SolverTraits<RS>;
-  constexpr int VS = MARCH_SLOTS * MARCH_THREADS;   // ring stride between variables
+  constexpr int VS = MARCH_SLOTS * SS;   // ring stride between variables
   double *upv[7] = {&up.d, &up.vx, &up.vy, &up.vz, &up.e, &up.by, &up.bz};
   double *lov[7] = {&lo.d, &lo.vx, &lo.vy, &lo.vz, &lo.e, &lo.by, &lo.bz};
 #pragma unroll
-  for (int v = 0; v < T::NV; ++v) recon_ring_var<RECON>(ring + v * VS, b0, *upv[T::member(v)], *lov[T::member(v)], oor);
+  for (int v = 0; v < T::NV; ++v) recon_ring_var<RECON, SS>(ring + v * VS, b0, *upv[T::member(v)], *lov[T::member(v)], oor);
   if constexpr (RECON == RECON_PPMX || RECON == RECON_WENOZ || RECON == RECON_TENO) {   // recon.hpp:78-108
     up.d = dmax(up.d, eos.dfloor);
     lo.d = dmax(lo.d, eos.dfloor);
@@ -340,19 +343,19 @@ __device__ __forceinline__ void ppm4_ring_cell(const double *__restrict__ ring, 
 // Cold side of the march kernels' deferred range guard (see flux_x1_kernel): one face repeated with the guarded operators.
 // The left state comes back from the thread's shared-memory copy (the hot path does not keep it live for this), the cell's
 // own states are re-reconstructed from the ring.
-template <int RECON, int RS>
+template <int RECON, int RS, int SS = MARCH_THREADS>
 __device__ __noinline__ void march_face_guarded(const double *__restrict__ ring, int b0, const double *__restrict__ lsm, double bni,
                                                 EosParams eos, State7 &up, Flux7 &fx) {
   State7 L, lo;
   L.d = lsm[0 * MARCH_THREADS]; L.vx = lsm[1 * MARCH_THREADS]; L.vy = lsm[2 * MARCH_THREADS]; L.vz = lsm[3 * MARCH_THREADS];
   L.e = lsm[4 * MARCH_THREADS]; L.by = lsm[5 * MARCH_THREADS]; L.bz = lsm[6 * MARCH_THREADS];
-  recon_ring_cell<RECON, RS>(ring, b0, eos, up, lo);
+  recon_ring_cell<RECON, RS, SS>(ring, b0, eos, up, lo);
   riemann_any<RS>(L, lo, bni, eos, fx);
 }
-template <int RECON, int RS>
+template <int RECON, int RS, int SS = MARCH_THREADS>
 __device__ __noinline__ void march_recon_guarded(const double *__restrict__ ring, int b0, EosParams eos, State7 &up) {
   State7 lo;
-  recon_ring_cell<RECON, RS>(ring, b0, eos, up, lo);
+  recon_ring_cell<RECON, RS, SS>(ring, b0, eos, up, lo);
 }
 __device__ __forceinline__ void store_left_state(double *lsm, const State7 &s) {
   lsm[0 * MARCH_THREADS] = s.d; lsm[1 * MARCH_THREADS] = s.vx; lsm[2 * MARCH_THREADS] = s.vy; lsm[3 * MARCH_THREADS] = s.vz;
@@ -560,6 +563,197 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
 }
 
 // ---------------------------------------------------------------------------------------
+// x2 / x3 sweeps, TMA form (5-point reconstructions, no flux+update fusion).  Same thread mapping, ring and arithmetic as
+// flux_march_kernel; what changes is who fetches the ring rows.  There every thread issues one 8-byte cp.async per variable
+// and step (7 LDGSTS + their addresses per thread and face); here ONE thread of the CTA issues one bulk-copy per variable and
+// row segment -- cp.async.bulk.shared.global through the TMA unit (SASS UBLKCP), up to ~1 KB each, completion counted in bytes
+// on an mbarrier -- and the other 127 threads only wait on that barrier.
+//   * A CTA owns 128 consecutive columns of the flattened (transverse, i) index space, i.e. at most three row segments of
+//     the array (rows of 64 columns or more).  Bulk copies need 16-byte aligned addresses and sizes, so each segment is fetched from its even-aligned start
+//     over an even number of doubles (rows start on 16-byte boundaries because n1 is even -- checked by the launcher); a thread
+//     reads its own column at a fixed offset `sidx` of the row buffer (MARCH_RB doubles per variable and slot).
+//   * full[slot]: mbarrier armed with the bytes of the row about to land in `slot`; every thread waits for the phase of the row
+//     c+2 it is about to read.  Re-use of a slot (the row fetched at step f overwrites the one last read at step f-1) is
+//     ordered by one __syncthreads per step, followed by a proxy fence in the issuing thread (generic reads before async writes).
+#define MARCH_RB 136     // row buffer: 128 columns + alignment slack of the segments (2 doubles each)
+#define MARCH_TMA_SEGS 3  // a CTA's 128 columns span at most 3 rows when a row has >= 64 columns
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(double *smem_dst, const double *gmem_src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int RECON, int RS, int DIR>
+__global__ void __launch_bounds__(MARCH_THREADS, AKB_MARCH_MINB)
+flux_march_tma_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const double *__restrict__ bcc,
+                      const double *__restrict__ bnf, double *__restrict__ flx, double *__restrict__ eyo,
+                      double *__restrict__ ezo, int seglen, int nseg) {
+  static_assert(DIR == 1 || DIR == 2, "march kernel handles x2 and x3");
+  static_assert(RECON >= RECON_PPM4, "the ring exists for the 5-point reconstructions");
+  using T = SolverTraits<RS>;
+  constexpr bool MHD = T::MHD;
+  constexpr bool IDEAL = T::IDEAL;
+  constexpr int NV = T::NV;
+  constexpr int VS = MARCH_SLOTS * MARCH_RB;
+  extern __shared__ double ring_all[];   // NV * MARCH_SLOTS * MARCH_RB (ring) + 7 * MARCH_THREADS (left state) + MARCH_SLOTS barriers; base 16-byte aligned
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(ring_all + NV * VS + 7 * MARCH_THREADS);
+  const int nc = g.nx1 + 2 * g.ext1;
+  const int nt = (DIR == 1) ? g.nx3 + 2 * g.ext3 : g.nx2 + 2 * g.ext2;
+  const int m = blockIdx.y / nseg, seg = blockIdx.y - m * nseg;       // block-uniform
+  const int ncol = nt * nc;
+  const int c0 = blockIdx.x * blockDim.x;                             // first column of the CTA (block-uniform)
+  const bool colok = c0 + (int)threadIdx.x < ncol;
+  const int col = colok ? c0 + (int)threadIdx.x : ncol - 1;           // idle threads shadow the last column (no stores)
+  const int tr = col / nc;
+  const int i = g.is - g.ext1 + (col - tr * nc);
+  const int fs0 = ((DIR == 1) ? g.js : g.ks) - g.next;
+  const int fe0 = ((DIR == 1) ? g.je + 1 : g.ke + 1) + g.next;
+  const int f_lo = fs0 + seg * seglen;
+  int f_hi = f_lo + seglen - 1;
+  if (f_hi > fe0) f_hi = fe0;
+  if (f_lo > f_hi) return;                                            // block-uniform
+  const long cc = g.cc;
+  const int s = (DIR == 1) ? g.n1 : g.n1 * g.n2;
+  int k, j;
+  if (DIR == 1) { k = g.ks - g.ext3 + tr; j = f_lo - 1; } else { j = g.js - g.ext2 + tr; k = f_lo - 1; }
+  int co = (k * g.n2 + j) * g.n1 + i;
+  int fo = (DIR == 1) ? (k * (g.n2 + 1) + f_lo) * g.n1 + i : (f_lo * g.n2 + j) * g.n1 + i;
+  const long fsz = (DIR == 1) ? g.f2 : g.f3;
+  const double *wb = w0 + (long)m * g.nvar * cc;
+  const double *bb = MHD ? bcc + (long)m * 3 * cc : wb;
+  const double *bnb = MHD ? bnf + (long)m * fsz : wb;
+  double *fb = flx + (long)m * g.nvar * fsz;
+  double *eyb = MHD ? eyo + (long)m * cc : nullptr;
+  double *ezb = MHD ? ezo + (long)m * cc : nullptr;
+  constexpr int ivx = IVX + DIR, ivy = IVX + (DIR + 1) % 3, ivz = IVX + (DIR + 2) % 3;
+  constexpr int iby = (DIR + 1) % 3, ibz = (DIR + 2) % 3;
+  auto vsrc = [&](int vv) -> const double * {
+    const int v = T::member(vv);
+    return v == 0 ? wb + IDN * cc : v == 1 ? wb + ivx * cc : v == 2 ? wb + ivy * cc : v == 3 ? wb + ivz * cc
+         : v == 4 ? wb + IEN * cc : v == 5 ? bb + iby * cc : bb + ibz * cc;
+  };
+  // the CTA's row segments (block-uniform): its 128 flattened columns cover at most MARCH_TMA_SEGS consecutive transverse rows
+  // (the launcher takes this kernel only when a row has at least 64 columns); segment q = nq columns of row trA+q starting at
+  // x1 index iq, fetched from the even-aligned index below it over an even number of doubles into offset doff[q] of the row buffer
+  const int trA = c0 / nc, cA = c0 - trA * nc;
+  int segn[MARCH_TMA_SEGS], seglen_[MARCH_TMA_SEGS], segoff[MARCH_TMA_SEGS], segrow[MARCH_TMA_SEGS], segpad[MARCH_TMA_SEGS];
+  int left = min((int)blockDim.x, ncol - c0), doff = 0, tot_len = 0;
+#pragma unroll
+  for (int q = 0; q < MARCH_TMA_SEGS; ++q) {
+    const int cq = (q == 0) ? cA : 0;
+    const int nq = max(0, min(left, nc - cq));
+    const int iq = g.is - g.ext1 + cq, iq_al = iq & ~1;
+    const int lq = nq > 0 ? (((iq - iq_al) + nq + 1) & ~1) : 0;
+    segn[q] = nq; seglen_[q] = lq; segoff[q] = doff; segpad[q] = iq - iq_al;
+    // cell offset of the aligned start at sweep index f_lo-1
+    segrow[q] = (DIR == 1) ? ((g.ks - g.ext3 + trA + q) * g.n2 + (f_lo - 1)) * g.n1 + iq_al
+                           : ((f_lo - 1) * g.n2 + (g.js - g.ext2 + trA + q)) * g.n1 + iq_al;
+    left -= nq; doff += lq; tot_len += lq;
+  }
+  const unsigned row_bytes = (unsigned)(NV * tot_len * 8);
+  int sidx = segpad[0];                  // idle threads shadow the CTA's first column
+  {
+    int t = (int)threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < MARCH_TMA_SEGS; ++q) {
+      if (colok && t >= 0 && t < segn[q]) sidx = segoff[q] + segpad[q] + t;
+      t -= segn[q];
+    }
+  }
+  auto fetch_row = [&](int slot, int r) {       // row (f_lo-1) + r of every variable into `slot`; one thread
+    mbar_expect_tx(full + slot, row_bytes);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double *dst = ring_all + v * VS + slot * MARCH_RB;
+      const double *src = vsrc(v) + r * s;
+#pragma unroll
+      for (int q = 0; q < MARCH_TMA_SEGS; ++q)
+        if (seglen_[q]) bulk_g2s(dst + segoff[q], src + segrow[q], (unsigned)(seglen_[q] * 8), full + slot);
+    }
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < MARCH_SLOTS; ++q) mbar_init(full + q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned phase = 0;                  // bit q = parity the next wait on slot q expects
+  // prologue: rows c-2 .. c+2+PF -> slots 0..S-1 (row c-2 in slot 0), c = f_lo-1
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int r = 0; r < MARCH_SLOTS; ++r)
+      if (r < 5 || (f_lo - 1) + (r - 2) <= f_hi + 2) fetch_row(r, r - 2);
+  }
+  const double *ring = ring_all + sidx;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) { mbar_wait(full + r, (phase >> r) & 1u); phase ^= 1u << r; }
+  State7 L, lo_unused;
+  {
+    bool oor0 = false;
+    recon_ring_cell<RECON, RS, MARCH_RB>(ring, 0, eos, L, lo_unused, &oor0);
+    if (oor0) { State7 lg; march_recon_guarded<RECON, RS, MARCH_RB>(ring, 0, eos, lg); L = lg; }
+  }
+  double *lsm = ring_all + NV * VS + threadIdx.x;
+  store_left_state(lsm, L);
+  int b0 = 1;
+  double bn_next = 0.0;
+  if constexpr (MHD) bn_next = __ldg(bnb + fo);
+  int r_next = 3 + MARCH_PF;           // next row to fetch, relative to sweep index f_lo-1: c+2+PF for c = f_lo
+  for (int f = f_lo; f <= f_hi; ++f) {
+    co += s;
+    const double bni = bn_next;
+    if constexpr (MHD) { if (f < f_hi) bn_next = __ldg(bnb + fo + s); }
+    int bn_slot = b0 + MARCH_SLOTS - 1; if (bn_slot >= MARCH_SLOTS) bn_slot -= MARCH_SLOTS;     // held row c-3, last read one step ago
+    __syncthreads();                   // every thread is done with that slot
+    if (threadIdx.x == 0 && f + MARCH_PF <= f_hi) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      fetch_row(bn_slot, r_next);
+    }
+    r_next += 1;
+    // this step reads rows c-2..c+2: the newest of them, c+2, sits in the slot 4 after b0
+    int b4 = b0 + 4; if (b4 >= MARCH_SLOTS) b4 -= MARCH_SLOTS;
+    mbar_wait(full + b4, (phase >> b4) & 1u);
+    phase ^= 1u << b4;
+    State7 up, lo;
+    bool oor = false;
+    recon_ring_cell<RECON, RS, MARCH_RB>(ring, b0, eos, up, lo, &oor);
+    Flux7 fx;
+    riemann_any<RS>(L, lo, bni, eos, fx, &oor);
+    if (oor) {
+      State7 ug; Flux7 fg;
+      march_face_guarded<RECON, RS, MARCH_RB>(ring, b0, lsm, bni, eos, ug, fg);
+      up = ug; fx = fg;
+    }
+    store_left_state(lsm, up);
+    if (colok) {
+      double *fp = fb + fo;
+      fp[IDN * fsz] = fx.d;
+      fp[ivx * fsz] = fx.mx;
+      fp[ivy * fsz] = fx.my;
+      fp[ivz * fsz] = fx.mz;
+      if constexpr (IDEAL) fp[IEN * fsz] = fx.e;
+      if constexpr (MHD) { eyb[co] = fx.ey; ezb[co] = fx.ez; }
+    }
+    L = up;
+    fo += s;
+    b0 = (b0 + 1 >= MARCH_SLOTS) ? 0 : b0 + 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Passive-scalar fluxes (mhd_fluxes.cpp:153-166,203-216,250-263; hydro_fluxes.cpp:126-138,...):
 // flx(n) = flx(IDN) * (flx(IDN) >= 0 ? wl(n) : wr(n)) over the faces of the ACTIVE transverse
 // range.  One thread per (face, scalar); only the upwind side is reconstructed (the value is the
@@ -632,6 +826,11 @@ struct SweepFork {
          cudaEventCreateWithFlags(&join[1], cudaEventDisableTiming) == cudaSuccess;
   }
 };
+// x2/x3 sweeps through flux_march_tma_kernel: process-wide switch, AKB_MARCH_TMA=0/1 at start-up, ak_mhd_set_march_tma at run time
+inline int &march_tma_flag() {
+  static int flag = [] { const char *v = getenv("AKB_MARCH_TMA"); return v ? (int)(v[0] == '1') : AKB_MARCH_TMA_DEFAULT; }();
+  return flag;
+}
 inline SweepFork *sweep_fork() {
   thread_local SweepFork f;
   return f.ok ? &f : nullptr;
@@ -653,6 +852,9 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
   if (ACC) acc = *accp;
   // ring + left-state copy (5-point reconstructions), + the previous face's fluxes (ACC)
   const size_t smem = sizeof(double) * (((RECON >= RECON_PPM4) ? (NV * MARCH_SLOTS + 7) : 0) + (ACC ? 5 : 0)) * MARCH_THREADS;
+  // TMA form of the marches (flux_march_tma_kernel): rows fetched by bulk copies; needs 16-byte aligned rows (n1 even, aligned bases)
+  const size_t smem_tma = sizeof(double) * ((size_t)NV * MARCH_SLOTS * MARCH_RB + 7 * MARCH_THREADS) + sizeof(unsigned long long) * MARCH_SLOTS;
+  const bool tma = march_tma_flag() && (g.n1 % 2 == 0) && (g.nx1 + 2 * g.ext1 >= 64) && ((((uintptr_t)a.w0) | ((uintptr_t)a.bcc0)) & 15) == 0 && RECON == RECON_PPM4 && !ACC;
   {  // x1
     constexpr int STEP = X1Step<RECON>::value - (ACC ? 1 : 0);
     const unsigned nc = g.nx1 + 2 + 2 * g.next + (RECON == RECON_PPM4 ? 1 : 0), plane = (unsigned)(g.nx2 + 2 * g.ext2) * nc;
@@ -669,18 +871,40 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
     const int nseg = (nf + 31 - (ACC ? 1 : 0)) / (32 - (ACC ? 1 : 0)), seglen = (nf + nseg - 1) / nseg;
     const long cols = (long)(g.nx3 + 2 * g.ext3) * (g.nx1 + 2 * g.ext1);
     if ((long)g.nmb * nseg > 65535 || (long)g.nvar * g.cc >= 0x7fffffffL) return cudaErrorInvalidConfiguration;
-    static bool attr1 = false;
-    if (!attr1 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 1, ACC ? 1 : 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr1 = true; }
-    flux_march_kernel<RECON, RS, 1, ACC ? 1 : 0><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st2>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg, acc);
+    bool done = false;
+    if constexpr (RECON == RECON_PPM4 && !ACC && !AKB_MARCH_CARRY) {   // instantiated for the headline reconstruction only (build time)
+      if (tma) {
+        static bool attr1t = false;
+        if (!attr1t) { cudaFuncSetAttribute(flux_march_tma_kernel<RECON, RS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma); attr1t = true; }
+        flux_march_tma_kernel<RECON, RS, 1><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem_tma, st2>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg);
+        done = true;
+      }
+    }
+    if (!done) {
+      static bool attr1 = false;
+      if (!attr1 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 1, ACC ? 1 : 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr1 = true; }
+      flux_march_kernel<RECON, RS, 1, ACC ? 1 : 0><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st2>>>(g, eos, a.w0, a.bcc0, a.b0x2f, a.flx2, a.e1x2, a.e3x2, seglen, nseg, acc);
+    }
   }
   if (g.three_d) {  // x3: (ey,ez) = (e2x3,e1x3)
     const int nf = g.nx3 + (ACC ? 0 : 1) + 2 * g.next;
     const int nseg = (nf + 31 - (ACC ? 1 : 0)) / (32 - (ACC ? 1 : 0)), seglen = (nf + nseg - 1) / nseg;
     const long cols = (long)(g.nx2 + 2 * g.ext2) * (g.nx1 + 2 * g.ext1);
     if ((long)g.nmb * nseg > 65535 || (long)g.nvar * g.cc >= 0x7fffffffL) return cudaErrorInvalidConfiguration;
-    static bool attr2 = false;
-    if (!attr2 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 2, ACC ? 2 : 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr2 = true; }
-    flux_march_kernel<RECON, RS, 2, ACC ? 2 : 0><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st3>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg, acc);
+    bool done = false;
+    if constexpr (RECON == RECON_PPM4 && !ACC && !AKB_MARCH_CARRY) {   // instantiated for the headline reconstruction only (build time)
+      if (tma) {
+        static bool attr2t = false;
+        if (!attr2t) { cudaFuncSetAttribute(flux_march_tma_kernel<RECON, RS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma); attr2t = true; }
+        flux_march_tma_kernel<RECON, RS, 2><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem_tma, st3>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg);
+        done = true;
+      }
+    }
+    if (!done) {
+      static bool attr2 = false;
+      if (!attr2 && smem) { cudaFuncSetAttribute(flux_march_kernel<RECON, RS, 2, ACC ? 2 : 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr2 = true; }
+      flux_march_kernel<RECON, RS, 2, ACC ? 2 : 0><<<dim3(nblocks(cols, MARCH_THREADS), (unsigned)(g.nmb * nseg)), MARCH_THREADS, smem, st3>>>(g, eos, a.w0, a.bcc0, a.b0x3f, a.flx3, a.e2x3, a.e1x3, seglen, nseg, acc);
+    }
   }
   if (sf) {   // join
     cudaEventRecord(sf->join[0], st2);

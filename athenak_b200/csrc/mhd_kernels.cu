@@ -542,6 +542,8 @@ cudaError_t launch_newdt(const Geom &g, const EosParams &eos, const Arrays &a, u
   return cudaGetLastError();
 }
 
+int set_march_tma(int on) { int &f = march_tma_flag(); const int old = f; f = on ? 1 : 0; return old; }
+
 cudaError_t launch_copy(const double *src, double *dst, long n, cudaStream_t st) {
   // 16-byte vector copy when both pointers allow it, scalar tail otherwise
   if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {

@@ -62,6 +62,7 @@ cudaError_t launch_fofc(const Geom &g, const EosParams &eos, const Arrays &a, do
                         unsigned char *flag, int *counter, cudaStream_t st);
 inline int internal_rsolver(int rsolver, int eos) { return rsolver + (eos == 1 ? 20 : 0); }
 cudaError_t launch_copy(const double *src, double *dst, long n, cudaStream_t st);
+int set_march_tma(int on);     // x2/x3 sweeps through the TMA bulk-copy form (flux_march_tma_kernel); returns the previous setting
 
 // fused stage tail (stage_tail.cu): corner EMFs + conserved update + CT + ConsToPrim (+ new dt) in one kernel, out of place
 // for the face field and the primitives; shell kernels for the outermost layer

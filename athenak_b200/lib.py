@@ -167,6 +167,7 @@ def load():
         "ak_sim_prims_newdt": [vp],
         "ak_sim_mesh_new_dt": [vp],
         "ak_small_d2h_sync": [vp, vp, C.c_long, vp],
+        "ak_mhd_set_march_tma": [ip],
         "ak_pipe_create": [C.POINTER(vp), ip, C.POINTER(vp)],
         "ak_pipe_wait": [vp, C.c_long],
         "ak_pipe_streams": [vp, C.POINTER(vp), C.POINTER(vp)],
@@ -223,7 +224,7 @@ EXPORTED = ("ak_mhd_create", "ak_mhd_destroy", "ak_last_error", "ak_mhd_copy_con
             "ak_mesh_create", "ak_mesh_create_smr", "ak_mesh_destroy", "ak_mesh_set_amr", "ak_mesh_adapt", "ak_mesh_amr_maps", "ak_amr_last_error", "ak_amr_criterion", "ak_amr_plan", "ak_amr_move", "ak_amr_repair_fc", "ak_smr_create", "ak_smr_destroy", "ak_smr_last_error",
             "ak_smr_coarse_cells", "ak_smr_counts", "ak_smr_restrict_cc", "ak_smr_exchange_cc", "ak_smr_prolongate_cc", "ak_smr_prolongate_cc_steps", "ak_smr_flux_correct_cc", "ak_smr_coarse_faces", "ak_smr_restrict_fc", "ak_smr_exchange_fc", "ak_smr_prolongate_fc_steps", "ak_smr_emf_correct", "ak_smr_fc_tables", "ak_mesh_last_error", "ak_mesh_info", "ak_mesh_tables",
             "ak_mesh_rank_tables", "ak_neighbor_index", "ak_pgen_blast", "ak_pgen_orszag_tang", "ak_selftest_divsqrt", "ak_peak_fp64",
-            "ak_sim_create", "ak_sim_destroy", "ak_sim_set_levels", "ak_sim_adapt", "ak_sim_execute_amr", "ak_sim_amr_status", "ak_sim_set_time", "ak_sim_prims_newdt", "ak_sim_mesh_new_dt", "ak_small_d2h_sync", "ak_pipe_create", "ak_pipe_submit", "ak_pipe_wait", "ak_pipe_streams", "ak_pipe_destroy", "ak_nccl_unique_id", "ak_sim_comm_init", "ak_sim_set_state",
+            "ak_sim_create", "ak_sim_destroy", "ak_sim_set_levels", "ak_sim_adapt", "ak_sim_execute_amr", "ak_sim_amr_status", "ak_sim_set_time", "ak_sim_prims_newdt", "ak_sim_mesh_new_dt", "ak_mhd_set_march_tma", "ak_small_d2h_sync", "ak_pipe_create", "ak_pipe_submit", "ak_pipe_wait", "ak_pipe_streams", "ak_pipe_destroy", "ak_nccl_unique_id", "ak_sim_comm_init", "ak_sim_set_state",
             "ak_sim_get_state", "ak_sim_get_prim", "ak_sim_initialize", "ak_sim_execute", "ak_sim_sync", "ak_sim_status", "ak_sim_arrays",
             "ak_sim_set_bcs", "ak_bcs_create", "ak_bcs_destroy", "ak_bcs_last_error", "ak_bcs_strictly_periodic",
             "ak_bcs_hydro", "ak_bcs_bfield", "ak_bcs_apply",

@@ -463,6 +463,9 @@ int ak_sim_sync(void *sim);
  * peer-memory ghost exchange active (0/1), exchanges done through it */
 int ak_sim_status(void *sim, double *st, long *cnt);
 int ak_sim_arrays(void *sim, ak_mhd_arrays *out);            /* the device arrays it owns */
+/* x2 / x3 flux sweeps (PPM4, rows of >= 64 columns, even n1) through the TMA bulk-copy kernel instead of per-thread cp.async.
+ * Process-wide; returns the previous setting; AKB_MARCH_TMA=0/1 sets the start-up value.  Results are bit-identical. */
+int ak_mhd_set_march_tma(int on);
 /* a few words device -> host, synchronously, by a kernel storing into mapped pinned memory instead of a D2H copy (which would
  * queue behind any bulk download in flight on the copy engine); bytes % 4 == 0 */
 int ak_small_d2h_sync(void *dst_host, const void *src_dev, long bytes, ak_stream_t s);

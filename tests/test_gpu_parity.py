@@ -400,3 +400,47 @@ def test_fluxes_bitwise_with_values_at_the_denormal_floor(recon, rs, nb):
     e.w0.copy_(torch.from_numpy(A.w0))
     e.bcc0.copy_(torch.from_numpy(A.bcc0))
     compare("unscaled state afterwards")
+
+
+@pytest.mark.parametrize("nx", [(64, 12, 12), (126, 8, 10), (200, 6, 6)])
+def test_tma_march_kernel_bitwise(nx):
+    """flux_march_tma_kernel (x2/x3 sweeps, ring rows fetched by cp.async.bulk / TMA, one issuing thread per CTA) against the
+    oracle and against the per-thread cp.async kernel on random states: rows of 66, 128 and 202 columns, so that a CTA's 128
+    columns span three, two and one-or-two array rows, with odd and even segment starts."""
+    from athenak_b200 import lib as _lib
+    from athenak_b200.mhd import MHD
+    L = O.lib()
+    E = _lib.load()
+    rng = np.random.default_rng(3)
+    cfg = O.make_cfg(1, 4, nx, "ppm4", "hlld")
+    A = O.Arrays(cfg)
+    A.w0[:] = rng.uniform(-1.0, 1.0, A.w0.shape)
+    A.w0[:, 0] = rng.uniform(0.5, 2.0, A.w0[:, 0].shape)
+    A.w0[:, 4] = rng.uniform(0.5, 2.0, A.w0[:, 4].shape)
+    A.bcc0[:] = rng.uniform(-1.0, 1.0, A.bcc0.shape)
+    for b in A.b0:
+        b[:] = rng.uniform(-1.0, 1.0, b.shape)
+    _, ngh, mbs, _ = O.uniform_mesh(nx, nx)
+    L.oracle_fluxes(C.byref(cfg), O.p(A.w0), O.p(A.bcc0), *[O.p(a) for a in A.b0], *[O.p(a) for a in A.flx], *[O.p(a) for a in A.fe])
+    drv = FakeDriver(0.25, 0.75, 0.25, 1.0e-3)
+    old = E.ak_mhd_set_march_tma(1)
+    try:
+        for on in (1, 0):
+            E.ak_mhd_set_march_tma(on)
+            e = make_engine(A, ngh, mbs, "ppm4", "hlld")
+            for t in e.uflx + e.femf:
+                t.fill_(float("nan"))
+            e.Fluxes(drv, 2)
+            torch.cuda.synchronize()
+            ng = cfg.ng
+            for q in range(3):
+                got = e.uflx[q].cpu().numpy()
+                w = ~np.isnan(got)                      # faces the sweep wrote
+                assert w.any() and np.array_equal(got[w], A.flx[q][w]), f"tma={on}: flux x{q + 1}"
+                assert not np.isnan(got[:, :, ng:-ng, ng:-ng, ng:-ng]).any()
+            for q in range(6):
+                got = e.femf[q].cpu().numpy()
+                w = ~np.isnan(got)
+                assert w.any() and np.array_equal(got[w], A.fe[q][w]), f"tma={on}: face emf {q}"
+    finally:
+        E.ak_mhd_set_march_tma(old)
