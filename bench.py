@@ -32,6 +32,7 @@ GAMMA = 1.6666667
 NG = 4
 DECK = os.path.join(ROOT, "tests", "decks", "blast3d.athinput")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "athena_blast")
+REF_BIN_CUDA = os.path.join(ROOT, "oracle", "_ref", "athena_blast_cuda")     # oracle/build_ref.sh cuda (the reference's own Kokkos-CUDA build)
 ALGO_BYTES_PER_CELL_STAGE = 256.0      # 32 FP64 words per active cell per stage
 METRIC = "Mcell-updates/s on 3D MHD blast 256^3/GPU"
 NCU_FLUX = os.path.join(ROOT, "profiles", "r02_flux_fp64.json")     # committed ncu summary the roofline's traffic / FP64 counts come from
@@ -53,9 +54,11 @@ def host_cores():
 # ----------------------------------------------------------------------------------------
 # reference CPU arm (unmodified reference binary built by oracle/build_ref.sh)
 
-def run_reference_cpu(n, ncycles, threads, timeout=1500):
+def run_reference_cpu(n, ncycles, threads, timeout=1500, binary=None):
     """Runs oracle/_ref/athena_blast at n^3 for ncycles; returns per-cycle wall seconds (from the
-    binary's own 'elapsed=' diagnostics) and its zone-cycles/cpu_second line."""
+    binary's own 'elapsed=' diagnostics) and its zone-cycles/cpu_second line.  binary: another build of the same
+    unmodified reference (the Kokkos-CUDA one for the reference_gpu leg)."""
+    REF_BIN = binary or globals()["REF_BIN"]
     if not os.path.exists(REF_BIN):
         return None
     env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="spread", OMP_PLACES="threads")
@@ -494,6 +497,55 @@ def bench_native(args):
     except Exception as ex:      # secondary block: never takes the headline down
         line["config3_ot"] = {"error": str(ex)[:200]}
 
+    # ---- the same headline run with the x2/x3 sweeps through the TMA bulk-copy kernel (flux_march_tma_kernel) --------------
+    try:
+        E = _lib.load()
+        prev = E.ak_mhd_set_march_tma(1)
+        st_ = make_sim(mesh, rank, world, dev, dist, **HEAD)
+        st_.set_state(hu0, hb1, hb2, hb3)
+        st_.initialize()
+        stt = torch.cuda.ExternalStream(st_.status()["stream"], device=dev)
+        kt = max(3, min(K, 10))
+        st_.execute(W)
+        sync_all(st_)
+        ev0.record(stt)
+        st_.execute(kt)
+        ev1.record(stt)
+        sync_all(st_)
+        mst = maxrank(ev0.elapsed_time(ev1))
+        E.ak_mhd_set_march_tma(prev)
+        # the default path over the same cycles, for a like-for-like ratio (the step gets slower as the blast's far-field shell grows)
+        sd_ = make_sim(mesh, rank, world, dev, dist, **HEAD)
+        sd_.set_state(hu0, hb1, hb2, hb3)
+        sd_.initialize()
+        sdd = torch.cuda.ExternalStream(sd_.status()["stream"], device=dev)
+        sd_.execute(W)
+        sync_all(sd_)
+        ev0.record(sdd)
+        sd_.execute(kt)
+        ev1.record(sdd)
+        sync_all(sd_)
+        msd = maxrank(ev0.elapsed_time(ev1))
+        line["tma_march"] = {"what": "headline workload with the x2/x3 flux sweeps fetching their ring rows by cp.async.bulk (TMA, SASS UBLKCP; "
+                                     "ak_mhd_set_march_tma) instead of per-thread cp.async; bit-identical results; same cycles for both figures",
+                             "value": cells * kt / (mst * 1e-3) / 1e6, "cp_async_value": cells * kt / (msd * 1e-3) / 1e6,
+                             "unit": "Mcell-updates/s", "steps": kt, "default": False}
+        del st_, sd_
+        torch.cuda.empty_cache()
+    except Exception as ex:      # secondary block
+        line["tma_march"] = {"error": str(ex)[:200]}
+
+    # ---- the reference's own GPU path on this device: its Kokkos-CUDA build of the same deck (oracle/build_ref.sh cuda) ----
+    if rank == 0 and world == 1 and os.path.exists(REF_BIN_CUDA) and not args.no_cpu_baseline:
+        try:
+            r = run_reference_cpu(n, 13, 1, timeout=600, binary=REF_BIN_CUDA)
+            pc = r["per_cycle"][3:-1] or r["per_cycle"]          # first cycles warm up, the last one includes the final output
+            line["reference_gpu"] = {"value": n ** 3 * len(pc) / sum(pc) / 1e6, "unit": "Mcell-updates/s", "kind": "reference",
+                                     "what": f"unmodified reference, Kokkos-CUDA build for sm_100 (oracle/_ref/athena_blast_cuda), {n}^3 single MeshBlock, "
+                                             f"{len(pc)} timed cycles after 3 warm-up, same device, per-cycle times from its own elapsed= diagnostics"}
+        except Exception as ex:
+            line["reference_gpu"] = {"value": None, "what": f"failed: {ex}"[:200]}
+
     # ---- per-kernel breakdown through the per-task C-ABI entry points -------------------------
     e = MHD(1, NG, (n, n, n), mb_size, nghbr, recon="ppm4", rsolver="hlld", gamma=GAMMA, my_rank=rank,
             gids_start=int(mesh.gids_start[rank]), device=dev)
@@ -576,8 +628,8 @@ def bench_native(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_cores()
         try:
-            ncpu, rate = pick_reference_size(threads, budget_s=25.0, ncycles=4)
-            r = run_reference_cpu(ncpu, 4, threads)
+            ncpu, rate = pick_reference_size(threads, budget_s=30.0, ncycles=6)
+            r = run_reference_cpu(ncpu, 6, threads)
             v = ncpu ** 3 * len(r["per_cycle"][1:]) / sum(r["per_cycle"][1:]) / 1e6
             line["cpu_baseline"] = {"value": v, "unit": "Mcell-updates/s", "cores": threads, "kind": "reference",
                                     "sample": f"{ncpu}^3 single MeshBlock, {len(r['per_cycle'][1:])} timed cycles after 1 warm-up, reference Kokkos::OpenMP build (oracle/_ref/athena_blast), all host threads"}
