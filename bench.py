@@ -628,7 +628,7 @@ def bench_native(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_cores()
         try:
-            ncpu, rate = pick_reference_size(threads, budget_s=30.0, ncycles=6)
+            ncpu, rate = pick_reference_size(threads, budget_s=45.0, ncycles=6)
             r = run_reference_cpu(ncpu, 6, threads)
             v = ncpu ** 3 * len(r["per_cycle"][1:]) / sum(r["per_cycle"][1:]) / 1e6
             line["cpu_baseline"] = {"value": v, "unit": "Mcell-updates/s", "cores": threads, "kind": "reference",
