@@ -26,6 +26,9 @@
 #ifndef AKB_MARCH_TMA_DEFAULT
 #define AKB_MARCH_TMA_DEFAULT 0   // x2/x3 sweeps of the 5-point reconstructions through flux_march_tma_kernel (AKB_MARCH_TMA=0/1 overrides)
 #endif
+#ifndef AKB_MARCH_SHARE
+#define AKB_MARCH_SHARE 1   // PPM4 x2/x3 sweeps: one interface evaluation per face, carried through shared memory (flux_march_kernel)
+#endif
 #ifndef AKB_MARCH_CARRY
 #define AKB_MARCH_CARRY 0   // PPM4 x2/x3 sweeps: carry the clamped interface value along the march.
                             // Measured SLOWER (1.12 vs 1.05 ms): -10% FP64 instructions but +14 live registers
@@ -122,15 +125,15 @@ __device__ __noinline__ void x1_face_guarded(const double *__restrict__ wc, cons
     for (int v = 0; v < T::NV; ++v) {
       const double *pv = vp[T::member(v)];
       const double q = __ldg(pv);
-      const double fl = ppm4_iface(__ldg(pv - 2), __ldg(pv - 1), q, __ldg(pv + 1));
+      const double fl = ppm4_iface(__ldg(pv - 2), __ldg(pv - 1), q, __ldg(pv + 1), AKB_COLD);
       const double fh = __shfl_down_sync(0xffffffffu, fl, 1);
       ppm4_mono(q, fl, fh, *upv[T::member(v)], *lov[T::member(v)]);
     }
   } else {
-    recon_cell<RECON, 0, T::MHD, T::IDEAL>(wc, bc, cc, 1, eos, up, lo);
+    recon_cell<RECON, 0, T::MHD, T::IDEAL>(wc, bc, cc, 1, eos, up, lo, AKB_COLD);
   }
   shift_up_state<RS>(up, L);
-  if (act) riemann_any<RS>(L, lo, bxi, eos, f);
+  if (act) riemann_any<RS>(L, lo, bxi, eos, f, AKB_COLD);
 }
 
 template <int RECON, int RS, bool ACC = false>
@@ -349,13 +352,45 @@ __device__ __noinline__ void march_face_guarded(const double *__restrict__ ring,
   State7 L, lo;
   L.d = lsm[0 * MARCH_THREADS]; L.vx = lsm[1 * MARCH_THREADS]; L.vy = lsm[2 * MARCH_THREADS]; L.vz = lsm[3 * MARCH_THREADS];
   L.e = lsm[4 * MARCH_THREADS]; L.by = lsm[5 * MARCH_THREADS]; L.bz = lsm[6 * MARCH_THREADS];
-  recon_ring_cell<RECON, RS, SS>(ring, b0, eos, up, lo);
-  riemann_any<RS>(L, lo, bni, eos, fx);
+  recon_ring_cell<RECON, RS, SS>(ring, b0, eos, up, lo, AKB_COLD);
+  riemann_any<RS>(L, lo, bni, eos, fx, AKB_COLD);
+}
+__device__ __forceinline__ void load_left_state(const double *lsm, State7 &s) {
+  s.d = lsm[0 * MARCH_THREADS]; s.vx = lsm[1 * MARCH_THREADS]; s.vy = lsm[2 * MARCH_THREADS]; s.vz = lsm[3 * MARCH_THREADS];
+  s.e = lsm[4 * MARCH_THREADS]; s.by = lsm[5 * MARCH_THREADS]; s.bz = lsm[6 * MARCH_THREADS];
+}
+// Repeat side of the plain march kernels' deferred range guard: the faces marked in `fix` (bit b = face f_lo + b) are solved again
+// from global memory with the guarded operators -- the upper state of the cell below, the lower state of the cell above, the
+// Riemann problem between them -- and their fluxes / face EMFs stored over the fast path's.  Same functions, same operands, so
+// an unflagged quantity comes out with the bits it had.  co0 / fo0: cell f_lo-1 and face f_lo of this thread's column.
+template <int RECON, int RS, int DIR>
+__device__ __noinline__ void march_fix_faces(unsigned fix, int f_lo, int f_hi, int co0, int fo0, int s, const double *__restrict__ wb,
+                                             const double *__restrict__ bb, const double *__restrict__ bnb, long cc, EosParams eos,
+                                             double *__restrict__ fb, long fsz, double *__restrict__ eyb, double *__restrict__ ezb) {
+  using T = SolverTraits<RS>;
+  constexpr int ivx = IVX + DIR, ivy = IVX + (DIR + 1) % 3, ivz = IVX + (DIR + 2) % 3;
+  while (fix) {
+    const int b = __ffs((int)fix) - 1;
+    fix &= fix - 1u;
+    if (f_lo + b > f_hi) break;
+    const int cb = co0 + b * s, ca = cb + s, fo = fo0 + b * s;     // cell below face f, cell above it, the face
+    State7 L, lo, unused;
+    recon_cell<RECON, DIR, T::MHD, T::IDEAL>(wb + cb, bb + cb, cc, s, eos, L, unused, AKB_COLD);
+    recon_cell<RECON, DIR, T::MHD, T::IDEAL>(wb + ca, bb + ca, cc, s, eos, unused, lo, AKB_COLD);
+    double bni = 0.0;
+    if constexpr (T::MHD) bni = __ldg(bnb + fo);
+    Flux7 fx;
+    riemann_any<RS>(L, lo, bni, eos, fx, AKB_COLD);
+    double *fp = fb + fo;
+    fp[IDN * fsz] = fx.d; fp[ivx * fsz] = fx.mx; fp[ivy * fsz] = fx.my; fp[ivz * fsz] = fx.mz;
+    if constexpr (T::IDEAL) fp[IEN * fsz] = fx.e;
+    if constexpr (T::MHD) { eyb[ca] = fx.ey; ezb[ca] = fx.ez; }
+  }
 }
 template <int RECON, int RS, int SS = MARCH_THREADS>
 __device__ __noinline__ void march_recon_guarded(const double *__restrict__ ring, int b0, EosParams eos, State7 &up) {
   State7 lo;
-  recon_ring_cell<RECON, RS, SS>(ring, b0, eos, up, lo);
+  recon_ring_cell<RECON, RS, SS>(ring, b0, eos, up, lo, AKB_COLD);
 }
 __device__ __forceinline__ void store_left_state(double *lsm, const State7 &s) {
   lsm[0 * MARCH_THREADS] = s.d; lsm[1 * MARCH_THREADS] = s.vx; lsm[2 * MARCH_THREADS] = s.vy; lsm[3 * MARCH_THREADS] = s.vz;
@@ -477,7 +512,95 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
   };
 
   State7 L, lo_unused;
-  if constexpr (RING) {
+  if constexpr (RING && RECON == RECON_PPM4 && ACC == 0 && AKB_MARCH_SHARE) {
+    // PPM4, plain sweep: shared-interface form of the march.  The clamped fourth-order value at the face between cells c and c+1 is
+    // ONE call ppm4_iface(q[c-1], q[c], q[c+1], q[c+2]) whether cell c asks for its upper value or cell c+1 for its lower one -- same
+    // function, same operands in the same order -- so each step evaluates only the interface ABOVE its cell and takes the one below
+    // from the previous step: 7 interface evaluations (division by 12, two clamps, the guard's tests) per face instead of 14.  The
+    // carried values live in the thread's shared memory next to the left state, not in registers (carried in registers the same
+    // idea lost in round 1: 1.05 -> 1.12 ms), and the stencil no longer reaches row c-2, so the ring is 5 rows instead of 6: the
+    // shared-memory footprint per CTA stays (6 NV + 7) x 128 doubles.  Range guard: faces are marked and solved again after the
+    // march (march_fix_faces); a flagged interface taints both cells it belongs to, i.e. faces f, f+1 and f+2.
+    constexpr int NS = 5;
+    constexpr int VS = NS * MARCH_THREADS;
+    double *ring = ring_all + threadIdx.x;
+    double *lsm = ring_all + NV * VS + threadIdx.x;      // left state of the next face
+    double *fsm = lsm + 7 * MARCH_THREADS;               // interface values at the lower face of the next cell
+    // rows f_lo-1 .. f_lo+2 -> slots 0..3 (the first cell's rows c-1 .. c+2); co = cell f_lo-1
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) cp_async8(ring + v * VS + r * MARCH_THREADS, vsrc(v) + (co + r * s));
+    }
+    cp_async_commit();
+    // meanwhile the cell below the first face, straight from global memory: both interfaces, its upper state (the first left
+    // state) and the interface it shares with cell f_lo
+    L.d = L.vx = L.vy = L.vz = L.e = L.by = L.bz = 0.0;
+    auto first_cell = [&](bool *oor) {
+      double *upv[7] = {&L.d, &L.vx, &L.vy, &L.vz, &L.e, &L.by, &L.bz};
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const double *p = vsrc(v) + co;
+        const double qm2 = __ldg(p - 2 * s), qm1 = __ldg(p - s), q = __ldg(p), qp1 = __ldg(p + s), qp2 = __ldg(p + 2 * s);
+        const double fl = ppm4_iface(qm2, qm1, q, qp1, oor), fh = ppm4_iface(qm1, q, qp1, qp2, oor);
+        double lo_v;
+        ppm4_mono(q, fl, fh, *upv[T::member(v)], lo_v);
+        fsm[v * MARCH_THREADS] = fh;
+      }
+    };
+    {
+      bool o0 = false;
+      first_cell(&o0);
+      if (o0) first_cell(AKB_COLD);
+    }
+    store_left_state(lsm, L);
+    cp_async_wait<0>();
+    unsigned fix = 0u;                // faces to be solved again after the march (bit f - f_lo)
+    const int co0 = co, fo0 = fo;     // cell f_lo-1 and face f_lo
+    int b0 = 0;                       // slot of row c-1 for the next cell (c = f_lo)
+    double bn_next = 0.0;
+    if constexpr (MHD) bn_next = __ldg(bnb + fo);
+    for (int f = f_lo; f <= f_hi; ++f) {
+      co += s;                        // cell c = f
+      const double bni = bn_next;
+      if constexpr (MHD) { if (f < f_hi) bn_next = __ldg(bnb + fo + s); }
+      int b1 = b0 + 1; if (b1 >= NS) b1 -= NS;
+      int b2 = b1 + 1; if (b2 >= NS) b2 -= NS;
+      int b3 = b2 + 1; if (b3 >= NS) b3 -= NS;
+      int b4 = b3 + 1; if (b4 >= NS) b4 -= NS;     // held row c-2: free
+      if (f + 1 <= f_hi) {            // row c+3, needed one step from now
+        const int ro = co + 3 * s;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) cp_async8(ring + v * VS + b4 * MARCH_THREADS, vsrc(v) + ro);
+      }
+      cp_async_commit();
+      cp_async_wait<1>();
+      State7 up, lo;
+      Flux7 fx;
+      bool orec = false, orie = false;
+      load_left_state(lsm, L);
+      {
+        double *upv[7] = {&up.d, &up.vx, &up.vy, &up.vz, &up.e, &up.by, &up.bz};
+        double *lov[7] = {&lo.d, &lo.vx, &lo.vy, &lo.vz, &lo.e, &lo.by, &lo.bz};
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const double *rv = ring + v * VS;
+          const double q = rv[b1 * MARCH_THREADS];
+          const double fh = ppm4_iface(rv[b0 * MARCH_THREADS], q, rv[b2 * MARCH_THREADS], rv[b3 * MARCH_THREADS], &orec);
+          ppm4_mono(q, fsm[v * MARCH_THREADS], fh, *upv[T::member(v)], *lov[T::member(v)]);
+          fsm[v * MARCH_THREADS] = fh;
+        }
+      }
+      store_left_state(lsm, up);
+      riemann_any<RS>(L, lo, bni, eos, fx, &orie);
+      fix |= ((orec ? 7u : 0u) | (orie ? 1u : 0u)) << (f - f_lo);     // bits past 31 fall off: those faces belong to the next segment
+      emit(f, fx, co, fo);
+      fo += s;
+      b0 = b1;
+    }
+    cp_async_wait<0>();
+    if (fix) march_fix_faces<RECON, RS, DIR>(fix, f_lo, f_hi, co0, fo0, s, wb, bb, bnb, cc, eos, fb, fsz, eyb, ezb);
+  } else if constexpr (RING) {
     constexpr int VS = MARCH_SLOTS * MARCH_THREADS;
     double *ring = ring_all + threadIdx.x;
     // prologue: rows c-2 .. c+2+PF -> slots 0..S-1 (row c-2 in slot 0), c = f_lo-1
@@ -499,8 +622,10 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       recon_ring_cell<RECON, RS>(ring, 0, eos, L, lo_unused, &oor0);
       if (oor0) { State7 lg; march_recon_guarded<RECON, RS>(ring, 0, eos, lg); L = lg; }
     }
-    double *lsm = ring_all + NV * VS + threadIdx.x;     // this thread's copy of the left state, for the cold path only
+    double *lsm = ring_all + NV * VS + threadIdx.x;     // this thread's copy of the left state
     store_left_state(lsm, L);
+    unsigned fix = 0u;                // faces to be solved again after the march (bit f - f_lo)
+    const int co0 = co, fo0 = fo;     // cell f_lo-1 and face f_lo
     int b0 = 1;                       // slot of row c-2 for the next cell (c = f_lo)
     // the normal field of a face is fetched one step ahead: issued next to its use it was the top stall site of the kernel
     double bn_next = 0.0;
@@ -519,10 +644,26 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       cp_async_commit();
       cp_async_wait<MARCH_PF>();
       State7 up, lo;
+      Flux7 fx;
+      if constexpr (ACC == 0 && !(RECON == RECON_PPM4 && AKB_MARCH_CARRY && MHD && IDEAL)) {
+        // Plain sweep: nothing but the flux of a face leaves the loop body, so a face whose arithmetic raised the range flag is only
+        // MARKED here and solved again after the march (march_fix_faces: both cells re-reconstructed from global memory with the
+        // guarded operators, flux and EMFs stored over the fast ones).  The loop then holds no call -- ptxas spilled ~25 more values
+        // per face around the in-loop repeat, and with 200 KB of the SM's 256 KB carved out for the rings those spills miss L1 --
+        // and the left state travels through the thread's shared-memory copy instead of 14 registers across the Riemann solve.
+        bool orec = false, orie = false;
+        load_left_state(lsm, L);
+        recon_ring_cell<RECON, RS>(ring, b0, eos, up, lo, &orec);
+        store_left_state(lsm, up);
+        riemann_any<RS>(L, lo, bni, eos, fx, &orie);
+        // a flagged reconstruction taints this face (lo) and the next one (up is its left state); bit 32 falls off: that face opens
+        // the next segment, whose thread reconstructs its own left state
+        fix |= ((orec ? 3u : 0u) | (orie ? 1u : 0u)) << (f - f_lo);
+        emit(f, fx, co, fo);
+      } else {
       bool oor = false;
       if constexpr (RECON == RECON_PPM4 && AKB_MARCH_CARRY && MHD && IDEAL) ppm4_ring_cell(ring, b0, fl, up, lo);
       else recon_ring_cell<RECON, RS>(ring, b0, eos, up, lo, &oor);
-      Flux7 fx;
       riemann_any<RS>(L, lo, bni, eos, fx, &oor);
       if (oor) {       // cold: an operand left the fast path's exact range (separate result objects keep up / fx in registers)
         State7 ug; Flux7 fg;
@@ -532,15 +673,19 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       store_left_state(lsm, up);
       emit(f, fx, co, fo);
       L = up;
+      }
       fo += s;
       b0 = (b0 + 1 >= MARCH_SLOTS) ? 0 : b0 + 1;
     }
     cp_async_wait<0>();
+    if constexpr (ACC == 0) {
+      if (fix) march_fix_faces<RECON, RS, DIR>(fix, f_lo, f_hi, co0, fo0, s, wb, bb, bnb, cc, eos, fb, fsz, eyb, ezb);
+    }
   } else {
     {
       bool oor0 = false;
       recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, L, lo_unused, &oor0);
-      if (oor0) recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, L, lo_unused);
+      if (oor0) recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, L, lo_unused, AKB_COLD);
     }
     for (int f = f_lo; f <= f_hi; ++f) {
       co += s;
@@ -552,8 +697,8 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       if constexpr (MHD) bni = __ldg(bnb + fo);
       riemann_any<RS>(L, lo, bni, eos, fx, &oor);
       if (oor) {       // cold: the guarded operators (L was verified when it was computed)
-        recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, up, lo);
-        riemann_any<RS>(L, lo, bni, eos, fx);
+        recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, up, lo, AKB_COLD);
+        riemann_any<RS>(L, lo, bni, eos, fx, AKB_COLD);
       }
       emit(f, fx, co, fo);
       L = up;

@@ -47,11 +47,17 @@ __global__ void selftest_kernel(long n, unsigned long long seed, int span, unsig
     b0 += differ(akb::drcp(b), r_ref);
     b1 += differ(akb::ddiv(a, b), q_ref);
     b2 += differ(akb::dsqrt(sb), s_ref);
+    // AKB_COLD: the operators of the repeat side of the deferred guard (scaled exact division first, the compiler's operator for
+    // what that form flags) must return the IEEE bits for every operand too, signs of zeros included
+    b0 += differ(akb::drcp(b, AKB_COLD), r_ref);
+    b1 += differ(akb::ddiv(a, b, AKB_COLD), q_ref);
+    b2 += differ(akb::dsqrt(sb, AKB_COLD), s_ref);
     {  // div_by: launch-uniform divisors of the path (12, 6 and awkward cell sizes), numerator over the drawn range
       const double ys[6] = {12.0, 6.0, 0.0050781250000000002, 1.0 / 3.0, 0.0129999999999999, 4.19921875};
       volatile double vy = ys[q % 6];
       const double y = vy, ry = 1.0 / vy, d_ref = va / vy;
       b3 += differ(akb::div_by(a, y, ry), d_ref);
+      b3 += differ(akb::div_by(a, y, ry, AKB_COLD), d_ref);
       // deferred form of the guard (flux sweeps, fused stage tail): whenever the flag stays clear the fast result must be the
       // IEEE one (up to the sign of a zero); a set flag sends the caller to the guarded operators checked above
       bool o1 = false, o2 = false, o3 = false, o4 = false;

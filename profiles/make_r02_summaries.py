@@ -54,6 +54,13 @@ for tag, fn in (("cp.async", "r02_flux_counts.csv"), ("tma", "r02_flux_counts_tm
         txt.append(f"{name:44s} {rec['ms_ncu']:.3f} ms  regs {rec['registers']:.0f}  warp-inst {rec['warp_inst']:.3e}  FP64 warp-inst {rec['fp64_warp_inst']:.3e} "
                    f"({100 * rec['fp64_warp_inst'] / rec['warp_inst']:.0f}%)  FP64 pipe {rec['fp64_pipe_pct_ncu']:.1f}%  warps active {rec['warps_active_pct']:.1f}%  "
                    f"DRAM {rec['dram_read_GB']:.3f} + {rec['dram_write_GB']:.3f} GB")
+        if "sass__inst_executed_local_loads" in e:      # later captures: spill traffic and the two dominant stall reasons
+            rec["local_loads"] = e["sass__inst_executed_local_loads"]; rec["local_stores"] = e["sass__inst_executed_local_stores"]
+            rec["stall_long_scoreboard"] = e.get("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio")
+            rec["stall_wait"] = e.get("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio")
+            rec["issue_active_pct"] = e.get("sm__issue_active.avg.pct_of_peak_sustained_elapsed")
+            txt.append(f"{'':44s} local loads {rec['local_loads']:.3e}  local stores {rec['local_stores']:.3e}  stalls per issue: long scoreboard "
+                       f"{rec['stall_long_scoreboard']:.2f}, wait {rec['stall_wait']:.2f}  issue active {rec['issue_active_pct']:.1f}%")
         if tag == "cp.async":
             out[name] = rec
 open(os.path.join(ROOT, "profiles", "r02_flux_counts.txt"), "w").write("\n".join(txt) + "\n")

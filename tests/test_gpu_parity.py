@@ -402,6 +402,47 @@ def test_fluxes_bitwise_with_values_at_the_denormal_floor(recon, rs, nb):
     compare("unscaled state afterwards")
 
 
+@pytest.mark.parametrize("nx", [(12, 40, 36), (70, 34, 8)])
+def test_repeat_side_of_the_range_guard_across_march_segments(nx):
+    """Repeat side of the sweeps' deferred range guard (x1: whole-warp repeat; x2/x3: faces marked during the march and solved
+    again afterwards by march_fix_faces, a flagged reconstruction marking the next face too) on extents whose x2/x3 marches are
+    cut into two segments (41, 37, 35 faces), random states with velocities and transverse fields scaled to the denormal floor,
+    to exact zeros and to subnormals cell by cell: every flux and face EMF equals the oracle's IEEE arithmetic bit for bit."""
+    L = O.lib()
+    rng = np.random.default_rng(17)
+    cfg = O.make_cfg(1, 4, nx, "ppm4", "hlld")
+    A = O.Arrays(cfg)
+    A.w0[:] = rng.uniform(-1.0, 1.0, A.w0.shape)
+    A.w0[:, 0] = rng.uniform(0.5, 2.0, A.w0[:, 0].shape)
+    A.w0[:, 4] = rng.uniform(0.5, 2.0, A.w0[:, 4].shape)
+    A.bcc0[:] = rng.uniform(-1.0, 1.0, A.bcc0.shape)
+    for b in A.b0:
+        b[:] = rng.uniform(-1.0, 1.0, b.shape)
+    shp = A.w0.shape[2:]
+    scale = 10.0 ** rng.choice([0.0, 0.0, 0.0, -155.0, -162.0, -300.0, -310.0, -320.0], size=shp)
+    scale[rng.uniform(size=shp) < 0.1] = 0.0
+    A.w0[:, 1:4] *= scale
+    A.bcc0[:, 1:3] *= scale
+    _, ngh, mbs, _ = O.uniform_mesh(nx, nx)
+    L.oracle_fluxes(C.byref(cfg), O.p(A.w0), O.p(A.bcc0), *[O.p(a) for a in A.b0], *[O.p(a) for a in A.flx], *[O.p(a) for a in A.fe])
+    drv = FakeDriver(0.25, 0.75, 0.25, 1.0e-3)
+    e = make_engine(A, ngh, mbs, "ppm4", "hlld")
+    for t in e.uflx + e.femf:
+        t.fill_(float("nan"))
+    e.Fluxes(drv, 2)
+    torch.cuda.synchronize()
+    ng = cfg.ng
+    for q in range(3):
+        got = e.uflx[q].cpu().numpy()
+        w = ~np.isnan(got)
+        assert w.any() and np.array_equal(got[w], A.flx[q][w]), f"flux x{q + 1}"
+        assert not np.isnan(got[:, :, ng:-ng, ng:-ng, ng:-ng]).any()
+    for q in range(6):
+        got = e.femf[q].cpu().numpy()
+        w = ~np.isnan(got)
+        assert w.any() and np.array_equal(got[w], A.fe[q][w]), f"face emf {q}"
+
+
 @pytest.mark.parametrize("nx", [(64, 12, 12), (126, 8, 10), (200, 6, 6)])
 def test_tma_march_kernel_bitwise(nx):
     """flux_march_tma_kernel (x2/x3 sweeps, ring rows fetched by cp.async.bulk / TMA, one issuing thread per CTA) against the
