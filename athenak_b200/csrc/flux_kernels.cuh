@@ -526,12 +526,16 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
     double *ring = ring_all + threadIdx.x;
     double *lsm = ring_all + NV * VS + threadIdx.x;      // left state of the next face
     double *fsm = lsm + 7 * MARCH_THREADS;               // interface values at the lower face of the next cell
+    // the face-normal field of the next face, fetched like the rows (two alternating slots).  As a register prefetch (__ldg one
+    // step ahead) the value was spilled the moment it was loaded and the STL waited out the load: 10 % of the kernel's stall samples
+    double *bsm = fsm + NV * MARCH_THREADS;
     // rows f_lo-1 .. f_lo+2 -> slots 0..3 (the first cell's rows c-1 .. c+2); co = cell f_lo-1
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) cp_async8(ring + v * VS + r * MARCH_THREADS, vsrc(v) + (co + r * s));
     }
+    if constexpr (MHD) cp_async8(bsm, bnb + fo);
     cp_async_commit();
     // meanwhile the cell below the first face, straight from global memory: both interfaces, its upper state (the first left
     // state) and the interface it shares with cell f_lo
@@ -556,25 +560,25 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
     store_left_state(lsm, L);
     cp_async_wait<0>();
     unsigned fix = 0u;                // faces to be solved again after the march (bit f - f_lo)
-    const int co0 = co, fo0 = fo;     // cell f_lo-1 and face f_lo
     int b0 = 0;                       // slot of row c-1 for the next cell (c = f_lo)
-    double bn_next = 0.0;
-    if constexpr (MHD) bn_next = __ldg(bnb + fo);
+    int bslot = 0;                    // slot of this face's normal field
     for (int f = f_lo; f <= f_hi; ++f) {
       co += s;                        // cell c = f
-      const double bni = bn_next;
-      if constexpr (MHD) { if (f < f_hi) bn_next = __ldg(bnb + fo + s); }
       int b1 = b0 + 1; if (b1 >= NS) b1 -= NS;
       int b2 = b1 + 1; if (b2 >= NS) b2 -= NS;
       int b3 = b2 + 1; if (b3 >= NS) b3 -= NS;
       int b4 = b3 + 1; if (b4 >= NS) b4 -= NS;     // held row c-2: free
-      if (f + 1 <= f_hi) {            // row c+3, needed one step from now
+      if (f + 1 <= f_hi) {            // row c+3 and the normal field of face f+1, needed one step from now
         const int ro = co + 3 * s;
 #pragma unroll
         for (int v = 0; v < NV; ++v) cp_async8(ring + v * VS + b4 * MARCH_THREADS, vsrc(v) + ro);
+        if constexpr (MHD) cp_async8(bsm + (bslot ^ 1) * MARCH_THREADS, bnb + fo + s);
       }
       cp_async_commit();
       cp_async_wait<1>();
+      double bni = 0.0;
+      if constexpr (MHD) bni = bsm[bslot * MARCH_THREADS];
+      bslot ^= 1;
       State7 up, lo;
       Flux7 fx;
       bool orec = false, orie = false;
@@ -599,7 +603,10 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       b0 = b1;
     }
     cp_async_wait<0>();
-    if (fix) march_fix_faces<RECON, RS, DIR>(fix, f_lo, f_hi, co0, fo0, s, wb, bb, bnb, cc, eos, fb, fsz, eyb, ezb);
+    if (fix) {     // co / fo have advanced by one row per face: cell f_lo-1 and face f_lo are that many rows back
+      const int nrow = (f_hi - f_lo + 1) * s;
+      march_fix_faces<RECON, RS, DIR>(fix, f_lo, f_hi, co - nrow, fo - nrow, s, wb, bb, bnb, cc, eos, fb, fsz, eyb, ezb);
+    }
   } else if constexpr (RING) {
     constexpr int VS = MARCH_SLOTS * MARCH_THREADS;
     double *ring = ring_all + threadIdx.x;
@@ -995,8 +1002,8 @@ static cudaError_t launch_fluxes_t(const Geom &g, const EosParams &eos, const Ar
   }
   AccArgs acc{};
   if (ACC) acc = *accp;
-  // ring + left-state copy (5-point reconstructions), + the previous face's fluxes (ACC)
-  const size_t smem = sizeof(double) * (((RECON >= RECON_PPM4) ? (NV * MARCH_SLOTS + 7) : 0) + (ACC ? 5 : 0)) * MARCH_THREADS;
+  // ring + left-state copy (5-point reconstructions), + the previous face's fluxes (ACC) or two slots of the face-normal field (plain PPM4 march)
+  const size_t smem = sizeof(double) * (((RECON >= RECON_PPM4) ? (NV * MARCH_SLOTS + 7) : 0) + (ACC ? 5 : 2)) * MARCH_THREADS;
   // TMA form of the marches (flux_march_tma_kernel): rows fetched by bulk copies; needs 16-byte aligned rows (n1 even, aligned bases)
   const size_t smem_tma = sizeof(double) * ((size_t)NV * MARCH_SLOTS * MARCH_RB + 7 * MARCH_THREADS) + sizeof(unsigned long long) * MARCH_SLOTS;
   const bool tma = march_tma_flag() && (g.n1 % 2 == 0) && (g.nx1 + 2 * g.ext1 >= 64) && ((((uintptr_t)a.w0) | ((uintptr_t)a.bcc0)) & 15) == 0 && RECON == RECON_PPM4 && !ACC;

@@ -13,7 +13,10 @@ def load(path):
     d = collections.OrderedDict()
     for r in rows[1:]:
         e = d.setdefault(r[iid], {"kernel": r[ik], "grid": r[ig]})
-        e[r[im]] = float(r[iv].replace(",", ""))
+        try:
+            e[r[im]] = float(r[iv].replace(",", ""))
+        except ValueError:      # "n/a": a metric this ncu build does not collect
+            pass
     return list(d.values())
 
 def short(k):
