@@ -70,12 +70,14 @@ halo_copy_kernel(const HaloDesc *__restrict__ descs, const int2 *__restrict__ ti
   double *arr = A.p[c];
   const long e1 = A.ext1[c], e2 = A.ext2[c], bs = A.bstride[c];
   const long qend = ((long)(tl.y + 1) * HALO_TILE < total) ? (long)(tl.y + 1) * HALO_TILE : total;
-  for (long q = (long)tl.y * HALO_TILE + threadIdx.x; q < qend; q += blockDim.x) {
-    long t = q;
-    const int i = (int)(t % ni); t /= ni;
-    const int j = (int)(t % nj); t /= nj;
-    const int k = (int)(t % nk);
-    const int v = (int)(t / nk);
+  // 32-bit index decode: a slab holds far fewer than 2^31 elements (checked by the launcher); the 64-bit divisions of the first
+  // version were most of the kernel's instructions
+  for (unsigned q = (unsigned)tl.y * HALO_TILE + threadIdx.x; q < (unsigned)qend; q += blockDim.x) {
+    unsigned t = q;
+    const int i = (int)(t % (unsigned)ni); t /= (unsigned)ni;
+    const int j = (int)(t % (unsigned)nj); t /= (unsigned)nj;
+    const int k = (int)(t % (unsigned)nk);
+    const int v = (int)(t / (unsigned)nk);
     const long a_idx = ((long)(d.lo[2] + k) * e2 + (d.lo[1] + j)) * e1 + (d.lo[0] + i) + v * varstride;
     const long base = (d.comp < 0) ? d.boff * nvar + v * per : d.boff;
     if (mode == HALO_LOCAL) {
@@ -407,6 +409,7 @@ static cudaError_t tile_table(HaloPlan *P, const std::vector<Desc> &host, const 
   std::vector<int2> t;
   for (size_t q = 0; q < host.size(); ++q) {
     const long total = count(host[q]);
+    if (total >= 0x7fffffffL) return cudaErrorInvalidConfiguration;      // the kernels decode element indices in 32 bits
     for (long c = 0; c * HALO_TILE < total; ++c) t.push_back(make_int2((int)q, (int)c));
   }
   HaloPlan::TileTab tab;
@@ -470,12 +473,12 @@ halo_push_kernel(const PushDesc *__restrict__ descs, const int2 *__restrict__ ti
   const long e1 = A.ext1[c], e2 = A.ext2[c];
   const long total = per * (cc ? nvar : 1);
   const long qend = ((long)(tl.y + 1) * HALO_TILE < total) ? (long)(tl.y + 1) * HALO_TILE : total;
-  for (long q = (long)tl.y * HALO_TILE + threadIdx.x; q < qend; q += blockDim.x) {
-    long t = q;
-    const int i = (int)(t % ni); t /= ni;
-    const int j = (int)(t % nj); t /= nj;
-    const int k = (int)(t % nk);
-    const long v = (t / nk) * (cc ? varstride : 0);
+  for (unsigned q = (unsigned)tl.y * HALO_TILE + threadIdx.x; q < (unsigned)qend; q += blockDim.x) {     // 32-bit decode, see halo_copy_kernel
+    unsigned t = q;
+    const int i = (int)(t % (unsigned)ni); t /= (unsigned)ni;
+    const int j = (int)(t % (unsigned)nj); t /= (unsigned)nj;
+    const int k = (int)(t % (unsigned)nk);
+    const long v = (long)(t / (unsigned)nk) * (cc ? varstride : 0);
     dst[((long)(d.dlo[2] + k) * e2 + (d.dlo[1] + j)) * e1 + (d.dlo[0] + i) + v] =
         src[((long)(d.lo[2] + k) * e2 + (d.lo[1] + j)) * e1 + (d.lo[0] + i) + v];
   }
