@@ -35,14 +35,15 @@ def test_guard_free_division_reproduces_the_gpu_difference_and_the_guard_removes
 
 
 def test_device_division_has_the_guard_at_every_site():
-    """The range guard lives inside ddiv / drcp / dsqrt (one policy for every call site) and is on by default."""
+    """The range guard lives inside ddiv / drcp / dsqrt (one policy for every call site) and is on by default; the repeat paths'
+    AKB_COLD mode (scaled exact division first) ends in the same cold operators."""
     src = open(os.path.join(os.path.dirname(TOOL), "..", "..", "athenak_b200", "csrc", "mhd_device.cuh")).read()
     assert re.search(r"#ifndef AKB_DIV_GUARD\s*\n#define AKB_DIV_GUARD 1", src)
     for fn, cold in (("double drcp(", "drcp_cold(x)"), ("double ddiv(", "ddiv_cold(a, b)"), ("double dsqrt(", "dsqrt_cold(x)")):
         body = src[src.index(fn):src.index(fn) + 1800]
         assert "#if AKB_DIV_GUARD" in body and cold in body, fn
     plm = src[src.index("void plm("):src.index("// ppm.hpp:44-77")]
-    assert "ddiv(dq2, dql + dqr, &o)" in plm and "ddiv(dq2, dql + dqr)" in plm and " / " not in "\n".join(l.split("//")[0] for l in plm.splitlines())
+    assert "ddiv(dq2, dql + dqr, &o)" in plm and "ddiv(dq2, dql + dqr, oor)" in plm and " / " not in "\n".join(l.split("//")[0] for l in plm.splitlines())
     # no call site may bypass the guard: every division / reciprocal / square root of the device arithmetic goes through the
     # guarded helpers (the cold helpers themselves, host-uniform constants and comments excepted)
     for name in ("mhd_device.cuh", "hydro_device.cuh", "iso_device.cuh", "c2p_device.cuh"):
