@@ -704,22 +704,32 @@ flux_march_kernel(Geom g, EosParams eos, const double *__restrict__ w0, const do
       recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, L, lo_unused, &oor0);
       if (oor0) recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, L, lo_unused, AKB_COLD);
     }
+    unsigned fix = 0u;                // plain sweep: faces to be solved again after the march (bit f - f_lo), as in the ring forms
+    const int co0 = co, fo0 = fo;     // cell f_lo-1 and face f_lo
     for (int f = f_lo; f <= f_hi; ++f) {
       co += s;
       State7 up, lo;
-      bool oor = false;
-      recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, up, lo, &oor);
+      bool orec = false, orie = false;
+      recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, up, lo, &orec);
       Flux7 fx;
       double bni = 0.0;
       if constexpr (MHD) bni = __ldg(bnb + fo);
-      riemann_any<RS>(L, lo, bni, eos, fx, &oor);
-      if (oor) {       // cold: the guarded operators (L was verified when it was computed)
-        recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, up, lo, AKB_COLD);
-        riemann_any<RS>(L, lo, bni, eos, fx, AKB_COLD);
+      riemann_any<RS>(L, lo, bni, eos, fx, &orie);
+      if constexpr (ACC == 0) {
+        // a flagged reconstruction taints this face (lo) and the next one (up is its left state)
+        fix |= ((orec ? 3u : 0u) | (orie ? 1u : 0u)) << (f - f_lo);
+      } else {
+        if (orec | orie) {       // fusion: the result feeds this step's divergence term, repeat in place (L was verified when it was computed)
+          recon_cell<RECON, DIR, MHD, IDEAL>(wb + co, bb + co, cc, s, eos, up, lo, AKB_COLD);
+          riemann_any<RS>(L, lo, bni, eos, fx, AKB_COLD);
+        }
       }
       emit(f, fx, co, fo);
       L = up;
       fo += s;
+    }
+    if constexpr (ACC == 0) {
+      if (fix) march_fix_faces<RECON, RS, DIR>(fix, f_lo, f_hi, co0, fo0, s, wb, bb, bnb, cc, eos, fb, fsz, eyb, ezb);
     }
   }
 }
