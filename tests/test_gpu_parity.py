@@ -402,12 +402,14 @@ def test_fluxes_bitwise_with_values_at_the_denormal_floor(recon, rs, nb):
     compare("unscaled state afterwards")
 
 
+@pytest.mark.parametrize("pattern", ["cells", "slab"])
 @pytest.mark.parametrize("nx", [(12, 40, 36), (70, 34, 8)])
-def test_repeat_side_of_the_range_guard_across_march_segments(nx):
+def test_repeat_side_of_the_range_guard_across_march_segments(nx, pattern):
     """Repeat side of the sweeps' deferred range guard (x1: whole-warp repeat; x2/x3: faces marked during the march and solved
     again afterwards by march_fix_faces, a flagged reconstruction marking the next face too) on extents whose x2/x3 marches are
     cut into two segments (41, 37, 35 faces), random states with velocities and transverse fields scaled to the denormal floor,
-    to exact zeros and to subnormals cell by cell: every flux and face EMF equals the oracle's IEEE arithmetic bit for bit."""
+    to exact zeros and to subnormals cell by cell ("cells") or over a contiguous slab ("slab": whole warps at the floor, which skip
+    the fast Riemann solve): every flux and face EMF equals the oracle's IEEE arithmetic bit for bit."""
     L = O.lib()
     rng = np.random.default_rng(17)
     cfg = O.make_cfg(1, 4, nx, "ppm4", "hlld")
@@ -419,8 +421,15 @@ def test_repeat_side_of_the_range_guard_across_march_segments(nx):
     for b in A.b0:
         b[:] = rng.uniform(-1.0, 1.0, b.shape)
     shp = A.w0.shape[2:]
-    scale = 10.0 ** rng.choice([0.0, 0.0, 0.0, -155.0, -162.0, -300.0, -310.0, -320.0], size=shp)
-    scale[rng.uniform(size=shp) < 0.1] = 0.0
+    if pattern == "cells":
+        scale = 10.0 ** rng.choice([0.0, 0.0, 0.0, -155.0, -162.0, -300.0, -310.0, -320.0], size=shp)
+        scale[rng.uniform(size=shp) < 0.1] = 0.0
+    else:
+        # a contiguous slab at the denormal floor (the blast's far-field shell): whole warps predict the repeat and skip the fast
+        # Riemann solve (at_floor, flux_kernels.cuh); its borders, a zero layer and the untouched half exercise the mixed warps
+        scale = np.ones(shp)
+        scale[shp[0] // 3:, shp[1] // 4:, :] = 10.0 ** rng.choice([-296.0, -300.0, -305.0], size=(shp[0] - shp[0] // 3, shp[1] - shp[1] // 4, shp[2]))
+        scale[-3:, :, :] = 0.0
     A.w0[:, 1:4] *= scale
     A.bcc0[:, 1:3] *= scale
     _, ngh, mbs, _ = O.uniform_mesh(nx, nx)
